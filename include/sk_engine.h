@@ -1,0 +1,269 @@
+/* sk_engine.h -- C ABI of the B200 photon-packet life-cycle engine (libskirt9_b200.so).
+ *
+ * This is the drop-in boundary for the one hot path of SKIRT 9 that this repository accelerates:
+ * MonteCarloSimulation::performLifeCycle() and everything it calls.  The
+ * reference has no C ABI of its own; the seam is the six call sites
+ *     parallel->call(Npp, [this](size_t i, size_t n){ performLifeCycle(i, n, primary, peel, store); })
+ * in SKIRT/core/MonteCarloSimulation.cpp:126-128,165-166,314,381,451,474, each followed by
+ * instrumentSystem()->flush(), wait() and mediumSystem()->communicateRadiationField().  Every entry
+ * point below names the reference function(s) whose work it takes over (paths relative to the
+ * reference root).  INTEGRATION.md shows the C++ shim a SKIRT maintainer would add on their side.
+ *
+ * Conventions: plain C types only; the caller owns every input array (the engine copies it to the
+ * device during the call); outputs are copied into caller-allocated host buffers; every function
+ * returns SK_OK or an error code and sk_last_error() gives the message (the reference throws
+ * FatalError; the shim rethrows).  All quantities are SI (m, W, rad), exactly the internal units of
+ * the reference.  All entry points are to be called from one host thread (the reference calls MPI
+ * from the parent thread only, SKIRT/mpi/ProcessManager.cpp:45).  There is NO CPU fallback: if no
+ * CUDA device is present sk_engine_create() fails with SK_ERR_CUDA.
+ *
+ * The same structs and the same function set (prefix sko_ instead of sk_engine_) are implemented by
+ * the CPU oracle in oracle/sk_oracle.c, which is test infrastructure only.
+ */
+#ifndef SK_ENGINE_H
+#define SK_ENGINE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SK_ABI_VERSION 1
+
+typedef struct sk_engine sk_engine_t;
+
+enum sk_status {
+    SK_OK = 0,
+    SK_ERR_INVALID = 1,     /* bad argument (reference: FATALERROR in setup) */
+    SK_ERR_UNSUPPORTED = 2, /* configuration outside the accelerated path (SURVEY.md 8a "OUT OF SCOPE") */
+    SK_ERR_CUDA = 3,        /* CUDA runtime failure / no device */
+    SK_ERR_STATE = 4        /* call sequence violated (e.g. run before grid/medium/sources are set) */
+};
+
+/* ---- Configuration: the digest of SKIRT/core/Configuration.cpp:30-377 the hot path reads ------- */
+typedef struct sk_config {
+    uint32_t seed;               /* Random::seed() (SKIRT/core/Random.hpp); Philox key word 0 */
+    int32_t force_scattering;    /* Configuration::forceScattering() (PhotonPacketOptions.hpp:63) */
+    int32_t min_scatt_events;    /* Configuration::minScattEvents() (PhotonPacketOptions.hpp:75) */
+    double path_length_bias;     /* Configuration::pathLengthBias() (PhotonPacketOptions.hpp:83) */
+    double min_weight_reduction; /* Configuration::minWeightReduction() (PhotonPacketOptions.hpp:69) */
+    int32_t device;              /* CUDA device ordinal this engine instance owns (one engine per GPU) */
+    int32_t reserved;
+} sk_config_t;
+
+/* ---- Wavelength grids: DisjointWavelengthGrid::bin (DisjointWavelengthGrid.cpp:332-341) -------- */
+typedef struct sk_wavelength_grid {
+    int32_t num_bins;       /* N = numBins() */
+    int32_t num_borders;    /* K = size of _borderv (N+1, or 2N for disjoint bins) */
+    const double* borders;  /* [K] ascending, DisjointWavelengthGrid::_borderv */
+    const int32_t* ell;     /* [K+1] DisjointWavelengthGrid::_ellv : border index -> bin index or -1 */
+    const double* lambda;   /* [N] characteristic wavelengths, _lambdav */
+    const double* dlambda;  /* [N] effective widths, _dlambdav */
+} sk_wavelength_grid_t;
+
+/* ---- Dust mix: DustMix tables (DustMix.cpp:47-246) for the Henyey-Greenstein scattering mode ---- */
+typedef struct sk_dustmix {
+    int32_t num_lambda;          /* size of the property grid */
+    int32_t reserved;
+    const double* lambda_border; /* [n] DustMix::_lambdav (geometric-mean borders, DustMix.cpp:91-98) */
+    const double* sigma_abs;     /* [n] DustMix::_sigmaabsv  (m2 per entity) */
+    const double* sigma_sca;     /* [n] DustMix::_sigmascav */
+    const double* asymmpar;      /* [n] DustMix::_asymmparv (already clamped to +-0.999999, DustMix.cpp:139-146) */
+    double mu;                   /* MaterialMix::mass(): dust mass per entity (kg) */
+} sk_dustmix_t;
+
+/* ---- Sources: SourceSystem / NormalizedSource / GeometricSource / PointSource ------------------- */
+enum sk_source_kind { SK_SRC_POINT = 1, SK_SRC_GEOMETRIC = 2 };
+enum sk_geometry_kind {
+    SK_GEOM_NONE = 0,
+    SK_GEOM_SHELL = 1,          /* ShellGeometry.cpp:14-28,43-57 p = {rmin, rmax, exponent, _smin, _sdiff, _tmin, _tmax} */
+    SK_GEOM_EXPDISK = 2,        /* ExpDiskGeometry.cpp:46-68   p = {hR, hz, Rmin, Rmax, zmax} */
+    SK_GEOM_RING = 3,           /* RingGeometry.cpp:56-68      p = {R0, w, hz} + radial cdf table */
+    SK_GEOM_SPIRAL_EXPDISK = 4  /* SpiralStructureGeometryDecorator.cpp:33-45,72-76 on ExpDisk:
+                                   p = {hR, hz, Rmin, Rmax, zmax, m(arms), pitch, R0, phi0, w, N(index)} */
+};
+enum sk_sed_kind {
+    SK_SED_TABULATED = 1, /* specificLuminosity by log-log interpolation of (lambda,p) (TabulatedSED) */
+    SK_SED_BLACKBODY = 2  /* specificLuminosity = Planck(lambda,T)/Ltot (BlackBodySED.cpp:38-41) */
+};
+enum sk_bias_kind {
+    SK_BIAS_NONE = 0,
+    SK_BIAS_LOGUNIFORM = 1, /* DefaultWavelengthDistribution.cpp:12-40  range = {min,max} */
+    SK_BIAS_OLIGO = 2       /* OligoWavelengthDistribution.cpp:13-38    discrete wavelengths */
+};
+#define SK_GEOM_MAX_PARAMS 12
+typedef struct sk_source {
+    int32_t kind;                /* sk_source_kind */
+    int32_t geometry;            /* sk_geometry_kind (SK_SRC_GEOMETRIC only) */
+    double luminosity;           /* Source::luminosity() (W) */
+    double source_weight;        /* Source::sourceWeight() */
+    double position[3];          /* PointSource position */
+    double geom_params[SK_GEOM_MAX_PARAMS];
+    int32_t geom_table_n;        /* RingGeometry::_Rv/_Xv size (0 if none) */
+    int32_t sed_kind;            /* sk_sed_kind */
+    const double* geom_table_x;  /* [geom_table_n] */
+    const double* geom_table_P;  /* [geom_table_n] */
+    int32_t sed_n;               /* size of the SED cdf tables */
+    int32_t bias_kind;           /* sk_bias_kind */
+    const double* sed_lambda;    /* [sed_n] SED::_lambdav */
+    const double* sed_p;         /* [sed_n] normalised pdf _pv */
+    const double* sed_P;         /* [sed_n] normalised cdf _Pv */
+    double sed_temperature;      /* blackbody T (K) */
+    double sed_norm;             /* blackbody: _Ltot of BlackBodySED.cpp:16 */
+    double wavelength_bias;      /* NormalizedSource::_xi (forced to 1 for oligochromatic) */
+    double bias_min, bias_max;   /* log-uniform bias distribution range */
+    int32_t oligo_n;             /* number of discrete wavelengths */
+    int32_t reserved;
+    const double* oligo_lambda;  /* [oligo_n] */
+    double oligo_probability;    /* OligoWavelengthDistribution::_probability */
+} sk_source_t;
+
+/* ---- Instruments: DistantInstrument / SEDInstrument / FrameInstrument / FullInstrument --------- */
+enum sk_instrument_kind { SK_INSTR_SED = 1, SK_INSTR_FRAME = 2, SK_INSTR_FULL = 3 };
+typedef struct sk_instrument {
+    int32_t kind;                   /* sk_instrument_kind */
+    int32_t wavelength_grid;        /* index into the grids given to sk_engine_set_wavelength_grids */
+    double inclination, azimuth, roll; /* rad (DistantInstrument.cpp:39-50) */
+    double distance;                /* m */
+    double radius;                  /* aperture radius (SEDInstrument / ApertureInstrument.cpp:24-43); 0 = none */
+    int32_t num_pixels_x, num_pixels_y;
+    double field_of_view_x, field_of_view_y, center_x, center_y; /* FrameInstrument.cpp:12-32 */
+    int32_t record_components;      /* Instrument::recordComponents */
+    int32_t num_scattering_levels;  /* Instrument::numScatteringLevels */
+    int32_t record_statistics;      /* Instrument::recordStatistics (SED bins; FluxRecorder.cpp:457-466) */
+    int32_t reserved;
+} sk_instrument_t;
+
+/* Detector array ids: the enum of SKIRT/core/FluxRecorder.cpp:26-56 without the polarisation entries. */
+enum sk_component {
+    SK_COMP_TOTAL = 0,
+    SK_COMP_TRANSPARENT = 1,
+    SK_COMP_PRIMARY_DIRECT = 2,
+    SK_COMP_PRIMARY_SCATTERED = 3,
+    SK_COMP_SECONDARY_DIRECT = 4,
+    SK_COMP_SECONDARY_SCATTERED = 5,
+    SK_COMP_SECONDARY_TRANSPARENT = 6,
+    SK_COMP_PRIMARY_SCATTERED_LEVEL = 7 /* + level-1 */
+};
+
+/* ---- Secondary (dust) emission: DustSecondarySource + EquilibriumDustEmissionCalculator -------- */
+typedef struct sk_secondary {
+    int32_t emission_grid;     /* wavelength grid index of Configuration::dustEmissionWLG() */
+    int32_t reserved;
+    double spatial_bias;       /* SecondaryEmissionOptions::spatialBias (DustSecondarySource.cpp:118-146) */
+    double wavelength_bias;    /* DustEmissionOptions::wavelengthBias */
+    double bias_min, bias_max; /* log-uniform bias distribution range (source wavelength range) */
+    double source_min, source_max; /* Configuration::sourceWavelengthRange: emission outside is suppressed */
+} sk_secondary_t;
+
+/* ---- Device-side event counters (the engine must count S, S_fwd, P_peel itself) -- */
+typedef struct sk_counters {
+    uint64_t packets;        /* histories launched with L > 0 */
+    uint64_t forward_paths;  /* setExtinctionOpticalDepths calls */
+    uint64_t forward_segments;
+    uint64_t replay_segments;/* segments re-walked to the interaction point (engine-internal; not algorithmic) */
+    uint64_t peel_paths;     /* getExtinctionOpticalDepth calls */
+    uint64_t peel_segments;
+    uint64_t scatterings;    /* simulateScattering calls */
+    uint64_t rf_deposits;    /* MediumSystem::storeRadiationField calls */
+    uint64_t detections;     /* FluxRecorder::detect calls that recorded */
+    uint64_t fallbacks;      /* tree: top-down relocations after a failed neighbour link */
+    uint64_t reserved[6];
+} sk_counters_t;
+
+/* ---- life cycle of the engine object ---------------------------------------------------------- */
+int sk_abi_version(void);
+const char* sk_last_error(void);
+
+/* Replaces nothing in the reference; allocates the per-GPU context the shim keeps next to
+ * MonteCarloSimulation (one engine per CUDA device / rank). */
+int sk_engine_create(const sk_config_t* config, sk_engine_t** out);
+void sk_engine_destroy(sk_engine_t* e);
+
+/* CartesianSpatialGrid::_xv/_yv/_zv (CartesianSpatialGrid.cpp:22-60); cell index m = k + Nz*j + Nz*Ny*i
+ * (CartesianSpatialGrid.cpp:210-213).  xv has nx+1 ascending borders, etc. */
+int sk_engine_set_grid_cartesian(sk_engine_t* e, int32_t nx, int32_t ny, int32_t nz, const double* xv,
+                                 const double* yv, const double* zv);
+
+/* TreeSpatialGrid::_nodev for an OctTreeNode tree (TreeSpatialGrid.cpp:33-49, OctTreeNode.cpp:22-35):
+ * extent = {xmin,ymin,zmin,xmax,ymax,zmax} of the root; first_child[l] = node index of the first of
+ * the 8 consecutive children of node l (child order OctTreeNode.cpp:22-35), or -1 when node l is a leaf.
+ * Cell index m = rank of the leaf in node order (TreeSpatialGrid::_cellindexv).  The engine derives its
+ * own device layout (lattice border tables, per-cell neighbour links) from this. */
+int sk_engine_set_grid_octree(sk_engine_t* e, const double extent[6], int32_t num_nodes, const int32_t* first_child);
+
+/* MediumState number densities and volumes for a single medium component
+ * (MediumState::numberDensity(m,0), MediumState::volume(m); MediumState.cpp:196-247). */
+int sk_engine_set_medium(sk_engine_t* e, int32_t num_cells, const double* number_density, const double* volume);
+
+int sk_engine_set_dustmix(sk_engine_t* e, const sk_dustmix_t* mix);
+
+/* All wavelength grids used by instruments, the radiation field and dust emission, addressed by index.
+ * rf_grid = index of Configuration::radiationFieldWLG() or -1 when no radiation field is stored. */
+int sk_engine_set_wavelength_grids(sk_engine_t* e, int32_t n, const sk_wavelength_grid_t* grids, int32_t rf_grid);
+
+/* SourceSystem::setupSelfAfter (SourceSystem.cpp:14-41): sources + SourceSystem::sourceBias(). */
+int sk_engine_set_sources(sk_engine_t* e, int32_t n, const sk_source_t* sources, double source_bias);
+
+/* InstrumentSystem::instruments(); allocates and zeroes the detector arrays
+ * (FluxRecorder::finalizeConfiguration, FluxRecorder.cpp:185-300).  has_medium_emission mirrors
+ * Instrument.cpp:23 (secondary component arrays exist only then). */
+int sk_engine_set_instruments(sk_engine_t* e, int32_t n, const sk_instrument_t* instruments, int32_t has_medium_emission);
+
+int sk_engine_set_secondary(sk_engine_t* e, const sk_secondary_t* sec);
+
+/* MediumSystem::clearRadiationField(primary) (MediumSystem.cpp:1279-1290). */
+int sk_engine_clear_rf(sk_engine_t* e, int32_t primary);
+
+/* SourceSystem::prepareForLaunch(numPackets) (SourceSystem.cpp:75-97). */
+int sk_engine_prepare_primary(sk_engine_t* e, uint64_t num_packets);
+
+/* SecondarySourceSystem::prepareForLaunch + DustSecondarySource::prepareLuminosities/preparePacketMap
+ * (SecondarySourceSystem.cpp:84-126, DustSecondarySource.cpp:26-146); computed on the device from the
+ * current radiation field.  Returns the total dust luminosity (W) in *luminosity. */
+int sk_engine_prepare_secondary(sk_engine_t* e, uint64_t num_packets, double* luminosity);
+
+/* THE hot path: performLifeCycle(firstIndex, numIndices, primary, peel, store)
+ * (MonteCarloSimulation.cpp:538-613) for histories [first, first+count) of the segment prepared by
+ * sk_engine_prepare_*; stream_id distinguishes the random streams of successive segments (Philox key
+ * word 1).  Returns after the device has finished (same semantics as Parallel::call returning) and
+ * includes InstrumentSystem::flush() (FluxRecorder.cpp:472-480). */
+int sk_engine_run_segment(sk_engine_t* e, uint64_t first, uint64_t count, int32_t primary, int32_t peel,
+                          int32_t store, uint32_t stream_id);
+/* Same, but only enqueues the work on the engine's stream; pair with sk_engine_synchronize(). */
+int sk_engine_launch_segment(sk_engine_t* e, uint64_t first, uint64_t count, int32_t primary, int32_t peel,
+                             int32_t store, uint32_t stream_id);
+int sk_engine_synchronize(sk_engine_t* e);
+/* Device time (ms) of the last segment kernel, measured with CUDA events on the engine's stream. */
+int sk_engine_last_kernel_ms(sk_engine_t* e, float* ms);
+
+/* MediumSystem::communicateRadiationField(primary) for the single-process case: _rf2 = _rf2c
+ * (MediumSystem.cpp:1304-1313).  Across GPUs the caller all-reduces the device buffer first
+ * (sk_engine_device_buffer + NCCL), exactly where the reference calls ProcessManager::sumToAll. */
+int sk_engine_communicate_rf(sk_engine_t* e, int32_t primary);
+
+/* MediumSystem::totalDustAbsorbedLuminosity(primary) (MediumSystem.cpp:1317-1356). */
+int sk_engine_absorbed_luminosity(sk_engine_t* e, int32_t primary, double* out);
+
+/* Outputs. which: 0 = _rf1, 1 = _rf2, 2 = _rf2c; out[m*Nrf + ell] (Table<2> row-major, MediumSystem.hpp:883-885). */
+int sk_engine_read_rf(sk_engine_t* e, int32_t which, double* out);
+/* FluxRecorder::_sed[component][ell] / _ifu[component][l + ell*Npix] (FluxRecorder.cpp:433).  For
+ * SK_COMP_TOTAL with recordComponents the engine returns the sum the reference forms in
+ * FluxRecorder::calibrateAndWrite (FluxRecorder.cpp:540-570). */
+int sk_engine_read_sed(sk_engine_t* e, int32_t instrument, int32_t component, double* out);
+int sk_engine_read_ifu(sk_engine_t* e, int32_t instrument, int32_t component, double* out);
+/* FluxRecorder::_wsed[k][ell], k = 0..4 (FluxRecorder.cpp:58-62). */
+int sk_engine_read_sed_stats(sk_engine_t* e, int32_t instrument, int32_t k, double* out);
+int sk_engine_counters(sk_engine_t* e, sk_counters_t* out, int32_t reset);
+
+/* Raw device buffers so that the rank's communicator (NCCL via torch.distributed in bench.py, or the
+ * shim's own ncclAllReduce) can reduce tallies in place: which = 0 rf1, 1 rf2, 2 rf2c, 3 = all
+ * detector arrays of all instruments (one contiguous block), 4 = all statistics arrays. */
+int sk_engine_device_buffer(sk_engine_t* e, int32_t which, void** device_ptr, uint64_t* num_doubles);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SK_ENGINE_H */

@@ -1,0 +1,1948 @@
+/* sk_oracle.c -- CPU ORACLE (TEST INFRASTRUCTURE ONLY) for the photon-packet life cycle.
+ *
+ * A plain-C, single-threaded restatement of the reference algorithm on the hot path named by
+ * BASELINE.json (SKIRT 9, MonteCarloSimulation::performLifeCycle and what it calls).  It exists so
+ * that tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg can check / time against it.
+ * Nothing under skirt9_b200/ (the product) may import, link or call this file.
+ *
+ * Parity pinning: the reference has no golden vectors or tests for this path.  The
+ * oracle is pinned instead against outputs of the unmodified reference compiled here into
+ * oracle/_ref (see oracle/Makefile, tests/golden/make_golden.py, tests/test_oracle_vs_reference.py):
+ * agreement is statistical (the reference draws from per-thread MT19937-64, this file and the CUDA
+ * engine draw from Philox4x32-10 keyed by history index), within the Monte-Carlo error the reference
+ * itself reports through recordStatistics.  Against the CUDA engine the agreement is deterministic
+ * (same draws, same arithmetic; differences only from summation order and libm ulps).
+ *
+ * Every function cites the reference file:line it follows (paths relative to /root/reference).
+ * The structs and the function set mirror include/sk_engine.h with the prefix sko_.
+ */
+#include "../include/sk_engine.h"
+
+#include <float.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+/* ------------------------------------------------------------------------------------------------ */
+/* engine object                                                                                    */
+/* ------------------------------------------------------------------------------------------------ */
+
+typedef struct {
+    sk_wavelength_grid_t g;
+} wlg_t;
+
+typedef struct {
+    sk_source_t s;
+} src_t;
+
+#define MAX_LEVELS 8
+#define NUM_COMP (SK_COMP_PRIMARY_SCATTERED_LEVEL + MAX_LEVELS)
+
+typedef struct {
+    sk_instrument_t d;
+    double kobs[3];
+    double costheta, sintheta, cosphi, sinphi, cosomega, sinomega;
+    double xpmin, xpsiz, ypmin, ypsiz, radius2;
+    int same_as_preceding;
+    int include_sed, include_ifu;
+    int record_total_only;
+    int nl;
+    size_t npix;
+    double* sed[NUM_COMP];
+    double* ifu[NUM_COMP];
+    double* wsed[5];
+    /* per-history statistics accumulator (FluxRecorder::ContributionList, FluxRecorder.hpp:327-339) */
+    int hist_active;
+    int hist_ell;
+    double hist_w;
+} instr_t;
+
+typedef struct {
+    int m;
+    double ds, s, tau;
+} seg_t;
+
+typedef struct sko_engine {
+    sk_config_t cfg;
+    /* grid */
+    int grid_kind; /* 1 cartesian, 2 octree */
+    int nx, ny, nz;
+    double *xv, *yv, *zv;
+    double extent[6];
+    double eps;
+    int nnodes;
+    int32_t* first_child;
+    double* node_box;    /* [6*nnodes] */
+    int32_t* cell_of_node;
+    int32_t* node_of_cell;
+    /* medium */
+    int ncells;
+    double *dens, *vol;
+    /* dust */
+    int nlam;
+    double *lam_border, *sig_abs, *sig_sca, *sig_ext, *gpar;
+    double mu;
+    /* wavelength grids */
+    int nwlg;
+    wlg_t* wlg;
+    int rf_grid;
+    int nrf;
+    double *rf1, *rf2, *rf2c;
+    /* sources */
+    int nsrc;
+    src_t* src;
+    double source_bias;
+    double *Lv, *Wv;
+    double Ltot;
+    uint64_t* Iv;
+    double Lpp;
+    uint64_t npackets;
+    /* instruments */
+    int ninstr;
+    instr_t* instr;
+    int has_medium_emission;
+    /* path buffer */
+    seg_t* segs;
+    int nsegs, capsegs;
+    sk_counters_t cnt;
+} sko_engine_t;
+
+static char g_err[512] = "";
+static int fail(int code, const char* msg)
+{
+    snprintf(g_err, sizeof g_err, "%s", msg);
+    return code;
+}
+const char* sko_last_error(void)
+{
+    return g_err;
+}
+int sko_abi_version(void)
+{
+    return SK_ABI_VERSION;
+}
+
+static double* dupd(const double* p, size_t n)
+{
+    double* q = (double*)malloc((n ? n : 1) * sizeof(double));
+    if (p) memcpy(q, p, n * sizeof(double));
+    return q;
+}
+static int32_t* dupi(const int32_t* p, size_t n)
+{
+    int32_t* q = (int32_t*)malloc((n ? n : 1) * sizeof(int32_t));
+    if (p) memcpy(q, p, n * sizeof(int32_t));
+    return q;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* random numbers: Philox4x32-10 (Salmon et al. 2011), replacing Random.cpp:20-56 (MT19937-64)      */
+/*   key = (seed, stream_id); counter = (history lo, history hi, block, 0); each block gives two    */
+/*   uniform deviates in the open interval (0,1) (Random.cpp:26-27 excludes 0 and 1 as well).       */
+/* ------------------------------------------------------------------------------------------------ */
+
+typedef struct {
+    uint32_t k0, k1;
+    uint32_t c0, c1, block;
+    int has_spare;
+    double spare;
+} rng_t;
+
+static void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1)
+{
+    for (int r = 0; r < 10; ++r)
+    {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c[0] = n0;
+        c[1] = n1;
+        c[2] = n2;
+        c[3] = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+static double u01(uint32_t lo, uint32_t hi)
+{
+    uint64_t x = ((uint64_t)hi << 32) | lo;
+    return ((double)(x >> 12) + 0.5) * (1.0 / 4503599627370496.0); /* 2^-52; result in (0,1) */
+}
+static void rng_init(rng_t* g, uint32_t seed, uint32_t stream, uint64_t history)
+{
+    g->k0 = seed;
+    g->k1 = stream;
+    g->c0 = (uint32_t)history;
+    g->c1 = (uint32_t)(history >> 32);
+    g->block = 0;
+    g->has_spare = 0;
+    g->spare = 0.;
+}
+/* Random::uniform, Random.cpp:70-73 */
+static double uniform(rng_t* g)
+{
+    if (g->has_spare)
+    {
+        g->has_spare = 0;
+        return g->spare;
+    }
+    uint32_t c[4] = {g->c0, g->c1, g->block, 0u};
+    philox4x32_10(c, g->k0, g->k1);
+    g->block++;
+    g->spare = u01(c[2], c[3]);
+    g->has_spare = 1;
+    return u01(c[0], c[1]);
+}
+/* Random::exponCutoff, Random.cpp:105-117 */
+static double expon_cutoff(rng_t* g, double xmax)
+{
+    if (xmax == 0.0)
+        return 0.0;
+    else if (xmax < 1e-10)
+        return uniform(g) * xmax;
+    double x = -log(1.0 - uniform(g) * (1.0 - exp(-xmax)));
+    while (x > xmax)
+    {
+        x = -log(1.0 - uniform(g) * (1.0 - exp(-xmax)));
+    }
+    return x;
+}
+/* Direction::Direction(theta,phi), SKIRT/utils/Direction.cpp:10-35 */
+static void direction_from_angles(double theta, double phi, double k[3])
+{
+    const double eps = 1e-8;
+    if (theta <= eps)
+    {
+        k[0] = 0;
+        k[1] = 0;
+        k[2] = 1;
+    }
+    else if (theta >= M_PI - eps)
+    {
+        k[0] = 0;
+        k[1] = 0;
+        k[2] = -1;
+    }
+    else
+    {
+        double sintheta = sin(theta);
+        k[0] = sintheta * cos(phi);
+        k[1] = sintheta * sin(phi);
+        k[2] = cos(theta);
+    }
+}
+/* Random::direction(), Random.cpp:121-126 */
+static void random_direction(rng_t* g, double k[3])
+{
+    double theta = acos(2.0 * uniform(g) - 1.0);
+    double phi = 2.0 * M_PI * uniform(g);
+    direction_from_angles(theta, phi, k);
+}
+/* Random::direction(bfk, costheta), Random.cpp:130-164 */
+static void random_direction_about(rng_t* g, const double k[3], double costheta, double knew[3])
+{
+    double phi = 2.0 * M_PI * uniform(g);
+    double cosphi = cos(phi);
+    double sinphi = sin(phi);
+    double sintheta = sqrt(fabs((1.0 - costheta) * (1.0 + costheta)));
+    double kx = k[0], ky = k[1], kz = k[2];
+    if (kz > 0.99999)
+    {
+        knew[0] = cosphi * sintheta;
+        knew[1] = sinphi * sintheta;
+        knew[2] = costheta;
+    }
+    else if (kz < -0.99999)
+    {
+        knew[0] = cosphi * sintheta;
+        knew[1] = sinphi * sintheta;
+        knew[2] = -costheta;
+    }
+    else
+    {
+        double root = sqrt((1.0 - kz) * (1.0 + kz));
+        knew[0] = sintheta / root * (-kx * kz * cosphi + ky * sinphi) + kx * costheta;
+        knew[1] = -sintheta / root * (ky * kz * cosphi + kx * sinphi) + ky * costheta;
+        knew[2] = root * sintheta * cosphi + kz * costheta;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* numerical helpers                                                                                */
+/* ------------------------------------------------------------------------------------------------ */
+
+/* NR::locateBasicImpl / locateClip / locateFail, SKIRT/utils/NR.hpp:130-191 */
+static int locate_basic(const double* xv, double x, int n)
+{
+    int jl = -1, ju = n;
+    while (ju - jl > 1)
+    {
+        int jm = (ju + jl) >> 1;
+        if (x < xv[jm])
+            ju = jm;
+        else
+            jl = jm;
+    }
+    return jl;
+}
+static int locate_clip(const double* xv, int n, double x)
+{
+    if (x < xv[0]) return 0;
+    return locate_basic(xv, x, n - 1);
+}
+static int locate_fail(const double* xv, int n, double x)
+{
+    if (x > xv[n - 1]) return -1;
+    return locate_basic(xv, x, n - 1);
+}
+/* NR::interpolateLinLin, NR.hpp:328-331 */
+static double interp_linlin(double x, double x1, double x2, double f1, double f2)
+{
+    return f1 + ((x - x1) / (x2 - x1)) * (f2 - f1);
+}
+/* NR::interpolateLogLog, NR.hpp:349-358 */
+static double interp_loglog(double x, double x1, double x2, double f1, double f2)
+{
+    if (f1 <= 0 || f2 <= 0)
+    {
+        if (x == x1) return f1;
+        if (x == x2) return f2;
+        return 0;
+    }
+    return f1 * exp(log(x / x1) / log(x2 / x1) * (log(f2 / f1)));
+}
+/* SpecialFunctions::gexp, SKIRT/utils/SpecialFunctions.cpp:822-836 */
+static double gexp(double p, double x)
+{
+    const double q = 1.0 - p;
+    if (q == 0.0)
+        return exp(x);
+    else if (fabs(q) < 1e-3)
+    {
+        double x2 = x * x;
+        return exp(x)
+               * (1.0 - 0.5 * x2 * q + 1.0 / 24.0 * x * x2 * (8.0 + 3.0 * x) * q * q
+                  - 1.0 / 48.0 * x2 * x2 * (12.0 + 8.0 * x + x2) * q * q * q);
+    }
+    else
+        return pow(1.0 + q * x, 1.0 / q);
+}
+/* SpecialFunctions::lnmean(x1,x2,lnx1,lnx2), SpecialFunctions.cpp:860-880 */
+static double lnmean4(double x1, double x2, double lnx1, double lnx2)
+{
+    if (x1 > x2)
+    {
+        double t = x1;
+        x1 = x2;
+        x2 = t;
+        t = lnx1;
+        lnx1 = lnx2;
+        lnx2 = t;
+    }
+    if (x1 <= 0) return 0.;
+    double x = x2 / x1 - 1.;
+    if (x < 1e-3)
+    {
+        return x1
+               / (1. - 1. / 2. * x + 1. / 3. * x * x - 1. / 4. * x * x * x + 1. / 5. * x * x * x * x
+                  - 1. / 6. * x * x * x * x * x);
+    }
+    else
+    {
+        return (x2 - x1) / (lnx2 - lnx1);
+    }
+}
+/* SpecialFunctions::LambertW1, SpecialFunctions.cpp:578-627 */
+static double lambert_w1(double z)
+{
+    const double eps = 1.0e-12;
+    const double em1 = 0.3678794411714423215955237701614608;
+    static const double c[12] = {-1.0,
+                                 2.331643981597124203363536062168,
+                                 -1.812187885639363490240191647568,
+                                 1.936631114492359755363277457668,
+                                 -2.353551201881614516821543561516,
+                                 3.066858901050631912893148922704,
+                                 -4.175335600258177138854984177460,
+                                 5.858023729874774148815053846119,
+                                 -8.401032217523977370984161688514,
+                                 12.250753501314460424,
+                                 -18.100697012472442755,
+                                 27.029044799010561650};
+    if (z == 0.0) return -DBL_MAX;
+    double q = z + em1;
+    double r = -sqrt(q);
+    double t8 = c[8] + r * (c[9] + r * (c[10] + r * c[11]));
+    double t5 = c[5] + r * (c[6] + r * (c[7] + r * t8));
+    double t1 = c[1] + r * (c[2] + r * (c[3] + r * (c[4] + r * t5)));
+    double w0 = c[0] + r * t1;
+    if (q < 3.0e-3) return w0;
+    double w, e, p, t;
+    if (z < -1e-6)
+        w = w0;
+    else
+    {
+        double l1 = log(-z);
+        double l2 = log(-l1);
+        w = l1 - l2 + l2 / l1;
+    }
+    for (int i = 0; i < 10; i++)
+    {
+        e = exp(w);
+        t = w * e - z;
+        p = w + 1.0;
+        t /= e * p - 0.5 * (p + 1.0) * t / p;
+        w -= t;
+        if (fabs(t) < eps * (1.0 + fabs(w))) return w;
+    }
+    return w; /* the reference throws here; unreachable for valid arguments */
+}
+/* PlanckFunction::value, SKIRT/utils/PlanckFunction.cpp:24-27 with Constants h, c, k */
+static double planck(double lambda, double T)
+{
+    const double h = 6.62606957e-34, c = 2.99792458e8, k = 1.3806488e-23;
+    double f1 = h * c / (k * T);
+    double f2 = 2.0 * h * c * c;
+    return f2 / pow(lambda, 5) / (exp(f1 / lambda) - 1.0);
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* setters                                                                                          */
+/* ------------------------------------------------------------------------------------------------ */
+
+int sko_create(const sk_config_t* config, sko_engine_t** out)
+{
+    if (!config || !out) return fail(SK_ERR_INVALID, "null argument");
+    sko_engine_t* e = (sko_engine_t*)calloc(1, sizeof *e);
+    e->cfg = *config;
+    e->rf_grid = -1;
+    e->capsegs = 1000; /* SpatialGridPath.cpp:14 INITIAL_CAPACITY */
+    e->segs = (seg_t*)malloc(e->capsegs * sizeof(seg_t));
+    *out = e;
+    return SK_OK;
+}
+
+static void free_instruments(sko_engine_t* e)
+{
+    for (int i = 0; i < e->ninstr; ++i)
+    {
+        for (int c = 0; c < NUM_COMP; ++c)
+        {
+            free(e->instr[i].sed[c]);
+            free(e->instr[i].ifu[c]);
+        }
+        for (int k = 0; k < 5; ++k) free(e->instr[i].wsed[k]);
+    }
+    free(e->instr);
+    e->instr = NULL;
+    e->ninstr = 0;
+}
+static void free_sources(sko_engine_t* e)
+{
+    for (int i = 0; i < e->nsrc; ++i)
+    {
+        sk_source_t* s = &e->src[i].s;
+        free((void*)s->geom_table_x);
+        free((void*)s->geom_table_P);
+        free((void*)s->sed_lambda);
+        free((void*)s->sed_p);
+        free((void*)s->sed_P);
+        free((void*)s->oligo_lambda);
+    }
+    free(e->src);
+    free(e->Lv);
+    free(e->Wv);
+    free(e->Iv);
+    e->src = NULL;
+    e->Lv = e->Wv = NULL;
+    e->Iv = NULL;
+    e->nsrc = 0;
+}
+static void free_wlg(sko_engine_t* e)
+{
+    for (int i = 0; i < e->nwlg; ++i)
+    {
+        free((void*)e->wlg[i].g.borders);
+        free((void*)e->wlg[i].g.ell);
+        free((void*)e->wlg[i].g.lambda);
+        free((void*)e->wlg[i].g.dlambda);
+    }
+    free(e->wlg);
+    e->wlg = NULL;
+    e->nwlg = 0;
+}
+static void free_grid(sko_engine_t* e)
+{
+    free(e->xv);
+    free(e->yv);
+    free(e->zv);
+    free(e->first_child);
+    free(e->node_box);
+    free(e->cell_of_node);
+    free(e->node_of_cell);
+    e->xv = e->yv = e->zv = e->node_box = NULL;
+    e->first_child = e->cell_of_node = e->node_of_cell = NULL;
+    e->grid_kind = 0;
+}
+
+void sko_destroy(sko_engine_t* e)
+{
+    if (!e) return;
+    free_instruments(e);
+    free_sources(e);
+    free_wlg(e);
+    free_grid(e);
+    free(e->dens);
+    free(e->vol);
+    free(e->lam_border);
+    free(e->sig_abs);
+    free(e->sig_sca);
+    free(e->sig_ext);
+    free(e->gpar);
+    free(e->rf1);
+    free(e->rf2);
+    free(e->rf2c);
+    free(e->segs);
+    free(e);
+}
+
+/* CartesianSpatialGrid setup, CartesianSpatialGrid.cpp:22-60 */
+int sko_set_grid_cartesian(sko_engine_t* e, int32_t nx, int32_t ny, int32_t nz, const double* xv, const double* yv,
+                           const double* zv)
+{
+    if (!e || nx < 1 || ny < 1 || nz < 1 || !xv || !yv || !zv) return fail(SK_ERR_INVALID, "bad cartesian grid");
+    free_grid(e);
+    e->grid_kind = 1;
+    e->nx = nx;
+    e->ny = ny;
+    e->nz = nz;
+    e->xv = dupd(xv, nx + 1);
+    e->yv = dupd(yv, ny + 1);
+    e->zv = dupd(zv, nz + 1);
+    e->extent[0] = xv[0];
+    e->extent[1] = yv[0];
+    e->extent[2] = zv[0];
+    e->extent[3] = xv[nx];
+    e->extent[4] = yv[ny];
+    e->extent[5] = zv[nz];
+    double dx = e->extent[3] - e->extent[0], dy = e->extent[4] - e->extent[1], dz = e->extent[5] - e->extent[2];
+    e->eps = 1e-12 * sqrt(dx * dx + dy * dy + dz * dz); /* CartesianSpatialGrid.cpp:102, Box.hpp:125-129 */
+    return SK_OK;
+}
+
+/* TreeSpatialGrid::setupSelfAfter, TreeSpatialGrid.cpp:23-49; OctTreeNode::createChildren, OctTreeNode.cpp:22-35 */
+int sko_set_grid_octree(sko_engine_t* e, const double extent[6], int32_t num_nodes, const int32_t* first_child)
+{
+    if (!e || !extent || num_nodes < 1 || !first_child) return fail(SK_ERR_INVALID, "bad octree");
+    free_grid(e);
+    e->grid_kind = 2;
+    memcpy(e->extent, extent, 6 * sizeof(double));
+    double dx = extent[3] - extent[0], dy = extent[4] - extent[1], dz = extent[5] - extent[2];
+    e->eps = 1e-12 * sqrt(dx * dx + dy * dy + dz * dz); /* TreeSpatialGrid.cpp:28 */
+    e->nnodes = num_nodes;
+    e->first_child = dupi(first_child, num_nodes);
+    e->node_box = (double*)malloc(6 * (size_t)num_nodes * sizeof(double));
+    e->cell_of_node = (int32_t*)malloc((size_t)num_nodes * sizeof(int32_t));
+    e->node_of_cell = (int32_t*)malloc((size_t)num_nodes * sizeof(int32_t));
+    char* seen = (char*)calloc(num_nodes, 1);
+    memcpy(e->node_box, extent, 6 * sizeof(double));
+    seen[0] = 1;
+    int m = 0;
+    for (int l = 0; l < num_nodes; ++l)
+    {
+        if (!seen[l])
+        {
+            free(seen);
+            return fail(SK_ERR_INVALID, "octree node list is not parent-before-child");
+        }
+        int fc = first_child[l];
+        if (fc < 0)
+        {
+            e->cell_of_node[l] = m;
+            e->node_of_cell[m] = l;
+            m++;
+            continue;
+        }
+        if (fc <= l || fc + 8 > num_nodes)
+        {
+            free(seen);
+            return fail(SK_ERR_INVALID, "octree child index out of range");
+        }
+        e->cell_of_node[l] = -1;
+        const double* b = e->node_box + 6 * (size_t)l;
+        double xmin = b[0], ymin = b[1], zmin = b[2], xmax = b[3], ymax = b[4], zmax = b[5];
+        double cx = 0.5 * (xmin + xmax), cy = 0.5 * (ymin + ymax), cz = 0.5 * (zmin + zmax); /* Box.hpp:135 */
+        for (int c = 0; c < 8; ++c)
+        {
+            double* cb = e->node_box + 6 * (size_t)(fc + c);
+            cb[0] = (c & 1) ? cx : xmin;
+            cb[3] = (c & 1) ? xmax : cx;
+            cb[1] = (c & 2) ? cy : ymin;
+            cb[4] = (c & 2) ? ymax : cy;
+            cb[2] = (c & 4) ? cz : zmin;
+            cb[5] = (c & 4) ? zmax : cz;
+            seen[fc + c] = 1;
+        }
+    }
+    free(seen);
+    e->ncells = 0; /* medium must be (re)set */
+    e->nx = m;     /* remember leaf count for validation */
+    return SK_OK;
+}
+
+static int grid_num_cells(const sko_engine_t* e)
+{
+    if (e->grid_kind == 1) return e->nx * e->ny * e->nz;
+    if (e->grid_kind == 2) return e->nx;
+    return 0;
+}
+
+int sko_set_medium(sko_engine_t* e, int32_t num_cells, const double* number_density, const double* volume)
+{
+    if (!e || !number_density) return fail(SK_ERR_INVALID, "null argument");
+    if (!e->grid_kind) return fail(SK_ERR_STATE, "set the grid before the medium");
+    if (num_cells != grid_num_cells(e)) return fail(SK_ERR_INVALID, "medium size does not match the grid");
+    free(e->dens);
+    free(e->vol);
+    e->ncells = num_cells;
+    e->dens = dupd(number_density, num_cells);
+    e->vol = volume ? dupd(volume, num_cells) : NULL;
+    return SK_OK;
+}
+
+int sko_set_dustmix(sko_engine_t* e, const sk_dustmix_t* mix)
+{
+    if (!e || !mix || mix->num_lambda < 2) return fail(SK_ERR_INVALID, "bad dust mix");
+    int n = mix->num_lambda;
+    free(e->lam_border);
+    free(e->sig_abs);
+    free(e->sig_sca);
+    free(e->sig_ext);
+    free(e->gpar);
+    e->nlam = n;
+    e->lam_border = dupd(mix->lambda_border, n);
+    e->sig_abs = dupd(mix->sigma_abs, n);
+    e->sig_sca = dupd(mix->sigma_sca, n);
+    e->gpar = dupd(mix->asymmpar, n);
+    e->sig_ext = (double*)malloc(n * sizeof(double));
+    for (int i = 0; i < n; ++i) e->sig_ext[i] = e->sig_abs[i] + e->sig_sca[i]; /* DustMix.cpp:160-163 */
+    e->mu = mix->mu;
+    return SK_OK;
+}
+
+static void alloc_rf(sko_engine_t* e)
+{
+    free(e->rf1);
+    free(e->rf2);
+    free(e->rf2c);
+    e->rf1 = e->rf2 = e->rf2c = NULL;
+    e->nrf = 0;
+    if (e->rf_grid >= 0 && e->ncells > 0)
+    {
+        e->nrf = e->wlg[e->rf_grid].g.num_bins;
+        size_t n = (size_t)e->ncells * e->nrf;
+        e->rf1 = (double*)calloc(n, sizeof(double));
+        e->rf2 = (double*)calloc(n, sizeof(double));
+        e->rf2c = (double*)calloc(n, sizeof(double));
+    }
+}
+
+int sko_set_wavelength_grids(sko_engine_t* e, int32_t n, const sk_wavelength_grid_t* grids, int32_t rf_grid)
+{
+    if (!e || n < 0 || (n && !grids) || rf_grid >= n) return fail(SK_ERR_INVALID, "bad wavelength grids");
+    if (rf_grid >= 0 && e->ncells <= 0) return fail(SK_ERR_STATE, "set the medium before a radiation field grid");
+    free_wlg(e);
+    e->wlg = (wlg_t*)calloc(n ? n : 1, sizeof(wlg_t));
+    e->nwlg = n;
+    for (int i = 0; i < n; ++i)
+    {
+        sk_wavelength_grid_t* g = &e->wlg[i].g;
+        *g = grids[i];
+        g->borders = dupd(grids[i].borders, g->num_borders);
+        g->ell = dupi(grids[i].ell, g->num_borders + 1);
+        g->lambda = dupd(grids[i].lambda, g->num_bins);
+        g->dlambda = dupd(grids[i].dlambda, g->num_bins);
+    }
+    e->rf_grid = rf_grid;
+    alloc_rf(e);
+    return SK_OK;
+}
+
+/* SourceSystem::setupSelfAfter, SourceSystem.cpp:14-41 */
+int sko_set_sources(sko_engine_t* e, int32_t n, const sk_source_t* sources, double source_bias)
+{
+    if (!e || n < 1 || !sources) return fail(SK_ERR_INVALID, "bad sources");
+    free_sources(e);
+    e->src = (src_t*)calloc(n, sizeof(src_t));
+    e->nsrc = n;
+    e->source_bias = source_bias;
+    for (int i = 0; i < n; ++i)
+    {
+        sk_source_t* s = &e->src[i].s;
+        *s = sources[i];
+        s->geom_table_x = s->geom_table_n ? dupd(sources[i].geom_table_x, s->geom_table_n) : NULL;
+        s->geom_table_P = s->geom_table_n ? dupd(sources[i].geom_table_P, s->geom_table_n) : NULL;
+        s->sed_lambda = s->sed_n ? dupd(sources[i].sed_lambda, s->sed_n) : NULL;
+        s->sed_p = s->sed_n ? dupd(sources[i].sed_p, s->sed_n) : NULL;
+        s->sed_P = s->sed_n ? dupd(sources[i].sed_P, s->sed_n) : NULL;
+        s->oligo_lambda = s->oligo_n ? dupd(sources[i].oligo_lambda, s->oligo_n) : NULL;
+    }
+    e->Lv = (double*)malloc(n * sizeof(double));
+    e->Wv = (double*)malloc(n * sizeof(double));
+    e->Iv = (uint64_t*)calloc(n + 1, sizeof(uint64_t));
+    double L = 0.;
+    for (int h = 0; h < n; ++h) L += sources[h].luminosity;
+    e->Ltot = L;
+    if (!L) return SK_OK;
+    double wLsum = 0., wsum = 0.;
+    for (int h = 0; h < n; ++h)
+    {
+        e->Lv[h] = sources[h].luminosity / L;
+        wLsum += sources[h].source_weight * e->Lv[h];
+        wsum += sources[h].source_weight;
+    }
+    double xi = source_bias;
+    for (int h = 0; h < n; ++h)
+        e->Wv[h] = (1 - xi) * (sources[h].source_weight * e->Lv[h]) / wLsum + xi * sources[h].source_weight / wsum;
+    return SK_OK;
+}
+
+/* DistantInstrument::setupSelfBefore (DistantInstrument.cpp:39-50), FrameInstrument::setupSelfBefore
+ * (FrameInstrument.cpp:12-32), FluxRecorder::finalizeConfiguration (FluxRecorder.cpp:185-300) */
+int sko_set_instruments(sko_engine_t* e, int32_t n, const sk_instrument_t* instruments, int32_t has_medium_emission)
+{
+    if (!e || n < 0 || (n && !instruments)) return fail(SK_ERR_INVALID, "bad instruments");
+    free_instruments(e);
+    e->instr = (instr_t*)calloc(n ? n : 1, sizeof(instr_t));
+    e->ninstr = n;
+    e->has_medium_emission = has_medium_emission;
+    for (int i = 0; i < n; ++i)
+    {
+        instr_t* q = &e->instr[i];
+        q->d = instruments[i];
+        const sk_instrument_t* d = &q->d;
+        if (d->wavelength_grid < 0 || d->wavelength_grid >= e->nwlg)
+            return fail(SK_ERR_INVALID, "instrument wavelength grid index out of range");
+        if (d->num_scattering_levels > MAX_LEVELS) return fail(SK_ERR_UNSUPPORTED, "too many scattering levels");
+        q->costheta = cos(d->inclination);
+        q->sintheta = sin(d->inclination);
+        q->cosphi = cos(d->azimuth);
+        q->sinphi = sin(d->azimuth);
+        q->cosomega = cos(d->roll);
+        q->sinomega = sin(d->roll);
+        direction_from_angles(d->inclination, d->azimuth, q->kobs);
+        q->include_sed = (d->kind == SK_INSTR_SED || d->kind == SK_INSTR_FULL);
+        q->include_ifu = (d->kind == SK_INSTR_FRAME || d->kind == SK_INSTR_FULL);
+        q->radius2 = d->radius * d->radius;
+        if (q->include_ifu)
+        {
+            q->xpmin = d->center_x - 0.5 * d->field_of_view_x;
+            q->xpsiz = d->field_of_view_x / d->num_pixels_x;
+            q->ypmin = d->center_y - 0.5 * d->field_of_view_y;
+            q->ypsiz = d->field_of_view_y / d->num_pixels_y;
+            q->npix = (size_t)d->num_pixels_x * d->num_pixels_y;
+        }
+        q->nl = e->wlg[d->wavelength_grid].g.num_bins;
+        q->record_total_only = !d->record_components;
+        /* DistantInstrument::determineSameObserverAsPreceding, DistantInstrument.cpp:54-62 */
+        q->same_as_preceding = 0;
+        if (i > 0)
+        {
+            const sk_instrument_t* p = &e->instr[i - 1].d;
+            if (d->distance == p->distance && d->inclination == p->inclination && d->azimuth == p->azimuth
+                && d->roll == p->roll)
+                q->same_as_preceding = 1;
+        }
+        size_t lensed = q->include_sed ? (size_t)q->nl : 0;
+        size_t lenifu = q->include_ifu ? q->npix * q->nl : 0;
+        for (int c = 0; c < NUM_COMP; ++c)
+        {
+            int need;
+            if (q->record_total_only)
+                need = (c == SK_COMP_TOTAL);
+            else if (c == SK_COMP_TRANSPARENT || c == SK_COMP_PRIMARY_DIRECT || c == SK_COMP_PRIMARY_SCATTERED)
+                need = 1;
+            else if (c == SK_COMP_SECONDARY_DIRECT || c == SK_COMP_SECONDARY_SCATTERED
+                     || c == SK_COMP_SECONDARY_TRANSPARENT)
+                need = has_medium_emission;
+            else if (c >= SK_COMP_PRIMARY_SCATTERED_LEVEL)
+                need = (c - SK_COMP_PRIMARY_SCATTERED_LEVEL) < d->num_scattering_levels;
+            else
+                need = 0;
+            if (need && lensed) q->sed[c] = (double*)calloc(lensed, sizeof(double));
+            if (need && lenifu) q->ifu[c] = (double*)calloc(lenifu, sizeof(double));
+        }
+        if (d->record_statistics && lensed)
+            for (int k = 0; k < 5; ++k) q->wsed[k] = (double*)calloc(lensed, sizeof(double));
+    }
+    return SK_OK;
+}
+
+int sko_set_secondary(sko_engine_t* e, const sk_secondary_t* sec)
+{
+    (void)e;
+    (void)sec;
+    return fail(SK_ERR_UNSUPPORTED, "secondary emission not implemented in the oracle yet");
+}
+
+/* MediumSystem::clearRadiationField, MediumSystem.cpp:1279-1290 */
+int sko_clear_rf(sko_engine_t* e, int32_t primary)
+{
+    if (!e) return fail(SK_ERR_INVALID, "null engine");
+    size_t n = (size_t)e->ncells * e->nrf;
+    if (!n) return SK_OK;
+    if (primary)
+    {
+        memset(e->rf1, 0, n * sizeof(double));
+        memset(e->rf2, 0, n * sizeof(double));
+    }
+    else
+        memset(e->rf2c, 0, n * sizeof(double));
+    return SK_OK;
+}
+
+/* SourceSystem::prepareForLaunch, SourceSystem.cpp:75-97 */
+int sko_prepare_primary(sko_engine_t* e, uint64_t num_packets)
+{
+    if (!e || !e->nsrc) return fail(SK_ERR_STATE, "no sources");
+    if (!e->Ltot) return fail(SK_ERR_INVALID, "Cannot launch primary source photon packets when total luminosity is zero");
+    int Ns = e->nsrc;
+    e->Iv[0] = 0;
+    double W = 0.;
+    for (int h = 1; h != Ns; ++h)
+    {
+        W += e->Wv[h - 1];
+        uint64_t idx = (uint64_t)round(W * (double)num_packets);
+        e->Iv[h] = idx < num_packets ? idx : num_packets;
+    }
+    e->Iv[Ns] = num_packets;
+    e->Lpp = e->Ltot / (double)num_packets;
+    e->npackets = num_packets;
+    return SK_OK;
+}
+
+int sko_prepare_secondary(sko_engine_t* e, uint64_t num_packets, double* luminosity)
+{
+    (void)e;
+    (void)num_packets;
+    (void)luminosity;
+    return fail(SK_ERR_UNSUPPORTED, "secondary emission not implemented in the oracle yet");
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* path segment generators                                                                          */
+/* ------------------------------------------------------------------------------------------------ */
+
+typedef struct {
+    int state; /* 0 Unknown, 1 Inside, 2 Outside (PathSegmentGenerator.hpp State) */
+    double rx, ry, rz, kx, ky, kz;
+    int m;
+    double ds;
+    int i, j, k; /* cartesian */
+    int node;    /* tree: current node or -1 */
+} gen_t;
+
+static int box_contains(const double* b, double x, double y, double z)
+{
+    /* Box::contains, SKIRT/utils/Box.hpp:99-109 (closed on all sides) */
+    return x >= b[0] && x <= b[3] && y >= b[1] && y <= b[4] && z >= b[2] && z <= b[5];
+}
+
+/* PathSegmentGenerator::moveInside, SKIRT/utils/PathSegmentGenerator.cpp:11-112 */
+static int move_inside(gen_t* g, const double* box, double eps)
+{
+    g->m = -1;
+    g->ds = 0.;
+    g->state = 2;
+    double cumds = 0.;
+    if (g->rx <= box[0])
+    {
+        if (g->kx <= 0.0)
+            return 0;
+        else
+        {
+            double ds = (box[0] - g->rx) / g->kx;
+            g->rx = box[0] + eps;
+            g->ry += g->ky * ds;
+            g->rz += g->kz * ds;
+            cumds += ds;
+        }
+    }
+    else if (g->rx >= box[3])
+    {
+        if (g->kx >= 0.0)
+            return 0;
+        else
+        {
+            double ds = (box[3] - g->rx) / g->kx;
+            g->rx = box[3] - eps;
+            g->ry += g->ky * ds;
+            g->rz += g->kz * ds;
+            cumds += ds;
+        }
+    }
+    if (g->ry <= box[1])
+    {
+        if (g->ky <= 0.0)
+            return 0;
+        else
+        {
+            double ds = (box[1] - g->ry) / g->ky;
+            g->rx += g->kx * ds;
+            g->ry = box[1] + eps;
+            g->rz += g->kz * ds;
+            cumds += ds;
+        }
+    }
+    else if (g->ry >= box[4])
+    {
+        if (g->ky >= 0.0)
+            return 0;
+        else
+        {
+            double ds = (box[4] - g->ry) / g->ky;
+            g->rx += g->kx * ds;
+            g->ry = box[4] - eps;
+            g->rz += g->kz * ds;
+            cumds += ds;
+        }
+    }
+    if (g->rz <= box[2])
+    {
+        if (g->kz <= 0.0)
+            return 0;
+        else
+        {
+            double ds = (box[2] - g->rz) / g->kz;
+            g->rx += g->kx * ds;
+            g->ry += g->ky * ds;
+            g->rz = box[2] + eps;
+            cumds += ds;
+        }
+    }
+    else if (g->rz >= box[5])
+    {
+        if (g->kz >= 0.0)
+            return 0;
+        else
+        {
+            double ds = (box[5] - g->rz) / g->kz;
+            g->rx += g->kx * ds;
+            g->ry += g->ky * ds;
+            g->rz = box[5] - eps;
+            cumds += ds;
+        }
+    }
+    if (!box_contains(box, g->rx, g->ry, g->rz)) return 0;
+    g->m = -1;
+    g->ds = cumds;
+    g->state = 1;
+    return 1;
+}
+
+static void gen_start(gen_t* g, const double r[3], const double k[3])
+{
+    g->state = 0;
+    g->rx = r[0];
+    g->ry = r[1];
+    g->rz = r[2];
+    g->kx = k[0];
+    g->ky = k[1];
+    g->kz = k[2];
+    g->node = -1;
+}
+
+/* CartesianSpatialGrid::MySegmentGenerator::next, CartesianSpatialGrid.cpp:95-162 */
+static int next_cartesian(const sko_engine_t* e, gen_t* g)
+{
+    switch (g->state)
+    {
+        case 0:
+        {
+            if (!move_inside(g, e->extent, e->eps)) return 0;
+            g->i = locate_clip(e->xv, e->nx + 1, g->rx);
+            g->j = locate_clip(e->yv, e->ny + 1, g->ry);
+            g->k = locate_clip(e->zv, e->nz + 1, g->rz);
+            if (g->ds > 0.) return 1;
+        }
+        /* fall through */
+        case 1:
+        {
+            int m = g->k + e->nz * g->j + e->nz * e->ny * g->i; /* CartesianSpatialGrid.cpp:210-213 */
+            double xE = (g->kx < 0.0) ? e->xv[g->i] : e->xv[g->i + 1];
+            double yE = (g->ky < 0.0) ? e->yv[g->j] : e->yv[g->j + 1];
+            double zE = (g->kz < 0.0) ? e->zv[g->k] : e->zv[g->k + 1];
+            double dsx = (fabs(g->kx) > 1e-15) ? (xE - g->rx) / g->kx : DBL_MAX;
+            double dsy = (fabs(g->ky) > 1e-15) ? (yE - g->ry) / g->ky : DBL_MAX;
+            double dsz = (fabs(g->kz) > 1e-15) ? (zE - g->rz) / g->kz : DBL_MAX;
+            if (dsx <= dsy && dsx <= dsz)
+            {
+                g->m = m;
+                g->ds = dsx;
+                g->rx = xE;
+                g->ry += g->ky * dsx;
+                g->rz += g->kz * dsx;
+                g->i += (g->kx < 0.0) ? -1 : 1;
+                if (g->i >= e->nx || g->i < 0) g->state = 2;
+            }
+            else if (dsy < dsx && dsy <= dsz)
+            {
+                g->m = m;
+                g->ds = dsy;
+                g->ry = yE;
+                g->rx += g->kx * dsy;
+                g->rz += g->kz * dsy;
+                g->j += (g->ky < 0.0) ? -1 : 1;
+                if (g->j >= e->ny || g->j < 0) g->state = 2;
+            }
+            else
+            {
+                g->m = m;
+                g->ds = dsz;
+                g->rz = zE;
+                g->rx += g->kx * dsz;
+                g->ry += g->ky * dsz;
+                g->k += (g->kz < 0.0) ? -1 : 1;
+                if (g->k >= e->nz || g->k < 0) g->state = 2;
+            }
+            return 1;
+        }
+        default: break;
+    }
+    return 0;
+}
+
+/* TreeNode::leafChild (TreeNode.cpp:65-76) with OctTreeNode::child (OctTreeNode.cpp:37-42) */
+static int tree_leaf_child(const sko_engine_t* e, double x, double y, double z)
+{
+    if (!box_contains(e->node_box, x, y, z)) return -1;
+    int node = 0;
+    while (e->first_child[node] >= 0)
+    {
+        int fc = e->first_child[node];
+        const double* c0 = e->node_box + 6 * (size_t)fc; /* CHILD_0->rmax() is the centre of the node */
+        int l = (x < c0[3] ? 0 : 1) + (y < c0[4] ? 0 : 2) + (z < c0[5] ? 0 : 4);
+        node = fc + l;
+    }
+    return node;
+}
+
+/* TreeSpatialGrid::MySegmentGenerator::next, TreeSpatialGrid.cpp:140-216.
+ * TreeNode::neighbor(wall, r) (TreeNode.cpp:103-112) returns the neighbouring leaf that contains r and the
+ * caller falls back to the top-down search when there is none; both give the leaf containing r (they can
+ * differ only when r lies exactly on a face shared by two candidate leaves), so the lookup is restated as
+ * the top-down search alone. */
+static int next_tree(sko_engine_t* e, gen_t* g)
+{
+    switch (g->state)
+    {
+        case 0:
+        {
+            if (!move_inside(g, e->extent, e->eps)) return 0;
+            g->node = tree_leaf_child(e, g->rx, g->ry, g->rz);
+            if (g->ds > 0.) return 1;
+        }
+        /* fall through */
+        case 1:
+        {
+            const double* b = e->node_box + 6 * (size_t)g->node;
+            double xnext = (g->kx < 0.0) ? b[0] : b[3];
+            double ynext = (g->ky < 0.0) ? b[1] : b[4];
+            double znext = (g->kz < 0.0) ? b[2] : b[5];
+            double dsx = (fabs(g->kx) > 1e-15) ? (xnext - g->rx) / g->kx : DBL_MAX;
+            double dsy = (fabs(g->ky) > 1e-15) ? (ynext - g->ry) / g->ky : DBL_MAX;
+            double dsz = (fabs(g->kz) > 1e-15) ? (znext - g->rz) / g->kz : DBL_MAX;
+            double ds;
+            if (dsx <= dsy && dsx <= dsz)
+                ds = dsx;
+            else if (dsy <= dsx && dsy <= dsz)
+                ds = dsy;
+            else
+                ds = dsz;
+            double adv = ds + e->eps;
+            g->rx += g->kx * adv;
+            g->ry += g->ky * adv;
+            g->rz += g->kz * adv;
+            g->m = e->cell_of_node[g->node];
+            g->ds = ds;
+            int oldnode = g->node;
+            g->node = tree_leaf_child(e, g->rx, g->ry, g->rz);
+            if (g->node == oldnode)
+            {
+                /* PathSegmentGenerator::propagateToNextAfter, PathSegmentGenerator.hpp:148-153 */
+                g->rx = nextafter(g->rx, (g->kx < 0.) ? -DBL_MAX : DBL_MAX);
+                g->ry = nextafter(g->ry, (g->ky < 0.) ? -DBL_MAX : DBL_MAX);
+                g->rz = nextafter(g->rz, (g->kz < 0.) ? -DBL_MAX : DBL_MAX);
+                g->node = tree_leaf_child(e, g->rx, g->ry, g->rz);
+            }
+            if (g->node < 0 || g->node == oldnode) g->state = 2;
+            return 1;
+        }
+        default: break;
+    }
+    return 0;
+}
+
+static int gen_next(sko_engine_t* e, gen_t* g)
+{
+    return e->grid_kind == 1 ? next_cartesian(e, g) : next_tree(e, g);
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* photon packet and medium functions                                                               */
+/* ------------------------------------------------------------------------------------------------ */
+
+typedef struct {
+    double lambda, W; /* PhotonPacket::_lambda, _W = L*lambda (PhotonPacket.hpp:337-340) */
+    double r[3], k[3];
+    int nscatt;
+    int primary_origin;
+    uint64_t history;
+    int has_tau;
+    double tau_obs;
+    int ilam; /* DustMix::indexForLambda(lambda), constant during the life cycle (no kinematics) */
+} packet_t;
+
+/* DustMix::indexForLambda, DustMix.cpp:276-279 */
+static int index_for_lambda(const sko_engine_t* e, double lambda)
+{
+    return locate_clip(e->lam_border, e->nlam, lambda);
+}
+
+/* DisjointWavelengthGrid::bin, DisjointWavelengthGrid.cpp:332-341 */
+static int wlg_bin(const sk_wavelength_grid_t* g, double lambda)
+{
+    /* std::upper_bound: first border strictly greater than lambda */
+    int lo = 0, hi = g->num_borders;
+    while (lo < hi)
+    {
+        int mid = (lo + hi) >> 1;
+        if (lambda < g->borders[mid])
+            hi = mid;
+        else
+            lo = mid + 1;
+    }
+    return g->ell[lo];
+}
+
+/* MediumSystem::setExtinctionOpticalDepths, single constant-section medium branch, MediumSystem.cpp:849-871;
+ * SpatialGridPath::addSegment, SpatialGridPath.cpp:41-48 */
+static void set_extinction_optical_depths(sko_engine_t* e, const packet_t* pp)
+{
+    gen_t g;
+    gen_start(&g, pp->r, pp->k);
+    e->nsegs = 0;
+    double s = 0.;
+    while (gen_next(e, &g))
+    {
+        if (g.ds > 0.)
+        {
+            if (e->nsegs == e->capsegs)
+            {
+                e->capsegs *= 2;
+                e->segs = (seg_t*)realloc(e->segs, e->capsegs * sizeof(seg_t));
+            }
+            s += g.ds;
+            seg_t* sg = &e->segs[e->nsegs++];
+            sg->m = g.m;
+            sg->ds = g.ds;
+            sg->s = s;
+            sg->tau = 0.;
+        }
+    }
+    double tau = 0.;
+    double section = e->sig_ext[pp->ilam];
+    for (int n = 0; n < e->nsegs; ++n)
+    {
+        seg_t* sg = &e->segs[n];
+        if (sg->m >= 0) tau += section * e->dens[sg->m] * sg->ds;
+        sg->tau = tau;
+    }
+    e->cnt.forward_paths++;
+    e->cnt.forward_segments += e->nsegs;
+}
+
+/* MediumSystem::getExtinctionOpticalDepth(pp, infinity), single-medium branch, MediumSystem.cpp:1192-1219 */
+static double get_extinction_optical_depth(sko_engine_t* e, const packet_t* ppp)
+{
+    double L = ppp->W / ppp->lambda;
+    if (L <= 0) return INFINITY;
+    double taumax = log(L) + 745;
+    gen_t g;
+    gen_start(&g, ppp->r, ppp->k);
+    double tau = 0.;
+    double section = e->sig_ext[ppp->ilam];
+    e->cnt.peel_paths++;
+    while (gen_next(e, &g))
+    {
+        e->cnt.peel_segments++;
+        if (g.m >= 0)
+        {
+            tau += section * e->dens[g.m] * g.ds;
+            if (tau >= taumax) return INFINITY;
+        }
+    }
+    return tau;
+}
+
+/* MonteCarloSimulation::storeRadiationField (constant perceived wavelength branch), MonteCarloSimulation.cpp:638-665;
+ * MediumSystem::storeRadiationField, MediumSystem.cpp:1294-1300 */
+static void store_radiation_field(sko_engine_t* e, int primary, const packet_t* pp)
+{
+    if (e->rf_grid < 0) return;
+    int ell = wlg_bin(&e->wlg[e->rf_grid].g, pp->lambda);
+    if (ell < 0) return;
+    double luminosity = pp->W / pp->lambda;
+    double lnExtBeg = 0.;
+    double extBeg = 1.;
+    double* rf = primary ? e->rf1 : e->rf2c;
+    for (int n = 0; n < e->nsegs; ++n)
+    {
+        const seg_t* sg = &e->segs[n];
+        double lnExtEnd = -sg->tau;
+        double extEnd = exp(lnExtEnd);
+        if (sg->m >= 0)
+        {
+            double extMean = lnmean4(extEnd, extBeg, lnExtEnd, lnExtBeg);
+            double Lds = luminosity * extMean * sg->ds;
+            rf[(size_t)sg->m * e->nrf + ell] += Lds;
+            e->cnt.rf_deposits++;
+        }
+        lnExtBeg = lnExtEnd;
+        extBeg = extEnd;
+    }
+}
+
+/* SpatialGridPath::findInteractionPoint, SpatialGridPath.cpp:164-206 (extinction-only members) */
+static void find_interaction_point(const sko_engine_t* e, double tauinteract, int* m_out, double* s_out)
+{
+    if (e->nsegs == 0)
+    {
+        *m_out = -1;
+        *s_out = 0.;
+        return;
+    }
+    /* std::upper_bound on the cumulative optical depth: first segment with tau > tauinteract */
+    int lo = 0, hi = e->nsegs;
+    while (lo < hi)
+    {
+        int mid = (lo + hi) >> 1;
+        if (tauinteract < e->segs[mid].tau)
+            hi = mid;
+        else
+            lo = mid + 1;
+    }
+    if (lo == 0)
+    {
+        *m_out = e->segs[0].m;
+        *s_out = interp_linlin(tauinteract, 0., e->segs[0].tau, 0., e->segs[0].s);
+    }
+    else if (lo < e->nsegs)
+    {
+        *m_out = e->segs[lo].m;
+        *s_out = interp_linlin(tauinteract, e->segs[lo - 1].tau, e->segs[lo].tau, e->segs[lo - 1].s, e->segs[lo].s);
+    }
+    else
+    {
+        *m_out = e->segs[lo - 1].m;
+        *s_out = e->segs[lo - 1].s;
+    }
+}
+
+/* DustMix.cpp:391-425: valueHG / integralHG / meanHG */
+static double value_hg(double g, double costheta)
+{
+    double t = 1. + g * g - 2. * g * costheta;
+    return (1. - g) * (1. + g) / sqrt(t * t * t);
+}
+static double integral_hg(double g, double cosalpha, double cosbeta)
+{
+    double ta = sqrt(1. + g * g - 2. * g * cosalpha);
+    double tb = sqrt(1. + g * g - 2. * g * cosbeta);
+    double f1 = (1. - g) * (1. + g) / g;
+    double f2 = (tb - ta) / (tb * ta);
+    return f1 * f2;
+}
+static double mean_hg(double g, double costheta)
+{
+    const double delta = 4. * M_PI / 180.;
+    double theta = acos(costheta);
+    double cosalpha = cos(theta - delta);
+    double cosbeta = cos(theta + delta);
+    if (theta < delta) return (integral_hg(g, 1., cosalpha) + integral_hg(g, 1., cosbeta)) / (2. - cosalpha - cosbeta);
+    if (theta > M_PI - delta)
+        return (integral_hg(g, cosalpha, -1.) + integral_hg(g, cosbeta, -1.)) / (2. + cosalpha + cosbeta);
+    return integral_hg(g, cosalpha, cosbeta) / (cosalpha - cosbeta);
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* instruments                                                                                      */
+/* ------------------------------------------------------------------------------------------------ */
+
+/* FluxRecorder::recordContributions for the SED arrays, FluxRecorder.cpp:962-986 */
+static void flush_history_stats(instr_t* q)
+{
+    if (q->hist_active && q->wsed[0])
+    {
+        double wn = 1.;
+        for (int k = 0; k <= 4; ++k)
+        {
+            q->wsed[k][q->hist_ell] += wn;
+            wn *= q->hist_w;
+        }
+    }
+    q->hist_active = 0;
+    q->hist_w = 0.;
+}
+
+/* Instrument::detect for SED/Frame/Full instruments: SEDInstrument.cpp:22-25 + ApertureInstrument.cpp:24-43,
+ * FrameInstrument.cpp:37-64, FluxRecorder::detect FluxRecorder.cpp:304-468 */
+static void detect(sko_engine_t* e, instr_t* q, packet_t* ppp)
+{
+    int l = 0;
+    double x = ppp->r[0], y = ppp->r[1], z = ppp->r[2];
+    if (q->d.kind == SK_INSTR_SED)
+    {
+        if (q->radius2)
+        {
+            double xpp = -q->sinphi * x + q->cosphi * y;
+            double ypp = -q->cosphi * q->costheta * x - q->sinphi * q->costheta * y + q->sintheta * z;
+            double radius2 = xpp * xpp + ypp * ypp;
+            if (radius2 > q->radius2) return;
+        }
+        l = 0;
+    }
+    else
+    {
+        double xpp = -q->sinphi * x + q->cosphi * y;
+        double ypp = -q->cosphi * q->costheta * x - q->sinphi * q->costheta * y + q->sintheta * z;
+        double xp = q->cosomega * xpp - q->sinomega * ypp;
+        double yp = q->sinomega * xpp + q->cosomega * ypp;
+        int i = (int)floor((xp - q->xpmin) / q->xpsiz);
+        int j = (int)floor((yp - q->ypmin) / q->ypsiz);
+        if (i < 0 || i >= q->d.num_pixels_x || j < 0 || j >= q->d.num_pixels_y)
+            l = -1;
+        else
+            l = i + q->d.num_pixels_x * j;
+    }
+    if (!q->include_sed && l < 0) return;
+
+    int ell = wlg_bin(&e->wlg[q->d.wavelength_grid].g, ppp->lambda);
+    if (ell < 0) return;
+
+    double L = ppp->W / ppp->lambda;
+    double tau;
+    if (ppp->has_tau)
+        tau = ppp->tau_obs;
+    else
+    {
+        tau = get_extinction_optical_depth(e, ppp);
+        ppp->tau_obs = tau;
+        ppp->has_tau = 1;
+    }
+    double Lext = L * exp(-tau);
+    e->cnt.detections++;
+
+    for (int pass = 0; pass < 2; ++pass)
+    {
+        double** arrays = pass == 0 ? q->sed : q->ifu;
+        size_t index;
+        if (pass == 0)
+        {
+            if (!q->include_sed) continue;
+            index = (size_t)ell;
+        }
+        else
+        {
+            if (!q->include_ifu || l < 0) continue;
+            index = (size_t)l + (size_t)ell * q->npix;
+        }
+        if (q->record_total_only)
+            arrays[SK_COMP_TOTAL][index] += Lext;
+        else if (ppp->primary_origin)
+        {
+            if (ppp->nscatt == 0)
+            {
+                arrays[SK_COMP_TRANSPARENT][index] += L;
+                arrays[SK_COMP_PRIMARY_DIRECT][index] += Lext;
+            }
+            else
+            {
+                arrays[SK_COMP_PRIMARY_SCATTERED][index] += Lext;
+                if (ppp->nscatt <= q->d.num_scattering_levels)
+                    arrays[SK_COMP_PRIMARY_SCATTERED_LEVEL + ppp->nscatt - 1][index] += Lext;
+            }
+        }
+        else
+        {
+            if (ppp->nscatt == 0)
+            {
+                arrays[SK_COMP_SECONDARY_TRANSPARENT][index] += L;
+                arrays[SK_COMP_SECONDARY_DIRECT][index] += Lext;
+            }
+            else
+                arrays[SK_COMP_SECONDARY_SCATTERED][index] += Lext;
+        }
+    }
+    if (q->d.record_statistics && q->include_sed)
+    {
+        q->hist_active = 1;
+        q->hist_ell = ell;
+        q->hist_w += Lext;
+    }
+}
+
+/* MonteCarloSimulation::peelOffEmission, MonteCarloSimulation.cpp:617-634; PhotonPacket::launchEmissionPeelOff,
+ * PhotonPacket.cpp:66-85 (isotropic emission: no angular bias) */
+static void peel_off_emission(sko_engine_t* e, const packet_t* pp)
+{
+    packet_t ppp;
+    memset(&ppp, 0, sizeof ppp);
+    for (int j = 0; j < e->ninstr; ++j)
+    {
+        instr_t* q = &e->instr[j];
+        if (!q->same_as_preceding)
+        {
+            ppp = *pp;
+            ppp.nscatt = 0;
+            memcpy(ppp.k, q->kobs, sizeof ppp.k);
+            ppp.has_tau = 0;
+        }
+        detect(e, q, &ppp);
+    }
+}
+
+/* MonteCarloSimulation::peelOffScattering (consolidated branch), MonteCarloSimulation.cpp:784-842;
+ * MediumSystem::peelOffScattering, MediumSystem.cpp:734-767; DustMix::peeloffScattering HG branch,
+ * DustMix.cpp:430-445; PhotonPacket::launchScatteringPeelOff, PhotonPacket.cpp:89-103 */
+static void peel_off_scattering(sko_engine_t* e, const packet_t* pp)
+{
+    const double glarge = 0.95;
+    packet_t ppp;
+    memset(&ppp, 0, sizeof ppp);
+    for (int j = 0; j < e->ninstr; ++j)
+    {
+        instr_t* q = &e->instr[j];
+        if (!q->same_as_preceding)
+        {
+            double costheta = pp->k[0] * q->kobs[0] + pp->k[1] * q->kobs[1] + pp->k[2] * q->kobs[2];
+            double g = e->gpar[pp->ilam];
+            double value = fabs(g) > glarge ? mean_hg(g, costheta) : value_hg(g, costheta);
+            double I = 0.;
+            I += value * 1.; /* single medium: weight wv[0] = 1, MediumSystem.cpp:703-708 */
+            ppp = *pp;
+            ppp.W = pp->W * I;
+            ppp.nscatt = pp->nscatt + 1;
+            memcpy(ppp.k, q->kobs, sizeof ppp.k);
+            ppp.has_tau = 0;
+        }
+        detect(e, q, &ppp);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* sources                                                                                          */
+/* ------------------------------------------------------------------------------------------------ */
+
+/* Random::cdfLogLog, Random.cpp:210-216 */
+static double sample_cdf_loglog(rng_t* g, const double* xv, const double* pv, const double* Pv, int n)
+{
+    double X = uniform(g);
+    int i = locate_clip(Pv, n, X);
+    double alpha = log(pv[i + 1] / pv[i]) / log(xv[i + 1] / xv[i]);
+    return xv[i] * gexp(-alpha, (X - Pv[i]) / (pv[i] * xv[i]));
+}
+/* Random::cdfLinLin, Random.cpp:201-206 */
+static double sample_cdf_linlin(rng_t* g, const double* xv, const double* Pv, int n)
+{
+    double X = uniform(g);
+    int i = locate_clip(Pv, n, X);
+    return interp_linlin(X, Pv[i], Pv[i + 1], xv[i], xv[i + 1]);
+}
+
+/* ContSED::specificLuminosity: BlackBodySED.cpp:38-41 / TabulatedSED.cpp:46-49 */
+static double specific_luminosity(const sk_source_t* s, double lambda)
+{
+    if (s->sed_kind == SK_SED_BLACKBODY) return planck(lambda, s->sed_temperature) / s->sed_norm;
+    int i = locate_fail(s->sed_lambda, s->sed_n, lambda);
+    if (i < 0) return 0.;
+    return interp_loglog(lambda, s->sed_lambda[i], s->sed_lambda[i + 1], s->sed_p[i], s->sed_p[i + 1]);
+}
+
+/* ExpDiskGeometry::randomCylRadius / randomZ, ExpDiskGeometry.cpp:46-68 */
+static double expdisk_random_R(rng_t* g, double hR, double Rmin, double Rmax)
+{
+    double R, X;
+    do
+    {
+        X = uniform(g);
+        R = hR * (-1.0 - lambert_w1((X - 1.0) / M_E));
+    } while ((Rmax > 0.0 && R >= Rmax) || R <= Rmin);
+    return R;
+}
+static double expdisk_random_z(rng_t* g, double hz, double zmax)
+{
+    double z, X;
+    do
+    {
+        X = uniform(g);
+        z = (X <= 0.5) ? hz * log(2.0 * X) : -hz * log(2.0 * (1.0 - X));
+    } while (zmax > 0.0 && fabs(z) >= zmax);
+    return z;
+}
+
+/* Geometry::generatePosition for the supported geometries */
+static void generate_position(rng_t* g, const sk_source_t* s, double r[3])
+{
+    const double* p = s->geom_params;
+    switch (s->geometry)
+    {
+        case SK_GEOM_SHELL:
+        {
+            /* ShellGeometry::randomRadius (ShellGeometry.cpp:43-57) + SpheGeometry::generatePosition (SpheGeometry.cpp:26-33) */
+            double pe = p[2], smin = p[3], sdiff = p[4], tmin = p[5], tmax = p[6];
+            double X = uniform(g);
+            double rad;
+            if (fabs(pe - 3.0) < 1e-2)
+            {
+                double sv = smin + X * sdiff;
+                rad = gexp(pe - 2.0, sv);
+            }
+            else
+            {
+                double zz = (1.0 - X) * tmin + X * tmax;
+                rad = pow(zz, 1.0 / (3.0 - pe));
+            }
+            double k[3];
+            random_direction(g, k);
+            r[0] = rad * k[0];
+            r[1] = rad * k[1];
+            r[2] = rad * k[2];
+            break;
+        }
+        case SK_GEOM_EXPDISK:
+        {
+            /* SepAxGeometry::generatePosition, SepAxGeometry.cpp:12-20 */
+            double R = expdisk_random_R(g, p[0], p[2], p[3]);
+            double phi = 2.0 * M_PI * uniform(g);
+            double z = expdisk_random_z(g, p[1], p[4]);
+            r[0] = R * cos(phi);
+            r[1] = R * sin(phi);
+            r[2] = z;
+            break;
+        }
+        case SK_GEOM_RING:
+        {
+            /* RingGeometry::randomCylRadius / randomZ, RingGeometry.cpp:56-68 */
+            double R = sample_cdf_linlin(g, s->geom_table_x, s->geom_table_P, s->geom_table_n);
+            double phi = 2.0 * M_PI * uniform(g);
+            double X = uniform(g);
+            double z = (X <= 0.5) ? p[2] * log(2.0 * X) : -p[2] * log(2.0 * (1.0 - X));
+            r[0] = R * cos(phi);
+            r[1] = R * sin(phi);
+            r[2] = z;
+            break;
+        }
+        case SK_GEOM_SPIRAL_EXPDISK:
+        {
+            /* SpiralStructureGeometryDecorator::generatePosition / perturbation,
+               SpiralStructureGeometryDecorator.cpp:33-45,72-76 */
+            double R0 = expdisk_random_R(g, p[0], p[2], p[3]);
+            double phi0 = 2.0 * M_PI * uniform(g);
+            double z = expdisk_random_z(g, p[1], p[4]);
+            double x0 = R0 * cos(phi0), y0 = R0 * sin(phi0);
+            double R = sqrt(x0 * x0 + y0 * y0); /* Position::cylindrical, Position.cpp:104-109 */
+            double m = p[5], pitch = p[6], Rz = p[7], phiz = p[8], w = p[9], N = p[10];
+            double tanp = tan(pitch);
+            double cn = sqrt(M_PI) * tgamma(N + 1.0) / tgamma(N + 0.5);
+            double c = 1.0 + (cn - 1.0) * w;
+            double phi, t;
+            do
+            {
+                phi = 2.0 * M_PI * uniform(g);
+                double gamma = log(R / Rz) / tanp + phiz + 0.5 * M_PI / m;
+                double perturbation = (1.0 - w) + w * cn * pow(sin(0.5 * m * (gamma - phi)), 2 * N);
+                t = uniform(g) * c / perturbation;
+            } while (t > 1);
+            r[0] = R * cos(phi);
+            r[1] = R * sin(phi);
+            r[2] = z;
+            break;
+        }
+        default: r[0] = r[1] = r[2] = 0.; break;
+    }
+}
+
+/* SourceSystem::launch (SourceSystem.cpp:101-113), NormalizedSource::launch (NormalizedSource.cpp:73-110),
+ * GeometricSource::launchNormalized (GeometricSource.cpp:66-82), PointSource::launchSpecialty (PointSource.cpp:32-42),
+ * PhotonPacket::launch (PhotonPacket.cpp:18-40) */
+static void launch_primary(sko_engine_t* e, rng_t* g, uint64_t history, packet_t* pp)
+{
+    /* std::upper_bound(_Iv, historyIndex) - 1 */
+    int lo = 0, hi = e->nsrc + 1;
+    while (lo < hi)
+    {
+        int mid = (lo + hi) >> 1;
+        if (history < e->Iv[mid])
+            hi = mid;
+        else
+            lo = mid + 1;
+    }
+    int h = lo - 1;
+    const sk_source_t* s = &e->src[h].s;
+    double weight = e->Lv[h] / e->Wv[h];
+    double L = e->Lpp * weight;
+
+    double lambda, w;
+    double xi = s->wavelength_bias;
+    if (!xi)
+    {
+        lambda = sample_cdf_loglog(g, s->sed_lambda, s->sed_p, s->sed_P, s->sed_n);
+        w = 1.;
+    }
+    else
+    {
+        if (uniform(g) > xi)
+            lambda = sample_cdf_loglog(g, s->sed_lambda, s->sed_p, s->sed_P, s->sed_n);
+        else if (s->bias_kind == SK_BIAS_OLIGO)
+        {
+            size_t index = (size_t)(uniform(g) * s->oligo_n); /* OligoWavelengthDistribution.cpp:34-38 */
+            lambda = s->oligo_lambda[index];
+        }
+        else
+        {
+            double logMin = log(s->bias_min);
+            double logWidth = log(s->bias_max) - log(s->bias_min);
+            lambda = exp(logMin + logWidth * uniform(g)); /* DefaultWavelengthDistribution.cpp:37-40 */
+        }
+        double sl = specific_luminosity(s, lambda);
+        if (!sl)
+            w = 0.;
+        else
+        {
+            double b;
+            if (s->bias_kind == SK_BIAS_OLIGO)
+                b = s->oligo_probability;
+            else
+            {
+                double logWidth = log(s->bias_max) - log(s->bias_min);
+                /* Range::containsFuzzy, SKIRT/utils/Range.hpp:56 */
+                if (lambda >= s->bias_min * (1 - 1e-14) && lambda <= s->bias_max * (1 + 1e-14))
+                    b = 1. / (logWidth * lambda);
+                else
+                    b = 0.;
+            }
+            w = sl / ((1 - xi) * sl + xi * b);
+        }
+    }
+    double Lw = L * w;
+    if (s->kind == SK_SRC_POINT)
+    {
+        pp->r[0] = s->position[0];
+        pp->r[1] = s->position[1];
+        pp->r[2] = s->position[2];
+    }
+    else
+        generate_position(g, s, pp->r);
+    random_direction(g, pp->k);
+    pp->lambda = lambda;
+    pp->W = Lw * lambda;
+    pp->nscatt = 0;
+    pp->primary_origin = 1;
+    pp->history = history;
+    pp->has_tau = 0;
+    pp->ilam = index_for_lambda(e, lambda);
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* the life cycle                                                                                   */
+/* ------------------------------------------------------------------------------------------------ */
+
+/* MonteCarloSimulation::simulateForcedPropagation, MonteCarloSimulation.cpp:696-742 */
+static void simulate_forced_propagation(sko_engine_t* e, rng_t* g, packet_t* pp, int* m_int)
+{
+    double taupath = e->nsegs ? e->segs[e->nsegs - 1].tau : 0.;
+    if (taupath <= 0.)
+    {
+        pp->W *= 0.;
+        *m_int = -1;
+        return;
+    }
+    double xi = e->cfg.path_length_bias;
+    double tau = 0.;
+    if (xi == 0.)
+        tau = expon_cutoff(g, taupath);
+    else
+    {
+        tau = uniform(g) < xi ? uniform(g) * taupath : expon_cutoff(g, taupath);
+        double p = -exp(-tau) / expm1(-taupath);
+        double q = (1.0 - xi) * p + xi / taupath;
+        double weight = p / q;
+        pp->W *= weight;
+    }
+    int m;
+    double s;
+    find_interaction_point(e, tau, &m, &s);
+    /* MediumSystem::albedoForScattering, MediumSystem.cpp:678-693 (single dust medium: ksca/kext) */
+    double albedo = 0.;
+    if (m >= 0)
+    {
+        double n = e->dens[m];
+        double ksca = n * e->sig_sca[pp->ilam];
+        double kext = n * e->sig_ext[pp->ilam];
+        albedo = kext > 0. ? ksca / kext : 0.;
+    }
+    pp->W *= -expm1(-taupath) * albedo;
+    /* PhotonPacket::propagate, PhotonPacket.cpp:107-111 */
+    pp->r[0] += s * pp->k[0];
+    pp->r[1] += s * pp->k[1];
+    pp->r[2] += s * pp->k[2];
+    *m_int = m;
+}
+
+/* MonteCarloSimulation::simulateNonForcedPropagation (MonteCarloSimulation.cpp:746-780) with
+ * MediumSystem::setInteractionPointUsingExtinction (MediumSystem.cpp:978-1010) */
+static int simulate_nonforced_propagation(sko_engine_t* e, rng_t* g, packet_t* pp)
+{
+    double tauinteract = -log(uniform(g)); /* Random::expon, Random.cpp:98-101 */
+    gen_t gen;
+    gen_start(&gen, pp->r, pp->k);
+    double tau = 0., s = 0.;
+    double section = e->sig_ext[pp->ilam];
+    e->cnt.forward_paths++;
+    while (gen_next(e, &gen))
+    {
+        e->cnt.forward_segments++;
+        double tau0 = tau, s0 = s;
+        double ds = gen.ds;
+        int m = gen.m;
+        if (m >= 0) tau += section * e->dens[m] * gen.ds;
+        s += ds;
+        if (tauinteract < tau)
+        {
+            double sint = interp_linlin(tauinteract, tau0, tau, s0, s);
+            double n = e->dens[m];
+            double ksca = n * e->sig_sca[pp->ilam];
+            double kext = n * e->sig_ext[pp->ilam];
+            double albedo = kext > 0. ? ksca / kext : 0.;
+            pp->W *= albedo;
+            pp->r[0] += sint * pp->k[0];
+            pp->r[1] += sint * pp->k[1];
+            pp->r[2] += sint * pp->k[2];
+            return 1;
+        }
+    }
+    return 0;
+}
+
+/* MediumSystem::simulateScattering (MediumSystem.cpp:796-823), DustMix::performScattering HG branch
+ * (DustMix.cpp:496-511), PhotonPacket::scatter (PhotonPacket.cpp:115-122) */
+static void simulate_scattering(sko_engine_t* e, rng_t* g, packet_t* pp)
+{
+    double gp = e->gpar[pp->ilam];
+    double knew[3];
+    if (fabs(gp) < 1e-6)
+        random_direction(g, knew);
+    else
+    {
+        double f = ((1.0 - gp) * (1.0 + gp)) / (1.0 - gp + 2.0 * gp * uniform(g));
+        double costheta = (1.0 + gp * gp - f * f) / (2.0 * gp);
+        random_direction_about(g, pp->k, costheta, knew);
+    }
+    pp->nscatt++;
+    memcpy(pp->k, knew, sizeof knew);
+    e->cnt.scatterings++;
+}
+
+/* MonteCarloSimulation::performLifeCycle for one history index, MonteCarloSimulation.cpp:538-613 */
+static void life_cycle(sko_engine_t* e, uint64_t history, int primary, int peel, int store, uint32_t stream_id)
+{
+    rng_t g;
+    rng_init(&g, e->cfg.seed, stream_id, history);
+    packet_t pp;
+    memset(&pp, 0, sizeof pp);
+    launch_primary(e, &g, history, &pp);
+    (void)primary;
+    if (pp.W / pp.lambda > 0)
+    {
+        e->cnt.packets++;
+        if (peel) peel_off_emission(e, &pp);
+        if (e->cfg.force_scattering)
+        {
+            double Lthreshold = (pp.W / pp.lambda) / e->cfg.min_weight_reduction;
+            int minScattEvents = e->cfg.min_scatt_events;
+            while (1)
+            {
+                set_extinction_optical_depths(e, &pp);
+                if (store) store_radiation_field(e, primary, &pp);
+                int m;
+                simulate_forced_propagation(e, &g, &pp, &m);
+                double L = pp.W / pp.lambda;
+                if (L <= 0 || (L <= Lthreshold && pp.nscatt >= minScattEvents)) break;
+                if (peel) peel_off_scattering(e, &pp);
+                simulate_scattering(e, &g, &pp);
+            }
+        }
+        else
+        {
+            while (1)
+            {
+                if (!simulate_nonforced_propagation(e, &g, &pp)) break;
+                if (pp.W / pp.lambda <= 0) break;
+                if (peel) peel_off_scattering(e, &pp);
+                simulate_scattering(e, &g, &pp);
+            }
+        }
+    }
+    /* per-history statistics: FluxRecorder::detect (FluxRecorder.cpp:457-466) flushes when the history changes */
+    for (int j = 0; j < e->ninstr; ++j) flush_history_stats(&e->instr[j]);
+}
+
+int sko_run_segment(sko_engine_t* e, uint64_t first, uint64_t count, int32_t primary, int32_t peel, int32_t store,
+                    uint32_t stream_id)
+{
+    if (!e) return fail(SK_ERR_INVALID, "null engine");
+    if (!e->grid_kind || !e->dens || !e->nlam || !e->nsrc) return fail(SK_ERR_STATE, "engine is not fully configured");
+    if (!primary) return fail(SK_ERR_UNSUPPORTED, "secondary emission not implemented in the oracle yet");
+    if (!e->npackets) return fail(SK_ERR_STATE, "call prepare_primary first");
+    if (store && e->rf_grid < 0) return fail(SK_ERR_STATE, "no radiation field grid configured");
+    if (store && !e->cfg.force_scattering)
+        return fail(SK_ERR_INVALID, "storing the radiation field requires forced scattering (Configuration.cpp:476-482)");
+    for (uint64_t i = first; i != first + count; ++i) life_cycle(e, i, primary, peel, store, stream_id);
+    return SK_OK;
+}
+
+/* MediumSystem::communicateRadiationField (single process), MediumSystem.cpp:1304-1313 */
+int sko_communicate_rf(sko_engine_t* e, int32_t primary)
+{
+    if (!e) return fail(SK_ERR_INVALID, "null engine");
+    if (!primary && e->rf2) memcpy(e->rf2, e->rf2c, (size_t)e->ncells * e->nrf * sizeof(double));
+    return SK_OK;
+}
+
+/* MediumSystem::totalDustAbsorbedLuminosity, MediumSystem.cpp:1317-1356 (single dust medium) */
+int sko_absorbed_luminosity(sko_engine_t* e, int32_t primary, double* out)
+{
+    if (!e || !out) return fail(SK_ERR_INVALID, "null argument");
+    if (e->rf_grid < 0) return fail(SK_ERR_STATE, "no radiation field");
+    const sk_wavelength_grid_t* g = &e->wlg[e->rf_grid].g;
+    const double* rf = primary ? e->rf1 : e->rf2;
+    double Labs = 0.;
+    for (int m = 0; m < e->ncells; ++m)
+    {
+        double sum = 0.;
+        for (int ell = 0; ell < e->nrf; ++ell)
+        {
+            int il = index_for_lambda(e, g->lambda[ell]);
+            sum += e->sig_abs[il] * e->dens[m] * rf[(size_t)m * e->nrf + ell];
+        }
+        Labs += sum;
+    }
+    *out = Labs;
+    return SK_OK;
+}
+
+int sko_read_rf(sko_engine_t* e, int32_t which, double* out)
+{
+    if (!e || !out) return fail(SK_ERR_INVALID, "null argument");
+    const double* src = which == 0 ? e->rf1 : which == 1 ? e->rf2 : e->rf2c;
+    if (!src) return fail(SK_ERR_STATE, "no radiation field");
+    memcpy(out, src, (size_t)e->ncells * e->nrf * sizeof(double));
+    return SK_OK;
+}
+
+static int read_array(sko_engine_t* e, int instrument, int component, int ifu, double* out)
+{
+    if (!e || !out || instrument < 0 || instrument >= e->ninstr || component < 0 || component >= NUM_COMP)
+        return fail(SK_ERR_INVALID, "bad instrument/component");
+    instr_t* q = &e->instr[instrument];
+    size_t len = ifu ? q->npix * q->nl : (size_t)q->nl;
+    double** arrays = ifu ? q->ifu : q->sed;
+    if (ifu ? !q->include_ifu : !q->include_sed) return fail(SK_ERR_INVALID, "instrument does not record this");
+    if (component == SK_COMP_TOTAL && !q->record_total_only)
+    {
+        /* FluxRecorder::calibrateAndWrite: total = direct + scattered (+ secondary), FluxRecorder.cpp:540-570 */
+        for (size_t i = 0; i < len; ++i)
+        {
+            double t = arrays[SK_COMP_PRIMARY_DIRECT][i] + arrays[SK_COMP_PRIMARY_SCATTERED][i];
+            if (arrays[SK_COMP_SECONDARY_DIRECT])
+                t += arrays[SK_COMP_SECONDARY_DIRECT][i] + arrays[SK_COMP_SECONDARY_SCATTERED][i];
+            out[i] = t;
+        }
+        return SK_OK;
+    }
+    if (!arrays[component]) return fail(SK_ERR_INVALID, "component not recorded");
+    memcpy(out, arrays[component], len * sizeof(double));
+    return SK_OK;
+}
+int sko_read_sed(sko_engine_t* e, int32_t instrument, int32_t component, double* out)
+{
+    return read_array(e, instrument, component, 0, out);
+}
+int sko_read_ifu(sko_engine_t* e, int32_t instrument, int32_t component, double* out)
+{
+    return read_array(e, instrument, component, 1, out);
+}
+int sko_read_sed_stats(sko_engine_t* e, int32_t instrument, int32_t k, double* out)
+{
+    if (!e || !out || instrument < 0 || instrument >= e->ninstr || k < 0 || k > 4)
+        return fail(SK_ERR_INVALID, "bad instrument/power");
+    instr_t* q = &e->instr[instrument];
+    if (!q->wsed[k]) return fail(SK_ERR_INVALID, "statistics not recorded");
+    memcpy(out, q->wsed[k], (size_t)q->nl * sizeof(double));
+    return SK_OK;
+}
+int sko_counters(sko_engine_t* e, sk_counters_t* out, int32_t reset)
+{
+    if (!e || !out) return fail(SK_ERR_INVALID, "null argument");
+    *out = e->cnt;
+    if (reset) memset(&e->cnt, 0, sizeof e->cnt);
+    return SK_OK;
+}
+
+/* test hooks: expose single building blocks so that unit tests can pin them one by one */
+double sko_test_uniform(uint32_t seed, uint32_t stream, uint64_t history, int index)
+{
+    rng_t g;
+    rng_init(&g, seed, stream, history);
+    double u = 0.;
+    for (int i = 0; i <= index; ++i) u = uniform(&g);
+    return u;
+}
+double sko_test_lnmean(double x1, double x2)
+{
+    return lnmean4(x1, x2, log(x1), log(x2));
+}
+double sko_test_lambert_w1(double z)
+{
+    return lambert_w1(z);
+}
+double sko_test_mean_hg(double g, double costheta)
+{
+    return mean_hg(g, costheta);
+}
+/* traces one path from r along k and returns the number of segments; m/ds are written up to cap entries */
+int sko_test_trace(sko_engine_t* e, const double r[3], const double k[3], int32_t* m, double* ds, int cap)
+{
+    gen_t g;
+    gen_start(&g, r, k);
+    int n = 0;
+    while (gen_next(e, &g))
+    {
+        if (n < cap)
+        {
+            m[n] = g.m;
+            ds[n] = g.ds;
+        }
+        n++;
+    }
+    return n;
+}

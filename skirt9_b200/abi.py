@@ -1,0 +1,343 @@
+"""ctypes mirror of include/sk_engine.h and a thin object wrapper around the C ABI.
+
+The wrapper is parametrised by (shared library, symbol prefix) so that the test-suite can drive the CPU
+oracle (prefix ``sko_``) through exactly the same Python code as the CUDA engine (prefix ``sk_engine_``).
+The product never loads the oracle: :func:`load_engine_library` only knows ``libskirt9_b200.so`` and fails
+loudly when it has not been built.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ENGINE_LIB_PATH = os.path.join(_HERE, "csrc", "libskirt9_b200.so")
+
+SK_OK, SK_ERR_INVALID, SK_ERR_UNSUPPORTED, SK_ERR_CUDA, SK_ERR_STATE = range(5)
+
+SK_SRC_POINT, SK_SRC_GEOMETRIC = 1, 2
+SK_GEOM_NONE, SK_GEOM_SHELL, SK_GEOM_EXPDISK, SK_GEOM_RING, SK_GEOM_SPIRAL_EXPDISK = range(5)
+SK_SED_TABULATED, SK_SED_BLACKBODY = 1, 2
+SK_BIAS_NONE, SK_BIAS_LOGUNIFORM, SK_BIAS_OLIGO = 0, 1, 2
+SK_INSTR_SED, SK_INSTR_FRAME, SK_INSTR_FULL = 1, 2, 3
+(SK_COMP_TOTAL, SK_COMP_TRANSPARENT, SK_COMP_PRIMARY_DIRECT, SK_COMP_PRIMARY_SCATTERED, SK_COMP_SECONDARY_DIRECT,
+ SK_COMP_SECONDARY_SCATTERED, SK_COMP_SECONDARY_TRANSPARENT, SK_COMP_PRIMARY_SCATTERED_LEVEL) = range(8)
+SK_GEOM_MAX_PARAMS = 12
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+
+
+class SkConfig(C.Structure):
+    _fields_ = [("seed", C.c_uint32), ("force_scattering", C.c_int32), ("min_scatt_events", C.c_int32),
+                ("path_length_bias", C.c_double), ("min_weight_reduction", C.c_double), ("device", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class SkWavelengthGrid(C.Structure):
+    _fields_ = [("num_bins", C.c_int32), ("num_borders", C.c_int32), ("borders", _dp), ("ell", _ip),
+                ("lambda_", _dp), ("dlambda", _dp)]
+
+
+class SkDustMix(C.Structure):
+    _fields_ = [("num_lambda", C.c_int32), ("reserved", C.c_int32), ("lambda_border", _dp), ("sigma_abs", _dp),
+                ("sigma_sca", _dp), ("asymmpar", _dp), ("mu", C.c_double)]
+
+
+class SkSource(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("geometry", C.c_int32), ("luminosity", C.c_double),
+                ("source_weight", C.c_double), ("position", C.c_double * 3),
+                ("geom_params", C.c_double * SK_GEOM_MAX_PARAMS), ("geom_table_n", C.c_int32),
+                ("sed_kind", C.c_int32), ("geom_table_x", _dp), ("geom_table_P", _dp), ("sed_n", C.c_int32),
+                ("bias_kind", C.c_int32), ("sed_lambda", _dp), ("sed_p", _dp), ("sed_P", _dp),
+                ("sed_temperature", C.c_double), ("sed_norm", C.c_double), ("wavelength_bias", C.c_double),
+                ("bias_min", C.c_double), ("bias_max", C.c_double), ("oligo_n", C.c_int32), ("reserved", C.c_int32),
+                ("oligo_lambda", _dp), ("oligo_probability", C.c_double)]
+
+
+class SkInstrument(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("wavelength_grid", C.c_int32), ("inclination", C.c_double),
+                ("azimuth", C.c_double), ("roll", C.c_double), ("distance", C.c_double), ("radius", C.c_double),
+                ("num_pixels_x", C.c_int32), ("num_pixels_y", C.c_int32), ("field_of_view_x", C.c_double),
+                ("field_of_view_y", C.c_double), ("center_x", C.c_double), ("center_y", C.c_double),
+                ("record_components", C.c_int32), ("num_scattering_levels", C.c_int32),
+                ("record_statistics", C.c_int32), ("reserved", C.c_int32)]
+
+
+class SkSecondary(C.Structure):
+    _fields_ = [("emission_grid", C.c_int32), ("reserved", C.c_int32), ("spatial_bias", C.c_double),
+                ("wavelength_bias", C.c_double), ("bias_min", C.c_double), ("bias_max", C.c_double),
+                ("source_min", C.c_double), ("source_max", C.c_double)]
+
+
+class SkCounters(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in
+                ("packets", "forward_paths", "forward_segments", "replay_segments", "peel_paths", "peel_segments",
+                 "scatterings", "rf_deposits", "detections", "fallbacks")] + [("reserved", C.c_uint64 * 6)]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_ if n != "reserved"}
+
+
+class SkError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"[sk status {code}] {msg}")
+        self.code = code
+
+
+def _d(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    return a, a.ctypes.data_as(_ip)
+
+
+def load_engine_library(path: Optional[str] = None) -> C.CDLL:
+    """Loads the CUDA engine; there is no fallback of any kind."""
+    path = path or ENGINE_LIB_PATH
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} has not been built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(the engine has no CPU fallback)")
+    return C.CDLL(path, mode=C.RTLD_GLOBAL)
+
+
+# names of the C ABI entry points after the prefix; include/sk_engine.h is the authority
+ABI_FUNCTIONS = ["create", "destroy", "set_grid_cartesian", "set_grid_octree", "set_medium", "set_dustmix",
+                 "set_wavelength_grids", "set_sources", "set_instruments", "set_secondary", "clear_rf",
+                 "prepare_primary", "prepare_secondary", "run_segment", "communicate_rf", "absorbed_luminosity",
+                 "read_rf", "read_sed", "read_ifu", "read_sed_stats", "counters"]
+ENGINE_ONLY_FUNCTIONS = ["launch_segment", "synchronize", "last_kernel_ms", "device_buffer"]
+
+
+class Engine:
+    """Object wrapper over the C ABI (``sk_engine_*`` by default)."""
+
+    def __init__(self, config: SkConfig, lib: Optional[C.CDLL] = None, prefix: str = "sk_engine_",
+                 misc_prefix: str = "sk_"):
+        self.lib = lib if lib is not None else load_engine_library()
+        self.prefix = prefix
+        self._last_error = getattr(self.lib, misc_prefix + "last_error")
+        self._last_error.restype = C.c_char_p
+        self._h = C.c_void_p()
+        self._keep = []
+        self.config = config
+        self._call("create", C.byref(config), C.byref(self._h))
+        self.num_cells = 0
+        self.num_rf = 0
+        self._instr = []
+        self._wlg = []
+
+    # -- plumbing -------------------------------------------------------------------------------
+    def _fn(self, name):
+        f = getattr(self.lib, self.prefix + name)
+        f.restype = C.c_int
+        return f
+
+    def _call(self, name, *args):
+        rc = self._fn(name)(*args)
+        if rc != SK_OK:
+            raise SkError(rc, (self._last_error() or b"").decode())
+
+    def close(self):
+        if self._h:
+            f = getattr(self.lib, self.prefix + "destroy")
+            f.restype = None
+            f(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- setters --------------------------------------------------------------------------------
+    def set_grid_cartesian(self, xv, yv, zv):
+        xv, px = _d(xv)
+        yv, py = _d(yv)
+        zv, pz = _d(zv)
+        self._call("set_grid_cartesian", self._h, C.c_int32(len(xv) - 1), C.c_int32(len(yv) - 1),
+                   C.c_int32(len(zv) - 1), px, py, pz)
+
+    def set_grid_octree(self, extent, first_child):
+        ext, pe = _d(extent)
+        fc, pf = _i(first_child)
+        self._call("set_grid_octree", self._h, pe, C.c_int32(len(fc)), pf)
+
+    def set_medium(self, number_density, volume=None):
+        n, pn = _d(number_density)
+        if volume is not None:
+            v, pv = _d(volume)
+        else:
+            pv = None
+        self._call("set_medium", self._h, C.c_int32(len(n)), pn, pv)
+        self.num_cells = len(n)
+
+    def set_dustmix(self, lambda_border, sigma_abs, sigma_sca, asymmpar, mu):
+        lb, p0 = _d(lambda_border)
+        sa, p1 = _d(sigma_abs)
+        ss, p2 = _d(sigma_sca)
+        g, p3 = _d(asymmpar)
+        mix = SkDustMix(len(lb), 0, p0, p1, p2, p3, mu)
+        self._call("set_dustmix", self._h, C.byref(mix))
+
+    def set_wavelength_grids(self, grids: Sequence[dict], rf_grid: int = -1):
+        """grids: dicts with keys borders, ell, lambda, dlambda (see host.DisjointWavelengthGrid.table())."""
+        arr = (SkWavelengthGrid * max(1, len(grids)))()
+        keep = []
+        for k, g in enumerate(grids):
+            b, pb = _d(g["borders"])
+            e, pe = _i(g["ell"])
+            l, pl = _d(g["lambda"])
+            d, pd = _d(g["dlambda"])
+            keep += [b, e, l, d]
+            arr[k] = SkWavelengthGrid(len(l), len(b), pb, pe, pl, pd)
+        self._call("set_wavelength_grids", self._h, C.c_int32(len(grids)), arr, C.c_int32(rf_grid))
+        self._wlg = [len(g["lambda"]) for g in grids]
+        self.num_rf = self._wlg[rf_grid] if rf_grid >= 0 else 0
+
+    def set_sources(self, sources: Sequence[dict], source_bias: float = 0.5):
+        arr = (SkSource * len(sources))()
+        keep = []
+        for k, s in enumerate(sources):
+            q = SkSource()
+            q.kind = s["kind"]
+            q.geometry = s.get("geometry", SK_GEOM_NONE)
+            q.luminosity = s["luminosity"]
+            q.source_weight = s.get("source_weight", 1.0)
+            q.position = (C.c_double * 3)(*s.get("position", (0., 0., 0.)))
+            gp = list(s.get("geom_params", ())) + [0.0] * SK_GEOM_MAX_PARAMS
+            q.geom_params = (C.c_double * SK_GEOM_MAX_PARAMS)(*gp[:SK_GEOM_MAX_PARAMS])
+            if s.get("geom_table_x") is not None:
+                a, pa = _d(s["geom_table_x"])
+                b, pb = _d(s["geom_table_P"])
+                keep += [a, b]
+                q.geom_table_n, q.geom_table_x, q.geom_table_P = len(a), pa, pb
+            q.sed_kind = s["sed_kind"]
+            a, pa = _d(s["sed_lambda"])
+            b, pb = _d(s["sed_p"])
+            c, pc = _d(s["sed_P"])
+            keep += [a, b, c]
+            q.sed_n, q.sed_lambda, q.sed_p, q.sed_P = len(a), pa, pb, pc
+            q.sed_temperature = s.get("sed_temperature", 0.0)
+            q.sed_norm = s.get("sed_norm", 1.0)
+            q.wavelength_bias = s.get("wavelength_bias", 0.0)
+            q.bias_kind = s.get("bias_kind", SK_BIAS_NONE)
+            q.bias_min = s.get("bias_min", 0.0)
+            q.bias_max = s.get("bias_max", 0.0)
+            if s.get("oligo_lambda") is not None:
+                a, pa = _d(s["oligo_lambda"])
+                keep.append(a)
+                q.oligo_n, q.oligo_lambda = len(a), pa
+                q.oligo_probability = s["oligo_probability"]
+            arr[k] = q
+        self._call("set_sources", self._h, C.c_int32(len(sources)), arr, C.c_double(source_bias))
+
+    def set_instruments(self, instruments: Sequence[dict], has_medium_emission: bool = False):
+        arr = (SkInstrument * max(1, len(instruments)))()
+        self._instr = []
+        for k, s in enumerate(instruments):
+            q = SkInstrument()
+            q.kind = s["kind"]
+            q.wavelength_grid = s.get("wavelength_grid", 0)
+            q.inclination = s.get("inclination", 0.0)
+            q.azimuth = s.get("azimuth", 0.0)
+            q.roll = s.get("roll", 0.0)
+            q.distance = s["distance"]
+            q.radius = s.get("radius", 0.0)
+            q.num_pixels_x = s.get("num_pixels_x", 0)
+            q.num_pixels_y = s.get("num_pixels_y", 0)
+            q.field_of_view_x = s.get("field_of_view_x", 0.0)
+            q.field_of_view_y = s.get("field_of_view_y", 0.0)
+            q.center_x = s.get("center_x", 0.0)
+            q.center_y = s.get("center_y", 0.0)
+            q.record_components = int(s.get("record_components", False))
+            q.num_scattering_levels = s.get("num_scattering_levels", 0)
+            q.record_statistics = int(s.get("record_statistics", False))
+            arr[k] = q
+            self._instr.append((self._wlg[q.wavelength_grid], q.num_pixels_x * q.num_pixels_y))
+        self._call("set_instruments", self._h, C.c_int32(len(instruments)), arr, C.c_int32(int(has_medium_emission)))
+
+    def set_secondary(self, emission_grid, spatial_bias, wavelength_bias, bias_min, bias_max, source_min, source_max):
+        sec = SkSecondary(emission_grid, 0, spatial_bias, wavelength_bias, bias_min, bias_max, source_min, source_max)
+        self._call("set_secondary", self._h, C.byref(sec))
+
+    # -- running --------------------------------------------------------------------------------
+    def clear_rf(self, primary=True):
+        self._call("clear_rf", self._h, C.c_int32(int(primary)))
+
+    def prepare_primary(self, num_packets):
+        self._call("prepare_primary", self._h, C.c_uint64(int(num_packets)))
+
+    def prepare_secondary(self, num_packets) -> float:
+        lum = C.c_double()
+        self._call("prepare_secondary", self._h, C.c_uint64(int(num_packets)), C.byref(lum))
+        return lum.value
+
+    def run_segment(self, first, count, primary=True, peel=True, store=False, stream_id=0):
+        self._call("run_segment", self._h, C.c_uint64(int(first)), C.c_uint64(int(count)), C.c_int32(int(primary)),
+                   C.c_int32(int(peel)), C.c_int32(int(store)), C.c_uint32(stream_id))
+
+    def launch_segment(self, first, count, primary=True, peel=True, store=False, stream_id=0):
+        self._call("launch_segment", self._h, C.c_uint64(int(first)), C.c_uint64(int(count)),
+                   C.c_int32(int(primary)), C.c_int32(int(peel)), C.c_int32(int(store)), C.c_uint32(stream_id))
+
+    def synchronize(self):
+        self._call("synchronize", self._h)
+
+    def last_kernel_ms(self) -> float:
+        ms = C.c_float()
+        self._call("last_kernel_ms", self._h, C.byref(ms))
+        return ms.value
+
+    def communicate_rf(self, primary=True):
+        self._call("communicate_rf", self._h, C.c_int32(int(primary)))
+
+    def absorbed_luminosity(self, primary=True) -> float:
+        out = C.c_double()
+        self._call("absorbed_luminosity", self._h, C.c_int32(int(primary)), C.byref(out))
+        return out.value
+
+    # -- outputs --------------------------------------------------------------------------------
+    def read_rf(self, which=0):
+        out = np.empty((self.num_cells, self.num_rf), dtype=np.float64)
+        self._call("read_rf", self._h, C.c_int32(which), out.ctypes.data_as(_dp))
+        return out
+
+    def read_sed(self, instrument=0, component=SK_COMP_TOTAL):
+        nl, _ = self._instr[instrument]
+        out = np.empty(nl, dtype=np.float64)
+        self._call("read_sed", self._h, C.c_int32(instrument), C.c_int32(component), out.ctypes.data_as(_dp))
+        return out
+
+    def read_ifu(self, instrument=0, component=SK_COMP_TOTAL):
+        nl, npix = self._instr[instrument]
+        out = np.empty((nl, npix), dtype=np.float64)
+        self._call("read_ifu", self._h, C.c_int32(instrument), C.c_int32(component), out.ctypes.data_as(_dp))
+        return out
+
+    def read_sed_stats(self, instrument=0):
+        nl, _ = self._instr[instrument]
+        out = np.empty((5, nl), dtype=np.float64)
+        for k in range(5):
+            row = np.empty(nl, dtype=np.float64)
+            self._call("read_sed_stats", self._h, C.c_int32(instrument), C.c_int32(k), row.ctypes.data_as(_dp))
+            out[k] = row
+        return out
+
+    def counters(self, reset=False) -> dict:
+        c = SkCounters()
+        self._call("counters", self._h, C.byref(c), C.c_int32(int(reset)))
+        return c.as_dict()
+
+    def device_buffer(self, which):
+        ptr = C.c_void_p()
+        n = C.c_uint64()
+        self._call("device_buffer", self._h, C.c_int32(which), C.byref(ptr), C.byref(n))
+        return ptr.value, n.value

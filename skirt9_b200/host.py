@@ -1,0 +1,749 @@
+"""Host-side mirror of the SKIRT 9 simulation items that feed the photon life cycle.
+
+Class and attribute names follow the reference (`SKIRT/core/*.hpp`) so that a model is written the way the
+corresponding ``.ski`` file reads.  Everything here is *setup* code that runs once on the host and ends in flat
+tables handed to the engine through the C ABI (include/sk_engine.h); the life cycle itself is never executed
+here -- there is no Python or CPU implementation of the hot path in the product.
+
+All quantities are SI, like the reference's internal units (`SKIRT/utils/Constants.hpp`).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+from scipy.special import erf, gamma as _gamma
+
+from . import abi
+
+# SKIRT/utils/Constants.hpp
+C_LIGHT = 2.99792458e8
+H_PLANCK = 6.62606957e-34
+K_BOLTZ = 1.3806488e-23
+PC = 3.08567758e16
+LSUN = 3.839e26
+MSUN = 1.9891e30
+MICRON = 1e-6
+
+
+# ---------------------------------------------------------------------------------------------------
+# numerical helpers (SKIRT/utils/NR.hpp, SpecialFunctions.cpp)
+# ---------------------------------------------------------------------------------------------------
+
+def gln(p, x):
+    """SpecialFunctions::gln, SpecialFunctions.cpp:798-811 (vectorised over x, scalar or array p)."""
+    p = np.asarray(p, dtype=float)
+    x = np.asarray(x, dtype=float)
+    q = 1.0 - p
+    lnx = np.log(x)
+    s = q * lnx
+    small = lnx * (1.0 + 0.5 * s + s * s / 6.0 + s * s * s / 24.0)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        big = (np.power(x, q) - 1.0) / q
+    return np.where(q == 0.0, lnx, np.where(np.abs(q) < 1e-3, small, big))
+
+
+def gln2(p, x1, x2):
+    """SpecialFunctions::gln2, SpecialFunctions.cpp:815-818."""
+    return x2 ** (1.0 - p) * gln(p, x1 / x2)
+
+
+def cdf2_loglog(xv, pv):
+    """NR::cdf2(loglog=true), SKIRT/utils/NR.cpp:25-60: returns (normalised pv, Pv, norm)."""
+    xv = np.asarray(xv, dtype=float)
+    pv = np.asarray(pv, dtype=float).copy()
+    n = len(xv) - 1
+    area = np.zeros(n)
+    ok = (pv[:-1] > 0) & (pv[1:] > 0)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        alpha = np.log(pv[1:] / pv[:-1]) / np.log(xv[1:] / xv[:-1])
+        a = pv[:-1] * xv[:-1] * gln(-alpha, xv[1:] / xv[:-1])
+    area[ok] = a[ok]
+    Pv = np.concatenate([[0.0], np.cumsum(area)])
+    norm = Pv[-1]
+    if norm > 0:
+        pv /= norm
+        Pv /= norm
+    Pv[-1] = 1.0
+    return pv, Pv, norm
+
+
+def planck(lam, T):
+    """PlanckFunction::value, SKIRT/utils/PlanckFunction.cpp:24-27."""
+    f1 = H_PLANCK * C_LIGHT / (K_BOLTZ * T)
+    f2 = 2.0 * H_PLANCK * C_LIGHT * C_LIGHT
+    return f2 / np.power(lam, 5) / np.expm1(f1 / lam)
+
+
+# ---------------------------------------------------------------------------------------------------
+# wavelength grids (DisjointWavelengthGrid.cpp:22-136)
+# ---------------------------------------------------------------------------------------------------
+
+class DisjointWavelengthGrid:
+    def __init__(self):
+        self.lambdav = self.borderv = self.ellv = self.dlambdav = None
+
+    def _set_range(self, lambdav, log_scale):
+        lam = np.sort(np.asarray(lambdav, dtype=float))
+        n = len(lam)
+        border = np.empty(n + 1)
+        if n == 1:
+            border[0], border[1] = lam[0] * 0.999, lam[0] * 1.001
+        elif log_scale:
+            border[0] = math.sqrt(lam[0] ** 3 / lam[1])
+            border[1:n] = np.sqrt(lam[:-1] * lam[1:])
+            border[n] = math.sqrt(lam[-1] ** 3 / lam[-2])
+        else:
+            border[0] = (3 * lam[0] - lam[1]) / 2
+            border[1:n] = (lam[:-1] + lam[1:]) / 2
+            border[n] = (3 * lam[-1] - lam[-2]) / 2
+        self.lambdav, self.borderv = lam, border
+        self.dlambdav = border[1:] - border[:-1]
+        self.ellv = np.concatenate([[-1], np.arange(n), [-1]]).astype(np.int32)
+
+    def _set_bins(self, lambdav, rel_half_width, constant_width):
+        lam = np.sort(np.asarray(lambdav, dtype=float))
+        n = len(lam)
+        if constant_width:
+            delta = lam[0] * rel_half_width
+            left, right = lam - delta, lam + delta
+        else:
+            left, right = lam * (1 - rel_half_width), lam * (1 + rel_half_width)
+        border = np.empty(2 * n)
+        border[0::2], border[1::2] = left, right
+        ell = np.full(2 * n + 1, -1, dtype=np.int32)
+        ell[1::2] = np.arange(n)
+        self.lambdav, self.borderv, self.ellv = lam, border, ell
+        self.dlambdav = right - left
+
+    @property
+    def num_bins(self):
+        return len(self.lambdav)
+
+    def wavelength_range(self):
+        return float(self.borderv[0]), float(self.borderv[-1])
+
+    def table(self):
+        return {"borders": self.borderv, "ell": self.ellv, "lambda": self.lambdav, "dlambda": self.dlambdav}
+
+
+class LogWavelengthGrid(DisjointWavelengthGrid):
+    """LogWavelengthGrid.cpp:12-24: N characteristic wavelengths from min to max inclusive."""
+
+    def __init__(self, minWavelength, maxWavelength, numWavelengths):
+        super().__init__()
+        n = numWavelengths - 1
+        lam = np.exp(math.log(minWavelength) + np.arange(n + 1) * (math.log(maxWavelength / minWavelength) / n))
+        self._set_range(lam, True)
+
+
+class ListWavelengthGrid(DisjointWavelengthGrid):
+    def __init__(self, wavelengths, log=True):
+        super().__init__()
+        self._set_range(wavelengths, log)
+
+
+class OligoWavelengthGrid(DisjointWavelengthGrid):
+    """OligoWavelengthGrid.cpp:25-31."""
+
+    def __init__(self, wavelengths):
+        super().__init__()
+        self._set_bins(wavelengths, 1e-3, True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# geometries
+# ---------------------------------------------------------------------------------------------------
+
+class ShellGeometry:
+    """ShellGeometry.cpp:14-57."""
+
+    def __init__(self, minRadius, maxRadius, exponent):
+        self.rmin, self.rmax, self.p = minRadius, maxRadius, exponent
+        self.smin = float(gln(self.p - 2.0, self.rmin))
+        self.sdiff = float(gln2(self.p - 2.0, self.rmax, self.rmin))
+        self.tmin = self.rmin ** (3.0 - self.p)
+        self.tmax = self.rmax ** (3.0 - self.p)
+        self.A = 0.25 / math.pi / self.sdiff
+
+    def density(self, x, y, z):
+        r = np.sqrt(x * x + y * y + z * z)
+        with np.errstate(divide="ignore"):
+            rho = self.A * np.power(r, -self.p)
+        return np.where((r < self.rmin) | (r > self.rmax), 0.0, rho)
+
+    def SigmaZ(self):
+        return 2.0 * self.A * float(gln2(self.p, self.rmax, self.rmin))
+
+    def source_fields(self):
+        return {"geometry": abi.SK_GEOM_SHELL,
+                "geom_params": [self.rmin, self.rmax, self.p, self.smin, self.sdiff, self.tmin, self.tmax]}
+
+
+class ExpDiskGeometry:
+    """ExpDiskGeometry.cpp:13-90."""
+
+    def __init__(self, scaleLength, scaleHeight, minRadius=0.0, maxRadius=0.0, maxZ=0.0):
+        self.hR, self.hz, self.Rmin, self.Rmax, self.zmax = scaleLength, scaleHeight, minRadius, maxRadius, maxZ
+        intz = -2.0 * self.hz * math.expm1(-self.zmax / self.hz) if self.zmax > 0 else 2.0 * self.hz
+        tmin = math.exp(-self.Rmin / self.hR) * (1 + self.Rmin / self.hR) if self.Rmin > 0 else 1.0
+        tmax = math.exp(-self.Rmax / self.hR) * (1 + self.Rmax / self.hR) if self.Rmax > 0 else 0.0
+        self.rho0 = 1.0 / (self.hR ** 2 * (tmin - tmax) * 2 * math.pi * intz)
+
+    def density_Rz(self, R, z):
+        absz = np.abs(z)
+        rho = self.rho0 * np.exp(-R / self.hR) * np.exp(-absz / self.hz)
+        out = np.zeros_like(rho)
+        ok = R >= self.Rmin
+        if self.Rmax > 0:
+            ok &= R <= self.Rmax
+        if self.zmax > 0:
+            ok &= absz <= self.zmax
+        out[ok] = rho[ok]
+        return out
+
+    def density(self, x, y, z):
+        return self.density_Rz(np.sqrt(x * x + y * y), z)
+
+    def SigmaZ(self):
+        if self.Rmin > 0:
+            return 0.0
+        if self.zmax > 0:
+            return -2.0 * self.rho0 * self.hz * math.expm1(-self.zmax / self.hz)
+        return 2.0 * self.rho0 * self.hz
+
+    def source_fields(self):
+        return {"geometry": abi.SK_GEOM_EXPDISK, "geom_params": [self.hR, self.hz, self.Rmin, self.Rmax, self.zmax]}
+
+
+class RingGeometry:
+    """RingGeometry.cpp:14-80."""
+
+    def __init__(self, ringRadius, width, height):
+        self.R0, self.w, self.hz = ringRadius, width, height
+        t = self.R0 / self.w / math.sqrt(2.0)
+        intz = 2.0 * self.hz
+        intR = self.w ** 2 * (math.exp(-t * t) + math.sqrt(math.pi) * t * (1.0 + math.erf(t)))
+        self.A = 1.0 / (2.0 * math.pi * intz * intR)
+        NRr = 330
+        self.Rv = np.linspace(max(0.0, self.R0 - 8 * self.w), self.R0 + 8 * self.w, NRr)
+        u = (self.R0 - self.Rv) / self.w / math.sqrt(2.0)
+        self.Xv = 4.0 * math.pi * self.A * self.hz * self.w ** 2 * (
+            math.exp(-t * t) - np.exp(-u * u) + math.sqrt(math.pi) * t * (math.erf(t) - erf(u)))
+        self.Xv[0], self.Xv[-1] = 0.0, 1.0
+
+    def density(self, x, y, z):
+        R = np.sqrt(x * x + y * y)
+        u = (R - self.R0) / (math.sqrt(2.0) * self.w)
+        return self.A * np.exp(-u * u) * np.exp(-np.abs(z) / self.hz)
+
+    def SigmaZ(self):
+        t = self.R0 / (math.sqrt(2.0) * self.w)
+        return 2.0 * self.A * self.hz * math.exp(-t * t)
+
+    def source_fields(self):
+        return {"geometry": abi.SK_GEOM_RING, "geom_params": [self.R0, self.w, self.hz],
+                "geom_table_x": self.Rv, "geom_table_P": self.Xv}
+
+
+class SpiralStructureGeometryDecorator:
+    """SpiralStructureGeometryDecorator.cpp:12-76 decorating an ExpDiskGeometry."""
+
+    def __init__(self, geometry: ExpDiskGeometry, numArms, pitchAngle, radiusZeroPoint, phaseZeroPoint,
+                 perturbationWeight, index):
+        self.geometry = geometry
+        self.m, self.p, self.R0, self.phi0, self.w, self.N = (numArms, pitchAngle, radiusZeroPoint, phaseZeroPoint,
+                                                              perturbationWeight, index)
+        self.tanp = math.tan(self.p)
+        self.cn = math.sqrt(math.pi) * _gamma(self.N + 1.0) / _gamma(self.N + 0.5)
+
+    def perturbation(self, R, phi):
+        with np.errstate(divide="ignore"):
+            g = np.log(R / self.R0) / self.tanp + self.phi0 + 0.5 * math.pi / self.m
+        return (1.0 - self.w) + self.w * self.cn * np.power(np.sin(0.5 * self.m * (g - phi)), 2 * self.N)
+
+    def density(self, x, y, z):
+        R = np.sqrt(x * x + y * y)
+        return self.geometry.density_Rz(R, z) * self.perturbation(R, np.arctan2(y, x))
+
+    def SigmaZ(self):
+        return self.geometry.SigmaZ()
+
+    def source_fields(self):
+        g = self.geometry
+        return {"geometry": abi.SK_GEOM_SPIRAL_EXPDISK,
+                "geom_params": [g.hR, g.hz, g.Rmin, g.Rmax, g.zmax, self.m, self.p, self.R0, self.phi0, self.w, self.N]}
+
+
+# ---------------------------------------------------------------------------------------------------
+# dust mix, medium
+# ---------------------------------------------------------------------------------------------------
+
+def _clamped_resample(lam, inlam, inval, loglog):
+    """NR::clampedResample<interpolateLogLog|interpolateLogLin>, NR.hpp (values clamped outside the table)."""
+    lam = np.asarray(lam, dtype=float)
+    inlam = np.asarray(inlam, dtype=float)
+    inval = np.asarray(inval, dtype=float)
+    if len(inlam) == 1:
+        return np.full_like(lam, inval[0])
+    lx = np.log(np.clip(lam, inlam[0], inlam[-1]))
+    if loglog and np.all(inval > 0):
+        return np.exp(np.interp(lx, np.log(inlam), np.log(inval)))
+    return np.interp(lx, np.log(inlam), inval)
+
+
+class MeanListDustMix:
+    """MeanListDustMix.cpp:12-27 + TabulatedDustMix.cpp:12-44 + DustMix::setupSelfAfter (DustMix.cpp:47-246)."""
+    MU = 1.5e-29  # kg per hydrogen atom
+
+    def __init__(self, wavelengths, extinctionCoefficients, albedos, asymmetryParameters):
+        o = np.argsort(wavelengths)
+        self.inlam = np.asarray(wavelengths, dtype=float)[o]
+        self.inkappa = np.asarray(extinctionCoefficients, dtype=float)[o]
+        self.inalbedo = np.asarray(albedos, dtype=float)[o]
+        self.ing = np.asarray(asymmetryParameters, dtype=float)[o]
+        self.lambda_border = None
+
+    def setup(self, wl_range, extra_wavelengths):
+        per_dex = 1000.0
+        kmin = math.floor(per_dex * math.log10(wl_range[0]))
+        kmax = math.ceil(per_dex * math.log10(wl_range[1]))
+        lam = np.power(10.0, np.arange(kmin, kmax + 1) / per_dex)
+        lam = np.unique(np.concatenate([lam, np.asarray(list(extra_wavelengths), dtype=float)]))
+        dm = 0.1
+        cutoff = lam[-1] > dm
+        if cutoff:
+            lam = lam[lam <= dm]
+            if lam[-1] != dm:
+                lam = np.append(lam, dm)
+            lam = np.append(lam, dm * 1.001)
+        self.lambdav = lam
+        self.lambda_border = lam.copy()
+        self.lambda_border[1:] = np.sqrt(lam[1:] * lam[:-1])
+        mu = self.MU
+        self.sigma_abs = _clamped_resample(lam, self.inlam, mu * self.inkappa * (1 - self.inalbedo), True)
+        self.sigma_sca = _clamped_resample(lam, self.inlam, mu * self.inkappa * self.inalbedo, True)
+        g = _clamped_resample(lam, self.inlam, self.ing, False)
+        self.asymmpar = np.where(np.abs(g) > 0.999999, np.copysign(0.999999, g), g)
+        if cutoff:
+            self.sigma_abs[-2:] = 0.0
+            self.sigma_sca[-2:] = 0.0
+        self.mu = mu
+
+    def index_for_lambda(self, lam):
+        """DustMix::indexForLambda = NR::locateClip(_lambdav, lambda), DustMix.cpp:276-279."""
+        i = np.searchsorted(self.lambda_border, lam, side="right") - 1
+        return np.clip(i, 0, len(self.lambda_border) - 2)
+
+    def section_ext(self, lam):
+        i = self.index_for_lambda(lam)
+        return self.sigma_abs[i] + self.sigma_sca[i]
+
+
+class GeometricMedium:
+    """GeometricMedium.cpp:14-20 with OpticalDepthMaterialNormalization (axis Z), .cpp:12-31."""
+
+    def __init__(self, geometry, materialMix, opticalDepth, wavelength):
+        self.geometry, self.mix = geometry, materialMix
+        self.tau, self.norm_wavelength = opticalDepth, wavelength
+        self.number = None
+
+    def setup(self):
+        section = float(self.mix.section_ext(self.norm_wavelength))
+        self.number = (self.tau / section) / self.geometry.SigmaZ()
+        self.mass = self.number * self.mix.mu
+
+    def number_density(self, x, y, z):
+        return self.number * self.geometry.density(x, y, z)
+
+
+# ---------------------------------------------------------------------------------------------------
+# spatial grids
+# ---------------------------------------------------------------------------------------------------
+
+class CartesianSpatialGrid:
+    """CartesianSpatialGrid.cpp:22-60 with LinMesh; cell index m = k + Nz*j + Nz*Ny*i (.cpp:210-213)."""
+
+    def __init__(self, minX, maxX, minY, maxY, minZ, maxZ, numX, numY, numZ):
+        self.xv = minX + (maxX - minX) * np.arange(numX + 1) / numX
+        self.yv = minY + (maxY - minY) * np.arange(numY + 1) / numY
+        self.zv = minZ + (maxZ - minZ) * np.arange(numZ + 1) / numZ
+        self.extent = (minX, minY, minZ, maxX, maxY, maxZ)
+
+    def setup(self, media, num_density_samples, rng):
+        pass
+
+    @property
+    def num_cells(self):
+        return (len(self.xv) - 1) * (len(self.yv) - 1) * (len(self.zv) - 1)
+
+    def cell_boxes(self):
+        nx, ny, nz = len(self.xv) - 1, len(self.yv) - 1, len(self.zv) - 1
+        i, j, k = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+        i, j, k = i.ravel(), j.ravel(), k.ravel()
+        return np.stack([self.xv[i], self.yv[j], self.zv[k], self.xv[i + 1], self.yv[j + 1], self.zv[k + 1]], axis=1)
+
+    def configure(self, engine):
+        engine.set_grid_cartesian(self.xv, self.yv, self.zv)
+
+
+class DensityTreePolicy:
+    """DensityTreePolicy.cpp:116-227 restricted to the dust-mass-fraction criterion."""
+
+    def __init__(self, minLevel, maxLevel, maxDustFraction):
+        self.minLevel, self.maxLevel, self.maxDustFraction = minLevel, maxLevel, maxDustFraction
+
+
+class PolicyTreeSpatialGrid:
+    """PolicyTreeSpatialGrid with treeType OctTree: TreeSpatialGrid.cpp:23-49, DensityTreePolicy.cpp:242-309,
+    OctTreeNode.cpp:22-35.  Nodes are kept in the reference's breadth-first `_nodev` order."""
+
+    def __init__(self, minX, maxX, minY, maxY, minZ, maxZ, policy: DensityTreePolicy):
+        self.extent = (minX, minY, minZ, maxX, maxY, maxZ)
+        self.policy = policy
+        self.first_child = None
+        self.boxes = None
+
+    def setup(self, media, num_density_samples, rng):
+        pol = self.policy
+        boxes = [np.array([self.extent], dtype=float)]
+        first_child = [np.array([-1], dtype=np.int64)]
+        level, lbeg, total = 0, 0, 1
+        cur = boxes[0]
+        while len(cur):
+            n = len(cur)
+            if level < pol.minLevel:
+                divide = np.ones(n, dtype=bool)
+            elif level >= pol.maxLevel:
+                divide = np.zeros(n, dtype=bool)
+            else:
+                # needsSubdivide: mean of numSamples random density samples times the node volume over the total
+                # dust mass, DensityTreePolicy.cpp:130-154,190-196 (mass density / total mass = geometry density)
+                rho = np.zeros(n)
+                for _ in range(num_density_samples):
+                    u = rng.random((n, 3))
+                    p = cur[:, :3] + u * (cur[:, 3:] - cur[:, :3])
+                    for med in media:
+                        rho += med.geometry.density(p[:, 0], p[:, 1], p[:, 2]) / len(media)
+                rho /= num_density_samples
+                vol = np.prod(cur[:, 3:] - cur[:, :3], axis=1)
+                divide = rho * vol > pol.maxDustFraction
+            idx = np.nonzero(divide)[0]
+            fc = np.full(n, -1, dtype=np.int64)
+            fc[idx] = total + 8 * np.arange(len(idx))
+            first_child[-1] = fc
+            par = cur[idx]
+            c = 0.5 * (par[:, :3] + par[:, 3:])  # Box::center, Box.hpp:135
+            kids = np.empty((len(idx), 8, 6))
+            for ch in range(8):
+                for ax in range(3):
+                    hi = (ch >> ax) & 1
+                    kids[:, ch, ax] = np.where(hi, c[:, ax], par[:, ax])
+                    kids[:, ch, ax + 3] = np.where(hi, par[:, ax + 3], c[:, ax])
+            cur = kids.reshape(-1, 6)
+            if len(cur):
+                boxes.append(cur)
+                first_child.append(np.full(len(cur), -1, dtype=np.int64))
+            lbeg = total
+            total += len(cur)
+            level += 1
+        self.boxes = np.concatenate(boxes)
+        self.first_child = np.concatenate(first_child).astype(np.int32)
+
+    @property
+    def num_cells(self):
+        return int((self.first_child < 0).sum())
+
+    def cell_boxes(self):
+        return self.boxes[self.first_child < 0]
+
+    def configure(self, engine):
+        engine.set_grid_octree(self.extent, self.first_child)
+
+
+class FileTreeSpatialGrid(PolicyTreeSpatialGrid):
+    """FileTreeSpatialGrid.cpp:22-78: rebuilds an octree from the 0/1 pre-order topology stream written by
+    TreeSpatialGridTopologyProbe (TreeSpatialGrid.cpp:232-251); nodes are created depth-first."""
+
+    def __init__(self, minX, maxX, minY, maxY, minZ, maxZ, topology: Sequence[int]):
+        super().__init__(minX, maxX, minY, maxY, minZ, maxZ, None)
+        self.topology = list(topology)
+
+    def setup(self, media, num_density_samples, rng):
+        topo = self.topology
+        boxes = [list(self.extent)]
+        first_child = [-1]
+        pos = [0]
+
+        def subdivide(node):
+            b = boxes[node]
+            c = [0.5 * (b[a] + b[a + 3]) for a in range(3)]
+            fc = len(boxes)
+            first_child[node] = fc
+            for ch in range(8):
+                nb = [0.0] * 6
+                for ax in range(3):
+                    hi = (ch >> ax) & 1
+                    nb[ax] = c[ax] if hi else b[ax]
+                    nb[ax + 3] = b[ax + 3] if hi else c[ax]
+                boxes.append(nb)
+                first_child.append(-1)
+            for ch in range(8):
+                flag = topo[pos[0]]
+                pos[0] += 1
+                if flag:
+                    subdivide(fc + ch)
+
+        # the first item is the number of children of the root (8 or 0)
+        nroot = topo[0]
+        pos[0] = 1
+        if nroot:
+            # FileTreeSpatialGrid subdivides the root, then reads one flag per child in order (depth first)
+            import sys
+            sys.setrecursionlimit(10000)
+            subdivide(0)
+        self.boxes = np.asarray(boxes, dtype=float)
+        self.first_child = np.asarray(first_child, dtype=np.int32)
+
+
+# ---------------------------------------------------------------------------------------------------
+# sources, SEDs
+# ---------------------------------------------------------------------------------------------------
+
+class BlackBodySED:
+    """BlackBodySED.cpp:12-65 + PlanckFunction::cdf (PlanckFunction.cpp:31-42)."""
+
+    def __init__(self, temperature):
+        self.T = temperature
+
+    def setup(self, source_range):
+        lo, hi = source_range
+        n = max(100, int(1000.0 * math.log10(hi / lo)))
+        self.lambdav = np.exp(math.log(lo) + np.arange(n + 1) * (math.log(hi / lo) / n))
+        pv = planck(self.lambdav, self.T)
+        self.pv, self.Pv, self.Ltot = cdf2_loglog(self.lambdav, pv)
+
+    def source_fields(self):
+        return {"sed_kind": abi.SK_SED_BLACKBODY, "sed_lambda": self.lambdav, "sed_p": self.pv, "sed_P": self.Pv,
+                "sed_temperature": self.T, "sed_norm": self.Ltot}
+
+    def specific_luminosity(self, lam):
+        return planck(np.asarray(lam, dtype=float), self.T) / self.Ltot
+
+
+@dataclass
+class PointSource:
+    position: Sequence[float]
+    sed: BlackBodySED
+    luminosity: float  # IntegratedLuminosityNormalization over the source range (W)
+    sourceWeight: float = 1.0
+    wavelengthBias: float = 0.5
+
+    def fields(self):
+        return {"kind": abi.SK_SRC_POINT, "position": tuple(self.position)}
+
+
+@dataclass
+class GeometricSource:
+    geometry: object
+    sed: BlackBodySED
+    luminosity: float
+    sourceWeight: float = 1.0
+    wavelengthBias: float = 0.5
+
+    def fields(self):
+        d = {"kind": abi.SK_SRC_GEOMETRIC}
+        d.update(self.geometry.source_fields())
+        return d
+
+
+# ---------------------------------------------------------------------------------------------------
+# instruments
+# ---------------------------------------------------------------------------------------------------
+
+@dataclass
+class Instrument:
+    instrumentName: str
+    distance: float
+    inclination: float = 0.0
+    azimuth: float = 0.0
+    roll: float = 0.0
+    kind: int = abi.SK_INSTR_SED
+    radius: float = 0.0
+    fieldOfViewX: float = 0.0
+    numPixelsX: int = 0
+    centerX: float = 0.0
+    fieldOfViewY: float = 0.0
+    numPixelsY: int = 0
+    centerY: float = 0.0
+    recordComponents: bool = False
+    numScatteringLevels: int = 0
+    recordStatistics: bool = False
+    wavelengthGrid: Optional[DisjointWavelengthGrid] = None
+
+    def fields(self, grid_index):
+        return {"kind": self.kind, "wavelength_grid": grid_index, "inclination": self.inclination,
+                "azimuth": self.azimuth, "roll": self.roll, "distance": self.distance, "radius": self.radius,
+                "num_pixels_x": self.numPixelsX, "num_pixels_y": self.numPixelsY,
+                "field_of_view_x": self.fieldOfViewX, "field_of_view_y": self.fieldOfViewY,
+                "center_x": self.centerX, "center_y": self.centerY, "record_components": self.recordComponents,
+                "num_scattering_levels": self.numScatteringLevels, "record_statistics": self.recordStatistics}
+
+
+def SEDInstrument(**kw):
+    return Instrument(kind=abi.SK_INSTR_SED, **kw)
+
+
+def FrameInstrument(**kw):
+    return Instrument(kind=abi.SK_INSTR_FRAME, **kw)
+
+
+def FullInstrument(**kw):
+    return Instrument(kind=abi.SK_INSTR_FULL, **kw)
+
+
+# ---------------------------------------------------------------------------------------------------
+# the simulation object
+# ---------------------------------------------------------------------------------------------------
+
+@dataclass
+class MonteCarloSimulation:
+    """Mirror of MonteCarloSimulation + Configuration for the accelerated modes
+    (OligoExtinctionOnly / ExtinctionOnly, with or without a stored radiation field)."""
+    sources: List[object]
+    medium: GeometricMedium
+    grid: object
+    instruments: List[Instrument]
+    numPackets: float
+    oligoWavelengths: Optional[Sequence[float]] = None  # oligochromatic when given
+    minWavelength: float = 0.09e-6  # SourceSystem::minWavelength / maxWavelength (panchromatic)
+    maxWavelength: float = 100e-6
+    defaultWavelengthGrid: Optional[DisjointWavelengthGrid] = None
+    radiationFieldWLG: Optional[DisjointWavelengthGrid] = None
+    storeRadiationField: bool = False
+    forceScattering: bool = True
+    minWeightReduction: float = 1e4
+    minScattEvents: int = 0
+    pathLengthBias: float = 0.5
+    sourceBias: float = 0.5
+    numDensitySamples: int = 100
+    seed: int = 0
+    setup_seed: int = 12345  # host-side sampling of densities / tree policy (numpy RNG)
+    density: Optional[np.ndarray] = field(default=None, repr=False)
+
+    def setup(self):
+        """Simulation::setup(): digests the hierarchy into the flat tables the engine needs."""
+        rng = np.random.default_rng(self.setup_seed)
+        oligo = self.oligoWavelengths is not None
+        if oligo:
+            self.defaultWavelengthGrid = OligoWavelengthGrid(self.oligoWavelengths)
+            self.source_range = self.defaultWavelengthGrid.wavelength_range()  # Configuration.cpp:60-65
+            if self.storeRadiationField:
+                self.radiationFieldWLG = self.defaultWavelengthGrid  # Configuration.cpp:249
+        else:
+            self.source_range = (self.minWavelength, self.maxWavelength)
+        # wavelength grids addressed by index
+        self.grids = []
+        for g in [self.defaultWavelengthGrid, self.radiationFieldWLG] + [i.wavelengthGrid for i in self.instruments]:
+            if g is not None and all(g is not h for h in self.grids):
+                self.grids.append(g)
+        # Configuration::simulationWavelengthRange / simulationWavelengths, Configuration.cpp:566-662
+        lo, hi = self.source_range
+        extra = [self.medium.norm_wavelength]
+        for g in self.grids:
+            a, b = g.wavelength_range()
+            lo, hi = min(lo, a), max(hi, b)
+            extra += list(g.lambdav)
+        if self.storeRadiationField and not oligo:
+            lo, hi = min(lo, 0.09e-6), max(hi, 2000e-6)
+        lo, hi = lo / 1.01, hi * 1.01
+        self.medium.mix.setup((lo, hi), extra)
+        self.medium.setup()
+        for s in self.sources:
+            s.sed.setup(self.source_range)
+        # grid and medium state (MediumSystem.cpp:286-399)
+        self.grid.setup([self.medium], self.numDensitySamples, rng)
+        boxes = self.grid.cell_boxes()
+        self.volume = np.prod(boxes[:, 3:] - boxes[:, :3], axis=1)
+        n = len(boxes)
+        dens = np.zeros(n)
+        if self.numDensitySamples == 1:
+            c = 0.5 * (boxes[:, :3] + boxes[:, 3:])
+            dens = self.medium.number_density(c[:, 0], c[:, 1], c[:, 2])
+        else:
+            for _ in range(self.numDensitySamples):
+                p = boxes[:, :3] + rng.random((n, 3)) * (boxes[:, 3:] - boxes[:, :3])
+                dens += self.medium.number_density(p[:, 0], p[:, 1], p[:, 2])
+            dens /= self.numDensitySamples
+        self.density = dens
+        return self
+
+    def config_struct(self, device=0):
+        xi = self.pathLengthBias if self.forceScattering else 0.0  # Configuration.cpp:497-504
+        force = self.forceScattering or self.storeRadiationField   # Configuration.cpp:476-482
+        return abi.SkConfig(self.seed, int(force), self.minScattEvents, xi, self.minWeightReduction, device, 0)
+
+    def configure(self, engine: abi.Engine):
+        """Hands every table to the engine (the extractor step of INTEGRATION.md)."""
+        oligo = self.oligoWavelengths is not None
+        self.grid.configure(engine)
+        engine.set_medium(self.density, self.volume)
+        mix = self.medium.mix
+        engine.set_dustmix(mix.lambda_border, mix.sigma_abs, mix.sigma_sca, mix.asymmpar, mix.mu)
+        rf = -1
+        if self.storeRadiationField:
+            rf = [k for k, g in enumerate(self.grids) if g is self.radiationFieldWLG][0]
+        engine.set_wavelength_grids([g.table() for g in self.grids], rf)
+        srcs = []
+        for s in self.sources:
+            d = s.fields()
+            d.update(s.sed.source_fields())
+            d["luminosity"] = s.luminosity
+            d["source_weight"] = s.sourceWeight
+            if oligo:
+                # NormalizedSource.cpp:27-31: always use the bias distribution; OligoWavelengthDistribution.cpp:13-38
+                g = self.defaultWavelengthGrid
+                d.update({"wavelength_bias": 1.0, "bias_kind": abi.SK_BIAS_OLIGO, "oligo_lambda": g.lambdav,
+                          "oligo_probability": 1.0 / g.num_bins / g.dlambdav[0]})
+            else:
+                d.update({"wavelength_bias": s.wavelengthBias, "bias_kind": abi.SK_BIAS_LOGUNIFORM,
+                          "bias_min": self.source_range[0], "bias_max": self.source_range[1]})
+            srcs.append(d)
+        engine.set_sources(srcs, self.sourceBias)
+        instr = []
+        for i in self.instruments:
+            g = i.wavelengthGrid if (i.wavelengthGrid is not None and not oligo) else self.defaultWavelengthGrid
+            instr.append(i.fields([k for k, h in enumerate(self.grids) if h is g][0]))
+        engine.set_instruments(instr, False)
+        return engine
+
+    def run(self, engine: abi.Engine, first=0, count=None, stream_id=0):
+        """MonteCarloSimulation::runPrimaryEmission, MonteCarloSimulation.cpp:104-138 (single rank)."""
+        n = int(self.numPackets)
+        store = self.storeRadiationField
+        if store:
+            engine.clear_rf(True)
+        engine.prepare_primary(n)
+        engine.run_segment(first, n if count is None else count, primary=True, peel=True, store=store,
+                           stream_id=stream_id)
+        if store:
+            engine.communicate_rf(True)
+
+    # -- calibration of raw tallies to the units the reference writes ------------------------------
+    def sed_flux_density(self, engine, instrument=0, component=abi.SK_COMP_TOTAL):
+        """FluxRecorder::calibrateAndWrite, FluxRecorder.cpp:672-708: F_lambda = L/(4 pi d^2)/dlambda (W/m2/m);
+        returned as F_nu in Jy (fluxOutputStyle Frequency, Units.cpp:557-567)."""
+        i = self.instruments[instrument]
+        oligo = self.oligoWavelengths is not None
+        g = i.wavelengthGrid if (i.wavelengthGrid is not None and not oligo) else self.defaultWavelengthGrid
+        L = engine.read_sed(instrument, component)
+        flam = L / (4 * math.pi * i.distance ** 2) / g.dlambdav
+        return flam * g.lambdav ** 2 / C_LIGHT * 1e26
+
+    def mean_intensity(self, engine, which=0):
+        """MediumSystem::meanIntensity, MediumSystem.cpp:1370-1380: J_lambda = rf/(4 pi V dlambda)."""
+        rf = engine.read_rf(which)
+        g = self.radiationFieldWLG
+        return rf / (4 * math.pi * self.volume[:, None] * g.dlambdav[None, :])
