@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""bench.py -- photon packets/s of the life-cycle hot path on BASELINE.json configs[1]
+(dusty spiral galaxy, ~9.3e5-cell octree, 50 wavelength bins, 256^2 FullInstrument, 1e8 packets per GPU).
+
+  python bench.py --gpus N --steps K --warmup W          # this repo's CUDA engine (one rank per GPU under torchrun)
+  python bench.py --impl reference --steps K --warmup W  # the UNMODIFIED reference (oracle/_ref) on the host cores
+
+A step = one primary-emission segment (MonteCarloSimulation::runPrimaryEmission): all histories of the rank's
+shard through the life-cycle kernel, then (N>1) the reduction of the instrument arrays over NCCL where the reference
+calls ProcessManager::sumToRoot (FluxRecorder.cpp:487-493).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "photon packets/sec"
+UNIT = "packets/s"
+SKI = os.path.join(ROOT, "tests", "golden", "ski", "cfg2.ski")
+REF_EXE = os.path.join(ROOT, "oracle", "_ref", "release", "SKIRT", "main", "skirt")
+WORKLOAD = "cfg2: dusty spiral (spiral exp-disk source, ring dust tau_Z=1), OctTree ~9.3e5 cells (levels 3-9), " \
+           "50 log wavelength bins 0.1-10 micron, FullInstrument 256x256 i=60deg, forced scattering, no RF"
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        d = json.load(open(p))
+        for key in ("hbm_gbs", "hbm_gb_s", "hbm_GBps"):
+            if key in d:
+                return float(d[key]), "measured (MEASURED_PEAKS.json)"
+        if isinstance(d.get("hbm"), dict) and "gbs" in d["hbm"]:
+            return float(d["hbm"]["gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        pass
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 3 + k and r[3 + k].lower().startswith("active")
+                                                         for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def run_reference_once(num_packets, threads, workdir):
+    """Times the unmodified reference on the same ski: returns packets/s from its own TimeLogger line."""
+    ski = os.path.join(workdir, "cfg2.ski")
+    text = open(SKI).read().replace('numPackets="1e6"', f'numPackets="{num_packets:g}"')
+    open(ski, "w").write(text)
+    out = os.path.join(workdir, "out")
+    os.makedirs(out, exist_ok=True)
+    subprocess.check_call([REF_EXE, "-t", str(threads), "-b", "-o", out, ski], stdout=subprocess.DEVNULL,
+                          stderr=subprocess.DEVNULL)
+    log = open(os.path.join(out, "cfg2_log.txt")).read()
+    m = re.search(r"Finished primary emission in ([0-9.]+) s", log)
+    return num_packets / float(m.group(1)), float(m.group(1))
+
+
+def run_port_once(num_packets):
+    """Fallback when oracle/_ref is absent: times the single-threaded C port of the oracle."""
+    from skirt9_b200 import configs
+    from tests.oracle_lib import OracleEngine
+    sim = configs.cfg2(num_packets=num_packets).setup()
+    e = sim.configure(OracleEngine(sim.config_struct()))
+    t = time.time()
+    sim.run(e)
+    dt = time.time() - t
+    return num_packets / dt, dt
+
+
+def cpu_baseline(sample_packets):
+    cores = os.cpu_count() or 1
+    if os.path.exists(REF_EXE):
+        with tempfile.TemporaryDirectory() as d:
+            rate, secs = run_reference_once(sample_packets, cores, d)
+        return {"value": rate, "unit": UNIT, "cores": cores, "kind": "reference",
+                "sample": f"unmodified SKIRT 9 (oracle/_ref) -t {cores}, same cfg2 ski, {sample_packets:g} packets, "
+                          f"'Finished primary emission in {secs:.1f} s'"}
+    rate, secs = run_port_once(min(sample_packets, 2e5))
+    return {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"oracle/sk_oracle.c single thread, {min(sample_packets, 2e5):g} packets in {secs:.1f} s"}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n = args.ref_packets
+    rates = []
+    with tempfile.TemporaryDirectory() as d:
+        have_ref = os.path.exists(REF_EXE)
+        for it in range(args.warmup + args.steps):
+            rate, secs = run_reference_once(n, cores, d) if have_ref else run_port_once(min(n, 2e5))
+            if it >= args.warmup:
+                rates.append((rate, secs))
+    value = sum(r for r, _ in rates) / len(rates)
+    ms = 1e3 * sum(s for _, s in rates) / len(rates)
+    kind = "reference" if have_ref else "port"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "packets_per_step": n, "timing": "reference TimeLogger 'Finished primary emission'"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores if have_ref else 1, "kind": kind,
+                             "sample": f"{n:g} packets per step, {'skirt -t %d' % cores if have_ref else 'C port, 1 thread'}"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def native_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from skirt9_b200 import abi, configs
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    packets_per_gpu = int(args.packets)
+    total = packets_per_gpu * world
+
+    sim = configs.cfg2(num_packets=total).setup()
+    engine = sim.configure(abi.Engine(sim.config_struct(device=local)))
+    stream = torch.cuda.ExternalStream(engine.cuda_stream(), device=local)
+    det = engine.device_tensor(3)
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=f"cuda:{local}")  # > 126 MB L2
+    first = rank * packets_per_gpu
+
+    def step(stream_id):
+        with torch.cuda.stream(stream):
+            flush.zero_()                      # L2 flush between iterations
+            engine.clear_instruments()
+            engine.prepare_primary(total)
+            engine.launch_segment(first, packets_per_gpu, True, True, False, stream_id)
+            if world > 1:
+                dist.all_reduce(det)           # FluxRecorder::calibrateAndWrite -> ProcessManager::sumToRoot
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for w in range(args.warmup):
+        step(w)
+        engine.synchronize()
+    engine.counters(reset=True)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms = []
+    ev0.record(stream)
+    for k in range(args.steps):
+        step(args.warmup + k)
+        engine.synchronize()                   # also reads back the kernel's own CUDA-event duration
+        kernel_ms.append(engine.last_kernel_ms())
+    ev1.record(stream)
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    cnt = engine.counters()
+
+    # ---- end-to-end through the public API with host buffers: tables H2D, run, tallies D2H, every step
+    e2e_steps = max(1, min(args.steps, 2))
+    h2d = (sim.grid.first_child.nbytes + sim.density.nbytes + sim.volume.nbytes
+           + sum(g.borderv.nbytes + g.ellv.nbytes + g.lambdav.nbytes + g.dlambdav.nbytes for g in sim.grids)
+           + 4 * sim.medium.mix.lambda_border.nbytes + sum(3 * s.sed.lambdav.nbytes for s in sim.sources))
+    d2h = 0
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        e2 = sim.configure(abi.Engine(sim.config_struct(device=local)))
+        e2.prepare_primary(total)
+        e2.run_segment(first, packets_per_gpu, True, True, False, 1000 + k)
+        if world > 1:
+            with torch.cuda.stream(torch.cuda.ExternalStream(e2.cuda_stream(), device=local)):
+                dist.all_reduce(e2.device_tensor(3))
+            e2.synchronize()
+        outs = [e2.read_sed(0, c) for c in (0, 1, 2, 3)] + [e2.read_ifu(0, c) for c in (0, 1, 2, 3)]
+        d2h = sum(o.nbytes for o in outs) + 2 * outs[4].nbytes  # total = direct + scattered is read as two arrays
+        e2.close()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+
+    if rank == 0:
+        ms_per_step = ms_total / args.steps
+        value = total / (ms_per_step * 1e-3)
+        pk = max(cnt["packets"], 1)
+        S = (cnt["forward_segments"] + cnt["peel_segments"]) / pk
+        S_fwd = cnt["forward_segments"] / pk
+        P_peel = cnt["peel_paths"] / pk
+        bytes_per_packet = 60.0 * S + 32.0 * P_peel + 64.0     # SURVEY.md 8d accounting (no RF store in cfg2)
+        kms = sum(kernel_ms) / len(kernel_ms)
+        achieved = bytes_per_packet * packets_per_gpu / (kms * 1e-3) / 1e9
+        peak, which = measured_peak()
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "packets_per_gpu": packets_per_gpu, "cells": int(sim.grid.num_cells),
+                           "l2": "256 MB buffer written between iterations", "sharding": "contiguous history blocks, "
+                           "replicated grid, NCCL all-reduce of the instrument arrays per step" if world > 1 else "single GPU"},
+                "e2e": {"value": total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                        "includes": "engine create + octree link build + all table uploads + kernel + read-back of 4 SED and 4 IFU arrays"},
+                "gpu_launches": args.steps,
+                "kernel": {"name": "sk_life_cycle_kernel<2>", "ms_per_launch": kms,
+                           "segments_per_packet": S, "forward_segments_per_packet": S_fwd,
+                           "replay_segments_per_packet": cnt["replay_segments"] / pk,
+                           "peel_paths_per_packet": P_peel, "scatterings_per_packet": cnt["scatterings"] / pk,
+                           "segments_per_s": (cnt["forward_segments"] + cnt["peel_segments"] + cnt["replay_segments"])
+                           / args.steps / (kms * 1e-3), "tree_fallbacks": cnt["fallbacks"]},
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": traffic, "peak_source": which,
+                             "bytes_per_packet": bytes_per_packet,
+                             "note": "algorithmic bytes (60 B/segment + 32 B/detection + 64 B/launch); the working set is "
+                                     "L2-resident so DRAM traffic is far lower: the kernel is latency/fp64-issue bound"},
+                "clocks": clocks}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args.cpu_packets)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--packets", type=float, default=1e8, help="packets per GPU per step (BASELINE configs[1]: 1e8)")
+    ap.add_argument("--cpu-packets", type=float, default=2e6, help="bounded sample for the cpu_baseline leg")
+    ap.add_argument("--ref-packets", type=float, default=1e6, help="packets per step of --impl reference")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        native_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -214,6 +214,10 @@ int sk_engine_set_instruments(sk_engine_t* e, int32_t n, const sk_instrument_t* 
 
 int sk_engine_set_secondary(sk_engine_t* e, const sk_secondary_t* sec);
 
+/* Zeroes all detector and statistics arrays (what FluxRecorder::finalizeConfiguration leaves behind,
+ * FluxRecorder.cpp:185-300) so that one engine can run several simulations back to back. */
+int sk_engine_clear_instruments(sk_engine_t* e);
+
 /* MediumSystem::clearRadiationField(primary) (MediumSystem.cpp:1279-1290). */
 int sk_engine_clear_rf(sk_engine_t* e, int32_t primary);
 
@@ -262,6 +266,9 @@ int sk_engine_counters(sk_engine_t* e, sk_counters_t* out, int32_t reset);
  * shim's own ncclAllReduce) can reduce tallies in place: which = 0 rf1, 1 rf2, 2 rf2c, 3 = all
  * detector arrays of all instruments (one contiguous block), 4 = all statistics arrays. */
 int sk_engine_device_buffer(sk_engine_t* e, int32_t which, void** device_ptr, uint64_t* num_doubles);
+/* The cudaStream_t all engine work is enqueued on (so that a caller can order its collectives and its CUDA
+ * events after the life-cycle kernel without a host synchronisation). */
+int sk_engine_cuda_stream(sk_engine_t* e, void** stream);
 
 #ifdef __cplusplus
 }

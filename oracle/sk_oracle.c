@@ -793,6 +793,24 @@ int sko_set_secondary(sko_engine_t* e, const sk_secondary_t* sec)
     return fail(SK_ERR_UNSUPPORTED, "secondary emission not implemented in the oracle yet");
 }
 
+int sko_clear_instruments(sko_engine_t* e)
+{
+    if (!e) return fail(SK_ERR_INVALID, "null engine");
+    for (int i = 0; i < e->ninstr; ++i)
+    {
+        instr_t* q = &e->instr[i];
+        size_t lensed = q->include_sed ? (size_t)q->nl : 0, lenifu = q->include_ifu ? q->npix * q->nl : 0;
+        for (int c = 0; c < NUM_COMP; ++c)
+        {
+            if (q->sed[c]) memset(q->sed[c], 0, lensed * sizeof(double));
+            if (q->ifu[c]) memset(q->ifu[c], 0, lenifu * sizeof(double));
+        }
+        for (int k = 0; k < 5; ++k)
+            if (q->wsed[k]) memset(q->wsed[k], 0, lensed * sizeof(double));
+    }
+    return SK_OK;
+}
+
 /* MediumSystem::clearRadiationField, MediumSystem.cpp:1279-1290 */
 int sko_clear_rf(sko_engine_t* e, int32_t primary)
 {
@@ -1945,4 +1963,10 @@ int sko_test_trace(sko_engine_t* e, const double r[3], const double k[3], int32_
         n++;
     }
     return n;
+}
+void sko_test_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3]};
+    philox4x32_10(c, key[0], key[1]);
+    memcpy(out, c, sizeof c);
 }

@@ -109,10 +109,10 @@ def load_engine_library(path: Optional[str] = None) -> C.CDLL:
 
 # names of the C ABI entry points after the prefix; include/sk_engine.h is the authority
 ABI_FUNCTIONS = ["create", "destroy", "set_grid_cartesian", "set_grid_octree", "set_medium", "set_dustmix",
-                 "set_wavelength_grids", "set_sources", "set_instruments", "set_secondary", "clear_rf",
+                 "set_wavelength_grids", "set_sources", "set_instruments", "set_secondary", "clear_instruments", "clear_rf",
                  "prepare_primary", "prepare_secondary", "run_segment", "communicate_rf", "absorbed_luminosity",
                  "read_rf", "read_sed", "read_ifu", "read_sed_stats", "counters"]
-ENGINE_ONLY_FUNCTIONS = ["launch_segment", "synchronize", "last_kernel_ms", "device_buffer"]
+ENGINE_ONLY_FUNCTIONS = ["launch_segment", "synchronize", "last_kernel_ms", "device_buffer", "cuda_stream"]
 
 
 class Engine:
@@ -269,6 +269,24 @@ class Engine:
         self._call("set_secondary", self._h, C.byref(sec))
 
     # -- running --------------------------------------------------------------------------------
+    def clear_instruments(self):
+        self._call("clear_instruments", self._h)
+
+    def cuda_stream(self) -> int:
+        p = C.c_void_p()
+        self._call("cuda_stream", self._h, C.byref(p))
+        return p.value or 0
+
+    def device_tensor(self, which):
+        """The engine's tally buffer `which` as a torch CUDA tensor sharing the memory (for NCCL collectives)."""
+        import torch
+        ptr, n = self.device_buffer(which)
+
+        class _Span:
+            __cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 3,
+                                        "strides": None}
+        return torch.as_tensor(_Span(), device=f"cuda:{self.config.device}")
+
     def clear_rf(self, primary=True):
         self._call("clear_rf", self._h, C.c_int32(int(primary)))
 

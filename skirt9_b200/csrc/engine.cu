@@ -1,0 +1,1027 @@
+// engine.cu -- host side of libskirt9_b200.so: the C ABI of include/sk_engine.h, the device memory layout
+// builder (octree links / lattice tables) and the kernel launches.  sm_100a only; no CPU fallback.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "sk_lifecycle.cuh"
+
+// ---------------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg)
+{
+    g_err = msg;
+    return code;
+}
+#define CK(call)                                                                                            \
+    do                                                                                                      \
+    {                                                                                                       \
+        cudaError_t _e = (call);                                                                            \
+        if (_e != cudaSuccess)                                                                              \
+            return fail(SK_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));                   \
+    } while (0)
+
+extern "C" const char* sk_last_error(void)
+{
+    return g_err.c_str();
+}
+extern "C" int sk_abi_version(void)
+{
+    return SK_ABI_VERSION;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------------
+#define SK_BLOCK 128
+#define SK_CHUNK 8
+
+template <int GRID>
+__global__ void __launch_bounds__(SK_BLOCK) sk_life_cycle_kernel(const SkDevModel M, const SkRunArgs A)
+{
+    extern __shared__ double smem[];
+    SkSmemTables T;
+    {
+        // stage the per-axis border tables (Cartesian borders / octree lattice) in shared memory
+        const int n0 = (GRID == 1 ? M.nx : M.nx) + 1, n1 = (GRID == 1 ? M.ny : M.nx) + 1,
+                  n2 = (GRID == 1 ? M.nz : M.nx) + 1;
+        if (M.lattice_in_smem)
+        {
+            for (int i = threadIdx.x; i < n0; i += blockDim.x) smem[i] = M.xv[i];
+            for (int i = threadIdx.x; i < n1; i += blockDim.x) smem[n0 + i] = M.yv[i];
+            for (int i = threadIdx.x; i < n2; i += blockDim.x) smem[n0 + n1 + i] = M.zv[i];
+            __syncthreads();
+            T.X = smem;
+            T.Y = smem + n0;
+            T.Z = smem + n0 + n1;
+        }
+        else
+        {
+            T.X = M.xv;
+            T.Y = M.yv;
+            T.Z = M.zv;
+        }
+    }
+    SkLocalCounters cnt;
+    memset(&cnt, 0, sizeof cnt);
+
+    // persistent threads: every thread draws chunks of history indices from a global dispenser; the tallies do
+    // not depend on which thread runs which history because the random stream is keyed by the history index
+    while (true)
+    {
+        unsigned long long base = atomicAdd(A.work_counter, (unsigned long long)SK_CHUNK);
+        if (base >= A.count) break;
+        unsigned long long end = base + SK_CHUNK < A.count ? base + SK_CHUNK : A.count;
+        for (unsigned long long h = base; h < end; ++h) sk_life_cycle<GRID>(M, T, A, cnt, A.first + h);
+    }
+
+    // counters: warp reduce, one atomic per warp and counter
+    unsigned int* c = reinterpret_cast<unsigned int*>(&cnt);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(SkLocalCounters) / sizeof(unsigned int)); ++i)
+    {
+        unsigned int v = __reduce_add_sync(0xffffffffu, c[i]);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&M.counters[i], (unsigned long long)v);
+    }
+}
+
+// MediumSystem::totalDustAbsorbedLuminosity, MediumSystem.cpp:1317-1356 (single dust medium, constant sections)
+__global__ void sk_absorbed_kernel(const double* __restrict__ rf, const double* __restrict__ dens_or_null,
+                                   const SkCellRec* __restrict__ cells, const double* __restrict__ kabs, int ncells,
+                                   int nrf, double* out)
+{
+    double sum = 0.;
+    for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < ncells; m += gridDim.x * blockDim.x)
+    {
+        double n = dens_or_null ? dens_or_null[m] : cells[m].dens;
+        double s = 0.;
+        for (int ell = 0; ell < nrf; ++ell) s += kabs[ell] * n * rf[(size_t)m * nrf + ell];
+        sum += s;
+    }
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, sum);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// engine object
+// ---------------------------------------------------------------------------------------------------
+struct HostInstr {
+    sk_instrument_t d;
+    int nl;
+    size_t npix;
+    bool include_sed, include_ifu, record_total_only;
+    long long sed_off[SK_NUM_COMP], ifu_off[SK_NUM_COMP];  // offsets (doubles) into the detector block, -1 = absent
+    long long wsed_off[5];
+};
+
+struct sk_engine {
+    sk_config_t cfg;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    SkDevModel M;
+    // owned device allocations by group
+    std::vector<void*> grid_allocs, medium_allocs, dust_allocs, wlg_allocs, src_allocs, instr_allocs, rf_allocs;
+    // host mirrors
+    int grid_kind = 0;
+    int grid_cells = 0;
+    std::vector<double> dens_host;
+    std::vector<SkCellRec> cellrec_host;  // octree records (links filled by set_grid, density by set_medium)
+    std::vector<double> dust_lam_border, dust_sig_abs;
+    std::vector<sk_wavelength_grid_t> wlg_host;
+    std::vector<std::vector<double>> wlg_lambda;
+    std::vector<double> Lv, Wv;
+    double Ltot = 0.;
+    uint64_t npackets = 0;
+    std::vector<HostInstr> instr;
+    double* det_block = nullptr;
+    size_t det_count = 0;
+    double* stat_block = nullptr;
+    size_t stat_count = 0;
+    unsigned long long* work_counter = nullptr;
+    double* scalar = nullptr;
+    int table_len[3] = {0, 0, 0};
+    size_t smem_bytes = 0;
+    float last_ms = 0.f;
+    bool timing_pending = false;
+};
+
+static void free_group(std::vector<void*>& v)
+{
+    for (void* p : v) cudaFree(p);
+    v.clear();
+}
+template <class T>
+static int upload(std::vector<void*>& group, const T* host, size_t n, T** out)
+{
+    T* d = nullptr;
+    CK(cudaMalloc(&d, std::max<size_t>(n, 1) * sizeof(T)));
+    group.push_back(d);
+    if (n) CK(cudaMemcpy(d, host, n * sizeof(T), cudaMemcpyHostToDevice));
+    *out = d;
+    return SK_OK;
+}
+template <class T>
+static int dalloc_zero(std::vector<void*>& group, size_t n, T** out)
+{
+    T* d = nullptr;
+    CK(cudaMalloc(&d, std::max<size_t>(n, 1) * sizeof(T)));
+    group.push_back(d);
+    CK(cudaMemset(d, 0, std::max<size_t>(n, 1) * sizeof(T)));
+    *out = d;
+    return SK_OK;
+}
+
+extern "C" int sk_engine_create(const sk_config_t* config, sk_engine_t** out)
+{
+    if (!config || !out) return fail(SK_ERR_INVALID, "null argument");
+    int ndev = 0;
+    cudaError_t err = cudaGetDeviceCount(&ndev);
+    if (err != cudaSuccess || ndev == 0)
+        return fail(SK_ERR_CUDA, "no CUDA device available (the engine has no CPU fallback)");
+    if (config->device < 0 || config->device >= ndev) return fail(SK_ERR_INVALID, "device ordinal out of range");
+    CK(cudaSetDevice(config->device));
+    sk_engine* e = new sk_engine();
+    e->cfg = *config;
+    memset(&e->M, 0, sizeof e->M);
+    e->M.seed = config->seed;
+    e->M.force_scattering = config->force_scattering;
+    e->M.min_scatt_events = config->min_scatt_events;
+    e->M.path_length_bias = config->path_length_bias;
+    e->M.min_weight_reduction = config->min_weight_reduction;
+    e->M.rf_grid = -1;
+    CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&e->ev0));
+    CK(cudaEventCreate(&e->ev1));
+    CK(cudaMalloc(&e->work_counter, sizeof(unsigned long long)));
+    CK(cudaMalloc(&e->scalar, sizeof(double)));
+    CK(cudaMalloc(&e->M.counters, 16 * sizeof(unsigned long long)));
+    CK(cudaMemset(e->M.counters, 0, 16 * sizeof(unsigned long long)));
+    *out = e;
+    return SK_OK;
+}
+
+extern "C" void sk_engine_destroy(sk_engine_t* e)
+{
+    if (!e) return;
+    cudaSetDevice(e->cfg.device);
+    cudaStreamSynchronize(e->stream);
+    free_group(e->grid_allocs);
+    free_group(e->medium_allocs);
+    free_group(e->dust_allocs);
+    free_group(e->wlg_allocs);
+    free_group(e->src_allocs);
+    free_group(e->instr_allocs);
+    free_group(e->rf_allocs);
+    cudaFree(e->work_counter);
+    cudaFree(e->scalar);
+    cudaFree(e->M.counters);
+    cudaEventDestroy(e->ev0);
+    cudaEventDestroy(e->ev1);
+    cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+static int set_tables(sk_engine* e, const double* xv, int nx1, const double* yv, int ny1, const double* zv, int nz1)
+{
+    double *dx, *dy, *dz;
+    if (int rc = upload(e->grid_allocs, xv, nx1, &dx)) return rc;
+    if (int rc = upload(e->grid_allocs, yv, ny1, &dy)) return rc;
+    if (int rc = upload(e->grid_allocs, zv, nz1, &dz)) return rc;
+    e->M.xv = dx;
+    e->M.yv = dy;
+    e->M.zv = dz;
+    e->table_len[0] = nx1;
+    e->table_len[1] = ny1;
+    e->table_len[2] = nz1;
+    size_t bytes = (size_t)(nx1 + ny1 + nz1) * sizeof(double);
+    // keep the tables in shared memory when they leave room for >= 4 CTAs per SM (227 KB per SM)
+    e->M.lattice_in_smem = bytes <= 48 * 1024 ? 1 : 0;
+    e->smem_bytes = e->M.lattice_in_smem ? bytes : 0;
+    return SK_OK;
+}
+
+extern "C" int sk_engine_set_grid_cartesian(sk_engine_t* e, int32_t nx, int32_t ny, int32_t nz, const double* xv,
+                                            const double* yv, const double* zv)
+{
+    if (!e || nx < 1 || ny < 1 || nz < 1 || !xv || !yv || !zv) return fail(SK_ERR_INVALID, "bad cartesian grid");
+    CK(cudaSetDevice(e->cfg.device));
+    free_group(e->grid_allocs);
+    e->grid_kind = 1;
+    e->M.grid_kind = 1;
+    e->M.nx = nx;
+    e->M.ny = ny;
+    e->M.nz = nz;
+    e->grid_cells = nx * ny * nz;
+    double ext[6] = {xv[0], yv[0], zv[0], xv[nx], yv[ny], zv[nz]};
+    memcpy(e->M.ext, ext, sizeof ext);
+    double dx = ext[3] - ext[0], dy = ext[4] - ext[1], dz = ext[5] - ext[2];
+    e->M.eps = 1e-12 * sqrt(dx * dx + dy * dy + dz * dz);  // CartesianSpatialGrid.cpp:102
+    e->M.ncells = 0;
+    return set_tables(e, xv, nx + 1, yv, ny + 1, zv, nz + 1);
+}
+
+// Builds the device layout of an octree from the reference's node list (TreeSpatialGrid::_nodev order):
+// integer lattice coordinates per node, per-axis lattice border tables computed with the reference's own
+// midpoint arithmetic (Box::center, Box.hpp:135, applied recursively as OctTreeNode::createChildren does),
+// and for every cell the six same-level-or-coarser neighbour links that replace TreeNode::_neighbors
+// (OctTreeNode::addNeighbors, OctTreeNode.cpp:46-138).
+extern "C" int sk_engine_set_grid_octree(sk_engine_t* e, const double extent[6], int32_t num_nodes,
+                                         const int32_t* first_child)
+{
+    if (!e || !extent || num_nodes < 1 || !first_child) return fail(SK_ERR_INVALID, "bad octree");
+    CK(cudaSetDevice(e->cfg.device));
+    const int nn = num_nodes;
+    std::vector<int> lev(nn, -1), parent(nn, -1);
+    lev[0] = 0;
+    int maxlev = 0;
+    for (int l = 0; l < nn; ++l)
+    {
+        if (lev[l] < 0) return fail(SK_ERR_INVALID, "octree node list is not parent-before-child");
+        int fc = first_child[l];
+        if (fc < 0) continue;
+        if (fc <= l || fc + 8 > nn) return fail(SK_ERR_INVALID, "octree child index out of range");
+        for (int c = 0; c < 8; ++c)
+        {
+            if (lev[fc + c] >= 0) return fail(SK_ERR_INVALID, "octree node has two parents");
+            lev[fc + c] = lev[l] + 1;
+            parent[fc + c] = l;
+        }
+        maxlev = std::max(maxlev, lev[l] + 1);
+    }
+    if (maxlev > SK_MAX_TREE_LEVEL) return fail(SK_ERR_UNSUPPORTED, "octree deeper than 15 levels");
+    if (nn > SK_LINK_INDEX_MASK) return fail(SK_ERR_UNSUPPORTED, "octree with more than 2^26 nodes");
+    const int N = 1 << maxlev;
+    // lattice coordinates
+    std::vector<int> ix(nn, 0), iy(nn, 0), iz(nn, 0);
+    for (int l = 0; l < nn; ++l)
+    {
+        int fc = first_child[l];
+        if (fc < 0) continue;
+        int half = N >> (lev[l] + 1);
+        for (int c = 0; c < 8; ++c)
+        {
+            ix[fc + c] = ix[l] + ((c & 1) ? half : 0);
+            iy[fc + c] = iy[l] + ((c & 2) ? half : 0);
+            iz[fc + c] = iz[l] + ((c & 4) ? half : 0);
+        }
+    }
+    // lattice border tables by recursive midpoints
+    std::vector<double> T[3];
+    for (int a = 0; a < 3; ++a)
+    {
+        T[a].assign(N + 1, 0.);
+        T[a][0] = extent[a];
+        T[a][N] = extent[a + 3];
+        for (int s = N; s > 1; s >>= 1)
+            for (int lo = 0; lo < N; lo += s) T[a][lo + s / 2] = 0.5 * (T[a][lo] + T[a][lo + s]);
+    }
+    // cells
+    std::vector<int> cell_of_node(nn, -1);
+    std::vector<int> node_of_cell;
+    for (int l = 0; l < nn; ++l)
+        if (first_child[l] < 0)
+        {
+            cell_of_node[l] = (int)node_of_cell.size();
+            node_of_cell.push_back(l);
+        }
+    const int nc = (int)node_of_cell.size();
+    std::vector<int32_t> node_child(nn);
+    for (int l = 0; l < nn; ++l) node_child[l] = first_child[l] >= 0 ? first_child[l] : -(cell_of_node[l] + 1);
+    // neighbour links: for lattice point (x,y,z) just across a wall find the deepest node of level <= L holding it
+    auto find_node = [&](int x, int y, int z, int L) -> int {
+        int node = 0;
+        while (first_child[node] >= 0 && lev[node] < L)
+        {
+            int half = N >> (lev[node] + 1);
+            int c = ((x - ix[node]) >= half ? 1 : 0) + ((y - iy[node]) >= half ? 2 : 0) + ((z - iz[node]) >= half ? 4 : 0);
+            node = first_child[node] + c;
+        }
+        return node;
+    };
+    e->cellrec_host.assign(nc, SkCellRec());
+    std::vector<uint32_t> coord(4 * (size_t)nc);
+    for (int m = 0; m < nc; ++m)
+    {
+        int l = node_of_cell[m];
+        int size = N >> lev[l];
+        coord[4 * (size_t)m + 0] = ix[l];
+        coord[4 * (size_t)m + 1] = iy[l];
+        coord[4 * (size_t)m + 2] = iz[l];
+        coord[4 * (size_t)m + 3] = lev[l];
+        SkCellRec& r = e->cellrec_host[m];
+        r.dens = 0.;
+        for (int w = 0; w < 6; ++w)
+        {
+            int x = ix[l], y = iy[l], z = iz[l];
+            int axis = w >> 1;
+            int* c = axis == 0 ? &x : axis == 1 ? &y : &z;
+            *c += (w & 1) ? size : -1;
+            if (*c < 0 || *c >= N)
+            {
+                r.link[w] = -1;
+                continue;
+            }
+            int nb = find_node(x, y, z, lev[l]);
+            if (first_child[nb] < 0)
+                r.link[w] = (lev[nb] << SK_LINK_LEVEL_SHIFT) | cell_of_node[nb];
+            else
+                r.link[w] = SK_LINK_INTERNAL | nb;
+        }
+    }
+    free_group(e->grid_allocs);
+    e->grid_kind = 2;
+    e->M.grid_kind = 2;
+    e->M.nx = N;
+    e->M.ny = N;
+    e->M.nz = N;
+    e->M.maxlevel = maxlev;
+    e->M.nnodes = nn;
+    e->grid_cells = nc;
+    e->M.ncells = 0;
+    memcpy(e->M.ext, extent, 6 * sizeof(double));
+    double dx = extent[3] - extent[0], dy = extent[4] - extent[1], dz = extent[5] - extent[2];
+    e->M.eps = 1e-12 * sqrt(dx * dx + dy * dy + dz * dz);  // TreeSpatialGrid.cpp:28
+    int32_t* d_child;
+    uint32_t* d_coord;
+    if (int rc = upload(e->grid_allocs, node_child.data(), (size_t)nn, &d_child)) return rc;
+    if (int rc = upload(e->grid_allocs, coord.data(), coord.size(), &d_coord)) return rc;
+    e->M.node_child = d_child;
+    e->M.cell_coord = d_coord;
+    return set_tables(e, T[0].data(), N + 1, T[1].data(), N + 1, T[2].data(), N + 1);
+}
+
+extern "C" int sk_engine_set_medium(sk_engine_t* e, int32_t num_cells, const double* number_density,
+                                    const double* volume)
+{
+    (void)volume;
+    if (!e || !number_density) return fail(SK_ERR_INVALID, "null argument");
+    if (!e->grid_kind) return fail(SK_ERR_STATE, "set the grid before the medium");
+    if (num_cells != e->grid_cells) return fail(SK_ERR_INVALID, "medium size does not match the grid");
+    CK(cudaSetDevice(e->cfg.device));
+    free_group(e->medium_allocs);
+    e->dens_host.assign(number_density, number_density + num_cells);
+    if (e->grid_kind == 1)
+    {
+        double* d;
+        if (int rc = upload(e->medium_allocs, number_density, (size_t)num_cells, &d)) return rc;
+        e->M.dens = d;
+        e->M.cells = nullptr;
+    }
+    else
+    {
+        for (int m = 0; m < num_cells; ++m) e->cellrec_host[m].dens = number_density[m];
+        SkCellRec* d;
+        if (int rc = upload(e->medium_allocs, e->cellrec_host.data(), (size_t)num_cells, &d)) return rc;
+        e->M.cells = d;
+        e->M.dens = nullptr;
+    }
+    e->M.ncells = num_cells;
+    return SK_OK;
+}
+
+extern "C" int sk_engine_set_dustmix(sk_engine_t* e, const sk_dustmix_t* mix)
+{
+    if (!e || !mix || mix->num_lambda < 2) return fail(SK_ERR_INVALID, "bad dust mix");
+    CK(cudaSetDevice(e->cfg.device));
+    free_group(e->dust_allocs);
+    int n = mix->num_lambda;
+    std::vector<double> ext(n);
+    for (int i = 0; i < n; ++i) ext[i] = mix->sigma_abs[i] + mix->sigma_sca[i];  // DustMix.cpp:160-163
+    double *a, *b, *c, *d, *g;
+    if (int rc = upload(e->dust_allocs, mix->lambda_border, (size_t)n, &a)) return rc;
+    if (int rc = upload(e->dust_allocs, mix->sigma_abs, (size_t)n, &b)) return rc;
+    if (int rc = upload(e->dust_allocs, mix->sigma_sca, (size_t)n, &c)) return rc;
+    if (int rc = upload(e->dust_allocs, ext.data(), (size_t)n, &d)) return rc;
+    if (int rc = upload(e->dust_allocs, mix->asymmpar, (size_t)n, &g)) return rc;
+    e->M.nlam = n;
+    e->M.lam_border = a;
+    e->M.sig_abs = b;
+    e->M.sig_sca = c;
+    e->M.sig_ext = d;
+    e->M.gpar = g;
+    e->dust_lam_border.assign(mix->lambda_border, mix->lambda_border + n);
+    e->dust_sig_abs.assign(mix->sigma_abs, mix->sigma_abs + n);
+    return SK_OK;
+}
+
+extern "C" int sk_engine_set_wavelength_grids(sk_engine_t* e, int32_t n, const sk_wavelength_grid_t* grids,
+                                              int32_t rf_grid)
+{
+    if (!e || n < 0 || (n && !grids) || rf_grid >= n) return fail(SK_ERR_INVALID, "bad wavelength grids");
+    if (rf_grid >= 0 && e->M.ncells <= 0) return fail(SK_ERR_STATE, "set the medium before a radiation field grid");
+    CK(cudaSetDevice(e->cfg.device));
+    free_group(e->wlg_allocs);
+    free_group(e->rf_allocs);
+    std::vector<SkDevWlg> dev(n ? n : 1);
+    e->wlg_host.assign(grids, grids + n);
+    e->wlg_lambda.clear();
+    for (int i = 0; i < n; ++i)
+    {
+        double *b, *l, *d;
+        int32_t* el;
+        if (int rc = upload(e->wlg_allocs, grids[i].borders, (size_t)grids[i].num_borders, &b)) return rc;
+        if (int rc = upload(e->wlg_allocs, grids[i].ell, (size_t)grids[i].num_borders + 1, &el)) return rc;
+        if (int rc = upload(e->wlg_allocs, grids[i].lambda, (size_t)grids[i].num_bins, &l)) return rc;
+        if (int rc = upload(e->wlg_allocs, grids[i].dlambda, (size_t)grids[i].num_bins, &d)) return rc;
+        dev[i].num_bins = grids[i].num_bins;
+        dev[i].num_borders = grids[i].num_borders;
+        dev[i].borders = b;
+        dev[i].ell = el;
+        dev[i].lambda = l;
+        dev[i].dlambda = d;
+        e->wlg_lambda.emplace_back(grids[i].lambda, grids[i].lambda + grids[i].num_bins);
+    }
+    SkDevWlg* dw;
+    if (int rc = upload(e->wlg_allocs, dev.data(), dev.size(), &dw)) return rc;
+    e->M.wlg = dw;
+    e->M.nwlg = n;
+    e->M.rf_grid = rf_grid;
+    e->M.nrf = 0;
+    e->M.rf1 = e->M.rf2 = e->M.rf2c = nullptr;
+    if (rf_grid >= 0)
+    {
+        e->M.nrf = grids[rf_grid].num_bins;
+        size_t cnt = (size_t)e->M.ncells * e->M.nrf;
+        if (int rc = dalloc_zero(e->rf_allocs, cnt, &e->M.rf1)) return rc;
+        if (int rc = dalloc_zero(e->rf_allocs, cnt, &e->M.rf2)) return rc;
+        if (int rc = dalloc_zero(e->rf_allocs, cnt, &e->M.rf2c)) return rc;
+    }
+    return SK_OK;
+}
+
+// SourceSystem::setupSelfAfter, SourceSystem.cpp:14-41
+extern "C" int sk_engine_set_sources(sk_engine_t* e, int32_t n, const sk_source_t* sources, double source_bias)
+{
+    if (!e || n < 1 || !sources) return fail(SK_ERR_INVALID, "bad sources");
+    CK(cudaSetDevice(e->cfg.device));
+    free_group(e->src_allocs);
+    double L = 0.;
+    for (int h = 0; h < n; ++h) L += sources[h].luminosity;
+    e->Ltot = L;
+    e->Lv.assign(n, 0.);
+    e->Wv.assign(n, 0.);
+    if (L)
+    {
+        double wLsum = 0., wsum = 0.;
+        for (int h = 0; h < n; ++h)
+        {
+            e->Lv[h] = sources[h].luminosity / L;
+            wLsum += sources[h].source_weight * e->Lv[h];
+            wsum += sources[h].source_weight;
+        }
+        for (int h = 0; h < n; ++h)
+            e->Wv[h] = (1 - source_bias) * (sources[h].source_weight * e->Lv[h]) / wLsum
+                       + source_bias * sources[h].source_weight / wsum;
+    }
+    std::vector<SkDevSource> dev(n);
+    for (int h = 0; h < n; ++h)
+    {
+        const sk_source_t& s = sources[h];
+        SkDevSource& d = dev[h];
+        memset(&d, 0, sizeof d);
+        if (s.kind != SK_SRC_POINT && s.kind != SK_SRC_GEOMETRIC) return fail(SK_ERR_UNSUPPORTED, "unknown source kind");
+        if (s.kind == SK_SRC_GEOMETRIC && (s.geometry < SK_GEOM_SHELL || s.geometry > SK_GEOM_SPIRAL_EXPDISK))
+            return fail(SK_ERR_UNSUPPORTED, "geometry has no device sampler");
+        if (s.sed_n < 2 || !s.sed_lambda || !s.sed_p || !s.sed_P) return fail(SK_ERR_INVALID, "source without SED tables");
+        d.kind = s.kind;
+        d.geometry = s.geometry;
+        d.sed_kind = s.sed_kind;
+        d.bias_kind = s.bias_kind;
+        memcpy(d.position, s.position, sizeof d.position);
+        memcpy(d.gp, s.geom_params, sizeof d.gp);
+        d.geom_table_n = s.geom_table_n;
+        d.sed_n = s.sed_n;
+        d.oligo_n = s.oligo_n;
+        double* p;
+        if (s.geom_table_n)
+        {
+            if (int rc = upload(e->src_allocs, s.geom_table_x, (size_t)s.geom_table_n, &p)) return rc;
+            d.geom_table_x = p;
+            if (int rc = upload(e->src_allocs, s.geom_table_P, (size_t)s.geom_table_n, &p)) return rc;
+            d.geom_table_P = p;
+        }
+        if (int rc = upload(e->src_allocs, s.sed_lambda, (size_t)s.sed_n, &p)) return rc;
+        d.sed_lambda = p;
+        if (int rc = upload(e->src_allocs, s.sed_p, (size_t)s.sed_n, &p)) return rc;
+        d.sed_p = p;
+        if (int rc = upload(e->src_allocs, s.sed_P, (size_t)s.sed_n, &p)) return rc;
+        d.sed_P = p;
+        if (s.oligo_n)
+        {
+            if (int rc = upload(e->src_allocs, s.oligo_lambda, (size_t)s.oligo_n, &p)) return rc;
+            d.oligo_lambda = p;
+        }
+        d.sed_temperature = s.sed_temperature;
+        d.sed_norm = s.sed_norm;
+        d.wavelength_bias = s.wavelength_bias;
+        d.bias_min = s.bias_min;
+        d.bias_max = s.bias_max;
+        d.oligo_probability = s.oligo_probability;
+        d.Lw = L ? e->Lv[h] / e->Wv[h] : 0.;
+    }
+    SkDevSource* ds;
+    if (int rc = upload(e->src_allocs, dev.data(), dev.size(), &ds)) return rc;
+    unsigned long long* iv;
+    if (int rc = dalloc_zero(e->src_allocs, (size_t)n + 1, &iv)) return rc;
+    e->M.src = ds;
+    e->M.Iv = iv;
+    e->M.nsrc = n;
+    e->npackets = 0;
+    return SK_OK;
+}
+
+// DistantInstrument::setupSelfBefore (DistantInstrument.cpp:39-50), FrameInstrument::setupSelfBefore
+// (FrameInstrument.cpp:12-32), FluxRecorder::finalizeConfiguration (FluxRecorder.cpp:185-300)
+extern "C" int sk_engine_set_instruments(sk_engine_t* e, int32_t n, const sk_instrument_t* instruments,
+                                         int32_t has_medium_emission)
+{
+    if (!e || n < 0 || (n && !instruments)) return fail(SK_ERR_INVALID, "bad instruments");
+    if (n > SK_MAX_INSTR) return fail(SK_ERR_UNSUPPORTED, "more than 8 instruments");
+    CK(cudaSetDevice(e->cfg.device));
+    free_group(e->instr_allocs);
+    e->instr.assign(n, HostInstr());
+    size_t det = 0, stat = 0;
+    for (int i = 0; i < n; ++i)
+    {
+        HostInstr& q = e->instr[i];
+        q.d = instruments[i];
+        const sk_instrument_t& d = q.d;
+        if (d.wavelength_grid < 0 || d.wavelength_grid >= e->M.nwlg)
+            return fail(SK_ERR_INVALID, "instrument wavelength grid index out of range");
+        if (d.num_scattering_levels > SK_MAX_LEVELS) return fail(SK_ERR_UNSUPPORTED, "too many scattering levels");
+        if (d.kind < SK_INSTR_SED || d.kind > SK_INSTR_FULL) return fail(SK_ERR_UNSUPPORTED, "unknown instrument kind");
+        q.include_sed = d.kind == SK_INSTR_SED || d.kind == SK_INSTR_FULL;
+        q.include_ifu = d.kind == SK_INSTR_FRAME || d.kind == SK_INSTR_FULL;
+        q.nl = e->wlg_host[d.wavelength_grid].num_bins;
+        q.npix = q.include_ifu ? (size_t)d.num_pixels_x * d.num_pixels_y : 0;
+        q.record_total_only = !d.record_components;
+        size_t lensed = q.include_sed ? (size_t)q.nl : 0, lenifu = q.include_ifu ? q.npix * q.nl : 0;
+        for (int c = 0; c < SK_NUM_COMP; ++c)
+        {
+            bool need;
+            if (q.record_total_only)
+                need = c == SK_COMP_TOTAL;
+            else if (c == SK_COMP_TRANSPARENT || c == SK_COMP_PRIMARY_DIRECT || c == SK_COMP_PRIMARY_SCATTERED)
+                need = true;
+            else if (c == SK_COMP_SECONDARY_DIRECT || c == SK_COMP_SECONDARY_SCATTERED || c == SK_COMP_SECONDARY_TRANSPARENT)
+                need = has_medium_emission != 0;
+            else if (c >= SK_COMP_PRIMARY_SCATTERED_LEVEL)
+                need = (c - SK_COMP_PRIMARY_SCATTERED_LEVEL) < d.num_scattering_levels;
+            else
+                need = false;
+            q.sed_off[c] = q.ifu_off[c] = -1;
+            if (need && lensed)
+            {
+                q.sed_off[c] = (long long)det;
+                det += lensed;
+            }
+            if (need && lenifu)
+            {
+                q.ifu_off[c] = (long long)det;
+                det += lenifu;
+            }
+        }
+        for (int k = 0; k < 5; ++k)
+        {
+            q.wsed_off[k] = -1;
+            if (d.record_statistics && lensed)
+            {
+                q.wsed_off[k] = (long long)stat;
+                stat += lensed;
+            }
+        }
+    }
+    if (int rc = dalloc_zero(e->instr_allocs, det, &e->det_block)) return rc;
+    if (int rc = dalloc_zero(e->instr_allocs, stat, &e->stat_block)) return rc;
+    e->det_count = det;
+    e->stat_count = stat;
+    std::vector<SkDevInstr> dev(n ? n : 1);
+    for (int i = 0; i < n; ++i)
+    {
+        const HostInstr& q = e->instr[i];
+        const sk_instrument_t& d = q.d;
+        SkDevInstr& v = dev[i];
+        memset(&v, 0, sizeof v);
+        v.kind = d.kind;
+        v.wlg = d.wavelength_grid;
+        v.nx = d.num_pixels_x;
+        v.ny = d.num_pixels_y;
+        v.num_levels = d.num_scattering_levels;
+        v.record_total_only = q.record_total_only;
+        v.record_stats = d.record_statistics;
+        v.include_sed = q.include_sed;
+        v.include_ifu = q.include_ifu;
+        v.nl = q.nl;
+        v.npix = q.npix;
+        v.costheta = cos(d.inclination);
+        v.sintheta = sin(d.inclination);
+        v.cosphi = cos(d.azimuth);
+        v.sinphi = sin(d.azimuth);
+        v.cosomega = cos(d.roll);
+        v.sinomega = sin(d.roll);
+        // Direction(inclination, azimuth), Direction.cpp:10-35
+        {
+            const double eps = 1e-8;
+            double th = d.inclination, ph = d.azimuth;
+            if (th <= eps)
+            {
+                v.kobs[0] = 0;
+                v.kobs[1] = 0;
+                v.kobs[2] = 1;
+            }
+            else if (th >= M_PI - eps)
+            {
+                v.kobs[0] = 0;
+                v.kobs[1] = 0;
+                v.kobs[2] = -1;
+            }
+            else
+            {
+                double st = sin(th);
+                v.kobs[0] = st * cos(ph);
+                v.kobs[1] = st * sin(ph);
+                v.kobs[2] = cos(th);
+            }
+        }
+        v.radius2 = d.radius * d.radius;
+        if (q.include_ifu)
+        {
+            v.xpmin = d.center_x - 0.5 * d.field_of_view_x;
+            v.xpsiz = d.field_of_view_x / d.num_pixels_x;
+            v.ypmin = d.center_y - 0.5 * d.field_of_view_y;
+            v.ypsiz = d.field_of_view_y / d.num_pixels_y;
+        }
+        v.same_as_preceding = 0;
+        if (i > 0)
+        {
+            const sk_instrument_t& p = e->instr[i - 1].d;  // DistantInstrument.cpp:54-62
+            if (d.distance == p.distance && d.inclination == p.inclination && d.azimuth == p.azimuth && d.roll == p.roll)
+                v.same_as_preceding = 1;
+        }
+        for (int c = 0; c < SK_NUM_COMP; ++c)
+        {
+            v.sed[c] = q.sed_off[c] >= 0 ? e->det_block + q.sed_off[c] : nullptr;
+            v.ifu[c] = q.ifu_off[c] >= 0 ? e->det_block + q.ifu_off[c] : nullptr;
+        }
+        for (int k = 0; k < 5; ++k) v.wsed[k] = q.wsed_off[k] >= 0 ? e->stat_block + q.wsed_off[k] : nullptr;
+    }
+    SkDevInstr* di;
+    if (int rc = upload(e->instr_allocs, dev.data(), dev.size(), &di)) return rc;
+    e->M.instr = di;
+    e->M.ninstr = n;
+    return SK_OK;
+}
+
+extern "C" int sk_engine_set_secondary(sk_engine_t* e, const sk_secondary_t* sec)
+{
+    (void)e;
+    (void)sec;
+    return fail(SK_ERR_UNSUPPORTED, "secondary emission is not implemented yet");
+}
+
+extern "C" int sk_engine_clear_instruments(sk_engine_t* e)
+{
+    if (!e) return fail(SK_ERR_INVALID, "null engine");
+    CK(cudaSetDevice(e->cfg.device));
+    if (e->det_count) CK(cudaMemsetAsync(e->det_block, 0, e->det_count * sizeof(double), e->stream));
+    if (e->stat_count) CK(cudaMemsetAsync(e->stat_block, 0, e->stat_count * sizeof(double), e->stream));
+    return SK_OK;
+}
+
+extern "C" int sk_engine_cuda_stream(sk_engine_t* e, void** stream)
+{
+    if (!e || !stream) return fail(SK_ERR_INVALID, "null argument");
+    *stream = (void*)e->stream;
+    return SK_OK;
+}
+
+extern "C" int sk_engine_clear_rf(sk_engine_t* e, int32_t primary)
+{
+    if (!e) return fail(SK_ERR_INVALID, "null engine");
+    CK(cudaSetDevice(e->cfg.device));
+    size_t bytes = (size_t)e->M.ncells * e->M.nrf * sizeof(double);
+    if (!bytes) return SK_OK;
+    if (primary)
+    {
+        CK(cudaMemsetAsync(e->M.rf1, 0, bytes, e->stream));
+        CK(cudaMemsetAsync(e->M.rf2, 0, bytes, e->stream));
+    }
+    else
+        CK(cudaMemsetAsync(e->M.rf2c, 0, bytes, e->stream));
+    return SK_OK;
+}
+
+// SourceSystem::prepareForLaunch, SourceSystem.cpp:75-97
+extern "C" int sk_engine_prepare_primary(sk_engine_t* e, uint64_t num_packets)
+{
+    if (!e || !e->M.nsrc) return fail(SK_ERR_STATE, "no sources");
+    if (!e->Ltot)
+        return fail(SK_ERR_INVALID, "Cannot launch primary source photon packets when total luminosity is zero");
+    if (!num_packets) return fail(SK_ERR_INVALID, "zero packets");
+    CK(cudaSetDevice(e->cfg.device));
+    int Ns = e->M.nsrc;
+    std::vector<unsigned long long> Iv(Ns + 1);
+    Iv[0] = 0;
+    double W = 0.;
+    for (int h = 1; h != Ns; ++h)
+    {
+        W += e->Wv[h - 1];
+        unsigned long long idx = (unsigned long long)std::round(W * (double)num_packets);
+        Iv[h] = std::min<unsigned long long>(idx, num_packets);
+    }
+    Iv[Ns] = num_packets;
+    CK(cudaMemcpyAsync(const_cast<unsigned long long*>(e->M.Iv), Iv.data(), Iv.size() * sizeof(unsigned long long),
+                       cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->M.Lpp = e->Ltot / (double)num_packets;
+    e->npackets = num_packets;
+    return SK_OK;
+}
+
+extern "C" int sk_engine_prepare_secondary(sk_engine_t* e, uint64_t num_packets, double* luminosity)
+{
+    (void)e;
+    (void)num_packets;
+    (void)luminosity;
+    return fail(SK_ERR_UNSUPPORTED, "secondary emission is not implemented yet");
+}
+
+static int g_num_sms = 0;
+
+extern "C" int sk_engine_launch_segment(sk_engine_t* e, uint64_t first, uint64_t count, int32_t primary,
+                                        int32_t peel, int32_t store, uint32_t stream_id)
+{
+    if (!e) return fail(SK_ERR_INVALID, "null engine");
+    if (!e->grid_kind || !e->M.ncells || !e->M.nlam || !e->M.nsrc)
+        return fail(SK_ERR_STATE, "engine is not fully configured");
+    if (!primary) return fail(SK_ERR_UNSUPPORTED, "secondary emission is not implemented yet");
+    if (!e->npackets) return fail(SK_ERR_STATE, "call sk_engine_prepare_primary first");
+    if (store && e->M.rf_grid < 0) return fail(SK_ERR_STATE, "no radiation field grid configured");
+    if (store && !e->M.force_scattering)
+        return fail(SK_ERR_INVALID, "storing the radiation field requires forced scattering (Configuration.cpp:476-482)");
+    CK(cudaSetDevice(e->cfg.device));
+    if (!g_num_sms)
+    {
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, e->cfg.device));
+        g_num_sms = prop.multiProcessorCount;
+    }
+    SkRunArgs A;
+    A.first = first;
+    A.count = count;
+    A.primary = primary;
+    A.peel = peel;
+    A.store = store;
+    A.stream_id = stream_id;
+    A.work_counter = e->work_counter;
+    CK(cudaMemsetAsync(e->work_counter, 0, sizeof(unsigned long long), e->stream));
+    // persistent grid: a multiple of the SM count, sized by the occupancy the kernel actually gets
+    int per_sm = 0;
+    auto kern = e->grid_kind == 1 ? sk_life_cycle_kernel<1> : sk_life_cycle_kernel<2>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SK_BLOCK, e->smem_bytes));
+    if (per_sm < 1) per_sm = 1;
+    unsigned long long want = (count + SK_CHUNK - 1) / SK_CHUNK;
+    unsigned long long threads_needed = want;
+    unsigned long long blocks_needed = (threads_needed + SK_BLOCK - 1) / SK_BLOCK;
+    unsigned long long grid = std::min<unsigned long long>((unsigned long long)g_num_sms * per_sm, std::max<unsigned long long>(blocks_needed, 1));
+    CK(cudaEventRecord(e->ev0, e->stream));
+    kern<<<(unsigned)grid, SK_BLOCK, e->smem_bytes, e->stream>>>(e->M, A);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(e->ev1, e->stream));
+    e->timing_pending = true;
+    return SK_OK;
+}
+
+extern "C" int sk_engine_synchronize(sk_engine_t* e)
+{
+    if (!e) return fail(SK_ERR_INVALID, "null engine");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaStreamSynchronize(e->stream));
+    if (e->timing_pending)
+    {
+        CK(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
+        e->timing_pending = false;
+    }
+    return SK_OK;
+}
+
+extern "C" int sk_engine_run_segment(sk_engine_t* e, uint64_t first, uint64_t count, int32_t primary, int32_t peel,
+                                     int32_t store, uint32_t stream_id)
+{
+    if (int rc = sk_engine_launch_segment(e, first, count, primary, peel, store, stream_id)) return rc;
+    return sk_engine_synchronize(e);
+}
+
+extern "C" int sk_engine_last_kernel_ms(sk_engine_t* e, float* ms)
+{
+    if (!e || !ms) return fail(SK_ERR_INVALID, "null argument");
+    *ms = e->last_ms;
+    return SK_OK;
+}
+
+extern "C" int sk_engine_communicate_rf(sk_engine_t* e, int32_t primary)
+{
+    if (!e) return fail(SK_ERR_INVALID, "null engine");
+    CK(cudaSetDevice(e->cfg.device));
+    if (!primary && e->M.rf2)
+    {
+        CK(cudaMemcpyAsync(e->M.rf2, e->M.rf2c, (size_t)e->M.ncells * e->M.nrf * sizeof(double),
+                           cudaMemcpyDeviceToDevice, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+    }
+    return SK_OK;
+}
+
+extern "C" int sk_engine_absorbed_luminosity(sk_engine_t* e, int32_t primary, double* out)
+{
+    if (!e || !out) return fail(SK_ERR_INVALID, "null argument");
+    if (e->M.rf_grid < 0) return fail(SK_ERR_STATE, "no radiation field");
+    CK(cudaSetDevice(e->cfg.device));
+    // kappa_abs per RF bin: DustMix::sectionAbs(lambda_ell) = _sigmaabsv[indexForLambda(lambda_ell)]
+    const std::vector<double>& lam = e->wlg_lambda[e->M.rf_grid];
+    std::vector<double> kabs(lam.size());
+    for (size_t i = 0; i < lam.size(); ++i)
+    {
+        const std::vector<double>& b = e->dust_lam_border;
+        int n = (int)b.size();
+        int idx;
+        if (lam[i] < b[0])
+            idx = 0;
+        else
+        {
+            int jl = -1, ju = n - 1;
+            while (ju - jl > 1)
+            {
+                int jm = (ju + jl) >> 1;
+                if (lam[i] < b[jm])
+                    ju = jm;
+                else
+                    jl = jm;
+            }
+            idx = jl;
+        }
+        kabs[i] = e->dust_sig_abs[idx];
+    }
+    double* dk = nullptr;
+    CK(cudaMalloc(&dk, kabs.size() * sizeof(double)));
+    CK(cudaMemcpyAsync(dk, kabs.data(), kabs.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemsetAsync(e->scalar, 0, sizeof(double), e->stream));
+    sk_absorbed_kernel<<<296, 256, 0, e->stream>>>(primary ? e->M.rf1 : e->M.rf2, e->M.dens, e->M.cells, dk,
+                                                   e->M.ncells, e->M.nrf, e->scalar);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, e->scalar, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    cudaFree(dk);
+    return SK_OK;
+}
+
+extern "C" int sk_engine_read_rf(sk_engine_t* e, int32_t which, double* out)
+{
+    if (!e || !out) return fail(SK_ERR_INVALID, "null argument");
+    const double* src = which == 0 ? e->M.rf1 : which == 1 ? e->M.rf2 : e->M.rf2c;
+    if (!src) return fail(SK_ERR_STATE, "no radiation field");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaMemcpyAsync(out, src, (size_t)e->M.ncells * e->M.nrf * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return SK_OK;
+}
+
+static int read_array(sk_engine* e, int instrument, int component, bool ifu, double* out)
+{
+    if (!e || !out || instrument < 0 || instrument >= (int)e->instr.size() || component < 0 || component >= SK_NUM_COMP)
+        return fail(SK_ERR_INVALID, "bad instrument/component");
+    CK(cudaSetDevice(e->cfg.device));
+    const HostInstr& q = e->instr[instrument];
+    if (ifu ? !q.include_ifu : !q.include_sed) return fail(SK_ERR_INVALID, "instrument does not record this");
+    size_t len = ifu ? q.npix * q.nl : (size_t)q.nl;
+    const long long* off = ifu ? q.ifu_off : q.sed_off;
+    auto fetch = [&](int c, double* dst) -> int {
+        CK(cudaMemcpyAsync(dst, e->det_block + off[c], len * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        return SK_OK;
+    };
+    if (component == SK_COMP_TOTAL && !q.record_total_only)
+    {
+        // FluxRecorder::calibrateAndWrite: total = direct + scattered (+ secondary), FluxRecorder.cpp:522-526
+        std::vector<double> tmp(len);
+        if (int rc = fetch(SK_COMP_PRIMARY_DIRECT, out)) return rc;
+        if (int rc = fetch(SK_COMP_PRIMARY_SCATTERED, tmp.data())) return rc;
+        for (size_t i = 0; i < len; ++i) out[i] += tmp[i];
+        if (off[SK_COMP_SECONDARY_DIRECT] >= 0)
+        {
+            std::vector<double> t2(len);
+            if (int rc = fetch(SK_COMP_SECONDARY_DIRECT, tmp.data())) return rc;
+            if (int rc = fetch(SK_COMP_SECONDARY_SCATTERED, t2.data())) return rc;
+            for (size_t i = 0; i < len; ++i) out[i] += tmp[i] + t2[i];
+        }
+        return SK_OK;
+    }
+    if (off[component] < 0) return fail(SK_ERR_INVALID, "component not recorded");
+    return fetch(component, out);
+}
+extern "C" int sk_engine_read_sed(sk_engine_t* e, int32_t instrument, int32_t component, double* out)
+{
+    return read_array(e, instrument, component, false, out);
+}
+extern "C" int sk_engine_read_ifu(sk_engine_t* e, int32_t instrument, int32_t component, double* out)
+{
+    return read_array(e, instrument, component, true, out);
+}
+extern "C" int sk_engine_read_sed_stats(sk_engine_t* e, int32_t instrument, int32_t k, double* out)
+{
+    if (!e || !out || instrument < 0 || instrument >= (int)e->instr.size() || k < 0 || k > 4)
+        return fail(SK_ERR_INVALID, "bad instrument/power");
+    const HostInstr& q = e->instr[instrument];
+    if (q.wsed_off[k] < 0) return fail(SK_ERR_INVALID, "statistics not recorded");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaMemcpyAsync(out, e->stat_block + q.wsed_off[k], (size_t)q.nl * sizeof(double), cudaMemcpyDeviceToHost,
+                       e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return SK_OK;
+}
+
+extern "C" int sk_engine_counters(sk_engine_t* e, sk_counters_t* out, int32_t reset)
+{
+    if (!e || !out) return fail(SK_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(e->cfg.device));
+    unsigned long long c[16];
+    CK(cudaMemcpyAsync(c, e->M.counters, sizeof c, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    memset(out, 0, sizeof *out);
+    out->packets = c[0];
+    out->forward_paths = c[1];
+    out->forward_segments = c[2];
+    out->replay_segments = c[3];
+    out->peel_paths = c[4];
+    out->peel_segments = c[5];
+    out->scatterings = c[6];
+    out->rf_deposits = c[7];
+    out->detections = c[8];
+    out->fallbacks = c[9];
+    if (reset) CK(cudaMemsetAsync(e->M.counters, 0, sizeof c, e->stream));
+    return SK_OK;
+}
+
+extern "C" int sk_engine_device_buffer(sk_engine_t* e, int32_t which, void** device_ptr, uint64_t* num_doubles)
+{
+    if (!e || !device_ptr || !num_doubles) return fail(SK_ERR_INVALID, "null argument");
+    size_t rfcount = (size_t)e->M.ncells * e->M.nrf;
+    switch (which)
+    {
+        case 0: *device_ptr = e->M.rf1; *num_doubles = rfcount; break;
+        case 1: *device_ptr = e->M.rf2; *num_doubles = rfcount; break;
+        case 2: *device_ptr = e->M.rf2c; *num_doubles = rfcount; break;
+        case 3: *device_ptr = e->det_block; *num_doubles = e->det_count; break;
+        case 4: *device_ptr = e->stat_block; *num_doubles = e->stat_count; break;
+        default: return fail(SK_ERR_INVALID, "unknown buffer");
+    }
+    return SK_OK;
+}

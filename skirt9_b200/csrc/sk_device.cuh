@@ -1,0 +1,406 @@
+// sk_device.cuh -- device-side data layout and building blocks of the photon life-cycle kernel (sm_100a).
+//
+// Layout in HBM:
+//   * octree: one 32-byte record per CELL {double density; int32 link[6]} -- exactly one 32 B sector per cell
+//     crossing; the cell geometry is NOT stored per cell: a cell is identified by its integer lattice coordinates
+//     (ix,iy,iz at the finest level, carried in registers) and its level, and its bounds come from three per-axis
+//     border tables X/Y/Z[2^maxLevel+1] that are staged in shared memory.  link[w] is the same-level-or-coarser
+//     neighbour across wall w: a cell index (+ its level) when that neighbour is a leaf, an internal node id
+//     otherwise (then a short descent through the 4-byte-per-node child table follows), -1 at the domain boundary.
+//   * Cartesian grid: border arrays in shared memory, density[m] 8 B per crossing, neighbours by index arithmetic.
+//   * tallies: fp64 arrays updated with native RED.F64 atomics.
+#pragma once
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+
+#include "../../include/sk_engine.h"
+
+#define SK_MAX_LEVELS 8
+#define SK_NUM_COMP (SK_COMP_PRIMARY_SCATTERED_LEVEL + SK_MAX_LEVELS)
+#define SK_MAX_INSTR 8
+#define SK_MAX_TREE_LEVEL 15
+#define SK_LINK_INTERNAL 0x40000000
+#define SK_LINK_LEVEL_SHIFT 26
+#define SK_LINK_INDEX_MASK 0x03FFFFFF
+
+struct __align__(32) SkCellRec {
+    double dens;
+    int32_t link[6];
+};
+
+struct SkDevWlg {
+    int32_t num_bins, num_borders;
+    const double* borders;
+    const int32_t* ell;
+    const double* lambda;
+    const double* dlambda;
+};
+
+struct SkDevSource {
+    int32_t kind, geometry, sed_kind, bias_kind;
+    double position[3];
+    double gp[SK_GEOM_MAX_PARAMS];
+    int32_t geom_table_n, sed_n, oligo_n, pad;
+    const double *geom_table_x, *geom_table_P;
+    const double *sed_lambda, *sed_p, *sed_P;
+    const double* oligo_lambda;
+    double sed_temperature, sed_norm, wavelength_bias, bias_min, bias_max, oligo_probability;
+    double Lw;  // _Lv[h]/_Wv[h]  (SourceSystem.cpp:105)
+};
+
+struct SkDevInstr {
+    int32_t kind, wlg, nx, ny, num_levels, record_total_only, record_stats, same_as_preceding;
+    int32_t include_sed, include_ifu, nl, pad;
+    unsigned long long npix;
+    double kobs[3];
+    double costheta, sintheta, cosphi, sinphi, cosomega, sinomega;
+    double xpmin, xpsiz, ypmin, ypsiz, radius2;
+    double* sed[SK_NUM_COMP];
+    double* ifu[SK_NUM_COMP];
+    double* wsed[5];
+};
+
+struct SkDevModel {
+    // configuration
+    uint32_t seed;
+    int32_t force_scattering, min_scatt_events;
+    double path_length_bias, min_weight_reduction;
+    // grid
+    int32_t grid_kind;  // 1 cartesian, 2 octree
+    int32_t nx, ny, nz; // cartesian bins; octree: lattice size per axis (2^maxlevel) in nx
+    int32_t maxlevel;
+    int32_t lattice_in_smem;
+    double ext[6];
+    double eps;
+    const double *xv, *yv, *zv;  // cartesian borders or octree lattice tables
+    const double* dens;          // cartesian: density per cell
+    const SkCellRec* cells;      // octree
+    const int32_t* node_child;   // octree: first child node id, or -(cell+1) for a leaf
+    const uint32_t* cell_coord;  // octree: 4 x uint32 per cell {ix,iy,iz,level}
+    int32_t ncells, nnodes;
+    // dust
+    int32_t nlam;
+    const double *lam_border, *sig_abs, *sig_sca, *sig_ext, *gpar;
+    // wavelength grids
+    const SkDevWlg* wlg;
+    int32_t nwlg, rf_grid, nrf;
+    double *rf1, *rf2, *rf2c;
+    // sources
+    const SkDevSource* src;
+    const unsigned long long* Iv;
+    int32_t nsrc;
+    double Lpp;
+    // instruments
+    const SkDevInstr* instr;
+    int32_t ninstr;
+    // counters
+    unsigned long long* counters;
+};
+
+struct SkRunArgs {
+    unsigned long long first, count;
+    int32_t primary, peel, store;
+    uint32_t stream_id;
+    unsigned long long* work_counter;  // dynamic history dispenser
+};
+
+// ---------------------------------------------------------------------------------------------------
+// Philox4x32-10 counter-based generator (replaces Random.cpp:20-56); identical to oracle/sk_oracle.c
+// ---------------------------------------------------------------------------------------------------
+struct SkRng {
+    uint32_t k0, k1, c0, c1, block;
+    int has_spare;
+    double spare;
+};
+
+__device__ __forceinline__ void sk_philox(uint32_t c[4], uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r)
+    {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        uint32_t n0 = hi1 ^ c[1] ^ k0;
+        uint32_t n2 = hi0 ^ c[3] ^ k1;
+        c[0] = n0;
+        c[1] = lo1;
+        c[2] = n2;
+        c[3] = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+__device__ __forceinline__ double sk_u01(uint32_t lo, uint32_t hi)
+{
+    unsigned long long x = ((unsigned long long)hi << 32) | lo;
+    return ((double)(x >> 12) + 0.5) * (1.0 / 4503599627370496.0);
+}
+__device__ __forceinline__ void sk_rng_init(SkRng& g, uint32_t seed, uint32_t stream, unsigned long long history)
+{
+    g.k0 = seed;
+    g.k1 = stream;
+    g.c0 = (uint32_t)history;
+    g.c1 = (uint32_t)(history >> 32);
+    g.block = 0;
+    g.has_spare = 0;
+    g.spare = 0.;
+}
+// Random::uniform, Random.cpp:70-73
+__device__ __noinline__ double sk_uniform(SkRng& g)
+{
+    if (g.has_spare)
+    {
+        g.has_spare = 0;
+        return g.spare;
+    }
+    uint32_t c[4] = {g.c0, g.c1, g.block, 0u};
+    sk_philox(c, g.k0, g.k1);
+    g.block++;
+    g.spare = sk_u01(c[2], c[3]);
+    g.has_spare = 1;
+    return sk_u01(c[0], c[1]);
+}
+// Random::exponCutoff, Random.cpp:105-117
+__device__ __forceinline__ double sk_expon_cutoff(SkRng& g, double xmax)
+{
+    if (xmax == 0.0)
+        return 0.0;
+    else if (xmax < 1e-10)
+        return sk_uniform(g) * xmax;
+    double x = -log(1.0 - sk_uniform(g) * (1.0 - exp(-xmax)));
+    while (x > xmax) x = -log(1.0 - sk_uniform(g) * (1.0 - exp(-xmax)));
+    return x;
+}
+// Direction::Direction(theta,phi), SKIRT/utils/Direction.cpp:10-35
+__device__ __forceinline__ void sk_direction_from_angles(double theta, double phi, double& kx, double& ky, double& kz)
+{
+    const double eps = 1e-8;
+    if (theta <= eps)
+    {
+        kx = 0;
+        ky = 0;
+        kz = 1;
+    }
+    else if (theta >= M_PI - eps)
+    {
+        kx = 0;
+        ky = 0;
+        kz = -1;
+    }
+    else
+    {
+        double sintheta = sin(theta);
+        kx = sintheta * cos(phi);
+        ky = sintheta * sin(phi);
+        kz = cos(theta);
+    }
+}
+// Random::direction(), Random.cpp:121-126
+__device__ __forceinline__ void sk_random_direction(SkRng& g, double& kx, double& ky, double& kz)
+{
+    double theta = acos(2.0 * sk_uniform(g) - 1.0);
+    double phi = 2.0 * M_PI * sk_uniform(g);
+    sk_direction_from_angles(theta, phi, kx, ky, kz);
+}
+// Random::direction(bfk, costheta), Random.cpp:130-164
+__device__ __forceinline__ void sk_random_direction_about(SkRng& g, double& kx, double& ky, double& kz, double costheta)
+{
+    double phi = 2.0 * M_PI * sk_uniform(g);
+    double cosphi = cos(phi);
+    double sinphi = sin(phi);
+    double sintheta = sqrt(fabs((1.0 - costheta) * (1.0 + costheta)));
+    double nx, ny, nz;
+    if (kz > 0.99999)
+    {
+        nx = cosphi * sintheta;
+        ny = sinphi * sintheta;
+        nz = costheta;
+    }
+    else if (kz < -0.99999)
+    {
+        nx = cosphi * sintheta;
+        ny = sinphi * sintheta;
+        nz = -costheta;
+    }
+    else
+    {
+        double root = sqrt((1.0 - kz) * (1.0 + kz));
+        nx = sintheta / root * (-kx * kz * cosphi + ky * sinphi) + kx * costheta;
+        ny = -sintheta / root * (ky * kz * cosphi + kx * sinphi) + ky * costheta;
+        nz = root * sintheta * cosphi + kz * costheta;
+    }
+    kx = nx;
+    ky = ny;
+    kz = nz;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// numerical helpers (NR.hpp:130-191,328-358; SpecialFunctions.cpp:578-627,822-880)
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int sk_locate_basic(const double* __restrict__ xv, double x, int n)
+{
+    int jl = -1, ju = n;
+    while (ju - jl > 1)
+    {
+        int jm = (ju + jl) >> 1;
+        if (x < xv[jm])
+            ju = jm;
+        else
+            jl = jm;
+    }
+    return jl;
+}
+__device__ __forceinline__ int sk_locate_clip(const double* __restrict__ xv, int n, double x)
+{
+    if (x < xv[0]) return 0;
+    return sk_locate_basic(xv, x, n - 1);
+}
+__device__ __forceinline__ int sk_locate_fail(const double* __restrict__ xv, int n, double x)
+{
+    if (x > xv[n - 1]) return -1;
+    return sk_locate_basic(xv, x, n - 1);
+}
+__device__ __forceinline__ double sk_interp_linlin(double x, double x1, double x2, double f1, double f2)
+{
+    return f1 + ((x - x1) / (x2 - x1)) * (f2 - f1);
+}
+__device__ __forceinline__ double sk_interp_loglog(double x, double x1, double x2, double f1, double f2)
+{
+    if (f1 <= 0 || f2 <= 0)
+    {
+        if (x == x1) return f1;
+        if (x == x2) return f2;
+        return 0;
+    }
+    return f1 * exp(log(x / x1) / log(x2 / x1) * (log(f2 / f1)));
+}
+__device__ __forceinline__ double sk_gexp(double p, double x)
+{
+    const double q = 1.0 - p;
+    if (q == 0.0)
+        return exp(x);
+    else if (fabs(q) < 1e-3)
+    {
+        double x2 = x * x;
+        return exp(x)
+               * (1.0 - 0.5 * x2 * q + 1.0 / 24.0 * x * x2 * (8.0 + 3.0 * x) * q * q
+                  - 1.0 / 48.0 * x2 * x2 * (12.0 + 8.0 * x + x2) * q * q * q);
+    }
+    else
+        return pow(1.0 + q * x, 1.0 / q);
+}
+__device__ __forceinline__ double sk_lnmean4(double x1, double x2, double lnx1, double lnx2)
+{
+    if (x1 > x2)
+    {
+        double t = x1;
+        x1 = x2;
+        x2 = t;
+        t = lnx1;
+        lnx1 = lnx2;
+        lnx2 = t;
+    }
+    if (x1 <= 0) return 0.;
+    double x = x2 / x1 - 1.;
+    if (x < 1e-3)
+    {
+        return x1
+               / (1. - 1. / 2. * x + 1. / 3. * x * x - 1. / 4. * x * x * x + 1. / 5. * x * x * x * x
+                  - 1. / 6. * x * x * x * x * x);
+    }
+    else
+        return (x2 - x1) / (lnx2 - lnx1);
+}
+__device__ __noinline__ double sk_lambert_w1(double z)
+{
+    const double eps = 1.0e-12;
+    const double em1 = 0.3678794411714423215955237701614608;
+    const double c[12] = {-1.0,
+                          2.331643981597124203363536062168,
+                          -1.812187885639363490240191647568,
+                          1.936631114492359755363277457668,
+                          -2.353551201881614516821543561516,
+                          3.066858901050631912893148922704,
+                          -4.175335600258177138854984177460,
+                          5.858023729874774148815053846119,
+                          -8.401032217523977370984161688514,
+                          12.250753501314460424,
+                          -18.100697012472442755,
+                          27.029044799010561650};
+    if (z == 0.0) return -DBL_MAX;
+    double q = z + em1;
+    double r = -sqrt(q);
+    double t8 = c[8] + r * (c[9] + r * (c[10] + r * c[11]));
+    double t5 = c[5] + r * (c[6] + r * (c[7] + r * t8));
+    double t1 = c[1] + r * (c[2] + r * (c[3] + r * (c[4] + r * t5)));
+    double w0 = c[0] + r * t1;
+    if (q < 3.0e-3) return w0;
+    double w, e, p, t;
+    if (z < -1e-6)
+        w = w0;
+    else
+    {
+        double l1 = log(-z);
+        double l2 = log(-l1);
+        w = l1 - l2 + l2 / l1;
+    }
+    for (int i = 0; i < 10; i++)
+    {
+        e = exp(w);
+        t = w * e - z;
+        p = w + 1.0;
+        t /= e * p - 0.5 * (p + 1.0) * t / p;
+        w -= t;
+        if (fabs(t) < eps * (1.0 + fabs(w))) return w;
+    }
+    return w;
+}
+// PlanckFunction::value, SKIRT/utils/PlanckFunction.cpp:24-27
+__device__ __forceinline__ double sk_planck(double lambda, double T)
+{
+    const double h = 6.62606957e-34, c = 2.99792458e8, k = 1.3806488e-23;
+    double f1 = h * c / (k * T);
+    double f2 = 2.0 * h * c * c;
+    return f2 / pow(lambda, 5) / (exp(f1 / lambda) - 1.0);
+}
+// DisjointWavelengthGrid::bin, DisjointWavelengthGrid.cpp:332-341
+__device__ __forceinline__ int sk_wlg_bin(const SkDevWlg& g, double lambda)
+{
+    int lo = 0, hi = g.num_borders;
+    while (lo < hi)
+    {
+        int mid = (lo + hi) >> 1;
+        if (lambda < g.borders[mid])
+            hi = mid;
+        else
+            lo = mid + 1;
+    }
+    return g.ell[lo];
+}
+// DustMix.cpp:391-425
+__device__ __forceinline__ double sk_value_hg(double g, double costheta)
+{
+    double t = 1. + g * g - 2. * g * costheta;
+    return (1. - g) * (1. + g) / sqrt(t * t * t);
+}
+__device__ __forceinline__ double sk_integral_hg(double g, double cosalpha, double cosbeta)
+{
+    double ta = sqrt(1. + g * g - 2. * g * cosalpha);
+    double tb = sqrt(1. + g * g - 2. * g * cosbeta);
+    double f1 = (1. - g) * (1. + g) / g;
+    double f2 = (tb - ta) / (tb * ta);
+    return f1 * f2;
+}
+__device__ __noinline__ double sk_mean_hg(double g, double costheta)
+{
+    const double delta = 4. * M_PI / 180.;
+    double theta = acos(costheta);
+    double cosalpha = cos(theta - delta);
+    double cosbeta = cos(theta + delta);
+    if (theta < delta)
+        return (sk_integral_hg(g, 1., cosalpha) + sk_integral_hg(g, 1., cosbeta)) / (2. - cosalpha - cosbeta);
+    if (theta > M_PI - delta)
+        return (sk_integral_hg(g, cosalpha, -1.) + sk_integral_hg(g, cosbeta, -1.)) / (2. + cosalpha + cosbeta);
+    return sk_integral_hg(g, cosalpha, cosbeta) / (cosalpha - cosbeta);
+}

@@ -1,0 +1,74 @@
+"""Small seeded models shared by the oracle tests (CPU) and the parity tests (GPU)."""
+import math
+
+import numpy as np
+
+from skirt9_b200 import abi, configs
+from skirt9_b200 import host as H
+
+DEG = math.pi / 180.0
+
+
+def small_cartesian(num_packets=20000, seed=3, **kw):
+    return configs.cfg1(num_packets=num_packets, seed=seed, num_density_samples=4, **kw)
+
+
+def small_octree(num_packets=20000, seed=5, **kw):
+    args = dict(max_level=6, max_dust_fraction=1e-4, num_pixels=32, num_wavelengths=8)
+    args.update(kw)
+    return configs.cfg2(num_packets=num_packets, seed=seed, **args)
+
+
+def two_sources_three_instruments(num_packets=20000, seed=11, force=True):
+    """Point + shell sources, SED (with aperture) + two frames that share one observer, scattering levels,
+    statistics, strongly forward-scattering dust (exercises the averaged HG peel-off), ragged 7x5x3 grid."""
+    pc = H.PC
+    mix = H.MeanListDustMix([0.1e-6, 1e-6, 10e-6], [2000.0, 1000.0, 100.0], [0.7, 0.6, 0.4], [0.97, 0.96, 0.2])
+    medium = H.GeometricMedium(H.ShellGeometry(0.05 * pc, 0.9 * pc, 1.0), mix, opticalDepth=3.0, wavelength=0.55e-6)
+    grid = H.CartesianSpatialGrid(-pc, pc, -0.8 * pc, 0.9 * pc, -0.5 * pc, 0.7 * pc, 7, 5, 3)
+    s1 = H.PointSource((0.1 * pc, -0.2 * pc, 0.05 * pc), H.BlackBodySED(8000.0), luminosity=2.0 * H.LSUN)
+    s2 = H.GeometricSource(H.ShellGeometry(0.2 * pc, 1.5 * pc, 2.0), H.BlackBodySED(3000.0), luminosity=1.0 * H.LSUN,
+                           sourceWeight=2.0)
+    wlg = H.LogWavelengthGrid(0.2e-6, 5e-6, 6)
+    i1 = H.SEDInstrument(instrumentName="sed", distance=1e6 * pc, inclination=30 * DEG, azimuth=40 * DEG,
+                         radius=0.6 * pc, recordComponents=True, numScatteringLevels=2, recordStatistics=True)
+    i2 = H.FrameInstrument(instrumentName="f1", distance=1e6 * pc, inclination=100 * DEG, azimuth=-20 * DEG,
+                           roll=15 * DEG, fieldOfViewX=2 * pc, numPixelsX=9, fieldOfViewY=1.5 * pc, numPixelsY=7,
+                           centerX=0.1 * pc, recordComponents=False)
+    i3 = H.FullInstrument(instrumentName="f2", distance=1e6 * pc, inclination=100 * DEG, azimuth=-20 * DEG,
+                          roll=15 * DEG, fieldOfViewX=1 * pc, numPixelsX=4, fieldOfViewY=1 * pc, numPixelsY=4,
+                          recordComponents=True, recordStatistics=True)
+    return H.MonteCarloSimulation(sources=[s1, s2], medium=medium, grid=grid, instruments=[i1, i2, i3],
+                                  numPackets=num_packets, minWavelength=0.15e-6, maxWavelength=8e-6,
+                                  defaultWavelengthGrid=wlg, storeRadiationField=force,
+                                  radiationFieldWLG=H.LogWavelengthGrid(0.15e-6, 8e-6, 5) if force else None,
+                                  forceScattering=force, numDensitySamples=3, seed=seed)
+
+
+def compare_engines(sim, a, b, rtol=1e-9):
+    """Asserts that two engines that ran the same simulation agree: event counters exactly, tallies to rtol."""
+    ca, cb = a.counters(), b.counters()
+    for key in ("packets", "forward_paths", "forward_segments", "peel_paths", "peel_segments", "scatterings",
+                "rf_deposits", "detections"):
+        assert ca[key] == cb[key], (key, ca[key], cb[key])
+    for j, ins in enumerate(sim.instruments):
+        comps = [abi.SK_COMP_TOTAL]
+        if ins.recordComponents:
+            comps += [abi.SK_COMP_TRANSPARENT, abi.SK_COMP_PRIMARY_DIRECT, abi.SK_COMP_PRIMARY_SCATTERED]
+            comps += [abi.SK_COMP_PRIMARY_SCATTERED_LEVEL + k for k in range(ins.numScatteringLevels)]
+        for c in comps:
+            if ins.kind in (abi.SK_INSTR_SED, abi.SK_INSTR_FULL):
+                x, y = a.read_sed(j, c), b.read_sed(j, c)
+                np.testing.assert_allclose(x, y, rtol=rtol, atol=1e-300, err_msg=f"sed instr {j} comp {c}")
+            if ins.kind in (abi.SK_INSTR_FRAME, abi.SK_INSTR_FULL):
+                x, y = a.read_ifu(j, c), b.read_ifu(j, c)
+                np.testing.assert_allclose(x, y, rtol=rtol, atol=rtol * max(y.max(), 1e-300),
+                                           err_msg=f"ifu instr {j} comp {c}")
+        if ins.recordStatistics and ins.kind in (abi.SK_INSTR_SED, abi.SK_INSTR_FULL):
+            x, y = a.read_sed_stats(j), b.read_sed_stats(j)
+            np.testing.assert_allclose(x, y, rtol=1e-8, atol=1e-300, err_msg=f"stats instr {j}")
+    if sim.storeRadiationField:
+        x, y = a.read_rf(0), b.read_rf(0)
+        np.testing.assert_allclose(x, y, rtol=rtol, atol=rtol * y.max())
+        la, lb = a.absorbed_luminosity(True), b.absorbed_luminosity(True)
+        assert abs(la - lb) <= 1e-9 * abs(lb)
