@@ -142,15 +142,13 @@ static int32_t* dupi(const int32_t* p, size_t n)
 
 /* ------------------------------------------------------------------------------------------------ */
 /* random numbers: Philox4x32-10 (Salmon et al. 2011), replacing Random.cpp:20-56 (MT19937-64)      */
-/*   key = (seed, stream_id); counter = (history lo, history hi, block, 0); each block gives two    */
-/*   uniform deviates in the open interval (0,1) (Random.cpp:26-27 excludes 0 and 1 as well).       */
+/*   key = (seed, stream_id); counter = (history lo, history hi, draw index, 0); each draw gives one */
+/*   uniform deviate in the open interval (0,1) (Random.cpp:26-27 excludes 0 and 1 as well).        */
 /* ------------------------------------------------------------------------------------------------ */
 
 typedef struct {
     uint32_t k0, k1;
-    uint32_t c0, c1, block;
-    int has_spare;
-    double spare;
+    uint32_t c0, c1, draw;
 } rng_t;
 
 static void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1)
@@ -182,23 +180,14 @@ static void rng_init(rng_t* g, uint32_t seed, uint32_t stream, uint64_t history)
     g->k1 = stream;
     g->c0 = (uint32_t)history;
     g->c1 = (uint32_t)(history >> 32);
-    g->block = 0;
-    g->has_spare = 0;
-    g->spare = 0.;
+    g->draw = 0;
 }
-/* Random::uniform, Random.cpp:70-73 */
+/* Random::uniform, Random.cpp:70-73: the n-th deviate of a history is Philox(counter = (history, n, 0)) */
 static double uniform(rng_t* g)
 {
-    if (g->has_spare)
-    {
-        g->has_spare = 0;
-        return g->spare;
-    }
-    uint32_t c[4] = {g->c0, g->c1, g->block, 0u};
+    uint32_t c[4] = {g->c0, g->c1, g->draw, 0u};
     philox4x32_10(c, g->k0, g->k1);
-    g->block++;
-    g->spare = u01(c[2], c[3]);
-    g->has_spare = 1;
+    g->draw++;
     return u01(c[0], c[1]);
 }
 /* Random::exponCutoff, Random.cpp:105-117 */

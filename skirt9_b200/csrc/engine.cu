@@ -41,46 +41,44 @@ extern "C" int sk_abi_version(void)
 // kernels
 // ---------------------------------------------------------------------------------------------------
 #define SK_BLOCK 128
-#define SK_CHUNK 8
+#define SK_WARPS_PER_BLOCK (SK_BLOCK / 32)
 
 template <int GRID>
 __global__ void __launch_bounds__(SK_BLOCK) sk_life_cycle_kernel(const SkDevModel M, const SkRunArgs A)
 {
     extern __shared__ double smem[];
     SkSmemTables T;
+    const int n0 = (GRID == 1 ? M.nx : M.nx) + 1, n1 = (GRID == 1 ? M.ny : M.nx) + 1, n2 = (GRID == 1 ? M.nz : M.nx) + 1;
+    int* lists;
+    if (M.lattice_in_smem)
     {
         // stage the per-axis border tables (Cartesian borders / octree lattice) in shared memory
-        const int n0 = (GRID == 1 ? M.nx : M.nx) + 1, n1 = (GRID == 1 ? M.ny : M.nx) + 1,
-                  n2 = (GRID == 1 ? M.nz : M.nx) + 1;
-        if (M.lattice_in_smem)
-        {
-            for (int i = threadIdx.x; i < n0; i += blockDim.x) smem[i] = M.xv[i];
-            for (int i = threadIdx.x; i < n1; i += blockDim.x) smem[n0 + i] = M.yv[i];
-            for (int i = threadIdx.x; i < n2; i += blockDim.x) smem[n0 + n1 + i] = M.zv[i];
-            __syncthreads();
-            T.X = smem;
-            T.Y = smem + n0;
-            T.Z = smem + n0 + n1;
-        }
-        else
-        {
-            T.X = M.xv;
-            T.Y = M.yv;
-            T.Z = M.zv;
-        }
+        for (int i = threadIdx.x; i < n0; i += blockDim.x) smem[i] = M.xv[i];
+        for (int i = threadIdx.x; i < n1; i += blockDim.x) smem[n0 + i] = M.yv[i];
+        for (int i = threadIdx.x; i < n2; i += blockDim.x) smem[n0 + n1 + i] = M.zv[i];
+        T.X = smem;
+        T.Y = smem + n0;
+        T.Z = smem + n0 + n1;
+        lists = reinterpret_cast<int*>(smem + n0 + n1 + n2);
     }
+    else
+    {
+        T.X = M.xv;
+        T.Y = M.yv;
+        T.Z = M.zv;
+        lists = reinterpret_cast<int*>(smem);
+    }
+    __syncthreads();
+    const int warp_in_block = threadIdx.x >> 5;
+    const size_t warp_global = (size_t)blockIdx.x * SK_WARPS_PER_BLOCK + warp_in_block;
+    SkPoolView P;
+    P.d = A.pool_d + warp_global * (size_t)(SK_ND * SK_POOL);
+    P.i = A.pool_i + warp_global * (size_t)(SK_NI * SK_POOL);
+    int* list = lists + warp_in_block * SK_POOL;
+
     SkLocalCounters cnt;
     memset(&cnt, 0, sizeof cnt);
-
-    // persistent threads: every thread draws chunks of history indices from a global dispenser; the tallies do
-    // not depend on which thread runs which history because the random stream is keyed by the history index
-    while (true)
-    {
-        unsigned long long base = atomicAdd(A.work_counter, (unsigned long long)SK_CHUNK);
-        if (base >= A.count) break;
-        unsigned long long end = base + SK_CHUNK < A.count ? base + SK_CHUNK : A.count;
-        for (unsigned long long h = base; h < end; ++h) sk_life_cycle<GRID>(M, T, A, cnt, A.first + h);
-    }
+    sk_warp_life_cycles<GRID>(M, T, A, P, list, cnt);
 
     // counters: warp reduce, one atomic per warp and counter
     unsigned int* c = reinterpret_cast<unsigned int*>(&cnt);
@@ -145,6 +143,9 @@ struct sk_engine {
     double* stat_block = nullptr;
     size_t stat_count = 0;
     unsigned long long* work_counter = nullptr;
+    double* pool_d = nullptr;
+    int32_t* pool_i = nullptr;
+    size_t pool_warps = 0;
     double* scalar = nullptr;
     int table_len[3] = {0, 0, 0};
     size_t smem_bytes = 0;
@@ -220,6 +221,8 @@ extern "C" void sk_engine_destroy(sk_engine_t* e)
     free_group(e->instr_allocs);
     free_group(e->rf_allocs);
     cudaFree(e->work_counter);
+    cudaFree(e->pool_d);
+    cudaFree(e->pool_i);
     cudaFree(e->scalar);
     cudaFree(e->M.counters);
     cudaEventDestroy(e->ev0);
@@ -822,18 +825,34 @@ extern "C" int sk_engine_launch_segment(sk_engine_t* e, uint64_t first, uint64_t
     A.stream_id = stream_id;
     A.work_counter = e->work_counter;
     CK(cudaMemsetAsync(e->work_counter, 0, sizeof(unsigned long long), e->stream));
-    // persistent grid: a multiple of the SM count, sized by the occupancy the kernel actually gets
+    // persistent grid: a multiple of the SM count, sized by the occupancy the kernel actually gets; every warp owns a
+    // pool of SK_POOL in-flight packets
     int per_sm = 0;
     auto kern = e->grid_kind == 1 ? sk_life_cycle_kernel<1> : sk_life_cycle_kernel<2>;
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SK_BLOCK, e->smem_bytes));
+    size_t smem = e->smem_bytes + (size_t)SK_WARPS_PER_BLOCK * SK_POOL * sizeof(int);
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SK_BLOCK, smem));
     if (per_sm < 1) per_sm = 1;
-    unsigned long long want = (count + SK_CHUNK - 1) / SK_CHUNK;
-    unsigned long long threads_needed = want;
-    unsigned long long blocks_needed = (threads_needed + SK_BLOCK - 1) / SK_BLOCK;
-    unsigned long long grid = std::min<unsigned long long>((unsigned long long)g_num_sms * per_sm, std::max<unsigned long long>(blocks_needed, 1));
+    unsigned long long warps_needed = (count + SK_POOL - 1) / SK_POOL;
+    unsigned long long blocks_needed = (warps_needed + SK_WARPS_PER_BLOCK - 1) / SK_WARPS_PER_BLOCK;
+    unsigned long long grid = std::min<unsigned long long>((unsigned long long)g_num_sms * per_sm,
+                                                           std::max<unsigned long long>(blocks_needed, 1));
+    size_t warps = (size_t)grid * SK_WARPS_PER_BLOCK;
+    if (warps > e->pool_warps)
+    {
+        cudaFree(e->pool_d);
+        cudaFree(e->pool_i);
+        e->pool_d = nullptr;
+        e->pool_i = nullptr;
+        e->pool_warps = 0;
+        CK(cudaMalloc(&e->pool_d, warps * (size_t)(SK_ND * SK_POOL) * sizeof(double)));
+        CK(cudaMalloc(&e->pool_i, warps * (size_t)(SK_NI * SK_POOL) * sizeof(int32_t)));
+        e->pool_warps = warps;
+    }
+    A.pool_d = e->pool_d;
+    A.pool_i = e->pool_i;
     CK(cudaEventRecord(e->ev0, e->stream));
-    kern<<<(unsigned)grid, SK_BLOCK, e->smem_bytes, e->stream>>>(e->M, A);
+    kern<<<(unsigned)grid, SK_BLOCK, smem, e->stream>>>(e->M, A);
     CK(cudaGetLastError());
     CK(cudaEventRecord(e->ev1, e->stream));
     e->timing_pending = true;

@@ -103,15 +103,15 @@ struct SkRunArgs {
     int32_t primary, peel, store;
     uint32_t stream_id;
     unsigned long long* work_counter;  // dynamic history dispenser
+    double* pool_d;                    // per-warp packet pools: [warp][SK_ND][SK_POOL]
+    int32_t* pool_i;                   // [warp][SK_NI][SK_POOL]
 };
 
 // ---------------------------------------------------------------------------------------------------
 // Philox4x32-10 counter-based generator (replaces Random.cpp:20-56); identical to oracle/sk_oracle.c
 // ---------------------------------------------------------------------------------------------------
 struct SkRng {
-    uint32_t k0, k1, c0, c1, block;
-    int has_spare;
-    double spare;
+    uint32_t k0, k1, c0, c1, draw;
 };
 
 __device__ __forceinline__ void sk_philox(uint32_t c[4], uint32_t k0, uint32_t k1)
@@ -136,29 +136,21 @@ __device__ __forceinline__ double sk_u01(uint32_t lo, uint32_t hi)
     unsigned long long x = ((unsigned long long)hi << 32) | lo;
     return ((double)(x >> 12) + 0.5) * (1.0 / 4503599627370496.0);
 }
-__device__ __forceinline__ void sk_rng_init(SkRng& g, uint32_t seed, uint32_t stream, unsigned long long history)
+__device__ __forceinline__ void sk_rng_init(SkRng& g, uint32_t seed, uint32_t stream, unsigned long long history,
+                                            uint32_t draw)
 {
     g.k0 = seed;
     g.k1 = stream;
     g.c0 = (uint32_t)history;
     g.c1 = (uint32_t)(history >> 32);
-    g.block = 0;
-    g.has_spare = 0;
-    g.spare = 0.;
+    g.draw = draw;
 }
-// Random::uniform, Random.cpp:70-73
+// Random::uniform, Random.cpp:70-73: the n-th deviate of a history is Philox(counter = (history, n, 0))
 __device__ __noinline__ double sk_uniform(SkRng& g)
 {
-    if (g.has_spare)
-    {
-        g.has_spare = 0;
-        return g.spare;
-    }
-    uint32_t c[4] = {g.c0, g.c1, g.block, 0u};
+    uint32_t c[4] = {g.c0, g.c1, g.draw, 0u};
     sk_philox(c, g.k0, g.k1);
-    g.block++;
-    g.spare = sk_u01(c[2], c[3]);
-    g.has_spare = 1;
+    g.draw++;
     return sk_u01(c[0], c[1]);
 }
 // Random::exponCutoff, Random.cpp:105-117

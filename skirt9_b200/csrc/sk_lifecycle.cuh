@@ -1,115 +1,140 @@
 // sk_lifecycle.cuh -- the photon life cycle on the device: MonteCarloSimulation::performLifeCycle
-// (SKIRT/core/MonteCarloSimulation.cpp:538-613) and everything it calls, restated for one CUDA thread per
-// in-flight history.  Paths are never materialised (the reference stores vector<Segment>, SpatialGridPath.hpp:93-115):
-// the forward path is walked once for the total optical depth (with the radiation-field deposits fused in) and
-// re-walked up to the sampled interaction point; both walks use identical arithmetic so they see identical segments.
+// (SKIRT/core/MonteCarloSimulation.cpp:538-613) and everything it calls.
+//
+// Execution model: a persistent kernel in which ONE WARP OWNS A POOL of SK_POOL in-flight
+// photon packets (state in a per-warp structure-of-arrays region of HBM/L2).  The warp advances its whole pool in
+// lock-step through the stages of the reference's forced-scattering loop; stages are of two kinds:
+//   * event stages (launch, peel-off set-up and detection, scattering, optical-depth sampling, interaction): every
+//     lane handles one packet of the pool, all lanes execute the same code -> no divergence;
+//   * trace stages (forward path to the boundary, re-walk to the interaction point, peel-off path to an observer):
+//     lanes are NOT bound to packets; each lane walks one ray cell by cell and, when its ray ends, immediately takes
+//     the next unprocessed ray of the stage from the warp's list -> the cell-crossing loop, which is >95 % of the work,
+//     stays converged although path lengths vary from 1 to several hundred segments.
+// Paths are never materialised (the reference stores vector<Segment>, SpatialGridPath.hpp:93-115): the forward path
+// is walked once for the total optical depth (radiation-field deposits fused in) and re-walked up to the sampled
+// interaction point; both walks use identical arithmetic so they see identical segments.
 #pragma once
 #include "sk_device.cuh"
 
-struct SkPacket {
-    double lambda, W;  // PhotonPacket::_lambda, _W = L*lambda (PhotonPacket.hpp:337-340)
-    double rx, ry, rz, kx, ky, kz;
-    int nscatt;
-    int primary_origin;
-    int ilam;          // DustMix::indexForLambda(lambda) (DustMix.cpp:276-279); constant without kinematics
-    double sig_ext;    // sectionExt at ilam
+#ifndef SK_POOL
+#define SK_POOL 256
+#endif
+
+// per-packet state: field-major arrays of SK_POOL entries per warp
+enum {
+    D_RX, D_RY, D_RZ, D_KX, D_KY, D_KZ, D_LAMBDA, D_W, D_LTHR, D_SIGEXT, D_TAUPATH, D_TAUINT, D_STOT, D_SINT,
+    D_PEELW, D_PTAU, D_LIMIT, D_HISTW0, SK_ND = D_HISTW0 + SK_MAX_INSTR
+};
+enum {
+    I_HLO, I_HHI, I_DRAW, I_NSCATT, I_STATE, I_ILAM, I_M, I_IX, I_IY, I_IZ, I_LEV, I_MINT, I_MIX, I_MIY, I_MIZ,
+    I_MLEV, I_NSEG, I_HELL0, SK_NI = I_HELL0 + SK_MAX_INSTR
+};
+// I_STATE bits
+#define SK_ST_LIVE 1
+#define SK_ST_SCATTER 2    // a scattering event is pending (peel-off of kind "scattering", then new direction)
+#define SK_ST_FOUND 4      // non-forced propagation: interaction point found
+
+struct SkPoolView {
+    double* d;
+    int32_t* i;
+    __device__ __forceinline__ double& D(int f, int s) const { return d[f * SK_POOL + s]; }
+    __device__ __forceinline__ int32_t& I(int f, int s) const { return i[f * SK_POOL + s]; }
 };
 
 struct SkLocalCounters {
     unsigned int packets, fwd_paths, fwd_segs, replay_segs, peel_paths, peel_segs, scatt, rf, det, fallbacks;
 };
 
-// Shared-memory staging of the per-axis border tables (Cartesian borders or octree lattice tables).
 struct SkSmemTables {
     const double *X, *Y, *Z;
 };
 
-// ---------------------------------------------------------------------------------------------------
-// Ray state + PathSegmentGenerator::moveInside (SKIRT/utils/PathSegmentGenerator.cpp:11-112)
-// ---------------------------------------------------------------------------------------------------
-struct SkRay {
-    double rx, ry, rz, kx, ky, kz;
+struct SkCellPos {
+    int m;           // cell index, -1 = outside / unknown
+    int ix, iy, iz;  // octree: lattice coordinates of the lower corner; Cartesian: bin indices i,j,k
+    int lev;
 };
 
+// ---------------------------------------------------------------------------------------------------
+// Geometry helpers
+// ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool sk_box_contains(const double* b, double x, double y, double z)
 {
     return x >= b[0] && x <= b[3] && y >= b[1] && y <= b[4] && z >= b[2] && z <= b[5];  // Box.hpp:99-109
 }
+__device__ __forceinline__ bool sk_box_strictly_inside(const double* b, double x, double y, double z)
+{
+    return x > b[0] && x < b[3] && y > b[1] && y < b[4] && z > b[2] && z < b[5];
+}
 
-__device__ __noinline__ bool sk_move_inside(SkRay& g, const double* box, double eps, double& cumds_out)
+// PathSegmentGenerator::moveInside, SKIRT/utils/PathSegmentGenerator.cpp:11-112
+__device__ __noinline__ bool sk_move_inside(double& rx, double& ry, double& rz, double kx, double ky, double kz,
+                                            const double* box, double eps, double& cumds_out)
 {
     double cumds = 0.;
-    if (g.rx <= box[0])
+    if (rx <= box[0])
     {
-        if (g.kx <= 0.0) return false;
-        double ds = (box[0] - g.rx) / g.kx;
-        g.rx = box[0] + eps;
-        g.ry += g.ky * ds;
-        g.rz += g.kz * ds;
+        if (kx <= 0.0) return false;
+        double ds = (box[0] - rx) / kx;
+        rx = box[0] + eps;
+        ry += ky * ds;
+        rz += kz * ds;
         cumds += ds;
     }
-    else if (g.rx >= box[3])
+    else if (rx >= box[3])
     {
-        if (g.kx >= 0.0) return false;
-        double ds = (box[3] - g.rx) / g.kx;
-        g.rx = box[3] - eps;
-        g.ry += g.ky * ds;
-        g.rz += g.kz * ds;
+        if (kx >= 0.0) return false;
+        double ds = (box[3] - rx) / kx;
+        rx = box[3] - eps;
+        ry += ky * ds;
+        rz += kz * ds;
         cumds += ds;
     }
-    if (g.ry <= box[1])
+    if (ry <= box[1])
     {
-        if (g.ky <= 0.0) return false;
-        double ds = (box[1] - g.ry) / g.ky;
-        g.rx += g.kx * ds;
-        g.ry = box[1] + eps;
-        g.rz += g.kz * ds;
+        if (ky <= 0.0) return false;
+        double ds = (box[1] - ry) / ky;
+        rx += kx * ds;
+        ry = box[1] + eps;
+        rz += kz * ds;
         cumds += ds;
     }
-    else if (g.ry >= box[4])
+    else if (ry >= box[4])
     {
-        if (g.ky >= 0.0) return false;
-        double ds = (box[4] - g.ry) / g.ky;
-        g.rx += g.kx * ds;
-        g.ry = box[4] - eps;
-        g.rz += g.kz * ds;
+        if (ky >= 0.0) return false;
+        double ds = (box[4] - ry) / ky;
+        rx += kx * ds;
+        ry = box[4] - eps;
+        rz += kz * ds;
         cumds += ds;
     }
-    if (g.rz <= box[2])
+    if (rz <= box[2])
     {
-        if (g.kz <= 0.0) return false;
-        double ds = (box[2] - g.rz) / g.kz;
-        g.rx += g.kx * ds;
-        g.ry += g.ky * ds;
-        g.rz = box[2] + eps;
+        if (kz <= 0.0) return false;
+        double ds = (box[2] - rz) / kz;
+        rx += kx * ds;
+        ry += ky * ds;
+        rz = box[2] + eps;
         cumds += ds;
     }
-    else if (g.rz >= box[5])
+    else if (rz >= box[5])
     {
-        if (g.kz >= 0.0) return false;
-        double ds = (box[5] - g.rz) / g.kz;
-        g.rx += g.kx * ds;
-        g.ry += g.ky * ds;
-        g.rz = box[5] - eps;
+        if (kz >= 0.0) return false;
+        double ds = (box[5] - rz) / kz;
+        rx += kx * ds;
+        ry += ky * ds;
+        rz = box[5] - eps;
         cumds += ds;
     }
-    if (!sk_box_contains(box, g.rx, g.ry, g.rz)) return false;
+    if (!sk_box_contains(box, rx, ry, rz)) return false;
     cumds_out = cumds;
     return true;
 }
 
-// ---------------------------------------------------------------------------------------------------
-// Octree cell location: TreeNode::leafChild (TreeNode.cpp:65-76) + OctTreeNode::child (OctTreeNode.cpp:37-42),
-// expressed on the integer lattice: a node is (ix,iy,iz,level), its centre is the lattice border at +half size.
-// ---------------------------------------------------------------------------------------------------
-struct SkTreePos {
-    int m;             // cell index, -1 = outside
-    int ix, iy, iz;    // lattice coordinates of the cell's lower corner
-    int lev;
-};
-
+// Octree cell location: TreeNode::leafChild (TreeNode.cpp:65-76) + OctTreeNode::child (OctTreeNode.cpp:37-42) on the
+// integer lattice: a node is (ix,iy,iz,level); its centre (CHILD_0->rmax) is the lattice border at +half size.
 __device__ __forceinline__ void sk_tree_descend(const SkDevModel& M, const SkSmemTables& T, int node, int ix, int iy,
-                                                int iz, int lev, double x, double y, double z, SkTreePos& out)
+                                                int iz, int lev, double x, double y, double z, SkCellPos& out)
 {
     int fc = __ldg(&M.node_child[node]);
     while (fc >= 0)
@@ -142,18 +167,28 @@ __device__ __forceinline__ void sk_tree_descend(const SkDevModel& M, const SkSme
     out.lev = lev;
 }
 
-__device__ __noinline__ void sk_tree_locate_root(const SkDevModel& M, const SkSmemTables& T, double x, double y,
-                                                 double z, SkTreePos& out)
+template <int GRID>
+__device__ __noinline__ void sk_locate(const SkDevModel& M, const SkSmemTables& T, double x, double y, double z,
+                                       SkCellPos& out)
 {
     if (!sk_box_contains(M.ext, x, y, z))
     {
         out.m = -1;
         return;
     }
-    sk_tree_descend(M, T, 0, 0, 0, 0, 0, x, y, z, out);
+    if (GRID == 1)
+    {
+        out.ix = sk_locate_clip(T.X, M.nx + 1, x);  // CartesianSpatialGrid.cpp:105-107
+        out.iy = sk_locate_clip(T.Y, M.ny + 1, y);
+        out.iz = sk_locate_clip(T.Z, M.nz + 1, z);
+        out.lev = 0;
+        out.m = out.iz + M.nz * out.iy + M.nz * M.ny * out.ix;
+    }
+    else
+        sk_tree_descend(M, T, 0, 0, 0, 0, 0, x, y, z, out);
 }
 
-__device__ __forceinline__ bool sk_tree_cell_contains(const SkDevModel& M, const SkSmemTables& T, const SkTreePos& p,
+__device__ __forceinline__ bool sk_tree_cell_contains(const SkDevModel& M, const SkSmemTables& T, const SkCellPos& p,
                                                       double x, double y, double z)
 {
     int size = 1 << (M.maxlevel - p.lev);
@@ -162,128 +197,105 @@ __device__ __forceinline__ bool sk_tree_cell_contains(const SkDevModel& M, const
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Path traversal.  `visit(m, dens, ds)` is called for every segment the reference generator would return
-// (m = -1 for the empty segment in front of the grid); it returns false to stop the walk early.
+// One cell crossing.  Returns the segment (m, dens, ds) and moves (r, p) to the next cell; `p.m < 0` afterwards
+// means the path has left the grid.
 //   Cartesian: CartesianSpatialGrid::MySegmentGenerator::next, CartesianSpatialGrid.cpp:95-162
-//   Octree:    TreeSpatialGrid::MySegmentGenerator::next, TreeSpatialGrid.cpp:140-216, with
-//              TreeNode::neighbor (TreeNode.cpp:103-112) served by the per-cell links
+//   Octree:    TreeSpatialGrid::MySegmentGenerator::next, TreeSpatialGrid.cpp:140-216, with TreeNode::neighbor
+//              (TreeNode.cpp:103-112) served by the per-cell links and the top-down search as the fall-back
 // ---------------------------------------------------------------------------------------------------
-template <class Visit>
-__device__ __forceinline__ void sk_trace_cartesian(const SkDevModel& M, const SkSmemTables& T, double rx, double ry,
-                                                   double rz, double kx, double ky, double kz, Visit&& visit)
+struct SkRayDir {
+    double kx, ky, kz;
+};
+
+template <int GRID>
+__device__ __forceinline__ void sk_step(const SkDevModel& M, const SkSmemTables& T, SkLocalCounters& cnt, double& rx,
+                                        double& ry, double& rz, const SkRayDir& k, SkCellPos& p, int& m_out,
+                                        double& dens_out, double& ds_out)
 {
-    SkRay g{rx, ry, rz, kx, ky, kz};
-    double cumds = 0.;
-    if (!sk_move_inside(g, M.ext, M.eps, cumds)) return;
-    int i = sk_locate_clip(T.X, M.nx + 1, g.rx);
-    int j = sk_locate_clip(T.Y, M.ny + 1, g.ry);
-    int k = sk_locate_clip(T.Z, M.nz + 1, g.rz);
-    if (cumds > 0.)
-        if (!visit(-1, 0., cumds)) return;
-    const int di = (kx < 0.0) ? -1 : 1, dj = (ky < 0.0) ? -1 : 1, dk = (kz < 0.0) ? -1 : 1;
-    const int oi = (kx < 0.0) ? 0 : 1, oj = (ky < 0.0) ? 0 : 1, ok = (kz < 0.0) ? 0 : 1;
-    const bool ux = fabs(kx) > 1e-15, uy = fabs(ky) > 1e-15, uz = fabs(kz) > 1e-15;
-    while (true)
+    if (GRID == 1)
     {
-        int m = k + M.nz * j + M.nz * M.ny * i;
+        int m = p.m;
         double dens = __ldg(&M.dens[m]);
-        double xE = T.X[i + oi];
-        double yE = T.Y[j + oj];
-        double zE = T.Z[k + ok];
-        double dsx = ux ? (xE - g.rx) / kx : DBL_MAX;
-        double dsy = uy ? (yE - g.ry) / ky : DBL_MAX;
-        double dsz = uz ? (zE - g.rz) / kz : DBL_MAX;
+        double xE = T.X[p.ix + ((k.kx < 0.0) ? 0 : 1)];
+        double yE = T.Y[p.iy + ((k.ky < 0.0) ? 0 : 1)];
+        double zE = T.Z[p.iz + ((k.kz < 0.0) ? 0 : 1)];
+        double dsx = (fabs(k.kx) > 1e-15) ? (xE - rx) / k.kx : DBL_MAX;
+        double dsy = (fabs(k.ky) > 1e-15) ? (yE - ry) / k.ky : DBL_MAX;
+        double dsz = (fabs(k.kz) > 1e-15) ? (zE - rz) / k.kz : DBL_MAX;
         double ds;
         bool outside;
         if (dsx <= dsy && dsx <= dsz)
         {
             ds = dsx;
-            g.rx = xE;
-            g.ry += ky * dsx;
-            g.rz += kz * dsx;
-            i += di;
-            outside = (i >= M.nx || i < 0);
+            rx = xE;
+            ry += k.ky * dsx;
+            rz += k.kz * dsx;
+            p.ix += (k.kx < 0.0) ? -1 : 1;
+            outside = (p.ix >= M.nx || p.ix < 0);
         }
         else if (dsy < dsx && dsy <= dsz)
         {
             ds = dsy;
-            g.ry = yE;
-            g.rx += kx * dsy;
-            g.rz += kz * dsy;
-            j += dj;
-            outside = (j >= M.ny || j < 0);
+            ry = yE;
+            rx += k.kx * dsy;
+            rz += k.kz * dsy;
+            p.iy += (k.ky < 0.0) ? -1 : 1;
+            outside = (p.iy >= M.ny || p.iy < 0);
         }
         else
         {
             ds = dsz;
-            g.rz = zE;
-            g.rx += kx * dsz;
-            g.ry += ky * dsz;
-            k += dk;
-            outside = (k >= M.nz || k < 0);
+            rz = zE;
+            rx += k.kx * dsz;
+            ry += k.ky * dsz;
+            p.iz += (k.kz < 0.0) ? -1 : 1;
+            outside = (p.iz >= M.nz || p.iz < 0);
         }
-        if (!visit(m, dens, ds)) return;
-        if (outside) return;
+        m_out = m;
+        dens_out = dens;
+        ds_out = ds;
+        p.m = outside ? -1 : p.iz + M.nz * p.iy + M.nz * M.ny * p.ix;
     }
-}
-
-template <class Visit>
-__device__ __forceinline__ void sk_trace_tree(const SkDevModel& M, const SkSmemTables& T, SkLocalCounters& cnt,
-                                              double rx, double ry, double rz, double kx, double ky, double kz,
-                                              Visit&& visit)
-{
-    SkRay g{rx, ry, rz, kx, ky, kz};
-    double cumds = 0.;
-    if (!sk_move_inside(g, M.ext, M.eps, cumds)) return;
-    SkTreePos p;
-    sk_tree_locate_root(M, T, g.rx, g.ry, g.rz, p);
-    if (cumds > 0.)
-        if (!visit(-1, 0., cumds)) return;
-    if (p.m < 0) return;  // cannot happen after a successful moveInside; the reference would dereference null
-    const bool ux = fabs(kx) > 1e-15, uy = fabs(ky) > 1e-15, uz = fabs(kz) > 1e-15;
-    const int wx = (kx < 0.0) ? 0 : 1, wy = (ky < 0.0) ? 2 : 3, wz = (kz < 0.0) ? 4 : 5;
-    const double eps = M.eps;
-    while (true)
+    else
     {
         // one 32-byte sector: density + the six neighbour links of the current cell
         const int4* rp = reinterpret_cast<const int4*>(&M.cells[p.m]);
         int4 a = __ldg(rp), b = __ldg(rp + 1);
         double dens = __hiloint2double(a.y, a.x);
         int size = 1 << (M.maxlevel - p.lev);
-        double xnext = T.X[p.ix + ((kx < 0.0) ? 0 : size)];
-        double ynext = T.Y[p.iy + ((ky < 0.0) ? 0 : size)];
-        double znext = T.Z[p.iz + ((kz < 0.0) ? 0 : size)];
-        double dsx = ux ? (xnext - g.rx) / kx : DBL_MAX;
-        double dsy = uy ? (ynext - g.ry) / ky : DBL_MAX;
-        double dsz = uz ? (znext - g.rz) / kz : DBL_MAX;
+        double xnext = T.X[p.ix + ((k.kx < 0.0) ? 0 : size)];
+        double ynext = T.Y[p.iy + ((k.ky < 0.0) ? 0 : size)];
+        double znext = T.Z[p.iz + ((k.kz < 0.0) ? 0 : size)];
+        double dsx = (fabs(k.kx) > 1e-15) ? (xnext - rx) / k.kx : DBL_MAX;
+        double dsy = (fabs(k.ky) > 1e-15) ? (ynext - ry) / k.ky : DBL_MAX;
+        double dsz = (fabs(k.kz) > 1e-15) ? (znext - rz) / k.kz : DBL_MAX;
         double ds;
         int wall;
         if (dsx <= dsy && dsx <= dsz)
         {
             ds = dsx;
-            wall = wx;
+            wall = (k.kx < 0.0) ? 0 : 1;
         }
         else if (dsy <= dsx && dsy <= dsz)
         {
             ds = dsy;
-            wall = wy;
+            wall = (k.ky < 0.0) ? 2 : 3;
         }
         else
         {
             ds = dsz;
-            wall = wz;
+            wall = (k.kz < 0.0) ? 4 : 5;
         }
-        double adv = ds + eps;
-        g.rx += kx * adv;
-        g.ry += ky * adv;
-        g.rz += kz * adv;
-        const int m_old = p.m;
-        bool go_on = visit(m_old, dens, ds);
-        if (!go_on) return;
+        double adv = ds + M.eps;
+        rx += k.kx * adv;
+        ry += k.ky * adv;
+        rz += k.kz * adv;
+        m_out = p.m;
+        dens_out = dens;
+        ds_out = ds;
 
-        // neighbour lookup through the link of the exit wall
         int link = wall == 0 ? a.z : wall == 1 ? a.w : wall == 2 ? b.x : wall == 3 ? b.y : wall == 4 ? b.z : b.w;
-        SkTreePos q;
+        SkCellPos q;
         q.m = -1;
         if (link >= 0)
         {
@@ -319,40 +331,30 @@ __device__ __forceinline__ void sk_trace_tree(const SkDevModel& M, const SkSmemT
                     iy += shift;
                 else
                     iz += shift;
-                sk_tree_descend(M, T, link & SK_LINK_INDEX_MASK, ix, iy, iz, p.lev, g.rx, g.ry, g.rz, q);
+                sk_tree_descend(M, T, link & SK_LINK_INDEX_MASK, ix, iy, iz, p.lev, rx, ry, rz, q);
             }
-            if (!sk_tree_cell_contains(M, T, q, g.rx, g.ry, g.rz)) q.m = -1;
+            if (!sk_tree_cell_contains(M, T, q, rx, ry, rz)) q.m = -1;
         }
         if (q.m < 0)
         {
             // `if (!_node) _node = _grid->root()->leafChild(r())`, TreeSpatialGrid.cpp:193
-            if (sk_box_contains(M.ext, g.rx, g.ry, g.rz))
+            if (sk_box_contains(M.ext, rx, ry, rz))
             {
                 cnt.fallbacks++;
-                sk_tree_locate_root(M, T, g.rx, g.ry, g.rz, q);
+                sk_locate<2>(M, T, rx, ry, rz, q);
             }
         }
-        if (q.m == m_old)
+        if (q.m == m_out)
         {
             // PathSegmentGenerator::propagateToNextAfter, PathSegmentGenerator.hpp:148-153
-            g.rx = nextafter(g.rx, (kx < 0.) ? -DBL_MAX : DBL_MAX);
-            g.ry = nextafter(g.ry, (ky < 0.) ? -DBL_MAX : DBL_MAX);
-            g.rz = nextafter(g.rz, (kz < 0.) ? -DBL_MAX : DBL_MAX);
-            sk_tree_locate_root(M, T, g.rx, g.ry, g.rz, q);
+            rx = nextafter(rx, (k.kx < 0.) ? -DBL_MAX : DBL_MAX);
+            ry = nextafter(ry, (k.ky < 0.) ? -DBL_MAX : DBL_MAX);
+            rz = nextafter(rz, (k.kz < 0.) ? -DBL_MAX : DBL_MAX);
+            sk_locate<2>(M, T, rx, ry, rz, q);
+            if (q.m == m_out) q.m = -1;
         }
-        if (q.m < 0 || q.m == m_old) return;
         p = q;
     }
-}
-
-template <int GRID, class Visit>
-__device__ __forceinline__ void sk_trace(const SkDevModel& M, const SkSmemTables& T, SkLocalCounters& cnt, double rx,
-                                         double ry, double rz, double kx, double ky, double kz, Visit&& visit)
-{
-    if (GRID == 1)
-        sk_trace_cartesian(M, T, rx, ry, rz, kx, ky, kz, visit);
-    else
-        sk_trace_tree(M, T, cnt, rx, ry, rz, kx, ky, kz, visit);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -476,7 +478,12 @@ __device__ __noinline__ void sk_generate_position(SkRng& g, const SkDevSource& s
     }
 }
 
-__device__ __noinline__ void sk_launch_primary(const SkDevModel& M, SkRng& g, unsigned long long history, SkPacket& pp)
+struct SkLaunch {
+    double lambda, W, rx, ry, rz, kx, ky, kz;
+    int ilam;
+};
+
+__device__ __noinline__ void sk_launch_primary(const SkDevModel& M, SkRng& g, unsigned long long history, SkLaunch& pp)
 {
     int lo = 0, hi = M.nsrc + 1;  // std::upper_bound(_Iv, historyIndex) - 1
     while (lo < hi)
@@ -542,73 +549,32 @@ __device__ __noinline__ void sk_launch_primary(const SkDevModel& M, SkRng& g, un
     sk_random_direction(g, pp.kx, pp.ky, pp.kz);
     pp.lambda = lambda;
     pp.W = Lw * lambda;  // PhotonPacket::launch, PhotonPacket.cpp:18-40
-    pp.nscatt = 0;
-    pp.primary_origin = 1;
     pp.ilam = sk_locate_clip(M.lam_border, M.nlam, lambda);
-    pp.sig_ext = M.sig_ext[pp.ilam];
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Instruments: Instrument::detect + FluxRecorder::detect (FluxRecorder.cpp:304-468)
+// Instruments
 // ---------------------------------------------------------------------------------------------------
-struct SkPeel {
-    double W;       // weight of the peel-off packet
-    int nscatt;
-    bool has_tau;
-    double tau;
-};
-
-template <int GRID>
-__device__ __forceinline__ double sk_observed_optical_depth(const SkDevModel& M, const SkSmemTables& T,
-                                                            SkLocalCounters& cnt, const SkPacket& pp, double W,
-                                                            const double* kobs)
+// First half of Instrument::detect / FluxRecorder::detect: does this instrument record a packet at (x,y,z) with
+// wavelength lambda?  SEDInstrument.cpp:22-25 + ApertureInstrument.cpp:24-43, FrameInstrument.cpp:45-64,
+// FluxRecorder.cpp:306-313.  Returns false when nothing is recorded (and no optical depth is needed).
+__device__ __forceinline__ bool sk_detect_geometry(const SkDevModel& M, const SkDevInstr& q, double x, double y,
+                                                   double z, double lambda, int& l, int& ell)
 {
-    // MediumSystem::getExtinctionOpticalDepth(pp, infinity), MediumSystem.cpp:1192-1219
-    double L = W / pp.lambda;
-    if (L <= 0) return INFINITY;
-    double taumax = log(L) + 745;
-    double tau = 0.;
-    const double section = pp.sig_ext;
-    bool inf = false;
-    unsigned int nseg = 0;
-    sk_trace<GRID>(M, T, cnt, pp.rx, pp.ry, pp.rz, kobs[0], kobs[1], kobs[2], [&](int m, double dens, double ds) {
-        nseg++;
-        if (m >= 0)
-        {
-            tau += section * dens * ds;
-            if (tau >= taumax)
-            {
-                inf = true;
-                return false;
-            }
-        }
-        return true;
-    });
-    cnt.peel_paths++;
-    cnt.peel_segs += nseg;
-    return inf ? INFINITY : tau;
-}
-
-template <int GRID>
-__device__ __forceinline__ void sk_detect(const SkDevModel& M, const SkSmemTables& T, SkLocalCounters& cnt,
-                                          const SkDevInstr& q, const SkPacket& pp, SkPeel& peel, double* hist_w,
-                                          int* hist_ell, int j)
-{
-    int l = 0;
-    double x = pp.rx, y = pp.ry, z = pp.rz;
+    l = 0;
     if (q.kind == SK_INSTR_SED)
     {
         if (q.radius2)
         {
-            double xpp = -q.sinphi * x + q.cosphi * y;  // ApertureInstrument.cpp:24-43
+            double xpp = -q.sinphi * x + q.cosphi * y;
             double ypp = -q.cosphi * q.costheta * x - q.sinphi * q.costheta * y + q.sintheta * z;
             double radius2 = xpp * xpp + ypp * ypp;
-            if (radius2 > q.radius2) return;
+            if (radius2 > q.radius2) return false;
         }
     }
     else
     {
-        double xpp = -q.sinphi * x + q.cosphi * y;  // FrameInstrument::pixelOnDetector, FrameInstrument.cpp:45-64
+        double xpp = -q.sinphi * x + q.cosphi * y;
         double ypp = -q.cosphi * q.costheta * x - q.sinphi * q.costheta * y + q.sintheta * z;
         double xp = q.cosomega * xpp - q.sinomega * ypp;
         double yp = q.sinomega * xpp + q.cosomega * ypp;
@@ -619,26 +585,21 @@ __device__ __forceinline__ void sk_detect(const SkDevModel& M, const SkSmemTable
         else
             l = i + q.nx * jj;
     }
-    if (!q.include_sed && l < 0) return;
-    int ell = sk_wlg_bin(M.wlg[q.wlg], pp.lambda);
-    if (ell < 0) return;
+    if (!q.include_sed && l < 0) return false;
+    ell = sk_wlg_bin(M.wlg[q.wlg], lambda);
+    return ell >= 0;
+}
 
-    double L = peel.W / pp.lambda;
-    if (!peel.has_tau)
-    {
-        peel.tau = sk_observed_optical_depth<GRID>(M, T, cnt, pp, peel.W, q.kobs);
-        peel.has_tau = true;
-    }
-    double Lext = L * exp(-peel.tau);
-    cnt.det++;
-
-    // component routing, FluxRecorder.cpp:345-380
+// Second half of FluxRecorder::detect (FluxRecorder.cpp:320-433): component routing and the tallies.
+__device__ __forceinline__ void sk_record(const SkDevInstr& q, int l, int ell, double L, double Lext, int nscatt,
+                                          bool primary_origin)
+{
     int c_ext, c_tr = -1, c_lev = -1;
     if (q.record_total_only)
         c_ext = SK_COMP_TOTAL;
-    else if (pp.primary_origin)
+    else if (primary_origin)
     {
-        if (peel.nscatt == 0)
+        if (nscatt == 0)
         {
             c_tr = SK_COMP_TRANSPARENT;
             c_ext = SK_COMP_PRIMARY_DIRECT;
@@ -646,12 +607,12 @@ __device__ __forceinline__ void sk_detect(const SkDevModel& M, const SkSmemTable
         else
         {
             c_ext = SK_COMP_PRIMARY_SCATTERED;
-            if (peel.nscatt <= q.num_levels) c_lev = SK_COMP_PRIMARY_SCATTERED_LEVEL + peel.nscatt - 1;
+            if (nscatt <= q.num_levels) c_lev = SK_COMP_PRIMARY_SCATTERED_LEVEL + nscatt - 1;
         }
     }
     else
     {
-        if (peel.nscatt == 0)
+        if (nscatt == 0)
         {
             c_tr = SK_COMP_SECONDARY_TRANSPARENT;
             c_ext = SK_COMP_SECONDARY_DIRECT;
@@ -672,269 +633,614 @@ __device__ __forceinline__ void sk_detect(const SkDevModel& M, const SkSmemTable
         if (c_tr >= 0) atomicAdd(&q.ifu[c_tr][index], L);
         if (c_lev >= 0) atomicAdd(&q.ifu[c_lev][index], Lext);
     }
-    if (q.record_stats && q.include_sed)
-    {
-        hist_w[j] += Lext;  // FluxRecorder.cpp:457-466: contributions of one history are summed per bin first
-        hist_ell[j] = ell;
-    }
-}
-
-// MonteCarloSimulation::peelOffEmission (.cpp:617-634) and peelOffScattering (.cpp:784-842, consolidated branch)
-template <int GRID>
-__device__ __forceinline__ void sk_peel_off(const SkDevModel& M, const SkSmemTables& T, SkLocalCounters& cnt,
-                                            const SkPacket& pp, bool scattering, double* hist_w, int* hist_ell)
-{
-    SkPeel peel;
-    peel.W = 0.;
-    peel.nscatt = 0;
-    peel.has_tau = false;
-    peel.tau = 0.;
-    for (int j = 0; j < M.ninstr; ++j)
-    {
-        const SkDevInstr& q = M.instr[j];
-        if (!q.same_as_preceding)
-        {
-            if (scattering)
-            {
-                // DustMix::peeloffScattering HG branch (DustMix.cpp:430-445); MediumSystem::peelOffScattering
-                // (MediumSystem.cpp:734-767) with the single-medium weight 1; launchScatteringPeelOff (PhotonPacket.cpp:89-103)
-                double costheta = pp.kx * q.kobs[0] + pp.ky * q.kobs[1] + pp.kz * q.kobs[2];
-                double gp = M.gpar[pp.ilam];
-                double value = fabs(gp) > 0.95 ? sk_mean_hg(gp, costheta) : sk_value_hg(gp, costheta);
-                double I = 0.;
-                I += value * 1.;
-                peel.W = pp.W * I;
-                peel.nscatt = pp.nscatt + 1;
-            }
-            else
-            {
-                peel.W = pp.W;  // launchEmissionPeelOff, PhotonPacket.cpp:66-85 (isotropic emission)
-                peel.nscatt = 0;
-            }
-            peel.has_tau = false;
-        }
-        sk_detect<GRID>(M, T, cnt, q, pp, peel, hist_w, hist_ell, j);
-    }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// One complete history.
+// Trace stage: walks all rays of `list[0..n)` with dynamic lane refill.
+//   MODE 0  forward path to the boundary: MediumSystem::setExtinctionOpticalDepths (MediumSystem.cpp:849-871) fused
+//           with MonteCarloSimulation::storeRadiationField (.cpp:638-665)
+//   MODE 1  walk to the interaction point: SpatialGridPath::findInteractionPoint (SpatialGridPath.cpp:164-206), or for
+//           non-forced scattering MediumSystem::setInteractionPointUsingExtinction (MediumSystem.cpp:978-1010)
+//   MODE 2  optical depth to the observer: MediumSystem::getExtinctionOpticalDepth (MediumSystem.cpp:1192-1219)
 // ---------------------------------------------------------------------------------------------------
-template <int GRID>
-__device__ __forceinline__ void sk_life_cycle(const SkDevModel& M, const SkSmemTables& T, const SkRunArgs& A,
-                                              SkLocalCounters& cnt, unsigned long long history)
+template <int GRID, int MODE>
+__device__ __forceinline__ void sk_trace_stage(const SkDevModel& M, const SkSmemTables& T, const SkRunArgs& A,
+                                               const SkPoolView& P, const int* list, int n, double obsx, double obsy,
+                                               double obsz, SkLocalCounters& cnt)
 {
-    SkRng g;
-    sk_rng_init(g, M.seed, A.stream_id, history);
-    SkPacket pp;
-    sk_launch_primary(M, g, history, pp);
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const bool forced = M.force_scattering != 0;
+    int head = 0;
+    bool active = false;
+    int slot = 0;
+    double rx = 0, ry = 0, rz = 0;
+    SkRayDir k{0, 0, 1};
+    SkCellPos p{-1, 0, 0, 0, 0};
+    double tau = 0, s = 0, limit = 0, section = 0;
+    int nseg = 0;
+    // MODE 0 extras
+    double lum = 0, lnExtBeg = 0, extBeg = 1;
+    int rf_ell = -1;
+    double* rf = nullptr;
+    // MODE 1 extras: the cell of the last accepted segment
+    SkCellPos lastp{-1, 0, 0, 0, 0};
 
-    double hist_w[SK_MAX_INSTR];
-    int hist_ell[SK_MAX_INSTR];
-#pragma unroll
-    for (int j = 0; j < SK_MAX_INSTR; ++j)
+    while (true)
     {
-        hist_w[j] = 0.;
-        hist_ell[j] = -1;
-    }
-
-    if (pp.W / pp.lambda > 0)
-    {
-        cnt.packets++;
-        if (A.peel) sk_peel_off<GRID>(M, T, cnt, pp, false, hist_w, hist_ell);
-
-        const double sig_sca = M.sig_sca[pp.ilam];
-        const double gp = M.gpar[pp.ilam];
-        int rf_ell = -1;
-        double* rf = nullptr;
-        if (A.store)
+        unsigned idle = __ballot_sync(0xffffffffu, !active);
+        if (idle)
         {
-            rf_ell = sk_wlg_bin(M.wlg[M.rf_grid], pp.lambda);  // MonteCarloSimulation.cpp:643
-            rf = A.primary ? M.rf1 : M.rf2c;
-        }
-
-        if (M.force_scattering)
-        {
-            const double Lthreshold = (pp.W / pp.lambda) / M.min_weight_reduction;
-            while (true)
+            if (!active)
             {
-                // ---- pass 1: MediumSystem::setExtinctionOpticalDepths (MediumSystem.cpp:849-871) fused with
-                //      MonteCarloSimulation::storeRadiationField (.cpp:638-665)
-                double tau = 0., s = 0.;
-                int last_m = -1;
-                unsigned int nseg = 0, nrf = 0;
-                const double section = pp.sig_ext;
-                const double luminosity = pp.W / pp.lambda;
-                double lnExtBeg = 0., extBeg = 1.;
-                const bool deposit = rf_ell >= 0;
-                sk_trace<GRID>(M, T, cnt, pp.rx, pp.ry, pp.rz, pp.kx, pp.ky, pp.kz, [&](int m, double dens, double ds) {
+                int idx = head + __popc(idle & lt_mask);
+                if (idx < n)
+                {
+                    slot = list[idx];
+                    active = true;
+                    rx = P.D(D_RX, slot);
+                    ry = P.D(D_RY, slot);
+                    rz = P.D(D_RZ, slot);
+                    if (MODE == 2)
+                    {
+                        k.kx = obsx;
+                        k.ky = obsy;
+                        k.kz = obsz;
+                    }
+                    else
+                    {
+                        k.kx = P.D(D_KX, slot);
+                        k.ky = P.D(D_KY, slot);
+                        k.kz = P.D(D_KZ, slot);
+                    }
+                    p.m = P.I(I_M, slot);
+                    p.ix = P.I(I_IX, slot);
+                    p.iy = P.I(I_IY, slot);
+                    p.iz = P.I(I_IZ, slot);
+                    p.lev = P.I(I_LEV, slot);
+                    section = P.D(D_SIGEXT, slot);
+                    tau = 0.;
+                    s = 0.;
+                    nseg = 0;
+                    if (MODE == 0)
+                    {
+                        lnExtBeg = 0.;
+                        extBeg = 1.;
+                        rf_ell = -1;
+                        if (A.store)
+                        {
+                            double lambda = P.D(D_LAMBDA, slot);
+                            rf_ell = sk_wlg_bin(M.wlg[M.rf_grid], lambda);  // MonteCarloSimulation.cpp:643
+                            rf = A.primary ? M.rf1 : M.rf2c;
+                            lum = P.D(D_W, slot) / lambda;
+                        }
+                    }
+                    if (MODE == 1)
+                    {
+                        limit = P.D(D_TAUINT, slot);
+                        lastp = p;
+                    }
+                    if (MODE == 2) limit = P.D(D_LIMIT, slot);
+                    if (p.m < 0)
+                    {
+                        // the path starts outside (or exactly on the border of) the grid: PathSegmentGenerator::moveInside
+                        double cumds = 0.;
+                        if (sk_move_inside(rx, ry, rz, k.kx, k.ky, k.kz, M.ext, M.eps, cumds))
+                        {
+                            sk_locate<GRID>(M, T, rx, ry, rz, p);
+                            if (cumds > 0.)
+                            {
+                                // the empty segment in front of the grid (m = -1)
+                                nseg++;
+                                s += cumds;
+                            }
+                        }
+                        // else: the path misses the grid; p.m stays -1 and the ray ends below without segments
+                    }
+                }
+            }
+            head += __popc(idle);
+            if (!__any_sync(0xffffffffu, active)) break;
+        }
+        if (active)
+        {
+            bool done = false;
+            if (p.m >= 0)
+            {
+                int m;
+                double dens, ds;
+                const SkCellPos cur = p;
+                sk_step<GRID>(M, T, cnt, rx, ry, rz, k, p, m, dens, ds);
+                if (MODE == 0)
+                {
                     if (ds > 0.)  // SpatialGridPath::addSegment, SpatialGridPath.cpp:41-48
                     {
                         nseg++;
                         s += ds;
-                        if (m >= 0) tau += section * dens * ds;
-                        last_m = m;
-                        if (deposit)
+                        tau += section * dens * ds;
+                        if (rf_ell >= 0)
                         {
                             double lnExtEnd = -tau;
                             double extEnd = exp(lnExtEnd);
-                            if (m >= 0)
-                            {
-                                double extMean = sk_lnmean4(extEnd, extBeg, lnExtEnd, lnExtBeg);
-                                double Lds = luminosity * extMean * ds;
-                                atomicAdd(&rf[(size_t)m * M.nrf + rf_ell], Lds);  // MediumSystem.cpp:1294-1300
-                                nrf++;
-                            }
+                            double extMean = sk_lnmean4(extEnd, extBeg, lnExtEnd, lnExtBeg);
+                            double Lds = lum * extMean * ds;
+                            atomicAdd(&rf[(size_t)m * M.nrf + rf_ell], Lds);  // MediumSystem.cpp:1294-1300
+                            cnt.rf++;
                             lnExtBeg = lnExtEnd;
                             extBeg = extEnd;
                         }
                     }
-                    return true;
-                });
-                cnt.fwd_paths++;
-                cnt.fwd_segs += nseg;
-                cnt.rf += nrf;
-
-                // ---- MonteCarloSimulation::simulateForcedPropagation, .cpp:696-742
-                const double taupath = tau;
-                if (!(nseg > 0 && taupath > 0.))
-                {
-                    pp.W *= 0.;
-                    break;
                 }
-                double xi = M.path_length_bias;
-                double tauint;
-                if (xi == 0.)
-                    tauint = sk_expon_cutoff(g, taupath);
-                else
+                else if (MODE == 1)
                 {
-                    tauint = sk_uniform(g) < xi ? sk_uniform(g) * taupath : sk_expon_cutoff(g, taupath);
-                    double p = -exp(-tauint) / expm1(-taupath);
-                    double q = (1.0 - xi) * p + xi / taupath;
-                    pp.W *= p / q;
-                }
-                // ---- pass 2: SpatialGridPath::findInteractionPoint (SpatialGridPath.cpp:164-206) by re-walking
-                int m_int = last_m;
-                double s_int = s;
-                {
-                    double tau2 = 0., s2 = 0.;
-                    unsigned int nre = 0;
-                    sk_trace<GRID>(M, T, cnt, pp.rx, pp.ry, pp.rz, pp.kx, pp.ky, pp.kz,
-                                   [&](int m, double dens, double ds) {
-                                       if (ds > 0.)
-                                       {
-                                           nre++;
-                                           double tau0 = tau2, s0 = s2;
-                                           s2 += ds;
-                                           if (m >= 0) tau2 += section * dens * ds;
-                                           if (tauint < tau2)
-                                           {
-                                               m_int = m;
-                                               s_int = sk_interp_linlin(tauint, tau0, tau2, s0, s2);
-                                               return false;
-                                           }
-                                       }
-                                       return true;
-                                   });
-                    cnt.replay_segs += nre;
-                }
-                // MediumSystem::albedoForScattering, MediumSystem.cpp:678-693
-                double albedo = 0.;
-                if (m_int >= 0)
-                {
-                    double n = GRID == 1 ? M.dens[m_int] : M.cells[m_int].dens;
-                    double ksca = n * sig_sca;
-                    double kext = n * pp.sig_ext;
-                    albedo = kext > 0. ? ksca / kext : 0.;
-                }
-                pp.W *= -expm1(-taupath) * albedo;
-                pp.rx += s_int * pp.kx;  // PhotonPacket::propagate, PhotonPacket.cpp:107-111
-                pp.ry += s_int * pp.ky;
-                pp.rz += s_int * pp.kz;
-
-                double L = pp.W / pp.lambda;
-                if (L <= 0 || (L <= Lthreshold && pp.nscatt >= M.min_scatt_events)) break;
-
-                if (A.peel) sk_peel_off<GRID>(M, T, cnt, pp, true, hist_w, hist_ell);
-
-                // MediumSystem::simulateScattering (.cpp:796-823) + DustMix::performScattering HG (DustMix.cpp:496-511)
-                if (fabs(gp) < 1e-6)
-                    sk_random_direction(g, pp.kx, pp.ky, pp.kz);
-                else
-                {
-                    double f = ((1.0 - gp) * (1.0 + gp)) / (1.0 - gp + 2.0 * gp * sk_uniform(g));
-                    double costheta = (1.0 + gp * gp - f * f) / (2.0 * gp);
-                    sk_random_direction_about(g, pp.kx, pp.ky, pp.kz, costheta);
-                }
-                pp.nscatt++;
-                cnt.scatt++;
-            }
-        }
-        else
-        {
-            // non-forced scattering: simulateNonForcedPropagation (.cpp:746-780) with
-            // MediumSystem::setInteractionPointUsingExtinction (MediumSystem.cpp:978-1010)
-            while (true)
-            {
-                double tauinteract = -log(sk_uniform(g));  // Random::expon
-                double tau = 0., s = 0.;
-                bool found = false;
-                int m_int = -1;
-                double s_int = 0.;
-                unsigned int nseg = 0;
-                const double section = pp.sig_ext;
-                sk_trace<GRID>(M, T, cnt, pp.rx, pp.ry, pp.rz, pp.kx, pp.ky, pp.kz, [&](int m, double dens, double ds) {
-                    nseg++;
-                    double tau0 = tau, s0 = s;
-                    if (m >= 0) tau += section * dens * ds;
-                    s += ds;
-                    if (tauinteract < tau)
+                    if (forced ? (ds > 0.) : true)
                     {
-                        found = true;
-                        m_int = m;
-                        s_int = sk_interp_linlin(tauinteract, tau0, tau, s0, s);
-                        return false;
+                        nseg++;
+                        double tau0 = tau, s0 = s;
+                        s += ds;
+                        tau += section * dens * ds;
+                        lastp = cur;
+                        if (limit < tau)
+                        {
+                            // interaction inside this segment: NR::interpolateLinLin
+                            P.D(D_SINT, slot) = sk_interp_linlin(limit, tau0, tau, s0, s);
+                            P.I(I_MINT, slot) = cur.m;
+                            P.I(I_MIX, slot) = cur.ix;
+                            P.I(I_MIY, slot) = cur.iy;
+                            P.I(I_MIZ, slot) = cur.iz;
+                            P.I(I_MLEV, slot) = cur.lev;
+                            P.I(I_STATE, slot) |= SK_ST_FOUND;
+                            done = true;
+                        }
                     }
-                    return true;
-                });
-                cnt.fwd_paths++;
-                cnt.fwd_segs += nseg;
-                if (!found) break;
-                double n = GRID == 1 ? M.dens[m_int] : M.cells[m_int].dens;
-                double ksca = n * sig_sca;
-                double kext = n * pp.sig_ext;
-                pp.W *= kext > 0. ? ksca / kext : 0.;
-                pp.rx += s_int * pp.kx;
-                pp.ry += s_int * pp.ky;
-                pp.rz += s_int * pp.kz;
-                if (pp.W / pp.lambda <= 0) break;
-                if (A.peel) sk_peel_off<GRID>(M, T, cnt, pp, true, hist_w, hist_ell);
-                if (fabs(gp) < 1e-6)
-                    sk_random_direction(g, pp.kx, pp.ky, pp.kz);
+                }
                 else
                 {
-                    double f = ((1.0 - gp) * (1.0 + gp)) / (1.0 - gp + 2.0 * gp * sk_uniform(g));
-                    double costheta = (1.0 + gp * gp - f * f) / (2.0 * gp);
-                    sk_random_direction_about(g, pp.kx, pp.ky, pp.kz, costheta);
+                    nseg++;
+                    tau += section * dens * ds;
+                    if (tau >= limit)
+                    {
+                        tau = INFINITY;  // MediumSystem.cpp:1215
+                        done = true;
+                    }
                 }
-                pp.nscatt++;
-                cnt.scatt++;
+            }
+            if (!done && p.m < 0)
+            {
+                // the path has left the grid (or never entered it)
+                done = true;
+                if (MODE == 1)
+                {
+                    // at or beyond the exit optical depth of the last segment: use the last segment
+                    // (SpatialGridPath.cpp:199-205); non-forced: no interaction (SK_ST_FOUND stays clear)
+                    P.D(D_SINT, slot) = s;
+                    P.I(I_MINT, slot) = lastp.m;
+                    P.I(I_MIX, slot) = lastp.ix;
+                    P.I(I_MIY, slot) = lastp.iy;
+                    P.I(I_MIZ, slot) = lastp.iz;
+                    P.I(I_MLEV, slot) = lastp.lev;
+                }
+            }
+            if (done)
+            {
+                active = false;
+                if (MODE == 0)
+                {
+                    P.D(D_TAUPATH, slot) = tau;
+                    P.D(D_STOT, slot) = s;
+                    P.I(I_NSEG, slot) = nseg;
+                    cnt.fwd_paths++;
+                    cnt.fwd_segs += nseg;
+                }
+                else if (MODE == 1)
+                {
+                    if (forced)
+                        cnt.replay_segs += nseg;
+                    else
+                    {
+                        cnt.fwd_paths++;
+                        cnt.fwd_segs += nseg;
+                    }
+                }
+                else
+                {
+                    P.D(D_PTAU, slot) = tau;
+                    cnt.peel_paths++;
+                    cnt.peel_segs += nseg;
+                }
             }
         }
     }
+    __syncwarp();
+}
 
-    // FluxRecorder::recordContributions for the SED arrays, FluxRecorder.cpp:962-986
+// ---------------------------------------------------------------------------------------------------
+// Event stages
+// ---------------------------------------------------------------------------------------------------
+// Ends a history: FluxRecorder::recordContributions for the SED arrays (FluxRecorder.cpp:962-986); frees the slot.
+__device__ __forceinline__ void sk_finish_history(const SkDevModel& M, const SkPoolView& P, int slot)
+{
     for (int j = 0; j < M.ninstr; ++j)
     {
-        if (hist_ell[j] >= 0)
+        const SkDevInstr& q = M.instr[j];
+        if (!q.record_stats) continue;
+        int ell = P.I(I_HELL0 + j, slot);
+        if (ell >= 0)
         {
-            const SkDevInstr& q = M.instr[j];
+            double w = P.D(D_HISTW0 + j, slot);
             double wn = 1.;
-            for (int k = 0; k <= 4; ++k)
+            for (int kk = 0; kk <= 4; ++kk)
             {
-                atomicAdd(&q.wsed[k][hist_ell[j]], wn);
-                wn *= hist_w[j];
+                atomicAdd(&q.wsed[kk][ell], wn);
+                wn *= w;
             }
         }
+    }
+    P.I(I_STATE, slot) = 0;
+}
+
+// Peel-off towards the observer group [j0, j1): MonteCarloSimulation::peelOffEmission (.cpp:617-634) /
+// peelOffScattering (.cpp:784-842, consolidated branch) split around the trace stage.
+template <int GRID>
+__device__ __forceinline__ void sk_peel_group(const SkDevModel& M, const SkSmemTables& T, const SkRunArgs& A,
+                                              const SkPoolView& P, int* list, int j0, int j1, SkLocalCounters& cnt)
+{
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const SkDevInstr& q0 = M.instr[j0];
+    const double ox = q0.kobs[0], oy = q0.kobs[1], oz = q0.kobs[2];
+    int n = 0;
+    // ---- set-up: weight of the peel-off packet and which packets need an optical depth at all
+    for (int base = 0; base < SK_POOL; base += 32)
+    {
+        int slot = base + lane;
+        int st = P.I(I_STATE, slot);
+        bool need = false;
+        if (st & SK_ST_LIVE)
+        {
+            double W = P.D(D_W, slot);
+            double lambda = P.D(D_LAMBDA, slot);
+            double peelW;
+            if (st & SK_ST_SCATTER)
+            {
+                // DustMix::peeloffScattering HG branch (DustMix.cpp:430-445); MediumSystem::peelOffScattering
+                // (MediumSystem.cpp:734-767) with the single-medium weight 1; launchScatteringPeelOff (PhotonPacket.cpp:89-103)
+                double costheta = P.D(D_KX, slot) * ox + P.D(D_KY, slot) * oy + P.D(D_KZ, slot) * oz;
+                double gp = M.gpar[P.I(I_ILAM, slot)];
+                double value = fabs(gp) > 0.95 ? sk_mean_hg(gp, costheta) : sk_value_hg(gp, costheta);
+                double I = 0.;
+                I += value * 1.;
+                peelW = W * I;
+            }
+            else
+                peelW = W;  // launchEmissionPeelOff, PhotonPacket.cpp:66-85 (isotropic emission)
+            P.D(D_PEELW, slot) = peelW;
+            double x = P.D(D_RX, slot), y = P.D(D_RY, slot), z = P.D(D_RZ, slot);
+            for (int j = j0; j < j1; ++j)
+            {
+                int l, ell;
+                if (sk_detect_geometry(M, M.instr[j], x, y, z, lambda, l, ell)) need = true;
+            }
+            if (need)
+            {
+                double L = peelW / lambda;
+                if (L <= 0)
+                {
+                    P.D(D_PTAU, slot) = INFINITY;  // MediumSystem.cpp:1196
+                    need = false;
+                }
+                else
+                    P.D(D_LIMIT, slot) = log(L) + 745;  // MediumSystem.cpp:1199
+            }
+        }
+        unsigned mask = __ballot_sync(0xffffffffu, need);
+        if (need) list[n + __popc(mask & lt_mask)] = slot;
+        n += __popc(mask);
+    }
+    __syncwarp();
+    sk_trace_stage<GRID, 2>(M, T, A, P, list, n, ox, oy, oz, cnt);
+    // ---- detection: FluxRecorder::detect, FluxRecorder.cpp:304-468
+    for (int base = 0; base < SK_POOL; base += 32)
+    {
+        int slot = base + lane;
+        int st = P.I(I_STATE, slot);
+        if (st & SK_ST_LIVE)
+        {
+            double lambda = P.D(D_LAMBDA, slot);
+            double x = P.D(D_RX, slot), y = P.D(D_RY, slot), z = P.D(D_RZ, slot);
+            double L = P.D(D_PEELW, slot) / lambda;
+            int nscatt = (st & SK_ST_SCATTER) ? P.I(I_NSCATT, slot) + 1 : 0;
+            for (int j = j0; j < j1; ++j)
+            {
+                const SkDevInstr& q = M.instr[j];
+                int l, ell;
+                if (!sk_detect_geometry(M, q, x, y, z, lambda, l, ell)) continue;
+                double Lext = L * exp(-P.D(D_PTAU, slot));
+                cnt.det++;
+                sk_record(q, l, ell, L, Lext, nscatt, A.primary != 0);
+                if (q.record_stats && q.include_sed)
+                {
+                    P.D(D_HISTW0 + j, slot) += Lext;  // FluxRecorder.cpp:457-466
+                    P.I(I_HELL0 + j, slot) = ell;
+                }
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The life cycles of one warp's pool.
+// ---------------------------------------------------------------------------------------------------
+template <int GRID>
+__device__ __forceinline__ void sk_warp_life_cycles(const SkDevModel& M, const SkSmemTables& T, const SkRunArgs& A,
+                                                    const SkPoolView& P, int* list, SkLocalCounters& cnt)
+{
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const bool forced = M.force_scattering != 0;
+    for (int base = 0; base < SK_POOL; base += 32) P.I(I_STATE, base + lane) = 0;
+    __syncwarp();
+    bool more = true;
+
+    while (true)
+    {
+        // ---- stage A: launch a history into every free slot (SourceSystem::launch)
+        int nlive = 0;
+        for (int base = 0; base < SK_POOL; base += 32)
+        {
+            int slot = base + lane;
+            int st = P.I(I_STATE, slot);
+            bool want = more && !(st & SK_ST_LIVE);
+            unsigned mask = __ballot_sync(0xffffffffu, want);
+            if (mask)
+            {
+                int cntw = __popc(mask);
+                unsigned long long b = 0;
+                if (lane == 0) b = atomicAdd(A.work_counter, (unsigned long long)cntw);
+                b = __shfl_sync(0xffffffffu, b, 0);
+                unsigned long long h = b + __popc(mask & lt_mask);
+                if (b + cntw >= A.count) more = false;
+                if (want && h < A.count)
+                {
+                    unsigned long long history = A.first + h;
+                    SkRng g;
+                    sk_rng_init(g, M.seed, A.stream_id, history, 0);
+                    SkLaunch pp;
+                    sk_launch_primary(M, g, history, pp);
+                    if (pp.W / pp.lambda > 0)  // MonteCarloSimulation.cpp:553
+                    {
+                        cnt.packets++;
+                        SkCellPos c;
+                        c.m = -1;
+                        c.ix = c.iy = c.iz = c.lev = 0;
+                        if (sk_box_strictly_inside(M.ext, pp.rx, pp.ry, pp.rz)) sk_locate<GRID>(M, T, pp.rx, pp.ry, pp.rz, c);
+                        P.D(D_RX, slot) = pp.rx;
+                        P.D(D_RY, slot) = pp.ry;
+                        P.D(D_RZ, slot) = pp.rz;
+                        P.D(D_KX, slot) = pp.kx;
+                        P.D(D_KY, slot) = pp.ky;
+                        P.D(D_KZ, slot) = pp.kz;
+                        P.D(D_LAMBDA, slot) = pp.lambda;
+                        P.D(D_W, slot) = pp.W;
+                        P.D(D_LTHR, slot) = (pp.W / pp.lambda) / M.min_weight_reduction;  // .cpp:563
+                        P.D(D_SIGEXT, slot) = M.sig_ext[pp.ilam];
+                        P.I(I_HLO, slot) = (int)(uint32_t)history;
+                        P.I(I_HHI, slot) = (int)(uint32_t)(history >> 32);
+                        P.I(I_DRAW, slot) = (int)g.draw;
+                        P.I(I_NSCATT, slot) = 0;
+                        P.I(I_ILAM, slot) = pp.ilam;
+                        P.I(I_M, slot) = c.m;
+                        P.I(I_IX, slot) = c.ix;
+                        P.I(I_IY, slot) = c.iy;
+                        P.I(I_IZ, slot) = c.iz;
+                        P.I(I_LEV, slot) = c.lev;
+                        for (int j = 0; j < M.ninstr; ++j)
+                        {
+                            P.D(D_HISTW0 + j, slot) = 0.;
+                            P.I(I_HELL0 + j, slot) = -1;
+                        }
+                        st = SK_ST_LIVE;
+                        P.I(I_STATE, slot) = st;
+                    }
+                }
+            }
+            nlive += __popc(__ballot_sync(0xffffffffu, (st & SK_ST_LIVE) != 0));
+        }
+        __syncwarp();
+        if (nlive == 0)
+        {
+            if (!more) break;
+            continue;
+        }
+
+        // ---- stage B: peel-off (emission for fresh packets, scattering for the others), one trace per observer
+        if (A.peel)
+        {
+            int j0 = 0;
+            while (j0 < M.ninstr)
+            {
+                int j1 = j0 + 1;
+                while (j1 < M.ninstr && M.instr[j1].same_as_preceding) j1++;
+                sk_peel_group<GRID>(M, T, A, P, list, j0, j1, cnt);
+                j0 = j1;
+            }
+        }
+
+        // ---- stage C: the pending scattering events: MediumSystem::simulateScattering (.cpp:796-823) +
+        //      DustMix::performScattering HG branch (DustMix.cpp:496-511); then the list of all live packets
+        int n = 0;
+        for (int base = 0; base < SK_POOL; base += 32)
+        {
+            int slot = base + lane;
+            int st = P.I(I_STATE, slot);
+            bool live = (st & SK_ST_LIVE) != 0;
+            if (live && (st & SK_ST_SCATTER))
+            {
+                SkRng g;
+                sk_rng_init(g, M.seed, A.stream_id,
+                            ((unsigned long long)(uint32_t)P.I(I_HHI, slot) << 32) | (uint32_t)P.I(I_HLO, slot),
+                            (uint32_t)P.I(I_DRAW, slot));
+                double gp = M.gpar[P.I(I_ILAM, slot)];
+                double kx = P.D(D_KX, slot), ky = P.D(D_KY, slot), kz = P.D(D_KZ, slot);
+                if (fabs(gp) < 1e-6)
+                    sk_random_direction(g, kx, ky, kz);
+                else
+                {
+                    double f = ((1.0 - gp) * (1.0 + gp)) / (1.0 - gp + 2.0 * gp * sk_uniform(g));
+                    double costheta = (1.0 + gp * gp - f * f) / (2.0 * gp);
+                    sk_random_direction_about(g, kx, ky, kz, costheta);
+                }
+                P.D(D_KX, slot) = kx;
+                P.D(D_KY, slot) = ky;
+                P.D(D_KZ, slot) = kz;
+                P.I(I_DRAW, slot) = (int)g.draw;
+                P.I(I_NSCATT, slot) += 1;
+                P.I(I_STATE, slot) = st & ~SK_ST_SCATTER;
+                cnt.scatt++;
+            }
+            unsigned mask = __ballot_sync(0xffffffffu, live);
+            if (live) list[n + __popc(mask & lt_mask)] = slot;
+            n += __popc(mask);
+        }
+        __syncwarp();
+
+        // ---- stage D: forward paths (forced scattering only)
+        if (forced) sk_trace_stage<GRID, 0>(M, T, A, P, list, n, 0., 0., 0., cnt);
+
+        // ---- stage E: sample the interaction optical depth: simulateForcedPropagation (.cpp:696-722) or
+        //      Random::expon for simulateNonForcedPropagation (.cpp:749)
+        n = 0;
+        for (int base = 0; base < SK_POOL; base += 32)
+        {
+            int slot = base + lane;
+            int st = P.I(I_STATE, slot);
+            bool live = (st & SK_ST_LIVE) != 0;
+            if (live)
+            {
+                SkRng g;
+                sk_rng_init(g, M.seed, A.stream_id,
+                            ((unsigned long long)(uint32_t)P.I(I_HHI, slot) << 32) | (uint32_t)P.I(I_HLO, slot),
+                            (uint32_t)P.I(I_DRAW, slot));
+                if (forced)
+                {
+                    double taupath = P.D(D_TAUPATH, slot);
+                    if (!(P.I(I_NSEG, slot) > 0 && taupath > 0.))
+                    {
+                        // no extinction along the path: the packet cannot scatter, terminate it (.cpp:702-706)
+                        sk_finish_history(M, P, slot);
+                        live = false;
+                    }
+                    else
+                    {
+                        double xi = M.path_length_bias;
+                        double tauint;
+                        if (xi == 0.)
+                            tauint = sk_expon_cutoff(g, taupath);
+                        else
+                        {
+                            tauint = sk_uniform(g) < xi ? sk_uniform(g) * taupath : sk_expon_cutoff(g, taupath);
+                            double pw = -exp(-tauint) / expm1(-taupath);
+                            double qw = (1.0 - xi) * pw + xi / taupath;
+                            P.D(D_W, slot) *= pw / qw;
+                        }
+                        P.D(D_TAUINT, slot) = tauint;
+                    }
+                }
+                else
+                    P.D(D_TAUINT, slot) = -log(sk_uniform(g));
+                if (live)
+                {
+                    P.I(I_DRAW, slot) = (int)g.draw;
+                    P.I(I_STATE, slot) = st & ~SK_ST_FOUND;
+                }
+            }
+            unsigned mask = __ballot_sync(0xffffffffu, live);
+            if (live) list[n + __popc(mask & lt_mask)] = slot;
+            n += __popc(mask);
+        }
+        __syncwarp();
+
+        // ---- stage F: walk to the interaction point
+        sk_trace_stage<GRID, 1>(M, T, A, P, list, n, 0., 0., 0., cnt);
+
+        // ---- stage G: the interaction: albedo weight, move, termination test (.cpp:724-741, 576-580)
+        for (int base = 0; base < SK_POOL; base += 32)
+        {
+            int slot = base + lane;
+            int st = P.I(I_STATE, slot);
+            if (st & SK_ST_LIVE)
+            {
+                bool alive = true;
+                if (!forced && !(st & SK_ST_FOUND)) alive = false;  // escaped, MonteCarloSimulation.cpp:594
+                if (alive)
+                {
+                    int m = P.I(I_MINT, slot);
+                    int ilam = P.I(I_ILAM, slot);
+                    // MediumSystem::albedoForScattering, MediumSystem.cpp:678-693
+                    double albedo = 0.;
+                    if (m >= 0)
+                    {
+                        double dn = GRID == 1 ? M.dens[m] : M.cells[m].dens;
+                        double ksca = dn * M.sig_sca[ilam];
+                        double kext = dn * P.D(D_SIGEXT, slot);
+                        albedo = kext > 0. ? ksca / kext : 0.;
+                    }
+                    double W = P.D(D_W, slot);
+                    if (forced)
+                        W *= -expm1(-P.D(D_TAUPATH, slot)) * albedo;
+                    else
+                        W *= albedo;
+                    double sint = P.D(D_SINT, slot);
+                    double kx = P.D(D_KX, slot), ky = P.D(D_KY, slot), kz = P.D(D_KZ, slot);
+                    double x = P.D(D_RX, slot) + sint * kx;  // PhotonPacket::propagate, PhotonPacket.cpp:107-111
+                    double y = P.D(D_RY, slot) + sint * ky;
+                    double z = P.D(D_RZ, slot) + sint * kz;
+                    P.D(D_W, slot) = W;
+                    P.D(D_RX, slot) = x;
+                    P.D(D_RY, slot) = y;
+                    P.D(D_RZ, slot) = z;
+                    double L = W / P.D(D_LAMBDA, slot);
+                    if (forced)
+                    {
+                        if (L <= 0 || (L <= P.D(D_LTHR, slot) && P.I(I_NSCATT, slot) >= M.min_scatt_events)) alive = false;
+                    }
+                    else if (L <= 0)
+                        alive = false;
+                    if (alive)
+                    {
+                        // the next paths start in the interaction cell unless rounding moved the point out of it
+                        SkCellPos c{m, P.I(I_MIX, slot), P.I(I_MIY, slot), P.I(I_MIZ, slot), P.I(I_MLEV, slot)};
+                        bool inside = m >= 0 && sk_box_strictly_inside(M.ext, x, y, z);
+                        if (inside)
+                        {
+                            if (GRID == 1)
+                                inside = x >= T.X[c.ix] && x < T.X[c.ix + 1] && y >= T.Y[c.iy] && y < T.Y[c.iy + 1]
+                                         && z >= T.Z[c.iz] && z < T.Z[c.iz + 1];
+                            else
+                            {
+                                int size = 1 << (M.maxlevel - c.lev);
+                                inside = x >= T.X[c.ix] && x < T.X[c.ix + size] && y >= T.Y[c.iy] && y < T.Y[c.iy + size]
+                                         && z >= T.Z[c.iz] && z < T.Z[c.iz + size];
+                            }
+                            if (!inside)
+                            {
+                                inside = sk_box_strictly_inside(M.ext, x, y, z);
+                                if (inside) sk_locate<GRID>(M, T, x, y, z, c);
+                            }
+                        }
+                        if (!inside) c.m = -1;
+                        P.I(I_M, slot) = c.m;
+                        P.I(I_IX, slot) = c.ix;
+                        P.I(I_IY, slot) = c.iy;
+                        P.I(I_IZ, slot) = c.iz;
+                        P.I(I_LEV, slot) = c.lev;
+                        P.I(I_STATE, slot) = SK_ST_LIVE | SK_ST_SCATTER;
+                    }
+                }
+                if (!alive) sk_finish_history(M, P, slot);
+            }
+        }
+        __syncwarp();
     }
 }
