@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(SK_BLOCK) sk_life_cycle_kernel(const SkDevMode
 
     SkLocalCounters cnt;
     memset(&cnt, 0, sizeof cnt);
-    sk_warp_life_cycles<GRID>(M, T, A, P, list, cnt);
+    sk_warp_life_cycles<GRID>(M, A.model, T, A, P, list, cnt);
 
     // counters: warp reduce, one atomic per warp and counter
     unsigned int* c = reinterpret_cast<unsigned int*>(&cnt);
@@ -145,6 +145,7 @@ struct sk_engine {
     unsigned long long* work_counter = nullptr;
     double* pool_d = nullptr;
     int32_t* pool_i = nullptr;
+    SkDevModel* model_dev = nullptr;
     size_t pool_warps = 0;
     double* scalar = nullptr;
     int table_len[3] = {0, 0, 0};
@@ -223,6 +224,7 @@ extern "C" void sk_engine_destroy(sk_engine_t* e)
     cudaFree(e->work_counter);
     cudaFree(e->pool_d);
     cudaFree(e->pool_i);
+    cudaFree(e->model_dev);
     cudaFree(e->scalar);
     cudaFree(e->M.counters);
     cudaEventDestroy(e->ev0);
@@ -375,7 +377,7 @@ extern "C" int sk_engine_set_grid_octree(sk_engine_t* e, const double extent[6],
             if (first_child[nb] < 0)
                 r.link[w] = (lev[nb] << SK_LINK_LEVEL_SHIFT) | cell_of_node[nb];
             else
-                r.link[w] = SK_LINK_INTERNAL | nb;
+                r.link[w] = SK_LINK_INTERNAL | (lev[nb] << SK_LINK_LEVEL_SHIFT) | first_child[nb];
         }
     }
     free_group(e->grid_allocs);
@@ -851,6 +853,9 @@ extern "C" int sk_engine_launch_segment(sk_engine_t* e, uint64_t first, uint64_t
     }
     A.pool_d = e->pool_d;
     A.pool_i = e->pool_i;
+    if (!e->model_dev) CK(cudaMalloc(&e->model_dev, sizeof(SkDevModel)));
+    CK(cudaMemcpyAsync(e->model_dev, &e->M, sizeof(SkDevModel), cudaMemcpyHostToDevice, e->stream));
+    A.model = e->model_dev;
     CK(cudaEventRecord(e->ev0, e->stream));
     kern<<<(unsigned)grid, SK_BLOCK, smem, e->stream>>>(e->M, A);
     CK(cudaGetLastError());

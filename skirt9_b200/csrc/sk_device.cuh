@@ -105,6 +105,7 @@ struct SkRunArgs {
     unsigned long long* work_counter;  // dynamic history dispenser
     double* pool_d;                    // per-warp packet pools: [warp][SK_ND][SK_POOL]
     int32_t* pool_i;                   // [warp][SK_NI][SK_POOL]
+    const SkDevModel* model;           // copy of the model in global memory for the cold, non-inlined paths
 };
 
 // ---------------------------------------------------------------------------------------------------

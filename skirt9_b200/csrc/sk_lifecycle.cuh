@@ -133,13 +133,14 @@ __device__ __noinline__ bool sk_move_inside(double& rx, double& ry, double& rz, 
 
 // Octree cell location: TreeNode::leafChild (TreeNode.cpp:65-76) + OctTreeNode::child (OctTreeNode.cpp:37-42) on the
 // integer lattice: a node is (ix,iy,iz,level); its centre (CHILD_0->rmax) is the lattice border at +half size.
-__device__ __forceinline__ void sk_tree_descend(const SkDevModel& M, const SkSmemTables& T, int node, int ix, int iy,
-                                                int iz, int lev, double x, double y, double z, SkCellPos& out)
+// `fc` is the node id of the first child of the node to descend from.
+__device__ __forceinline__ void sk_tree_descend(const int32_t* __restrict__ node_child, int maxlevel,
+                                                const SkSmemTables& T, int fc, int ix, int iy, int iz, int lev,
+                                                double x, double y, double z, SkCellPos& out)
 {
-    int fc = __ldg(&M.node_child[node]);
     while (fc >= 0)
     {
-        int half = 1 << (M.maxlevel - lev - 1);
+        int half = 1 << (maxlevel - lev - 1);
         int l = 0;
         if (!(x < T.X[ix + half]))
         {
@@ -157,8 +158,7 @@ __device__ __forceinline__ void sk_tree_descend(const SkDevModel& M, const SkSme
             iz += half;
         }
         lev++;
-        node = fc + l;
-        fc = __ldg(&M.node_child[node]);
+        fc = __ldg(&node_child[fc + l]);
     }
     out.m = -(fc + 1);
     out.ix = ix;
@@ -167,33 +167,47 @@ __device__ __forceinline__ void sk_tree_descend(const SkDevModel& M, const SkSme
     out.lev = lev;
 }
 
+// Cold path: locates the cell holding (x,y,z) from scratch.  Takes the model through a pointer to its copy in
+// global memory so that the kernel-parameter copy never has its address taken (that would force it into local memory).
 template <int GRID>
-__device__ __noinline__ void sk_locate(const SkDevModel& M, const SkSmemTables& T, double x, double y, double z,
-                                       SkCellPos& out)
+__device__ __noinline__ void sk_locate(const SkDevModel* __restrict__ Mg, const SkSmemTables& T, double x, double y,
+                                       double z, SkCellPos& out)
 {
-    if (!sk_box_contains(M.ext, x, y, z))
+    if (!sk_box_contains(Mg->ext, x, y, z))
     {
         out.m = -1;
         return;
     }
     if (GRID == 1)
     {
-        out.ix = sk_locate_clip(T.X, M.nx + 1, x);  // CartesianSpatialGrid.cpp:105-107
-        out.iy = sk_locate_clip(T.Y, M.ny + 1, y);
-        out.iz = sk_locate_clip(T.Z, M.nz + 1, z);
+        out.ix = sk_locate_clip(T.X, Mg->nx + 1, x);  // CartesianSpatialGrid.cpp:105-107
+        out.iy = sk_locate_clip(T.Y, Mg->ny + 1, y);
+        out.iz = sk_locate_clip(T.Z, Mg->nz + 1, z);
         out.lev = 0;
-        out.m = out.iz + M.nz * out.iy + M.nz * M.ny * out.ix;
+        out.m = out.iz + Mg->nz * out.iy + Mg->nz * Mg->ny * out.ix;
     }
     else
-        sk_tree_descend(M, T, 0, 0, 0, 0, 0, x, y, z, out);
+        sk_tree_descend(Mg->node_child, Mg->maxlevel, T, __ldg(&Mg->node_child[0]), 0, 0, 0, 0, x, y, z, out);
 }
 
-__device__ __forceinline__ bool sk_tree_cell_contains(const SkDevModel& M, const SkSmemTables& T, const SkCellPos& p,
-                                                      double x, double y, double z)
+// Cold path of the octree step: the full neighbour search of TreeSpatialGrid.cpp:190-207 for the situations the
+// fast path does not decide itself (domain boundary, near-ties between exit walls, grazing directions):
+// the leaf containing the new position (TreeNode::neighbor + root()->leafChild fall-back), the nextafter escape
+// when stuck in the same cell, and termination.
+__device__ __noinline__ void sk_tree_step_rare(const SkDevModel* __restrict__ Mg, const SkSmemTables& T, double& rx,
+                                               double& ry, double& rz, double kx, double ky, double kz, int m_old,
+                                               SkCellPos& q)
 {
-    int size = 1 << (M.maxlevel - p.lev);
-    return x >= T.X[p.ix] && x <= T.X[p.ix + size] && y >= T.Y[p.iy] && y <= T.Y[p.iy + size] && z >= T.Z[p.iz]
-           && z <= T.Z[p.iz + size];
+    sk_locate<2>(Mg, T, rx, ry, rz, q);
+    if (q.m == m_old)
+    {
+        // PathSegmentGenerator::propagateToNextAfter, PathSegmentGenerator.hpp:148-153
+        rx = nextafter(rx, (kx < 0.) ? -DBL_MAX : DBL_MAX);
+        ry = nextafter(ry, (ky < 0.) ? -DBL_MAX : DBL_MAX);
+        rz = nextafter(rz, (kz < 0.) ? -DBL_MAX : DBL_MAX);
+        sk_locate<2>(Mg, T, rx, ry, rz, q);
+        if (q.m == m_old) q.m = -1;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -201,16 +215,28 @@ __device__ __forceinline__ bool sk_tree_cell_contains(const SkDevModel& M, const
 // means the path has left the grid.
 //   Cartesian: CartesianSpatialGrid::MySegmentGenerator::next, CartesianSpatialGrid.cpp:95-162
 //   Octree:    TreeSpatialGrid::MySegmentGenerator::next, TreeSpatialGrid.cpp:140-216, with TreeNode::neighbor
-//              (TreeNode.cpp:103-112) served by the per-cell links and the top-down search as the fall-back
+//              (TreeNode.cpp:103-112) served by the per-cell links
+// The ray carries the reciprocals of its direction components (0 where the reference treats the component as
+// zero, fabs(k) <= 1e-15), so the exit distances cost a multiplication instead of a division per axis.
 // ---------------------------------------------------------------------------------------------------
 struct SkRayDir {
     double kx, ky, kz;
+    double ikx, iky, ikz;
+    __device__ __forceinline__ void set(double x, double y, double z)
+    {
+        kx = x;
+        ky = y;
+        kz = z;
+        ikx = (fabs(x) > 1e-15) ? 1.0 / x : 0.;
+        iky = (fabs(y) > 1e-15) ? 1.0 / y : 0.;
+        ikz = (fabs(z) > 1e-15) ? 1.0 / z : 0.;
+    }
 };
 
 template <int GRID>
-__device__ __forceinline__ void sk_step(const SkDevModel& M, const SkSmemTables& T, SkLocalCounters& cnt, double& rx,
-                                        double& ry, double& rz, const SkRayDir& k, SkCellPos& p, int& m_out,
-                                        double& dens_out, double& ds_out)
+__device__ __forceinline__ void sk_step(const SkDevModel& M, const SkDevModel* __restrict__ Mg, const SkSmemTables& T,
+                                        SkLocalCounters& cnt, double& rx, double& ry, double& rz, const SkRayDir& k,
+                                        SkCellPos& p, int& m_out, double& dens_out, double& ds_out)
 {
     if (GRID == 1)
     {
@@ -219,9 +245,9 @@ __device__ __forceinline__ void sk_step(const SkDevModel& M, const SkSmemTables&
         double xE = T.X[p.ix + ((k.kx < 0.0) ? 0 : 1)];
         double yE = T.Y[p.iy + ((k.ky < 0.0) ? 0 : 1)];
         double zE = T.Z[p.iz + ((k.kz < 0.0) ? 0 : 1)];
-        double dsx = (fabs(k.kx) > 1e-15) ? (xE - rx) / k.kx : DBL_MAX;
-        double dsy = (fabs(k.ky) > 1e-15) ? (yE - ry) / k.ky : DBL_MAX;
-        double dsz = (fabs(k.kz) > 1e-15) ? (zE - rz) / k.kz : DBL_MAX;
+        double dsx = (k.ikx != 0.) ? (xE - rx) * k.ikx : DBL_MAX;
+        double dsy = (k.iky != 0.) ? (yE - ry) * k.iky : DBL_MAX;
+        double dsz = (k.ikz != 0.) ? (zE - rz) * k.ikz : DBL_MAX;
         double ds;
         bool outside;
         if (dsx <= dsy && dsx <= dsz)
@@ -260,100 +286,73 @@ __device__ __forceinline__ void sk_step(const SkDevModel& M, const SkSmemTables&
     {
         // one 32-byte sector: density + the six neighbour links of the current cell
         const int4* rp = reinterpret_cast<const int4*>(&M.cells[p.m]);
-        int4 a = __ldg(rp), b = __ldg(rp + 1);
-        double dens = __hiloint2double(a.y, a.x);
-        int size = 1 << (M.maxlevel - p.lev);
-        double xnext = T.X[p.ix + ((k.kx < 0.0) ? 0 : size)];
-        double ynext = T.Y[p.iy + ((k.ky < 0.0) ? 0 : size)];
-        double znext = T.Z[p.iz + ((k.kz < 0.0) ? 0 : size)];
-        double dsx = (fabs(k.kx) > 1e-15) ? (xnext - rx) / k.kx : DBL_MAX;
-        double dsy = (fabs(k.ky) > 1e-15) ? (ynext - ry) / k.ky : DBL_MAX;
-        double dsz = (fabs(k.kz) > 1e-15) ? (znext - rz) / k.kz : DBL_MAX;
-        double ds;
-        int wall;
-        if (dsx <= dsy && dsx <= dsz)
-        {
-            ds = dsx;
-            wall = (k.kx < 0.0) ? 0 : 1;
-        }
-        else if (dsy <= dsx && dsy <= dsz)
-        {
-            ds = dsy;
-            wall = (k.ky < 0.0) ? 2 : 3;
-        }
-        else
-        {
-            ds = dsz;
-            wall = (k.kz < 0.0) ? 4 : 5;
-        }
-        double adv = ds + M.eps;
+        const int4 a = __ldg(rp), b = __ldg(rp + 1);
+        const int size = 1 << (M.maxlevel - p.lev);
+        const bool nx = k.kx < 0.0, ny = k.ky < 0.0, nz = k.kz < 0.0;
+        const double xnext = T.X[p.ix + (nx ? 0 : size)];
+        const double ynext = T.Y[p.iy + (ny ? 0 : size)];
+        const double znext = T.Z[p.iz + (nz ? 0 : size)];
+        const double dsx = (k.ikx != 0.) ? (xnext - rx) * k.ikx : DBL_MAX;
+        const double dsy = (k.iky != 0.) ? (ynext - ry) * k.iky : DBL_MAX;
+        const double dsz = (k.ikz != 0.) ? (znext - rz) * k.ikz : DBL_MAX;
+        // exit wall: x if dsx<=dsy && dsx<=dsz, else y if dsy<=dsx && dsy<=dsz, else z (TreeSpatialGrid.cpp:160-178)
+        const bool takex = dsx <= dsy && dsx <= dsz;
+        const bool takey = !takex && dsy <= dsx && dsy <= dsz;
+        const double ds = takex ? dsx : takey ? dsy : dsz;
+        const double other = takex ? fmin(dsy, dsz) : takey ? fmin(dsx, dsz) : fmin(dsx, dsy);
+        const double kexit = takex ? k.kx : takey ? k.ky : k.kz;
+        const int lx = nx ? a.z : a.w, ly = ny ? b.x : b.y, lz = nz ? b.z : b.w;
+        const int link = takex ? lx : takey ? ly : lz;
+        const double adv = ds + M.eps;
         rx += k.kx * adv;
         ry += k.ky * adv;
         rz += k.kz * adv;
         m_out = p.m;
-        dens_out = dens;
+        dens_out = __hiloint2double(a.y, a.x);
         ds_out = ds;
-
-        int link = wall == 0 ? a.z : wall == 1 ? a.w : wall == 2 ? b.x : wall == 3 ? b.y : wall == 4 ? b.z : b.w;
-        SkCellPos q;
-        q.m = -1;
-        if (link >= 0)
+        // The link decides the next cell unless the new position may also have crossed a second wall (the exit
+        // distances of two walls differ by less than a few eps), the direction grazes the exit wall (the eps advance may
+        // be lost to rounding), or the path reaches the domain boundary; those cases take the reference's full search.
+        const bool rare = link < 0 || !(other - ds > 4. * M.eps) || !(fabs(kexit) > 1e-3);
+        if (!rare)
         {
-            int axis = wall >> 1;
-            bool neg = !(wall & 1);
+            // step to the lattice point just across the exit wall, then align to the neighbour's level
+            int ix = p.ix, iy = p.iy, iz = p.iz;
+            if (takex)
+                ix += nx ? -1 : size;
+            else if (takey)
+                iy += ny ? -1 : size;
+            else
+                iz += nz ? -1 : size;
+            const int nlev = (link >> SK_LINK_LEVEL_SHIFT) & 15;
+            const int mask = ~((1 << (M.maxlevel - nlev)) - 1);
+            ix &= mask;
+            iy &= mask;
+            iz &= mask;
+            const int idx = link & SK_LINK_INDEX_MASK;
             if (!(link & SK_LINK_INTERNAL))
             {
-                // leaf neighbour at the same or a coarser level
-                q.lev = (link >> SK_LINK_LEVEL_SHIFT) & 15;
-                q.m = link & SK_LINK_INDEX_MASK;
-                int nsize = 1 << (M.maxlevel - q.lev);
-                int mask = ~(nsize - 1);
-                q.ix = p.ix & mask;
-                q.iy = p.iy & mask;
-                q.iz = p.iz & mask;
-                int c = (axis == 0 ? p.ix : axis == 1 ? p.iy : p.iz);
-                c = neg ? c - nsize : c + size;
-                if (axis == 0)
-                    q.ix = c;
-                else if (axis == 1)
-                    q.iy = c;
-                else
-                    q.iz = c;
+                p.m = idx;  // leaf neighbour at the same or a coarser level
+                p.ix = ix;
+                p.iy = iy;
+                p.iz = iz;
+                p.lev = nlev;
             }
             else
-            {
-                // internal neighbour node of the same level: descend to the leaf that holds the new position
-                int ix = p.ix, iy = p.iy, iz = p.iz;
-                int shift = neg ? -size : size;
-                if (axis == 0)
-                    ix += shift;
-                else if (axis == 1)
-                    iy += shift;
-                else
-                    iz += shift;
-                sk_tree_descend(M, T, link & SK_LINK_INDEX_MASK, ix, iy, iz, p.lev, rx, ry, rz, q);
-            }
-            if (!sk_tree_cell_contains(M, T, q, rx, ry, rz)) q.m = -1;
+                sk_tree_descend(M.node_child, M.maxlevel, T, idx, ix, iy, iz, nlev, rx, ry, rz, p);
         }
-        if (q.m < 0)
+        else
         {
-            // `if (!_node) _node = _grid->root()->leafChild(r())`, TreeSpatialGrid.cpp:193
-            if (sk_box_contains(M.ext, rx, ry, rz))
-            {
-                cnt.fallbacks++;
-                sk_locate<2>(M, T, rx, ry, rz, q);
-            }
+            // (copies confine the address-taken variables, which live in local memory, to this cold branch)
+            cnt.fallbacks++;
+            double tx = rx, ty = ry, tz = rz;
+            SkCellPos q;
+            sk_tree_step_rare(Mg, T, tx, ty, tz, k.kx, k.ky, k.kz, p.m, q);
+            rx = tx;
+            ry = ty;
+            rz = tz;
+            p = q;
         }
-        if (q.m == m_out)
-        {
-            // PathSegmentGenerator::propagateToNextAfter, PathSegmentGenerator.hpp:148-153
-            rx = nextafter(rx, (k.kx < 0.) ? -DBL_MAX : DBL_MAX);
-            ry = nextafter(ry, (k.ky < 0.) ? -DBL_MAX : DBL_MAX);
-            rz = nextafter(rz, (k.kz < 0.) ? -DBL_MAX : DBL_MAX);
-            sk_locate<2>(M, T, rx, ry, rz, q);
-            if (q.m == m_out) q.m = -1;
-        }
-        p = q;
     }
 }
 
@@ -483,8 +482,10 @@ struct SkLaunch {
     int ilam;
 };
 
-__device__ __noinline__ void sk_launch_primary(const SkDevModel& M, SkRng& g, unsigned long long history, SkLaunch& pp)
+__device__ __noinline__ void sk_launch_primary(const SkDevModel* __restrict__ Mg, SkRng& g, unsigned long long history,
+                                               SkLaunch& pp)
 {
+    const SkDevModel& M = *Mg;
     int lo = 0, hi = M.nsrc + 1;  // std::upper_bound(_Iv, historyIndex) - 1
     while (lo < hi)
     {
@@ -637,120 +638,166 @@ __device__ __forceinline__ void sk_record(const SkDevInstr& q, int l, int ell, d
 
 // ---------------------------------------------------------------------------------------------------
 // Trace stage: walks all rays of `list[0..n)` with dynamic lane refill.
-//   MODE 0  forward path to the boundary: MediumSystem::setExtinctionOpticalDepths (MediumSystem.cpp:849-871) fused
-//           with MonteCarloSimulation::storeRadiationField (.cpp:638-665)
+//   MODE 0  forward path to the boundary: MediumSystem::setExtinctionOpticalDepths (MediumSystem.cpp:849-871); with
+//           STORE fused with MonteCarloSimulation::storeRadiationField (.cpp:638-665)
 //   MODE 1  walk to the interaction point: SpatialGridPath::findInteractionPoint (SpatialGridPath.cpp:164-206), or for
 //           non-forced scattering MediumSystem::setInteractionPointUsingExtinction (MediumSystem.cpp:978-1010)
 //   MODE 2  optical depth to the observer: MediumSystem::getExtinctionOpticalDepth (MediumSystem.cpp:1192-1219)
+// Structure: a compact inner loop that only crosses cells, and an outer service block (store the results of finished
+// rays, load new rays) that is entered when at least SK_REFILL_MIN lanes are idle, so that its cost is shared.
 // ---------------------------------------------------------------------------------------------------
-template <int GRID, int MODE>
-__device__ __forceinline__ void sk_trace_stage(const SkDevModel& M, const SkSmemTables& T, const SkRunArgs& A,
-                                               const SkPoolView& P, const int* list, int n, double obsx, double obsy,
-                                               double obsz, SkLocalCounters& cnt)
+#ifndef SK_REFILL_MIN
+#define SK_REFILL_MIN 6
+#endif
+
+template <int GRID, int MODE, bool STORE>
+__device__ __forceinline__ void sk_trace_stage(const SkDevModel& M, const SkDevModel* __restrict__ Mg,
+                                               const SkSmemTables& T, const SkRunArgs& A, const SkPoolView& P,
+                                               const int* list, int n, const SkRayDir& obs, SkLocalCounters& cnt)
 {
     const unsigned lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     const bool forced = M.force_scattering != 0;
     int head = 0;
-    bool active = false;
+    bool active = false, pending = false;
     int slot = 0;
     double rx = 0, ry = 0, rz = 0;
-    SkRayDir k{0, 0, 1};
+    SkRayDir k;
+    k.set(0., 0., 1.);
     SkCellPos p{-1, 0, 0, 0, 0};
     double tau = 0, s = 0, limit = 0, section = 0;
     int nseg = 0;
-    // MODE 0 extras
+    // MODE 0 + STORE extras
     double lum = 0, lnExtBeg = 0, extBeg = 1;
     int rf_ell = -1;
     double* rf = nullptr;
-    // MODE 1 extras: the cell of the last accepted segment
-    SkCellPos lastp{-1, 0, 0, 0, 0};
+    // MODE 1 results
+    SkCellPos hit{-1, 0, 0, 0, 0};
+    double s_int = 0;
+    bool found = false;
 
     while (true)
     {
-        unsigned idle = __ballot_sync(0xffffffffu, !active);
-        if (idle)
+        // ---------------- service block: results of finished rays out, new rays in
+        if (pending)
         {
-            if (!active)
+            pending = false;
+            if (MODE == 0)
             {
-                int idx = head + __popc(idle & lt_mask);
-                if (idx < n)
+                P.D(D_TAUPATH, slot) = tau;
+                P.D(D_STOT, slot) = s;
+                P.I(I_NSEG, slot) = nseg;
+                cnt.fwd_paths++;
+                cnt.fwd_segs += nseg;
+            }
+            else if (MODE == 1)
+            {
+                P.D(D_SINT, slot) = s_int;
+                P.I(I_MINT, slot) = hit.m;
+                P.I(I_MIX, slot) = hit.ix;
+                P.I(I_MIY, slot) = hit.iy;
+                P.I(I_MIZ, slot) = hit.iz;
+                P.I(I_MLEV, slot) = hit.lev;
+                if (found) P.I(I_STATE, slot) |= SK_ST_FOUND;
+                if (forced)
+                    cnt.replay_segs += nseg;
+                else
                 {
-                    slot = list[idx];
-                    active = true;
-                    rx = P.D(D_RX, slot);
-                    ry = P.D(D_RY, slot);
-                    rz = P.D(D_RZ, slot);
-                    if (MODE == 2)
+                    cnt.fwd_paths++;
+                    cnt.fwd_segs += nseg;
+                }
+            }
+            else
+            {
+                P.D(D_PTAU, slot) = tau;
+                cnt.peel_paths++;
+                cnt.peel_segs += nseg;
+            }
+        }
+        {
+            unsigned idle = __ballot_sync(0xffffffffu, !active);
+            int idx = head + __popc(idle & lt_mask);
+            head += __popc(idle);
+            if (!active && idx < n)
+            {
+                slot = list[idx];
+                active = true;
+                rx = P.D(D_RX, slot);
+                ry = P.D(D_RY, slot);
+                rz = P.D(D_RZ, slot);
+                if (MODE == 2)
+                    k = obs;
+                else
+                    k.set(P.D(D_KX, slot), P.D(D_KY, slot), P.D(D_KZ, slot));
+                p.m = P.I(I_M, slot);
+                p.ix = P.I(I_IX, slot);
+                p.iy = P.I(I_IY, slot);
+                p.iz = P.I(I_IZ, slot);
+                p.lev = P.I(I_LEV, slot);
+                section = P.D(D_SIGEXT, slot);
+                tau = 0.;
+                s = 0.;
+                nseg = 0;
+                if (MODE == 0 && STORE)
+                {
+                    lnExtBeg = 0.;
+                    extBeg = 1.;
+                    double lambda = P.D(D_LAMBDA, slot);
+                    rf_ell = sk_wlg_bin(M.wlg[M.rf_grid], lambda);  // MonteCarloSimulation.cpp:643
+                    rf = A.primary ? M.rf1 : M.rf2c;
+                    lum = P.D(D_W, slot) / lambda;
+                }
+                if (MODE == 1)
+                {
+                    limit = P.D(D_TAUINT, slot);
+                    hit = p;
+                    found = false;
+                    s_int = 0.;
+                }
+                if (MODE == 2) limit = P.D(D_LIMIT, slot);
+                if (p.m < 0)
+                {
+                    // the path starts outside (or exactly on the border of) the grid: PathSegmentGenerator::moveInside
+                    double cumds = 0.;
+                    double tx = rx, ty = ry, tz = rz;
+                    if (sk_move_inside(tx, ty, tz, k.kx, k.ky, k.kz, Mg->ext, M.eps, cumds))
                     {
-                        k.kx = obsx;
-                        k.ky = obsy;
-                        k.kz = obsz;
-                    }
-                    else
-                    {
-                        k.kx = P.D(D_KX, slot);
-                        k.ky = P.D(D_KY, slot);
-                        k.kz = P.D(D_KZ, slot);
-                    }
-                    p.m = P.I(I_M, slot);
-                    p.ix = P.I(I_IX, slot);
-                    p.iy = P.I(I_IY, slot);
-                    p.iz = P.I(I_IZ, slot);
-                    p.lev = P.I(I_LEV, slot);
-                    section = P.D(D_SIGEXT, slot);
-                    tau = 0.;
-                    s = 0.;
-                    nseg = 0;
-                    if (MODE == 0)
-                    {
-                        lnExtBeg = 0.;
-                        extBeg = 1.;
-                        rf_ell = -1;
-                        if (A.store)
+                        SkCellPos q;
+                        sk_locate<GRID>(Mg, T, tx, ty, tz, q);
+                        rx = tx;
+                        ry = ty;
+                        rz = tz;
+                        p = q;
+                        if (cumds > 0.)
                         {
-                            double lambda = P.D(D_LAMBDA, slot);
-                            rf_ell = sk_wlg_bin(M.wlg[M.rf_grid], lambda);  // MonteCarloSimulation.cpp:643
-                            rf = A.primary ? M.rf1 : M.rf2c;
-                            lum = P.D(D_W, slot) / lambda;
+                            // the empty segment in front of the grid (m = -1)
+                            nseg++;
+                            s += cumds;
                         }
                     }
-                    if (MODE == 1)
-                    {
-                        limit = P.D(D_TAUINT, slot);
-                        lastp = p;
-                    }
-                    if (MODE == 2) limit = P.D(D_LIMIT, slot);
                     if (p.m < 0)
                     {
-                        // the path starts outside (or exactly on the border of) the grid: PathSegmentGenerator::moveInside
-                        double cumds = 0.;
-                        if (sk_move_inside(rx, ry, rz, k.kx, k.ky, k.kz, M.ext, M.eps, cumds))
-                        {
-                            sk_locate<GRID>(M, T, rx, ry, rz, p);
-                            if (cumds > 0.)
-                            {
-                                // the empty segment in front of the grid (m = -1)
-                                nseg++;
-                                s += cumds;
-                            }
-                        }
-                        // else: the path misses the grid; p.m stays -1 and the ray ends below without segments
+                        // the path misses the grid: no segments
+                        active = false;
+                        pending = true;
+                        if (MODE == 1) s_int = s;
                     }
                 }
             }
-            head += __popc(idle);
-            if (!__any_sync(0xffffffffu, active)) break;
+            if (!__any_sync(0xffffffffu, active || pending)) break;
         }
-        if (active)
+        // ---------------- inner loop: cross cells until enough lanes have finished their ray
+        const int want_idle = head < n ? SK_REFILL_MIN : 32;
+        int nidle;
+        do
         {
-            bool done = false;
-            if (p.m >= 0)
+            if (active)
             {
                 int m;
                 double dens, ds;
                 const SkCellPos cur = p;
-                sk_step<GRID>(M, T, cnt, rx, ry, rz, k, p, m, dens, ds);
+                sk_step<GRID>(M, Mg, T, cnt, rx, ry, rz, k, p, m, dens, ds);
+                bool done = false;
                 if (MODE == 0)
                 {
                     if (ds > 0.)  // SpatialGridPath::addSegment, SpatialGridPath.cpp:41-48
@@ -758,7 +805,7 @@ __device__ __forceinline__ void sk_trace_stage(const SkDevModel& M, const SkSmem
                         nseg++;
                         s += ds;
                         tau += section * dens * ds;
-                        if (rf_ell >= 0)
+                        if (STORE && rf_ell >= 0)
                         {
                             double lnExtEnd = -tau;
                             double extEnd = exp(lnExtEnd);
@@ -779,17 +826,11 @@ __device__ __forceinline__ void sk_trace_stage(const SkDevModel& M, const SkSmem
                         double tau0 = tau, s0 = s;
                         s += ds;
                         tau += section * dens * ds;
-                        lastp = cur;
+                        hit = cur;
                         if (limit < tau)
                         {
-                            // interaction inside this segment: NR::interpolateLinLin
-                            P.D(D_SINT, slot) = sk_interp_linlin(limit, tau0, tau, s0, s);
-                            P.I(I_MINT, slot) = cur.m;
-                            P.I(I_MIX, slot) = cur.ix;
-                            P.I(I_MIY, slot) = cur.iy;
-                            P.I(I_MIZ, slot) = cur.iz;
-                            P.I(I_MLEV, slot) = cur.lev;
-                            P.I(I_STATE, slot) |= SK_ST_FOUND;
+                            s_int = sk_interp_linlin(limit, tau0, tau, s0, s);  // interaction inside this segment
+                            found = true;
                             done = true;
                         }
                     }
@@ -804,52 +845,21 @@ __device__ __forceinline__ void sk_trace_stage(const SkDevModel& M, const SkSmem
                         done = true;
                     }
                 }
-            }
-            if (!done && p.m < 0)
-            {
-                // the path has left the grid (or never entered it)
-                done = true;
-                if (MODE == 1)
+                if (!done && p.m < 0)
                 {
-                    // at or beyond the exit optical depth of the last segment: use the last segment
-                    // (SpatialGridPath.cpp:199-205); non-forced: no interaction (SK_ST_FOUND stays clear)
-                    P.D(D_SINT, slot) = s;
-                    P.I(I_MINT, slot) = lastp.m;
-                    P.I(I_MIX, slot) = lastp.ix;
-                    P.I(I_MIY, slot) = lastp.iy;
-                    P.I(I_MIZ, slot) = lastp.iz;
-                    P.I(I_MLEV, slot) = lastp.lev;
+                    // the path has left the grid; MODE 1: at or beyond the exit optical depth of the last segment ->
+                    // use the last segment (SpatialGridPath.cpp:199-205); non-forced: no interaction
+                    done = true;
+                    if (MODE == 1) s_int = s;
+                }
+                if (done)
+                {
+                    active = false;
+                    pending = true;
                 }
             }
-            if (done)
-            {
-                active = false;
-                if (MODE == 0)
-                {
-                    P.D(D_TAUPATH, slot) = tau;
-                    P.D(D_STOT, slot) = s;
-                    P.I(I_NSEG, slot) = nseg;
-                    cnt.fwd_paths++;
-                    cnt.fwd_segs += nseg;
-                }
-                else if (MODE == 1)
-                {
-                    if (forced)
-                        cnt.replay_segs += nseg;
-                    else
-                    {
-                        cnt.fwd_paths++;
-                        cnt.fwd_segs += nseg;
-                    }
-                }
-                else
-                {
-                    P.D(D_PTAU, slot) = tau;
-                    cnt.peel_paths++;
-                    cnt.peel_segs += nseg;
-                }
-            }
-        }
+            nidle = __popc(__ballot_sync(0xffffffffu, !active));
+        } while (nidle < want_idle);
     }
     __syncwarp();
 }
@@ -882,7 +892,8 @@ __device__ __forceinline__ void sk_finish_history(const SkDevModel& M, const SkP
 // Peel-off towards the observer group [j0, j1): MonteCarloSimulation::peelOffEmission (.cpp:617-634) /
 // peelOffScattering (.cpp:784-842, consolidated branch) split around the trace stage.
 template <int GRID>
-__device__ __forceinline__ void sk_peel_group(const SkDevModel& M, const SkSmemTables& T, const SkRunArgs& A,
+__device__ __forceinline__ void sk_peel_group(const SkDevModel& M, const SkDevModel* __restrict__ Mg,
+                                              const SkSmemTables& T, const SkRunArgs& A,
                                               const SkPoolView& P, int* list, int j0, int j1, SkLocalCounters& cnt)
 {
     const unsigned lane = threadIdx.x & 31;
@@ -891,6 +902,7 @@ __device__ __forceinline__ void sk_peel_group(const SkDevModel& M, const SkSmemT
     const double ox = q0.kobs[0], oy = q0.kobs[1], oz = q0.kobs[2];
     int n = 0;
     // ---- set-up: weight of the peel-off packet and which packets need an optical depth at all
+#pragma unroll 1
     for (int base = 0; base < SK_POOL; base += 32)
     {
         int slot = base + lane;
@@ -938,8 +950,11 @@ __device__ __forceinline__ void sk_peel_group(const SkDevModel& M, const SkSmemT
         n += __popc(mask);
     }
     __syncwarp();
-    sk_trace_stage<GRID, 2>(M, T, A, P, list, n, ox, oy, oz, cnt);
+    SkRayDir obs;
+    obs.set(ox, oy, oz);
+    sk_trace_stage<GRID, 2, false>(M, Mg, T, A, P, list, n, obs, cnt);
     // ---- detection: FluxRecorder::detect, FluxRecorder.cpp:304-468
+#pragma unroll 1
     for (int base = 0; base < SK_POOL; base += 32)
     {
         int slot = base + lane;
@@ -973,12 +988,14 @@ __device__ __forceinline__ void sk_peel_group(const SkDevModel& M, const SkSmemT
 // The life cycles of one warp's pool.
 // ---------------------------------------------------------------------------------------------------
 template <int GRID>
-__device__ __forceinline__ void sk_warp_life_cycles(const SkDevModel& M, const SkSmemTables& T, const SkRunArgs& A,
+__device__ __forceinline__ void sk_warp_life_cycles(const SkDevModel& M, const SkDevModel* __restrict__ Mg,
+                                                    const SkSmemTables& T, const SkRunArgs& A,
                                                     const SkPoolView& P, int* list, SkLocalCounters& cnt)
 {
     const unsigned lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     const bool forced = M.force_scattering != 0;
+#pragma unroll 1
     for (int base = 0; base < SK_POOL; base += 32) P.I(I_STATE, base + lane) = 0;
     __syncwarp();
     bool more = true;
@@ -987,7 +1004,8 @@ __device__ __forceinline__ void sk_warp_life_cycles(const SkDevModel& M, const S
     {
         // ---- stage A: launch a history into every free slot (SourceSystem::launch)
         int nlive = 0;
-        for (int base = 0; base < SK_POOL; base += 32)
+    #pragma unroll 1
+    for (int base = 0; base < SK_POOL; base += 32)
         {
             int slot = base + lane;
             int st = P.I(I_STATE, slot);
@@ -1007,14 +1025,14 @@ __device__ __forceinline__ void sk_warp_life_cycles(const SkDevModel& M, const S
                     SkRng g;
                     sk_rng_init(g, M.seed, A.stream_id, history, 0);
                     SkLaunch pp;
-                    sk_launch_primary(M, g, history, pp);
+                    sk_launch_primary(Mg, g, history, pp);
                     if (pp.W / pp.lambda > 0)  // MonteCarloSimulation.cpp:553
                     {
                         cnt.packets++;
                         SkCellPos c;
                         c.m = -1;
                         c.ix = c.iy = c.iz = c.lev = 0;
-                        if (sk_box_strictly_inside(M.ext, pp.rx, pp.ry, pp.rz)) sk_locate<GRID>(M, T, pp.rx, pp.ry, pp.rz, c);
+                        if (sk_box_strictly_inside(M.ext, pp.rx, pp.ry, pp.rz)) sk_locate<GRID>(Mg, T, pp.rx, pp.ry, pp.rz, c);
                         P.D(D_RX, slot) = pp.rx;
                         P.D(D_RY, slot) = pp.ry;
                         P.D(D_RZ, slot) = pp.rz;
@@ -1062,7 +1080,7 @@ __device__ __forceinline__ void sk_warp_life_cycles(const SkDevModel& M, const S
             {
                 int j1 = j0 + 1;
                 while (j1 < M.ninstr && M.instr[j1].same_as_preceding) j1++;
-                sk_peel_group<GRID>(M, T, A, P, list, j0, j1, cnt);
+                sk_peel_group<GRID>(M, Mg, T, A, P, list, j0, j1, cnt);
                 j0 = j1;
             }
         }
@@ -1070,7 +1088,8 @@ __device__ __forceinline__ void sk_warp_life_cycles(const SkDevModel& M, const S
         // ---- stage C: the pending scattering events: MediumSystem::simulateScattering (.cpp:796-823) +
         //      DustMix::performScattering HG branch (DustMix.cpp:496-511); then the list of all live packets
         int n = 0;
-        for (int base = 0; base < SK_POOL; base += 32)
+    #pragma unroll 1
+    for (int base = 0; base < SK_POOL; base += 32)
         {
             int slot = base + lane;
             int st = P.I(I_STATE, slot);
@@ -1106,12 +1125,21 @@ __device__ __forceinline__ void sk_warp_life_cycles(const SkDevModel& M, const S
         __syncwarp();
 
         // ---- stage D: forward paths (forced scattering only)
-        if (forced) sk_trace_stage<GRID, 0>(M, T, A, P, list, n, 0., 0., 0., cnt);
+        SkRayDir nodir;
+        nodir.set(0., 0., 1.);
+        if (forced)
+        {
+            if (A.store)
+                sk_trace_stage<GRID, 0, true>(M, Mg, T, A, P, list, n, nodir, cnt);
+            else
+                sk_trace_stage<GRID, 0, false>(M, Mg, T, A, P, list, n, nodir, cnt);
+        }
 
         // ---- stage E: sample the interaction optical depth: simulateForcedPropagation (.cpp:696-722) or
         //      Random::expon for simulateNonForcedPropagation (.cpp:749)
         n = 0;
-        for (int base = 0; base < SK_POOL; base += 32)
+    #pragma unroll 1
+    for (int base = 0; base < SK_POOL; base += 32)
         {
             int slot = base + lane;
             int st = P.I(I_STATE, slot);
@@ -1162,10 +1190,11 @@ __device__ __forceinline__ void sk_warp_life_cycles(const SkDevModel& M, const S
         __syncwarp();
 
         // ---- stage F: walk to the interaction point
-        sk_trace_stage<GRID, 1>(M, T, A, P, list, n, 0., 0., 0., cnt);
+        sk_trace_stage<GRID, 1, false>(M, Mg, T, A, P, list, n, nodir, cnt);
 
         // ---- stage G: the interaction: albedo weight, move, termination test (.cpp:724-741, 576-580)
-        for (int base = 0; base < SK_POOL; base += 32)
+    #pragma unroll 1
+    for (int base = 0; base < SK_POOL; base += 32)
         {
             int slot = base + lane;
             int st = P.I(I_STATE, slot);
@@ -1226,7 +1255,7 @@ __device__ __forceinline__ void sk_warp_life_cycles(const SkDevModel& M, const S
                             if (!inside)
                             {
                                 inside = sk_box_strictly_inside(M.ext, x, y, z);
-                                if (inside) sk_locate<GRID>(M, T, x, y, z, c);
+                                if (inside) sk_locate<GRID>(Mg, T, x, y, z, c);
                             }
                         }
                         if (!inside) c.m = -1;
