@@ -467,9 +467,13 @@ class FileTreeSpatialGrid(PolicyTreeSpatialGrid):
     """FileTreeSpatialGrid.cpp:22-78: rebuilds an octree from the 0/1 pre-order topology stream written by
     TreeSpatialGridTopologyProbe (TreeSpatialGrid.cpp:232-251); nodes are created depth-first."""
 
-    def __init__(self, minX, maxX, minY, maxY, minZ, maxZ, topology: Sequence[int]):
+    def __init__(self, minX, maxX, minY, maxY, minZ, maxZ, topology: Sequence[int], policyOrder: bool = False):
+        """policyOrder=True renumbers the nodes breadth-first, level by level, the way DensityTreePolicy::constructTree
+        (DensityTreePolicy.cpp:242-309) created them in the run that exported the topology, so that cell indices match
+        that run's per-cell output files."""
         super().__init__(minX, maxX, minY, maxY, minZ, maxZ, None)
         self.topology = list(topology)
+        self.policyOrder = policyOrder
 
     def setup(self, media, num_density_samples, rng):
         topo = self.topology
@@ -477,7 +481,12 @@ class FileTreeSpatialGrid(PolicyTreeSpatialGrid):
         first_child = [-1]
         pos = [0]
 
-        def subdivide(node):
+        def subdivide_if_needed(node):
+            # subdivideNodeIfNeeded, FileTreeSpatialGrid.cpp:20-37: one flag per node, pre-order
+            flag = topo[pos[0]]
+            pos[0] += 1
+            if not flag:
+                return
             b = boxes[node]
             c = [0.5 * (b[a] + b[a + 3]) for a in range(3)]
             fc = len(boxes)
@@ -491,21 +500,26 @@ class FileTreeSpatialGrid(PolicyTreeSpatialGrid):
                 boxes.append(nb)
                 first_child.append(-1)
             for ch in range(8):
-                flag = topo[pos[0]]
-                pos[0] += 1
-                if flag:
-                    subdivide(fc + ch)
+                subdivide_if_needed(fc + ch)
 
-        # the first item is the number of children of the root (8 or 0)
-        nroot = topo[0]
+        # the first item is the number of children of the root (8 or 0), then the root's own flag follows
+        if topo[0] not in (0, 8):
+            raise ValueError("only octree topologies are supported")
         pos[0] = 1
-        if nroot:
-            # FileTreeSpatialGrid subdivides the root, then reads one flag per child in order (depth first)
-            import sys
-            sys.setrecursionlimit(10000)
-            subdivide(0)
+        subdivide_if_needed(0)
         self.boxes = np.asarray(boxes, dtype=float)
         self.first_child = np.asarray(first_child, dtype=np.int32)
+        if self.policyOrder:
+            fc = self.first_child
+            order = [0]
+            for node in order:  # breadth-first queue: children are appended when their parent is visited
+                if fc[node] >= 0:
+                    order.extend(range(fc[node], fc[node] + 8))
+            order = np.asarray(order)
+            newid = np.empty(len(order), dtype=np.int64)
+            newid[order] = np.arange(len(order))
+            self.boxes = self.boxes[order]
+            self.first_child = np.where(fc[order] >= 0, newid[np.maximum(fc[order], 0)], -1).astype(np.int32)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -669,7 +683,12 @@ class MonteCarloSimulation:
         self.volume = np.prod(boxes[:, 3:] - boxes[:, :3], axis=1)
         n = len(boxes)
         dens = np.zeros(n)
-        if self.numDensitySamples == 1:
+        if self.density is not None:
+            # medium state imported from a SpatialCellPropertiesProbe file of a reference run (tests/golden)
+            if len(self.density) != n:
+                raise ValueError("imported density does not match the grid")
+            dens = np.asarray(self.density, dtype=float)
+        elif self.numDensitySamples == 1:
             c = 0.5 * (boxes[:, :3] + boxes[:, 3:])
             dens = self.medium.number_density(c[:, 0], c[:, 1], c[:, 2])
         else:
@@ -741,6 +760,24 @@ class MonteCarloSimulation:
         L = engine.read_sed(instrument, component)
         flam = L / (4 * math.pi * i.distance ** 2) / g.dlambdav
         return flam * g.lambdav ** 2 / C_LIGHT * 1e26
+
+    def surface_brightness(self, engine, instrument=0, component=abi.SK_COMP_TOTAL):
+        """FluxRecorder::calibrateAndWrite, FluxRecorder.cpp:503-506,740-749: per-pixel F_lambda / Omega_pixel with
+        Omega = 4 atan(dx/2d) atan(dy/2d); returned as [ell][j][i] in MJy/sr (fluxOutputStyle Frequency,
+        Units.cpp:599-609), the layout and unit of the reference's FITS cubes."""
+        i = self.instruments[instrument]
+        oligo = self.oligoWavelengths is not None
+        g = i.wavelengthGrid if (i.wavelengthGrid is not None and not oligo) else self.defaultWavelengthGrid
+        L = engine.read_ifu(instrument, component).reshape(g.num_bins, i.numPixelsY, i.numPixelsX)
+        omega = 4.0 * math.atan(0.5 * i.fieldOfViewX / i.numPixelsX / i.distance) \
+            * math.atan(0.5 * i.fieldOfViewY / i.numPixelsY / i.distance)
+        flam = L / (4 * math.pi * i.distance ** 2) / g.dlambdav[:, None, None] / omega
+        return flam * (g.lambdav ** 2)[:, None, None] / C_LIGHT * 1e26 * 1e-6
+
+    def mean_intensity_nu(self, engine, which=0):
+        """J_nu in W/m2/Hz/sr as RadiationFieldProbe writes it with fluxOutputStyle Frequency (Units.cpp:641-651)."""
+        g = self.radiationFieldWLG
+        return self.mean_intensity(engine, which) * (g.lambdav ** 2)[None, :] / C_LIGHT
 
     def mean_intensity(self, engine, which=0):
         """MediumSystem::meanIntensity, MediumSystem.cpp:1370-1380: J_lambda = rf/(4 pi V dlambda)."""

@@ -1,0 +1,169 @@
+#!/usr/bin/env python
+"""Generates the golden fixtures under tests/golden/ by RUNNING THE UNMODIFIED REFERENCE (oracle/_ref, built from
+/root/reference by oracle/ref.mk) on the ski files under tests/golden/ski/ with `-t 1` (bit-reproducible).
+
+The reference has no tests or golden vectors of its own, so these outputs ARE the pin of the oracle:
+each fixture holds both the reference's INPUTS as the reference itself sampled them (per-cell densities from
+SpatialCellPropertiesProbe, the octree topology from TreeSpatialGridTopologyProbe) and its OUTPUTS (SED columns,
+Sigma w^k statistics, calibrated frames, per-cell mean intensity, convergence log values), so that the oracle and the
+CUDA engine can be run on IDENTICAL inputs and compared within the Monte-Carlo tolerance the reference's own
+statistics define.
+
+    python tests/golden/make_golden.py [cfg1 cfg2s cfg4s cfg5s]
+
+Only this script needs oracle/_ref; the tests read the committed .npz files.
+"""
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+SKIRT = os.path.join(ROOT, "oracle", "_ref", "release", "SKIRT", "main", "skirt")
+
+
+def read_fits_cube(path):
+    """Primary HDU of a SKIRT frame file: BITPIX=-32 big-endian float32 (FITSInOut.cpp:160,194)."""
+    raw = open(path, "rb").read()
+    cards = {}
+    pos = 0
+    while True:
+        block = raw[pos:pos + 2880].decode("ascii")
+        pos += 2880
+        done = False
+        for i in range(0, 2880, 80):
+            c = block[i:i + 80]
+            if c.startswith("END"):
+                done = True
+                break
+            if "=" in c[:10]:
+                cards[c[:8].strip()] = c[10:].split("/")[0].strip().strip("'").strip()
+        if done:
+            break
+    nx, ny = int(cards["NAXIS1"]), int(cards["NAXIS2"])
+    nz = int(cards.get("NAXIS3", 1))
+    data = np.frombuffer(raw, dtype=">f4", count=nx * ny * nz, offset=pos).astype(np.float32)
+    return data.reshape(nz, ny, nx), cards
+
+
+def read_columns(path):
+    return np.loadtxt(path, comments="#", ndmin=2)
+
+
+def run_reference(ski_name, workdir, extra_inputs=None, threads=1):
+    ski = os.path.join(HERE, "ski", ski_name + ".ski")
+    for name, text in (extra_inputs or {}).items():
+        open(os.path.join(workdir, name), "w").write(text)
+    subprocess.check_call([SKIRT, "-t", str(threads), "-b", "-i", workdir, "-o", workdir, ski],
+                          stdout=subprocess.DEVNULL)
+    return open(os.path.join(workdir, ski_name + "_log.txt")).read()
+
+
+def frames(workdir, prefix, names):
+    out = {}
+    for n in names:
+        p = os.path.join(workdir, f"{prefix}_{n}.fits")
+        if os.path.exists(p):
+            out["frame_" + n] = read_fits_cube(p)[0]
+    return out
+
+
+def parse_topology(path):
+    return np.array([int(t) for t in open(path).read().split("\n") if t and not t.startswith("#")], dtype=np.int8)
+
+
+def make_cfg1():
+    with tempfile.TemporaryDirectory() as d:
+        log = run_reference("cfg1", d)
+        sed = read_columns(os.path.join(d, "cfg1_i60_sed.dat"))
+        stats = read_columns(os.path.join(d, "cfg1_i60_sedstats.dat"))
+        cells = read_columns(os.path.join(d, "cfg1_cells_cellprops.dat"))
+        rfJ = read_columns(os.path.join(d, "cfg1_rf_J.dat"))
+        out = dict(sed=sed, sedstats=stats, mass_density_msun_pc3=cells[:, 6], cell_center_pc=cells[:, 1:4].astype(np.float32),
+                   cell_volume_pc3=cells[:, 4], J_nu=rfJ[:, 1:], num_packets=1e6,
+                   seconds=float(re.search(r"Finished primary emission in ([0-9.]+) s", log).group(1)))
+        out.update(frames(d, "cfg1_i60", ["total", "transparent", "primarydirect", "primaryscattered", "stats0",
+                                          "stats1", "stats2"]))
+    np.savez_compressed(os.path.join(HERE, "cfg1_ref.npz"), **out)
+    print("cfg1:", {k: np.shape(v) for k, v in out.items()})
+
+
+def make_cfg2s():
+    with tempfile.TemporaryDirectory() as d:
+        log = run_reference("cfg2s", d)
+        sed = read_columns(os.path.join(d, "cfg2s_i60_sed.dat"))
+        stats = read_columns(os.path.join(d, "cfg2s_i60_sedstats.dat"))
+        cells = read_columns(os.path.join(d, "cfg2s_cells_cellprops.dat"))
+        topo = parse_topology(os.path.join(d, "cfg2s_topo_treetop.dat"))
+        out = dict(sed=sed, sedstats=stats, mass_density_msun_pc3=cells[:, 6], cell_center_pc=cells[:, 1:4],
+                   cell_volume_pc3=cells[:, 4], topology=topo, num_packets=1e6,
+                   seconds=float(re.search(r"Finished primary emission in ([0-9.]+) s", log).group(1)))
+        out.update(frames(d, "cfg2s_i60", ["total", "transparent", "primarydirect", "primaryscattered", "stats0",
+                                           "stats1", "stats2"]))
+    np.savez_compressed(os.path.join(HERE, "cfg2s_ref.npz"), **out)
+    print("cfg2s:", {k: np.shape(v) for k, v in out.items()})
+
+
+def make_cfg4s():
+    with tempfile.TemporaryDirectory() as d:
+        log = run_reference("cfg4s", d)
+        sed = read_columns(os.path.join(d, "cfg4s_sed_sed.dat"))
+        cells = read_columns(os.path.join(d, "cfg4s_cells_cellprops.dat"))
+        topo = parse_topology(os.path.join(d, "cfg4s_topo_treetop.dat"))
+        rfJ = read_columns(os.path.join(d, "cfg4s_rf_J.dat"))
+        T = read_columns(os.path.join(d, "cfg4s_temp_T.dat"))
+        # convergence log lines, MonteCarloSimulation.cpp:193-214
+        prim = [float(x) for x in re.findall(r"absorbed primary luminosity: ([0-9.eE+-]+) Lsun", log)]
+        sec = [float(x) for x in re.findall(r"absorbed secondary luminosity: ([0-9.eE+-]+) Lsun", log)]
+        conv = re.search(r"Convergence reached after (\d+) iterations", log)
+        out = dict(sed=sed, mass_density_msun_pc3=cells[:, 6], cell_center_pc=cells[:, 1:4], cell_volume_pc3=cells[:, 4],
+                   topology=topo, J_nu=rfJ[:, 1:].astype(np.float32), temperature=T[:, 1], absorbed_primary_lsun=np.array(prim),
+                   absorbed_secondary_lsun=np.array(sec), converged_after=int(conv.group(1)) if conv else -1,
+                   num_packets=2e5, log_tail=np.array(log[-6000:]))
+    np.savez_compressed(os.path.join(HERE, "cfg4s_ref.npz"), **out)
+    print("cfg4s:", {k: np.shape(v) for k, v in out.items()}, prim, sec, conv and conv.group(0))
+
+
+def sph_particles(n=6000, seed=12345):
+    """SURVEY.md 8d cfg5 recipe scaled down: columns x y z h M (pc, pc, pc, pc, Msun)."""
+    rng = np.random.default_rng(seed)
+    R = rng.gamma(2.0, 3000.0, size=4 * n)
+    R = R[R < 15000.0][:n]
+    phi = rng.uniform(0, 2 * np.pi, size=n)
+    z = np.clip(rng.laplace(0.0, 250.0, size=n), -1900.0, 1900.0)
+    h = 400.0 * (1 + R / 8000.0)
+    M = np.full(n, 1e3)
+    return np.stack([R * np.cos(phi), R * np.sin(phi), z, h, M], axis=1)
+
+
+def sph_text(p):
+    head = "# column 1: x (pc)\n# column 2: y (pc)\n# column 3: z (pc)\n# column 4: h (pc)\n# column 5: M (Msun)\n"
+    return head + "\n".join(" ".join("%.8e" % v for v in row) for row in p) + "\n"
+
+
+def make_cfg5s():
+    p = sph_particles()
+    with tempfile.TemporaryDirectory() as d:
+        log = run_reference("cfg5s", d, {"sph.txt": sph_text(p)})
+        sed = read_columns(os.path.join(d, "cfg5s_i60_sed.dat"))
+        stats = read_columns(os.path.join(d, "cfg5s_i60_sedstats.dat"))
+        cells = read_columns(os.path.join(d, "cfg5s_cells_cellprops.dat"))
+        out = dict(sed=sed, sedstats=stats, particles=p, mass_density_msun_pc3=cells[:, 6], cell_center_pc=cells[:, 1:4],
+                   cell_volume_pc3=cells[:, 4], num_packets=2e5,
+                   seconds=float(re.search(r"Finished primary emission in ([0-9.]+) s", log).group(1)))
+        out.update(frames(d, "cfg5s_i60", ["total", "transparent", "primarydirect", "primaryscattered", "stats0",
+                                           "stats1", "stats2"]))
+    np.savez_compressed(os.path.join(HERE, "cfg5s_ref.npz"), **out)
+    print("cfg5s:", {k: np.shape(v) for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    if not os.path.exists(SKIRT):
+        raise SystemExit("oracle/_ref is not built: run `make -C oracle -f ref.mk -j8` where /root/reference exists")
+    todo = sys.argv[1:] or ["cfg1", "cfg2s"]
+    for name in todo:
+        globals()["make_" + name]()
