@@ -100,7 +100,7 @@ def _i(a):
 
 def load_engine_library(path: Optional[str] = None) -> C.CDLL:
     """Loads the CUDA engine; there is no fallback of any kind."""
-    path = path or ENGINE_LIB_PATH
+    path = path or os.environ.get("SK_ENGINE_LIB") or ENGINE_LIB_PATH  # SK_ENGINE_LIB: kernel-variant experiments
     if not os.path.exists(path):
         raise RuntimeError(f"{path} has not been built: run `python -c 'import __graft_entry__ as g; g.build()'` "
                            "(the engine has no CPU fallback)")

@@ -40,11 +40,16 @@ extern "C" int sk_abi_version(void)
 // ---------------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------------
+#ifndef SK_BLOCK
 #define SK_BLOCK 128
+#endif
+#ifndef SK_MINBLOCKS
+#define SK_MINBLOCKS 4
+#endif
 #define SK_WARPS_PER_BLOCK (SK_BLOCK / 32)
 
 template <int GRID>
-__global__ void __launch_bounds__(SK_BLOCK) sk_life_cycle_kernel(const SkDevModel M, const SkRunArgs A)
+__global__ void __launch_bounds__(SK_BLOCK, SK_MINBLOCKS) sk_life_cycle_kernel(const SkDevModel M, const SkRunArgs A)
 {
     extern __shared__ double smem[];
     SkSmemTables T;
