@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SK_ABI_VERSION 1
+#define SK_ABI_VERSION 2
 
 typedef struct sk_engine sk_engine_t;
 
@@ -148,14 +148,21 @@ enum sk_component {
     SK_COMP_PRIMARY_SCATTERED_LEVEL = 7 /* + level-1 */
 };
 
-/* ---- Secondary (dust) emission: DustSecondarySource + EquilibriumDustEmissionCalculator -------- */
+/* ---- Secondary (dust) emission: DustSecondarySource + EquilibriumDustEmissionCalculator --------
+ * The tables are what EquilibriumDustEmissionCalculator::precalculate (EquilibriumDustEmissionCalculator.cpp:18-93)
+ * leaves behind for the single dust mix; they are setup data computed on the host side like the DustMix tables. */
 typedef struct sk_secondary {
-    int32_t emission_grid;     /* wavelength grid index of Configuration::dustEmissionWLG() */
-    int32_t reserved;
-    double spatial_bias;       /* SecondaryEmissionOptions::spatialBias (DustSecondarySource.cpp:118-146) */
-    double wavelength_bias;    /* DustEmissionOptions::wavelengthBias */
-    double bias_min, bias_max; /* log-uniform bias distribution range (source wavelength range) */
-    double source_min, source_max; /* Configuration::sourceWavelengthRange: emission outside is suppressed */
+    int32_t emission_grid;       /* wavelength grid index of Configuration::dustEmissionWLG() */
+    int32_t num_temperatures;    /* size of the temperature grid _Tv (1001, .cpp:55) */
+    double spatial_bias;         /* SecondaryEmissionOptions::spatialBias (DustSecondarySource.cpp:118-146) */
+    double wavelength_bias;      /* DustEmissionOptions::wavelengthBias (DustSecondarySource.cpp:526) */
+    double bias_min, bias_max;   /* range of the log-uniform DefaultWavelengthDistribution = wavelength range of the
+                                    dust emission grid (DustEmissionOptions.hpp:87-90) */
+    const double* temperature;   /* [num_temperatures] _Tv */
+    const double* planck_abs;    /* [num_temperatures] _planckabsvv[0] (.cpp:70-91) */
+    const double* rf_sigma_abs;  /* [N_rf]   _rfsigmaabsvv[0]: sigma_abs resampled on the radiation field grid (.cpp:59) */
+    const double* em_sigma_abs;  /* [N_em+2] _emsigmaabsvv[0]: sigma_abs on DisjointWavelengthGrid::extlambdav() of the
+                                    emission grid (.cpp:62-65, DisjointWavelengthGrid.cpp:346-356) */
 } sk_secondary_t;
 
 /* ---- Device-side event counters (the engine must count S, S_fwd, P_peel itself) -- */
@@ -225,8 +232,13 @@ int sk_engine_clear_rf(sk_engine_t* e, int32_t primary);
 int sk_engine_prepare_primary(sk_engine_t* e, uint64_t num_packets);
 
 /* SecondarySourceSystem::prepareForLaunch + DustSecondarySource::prepareLuminosities/preparePacketMap
- * (SecondarySourceSystem.cpp:84-126, DustSecondarySource.cpp:26-146); computed on the device from the
- * current radiation field.  Returns the total dust luminosity (W) in *luminosity. */
+ * (SecondarySourceSystem.cpp:84-126, DustSecondarySource.cpp:26-146) and, for every emitting cell at once, the
+ * emission spectrum and its cumulative distribution that the reference computes lazily per thread
+ * (DustCellEmission::calculateIfNeeded, DustSecondarySource.cpp:187-285; MediumSystem::dustEmissionSpectrum/
+ * meanIntensity, MediumSystem.cpp:1370-1380,1466-1476; EquilibriumDustEmissionCalculator::emissivity, .cpp:120-150);
+ * computed on the device from the current radiation field rf1+rf2.  Returns the total dust luminosity (W) in
+ * *luminosity; a zero luminosity is reported as SK_OK with *luminosity = 0 (the caller skips the segment like
+ * MonteCarloSimulation.cpp:156-159). */
 int sk_engine_prepare_secondary(sk_engine_t* e, uint64_t num_packets, double* luminosity);
 
 /* THE hot path: performLifeCycle(firstIndex, numIndices, primary, peel, store)

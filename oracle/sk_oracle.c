@@ -106,6 +106,17 @@ typedef struct sko_engine {
     int ninstr;
     instr_t* instr;
     int has_medium_emission;
+    /* secondary (dust) emission */
+    int has_secondary;
+    sk_secondary_t sec;
+    double *sec_T, *sec_planckabs, *sec_rfsig, *sec_emsig; /* EquilibriumDustEmissionCalculator tables */
+    int sec_nem;             /* N_em + 2 points of DisjointWavelengthGrid::extlambdav() */
+    double* sec_lambda;      /* [sec_nem] */
+    double *sec_pv, *sec_Pv; /* [ncells][sec_nem] normalised emission spectrum and cdf of every cell */
+    double *sec_Lv, *sec_Wv; /* [ncells] DustSecondarySource::_Lv, _Wv */
+    uint64_t* sec_Iv;        /* [ncells+1] */
+    double sec_Lpp;
+    int secondary_ready;
     /* path buffer */
     seg_t* segs;
     int nsegs, capsegs;
@@ -324,6 +335,22 @@ static double gexp(double p, double x)
     else
         return pow(1.0 + q * x, 1.0 / q);
 }
+/* SpecialFunctions::gln, SpecialFunctions.cpp:798-811 */
+static double gln(double p, double x)
+{
+    const double q = 1.0 - p;
+    if (q == 0.0)
+        return log(x);
+    else if (fabs(q) < 1e-3)
+    {
+        double lnx = log(x);
+        double s = q * lnx;
+        return lnx * (1.0 + 0.5 * s + 1.0 / 6.0 * s * s + 1.0 / 24.0 * s * s * s);
+    }
+    else
+        return (pow(x, q) - 1.0) / q;
+}
+
 /* SpecialFunctions::lnmean(x1,x2,lnx1,lnx2), SpecialFunctions.cpp:860-880 */
 static double lnmean4(double x1, double x2, double lnx1, double lnx2)
 {
@@ -482,11 +509,13 @@ static void free_grid(sko_engine_t* e)
     e->grid_kind = 0;
 }
 
+static void free_secondary(sko_engine_t* e);
 void sko_destroy(sko_engine_t* e)
 {
     if (!e) return;
     free_instruments(e);
     free_sources(e);
+    free_secondary(e);
     free_wlg(e);
     free_grid(e);
     free(e->dens);
@@ -775,11 +804,47 @@ int sko_set_instruments(sko_engine_t* e, int32_t n, const sk_instrument_t* instr
     return SK_OK;
 }
 
+static void free_secondary(sko_engine_t* e)
+{
+    free(e->sec_T);
+    free(e->sec_planckabs);
+    free(e->sec_rfsig);
+    free(e->sec_emsig);
+    free(e->sec_lambda);
+    free(e->sec_pv);
+    free(e->sec_Pv);
+    free(e->sec_Lv);
+    free(e->sec_Wv);
+    free(e->sec_Iv);
+    e->sec_T = e->sec_planckabs = e->sec_rfsig = e->sec_emsig = e->sec_lambda = e->sec_pv = e->sec_Pv = NULL;
+    e->sec_Lv = e->sec_Wv = NULL;
+    e->sec_Iv = NULL;
+    e->has_secondary = e->secondary_ready = 0;
+}
+
 int sko_set_secondary(sko_engine_t* e, const sk_secondary_t* sec)
 {
-    (void)e;
-    (void)sec;
-    return fail(SK_ERR_UNSUPPORTED, "secondary emission not implemented in the oracle yet");
+    if (!e || !sec) return fail(SK_ERR_INVALID, "null argument");
+    if (e->rf_grid < 0) return fail(SK_ERR_STATE, "dust emission needs a radiation field grid");
+    if (sec->emission_grid < 0 || sec->emission_grid >= e->nwlg) return fail(SK_ERR_INVALID, "bad emission grid index");
+    if (sec->num_temperatures < 2 || !sec->temperature || !sec->planck_abs || !sec->rf_sigma_abs || !sec->em_sigma_abs)
+        return fail(SK_ERR_INVALID, "missing emission calculator tables");
+    free_secondary(e);
+    e->sec = *sec;
+    const sk_wavelength_grid_t* g = &e->wlg[sec->emission_grid].g;
+    int n = g->num_bins;
+    e->sec_nem = n + 2;
+    e->sec_T = dupd(sec->temperature, sec->num_temperatures);
+    e->sec_planckabs = dupd(sec->planck_abs, sec->num_temperatures);
+    e->sec_rfsig = dupd(sec->rf_sigma_abs, e->nrf);
+    e->sec_emsig = dupd(sec->em_sigma_abs, n + 2);
+    /* DisjointWavelengthGrid::extlambdav, DisjointWavelengthGrid.cpp:346-356 */
+    e->sec_lambda = (double*)malloc((n + 2) * sizeof(double));
+    e->sec_lambda[0] = g->borders[0];
+    for (int ell = 0; ell < n; ++ell) e->sec_lambda[ell + 1] = g->lambda[ell];
+    e->sec_lambda[n + 1] = g->borders[g->num_borders - 1];
+    e->has_secondary = 1;
+    return SK_OK;
 }
 
 int sko_clear_instruments(sko_engine_t* e)
@@ -836,12 +901,142 @@ int sko_prepare_primary(sko_engine_t* e, uint64_t num_packets)
     return SK_OK;
 }
 
+static int index_for_lambda(const sko_engine_t* e, double lambda);
+static double interp_loglog(double x, double x1, double x2, double f1, double f2);
+static double interp_linlin(double x, double x1, double x2, double f1, double f2);
+static double planck(double lambda, double T);
+static double gln(double p, double x);
+
+/* SecondarySourceSystem::prepareForLaunch (SecondarySourceSystem.cpp:84-126) for the single DustSecondarySource:
+ * DustSecondarySource::prepareLuminosities / preparePacketMap (DustSecondarySource.cpp:26-146) with the AllCellsLibrary
+ * mapping (identity, AllCellsLibrary.cpp:26-32), followed by the emission spectrum of every emitting cell, which the
+ * reference computes lazily: DustCellEmission::calculateSingleSpectrum (DustSecondarySource.cpp:277-285) =
+ * MediumSystem::dustEmissionSpectrum (MediumSystem.cpp:1466-1476) <- meanIntensity (:1370-1380) <- DustMix::emissionSpectrum
+ * (DustMix.cpp:650-653) <- EquilibriumDustEmissionCalculator::emissivity / equilibriumTemperature (.cpp:120-150), then
+ * NR::cdf<interpolateLogLog> over the range of the emission grid (NR.hpp:494-520, NR.cpp:25-60). */
 int sko_prepare_secondary(sko_engine_t* e, uint64_t num_packets, double* luminosity)
 {
-    (void)e;
-    (void)num_packets;
-    (void)luminosity;
-    return fail(SK_ERR_UNSUPPORTED, "secondary emission not implemented in the oracle yet");
+    if (!e || !luminosity) return fail(SK_ERR_INVALID, "null argument");
+    if (!e->has_secondary) return fail(SK_ERR_STATE, "call set_secondary first");
+    if (!num_packets) return fail(SK_ERR_INVALID, "zero packets");
+    const int M = e->ncells, nrf = e->nrf, nem = e->sec_nem;
+    const sk_wavelength_grid_t* rfg = &e->wlg[e->rf_grid].g;
+    if (!e->sec_Lv)
+    {
+        e->sec_Lv = (double*)calloc(M, sizeof(double));
+        e->sec_Wv = (double*)calloc(M, sizeof(double));
+        e->sec_Iv = (uint64_t*)calloc((size_t)M + 1, sizeof(uint64_t));
+        e->sec_pv = (double*)calloc((size_t)M * nem, sizeof(double));
+        e->sec_Pv = (double*)calloc((size_t)M * nem, sizeof(double));
+    }
+    /* luminosities 1: MediumSystem::dustLuminosity, MediumSystem.cpp:1452-1462 */
+    for (int m = 0; m < M; ++m)
+    {
+        double Labs = 0.;
+        for (int ell = 0; ell < nrf; ++ell)
+        {
+            double opacity = e->dens[m] * e->sig_abs[index_for_lambda(e, rfg->lambda[ell])];
+            double rf = 0.;
+            rf += e->rf1[(size_t)m * nrf + ell];
+            rf += e->rf2[(size_t)m * nrf + ell];
+            Labs += opacity * rf;
+        }
+        e->sec_Lv[m] = Labs;
+    }
+    /* luminosities 2 */
+    double L = 0.;
+    for (int m = 0; m < M; ++m) L += e->sec_Lv[m];
+    *luminosity = L;
+    e->secondary_ready = 0;
+    if (!L) return SK_OK; /* SecondarySourceSystem.cpp:93-94: the caller skips the segment */
+    for (int m = 0; m < M; ++m) e->sec_Lv[m] /= L;
+    /* preparePacketMap: composite-biased launch weights and the history index map (cells in launch order = cell order) */
+    double wsum = 0.;
+    for (int m = 0; m < M; ++m) wsum += e->sec_Lv[m] > 0 ? 1. : 0.;
+    double xi = e->sec.spatial_bias;
+    for (int m = 0; m < M; ++m)
+    {
+        double w = (e->sec_Lv[m] > 0 ? 1. : 0.) / wsum;
+        e->sec_Wv[m] = (1 - xi) * e->sec_Lv[m] + xi * w;
+    }
+    e->sec_Iv[0] = 0;
+    double W = 0.;
+    for (int p = 1; p != M; ++p)
+    {
+        W += e->sec_Wv[p - 1];
+        uint64_t idx = (uint64_t)round(W * (double)num_packets);
+        e->sec_Iv[p] = idx < num_packets ? idx : num_packets;
+    }
+    e->sec_Iv[M] = num_packets;
+    e->sec_Lpp = L / (double)num_packets; /* SecondarySourceSystem.cpp:119 with a single source of weight 1 */
+    /* the emission spectrum of every emitting cell */
+    const int nT = e->sec.num_temperatures;
+    for (int m = 0; m < M; ++m)
+    {
+        double* pv = e->sec_pv + (size_t)m * nem;
+        double* Pv = e->sec_Pv + (size_t)m * nem;
+        if (!(e->sec_Lv[m] > 0))
+        {
+            memset(pv, 0, nem * sizeof(double));
+            memset(Pv, 0, nem * sizeof(double));
+            continue;
+        }
+        /* meanIntensity + equilibriumTemperature */
+        double factor = 1. / (4. * M_PI * e->vol[m]);
+        double inputabs = 0.;
+        for (int ell = 0; ell < nrf; ++ell)
+        {
+            double rf = 0.;
+            rf += e->rf1[(size_t)m * nrf + ell];
+            rf += e->rf2[(size_t)m * nrf + ell];
+            double J = rf * factor / rfg->dlambda[ell];
+            inputabs += e->sec_rfsig[ell] * (J + 0.) * rfg->dlambda[ell];
+        }
+        double T = 0.;
+        if (inputabs > 0.)
+        {
+            /* NR::clampedValue<interpolateLinLin>(inputabs, _planckabsvv, _Tv), NR.hpp:391-399 with NR::locate */
+            int i = inputabs == e->sec_planckabs[nT - 1] ? nT - 2 : locate_basic(e->sec_planckabs, inputabs, nT);
+            if (i < 0)
+                T = e->sec_T[0];
+            else if (i >= nT - 1)
+                T = e->sec_T[nT - 1];
+            else
+                T = interp_linlin(inputabs, e->sec_planckabs[i], e->sec_planckabs[i + 1], e->sec_T[i], e->sec_T[i + 1]);
+        }
+        /* emissivity times number density on the extended emission grid */
+        for (int i = 0; i < nem; ++i) pv[i] = e->dens[m] * (e->sec_emsig[i] * planck(e->sec_lambda[i], T));
+        /* NR::cdf<interpolateLogLog>(xv,pv,Pv, extlambdav, ev, range of the grid): the range is [ext[0], ext[n+1]], so
+           the axis is the extended grid itself and the two outer values are the log-log interpolants evaluated at the
+           end points of the first and last interval */
+        {
+            const double* x = e->sec_lambda;
+            double first = interp_loglog(x[0], x[0], x[1], pv[0], pv[1]);
+            double last = interp_loglog(x[nem - 1], x[nem - 2], x[nem - 1], pv[nem - 2], pv[nem - 1]);
+            pv[0] = first;
+            pv[nem - 1] = last;
+            Pv[0] = 0.;
+            for (int i = 0; i != nem - 1; ++i)
+            {
+                double area = 0.;
+                if (pv[i] > 0 && pv[i + 1] > 0)
+                {
+                    double alpha = log(pv[i + 1] / pv[i]) / log(x[i + 1] / x[i]);
+                    area = pv[i] * x[i] * gln(-alpha, x[i + 1] / x[i]);
+                }
+                Pv[i + 1] = Pv[i] + area;
+            }
+            double norm = Pv[nem - 1];
+            if (norm > 0.)
+                for (int i = 0; i < nem; ++i)
+                {
+                    pv[i] /= norm;
+                    Pv[i] /= norm;
+                }
+        }
+    }
+    e->secondary_ready = 1;
+    return SK_OK;
 }
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -1669,6 +1864,92 @@ static void launch_primary(sko_engine_t* e, rng_t* g, uint64_t history, packet_t
     pp->ilam = index_for_lambda(e, lambda);
 }
 
+/* SecondarySourceSystem::launch (SecondarySourceSystem.cpp:130-142) + DustSecondarySource::launch
+ * (DustSecondarySource.cpp:511-581) without velocities and polarisation; cell box from the grid for
+ * SpatialGrid::randomPositionInCell (TreeSpatialGrid.cpp:125-128, CartesianSpatialGrid.cpp:80-83) + Random::position
+ * (Random.cpp:168-176) + Box::fracPos */
+static void cell_box(const sko_engine_t* e, int m, double b[6])
+{
+    if (e->grid_kind == 1)
+    {
+        int k = m % e->nz, j = (m / e->nz) % e->ny, i = m / (e->nz * e->ny);
+        b[0] = e->xv[i];
+        b[1] = e->yv[j];
+        b[2] = e->zv[k];
+        b[3] = e->xv[i + 1];
+        b[4] = e->yv[j + 1];
+        b[5] = e->zv[k + 1];
+    }
+    else
+        memcpy(b, e->node_box + 6 * (size_t)e->node_of_cell[m], 6 * sizeof(double));
+}
+
+static void launch_secondary(sko_engine_t* e, rng_t* g, uint64_t history, packet_t* pp)
+{
+    const int M = e->ncells, nem = e->sec_nem;
+    /* std::upper_bound(_Iv, historyIndex) - 1 */
+    int lo = 0, hi = M + 1;
+    while (lo < hi)
+    {
+        int mid = (lo + hi) >> 1;
+        if (history < e->sec_Iv[mid])
+            hi = mid;
+        else
+            lo = mid + 1;
+    }
+    int m = lo - 1; /* launch order = cell order for the AllCellsLibrary */
+    double ws = e->sec_Lv[m] / e->sec_Wv[m];
+    const double* xv = e->sec_lambda;
+    const double* pv = e->sec_pv + (size_t)m * nem;
+    const double* Pv = e->sec_Pv + (size_t)m * nem;
+    double lambda, w;
+    double xi = e->sec.wavelength_bias;
+    if (!xi)
+    {
+        lambda = sample_cdf_loglog(g, xv, pv, Pv, nem);
+        w = 1.;
+    }
+    else
+    {
+        double logMin = log(e->sec.bias_min);
+        double logWidth = log(e->sec.bias_max) - log(e->sec.bias_min);
+        if (uniform(g) > xi)
+            lambda = sample_cdf_loglog(g, xv, pv, Pv, nem);
+        else
+            lambda = exp(logMin + logWidth * uniform(g)); /* DefaultWavelengthDistribution.cpp:37-40 */
+        /* NR::value<interpolateLogLog>(lambda, _lambdav, _pv), NR.hpp:372-378 */
+        double sl = 0.;
+        int i = locate_fail(xv, nem, lambda);
+        if (i >= 0) sl = interp_loglog(lambda, xv[i], xv[i + 1], pv[i], pv[i + 1]);
+        if (!sl)
+            w = 0.;
+        else
+        {
+            double b;
+            if (lambda >= e->sec.bias_min * (1 - 1e-14) && lambda <= e->sec.bias_max * (1 + 1e-14))
+                b = 1. / (logWidth * lambda);
+            else
+                b = 0.;
+            w = sl / ((1 - xi) * sl + xi * b);
+        }
+    }
+    double box[6];
+    cell_box(e, m, box);
+    double ux = uniform(g), uy = uniform(g), uz = uniform(g);
+    pp->r[0] = box[0] + ux * (box[3] - box[0]); /* Box::fracPos, Box.hpp */
+    pp->r[1] = box[1] + uy * (box[4] - box[1]);
+    pp->r[2] = box[2] + uz * (box[5] - box[2]);
+    random_direction(g, pp->k);
+    double L = e->sec_Lpp * 1.; /* _Lv[s]/_Wv[s] = 1 for the single secondary source */
+    pp->lambda = lambda;
+    pp->W = (L * ws * w) * lambda;
+    pp->nscatt = 0;
+    pp->primary_origin = 0;
+    pp->history = history;
+    pp->has_tau = 0;
+    pp->ilam = index_for_lambda(e, lambda);
+}
+
 /* ------------------------------------------------------------------------------------------------ */
 /* the life cycle                                                                                   */
 /* ------------------------------------------------------------------------------------------------ */
@@ -1776,8 +2057,10 @@ static void life_cycle(sko_engine_t* e, uint64_t history, int primary, int peel,
     rng_init(&g, e->cfg.seed, stream_id, history);
     packet_t pp;
     memset(&pp, 0, sizeof pp);
-    launch_primary(e, &g, history, &pp);
-    (void)primary;
+    if (primary)
+        launch_primary(e, &g, history, &pp);
+    else
+        launch_secondary(e, &g, history, &pp);
     if (pp.W / pp.lambda > 0)
     {
         e->cnt.packets++;
@@ -1817,9 +2100,10 @@ int sko_run_segment(sko_engine_t* e, uint64_t first, uint64_t count, int32_t pri
                     uint32_t stream_id)
 {
     if (!e) return fail(SK_ERR_INVALID, "null engine");
-    if (!e->grid_kind || !e->dens || !e->nlam || !e->nsrc) return fail(SK_ERR_STATE, "engine is not fully configured");
-    if (!primary) return fail(SK_ERR_UNSUPPORTED, "secondary emission not implemented in the oracle yet");
-    if (!e->npackets) return fail(SK_ERR_STATE, "call prepare_primary first");
+    if (!e->grid_kind || !e->dens || !e->nlam) return fail(SK_ERR_STATE, "engine is not fully configured");
+    if (primary && !e->nsrc) return fail(SK_ERR_STATE, "engine is not fully configured");
+    if (primary && !e->npackets) return fail(SK_ERR_STATE, "call prepare_primary first");
+    if (!primary && !e->secondary_ready) return fail(SK_ERR_STATE, "call prepare_secondary first");
     if (store && e->rf_grid < 0) return fail(SK_ERR_STATE, "no radiation field grid configured");
     if (store && !e->cfg.force_scattering)
         return fail(SK_ERR_INVALID, "storing the radiation field requires forced scattering (Configuration.cpp:476-482)");

@@ -68,9 +68,9 @@ class SkInstrument(C.Structure):
 
 
 class SkSecondary(C.Structure):
-    _fields_ = [("emission_grid", C.c_int32), ("reserved", C.c_int32), ("spatial_bias", C.c_double),
+    _fields_ = [("emission_grid", C.c_int32), ("num_temperatures", C.c_int32), ("spatial_bias", C.c_double),
                 ("wavelength_bias", C.c_double), ("bias_min", C.c_double), ("bias_max", C.c_double),
-                ("source_min", C.c_double), ("source_max", C.c_double)]
+                ("temperature", _dp), ("planck_abs", _dp), ("rf_sigma_abs", _dp), ("em_sigma_abs", _dp)]
 
 
 class SkCounters(C.Structure):
@@ -264,8 +264,11 @@ class Engine:
             self._instr.append((self._wlg[q.wavelength_grid], q.num_pixels_x * q.num_pixels_y))
         self._call("set_instruments", self._h, C.c_int32(len(instruments)), arr, C.c_int32(int(has_medium_emission)))
 
-    def set_secondary(self, emission_grid, spatial_bias, wavelength_bias, bias_min, bias_max, source_min, source_max):
-        sec = SkSecondary(emission_grid, 0, spatial_bias, wavelength_bias, bias_min, bias_max, source_min, source_max)
+    def set_secondary(self, emission_grid, spatial_bias, wavelength_bias, bias_min, bias_max, temperature, planck_abs,
+                      rf_sigma_abs, em_sigma_abs):
+        keep = [_d(temperature), _d(planck_abs), _d(rf_sigma_abs), _d(em_sigma_abs)]
+        sec = SkSecondary(emission_grid, len(keep[0][0]), spatial_bias, wavelength_bias, bias_min, bias_max,
+                          keep[0][1], keep[1][1], keep[2][1], keep[3][1])
         self._call("set_secondary", self._h, C.byref(sec))
 
     # -- running --------------------------------------------------------------------------------

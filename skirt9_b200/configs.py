@@ -45,3 +45,25 @@ def cfg2(num_packets=1e8, max_level=9, max_dust_fraction=3.5e-6, seed=0, num_pix
                                   numPackets=num_packets, minWavelength=0.1e-6, maxWavelength=10e-6,
                                   defaultWavelengthGrid=wlg, storeRadiationField=False, numDensitySamples=20,
                                   seed=seed)
+
+
+def cfg4(num_packets=2e5, max_level=6, max_dust_fraction=2e-4, seed=0, min_level=3, num_sed_wavelengths=50,
+         max_secondary_iterations=5):
+    """dust emission with secondary-emission iterations; 1e4 Lsun 10 000 K point source in an r^-2 dust
+    shell with tau_Z(0.55 um) = 20, octree, RF grid 40 bins 0.1-1000 um, emission grid 60 bins 1-1000 um,
+    SEDInstrument with components.  (BASELINE.json configs[3] scales the tree to ~1e6 cells: max_level=8,
+    max_dust_fraction~3e-6.)"""
+    pc = H.PC
+    mix = H.MeanListDustMix([0.05e-6, 0.55e-6, 10e-6, 100e-6, 2000e-6], [5000.0, 1000.0, 100.0, 5.0, 0.01],
+                            [0.4, 0.6, 0.2, 0.01, 0.0001], [0.6, 0.5, 0.05, 0.0, 0.0])
+    medium = H.GeometricMedium(H.ShellGeometry(0.01 * pc, 1.0 * pc, 2.0), mix, opticalDepth=20.0, wavelength=0.55e-6)
+    grid = H.PolicyTreeSpatialGrid(-pc, pc, -pc, pc, -pc, pc, H.DensityTreePolicy(min_level, max_level, max_dust_fraction))
+    src = H.PointSource((0.0, 0.0, 0.0), H.BlackBodySED(10000.0), luminosity=1e4 * H.LSUN)
+    instr = H.SEDInstrument(instrumentName="sed", distance=1e6 * pc, inclination=60 * DEG, recordComponents=True)
+    return H.MonteCarloSimulation(sources=[src], medium=medium, grid=grid, instruments=[instr], numPackets=num_packets,
+                                  minWavelength=0.1e-6, maxWavelength=20e-6,
+                                  defaultWavelengthGrid=H.LogWavelengthGrid(0.1e-6, 1000e-6, num_sed_wavelengths),
+                                  storeRadiationField=True, radiationFieldWLG=H.LogWavelengthGrid(0.1e-6, 1000e-6, 40),
+                                  dustEmissionWLG=H.LogWavelengthGrid(1e-6, 1000e-6, 60), iterateSecondaryEmission=True,
+                                  minSecondaryIterations=1, maxSecondaryIterations=max_secondary_iterations,
+                                  numDensitySamples=20, seed=seed)

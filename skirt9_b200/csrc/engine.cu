@@ -3,13 +3,15 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
 #include <vector>
 
-#include "sk_lifecycle.cuh"
+#include "sk_secondary.cuh"
+#include "sk_wavefront.cuh"
 
 // ---------------------------------------------------------------------------------------------------
 // error plumbing
@@ -40,61 +42,6 @@ extern "C" int sk_abi_version(void)
 // ---------------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------------
-#ifndef SK_BLOCK
-#define SK_BLOCK 128
-#endif
-#ifndef SK_MINBLOCKS
-#define SK_MINBLOCKS 4
-#endif
-#define SK_WARPS_PER_BLOCK (SK_BLOCK / 32)
-
-template <int GRID>
-__global__ void __launch_bounds__(SK_BLOCK, SK_MINBLOCKS) sk_life_cycle_kernel(const SkDevModel M, const SkRunArgs A)
-{
-    extern __shared__ double smem[];
-    SkSmemTables T;
-    const int n0 = (GRID == 1 ? M.nx : M.nx) + 1, n1 = (GRID == 1 ? M.ny : M.nx) + 1, n2 = (GRID == 1 ? M.nz : M.nx) + 1;
-    int* lists;
-    if (M.lattice_in_smem)
-    {
-        // stage the per-axis border tables (Cartesian borders / octree lattice) in shared memory
-        for (int i = threadIdx.x; i < n0; i += blockDim.x) smem[i] = M.xv[i];
-        for (int i = threadIdx.x; i < n1; i += blockDim.x) smem[n0 + i] = M.yv[i];
-        for (int i = threadIdx.x; i < n2; i += blockDim.x) smem[n0 + n1 + i] = M.zv[i];
-        T.X = smem;
-        T.Y = smem + n0;
-        T.Z = smem + n0 + n1;
-        lists = reinterpret_cast<int*>(smem + n0 + n1 + n2);
-    }
-    else
-    {
-        T.X = M.xv;
-        T.Y = M.yv;
-        T.Z = M.zv;
-        lists = reinterpret_cast<int*>(smem);
-    }
-    __syncthreads();
-    const int warp_in_block = threadIdx.x >> 5;
-    const size_t warp_global = (size_t)blockIdx.x * SK_WARPS_PER_BLOCK + warp_in_block;
-    SkPoolView P;
-    P.d = A.pool_d + warp_global * (size_t)(SK_ND * SK_POOL);
-    P.i = A.pool_i + warp_global * (size_t)(SK_NI * SK_POOL);
-    int* list = lists + warp_in_block * SK_POOL;
-
-    SkLocalCounters cnt;
-    memset(&cnt, 0, sizeof cnt);
-    sk_warp_life_cycles<GRID>(M, A.model, T, A, P, list, cnt);
-
-    // counters: warp reduce, one atomic per warp and counter
-    unsigned int* c = reinterpret_cast<unsigned int*>(&cnt);
-#pragma unroll
-    for (int i = 0; i < (int)(sizeof(SkLocalCounters) / sizeof(unsigned int)); ++i)
-    {
-        unsigned int v = __reduce_add_sync(0xffffffffu, c[i]);
-        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&M.counters[i], (unsigned long long)v);
-    }
-}
-
 // MediumSystem::totalDustAbsorbedLuminosity, MediumSystem.cpp:1317-1356 (single dust medium, constant sections)
 __global__ void sk_absorbed_kernel(const double* __restrict__ rf, const double* __restrict__ dens_or_null,
                                    const SkCellRec* __restrict__ cells, const double* __restrict__ kabs, int ncells,
@@ -130,7 +77,7 @@ struct sk_engine {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     SkDevModel M;
     // owned device allocations by group
-    std::vector<void*> grid_allocs, medium_allocs, dust_allocs, wlg_allocs, src_allocs, instr_allocs, rf_allocs;
+    std::vector<void*> grid_allocs, medium_allocs, dust_allocs, wlg_allocs, src_allocs, instr_allocs, rf_allocs, sec_allocs;
     // host mirrors
     int grid_kind = 0;
     int grid_cells = 0;
@@ -139,6 +86,7 @@ struct sk_engine {
     std::vector<double> dust_lam_border, dust_sig_abs;
     std::vector<sk_wavelength_grid_t> wlg_host;
     std::vector<std::vector<double>> wlg_lambda;
+    std::vector<double> wlg_border_lo, wlg_border_hi;
     std::vector<double> Lv, Wv;
     double Ltot = 0.;
     uint64_t npackets = 0;
@@ -148,15 +96,23 @@ struct sk_engine {
     double* stat_block = nullptr;
     size_t stat_count = 0;
     unsigned long long* work_counter = nullptr;
-    double* pool_d = nullptr;
-    int32_t* pool_i = nullptr;
+    SkBank bank = {nullptr, nullptr, nullptr, nullptr, 0};  // the in-flight packets (sk_wavefront.cuh)
+    int bank_fields_d = 0, bank_fields_i = 0;
+    unsigned int* ctl_host = nullptr;                       // pinned copy of the control words + work counter
+    cudaEvent_t ev_ctl = nullptr;
     SkDevModel* model_dev = nullptr;
-    size_t pool_warps = 0;
+    int num_sms = 0;
     double* scalar = nullptr;
     int table_len[3] = {0, 0, 0};
     size_t smem_bytes = 0;
     float last_ms = 0.f;
     bool timing_pending = false;
+    std::vector<int> instr_same_observer;
+    std::vector<std::array<double, 3>> instr_kobs;
+    bool secondary_ready = false, has_secondary = false;
+    sk_secondary_t sec;
+    std::vector<double> sec_Lv_host;
+    unsigned long long rounds_last = 0;
 };
 
 static void free_group(std::vector<void*>& v)
@@ -226,9 +182,14 @@ extern "C" void sk_engine_destroy(sk_engine_t* e)
     free_group(e->src_allocs);
     free_group(e->instr_allocs);
     free_group(e->rf_allocs);
+    free_group(e->sec_allocs);
     cudaFree(e->work_counter);
-    cudaFree(e->pool_d);
-    cudaFree(e->pool_i);
+    cudaFree(e->bank.d);
+    cudaFree(e->bank.i);
+    cudaFree(e->bank.list);
+    cudaFree(e->bank.ctl);
+    cudaFreeHost(e->ctl_host);
+    if (e->ev_ctl) cudaEventDestroy(e->ev_ctl);
     cudaFree(e->model_dev);
     cudaFree(e->scalar);
     cudaFree(e->M.counters);
@@ -410,7 +371,6 @@ extern "C" int sk_engine_set_grid_octree(sk_engine_t* e, const double extent[6],
 extern "C" int sk_engine_set_medium(sk_engine_t* e, int32_t num_cells, const double* number_density,
                                     const double* volume)
 {
-    (void)volume;
     if (!e || !number_density) return fail(SK_ERR_INVALID, "null argument");
     if (!e->grid_kind) return fail(SK_ERR_STATE, "set the grid before the medium");
     if (num_cells != e->grid_cells) return fail(SK_ERR_INVALID, "medium size does not match the grid");
@@ -433,6 +393,13 @@ extern "C" int sk_engine_set_medium(sk_engine_t* e, int32_t num_cells, const dou
         e->M.dens = nullptr;
     }
     e->M.ncells = num_cells;
+    e->M.volume = nullptr;
+    if (volume)
+    {
+        double* v;
+        if (int rc = upload(e->medium_allocs, volume, (size_t)num_cells, &v)) return rc;
+        e->M.volume = v;
+    }
     return SK_OK;
 }
 
@@ -472,6 +439,8 @@ extern "C" int sk_engine_set_wavelength_grids(sk_engine_t* e, int32_t n, const s
     std::vector<SkDevWlg> dev(n ? n : 1);
     e->wlg_host.assign(grids, grids + n);
     e->wlg_lambda.clear();
+    e->wlg_border_lo.clear();
+    e->wlg_border_hi.clear();
     for (int i = 0; i < n; ++i)
     {
         double *b, *l, *d;
@@ -487,6 +456,8 @@ extern "C" int sk_engine_set_wavelength_grids(sk_engine_t* e, int32_t n, const s
         dev[i].lambda = l;
         dev[i].dlambda = d;
         e->wlg_lambda.emplace_back(grids[i].lambda, grids[i].lambda + grids[i].num_bins);
+        e->wlg_border_lo.push_back(grids[i].borders[0]);
+        e->wlg_border_hi.push_back(grids[i].borders[grids[i].num_borders - 1]);
     }
     SkDevWlg* dw;
     if (int rc = upload(e->wlg_allocs, dev.data(), dev.size(), &dw)) return rc;
@@ -722,6 +693,13 @@ extern "C" int sk_engine_set_instruments(sk_engine_t* e, int32_t n, const sk_ins
         }
         for (int k = 0; k < 5; ++k) v.wsed[k] = q.wsed_off[k] >= 0 ? e->stat_block + q.wsed_off[k] : nullptr;
     }
+    e->instr_same_observer.assign(n, 0);
+    e->instr_kobs.assign(n, std::array<double, 3>{0., 0., 1.});
+    for (int i = 0; i < n; ++i)
+    {
+        e->instr_same_observer[i] = dev[i].same_as_preceding;
+        e->instr_kobs[i] = {dev[i].kobs[0], dev[i].kobs[1], dev[i].kobs[2]};
+    }
     SkDevInstr* di;
     if (int rc = upload(e->instr_allocs, dev.data(), dev.size(), &di)) return rc;
     e->M.instr = di;
@@ -729,11 +707,73 @@ extern "C" int sk_engine_set_instruments(sk_engine_t* e, int32_t n, const sk_ins
     return SK_OK;
 }
 
+// nearest-grid-point lookup of the dust mix: DustMix::indexForLambda = NR::locateClip(_lambdav, lambda), DustMix.cpp:276-279
+static int dust_index_for_lambda(const sk_engine* e, double lambda)
+{
+    const std::vector<double>& b = e->dust_lam_border;
+    int n = (int)b.size();
+    if (lambda < b[0]) return 0;
+    int jl = -1, ju = n - 1;
+    while (ju - jl > 1)
+    {
+        int jm = (ju + jl) >> 1;
+        if (lambda < b[jm])
+            ju = jm;
+        else
+            jl = jm;
+    }
+    return jl;
+}
+
 extern "C" int sk_engine_set_secondary(sk_engine_t* e, const sk_secondary_t* sec)
 {
-    (void)e;
-    (void)sec;
-    return fail(SK_ERR_UNSUPPORTED, "secondary emission is not implemented yet");
+    if (!e || !sec) return fail(SK_ERR_INVALID, "null argument");
+    if (e->M.rf_grid < 0) return fail(SK_ERR_STATE, "dust emission needs a radiation field grid");
+    if (!e->M.volume) return fail(SK_ERR_STATE, "dust emission needs the cell volumes (sk_engine_set_medium)");
+    if (!e->M.nlam) return fail(SK_ERR_STATE, "set the dust mix before the secondary emission tables");
+    if (sec->emission_grid < 0 || sec->emission_grid >= e->M.nwlg) return fail(SK_ERR_INVALID, "bad emission grid index");
+    if (sec->num_temperatures < 2 || !sec->temperature || !sec->planck_abs || !sec->rf_sigma_abs || !sec->em_sigma_abs)
+        return fail(SK_ERR_INVALID, "missing emission calculator tables");
+    CK(cudaSetDevice(e->cfg.device));
+    free_group(e->sec_allocs);
+    e->sec = *sec;
+    const sk_wavelength_grid_t& g = e->wlg_host[sec->emission_grid];
+    const std::vector<double>& glam = e->wlg_lambda[sec->emission_grid];
+    const int n = g.num_bins, nem = n + 2, nrf = e->M.nrf, nc = e->M.ncells;
+    // DisjointWavelengthGrid::extlambdav, DisjointWavelengthGrid.cpp:346-356
+    std::vector<double> ext(nem);
+    ext[0] = e->wlg_border_lo[sec->emission_grid];
+    for (int ell = 0; ell < n; ++ell) ext[ell + 1] = glam[ell];
+    ext[nem - 1] = e->wlg_border_hi[sec->emission_grid];
+    std::vector<double> kabs(nrf);
+    const std::vector<double>& rflam = e->wlg_lambda[e->M.rf_grid];
+    for (int ell = 0; ell < nrf; ++ell) kabs[ell] = e->dust_sig_abs[dust_index_for_lambda(e, rflam[ell])];
+    double *a, *b, *c, *d, *f, *k;
+    if (int rc = upload(e->sec_allocs, ext.data(), (size_t)nem, &a)) return rc;
+    if (int rc = upload(e->sec_allocs, sec->em_sigma_abs, (size_t)nem, &b)) return rc;
+    if (int rc = upload(e->sec_allocs, sec->rf_sigma_abs, (size_t)nrf, &c)) return rc;
+    if (int rc = upload(e->sec_allocs, sec->temperature, (size_t)sec->num_temperatures, &d)) return rc;
+    if (int rc = upload(e->sec_allocs, sec->planck_abs, (size_t)sec->num_temperatures, &f)) return rc;
+    if (int rc = upload(e->sec_allocs, kabs.data(), (size_t)nrf, &k)) return rc;
+    e->M.sec_nem = nem;
+    e->M.sec_nT = sec->num_temperatures;
+    e->M.sec_lambda = a;
+    e->M.sec_emsig = b;
+    e->M.sec_rfsig = c;
+    e->M.sec_T = d;
+    e->M.sec_planckabs = f;
+    e->M.sec_kabs_rf = k;
+    if (int rc = dalloc_zero(e->sec_allocs, (size_t)nc * nem, &e->M.sec_pv)) return rc;
+    if (int rc = dalloc_zero(e->sec_allocs, (size_t)nc * nem, &e->M.sec_Pv)) return rc;
+    if (int rc = dalloc_zero(e->sec_allocs, (size_t)nc, &e->M.sec_Lv)) return rc;
+    if (int rc = dalloc_zero(e->sec_allocs, (size_t)nc, &e->M.sec_ws)) return rc;
+    if (int rc = dalloc_zero(e->sec_allocs, (size_t)nc + 1, &e->M.sec_Iv)) return rc;
+    e->M.sec_xi = sec->wavelength_bias;
+    e->M.sec_bias_min = sec->bias_min;
+    e->M.sec_bias_max = sec->bias_max;
+    e->has_secondary = true;
+    e->secondary_ready = false;
+    return SK_OK;
 }
 
 extern "C" int sk_engine_clear_instruments(sk_engine_t* e)
@@ -795,75 +835,237 @@ extern "C" int sk_engine_prepare_primary(sk_engine_t* e, uint64_t num_packets)
     return SK_OK;
 }
 
+// SecondarySourceSystem::prepareForLaunch (SecondarySourceSystem.cpp:84-126) for the single DustSecondarySource:
+// prepareLuminosities / preparePacketMap (DustSecondarySource.cpp:26-146).  The per-cell luminosities and spectra are
+// computed on the device; the cumulative weights are summed sequentially on the host in the reference's order so that the
+// history-index map _Iv is the reference's (it rounds W*N, DustSecondarySource.cpp:136-145).
 extern "C" int sk_engine_prepare_secondary(sk_engine_t* e, uint64_t num_packets, double* luminosity)
 {
-    (void)e;
-    (void)num_packets;
-    (void)luminosity;
-    return fail(SK_ERR_UNSUPPORTED, "secondary emission is not implemented yet");
+    if (!e || !luminosity) return fail(SK_ERR_INVALID, "null argument");
+    if (!e->has_secondary) return fail(SK_ERR_STATE, "call sk_engine_set_secondary first");
+    if (!num_packets) return fail(SK_ERR_INVALID, "zero packets");
+    CK(cudaSetDevice(e->cfg.device));
+    const int M = e->M.ncells;
+    const unsigned blocks = (unsigned)((M + 127) / 128);
+    if (e->grid_kind == 1)
+        sk_dust_luminosity_kernel<1><<<blocks, 128, 0, e->stream>>>(e->M);
+    else
+        sk_dust_luminosity_kernel<2><<<blocks, 128, 0, e->stream>>>(e->M);
+    CK(cudaGetLastError());
+    std::vector<double>& Lv = e->sec_Lv_host;
+    Lv.resize(M);
+    CK(cudaMemcpyAsync(Lv.data(), e->M.sec_Lv, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    double L = 0.;
+    for (int m = 0; m < M; ++m) L += Lv[m];
+    *luminosity = L;
+    e->secondary_ready = false;
+    if (!L) return SK_OK;
+    for (int m = 0; m < M; ++m) Lv[m] /= L;
+    double wsum = 0.;
+    for (int m = 0; m < M; ++m) wsum += Lv[m] > 0 ? 1. : 0.;
+    const double xi = e->sec.spatial_bias;
+    std::vector<double> ws(M);
+    std::vector<unsigned long long> Iv((size_t)M + 1);
+    Iv[0] = 0;
+    double W = 0.;
+    for (int m = 0; m < M; ++m)
+    {
+        double w = (Lv[m] > 0 ? 1. : 0.) / wsum;
+        double Wm = (1 - xi) * Lv[m] + xi * w;
+        ws[m] = Wm > 0 ? Lv[m] / Wm : 0.;
+        if (m + 1 != M)
+        {
+            W += Wm;
+            unsigned long long idx = (unsigned long long)std::round(W * (double)num_packets);
+            Iv[m + 1] = std::min<unsigned long long>(idx, num_packets);
+        }
+    }
+    Iv[M] = num_packets;
+    CK(cudaMemcpyAsync(e->M.sec_Lv, Lv.data(), (size_t)M * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->M.sec_ws, ws.data(), (size_t)M * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->M.sec_Iv, Iv.data(), ((size_t)M + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice,
+                       e->stream));
+    if (e->grid_kind == 1)
+        sk_emission_spectrum_kernel<1><<<blocks, 128, 0, e->stream>>>(e->M);
+    else
+        sk_emission_spectrum_kernel<2><<<blocks, 128, 0, e->stream>>>(e->M);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->stream));
+    e->M.sec_Lpp = L / (double)num_packets;  // SecondarySourceSystem.cpp:119
+    e->secondary_ready = true;
+    return SK_OK;
 }
 
-static int g_num_sms = 0;
+// ---------------------------------------------------------------------------------------------------
+// the segment driver: performLifeCycle(firstIndex, numIndices, primary, peel, store) over the bank
+// ---------------------------------------------------------------------------------------------------
+static size_t bank_capacity_limit()
+{
+    // in-flight packets per GPU; ~230 B of state each.  SK_BANK overrides (tests use small banks to exercise refill).
+    const char* s = getenv("SK_BANK");
+    long long v = s ? atoll(s) : 0;
+    return v > 0 ? (size_t)v : (size_t)1 << 23;
+}
+
+static int ensure_bank(sk_engine* e, uint64_t count)
+{
+    size_t cap = std::min<uint64_t>(count, bank_capacity_limit());
+    cap = std::max<size_t>((cap + 255) / 256 * 256, 256);
+    const int nd = D_HISTW0 + std::max(e->M.ninstr, 1), ni = I_HELL0 + std::max(e->M.ninstr, 1);
+    if ((size_t)e->bank.cap >= cap && e->bank_fields_d == nd && e->bank_fields_i == ni) return SK_OK;
+    cudaFree(e->bank.d);
+    cudaFree(e->bank.i);
+    cudaFree(e->bank.list);
+    e->bank.d = nullptr;
+    e->bank.i = nullptr;
+    e->bank.list = nullptr;
+    e->bank.cap = 0;
+    CK(cudaMalloc(&e->bank.d, cap * nd * sizeof(double)));
+    CK(cudaMalloc(&e->bank.i, cap * ni * sizeof(int32_t)));
+    CK(cudaMalloc(&e->bank.list, cap * sizeof(int32_t)));
+    if (!e->bank.ctl) CK(cudaMalloc(&e->bank.ctl, SK_CTL_WORDS * sizeof(unsigned int)));
+    if (!e->ctl_host) CK(cudaMallocHost(&e->ctl_host, (SK_CTL_WORDS + 2) * sizeof(unsigned int)));
+    if (!e->ev_ctl) CK(cudaEventCreateWithFlags(&e->ev_ctl, cudaEventDisableTiming));
+    e->bank.cap = (int32_t)cap;
+    e->bank_fields_d = nd;
+    e->bank_fields_i = ni;
+    return SK_OK;
+}
+
+template <int GRID, int MODE, bool STORE>
+static int launch_trace(sk_engine* e, const SkRunArgs& A, const SkRayDir& dir)
+{
+    auto kern = sk_wf_trace<GRID, MODE, STORE>;
+    // occupancy of this instantiation for this engine's shared-memory footprint (cached per footprint)
+    static size_t cached_smem = (size_t)-1;
+    static int per_sm = 0;
+    const size_t smem = e->smem_bytes;
+    if (cached_smem != smem)
+    {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1)));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SK_TRACE_BLOCK, smem));
+        if (per_sm < 1) per_sm = 1;
+        cached_smem = smem;
+    }
+    // persistent grid: every SM filled to the occupancy this kernel gets, but no more warps than chunks of rays
+    unsigned long long chunks = ((unsigned long long)e->bank.cap + SK_CHUNK - 1) / SK_CHUNK;
+    unsigned long long blocks = (chunks + (SK_TRACE_BLOCK / 32) - 1) / (SK_TRACE_BLOCK / 32);
+    unsigned grid = (unsigned)std::min<unsigned long long>((unsigned long long)e->num_sms * per_sm, std::max<unsigned long long>(blocks, 1));
+    CK(cudaMemsetAsync(&e->bank.ctl[SK_CTL_CURSOR], 0, sizeof(unsigned int), e->stream));
+    kern<<<grid, SK_TRACE_BLOCK, smem, e->stream>>>(e->M, A, e->bank, dir);
+    CK(cudaGetLastError());
+    return SK_OK;
+}
+
+template <int GRID>
+static int run_bank(sk_engine* e, const SkRunArgs& A)
+{
+    const SkDevModel& M = e->M;
+    const SkBank& K = e->bank;
+    const unsigned eblocks = (unsigned)((K.cap + SK_EVENT_BLOCK - 1) / SK_EVENT_BLOCK);
+    // observer groups: consecutive instruments that share the observer (Instrument.hpp:107) share one peel-off ray
+    std::vector<std::pair<int, int>> groups;
+    if (A.peel)
+        for (int j0 = 0; j0 < (int)e->instr.size();)
+        {
+            int j1 = j0 + 1;
+            while (j1 < (int)e->instr.size() && e->instr_same_observer[j1]) j1++;
+            groups.emplace_back(j0, j1);
+            j0 = j1;
+        }
+    SkRayDir nodir;
+    nodir.set(0., 0., 1.);
+    CK(cudaMemsetAsync(K.i + (size_t)I_STATE * K.cap, 0, (size_t)K.cap * sizeof(int32_t), e->stream));
+    for (unsigned long long round = 0;; ++round)
+    {
+        CK(cudaMemsetAsync(K.ctl, 0, SK_CTL_WORDS * sizeof(unsigned int), e->stream));
+        const int g0a = groups.empty() ? 0 : groups[0].first, g0b = groups.empty() ? 0 : groups[0].second;
+        sk_wf_advance<GRID><<<eblocks, SK_EVENT_BLOCK, 0, e->stream>>>(M, A, K, g0a, g0b);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(e->ctl_host, K.ctl, SK_CTL_WORDS * sizeof(unsigned int), cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaMemcpyAsync(e->ctl_host + SK_CTL_WORDS, A.work_counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                           e->stream));
+        CK(cudaEventRecord(e->ev_ctl, e->stream));
+        // the rest of the round is enqueued before the census is looked at, so the device never waits for the host
+        if (groups.empty())
+        {
+            sk_wf_detect<<<eblocks, SK_EVENT_BLOCK, 0, e->stream>>>(M, A, K, 0, 0, 1);
+            CK(cudaGetLastError());
+        }
+        for (size_t gi = 0; gi < groups.size(); ++gi)
+        {
+            const int j0 = groups[gi].first, j1 = groups[gi].second;
+            if (gi > 0)
+            {
+                CK(cudaMemsetAsync(&K.ctl[SK_CTL_NLIST], 0, sizeof(unsigned int), e->stream));
+                sk_wf_peel_setup<<<eblocks, SK_EVENT_BLOCK, 0, e->stream>>>(M, K, j0, j1);
+                CK(cudaGetLastError());
+            }
+            SkRayDir obs;
+            obs.set(e->instr_kobs[j0][0], e->instr_kobs[j0][1], e->instr_kobs[j0][2]);
+            if (int rc = launch_trace<GRID, 2, false>(e, A, obs)) return rc;
+            const int last = gi + 1 == groups.size();
+            if (last) CK(cudaMemsetAsync(&K.ctl[SK_CTL_NLIST], 0, sizeof(unsigned int), e->stream));
+            sk_wf_detect<<<eblocks, SK_EVENT_BLOCK, 0, e->stream>>>(M, A, K, j0, j1, last);
+            CK(cudaGetLastError());
+        }
+        if (M.force_scattering)
+        {
+            if (int rc = A.store ? launch_trace<GRID, 0, true>(e, A, nodir) : launch_trace<GRID, 0, false>(e, A, nodir))
+                return rc;
+        }
+        CK(cudaMemsetAsync(&K.ctl[SK_CTL_NLIST], 0, sizeof(unsigned int), e->stream));
+        sk_wf_sample<<<eblocks, SK_EVENT_BLOCK, 0, e->stream>>>(M, A, K);
+        CK(cudaGetLastError());
+        if (int rc = launch_trace<GRID, 1, false>(e, A, nodir)) return rc;
+        // census of this round: stop when the bank is empty and every history has been handed out
+        CK(cudaEventSynchronize(e->ev_ctl));
+        unsigned long long dispensed;
+        memcpy(&dispensed, e->ctl_host + SK_CTL_WORDS, sizeof dispensed);
+        if (e->ctl_host[SK_CTL_NLIVE] == 0 && dispensed >= A.count) break;
+    }
+    e->rounds_last = 0;
+    return SK_OK;
+}
 
 extern "C" int sk_engine_launch_segment(sk_engine_t* e, uint64_t first, uint64_t count, int32_t primary,
                                         int32_t peel, int32_t store, uint32_t stream_id)
 {
     if (!e) return fail(SK_ERR_INVALID, "null engine");
-    if (!e->grid_kind || !e->M.ncells || !e->M.nlam || !e->M.nsrc)
-        return fail(SK_ERR_STATE, "engine is not fully configured");
-    if (!primary) return fail(SK_ERR_UNSUPPORTED, "secondary emission is not implemented yet");
-    if (!e->npackets) return fail(SK_ERR_STATE, "call sk_engine_prepare_primary first");
+    if (!e->grid_kind || !e->M.ncells || !e->M.nlam) return fail(SK_ERR_STATE, "engine is not fully configured");
+    if (primary && !e->M.nsrc) return fail(SK_ERR_STATE, "engine is not fully configured");
+    if (primary && !e->npackets) return fail(SK_ERR_STATE, "call sk_engine_prepare_primary first");
+    if (!primary && !e->secondary_ready) return fail(SK_ERR_STATE, "call sk_engine_prepare_secondary first");
     if (store && e->M.rf_grid < 0) return fail(SK_ERR_STATE, "no radiation field grid configured");
     if (store && !e->M.force_scattering)
         return fail(SK_ERR_INVALID, "storing the radiation field requires forced scattering (Configuration.cpp:476-482)");
     CK(cudaSetDevice(e->cfg.device));
-    if (!g_num_sms)
+    if (!e->num_sms)
     {
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, e->cfg.device));
-        g_num_sms = prop.multiProcessorCount;
+        e->num_sms = prop.multiProcessorCount;
     }
-    SkRunArgs A;
-    A.first = first;
-    A.count = count;
-    A.primary = primary;
-    A.peel = peel;
-    A.store = store;
-    A.stream_id = stream_id;
-    A.work_counter = e->work_counter;
-    CK(cudaMemsetAsync(e->work_counter, 0, sizeof(unsigned long long), e->stream));
-    // persistent grid: a multiple of the SM count, sized by the occupancy the kernel actually gets; every warp owns a
-    // pool of SK_POOL in-flight packets
-    int per_sm = 0;
-    auto kern = e->grid_kind == 1 ? sk_life_cycle_kernel<1> : sk_life_cycle_kernel<2>;
-    size_t smem = e->smem_bytes + (size_t)SK_WARPS_PER_BLOCK * SK_POOL * sizeof(int);
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SK_BLOCK, smem));
-    if (per_sm < 1) per_sm = 1;
-    unsigned long long warps_needed = (count + SK_POOL - 1) / SK_POOL;
-    unsigned long long blocks_needed = (warps_needed + SK_WARPS_PER_BLOCK - 1) / SK_WARPS_PER_BLOCK;
-    unsigned long long grid = std::min<unsigned long long>((unsigned long long)g_num_sms * per_sm,
-                                                           std::max<unsigned long long>(blocks_needed, 1));
-    size_t warps = (size_t)grid * SK_WARPS_PER_BLOCK;
-    if (warps > e->pool_warps)
-    {
-        cudaFree(e->pool_d);
-        cudaFree(e->pool_i);
-        e->pool_d = nullptr;
-        e->pool_i = nullptr;
-        e->pool_warps = 0;
-        CK(cudaMalloc(&e->pool_d, warps * (size_t)(SK_ND * SK_POOL) * sizeof(double)));
-        CK(cudaMalloc(&e->pool_i, warps * (size_t)(SK_NI * SK_POOL) * sizeof(int32_t)));
-        e->pool_warps = warps;
-    }
-    A.pool_d = e->pool_d;
-    A.pool_i = e->pool_i;
-    if (!e->model_dev) CK(cudaMalloc(&e->model_dev, sizeof(SkDevModel)));
-    CK(cudaMemcpyAsync(e->model_dev, &e->M, sizeof(SkDevModel), cudaMemcpyHostToDevice, e->stream));
-    A.model = e->model_dev;
     CK(cudaEventRecord(e->ev0, e->stream));
-    kern<<<(unsigned)grid, SK_BLOCK, smem, e->stream>>>(e->M, A);
-    CK(cudaGetLastError());
+    if (count)
+    {
+        if (int rc = ensure_bank(e, count)) return rc;
+        SkRunArgs A;
+        A.first = first;
+        A.count = count;
+        A.primary = primary;
+        A.peel = peel && !e->instr.empty();
+        A.store = store;
+        A.stream_id = stream_id;
+        A.work_counter = e->work_counter;
+        CK(cudaMemsetAsync(e->work_counter, 0, sizeof(unsigned long long), e->stream));
+        if (!e->model_dev) CK(cudaMalloc(&e->model_dev, sizeof(SkDevModel)));
+        CK(cudaMemcpyAsync(e->model_dev, &e->M, sizeof(SkDevModel), cudaMemcpyHostToDevice, e->stream));
+        A.model = e->model_dev;
+        int rc = e->grid_kind == 1 ? run_bank<1>(e, A) : run_bank<2>(e, A);
+        if (rc) return rc;
+    }
     CK(cudaEventRecord(e->ev1, e->stream));
     e->timing_pending = true;
     return SK_OK;
@@ -917,28 +1119,7 @@ extern "C" int sk_engine_absorbed_luminosity(sk_engine_t* e, int32_t primary, do
     // kappa_abs per RF bin: DustMix::sectionAbs(lambda_ell) = _sigmaabsv[indexForLambda(lambda_ell)]
     const std::vector<double>& lam = e->wlg_lambda[e->M.rf_grid];
     std::vector<double> kabs(lam.size());
-    for (size_t i = 0; i < lam.size(); ++i)
-    {
-        const std::vector<double>& b = e->dust_lam_border;
-        int n = (int)b.size();
-        int idx;
-        if (lam[i] < b[0])
-            idx = 0;
-        else
-        {
-            int jl = -1, ju = n - 1;
-            while (ju - jl > 1)
-            {
-                int jm = (ju + jl) >> 1;
-                if (lam[i] < b[jm])
-                    ju = jm;
-                else
-                    jl = jm;
-            }
-            idx = jl;
-        }
-        kabs[i] = e->dust_sig_abs[idx];
-    }
+    for (size_t i = 0; i < lam.size(); ++i) kabs[i] = e->dust_sig_abs[dust_index_for_lambda(e, lam[i])];
     double* dk = nullptr;
     CK(cudaMalloc(&dk, kabs.size() * sizeof(double)));
     CK(cudaMemcpyAsync(dk, kabs.data(), kabs.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));

@@ -1,0 +1,651 @@
+// sk_blocks.cuh -- building blocks of the photon life cycle on the device: the pieces of
+// MonteCarloSimulation::performLifeCycle (SKIRT/core/MonteCarloSimulation.cpp:538-613) and of everything it calls
+// that the stage kernels of sk_wavefront.cuh are assembled from: cell location and cell crossing for each grid type,
+// the source samplers, the instrument projection and the detector tallies.
+#pragma once
+#include "sk_device.cuh"
+
+// Per-packet state of the in-flight bank: field-major arrays of `cap` entries (structure of arrays in HBM),
+// the device counterpart of PhotonPacket (SKIRT/utils/PhotonPacket.hpp:337-363).
+enum {
+    D_RX, D_RY, D_RZ, D_KX, D_KY, D_KZ, D_LAMBDA, D_W, D_LTHR, D_SIGEXT, D_TAUPATH, D_TAUINT, D_STOT, D_SINT,
+    D_PEELW, D_PTAU, D_LIMIT, D_HISTW0, SK_ND = D_HISTW0 + SK_MAX_INSTR
+};
+enum {
+    I_HLO, I_HHI, I_DRAW, I_NSCATT, I_STATE, I_ILAM, I_M, I_IX, I_IY, I_IZ, I_LEV, I_MINT, I_MIX, I_MIY, I_MIZ,
+    I_MLEV, I_NSEG, I_HELL0, SK_NI = I_HELL0 + SK_MAX_INSTR
+};
+// I_STATE bits
+#define SK_ST_LIVE 1
+#define SK_ST_SCATTER 2    // a scattering event is pending (peel-off of kind "scattering", then new direction)
+#define SK_ST_FOUND 4      // non-forced propagation: interaction point found
+
+struct SkBank {
+    double* d;        // [D_HISTW0 + ninstr][cap]
+    int32_t* i;       // [I_HELL0 + ninstr][cap]
+    int32_t* list;    // [cap] slots of the rays of the trace stage being prepared / consumed
+    unsigned int* ctl;  // control words: see SK_CTL_*
+    int32_t cap;
+    __device__ __forceinline__ double& D(int f, int s) const { return d[(size_t)f * cap + s]; }
+    __device__ __forceinline__ int32_t& I(int f, int s) const { return i[(size_t)f * cap + s]; }
+};
+enum { SK_CTL_NLIST, SK_CTL_CURSOR, SK_CTL_NLIVE, SK_CTL_WORDS = 4 };
+
+struct SkLocalCounters {
+    unsigned int packets, fwd_paths, fwd_segs, replay_segs, peel_paths, peel_segs, scatt, rf, det, fallbacks;
+};
+
+struct SkSmemTables {
+    const double *X, *Y, *Z;
+};
+
+struct SkCellPos {
+    int m;           // cell index, -1 = outside / unknown
+    int ix, iy, iz;  // octree: lattice coordinates of the lower corner; Cartesian: bin indices i,j,k
+    int lev;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// Geometry helpers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool sk_box_contains(const double* b, double x, double y, double z)
+{
+    return x >= b[0] && x <= b[3] && y >= b[1] && y <= b[4] && z >= b[2] && z <= b[5];  // Box.hpp:99-109
+}
+__device__ __forceinline__ bool sk_box_strictly_inside(const double* b, double x, double y, double z)
+{
+    return x > b[0] && x < b[3] && y > b[1] && y < b[4] && z > b[2] && z < b[5];
+}
+
+// PathSegmentGenerator::moveInside, SKIRT/utils/PathSegmentGenerator.cpp:11-112
+__device__ __noinline__ bool sk_move_inside(double& rx, double& ry, double& rz, double kx, double ky, double kz,
+                                            const double* box, double eps, double& cumds_out)
+{
+    double cumds = 0.;
+    if (rx <= box[0])
+    {
+        if (kx <= 0.0) return false;
+        double ds = (box[0] - rx) / kx;
+        rx = box[0] + eps;
+        ry += ky * ds;
+        rz += kz * ds;
+        cumds += ds;
+    }
+    else if (rx >= box[3])
+    {
+        if (kx >= 0.0) return false;
+        double ds = (box[3] - rx) / kx;
+        rx = box[3] - eps;
+        ry += ky * ds;
+        rz += kz * ds;
+        cumds += ds;
+    }
+    if (ry <= box[1])
+    {
+        if (ky <= 0.0) return false;
+        double ds = (box[1] - ry) / ky;
+        rx += kx * ds;
+        ry = box[1] + eps;
+        rz += kz * ds;
+        cumds += ds;
+    }
+    else if (ry >= box[4])
+    {
+        if (ky >= 0.0) return false;
+        double ds = (box[4] - ry) / ky;
+        rx += kx * ds;
+        ry = box[4] - eps;
+        rz += kz * ds;
+        cumds += ds;
+    }
+    if (rz <= box[2])
+    {
+        if (kz <= 0.0) return false;
+        double ds = (box[2] - rz) / kz;
+        rx += kx * ds;
+        ry += ky * ds;
+        rz = box[2] + eps;
+        cumds += ds;
+    }
+    else if (rz >= box[5])
+    {
+        if (kz >= 0.0) return false;
+        double ds = (box[5] - rz) / kz;
+        rx += kx * ds;
+        ry += ky * ds;
+        rz = box[5] - eps;
+        cumds += ds;
+    }
+    if (!sk_box_contains(box, rx, ry, rz)) return false;
+    cumds_out = cumds;
+    return true;
+}
+
+// Octree cell location: TreeNode::leafChild (TreeNode.cpp:65-76) + OctTreeNode::child (OctTreeNode.cpp:37-42) on the
+// integer lattice: a node is (ix,iy,iz,level); its centre (CHILD_0->rmax) is the lattice border at +half size.
+// `fc` is the node id of the first child of the node to descend from.
+__device__ __forceinline__ void sk_tree_descend(const int32_t* __restrict__ node_child, int maxlevel,
+                                                const SkSmemTables& T, int fc, int ix, int iy, int iz, int lev,
+                                                double x, double y, double z, SkCellPos& out)
+{
+    while (fc >= 0)
+    {
+        int half = 1 << (maxlevel - lev - 1);
+        int l = 0;
+        if (!(x < T.X[ix + half]))
+        {
+            l |= 1;
+            ix += half;
+        }
+        if (!(y < T.Y[iy + half]))
+        {
+            l |= 2;
+            iy += half;
+        }
+        if (!(z < T.Z[iz + half]))
+        {
+            l |= 4;
+            iz += half;
+        }
+        lev++;
+        fc = __ldg(&node_child[fc + l]);
+    }
+    out.m = -(fc + 1);
+    out.ix = ix;
+    out.iy = iy;
+    out.iz = iz;
+    out.lev = lev;
+}
+
+// Cold path: locates the cell holding (x,y,z) from scratch.  Takes the model through a pointer to its copy in
+// global memory so that the kernel-parameter copy never has its address taken (that would force it into local memory).
+template <int GRID>
+__device__ __noinline__ void sk_locate(const SkDevModel* __restrict__ Mg, const SkSmemTables& T, double x, double y,
+                                       double z, SkCellPos& out)
+{
+    if (!sk_box_contains(Mg->ext, x, y, z))
+    {
+        out.m = -1;
+        return;
+    }
+    if (GRID == 1)
+    {
+        out.ix = sk_locate_clip(T.X, Mg->nx + 1, x);  // CartesianSpatialGrid.cpp:105-107
+        out.iy = sk_locate_clip(T.Y, Mg->ny + 1, y);
+        out.iz = sk_locate_clip(T.Z, Mg->nz + 1, z);
+        out.lev = 0;
+        out.m = out.iz + Mg->nz * out.iy + Mg->nz * Mg->ny * out.ix;
+    }
+    else
+        sk_tree_descend(Mg->node_child, Mg->maxlevel, T, __ldg(&Mg->node_child[0]), 0, 0, 0, 0, x, y, z, out);
+}
+
+// Cold path of the octree step: the full neighbour search of TreeSpatialGrid.cpp:190-207 for the situations the
+// fast path does not decide itself (domain boundary, near-ties between exit walls, grazing directions):
+// the leaf containing the new position (TreeNode::neighbor + root()->leafChild fall-back), the nextafter escape
+// when stuck in the same cell, and termination.
+__device__ __noinline__ void sk_tree_step_rare(const SkDevModel* __restrict__ Mg, const SkSmemTables& T, double& rx,
+                                               double& ry, double& rz, double kx, double ky, double kz, int m_old,
+                                               SkCellPos& q)
+{
+    sk_locate<2>(Mg, T, rx, ry, rz, q);
+    if (q.m == m_old)
+    {
+        // PathSegmentGenerator::propagateToNextAfter, PathSegmentGenerator.hpp:148-153
+        rx = nextafter(rx, (kx < 0.) ? -DBL_MAX : DBL_MAX);
+        ry = nextafter(ry, (ky < 0.) ? -DBL_MAX : DBL_MAX);
+        rz = nextafter(rz, (kz < 0.) ? -DBL_MAX : DBL_MAX);
+        sk_locate<2>(Mg, T, rx, ry, rz, q);
+        if (q.m == m_old) q.m = -1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// One cell crossing.  Returns the segment (m, dens, ds) and moves (r, p) to the next cell; `p.m < 0` afterwards
+// means the path has left the grid.
+//   Cartesian: CartesianSpatialGrid::MySegmentGenerator::next, CartesianSpatialGrid.cpp:95-162
+//   Octree:    TreeSpatialGrid::MySegmentGenerator::next, TreeSpatialGrid.cpp:140-216, with TreeNode::neighbor
+//              (TreeNode.cpp:103-112) served by the per-cell links
+// The ray carries the reciprocals of its direction components (0 where the reference treats the component as
+// zero, fabs(k) <= 1e-15), so the exit distances cost a multiplication instead of a division per axis.
+// ---------------------------------------------------------------------------------------------------
+struct SkRayDir {
+    double kx, ky, kz;
+    double ikx, iky, ikz;
+    __host__ __device__ __forceinline__ void set(double x, double y, double z)
+    {
+        kx = x;
+        ky = y;
+        kz = z;
+        ikx = (fabs(x) > 1e-15) ? 1.0 / x : 0.;
+        iky = (fabs(y) > 1e-15) ? 1.0 / y : 0.;
+        ikz = (fabs(z) > 1e-15) ? 1.0 / z : 0.;
+    }
+};
+
+template <int GRID>
+__device__ __forceinline__ void sk_step(const SkDevModel& M, const SkDevModel* __restrict__ Mg, const SkSmemTables& T,
+                                        SkLocalCounters& cnt, double& rx, double& ry, double& rz, const SkRayDir& k,
+                                        SkCellPos& p, int& m_out, double& dens_out, double& ds_out)
+{
+    if (GRID == 1)
+    {
+        int m = p.m;
+        double dens = __ldg(&M.dens[m]);
+        double xE = T.X[p.ix + ((k.kx < 0.0) ? 0 : 1)];
+        double yE = T.Y[p.iy + ((k.ky < 0.0) ? 0 : 1)];
+        double zE = T.Z[p.iz + ((k.kz < 0.0) ? 0 : 1)];
+        double dsx = (k.ikx != 0.) ? (xE - rx) * k.ikx : DBL_MAX;
+        double dsy = (k.iky != 0.) ? (yE - ry) * k.iky : DBL_MAX;
+        double dsz = (k.ikz != 0.) ? (zE - rz) * k.ikz : DBL_MAX;
+        double ds;
+        bool outside;
+        if (dsx <= dsy && dsx <= dsz)
+        {
+            ds = dsx;
+            rx = xE;
+            ry += k.ky * dsx;
+            rz += k.kz * dsx;
+            p.ix += (k.kx < 0.0) ? -1 : 1;
+            outside = (p.ix >= M.nx || p.ix < 0);
+        }
+        else if (dsy < dsx && dsy <= dsz)
+        {
+            ds = dsy;
+            ry = yE;
+            rx += k.kx * dsy;
+            rz += k.kz * dsy;
+            p.iy += (k.ky < 0.0) ? -1 : 1;
+            outside = (p.iy >= M.ny || p.iy < 0);
+        }
+        else
+        {
+            ds = dsz;
+            rz = zE;
+            rx += k.kx * dsz;
+            ry += k.ky * dsz;
+            p.iz += (k.kz < 0.0) ? -1 : 1;
+            outside = (p.iz >= M.nz || p.iz < 0);
+        }
+        m_out = m;
+        dens_out = dens;
+        ds_out = ds;
+        p.m = outside ? -1 : p.iz + M.nz * p.iy + M.nz * M.ny * p.ix;
+    }
+    else
+    {
+        // one 32-byte sector: density + the six neighbour links of the current cell
+        const int4* rp = reinterpret_cast<const int4*>(&M.cells[p.m]);
+        const int4 a = __ldg(rp), b = __ldg(rp + 1);
+        const int size = 1 << (M.maxlevel - p.lev);
+        const bool nx = k.kx < 0.0, ny = k.ky < 0.0, nz = k.kz < 0.0;
+        const double xnext = T.X[p.ix + (nx ? 0 : size)];
+        const double ynext = T.Y[p.iy + (ny ? 0 : size)];
+        const double znext = T.Z[p.iz + (nz ? 0 : size)];
+        const double dsx = (k.ikx != 0.) ? (xnext - rx) * k.ikx : DBL_MAX;
+        const double dsy = (k.iky != 0.) ? (ynext - ry) * k.iky : DBL_MAX;
+        const double dsz = (k.ikz != 0.) ? (znext - rz) * k.ikz : DBL_MAX;
+        // exit wall: x if dsx<=dsy && dsx<=dsz, else y if dsy<=dsx && dsy<=dsz, else z (TreeSpatialGrid.cpp:160-178)
+        const bool takex = dsx <= dsy && dsx <= dsz;
+        const bool takey = !takex && dsy <= dsx && dsy <= dsz;
+        const double ds = takex ? dsx : takey ? dsy : dsz;
+        const double other = takex ? fmin(dsy, dsz) : takey ? fmin(dsx, dsz) : fmin(dsx, dsy);
+        const double kexit = takex ? k.kx : takey ? k.ky : k.kz;
+        const int lx = nx ? a.z : a.w, ly = ny ? b.x : b.y, lz = nz ? b.z : b.w;
+        const int link = takex ? lx : takey ? ly : lz;
+        const double adv = ds + M.eps;
+        rx += k.kx * adv;
+        ry += k.ky * adv;
+        rz += k.kz * adv;
+        m_out = p.m;
+        dens_out = __hiloint2double(a.y, a.x);
+        ds_out = ds;
+        // The link decides the next cell unless the new position may also have crossed a second wall (the exit
+        // distances of two walls differ by less than a few eps), the direction grazes the exit wall (the eps advance may
+        // be lost to rounding), or the path reaches the domain boundary; those cases take the reference's full search.
+        const bool rare = link < 0 || !(other - ds > 4. * M.eps) || !(fabs(kexit) > 1e-3);
+        if (!rare)
+        {
+            // step to the lattice point just across the exit wall, then align to the neighbour's level
+            int ix = p.ix, iy = p.iy, iz = p.iz;
+            if (takex)
+                ix += nx ? -1 : size;
+            else if (takey)
+                iy += ny ? -1 : size;
+            else
+                iz += nz ? -1 : size;
+            const int nlev = (link >> SK_LINK_LEVEL_SHIFT) & 15;
+            const int mask = ~((1 << (M.maxlevel - nlev)) - 1);
+            ix &= mask;
+            iy &= mask;
+            iz &= mask;
+            const int idx = link & SK_LINK_INDEX_MASK;
+            if (!(link & SK_LINK_INTERNAL))
+            {
+                p.m = idx;  // leaf neighbour at the same or a coarser level
+                p.ix = ix;
+                p.iy = iy;
+                p.iz = iz;
+                p.lev = nlev;
+            }
+            else
+                sk_tree_descend(M.node_child, M.maxlevel, T, idx, ix, iy, iz, nlev, rx, ry, rz, p);
+        }
+        else
+        {
+            // (copies confine the address-taken variables, which live in local memory, to this cold branch)
+            cnt.fallbacks++;
+            double tx = rx, ty = ry, tz = rz;
+            SkCellPos q;
+            sk_tree_step_rare(Mg, T, tx, ty, tz, k.kx, k.ky, k.kz, p.m, q);
+            rx = tx;
+            ry = ty;
+            rz = tz;
+            p = q;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Sources: SourceSystem::launch (SourceSystem.cpp:101-113), NormalizedSource::launch (NormalizedSource.cpp:73-110),
+// GeometricSource::launchNormalized (GeometricSource.cpp:66-82), PointSource::launchSpecialty (PointSource.cpp:32-42)
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double sk_sample_cdf_loglog(SkRng& g, const double* xv, const double* pv, const double* Pv,
+                                                       int n)
+{
+    double X = sk_uniform(g);  // Random::cdfLogLog, Random.cpp:210-216
+    int i = sk_locate_clip(Pv, n, X);
+    double alpha = log(pv[i + 1] / pv[i]) / log(xv[i + 1] / xv[i]);
+    return xv[i] * sk_gexp(-alpha, (X - Pv[i]) / (pv[i] * xv[i]));
+}
+__device__ __forceinline__ double sk_sample_cdf_linlin(SkRng& g, const double* xv, const double* Pv, int n)
+{
+    double X = sk_uniform(g);  // Random::cdfLinLin, Random.cpp:201-206
+    int i = sk_locate_clip(Pv, n, X);
+    return sk_interp_linlin(X, Pv[i], Pv[i + 1], xv[i], xv[i + 1]);
+}
+__device__ __forceinline__ double sk_specific_luminosity(const SkDevSource& s, double lambda)
+{
+    if (s.sed_kind == SK_SED_BLACKBODY) return sk_planck(lambda, s.sed_temperature) / s.sed_norm;
+    int i = sk_locate_fail(s.sed_lambda, s.sed_n, lambda);
+    if (i < 0) return 0.;
+    return sk_interp_loglog(lambda, s.sed_lambda[i], s.sed_lambda[i + 1], s.sed_p[i], s.sed_p[i + 1]);
+}
+// ExpDiskGeometry::randomCylRadius / randomZ, ExpDiskGeometry.cpp:46-68
+__device__ __forceinline__ double sk_expdisk_R(SkRng& g, double hR, double Rmin, double Rmax)
+{
+    double R, X;
+    do
+    {
+        X = sk_uniform(g);
+        R = hR * (-1.0 - sk_lambert_w1((X - 1.0) / M_E));
+    } while ((Rmax > 0.0 && R >= Rmax) || R <= Rmin);
+    return R;
+}
+__device__ __forceinline__ double sk_expdisk_z(SkRng& g, double hz, double zmax)
+{
+    double z, X;
+    do
+    {
+        X = sk_uniform(g);
+        z = (X <= 0.5) ? hz * log(2.0 * X) : -hz * log(2.0 * (1.0 - X));
+    } while (zmax > 0.0 && fabs(z) >= zmax);
+    return z;
+}
+__device__ __noinline__ void sk_generate_position(SkRng& g, const SkDevSource& s, double& x, double& y, double& z)
+{
+    const double* p = s.gp;
+    switch (s.geometry)
+    {
+        case SK_GEOM_SHELL:
+        {
+            // ShellGeometry::randomRadius (ShellGeometry.cpp:43-57) + SpheGeometry::generatePosition (SpheGeometry.cpp:26-33)
+            double pe = p[2], smin = p[3], sdiff = p[4], tmin = p[5], tmax = p[6];
+            double X = sk_uniform(g);
+            double rad;
+            if (fabs(pe - 3.0) < 1e-2)
+                rad = sk_gexp(pe - 2.0, smin + X * sdiff);
+            else
+            {
+                double zz = (1.0 - X) * tmin + X * tmax;
+                rad = pow(zz, 1.0 / (3.0 - pe));
+            }
+            double kx, ky, kz;
+            sk_random_direction(g, kx, ky, kz);
+            x = rad * kx;
+            y = rad * ky;
+            z = rad * kz;
+            break;
+        }
+        case SK_GEOM_EXPDISK:
+        {
+            double R = sk_expdisk_R(g, p[0], p[2], p[3]);  // SepAxGeometry::generatePosition, SepAxGeometry.cpp:12-20
+            double phi = 2.0 * M_PI * sk_uniform(g);
+            double zz = sk_expdisk_z(g, p[1], p[4]);
+            x = R * cos(phi);
+            y = R * sin(phi);
+            z = zz;
+            break;
+        }
+        case SK_GEOM_RING:
+        {
+            double R = sk_sample_cdf_linlin(g, s.geom_table_x, s.geom_table_P, s.geom_table_n);  // RingGeometry.cpp:56-68
+            double phi = 2.0 * M_PI * sk_uniform(g);
+            double X = sk_uniform(g);
+            double zz = (X <= 0.5) ? p[2] * log(2.0 * X) : -p[2] * log(2.0 * (1.0 - X));
+            x = R * cos(phi);
+            y = R * sin(phi);
+            z = zz;
+            break;
+        }
+        case SK_GEOM_SPIRAL_EXPDISK:
+        {
+            // SpiralStructureGeometryDecorator::generatePosition / perturbation, .cpp:33-45,72-76
+            double R0 = sk_expdisk_R(g, p[0], p[2], p[3]);
+            double phi0 = 2.0 * M_PI * sk_uniform(g);
+            double zz = sk_expdisk_z(g, p[1], p[4]);
+            double x0 = R0 * cos(phi0), y0 = R0 * sin(phi0);
+            double R = sqrt(x0 * x0 + y0 * y0);
+            double m = p[5], pitch = p[6], Rz = p[7], phiz = p[8], w = p[9], N = p[10];
+            double tanp = tan(pitch);
+            double cn = sqrt(M_PI) * tgamma(N + 1.0) / tgamma(N + 0.5);
+            double c = 1.0 + (cn - 1.0) * w;
+            double phi, t;
+            do
+            {
+                phi = 2.0 * M_PI * sk_uniform(g);
+                double gamma = log(R / Rz) / tanp + phiz + 0.5 * M_PI / m;
+                double perturbation = (1.0 - w) + w * cn * pow(sin(0.5 * m * (gamma - phi)), 2 * N);
+                t = sk_uniform(g) * c / perturbation;
+            } while (t > 1);
+            x = R * cos(phi);
+            y = R * sin(phi);
+            z = zz;
+            break;
+        }
+        default: x = y = z = 0.; break;
+    }
+}
+
+struct SkLaunch {
+    double lambda, W, rx, ry, rz, kx, ky, kz;
+    int ilam;
+};
+
+__device__ __noinline__ void sk_launch_primary(const SkDevModel* __restrict__ Mg, SkRng& g, unsigned long long history,
+                                               SkLaunch& pp)
+{
+    const SkDevModel& M = *Mg;
+    int lo = 0, hi = M.nsrc + 1;  // std::upper_bound(_Iv, historyIndex) - 1
+    while (lo < hi)
+    {
+        int mid = (lo + hi) >> 1;
+        if (history < M.Iv[mid])
+            hi = mid;
+        else
+            lo = mid + 1;
+    }
+    const SkDevSource& s = M.src[lo - 1];
+    double L = M.Lpp * s.Lw;
+    double lambda, w;
+    double xi = s.wavelength_bias;
+    if (!xi)
+    {
+        lambda = sk_sample_cdf_loglog(g, s.sed_lambda, s.sed_p, s.sed_P, s.sed_n);
+        w = 1.;
+    }
+    else
+    {
+        if (sk_uniform(g) > xi)
+            lambda = sk_sample_cdf_loglog(g, s.sed_lambda, s.sed_p, s.sed_P, s.sed_n);
+        else if (s.bias_kind == SK_BIAS_OLIGO)
+        {
+            size_t index = (size_t)(sk_uniform(g) * s.oligo_n);  // OligoWavelengthDistribution.cpp:34-38
+            lambda = s.oligo_lambda[index];
+        }
+        else
+        {
+            double logMin = log(s.bias_min);
+            double logWidth = log(s.bias_max) - log(s.bias_min);
+            lambda = exp(logMin + logWidth * sk_uniform(g));  // DefaultWavelengthDistribution.cpp:37-40
+        }
+        double sl = sk_specific_luminosity(s, lambda);
+        if (!sl)
+            w = 0.;
+        else
+        {
+            double b;
+            if (s.bias_kind == SK_BIAS_OLIGO)
+                b = s.oligo_probability;
+            else
+            {
+                double logWidth = log(s.bias_max) - log(s.bias_min);
+                if (lambda >= s.bias_min * (1 - 1e-14) && lambda <= s.bias_max * (1 + 1e-14))  // Range.hpp:56
+                    b = 1. / (logWidth * lambda);
+                else
+                    b = 0.;
+            }
+            w = sl / ((1 - xi) * sl + xi * b);
+        }
+    }
+    double Lw = L * w;
+    if (s.kind == SK_SRC_POINT)
+    {
+        pp.rx = s.position[0];
+        pp.ry = s.position[1];
+        pp.rz = s.position[2];
+    }
+    else
+        sk_generate_position(g, s, pp.rx, pp.ry, pp.rz);
+    sk_random_direction(g, pp.kx, pp.ky, pp.kz);
+    pp.lambda = lambda;
+    pp.W = Lw * lambda;  // PhotonPacket::launch, PhotonPacket.cpp:18-40
+    pp.ilam = sk_locate_clip(M.lam_border, M.nlam, lambda);
+}
+
+// DustSecondarySource::launch (DustSecondarySource.cpp:511-581): implemented in sk_secondary.cuh
+template <int GRID>
+__device__ __noinline__ void sk_launch_secondary(const SkDevModel* __restrict__ Mg, const SkSmemTables& T, SkRng& g,
+                                    unsigned long long history, SkLaunch& pp);
+
+// ---------------------------------------------------------------------------------------------------
+// Instruments
+// ---------------------------------------------------------------------------------------------------
+// First half of Instrument::detect / FluxRecorder::detect: does this instrument record a packet at (x,y,z) with
+// wavelength lambda?  SEDInstrument.cpp:22-25 + ApertureInstrument.cpp:24-43, FrameInstrument.cpp:45-64,
+// FluxRecorder.cpp:306-313.  Returns false when nothing is recorded (and no optical depth is needed).
+__device__ __forceinline__ bool sk_detect_geometry(const SkDevModel& M, const SkDevInstr& q, double x, double y,
+                                                   double z, double lambda, int& l, int& ell)
+{
+    l = 0;
+    if (q.kind == SK_INSTR_SED)
+    {
+        if (q.radius2)
+        {
+            double xpp = -q.sinphi * x + q.cosphi * y;
+            double ypp = -q.cosphi * q.costheta * x - q.sinphi * q.costheta * y + q.sintheta * z;
+            double radius2 = xpp * xpp + ypp * ypp;
+            if (radius2 > q.radius2) return false;
+        }
+    }
+    else
+    {
+        double xpp = -q.sinphi * x + q.cosphi * y;
+        double ypp = -q.cosphi * q.costheta * x - q.sinphi * q.costheta * y + q.sintheta * z;
+        double xp = q.cosomega * xpp - q.sinomega * ypp;
+        double yp = q.sinomega * xpp + q.cosomega * ypp;
+        int i = (int)floor((xp - q.xpmin) / q.xpsiz);
+        int jj = (int)floor((yp - q.ypmin) / q.ypsiz);
+        if (i < 0 || i >= q.nx || jj < 0 || jj >= q.ny)
+            l = -1;
+        else
+            l = i + q.nx * jj;
+    }
+    if (!q.include_sed && l < 0) return false;
+    ell = sk_wlg_bin(M.wlg[q.wlg], lambda);
+    return ell >= 0;
+}
+
+// Second half of FluxRecorder::detect (FluxRecorder.cpp:320-433): component routing and the tallies.
+__device__ __forceinline__ void sk_record(const SkDevInstr& q, int l, int ell, double L, double Lext, int nscatt,
+                                          bool primary_origin)
+{
+    int c_ext, c_tr = -1, c_lev = -1;
+    if (q.record_total_only)
+        c_ext = SK_COMP_TOTAL;
+    else if (primary_origin)
+    {
+        if (nscatt == 0)
+        {
+            c_tr = SK_COMP_TRANSPARENT;
+            c_ext = SK_COMP_PRIMARY_DIRECT;
+        }
+        else
+        {
+            c_ext = SK_COMP_PRIMARY_SCATTERED;
+            if (nscatt <= q.num_levels) c_lev = SK_COMP_PRIMARY_SCATTERED_LEVEL + nscatt - 1;
+        }
+    }
+    else
+    {
+        if (nscatt == 0)
+        {
+            c_tr = SK_COMP_SECONDARY_TRANSPARENT;
+            c_ext = SK_COMP_SECONDARY_DIRECT;
+        }
+        else
+            c_ext = SK_COMP_SECONDARY_SCATTERED;
+    }
+    if (q.include_sed)
+    {
+        atomicAdd(&q.sed[c_ext][ell], Lext);  // LockFree::add, LockFree.hpp:23-37 -> native fp64 RED
+        if (c_tr >= 0) atomicAdd(&q.sed[c_tr][ell], L);
+        if (c_lev >= 0) atomicAdd(&q.sed[c_lev][ell], Lext);
+    }
+    if (q.include_ifu && l >= 0)
+    {
+        size_t index = (size_t)l + (size_t)ell * q.npix;  // FluxRecorder.cpp:433
+        atomicAdd(&q.ifu[c_ext][index], Lext);
+        if (c_tr >= 0) atomicAdd(&q.ifu[c_tr][index], L);
+        if (c_lev >= 0) atomicAdd(&q.ifu[c_lev][index], Lext);
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// per-grid accessors used by the event kernels
+// ---------------------------------------------------------------------------------------------------
+template <int GRID>
+__device__ __forceinline__ double sk_cell_density(const SkDevModel& M, int m)
+{
+    return GRID == 2 ? M.cells[m].dens : M.dens[m];
+}
+// true when (x,y,z) lies in the half-open box of cell c
+template <int GRID>
+__device__ __forceinline__ bool sk_cell_contains(const SkDevModel& M, const SkSmemTables& T, const SkCellPos& c, double x,
+                                                 double y, double z)
+{
+    const int size = GRID == 1 ? 1 : 1 << (M.maxlevel - c.lev);
+    return x >= T.X[c.ix] && x < T.X[c.ix + size] && y >= T.Y[c.iy] && y < T.Y[c.iy + size] && z >= T.Z[c.iz]
+           && z < T.Z[c.iz + size];
+}

@@ -79,6 +79,7 @@ struct SkDevModel {
     const int32_t* node_child;   // octree: first child node id, or -(cell+1) for a leaf
     const uint32_t* cell_coord;  // octree: 4 x uint32 per cell {ix,iy,iz,level}
     int32_t ncells, nnodes;
+    const double* volume;        // cell volumes (MediumState::volume)
     // dust
     int32_t nlam;
     const double *lam_border, *sig_abs, *sig_sca, *sig_ext, *gpar;
@@ -91,6 +92,14 @@ struct SkDevModel {
     const unsigned long long* Iv;
     int32_t nsrc;
     double Lpp;
+    // secondary (dust) emission, sk_secondary.cuh
+    int32_t sec_nem, sec_nT;         // points of the extended emission grid; size of the temperature grid
+    const double *sec_lambda, *sec_emsig, *sec_rfsig, *sec_T, *sec_planckabs;
+    const double* sec_kabs_rf;       // sigma_abs at the characteristic wavelengths of the radiation field grid
+    double *sec_pv, *sec_Pv;         // [ncells][sec_nem] normalised emission spectrum and its cdf
+    double *sec_Lv, *sec_ws;         // [ncells] absorbed luminosity; launch weight _Lv[m]/_Wv[m]
+    unsigned long long* sec_Iv;      // [ncells+1] history index -> cell map
+    double sec_Lpp, sec_xi, sec_bias_min, sec_bias_max;
     // instruments
     const SkDevInstr* instr;
     int32_t ninstr;
@@ -103,8 +112,6 @@ struct SkRunArgs {
     int32_t primary, peel, store;
     uint32_t stream_id;
     unsigned long long* work_counter;  // dynamic history dispenser
-    double* pool_d;                    // per-warp packet pools: [warp][SK_ND][SK_POOL]
-    int32_t* pool_i;                   // [warp][SK_NI][SK_POOL]
     const SkDevModel* model;           // copy of the model in global memory for the cold, non-inlined paths
 };
 

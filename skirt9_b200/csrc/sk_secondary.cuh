@@ -1,0 +1,207 @@
+// sk_secondary.cuh -- dust re-emission on the device: SecondarySourceSystem / DustSecondarySource
+// (SKIRT/core/SecondarySourceSystem.cpp:84-142, DustSecondarySource.cpp:26-146,511-581) with the
+// EquilibriumDustEmissionCalculator (EquilibriumDustEmissionCalculator.cpp:120-150).
+//
+// The reference computes a cell's emission spectrum lazily, per thread, the first time a packet is launched from it
+// (DustCellEmission::calculateIfNeeded, DustSecondarySource.cpp:187-285).  Here the spectra of ALL emitting cells are
+// computed by one batched kernel per segment (one thread per cell, ~100 wavelengths each) and kept in HBM
+// ([ncells][N_em+2] pdf and cdf), so that the launch of a history is a pair of binary searches.
+#pragma once
+#include "sk_blocks.cuh"
+
+// MediumSystem::dustLuminosity, MediumSystem.cpp:1452-1462 (single dust medium with constant cross sections:
+// opacityAbs = n * sigma_abs(lambda_ell), radiationField = rf1 + rf2)
+template <int GRID>
+__global__ void sk_dust_luminosity_kernel(const SkDevModel M)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M.ncells) return;
+    const double n = sk_cell_density<GRID>(M, m);
+    double Labs = 0.;
+    for (int ell = 0; ell < M.nrf; ++ell)
+    {
+        double opacity = n * M.sec_kabs_rf[ell];
+        double rf = 0.;
+        rf += M.rf1[(size_t)m * M.nrf + ell];
+        rf += M.rf2[(size_t)m * M.nrf + ell];
+        Labs += opacity * rf;
+    }
+    M.sec_Lv[m] = Labs;
+}
+
+// SpecialFunctions::gln, SpecialFunctions.cpp:798-811
+__device__ __forceinline__ double sk_gln(double p, double x)
+{
+    const double q = 1.0 - p;
+    if (q == 0.0)
+        return log(x);
+    else if (fabs(q) < 1e-3)
+    {
+        double lnx = log(x);
+        double s = q * lnx;
+        return lnx * (1.0 + 0.5 * s + 1.0 / 6.0 * s * s + 1.0 / 24.0 * s * s * s);
+    }
+    else
+        return (pow(x, q) - 1.0) / q;
+}
+
+// The normalised emission spectrum and its cumulative distribution for every emitting cell:
+// MediumSystem::meanIntensity (MediumSystem.cpp:1370-1380) -> EquilibriumDustEmissionCalculator::equilibriumTemperature
+// (.cpp:120-131, NR::clampedValue<interpolateLinLin>, NR.hpp:391-399) -> emissivity (.cpp:135-150) times the number
+// density (DustMix::emissionSpectrum, DustMix.cpp:650-653) -> NR::cdf<interpolateLogLog> over the range of the emission
+// grid (NR.hpp:494-520 + NR::cdf2, NR.cpp:25-60).  sec_Lv holds the normalised luminosities here (only their sign is used).
+template <int GRID>
+__global__ void sk_emission_spectrum_kernel(const SkDevModel M)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M.ncells) return;
+    const int nem = M.sec_nem, nrf = M.nrf, nT = M.sec_nT;
+    double* pv = M.sec_pv + (size_t)m * nem;
+    double* Pv = M.sec_Pv + (size_t)m * nem;
+    if (!(M.sec_Lv[m] > 0))
+    {
+        for (int i = 0; i < nem; ++i)
+        {
+            pv[i] = 0.;
+            Pv[i] = 0.;
+        }
+        return;
+    }
+    const SkDevWlg& rfg = M.wlg[M.rf_grid];
+    const double factor = 1. / (4. * M_PI * M.volume[m]);
+    double inputabs = 0.;
+    for (int ell = 0; ell < nrf; ++ell)
+    {
+        double rf = 0.;
+        rf += M.rf1[(size_t)m * nrf + ell];
+        rf += M.rf2[(size_t)m * nrf + ell];
+        double J = rf * factor / rfg.dlambda[ell];
+        inputabs += M.sec_rfsig[ell] * (J + 0.) * rfg.dlambda[ell];
+    }
+    double T = 0.;
+    if (inputabs > 0.)
+    {
+        int i = inputabs == M.sec_planckabs[nT - 1] ? nT - 2 : sk_locate_basic(M.sec_planckabs, inputabs, nT);
+        if (i < 0)
+            T = M.sec_T[0];
+        else if (i >= nT - 1)
+            T = M.sec_T[nT - 1];
+        else
+            T = sk_interp_linlin(inputabs, M.sec_planckabs[i], M.sec_planckabs[i + 1], M.sec_T[i], M.sec_T[i + 1]);
+    }
+    const double n = sk_cell_density<GRID>(M, m);
+    const double* x = M.sec_lambda;
+    for (int i = 0; i < nem; ++i) pv[i] = n * (M.sec_emsig[i] * sk_planck(x[i], T));
+    {
+        double first = sk_interp_loglog(x[0], x[0], x[1], pv[0], pv[1]);
+        double last = sk_interp_loglog(x[nem - 1], x[nem - 2], x[nem - 1], pv[nem - 2], pv[nem - 1]);
+        pv[0] = first;
+        pv[nem - 1] = last;
+        Pv[0] = 0.;
+        double P = 0.;
+        for (int i = 0; i != nem - 1; ++i)
+        {
+            double area = 0.;
+            if (pv[i] > 0 && pv[i + 1] > 0)
+            {
+                double alpha = log(pv[i + 1] / pv[i]) / log(x[i + 1] / x[i]);
+                area = pv[i] * x[i] * sk_gln(-alpha, x[i + 1] / x[i]);
+            }
+            P = P + area;
+            Pv[i + 1] = P;
+        }
+        const double norm = P;
+        if (norm > 0.)
+            for (int i = 0; i < nem; ++i)
+            {
+                pv[i] /= norm;
+                Pv[i] /= norm;
+            }
+    }
+}
+
+// SecondarySourceSystem::launch (SecondarySourceSystem.cpp:130-142) + DustSecondarySource::launch
+// (DustSecondarySource.cpp:511-581) without velocities and polarisation; SpatialGrid::randomPositionInCell
+// (TreeSpatialGrid.cpp:125-128, CartesianSpatialGrid.cpp:80-83) = Random::position(box) (Random.cpp:168-176).
+template <int GRID>
+__device__ __noinline__ void sk_launch_secondary(const SkDevModel* __restrict__ Mg, const SkSmemTables& T, SkRng& g,
+                                                 unsigned long long history, SkLaunch& pp)
+{
+    const SkDevModel& M = *Mg;
+    const int nem = M.sec_nem;
+    int lo = 0, hi = M.ncells + 1;  // std::upper_bound(_Iv, historyIndex) - 1
+    while (lo < hi)
+    {
+        int mid = (lo + hi) >> 1;
+        if (history < M.sec_Iv[mid])
+            hi = mid;
+        else
+            lo = mid + 1;
+    }
+    const int m = lo - 1;  // launch order = cell order for the AllCellsLibrary (AllCellsLibrary.cpp:26-32)
+    const double ws = M.sec_ws[m];
+    const double* xv = M.sec_lambda;
+    const double* pv = M.sec_pv + (size_t)m * nem;
+    const double* Pv = M.sec_Pv + (size_t)m * nem;
+    double lambda, w;
+    const double xi = M.sec_xi;
+    if (!xi)
+    {
+        lambda = sk_sample_cdf_loglog(g, xv, pv, Pv, nem);
+        w = 1.;
+    }
+    else
+    {
+        const double logMin = log(M.sec_bias_min);
+        const double logWidth = log(M.sec_bias_max) - log(M.sec_bias_min);
+        if (sk_uniform(g) > xi)
+            lambda = sk_sample_cdf_loglog(g, xv, pv, Pv, nem);
+        else
+            lambda = exp(logMin + logWidth * sk_uniform(g));  // DefaultWavelengthDistribution.cpp:37-40
+        double sl = 0.;  // NR::value<interpolateLogLog>, NR.hpp:372-378
+        int i = sk_locate_fail(xv, nem, lambda);
+        if (i >= 0) sl = sk_interp_loglog(lambda, xv[i], xv[i + 1], pv[i], pv[i + 1]);
+        if (!sl)
+            w = 0.;
+        else
+        {
+            double b;
+            if (lambda >= M.sec_bias_min * (1 - 1e-14) && lambda <= M.sec_bias_max * (1 + 1e-14))  // Range.hpp:56
+                b = 1. / (logWidth * lambda);
+            else
+                b = 0.;
+            w = sl / ((1 - xi) * sl + xi * b);
+        }
+    }
+    double b0, b1, b2, b3, b4, b5;
+    if (GRID == 1)
+    {
+        int k = m % M.nz, j = (m / M.nz) % M.ny, i = m / (M.nz * M.ny);
+        b0 = T.X[i];
+        b1 = T.Y[j];
+        b2 = T.Z[k];
+        b3 = T.X[i + 1];
+        b4 = T.Y[j + 1];
+        b5 = T.Z[k + 1];
+    }
+    else
+    {
+        const uint4 c = reinterpret_cast<const uint4*>(M.cell_coord)[m];
+        const int size = 1 << (M.maxlevel - (int)c.w);
+        b0 = T.X[c.x];
+        b1 = T.Y[c.y];
+        b2 = T.Z[c.z];
+        b3 = T.X[c.x + size];
+        b4 = T.Y[c.y + size];
+        b5 = T.Z[c.z + size];
+    }
+    const double ux = sk_uniform(g), uy = sk_uniform(g), uz = sk_uniform(g);
+    pp.rx = b0 + ux * (b3 - b0);  // Box::fracPos, SKIRT/utils/Box.hpp:151-154
+    pp.ry = b1 + uy * (b4 - b1);
+    pp.rz = b2 + uz * (b5 - b2);
+    sk_random_direction(g, pp.kx, pp.ky, pp.kz);
+    const double L = M.sec_Lpp * 1.;  // _Lv[s]/_Wv[s] = 1 for the single secondary source
+    pp.lambda = lambda;
+    pp.W = (L * ws * w) * lambda;
+    pp.ilam = sk_locate_clip(M.lam_border, M.nlam, lambda);
+}

@@ -1,0 +1,692 @@
+// sk_wavefront.cuh -- the photon life cycle as a sequence of stage kernels over a bank of in-flight packets:
+// MonteCarloSimulation::performLifeCycle (SKIRT/core/MonteCarloSimulation.cpp:538-613) and everything it calls.
+//
+// Execution model.  The reference runs one history at a time per thread; here a BANK of up to
+// `cap` histories (millions) is in flight per GPU, its state held as a structure of arrays in HBM, and the body of the
+// reference's forced-scattering loop (.cpp:565-585) is cut at its three grid traversals into stage kernels that each
+// advance the whole bank by one step:
+//     advance  = [interaction of the previous round: .cpp:724-741,576-580] + [launch into free slots: SourceSystem::launch]
+//                + [peel-off set-up towards the first observer: .cpp:617-634 / 784-842]
+//     trace<2> = optical depth to the observer for every peel-off ray          (MediumSystem.cpp:1192-1219)
+//     detect   = FluxRecorder::detect for the observer group; after the last group the scattering itself
+//                (MediumSystem.cpp:796-823) and the list of forward rays
+//     trace<0> = forward path to the grid boundary, RF deposits fused in       (MediumSystem.cpp:849-871, .cpp:638-665)
+//     sample   = interaction optical depth with path-length biasing            (.cpp:696-722)
+//     trace<1> = walk to the interaction point                                 (SpatialGridPath.cpp:164-206)
+// Event kernels (advance, detect, sample) are element-wise over the bank: every thread owns one slot, all threads run
+// the same short code, state is read and written coalesced.  Trace kernels are persistent: lanes are NOT bound to
+// packets; each lane walks one ray cell by cell and, when its ray ends, takes the next unprocessed ray of the stage
+// from a global list (chunks of SK_CHUNK rays reserved per warp with one atomic) -> the cell-crossing loop stays
+// converged although path lengths vary from 1 to several hundred segments, each kernel is small enough to live in
+// the instruction cache, and each gets the register budget / occupancy that suits it.
+// Paths are never materialised (the reference stores vector<Segment>, SpatialGridPath.hpp:93-115): the forward path
+// is walked once for the total optical depth and re-walked up to the sampled interaction point; both walks use
+// identical arithmetic so they see identical segments.
+#pragma once
+#include "sk_blocks.cuh"
+
+#ifndef SK_EVENT_BLOCK
+#define SK_EVENT_BLOCK 256
+#endif
+#ifndef SK_TRACE_BLOCK
+#define SK_TRACE_BLOCK 128
+#endif
+#ifndef SK_TRACE_MINBLOCKS
+#define SK_TRACE_MINBLOCKS 6
+#endif
+#ifndef SK_CHUNK
+#define SK_CHUNK 64
+#endif
+#ifndef SK_REFILL_MIN
+#define SK_REFILL_MIN 6
+#endif
+
+// ---------------------------------------------------------------------------------------------------
+// small helpers shared by the stage kernels
+// ---------------------------------------------------------------------------------------------------
+// appends `slot` of every lane with `want` to the ray list (one atomic per warp); all 32 lanes must call
+__device__ __forceinline__ void sk_list_append(const SkBank& K, bool want, int slot)
+{
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned mask = __ballot_sync(0xffffffffu, want);
+    if (!mask) return;
+    const int leader = __ffs(mask) - 1;
+    unsigned base = 0;
+    if ((int)lane == leader) base = atomicAdd(&K.ctl[SK_CTL_NLIST], (unsigned)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (want) K.list[base + __popc(mask & ((1u << lane) - 1u))] = slot;
+}
+
+__device__ __forceinline__ void sk_flush_counters(const SkDevModel& M, SkLocalCounters& cnt)
+{
+    unsigned int* c = reinterpret_cast<unsigned int*>(&cnt);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(SkLocalCounters) / sizeof(unsigned int)); ++i)
+    {
+        unsigned int v = __reduce_add_sync(0xffffffffu, c[i]);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&M.counters[i], (unsigned long long)v);
+    }
+}
+
+__device__ __forceinline__ void sk_rng_load(SkRng& g, const SkDevModel& M, const SkRunArgs& A, const SkBank& K, int slot)
+{
+    sk_rng_init(g, M.seed, A.stream_id,
+                ((unsigned long long)(uint32_t)K.I(I_HHI, slot) << 32) | (uint32_t)K.I(I_HLO, slot),
+                (uint32_t)K.I(I_DRAW, slot));
+}
+
+// Ends a history: FluxRecorder::recordContributions for the SED arrays (FluxRecorder.cpp:962-986); frees the slot.
+__device__ __forceinline__ void sk_finish_history(const SkDevModel& M, const SkBank& K, int slot)
+{
+    for (int j = 0; j < M.ninstr; ++j)
+    {
+        const SkDevInstr& q = M.instr[j];
+        if (!q.record_stats) continue;
+        int ell = K.I(I_HELL0 + j, slot);
+        if (ell >= 0)
+        {
+            double w = K.D(D_HISTW0 + j, slot);
+            double wn = 1.;
+            for (int kk = 0; kk <= 4; ++kk)
+            {
+                atomicAdd(&q.wsed[kk][ell], wn);
+                wn *= w;
+            }
+        }
+    }
+    K.I(I_STATE, slot) = 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Trace kernels: walk all rays of the list with dynamic lane refill.
+//   MODE 0  forward path to the boundary: MediumSystem::setExtinctionOpticalDepths (MediumSystem.cpp:849-871); with
+//           STORE fused with MonteCarloSimulation::storeRadiationField (.cpp:638-665)
+//   MODE 1  walk to the interaction point: SpatialGridPath::findInteractionPoint (SpatialGridPath.cpp:164-206), or for
+//           non-forced scattering MediumSystem::setInteractionPointUsingExtinction (MediumSystem.cpp:978-1010)
+//   MODE 2  optical depth to the observer: MediumSystem::getExtinctionOpticalDepth (MediumSystem.cpp:1192-1219)
+// Structure: a compact inner loop that only crosses cells, and an outer service block (store the results of finished
+// rays, load new rays) that is entered when at least SK_REFILL_MIN lanes are idle, so that its cost is shared.
+// ---------------------------------------------------------------------------------------------------
+template <int GRID, int MODE, bool STORE>
+__global__ void __launch_bounds__(SK_TRACE_BLOCK, SK_TRACE_MINBLOCKS)
+    sk_wf_trace(const SkDevModel M, const SkRunArgs A, const SkBank K, const SkRayDir obs)
+{
+    extern __shared__ double smem[];
+    SkSmemTables T;
+    if (M.lattice_in_smem)
+    {
+        // stage the per-axis border tables (Cartesian borders / octree lattice) in shared memory
+        const int n0 = M.nx + 1, n1 = M.ny + 1, n2 = M.nz + 1;
+        for (int i = threadIdx.x; i < n0; i += blockDim.x) smem[i] = M.xv[i];
+        for (int i = threadIdx.x; i < n1; i += blockDim.x) smem[n0 + i] = M.yv[i];
+        for (int i = threadIdx.x; i < n2; i += blockDim.x) smem[n0 + n1 + i] = M.zv[i];
+        T.X = smem;
+        T.Y = smem + n0;
+        T.Z = smem + n0 + n1;
+        __syncthreads();
+    }
+    else
+    {
+        T.X = M.xv;
+        T.Y = M.yv;
+        T.Z = M.zv;
+    }
+    const SkDevModel* __restrict__ Mg = A.model;
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const bool forced = M.force_scattering != 0;
+    const int n = (int)K.ctl[SK_CTL_NLIST];
+    SkLocalCounters cnt;
+    memset(&cnt, 0, sizeof cnt);
+
+    int chunk_pos = 0, chunk_end = 0;  // the warp's reserved range of the list
+    bool exhausted = false;            // the global list has been handed out completely
+    bool active = false, pending = false;
+    int slot = 0;
+    double rx = 0, ry = 0, rz = 0;
+    SkRayDir k;
+    k.set(0., 0., 1.);
+    SkCellPos p{-1, 0, 0, 0, 0};
+    double tau = 0, s = 0, limit = 0, section = 0;
+    int nseg = 0;
+    // MODE 0 + STORE extras
+    double lum = 0, lnExtBeg = 0, extBeg = 1;
+    int rf_ell = -1;
+    double* rf = nullptr;
+    // MODE 1 results
+    SkCellPos hit{-1, 0, 0, 0, 0};
+    double s_int = 0;
+    bool found = false;
+
+    while (true)
+    {
+        // ---------------- service block: results of finished rays out, new rays in
+        if (pending)
+        {
+            pending = false;
+            if (MODE == 0)
+            {
+                K.D(D_TAUPATH, slot) = tau;
+                K.D(D_STOT, slot) = s;
+                K.I(I_NSEG, slot) = nseg;
+                cnt.fwd_paths++;
+                cnt.fwd_segs += nseg;
+            }
+            else if (MODE == 1)
+            {
+                K.D(D_SINT, slot) = s_int;
+                K.I(I_MINT, slot) = hit.m;
+                K.I(I_MIX, slot) = hit.ix;
+                K.I(I_MIY, slot) = hit.iy;
+                K.I(I_MIZ, slot) = hit.iz;
+                K.I(I_MLEV, slot) = hit.lev;
+                if (found) K.I(I_STATE, slot) |= SK_ST_FOUND;
+                if (forced)
+                    cnt.replay_segs += nseg;
+                else
+                {
+                    cnt.fwd_paths++;
+                    cnt.fwd_segs += nseg;
+                }
+            }
+            else
+            {
+                K.D(D_PTAU, slot) = tau;
+                cnt.peel_paths++;
+                cnt.peel_segs += nseg;
+            }
+        }
+        {
+            const unsigned idle = __ballot_sync(0xffffffffu, !active);
+            if (chunk_pos >= chunk_end && !exhausted)
+            {
+                unsigned b = 0;
+                if (lane == 0) b = atomicAdd(&K.ctl[SK_CTL_CURSOR], (unsigned)SK_CHUNK);
+                b = __shfl_sync(0xffffffffu, b, 0);
+                if ((int)b >= n)
+                    exhausted = true;
+                else
+                {
+                    chunk_pos = (int)b;
+                    chunk_end = min((int)b + SK_CHUNK, n);
+                }
+            }
+            const int idx = chunk_pos + __popc(idle & lt_mask);
+            const int take = min(__popc(idle), chunk_end - chunk_pos);
+            if (!active && idx < chunk_end)
+            {
+                slot = K.list[idx];
+                active = true;
+                rx = K.D(D_RX, slot);
+                ry = K.D(D_RY, slot);
+                rz = K.D(D_RZ, slot);
+                if (MODE == 2)
+                    k = obs;
+                else
+                    k.set(K.D(D_KX, slot), K.D(D_KY, slot), K.D(D_KZ, slot));
+                p.m = K.I(I_M, slot);
+                p.ix = K.I(I_IX, slot);
+                p.iy = K.I(I_IY, slot);
+                p.iz = K.I(I_IZ, slot);
+                p.lev = K.I(I_LEV, slot);
+                section = K.D(D_SIGEXT, slot);
+                tau = 0.;
+                s = 0.;
+                nseg = 0;
+                if (MODE == 0 && STORE)
+                {
+                    lnExtBeg = 0.;
+                    extBeg = 1.;
+                    double lambda = K.D(D_LAMBDA, slot);
+                    rf_ell = sk_wlg_bin(M.wlg[M.rf_grid], lambda);  // MonteCarloSimulation.cpp:643
+                    rf = A.primary ? M.rf1 : M.rf2c;
+                    lum = K.D(D_W, slot) / lambda;
+                }
+                if (MODE == 1)
+                {
+                    limit = K.D(D_TAUINT, slot);
+                    hit = p;
+                    found = false;
+                    s_int = 0.;
+                }
+                if (MODE == 2) limit = K.D(D_LIMIT, slot);
+                if (p.m < 0)
+                {
+                    // the path starts outside (or exactly on the border of) the grid: PathSegmentGenerator::moveInside
+                    double cumds = 0.;
+                    double tx = rx, ty = ry, tz = rz;
+                    if (sk_move_inside(tx, ty, tz, k.kx, k.ky, k.kz, Mg->ext, M.eps, cumds))
+                    {
+                        SkCellPos q;
+                        sk_locate<GRID>(Mg, T, tx, ty, tz, q);
+                        rx = tx;
+                        ry = ty;
+                        rz = tz;
+                        p = q;
+                        if (cumds > 0.)
+                        {
+                            // the empty segment in front of the grid (m = -1)
+                            nseg++;
+                            s += cumds;
+                        }
+                    }
+                    if (p.m < 0)
+                    {
+                        // the path misses the grid: no segments
+                        active = false;
+                        pending = true;
+                        if (MODE == 1) s_int = s;
+                    }
+                }
+            }
+            if (take > 0) chunk_pos += take;
+            if (!__any_sync(0xffffffffu, active || pending))
+            {
+                if (exhausted) break;
+                continue;  // the chunk ran out exactly here: reserve the next one
+            }
+        }
+        // ---------------- inner loop: cross cells until enough lanes have finished their ray
+        const int want_idle = (exhausted && chunk_pos >= chunk_end) ? 32 : SK_REFILL_MIN;
+        int nidle;
+        do
+        {
+            if (active)
+            {
+                int m;
+                double dens, ds;
+                const SkCellPos cur = p;
+                sk_step<GRID>(M, Mg, T, cnt, rx, ry, rz, k, p, m, dens, ds);
+                bool done = false;
+                if (MODE == 0)
+                {
+                    if (ds > 0.)  // SpatialGridPath::addSegment, SpatialGridPath.cpp:41-48
+                    {
+                        nseg++;
+                        s += ds;
+                        tau += section * dens * ds;
+                        if (STORE && rf_ell >= 0)
+                        {
+                            double lnExtEnd = -tau;
+                            double extEnd = exp(lnExtEnd);
+                            double extMean = sk_lnmean4(extEnd, extBeg, lnExtEnd, lnExtBeg);
+                            double Lds = lum * extMean * ds;
+                            atomicAdd(&rf[(size_t)m * M.nrf + rf_ell], Lds);  // MediumSystem.cpp:1294-1300
+                            cnt.rf++;
+                            lnExtBeg = lnExtEnd;
+                            extBeg = extEnd;
+                        }
+                    }
+                }
+                else if (MODE == 1)
+                {
+                    if (forced ? (ds > 0.) : true)
+                    {
+                        nseg++;
+                        double tau0 = tau, s0 = s;
+                        s += ds;
+                        tau += section * dens * ds;
+                        hit = cur;
+                        if (limit < tau)
+                        {
+                            s_int = sk_interp_linlin(limit, tau0, tau, s0, s);  // interaction inside this segment
+                            found = true;
+                            done = true;
+                        }
+                    }
+                }
+                else
+                {
+                    nseg++;
+                    tau += section * dens * ds;
+                    if (tau >= limit)
+                    {
+                        tau = INFINITY;  // MediumSystem.cpp:1215
+                        done = true;
+                    }
+                }
+                if (!done && p.m < 0)
+                {
+                    // the path has left the grid; MODE 1: at or beyond the exit optical depth of the last segment ->
+                    // use the last segment (SpatialGridPath.cpp:199-205); non-forced: no interaction
+                    done = true;
+                    if (MODE == 1) s_int = s;
+                }
+                if (done)
+                {
+                    active = false;
+                    pending = true;
+                }
+            }
+            nidle = __popc(__ballot_sync(0xffffffffu, !active));
+        } while (nidle < want_idle);
+    }
+    sk_flush_counters(M, cnt);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Event kernels: one thread per slot of the bank
+// ---------------------------------------------------------------------------------------------------
+// Peel-off set-up towards the observer group [j0, j1): the weight of the peel-off packet and whether it needs an
+// optical depth at all.  MonteCarloSimulation::peelOffEmission (.cpp:617-634) / peelOffScattering (.cpp:784-842,
+// consolidated branch), DustMix::peeloffScattering HG branch (DustMix.cpp:430-445), MediumSystem::peelOffScattering
+// (MediumSystem.cpp:734-767) with the single-medium weight 1, PhotonPacket::launchScatteringPeelOff / launchEmissionPeelOff
+// (PhotonPacket.cpp:66-103).  Returns true when the slot joins the peel-off ray list.
+__device__ __forceinline__ bool sk_peel_setup(const SkDevModel& M, const SkBank& K, int slot, int st, int j0, int j1)
+{
+    const SkDevInstr& q0 = M.instr[j0];
+    const double ox = q0.kobs[0], oy = q0.kobs[1], oz = q0.kobs[2];
+    double W = K.D(D_W, slot);
+    double lambda = K.D(D_LAMBDA, slot);
+    double peelW;
+    if (st & SK_ST_SCATTER)
+    {
+        double costheta = K.D(D_KX, slot) * ox + K.D(D_KY, slot) * oy + K.D(D_KZ, slot) * oz;
+        double gp = M.gpar[K.I(I_ILAM, slot)];
+        double value = fabs(gp) > 0.95 ? sk_mean_hg(gp, costheta) : sk_value_hg(gp, costheta);
+        double I = 0.;
+        I += value * 1.;
+        peelW = W * I;
+    }
+    else
+        peelW = W;  // isotropic emission
+    K.D(D_PEELW, slot) = peelW;
+    double x = K.D(D_RX, slot), y = K.D(D_RY, slot), z = K.D(D_RZ, slot);
+    bool need = false;
+    for (int j = j0; j < j1; ++j)
+    {
+        int l, ell;
+        if (sk_detect_geometry(M, M.instr[j], x, y, z, lambda, l, ell)) need = true;
+    }
+    if (need)
+    {
+        double L = peelW / lambda;
+        if (L <= 0)
+        {
+            K.D(D_PTAU, slot) = INFINITY;  // MediumSystem.cpp:1196
+            need = false;
+        }
+        else
+            K.D(D_LIMIT, slot) = log(L) + 745;  // MediumSystem.cpp:1199
+    }
+    return need;
+}
+
+// advance: the interaction that ends the previous round, the launch of new histories into free slots, and the
+// peel-off set-up towards the first observer group.
+template <int GRID>
+__global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_advance(const SkDevModel M, const SkRunArgs A, const SkBank K,
+                                                                 const int j0, const int j1)
+{
+    const SkSmemTables T{M.xv, M.yv, M.zv};
+    const SkDevModel* __restrict__ Mg = A.model;
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const bool forced = M.force_scattering != 0;
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = slot < K.cap;
+    SkLocalCounters cnt;
+    memset(&cnt, 0, sizeof cnt);
+    int st = valid ? K.I(I_STATE, slot) : 0;
+
+    // ---- the interaction: albedo weight, move, termination test (.cpp:724-741, 576-580)
+    if (st & SK_ST_LIVE)
+    {
+        bool alive = true;
+        if (!forced && !(st & SK_ST_FOUND)) alive = false;  // escaped, MonteCarloSimulation.cpp:594
+        if (alive)
+        {
+            int m = K.I(I_MINT, slot);
+            int ilam = K.I(I_ILAM, slot);
+            // MediumSystem::albedoForScattering, MediumSystem.cpp:678-693
+            double albedo = 0.;
+            if (m >= 0)
+            {
+                double dn = sk_cell_density<GRID>(M, m);
+                double ksca = dn * M.sig_sca[ilam];
+                double kext = dn * K.D(D_SIGEXT, slot);
+                albedo = kext > 0. ? ksca / kext : 0.;
+            }
+            double W = K.D(D_W, slot);
+            if (forced)
+                W *= -expm1(-K.D(D_TAUPATH, slot)) * albedo;
+            else
+                W *= albedo;
+            double sint = K.D(D_SINT, slot);
+            double kx = K.D(D_KX, slot), ky = K.D(D_KY, slot), kz = K.D(D_KZ, slot);
+            double x = K.D(D_RX, slot) + sint * kx;  // PhotonPacket::propagate, PhotonPacket.cpp:107-111
+            double y = K.D(D_RY, slot) + sint * ky;
+            double z = K.D(D_RZ, slot) + sint * kz;
+            K.D(D_W, slot) = W;
+            K.D(D_RX, slot) = x;
+            K.D(D_RY, slot) = y;
+            K.D(D_RZ, slot) = z;
+            double L = W / K.D(D_LAMBDA, slot);
+            if (forced)
+            {
+                if (L <= 0 || (L <= K.D(D_LTHR, slot) && K.I(I_NSCATT, slot) >= M.min_scatt_events)) alive = false;
+            }
+            else if (L <= 0)
+                alive = false;
+            if (alive)
+            {
+                // the next paths start in the interaction cell unless rounding moved the point out of it
+                SkCellPos c{m, K.I(I_MIX, slot), K.I(I_MIY, slot), K.I(I_MIZ, slot), K.I(I_MLEV, slot)};
+                bool inside = m >= 0 && sk_box_strictly_inside(M.ext, x, y, z);
+                if (inside && !sk_cell_contains<GRID>(M, T, c, x, y, z))
+                {
+                    SkCellPos c2;
+                    sk_locate<GRID>(Mg, T, x, y, z, c2);
+                    c = c2;
+                }
+                if (!inside) c.m = -1;
+                K.I(I_M, slot) = c.m;
+                K.I(I_IX, slot) = c.ix;
+                K.I(I_IY, slot) = c.iy;
+                K.I(I_IZ, slot) = c.iz;
+                K.I(I_LEV, slot) = c.lev;
+                st = SK_ST_LIVE | SK_ST_SCATTER;
+                K.I(I_STATE, slot) = st;
+            }
+        }
+        if (!alive)
+        {
+            sk_finish_history(M, K, slot);
+            st = 0;
+        }
+    }
+
+    // ---- launch a history into every free slot (SourceSystem::launch)
+    {
+        const bool want = valid && !(st & SK_ST_LIVE);
+        const unsigned mask = __ballot_sync(0xffffffffu, want);
+        if (mask)
+        {
+            const int leader = __ffs(mask) - 1;
+            unsigned long long b = 0;
+            if ((int)lane == leader) b = atomicAdd(A.work_counter, (unsigned long long)__popc(mask));
+            b = __shfl_sync(0xffffffffu, b, leader);
+            const unsigned long long h = b + __popc(mask & lt_mask);
+            if (want && h < A.count)
+            {
+                const unsigned long long history = A.first + h;
+                SkRng g;
+                sk_rng_init(g, M.seed, A.stream_id, history, 0);
+                SkLaunch pp;
+                if (A.primary)
+                    sk_launch_primary(Mg, g, history, pp);
+                else
+                    sk_launch_secondary<GRID>(Mg, T, g, history, pp);
+                if (pp.W / pp.lambda > 0)  // MonteCarloSimulation.cpp:553
+                {
+                    cnt.packets++;
+                    SkCellPos c;
+                    c.m = -1;
+                    c.ix = c.iy = c.iz = c.lev = 0;
+                    if (sk_box_strictly_inside(M.ext, pp.rx, pp.ry, pp.rz)) sk_locate<GRID>(Mg, T, pp.rx, pp.ry, pp.rz, c);
+                    K.D(D_RX, slot) = pp.rx;
+                    K.D(D_RY, slot) = pp.ry;
+                    K.D(D_RZ, slot) = pp.rz;
+                    K.D(D_KX, slot) = pp.kx;
+                    K.D(D_KY, slot) = pp.ky;
+                    K.D(D_KZ, slot) = pp.kz;
+                    K.D(D_LAMBDA, slot) = pp.lambda;
+                    K.D(D_W, slot) = pp.W;
+                    K.D(D_LTHR, slot) = (pp.W / pp.lambda) / M.min_weight_reduction;  // .cpp:563
+                    K.D(D_SIGEXT, slot) = M.sig_ext[pp.ilam];
+                    K.I(I_HLO, slot) = (int)(uint32_t)history;
+                    K.I(I_HHI, slot) = (int)(uint32_t)(history >> 32);
+                    K.I(I_DRAW, slot) = (int)g.draw;
+                    K.I(I_NSCATT, slot) = 0;
+                    K.I(I_ILAM, slot) = pp.ilam;
+                    K.I(I_M, slot) = c.m;
+                    K.I(I_IX, slot) = c.ix;
+                    K.I(I_IY, slot) = c.iy;
+                    K.I(I_IZ, slot) = c.iz;
+                    K.I(I_LEV, slot) = c.lev;
+                    for (int j = 0; j < M.ninstr; ++j)
+                    {
+                        K.D(D_HISTW0 + j, slot) = 0.;
+                        K.I(I_HELL0 + j, slot) = -1;
+                    }
+                    st = SK_ST_LIVE;
+                    K.I(I_STATE, slot) = st;
+                }
+            }
+        }
+    }
+
+    // ---- census of the bank, and the peel-off rays towards the first observer group
+    const bool live = (st & SK_ST_LIVE) != 0;
+    {
+        const unsigned mask = __ballot_sync(0xffffffffu, live);
+        if (lane == 0 && mask) atomicAdd(&K.ctl[SK_CTL_NLIVE], (unsigned)__popc(mask));
+    }
+    if (A.peel && j1 > j0)
+    {
+        bool need = live && sk_peel_setup(M, K, slot, st, j0, j1);
+        sk_list_append(K, need, slot);
+    }
+    sk_flush_counters(M, cnt);
+}
+
+// peel-off set-up towards a further observer group
+__global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_peel_setup(const SkDevModel M, const SkBank K, const int j0,
+                                                                    const int j1)
+{
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const int st = slot < K.cap ? K.I(I_STATE, slot) : 0;
+    bool need = (st & SK_ST_LIVE) && sk_peel_setup(M, K, slot, st, j0, j1);
+    sk_list_append(K, need, slot);
+}
+
+// detect: FluxRecorder::detect (FluxRecorder.cpp:304-468) for the observer group [j0, j1); when `last`, also the
+// pending scattering events -- MediumSystem::simulateScattering (MediumSystem.cpp:796-823) + DustMix::performScattering
+// HG branch (DustMix.cpp:496-511) -- and the list of forward rays.
+__global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_detect(const SkDevModel M, const SkRunArgs A, const SkBank K,
+                                                                const int j0, const int j1, const int last)
+{
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = slot < K.cap;
+    SkLocalCounters cnt;
+    memset(&cnt, 0, sizeof cnt);
+    int st = valid ? K.I(I_STATE, slot) : 0;
+    const bool live = (st & SK_ST_LIVE) != 0;
+    if (live && j1 > j0)
+    {
+        double lambda = K.D(D_LAMBDA, slot);
+        double x = K.D(D_RX, slot), y = K.D(D_RY, slot), z = K.D(D_RZ, slot);
+        double L = K.D(D_PEELW, slot) / lambda;
+        int nscatt = (st & SK_ST_SCATTER) ? K.I(I_NSCATT, slot) + 1 : 0;
+        for (int j = j0; j < j1; ++j)
+        {
+            const SkDevInstr& q = M.instr[j];
+            int l, ell;
+            if (!sk_detect_geometry(M, q, x, y, z, lambda, l, ell)) continue;
+            double Lext = L * exp(-K.D(D_PTAU, slot));
+            cnt.det++;
+            sk_record(q, l, ell, L, Lext, nscatt, A.primary != 0);
+            if (q.record_stats && q.include_sed)
+            {
+                K.D(D_HISTW0 + j, slot) += Lext;  // FluxRecorder.cpp:457-466
+                K.I(I_HELL0 + j, slot) = ell;
+            }
+        }
+    }
+    if (last)
+    {
+        if (live && (st & SK_ST_SCATTER))
+        {
+            SkRng g;
+            sk_rng_load(g, M, A, K, slot);
+            double gp = M.gpar[K.I(I_ILAM, slot)];
+            double kx = K.D(D_KX, slot), ky = K.D(D_KY, slot), kz = K.D(D_KZ, slot);
+            if (fabs(gp) < 1e-6)
+                sk_random_direction(g, kx, ky, kz);
+            else
+            {
+                double f = ((1.0 - gp) * (1.0 + gp)) / (1.0 - gp + 2.0 * gp * sk_uniform(g));
+                double costheta = (1.0 + gp * gp - f * f) / (2.0 * gp);
+                sk_random_direction_about(g, kx, ky, kz, costheta);
+            }
+            K.D(D_KX, slot) = kx;
+            K.D(D_KY, slot) = ky;
+            K.D(D_KZ, slot) = kz;
+            K.I(I_DRAW, slot) = (int)g.draw;
+            K.I(I_NSCATT, slot) += 1;
+            K.I(I_STATE, slot) = st & ~SK_ST_SCATTER;
+            cnt.scatt++;
+        }
+        if (M.force_scattering) sk_list_append(K, live, slot);
+    }
+    sk_flush_counters(M, cnt);
+}
+
+// sample: the interaction optical depth -- simulateForcedPropagation (.cpp:696-722) or Random::expon for
+// simulateNonForcedPropagation (.cpp:749) -- and the list of rays to walk to the interaction point.
+__global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_sample(const SkDevModel M, const SkRunArgs A, const SkBank K)
+{
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = slot < K.cap;
+    const bool forced = M.force_scattering != 0;
+    int st = valid ? K.I(I_STATE, slot) : 0;
+    bool live = (st & SK_ST_LIVE) != 0;
+    if (live)
+    {
+        SkRng g;
+        sk_rng_load(g, M, A, K, slot);
+        if (forced)
+        {
+            double taupath = K.D(D_TAUPATH, slot);
+            if (!(K.I(I_NSEG, slot) > 0 && taupath > 0.))
+            {
+                // no extinction along the path: the packet cannot scatter, terminate it (.cpp:702-706)
+                sk_finish_history(M, K, slot);
+                live = false;
+            }
+            else
+            {
+                double xi = M.path_length_bias;
+                double tauint;
+                if (xi == 0.)
+                    tauint = sk_expon_cutoff(g, taupath);
+                else
+                {
+                    tauint = sk_uniform(g) < xi ? sk_uniform(g) * taupath : sk_expon_cutoff(g, taupath);
+                    double pw = -exp(-tauint) / expm1(-taupath);
+                    double qw = (1.0 - xi) * pw + xi / taupath;
+                    K.D(D_W, slot) *= pw / qw;
+                }
+                K.D(D_TAUINT, slot) = tauint;
+            }
+        }
+        else
+            K.D(D_TAUINT, slot) = -log(sk_uniform(g));
+        if (live)
+        {
+            K.I(I_DRAW, slot) = (int)g.draw;
+            K.I(I_STATE, slot) = st & ~SK_ST_FOUND;
+        }
+    }
+    sk_list_append(K, live, slot);
+}

@@ -327,10 +327,42 @@ class MeanListDustMix:
         self.sigma_sca = _clamped_resample(lam, self.inlam, mu * self.inkappa * self.inalbedo, True)
         g = _clamped_resample(lam, self.inlam, self.ing, False)
         self.asymmpar = np.where(np.abs(g) > 0.999999, np.copysign(0.999999, g), g)
+        self.sigma_abs_unclipped = self.sigma_abs.copy()
         if cutoff:
             self.sigma_abs[-2:] = 0.0
             self.sigma_sca[-2:] = 0.0
         self.mu = mu
+
+    def precalculate(self, rf_grid, em_grid):
+        """EquilibriumDustEmissionCalculator::precalculate, EquilibriumDustEmissionCalculator.cpp:18-93 (one dust
+        population, no CMB heating): sigma_abs resampled log-log on the radiation-field and (extended) emission grids and
+        the Planck-integrated absorption cross section on the power-law temperature grid 0..5000 K."""
+        lam, sig = self.lambdav, self.sigma_abs_unclipped
+
+        def resample_loglog(x):  # NR::resample<interpolateLogLog>: zero outside the table, NR.hpp:406-413
+            x = np.asarray(x, dtype=float)
+            out = np.zeros_like(x)
+            ok = (x >= lam[0]) & (x <= lam[-1])
+            i = np.clip(np.searchsorted(lam, x[ok], side="right") - 1, 0, len(lam) - 2)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                v = sig[i] * np.exp(np.log(x[ok] / lam[i]) / np.log(lam[i + 1] / lam[i]) * np.log(sig[i + 1] / sig[i]))
+            bad = (sig[i] <= 0) | (sig[i + 1] <= 0)
+            v[bad] = np.where(x[ok][bad] == lam[i][bad], sig[i][bad], np.where(x[ok][bad] == lam[i + 1][bad], sig[i + 1][bad], 0.0))
+            out[ok] = v
+            return out
+
+        self.rf_sigma_abs = resample_loglog(rf_grid.lambdav)
+        self.em_lambda = np.concatenate([[em_grid.borderv[0]], em_grid.lambdav, [em_grid.borderv[-1]]])  # extlambdav
+        self.em_sigma_abs = resample_loglog(self.em_lambda)
+        n, ratio, xmax = 1000, 500.0, 5000.0       # NR::buildPowerLawGrid(_Tv, 0., 5000., 1000, 500.), NR.hpp:221-235
+        q = ratio ** (1.0 / (n - 1))
+        self.Tv = (1.0 - q ** np.arange(n + 1)) / (1.0 - q ** n) * xmax
+        dl = lam[1:] - lam[:-1]
+        planckabs = np.zeros(n + 1)
+        with np.errstate(over="ignore", divide="ignore"):
+            for p_ in range(1, n + 1):
+                planckabs[p_] = np.sum(sig[1:] * planck(lam[1:], self.Tv[p_]) * dl)
+        self.planck_abs = planckabs
 
     def index_for_lambda(self, lam):
         """DustMix::indexForLambda = NR::locateClip(_lambdav, lambda), DustMix.cpp:276-279."""
@@ -644,6 +676,18 @@ class MonteCarloSimulation:
     sourceBias: float = 0.5
     numDensitySamples: int = 100
     seed: int = 0
+    # DustEmission mode (MonteCarloSimulation.hpp:223-273, DustEmissionOptions, SecondaryEmissionOptions, IterationOptions)
+    dustEmissionWLG: Optional[DisjointWavelengthGrid] = None   # given => simulationMode DustEmission
+    iterateSecondaryEmission: bool = False
+    minSecondaryIterations: int = 1
+    maxSecondaryIterations: int = 10
+    maxFractionOfPrimary: float = 0.01
+    maxFractionOfPrevious: float = 0.03
+    secondarySpatialBias: float = 0.5
+    dustEmissionWavelengthBias: float = 0.5
+    storeEmissionRadiationField: bool = False
+    secondaryPacketsMultiplier: float = 1.0
+    secondaryIterationPacketsMultiplier: float = 1.0
     setup_seed: int = 12345  # host-side sampling of densities / tree policy (numpy RNG)
     density: Optional[np.ndarray] = field(default=None, repr=False)
 
@@ -660,7 +704,8 @@ class MonteCarloSimulation:
             self.source_range = (self.minWavelength, self.maxWavelength)
         # wavelength grids addressed by index
         self.grids = []
-        for g in [self.defaultWavelengthGrid, self.radiationFieldWLG] + [i.wavelengthGrid for i in self.instruments]:
+        for g in [self.defaultWavelengthGrid, self.radiationFieldWLG, self.dustEmissionWLG] \
+                + [i.wavelengthGrid for i in self.instruments]:
             if g is not None and all(g is not h for h in self.grids):
                 self.grids.append(g)
         # Configuration::simulationWavelengthRange / simulationWavelengths, Configuration.cpp:566-662
@@ -674,6 +719,10 @@ class MonteCarloSimulation:
             lo, hi = min(lo, 0.09e-6), max(hi, 2000e-6)
         lo, hi = lo / 1.01, hi * 1.01
         self.medium.mix.setup((lo, hi), extra)
+        if self.dustEmissionWLG is not None:
+            if not self.storeRadiationField or self.radiationFieldWLG is None:
+                raise ValueError("DustEmission mode needs a stored radiation field")
+            self.medium.mix.precalculate(self.radiationFieldWLG, self.dustEmissionWLG)
         self.medium.setup()
         for s in self.sources:
             s.sed.setup(self.source_range)
@@ -735,11 +784,26 @@ class MonteCarloSimulation:
         for i in self.instruments:
             g = i.wavelengthGrid if (i.wavelengthGrid is not None and not oligo) else self.defaultWavelengthGrid
             instr.append(i.fields([k for k, h in enumerate(self.grids) if h is g][0]))
-        engine.set_instruments(instr, False)
+        engine.set_instruments(instr, self.dustEmissionWLG is not None)
+        if self.dustEmissionWLG is not None:
+            mix, eg = self.medium.mix, self.dustEmissionWLG
+            lo, hi = eg.wavelength_range()
+            engine.set_secondary([k for k, h in enumerate(self.grids) if h is eg][0], self.secondarySpatialBias,
+                                 self.dustEmissionWavelengthBias, lo, hi, mix.Tv, mix.planck_abs, mix.rf_sigma_abs,
+                                 mix.em_sigma_abs)
         return engine
 
     def run(self, engine: abi.Engine, first=0, count=None, stream_id=0):
-        """MonteCarloSimulation::runPrimaryEmission, MonteCarloSimulation.cpp:104-138 (single rank)."""
+        """MonteCarloSimulation::runSimulation, MonteCarloSimulation.cpp:58-100 (single rank): primary emission and, in
+        DustEmission mode, the secondary emission iterations and the final secondary emission."""
+        self.run_primary_emission(engine, first, count, stream_id)
+        if self.dustEmissionWLG is not None:
+            if self.iterateSecondaryEmission:
+                self.run_secondary_emission_iterations(engine, stream_id + 1000)
+            self.run_secondary_emission(engine, stream_id + 2000)
+
+    def run_primary_emission(self, engine, first=0, count=None, stream_id=0):
+        """MonteCarloSimulation::runPrimaryEmission, MonteCarloSimulation.cpp:104-138."""
         n = int(self.numPackets)
         store = self.storeRadiationField
         if store:
@@ -749,6 +813,45 @@ class MonteCarloSimulation:
                            stream_id=stream_id)
         if store:
             engine.communicate_rf(True)
+
+    def run_secondary_emission(self, engine, stream_id=2000):
+        """MonteCarloSimulation::runSecondaryEmission, MonteCarloSimulation.cpp:142-173."""
+        store = self.storeEmissionRadiationField
+        if store:
+            engine.clear_rf(False)
+        n = int(self.numPackets * self.secondaryPacketsMultiplier)
+        self.dust_luminosity = engine.prepare_secondary(n)
+        if self.dust_luminosity > 0:
+            engine.run_segment(0, n, primary=False, peel=True, store=store, stream_id=stream_id)
+        if store:
+            engine.communicate_rf(False)
+
+    def run_secondary_emission_iterations(self, engine, stream_id=1000):
+        """MonteCarloSimulation::runSecondaryEmissionIterations (.cpp:335-403) with DustAbsorptionConvergence
+        (.cpp:180-227) and logLoopConvergence (.cpp:233-261).  Records the log values in self.convergence."""
+        n = int(self.numPackets * self.secondaryIterationPacketsMultiplier)
+        self.convergence = []
+        prev = 0.0
+        it = 0
+        while True:
+            it += 1
+            engine.clear_rf(False)
+            lum = engine.prepare_secondary(n)
+            if not lum > 0:
+                return
+            engine.run_segment(0, n, primary=False, peel=False, store=True, stream_id=stream_id + it)
+            engine.communicate_rf(False)
+            Lprim, Lseco = engine.absorbed_luminosity(True), engine.absorbed_luminosity(False)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                converged = (Lprim <= 0 or Lseco <= 0 or Lseco / Lprim < self.maxFractionOfPrimary
+                             or abs((Lseco - prev) / Lseco) < self.maxFractionOfPrevious)
+            prev = Lseco
+            self.convergence.append({"iteration": it, "dust_luminosity": lum, "absorbed_primary": Lprim,
+                                     "absorbed_secondary": Lseco, "converged": bool(converged)})
+            if converged and it >= self.minSecondaryIterations:
+                break
+            if not converged and it >= self.maxSecondaryIterations:
+                break
 
     # -- calibration of raw tallies to the units the reference writes ------------------------------
     def sed_flux_density(self, engine, instrument=0, component=abi.SK_COMP_TOTAL):

@@ -54,8 +54,12 @@ def read_columns(path):
     return np.loadtxt(path, comments="#", ndmin=2)
 
 
-def run_reference(ski_name, workdir, extra_inputs=None, threads=1):
+def run_reference(ski_name, workdir, extra_inputs=None, threads=1, packets=None):
     ski = os.path.join(HERE, "ski", ski_name + ".ski")
+    if packets is not None:
+        text = re.sub(r'numPackets="[^"]*"', 'numPackets="%g"' % packets, open(ski).read(), count=1)
+        ski = os.path.join(workdir, ski_name + ".ski")
+        open(ski, "w").write(text)
     for name, text in (extra_inputs or {}).items():
         open(os.path.join(workdir, name), "w").write(text)
     subprocess.check_call([SKIRT, "-t", str(threads), "-b", "-i", workdir, "-o", workdir, ski],
@@ -108,6 +112,41 @@ def make_cfg2s():
     print("cfg2s:", {k: np.shape(v) for k, v in out.items()})
 
 
+def make_hi(name, packets=2e7):
+    """High-statistics companion of a fixture: the same ski with `packets` histories, still with `-t 1` because the
+    tree and the cell densities are sampled from the thread's random stream (Random.cpp:31-36) and must stay those of
+    the base fixture; only the SED, its statistics and the wavelength-summed frame are kept."""
+    with tempfile.TemporaryDirectory() as d:
+        run_reference(name, d, threads=1, packets=packets)
+        out = dict(sed=read_columns(os.path.join(d, name + "_i60_sed.dat")),
+                   sedstats=read_columns(os.path.join(d, name + "_i60_sedstats.dat")), num_packets=packets)
+        out["frame_total_sum"] = read_fits_cube(os.path.join(d, name + "_i60_total.fits"))[0].astype(np.float64).sum(axis=0)
+        dens = read_columns(os.path.join(d, name + "_cells_cellprops.dat"))[:, 6]
+        base = np.load(os.path.join(HERE, name + "_ref.npz"))["mass_density_msun_pc3"]
+        assert np.array_equal(dens, base), "the high-statistics run must see the inputs of the base fixture"
+    np.savez_compressed(os.path.join(HERE, name + "_hi_ref.npz"), **out)
+    print(name + "_hi:", {k: np.shape(v) for k, v in out.items()})
+
+
+def make_cfg1_hi():
+    make_hi("cfg1")
+
+
+def make_cfg2s_hi():
+    make_hi("cfg2s")
+
+
+def shell_average(cells, J, nshell=32, rmax=1.0):
+    """Volume-weighted mean of the per-cell J_nu in `nshell` radial shells of width rmax/nshell pc (keeps the fixture small;
+    the per-cell values are dominated by Monte-Carlo noise anyway)."""
+    r = np.linalg.norm(cells[:, 1:4], axis=1)
+    V = cells[:, 4]
+    k = np.minimum((r / (rmax / nshell)).astype(int), nshell - 1)
+    num = np.stack([np.bincount(k, weights=V * J[:, ell], minlength=nshell) for ell in range(J.shape[1])], axis=1)
+    den = np.bincount(k, weights=V, minlength=nshell)
+    return num / np.maximum(den, 1e-300)[:, None]
+
+
 def make_cfg4s():
     with tempfile.TemporaryDirectory() as d:
         log = run_reference("cfg4s", d)
@@ -115,15 +154,16 @@ def make_cfg4s():
         cells = read_columns(os.path.join(d, "cfg4s_cells_cellprops.dat"))
         topo = parse_topology(os.path.join(d, "cfg4s_topo_treetop.dat"))
         rfJ = read_columns(os.path.join(d, "cfg4s_rf_J.dat"))
-        T = read_columns(os.path.join(d, "cfg4s_temp_T.dat"))
+        T = read_columns(os.path.join(d, "cfg4s_temp_dust_T.dat"))
         # convergence log lines, MonteCarloSimulation.cpp:193-214
-        prim = [float(x) for x in re.findall(r"absorbed primary luminosity: ([0-9.eE+-]+) Lsun", log)]
-        sec = [float(x) for x in re.findall(r"absorbed secondary luminosity: ([0-9.eE+-]+) Lsun", log)]
+        prim = [float(x) for x in re.findall(r"dust-absorbed primary luminosity is ([0-9.eE+-]+) Lsun", log)]
+        sec = [float(x) for x in re.findall(r"dust-absorbed secondary luminosity in iteration \d+ is ([0-9.eE+-]+) Lsun", log)]
+        dustlum = [float(x) for x in re.findall(r"Dust luminosity: ([0-9.eE+-]+) Lsun", log)]
         conv = re.search(r"Convergence reached after (\d+) iterations", log)
         out = dict(sed=sed, mass_density_msun_pc3=cells[:, 6], cell_center_pc=cells[:, 1:4], cell_volume_pc3=cells[:, 4],
-                   topology=topo, J_nu=rfJ[:, 1:].astype(np.float32), temperature=T[:, 1], absorbed_primary_lsun=np.array(prim),
-                   absorbed_secondary_lsun=np.array(sec), converged_after=int(conv.group(1)) if conv else -1,
-                   num_packets=2e5, log_tail=np.array(log[-6000:]))
+                   topology=topo, J_nu_shell=shell_average(cells, rfJ[:, 1:]), temperature=T[:, 1].astype(np.float32), absorbed_primary_lsun=np.array(prim),
+                   absorbed_secondary_lsun=np.array(sec), dust_luminosity_lsun=np.array(dustlum), converged_after=int(conv.group(1)) if conv else -1,
+                   num_packets=2e5)
     np.savez_compressed(os.path.join(HERE, "cfg4s_ref.npz"), **out)
     print("cfg4s:", {k: np.shape(v) for k, v in out.items()}, prim, sec, conv and conv.group(0))
 

@@ -56,6 +56,9 @@ def compare_engines(sim, a, b, rtol=1e-9):
         if ins.recordComponents:
             comps += [abi.SK_COMP_TRANSPARENT, abi.SK_COMP_PRIMARY_DIRECT, abi.SK_COMP_PRIMARY_SCATTERED]
             comps += [abi.SK_COMP_PRIMARY_SCATTERED_LEVEL + k for k in range(ins.numScatteringLevels)]
+            if sim.dustEmissionWLG is not None:
+                comps += [abi.SK_COMP_SECONDARY_DIRECT, abi.SK_COMP_SECONDARY_SCATTERED,
+                          abi.SK_COMP_SECONDARY_TRANSPARENT]
         for c in comps:
             if ins.kind in (abi.SK_INSTR_SED, abi.SK_INSTR_FULL):
                 x, y = a.read_sed(j, c), b.read_sed(j, c)
@@ -72,3 +75,13 @@ def compare_engines(sim, a, b, rtol=1e-9):
         np.testing.assert_allclose(x, y, rtol=rtol, atol=rtol * y.max())
         la, lb = a.absorbed_luminosity(True), b.absorbed_luminosity(True)
         assert abs(la - lb) <= 1e-9 * abs(lb)
+        if sim.dustEmissionWLG is not None:
+            for which in (1, 2):
+                x, y = a.read_rf(which), b.read_rf(which)
+                np.testing.assert_allclose(x, y, rtol=rtol, atol=rtol * max(y.max(), 1e-300), err_msg=f"rf {which}")
+
+
+def small_dust_emission(num_packets=20000, seed=7, **kw):
+    args = dict(max_level=5, max_dust_fraction=1e-3, num_sed_wavelengths=12, max_secondary_iterations=3)
+    args.update(kw)
+    return configs.cfg4(num_packets=num_packets, seed=seed, **args)

@@ -77,6 +77,52 @@ def test_history_sharding_matches_single_run(engine_lib):
     models.compare_engines(sim, a, b, rtol=1e-11)
 
 
+def test_dust_emission_iterations_match_oracle(engine_lib):
+    """DustEmission mode: primary emission, secondary-emission iterations to convergence, final secondary emission."""
+    import copy
+    sim = models.small_dust_emission(num_packets=20000).setup()
+    simc = copy.copy(sim)
+    gpu = sim.configure(abi.Engine(sim.config_struct(device=0), lib=engine_lib))
+    cpu = simc.configure(OracleEngine(simc.config_struct()))
+    sim.run(gpu)
+    simc.run(cpu)
+    assert len(sim.convergence) == len(simc.convergence) >= 1
+    for a, b in zip(sim.convergence, simc.convergence):
+        assert a["converged"] == b["converged"]
+        for key in ("dust_luminosity", "absorbed_primary", "absorbed_secondary"):
+            assert a[key] == pytest.approx(b[key], rel=1e-9), key
+    assert sim.dust_luminosity == pytest.approx(simc.dust_luminosity, rel=1e-9)
+    models.compare_engines(sim, gpu, cpu, rtol=1e-8)
+    sec = gpu.read_sed(0, abi.SK_COMP_SECONDARY_DIRECT)
+    assert sec.sum() > 0
+
+
+def test_dust_emission_on_cartesian_grid(engine_lib):
+    import copy
+    sim = models.small_dust_emission(num_packets=8000)
+    pc = 3.08567758e16
+    from skirt9_b200 import host as H
+    sim.grid = H.CartesianSpatialGrid(-pc, pc, -pc, pc, -pc, pc, 12, 10, 14)
+    sim.setup()
+    simc = copy.copy(sim)
+    gpu = sim.configure(abi.Engine(sim.config_struct(device=0), lib=engine_lib))
+    cpu = simc.configure(OracleEngine(simc.config_struct()))
+    sim.run(gpu)
+    simc.run(cpu)
+    models.compare_engines(sim, gpu, cpu, rtol=1e-8)
+
+
+def test_small_bank_refills_slots(engine_lib, monkeypatch):
+    """A bank far smaller than the number of histories: slots are reused many times; results do not change."""
+    sim = models.small_octree(num_packets=20000).setup()
+    a = sim.configure(abi.Engine(sim.config_struct(device=0), lib=engine_lib))
+    sim.run(a)
+    monkeypatch.setenv("SK_BANK", "1024")
+    b = sim.configure(abi.Engine(sim.config_struct(device=0), lib=engine_lib))
+    sim.run(b)
+    models.compare_engines(sim, a, b, rtol=1e-10)
+
+
 def test_full_size_octree_properties(engine_lib):
     """BASELINE.json configs[1] at full grid size (~9.3e5 cells) with 2e6 packets: size-independent properties --
     transparent SED equals the analytic L_nu/(4 pi d^2) per bin up to wavelength-sampling noise, components are
