@@ -188,12 +188,13 @@ def native_arm(args):
     if sampler:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms = []
+    kernel_ms, stage_ms = [], []
     ev0.record(stream)
     for k in range(args.steps):
         step(args.warmup + k)
-        engine.synchronize()                   # also reads back the kernel's own CUDA-event duration
+        engine.synchronize()                   # also reads back the engine's own CUDA-event durations
         kernel_ms.append(engine.last_kernel_ms())
+        stage_ms.append(engine.last_stage_ms())
     ev1.record(stream)
     barrier()
     ms_total = ev0.elapsed_time(ev1)
@@ -205,7 +206,7 @@ def native_arm(args):
     cnt = engine.counters()
 
     # ---- end-to-end through the public API with host buffers: tables H2D, run, tallies D2H, every step
-    e2e_steps = max(1, min(args.steps, 2))
+    e2e_steps = 0 if args.no_e2e else max(1, min(args.steps, 2))
     h2d = (sim.grid.first_child.nbytes + sim.density.nbytes + sim.volume.nbytes
            + sum(g.borderv.nbytes + g.ellv.nbytes + g.lambdav.nbytes + g.dlambdav.nbytes for g in sim.grids)
            + 4 * sim.medium.mix.lambda_border.nbytes + sum(3 * s.sed.lambdav.nbytes for s in sim.sources))
@@ -224,7 +225,7 @@ def native_arm(args):
         d2h = sum(o.nbytes for o in outs) + 2 * outs[4].nbytes  # total = direct + scattered is read as two arrays
         e2.close()
     barrier()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    e2e_s = (time.perf_counter() - t0) / max(e2e_steps, 1)
     te = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local}")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -239,7 +240,18 @@ def native_arm(args):
         P_peel = cnt["peel_paths"] / pk
         bytes_per_packet = 60.0 * S + 32.0 * P_peel + 64.0     # SURVEY.md 8d accounting (no RF store in cfg2)
         kms = sum(kernel_ms) / len(kernel_ms)
-        achieved = bytes_per_packet * packets_per_gpu / (kms * 1e-3) / 1e9
+        stages = {k: sum(d[k] for d in stage_ms) / len(stage_ms) for k in stage_ms[0]}
+        # the dominant kernel: the trace kernel with the largest share of the step; its algorithmic bytes are 60 B per
+        # segment it crosses (cell bounds 48 B + density 8 B + link 4 B), its time the sum of its launches
+        seg = {"trace_forward": cnt["forward_segments"], "trace_interaction": cnt["replay_segments"],
+               "trace_peel": cnt["peel_segments"]}
+        dom = max(seg, key=lambda k: stages[k])
+        dom_name = {"trace_forward": "sk_wf_trace<2,0,false>", "trace_interaction": "sk_wf_trace<2,1,false>",
+                    "trace_peel": "sk_wf_trace<2,2,false>"}[dom]
+        dom_bytes = 60.0 * seg[dom] / args.steps
+        dom_launches = cnt["rounds"] / args.steps
+        achieved = dom_bytes / (stages[dom] * 1e-3) / 1e9
+        whole_step = bytes_per_packet * packets_per_gpu / (kms * 1e-3) / 1e9
         peak, which = measured_peak()
         traffic = None
         try:
@@ -252,20 +264,27 @@ def native_arm(args):
                 "config": {"workload": WORKLOAD, "packets_per_gpu": packets_per_gpu, "cells": int(sim.grid.num_cells),
                            "l2": "256 MB buffer written between iterations", "sharding": "contiguous history blocks, "
                            "replicated grid, NCCL all-reduce of the instrument arrays per step" if world > 1 else "single GPU"},
-                "e2e": {"value": total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                        "includes": "engine create + octree link build + all table uploads + kernel + read-back of 4 SED and 4 IFU arrays"},
-                "gpu_launches": args.steps,
-                "kernel": {"name": "sk_life_cycle_kernel<2>", "ms_per_launch": kms,
+                "e2e": {"value": total / e2e_s if e2e_steps else None, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                        "includes": "engine create + octree link build + all table uploads + all stage kernels + read-back of 4 SED and 4 IFU arrays"},
+                "gpu_launches": int(cnt["kernel_launches"]),
+                "kernel": {"name": dom_name, "launches_per_step": dom_launches, "ms_per_step": stages[dom],
+                           "ms_per_launch": stages[dom] / max(dom_launches, 1), "share_of_step": stages[dom] / kms,
+                           "stage_ms_per_step": stages, "step_ms": kms,
                            "segments_per_packet": S, "forward_segments_per_packet": S_fwd,
                            "replay_segments_per_packet": cnt["replay_segments"] / pk,
                            "peel_paths_per_packet": P_peel, "scatterings_per_packet": cnt["scatterings"] / pk,
                            "segments_per_s": (cnt["forward_segments"] + cnt["peel_segments"] + cnt["replay_segments"])
-                           / args.steps / (kms * 1e-3), "tree_fallbacks": cnt["fallbacks"]},
+                           / args.steps / (kms * 1e-3), "tree_fallbacks_per_packet": cnt["fallbacks"] / pk,
+                           "rounds_per_step": cnt["rounds"] / args.steps},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "peak_source": which,
+                             "bytes_per_launch": dom_bytes / max(dom_launches, 1),
+                             "whole_step_achieved": whole_step, "whole_step_frac": whole_step / peak,
                              "bytes_per_packet": bytes_per_packet,
-                             "note": "algorithmic bytes (60 B/segment + 32 B/detection + 64 B/launch); the working set is "
-                                     "L2-resident so DRAM traffic is far lower: the kernel is latency/fp64-issue bound"},
+                             "note": "achieved = 60 B x segments crossed by the dominant trace kernel / its CUDA-event time; "
+                                     "whole_step = (60 B/segment + 32 B/detection + 64 B/launch) x packets / step time. The "
+                                     "30 MB of cell records are L2-resident, so DRAM traffic is far below the algorithmic "
+                                     "bytes: the kernel is latency / fp64-issue bound, not HBM bound"},
                 "clocks": clocks}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.cpu_packets)
@@ -284,6 +303,7 @@ def main():
     ap.add_argument("--cpu-packets", type=float, default=2e6, help="bounded sample for the cpu_baseline leg")
     ap.add_argument("--ref-packets", type=float, default=1e6, help="packets per step of --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs only)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

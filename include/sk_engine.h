@@ -82,7 +82,8 @@ enum sk_geometry_kind {
     SK_GEOM_EXPDISK = 2,        /* ExpDiskGeometry.cpp:46-68   p = {hR, hz, Rmin, Rmax, zmax} */
     SK_GEOM_RING = 3,           /* RingGeometry.cpp:56-68      p = {R0, w, hz} + radial cdf table */
     SK_GEOM_SPIRAL_EXPDISK = 4  /* SpiralStructureGeometryDecorator.cpp:33-45,72-76 on ExpDisk:
-                                   p = {hR, hz, Rmin, Rmax, zmax, m(arms), pitch, R0, phi0, w, N(index)} */
+                                   p = {hR, hz, Rmin, Rmax, zmax, m(arms), tan(pitch) = _tanp, R0, phi0, w, N(index),
+                                        _cn} with the setup values of SpiralStructureGeometryDecorator.cpp:12-20 */
 };
 enum sk_sed_kind {
     SK_SED_TABULATED = 1, /* specificLuminosity by log-log interpolation of (lambda,p) (TabulatedSED) */
@@ -177,7 +178,9 @@ typedef struct sk_counters {
     uint64_t rf_deposits;    /* MediumSystem::storeRadiationField calls */
     uint64_t detections;     /* FluxRecorder::detect calls that recorded */
     uint64_t fallbacks;      /* tree: top-down relocations after a failed neighbour link */
-    uint64_t reserved[6];
+    uint64_t kernel_launches;/* kernels launched by sk_engine_launch_segment / prepare_secondary (host-side count) */
+    uint64_t rounds;         /* rounds of the stage sequence over the bank */
+    uint64_t reserved[4];
 } sk_counters_t;
 
 /* ---- life cycle of the engine object ---------------------------------------------------------- */
@@ -252,8 +255,13 @@ int sk_engine_run_segment(sk_engine_t* e, uint64_t first, uint64_t count, int32_
 int sk_engine_launch_segment(sk_engine_t* e, uint64_t first, uint64_t count, int32_t primary, int32_t peel,
                              int32_t store, uint32_t stream_id);
 int sk_engine_synchronize(sk_engine_t* e);
-/* Device time (ms) of the last segment kernel, measured with CUDA events on the engine's stream. */
+/* Device time (ms) of the last segment (all its stage kernels), measured with CUDA events on the engine's stream. */
 int sk_engine_last_kernel_ms(sk_engine_t* e, float* ms);
+/* Device time (ms) of the last segment per stage kernel, summed over the rounds (CUDA events around every launch):
+ * out[SK_STAGE_*]. */
+enum sk_stage { SK_STAGE_ADVANCE = 0, SK_STAGE_LAUNCH, SK_STAGE_PEEL_SETUP, SK_STAGE_DETECT, SK_STAGE_SAMPLE, SK_STAGE_TRACE_FORWARD,
+                SK_STAGE_TRACE_INTERACTION, SK_STAGE_TRACE_PEEL, SK_STAGE_COUNT };
+int sk_engine_last_stage_ms(sk_engine_t* e, float out[SK_STAGE_COUNT]);
 
 /* MediumSystem::communicateRadiationField(primary) for the single-process case: _rf2 = _rf2c
  * (MediumSystem.cpp:1304-1313).  Across GPUs the caller all-reduces the device buffer first

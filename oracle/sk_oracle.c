@@ -1762,9 +1762,7 @@ static void generate_position(rng_t* g, const sk_source_t* s, double r[3])
             double z = expdisk_random_z(g, p[1], p[4]);
             double x0 = R0 * cos(phi0), y0 = R0 * sin(phi0);
             double R = sqrt(x0 * x0 + y0 * y0); /* Position::cylindrical, Position.cpp:104-109 */
-            double m = p[5], pitch = p[6], Rz = p[7], phiz = p[8], w = p[9], N = p[10];
-            double tanp = tan(pitch);
-            double cn = sqrt(M_PI) * tgamma(N + 1.0) / tgamma(N + 0.5);
+            double m = p[5], tanp = p[6], Rz = p[7], phiz = p[8], w = p[9], N = p[10], cn = p[11];
             double c = 1.0 + (cn - 1.0) * w;
             double phi, t;
             do

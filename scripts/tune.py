@@ -28,7 +28,8 @@ for path in libs:
         e.clear_instruments()
         e.run_segment(0, packets, True, True, False, k)
         ms.append(e.last_kernel_ms())
+    stages = {k: round(v, 1) for k, v in e.last_stage_ms().items()}
     c = e.counters()
     print(json.dumps({"variant": os.path.basename(path)[4:-3], "packets": packets, "ms": ms,
-                      "pkt_per_s": packets / (min(ms[1:]) * 1e-3), "fallbacks_per_pkt": c["fallbacks"] / c["packets"]}), flush=True)
+                      "pkt_per_s": packets / (min(ms[1:]) * 1e-3), "stages_ms": stages, "rounds": c["rounds"] / 3}), flush=True)
     e.close()

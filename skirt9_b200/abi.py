@@ -76,7 +76,8 @@ class SkSecondary(C.Structure):
 class SkCounters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in
                 ("packets", "forward_paths", "forward_segments", "replay_segments", "peel_paths", "peel_segments",
-                 "scatterings", "rf_deposits", "detections", "fallbacks")] + [("reserved", C.c_uint64 * 6)]
+                 "scatterings", "rf_deposits", "detections", "fallbacks", "kernel_launches", "rounds")] \
+        + [("reserved", C.c_uint64 * 4)]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_ if n != "reserved"}
@@ -112,7 +113,7 @@ ABI_FUNCTIONS = ["create", "destroy", "set_grid_cartesian", "set_grid_octree", "
                  "set_wavelength_grids", "set_sources", "set_instruments", "set_secondary", "clear_instruments", "clear_rf",
                  "prepare_primary", "prepare_secondary", "run_segment", "communicate_rf", "absorbed_luminosity",
                  "read_rf", "read_sed", "read_ifu", "read_sed_stats", "counters"]
-ENGINE_ONLY_FUNCTIONS = ["launch_segment", "synchronize", "last_kernel_ms", "device_buffer", "cuda_stream"]
+ENGINE_ONLY_FUNCTIONS = ["launch_segment", "synchronize", "last_kernel_ms", "last_stage_ms", "device_buffer", "cuda_stream"]
 
 
 class Engine:
@@ -311,6 +312,13 @@ class Engine:
 
     def synchronize(self):
         self._call("synchronize", self._h)
+
+    STAGES = ("advance", "launch", "peel_setup", "detect", "sample", "trace_forward", "trace_interaction", "trace_peel")
+
+    def last_stage_ms(self) -> dict:
+        out = (C.c_float * len(self.STAGES))()
+        self._call("last_stage_ms", self._h, out)
+        return dict(zip(self.STAGES, [float(x) for x in out]))
 
     def last_kernel_ms(self) -> float:
         ms = C.c_float()

@@ -96,7 +96,7 @@ struct sk_engine {
     double* stat_block = nullptr;
     size_t stat_count = 0;
     unsigned long long* work_counter = nullptr;
-    SkBank bank = {nullptr, nullptr, nullptr, nullptr, 0};  // the in-flight packets (sk_wavefront.cuh)
+    SkBank bank = {nullptr, nullptr, nullptr, nullptr, nullptr, 0};  // the in-flight packets (sk_wavefront.cuh)
     int bank_fields_d = 0, bank_fields_i = 0;
     unsigned int* ctl_host = nullptr;                       // pinned copy of the control words + work counter
     cudaEvent_t ev_ctl = nullptr;
@@ -109,11 +109,36 @@ struct sk_engine {
     bool timing_pending = false;
     std::vector<int> instr_same_observer;
     std::vector<std::array<double, 3>> instr_kobs;
-    bool secondary_ready = false, has_secondary = false;
+    bool secondary_ready = false, has_secondary = false, l2_policy_set = false;
     sk_secondary_t sec;
     std::vector<double> sec_Lv_host;
-    unsigned long long rounds_last = 0;
+    unsigned long long rounds_total = 0, launches_total = 0;
+    // per-stage timing of the last segment: event pairs around every launch
+    std::vector<cudaEvent_t> stage_events;  // pool, grown on demand
+    std::vector<int> stage_of_pair;         // stage id of pair i (events 2i, 2i+1) in the current segment
+    float stage_ms[SK_STAGE_COUNT] = {0};
 };
+
+static int stage_begin(sk_engine* e, int stage)
+{
+    size_t i = e->stage_of_pair.size();
+    while (e->stage_events.size() < 2 * (i + 1))
+    {
+        cudaEvent_t ev;
+        CK(cudaEventCreate(&ev));
+        e->stage_events.push_back(ev);
+    }
+    e->stage_of_pair.push_back(stage);
+    CK(cudaEventRecord(e->stage_events[2 * i], e->stream));
+    e->launches_total++;
+    return SK_OK;
+}
+static int stage_end(sk_engine* e)
+{
+    size_t i = e->stage_of_pair.size() - 1;
+    CK(cudaEventRecord(e->stage_events[2 * i + 1], e->stream));
+    return SK_OK;
+}
 
 static void free_group(std::vector<void*>& v)
 {
@@ -187,9 +212,11 @@ extern "C" void sk_engine_destroy(sk_engine_t* e)
     cudaFree(e->bank.d);
     cudaFree(e->bank.i);
     cudaFree(e->bank.list);
+    cudaFree(e->bank.free_list);
     cudaFree(e->bank.ctl);
     cudaFreeHost(e->ctl_host);
     if (e->ev_ctl) cudaEventDestroy(e->ev_ctl);
+    for (cudaEvent_t ev : e->stage_events) cudaEventDestroy(ev);
     cudaFree(e->model_dev);
     cudaFree(e->scalar);
     cudaFree(e->M.counters);
@@ -393,6 +420,7 @@ extern "C" int sk_engine_set_medium(sk_engine_t* e, int32_t num_cells, const dou
         e->M.dens = nullptr;
     }
     e->M.ncells = num_cells;
+    e->l2_policy_set = false;
     e->M.volume = nullptr;
     if (volume)
     {
@@ -917,13 +945,16 @@ static int ensure_bank(sk_engine* e, uint64_t count)
     cudaFree(e->bank.d);
     cudaFree(e->bank.i);
     cudaFree(e->bank.list);
+    cudaFree(e->bank.free_list);
     e->bank.d = nullptr;
     e->bank.i = nullptr;
     e->bank.list = nullptr;
+    e->bank.free_list = nullptr;
     e->bank.cap = 0;
     CK(cudaMalloc(&e->bank.d, cap * nd * sizeof(double)));
     CK(cudaMalloc(&e->bank.i, cap * ni * sizeof(int32_t)));
     CK(cudaMalloc(&e->bank.list, cap * sizeof(int32_t)));
+    CK(cudaMalloc(&e->bank.free_list, cap * sizeof(int32_t)));
     if (!e->bank.ctl) CK(cudaMalloc(&e->bank.ctl, SK_CTL_WORDS * sizeof(unsigned int)));
     if (!e->ctl_host) CK(cudaMallocHost(&e->ctl_host, (SK_CTL_WORDS + 2) * sizeof(unsigned int)));
     if (!e->ev_ctl) CK(cudaEventCreateWithFlags(&e->ev_ctl, cudaEventDisableTiming));
@@ -933,10 +964,10 @@ static int ensure_bank(sk_engine* e, uint64_t count)
     return SK_OK;
 }
 
-template <int GRID, int MODE, bool STORE>
-static int launch_trace(sk_engine* e, const SkRunArgs& A, const SkRayDir& dir)
+template <int GRID, int MODE, bool STORE, bool SMEMT>
+static int launch_trace_impl(sk_engine* e, const SkRunArgs& A, const SkRayDir& dir)
 {
-    auto kern = sk_wf_trace<GRID, MODE, STORE>;
+    auto kern = sk_wf_trace<GRID, MODE, STORE, SMEMT>;
     // occupancy of this instantiation for this engine's shared-memory footprint (cached per footprint)
     static size_t cached_smem = (size_t)-1;
     static int per_sm = 0;
@@ -953,9 +984,18 @@ static int launch_trace(sk_engine* e, const SkRunArgs& A, const SkRayDir& dir)
     unsigned long long blocks = (chunks + (SK_TRACE_BLOCK / 32) - 1) / (SK_TRACE_BLOCK / 32);
     unsigned grid = (unsigned)std::min<unsigned long long>((unsigned long long)e->num_sms * per_sm, std::max<unsigned long long>(blocks, 1));
     CK(cudaMemsetAsync(&e->bank.ctl[SK_CTL_CURSOR], 0, sizeof(unsigned int), e->stream));
+    if (int rc = stage_begin(e, MODE == 0 ? SK_STAGE_TRACE_FORWARD : MODE == 1 ? SK_STAGE_TRACE_INTERACTION : SK_STAGE_TRACE_PEEL))
+        return rc;
     kern<<<grid, SK_TRACE_BLOCK, smem, e->stream>>>(e->M, A, e->bank, dir);
     CK(cudaGetLastError());
-    return SK_OK;
+    return stage_end(e);
+}
+
+template <int GRID, int MODE, bool STORE>
+static int launch_trace(sk_engine* e, const SkRunArgs& A, const SkRayDir& dir)
+{
+    return e->M.lattice_in_smem ? launch_trace_impl<GRID, MODE, STORE, true>(e, A, dir)
+                                : launch_trace_impl<GRID, MODE, STORE, false>(e, A, dir);
 }
 
 template <int GRID>
@@ -974,6 +1014,23 @@ static int run_bank(sk_engine* e, const SkRunArgs& A)
             groups.emplace_back(j0, j1);
             j0 = j1;
         }
+    // detect is a persistent grid-stride kernel with the SED arrays of the observer group in shared memory
+    const unsigned dblocks = std::min<unsigned>(eblocks, (unsigned)e->num_sms * 8u);
+    auto launch_detect = [&](int j0, int j1, int last) -> int {
+        int nl = 0;
+        for (int j = j0; j < j1; ++j)
+            if (e->instr[j].include_sed) nl = std::max(nl, e->instr[j].nl);
+        size_t smem = (size_t)(j1 - j0) * SK_NUM_COMP * nl * sizeof(double);
+        if (smem > 40 * 1024)  // too many bins for shared memory: add straight to the global arrays
+        {
+            nl = 0;
+            smem = 0;
+        }
+        if (int rc = stage_begin(e, SK_STAGE_DETECT)) return rc;
+        sk_wf_detect<<<dblocks, SK_EVENT_BLOCK, smem, e->stream>>>(M, A, K, j0, j1, last, nl);
+        CK(cudaGetLastError());
+        return stage_end(e);
+    };
     SkRayDir nodir;
     nodir.set(0., 0., 1.);
     CK(cudaMemsetAsync(K.i + (size_t)I_STATE * K.cap, 0, (size_t)K.cap * sizeof(int32_t), e->stream));
@@ -981,8 +1038,14 @@ static int run_bank(sk_engine* e, const SkRunArgs& A)
     {
         CK(cudaMemsetAsync(K.ctl, 0, SK_CTL_WORDS * sizeof(unsigned int), e->stream));
         const int g0a = groups.empty() ? 0 : groups[0].first, g0b = groups.empty() ? 0 : groups[0].second;
+        if (int rc = stage_begin(e, SK_STAGE_ADVANCE)) return rc;
         sk_wf_advance<GRID><<<eblocks, SK_EVENT_BLOCK, 0, e->stream>>>(M, A, K, g0a, g0b);
         CK(cudaGetLastError());
+        if (int rc = stage_end(e)) return rc;
+        if (int rc = stage_begin(e, SK_STAGE_LAUNCH)) return rc;
+        sk_wf_launch<GRID><<<eblocks, SK_EVENT_BLOCK, 0, e->stream>>>(M, A, K, g0a, g0b);
+        CK(cudaGetLastError());
+        if (int rc = stage_end(e)) return rc;
         CK(cudaMemcpyAsync(e->ctl_host, K.ctl, SK_CTL_WORDS * sizeof(unsigned int), cudaMemcpyDeviceToHost, e->stream));
         CK(cudaMemcpyAsync(e->ctl_host + SK_CTL_WORDS, A.work_counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                            e->stream));
@@ -990,8 +1053,7 @@ static int run_bank(sk_engine* e, const SkRunArgs& A)
         // the rest of the round is enqueued before the census is looked at, so the device never waits for the host
         if (groups.empty())
         {
-            sk_wf_detect<<<eblocks, SK_EVENT_BLOCK, 0, e->stream>>>(M, A, K, 0, 0, 1);
-            CK(cudaGetLastError());
+            if (int rc = launch_detect(0, 0, 1)) return rc;
         }
         for (size_t gi = 0; gi < groups.size(); ++gi)
         {
@@ -999,16 +1061,17 @@ static int run_bank(sk_engine* e, const SkRunArgs& A)
             if (gi > 0)
             {
                 CK(cudaMemsetAsync(&K.ctl[SK_CTL_NLIST], 0, sizeof(unsigned int), e->stream));
+                if (int rc = stage_begin(e, SK_STAGE_PEEL_SETUP)) return rc;
                 sk_wf_peel_setup<<<eblocks, SK_EVENT_BLOCK, 0, e->stream>>>(M, K, j0, j1);
                 CK(cudaGetLastError());
+                if (int rc = stage_end(e)) return rc;
             }
             SkRayDir obs;
             obs.set(e->instr_kobs[j0][0], e->instr_kobs[j0][1], e->instr_kobs[j0][2]);
             if (int rc = launch_trace<GRID, 2, false>(e, A, obs)) return rc;
             const int last = gi + 1 == groups.size();
             if (last) CK(cudaMemsetAsync(&K.ctl[SK_CTL_NLIST], 0, sizeof(unsigned int), e->stream));
-            sk_wf_detect<<<eblocks, SK_EVENT_BLOCK, 0, e->stream>>>(M, A, K, j0, j1, last);
-            CK(cudaGetLastError());
+            if (int rc = launch_detect(j0, j1, last)) return rc;
         }
         if (M.force_scattering)
         {
@@ -1016,16 +1079,18 @@ static int run_bank(sk_engine* e, const SkRunArgs& A)
                 return rc;
         }
         CK(cudaMemsetAsync(&K.ctl[SK_CTL_NLIST], 0, sizeof(unsigned int), e->stream));
+        if (int rc = stage_begin(e, SK_STAGE_SAMPLE)) return rc;
         sk_wf_sample<<<eblocks, SK_EVENT_BLOCK, 0, e->stream>>>(M, A, K);
         CK(cudaGetLastError());
+        if (int rc = stage_end(e)) return rc;
         if (int rc = launch_trace<GRID, 1, false>(e, A, nodir)) return rc;
         // census of this round: stop when the bank is empty and every history has been handed out
         CK(cudaEventSynchronize(e->ev_ctl));
         unsigned long long dispensed;
         memcpy(&dispensed, e->ctl_host + SK_CTL_WORDS, sizeof dispensed);
+        e->rounds_total++;
         if (e->ctl_host[SK_CTL_NLIVE] == 0 && dispensed >= A.count) break;
     }
-    e->rounds_last = 0;
     return SK_OK;
 }
 
@@ -1047,7 +1112,33 @@ extern "C" int sk_engine_launch_segment(sk_engine_t* e, uint64_t first, uint64_t
         CK(cudaGetDeviceProperties(&prop, e->cfg.device));
         e->num_sms = prop.multiProcessorCount;
     }
+    if (!e->l2_policy_set)
+    {
+        // keep the cell records (the random-access working set of the crossing loops) resident in L2 while the packet
+        // bank streams through it: persisting access-policy window on the engine's stream
+        const void* base = e->grid_kind == 2 ? (const void*)e->M.cells : (const void*)e->M.dens;
+        size_t bytes = e->grid_kind == 2 ? (size_t)e->M.ncells * sizeof(SkCellRec) : (size_t)e->M.ncells * sizeof(double);
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, e->cfg.device));
+        size_t window = std::min<size_t>(bytes, (size_t)prop.accessPolicyMaxWindowSize);
+        size_t carve = std::min<size_t>(window, (size_t)prop.persistingL2CacheMaxSize);
+        if (window && carve && !getenv("SK_NO_L2_PERSIST"))
+        {
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+            cudaStreamAttrValue attr;
+            memset(&attr, 0, sizeof attr);
+            attr.accessPolicyWindow.base_ptr = const_cast<void*>(base);
+            attr.accessPolicyWindow.num_bytes = window;
+            attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)window);
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            cudaStreamSetAttribute(e->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+            cudaGetLastError();  // the policy is an optimisation: failure to set it is not an error
+        }
+        e->l2_policy_set = true;
+    }
     CK(cudaEventRecord(e->ev0, e->stream));
+    e->stage_of_pair.clear();
     if (count)
     {
         if (int rc = ensure_bank(e, count)) return rc;
@@ -1079,6 +1170,13 @@ extern "C" int sk_engine_synchronize(sk_engine_t* e)
     if (e->timing_pending)
     {
         CK(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
+        for (int k = 0; k < SK_STAGE_COUNT; ++k) e->stage_ms[k] = 0.f;
+        for (size_t i = 0; i < e->stage_of_pair.size(); ++i)
+        {
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, e->stage_events[2 * i], e->stage_events[2 * i + 1]));
+            e->stage_ms[e->stage_of_pair[i]] += ms;
+        }
         e->timing_pending = false;
     }
     return SK_OK;
@@ -1095,6 +1193,13 @@ extern "C" int sk_engine_last_kernel_ms(sk_engine_t* e, float* ms)
 {
     if (!e || !ms) return fail(SK_ERR_INVALID, "null argument");
     *ms = e->last_ms;
+    return SK_OK;
+}
+
+extern "C" int sk_engine_last_stage_ms(sk_engine_t* e, float out[SK_STAGE_COUNT])
+{
+    if (!e || !out) return fail(SK_ERR_INVALID, "null argument");
+    for (int k = 0; k < SK_STAGE_COUNT; ++k) out[k] = e->stage_ms[k];
     return SK_OK;
 }
 
@@ -1216,7 +1321,13 @@ extern "C" int sk_engine_counters(sk_engine_t* e, sk_counters_t* out, int32_t re
     out->rf_deposits = c[7];
     out->detections = c[8];
     out->fallbacks = c[9];
-    if (reset) CK(cudaMemsetAsync(e->M.counters, 0, sizeof c, e->stream));
+    out->kernel_launches = e->launches_total;
+    out->rounds = e->rounds_total;
+    if (reset)
+    {
+        CK(cudaMemsetAsync(e->M.counters, 0, sizeof c, e->stream));
+        e->launches_total = e->rounds_total = 0;
+    }
     return SK_OK;
 }
 

@@ -24,12 +24,13 @@ struct SkBank {
     double* d;        // [D_HISTW0 + ninstr][cap]
     int32_t* i;       // [I_HELL0 + ninstr][cap]
     int32_t* list;    // [cap] slots of the rays of the trace stage being prepared / consumed
+    int32_t* free_list;  // [cap] free slots found by the advance kernel, filled by the launch kernel
     unsigned int* ctl;  // control words: see SK_CTL_*
     int32_t cap;
     __device__ __forceinline__ double& D(int f, int s) const { return d[(size_t)f * cap + s]; }
     __device__ __forceinline__ int32_t& I(int f, int s) const { return i[(size_t)f * cap + s]; }
 };
-enum { SK_CTL_NLIST, SK_CTL_CURSOR, SK_CTL_NLIVE, SK_CTL_WORDS = 4 };
+enum { SK_CTL_NLIST, SK_CTL_CURSOR, SK_CTL_NLIVE, SK_CTL_NFREE, SK_CTL_WORDS = 4 };
 
 struct SkLocalCounters {
     unsigned int packets, fwd_paths, fwd_segs, replay_segs, peel_paths, peel_segs, scatt, rf, det, fallbacks;
@@ -446,9 +447,7 @@ __device__ __noinline__ void sk_generate_position(SkRng& g, const SkDevSource& s
             double zz = sk_expdisk_z(g, p[1], p[4]);
             double x0 = R0 * cos(phi0), y0 = R0 * sin(phi0);
             double R = sqrt(x0 * x0 + y0 * y0);
-            double m = p[5], pitch = p[6], Rz = p[7], phiz = p[8], w = p[9], N = p[10];
-            double tanp = tan(pitch);
-            double cn = sqrt(M_PI) * tgamma(N + 1.0) / tgamma(N + 0.5);
+            double m = p[5], tanp = p[6], Rz = p[7], phiz = p[8], w = p[9], N = p[10], cn = p[11];
             double c = 1.0 + (cn - 1.0) * w;
             double phi, t;
             do
@@ -587,8 +586,10 @@ __device__ __forceinline__ bool sk_detect_geometry(const SkDevModel& M, const Sk
 }
 
 // Second half of FluxRecorder::detect (FluxRecorder.cpp:320-433): component routing and the tallies.
+// `sed_sm` (optional) is the block's shared-memory copy [SK_NUM_COMP][nl_stride] of this instrument's SED arrays: all
+// packets of a round hit the same few hundred SED bins, so they are combined per block before they reach the L2 atomics.
 __device__ __forceinline__ void sk_record(const SkDevInstr& q, int l, int ell, double L, double Lext, int nscatt,
-                                          bool primary_origin)
+                                          bool primary_origin, double* sed_sm, int nl_stride)
 {
     int c_ext, c_tr = -1, c_lev = -1;
     if (q.record_total_only)
@@ -618,9 +619,18 @@ __device__ __forceinline__ void sk_record(const SkDevInstr& q, int l, int ell, d
     }
     if (q.include_sed)
     {
-        atomicAdd(&q.sed[c_ext][ell], Lext);  // LockFree::add, LockFree.hpp:23-37 -> native fp64 RED
-        if (c_tr >= 0) atomicAdd(&q.sed[c_tr][ell], L);
-        if (c_lev >= 0) atomicAdd(&q.sed[c_lev][ell], Lext);
+        if (sed_sm)
+        {
+            atomicAdd(&sed_sm[c_ext * nl_stride + ell], Lext);
+            if (c_tr >= 0) atomicAdd(&sed_sm[c_tr * nl_stride + ell], L);
+            if (c_lev >= 0) atomicAdd(&sed_sm[c_lev * nl_stride + ell], Lext);
+        }
+        else
+        {
+            atomicAdd(&q.sed[c_ext][ell], Lext);  // LockFree::add, LockFree.hpp:23-37 -> native fp64 RED
+            if (c_tr >= 0) atomicAdd(&q.sed[c_tr][ell], L);
+            if (c_lev >= 0) atomicAdd(&q.sed[c_lev][ell], Lext);
+        }
     }
     if (q.include_ifu && l >= 0)
     {
@@ -630,7 +640,6 @@ __device__ __forceinline__ void sk_record(const SkDevInstr& q, int l, int ell, d
         if (c_lev >= 0) atomicAdd(&q.ifu[c_lev][index], Lext);
     }
 }
-
 
 // ---------------------------------------------------------------------------------------------------
 // per-grid accessors used by the event kernels

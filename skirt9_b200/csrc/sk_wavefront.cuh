@@ -107,15 +107,16 @@ __device__ __forceinline__ void sk_finish_history(const SkDevModel& M, const SkB
 // Structure: a compact inner loop that only crosses cells, and an outer service block (store the results of finished
 // rays, load new rays) that is entered when at least SK_REFILL_MIN lanes are idle, so that its cost is shared.
 // ---------------------------------------------------------------------------------------------------
-template <int GRID, int MODE, bool STORE>
+template <int GRID, int MODE, bool STORE, bool TABLES_IN_SMEM>
 __global__ void __launch_bounds__(SK_TRACE_BLOCK, SK_TRACE_MINBLOCKS)
     sk_wf_trace(const SkDevModel M, const SkRunArgs A, const SkBank K, const SkRayDir obs)
 {
     extern __shared__ double smem[];
     SkSmemTables T;
-    if (M.lattice_in_smem)
+    if (TABLES_IN_SMEM)
     {
-        // stage the per-axis border tables (Cartesian borders / octree lattice) in shared memory
+        // stage the per-axis border tables (Cartesian borders / octree lattice) in shared memory; the instantiation is
+        // separate from the global-memory one so that the lookups in the crossing loop compile to LDS
         const int n0 = M.nx + 1, n1 = M.ny + 1, n2 = M.nz + 1;
         for (int i = threadIdx.x; i < n0; i += blockDim.x) smem[i] = M.xv[i];
         for (int i = threadIdx.x; i < n1; i += blockDim.x) smem[n0 + i] = M.yv[i];
@@ -412,8 +413,8 @@ __device__ __forceinline__ bool sk_peel_setup(const SkDevModel& M, const SkBank&
     return need;
 }
 
-// advance: the interaction that ends the previous round, the launch of new histories into free slots, and the
-// peel-off set-up towards the first observer group.
+// advance: the interaction that ends the previous round and, for the surviving packets, the peel-off set-up towards
+// the first observer group; free slots are collected for the launch kernel.
 template <int GRID>
 __global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_advance(const SkDevModel M, const SkRunArgs A, const SkBank K,
                                                                  const int j0, const int j1)
@@ -496,63 +497,17 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_advance(const SkDevModel
         }
     }
 
-    // ---- launch a history into every free slot (SourceSystem::launch)
+    // ---- free slots go to the launch kernel through a compact list (the launch code then runs with full warps)
     {
-        const bool want = valid && !(st & SK_ST_LIVE);
-        const unsigned mask = __ballot_sync(0xffffffffu, want);
+        const bool isfree = valid && !(st & SK_ST_LIVE);
+        const unsigned mask = __ballot_sync(0xffffffffu, isfree);
         if (mask)
         {
             const int leader = __ffs(mask) - 1;
-            unsigned long long b = 0;
-            if ((int)lane == leader) b = atomicAdd(A.work_counter, (unsigned long long)__popc(mask));
-            b = __shfl_sync(0xffffffffu, b, leader);
-            const unsigned long long h = b + __popc(mask & lt_mask);
-            if (want && h < A.count)
-            {
-                const unsigned long long history = A.first + h;
-                SkRng g;
-                sk_rng_init(g, M.seed, A.stream_id, history, 0);
-                SkLaunch pp;
-                if (A.primary)
-                    sk_launch_primary(Mg, g, history, pp);
-                else
-                    sk_launch_secondary<GRID>(Mg, T, g, history, pp);
-                if (pp.W / pp.lambda > 0)  // MonteCarloSimulation.cpp:553
-                {
-                    cnt.packets++;
-                    SkCellPos c;
-                    c.m = -1;
-                    c.ix = c.iy = c.iz = c.lev = 0;
-                    if (sk_box_strictly_inside(M.ext, pp.rx, pp.ry, pp.rz)) sk_locate<GRID>(Mg, T, pp.rx, pp.ry, pp.rz, c);
-                    K.D(D_RX, slot) = pp.rx;
-                    K.D(D_RY, slot) = pp.ry;
-                    K.D(D_RZ, slot) = pp.rz;
-                    K.D(D_KX, slot) = pp.kx;
-                    K.D(D_KY, slot) = pp.ky;
-                    K.D(D_KZ, slot) = pp.kz;
-                    K.D(D_LAMBDA, slot) = pp.lambda;
-                    K.D(D_W, slot) = pp.W;
-                    K.D(D_LTHR, slot) = (pp.W / pp.lambda) / M.min_weight_reduction;  // .cpp:563
-                    K.D(D_SIGEXT, slot) = M.sig_ext[pp.ilam];
-                    K.I(I_HLO, slot) = (int)(uint32_t)history;
-                    K.I(I_HHI, slot) = (int)(uint32_t)(history >> 32);
-                    K.I(I_DRAW, slot) = (int)g.draw;
-                    K.I(I_NSCATT, slot) = 0;
-                    K.I(I_ILAM, slot) = pp.ilam;
-                    K.I(I_M, slot) = c.m;
-                    K.I(I_IX, slot) = c.ix;
-                    K.I(I_IY, slot) = c.iy;
-                    K.I(I_IZ, slot) = c.iz;
-                    K.I(I_LEV, slot) = c.lev;
-                    for (int j = 0; j < M.ninstr; ++j)
-                    {
-                        K.D(D_HISTW0 + j, slot) = 0.;
-                        K.I(I_HELL0 + j, slot) = -1;
-                    }
-                    st = SK_ST_LIVE;
-                    K.I(I_STATE, slot) = st;
-                }
-            }
+            unsigned base = 0;
+            if ((int)lane == leader) base = atomicAdd(&K.ctl[SK_CTL_NFREE], (unsigned)__popc(mask));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (isfree) K.free_list[base + __popc(mask & lt_mask)] = slot;
         }
     }
 
@@ -570,6 +525,91 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_advance(const SkDevModel
     sk_flush_counters(M, cnt);
 }
 
+// launch: a new history into every free slot collected by `advance` (SourceSystem::launch, SourceSystem.cpp:101-113 /
+// SecondarySourceSystem::launch, SecondarySourceSystem.cpp:130-142), then its emission peel-off set-up
+// (MonteCarloSimulation::peelOffEmission, .cpp:617-634).  One thread per entry of the free list.
+template <int GRID>
+__global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_launch(const SkDevModel M, const SkRunArgs A, const SkBank K,
+                                                                const int j0, const int j1)
+{
+    const SkSmemTables T{M.xv, M.yv, M.zv};
+    const SkDevModel* __restrict__ Mg = A.model;
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const unsigned nfree = K.ctl[SK_CTL_NFREE];
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx - lane >= nfree) return;  // the whole warp is beyond the list
+    const bool want = idx < nfree;
+    const int slot = want ? K.free_list[idx] : 0;
+    SkLocalCounters cnt;
+    memset(&cnt, 0, sizeof cnt);
+    bool live = false;
+    {
+        const unsigned mask = __ballot_sync(0xffffffffu, want);
+        const int leader = __ffs(mask) - 1;
+        unsigned long long b = 0;
+        if ((int)lane == leader) b = atomicAdd(A.work_counter, (unsigned long long)__popc(mask));
+        b = __shfl_sync(0xffffffffu, b, leader);
+        const unsigned long long h = b + __popc(mask & lt_mask);
+        if (want && h < A.count)
+        {
+            const unsigned long long history = A.first + h;
+            SkRng g;
+            sk_rng_init(g, M.seed, A.stream_id, history, 0);
+            SkLaunch pp;
+            if (A.primary)
+                sk_launch_primary(Mg, g, history, pp);
+            else
+                sk_launch_secondary<GRID>(Mg, T, g, history, pp);
+            if (pp.W / pp.lambda > 0)  // MonteCarloSimulation.cpp:553
+            {
+                cnt.packets++;
+                SkCellPos c;
+                c.m = -1;
+                c.ix = c.iy = c.iz = c.lev = 0;
+                if (sk_box_strictly_inside(M.ext, pp.rx, pp.ry, pp.rz)) sk_locate<GRID>(Mg, T, pp.rx, pp.ry, pp.rz, c);
+                K.D(D_RX, slot) = pp.rx;
+                K.D(D_RY, slot) = pp.ry;
+                K.D(D_RZ, slot) = pp.rz;
+                K.D(D_KX, slot) = pp.kx;
+                K.D(D_KY, slot) = pp.ky;
+                K.D(D_KZ, slot) = pp.kz;
+                K.D(D_LAMBDA, slot) = pp.lambda;
+                K.D(D_W, slot) = pp.W;
+                K.D(D_LTHR, slot) = (pp.W / pp.lambda) / M.min_weight_reduction;  // .cpp:563
+                K.D(D_SIGEXT, slot) = M.sig_ext[pp.ilam];
+                K.I(I_HLO, slot) = (int)(uint32_t)history;
+                K.I(I_HHI, slot) = (int)(uint32_t)(history >> 32);
+                K.I(I_DRAW, slot) = (int)g.draw;
+                K.I(I_NSCATT, slot) = 0;
+                K.I(I_ILAM, slot) = pp.ilam;
+                K.I(I_M, slot) = c.m;
+                K.I(I_IX, slot) = c.ix;
+                K.I(I_IY, slot) = c.iy;
+                K.I(I_IZ, slot) = c.iz;
+                K.I(I_LEV, slot) = c.lev;
+                for (int j = 0; j < M.ninstr; ++j)
+                {
+                    K.D(D_HISTW0 + j, slot) = 0.;
+                    K.I(I_HELL0 + j, slot) = -1;
+                }
+                K.I(I_STATE, slot) = SK_ST_LIVE;
+                live = true;
+            }
+        }
+    }
+    {
+        const unsigned mask = __ballot_sync(0xffffffffu, live);
+        if (lane == 0 && mask) atomicAdd(&K.ctl[SK_CTL_NLIVE], (unsigned)__popc(mask));
+    }
+    if (A.peel && j1 > j0)
+    {
+        bool need = live && sk_peel_setup(M, K, slot, SK_ST_LIVE, j0, j1);
+        sk_list_append(K, need, slot);
+    }
+    sk_flush_counters(M, cnt);
+}
+
 // peel-off set-up towards a further observer group
 __global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_peel_setup(const SkDevModel M, const SkBank K, const int j0,
                                                                     const int j1)
@@ -582,64 +622,86 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_peel_setup(const SkDevMo
 
 // detect: FluxRecorder::detect (FluxRecorder.cpp:304-468) for the observer group [j0, j1); when `last`, also the
 // pending scattering events -- MediumSystem::simulateScattering (MediumSystem.cpp:796-823) + DustMix::performScattering
-// HG branch (DustMix.cpp:496-511) -- and the list of forward rays.
+// HG branch (DustMix.cpp:496-511) -- and the list of forward rays.  Persistent grid-stride kernel: each block keeps the
+// SED arrays of the group in shared memory (nl_stride > 0) and adds them to the global arrays once at its end.
 __global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_detect(const SkDevModel M, const SkRunArgs A, const SkBank K,
-                                                                const int j0, const int j1, const int last)
+                                                                const int j0, const int j1, const int last,
+                                                                const int nl_stride)
 {
-    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = slot < K.cap;
+    extern __shared__ double sed_sm[];
+    const int per_instr = SK_NUM_COMP * nl_stride;
+    for (int i = threadIdx.x; i < (j1 - j0) * per_instr; i += blockDim.x) sed_sm[i] = 0.;
+    __syncthreads();
     SkLocalCounters cnt;
     memset(&cnt, 0, sizeof cnt);
-    int st = valid ? K.I(I_STATE, slot) : 0;
-    const bool live = (st & SK_ST_LIVE) != 0;
-    if (live && j1 > j0)
+    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < K.cap; slot += gridDim.x * blockDim.x)
     {
-        double lambda = K.D(D_LAMBDA, slot);
-        double x = K.D(D_RX, slot), y = K.D(D_RY, slot), z = K.D(D_RZ, slot);
-        double L = K.D(D_PEELW, slot) / lambda;
-        int nscatt = (st & SK_ST_SCATTER) ? K.I(I_NSCATT, slot) + 1 : 0;
-        for (int j = j0; j < j1; ++j)
+        int st = K.I(I_STATE, slot);
+        const bool live = (st & SK_ST_LIVE) != 0;
+        if (live && j1 > j0)
         {
-            const SkDevInstr& q = M.instr[j];
-            int l, ell;
-            if (!sk_detect_geometry(M, q, x, y, z, lambda, l, ell)) continue;
-            double Lext = L * exp(-K.D(D_PTAU, slot));
-            cnt.det++;
-            sk_record(q, l, ell, L, Lext, nscatt, A.primary != 0);
-            if (q.record_stats && q.include_sed)
+            double lambda = K.D(D_LAMBDA, slot);
+            double x = K.D(D_RX, slot), y = K.D(D_RY, slot), z = K.D(D_RZ, slot);
+            double L = K.D(D_PEELW, slot) / lambda;
+            int nscatt = (st & SK_ST_SCATTER) ? K.I(I_NSCATT, slot) + 1 : 0;
+            for (int j = j0; j < j1; ++j)
             {
-                K.D(D_HISTW0 + j, slot) += Lext;  // FluxRecorder.cpp:457-466
-                K.I(I_HELL0 + j, slot) = ell;
+                const SkDevInstr& q = M.instr[j];
+                int l, ell;
+                if (!sk_detect_geometry(M, q, x, y, z, lambda, l, ell)) continue;
+                double Lext = L * exp(-K.D(D_PTAU, slot));
+                cnt.det++;
+                sk_record(q, l, ell, L, Lext, nscatt, A.primary != 0, nl_stride ? sed_sm + (j - j0) * per_instr : nullptr,
+                          nl_stride);
+                if (q.record_stats && q.include_sed)
+                {
+                    K.D(D_HISTW0 + j, slot) += Lext;  // FluxRecorder.cpp:457-466
+                    K.I(I_HELL0 + j, slot) = ell;
+                }
             }
         }
-    }
-    if (last)
-    {
-        if (live && (st & SK_ST_SCATTER))
+        if (last)
         {
-            SkRng g;
-            sk_rng_load(g, M, A, K, slot);
-            double gp = M.gpar[K.I(I_ILAM, slot)];
-            double kx = K.D(D_KX, slot), ky = K.D(D_KY, slot), kz = K.D(D_KZ, slot);
-            if (fabs(gp) < 1e-6)
-                sk_random_direction(g, kx, ky, kz);
-            else
+            if (live && (st & SK_ST_SCATTER))
             {
-                double f = ((1.0 - gp) * (1.0 + gp)) / (1.0 - gp + 2.0 * gp * sk_uniform(g));
-                double costheta = (1.0 + gp * gp - f * f) / (2.0 * gp);
-                sk_random_direction_about(g, kx, ky, kz, costheta);
+                SkRng g;
+                sk_rng_load(g, M, A, K, slot);
+                double gp = M.gpar[K.I(I_ILAM, slot)];
+                double kx = K.D(D_KX, slot), ky = K.D(D_KY, slot), kz = K.D(D_KZ, slot);
+                if (fabs(gp) < 1e-6)
+                    sk_random_direction(g, kx, ky, kz);
+                else
+                {
+                    double f = ((1.0 - gp) * (1.0 + gp)) / (1.0 - gp + 2.0 * gp * sk_uniform(g));
+                    double costheta = (1.0 + gp * gp - f * f) / (2.0 * gp);
+                    sk_random_direction_about(g, kx, ky, kz, costheta);
+                }
+                K.D(D_KX, slot) = kx;
+                K.D(D_KY, slot) = ky;
+                K.D(D_KZ, slot) = kz;
+                K.I(I_DRAW, slot) = (int)g.draw;
+                K.I(I_NSCATT, slot) += 1;
+                K.I(I_STATE, slot) = st & ~SK_ST_SCATTER;
+                cnt.scatt++;
             }
-            K.D(D_KX, slot) = kx;
-            K.D(D_KY, slot) = ky;
-            K.D(D_KZ, slot) = kz;
-            K.I(I_DRAW, slot) = (int)g.draw;
-            K.I(I_NSCATT, slot) += 1;
-            K.I(I_STATE, slot) = st & ~SK_ST_SCATTER;
-            cnt.scatt++;
+            if (M.force_scattering) sk_list_append(K, live, slot);
         }
-        if (M.force_scattering) sk_list_append(K, live, slot);
     }
     sk_flush_counters(M, cnt);
+    if (nl_stride)
+    {
+        __syncthreads();
+        for (int i = threadIdx.x; i < (j1 - j0) * per_instr; i += blockDim.x)
+        {
+            const double v = sed_sm[i];
+            if (v != 0.)
+            {
+                const SkDevInstr& q = M.instr[j0 + i / per_instr];
+                const int c = (i % per_instr) / nl_stride, ell = i % nl_stride;
+                atomicAdd(&q.sed[c][ell], v);
+            }
+        }
+    }
 }
 
 // sample: the interaction optical depth -- simulateForcedPropagation (.cpp:696-722) or Random::expon for

@@ -274,7 +274,8 @@ class SpiralStructureGeometryDecorator:
     def source_fields(self):
         g = self.geometry
         return {"geometry": abi.SK_GEOM_SPIRAL_EXPDISK,
-                "geom_params": [g.hR, g.hz, g.Rmin, g.Rmax, g.zmax, self.m, self.p, self.R0, self.phi0, self.w, self.N]}
+                "geom_params": [g.hR, g.hz, g.Rmin, g.Rmax, g.zmax, self.m, self.tanp, self.R0, self.phi0, self.w, self.N,
+                                self.cn]}
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -129,7 +129,7 @@ def check_cfg2s(sim, e, g, n, nsigma=4.0):
     blk = lambda x: x.reshape(8, 8, 8, 8).sum(axis=(1, 3))
     a, b = blk(a), blk(b)
     ok = b > 0.05 * b.max()
-    np.testing.assert_allclose(a[ok], b[ok], rtol=0.05 * max(1.0, scale))
+    np.testing.assert_allclose(a[ok], b[ok], rtol=0.08 * max(1.0, scale))   # the base fixture has 1e6 packets
     assert a.sum() == pytest.approx(b.sum(), rel=0.005 * max(1.0, scale))
     c = blk(hi["frame_total_sum"])
     scale_hi = max(1.0, math.sqrt(hi["num_packets"] / n))
