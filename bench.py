@@ -145,7 +145,7 @@ def native_arm(args):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from skirt9_b200 import abi, configs
+    from skirt9_b200 import abi, configs, parallel
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -163,7 +163,8 @@ def native_arm(args):
     stream = torch.cuda.ExternalStream(engine.cuda_stream(), device=local)
     det = engine.device_tensor(3)
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=f"cuda:{local}")  # > 126 MB L2
-    first = rank * packets_per_gpu
+    first, count = parallel.history_block(total, rank, world)   # contiguous block of this rank
+    assert count == packets_per_gpu
 
     def step(stream_id):
         with torch.cuda.stream(stream):

@@ -2197,6 +2197,17 @@ int sko_counters(sko_engine_t* e, sk_counters_t* out, int32_t reset)
     return SK_OK;
 }
 
+/* Counterpart of sk_engine_device_buffer for the radiation field tables (host memory here), so that the multi-rank tests
+ * can all-reduce them in place exactly where the reference calls ProcessManager::sumToAll (MediumSystem.cpp:1304-1313). */
+int sko_device_buffer(sko_engine_t* e, int32_t which, void** ptr, uint64_t* num_doubles)
+{
+    if (!e || !ptr || !num_doubles) return fail(SK_ERR_INVALID, "null argument");
+    if (which < 0 || which > 2) return fail(SK_ERR_UNSUPPORTED, "the oracle exposes only the radiation field tables");
+    *ptr = which == 0 ? e->rf1 : which == 1 ? e->rf2 : e->rf2c;
+    *num_doubles = (uint64_t)e->ncells * e->nrf;
+    return SK_OK;
+}
+
 /* test hooks: expose single building blocks so that unit tests can pin them one by one */
 double sko_test_uniform(uint32_t seed, uint32_t stream, uint64_t history, int index)
 {

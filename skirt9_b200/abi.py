@@ -282,9 +282,14 @@ class Engine:
         return p.value or 0
 
     def device_tensor(self, which):
-        """The engine's tally buffer `which` as a torch CUDA tensor sharing the memory (for NCCL collectives)."""
+        """The tally buffer `which` (0 rf1, 1 rf2, 2 rf2c, 3 detector block, 4 statistics block) as a torch tensor that
+        SHARES the engine's memory, for in-place collectives: a CUDA tensor for the engine (NCCL); the test-only CPU
+        oracle hands out host memory (gloo)."""
         import torch
         ptr, n = self.device_buffer(which)
+        if self.prefix != "sk_engine_":
+            arr = np.ctypeslib.as_array(C.cast(ptr, _dp), shape=(int(n),))
+            return torch.from_numpy(arr)
 
         class _Span:
             __cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 3,

@@ -794,28 +794,35 @@ class MonteCarloSimulation:
                                  mix.em_sigma_abs)
         return engine
 
-    def run(self, engine: abi.Engine, first=0, count=None, stream_id=0):
-        """MonteCarloSimulation::runSimulation, MonteCarloSimulation.cpp:58-100 (single rank): primary emission and, in
-        DustEmission mode, the secondary emission iterations and the final secondary emission."""
-        self.run_primary_emission(engine, first, count, stream_id)
+    def run(self, engine: abi.Engine, first=0, count=None, stream_id=0, comm=None):
+        """MonteCarloSimulation::runSimulation, MonteCarloSimulation.cpp:58-100: primary emission and, in DustEmission
+        mode, the secondary emission iterations and the final secondary emission.  `comm` (skirt9_b200.parallel.Comm)
+        shards the histories of every segment over the ranks and performs the reference's reductions."""
+        self.run_primary_emission(engine, first, count, stream_id, comm)
         if self.dustEmissionWLG is not None:
             if self.iterateSecondaryEmission:
-                self.run_secondary_emission_iterations(engine, stream_id + 1000)
-            self.run_secondary_emission(engine, stream_id + 2000)
+                self.run_secondary_emission_iterations(engine, stream_id + 1000, comm)
+            self.run_secondary_emission(engine, stream_id + 2000, comm)
+        if comm is not None:
+            comm.allreduce_detectors(engine)   # FluxRecorder::calibrateAndWrite, FluxRecorder.cpp:487-493
 
-    def run_primary_emission(self, engine, first=0, count=None, stream_id=0):
+    def run_primary_emission(self, engine, first=0, count=None, stream_id=0, comm=None):
         """MonteCarloSimulation::runPrimaryEmission, MonteCarloSimulation.cpp:104-138."""
         n = int(self.numPackets)
         store = self.storeRadiationField
         if store:
             engine.clear_rf(True)
         engine.prepare_primary(n)
+        if comm is not None:
+            first, count = comm.block(n)
         engine.run_segment(first, n if count is None else count, primary=True, peel=True, store=store,
                            stream_id=stream_id)
         if store:
+            if comm is not None:
+                comm.allreduce_rf(engine, True)
             engine.communicate_rf(True)
 
-    def run_secondary_emission(self, engine, stream_id=2000):
+    def run_secondary_emission(self, engine, stream_id=2000, comm=None):
         """MonteCarloSimulation::runSecondaryEmission, MonteCarloSimulation.cpp:142-173."""
         store = self.storeEmissionRadiationField
         if store:
@@ -823,11 +830,14 @@ class MonteCarloSimulation:
         n = int(self.numPackets * self.secondaryPacketsMultiplier)
         self.dust_luminosity = engine.prepare_secondary(n)
         if self.dust_luminosity > 0:
-            engine.run_segment(0, n, primary=False, peel=True, store=store, stream_id=stream_id)
+            first, count = comm.block(n) if comm is not None else (0, n)
+            engine.run_segment(first, count, primary=False, peel=True, store=store, stream_id=stream_id)
         if store:
+            if comm is not None:
+                comm.allreduce_rf(engine, False)
             engine.communicate_rf(False)
 
-    def run_secondary_emission_iterations(self, engine, stream_id=1000):
+    def run_secondary_emission_iterations(self, engine, stream_id=1000, comm=None):
         """MonteCarloSimulation::runSecondaryEmissionIterations (.cpp:335-403) with DustAbsorptionConvergence
         (.cpp:180-227) and logLoopConvergence (.cpp:233-261).  Records the log values in self.convergence."""
         n = int(self.numPackets * self.secondaryIterationPacketsMultiplier)
@@ -840,7 +850,10 @@ class MonteCarloSimulation:
             lum = engine.prepare_secondary(n)
             if not lum > 0:
                 return
-            engine.run_segment(0, n, primary=False, peel=False, store=True, stream_id=stream_id + it)
+            first, count = comm.block(n) if comm is not None else (0, n)
+            engine.run_segment(first, count, primary=False, peel=False, store=True, stream_id=stream_id + it)
+            if comm is not None:
+                comm.allreduce_rf(engine, False)
             engine.communicate_rf(False)
             Lprim, Lseco = engine.absorbed_luminosity(True), engine.absorbed_luminosity(False)
             with np.errstate(divide="ignore", invalid="ignore"):
