@@ -214,17 +214,27 @@ def native_arm(args):
     d2h = 0
     barrier()
     t0 = time.perf_counter()
+    e2e_parts = {"configure_s": 0.0, "run_s": 0.0, "read_s": 0.0}
     for k in range(e2e_steps):
+        ta = time.perf_counter()
         e2 = sim.configure(abi.Engine(sim.config_struct(device=local)))
+        tb = time.perf_counter()
         e2.prepare_primary(total)
         e2.run_segment(first, packets_per_gpu, True, True, False, 1000 + k)
         if world > 1:
             with torch.cuda.stream(torch.cuda.ExternalStream(e2.cuda_stream(), device=local)):
                 dist.all_reduce(e2.device_tensor(3))
             e2.synchronize()
+        tc = time.perf_counter()
         outs = [e2.read_sed(0, c) for c in (0, 1, 2, 3)] + [e2.read_ifu(0, c) for c in (0, 1, 2, 3)]
-        d2h = sum(o.nbytes for o in outs) + 2 * outs[4].nbytes  # total = direct + scattered is read as two arrays
+        d2h = sum(o.nbytes for o in outs)
+        td0 = time.perf_counter()
         e2.close()
+        td = time.perf_counter()
+        e2e_parts["close_s"] = e2e_parts.get("close_s", 0.0) + (td - td0) / e2e_steps
+        e2e_parts["configure_s"] += (tb - ta) / e2e_steps
+        e2e_parts["run_s"] += (tc - tb) / e2e_steps
+        e2e_parts["read_s"] += (td - tc) / e2e_steps
     barrier()
     e2e_s = (time.perf_counter() - t0) / max(e2e_steps, 1)
     te = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local}")
@@ -266,7 +276,8 @@ def native_arm(args):
                            "l2": "256 MB buffer written between iterations", "sharding": "contiguous history blocks, "
                            "replicated grid, NCCL all-reduce of the instrument arrays per step" if world > 1 else "single GPU"},
                 "e2e": {"value": total / e2e_s if e2e_steps else None, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                        "includes": "engine create + octree link build + all table uploads + all stage kernels + read-back of 4 SED and 4 IFU arrays"},
+                        "includes": "engine create + octree link build + all table uploads + all stage kernels + read-back of 4 SED and 4 IFU arrays",
+                        "parts": e2e_parts},
                 "gpu_launches": int(cnt["kernel_launches"]),
                 "kernel": {"name": dom_name, "launches_per_step": dom_launches, "ms_per_step": stages[dom],
                            "ms_per_launch": stages[dom] / max(dom_launches, 1), "share_of_step": stages[dom] / kms,

@@ -42,6 +42,66 @@ extern "C" int sk_abi_version(void)
 // ---------------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------------
+// Octree neighbour links, one thread per cell: for the lattice point just across each wall find the deepest node of
+// level <= the cell's level that holds it (replaces TreeNode::_neighbors built by OctTreeNode::addNeighbors,
+// OctTreeNode.cpp:46-138)
+__global__ void sk_build_links_kernel(const int32_t* __restrict__ first_child, const int32_t* __restrict__ node_child,
+                                      const uint32_t* __restrict__ node_coord, const int32_t* __restrict__ node_of_cell,
+                                      int ncells, int N, int maxlev, SkCellRec* __restrict__ cells,
+                                      uint32_t* __restrict__ cell_coord)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= ncells) return;
+    const int l = node_of_cell[m];
+    const uint4 c = reinterpret_cast<const uint4*>(node_coord)[l];
+    reinterpret_cast<uint4*>(cell_coord)[m] = c;
+    const int lev = (int)c.w, size = N >> lev;
+    SkCellRec r;
+    r.dens = 0.;
+    for (int w = 0; w < 6; ++w)
+    {
+        int x = (int)c.x, y = (int)c.y, z = (int)c.z;
+        const int axis = w >> 1;
+        int& t = axis == 0 ? x : axis == 1 ? y : z;
+        t += (w & 1) ? size : -1;
+        if (t < 0 || t >= N)
+        {
+            r.link[w] = -1;
+            continue;
+        }
+        int node = 0, nlev = 0, nx = 0, ny = 0, nz = 0;
+        while (first_child[node] >= 0 && nlev < lev)
+        {
+            const int half = N >> (nlev + 1);
+            const int ch = ((x - nx) >= half ? 1 : 0) + ((y - ny) >= half ? 2 : 0) + ((z - nz) >= half ? 4 : 0);
+            nx += (ch & 1) ? half : 0;
+            ny += (ch & 2) ? half : 0;
+            nz += (ch & 4) ? half : 0;
+            node = first_child[node] + ch;
+            nlev++;
+        }
+        const int nc = node_child[node];
+        r.link[w] = nc < 0 ? ((nlev << SK_LINK_LEVEL_SHIFT) | (-(nc + 1)))
+                           : (SK_LINK_INTERNAL | (nlev << SK_LINK_LEVEL_SHIFT) | nc);
+    }
+    cells[m] = r;
+}
+__global__ void sk_set_density_kernel(SkCellRec* __restrict__ cells, const double* __restrict__ dens, int ncells)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m < ncells) cells[m].dens = dens[m];
+}
+__global__ void sk_sum_kernel(double* __restrict__ out, const double* __restrict__ a, const double* __restrict__ b,
+                              const double* __restrict__ c, const double* __restrict__ d, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    {
+        double v = a[i] + b[i];
+        if (c) v += c[i] + d[i];
+        out[i] = v;
+    }
+}
+
 // MediumSystem::totalDustAbsorbedLuminosity, MediumSystem.cpp:1317-1356 (single dust medium, constant sections)
 __global__ void sk_absorbed_kernel(const double* __restrict__ rf, const double* __restrict__ dens_or_null,
                                    const SkCellRec* __restrict__ cells, const double* __restrict__ kabs, int ncells,
@@ -82,7 +142,6 @@ struct sk_engine {
     int grid_kind = 0;
     int grid_cells = 0;
     std::vector<double> dens_host;
-    std::vector<SkCellRec> cellrec_host;  // octree records (links filled by set_grid, density by set_medium)
     std::vector<double> dust_lam_border, dust_sig_abs;
     std::vector<sk_wavelength_grid_t> wlg_host;
     std::vector<std::vector<double>> wlg_lambda;
@@ -110,6 +169,10 @@ struct sk_engine {
     std::vector<int> instr_same_observer;
     std::vector<std::array<double, 3>> instr_kobs;
     bool secondary_ready = false, has_secondary = false, l2_policy_set = false;
+    void* pinned = nullptr;
+    cudaEvent_t pin_ev[2] = {nullptr, nullptr};
+    double* scratch = nullptr;
+    size_t scratch_len = 0;
     sk_secondary_t sec;
     std::vector<double> sec_Lv_host;
     unsigned long long rounds_total = 0, launches_total = 0;
@@ -218,6 +281,10 @@ extern "C" void sk_engine_destroy(sk_engine_t* e)
     if (e->ev_ctl) cudaEventDestroy(e->ev_ctl);
     for (cudaEvent_t ev : e->stage_events) cudaEventDestroy(ev);
     cudaFree(e->model_dev);
+    cudaFree(e->scratch);
+    if (e->pinned) cudaFreeHost(e->pinned);
+    if (e->pin_ev[0]) cudaEventDestroy(e->pin_ev[0]);
+    if (e->pin_ev[1]) cudaEventDestroy(e->pin_ev[1]);
     cudaFree(e->scalar);
     cudaFree(e->M.counters);
     cudaEventDestroy(e->ev0);
@@ -262,6 +329,7 @@ extern "C" int sk_engine_set_grid_cartesian(sk_engine_t* e, int32_t nx, int32_t 
     double dx = ext[3] - ext[0], dy = ext[4] - ext[1], dz = ext[5] - ext[2];
     e->M.eps = 1e-12 * sqrt(dx * dx + dy * dy + dz * dz);  // CartesianSpatialGrid.cpp:102
     e->M.ncells = 0;
+    e->M.cells = nullptr;
     return set_tables(e, xv, nx + 1, yv, ny + 1, zv, nz + 1);
 }
 
@@ -332,46 +400,13 @@ extern "C" int sk_engine_set_grid_octree(sk_engine_t* e, const double extent[6],
     const int nc = (int)node_of_cell.size();
     std::vector<int32_t> node_child(nn);
     for (int l = 0; l < nn; ++l) node_child[l] = first_child[l] >= 0 ? first_child[l] : -(cell_of_node[l] + 1);
-    // neighbour links: for lattice point (x,y,z) just across a wall find the deepest node of level <= L holding it
-    auto find_node = [&](int x, int y, int z, int L) -> int {
-        int node = 0;
-        while (first_child[node] >= 0 && lev[node] < L)
-        {
-            int half = N >> (lev[node] + 1);
-            int c = ((x - ix[node]) >= half ? 1 : 0) + ((y - iy[node]) >= half ? 2 : 0) + ((z - iz[node]) >= half ? 4 : 0);
-            node = first_child[node] + c;
-        }
-        return node;
-    };
-    e->cellrec_host.assign(nc, SkCellRec());
-    std::vector<uint32_t> coord(4 * (size_t)nc);
-    for (int m = 0; m < nc; ++m)
+    std::vector<uint32_t> node_coord(4 * (size_t)nn);
+    for (int l = 0; l < nn; ++l)
     {
-        int l = node_of_cell[m];
-        int size = N >> lev[l];
-        coord[4 * (size_t)m + 0] = ix[l];
-        coord[4 * (size_t)m + 1] = iy[l];
-        coord[4 * (size_t)m + 2] = iz[l];
-        coord[4 * (size_t)m + 3] = lev[l];
-        SkCellRec& r = e->cellrec_host[m];
-        r.dens = 0.;
-        for (int w = 0; w < 6; ++w)
-        {
-            int x = ix[l], y = iy[l], z = iz[l];
-            int axis = w >> 1;
-            int* c = axis == 0 ? &x : axis == 1 ? &y : &z;
-            *c += (w & 1) ? size : -1;
-            if (*c < 0 || *c >= N)
-            {
-                r.link[w] = -1;
-                continue;
-            }
-            int nb = find_node(x, y, z, lev[l]);
-            if (first_child[nb] < 0)
-                r.link[w] = (lev[nb] << SK_LINK_LEVEL_SHIFT) | cell_of_node[nb];
-            else
-                r.link[w] = SK_LINK_INTERNAL | (lev[nb] << SK_LINK_LEVEL_SHIFT) | first_child[nb];
-        }
+        node_coord[4 * (size_t)l + 0] = ix[l];
+        node_coord[4 * (size_t)l + 1] = iy[l];
+        node_coord[4 * (size_t)l + 2] = iz[l];
+        node_coord[4 * (size_t)l + 3] = lev[l];
     }
     free_group(e->grid_allocs);
     e->grid_kind = 2;
@@ -386,12 +421,30 @@ extern "C" int sk_engine_set_grid_octree(sk_engine_t* e, const double extent[6],
     memcpy(e->M.ext, extent, 6 * sizeof(double));
     double dx = extent[3] - extent[0], dy = extent[4] - extent[1], dz = extent[5] - extent[2];
     e->M.eps = 1e-12 * sqrt(dx * dx + dy * dy + dz * dz);  // TreeSpatialGrid.cpp:28
-    int32_t* d_child;
-    uint32_t* d_coord;
+    int32_t *d_child, *d_first, *d_nodeofcell;
+    uint32_t *d_coord, *d_nodecoord;
+    SkCellRec* d_cells;
     if (int rc = upload(e->grid_allocs, node_child.data(), (size_t)nn, &d_child)) return rc;
-    if (int rc = upload(e->grid_allocs, coord.data(), coord.size(), &d_coord)) return rc;
+    if (int rc = dalloc_zero(e->grid_allocs, 4 * (size_t)nc, &d_coord)) return rc;
+    if (int rc = dalloc_zero(e->grid_allocs, (size_t)nc, &d_cells)) return rc;
+    // the link builder runs on the device; its inputs are scratch
+    std::vector<void*> scratch;
+    int rc = upload(scratch, first_child, (size_t)nn, &d_first);
+    if (!rc) rc = upload(scratch, node_coord.data(), node_coord.size(), &d_nodecoord);
+    if (!rc) rc = upload(scratch, node_of_cell.data(), (size_t)nc, &d_nodeofcell);
+    if (!rc)
+    {
+        sk_build_links_kernel<<<(nc + 127) / 128, 128, 0, e->stream>>>(d_first, d_child, d_nodecoord, d_nodeofcell, nc, N,
+                                                                      maxlev, d_cells, d_coord);
+        cudaError_t err = cudaGetLastError();
+        if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+        if (err != cudaSuccess) rc = fail(SK_ERR_CUDA, std::string("octree link builder: ") + cudaGetErrorString(err));
+    }
+    free_group(scratch);
+    if (rc) return rc;
     e->M.node_child = d_child;
     e->M.cell_coord = d_coord;
+    e->M.cells = d_cells;
     return set_tables(e, T[0].data(), N + 1, T[1].data(), N + 1, T[2].data(), N + 1);
 }
 
@@ -409,14 +462,15 @@ extern "C" int sk_engine_set_medium(sk_engine_t* e, int32_t num_cells, const dou
         double* d;
         if (int rc = upload(e->medium_allocs, number_density, (size_t)num_cells, &d)) return rc;
         e->M.dens = d;
-        e->M.cells = nullptr;
     }
     else
     {
-        for (int m = 0; m < num_cells; ++m) e->cellrec_host[m].dens = number_density[m];
-        SkCellRec* d;
-        if (int rc = upload(e->medium_allocs, e->cellrec_host.data(), (size_t)num_cells, &d)) return rc;
-        e->M.cells = d;
+        // the cell records (links) live with the grid; the density is written into them in place
+        double* d;
+        if (int rc = upload(e->medium_allocs, number_density, (size_t)num_cells, &d)) return rc;
+        sk_set_density_kernel<<<(num_cells + 255) / 256, 256, 0, e->stream>>>(const_cast<SkCellRec*>(e->M.cells), d, num_cells);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(e->stream));
         e->M.dens = nullptr;
     }
     e->M.ncells = num_cells;
@@ -1238,14 +1292,51 @@ extern "C" int sk_engine_absorbed_luminosity(sk_engine_t* e, int32_t primary, do
     return SK_OK;
 }
 
+static int fetch_doubles(sk_engine* e, const double* dev, size_t n, double* out);
 extern "C" int sk_engine_read_rf(sk_engine_t* e, int32_t which, double* out)
 {
     if (!e || !out) return fail(SK_ERR_INVALID, "null argument");
     const double* src = which == 0 ? e->M.rf1 : which == 1 ? e->M.rf2 : e->M.rf2c;
     if (!src) return fail(SK_ERR_STATE, "no radiation field");
     CK(cudaSetDevice(e->cfg.device));
-    CK(cudaMemcpyAsync(out, src, (size_t)e->M.ncells * e->M.nrf * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
+    return fetch_doubles(e, src, (size_t)e->M.ncells * e->M.nrf, out);
+}
+
+// device -> caller buffer through a pinned staging buffer (pageable destinations otherwise crawl at page-fault speed)
+static int fetch_doubles(sk_engine* e, const double* dev, size_t n, double* out)
+{
+    const size_t bytes = n * sizeof(double);
+    if (bytes < ((size_t)1 << 16))
+    {
+        CK(cudaMemcpyAsync(out, dev, bytes, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        return SK_OK;
+    }
+    const size_t chunk = (size_t)32 << 20;
+    if (!e->pinned)
+    {
+        CK(cudaMallocHost(&e->pinned, 2 * chunk));
+        CK(cudaEventCreateWithFlags(&e->pin_ev[0], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&e->pin_ev[1], cudaEventDisableTiming));
+    }
+    // double-buffered: the copy of chunk i+1 over PCIe overlaps the host memcpy of chunk i
+    size_t nchunks = (bytes + chunk - 1) / chunk;
+    for (size_t i = 0; i <= nchunks; ++i)
+    {
+        if (i < nchunks)
+        {
+            size_t off = i * chunk, len = std::min(chunk, bytes - off);
+            CK(cudaMemcpyAsync((char*)e->pinned + (i & 1) * chunk, (const char*)dev + off, len, cudaMemcpyDeviceToHost,
+                               e->stream));
+            CK(cudaEventRecord(e->pin_ev[i & 1], e->stream));
+        }
+        if (i > 0)
+        {
+            size_t j = i - 1, off = j * chunk, len = std::min(chunk, bytes - off);
+            CK(cudaEventSynchronize(e->pin_ev[j & 1]));
+            memcpy((char*)out + off, (char*)e->pinned + (j & 1) * chunk, len);
+        }
+    }
     return SK_OK;
 }
 
@@ -1258,29 +1349,29 @@ static int read_array(sk_engine* e, int instrument, int component, bool ifu, dou
     if (ifu ? !q.include_ifu : !q.include_sed) return fail(SK_ERR_INVALID, "instrument does not record this");
     size_t len = ifu ? q.npix * q.nl : (size_t)q.nl;
     const long long* off = ifu ? q.ifu_off : q.sed_off;
-    auto fetch = [&](int c, double* dst) -> int {
-        CK(cudaMemcpyAsync(dst, e->det_block + off[c], len * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-        CK(cudaStreamSynchronize(e->stream));
-        return SK_OK;
-    };
     if (component == SK_COMP_TOTAL && !q.record_total_only)
     {
-        // FluxRecorder::calibrateAndWrite: total = direct + scattered (+ secondary), FluxRecorder.cpp:522-526
-        std::vector<double> tmp(len);
-        if (int rc = fetch(SK_COMP_PRIMARY_DIRECT, out)) return rc;
-        if (int rc = fetch(SK_COMP_PRIMARY_SCATTERED, tmp.data())) return rc;
-        for (size_t i = 0; i < len; ++i) out[i] += tmp[i];
-        if (off[SK_COMP_SECONDARY_DIRECT] >= 0)
+        // FluxRecorder::calibrateAndWrite: total = direct + scattered (+ secondary), FluxRecorder.cpp:522-526; summed on
+        // the device into scratch, one transfer
+        if (e->scratch_len < len)
         {
-            std::vector<double> t2(len);
-            if (int rc = fetch(SK_COMP_SECONDARY_DIRECT, tmp.data())) return rc;
-            if (int rc = fetch(SK_COMP_SECONDARY_SCATTERED, t2.data())) return rc;
-            for (size_t i = 0; i < len; ++i) out[i] += tmp[i] + t2[i];
+            cudaFree(e->scratch);
+            e->scratch = nullptr;
+            e->scratch_len = 0;
+            CK(cudaMalloc(&e->scratch, len * sizeof(double)));
+            e->scratch_len = len;
         }
-        return SK_OK;
+        const bool sec = off[SK_COMP_SECONDARY_DIRECT] >= 0;
+        unsigned blocks = (unsigned)std::min<size_t>((len + 255) / 256, 4096);
+        sk_sum_kernel<<<blocks, 256, 0, e->stream>>>(e->scratch, e->det_block + off[SK_COMP_PRIMARY_DIRECT],
+                                                     e->det_block + off[SK_COMP_PRIMARY_SCATTERED],
+                                                     sec ? e->det_block + off[SK_COMP_SECONDARY_DIRECT] : nullptr,
+                                                     sec ? e->det_block + off[SK_COMP_SECONDARY_SCATTERED] : nullptr, len);
+        CK(cudaGetLastError());
+        return fetch_doubles(e, e->scratch, len, out);
     }
     if (off[component] < 0) return fail(SK_ERR_INVALID, "component not recorded");
-    return fetch(component, out);
+    return fetch_doubles(e, e->det_block + off[component], len, out);
 }
 extern "C" int sk_engine_read_sed(sk_engine_t* e, int32_t instrument, int32_t component, double* out)
 {
