@@ -1,0 +1,627 @@
+// GpuLifeCycle.cpp -- see GpuLifeCycle.hpp.  C++14 like the reference.
+//
+// The data the engine needs lives in private members of a dozen reference classes.  A maintainer would
+// add `friend class GpuLifeCycle;` to those classes; because this repository must not modify or copy the reference, this
+// one translation unit instead sees the reference headers with `private`/`protected` mapped to `public` (the standard
+// library headers are included first so that they are unaffected; access specifiers do not change object layout).
+
+// ---- standard library first (see above)
+#include <algorithm>
+#include <array>
+#include <atomic>
+#include <cmath>
+#include <complex>
+#include <condition_variable>
+#include <cstring>
+#include <fstream>
+#include <functional>
+#include <iostream>
+#include <limits>
+#include <list>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <numeric>
+#include <random>
+#include <set>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <tuple>
+#include <typeinfo>
+#include <unordered_map>
+#include <unordered_set>
+#include <utility>
+#include <valarray>
+#include <vector>
+
+#define private public
+#define protected public
+#include "AllCellsLibrary.hpp"
+#include "BlackBodySED.hpp"
+#include "CartesianSpatialGrid.hpp"
+#include "Configuration.hpp"
+#include "DefaultWavelengthDistribution.hpp"
+#include "DisjointWavelengthGrid.hpp"
+#include "DistantInstrument.hpp"
+#include "DustMix.hpp"
+#include "ExpDiskGeometry.hpp"
+#include "FatalError.hpp"
+#include "FluxRecorder.hpp"
+#include "FrameInstrument.hpp"
+#include "FullInstrument.hpp"
+#include "GeometricSource.hpp"
+#include "InstrumentSystem.hpp"
+#include "Log.hpp"
+#include "Medium.hpp"
+#include "MediumSystem.hpp"
+#include "MonteCarloSimulation.hpp"
+#include "OctTreeNode.hpp"
+#include "OligoWavelengthDistribution.hpp"
+#include "PointSource.hpp"
+#include "ProbeSystem.hpp"
+#include "ProcessManager.hpp"
+#include "Random.hpp"
+#include "RingGeometry.hpp"
+#include "SEDInstrument.hpp"
+#include "SecondarySourceSystem.hpp"
+#include "ShellGeometry.hpp"
+#include "SourceSystem.hpp"
+#include "SpiralStructureGeometryDecorator.hpp"
+#include "StringUtils.hpp"
+#include "TabulatedSED.hpp"
+#include "TimeLogger.hpp"
+#include "TreeSpatialGrid.hpp"
+#include "Units.hpp"
+#undef private
+#undef protected
+
+#include "GpuLifeCycle.hpp"
+
+////////////////////////////////////////////////////////////////////
+
+namespace
+{
+    // detector array ids of the reference (anonymous enum in FluxRecorder.cpp:26-56)
+    enum { RefTotal = 0, RefTransparent, RefPrimaryDirect, RefPrimaryScattered, RefSecondaryDirect, RefSecondaryScattered,
+           RefSecondaryTransparent, RefPrimaryScatteredLevel = 28 };
+
+    int refComponent(int c)
+    {
+        switch (c)
+        {
+            case SK_COMP_TOTAL: return RefTotal;
+            case SK_COMP_TRANSPARENT: return RefTransparent;
+            case SK_COMP_PRIMARY_DIRECT: return RefPrimaryDirect;
+            case SK_COMP_PRIMARY_SCATTERED: return RefPrimaryScattered;
+            case SK_COMP_SECONDARY_DIRECT: return RefSecondaryDirect;
+            case SK_COMP_SECONDARY_SCATTERED: return RefSecondaryScattered;
+            case SK_COMP_SECONDARY_TRANSPARENT: return RefSecondaryTransparent;
+            default: return RefPrimaryScatteredLevel + (c - SK_COMP_PRIMARY_SCATTERED_LEVEL);
+        }
+    }
+
+    const double* ptr(const Array& a) { return &a[0]; }
+
+    // the geometries that have a device-side sampler (include/sk_engine.h sk_geometry_kind)
+    bool fillGeometry(const Geometry* geom, sk_source_t& s)
+    {
+        if (auto g = dynamic_cast<const ShellGeometry*>(geom))
+        {
+            s.geometry = SK_GEOM_SHELL;
+            double p[] = {g->minRadius(), g->maxRadius(), g->exponent(), g->_smin, g->_sdiff, g->_tmin, g->_tmax};
+            std::copy(p, p + 7, s.geom_params);
+            return true;
+        }
+        if (auto g = dynamic_cast<const ExpDiskGeometry*>(geom))
+        {
+            s.geometry = SK_GEOM_EXPDISK;
+            double p[] = {g->scaleLength(), g->scaleHeight(), g->minRadius(), g->maxRadius(), g->maxZ()};
+            std::copy(p, p + 5, s.geom_params);
+            return true;
+        }
+        if (auto g = dynamic_cast<const RingGeometry*>(geom))
+        {
+            s.geometry = SK_GEOM_RING;
+            double p[] = {g->ringRadius(), g->width(), g->height()};
+            std::copy(p, p + 3, s.geom_params);
+            s.geom_table_n = static_cast<int>(g->_Rv.size());
+            s.geom_table_x = ptr(g->_Rv);
+            s.geom_table_P = ptr(g->_Xv);
+            return true;
+        }
+        if (auto g = dynamic_cast<const SpiralStructureGeometryDecorator*>(geom))
+        {
+            auto d = dynamic_cast<const ExpDiskGeometry*>(g->geometry());
+            if (!d) return false;
+            s.geometry = SK_GEOM_SPIRAL_EXPDISK;
+            double p[] = {d->scaleLength(), d->scaleHeight(), d->minRadius(), d->maxRadius(), d->maxZ(),
+                          static_cast<double>(g->numArms()), g->_tanp, g->radiusZeroPoint(), g->phaseZeroPoint(),
+                          g->perturbationWeight(), static_cast<double>(g->index()), g->_cn};
+            std::copy(p, p + 12, s.geom_params);
+            return true;
+        }
+        return false;
+    }
+}
+
+////////////////////////////////////////////////////////////////////
+
+GpuLifeCycle::GpuLifeCycle(MonteCarloSimulation* sim, int device) : _sim(sim), _device(device) {}
+
+GpuLifeCycle::~GpuLifeCycle()
+{
+    if (_e) sk_engine_destroy(_e);
+}
+
+void GpuLifeCycle::check(int rc) const
+{
+    // the reference reports errors as FatalError exceptions (SkirtCommandLineHandler.cpp:372-400)
+    if (rc != SK_OK) throw FATALERROR(string("GPU life-cycle engine: ") + sk_last_error());
+}
+
+////////////////////////////////////////////////////////////////////
+
+std::string GpuLifeCycle::unsupportedReason() const
+{
+    auto config = _sim->_config;
+    auto ms = _sim->mediumSystem();
+    if (!config->hasMedium() || !ms) return "no medium";
+    if (ms->numMedia() != 1 || !config->hasSingleConstantSectionMedium()) return "more than one medium or variable cross sections";
+    if (config->hasPolarization()) return "polarization";
+    if (config->hasMovingMedia()) return "moving media";
+    if (!config->hasConstantPerceivedWavelength()) return "wavelengths that change during the life cycle";
+    if (config->explicitAbsorption()) return "explicit absorption";
+    if (config->hasDynamicState()) return "dynamic medium state";
+    if (config->hasPrimaryIterations() || config->hasMergedIterations()) return "primary / merged iterations";
+    if (config->hasGasEmission()) return "gas emission";
+    if (config->hasStochasticDustEmission()) return "stochastic dust emission";
+    if (config->includeHeatingByCMB()) return "CMB heating";
+    if (config->redshift() != 0.) return "nonzero redshift";
+    if (ProcessManager::isMultiProc()) return "MPI (use one engine per rank through the C ABI instead)";
+    auto mix = dynamic_cast<const DustMix*>(ms->media()[0]->mix());
+    if (!mix || mix->scatteringMode() != DustMix::ScatteringMode::HenyeyGreenstein) return "a material mix other than a Henyey-Greenstein dust mix";
+    auto grid = ms->grid();
+    auto tree = dynamic_cast<TreeSpatialGrid*>(grid);
+    if (!dynamic_cast<CartesianSpatialGrid*>(grid) && !(tree && dynamic_cast<OctTreeNode*>(tree->_nodev[0])))
+        return "spatial grid " + grid->type();
+    for (auto source : _sim->sourceSystem()->sources())
+    {
+        auto ns = dynamic_cast<NormalizedSource*>(source);
+        if (!ns) return "source " + source->type();
+        if (!dynamic_cast<BlackBodySED*>(ns->sed()) && !dynamic_cast<TabulatedSED*>(ns->sed())) return "SED " + ns->sed()->type();
+        if (!ns->_oligochromatic && ns->_xi && !dynamic_cast<DefaultWavelengthDistribution*>(ns->_biasDistribution))
+            return "wavelength bias distribution " + ns->_biasDistribution->type();
+        if (auto ps = dynamic_cast<PointSource*>(source))
+        {
+            if (ps->angularDistribution() || ps->polarizationProfile()) return "anisotropic or polarized point source";
+            if (ps->velocityX() || ps->velocityY() || ps->velocityZ()) return "moving source";
+        }
+        else if (auto gs = dynamic_cast<GeometricSource*>(source))
+        {
+            sk_source_t probe;
+            memset(&probe, 0, sizeof probe);
+            if (!fillGeometry(gs->geometry(), probe)) return "source geometry " + gs->geometry()->type();
+            if (gs->velocityMagnitude()) return "moving source";
+        }
+        else
+            return "source " + source->type();
+    }
+    for (auto ins : _sim->instrumentSystem()->instruments())
+    {
+        if (!dynamic_cast<SEDInstrument*>(ins) && !dynamic_cast<FullInstrument*>(ins)
+            && !(dynamic_cast<FrameInstrument*>(ins) && ins->type() == "FrameInstrument"))
+            return "instrument " + ins->type();
+        if (ins->recordPolarization()) return "polarization recording";
+        if (!dynamic_cast<const DisjointWavelengthGrid*>(ins->_recorder->_lambdagrid)) return "instrument wavelength grid that is not disjoint";
+    }
+    if (_sim->instrumentSystem()->instruments().size() > 8) return "more than 8 instruments";
+    if (config->hasSecondaryEmission())
+    {
+        if (!config->hasDustEmission()) return "secondary emission other than dust";
+        if (!dynamic_cast<AllCellsLibrary*>(config->cellLibrary())) return "spatial cell library " + config->cellLibrary()->type();
+        if (config->dustEmissionWavelengthBias()
+            && !dynamic_cast<DefaultWavelengthDistribution*>(config->dustEmissionWavelengthBiasDistribution()))
+            return "dust emission wavelength bias distribution";
+        if (_sim->_secondarySourceSystem->numSources() != 1) return "more than one secondary source";
+    }
+    return std::string();
+}
+
+////////////////////////////////////////////////////////////////////
+
+void GpuLifeCycle::configure()
+{
+    auto config = _sim->_config;
+    auto ms = _sim->mediumSystem();
+
+    // ---- Configuration digest (Configuration.cpp:30-377)
+    sk_config_t c;
+    memset(&c, 0, sizeof c);
+    c.seed = static_cast<uint32_t>(_sim->random()->seed());
+    c.force_scattering = config->forceScattering();
+    c.min_scatt_events = config->minScattEvents();
+    c.path_length_bias = config->pathLengthBias();
+    c.min_weight_reduction = config->minWeightReduction();
+    c.device = _device;
+    check(sk_engine_create(&c, &_e));
+
+    // ---- spatial grid
+    if (auto g = dynamic_cast<CartesianSpatialGrid*>(ms->grid()))
+    {
+        check(sk_engine_set_grid_cartesian(_e, g->_Nx, g->_Ny, g->_Nz, ptr(g->_xv), ptr(g->_yv), ptr(g->_zv)));
+    }
+    else
+    {
+        auto t = dynamic_cast<TreeSpatialGrid*>(ms->grid());
+        size_t n = t->_nodev.size();
+        vector<int32_t> firstChild(n);
+        for (size_t l = 0; l != n; ++l)
+        {
+            auto node = t->_nodev[l];
+            firstChild[l] = node->isChildless() ? -1 : node->children()[0]->id();
+        }
+        Box b = t->extent();
+        double ext[6] = {b.xmin(), b.ymin(), b.zmin(), b.xmax(), b.ymax(), b.zmax()};
+        check(sk_engine_set_grid_octree(_e, ext, static_cast<int32_t>(n), firstChild.data()));
+    }
+
+    // ---- medium state (MediumState.cpp:196-247)
+    int M = ms->numCells();
+    vector<double> nv(M), Vv(M);
+    for (int m = 0; m != M; ++m)
+    {
+        nv[m] = ms->numberDensity(m, 0);
+        Vv[m] = ms->volume(m);
+    }
+    check(sk_engine_set_medium(_e, M, nv.data(), Vv.data()));
+
+    // ---- dust mix tables (DustMix.cpp:47-246)
+    auto mix = dynamic_cast<const DustMix*>(ms->media()[0]->mix());
+    sk_dustmix_t d;
+    memset(&d, 0, sizeof d);
+    d.num_lambda = static_cast<int32_t>(mix->_lambdav.size());
+    d.lambda_border = ptr(mix->_lambdav);
+    d.sigma_abs = ptr(mix->_sigmaabsv);
+    d.sigma_sca = ptr(mix->_sigmascav);
+    d.asymmpar = ptr(mix->_asymmparv);
+    d.mu = mix->mass();
+    check(sk_engine_set_dustmix(_e, &d));
+
+    // ---- wavelength grids: every distinct grid used by the instruments, the radiation field and dust emission
+    vector<DisjointWavelengthGrid*> grids;
+    auto gridIndex = [&grids](DisjointWavelengthGrid* g) {
+        auto it = std::find(grids.begin(), grids.end(), g);
+        if (it != grids.end()) return static_cast<int>(it - grids.begin());
+        grids.push_back(g);
+        return static_cast<int>(grids.size()) - 1;
+    };
+    int rfGrid = config->hasRadiationField() ? gridIndex(config->radiationFieldWLG()) : -1;
+    int emGrid = config->hasDustEmission() ? gridIndex(config->dustEmissionWLG()) : -1;
+    vector<int> insGrid;
+    for (auto ins : _sim->instrumentSystem()->instruments())
+        insGrid.push_back(gridIndex(const_cast<DisjointWavelengthGrid*>(dynamic_cast<const DisjointWavelengthGrid*>(ins->_recorder->_lambdagrid))));
+    vector<sk_wavelength_grid_t> wg(grids.size());
+    vector<vector<int32_t>> ellv(grids.size());
+    for (size_t i = 0; i != grids.size(); ++i)
+    {
+        auto g = grids[i];
+        ellv[i].assign(g->_ellv.begin(), g->_ellv.end());
+        wg[i].num_bins = g->numBins();
+        wg[i].num_borders = static_cast<int32_t>(g->_borderv.size());
+        wg[i].borders = ptr(g->_borderv);
+        wg[i].ell = ellv[i].data();
+        wg[i].lambda = ptr(g->_lambdav);
+        wg[i].dlambda = ptr(g->_dlambdav);
+    }
+    check(sk_engine_set_wavelength_grids(_e, static_cast<int32_t>(wg.size()), wg.data(), rfGrid));
+
+    // ---- primary sources (SourceSystem.cpp:14-41, NormalizedSource.cpp:20-70)
+    auto ss = _sim->sourceSystem();
+    vector<sk_source_t> sv(ss->sources().size());
+    vector<double> oligoLambda;
+    if (config->oligochromatic())
+    {
+        auto od = dynamic_cast<OligoWavelengthDistribution*>(config->oligoWavelengthBiasDistribution());
+        oligoLambda.assign(begin(od->_wavelengths), end(od->_wavelengths));
+    }
+    for (size_t h = 0; h != sv.size(); ++h)
+    {
+        auto ns = dynamic_cast<NormalizedSource*>(ss->sources()[h]);
+        sk_source_t& s = sv[h];
+        memset(&s, 0, sizeof s);
+        s.luminosity = ns->luminosity();
+        s.source_weight = ns->sourceWeight();
+        if (auto ps = dynamic_cast<PointSource*>(ns))
+        {
+            s.kind = SK_SRC_POINT;
+            s.position[0] = ps->positionX();
+            s.position[1] = ps->positionY();
+            s.position[2] = ps->positionZ();
+        }
+        else
+        {
+            s.kind = SK_SRC_GEOMETRIC;
+            fillGeometry(dynamic_cast<GeometricSource*>(ns)->geometry(), s);
+        }
+        if (auto bb = dynamic_cast<BlackBodySED*>(ns->sed()))
+        {
+            s.sed_kind = SK_SED_BLACKBODY;
+            s.sed_n = static_cast<int32_t>(bb->_lambdav.size());
+            s.sed_lambda = ptr(bb->_lambdav);
+            s.sed_p = ptr(bb->_pv);
+            s.sed_P = ptr(bb->_Pv);
+            s.sed_temperature = bb->temperature();
+            s.sed_norm = bb->_Ltot;
+        }
+        else
+        {
+            auto ts = dynamic_cast<TabulatedSED*>(ns->sed());
+            s.sed_kind = SK_SED_TABULATED;
+            s.sed_n = static_cast<int32_t>(ts->_lambdav.size());
+            s.sed_lambda = ptr(ts->_lambdav);
+            s.sed_p = ptr(ts->_pv);
+            s.sed_P = ptr(ts->_Pv);
+        }
+        s.wavelength_bias = ns->_xi;
+        if (ns->_oligochromatic)
+        {
+            auto od = dynamic_cast<OligoWavelengthDistribution*>(ns->_biasDistribution);
+            s.bias_kind = SK_BIAS_OLIGO;
+            s.oligo_n = static_cast<int32_t>(oligoLambda.size());
+            s.oligo_lambda = oligoLambda.data();
+            s.oligo_probability = od->_probability;
+        }
+        else if (ns->_xi)
+        {
+            auto dd = dynamic_cast<DefaultWavelengthDistribution*>(ns->_biasDistribution);
+            s.bias_kind = SK_BIAS_LOGUNIFORM;
+            s.bias_min = dd->_range.min();
+            s.bias_max = dd->_range.max();
+        }
+    }
+    check(sk_engine_set_sources(_e, static_cast<int32_t>(sv.size()), sv.data(), ss->sourceBias()));
+
+    // ---- instruments (DistantInstrument.cpp:13-77, FrameInstrument.cpp:12-32, FluxRecorder.cpp:185-300)
+    vector<sk_instrument_t> iv(_sim->instrumentSystem()->instruments().size());
+    for (size_t i = 0; i != iv.size(); ++i)
+    {
+        auto ins = _sim->instrumentSystem()->instruments()[i];
+        auto di = dynamic_cast<DistantInstrument*>(ins);
+        sk_instrument_t& q = iv[i];
+        memset(&q, 0, sizeof q);
+        q.wavelength_grid = insGrid[i];
+        q.inclination = di->inclination();
+        q.azimuth = di->azimuth();
+        q.roll = di->roll();
+        q.distance = di->distance();
+        if (auto si = dynamic_cast<SEDInstrument*>(ins))
+        {
+            q.kind = SK_INSTR_SED;
+            q.radius = si->radius();
+        }
+        else
+        {
+            auto fi = dynamic_cast<FrameInstrument*>(ins);
+            q.kind = dynamic_cast<FullInstrument*>(ins) ? SK_INSTR_FULL : SK_INSTR_FRAME;
+            q.num_pixels_x = fi->numPixelsX();
+            q.num_pixels_y = fi->numPixelsY();
+            q.field_of_view_x = fi->fieldOfViewX();
+            q.field_of_view_y = fi->fieldOfViewY();
+            q.center_x = fi->centerX();
+            q.center_y = fi->centerY();
+        }
+        q.record_components = !ins->_recorder->_recordTotalOnly;
+        q.num_scattering_levels = ins->numScatteringLevels();
+        q.record_statistics = ins->recordStatistics();
+    }
+    check(sk_engine_set_instruments(_e, static_cast<int32_t>(iv.size()), iv.data(), config->hasSecondaryEmission()));
+
+    // ---- dust emission (EquilibriumDustEmissionCalculator.cpp:18-93)
+    if (config->hasSecondaryEmission())
+    {
+        auto& calc = mix->_calc;
+        sk_secondary_t sec;
+        memset(&sec, 0, sizeof sec);
+        sec.emission_grid = emGrid;
+        sec.num_temperatures = static_cast<int32_t>(calc._Tv.size());
+        sec.spatial_bias = config->secondarySpatialBias();
+        sec.wavelength_bias = config->dustEmissionWavelengthBias();
+        Range r = config->dustEmissionWLG()->wavelengthRange();
+        sec.bias_min = r.min();
+        sec.bias_max = r.max();
+        sec.temperature = ptr(calc._Tv);
+        sec.planck_abs = ptr(calc._planckabsvv[0]);
+        sec.rf_sigma_abs = ptr(calc._rfsigmaabsvv[0]);
+        sec.em_sigma_abs = ptr(calc._emsigmaabsvv[0]);
+        check(sk_engine_set_secondary(_e, &sec));
+    }
+}
+
+////////////////////////////////////////////////////////////////////
+
+// MonteCarloSimulation::runSimulation, MonteCarloSimulation.cpp:58-100
+void GpuLifeCycle::runSimulation()
+{
+    auto config = _sim->_config;
+    {
+        TimeLogger logger(_sim->log(), "the run");
+        runPrimaryEmission();
+        if (config->hasSecondaryEmission())
+        {
+            if (config->hasSecondaryIterations()) runSecondaryEmissionIterations();
+            runSecondaryEmission();
+        }
+    }
+    check(sk_engine_counters(_e, &_counters, 0));
+    {
+        TimeLogger logger(_sim->log(), "final output");
+        returnRadiationField();
+        _sim->probeSystem()->probeRun();
+        returnDetectors();
+        _sim->instrumentSystem()->flush();
+        _sim->instrumentSystem()->write();
+    }
+}
+
+// MonteCarloSimulation::runPrimaryEmission, MonteCarloSimulation.cpp:104-138
+void GpuLifeCycle::runPrimaryEmission()
+{
+    auto config = _sim->_config;
+    string segment = "primary emission";
+    TimeLogger logger(_sim->log(), segment);
+    if (config->hasRadiationField()) check(sk_engine_clear_rf(_e, 1));
+    size_t Npp = config->numPrimaryPackets();
+    if (!Npp)
+        _sim->log()->warning("Skipping primary emission because no photon packets were requested");
+    else if (!_sim->sourceSystem()->luminosity())
+        _sim->log()->warning("Skipping primary emission because the total luminosity of primary sources is zero");
+    else
+    {
+        _sim->log()->info("Launching " + StringUtils::toString(static_cast<double>(Npp)) + " primary emission photon packets on the GPU");
+        check(sk_engine_prepare_primary(_e, Npp));
+        check(sk_engine_run_segment(_e, 0, Npp, 1, 1, config->hasRadiationField(), _segment++));
+    }
+    if (config->hasRadiationField()) check(sk_engine_communicate_rf(_e, 1));
+}
+
+// MonteCarloSimulation::runSecondaryEmission, MonteCarloSimulation.cpp:142-173
+void GpuLifeCycle::runSecondaryEmission()
+{
+    auto config = _sim->_config;
+    string segment = "secondary emission";
+    TimeLogger logger(_sim->log(), segment);
+    bool storeRF = config->storeEmissionRadiationField();
+    if (storeRF) check(sk_engine_clear_rf(_e, 0));
+    size_t Npp = config->numSecondaryPackets();
+    double L = 0.;
+    if (!Npp)
+        _sim->log()->warning("Skipping secondary emission because no photon packets were requested");
+    else
+    {
+        check(sk_engine_prepare_secondary(_e, Npp, &L));
+        if (!L)
+            _sim->log()->warning("Skipping secondary emission because the total luminosity of secondary sources is zero");
+        else
+        {
+            auto units = _sim->units();
+            _sim->log()->info("Dust luminosity: " + StringUtils::toString(units->obolluminosity(L), 'g') + " " + units->ubolluminosity());
+            check(sk_engine_run_segment(_e, 0, Npp, 0, 1, storeRF, _segment++));
+        }
+    }
+    if (storeRF) check(sk_engine_communicate_rf(_e, 0));
+}
+
+// MonteCarloSimulation::runSecondaryEmissionIterations (.cpp:335-403) with DustAbsorptionConvergence (.cpp:180-227) and
+// logLoopConvergence (.cpp:233-261); the log lines are the reference's
+void GpuLifeCycle::runSecondaryEmissionIterations()
+{
+    auto config = _sim->_config;
+    auto log = _sim->log();
+    auto units = _sim->units();
+    size_t Npp = config->numSecondaryIterationPackets();
+    int minIters = config->minSecondaryIterations();
+    int maxIters = config->maxSecondaryIterations();
+    double fractionOfPrimary = config->maxFractionOfPrimary();
+    double fractionOfPrevious = config->maxFractionOfPrevious();
+    double prevLabsseco = 0.;
+    int iter = 0;
+    while (true)
+    {
+        ++iter;
+        bool converged = true;
+        {
+            string segment = "secondary emission iteration " + std::to_string(iter);
+            TimeLogger logger(log, segment);
+            check(sk_engine_clear_rf(_e, 0));
+            double L = 0.;
+            check(sk_engine_prepare_secondary(_e, Npp, &L));
+            if (!L)
+            {
+                log->warning("Skipping secondary emission iterations because the total luminosity of secondary sources is zero");
+                return;
+            }
+            log->info("Dust luminosity: " + StringUtils::toString(units->obolluminosity(L), 'g') + " " + units->ubolluminosity());
+            check(sk_engine_run_segment(_e, 0, Npp, 0, 0, 1, _segment++));
+            check(sk_engine_communicate_rf(_e, 0));
+
+            double Labsprim = 0., Labsseco = 0.;
+            check(sk_engine_absorbed_luminosity(_e, 1, &Labsprim));
+            check(sk_engine_absorbed_luminosity(_e, 0, &Labsseco));
+            log->info("The total dust-absorbed primary luminosity is " + StringUtils::toString(units->obolluminosity(Labsprim), 'g')
+                      + " " + units->ubolluminosity());
+            log->info("The total dust-absorbed secondary luminosity in iteration " + std::to_string(iter) + " is "
+                      + StringUtils::toString(units->obolluminosity(Labsseco), 'g') + " " + units->ubolluminosity());
+            if (Labsprim > 0. && Labsseco > 0.)
+            {
+                if (iter == 1)
+                    log->info("--> absorbed secondary luminosity is " + StringUtils::toString(Labsseco / Labsprim * 100., 'f', 2)
+                              + "% of absorbed primary luminosity (convergence criterion is "
+                              + StringUtils::toString(fractionOfPrimary * 100., 'f', 2) + "%)");
+                else
+                    log->info("--> absorbed secondary luminosity changed by "
+                              + StringUtils::toString(std::abs((Labsseco - prevLabsseco) / Labsseco) * 100., 'f', 2)
+                              + "% compared to previous iteration (convergence criterion is "
+                              + StringUtils::toString(fractionOfPrevious * 100., 'f', 2) + "%)");
+            }
+            converged = Labsprim <= 0. || Labsseco <= 0. || Labsseco / Labsprim < fractionOfPrimary
+                        || std::abs((Labsseco - prevLabsseco) / Labsseco) < fractionOfPrevious;
+            prevLabsseco = Labsseco;
+        }
+        // probes that fire after every iteration read the radiation field from the reference's tables
+        returnRadiationField();
+        _sim->probeSystem()->probeSecondary(iter);
+
+        if (converged && iter < minIters)
+        {
+            log->info("Convergence reached but continuing until " + std::to_string(minIters) + " iterations have been performed");
+            continue;
+        }
+        if (converged)
+        {
+            log->info("Convergence reached after " + std::to_string(iter) + " iterations");
+            break;
+        }
+        if (iter < maxIters)
+        {
+            log->info("Convergence not yet reached after " + std::to_string(iter) + " iterations");
+            continue;
+        }
+        log->error("Convergence not yet reached after " + std::to_string(iter) + " iterations");
+        break;
+    }
+}
+
+////////////////////////////////////////////////////////////////////
+
+// the radiation field tables of the reference (MediumSystem.hpp:883-885) for its probes
+void GpuLifeCycle::returnRadiationField()
+{
+    auto ms = _sim->mediumSystem();
+    if (!_sim->_config->hasRadiationField()) return;
+    if (ms->_rf1.size()) check(sk_engine_read_rf(_e, 0, &ms->_rf1.data()[0]));
+    if (ms->_rf2.size()) check(sk_engine_read_rf(_e, 1, &ms->_rf2.data()[0]));
+}
+
+// the detector arrays of every FluxRecorder (FluxRecorder.hpp:396-404) before FluxRecorder::calibrateAndWrite
+void GpuLifeCycle::returnDetectors()
+{
+    auto& instruments = _sim->instrumentSystem()->instruments();
+    for (size_t i = 0; i != instruments.size(); ++i)
+    {
+        auto rec = instruments[i]->_recorder;
+        int numComp = static_cast<int>(rec->_sed.size());
+        for (int c = 0; c != SK_COMP_PRIMARY_SCATTERED_LEVEL + 8; ++c)
+        {
+            int rc = refComponent(c);
+            if (rc >= numComp) continue;
+            // in the reference the Total array exists only when components are not recorded (FluxRecorder.cpp:214-218)
+            if (rec->_sed[rc].size()) check(sk_engine_read_sed(_e, static_cast<int32_t>(i), c, &rec->_sed[rc][0]));
+            if (rec->_ifu[rc].size()) check(sk_engine_read_ifu(_e, static_cast<int32_t>(i), c, &rec->_ifu[rc][0]));
+        }
+        for (size_t k = 0; k != rec->_wsed.size(); ++k)
+            if (rec->_wsed[k].size()) check(sk_engine_read_sed_stats(_e, static_cast<int32_t>(i), static_cast<int32_t>(k), &rec->_wsed[k][0]));
+        if (!rec->_wifu.empty() && rec->_wifu[0].size())
+            _sim->log()->warning("Per-pixel statistics (stats*.fits) are not recorded by the GPU life cycle; the frames stay zero");
+    }
+}

@@ -26,32 +26,8 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 SKIRT = os.path.join(ROOT, "oracle", "_ref", "release", "SKIRT", "main", "skirt")
 
 
-def read_fits_cube(path):
-    """Primary HDU of a SKIRT frame file: BITPIX=-32 big-endian float32 (FITSInOut.cpp:160,194)."""
-    raw = open(path, "rb").read()
-    cards = {}
-    pos = 0
-    while True:
-        block = raw[pos:pos + 2880].decode("ascii")
-        pos += 2880
-        done = False
-        for i in range(0, 2880, 80):
-            c = block[i:i + 80]
-            if c.startswith("END"):
-                done = True
-                break
-            if "=" in c[:10]:
-                cards[c[:8].strip()] = c[10:].split("/")[0].strip().strip("'").strip()
-        if done:
-            break
-    nx, ny = int(cards["NAXIS1"]), int(cards["NAXIS2"])
-    nz = int(cards.get("NAXIS3", 1))
-    data = np.frombuffer(raw, dtype=">f4", count=nx * ny * nz, offset=pos).astype(np.float32)
-    return data.reshape(nz, ny, nx), cards
-
-
-def read_columns(path):
-    return np.loadtxt(path, comments="#", ndmin=2)
+sys.path.insert(0, ROOT)
+from tests.skirt_files import read_columns, read_fits_cube  # noqa: E402
 
 
 def run_reference(ski_name, workdir, extra_inputs=None, threads=1, packets=None):

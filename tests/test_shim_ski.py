@@ -1,0 +1,114 @@
+"""The drop-in itself: shim/_build/skirt_b200 = the UNMODIFIED reference (its .ski reader, setup code, probes, FITS and text
+writers, linked from the reference's object files) with the photon life cycle handed to the GPU engine by the C++ shim
+shim/GpuLifeCycle.cpp.  The very .ski files the golden fixtures were produced from are run unchanged, and the output
+FILES are compared with what the reference's own CPU life cycle wrote for them (tests/golden/*.npz).  `-t 1` makes the
+reference's setup (tree construction, density sampling) identical to the fixture run, so the densities agree bit for bit
+and only the random streams of the life cycle differ."""
+import math
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests.skirt_files import read_columns, read_fits_cube
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "shim", "_build", "skirt_b200")
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+pytestmark = pytest.mark.gpu
+
+
+def run_ski(name, tmp_path, packets):
+    if not os.path.exists(EXE):
+        pytest.fail("shim/_build/skirt_b200 has not been built (make -C shim, where /root/reference exists)")
+    text = open(os.path.join(GOLD, "ski", name + ".ski")).read()
+    text = re.sub(r'numPackets="[^"]*"', 'numPackets="%g"' % packets, text, count=1)
+    ski = tmp_path / (name + ".ski")
+    ski.write_text(text)
+    subprocess.check_call([EXE, "-t", "1", "-b", "-o", str(tmp_path), str(ski)], stdout=subprocess.DEVNULL)
+    log = (tmp_path / (name + "_log.txt")).read_text()
+    assert "GPU life cycle:" in log, log[-2000:]
+    return log
+
+
+def rel_error(stats_row):
+    n, w1, w2 = stats_row[0], stats_row[1], stats_row[2]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.sqrt(np.maximum(w2 / (w1 * w1) - 1.0 / np.maximum(n, 1), 0.0))
+
+
+def test_cfg1_ski_runs_unchanged(tmp_path):
+    g = np.load(os.path.join(GOLD, "cfg1_ref.npz"))
+    hi = np.load(os.path.join(GOLD, "cfg1_hi_ref.npz"))
+    n = 4e6
+    log = run_ski("cfg1", tmp_path, n)
+    assert re.search(r"Finished primary emission in [0-9.]+ s", log)
+    sed = read_columns(tmp_path / "cfg1_i60_sed.dat")[0]
+    stats = read_columns(tmp_path / "cfg1_i60_sedstats.dat")[0]
+    cells = read_columns(tmp_path / "cfg1_cells_cellprops.dat")
+    # same setup as the fixture run: the reference's own density sampling, bit for bit
+    np.testing.assert_array_equal(cells[:, 6], g["mass_density_msun_pc3"])
+    assert stats[1] == n
+    ref = g["sed"][0]
+    assert sed[2] == pytest.approx(ref[2], rel=1e-8)     # transparent flux: noise free
+    assert sed[3] == pytest.approx(ref[3], rel=1e-8)     # direct flux: same densities, same optical depth
+    for r in (g, hi):
+        tol = 4.0 * math.hypot(rel_error(r["sedstats"][0, 1:]), rel_error(stats[1:]))
+        assert abs(sed[1] - r["sed"][0, 1]) <= tol * r["sed"][0, 1]
+        assert abs(sed[4] - r["sed"][0, 4]) <= tol * r["sed"][0, 1]
+    for comp in ("transparent", "primarydirect"):
+        frame, cards = read_fits_cube(tmp_path / f"cfg1_i60_{comp}.fits")
+        np.testing.assert_allclose(frame, g["frame_" + comp], rtol=3e-6)
+        assert cards["BUNIT"] == "MJy/sr"
+    total, _ = read_fits_cube(tmp_path / "cfg1_i60_total.fits")
+    assert total.sum() == pytest.approx(hi["frame_total_sum"].sum(), rel=2e-3)
+    # the radiation field probe of the reference, fed from the engine's tally
+    J = read_columns(tmp_path / "cfg1_rf_J.dat")[:, 1]
+    assert J.sum() == pytest.approx(g["J_nu"][:, 0].sum(), rel=0.004)
+
+
+def test_cfg2s_ski_octree_runs_unchanged(tmp_path):
+    g = np.load(os.path.join(GOLD, "cfg2s_ref.npz"))
+    hi = np.load(os.path.join(GOLD, "cfg2s_hi_ref.npz"))
+    n = 4e6
+    run_ski("cfg2s", tmp_path, n)
+    sed = read_columns(tmp_path / "cfg2s_i60_sed.dat")
+    stats = read_columns(tmp_path / "cfg2s_i60_sedstats.dat")
+    cells = read_columns(tmp_path / "cfg2s_cells_cellprops.dat")
+    np.testing.assert_array_equal(cells[:, 6], g["mass_density_msun_pc3"])   # same tree, same densities
+    np.testing.assert_allclose(sed[:, 0], g["sed"][:, 0], rtol=1e-9)
+    r_own = rel_error(stats[:, 1:].T)
+    for r in (g, hi):
+        tol = 4.0 * np.hypot(rel_error(r["sedstats"][:, 1:].T), r_own)
+        for col in (1, 2, 3, 4):
+            bound = tol * np.maximum(r["sed"][:, col], r["sed"][:, 1])
+            assert np.all(np.abs(sed[:, col] - r["sed"][:, col]) <= bound), col
+    total, _ = read_fits_cube(tmp_path / "cfg2s_i60_total.fits")
+    assert total.astype(float).sum() == pytest.approx(hi["frame_total_sum"].sum(), rel=3e-3)
+
+
+def test_cfg4s_ski_dust_emission_runs_unchanged(tmp_path):
+    g = np.load(os.path.join(GOLD, "cfg4s_ref.npz"))
+    n = 2e6
+    log = run_ski("cfg4s", tmp_path, n)
+    prim = [float(x) for x in re.findall(r"dust-absorbed primary luminosity is ([0-9.eE+-]+) Lsun", log)]
+    sec = [float(x) for x in re.findall(r"dust-absorbed secondary luminosity in iteration \d+ is ([0-9.eE+-]+) Lsun", log)]
+    conv = re.search(r"Convergence reached after (\d+) iterations", log)
+    assert conv and int(conv.group(1)) == int(g["converged_after"])
+    np.testing.assert_allclose(prim, g["absorbed_primary_lsun"], rtol=0.004)
+    np.testing.assert_allclose(sec, g["absorbed_secondary_lsun"], rtol=0.02)
+    sed = read_columns(tmp_path / "cfg4s_sed_sed.dat")
+    ref = g["sed"]
+    peak = ref[:, 1].max()
+    for col in range(1, 8):
+        ok = ref[:, col] > 0.02 * ref[:, col].max()
+        np.testing.assert_allclose(sed[ok, col], ref[ok, col], rtol=0.12, atol=0.003 * peak, err_msg=f"column {col}")
+        assert sed[:, col].sum() == pytest.approx(ref[:, col].sum(), rel=0.02)
+    # the reference's TemperatureProbe evaluated on the radiation field the engine handed back
+    T = read_columns(tmp_path / "cfg4s_temp_dust_T.dat")[:, 1]
+    ok = g["temperature"] > 0
+    assert np.median(np.abs(T[ok] / g["temperature"][ok] - 1)) < 0.02
+    assert np.array_equal(T > 0, g["temperature"] > 0) or np.mean((T > 0) != ok) < 0.01
