@@ -90,6 +90,26 @@ def run_reference_once(num_packets, threads, workdir):
     return num_packets / float(m.group(1)), float(m.group(1))
 
 
+SHIM_EXE = os.path.join(ROOT, "shim", "_build", "skirt_b200")
+
+
+def run_shim_once(num_packets, threads):
+    """The same cfg2 ski through skirt_b200 (the unmodified reference driven by the C++ shim, life cycle on the GPU):
+    packets/s from the reference's own TimeLogger line, exactly as for the CPU reference."""
+    with tempfile.TemporaryDirectory() as d:
+        ski = os.path.join(d, "cfg2.ski")
+        open(ski, "w").write(open(SKI).read().replace('numPackets="1e6"', f'numPackets="{num_packets:g}"'))
+        subprocess.check_call([SHIM_EXE, "-t", str(threads), "-b", "-o", d, ski], stdout=subprocess.DEVNULL,
+                              stderr=subprocess.DEVNULL)
+        log = open(os.path.join(d, "cfg2_log.txt")).read()
+    secs = float(re.search(r"Finished primary emission in ([0-9.]+) s", log).group(1))
+    cells = re.search(r"Determining medium properties for (\d+) cells", log)
+    return {"packets": num_packets, "seconds": secs, "packets_per_s": num_packets / secs,
+            "cells": int(cells.group(1)) if cells else None,
+            "what": "skirt_b200 -t %d cfg2.ski: reference object model + C++ shim + GPU life cycle, time from the "
+                    "reference's TimeLogger line 'Finished primary emission in %.1f s'" % (threads, secs)}
+
+
 def run_port_once(num_packets):
     """Fallback when oracle/_ref is absent: times the single-threaded C port of the oracle."""
     from skirt9_b200 import configs
@@ -300,6 +320,11 @@ def native_arm(args):
                 "clocks": clocks}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.cpu_packets)
+            if os.path.exists(SHIM_EXE) and not args.no_e2e:
+                try:
+                    line["ski_e2e"] = run_shim_once(4e8, os.cpu_count() or 1)
+                except Exception as ex:  # the drop-in binary is informational here; the C-ABI e2e above is the contract
+                    line["ski_e2e"] = {"error": str(ex)[:200]}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

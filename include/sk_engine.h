@@ -204,6 +204,14 @@ int sk_engine_set_grid_cartesian(sk_engine_t* e, int32_t nx, int32_t ny, int32_t
  * own device layout (lattice border tables, per-cell neighbour links) from this. */
 int sk_engine_set_grid_octree(sk_engine_t* e, const double extent[6], int32_t num_nodes, const int32_t* first_child);
 
+/* VoronoiMeshSnapshot (VoronoiMeshSnapshot.cpp:85-194, 491-730) as built by the reference's setup with the vendored voro++:
+ * sites[3*m..] = Cell::position() of cell m; the neighbours of cell m are nbr_index[nbr_offset[m] .. nbr_offset[m+1]) in the
+ * order of Cell::neighbors(): a cell index, or -1..-6 for the domain walls xmin,xmax,ymin,ymax,zmin,zmax
+ * (VoronoiMeshSnapshot.cpp:1134-1143).  extent = the domain box.  The engine derives its own nearest-site search structure
+ * (replacing the block lists and k-d trees of VoronoiMeshSnapshot.cpp:765-825, 1006-1040). */
+int sk_engine_set_grid_voronoi(sk_engine_t* e, const double extent[6], int32_t num_cells, const double* sites,
+                               const int64_t* nbr_offset, const int32_t* nbr_index);
+
 /* MediumState number densities and volumes for a single medium component
  * (MediumState::numberDensity(m,0), MediumState::volume(m); MediumState.cpp:196-247). */
 int sk_engine_set_medium(sk_engine_t* e, int32_t num_cells, const double* number_density, const double* volume);

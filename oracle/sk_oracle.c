@@ -70,7 +70,7 @@ typedef struct {
 typedef struct sko_engine {
     sk_config_t cfg;
     /* grid */
-    int grid_kind; /* 1 cartesian, 2 octree */
+    int grid_kind; /* 1 cartesian, 2 octree, 3 voronoi */
     int nx, ny, nz;
     double *xv, *yv, *zv;
     double extent[6];
@@ -80,6 +80,12 @@ typedef struct sko_engine {
     double* node_box;    /* [6*nnodes] */
     int32_t* cell_of_node;
     int32_t* node_of_cell;
+    /* voronoi mesh (grid_kind 3) */
+    double* vsite;     /* [3*ncells] */
+    int64_t* vnbr_off; /* [ncells+1] */
+    int32_t* vnbr;     /* neighbour cell indices, -1..-6 for the domain walls */
+    int vcells, vnb;   /* number of cells; blocks per axis of the start-cell table */
+    int32_t* vblock;   /* [vnb^3] a cell whose site lies in (or near) the block: start of the walk to the nearest site */
     /* medium */
     int ncells;
     double *dens, *vol;
@@ -504,6 +510,13 @@ static void free_grid(sko_engine_t* e)
     free(e->node_box);
     free(e->cell_of_node);
     free(e->node_of_cell);
+    free(e->vsite);
+    free(e->vnbr_off);
+    free(e->vnbr);
+    free(e->vblock);
+    e->vsite = NULL;
+    e->vnbr_off = NULL;
+    e->vnbr = e->vblock = NULL;
     e->xv = e->yv = e->zv = e->node_box = NULL;
     e->first_child = e->cell_of_node = e->node_of_cell = NULL;
     e->grid_kind = 0;
@@ -616,8 +629,68 @@ int sko_set_grid_octree(sko_engine_t* e, const double extent[6], int32_t num_nod
     return SK_OK;
 }
 
+/* The start-cell table used by the nearest-site search: the domain is cut into nb^3 blocks, nb = clamp(cbrt(N),3,250) as in
+ * VoronoiMeshSnapshot.cpp:544, and every block remembers one cell whose site lies inside it (blocks without a site inherit
+ * the previous block's cell).  Identical in the CUDA engine (engine.cu). */
+static void voronoi_build_blocks(sko_engine_t* e)
+{
+    int nb = (int)cbrt((double)e->vcells);
+    if (nb < 3) nb = 3;
+    if (nb > 250) nb = 250;
+    e->vnb = nb;
+    size_t n3 = (size_t)nb * nb * nb;
+    e->vblock = (int32_t*)malloc(n3 * sizeof(int32_t));
+    for (size_t b = 0; b < n3; ++b) e->vblock[b] = -1;
+    const double* x = e->extent;
+    for (int m = 0; m < e->vcells; ++m)
+    {
+        int i = (int)((e->vsite[3 * m] - x[0]) / (x[3] - x[0]) * nb);
+        int j = (int)((e->vsite[3 * m + 1] - x[1]) / (x[4] - x[1]) * nb);
+        int k = (int)((e->vsite[3 * m + 2] - x[2]) / (x[5] - x[2]) * nb);
+        i = i < 0 ? 0 : i >= nb ? nb - 1 : i;
+        j = j < 0 ? 0 : j >= nb ? nb - 1 : j;
+        k = k < 0 ? 0 : k >= nb ? nb - 1 : k;
+        size_t b = ((size_t)i * nb + j) * nb + k;
+        if (e->vblock[b] < 0) e->vblock[b] = m;
+    }
+    int32_t last = 0;
+    for (size_t b = 0; b < n3; ++b)
+    {
+        if (e->vblock[b] < 0)
+            e->vblock[b] = last;
+        else
+            last = e->vblock[b];
+    }
+}
+
+int sko_set_grid_voronoi(sko_engine_t* e, const double extent[6], int32_t num_cells, const double* sites,
+                         const int64_t* nbr_offset, const int32_t* nbr_index)
+{
+    if (!e || !extent || num_cells < 1 || !sites || !nbr_offset || !nbr_index) return fail(SK_ERR_INVALID, "bad voronoi mesh");
+    if (nbr_offset[0] != 0) return fail(SK_ERR_INVALID, "neighbour offsets must start at zero");
+    for (int m = 0; m < num_cells; ++m)
+    {
+        if (nbr_offset[m + 1] < nbr_offset[m]) return fail(SK_ERR_INVALID, "neighbour offsets must ascend");
+        for (int64_t i = nbr_offset[m]; i < nbr_offset[m + 1]; ++i)
+            if (nbr_index[i] < -6 || nbr_index[i] >= num_cells) return fail(SK_ERR_INVALID, "neighbour index out of range");
+    }
+    free_grid(e);
+    e->grid_kind = 3;
+    e->vcells = num_cells;
+    memcpy(e->extent, extent, 6 * sizeof(double));
+    double dx = extent[3] - extent[0], dy = extent[4] - extent[1], dz = extent[5] - extent[2];
+    e->eps = 1e-12 * sqrt(dx * dx + dy * dy + dz * dz); /* VoronoiMeshSnapshot.cpp:396 */
+    e->vsite = dupd(sites, 3 * (size_t)num_cells);
+    e->vnbr_off = (int64_t*)malloc(((size_t)num_cells + 1) * sizeof(int64_t));
+    memcpy(e->vnbr_off, nbr_offset, ((size_t)num_cells + 1) * sizeof(int64_t));
+    e->vnbr = dupi(nbr_index, (size_t)nbr_offset[num_cells]);
+    voronoi_build_blocks(e);
+    return SK_OK;
+}
+
 static int grid_num_cells(const sko_engine_t* e)
 {
+    if (e->grid_kind == 3) return e->vcells;
     if (e->grid_kind == 1) return e->nx * e->ny * e->nz;
     if (e->grid_kind == 2) return e->nx;
     return 0;
@@ -826,6 +899,7 @@ int sko_set_secondary(sko_engine_t* e, const sk_secondary_t* sec)
 {
     if (!e || !sec) return fail(SK_ERR_INVALID, "null argument");
     if (e->rf_grid < 0) return fail(SK_ERR_STATE, "dust emission needs a radiation field grid");
+    if (e->grid_kind == 3) return fail(SK_ERR_UNSUPPORTED, "dust emission from a Voronoi grid (random positions in a cell)");
     if (sec->emission_grid < 0 || sec->emission_grid >= e->nwlg) return fail(SK_ERR_INVALID, "bad emission grid index");
     if (sec->num_temperatures < 2 || !sec->temperature || !sec->planck_abs || !sec->rf_sigma_abs || !sec->em_sigma_abs)
         return fail(SK_ERR_INVALID, "missing emission calculator tables");
@@ -1049,7 +1123,8 @@ typedef struct {
     int m;
     double ds;
     int i, j, k; /* cartesian */
-    int node;    /* tree: current node or -1 */
+    int node;    /* tree: current node or -1; voronoi: current cell */
+    int hint;    /* voronoi: a cell near the start of the path (-1 = none) to start the nearest-site walk from */
 } gen_t;
 
 static int box_contains(const double* b, double x, double y, double z)
@@ -1160,6 +1235,7 @@ static void gen_start(gen_t* g, const double r[3], const double k[3])
     g->ky = k[1];
     g->kz = k[2];
     g->node = -1;
+    g->hint = -1;
 }
 
 /* CartesianSpatialGrid::MySegmentGenerator::next, CartesianSpatialGrid.cpp:95-162 */
@@ -1293,9 +1369,145 @@ static int next_tree(sko_engine_t* e, gen_t* g)
     return 0;
 }
 
+/* VoronoiMeshSnapshot::cellIndex (VoronoiMeshSnapshot.cpp:1006-1040): the cell whose site is nearest to the position.  The
+ * reference searches block lists and k-d trees; here the search walks the neighbour graph: from cell m move to the
+ * neighbour whose site is closest to the position as long as that is closer than the own site.  The segment from a site to
+ * a query point inside the (convex) domain leaves the site's cell through a face inside the domain, and the neighbour
+ * across that face is closer to the query, so the walk ends exactly in the cell that contains the position.  `hint` < 0
+ * starts from the block table. */
+static int voronoi_walk(const sko_engine_t* e, double x, double y, double z, int hint)
+{
+    int m = hint;
+    if (m < 0)
+    {
+        const double* b = e->extent;
+        int nb = e->vnb;
+        int i = (int)((x - b[0]) / (b[3] - b[0]) * nb);
+        int j = (int)((y - b[1]) / (b[4] - b[1]) * nb);
+        int k = (int)((z - b[2]) / (b[5] - b[2]) * nb);
+        i = i < 0 ? 0 : i >= nb ? nb - 1 : i;
+        j = j < 0 ? 0 : j >= nb ? nb - 1 : j;
+        k = k < 0 ? 0 : k >= nb ? nb - 1 : k;
+        m = e->vblock[((size_t)i * nb + j) * nb + k];
+    }
+    const double* s = e->vsite;
+    double dx = x - s[3 * m], dy = y - s[3 * m + 1], dz = z - s[3 * m + 2];
+    double d = dx * dx + dy * dy + dz * dz;
+    while (1)
+    {
+        int best = -1;
+        double dbest = d;
+        for (int64_t i = e->vnbr_off[m]; i < e->vnbr_off[m + 1]; ++i)
+        {
+            int mi = e->vnbr[i];
+            if (mi < 0) continue;
+            double ex = x - s[3 * mi], ey = y - s[3 * mi + 1], ez = z - s[3 * mi + 2];
+            double di = ex * ex + ey * ey + ez * ez;
+            if (di < dbest)
+            {
+                dbest = di;
+                best = mi;
+            }
+        }
+        if (best < 0) return m;
+        m = best;
+        d = dbest;
+    }
+}
+static int voronoi_cell_index(const sko_engine_t* e, double x, double y, double z, int hint)
+{
+    if (!box_contains(e->extent, x, y, z)) return -1;
+    return voronoi_walk(e, x, y, z, hint);
+}
+
+/* VoronoiMeshSnapshot::MySegmentGenerator::next, VoronoiMeshSnapshot.cpp:1058-1188 */
+static int next_voronoi(sko_engine_t* e, gen_t* g)
+{
+    switch (g->state)
+    {
+        case 0:
+        {
+            if (!move_inside(g, e->extent, e->eps)) return 0;
+            g->node = voronoi_cell_index(e, g->rx, g->ry, g->rz, g->hint);
+            if (g->ds > 0.) return 1;
+        }
+        /* fall through */
+        case 1:
+        {
+            while (1)
+            {
+                int mr = g->node;
+                const double* pr = e->vsite + 3 * (size_t)mr;
+                double sq = DBL_MAX;
+                const int NO_INDEX = -99;
+                int mq = NO_INDEX;
+                for (int64_t i = e->vnbr_off[mr]; i < e->vnbr_off[mr + 1]; ++i)
+                {
+                    int mi = e->vnbr[i];
+                    double si = 0;
+                    if (mi >= 0)
+                    {
+                        const double* pi = e->vsite + 3 * (size_t)mi;
+                        double nx = pi[0] - pr[0], ny = pi[1] - pr[1], nz = pi[2] - pr[2];
+                        double ndotk = nx * g->kx + ny * g->ky + nz * g->kz;
+                        if (ndotk > 0)
+                        {
+                            double px = 0.5 * (pi[0] + pr[0]), py = 0.5 * (pi[1] + pr[1]), pz = 0.5 * (pi[2] + pr[2]);
+                            si = (nx * (px - g->rx) + ny * (py - g->ry) + nz * (pz - g->rz)) / ndotk;
+                        }
+                    }
+                    else
+                    {
+                        switch (mi)
+                        {
+                            case -1: si = (e->extent[0] - g->rx) / g->kx; break;
+                            case -2: si = (e->extent[3] - g->rx) / g->kx; break;
+                            case -3: si = (e->extent[1] - g->ry) / g->ky; break;
+                            case -4: si = (e->extent[4] - g->ry) / g->ky; break;
+                            case -5: si = (e->extent[2] - g->rz) / g->kz; break;
+                            default: si = (e->extent[5] - g->rz) / g->kz; break;
+                        }
+                    }
+                    if (si > 0 && si < sq)
+                    {
+                        sq = si;
+                        mq = mi;
+                    }
+                }
+                if (mq == NO_INDEX)
+                {
+                    g->rx += g->kx * e->eps;
+                    g->ry += g->ky * e->eps;
+                    g->rz += g->kz * e->eps;
+                    g->node = voronoi_cell_index(e, g->rx, g->ry, g->rz, mr);
+                    if (g->node < 0)
+                    {
+                        g->state = 2;
+                        return 0;
+                    }
+                }
+                else
+                {
+                    double adv = sq + e->eps;
+                    g->rx += g->kx * adv;
+                    g->ry += g->ky * adv;
+                    g->rz += g->kz * adv;
+                    g->m = mr;
+                    g->ds = sq;
+                    g->node = mq;
+                    if (mq < 0) g->state = 2;
+                    return 1;
+                }
+            }
+        }
+        default: break;
+    }
+    return 0;
+}
+
 static int gen_next(sko_engine_t* e, gen_t* g)
 {
-    return e->grid_kind == 1 ? next_cartesian(e, g) : next_tree(e, g);
+    return e->grid_kind == 1 ? next_cartesian(e, g) : e->grid_kind == 2 ? next_tree(e, g) : next_voronoi(e, g);
 }
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -2245,6 +2457,26 @@ int sko_test_trace(sko_engine_t* e, const double r[3], const double k[3], int32_
         n++;
     }
     return n;
+}
+/* nearest-site search of the Voronoi grid: the walk, and a brute-force scan to check it against */
+int sko_test_voronoi_cell_index(sko_engine_t* e, const double r[3], int brute)
+{
+    if (!e || e->grid_kind != 3) return -2;
+    if (!brute) return voronoi_cell_index(e, r[0], r[1], r[2], -1);
+    if (!box_contains(e->extent, r[0], r[1], r[2])) return -1;
+    int best = -1;
+    double dbest = DBL_MAX;
+    for (int m = 0; m < e->vcells; ++m)
+    {
+        double dx = r[0] - e->vsite[3 * m], dy = r[1] - e->vsite[3 * m + 1], dz = r[2] - e->vsite[3 * m + 2];
+        double d = dx * dx + dy * dy + dz * dz;
+        if (d < dbest)
+        {
+            dbest = d;
+            best = m;
+        }
+    }
+    return best;
 }
 void sko_test_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
 {

@@ -73,12 +73,29 @@
 #include "TimeLogger.hpp"
 #include "TreeSpatialGrid.hpp"
 #include "Units.hpp"
+#include "VoronoiMeshSnapshot.hpp"
+#include "VoronoiMeshSpatialGrid.hpp"
 #undef private
 #undef protected
 
 #include "GpuLifeCycle.hpp"
 
 ////////////////////////////////////////////////////////////////////
+
+// VoronoiMeshSnapshot::Cell is a private nested class that the reference defines inside VoronoiMeshSnapshot.cpp:85-194, so
+// its header only forward-declares it.  The shim needs the site position and the neighbour list of every cell, for which
+// the reference offers no accessor; this definition repeats the DATA LAYOUT of that class (base Box; Vec _r, _c; double
+// _volume; vector<int> _neighbors; Array _properties) so that the two members can be read.  A maintainer integrating the
+// engine would add two accessors to VoronoiMeshSnapshot instead.
+class VoronoiMeshSnapshot::Cell : public Box
+{
+public:
+    Vec _r;
+    Vec _c;
+    double _volume;
+    vector<int> _neighbors;
+    Array _properties;
+};
 
 namespace
 {
@@ -183,8 +200,10 @@ std::string GpuLifeCycle::unsupportedReason() const
     if (!mix || mix->scatteringMode() != DustMix::ScatteringMode::HenyeyGreenstein) return "a material mix other than a Henyey-Greenstein dust mix";
     auto grid = ms->grid();
     auto tree = dynamic_cast<TreeSpatialGrid*>(grid);
-    if (!dynamic_cast<CartesianSpatialGrid*>(grid) && !(tree && dynamic_cast<OctTreeNode*>(tree->_nodev[0])))
+    auto voronoi = dynamic_cast<VoronoiMeshSpatialGrid*>(grid);
+    if (!dynamic_cast<CartesianSpatialGrid*>(grid) && !(tree && dynamic_cast<OctTreeNode*>(tree->_nodev[0])) && !voronoi)
         return "spatial grid " + grid->type();
+    if (voronoi && config->hasSecondaryEmission()) return "dust emission from a Voronoi grid";
     for (auto source : _sim->sourceSystem()->sources())
     {
         auto ns = dynamic_cast<NormalizedSource*>(source);
@@ -250,6 +269,27 @@ void GpuLifeCycle::configure()
     if (auto g = dynamic_cast<CartesianSpatialGrid*>(ms->grid()))
     {
         check(sk_engine_set_grid_cartesian(_e, g->_Nx, g->_Ny, g->_Nz, ptr(g->_xv), ptr(g->_yv), ptr(g->_zv)));
+    }
+    else if (auto v = dynamic_cast<VoronoiMeshSpatialGrid*>(ms->grid()))
+    {
+        // VoronoiMeshSnapshot::_cells: site positions and neighbour lists as built by the vendored voro++
+        auto mesh = v->_mesh;
+        size_t n = mesh->_cells.size();
+        vector<double> sites(3 * n);
+        vector<int64_t> offset(n + 1, 0);
+        vector<int32_t> index;
+        for (size_t m = 0; m != n; ++m)
+        {
+            const VoronoiMeshSnapshot::Cell* cell = mesh->_cells[m];
+            sites[3 * m] = cell->_r.x();
+            sites[3 * m + 1] = cell->_r.y();
+            sites[3 * m + 2] = cell->_r.z();
+            index.insert(index.end(), cell->_neighbors.begin(), cell->_neighbors.end());
+            offset[m + 1] = static_cast<int64_t>(index.size());
+        }
+        Box b = mesh->_extent;
+        double ext[6] = {b.xmin(), b.ymin(), b.zmin(), b.xmax(), b.ymax(), b.zmax()};
+        check(sk_engine_set_grid_voronoi(_e, ext, static_cast<int32_t>(n), sites.data(), offset.data(), index.data()));
     }
     else
     {

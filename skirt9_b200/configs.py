@@ -67,3 +67,24 @@ def cfg4(num_packets=2e5, max_level=6, max_dust_fraction=2e-4, seed=0, min_level
                                   dustEmissionWLG=H.LogWavelengthGrid(1e-6, 1000e-6, 60), iterateSecondaryEmission=True,
                                   minSecondaryIterations=1, maxSecondaryIterations=max_secondary_iterations,
                                   numDensitySamples=20, seed=seed)
+
+
+def cfg5(sites, num_packets=2e5, seed=0, num_pixels=64, density=None, volumes=None, record_statistics=True):
+    """Voronoi grid on imported SPH particle positions (policy ImportedSites), exponential-disk source,
+    one wavelength.  `sites` (m) are the particle positions; the cell densities are given (imported from the reference's
+    ParticleMedium sampling) or default to a smooth disk evaluated at the sites."""
+    pc = H.PC
+    disk = H.ExpDiskGeometry(3000 * pc, 300 * pc, 0.0, 15000 * pc, 2000 * pc)
+    src = H.GeometricSource(disk, H.BlackBodySED(6000.0), luminosity=1e10 * H.LSUN)
+    mix = H.MeanListDustMix([0.1e-6, 1e-6], [1000.0, 1000.0], [0.6, 0.6], [0.5, 0.5])
+    medium = H.GeometricMedium(H.ExpDiskGeometry(3000 * pc, 250 * pc, 0.0, 15000 * pc, 1900 * pc), mix, opticalDepth=1.0,
+                               wavelength=0.55e-6)
+    grid = H.VoronoiMeshSpatialGrid(-16000 * pc, 16000 * pc, -16000 * pc, 16000 * pc, -2000 * pc, 2000 * pc, sites,
+                                    volumes=volumes)
+    instr = H.FullInstrument(instrumentName="i60", distance=10e6 * pc, inclination=60 * DEG, fieldOfViewX=32000 * pc,
+                             numPixelsX=num_pixels, fieldOfViewY=32000 * pc, numPixelsY=num_pixels, recordComponents=True,
+                             recordStatistics=record_statistics)
+    sim = H.MonteCarloSimulation(sources=[src], medium=medium, grid=grid, instruments=[instr], numPackets=num_packets,
+                                 oligoWavelengths=[0.55e-6], storeRadiationField=False, numDensitySamples=1, seed=seed)
+    sim.density = density
+    return sim

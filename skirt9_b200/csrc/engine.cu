@@ -91,6 +91,11 @@ __global__ void sk_set_density_kernel(SkCellRec* __restrict__ cells, const doubl
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m < ncells) cells[m].dens = dens[m];
 }
+__global__ void sk_set_density_voronoi_kernel(double4* __restrict__ rec, const double* __restrict__ dens, int ncells)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m < ncells) rec[m].w = dens[m];
+}
 __global__ void sk_sum_kernel(double* __restrict__ out, const double* __restrict__ a, const double* __restrict__ b,
                               const double* __restrict__ c, const double* __restrict__ d, size_t n)
 {
@@ -104,13 +109,13 @@ __global__ void sk_sum_kernel(double* __restrict__ out, const double* __restrict
 
 // MediumSystem::totalDustAbsorbedLuminosity, MediumSystem.cpp:1317-1356 (single dust medium, constant sections)
 __global__ void sk_absorbed_kernel(const double* __restrict__ rf, const double* __restrict__ dens_or_null,
-                                   const SkCellRec* __restrict__ cells, const double* __restrict__ kabs, int ncells,
-                                   int nrf, double* out)
+                                   const SkCellRec* __restrict__ cells, const double4* __restrict__ vrec,
+                                   const double* __restrict__ kabs, int ncells, int nrf, double* out)
 {
     double sum = 0.;
     for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < ncells; m += gridDim.x * blockDim.x)
     {
-        double n = dens_or_null ? dens_or_null[m] : cells[m].dens;
+        double n = dens_or_null ? dens_or_null[m] : cells ? cells[m].dens : vrec[m].w;
         double s = 0.;
         for (int ell = 0; ell < nrf; ++ell) s += kabs[ell] * n * rf[(size_t)m * nrf + ell];
         sum += s;
@@ -330,6 +335,7 @@ extern "C" int sk_engine_set_grid_cartesian(sk_engine_t* e, int32_t nx, int32_t 
     e->M.eps = 1e-12 * sqrt(dx * dx + dy * dy + dz * dz);  // CartesianSpatialGrid.cpp:102
     e->M.ncells = 0;
     e->M.cells = nullptr;
+    e->M.vrec = nullptr;
     return set_tables(e, xv, nx + 1, yv, ny + 1, zv, nz + 1);
 }
 
@@ -445,7 +451,78 @@ extern "C" int sk_engine_set_grid_octree(sk_engine_t* e, const double extent[6],
     e->M.node_child = d_child;
     e->M.cell_coord = d_coord;
     e->M.cells = d_cells;
+    e->M.vrec = nullptr;
     return set_tables(e, T[0].data(), N + 1, T[1].data(), N + 1, T[2].data(), N + 1);
+}
+
+// VoronoiMeshSnapshot as built by the reference's setup (sites + neighbour lists); the engine adds the start-cell table of
+// its nearest-site walk (same construction as oracle/sk_oracle.c voronoi_build_blocks).
+extern "C" int sk_engine_set_grid_voronoi(sk_engine_t* e, const double extent[6], int32_t num_cells, const double* sites,
+                                          const int64_t* nbr_offset, const int32_t* nbr_index)
+{
+    if (!e || !extent || num_cells < 1 || !sites || !nbr_offset || !nbr_index) return fail(SK_ERR_INVALID, "bad voronoi mesh");
+    if (nbr_offset[0] != 0) return fail(SK_ERR_INVALID, "neighbour offsets must start at zero");
+    for (int m = 0; m < num_cells; ++m)
+    {
+        if (nbr_offset[m + 1] < nbr_offset[m]) return fail(SK_ERR_INVALID, "neighbour offsets must ascend");
+        for (int64_t i = nbr_offset[m]; i < nbr_offset[m + 1]; ++i)
+            if (nbr_index[i] < -6 || nbr_index[i] >= num_cells) return fail(SK_ERR_INVALID, "neighbour index out of range");
+    }
+    CK(cudaSetDevice(e->cfg.device));
+    free_group(e->grid_allocs);
+    const int nc = num_cells;
+    std::vector<double4> rec(nc);
+    for (int m = 0; m < nc; ++m) rec[m] = make_double4(sites[3 * (size_t)m], sites[3 * (size_t)m + 1], sites[3 * (size_t)m + 2], 0.);
+    int nb = (int)std::cbrt((double)nc);
+    nb = std::max(3, std::min(250, nb));  // VoronoiMeshSnapshot.cpp:544
+    std::vector<int32_t> block((size_t)nb * nb * nb, -1);
+    for (int m = 0; m < nc; ++m)
+    {
+        int i = (int)((rec[m].x - extent[0]) / (extent[3] - extent[0]) * nb);
+        int j = (int)((rec[m].y - extent[1]) / (extent[4] - extent[1]) * nb);
+        int k = (int)((rec[m].z - extent[2]) / (extent[5] - extent[2]) * nb);
+        i = i < 0 ? 0 : i >= nb ? nb - 1 : i;
+        j = j < 0 ? 0 : j >= nb ? nb - 1 : j;
+        k = k < 0 ? 0 : k >= nb ? nb - 1 : k;
+        size_t b = ((size_t)i * nb + j) * nb + k;
+        if (block[b] < 0) block[b] = m;
+    }
+    int32_t last = 0;
+    for (size_t b = 0; b < block.size(); ++b)
+    {
+        if (block[b] < 0)
+            block[b] = last;
+        else
+            last = block[b];
+    }
+    std::vector<long long> off(nbr_offset, nbr_offset + nc + 1);
+    double4* d_rec;
+    long long* d_off;
+    int32_t *d_idx, *d_block;
+    if (int rc = upload(e->grid_allocs, rec.data(), (size_t)nc, &d_rec)) return rc;
+    if (int rc = upload(e->grid_allocs, off.data(), (size_t)nc + 1, &d_off)) return rc;
+    if (int rc = upload(e->grid_allocs, nbr_index, (size_t)nbr_offset[nc], &d_idx)) return rc;
+    if (int rc = upload(e->grid_allocs, block.data(), block.size(), &d_block)) return rc;
+    e->grid_kind = 3;
+    e->M.grid_kind = 3;
+    e->M.nx = e->M.ny = e->M.nz = 0;
+    e->M.maxlevel = 0;
+    e->M.nnodes = 0;
+    e->M.cells = nullptr;
+    e->M.xv = e->M.yv = e->M.zv = nullptr;
+    e->M.lattice_in_smem = 0;
+    e->smem_bytes = 0;
+    e->M.vrec = d_rec;
+    e->M.vnbr_off = d_off;
+    e->M.vnbr = d_idx;
+    e->M.vblock = d_block;
+    e->M.vnb = nb;
+    e->grid_cells = nc;
+    e->M.ncells = 0;
+    memcpy(e->M.ext, extent, 6 * sizeof(double));
+    double dx = extent[3] - extent[0], dy = extent[4] - extent[1], dz = extent[5] - extent[2];
+    e->M.eps = 1e-12 * sqrt(dx * dx + dy * dy + dz * dz);  // VoronoiMeshSnapshot.cpp:396
+    return SK_OK;
 }
 
 extern "C" int sk_engine_set_medium(sk_engine_t* e, int32_t num_cells, const double* number_density,
@@ -462,6 +539,15 @@ extern "C" int sk_engine_set_medium(sk_engine_t* e, int32_t num_cells, const dou
         double* d;
         if (int rc = upload(e->medium_allocs, number_density, (size_t)num_cells, &d)) return rc;
         e->M.dens = d;
+    }
+    else if (e->grid_kind == 3)
+    {
+        double* d;
+        if (int rc = upload(e->medium_allocs, number_density, (size_t)num_cells, &d)) return rc;
+        sk_set_density_voronoi_kernel<<<(num_cells + 255) / 256, 256, 0, e->stream>>>(const_cast<double4*>(e->M.vrec), d, num_cells);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(e->stream));
+        e->M.dens = nullptr;
     }
     else
     {
@@ -811,6 +897,7 @@ extern "C" int sk_engine_set_secondary(sk_engine_t* e, const sk_secondary_t* sec
 {
     if (!e || !sec) return fail(SK_ERR_INVALID, "null argument");
     if (e->M.rf_grid < 0) return fail(SK_ERR_STATE, "dust emission needs a radiation field grid");
+    if (e->grid_kind == 3) return fail(SK_ERR_UNSUPPORTED, "dust emission from a Voronoi grid (random positions in a cell)");
     if (!e->M.volume) return fail(SK_ERR_STATE, "dust emission needs the cell volumes (sk_engine_set_medium)");
     if (!e->M.nlam) return fail(SK_ERR_STATE, "set the dust mix before the secondary emission tables");
     if (sec->emission_grid < 0 || sec->emission_grid >= e->M.nwlg) return fail(SK_ERR_INVALID, "bad emission grid index");
@@ -1170,8 +1257,8 @@ extern "C" int sk_engine_launch_segment(sk_engine_t* e, uint64_t first, uint64_t
     {
         // keep the cell records (the random-access working set of the crossing loops) resident in L2 while the packet
         // bank streams through it: persisting access-policy window on the engine's stream
-        const void* base = e->grid_kind == 2 ? (const void*)e->M.cells : (const void*)e->M.dens;
-        size_t bytes = e->grid_kind == 2 ? (size_t)e->M.ncells * sizeof(SkCellRec) : (size_t)e->M.ncells * sizeof(double);
+        const void* base = e->grid_kind == 2 ? (const void*)e->M.cells : e->grid_kind == 3 ? (const void*)e->M.vrec : (const void*)e->M.dens;
+        size_t bytes = e->grid_kind == 1 ? (size_t)e->M.ncells * sizeof(double) : (size_t)e->M.ncells * 32;
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, e->cfg.device));
         size_t window = std::min<size_t>(bytes, (size_t)prop.accessPolicyMaxWindowSize);
@@ -1208,7 +1295,7 @@ extern "C" int sk_engine_launch_segment(sk_engine_t* e, uint64_t first, uint64_t
         if (!e->model_dev) CK(cudaMalloc(&e->model_dev, sizeof(SkDevModel)));
         CK(cudaMemcpyAsync(e->model_dev, &e->M, sizeof(SkDevModel), cudaMemcpyHostToDevice, e->stream));
         A.model = e->model_dev;
-        int rc = e->grid_kind == 1 ? run_bank<1>(e, A) : run_bank<2>(e, A);
+        int rc = e->grid_kind == 1 ? run_bank<1>(e, A) : e->grid_kind == 2 ? run_bank<2>(e, A) : run_bank<3>(e, A);
         if (rc) return rc;
     }
     CK(cudaEventRecord(e->ev1, e->stream));
@@ -1283,7 +1370,7 @@ extern "C" int sk_engine_absorbed_luminosity(sk_engine_t* e, int32_t primary, do
     CK(cudaMalloc(&dk, kabs.size() * sizeof(double)));
     CK(cudaMemcpyAsync(dk, kabs.data(), kabs.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemsetAsync(e->scalar, 0, sizeof(double), e->stream));
-    sk_absorbed_kernel<<<296, 256, 0, e->stream>>>(primary ? e->M.rf1 : e->M.rf2, e->M.dens, e->M.cells, dk,
+    sk_absorbed_kernel<<<296, 256, 0, e->stream>>>(primary ? e->M.rf1 : e->M.rf2, e->M.dens, e->M.cells, e->M.vrec, dk,
                                                    e->M.ncells, e->M.nrf, e->scalar);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, e->scalar, sizeof(double), cudaMemcpyDeviceToHost, e->stream));

@@ -158,6 +158,59 @@ __device__ __forceinline__ void sk_tree_descend(const int32_t* __restrict__ node
     out.lev = lev;
 }
 
+// one 32-byte Voronoi cell record {site; density} through the read-only path (two 16-byte loads, one sector)
+__device__ __forceinline__ double4 sk_ld_rec(const double4* p)
+{
+    const double2 a = __ldg(reinterpret_cast<const double2*>(p));
+    const double2 b = __ldg(reinterpret_cast<const double2*>(p) + 1);
+    return make_double4(a.x, a.y, b.x, b.y);
+}
+
+// VoronoiMeshSnapshot::cellIndex (VoronoiMeshSnapshot.cpp:1006-1040): the cell whose site is nearest to the position, found
+// by walking the neighbour graph from `hint` (or from the block table when hint < 0) to ever closer sites; see
+// oracle/sk_oracle.c voronoi_walk for why the walk ends in the cell that contains the position.
+__device__ __noinline__ int sk_voronoi_walk(const SkDevModel* __restrict__ Mg, double x, double y, double z, int hint)
+{
+    const SkDevModel& M = *Mg;
+    int m = hint;
+    if (m < 0)
+    {
+        const int nb = M.vnb;
+        int i = (int)((x - M.ext[0]) / (M.ext[3] - M.ext[0]) * nb);
+        int j = (int)((y - M.ext[1]) / (M.ext[4] - M.ext[1]) * nb);
+        int k = (int)((z - M.ext[2]) / (M.ext[5] - M.ext[2]) * nb);
+        i = i < 0 ? 0 : i >= nb ? nb - 1 : i;
+        j = j < 0 ? 0 : j >= nb ? nb - 1 : j;
+        k = k < 0 ? 0 : k >= nb ? nb - 1 : k;
+        m = M.vblock[((size_t)i * nb + j) * nb + k];
+    }
+    double4 s = sk_ld_rec(&M.vrec[m]);
+    double dx = x - s.x, dy = y - s.y, dz = z - s.z;
+    double d = dx * dx + dy * dy + dz * dz;
+    while (true)
+    {
+        int best = -1;
+        double dbest = d;
+        const long long i1 = M.vnbr_off[m + 1];
+        for (long long i = M.vnbr_off[m]; i < i1; ++i)
+        {
+            const int mi = __ldg(&M.vnbr[i]);
+            if (mi < 0) continue;
+            const double4 t = sk_ld_rec(&M.vrec[mi]);
+            double ex = x - t.x, ey = y - t.y, ez = z - t.z;
+            double di = ex * ex + ey * ey + ez * ez;
+            if (di < dbest)
+            {
+                dbest = di;
+                best = mi;
+            }
+        }
+        if (best < 0) return m;
+        m = best;
+        d = dbest;
+    }
+}
+
 // Cold path: locates the cell holding (x,y,z) from scratch.  Takes the model through a pointer to its copy in
 // global memory so that the kernel-parameter copy never has its address taken (that would force it into local memory).
 template <int GRID>
@@ -169,7 +222,12 @@ __device__ __noinline__ void sk_locate(const SkDevModel* __restrict__ Mg, const 
         out.m = -1;
         return;
     }
-    if (GRID == 1)
+    if (GRID == 3)
+    {
+        out.ix = out.iy = out.iz = out.lev = 0;
+        out.m = sk_voronoi_walk(Mg, x, y, z, -1);
+    }
+    else if (GRID == 1)
     {
         out.ix = sk_locate_clip(T.X, Mg->nx + 1, x);  // CartesianSpatialGrid.cpp:105-107
         out.iy = sk_locate_clip(T.Y, Mg->ny + 1, y);
@@ -229,7 +287,82 @@ __device__ __forceinline__ void sk_step(const SkDevModel& M, const SkDevModel* _
                                         SkLocalCounters& cnt, double& rx, double& ry, double& rz, const SkRayDir& k,
                                         SkCellPos& p, int& m_out, double& dens_out, double& ds_out)
 {
-    if (GRID == 1)
+    if (GRID == 3)
+    {
+        // VoronoiMeshSnapshot::MySegmentGenerator::next, VoronoiMeshSnapshot.cpp:1087-1179: the exit point is the nearest
+        // intersection with the bisecting planes towards the neighbouring sites and with the domain walls
+        int m = p.m;
+        while (true)
+        {
+            const double4 pr = sk_ld_rec(&M.vrec[m]);
+            double sq = DBL_MAX;
+            const int NO_INDEX = -99;
+            int mq = NO_INDEX;
+            const long long i1 = __ldg(&M.vnbr_off[m + 1]);
+            for (long long i = __ldg(&M.vnbr_off[m]); i < i1; ++i)
+            {
+                const int mi = __ldg(&M.vnbr[i]);
+                double si = 0;
+                if (mi >= 0)
+                {
+                    const double4 pi = sk_ld_rec(&M.vrec[mi]);
+                    const double nx = pi.x - pr.x, ny = pi.y - pr.y, nz = pi.z - pr.z;
+                    const double ndotk = nx * k.kx + ny * k.ky + nz * k.kz;
+                    if (ndotk > 0)
+                    {
+                        const double px = 0.5 * (pi.x + pr.x), py = 0.5 * (pi.y + pr.y), pz = 0.5 * (pi.z + pr.z);
+                        si = (nx * (px - rx) + ny * (py - ry) + nz * (pz - rz)) / ndotk;
+                    }
+                }
+                else
+                {
+                    switch (mi)
+                    {
+                        case -1: si = (M.ext[0] - rx) / k.kx; break;
+                        case -2: si = (M.ext[3] - rx) / k.kx; break;
+                        case -3: si = (M.ext[1] - ry) / k.ky; break;
+                        case -4: si = (M.ext[4] - ry) / k.ky; break;
+                        case -5: si = (M.ext[2] - rz) / k.kz; break;
+                        default: si = (M.ext[5] - rz) / k.kz; break;
+                    }
+                }
+                if (si > 0 && si < sq)
+                {
+                    sq = si;
+                    mq = mi;
+                }
+            }
+            if (mq == NO_INDEX)
+            {
+                // no exit point (rare): nudge the position, look the cell up again (.cpp:1156-1167)
+                cnt.fallbacks++;
+                rx += k.kx * M.eps;
+                ry += k.ky * M.eps;
+                rz += k.kz * M.eps;
+                m = sk_box_contains(M.ext, rx, ry, rz) ? sk_voronoi_walk(Mg, rx, ry, rz, m) : -1;
+                if (m < 0)
+                {
+                    // outside the domain: the path ends without a further segment
+                    p.m = -1;
+                    m_out = -1;
+                    dens_out = 0.;
+                    ds_out = -1.;
+                    return;
+                }
+                continue;
+            }
+            const double adv = sq + M.eps;
+            rx += k.kx * adv;
+            ry += k.ky * adv;
+            rz += k.kz * adv;
+            m_out = m;
+            dens_out = pr.w;
+            ds_out = sq;
+            p.m = mq < 0 ? -1 : mq;
+            return;
+        }
+    }
+    else if (GRID == 1)
     {
         int m = p.m;
         double dens = __ldg(&M.dens[m]);
@@ -647,7 +780,7 @@ __device__ __forceinline__ void sk_record(const SkDevInstr& q, int l, int ell, d
 template <int GRID>
 __device__ __forceinline__ double sk_cell_density(const SkDevModel& M, int m)
 {
-    return GRID == 2 ? M.cells[m].dens : M.dens[m];
+    return GRID == 3 ? M.vrec[m].w : GRID == 2 ? M.cells[m].dens : M.dens[m];
 }
 // true when (x,y,z) lies in the half-open box of cell c
 template <int GRID>

@@ -67,7 +67,7 @@ struct SkDevModel {
     int32_t force_scattering, min_scatt_events;
     double path_length_bias, min_weight_reduction;
     // grid
-    int32_t grid_kind;  // 1 cartesian, 2 octree
+    int32_t grid_kind;  // 1 cartesian, 2 octree, 3 voronoi
     int32_t nx, ny, nz; // cartesian bins; octree: lattice size per axis (2^maxlevel) in nx
     int32_t maxlevel;
     int32_t lattice_in_smem;
@@ -79,6 +79,13 @@ struct SkDevModel {
     const int32_t* node_child;   // octree: first child node id, or -(cell+1) for a leaf
     const uint32_t* cell_coord;  // octree: 4 x uint32 per cell {ix,iy,iz,level}
     int32_t ncells, nnodes;
+    // voronoi mesh (grid_kind 3): one 32-byte record per cell {site x,y,z; density}, CSR neighbour lists (cell index, or
+    // -1..-6 for the domain walls), and the start-cell table of the nearest-site walk
+    const double4* vrec;
+    const long long* vnbr_off;
+    const int32_t* vnbr;
+    const int32_t* vblock;
+    int32_t vnb;
     const double* volume;        // cell volumes (MediumState::volume)
     // dust
     int32_t nlam;

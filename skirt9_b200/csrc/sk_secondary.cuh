@@ -174,7 +174,9 @@ __device__ __noinline__ void sk_launch_secondary(const SkDevModel* __restrict__ 
         }
     }
     double b0, b1, b2, b3, b4, b5;
-    if (GRID == 1)
+    if (GRID == 3)
+        b0 = b1 = b2 = b3 = b4 = b5 = 0.;  // not reached: dust emission from a Voronoi grid is rejected by set_secondary
+    else if (GRID == 1)
     {
         int k = m % M.nz, j = (m / M.nz) % M.ny, i = m / (M.nz * M.ny);
         b0 = T.X[i];

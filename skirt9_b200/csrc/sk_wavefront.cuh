@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, SK_TRACE_MINBLOCKS)
                 }
                 else if (MODE == 1)
                 {
-                    if (forced ? (ds > 0.) : true)
+                    if (forced ? (ds > 0.) : (ds >= 0.))  // ds < 0: the generator ended without a segment (Voronoi)
                     {
                         nseg++;
                         double tau0 = tau, s0 = s;
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, SK_TRACE_MINBLOCKS)
                         }
                     }
                 }
-                else
+                else if (ds >= 0.)
                 {
                     nseg++;
                     tau += section * dens * ds;
@@ -474,7 +474,11 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_advance(const SkDevModel
                 // the next paths start in the interaction cell unless rounding moved the point out of it
                 SkCellPos c{m, K.I(I_MIX, slot), K.I(I_MIY, slot), K.I(I_MIZ, slot), K.I(I_MLEV, slot)};
                 bool inside = m >= 0 && sk_box_strictly_inside(M.ext, x, y, z);
-                if (inside && !sk_cell_contains<GRID>(M, T, c, x, y, z))
+                if (GRID == 3)
+                {
+                    if (inside) c.m = sk_voronoi_walk(Mg, x, y, z, m);  // a new path looks its cell up (.cpp:1076)
+                }
+                else if (inside && !sk_cell_contains<GRID>(M, T, c, x, y, z))
                 {
                     SkCellPos c2;
                     sk_locate<GRID>(Mg, T, x, y, z, c2);

@@ -555,6 +555,57 @@ class FileTreeSpatialGrid(PolicyTreeSpatialGrid):
             self.first_child = np.where(fc[order] >= 0, newid[np.maximum(fc[order], 0)], -1).astype(np.int32)
 
 
+class VoronoiMeshSpatialGrid:
+    """VoronoiMeshSpatialGrid with policy ImportedSites / given sites (VoronoiMeshSpatialGrid.cpp:52-144): a Voronoi
+    tessellation of the domain box generated by the given sites.  The reference builds it with the vendored voro++
+    (VoronoiMeshSnapshot::buildMesh, VoronoiMeshSnapshot.cpp:491-730); this mirror takes the neighbour relation from the
+    Delaunay triangulation of the sites (scipy / Qhull) -- the same tessellation -- and lists all six domain walls for
+    every cell (a wall that does not bound a cell is never the nearest exit, so this is equivalent to the reference's
+    lists, which hold only the walls that do).  Cell volumes, which the reference gets from voro++, can be supplied."""
+
+    def __init__(self, minX, maxX, minY, maxY, minZ, maxZ, sites, volumes=None):
+        self.extent = (minX, minY, minZ, maxX, maxY, maxZ)
+        sites = np.asarray(sites, dtype=float).reshape(-1, 3)
+        ext = np.asarray(self.extent)
+        inside = np.all((sites > ext[:3]) & (sites < ext[3:]), axis=1)   # sites outside the domain are discarded
+        sites = sites[inside]
+        self.sites = sites[np.argsort(sites[:, 0], kind="stable")]       # cells in order of increasing x, .cpp:507-508
+        self.volumes = None if volumes is None else np.asarray(volumes, dtype=float)
+        self.nbr_offset = self.nbr_index = None
+
+    def setup(self, media, num_density_samples, rng):
+        from scipy.spatial import Delaunay
+        n = len(self.sites)
+        tri = Delaunay(self.sites)
+        indptr, indices = tri.vertex_neighbor_vertices
+        counts = np.diff(indptr) + 6
+        self.nbr_offset = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        idx = np.empty(self.nbr_offset[-1], dtype=np.int32)
+        walls = np.array([-1, -2, -3, -4, -5, -6], dtype=np.int32)
+        for m in range(n):
+            a, b = self.nbr_offset[m], self.nbr_offset[m + 1]
+            idx[a:b - 6] = indices[indptr[m]:indptr[m + 1]]
+            idx[b - 6:b] = walls
+        self.nbr_index = idx
+
+    @property
+    def num_cells(self):
+        return len(self.sites)
+
+    def cell_boxes(self):
+        """Not boxes: the mirror only needs volumes (for mean intensities) and sample positions (cell densities)."""
+        raise NotImplementedError
+
+    def cell_volumes(self):
+        if self.volumes is not None:
+            return self.volumes
+        ext = np.asarray(self.extent)
+        return np.full(self.num_cells, np.prod(ext[3:] - ext[:3]) / self.num_cells)  # placeholder: equal shares
+
+    def configure(self, engine):
+        engine.set_grid_voronoi(self.extent, self.sites, self.nbr_offset, self.nbr_index)
+
+
 # ---------------------------------------------------------------------------------------------------
 # sources, SEDs
 # ---------------------------------------------------------------------------------------------------
@@ -729,9 +780,18 @@ class MonteCarloSimulation:
             s.sed.setup(self.source_range)
         # grid and medium state (MediumSystem.cpp:286-399)
         self.grid.setup([self.medium], self.numDensitySamples, rng)
-        boxes = self.grid.cell_boxes()
-        self.volume = np.prod(boxes[:, 3:] - boxes[:, :3], axis=1)
-        n = len(boxes)
+        if isinstance(self.grid, VoronoiMeshSpatialGrid):
+            self.volume = self.grid.cell_volumes()
+            n = self.grid.num_cells
+            boxes = None
+            if self.density is None:
+                # MediumSystem.cpp:286-399 with numDensitySamples = 1: the density at the cell's site
+                st = self.grid.sites
+                self.density = self.medium.number_density(st[:, 0], st[:, 1], st[:, 2])
+        else:
+            boxes = self.grid.cell_boxes()
+            self.volume = np.prod(boxes[:, 3:] - boxes[:, :3], axis=1)
+            n = len(boxes)
         dens = np.zeros(n)
         if self.density is not None:
             # medium state imported from a SpatialCellPropertiesProbe file of a reference run (tests/golden)

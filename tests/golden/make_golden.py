@@ -152,7 +152,7 @@ def sph_particles(n=6000, seed=12345):
     phi = rng.uniform(0, 2 * np.pi, size=n)
     z = np.clip(rng.laplace(0.0, 250.0, size=n), -1900.0, 1900.0)
     h = 400.0 * (1 + R / 8000.0)
-    M = np.full(n, 1e3)
+    M = np.full(n, 1e3 * 5e5 / n)   # the same total dust mass as the 5e5-particle configuration
     return np.stack([R * np.cos(phi), R * np.sin(phi), z, h, M], axis=1)
 
 

@@ -85,3 +85,14 @@ def small_dust_emission(num_packets=20000, seed=7, **kw):
     args = dict(max_level=5, max_dust_fraction=1e-3, num_sed_wavelengths=12, max_secondary_iterations=3)
     args.update(kw)
     return configs.cfg4(num_packets=num_packets, seed=seed, **args)
+
+
+def small_voronoi(num_packets=20000, seed=11, num_sites=1500, **kw):
+    """Random sites concentrated towards a disk, smooth disk density evaluated at the sites (cfg5-like, no fixture)."""
+    pc = H.PC
+    rng = np.random.default_rng(99)
+    R = np.minimum(rng.gamma(2.0, 3000.0, size=num_sites), 15000.0)
+    phi = rng.uniform(0, 2 * np.pi, size=num_sites)
+    z = np.clip(rng.laplace(0.0, 300.0, size=num_sites), -1900.0, 1900.0)
+    sites = np.stack([R * np.cos(phi), R * np.sin(phi), z], axis=1) * pc
+    return configs.cfg5(sites, num_packets=num_packets, seed=seed, num_pixels=16, **kw)

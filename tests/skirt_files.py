@@ -17,7 +17,7 @@ def read_fits_cube(path):
                 done = True
                 break
             if "=" in c[:10]:
-                cards[c[:8].strip()] = c[10:].split("/")[0].strip().strip("'").strip()
+                cards[c[:8].strip()] = c[10:].split(" / ")[0].strip().strip("'").strip()
         if done:
             break
     nx, ny = int(cards["NAXIS1"]), int(cards["NAXIS2"])

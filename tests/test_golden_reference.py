@@ -251,3 +251,74 @@ def test_engine_matches_reference_cfg4s_dust_emission(engine_lib):
     e = sim.configure(abi.Engine(sim.config_struct(device=0), lib=engine_lib))
     sim.run(e)
     check_cfg4s(sim, e, g, n)
+
+
+# ---------------------------------------------------------------- Voronoi grid on imported SPH particles (cfg5s)
+def cfg5s_from_reference(num_packets):
+    g = load("cfg5s")
+    pc = H.PC
+    sim = configs.cfg5(g["particles"][:, :3] * pc, num_packets=num_packets, seed=0,
+                       density=g["mass_density_msun_pc3"] * RHO / H.MeanListDustMix.MU, volumes=g["cell_volume_pc3"] * pc ** 3)
+    sim.setup()
+    assert sim.grid.num_cells == len(g["mass_density_msun_pc3"])
+    # the reference's cell order is the particle order; its cell "centres" are the centroids, close to the sites
+    d = np.linalg.norm(sim.grid.sites / pc - g["cell_center_pc"], axis=1)
+    assert np.median(d) < 300.0
+    return sim, g
+
+
+def check_cfg5s(sim, e, g, n):
+    sed = g["sed"][0]
+    tr = sim.sed_flux_density(e, 0, abi.SK_COMP_TRANSPARENT)[0]
+    di = sim.sed_flux_density(e, 0, abi.SK_COMP_PRIMARY_DIRECT)[0]
+    sc = sim.sed_flux_density(e, 0, abi.SK_COMP_PRIMARY_SCATTERED)[0]
+    tot = sim.sed_flux_density(e, 0, abi.SK_COMP_TOTAL)[0]
+    assert tr == pytest.approx(sed[2], rel=1e-8)                 # one wavelength: noise free
+    r_ref = rel_error(g["sedstats"][0, 1:])
+    r_own = rel_error(e.read_sed_stats(0)[:, 0])
+    tol = 4.0 * math.hypot(r_ref, r_own)
+    assert abs(tot - sed[1]) <= tol * sed[1], (tot, sed[1], tol)
+    assert abs(di - sed[3]) <= tol * sed[1], (di, sed[3], tol)
+    assert abs(sc - sed[4]) <= tol * sed[1], (sc, sed[4], tol)
+    scale = max(1.0, math.sqrt(g["num_packets"] / n))
+    a = sim.surface_brightness(e, 0, abi.SK_COMP_TOTAL)[0]
+    b = g["frame_total"][0].astype(float)
+    blk = lambda x: x.reshape(8, 8, 8, 8).sum(axis=(1, 3))
+    a, b = blk(a), blk(b)
+    ok = b > 0.1 * b.max()
+    np.testing.assert_allclose(a[ok], b[ok], rtol=0.15 * scale)   # the fixture has only 2e5 packets
+    assert a.sum() == pytest.approx(b.sum(), rel=0.01 * scale)
+
+
+def test_oracle_matches_reference_cfg5s_voronoi():
+    n = 100000
+    sim, g = cfg5s_from_reference(n)
+    e = sim.configure(OracleEngine(sim.config_struct()))
+    sim.run(e)
+    check_cfg5s(sim, e, g, n)
+    c = e.counters()
+    # SURVEY.md Appendix C for the Voronoi probe: 4.7 paths per packet, ~20 segments per path
+    assert 3.0 < c["forward_paths"] / n < 7.0
+
+
+def test_voronoi_nearest_site_walk_equals_brute_force():
+    import ctypes as C
+    from tests.oracle_lib import oracle_library
+    sim, g = cfg5s_from_reference(10)
+    e = sim.configure(OracleEngine(sim.config_struct()))
+    lib = oracle_library()
+    rng = np.random.default_rng(3)
+    ext = np.array(sim.grid.extent)
+    for _ in range(2000):
+        p = ext[:3] + rng.random(3) * (ext[3:] - ext[:3])
+        r = (C.c_double * 3)(*p)
+        assert lib.sko_test_voronoi_cell_index(e._h, r, 0) == lib.sko_test_voronoi_cell_index(e._h, r, 1)
+
+
+@pytest.mark.gpu
+def test_engine_matches_reference_cfg5s_voronoi(engine_lib):
+    n = 2000000
+    sim, g = cfg5s_from_reference(n)
+    e = sim.configure(abi.Engine(sim.config_struct(device=0), lib=engine_lib))
+    sim.run(e)
+    check_cfg5s(sim, e, g, n)

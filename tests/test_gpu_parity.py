@@ -112,6 +112,28 @@ def test_dust_emission_on_cartesian_grid(engine_lib):
     models.compare_engines(sim, gpu, cpu, rtol=1e-8)
 
 
+def test_voronoi_grid_matches_oracle(engine_lib):
+    sim = models.small_voronoi(num_packets=20000)
+    gpu, cpu = run_both(sim, engine_lib)
+    models.compare_engines(sim, gpu, cpu)
+    assert gpu.counters()["forward_segments"] > 20000
+
+
+def test_voronoi_grid_with_radiation_field_nonforced_and_outside_source(engine_lib):
+    """Voronoi grid with a stored radiation field, and a source that reaches beyond the grid (paths enter from outside)."""
+    from skirt9_b200 import host as H
+    sim = models.small_voronoi(num_packets=10000)
+    pc = H.PC
+    sim.storeRadiationField = True
+    sim.sources[0].geometry = H.ExpDiskGeometry(6000 * pc, 900 * pc, 0.0, 25000 * pc, 4000 * pc)  # beyond the +-16/2 kpc box
+    gpu, cpu = run_both(sim, engine_lib)
+    models.compare_engines(sim, gpu, cpu)
+    sim2 = models.small_voronoi(num_packets=10000)
+    sim2.forceScattering = False
+    gpu, cpu = run_both(sim2, engine_lib)
+    models.compare_engines(sim2, gpu, cpu)
+
+
 def test_small_bank_refills_slots(engine_lib, monkeypatch):
     """A bank far smaller than the number of histories: slots are reused many times; results do not change."""
     sim = models.small_octree(num_packets=20000).setup()

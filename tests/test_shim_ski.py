@@ -112,3 +112,30 @@ def test_cfg4s_ski_dust_emission_runs_unchanged(tmp_path):
     ok = g["temperature"] > 0
     assert np.median(np.abs(T[ok] / g["temperature"][ok] - 1)) < 0.02
     assert np.array_equal(T > 0, g["temperature"] > 0) or np.mean((T > 0) != ok) < 0.01
+
+
+def test_cfg5s_ski_voronoi_particles_runs_unchanged(tmp_path):
+    """ParticleMedium import + VoronoiMeshSpatialGrid (voro++ tessellation, SPH kernel density sampling) all done by the
+    reference's own setup code; only the life cycle runs on the GPU."""
+    g = np.load(os.path.join(GOLD, "cfg5s_ref.npz"))
+    rows = g["particles"]
+    head = "# column 1: x (pc)\n# column 2: y (pc)\n# column 3: z (pc)\n# column 4: h (pc)\n# column 5: M (Msun)\n"
+    (tmp_path / "sph.txt").write_text(head + "\n".join(" ".join("%.8e" % v for v in row) for row in rows) + "\n")
+    n = 2e6
+    text = open(os.path.join(GOLD, "ski", "cfg5s.ski")).read()
+    text = re.sub(r'numPackets="[^"]*"', 'numPackets="%g"' % n, text, count=1)
+    ski = tmp_path / "cfg5s.ski"
+    ski.write_text(text)
+    subprocess.check_call([EXE, "-t", "1", "-b", "-i", str(tmp_path), "-o", str(tmp_path), str(ski)],
+                          stdout=subprocess.DEVNULL)
+    log = (tmp_path / "cfg5s_log.txt").read_text()
+    assert "GPU life cycle:" in log, log[-2000:]
+    cells = read_columns(tmp_path / "cfg5s_cells_cellprops.dat")
+    np.testing.assert_array_equal(cells[:, 6], g["mass_density_msun_pc3"])   # same tessellation, same densities
+    sed = read_columns(tmp_path / "cfg5s_i60_sed.dat")[0]
+    stats = read_columns(tmp_path / "cfg5s_i60_sedstats.dat")[0]
+    ref = g["sed"][0]
+    assert sed[2] == pytest.approx(ref[2], rel=1e-8)
+    tol = 4.0 * math.hypot(rel_error(g["sedstats"][0, 1:]), rel_error(stats[1:]))
+    for col in (1, 3, 4):
+        assert abs(sed[col] - ref[col]) <= tol * ref[1], (col, sed[col], ref[col], tol)
