@@ -506,8 +506,14 @@ __device__ __forceinline__ void sk_step(const SkDevModel& M, const SkDevModel* _
         // The link decides the next cell unless the new position may also have crossed a second wall (the exit
         // distances of two walls differ by less than a few eps), the direction grazes the exit wall (the eps advance may
         // be lost to rounding), or the path reaches the domain boundary; those cases take the reference's full search.
+        // The common way for a path to end: there is no neighbour across the exit wall and the new position lies outside
+        // the domain, so TreeNode::neighbor() and root()->leafChild() both come back empty (TreeSpatialGrid.cpp:190-205).
+        if (link < 0 && !sk_box_contains(M.ext, rx, ry, rz))
+        {
+            p.m = -1;
+            return;
+        }
         const bool rare = link < 0 || !(other - ds > 4. * M.eps) || !(fabs(kexit) > 1e-3);
-        const int oldlev = p.lev;
         if (!rare)
         {
             // step to the lattice point just across the exit wall, then align to the neighbour's level
