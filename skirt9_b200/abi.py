@@ -357,9 +357,13 @@ class Engine:
         self._call("read_sed", self._h, C.c_int32(instrument), C.c_int32(component), out.ctypes.data_as(_dp))
         return out
 
-    def read_ifu(self, instrument=0, component=SK_COMP_TOTAL):
+    def read_ifu(self, instrument=0, component=SK_COMP_TOTAL, out=None):
+        """[ell][pixel] tallies; `out` may be a caller-owned C-contiguous float64 array of that shape (the way the C++ shim
+        reads straight into FluxRecorder's arrays)."""
         nl, npix = self._instr[instrument]
-        out = np.empty((nl, npix), dtype=np.float64)
+        if out is None:
+            out = np.empty((nl, npix), dtype=np.float64)
+        assert out.shape == (nl, npix) and out.dtype == np.float64 and out.flags["C_CONTIGUOUS"]
         self._call("read_ifu", self._h, C.c_int32(instrument), C.c_int32(component), out.ctypes.data_as(_dp))
         return out
 

@@ -514,6 +514,9 @@ __device__ __forceinline__ void sk_step(const SkDevModel& M, const SkDevModel* _
             return;
         }
         const bool rare = link < 0 || !(other - ds > 4. * M.eps) || !(fabs(kexit) > 1e-3);
+#if SK_CARRY_BORDERS
+        const int oldlev = p.lev;
+#endif
         if (!rare)
         {
             // step to the lattice point just across the exit wall, then align to the neighbour's level

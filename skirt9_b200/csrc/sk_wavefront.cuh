@@ -44,17 +44,68 @@
 // ---------------------------------------------------------------------------------------------------
 // small helpers shared by the stage kernels
 // ---------------------------------------------------------------------------------------------------
-// appends `slot` of every lane with `want` to the ray list (one atomic per warp); all 32 lanes must call
-__device__ __forceinline__ void sk_list_append(const SkBank& K, bool want, int slot)
+// Appends `slot` of every thread with `want` to a list whose length is the control word `ctl_word` -- ONE atomic per
+// block: all warps of all SMs adding to the same address is what otherwise bounds the element-wise kernels (the L2 atomic
+// unit serialises per address).  Every thread of the block must call (uses two block barriers); `nlive`, when not null,
+// is a census counter that receives the block's number of `count_live` threads in the same pass.
+__device__ __forceinline__ void sk_block_append(int32_t* list, unsigned int* ctl_word, bool want, int slot,
+                                                unsigned int* nlive = nullptr, bool count_live = false,
+                                                unsigned long long* live_counter = nullptr)
 {
-    const unsigned lane = threadIdx.x & 31;
+    __shared__ unsigned int s_cnt[2][SK_EVENT_BLOCK / 32];
+    __shared__ unsigned int s_base;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned mask = __ballot_sync(0xffffffffu, want);
-    if (!mask) return;
-    const int leader = __ffs(mask) - 1;
-    unsigned base = 0;
-    if ((int)lane == leader) base = atomicAdd(&K.ctl[SK_CTL_NLIST], (unsigned)__popc(mask));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (want) K.list[base + __popc(mask & ((1u << lane) - 1u))] = slot;
+    const unsigned live = nlive ? __ballot_sync(0xffffffffu, count_live) : 0u;
+    if (lane == 0)
+    {
+        s_cnt[0][warp] = __popc(mask);
+        s_cnt[1][warp] = __popc(live);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        unsigned total = 0, tlive = 0;
+        for (int w = 0; w < SK_EVENT_BLOCK / 32; ++w)
+        {
+            const unsigned c = s_cnt[0][w];
+            s_cnt[0][w] = total;  // exclusive prefix
+            total += c;
+            tlive += s_cnt[1][w];
+        }
+        s_base = total ? atomicAdd(ctl_word, total) : 0u;
+        if (nlive && tlive) atomicAdd(nlive, tlive);
+        if (live_counter && tlive) atomicAdd(live_counter, (unsigned long long)tlive);
+    }
+    __syncthreads();
+    if (want) list[s_base + s_cnt[0][warp] + __popc(mask & ((1u << lane) - 1u))] = slot;
+    __syncthreads();  // the shared words are reused by the next call
+}
+
+// Reserves one index of a 64-bit counter for every thread with `want` (the history dispenser), one atomic per block.
+__device__ __forceinline__ unsigned long long sk_block_reserve(unsigned long long* counter, bool want)
+{
+    __shared__ unsigned int r_cnt[SK_EVENT_BLOCK / 32];
+    __shared__ unsigned long long r_base;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned mask = __ballot_sync(0xffffffffu, want);
+    if (lane == 0) r_cnt[warp] = __popc(mask);
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        unsigned total = 0;
+        for (int w = 0; w < SK_EVENT_BLOCK / 32; ++w)
+        {
+            const unsigned c = r_cnt[w];
+            r_cnt[w] = total;
+            total += c;
+        }
+        r_base = total ? atomicAdd(counter, (unsigned long long)total) : 0ull;
+    }
+    __syncthreads();
+    const unsigned long long h = r_base + r_cnt[warp] + __popc(mask & ((1u << lane) - 1u));
+    __syncthreads();
+    return h;
 }
 
 __device__ __forceinline__ void sk_flush_counters(const SkDevModel& M, SkLocalCounters& cnt)
@@ -377,17 +428,17 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, SK_TRACE_MINBLOCKS)
 // consolidated branch), DustMix::peeloffScattering HG branch (DustMix.cpp:430-445), MediumSystem::peelOffScattering
 // (MediumSystem.cpp:734-767) with the single-medium weight 1, PhotonPacket::launchScatteringPeelOff / launchEmissionPeelOff
 // (PhotonPacket.cpp:66-103).  Returns true when the slot joins the peel-off ray list.
-__device__ __forceinline__ bool sk_peel_setup(const SkDevModel& M, const SkBank& K, int slot, int st, int j0, int j1)
+__device__ __forceinline__ bool sk_peel_setup_values(const SkDevModel& M, const SkBank& K, int slot, bool scattering,
+                                                     int j0, int j1, double W, double lambda, double x, double y, double z,
+                                                     double kx, double ky, double kz, int ilam)
 {
     const SkDevInstr& q0 = M.instr[j0];
     const double ox = q0.kobs[0], oy = q0.kobs[1], oz = q0.kobs[2];
-    double W = K.D(D_W, slot);
-    double lambda = K.D(D_LAMBDA, slot);
     double peelW;
-    if (st & SK_ST_SCATTER)
+    if (scattering)
     {
-        double costheta = K.D(D_KX, slot) * ox + K.D(D_KY, slot) * oy + K.D(D_KZ, slot) * oz;
-        double gp = M.gpar[K.I(I_ILAM, slot)];
+        double costheta = kx * ox + ky * oy + kz * oz;
+        double gp = M.gpar[ilam];
         double value = fabs(gp) > 0.95 ? sk_mean_hg(gp, costheta) : sk_value_hg(gp, costheta);
         double I = 0.;
         I += value * 1.;
@@ -396,7 +447,6 @@ __device__ __forceinline__ bool sk_peel_setup(const SkDevModel& M, const SkBank&
     else
         peelW = W;  // isotropic emission
     K.D(D_PEELW, slot) = peelW;
-    double x = K.D(D_RX, slot), y = K.D(D_RY, slot), z = K.D(D_RZ, slot);
     bool need = false;
     for (int j = j0; j < j1; ++j)
     {
@@ -416,6 +466,12 @@ __device__ __forceinline__ bool sk_peel_setup(const SkDevModel& M, const SkBank&
     }
     return need;
 }
+__device__ __forceinline__ bool sk_peel_setup(const SkDevModel& M, const SkBank& K, int slot, int st, int j0, int j1)
+{
+    return sk_peel_setup_values(M, K, slot, (st & SK_ST_SCATTER) != 0, j0, j1, K.D(D_W, slot), K.D(D_LAMBDA, slot),
+                                K.D(D_RX, slot), K.D(D_RY, slot), K.D(D_RZ, slot), K.D(D_KX, slot), K.D(D_KY, slot),
+                                K.D(D_KZ, slot), K.I(I_ILAM, slot));
+}
 
 // advance: the interaction that ends the previous round and, for the surviving packets, the peel-off set-up towards
 // the first observer group; free slots are collected for the launch kernel.
@@ -425,14 +481,22 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_advance(const SkDevModel
 {
     const SkSmemTables T{M.xv, M.yv, M.zv};
     const SkDevModel* __restrict__ Mg = A.model;
-    const unsigned lane = threadIdx.x & 31;
-    const unsigned lt_mask = (1u << lane) - 1u;
     const bool forced = M.force_scattering != 0;
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = slot < K.cap;
-    SkLocalCounters cnt;
-    memset(&cnt, 0, sizeof cnt);
     int st = valid ? K.I(I_STATE, slot) : 0;
+
+    // Every field the interaction needs is requested before the first use, for live and dead slots alike: the kernel is a
+    // streaming pass over the bank, and its speed is the number of loads in flight, not the instruction count.
+    const int sl = valid ? slot : 0;
+    const int m = K.I(I_MINT, sl), ilam = K.I(I_ILAM, sl), nscatt = K.I(I_NSCATT, sl);
+    const int mix = K.I(I_MIX, sl), miy = K.I(I_MIY, sl), miz = K.I(I_MIZ, sl), mlev = K.I(I_MLEV, sl);
+    const double sigext = K.D(D_SIGEXT, sl), W0 = K.D(D_W, sl), taupath = K.D(D_TAUPATH, sl), sint = K.D(D_SINT, sl);
+    const double kx = K.D(D_KX, sl), ky = K.D(D_KY, sl), kz = K.D(D_KZ, sl);
+    const double rx0 = K.D(D_RX, sl), ry0 = K.D(D_RY, sl), rz0 = K.D(D_RZ, sl);
+    const double lambda = K.D(D_LAMBDA, sl), lthr = K.D(D_LTHR, sl);
+    bool survivor = false;
+    double W = W0, x = rx0, y = ry0, z = rz0;
 
     // ---- the interaction: albedo weight, move, termination test (.cpp:724-741, 576-580)
     if (st & SK_ST_LIVE)
@@ -441,42 +505,37 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_advance(const SkDevModel
         if (!forced && !(st & SK_ST_FOUND)) alive = false;  // escaped, MonteCarloSimulation.cpp:594
         if (alive)
         {
-            int m = K.I(I_MINT, slot);
-            int ilam = K.I(I_ILAM, slot);
             // MediumSystem::albedoForScattering, MediumSystem.cpp:678-693
             double albedo = 0.;
             if (m >= 0)
             {
                 double dn = sk_cell_density<GRID>(M, m);
                 double ksca = dn * M.sig_sca[ilam];
-                double kext = dn * K.D(D_SIGEXT, slot);
+                double kext = dn * sigext;
                 albedo = kext > 0. ? ksca / kext : 0.;
             }
-            double W = K.D(D_W, slot);
             if (forced)
-                W *= -expm1(-K.D(D_TAUPATH, slot)) * albedo;
+                W *= -expm1(-taupath) * albedo;
             else
                 W *= albedo;
-            double sint = K.D(D_SINT, slot);
-            double kx = K.D(D_KX, slot), ky = K.D(D_KY, slot), kz = K.D(D_KZ, slot);
-            double x = K.D(D_RX, slot) + sint * kx;  // PhotonPacket::propagate, PhotonPacket.cpp:107-111
-            double y = K.D(D_RY, slot) + sint * ky;
-            double z = K.D(D_RZ, slot) + sint * kz;
+            x = rx0 + sint * kx;  // PhotonPacket::propagate, PhotonPacket.cpp:107-111
+            y = ry0 + sint * ky;
+            z = rz0 + sint * kz;
             K.D(D_W, slot) = W;
             K.D(D_RX, slot) = x;
             K.D(D_RY, slot) = y;
             K.D(D_RZ, slot) = z;
-            double L = W / K.D(D_LAMBDA, slot);
+            double L = W / lambda;
             if (forced)
             {
-                if (L <= 0 || (L <= K.D(D_LTHR, slot) && K.I(I_NSCATT, slot) >= M.min_scatt_events)) alive = false;
+                if (L <= 0 || (L <= lthr && nscatt >= M.min_scatt_events)) alive = false;
             }
             else if (L <= 0)
                 alive = false;
             if (alive)
             {
                 // the next paths start in the interaction cell unless rounding moved the point out of it
-                SkCellPos c{m, K.I(I_MIX, slot), K.I(I_MIY, slot), K.I(I_MIZ, slot), K.I(I_MLEV, slot)};
+                SkCellPos c{m, mix, miy, miz, mlev};
                 bool inside = m >= 0 && sk_box_strictly_inside(M.ext, x, y, z);
                 if (GRID == 3)
                 {
@@ -496,6 +555,7 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_advance(const SkDevModel
                 K.I(I_LEV, slot) = c.lev;
                 st = SK_ST_LIVE | SK_ST_SCATTER;
                 K.I(I_STATE, slot) = st;
+                survivor = true;
             }
         }
         if (!alive)
@@ -505,32 +565,15 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_advance(const SkDevModel
         }
     }
 
-    // ---- free slots go to the launch kernel through a compact list (the launch code then runs with full warps)
-    {
-        const bool isfree = valid && !(st & SK_ST_LIVE);
-        const unsigned mask = __ballot_sync(0xffffffffu, isfree);
-        if (mask)
-        {
-            const int leader = __ffs(mask) - 1;
-            unsigned base = 0;
-            if ((int)lane == leader) base = atomicAdd(&K.ctl[SK_CTL_NFREE], (unsigned)__popc(mask));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (isfree) K.free_list[base + __popc(mask & lt_mask)] = slot;
-        }
-    }
-
-    // ---- census of the bank, and the peel-off rays towards the first observer group
+    // ---- free slots go to the launch kernel through a compact list (the launch code then runs with full warps); the
+    //      census of the survivors rides along
     const bool live = (st & SK_ST_LIVE) != 0;
-    {
-        const unsigned mask = __ballot_sync(0xffffffffu, live);
-        if (lane == 0 && mask) atomicAdd(&K.ctl[SK_CTL_NLIVE], (unsigned)__popc(mask));
-    }
+    sk_block_append(K.free_list, &K.ctl[SK_CTL_NFREE], valid && !live, slot, &K.ctl[SK_CTL_NLIVE], live);
     if (A.peel && j1 > j0)
     {
-        bool need = live && sk_peel_setup(M, K, slot, st, j0, j1);
-        sk_list_append(K, need, slot);
+        bool need = survivor && sk_peel_setup_values(M, K, slot, true, j0, j1, W, lambda, x, y, z, kx, ky, kz, ilam);
+        sk_block_append(K.list, &K.ctl[SK_CTL_NLIST], need, slot);
     }
-    sk_flush_counters(M, cnt);
 }
 
 // launch: a new history into every free slot collected by `advance` (SourceSystem::launch, SourceSystem.cpp:101-113 /
@@ -542,23 +585,14 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_launch(const SkDevModel 
 {
     const SkSmemTables T{M.xv, M.yv, M.zv};
     const SkDevModel* __restrict__ Mg = A.model;
-    const unsigned lane = threadIdx.x & 31;
-    const unsigned lt_mask = (1u << lane) - 1u;
     const unsigned nfree = K.ctl[SK_CTL_NFREE];
+    if (blockIdx.x * blockDim.x >= nfree) return;  // the whole block is beyond the list
     const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx - lane >= nfree) return;  // the whole warp is beyond the list
     const bool want = idx < nfree;
     const int slot = want ? K.free_list[idx] : 0;
-    SkLocalCounters cnt;
-    memset(&cnt, 0, sizeof cnt);
     bool live = false;
     {
-        const unsigned mask = __ballot_sync(0xffffffffu, want);
-        const int leader = __ffs(mask) - 1;
-        unsigned long long b = 0;
-        if ((int)lane == leader) b = atomicAdd(A.work_counter, (unsigned long long)__popc(mask));
-        b = __shfl_sync(0xffffffffu, b, leader);
-        const unsigned long long h = b + __popc(mask & lt_mask);
+        const unsigned long long h = sk_block_reserve(A.work_counter, want);
         if (want && h < A.count)
         {
             const unsigned long long history = A.first + h;
@@ -571,7 +605,6 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_launch(const SkDevModel 
                 sk_launch_secondary<GRID>(Mg, T, g, history, pp);
             if (pp.W / pp.lambda > 0)  // MonteCarloSimulation.cpp:553
             {
-                cnt.packets++;
                 SkCellPos c;
                 c.m = -1;
                 c.ix = c.iy = c.iz = c.lev = 0;
@@ -607,15 +640,10 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_launch(const SkDevModel 
         }
     }
     {
-        const unsigned mask = __ballot_sync(0xffffffffu, live);
-        if (lane == 0 && mask) atomicAdd(&K.ctl[SK_CTL_NLIVE], (unsigned)__popc(mask));
+        const bool need = A.peel && j1 > j0 && live && sk_peel_setup(M, K, slot, SK_ST_LIVE, j0, j1);
+        // (the launched packets are counted -- sk_counters_t::packets -- in the same pass)
+        sk_block_append(K.list, &K.ctl[SK_CTL_NLIST], need, slot, &K.ctl[SK_CTL_NLIVE], live, &M.counters[0]);
     }
-    if (A.peel && j1 > j0)
-    {
-        bool need = live && sk_peel_setup(M, K, slot, SK_ST_LIVE, j0, j1);
-        sk_list_append(K, need, slot);
-    }
-    sk_flush_counters(M, cnt);
 }
 
 // peel-off set-up towards a further observer group
@@ -625,7 +653,7 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_peel_setup(const SkDevMo
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     const int st = slot < K.cap ? K.I(I_STATE, slot) : 0;
     bool need = (st & SK_ST_LIVE) && sk_peel_setup(M, K, slot, st, j0, j1);
-    sk_list_append(K, need, slot);
+    sk_block_append(K.list, &K.ctl[SK_CTL_NLIST], need, slot);
 }
 
 // detect: FluxRecorder::detect (FluxRecorder.cpp:304-468) for the observer group [j0, j1); when `last`, also the
@@ -692,7 +720,7 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_detect(const SkDevModel 
                 K.I(I_STATE, slot) = st & ~SK_ST_SCATTER;
                 cnt.scatt++;
             }
-            if (M.force_scattering) sk_list_append(K, live, slot);
+            if (M.force_scattering) sk_block_append(K.list, &K.ctl[SK_CTL_NLIST], live, slot);
         }
     }
     sk_flush_counters(M, cnt);
@@ -758,5 +786,5 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_sample(const SkDevModel 
             K.I(I_STATE, slot) = st & ~SK_ST_FOUND;
         }
     }
-    sk_list_append(K, live, slot);
+    sk_block_append(K.list, &K.ctl[SK_CTL_NLIST], live, slot);
 }
