@@ -160,7 +160,7 @@ struct sk_engine {
     double* stat_block = nullptr;
     size_t stat_count = 0;
     unsigned long long* work_counter = nullptr;
-    SkBank bank = {nullptr, nullptr, nullptr, nullptr, nullptr, 0};  // the in-flight packets (sk_wavefront.cuh)
+    SkBank bank = {nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0};  // the in-flight packets (sk_wavefront.cuh)
     int bank_fields_d = 0, bank_fields_i = 0;
     unsigned int* ctl_host = nullptr;                       // pinned copy of the control words + work counter
     cudaEvent_t ev_ctl = nullptr;
@@ -1081,7 +1081,8 @@ static int ensure_bank(sk_engine* e, uint64_t count)
 {
     size_t cap = std::min<uint64_t>(count, bank_capacity_limit());
     cap = std::max<size_t>((cap + 255) / 256 * 256, 256);
-    const int nd = D_HISTW0 + std::max(e->M.ninstr, 1), ni = I_HELL0 + std::max(e->M.ninstr, 1);
+    const int nd = SK_BANK_FIELDS_D(e->M.ninstr), ni = SK_BANK_FIELDS_I(e->M.ninstr);
+    e->bank.n = (int32_t)cap;
     if ((size_t)e->bank.cap >= cap && e->bank_fields_d == nd && e->bank_fields_i == ni) return SK_OK;
     cudaFree(e->bank.d);
     cudaFree(e->bank.i);
@@ -1121,7 +1122,7 @@ static int launch_trace_impl(sk_engine* e, const SkRunArgs& A, const SkRayDir& d
         cached_smem = smem;
     }
     // persistent grid: every SM filled to the occupancy this kernel gets, but no more warps than chunks of rays
-    unsigned long long chunks = ((unsigned long long)e->bank.cap + SK_CHUNK - 1) / SK_CHUNK;
+    unsigned long long chunks = ((unsigned long long)e->bank.n + SK_CHUNK - 1) / SK_CHUNK;
     unsigned long long blocks = (chunks + (SK_TRACE_BLOCK / 32) - 1) / (SK_TRACE_BLOCK / 32);
     unsigned grid = (unsigned)std::min<unsigned long long>((unsigned long long)e->num_sms * per_sm, std::max<unsigned long long>(blocks, 1));
     CK(cudaMemsetAsync(&e->bank.ctl[SK_CTL_CURSOR], 0, sizeof(unsigned int), e->stream));
@@ -1144,7 +1145,7 @@ static int run_bank(sk_engine* e, const SkRunArgs& A)
 {
     const SkDevModel& M = e->M;
     const SkBank& K = e->bank;
-    const unsigned eblocks = (unsigned)((K.cap + SK_EVENT_BLOCK - 1) / SK_EVENT_BLOCK);
+    unsigned eblocks = (unsigned)((K.n + SK_EVENT_BLOCK - 1) / SK_EVENT_BLOCK);
     // observer groups: consecutive instruments that share the observer (Instrument.hpp:107) share one peel-off ray
     std::vector<std::pair<int, int>> groups;
     if (A.peel)
@@ -1156,8 +1157,8 @@ static int run_bank(sk_engine* e, const SkRunArgs& A)
             j0 = j1;
         }
     // detect is a persistent grid-stride kernel with the SED arrays of the observer group in shared memory
-    const unsigned dblocks = std::min<unsigned>(eblocks, (unsigned)e->num_sms * 8u);
     auto launch_detect = [&](int j0, int j1, int last) -> int {
+        const unsigned dblocks = std::min<unsigned>(eblocks, (unsigned)e->num_sms * 8u);
         int nl = 0;
         for (int j = j0; j < j1; ++j)
             if (e->instr[j].include_sed) nl = std::max(nl, e->instr[j].nl);
@@ -1174,7 +1175,7 @@ static int run_bank(sk_engine* e, const SkRunArgs& A)
     };
     SkRayDir nodir;
     nodir.set(0., 0., 1.);
-    CK(cudaMemsetAsync(K.i + (size_t)I_STATE * K.cap, 0, (size_t)K.cap * sizeof(int32_t), e->stream));
+    CK(cudaMemsetAsync(K.i + (size_t)I_STATE * K.cap, 0, (size_t)K.n * sizeof(int32_t), e->stream));
     for (unsigned long long round = 0;; ++round)
     {
         CK(cudaMemsetAsync(K.ctl, 0, SK_CTL_WORDS * sizeof(unsigned int), e->stream));
@@ -1230,7 +1231,23 @@ static int run_bank(sk_engine* e, const SkRunArgs& A)
         unsigned long long dispensed;
         memcpy(&dispensed, e->ctl_host + SK_CTL_WORDS, sizeof dispensed);
         e->rounds_total++;
-        if (e->ctl_host[SK_CTL_NLIVE] == 0 && dispensed >= A.count) break;
+        const unsigned nlive = e->ctl_host[SK_CTL_NLIVE];
+        if (nlive == 0 && dispensed >= A.count) break;
+        // draining: pack the survivors into the head of the bank when fewer than half of the slots in use are alive
+        if (dispensed >= A.count && (size_t)nlive * 2 < (size_t)K.n && K.n > SK_EVENT_BLOCK)
+        {
+            const int n_new = (int)std::max<size_t>(((size_t)nlive + SK_EVENT_BLOCK - 1) / SK_EVENT_BLOCK * SK_EVENT_BLOCK, SK_EVENT_BLOCK);
+            CK(cudaMemsetAsync(K.ctl, 0, SK_CTL_WORDS * sizeof(unsigned int), e->stream));
+            sk_wf_partition<<<eblocks, SK_EVENT_BLOCK, 0, e->stream>>>(K, n_new);
+            CK(cudaGetLastError());
+            // at most the survivors of the tail move; the kernel reads the actual count from the control word
+            const unsigned mblocks = (unsigned)(((size_t)nlive + SK_EVENT_BLOCK - 1) / SK_EVENT_BLOCK);
+            sk_wf_move<<<std::max(mblocks, 1u), SK_EVENT_BLOCK, 0, e->stream>>>(K, e->bank_fields_d, e->bank_fields_i);
+            CK(cudaGetLastError());
+            e->launches_total += 2;
+            e->bank.n = n_new;
+            eblocks = (unsigned)((K.n + SK_EVENT_BLOCK - 1) / SK_EVENT_BLOCK);
+        }
     }
     return SK_OK;
 }

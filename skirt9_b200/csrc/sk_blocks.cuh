@@ -26,11 +26,14 @@ struct SkBank {
     int32_t* list;    // [cap] slots of the rays of the trace stage being prepared / consumed
     int32_t* free_list;  // [cap] free slots found by the advance kernel, filled by the launch kernel
     unsigned int* ctl;  // control words: see SK_CTL_*
-    int32_t cap;
+    int32_t cap;      // allocated slots = stride of the field-major arrays
+    int32_t n;        // slots in use [0, n): the whole bank while histories are handed out, shrinking while it drains
     __device__ __forceinline__ double& D(int f, int s) const { return d[(size_t)f * cap + s]; }
     __device__ __forceinline__ int32_t& I(int f, int s) const { return i[(size_t)f * cap + s]; }
 };
 enum { SK_CTL_NLIST, SK_CTL_CURSOR, SK_CTL_NLIVE, SK_CTL_NFREE, SK_CTL_WORDS = 4 };
+#define SK_BANK_FIELDS_D(ninstr) (D_HISTW0 + ((ninstr) > 0 ? (ninstr) : 1))
+#define SK_BANK_FIELDS_I(ninstr) (I_HELL0 + ((ninstr) > 0 ? (ninstr) : 1))
 
 struct SkLocalCounters {
     unsigned int packets, fwd_paths, fwd_segs, replay_segs, peel_paths, peel_segs, scatt, rf, det, fallbacks;

@@ -161,7 +161,10 @@ __device__ __forceinline__ void sk_rng_init(SkRng& g, uint32_t seed, uint32_t st
     g.draw = draw;
 }
 // Random::uniform, Random.cpp:70-73: the n-th deviate of a history is Philox(counter = (history, n, 0))
-__device__ __noinline__ double sk_uniform(SkRng& g)
+#ifndef SK_UNIFORM_INLINE
+#define SK_UNIFORM_INLINE __noinline__
+#endif
+__device__ SK_UNIFORM_INLINE double sk_uniform(SkRng& g)
 {
     uint32_t c[4] = {g.c0, g.c1, g.draw, 0u};
     sk_philox(c, g.k0, g.k1);

@@ -40,6 +40,9 @@
 #ifndef SK_REFILL_MIN
 #define SK_REFILL_MIN 6
 #endif
+#ifndef SK_REFILL_MIN_SHORT
+#define SK_REFILL_MIN_SHORT 12  // walks to the interaction point are short (a dozen cells): refill threshold of their own
+#endif
 
 // ---------------------------------------------------------------------------------------------------
 // small helpers shared by the stage kernels
@@ -343,7 +346,7 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, SK_TRACE_MINBLOCKS)
             }
         }
         // ---------------- inner loop: cross cells until enough lanes have finished their ray
-        const int want_idle = (exhausted && chunk_pos >= chunk_end) ? 32 : SK_REFILL_MIN;
+        const int want_idle = (exhausted && chunk_pos >= chunk_end) ? 32 : (MODE == 1 ? SK_REFILL_MIN_SHORT : SK_REFILL_MIN);
         int nidle;
         do
         {
@@ -483,7 +486,7 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_advance(const SkDevModel
     const SkDevModel* __restrict__ Mg = A.model;
     const bool forced = M.force_scattering != 0;
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = slot < K.cap;
+    const bool valid = slot < K.n;
     int st = valid ? K.I(I_STATE, slot) : 0;
 
     // Every field the interaction needs is requested before the first use, for live and dead slots alike: the kernel is a
@@ -579,8 +582,11 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_advance(const SkDevModel
 // launch: a new history into every free slot collected by `advance` (SourceSystem::launch, SourceSystem.cpp:101-113 /
 // SecondarySourceSystem::launch, SecondarySourceSystem.cpp:130-142), then its emission peel-off set-up
 // (MonteCarloSimulation::peelOffEmission, .cpp:617-634).  One thread per entry of the free list.
+#ifndef SK_LAUNCH_MINBLOCKS
+#define SK_LAUNCH_MINBLOCKS 4
+#endif
 template <int GRID>
-__global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_launch(const SkDevModel M, const SkRunArgs A, const SkBank K,
+__global__ void __launch_bounds__(SK_EVENT_BLOCK, SK_LAUNCH_MINBLOCKS) sk_wf_launch(const SkDevModel M, const SkRunArgs A, const SkBank K,
                                                                 const int j0, const int j1)
 {
     const SkSmemTables T{M.xv, M.yv, M.zv};
@@ -651,7 +657,7 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_peel_setup(const SkDevMo
                                                                     const int j1)
 {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-    const int st = slot < K.cap ? K.I(I_STATE, slot) : 0;
+    const int st = slot < K.n ? K.I(I_STATE, slot) : 0;
     bool need = (st & SK_ST_LIVE) && sk_peel_setup(M, K, slot, st, j0, j1);
     sk_block_append(K.list, &K.ctl[SK_CTL_NLIST], need, slot);
 }
@@ -670,7 +676,7 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_detect(const SkDevModel 
     __syncthreads();
     SkLocalCounters cnt;
     memset(&cnt, 0, sizeof cnt);
-    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < K.cap; slot += gridDim.x * blockDim.x)
+    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < K.n; slot += gridDim.x * blockDim.x)
     {
         int st = K.I(I_STATE, slot);
         const bool live = (st & SK_ST_LIVE) != 0;
@@ -745,7 +751,7 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_detect(const SkDevModel 
 __global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_sample(const SkDevModel M, const SkRunArgs A, const SkBank K)
 {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = slot < K.cap;
+    const bool valid = slot < K.n;
     const bool forced = M.force_scattering != 0;
     int st = valid ? K.I(I_STATE, slot) : 0;
     bool live = (st & SK_ST_LIVE) != 0;
@@ -787,4 +793,30 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_sample(const SkDevModel 
         }
     }
     sk_block_append(K.list, &K.ctl[SK_CTL_NLIST], live, slot);
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// Draining: once every history of the segment has been handed out the bank empties geometrically (a packet survives a
+// round with probability ~3/4) over several dozen rounds.  So that the element-wise kernels and the trace grids shrink with
+// it, the live packets are packed into the head of the bank whenever fewer than half of the slots in use are alive:
+// partition lists the live slots of the tail [n_new, n) and the dead slots of the head [0, n_new), move copies the former
+// into the latter (all fields), after which the bank is [0, n_new).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_partition(const SkBank K, const int n_new)
+{
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = slot < K.n;
+    const bool live = valid && (K.I(I_STATE, slot) & SK_ST_LIVE);
+    sk_block_append(K.list, &K.ctl[SK_CTL_NLIST], live && slot >= n_new, slot);       // sources
+    sk_block_append(K.free_list, &K.ctl[SK_CTL_NFREE], valid && !live && slot < n_new, slot);  // destinations
+}
+__global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_move(const SkBank K, const int nd, const int ni)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K.ctl[SK_CTL_NLIST]) return;
+    const int src = K.list[i], dst = K.free_list[i];
+    for (int f = 0; f < nd; ++f) K.D(f, dst) = K.D(f, src);
+    for (int f = 0; f < ni; ++f) K.I(f, dst) = K.I(f, src);
+    K.I(I_STATE, src) = 0;
 }
