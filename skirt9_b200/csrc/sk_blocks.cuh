@@ -285,22 +285,6 @@ struct SkRayDir {
     }
 };
 
-#ifndef SK_PREFETCH_LINKS
-#define SK_PREFETCH_LINKS 0  // measured: prefetching the candidate records adds L1 wavefronts, the loop's bottleneck (-30 %)
-#endif
-__device__ __forceinline__ void sk_prefetch_link(const SkDevModel& M, int link)
-{
-    if (link >= 0)
-    {
-        const int idx = link & SK_LINK_INDEX_MASK;
-        const void* ptr = (link & SK_LINK_INTERNAL) ? (const void*)(M.node_child + idx) : (const void*)(M.cells + idx);
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
-    }
-}
-
-#ifndef SK_CARRY_BORDERS
-#define SK_CARRY_BORDERS 0  // measured: carrying the exit borders costs more (registers, predicated look-ups) than it saves (-8 %)
-#endif
 // one 32-byte record with a single 256-bit load through the read-only path (LDG.E.256 on sm_100a): half the L1 tag
 // look-ups of two 128-bit loads, and the L1 data pipe is what bounds the crossing loop
 __device__ __forceinline__ void sk_ld256(const void* p, int4& a, int4& b)
@@ -311,27 +295,10 @@ __device__ __forceinline__ void sk_ld256(const void* p, int4& a, int4& b)
     b = make_int4((int)(unsigned)q2, (int)(q2 >> 32), (int)(unsigned)q3, (int)(q3 >> 32));
 }
 
-// The borders of the current cell that the ray is heading for (its candidate exit planes), carried in registers along the
-// ray: after a crossing into a cell of the same size only the border on the crossed axis changes, so the crossing loop
-// does one table look-up instead of three most of the time (the shared-memory look-ups are random, i.e. bank-conflicted).
-struct SkExitBorders {
-    double x, y, z;
-};
-template <int GRID>
-__device__ __forceinline__ void sk_exit_borders(const SkDevModel& M, const SkSmemTables& T, const SkRayDir& k,
-                                                const SkCellPos& p, SkExitBorders& e)
-{
-    if (GRID == 3 || p.m < 0) return;
-    const int size = GRID == 1 ? 1 : 1 << (M.maxlevel - p.lev);
-    e.x = T.X[p.ix + ((k.kx < 0.0) ? 0 : size)];
-    e.y = T.Y[p.iy + ((k.ky < 0.0) ? 0 : size)];
-    e.z = T.Z[p.iz + ((k.kz < 0.0) ? 0 : size)];
-}
-
 template <int GRID>
 __device__ __forceinline__ void sk_step(const SkDevModel& M, const SkDevModel* __restrict__ Mg, const SkSmemTables& T,
                                         SkLocalCounters& cnt, double& rx, double& ry, double& rz, const SkRayDir& k,
-                                        SkCellPos& p, SkExitBorders& eb, int& m_out, double& dens_out, double& ds_out)
+                                        SkCellPos& p, int& m_out, double& dens_out, double& ds_out)
 {
     if (GRID == 3)
     {
@@ -412,13 +379,9 @@ __device__ __forceinline__ void sk_step(const SkDevModel& M, const SkDevModel* _
     {
         int m = p.m;
         double dens = __ldg(&M.dens[m]);
-#if SK_CARRY_BORDERS
-        const double xE = eb.x, yE = eb.y, zE = eb.z;
-#else
         double xE = T.X[p.ix + ((k.kx < 0.0) ? 0 : 1)];
         double yE = T.Y[p.iy + ((k.ky < 0.0) ? 0 : 1)];
         double zE = T.Z[p.iz + ((k.kz < 0.0) ? 0 : 1)];
-#endif
         double dsx = (k.ikx != 0.) ? (xE - rx) * k.ikx : DBL_MAX;
         double dsy = (k.iky != 0.) ? (yE - ry) * k.iky : DBL_MAX;
         double dsz = (k.ikz != 0.) ? (zE - rz) * k.ikz : DBL_MAX;
@@ -432,9 +395,6 @@ __device__ __forceinline__ void sk_step(const SkDevModel& M, const SkDevModel* _
             rz += k.kz * dsx;
             p.ix += (k.kx < 0.0) ? -1 : 1;
             outside = (p.ix >= M.nx || p.ix < 0);
-#if SK_CARRY_BORDERS
-            if (!outside) eb.x = T.X[p.ix + ((k.kx < 0.0) ? 0 : 1)];
-#endif
         }
         else if (dsy < dsx && dsy <= dsz)
         {
@@ -444,9 +404,6 @@ __device__ __forceinline__ void sk_step(const SkDevModel& M, const SkDevModel* _
             rz += k.kz * dsy;
             p.iy += (k.ky < 0.0) ? -1 : 1;
             outside = (p.iy >= M.ny || p.iy < 0);
-#if SK_CARRY_BORDERS
-            if (!outside) eb.y = T.Y[p.iy + ((k.ky < 0.0) ? 0 : 1)];
-#endif
         }
         else
         {
@@ -456,9 +413,6 @@ __device__ __forceinline__ void sk_step(const SkDevModel& M, const SkDevModel* _
             ry += k.ky * dsz;
             p.iz += (k.kz < 0.0) ? -1 : 1;
             outside = (p.iz >= M.nz || p.iz < 0);
-#if SK_CARRY_BORDERS
-            if (!outside) eb.z = T.Z[p.iz + ((k.kz < 0.0) ? 0 : 1)];
-#endif
         }
         m_out = m;
         dens_out = dens;
@@ -472,13 +426,9 @@ __device__ __forceinline__ void sk_step(const SkDevModel& M, const SkDevModel* _
         sk_ld256(&M.cells[p.m], a, b);
         const int size = 1 << (M.maxlevel - p.lev);
         const bool nx = k.kx < 0.0, ny = k.ky < 0.0, nz = k.kz < 0.0;
-#if SK_CARRY_BORDERS
-        const double xnext = eb.x, ynext = eb.y, znext = eb.z;
-#else
         const double xnext = T.X[p.ix + (nx ? 0 : size)];
         const double ynext = T.Y[p.iy + (ny ? 0 : size)];
         const double znext = T.Z[p.iz + (nz ? 0 : size)];
-#endif
         const double dsx = (k.ikx != 0.) ? (xnext - rx) * k.ikx : DBL_MAX;
         const double dsy = (k.iky != 0.) ? (ynext - ry) * k.iky : DBL_MAX;
         const double dsz = (k.ikz != 0.) ? (znext - rz) * k.ikz : DBL_MAX;
@@ -489,15 +439,6 @@ __device__ __forceinline__ void sk_step(const SkDevModel& M, const SkDevModel* _
         const double other = takex ? fmin(dsy, dsz) : takey ? fmin(dsx, dsz) : fmin(dsx, dsy);
         const double kexit = takex ? k.kx : takey ? k.ky : k.kz;
         const int lx = nx ? a.z : a.w, ly = ny ? b.x : b.y, lz = nz ? b.z : b.w;
-#if SK_PREFETCH_LINKS
-        // The next record is known only after the exit wall has been chosen, and its L2 latency is the longest stall of the
-        // loop: start the three candidates (the neighbours across the walls the ray is heading for) on their way into L1
-        // now, so that the one that is needed arrives while the exit arithmetic runs.  A link to an internal node prefetches
-        // the 32-byte row of its eight children instead.
-        sk_prefetch_link(M, lx);
-        sk_prefetch_link(M, ly);
-        sk_prefetch_link(M, lz);
-#endif
         const int link = takex ? lx : takey ? ly : lz;
         const double adv = ds + M.eps;
         rx += k.kx * adv;
@@ -517,9 +458,6 @@ __device__ __forceinline__ void sk_step(const SkDevModel& M, const SkDevModel* _
             return;
         }
         const bool rare = link < 0 || !(other - ds > 4. * M.eps) || !(fabs(kexit) > 1e-3);
-#if SK_CARRY_BORDERS
-        const int oldlev = p.lev;
-#endif
         if (!rare)
         {
             // step to the lattice point just across the exit wall, then align to the neighbour's level
@@ -546,16 +484,6 @@ __device__ __forceinline__ void sk_step(const SkDevModel& M, const SkDevModel* _
             }
             else
                 sk_tree_descend(M.node_child, M.maxlevel, T, idx, ix, iy, iz, nlev, rx, ry, rz, p);
-#if SK_CARRY_BORDERS
-            // the exit borders of the new cell: all three when the cell size changed, else only the crossed axis
-            {
-                const int nsize = 1 << (M.maxlevel - p.lev);
-                const bool all = p.lev != oldlev;
-                if (all || takex) eb.x = T.X[p.ix + (nx ? 0 : nsize)];
-                if (all || takey) eb.y = T.Y[p.iy + (ny ? 0 : nsize)];
-                if (all || !(takex || takey)) eb.z = T.Z[p.iz + (nz ? 0 : nsize)];
-            }
-#endif
         }
         else
         {
@@ -568,9 +496,6 @@ __device__ __forceinline__ void sk_step(const SkDevModel& M, const SkDevModel* _
             ry = ty;
             rz = tz;
             p = q;
-#if SK_CARRY_BORDERS
-            sk_exit_borders<2>(M, T, k, p, eb);
-#endif
         }
     }
 }

@@ -202,7 +202,6 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, SK_TRACE_MINBLOCKS)
     SkRayDir k;
     k.set(0., 0., 1.);
     SkCellPos p{-1, 0, 0, 0, 0};
-    SkExitBorders eb{0., 0., 0.};
     double tau = 0, s = 0, limit = 0, section = 0;
     int nseg = 0;
     // MODE 0 + STORE extras
@@ -334,9 +333,6 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, SK_TRACE_MINBLOCKS)
                         if (MODE == 1) s_int = s;
                     }
                 }
-#if SK_CARRY_BORDERS
-                if (active) sk_exit_borders<GRID>(M, T, k, p, eb);
-#endif
             }
             if (take > 0) chunk_pos += take;
             if (!__any_sync(0xffffffffu, active || pending))
@@ -355,7 +351,7 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, SK_TRACE_MINBLOCKS)
                 int m;
                 double dens, ds;
                 const SkCellPos cur = p;
-                sk_step<GRID>(M, Mg, T, cnt, rx, ry, rz, k, p, eb, m, dens, ds);
+                sk_step<GRID>(M, Mg, T, cnt, rx, ry, rz, k, p, m, dens, ds);
                 bool done = false;
                 if (MODE == 0)
                 {
