@@ -631,6 +631,48 @@ class BlackBodySED:
         return planck(np.asarray(lam, dtype=float), self.T) / self.Ltot
 
 
+def cdf_loglog_range(inx, inp, lo, hi):
+    """NR::cdf<interpolateLogLog>(xv, pv, Pv, inxv, inpv, range), NR.hpp:494-520: the tabulated pdf restricted to [lo, hi]
+    with log-log interpolated end points; returns (xv, pv, Pv, norm)."""
+    inx, inp = np.asarray(inx, dtype=float), np.asarray(inp, dtype=float)
+
+    def interp(x, i):  # NR::interpolateLogLog between points i-1 and i
+        x1, x2, f1, f2 = inx[i - 1], inx[i], inp[i - 1], inp[i]
+        if f1 <= 0 or f2 <= 0:
+            return f1 if x == x1 else f2 if x == x2 else 0.0
+        return f1 * math.exp(math.log(x / x1) / math.log(x2 / x1) * math.log(f2 / f1))
+
+    min_right = int(np.searchsorted(inx, lo, side="right"))
+    max_right = int(np.searchsorted(inx, hi, side="left"))
+    xv = np.concatenate([[lo], inx[min_right:max_right], [hi]])
+    pv = np.empty(len(xv))
+    pv[0] = 0.0 if min_right == 0 else interp(lo, min_right)
+    pv[1:-1] = inp[min_right:max_right]
+    pv[-1] = 0.0 if max_right == len(inx) else interp(hi, max_right)
+    pv, Pv, norm = cdf2_loglog(xv, pv)
+    return xv, pv, Pv, norm
+
+
+class ListSED:
+    """ListSED.cpp:12-24 + TabulatedSED.cpp:12-35: a tabulated SED (wavelengths in m, specific luminosities per unit
+    wavelength in arbitrary units), normalised over the source wavelength range."""
+
+    def __init__(self, wavelengths, specificLuminosities):
+        o = np.argsort(wavelengths)
+        self.inlam = np.asarray(wavelengths, dtype=float)[o]
+        self.inp = np.asarray(specificLuminosities, dtype=float)[o]
+
+    def setup(self, source_range):
+        self.lambdav, self.pv, self.Pv, self.norm = cdf_loglog_range(self.inlam, self.inp, *source_range)
+
+    def source_fields(self):
+        return {"sed_kind": abi.SK_SED_TABULATED, "sed_lambda": self.lambdav, "sed_p": self.pv, "sed_P": self.Pv}
+
+    def specific_luminosity(self, lam):
+        lam = np.asarray(lam, dtype=float)
+        return np.exp(np.interp(np.log(lam), np.log(self.inlam), np.log(self.inp))) / self.norm
+
+
 @dataclass
 class PointSource:
     position: Sequence[float]

@@ -96,3 +96,23 @@ def small_voronoi(num_packets=20000, seed=11, num_sites=1500, **kw):
     z = np.clip(rng.laplace(0.0, 300.0, size=num_sites), -1900.0, 1900.0)
     sites = np.stack([R * np.cos(phi), R * np.sin(phi), z], axis=1) * pc
     return configs.cfg5(sites, num_packets=num_packets, seed=seed, num_pixels=16, **kw)
+
+
+def tabulated_sed_ring_source_high_g(num_packets=20000, seed=13):
+    """A ring-shaped source with a tabulated (ListSED) spectrum next to a point source, and a strongly forward-scattering
+    dust mix (g = 0.97 > 0.95: the peel-off uses the +-4 degree averaged phase function, DustMix.cpp:395-445)."""
+    pc = H.PC
+    mix = H.MeanListDustMix([0.1e-6, 1e-6, 10e-6], [2000.0, 800.0, 60.0], [0.7, 0.6, 0.4], [0.97, 0.96, 0.3])
+    medium = H.GeometricMedium(H.ShellGeometry(0.05 * pc, 1.0 * pc, 1.0), mix, opticalDepth=2.0, wavelength=0.55e-6)
+    grid = H.PolicyTreeSpatialGrid(-pc, pc, -pc, pc, -pc, pc, H.DensityTreePolicy(2, 5, 2e-3))
+    sed = H.ListSED([0.12e-6, 0.3e-6, 0.8e-6, 2e-6, 9e-6], [0.2, 1.0, 3.0, 1.5, 0.1])
+    s1 = H.GeometricSource(H.RingGeometry(0.5 * pc, 0.1 * pc, 0.05 * pc), sed, luminosity=2.0 * H.LSUN)
+    s2 = H.PointSource((0.1 * pc, 0.0, -0.2 * pc), H.BlackBodySED(8000.0), luminosity=1.0 * H.LSUN)
+    wlg = H.LogWavelengthGrid(0.15e-6, 8e-6, 7)
+    i1 = H.FullInstrument(instrumentName="f", distance=1e6 * pc, inclination=75 * DEG, azimuth=10 * DEG, fieldOfViewX=2.4 * pc,
+                          numPixelsX=12, fieldOfViewY=2.4 * pc, numPixelsY=12, recordComponents=True, numScatteringLevels=3,
+                          recordStatistics=True)
+    return H.MonteCarloSimulation(sources=[s1, s2], medium=medium, grid=grid, instruments=[i1], numPackets=num_packets,
+                                  minWavelength=0.15e-6, maxWavelength=8e-6, defaultWavelengthGrid=wlg,
+                                  storeRadiationField=True, radiationFieldWLG=H.LogWavelengthGrid(0.15e-6, 8e-6, 5),
+                                  numDensitySamples=3, seed=seed)

@@ -134,6 +134,13 @@ def test_voronoi_grid_with_radiation_field_nonforced_and_outside_source(engine_l
     models.compare_engines(sim2, gpu, cpu)
 
 
+def test_tabulated_sed_ring_source_and_forward_peaked_scattering(engine_lib):
+    sim = models.tabulated_sed_ring_source_high_g(num_packets=20000)
+    gpu, cpu = run_both(sim, engine_lib)
+    models.compare_engines(sim, gpu, cpu)
+    assert gpu.read_sed(0, abi.SK_COMP_PRIMARY_SCATTERED_LEVEL + 2).sum() > 0
+
+
 def test_small_bank_refills_slots(engine_lib, monkeypatch):
     """A bank far smaller than the number of histories: slots are reused many times; results do not change."""
     sim = models.small_octree(num_packets=20000).setup()
