@@ -133,7 +133,9 @@ typedef struct sk_instrument {
     double field_of_view_x, field_of_view_y, center_x, center_y; /* FrameInstrument.cpp:12-32 */
     int32_t record_components;      /* Instrument::recordComponents */
     int32_t num_scattering_levels;  /* Instrument::numScatteringLevels */
-    int32_t record_statistics;      /* Instrument::recordStatistics (SED bins; FluxRecorder.cpp:457-466) */
+    int32_t record_statistics;      /* Instrument::recordStatistics: Sum w^k per SED bin and per frame pixel, with the
+                                       contributions of one history to the same bin combined first
+                                       (FluxRecorder.cpp:457-466, 962-1014) */
     int32_t reserved;
 } sk_instrument_t;
 
@@ -288,6 +290,8 @@ int sk_engine_read_sed(sk_engine_t* e, int32_t instrument, int32_t component, do
 int sk_engine_read_ifu(sk_engine_t* e, int32_t instrument, int32_t component, double* out);
 /* FluxRecorder::_wsed[k][ell], k = 0..4 (FluxRecorder.cpp:58-62). */
 int sk_engine_read_sed_stats(sk_engine_t* e, int32_t instrument, int32_t k, double* out);
+/* FluxRecorder::_wifu[k][l + ell*Npix], k = 0..4: the same statistics per frame pixel (FluxRecorder.cpp:990-1013). */
+int sk_engine_read_ifu_stats(sk_engine_t* e, int32_t instrument, int32_t k, double* out);
 int sk_engine_counters(sk_engine_t* e, sk_counters_t* out, int32_t reset);
 
 /* Raw device buffers so that the rank's communicator (NCCL via torch.distributed in bench.py, or the

@@ -56,10 +56,15 @@ typedef struct {
     double* sed[NUM_COMP];
     double* ifu[NUM_COMP];
     double* wsed[5];
+    double* wifu[5];
     /* per-history statistics accumulator (FluxRecorder::ContributionList, FluxRecorder.hpp:327-339) */
     int hist_active;
     int hist_ell;
     double hist_w;
+    /* the history's contributions per frame pixel: index l + ell*Npix and summed weight, in order of first detection */
+    int hist_npix, hist_cappix;
+    size_t* hist_lell;
+    double* hist_wpix;
 } instr_t;
 
 typedef struct {
@@ -462,6 +467,9 @@ static void free_instruments(sko_engine_t* e)
             free(e->instr[i].ifu[c]);
         }
         for (int k = 0; k < 5; ++k) free(e->instr[i].wsed[k]);
+        for (int k = 0; k < 5; ++k) free(e->instr[i].wifu[k]);
+        free(e->instr[i].hist_lell);
+        free(e->instr[i].hist_wpix);
     }
     free(e->instr);
     e->instr = NULL;
@@ -873,6 +881,8 @@ int sko_set_instruments(sko_engine_t* e, int32_t n, const sk_instrument_t* instr
         }
         if (d->record_statistics && lensed)
             for (int k = 0; k < 5; ++k) q->wsed[k] = (double*)calloc(lensed, sizeof(double));
+        if (d->record_statistics && lenifu)
+            for (int k = 0; k < 5; ++k) q->wifu[k] = (double*)calloc(lenifu, sizeof(double));
     }
     return SK_OK;
 }
@@ -934,7 +944,10 @@ int sko_clear_instruments(sko_engine_t* e)
             if (q->ifu[c]) memset(q->ifu[c], 0, lenifu * sizeof(double));
         }
         for (int k = 0; k < 5; ++k)
+        {
             if (q->wsed[k]) memset(q->wsed[k], 0, lensed * sizeof(double));
+            if (q->wifu[k]) memset(q->wifu[k], 0, lenifu * sizeof(double));
+        }
     }
     return SK_OK;
 }
@@ -1715,6 +1728,18 @@ static void flush_history_stats(instr_t* q)
     }
     q->hist_active = 0;
     q->hist_w = 0.;
+    /* FluxRecorder::recordContributions for the frame, FluxRecorder.cpp:990-1013 (the list already holds one entry per
+       pixel and wavelength bin, which is what sorting and grouping the raw contributions produces) */
+    for (int i = 0; i < q->hist_npix; ++i)
+    {
+        double wn = 1.;
+        for (int k = 0; k <= 4; ++k)
+        {
+            q->wifu[k][q->hist_lell[i]] += wn;
+            wn *= q->hist_wpix[i];
+        }
+    }
+    q->hist_npix = 0;
 }
 
 /* Instrument::detect for SED/Frame/Full instruments: SEDInstrument.cpp:22-25 + ApertureInstrument.cpp:24-43,
@@ -1811,6 +1836,25 @@ static void detect(sko_engine_t* e, instr_t* q, packet_t* ppp)
         q->hist_active = 1;
         q->hist_ell = ell;
         q->hist_w += Lext;
+    }
+    if (q->d.record_statistics && q->include_ifu && l >= 0)
+    {
+        size_t lell = (size_t)l + (size_t)ell * q->npix;
+        int i = 0;
+        while (i < q->hist_npix && q->hist_lell[i] != lell) i++;
+        if (i == q->hist_npix)
+        {
+            if (q->hist_npix == q->hist_cappix)
+            {
+                q->hist_cappix = q->hist_cappix ? 2 * q->hist_cappix : 64;
+                q->hist_lell = (size_t*)realloc(q->hist_lell, q->hist_cappix * sizeof(size_t));
+                q->hist_wpix = (double*)realloc(q->hist_wpix, q->hist_cappix * sizeof(double));
+            }
+            q->hist_lell[i] = lell;
+            q->hist_wpix[i] = 0.;
+            q->hist_npix++;
+        }
+        q->hist_wpix[i] += Lext;
     }
 }
 
@@ -2399,6 +2443,15 @@ int sko_read_sed_stats(sko_engine_t* e, int32_t instrument, int32_t k, double* o
     instr_t* q = &e->instr[instrument];
     if (!q->wsed[k]) return fail(SK_ERR_INVALID, "statistics not recorded");
     memcpy(out, q->wsed[k], (size_t)q->nl * sizeof(double));
+    return SK_OK;
+}
+int sko_read_ifu_stats(sko_engine_t* e, int32_t instrument, int32_t k, double* out)
+{
+    if (!e || !out || instrument < 0 || instrument >= e->ninstr || k < 0 || k > 4)
+        return fail(SK_ERR_INVALID, "bad instrument/power");
+    instr_t* q = &e->instr[instrument];
+    if (!q->wifu[k]) return fail(SK_ERR_INVALID, "statistics not recorded");
+    memcpy(out, q->wifu[k], q->npix * (size_t)q->nl * sizeof(double));
     return SK_OK;
 }
 int sko_counters(sko_engine_t* e, sk_counters_t* out, int32_t reset)

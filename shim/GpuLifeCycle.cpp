@@ -661,7 +661,7 @@ void GpuLifeCycle::returnDetectors()
         }
         for (size_t k = 0; k != rec->_wsed.size(); ++k)
             if (rec->_wsed[k].size()) check(sk_engine_read_sed_stats(_e, static_cast<int32_t>(i), static_cast<int32_t>(k), &rec->_wsed[k][0]));
-        if (!rec->_wifu.empty() && rec->_wifu[0].size())
-            _sim->log()->warning("Per-pixel statistics (stats*.fits) are not recorded by the GPU life cycle; the frames stay zero");
+        for (size_t k = 0; k != rec->_wifu.size(); ++k)
+            if (rec->_wifu[k].size()) check(sk_engine_read_ifu_stats(_e, static_cast<int32_t>(i), static_cast<int32_t>(k), &rec->_wifu[k][0]));
     }
 }

@@ -112,7 +112,7 @@ def load_engine_library(path: Optional[str] = None) -> C.CDLL:
 ABI_FUNCTIONS = ["create", "destroy", "set_grid_cartesian", "set_grid_octree", "set_grid_voronoi", "set_medium", "set_dustmix",
                  "set_wavelength_grids", "set_sources", "set_instruments", "set_secondary", "clear_instruments", "clear_rf",
                  "prepare_primary", "prepare_secondary", "run_segment", "communicate_rf", "absorbed_luminosity",
-                 "read_rf", "read_sed", "read_ifu", "read_sed_stats", "counters"]
+                 "read_rf", "read_sed", "read_ifu", "read_sed_stats", "read_ifu_stats", "counters"]
 ENGINE_ONLY_FUNCTIONS = ["launch_segment", "synchronize", "last_kernel_ms", "last_stage_ms", "device_buffer", "cuda_stream"]
 
 
@@ -374,6 +374,14 @@ class Engine:
             row = np.empty(nl, dtype=np.float64)
             self._call("read_sed_stats", self._h, C.c_int32(instrument), C.c_int32(k), row.ctypes.data_as(_dp))
             out[k] = row
+        return out
+
+    def read_ifu_stats(self, instrument=0):
+        """Sum w^k per frame pixel, k = 0..4: [k][ell][pixel] (FluxRecorder::_wifu)."""
+        nl, npix = self._instr[instrument]
+        out = np.empty((5, nl, npix), dtype=np.float64)
+        for k in range(5):
+            self._call("read_ifu_stats", self._h, C.c_int32(instrument), C.c_int32(k), out[k].ctypes.data_as(_dp))
         return out
 
     def counters(self, reset=False) -> dict:

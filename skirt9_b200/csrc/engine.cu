@@ -133,7 +133,8 @@ struct HostInstr {
     size_t npix;
     bool include_sed, include_ifu, record_total_only;
     long long sed_off[SK_NUM_COMP], ifu_off[SK_NUM_COMP];  // offsets (doubles) into the detector block, -1 = absent
-    long long wsed_off[5];
+    long long wsed_off[5], wifu_off[5];
+    int pix_slot = -1;
 };
 
 struct sk_engine {
@@ -174,6 +175,7 @@ struct sk_engine {
     std::vector<int> instr_same_observer;
     std::vector<std::array<double, 3>> instr_kobs;
     bool secondary_ready = false, has_secondary = false, l2_policy_set = false;
+    int num_pix_lists = 0;
     void* pinned = nullptr;
     cudaEvent_t pin_ev[2] = {nullptr, nullptr};
     double* scratch = nullptr;
@@ -737,6 +739,7 @@ extern "C" int sk_engine_set_instruments(sk_engine_t* e, int32_t n, const sk_ins
     free_group(e->instr_allocs);
     e->instr.assign(n, HostInstr());
     size_t det = 0, stat = 0;
+    int num_pix_lists = 0;
     for (int i = 0; i < n; ++i)
     {
         HostInstr& q = e->instr[i];
@@ -775,6 +778,21 @@ extern "C" int sk_engine_set_instruments(sk_engine_t* e, int32_t n, const sk_ins
             {
                 q.ifu_off[c] = (long long)det;
                 det += lenifu;
+            }
+        }
+        q.pix_slot = -1;
+        if (d.record_statistics && lenifu)
+        {
+            if (lenifu > (size_t)0x7fffffff) return fail(SK_ERR_UNSUPPORTED, "per-pixel statistics on a frame with more than 2^31 pixel bins");
+            q.pix_slot = num_pix_lists++;
+        }
+        for (int k = 0; k < 5; ++k)
+        {
+            q.wifu_off[k] = -1;
+            if (q.pix_slot >= 0)
+            {
+                q.wifu_off[k] = (long long)stat;
+                stat += lenifu;
             }
         }
         for (int k = 0; k < 5; ++k)
@@ -860,6 +878,8 @@ extern "C" int sk_engine_set_instruments(sk_engine_t* e, int32_t n, const sk_ins
             v.ifu[c] = q.ifu_off[c] >= 0 ? e->det_block + q.ifu_off[c] : nullptr;
         }
         for (int k = 0; k < 5; ++k) v.wsed[k] = q.wsed_off[k] >= 0 ? e->stat_block + q.wsed_off[k] : nullptr;
+        for (int k = 0; k < 5; ++k) v.wifu[k] = q.wifu_off[k] >= 0 ? e->stat_block + q.wifu_off[k] : nullptr;
+        v.pix_slot = q.pix_slot;
     }
     e->instr_same_observer.assign(n, 0);
     e->instr_kobs.assign(n, std::array<double, 3>{0., 0., 1.});
@@ -872,6 +892,9 @@ extern "C" int sk_engine_set_instruments(sk_engine_t* e, int32_t n, const sk_ins
     if (int rc = upload(e->instr_allocs, dev.data(), dev.size(), &di)) return rc;
     e->M.instr = di;
     e->M.ninstr = n;
+    e->num_pix_lists = num_pix_lists;
+    e->M.pix_base_d = SK_BANK_FIELDS_D(n);
+    e->M.pix_base_i = SK_BANK_FIELDS_I(n);
     return SK_OK;
 }
 
@@ -1081,7 +1104,8 @@ static int ensure_bank(sk_engine* e, uint64_t count)
 {
     size_t cap = std::min<uint64_t>(count, bank_capacity_limit());
     cap = std::max<size_t>((cap + 255) / 256 * 256, 256);
-    const int nd = SK_BANK_FIELDS_D(e->M.ninstr), ni = SK_BANK_FIELDS_I(e->M.ninstr);
+    const int nd = SK_BANK_FIELDS_D(e->M.ninstr) + e->num_pix_lists * SK_PIX_K;
+    const int ni = SK_BANK_FIELDS_I(e->M.ninstr) + e->num_pix_lists * (SK_PIX_K + 1);
     e->bank.n = (int32_t)cap;
     if ((size_t)e->bank.cap >= cap && e->bank_fields_d == nd && e->bank_fields_i == ni) return SK_OK;
     cudaFree(e->bank.d);
@@ -1496,6 +1520,16 @@ extern "C" int sk_engine_read_sed_stats(sk_engine_t* e, int32_t instrument, int3
                        e->stream));
     CK(cudaStreamSynchronize(e->stream));
     return SK_OK;
+}
+
+extern "C" int sk_engine_read_ifu_stats(sk_engine_t* e, int32_t instrument, int32_t k, double* out)
+{
+    if (!e || !out || instrument < 0 || instrument >= (int)e->instr.size() || k < 0 || k > 4)
+        return fail(SK_ERR_INVALID, "bad instrument/power");
+    const HostInstr& q = e->instr[instrument];
+    if (q.wifu_off[k] < 0) return fail(SK_ERR_INVALID, "statistics not recorded");
+    CK(cudaSetDevice(e->cfg.device));
+    return fetch_doubles(e, e->stat_block + q.wifu_off[k], q.npix * (size_t)q.nl, out);
 }
 
 extern "C" int sk_engine_counters(sk_engine_t* e, sk_counters_t* out, int32_t reset)

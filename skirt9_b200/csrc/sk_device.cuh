@@ -19,6 +19,9 @@
 #define SK_MAX_LEVELS 8
 #define SK_NUM_COMP (SK_COMP_PRIMARY_SCATTERED_LEVEL + SK_MAX_LEVELS)
 #define SK_MAX_INSTR 8
+#ifndef SK_PIX_K
+#define SK_PIX_K 32  // distinct frame pixels one history can hold before its oldest entry is recorded early
+#endif
 #define SK_MAX_TREE_LEVEL 15
 #define SK_LINK_INTERNAL 0x40000000
 #define SK_LINK_LEVEL_SHIFT 26
@@ -59,6 +62,9 @@ struct SkDevInstr {
     double* sed[SK_NUM_COMP];
     double* ifu[SK_NUM_COMP];
     double* wsed[5];
+    double* wifu[5];    // per-pixel statistics (FluxRecorder::_wifu) or null
+    int32_t pix_slot;   // index of this instrument's per-history pixel list in the bank, or -1
+    int32_t pad2;
 };
 
 struct SkDevModel {
@@ -110,6 +116,7 @@ struct SkDevModel {
     // instruments
     const SkDevInstr* instr;
     int32_t ninstr;
+    int32_t pix_base_d, pix_base_i;  // first bank field of the per-history pixel lists (SK_PIX_K entries per instrument)
     // counters
     unsigned long long* counters;
 };

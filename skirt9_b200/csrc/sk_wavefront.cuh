@@ -129,6 +129,37 @@ __device__ __forceinline__ void sk_rng_load(SkRng& g, const SkDevModel& M, const
                 (uint32_t)K.I(I_DRAW, slot));
 }
 
+__device__ __forceinline__ void sk_record_pixel_stats(const SkDevInstr& q, int lell, double w)
+{
+    double wn = 1.;
+    for (int kk = 0; kk <= 4; ++kk)
+    {
+        atomicAdd(&q.wifu[kk][lell], wn);
+        wn *= w;
+    }
+}
+// A detection's contribution to the history's pixel list (ContributionList::addContribution, FluxRecorder.hpp:331, with the
+// grouping of FluxRecorder.cpp:996-999 done on insertion).  A history that reaches more than SK_PIX_K distinct pixels has
+// its oldest entry recorded early.
+__device__ __forceinline__ void sk_add_pixel_contribution(const SkDevModel& M, const SkBank& K, const SkDevInstr& q,
+                                                          int slot, int lell, double w)
+{
+    const int fi = M.pix_base_i + q.pix_slot * (SK_PIX_K + 1), fd = M.pix_base_d + q.pix_slot * SK_PIX_K;
+    const int total = K.I(fi + SK_PIX_K, slot);
+    const int n = min(total, SK_PIX_K);
+    for (int i = 0; i < n; ++i)
+        if (K.I(fi + i, slot) == lell)
+        {
+            K.D(fd + i, slot) += w;
+            return;
+        }
+    const int at = total % SK_PIX_K;
+    if (total >= SK_PIX_K) sk_record_pixel_stats(q, K.I(fi + at, slot), K.D(fd + at, slot));
+    K.I(fi + at, slot) = lell;
+    K.D(fd + at, slot) = w;
+    K.I(fi + SK_PIX_K, slot) = total + 1;
+}
+
 // Ends a history: FluxRecorder::recordContributions for the SED arrays (FluxRecorder.cpp:962-986); frees the slot.
 __device__ __forceinline__ void sk_finish_history(const SkDevModel& M, const SkBank& K, int slot)
 {
@@ -147,6 +178,15 @@ __device__ __forceinline__ void sk_finish_history(const SkDevModel& M, const SkB
                 wn *= w;
             }
         }
+    }
+    // the same per frame pixel (FluxRecorder.cpp:990-1013): the history's list holds one entry per pixel and bin
+    for (int j = 0; j < M.ninstr; ++j)
+    {
+        const SkDevInstr& q = M.instr[j];
+        if (q.pix_slot < 0) continue;
+        const int fi = M.pix_base_i + q.pix_slot * (SK_PIX_K + 1), fd = M.pix_base_d + q.pix_slot * SK_PIX_K;
+        const int n = min(K.I(fi + SK_PIX_K, slot), SK_PIX_K);
+        for (int i = 0; i < n; ++i) sk_record_pixel_stats(q, K.I(fi + i, slot), K.D(fd + i, slot));
     }
     K.I(I_STATE, slot) = 0;
 }
@@ -635,6 +675,8 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK, SK_LAUNCH_MINBLOCKS) sk_wf_lau
                 {
                     K.D(D_HISTW0 + j, slot) = 0.;
                     K.I(I_HELL0 + j, slot) = -1;
+                    const int ps = M.instr[j].pix_slot;
+                    if (ps >= 0) K.I(M.pix_base_i + ps * (SK_PIX_K + 1) + SK_PIX_K, slot) = 0;
                 }
                 K.I(I_STATE, slot) = SK_ST_LIVE;
                 live = true;
@@ -696,6 +738,7 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_detect(const SkDevModel 
                     K.D(D_HISTW0 + j, slot) += Lext;  // FluxRecorder.cpp:457-466
                     K.I(I_HELL0 + j, slot) = ell;
                 }
+                if (q.pix_slot >= 0 && l >= 0) sk_add_pixel_contribution(M, K, q, slot, l + ell * (int)q.npix, Lext);
             }
         }
         if (last)

@@ -123,6 +123,22 @@ def shell_average(cells, J, nshell=32, rmax=1.0):
     return num / np.maximum(den, 1e-300)[:, None]
 
 
+def make_cfg6m():
+    """The multi-feature ski: every output file the reference writes, with 4e6 packets (-t 1)."""
+    with tempfile.TemporaryDirectory() as d:
+        run_reference("cfg6m", d, packets=4e6)
+        out = dict(sed_sed=read_columns(os.path.join(d, "cfg6m_sed_sed.dat")),
+                   sed_stats=read_columns(os.path.join(d, "cfg6m_sed_sedstats.dat")),
+                   full_sed=read_columns(os.path.join(d, "cfg6m_full_sed.dat")),
+                   frame_total=read_fits_cube(os.path.join(d, "cfg6m_frame_total.fits"))[0],
+                   mass_density_msun_pc3=read_columns(os.path.join(d, "cfg6m_cells_cellprops.dat"))[:, 6],
+                   J_nu=read_columns(os.path.join(d, "cfg6m_rf_J.dat"))[:, 1:].astype(np.float32), num_packets=4e6)
+        for c in ("total", "transparent", "primarydirect", "primaryscattered"):
+            out["full_" + c] = read_fits_cube(os.path.join(d, f"cfg6m_full_{c}.fits"))[0]
+    np.savez_compressed(os.path.join(HERE, "cfg6m_ref.npz"), **out)
+    print("cfg6m:", {k: np.shape(v) for k, v in out.items()})
+
+
 def make_cfg4s():
     with tempfile.TemporaryDirectory() as d:
         log = run_reference("cfg4s", d)

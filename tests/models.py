@@ -70,6 +70,11 @@ def compare_engines(sim, a, b, rtol=1e-9):
         if ins.recordStatistics and ins.kind in (abi.SK_INSTR_SED, abi.SK_INSTR_FULL):
             x, y = a.read_sed_stats(j), b.read_sed_stats(j)
             np.testing.assert_allclose(x, y, rtol=1e-8, atol=1e-300, err_msg=f"stats instr {j}")
+        if ins.recordStatistics and ins.kind in (abi.SK_INSTR_FRAME, abi.SK_INSTR_FULL):
+            x, y = a.read_ifu_stats(j), b.read_ifu_stats(j)
+            np.testing.assert_array_equal(x[0], y[0], err_msg=f"pixel counts instr {j}")   # histories per pixel: integers
+            for k in range(1, 5):
+                np.testing.assert_allclose(x[k], y[k], rtol=1e-8, atol=1e-8 * y[k].max(), err_msg=f"pixel stats {k} instr {j}")
     if sim.storeRadiationField:
         x, y = a.read_rf(0), b.read_rf(0)
         np.testing.assert_allclose(x, y, rtol=rtol, atol=rtol * y.max())

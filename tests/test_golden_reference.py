@@ -93,6 +93,18 @@ def check_cfg1(sim, e, g, n):
     scale = math.sqrt(g["num_packets"] / n)
     ok = b > 0.02 * b.max()
     assert np.all(np.abs(a - b)[ok] <= 5.0 * r_blk[ok] * math.hypot(1.0, scale) * b[ok] + 1e-3 * b.max())
+    # per-pixel statistics (stats0/1/2.fits of the reference = Sum w^k per pixel, uncalibrated): the number of histories
+    # seen per pixel scales with the number of packets; Sum w is the total frame
+    st = e.read_ifu_stats(0)
+    ratio = n / float(g["num_packets"])
+    s0, s0ref = blk(st[0][0].reshape(64, 64)), blk(g["frame_stats0"][0].astype(float))
+    okc = s0ref > 2000
+    np.testing.assert_allclose(s0[okc] / ratio, s0ref[okc], rtol=0.05 * math.hypot(1.0, scale))
+    assert st[0].sum() / ratio == pytest.approx(float(g["frame_stats0"].sum()), rel=0.005 * math.hypot(1.0, scale))
+    # the files hold c^k Sum w^k with a common scale c (FluxRecorder.cpp:826-845): compare the scale-free Sum w^2/(Sum w)^2
+    s1, s2 = blk(st[1][0].reshape(64, 64)), blk(st[2][0].reshape(64, 64))
+    s1ref, s2ref = blk(g["frame_stats1"][0].astype(float)), blk(g["frame_stats2"][0].astype(float))
+    np.testing.assert_allclose((s2 / s1 ** 2)[okc] * ratio, (s2ref / s1ref ** 2)[okc], rtol=0.10 * math.hypot(1.0, scale))
     # radiation field: J per cell in radial shells (noise per cell ~ several % at 1e6 packets; per shell < 1 %)
     J = sim.mean_intensity_nu(e, 0)[:, 0]
     Jref = g["J_nu"][:, 0]

@@ -156,3 +156,19 @@ def test_tabulated_sed_and_ring_source_known_answers():
     assert tr.sum() == pytest.approx(sim.sources[0].luminosity, rel=0.01)
     # the direct frame (no extinction to speak of at the rim) shows the ring: flux-weighted mean projected radius
     assert e.counters()["packets"] == 40000
+
+
+def test_per_pixel_statistics_group_a_history_before_exponentiation():
+    """FluxRecorder.cpp:990-1013: Sum w^1 per pixel is the total frame; Sum w^0 counts histories, not detections, so with
+    coarse pixels it is smaller than the number of detections that fell on the frame."""
+    sim = models.small_cartesian(num_packets=5000, record_statistics=True)
+    sim.instruments[0].numPixelsX = sim.instruments[0].numPixelsY = 4      # coarse: repeated hits of one history
+    sim.setup()
+    e = sim.configure(OracleEngine(sim.config_struct()))
+    sim.run(e)
+    st = e.read_ifu_stats(0)
+    total = e.read_ifu(0, abi.SK_COMP_TOTAL)
+    np.testing.assert_allclose(st[1], total, rtol=1e-10, atol=1e-12 * total.max())
+    assert st[0].sum() < e.counters()["detections"]
+    assert st[0].sum() >= 5000                                             # every history is seen at least once
+    assert np.all(st[2] <= st[1] ** 2 + 1e-9 * (st[1] ** 2).max())          # Sum w^2 <= (Sum w)^2

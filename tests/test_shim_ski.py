@@ -65,6 +65,10 @@ def test_cfg1_ski_runs_unchanged(tmp_path):
         assert cards["BUNIT"] == "MJy/sr"
     total, _ = read_fits_cube(tmp_path / "cfg1_i60_total.fits")
     assert total.sum() == pytest.approx(hi["frame_total_sum"].sum(), rel=2e-3)
+    # per-pixel statistics frames written by the reference from the engine's Sum w^k tallies: histories per pixel
+    s0, _ = read_fits_cube(tmp_path / "cfg1_i60_stats0.fits")
+    assert s0.astype(float).sum() / (n / 1e6) == pytest.approx(float(g["frame_stats0"].sum()), rel=0.005)
+    assert s0.max() > 0 and (tmp_path / "cfg1_i60_stats4.fits").exists()
     # the radiation field probe of the reference, fed from the engine's tally
     J = read_columns(tmp_path / "cfg1_rf_J.dat")[:, 1]
     assert J.sum() == pytest.approx(g["J_nu"][:, 0].sum(), rel=0.004)
@@ -139,3 +143,42 @@ def test_cfg5s_ski_voronoi_particles_runs_unchanged(tmp_path):
     tol = 4.0 * math.hypot(rel_error(g["sedstats"][0, 1:]), rel_error(stats[1:]))
     for col in (1, 3, 4):
         assert abs(sed[col] - ref[col]) <= tol * ref[1], (col, sed[col], ref[col], tol)
+
+
+def test_cfg6m_ski_many_features_runs_unchanged(tmp_path):
+    """Two sources (ring + ListSED, point + blackbody), forward-peaked dust, stored radiation field, three instruments on two
+    lines of sight with aperture, scattering levels, statistics, roll, offsets and an instrument-specific wavelength grid."""
+    g = np.load(os.path.join(GOLD, "cfg6m_ref.npz"))
+    n = 4e6
+    run_ski("cfg6m", tmp_path, n)
+    cells = read_columns(tmp_path / "cfg6m_cells_cellprops.dat")
+    np.testing.assert_array_equal(cells[:, 6], g["mass_density_msun_pc3"])
+    stats = read_columns(tmp_path / "cfg6m_sed_sedstats.dat")
+    sed = read_columns(tmp_path / "cfg6m_sed_sed.dat")
+    ref = g["sed_sed"]
+    tol = 4.5 * np.hypot(rel_error(g["sed_stats"][:, 1:].T), rel_error(stats[:, 1:].T))
+    # columns: total, transparent, direct, scattered, (3 secondary), 1-times and 2-times scattered
+    for col in (1, 2, 3, 4, 8, 9):
+        bound = tol * np.maximum(ref[:, col], ref[:, 1])
+        assert np.all(np.abs(sed[:, col] - ref[:, col]) <= bound), (col, sed[:, col] / ref[:, col] - 1, tol)
+    assert np.all(sed[:, 5:8] == 0)
+    # the FullInstrument has its own 4-bin wavelength grid
+    fsed, fref = read_columns(tmp_path / "cfg6m_full_sed.dat"), g["full_sed"]
+    assert fsed.shape == fref.shape == (4, 8)
+    np.testing.assert_allclose(fsed[:, 0], fref[:, 0], rtol=1e-9)
+    np.testing.assert_allclose(fsed[:, 1:5], fref[:, 1:5], rtol=0.03)
+    # frames: the rolled off-centre frame (total only) and the components of the full instrument
+    frame, _ = read_fits_cube(tmp_path / "cfg6m_frame_total.fits")
+    assert frame.shape == g["frame_total"].shape == (7, 14, 18)
+    a, b = frame.astype(float).sum(axis=0), g["frame_total"].astype(float).sum(axis=0)
+    ok = b > 0.05 * b.max()
+    np.testing.assert_allclose(a[ok], b[ok], rtol=0.08)
+    assert a.sum() == pytest.approx(b.sum(), rel=0.005)
+    for comp in ("total", "transparent", "primarydirect", "primaryscattered"):
+        x, _ = read_fits_cube(tmp_path / f"cfg6m_full_{comp}.fits")
+        y = g["full_" + comp]
+        assert x.shape == y.shape == (4, 8, 8)
+        assert x.astype(float).sum() == pytest.approx(y.astype(float).sum(), rel=0.01), comp
+    # the reference's radiation field probe on the engine's tally
+    J = read_columns(tmp_path / "cfg6m_rf_J.dat")[:, 1:]
+    np.testing.assert_allclose(J.sum(axis=0), g["J_nu"].astype(float).sum(axis=0), rtol=0.01)
