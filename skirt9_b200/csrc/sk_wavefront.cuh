@@ -34,6 +34,9 @@
 #ifndef SK_TRACE_MINBLOCKS
 #define SK_TRACE_MINBLOCKS 6
 #endif
+#ifndef SK_TRACE_MINBLOCKS_PEEL
+#define SK_TRACE_MINBLOCKS_PEEL 8   // the peel-off kernel keeps its (shared) direction in parameter space: fewer registers
+#endif
 #ifndef SK_CHUNK
 #define SK_CHUNK 64
 #endif
@@ -202,7 +205,7 @@ __device__ __forceinline__ void sk_finish_history(const SkDevModel& M, const SkB
 // rays, load new rays) that is entered when at least SK_REFILL_MIN lanes are idle, so that its cost is shared.
 // ---------------------------------------------------------------------------------------------------
 template <int GRID, int MODE, bool STORE, bool TABLES_IN_SMEM>
-__global__ void __launch_bounds__(SK_TRACE_BLOCK, SK_TRACE_MINBLOCKS)
+__global__ void __launch_bounds__(SK_TRACE_BLOCK, MODE == 2 ? SK_TRACE_MINBLOCKS_PEEL : SK_TRACE_MINBLOCKS)
     sk_wf_trace(const SkDevModel M, const SkRunArgs A, const SkBank K, const SkRayDir obs)
 {
     extern __shared__ double smem[];
@@ -239,8 +242,9 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, SK_TRACE_MINBLOCKS)
     bool active = false, pending = false;
     int slot = 0;
     double rx = 0, ry = 0, rz = 0;
-    SkRayDir k;
-    k.set(0., 0., 1.);
+    SkRayDir kray;  // direction of the lane's ray; all peel-off rays (MODE 2) share the observer's direction, which stays in
+    kray.set(0., 0., 1.);  // the kernel's parameter space: no per-lane registers, uniform sign tests
+    const SkRayDir& k = MODE == 2 ? obs : kray;
     SkCellPos p{-1, 0, 0, 0, 0};
     double tau = 0, s = 0, limit = 0, section = 0;
     int nseg = 0;
@@ -315,10 +319,7 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, SK_TRACE_MINBLOCKS)
                 rx = K.D(D_RX, slot);
                 ry = K.D(D_RY, slot);
                 rz = K.D(D_RZ, slot);
-                if (MODE == 2)
-                    k = obs;
-                else
-                    k.set(K.D(D_KX, slot), K.D(D_KY, slot), K.D(D_KZ, slot));
+                if (MODE != 2) kray.set(K.D(D_KX, slot), K.D(D_KY, slot), K.D(D_KZ, slot));
                 p.m = K.I(I_M, slot);
                 p.ix = K.I(I_IX, slot);
                 p.iy = K.I(I_IY, slot);
