@@ -87,7 +87,28 @@ def run_reference_once(num_packets, threads, workdir):
                           stderr=subprocess.DEVNULL)
     log = open(os.path.join(out, "cfg2_log.txt")).read()
     m = re.search(r"Finished primary emission in ([0-9.]+) s", log)
+    LAST_REFERENCE_SETUP.clear()
+    LAST_REFERENCE_SETUP.update(reference_setup_times(log, threads))
     return num_packets / float(m.group(1)), float(m.group(1))
+
+
+LAST_REFERENCE_SETUP = {}
+
+
+def reference_setup_times(log, threads):
+    """Grid construction and medium-state sampling times of a reference run, from the millisecond time stamps of its log
+    ('Constructing the spatial tree grid...' -> 'Finished construction of the spatial tree grid';
+    'Determining medium properties for N cells...' -> 'Done determining medium properties')."""
+    def stamp(pattern):
+        m = re.search(r"\d+/\d+/\d+ (\d+):(\d+):(\d+\.\d+)\s+" + pattern, log)
+        return None if m is None else 3600 * int(m.group(1)) + 60 * int(m.group(2)) + float(m.group(3))
+    t = [stamp(p) for p in ("Constructing the spatial tree grid", "Finished construction of the spatial tree grid",
+                            r"Determining medium properties for \d+ cells", "Done determining medium properties")]
+    if any(v is None for v in t):
+        return {}
+    cells = re.search(r"Determining medium properties for (\d+) cells", log)
+    return {"threads": threads, "cells": int(cells.group(1)), "construct_tree_s": (t[1] - t[0]) % 86400,
+            "medium_properties_s": (t[3] - t[2]) % 86400}
 
 
 SHIM_EXE = os.path.join(ROOT, "shim", "_build", "skirt_b200")
@@ -159,6 +180,30 @@ def reference_arm(args):
                              "sample": f"{n:g} packets per step, {'skirt -t %d' % cores if have_ref else 'C port, 1 thread'}"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def device_setup_times(device):
+    """SURVEY.md 8f row f2 on the bench workload: DensityTreePolicy::constructTree and the density sampling of
+    MediumSystem::setupSelfAfter as CUDA kernels (sk_engine_build_octree / sk_engine_sample_medium), host wall time around
+    the blocking C-ABI calls, best of 3 after a warm-up."""
+    from skirt9_b200 import abi, configs
+    sim = configs.cfg2(num_packets=1000)
+    sim.deviceSetup = True
+    sim.setup()
+    e = abi.Engine(sim.config_struct(device=device))
+    geom, pol = sim.medium.density_geometry(), sim.grid.tree_policy(sim.numDensitySamples)
+    e.build_octree(sim.grid.extent, pol, [geom])
+    best = [1e9, 1e9]
+    for _ in range(3):
+        t0 = time.perf_counter()
+        nn, nc = e.build_octree(sim.grid.extent, pol, [geom])
+        t1 = time.perf_counter()
+        e.sample_medium(geom, sim.numDensitySamples, nc)
+        t2 = time.perf_counter()
+        best = [min(best[0], t1 - t0), min(best[1], t2 - t1)]
+    e.close()
+    return {"nodes": nn, "cells": nc, "num_density_samples": sim.numDensitySamples, "device_build_octree_s": best[0],
+            "device_sample_medium_s": best[1]}
 
 
 def native_arm(args):
@@ -241,8 +286,13 @@ def native_arm(args):
     e2e_parts = {"configure_s": 0.0, "run_s": 0.0, "read_s": 0.0}
     for k in range(e2e_steps):
         ta = time.perf_counter()
-        e2 = sim.configure(abi.Engine(sim.config_struct(device=local)))
+        e2 = abi.Engine(sim.config_struct(device=local))
+        tcreate = time.perf_counter() - ta
+        sim.configure(e2)
         tb = time.perf_counter()
+        detail = dict(sim.last_configure_parts, create=tcreate)
+        for kk, vv in detail.items():
+            e2e_parts["configure_" + kk + "_s"] = e2e_parts.get("configure_" + kk + "_s", 0.0) + vv / e2e_steps
         e2.prepare_primary(total)
         e2.run_segment(first, packets_per_gpu, True, True, False, 1000 + k)
         if world > 1:
@@ -324,6 +374,9 @@ def native_arm(args):
                 "clocks": clocks}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.cpu_packets)
+            line["setup"] = device_setup_times(local)
+            if LAST_REFERENCE_SETUP:
+                line["setup"]["reference_cpu"] = dict(LAST_REFERENCE_SETUP)
             if os.path.exists(SHIM_EXE) and not args.no_e2e:
                 try:
                     line["ski_e2e"] = run_shim_once(4e8, os.cpu_count() or 1)

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SK_ABI_VERSION 2
+#define SK_ABI_VERSION 3
 
 typedef struct sk_engine sk_engine_t;
 
@@ -168,6 +168,34 @@ typedef struct sk_secondary {
                                     emission grid (.cpp:62-65, DisjointWavelengthGrid.cpp:346-356) */
 } sk_secondary_t;
 
+/* ---- Setup on the device: octree construction and medium-state sampling ----
+ * A medium component as the tree policy and the density sampler see it: a normalised Geometry (density integrates to one)
+ * times a total number of entities / a total mass (GeometricMedium.cpp:14-40).  p[] holds what Geometry::density needs:
+ *   SK_GEOM_SHELL           {rmin, rmax, exponent, _A}                                   ShellGeometry.cpp:30-36
+ *   SK_GEOM_EXPDISK         {hR, hz, Rmin, Rmax, zmax, _rho0}                            ExpDiskGeometry.cpp:32-42
+ *   SK_GEOM_RING            {R0, w, hz, _A}                                              RingGeometry.cpp:39-43
+ *   SK_GEOM_SPIRAL_EXPDISK  {hR, hz, Rmin, Rmax, zmax, _rho0, m, _tanp, R0, phi0, w, N, _cn}
+ *                                                                     SpiralStructureGeometryDecorator.cpp:24-29,71-75 */
+#define SK_DENSITY_MAX_PARAMS 16
+typedef struct sk_density_geometry {
+    int32_t geometry;  /* sk_geometry_kind */
+    int32_t reserved;
+    double number;     /* Medium::number(): number density = number * Geometry::density(r) */
+    double mass;       /* Medium::mass():   mass density   = mass   * Geometry::density(r) */
+    double p[SK_DENSITY_MAX_PARAMS];
+} sk_density_geometry_t;
+
+/* DensityTreePolicy (DensityTreePolicy.cpp:116-227), dust criteria; a criterion with value 0 is disabled. */
+typedef struct sk_tree_policy {
+    int32_t min_level, max_level;       /* TreePolicy::minLevel / maxLevel */
+    int32_t num_samples;                /* SamplingOptions::numDensitySamples (DensityTreePolicy.cpp:76) */
+    int32_t reserved;
+    double max_dust_fraction;           /* delta = M_node / M_dust > maxDustFraction             (.cpp:192-196) */
+    double max_dust_optical_depth;      /* tau = kappa * rho * diagonal > maxDustOpticalDepth    (.cpp:199-203) */
+    double max_dust_density_dispersion; /* q = (rhomax-rhomin)/rhomax > maxDustDensityDispersion (.cpp:206-210) */
+    double dust_kappa;                  /* DensityTreePolicy::_dustKappa (.cpp:88-97) */
+} sk_tree_policy_t;
+
 /* ---- Device-side event counters (the engine must count S, S_fwd, P_peel itself) -- */
 typedef struct sk_counters {
     uint64_t packets;        /* histories launched with L > 0 */
@@ -217,6 +245,28 @@ int sk_engine_set_grid_voronoi(sk_engine_t* e, const double extent[6], int32_t n
 /* MediumState number densities and volumes for a single medium component
  * (MediumState::numberDensity(m,0), MediumState::volume(m); MediumState.cpp:196-247). */
 int sk_engine_set_medium(sk_engine_t* e, int32_t num_cells, const double* number_density, const double* volume);
+
+/* DensityTreePolicy::constructTree (DensityTreePolicy.cpp:242-309) with OctTreeNode::createChildren (OctTreeNode.cpp:22-35),
+ * on the device: level by level, every node of the level is evaluated by needsSubdivide (.cpp:116-227: num_samples
+ * random positions in the node, Random::position(Box) Random.cpp:168-176, dust mass density summed over the media) and the
+ * flagged nodes get 8 children appended in node order, so that the node list has the reference's breadth-first order.
+ * The random positions come from the engine's counter-based generator (key = (seed, 0x54524545 "TREE"), counter =
+ * (node index, draw)); the reference draws from its thread-local Mersenne twisters, so the two trees agree statistically,
+ * not node by node.  Leaves the engine in the state sk_engine_set_grid_octree would (tables, neighbour links). */
+int sk_engine_build_octree(sk_engine_t* e, const double extent[6], const sk_tree_policy_t* policy, int32_t num_media,
+                           const sk_density_geometry_t* media, uint64_t* num_nodes, uint64_t* num_cells);
+/* The first_child array of the octree the engine holds (same meaning as in sk_engine_set_grid_octree), e.g. for
+ * TreeSpatialGridTopologyProbe (TreeSpatialGrid.cpp:232-251) or to rebuild the reference's TreeNode objects. */
+int sk_engine_read_octree(sk_engine_t* e, int32_t* first_child);
+
+/* MediumSystem::setupSelfAfter's cell loop (MediumSystem.cpp:286-330) for one geometric medium on a Cartesian or octree
+ * grid: volume(m) = SpatialGrid::volume(m), numberDensity(m) = PropertySampler::density (MediumSystem.cpp:80-106): the
+ * density at the cell centre for num_samples = 1, else the mean over num_samples random positions in the cell
+ * (TreeSpatialGrid::randomPositionInCell, TreeSpatialGrid.cpp:125-128).  Generator key = (seed, 0x43454c4c "CELL"),
+ * counter = (cell index, draw).  Replaces sk_engine_set_medium. */
+int sk_engine_sample_medium(sk_engine_t* e, const sk_density_geometry_t* medium, int32_t num_samples);
+/* MediumState::numberDensity(m,0) and MediumState::volume(m) as the engine holds them (either array may be NULL). */
+int sk_engine_read_medium(sk_engine_t* e, double* number_density, double* volume);
 
 int sk_engine_set_dustmix(sk_engine_t* e, const sk_dustmix_t* mix);
 

@@ -717,6 +717,223 @@ int sko_set_medium(sko_engine_t* e, int32_t num_cells, const double* number_dens
     return SK_OK;
 }
 
+/* ------------------------------------------------------------------------------------------------ */
+/* setup: octree construction by the density policy and medium-state sampling  */
+/* ------------------------------------------------------------------------------------------------ */
+
+/* Geometry::density(Position): ShellGeometry.cpp:30-36 (through SpheGeometry), ExpDiskGeometry.cpp:32-42 and
+ * RingGeometry.cpp:39-43 (through AxGeometry), SpiralStructureGeometryDecorator.cpp:24-29,71-75 */
+static double geom_density(const sk_density_geometry_t* g, double x, double y, double z)
+{
+    const double* p = g->p;
+    switch (g->geometry)
+    {
+        case SK_GEOM_SHELL:
+        {
+            double r = sqrt(x * x + y * y + z * z);
+            if (r < p[0] || r > p[1]) return 0.0;
+            return p[3] * pow(r, -p[2]);
+        }
+        case SK_GEOM_EXPDISK:
+        case SK_GEOM_SPIRAL_EXPDISK:
+        {
+            double R = sqrt(x * x + y * y);
+            double absz = fabs(z);
+            double rho;
+            if (p[3] > 0.0 && R > p[3])
+                rho = 0.0;
+            else if (p[4] > 0.0 && absz > p[4])
+                rho = 0.0;
+            else if (R < p[2])
+                rho = 0.0;
+            else
+                rho = p[5] * exp(-R / p[0]) * exp(-absz / p[1]);
+            if (g->geometry == SK_GEOM_EXPDISK) return rho;
+            double phi = atan2(y, x);
+            double m = p[6], tanp = p[7], R0 = p[8], phi0 = p[9], w = p[10], N = p[11], cn = p[12];
+            double gamma = log(R / R0) / tanp + phi0 + 0.5 * M_PI / m;
+            double perturbation = (1.0 - w) + w * cn * pow(sin(0.5 * m * (gamma - phi)), 2 * N);
+            return rho * perturbation;
+        }
+        case SK_GEOM_RING:
+        {
+            double R = sqrt(x * x + y * y);
+            double u = (R - p[0]) / (M_SQRT2 * p[1]);
+            return p[3] * exp(-u * u) * exp(-fabs(z) / p[2]);
+        }
+    }
+    return 0.0;
+}
+
+/* DensityTreePolicy::needsSubdivide, DensityTreePolicy.cpp:116-227 (dust criteria; samples from the stream
+ * (seed, "TREE") with counter = node index) */
+static int needs_subdivide(const sk_tree_policy_t* pol, int nmedia, const sk_density_geometry_t* media, double dust_mass,
+                           uint32_t seed, int node, int level, const double* box)
+{
+    if (level < pol->min_level) return 1;
+    if (level >= pol->max_level) return 0;
+    rng_t g;
+    rng_init(&g, seed, 0x54524545u, (uint64_t)node);
+    double rhosum = 0., rhomin = DBL_MAX, rhomax = 0.;
+    for (int i = 0; i != pol->num_samples; ++i)
+    {
+        /* Random::position(Box), Random.cpp:168-176 */
+        double ux = uniform(&g);
+        double uy = uniform(&g);
+        double uz = uniform(&g);
+        double x = box[0] + ux * (box[3] - box[0]);
+        double y = box[1] + uy * (box[4] - box[1]);
+        double z = box[2] + uz * (box[5] - box[2]);
+        double rhoi = 0.;
+        for (int h = 0; h < nmedia; ++h) rhoi += media[h].mass * geom_density(&media[h], x, y, z);
+        rhosum += rhoi;
+        if (rhoi < rhomin) rhomin = rhoi;
+        if (rhoi > rhomax) rhomax = rhoi;
+    }
+    double rho = rhosum / pol->num_samples;
+    double dx = box[3] - box[0], dy = box[4] - box[1], dz = box[5] - box[2];
+    double V = dx * dy * dz;
+    double M = rho * V;
+    if (pol->max_dust_fraction > 0. && M / dust_mass > pol->max_dust_fraction) return 1;
+    if (pol->max_dust_optical_depth > 0. && pol->dust_kappa * rho * sqrt(dx * dx + dy * dy + dz * dz) > pol->max_dust_optical_depth)
+        return 1;
+    if (pol->max_dust_density_dispersion > 0.)
+    {
+        double q = rhomax > 0 ? (rhomax - rhomin) / rhomax : 0.;
+        if (q > pol->max_dust_density_dispersion) return 1;
+    }
+    return 0;
+}
+
+/* DensityTreePolicy::constructTree, DensityTreePolicy.cpp:242-309: breadth-first, level by level; then the grid is set
+ * as by sko_set_grid_octree */
+int sko_build_octree(sko_engine_t* e, const double extent[6], const sk_tree_policy_t* pol, int32_t num_media,
+                     const sk_density_geometry_t* media, uint64_t* num_nodes, uint64_t* num_cells)
+{
+    if (!e || !extent || !pol || !media || num_media < 1) return fail(SK_ERR_INVALID, "bad tree policy");
+    double dust_mass = 0.;
+    for (int h = 0; h < num_media; ++h) dust_mass += media[h].mass;
+    size_t cap = 1024, nn = 1;
+    int32_t* fc = (int32_t*)malloc(cap * sizeof(int32_t));
+    int32_t* lev = (int32_t*)malloc(cap * sizeof(int32_t));
+    double* box = (double*)malloc(6 * cap * sizeof(double));
+    memcpy(box, extent, 6 * sizeof(double));
+    lev[0] = 0;
+    size_t lbeg = 0, lend = 1;
+    while (lend != lbeg)
+    {
+        for (size_t l = lbeg; l != lend; ++l)
+        {
+            fc[l] = -1;
+            if (!needs_subdivide(pol, num_media, media, dust_mass, (uint32_t)e->cfg.seed, (int)l, lev[l], box + 6 * l)) continue;
+            if (nn + 8 > cap)
+            {
+                cap *= 2;
+                fc = (int32_t*)realloc(fc, cap * sizeof(int32_t));
+                lev = (int32_t*)realloc(lev, cap * sizeof(int32_t));
+                box = (double*)realloc(box, 6 * cap * sizeof(double));
+            }
+            fc[l] = (int32_t)nn;
+            const double* b = box + 6 * l;
+            double cx = 0.5 * (b[0] + b[3]), cy = 0.5 * (b[1] + b[4]), cz = 0.5 * (b[2] + b[5]); /* Box.hpp:135 */
+            for (int c = 0; c < 8; ++c) /* OctTreeNode::createChildren, OctTreeNode.cpp:22-35 */
+            {
+                double* cb = box + 6 * (nn + c);
+                cb[0] = (c & 1) ? cx : b[0];
+                cb[3] = (c & 1) ? b[3] : cx;
+                cb[1] = (c & 2) ? cy : b[1];
+                cb[4] = (c & 2) ? b[4] : cy;
+                cb[2] = (c & 4) ? cz : b[2];
+                cb[5] = (c & 4) ? b[5] : cz;
+                lev[nn + c] = lev[l] + 1;
+            }
+            nn += 8;
+        }
+        lbeg = lend;
+        lend = nn;
+    }
+    int rc = sko_set_grid_octree(e, extent, (int32_t)nn, fc);
+    free(fc);
+    free(lev);
+    free(box);
+    if (rc) return rc;
+    if (num_nodes) *num_nodes = nn;
+    if (num_cells) *num_cells = (uint64_t)e->nx;
+    return SK_OK;
+}
+
+int sko_read_octree(sko_engine_t* e, int32_t* first_child)
+{
+    if (!e || !first_child || e->grid_kind != 2) return fail(SK_ERR_STATE, "the engine holds no octree");
+    memcpy(first_child, e->first_child, (size_t)e->nnodes * sizeof(int32_t));
+    return SK_OK;
+}
+
+/* MediumSystem::setupSelfAfter cell loop, MediumSystem.cpp:286-330, with PropertySampler (MediumSystem.cpp:46-106):
+ * samples from the stream (seed, "CELL") with counter = cell index */
+int sko_sample_medium(sko_engine_t* e, const sk_density_geometry_t* medium, int32_t num_samples)
+{
+    if (!e || !medium || num_samples < 1) return fail(SK_ERR_INVALID, "bad medium");
+    if (e->grid_kind != 1 && e->grid_kind != 2) return fail(SK_ERR_UNSUPPORTED, "density sampling needs a Cartesian or octree grid");
+    int nc = grid_num_cells(e);
+    free(e->dens);
+    free(e->vol);
+    e->dens = (double*)malloc((size_t)nc * sizeof(double));
+    e->vol = (double*)malloc((size_t)nc * sizeof(double));
+    e->ncells = nc;
+    for (int m = 0; m < nc; ++m)
+    {
+        double b[6];
+        if (e->grid_kind == 1)
+        {
+            int k = m % e->nz, j = (m / e->nz) % e->ny, i = m / (e->nz * e->ny);
+            b[0] = e->xv[i];
+            b[3] = e->xv[i + 1];
+            b[1] = e->yv[j];
+            b[4] = e->yv[j + 1];
+            b[2] = e->zv[k];
+            b[5] = e->zv[k + 1];
+        }
+        else
+            memcpy(b, e->node_box + 6 * (size_t)e->node_of_cell[m], sizeof b);
+        double n;
+        if (num_samples == 1)
+            n = medium->number * geom_density(medium, 0.5 * (b[0] + b[3]), 0.5 * (b[1] + b[4]), 0.5 * (b[2] + b[5]));
+        else
+        {
+            rng_t g;
+            rng_init(&g, (uint32_t)e->cfg.seed, 0x43454c4cu, (uint64_t)m);
+            double sum = 0.;
+            for (int i = 0; i != num_samples; ++i)
+            {
+                double ux = uniform(&g);
+                double uy = uniform(&g);
+                double uz = uniform(&g);
+                double x = b[0] + ux * (b[3] - b[0]);
+                double y = b[1] + uy * (b[4] - b[1]);
+                double z = b[2] + uz * (b[5] - b[2]);
+                sum += medium->number * geom_density(medium, x, y, z);
+            }
+            n = sum / num_samples;
+        }
+        e->dens[m] = n;
+        e->vol[m] = (b[3] - b[0]) * (b[4] - b[1]) * (b[5] - b[2]);
+    }
+    return SK_OK;
+}
+
+int sko_read_medium(sko_engine_t* e, double* number_density, double* volume)
+{
+    if (!e || !e->ncells) return fail(SK_ERR_STATE, "the engine holds no medium state");
+    if (number_density) memcpy(number_density, e->dens, (size_t)e->ncells * sizeof(double));
+    if (volume)
+    {
+        if (!e->vol) return fail(SK_ERR_STATE, "the engine holds no cell volumes");
+        memcpy(volume, e->vol, (size_t)e->ncells * sizeof(double));
+    }
+    return SK_OK;
+}
+
 int sko_set_dustmix(sko_engine_t* e, const sk_dustmix_t* mix)
 {
     if (!e || !mix || mix->num_lambda < 2) return fail(SK_ERR_INVALID, "bad dust mix");

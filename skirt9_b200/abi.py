@@ -73,6 +73,30 @@ class SkSecondary(C.Structure):
                 ("temperature", _dp), ("planck_abs", _dp), ("rf_sigma_abs", _dp), ("em_sigma_abs", _dp)]
 
 
+SK_DENSITY_MAX_PARAMS = 16
+
+
+class SkDensityGeometry(C.Structure):
+    _fields_ = [("geometry", C.c_int32), ("reserved", C.c_int32), ("number", C.c_double), ("mass", C.c_double),
+                ("p", C.c_double * SK_DENSITY_MAX_PARAMS)]
+
+    @classmethod
+    def make(cls, geometry, params, number=1.0, mass=1.0):
+        g = cls()
+        g.geometry, g.number, g.mass = int(geometry), float(number), float(mass)
+        if len(params) > SK_DENSITY_MAX_PARAMS:
+            raise ValueError("too many density parameters")
+        for k, v in enumerate(params):
+            g.p[k] = float(v)
+        return g
+
+
+class SkTreePolicy(C.Structure):
+    _fields_ = [("min_level", C.c_int32), ("max_level", C.c_int32), ("num_samples", C.c_int32), ("reserved", C.c_int32),
+                ("max_dust_fraction", C.c_double), ("max_dust_optical_depth", C.c_double),
+                ("max_dust_density_dispersion", C.c_double), ("dust_kappa", C.c_double)]
+
+
 class SkCounters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in
                 ("packets", "forward_paths", "forward_segments", "replay_segments", "peel_paths", "peel_segments",
@@ -113,6 +137,7 @@ ABI_FUNCTIONS = ["create", "destroy", "set_grid_cartesian", "set_grid_octree", "
                  "set_wavelength_grids", "set_sources", "set_instruments", "set_secondary", "clear_instruments", "clear_rf",
                  "prepare_primary", "prepare_secondary", "run_segment", "communicate_rf", "absorbed_luminosity",
                  "read_rf", "read_sed", "read_ifu", "read_sed_stats", "read_ifu_stats", "counters"]
+SETUP_FUNCTIONS = ["build_octree", "read_octree", "sample_medium", "read_medium"]
 ENGINE_ONLY_FUNCTIONS = ["launch_segment", "synchronize", "last_kernel_ms", "last_stage_ms", "device_buffer", "cuda_stream"]
 
 
@@ -130,6 +155,7 @@ class Engine:
         self.config = config
         self._call("create", C.byref(config), C.byref(self._h))
         self.num_cells = 0
+        self.num_nodes = 0
         self.num_rf = 0
         self._instr = []
         self._wlg = []
@@ -170,6 +196,32 @@ class Engine:
         ext, pe = _d(extent)
         fc, pf = _i(first_child)
         self._call("set_grid_octree", self._h, pe, C.c_int32(len(fc)), pf)
+        self.num_nodes = len(fc)
+
+    def build_octree(self, extent, policy: SkTreePolicy, media: Sequence[SkDensityGeometry]):
+        """DensityTreePolicy::constructTree on the engine's side; returns (num_nodes, num_cells)."""
+        ext, pe = _d(extent)
+        arr = (SkDensityGeometry * len(media))(*media)
+        nn, nc = C.c_uint64(), C.c_uint64()
+        self._call("build_octree", self._h, pe, C.byref(policy), C.c_int32(len(media)), arr, C.byref(nn), C.byref(nc))
+        self.num_nodes = int(nn.value)
+        self.num_grid_cells = int(nc.value)
+        return self.num_nodes, self.num_grid_cells
+
+    def read_octree(self):
+        out = np.empty(max(self.num_nodes, 1), dtype=np.int32)
+        self._call("read_octree", self._h, out.ctypes.data_as(_ip))
+        return out[:self.num_nodes]
+
+    def sample_medium(self, medium: SkDensityGeometry, num_samples: int, num_cells: int):
+        self._call("sample_medium", self._h, C.byref(medium), C.c_int32(num_samples))
+        self.num_cells = num_cells
+
+    def read_medium(self):
+        dens = np.empty(self.num_cells)
+        vol = np.empty(self.num_cells)
+        self._call("read_medium", self._h, dens.ctypes.data_as(_dp), vol.ctypes.data_as(_dp))
+        return dens, vol
 
     def set_grid_voronoi(self, extent, sites, nbr_offset, nbr_index):
         ext, pe = _d(extent)

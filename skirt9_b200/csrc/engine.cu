@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <array>
+#include <cfloat>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -11,6 +12,7 @@
 #include <vector>
 
 #include "sk_secondary.cuh"
+#include "sk_setup.cuh"
 #include "sk_wavefront.cuh"
 
 // ---------------------------------------------------------------------------------------------------
@@ -169,6 +171,7 @@ struct sk_engine {
     int num_sms = 0;
     double* scalar = nullptr;
     int table_len[3] = {0, 0, 0};
+    const int32_t* first_child_dev = nullptr;  // octree: first_child per node (owned by grid_allocs)
     size_t smem_bytes = 0;
     float last_ms = 0.f;
     bool timing_pending = false;
@@ -346,6 +349,56 @@ extern "C" int sk_engine_set_grid_cartesian(sk_engine_t* e, int32_t nx, int32_t 
 // midpoint arithmetic (Box::center, Box.hpp:135, applied recursively as OctTreeNode::createChildren does),
 // and for every cell the six same-level-or-coarser neighbour links that replace TreeNode::_neighbors
 // (OctTreeNode::addNeighbors, OctTreeNode.cpp:46-138).
+// lattice border tables by recursive midpoints: the doubles Box::center (Box.hpp:135) yields level by level
+static void midpoint_tables(const double extent[6], int N, std::vector<double> T[3])
+{
+    for (int a = 0; a < 3; ++a)
+    {
+        T[a].assign(N + 1, 0.);
+        T[a][0] = extent[a];
+        T[a][N] = extent[a + 3];
+        for (int s = N; s > 1; s >>= 1)
+            for (int lo = 0; lo < N; lo += s) T[a][lo + s / 2] = 0.5 * (T[a][lo] + T[a][lo + s]);
+    }
+}
+
+// Common tail of sk_engine_set_grid_octree and sk_engine_build_octree: the node arrays are on the device (d_first and
+// d_child already owned by grid_allocs, d_nodecoord = {ix,iy,iz,level} in units of the finest level, d_nodeofcell scratch)
+static int finish_octree(sk_engine* e, const double extent[6], int nn, int nc, int maxlev, const int32_t* d_first,
+                         const int32_t* d_child, const uint32_t* d_nodecoord, const int32_t* d_nodeofcell)
+{
+    const int N = 1 << maxlev;
+    std::vector<double> T[3];
+    midpoint_tables(extent, N, T);
+    e->grid_kind = 2;
+    e->M.grid_kind = 2;
+    e->M.nx = N;
+    e->M.ny = N;
+    e->M.nz = N;
+    e->M.maxlevel = maxlev;
+    e->M.nnodes = nn;
+    e->grid_cells = nc;
+    e->M.ncells = 0;
+    memcpy(e->M.ext, extent, 6 * sizeof(double));
+    double dx = extent[3] - extent[0], dy = extent[4] - extent[1], dz = extent[5] - extent[2];
+    e->M.eps = 1e-12 * sqrt(dx * dx + dy * dy + dz * dz);  // TreeSpatialGrid.cpp:28
+    uint32_t* d_coord;
+    SkCellRec* d_cells;
+    if (int rc = dalloc_zero(e->grid_allocs, 4 * (size_t)nc, &d_coord)) return rc;
+    if (int rc = dalloc_zero(e->grid_allocs, (size_t)nc, &d_cells)) return rc;
+    sk_build_links_kernel<<<(nc + 127) / 128, 128, 0, e->stream>>>(d_first, d_child, d_nodecoord, d_nodeofcell, nc, N, maxlev,
+                                                                  d_cells, d_coord);
+    cudaError_t err = cudaGetLastError();
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+    if (err != cudaSuccess) return fail(SK_ERR_CUDA, std::string("octree link builder: ") + cudaGetErrorString(err));
+    e->M.node_child = d_child;
+    e->M.cell_coord = d_coord;
+    e->M.cells = d_cells;
+    e->M.vrec = nullptr;
+    e->first_child_dev = d_first;
+    return set_tables(e, T[0].data(), N + 1, T[1].data(), N + 1, T[2].data(), N + 1);
+}
+
 extern "C" int sk_engine_set_grid_octree(sk_engine_t* e, const double extent[6], int32_t num_nodes,
                                          const int32_t* first_child)
 {
@@ -386,16 +439,6 @@ extern "C" int sk_engine_set_grid_octree(sk_engine_t* e, const double extent[6],
             iz[fc + c] = iz[l] + ((c & 4) ? half : 0);
         }
     }
-    // lattice border tables by recursive midpoints
-    std::vector<double> T[3];
-    for (int a = 0; a < 3; ++a)
-    {
-        T[a].assign(N + 1, 0.);
-        T[a][0] = extent[a];
-        T[a][N] = extent[a + 3];
-        for (int s = N; s > 1; s >>= 1)
-            for (int lo = 0; lo < N; lo += s) T[a][lo + s / 2] = 0.5 * (T[a][lo] + T[a][lo + s]);
-    }
     // cells
     std::vector<int> cell_of_node(nn, -1);
     std::vector<int> node_of_cell;
@@ -417,44 +460,16 @@ extern "C" int sk_engine_set_grid_octree(sk_engine_t* e, const double extent[6],
         node_coord[4 * (size_t)l + 3] = lev[l];
     }
     free_group(e->grid_allocs);
-    e->grid_kind = 2;
-    e->M.grid_kind = 2;
-    e->M.nx = N;
-    e->M.ny = N;
-    e->M.nz = N;
-    e->M.maxlevel = maxlev;
-    e->M.nnodes = nn;
-    e->grid_cells = nc;
-    e->M.ncells = 0;
-    memcpy(e->M.ext, extent, 6 * sizeof(double));
-    double dx = extent[3] - extent[0], dy = extent[4] - extent[1], dz = extent[5] - extent[2];
-    e->M.eps = 1e-12 * sqrt(dx * dx + dy * dy + dz * dz);  // TreeSpatialGrid.cpp:28
     int32_t *d_child, *d_first, *d_nodeofcell;
-    uint32_t *d_coord, *d_nodecoord;
-    SkCellRec* d_cells;
+    uint32_t* d_nodecoord;
     if (int rc = upload(e->grid_allocs, node_child.data(), (size_t)nn, &d_child)) return rc;
-    if (int rc = dalloc_zero(e->grid_allocs, 4 * (size_t)nc, &d_coord)) return rc;
-    if (int rc = dalloc_zero(e->grid_allocs, (size_t)nc, &d_cells)) return rc;
-    // the link builder runs on the device; its inputs are scratch
+    if (int rc = upload(e->grid_allocs, first_child, (size_t)nn, &d_first)) return rc;
     std::vector<void*> scratch;
-    int rc = upload(scratch, first_child, (size_t)nn, &d_first);
-    if (!rc) rc = upload(scratch, node_coord.data(), node_coord.size(), &d_nodecoord);
+    int rc = upload(scratch, node_coord.data(), node_coord.size(), &d_nodecoord);
     if (!rc) rc = upload(scratch, node_of_cell.data(), (size_t)nc, &d_nodeofcell);
-    if (!rc)
-    {
-        sk_build_links_kernel<<<(nc + 127) / 128, 128, 0, e->stream>>>(d_first, d_child, d_nodecoord, d_nodeofcell, nc, N,
-                                                                      maxlev, d_cells, d_coord);
-        cudaError_t err = cudaGetLastError();
-        if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
-        if (err != cudaSuccess) rc = fail(SK_ERR_CUDA, std::string("octree link builder: ") + cudaGetErrorString(err));
-    }
+    if (!rc) rc = finish_octree(e, extent, nn, nc, maxlev, d_first, d_child, d_nodecoord, d_nodeofcell);
     free_group(scratch);
-    if (rc) return rc;
-    e->M.node_child = d_child;
-    e->M.cell_coord = d_coord;
-    e->M.cells = d_cells;
-    e->M.vrec = nullptr;
-    return set_tables(e, T[0].data(), N + 1, T[1].data(), N + 1, T[2].data(), N + 1);
+    return rc;
 }
 
 // VoronoiMeshSnapshot as built by the reference's setup (sites + neighbour lists); the engine adds the start-cell table of
@@ -570,6 +585,265 @@ extern "C" int sk_engine_set_medium(sk_engine_t* e, int32_t num_cells, const dou
         if (int rc = upload(e->medium_allocs, volume, (size_t)num_cells, &v)) return rc;
         e->M.volume = v;
     }
+    return SK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// setup on the device (sk_setup.cuh)
+// ---------------------------------------------------------------------------------------------------
+static int to_dev_geom(const sk_density_geometry_t& in, SkDevGeom& out)
+{
+    if (in.geometry < SK_GEOM_SHELL || in.geometry > SK_GEOM_SPIRAL_EXPDISK)
+        return fail(SK_ERR_UNSUPPORTED, "geometry kind without a device density function");
+    out.kind = in.geometry;
+    out.pad = 0;
+    out.number = in.number;
+    out.mass = in.mass;
+    memcpy(out.p, in.p, sizeof out.p);
+    return SK_OK;
+}
+// exclusive scan of n int32 on the engine's stream; sums = scratch for ceil(n/1024) block sums, total = device int32
+static int exclusive_scan(sk_engine* e, const int32_t* in, int32_t* out, int n, int32_t* sums, int32_t* total)
+{
+    const int nb = (n + SK_SCAN_BLOCK - 1) / SK_SCAN_BLOCK;
+    sk_scan_block_kernel<<<nb, SK_SCAN_BLOCK, 0, e->stream>>>(in, out, sums, n);
+    sk_scan_sums_kernel<<<1, SK_SCAN_BLOCK, 0, e->stream>>>(sums, nb, total);
+    sk_scan_add_kernel<<<nb, SK_SCAN_BLOCK, 0, e->stream>>>(out, sums, n);
+    CK(cudaGetLastError());
+    return SK_OK;
+}
+namespace
+{
+    // device arrays of the growing node list
+    struct TreeArrays {
+        uint4* coord = nullptr;
+        int32_t* first = nullptr;
+        size_t cap = 0;
+        ~TreeArrays()
+        {
+            cudaFree(coord);
+            cudaFree(first);
+        }
+    };
+}
+static int grow_tree(sk_engine* e, TreeArrays& A, size_t need, size_t used)
+{
+    if (need <= A.cap) return SK_OK;
+    size_t cap = std::max<size_t>(need, 2 * A.cap);
+    uint4* c = nullptr;
+    int32_t* f = nullptr;
+    CK(cudaMalloc(&c, cap * sizeof(uint4)));
+    cudaError_t err = cudaMalloc(&f, cap * sizeof(int32_t));
+    if (err != cudaSuccess)
+    {
+        cudaFree(c);
+        return fail(SK_ERR_CUDA, std::string("octree node list: ") + cudaGetErrorString(err));
+    }
+    if (used)
+    {
+        cudaMemcpyAsync(c, A.coord, used * sizeof(uint4), cudaMemcpyDeviceToDevice, e->stream);
+        cudaMemcpyAsync(f, A.first, used * sizeof(int32_t), cudaMemcpyDeviceToDevice, e->stream);
+        cudaStreamSynchronize(e->stream);
+    }
+    cudaFree(A.coord);
+    cudaFree(A.first);
+    A.coord = c;
+    A.first = f;
+    A.cap = cap;
+    return SK_OK;
+}
+
+extern "C" int sk_engine_build_octree(sk_engine_t* e, const double extent[6], const sk_tree_policy_t* policy, int32_t num_media,
+                                      const sk_density_geometry_t* media, uint64_t* num_nodes, uint64_t* num_cells)
+{
+    if (!e || !extent || !policy || !media) return fail(SK_ERR_INVALID, "null argument");
+    if (num_media < 1 || num_media > SK_SETUP_MAX_MEDIA) return fail(SK_ERR_UNSUPPORTED, "1..8 media components");
+    if (policy->min_level < 0 || policy->max_level < policy->min_level) return fail(SK_ERR_INVALID, "bad tree levels");
+    if (policy->max_level > SK_MAX_TREE_LEVEL) return fail(SK_ERR_UNSUPPORTED, "octree deeper than 15 levels");
+    if (policy->num_samples < 1) return fail(SK_ERR_INVALID, "numDensitySamples must be positive");
+    if (!(extent[3] > extent[0] && extent[4] > extent[1] && extent[5] > extent[2])) return fail(SK_ERR_INVALID, "empty extent");
+    CK(cudaSetDevice(e->cfg.device));
+    SkDevGeomSet G;
+    memset(&G, 0, sizeof G);
+    G.n = num_media;
+    double dust_mass = 0.;
+    for (int h = 0; h < num_media; ++h)
+    {
+        if (int rc = to_dev_geom(media[h], G.g[h])) return rc;
+        dust_mass += media[h].mass;  // DensityTreePolicy::_dustMass, DensityTreePolicy.cpp:84-86
+    }
+    if (!(dust_mass > 0.)) return fail(SK_ERR_INVALID, "the media hold no dust mass");
+
+    const int maxL = policy->max_level, NL = 1 << maxL;
+    std::vector<double> T[3];
+    midpoint_tables(extent, NL, T);
+    std::vector<void*> scratch;
+    struct Guard {
+        std::vector<void*>& v;
+        ~Guard() { free_group(v); }
+    } guard{scratch};
+    double *dx, *dy, *dz;
+    if (int rc = upload(scratch, T[0].data(), T[0].size(), &dx)) return rc;
+    if (int rc = upload(scratch, T[1].data(), T[1].size(), &dy)) return rc;
+    if (int rc = upload(scratch, T[2].data(), T[2].size(), &dz)) return rc;
+    int32_t* d_total;
+    if (int rc = dalloc_zero(scratch, 1, &d_total)) return rc;
+    SkTreeBuild B;
+    B.xv = dx;
+    B.yv = dy;
+    B.zv = dz;
+    B.N = NL;
+    B.min_level = policy->min_level;
+    B.max_level = policy->max_level;
+    B.num_samples = policy->num_samples;
+    B.max_fraction = policy->max_dust_fraction;
+    B.max_tau = policy->max_dust_optical_depth;
+    B.max_dispersion = policy->max_dust_density_dispersion;
+    B.kappa = policy->dust_kappa;
+    B.dust_mass = dust_mass;
+    B.seed = (uint32_t)e->cfg.seed;
+
+    TreeArrays A;
+    if (int rc = grow_tree(e, A, 1 << 16, 0)) return rc;
+    const uint4 root = make_uint4(0, 0, 0, 0);
+    CK(cudaMemcpyAsync(A.coord, &root, sizeof root, cudaMemcpyHostToDevice, e->stream));
+    // level-wise scratch, grown with the widest level
+    int32_t *d_divide = nullptr, *d_rank = nullptr, *d_sums = nullptr;
+    size_t level_cap = 0;
+    std::vector<void*> level_scratch;
+    Guard guard2{level_scratch};
+    size_t lbeg = 0, lend = 1;
+    int level = 0, maxlev = 0;
+    while (lend != lbeg)  // DensityTreePolicy::constructTree, DensityTreePolicy.cpp:260-303
+    {
+        const int n = (int)(lend - lbeg);
+        if ((size_t)n > level_cap)
+        {
+            free_group(level_scratch);
+            level_cap = std::max<size_t>(2 * (size_t)n, 1 << 16);
+            if (int rc = dalloc_zero(level_scratch, level_cap, &d_divide)) return rc;
+            if (int rc = dalloc_zero(level_scratch, level_cap, &d_rank)) return rc;
+            if (int rc = dalloc_zero(level_scratch, level_cap / SK_SCAN_BLOCK + 2, &d_sums)) return rc;
+        }
+        sk_tree_evaluate_kernel<<<(n + 127) / 128, 128, 0, e->stream>>>(B, G, A.coord, (int)lbeg, (int)lend, d_divide);
+        CK(cudaGetLastError());
+        if (int rc = exclusive_scan(e, d_divide, d_rank, n, d_sums, d_total)) return rc;
+        int32_t ndiv = 0;
+        CK(cudaMemcpyAsync(&ndiv, d_total, sizeof ndiv, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        const size_t nn_new = lend + 8 * (size_t)ndiv;
+        if (nn_new > (size_t)SK_LINK_INDEX_MASK) return fail(SK_ERR_UNSUPPORTED, "octree with more than 2^26 nodes");
+        if (int rc = grow_tree(e, A, nn_new, lend)) return rc;
+        sk_tree_subdivide_kernel<<<(n + 127) / 128, 128, 0, e->stream>>>(NL, A.coord, A.first, (int)lbeg, (int)lend, d_divide,
+                                                                        d_rank);
+        CK(cudaGetLastError());
+        if (ndiv) maxlev = level + 1;
+        level++;
+        lbeg = lend;
+        lend = nn_new;
+    }
+    const int nn = (int)lend;
+    // cells = leaves in node order; lattice coordinates in units of the deepest level reached
+    int32_t *d_leaf, *d_cellrank, *d_sums2, *d_child, *d_first, *d_nodeofcell;
+    if (int rc = dalloc_zero(scratch, (size_t)nn, &d_leaf)) return rc;
+    if (int rc = dalloc_zero(scratch, (size_t)nn, &d_cellrank)) return rc;
+    if (int rc = dalloc_zero(scratch, (size_t)nn / SK_SCAN_BLOCK + 2, &d_sums2)) return rc;
+    sk_tree_leaf_flags_kernel<<<(nn + 255) / 256, 256, 0, e->stream>>>(A.coord, A.first, nn, maxL - maxlev, d_leaf);
+    CK(cudaGetLastError());
+    if (int rc = exclusive_scan(e, d_leaf, d_cellrank, nn, d_sums2, d_total)) return rc;
+    int32_t nc = 0;
+    CK(cudaMemcpyAsync(&nc, d_total, sizeof nc, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    free_group(e->grid_allocs);
+    if (int rc = dalloc_zero(e->grid_allocs, (size_t)nn, &d_child)) return rc;
+    if (int rc = dalloc_zero(e->grid_allocs, (size_t)nn, &d_first)) return rc;
+    if (int rc = dalloc_zero(scratch, (size_t)nc, &d_nodeofcell)) return rc;
+    CK(cudaMemcpyAsync(d_first, A.first, (size_t)nn * sizeof(int32_t), cudaMemcpyDeviceToDevice, e->stream));
+    sk_tree_number_cells_kernel<<<(nn + 255) / 256, 256, 0, e->stream>>>(A.first, d_cellrank, nn, d_child, d_nodeofcell);
+    CK(cudaGetLastError());
+    if (int rc = finish_octree(e, extent, nn, nc, maxlev, d_first, d_child, reinterpret_cast<const uint32_t*>(A.coord), d_nodeofcell))
+        return rc;
+    if (num_nodes) *num_nodes = (uint64_t)nn;
+    if (num_cells) *num_cells = (uint64_t)nc;
+    return SK_OK;
+}
+
+extern "C" int sk_engine_read_octree(sk_engine_t* e, int32_t* first_child)
+{
+    if (!e || !first_child) return fail(SK_ERR_INVALID, "null argument");
+    if (e->grid_kind != 2 || !e->first_child_dev) return fail(SK_ERR_STATE, "the engine holds no octree");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaMemcpyAsync(first_child, e->first_child_dev, (size_t)e->M.nnodes * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return SK_OK;
+}
+
+extern "C" int sk_engine_sample_medium(sk_engine_t* e, const sk_density_geometry_t* medium, int32_t num_samples)
+{
+    if (!e || !medium) return fail(SK_ERR_INVALID, "null argument");
+    if (num_samples < 1) return fail(SK_ERR_INVALID, "numDensitySamples must be positive");
+    if (e->grid_kind != 1 && e->grid_kind != 2)
+        return fail(e->grid_kind ? SK_ERR_UNSUPPORTED : SK_ERR_STATE, "density sampling needs a Cartesian or octree grid");
+    SkDevGeom g;
+    if (int rc = to_dev_geom(*medium, g)) return rc;
+    CK(cudaSetDevice(e->cfg.device));
+    free_group(e->medium_allocs);
+    const int nc = e->grid_cells;
+    double *d_vol, *d_dens = nullptr;
+    if (int rc = dalloc_zero(e->medium_allocs, (size_t)nc, &d_vol)) return rc;
+    if (e->grid_kind == 1)
+    {
+        if (int rc = dalloc_zero(e->medium_allocs, (size_t)nc, &d_dens)) return rc;
+        sk_sample_medium_kernel<1><<<(nc + 127) / 128, 128, 0, e->stream>>>(e->M, g, num_samples, (uint32_t)e->cfg.seed, nc, nullptr,
+                                                                            d_dens, d_vol);
+    }
+    else
+        sk_sample_medium_kernel<2><<<(nc + 127) / 128, 128, 0, e->stream>>>(e->M, g, num_samples, (uint32_t)e->cfg.seed, nc,
+                                                                            const_cast<SkCellRec*>(e->M.cells), nullptr, d_vol);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->stream));
+    e->dens_host.clear();
+    e->M.dens = d_dens;
+    e->M.volume = d_vol;
+    e->M.ncells = nc;
+    e->l2_policy_set = false;
+    return SK_OK;
+}
+
+extern "C" int sk_engine_read_medium(sk_engine_t* e, double* number_density, double* volume)
+{
+    if (!e) return fail(SK_ERR_INVALID, "null argument");
+    if (!e->M.ncells) return fail(SK_ERR_STATE, "the engine holds no medium state");
+    CK(cudaSetDevice(e->cfg.device));
+    const int nc = e->M.ncells;
+    if (number_density)
+    {
+        if (e->M.dens)
+            CK(cudaMemcpyAsync(number_density, e->M.dens, (size_t)nc * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+        else
+        {
+            std::vector<void*> scratch;
+            double* d;
+            int rc = dalloc_zero(scratch, (size_t)nc, &d);
+            if (!rc)
+            {
+                sk_gather_density_kernel<<<(nc + 255) / 256, 256, 0, e->stream>>>(e->M.cells, e->M.vrec, nc, d);
+                cudaError_t err = cudaGetLastError();
+                if (err == cudaSuccess)
+                    err = cudaMemcpyAsync(number_density, d, (size_t)nc * sizeof(double), cudaMemcpyDeviceToHost, e->stream);
+                if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+                if (err != cudaSuccess) rc = fail(SK_ERR_CUDA, std::string("read medium: ") + cudaGetErrorString(err));
+            }
+            free_group(scratch);
+            if (rc) return rc;
+        }
+    }
+    if (volume)
+    {
+        if (!e->M.volume) return fail(SK_ERR_STATE, "the engine holds no cell volumes");
+        CK(cudaMemcpyAsync(volume, e->M.volume, (size_t)nc * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    }
+    CK(cudaStreamSynchronize(e->stream));
     return SK_OK;
 }
 

@@ -1,0 +1,343 @@
+// sk_setup.cuh -- setup on the device: octree construction by the density policy and sampling of the
+// medium state, the two steps of the reference's setup that scale with the number of cells.
+//
+//   DensityTreePolicy::constructTree / needsSubdivide     SKIRT/core/DensityTreePolicy.cpp:116-309
+//   OctTreeNode::createChildren                           SKIRT/core/OctTreeNode.cpp:22-35
+//   MediumSystem::setupSelfAfter (cell loop)              SKIRT/core/MediumSystem.cpp:286-330, PropertySampler :46-106
+//   Geometry::density of the supported geometries         ShellGeometry.cpp:30-36, ExpDiskGeometry.cpp:32-42,
+//                                                         RingGeometry.cpp:39-43, SpiralStructureGeometryDecorator.cpp:24-29,71-75
+//
+// The tree grows level by level like the reference's node list: one thread evaluates one node of the level (its samples
+// in sequence, so that the sum has the order of the reference's loop), an exclusive scan of the flags ranks the nodes to
+// divide, and the children are appended in that order -- the breadth-first node numbering of constructTree.  Node boxes
+// are never stored: a node is its lattice coordinate at the finest level the policy allows, and its borders are entries
+// of the per-axis midpoint tables (the same doubles the reference obtains from Box::center recursively).
+#pragma once
+#include "sk_device.cuh"
+
+#define SK_SETUP_MAX_MEDIA 8
+#define SK_STREAM_TREE 0x54524545u  // "TREE"
+#define SK_STREAM_CELL 0x43454c4cu  // "CELL"
+
+struct SkDevGeom {
+    int32_t kind, pad;
+    double number, mass;
+    double p[SK_DENSITY_MAX_PARAMS];
+};
+struct SkDevGeomSet {
+    int32_t n, pad;
+    SkDevGeom g[SK_SETUP_MAX_MEDIA];
+};
+
+// Geometry::density(Position) of a normalised geometry
+__device__ __forceinline__ double sk_geom_density(const SkDevGeom& g, double x, double y, double z)
+{
+    const double* p = g.p;
+    switch (g.kind)
+    {
+        case SK_GEOM_SHELL:
+        {
+            // SpheGeometry::density(Position) -> ShellGeometry::density(r), ShellGeometry.cpp:30-36
+            double r = sqrt(x * x + y * y + z * z);
+            if (r < p[0] || r > p[1]) return 0.0;
+            return p[3] * pow(r, -p[2]);
+        }
+        case SK_GEOM_EXPDISK:
+        case SK_GEOM_SPIRAL_EXPDISK:
+        {
+            // ExpDiskGeometry::density(R,z), ExpDiskGeometry.cpp:32-42
+            double R = sqrt(x * x + y * y);
+            double absz = fabs(z);
+            double rho;
+            if (p[3] > 0.0 && R > p[3])
+                rho = 0.0;
+            else if (p[4] > 0.0 && absz > p[4])
+                rho = 0.0;
+            else if (R < p[2])
+                rho = 0.0;
+            else
+                rho = p[5] * exp(-R / p[0]) * exp(-absz / p[1]);
+            if (g.kind == SK_GEOM_EXPDISK) return rho;
+            // SpiralStructureGeometryDecorator::density / perturbation, .cpp:24-29,71-75; Vec::cylindrical: phi = atan2(y,x)
+            double phi = atan2(y, x);
+            double m = p[6], tanp = p[7], R0 = p[8], phi0 = p[9], w = p[10], N = p[11], cn = p[12];
+            double gamma = log(R / R0) / tanp + phi0 + 0.5 * M_PI / m;
+            double perturbation = (1.0 - w) + w * cn * pow(sin(0.5 * m * (gamma - phi)), 2 * N);
+            return rho * perturbation;
+        }
+        case SK_GEOM_RING:
+        {
+            // RingGeometry::density(R,z), RingGeometry.cpp:39-43
+            double R = sqrt(x * x + y * y);
+            double u = (R - p[0]) / (M_SQRT2 * p[1]);
+            return p[3] * exp(-u * u) * exp(-fabs(z) / p[2]);
+        }
+    }
+    return 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// exclusive scan of int32 flags (three passes; block = 1024 items)
+// ---------------------------------------------------------------------------------------------------
+#define SK_SCAN_BLOCK 1024
+__global__ void __launch_bounds__(SK_SCAN_BLOCK) sk_scan_block_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out,
+                                                                      int32_t* __restrict__ block_sum, int n)
+{
+    __shared__ int32_t warp_sum[32];
+    const int i = blockIdx.x * SK_SCAN_BLOCK + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int32_t v = i < n ? in[i] : 0;
+    int32_t incl = v;
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        int32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sum[warp] = incl;
+    __syncthreads();
+    if (warp == 0)
+    {
+        int32_t w = warp_sum[lane];
+        int32_t wi = w;
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            int32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        warp_sum[lane] = wi - w;  // exclusive over warps
+        if (lane == 31) block_sum[blockIdx.x] = wi;
+    }
+    __syncthreads();
+    if (i < n) out[i] = warp_sum[warp] + incl - v;
+}
+// one block: exclusive scan of the block sums in place, total to *total
+__global__ void __launch_bounds__(SK_SCAN_BLOCK) sk_scan_sums_kernel(int32_t* __restrict__ block_sum, int nblocks,
+                                                                     int32_t* __restrict__ total)
+{
+    __shared__ int32_t warp_sum[32];
+    __shared__ int32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < nblocks; base += SK_SCAN_BLOCK)
+    {
+        const int i = base + threadIdx.x;
+        int32_t v = i < nblocks ? block_sum[i] : 0;
+        int32_t incl = v;
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            int32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_sum[warp] = incl;
+        __syncthreads();
+        if (warp == 0)
+        {
+            int32_t w = warp_sum[lane];
+            int32_t wi = w;
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                int32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            warp_sum[lane] = wi - w;
+        }
+        __syncthreads();
+        const int32_t c = carry;
+        if (i < nblocks) block_sum[i] = c + warp_sum[warp] + incl - v;
+        __syncthreads();
+        if (threadIdx.x == SK_SCAN_BLOCK - 1) carry = c + warp_sum[warp] + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+__global__ void __launch_bounds__(SK_SCAN_BLOCK) sk_scan_add_kernel(int32_t* __restrict__ out,
+                                                                    const int32_t* __restrict__ block_sum, int n)
+{
+    const int i = blockIdx.x * SK_SCAN_BLOCK + threadIdx.x;
+    if (i < n) out[i] += block_sum[blockIdx.x];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// octree construction
+// ---------------------------------------------------------------------------------------------------
+struct SkTreeBuild {
+    const double *xv, *yv, *zv;  // midpoint tables at the policy's finest level, N+1 entries each
+    int N;                       // 1 << max_level
+    int min_level, max_level, num_samples;
+    double max_fraction, max_tau, max_dispersion, kappa, dust_mass;
+    uint32_t seed;
+};
+
+// DensityTreePolicy::needsSubdivide for the nodes [lbeg, lend) of one level, DensityTreePolicy.cpp:116-227
+__global__ void __launch_bounds__(128) sk_tree_evaluate_kernel(SkTreeBuild B, SkDevGeomSet G, const uint4* __restrict__ coord,
+                                                               int lbeg, int lend, int32_t* __restrict__ divide)
+{
+    const int l = lbeg + blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= lend) return;
+    const uint4 c = coord[l];
+    const int lev = (int)c.w;
+    int flag = 0;
+    if (lev < B.min_level)
+        flag = 1;
+    else if (lev < B.max_level)
+    {
+        const int size = B.N >> lev;
+        const double xmin = B.xv[c.x], xmax = B.xv[c.x + size];
+        const double ymin = B.yv[c.y], ymax = B.yv[c.y + size];
+        const double zmin = B.zv[c.z], zmax = B.zv[c.z + size];
+        SkRng g;
+        sk_rng_init(g, B.seed, SK_STREAM_TREE, (unsigned long long)l, 0);
+        double rhosum = 0., rhomin = DBL_MAX, rhomax = 0.;
+        for (int i = 0; i != B.num_samples; ++i)
+        {
+            // Random::position(Box), Random.cpp:168-176 with Box::fracPos
+            double ux = sk_uniform(g);
+            double uy = sk_uniform(g);
+            double uz = sk_uniform(g);
+            double x = xmin + ux * (xmax - xmin);
+            double y = ymin + uy * (ymax - ymin);
+            double z = zmin + uz * (zmax - zmin);
+            double rhoi = 0.;
+            for (int h = 0; h < G.n; ++h) rhoi += G.g[h].mass * sk_geom_density(G.g[h], x, y, z);
+            rhosum += rhoi;
+            if (rhoi < rhomin) rhomin = rhoi;
+            if (rhoi > rhomax) rhomax = rhoi;
+        }
+        const double rho = rhosum / B.num_samples;
+        const double dx = xmax - xmin, dy = ymax - ymin, dz = zmax - zmin;
+        const double V = dx * dy * dz;  // Box::volume
+        const double M = rho * V;
+        if (B.max_fraction > 0. && M / B.dust_mass > B.max_fraction) flag = 1;
+        if (B.max_tau > 0. && B.kappa * rho * sqrt(dx * dx + dy * dy + dz * dz) > B.max_tau) flag = 1;
+        if (B.max_dispersion > 0.)
+        {
+            double q = rhomax > 0 ? (rhomax - rhomin) / rhomax : 0.;
+            if (q > B.max_dispersion) flag = 1;
+        }
+    }
+    divide[l - lbeg] = flag;
+}
+
+// TreeNode::subdivide -> OctTreeNode::createChildren (OctTreeNode.cpp:22-35) for the flagged nodes of the level; the
+// children of the r-th flagged node become nodes lend + 8r .. lend + 8r + 7 (child c: bit 0 = upper x half, bit 1 = y,
+// bit 2 = z)
+__global__ void __launch_bounds__(128) sk_tree_subdivide_kernel(int N, uint4* __restrict__ coord, int32_t* __restrict__ first_child,
+                                                                int lbeg, int lend, const int32_t* __restrict__ divide,
+                                                                const int32_t* __restrict__ rank)
+{
+    const int l = lbeg + blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= lend) return;
+    if (!divide[l - lbeg])
+    {
+        first_child[l] = -1;
+        return;
+    }
+    const int fc = lend + 8 * rank[l - lbeg];
+    first_child[l] = fc;
+    const uint4 c = coord[l];
+    const unsigned half = (unsigned)(N >> ((int)c.w + 1));
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch)
+        coord[fc + ch] = make_uint4(c.x + ((ch & 1) ? half : 0u), c.y + ((ch & 2) ? half : 0u), c.z + ((ch & 4) ? half : 0u),
+                                    c.w + 1u);
+}
+
+// after the last level: rescale the lattice coordinates to the deepest level actually reached, flag the leaves
+__global__ void sk_tree_leaf_flags_kernel(uint4* __restrict__ coord, const int32_t* __restrict__ first_child, int nn, int shift,
+                                          int32_t* __restrict__ leaf)
+{
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nn) return;
+    if (shift)
+    {
+        uint4 c = coord[l];
+        c.x >>= shift;
+        c.y >>= shift;
+        c.z >>= shift;
+        coord[l] = c;
+    }
+    leaf[l] = first_child[l] < 0 ? 1 : 0;
+}
+// TreeSpatialGrid::_cellindexv / _idv (TreeSpatialGrid.cpp:40-48): cells are the leaves in node order
+__global__ void sk_tree_number_cells_kernel(const int32_t* __restrict__ first_child, const int32_t* __restrict__ cell_rank, int nn,
+                                            int32_t* __restrict__ node_child, int32_t* __restrict__ node_of_cell)
+{
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nn) return;
+    const int fc = first_child[l];
+    if (fc >= 0)
+        node_child[l] = fc;
+    else
+    {
+        const int m = cell_rank[l];
+        node_child[l] = -(m + 1);
+        node_of_cell[m] = l;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// medium state: volume and sampled number density per cell, MediumSystem.cpp:286-330 with PropertySampler :80-106
+// ---------------------------------------------------------------------------------------------------
+template <int GRID>
+__global__ void __launch_bounds__(128) sk_sample_medium_kernel(SkDevModel M, SkDevGeom g, int num_samples, uint32_t seed, int ncells,
+                                                               SkCellRec* __restrict__ cells, double* __restrict__ dens,
+                                                               double* __restrict__ volume)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= ncells) return;
+    int ix, iy, iz, size;
+    if (GRID == 1)
+    {
+        // m = k + Nz*j + Nz*Ny*i, CartesianSpatialGrid.cpp:210-213
+        iz = m % M.nz;
+        iy = (m / M.nz) % M.ny;
+        ix = m / (M.nz * M.ny);
+        size = 1;
+    }
+    else
+    {
+        const uint4 c = reinterpret_cast<const uint4*>(M.cell_coord)[m];
+        ix = (int)c.x;
+        iy = (int)c.y;
+        iz = (int)c.z;
+        size = 1 << (M.maxlevel - (int)c.w);
+    }
+    const double xmin = M.xv[ix], xmax = M.xv[ix + size];
+    const double ymin = M.yv[iy], ymax = M.yv[iy + size];
+    const double zmin = M.zv[iz], zmax = M.zv[iz + size];
+    double n;
+    if (num_samples == 1)
+    {
+        // SpatialGrid::centralPositionInCell = Box::center, Box.hpp:135
+        n = g.number * sk_geom_density(g, 0.5 * (xmin + xmax), 0.5 * (ymin + ymax), 0.5 * (zmin + zmax));
+    }
+    else
+    {
+        SkRng r;
+        sk_rng_init(r, seed, SK_STREAM_CELL, (unsigned long long)m, 0);
+        double sum = 0.;
+        for (int i = 0; i != num_samples; ++i)
+        {
+            double ux = sk_uniform(r);
+            double uy = sk_uniform(r);
+            double uz = sk_uniform(r);
+            double x = xmin + ux * (xmax - xmin);
+            double y = ymin + uy * (ymax - ymin);
+            double z = zmin + uz * (zmax - zmin);
+            sum += g.number * sk_geom_density(g, x, y, z);
+        }
+        n = sum / num_samples;
+    }
+    volume[m] = (xmax - xmin) * (ymax - ymin) * (zmax - zmin);
+    if (GRID == 1)
+        dens[m] = n;
+    else
+        cells[m].dens = n;
+}
+__global__ void sk_gather_density_kernel(const SkCellRec* __restrict__ cells, const double4* __restrict__ vrec, int ncells,
+                                         double* __restrict__ out)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m < ncells) out[m] = cells ? cells[m].dens : vrec[m].w;
+}

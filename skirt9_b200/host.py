@@ -10,6 +10,7 @@ All quantities are SI, like the reference's internal units (`SKIRT/utils/Constan
 from __future__ import annotations
 
 import math
+import time
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence
 
@@ -177,6 +178,9 @@ class ShellGeometry:
     def SigmaZ(self):
         return 2.0 * self.A * float(gln2(self.p, self.rmax, self.rmin))
 
+    def density_fields(self):
+        return abi.SK_GEOM_SHELL, [self.rmin, self.rmax, self.p, self.A]
+
     def source_fields(self):
         return {"geometry": abi.SK_GEOM_SHELL,
                 "geom_params": [self.rmin, self.rmax, self.p, self.smin, self.sdiff, self.tmin, self.tmax]}
@@ -214,6 +218,9 @@ class ExpDiskGeometry:
             return -2.0 * self.rho0 * self.hz * math.expm1(-self.zmax / self.hz)
         return 2.0 * self.rho0 * self.hz
 
+    def density_fields(self):
+        return abi.SK_GEOM_EXPDISK, [self.hR, self.hz, self.Rmin, self.Rmax, self.zmax, self.rho0]
+
     def source_fields(self):
         return {"geometry": abi.SK_GEOM_EXPDISK, "geom_params": [self.hR, self.hz, self.Rmin, self.Rmax, self.zmax]}
 
@@ -243,6 +250,9 @@ class RingGeometry:
         t = self.R0 / (math.sqrt(2.0) * self.w)
         return 2.0 * self.A * self.hz * math.exp(-t * t)
 
+    def density_fields(self):
+        return abi.SK_GEOM_RING, [self.R0, self.w, self.hz, self.A]
+
     def source_fields(self):
         return {"geometry": abi.SK_GEOM_RING, "geom_params": [self.R0, self.w, self.hz],
                 "geom_table_x": self.Rv, "geom_table_P": self.Xv}
@@ -270,6 +280,11 @@ class SpiralStructureGeometryDecorator:
 
     def SigmaZ(self):
         return self.geometry.SigmaZ()
+
+    def density_fields(self):
+        g = self.geometry
+        return abi.SK_GEOM_SPIRAL_EXPDISK, [g.hR, g.hz, g.Rmin, g.Rmax, g.zmax, g.rho0, self.m, self.tanp, self.R0,
+                                            self.phi0, self.w, self.N, self.cn]
 
     def source_fields(self):
         g = self.geometry
@@ -391,6 +406,11 @@ class GeometricMedium:
     def number_density(self, x, y, z):
         return self.number * self.geometry.density(x, y, z)
 
+    def density_geometry(self):
+        """The medium as sk_engine_build_octree / sk_engine_sample_medium take it (include/sk_engine.h)."""
+        kind, params = self.geometry.density_fields()
+        return abi.SkDensityGeometry.make(kind, params, self.number, self.mass)
+
 
 # ---------------------------------------------------------------------------------------------------
 # spatial grids
@@ -494,6 +514,39 @@ class PolicyTreeSpatialGrid:
 
     def configure(self, engine):
         engine.set_grid_octree(self.extent, self.first_child)
+
+    def tree_policy(self, num_density_samples):
+        pol = self.policy
+        return abi.SkTreePolicy(pol.minLevel, pol.maxLevel, num_density_samples, 0, pol.maxDustFraction, 0.0, 0.0, 0.0)
+
+    def adopt(self, first_child):
+        """Takes over a node list built elsewhere (sk_engine_build_octree) and derives the node boxes from it."""
+        self.first_child = np.asarray(first_child, dtype=np.int32)
+        self.boxes = boxes_from_first_child(self.extent, self.first_child)
+
+
+def boxes_from_first_child(extent, first_child):
+    """Node boxes of a breadth-first octree node list by Box::center recursion (Box.hpp:135, OctTreeNode.cpp:22-35)."""
+    fc = np.asarray(first_child, dtype=np.int64)
+    boxes = np.empty((len(fc), 6))
+    boxes[0] = extent
+    level = np.array([0])
+    while len(level):
+        par = level[fc[level] >= 0]
+        if not len(par):
+            break
+        b = boxes[par]
+        c = 0.5 * (b[:, :3] + b[:, 3:])
+        kids = np.empty((len(par), 8, 6))
+        for ch in range(8):
+            for ax in range(3):
+                hi = (ch >> ax) & 1
+                kids[:, ch, ax] = c[:, ax] if hi else b[:, ax]
+                kids[:, ch, ax + 3] = b[:, ax + 3] if hi else c[:, ax]
+        idx = (fc[par][:, None] + np.arange(8)[None, :]).ravel()
+        boxes[idx] = kids.reshape(-1, 6)
+        level = idx
+    return boxes
 
 
 class FileTreeSpatialGrid(PolicyTreeSpatialGrid):
@@ -783,6 +836,9 @@ class MonteCarloSimulation:
     secondaryPacketsMultiplier: float = 1.0
     secondaryIterationPacketsMultiplier: float = 1.0
     setup_seed: int = 12345  # host-side sampling of densities / tree policy (numpy RNG)
+    # build the octree and sample the medium state on the engine's side
+    # (sk_engine_build_octree / sk_engine_sample_medium) instead of with the numpy code of setup()
+    deviceSetup: bool = False
     density: Optional[np.ndarray] = field(default=None, repr=False)
 
     def setup(self):
@@ -821,6 +877,14 @@ class MonteCarloSimulation:
         for s in self.sources:
             s.sed.setup(self.source_range)
         # grid and medium state (MediumSystem.cpp:286-399)
+        if self.deviceSetup:
+            if not isinstance(self.grid, (CartesianSpatialGrid, PolicyTreeSpatialGrid)) \
+                    or isinstance(self.grid, FileTreeSpatialGrid):
+                raise ValueError("deviceSetup needs a Cartesian or policy octree grid")
+            if isinstance(self.grid, CartesianSpatialGrid):
+                self.grid.setup([self.medium], self.numDensitySamples, rng)
+            self.density = self.volume = None  # both come from the engine in configure()
+            return self
         self.grid.setup([self.medium], self.numDensitySamples, rng)
         if isinstance(self.grid, VoronoiMeshSpatialGrid):
             self.volume = self.grid.cell_volumes()
@@ -859,8 +923,26 @@ class MonteCarloSimulation:
     def configure(self, engine: abi.Engine):
         """Hands every table to the engine (the extractor step of INTEGRATION.md)."""
         oligo = self.oligoWavelengths is not None
-        self.grid.configure(engine)
-        engine.set_medium(self.density, self.volume)
+        marks = [("start", time.perf_counter())]
+
+        def mark(name):
+            marks.append((name, time.perf_counter()))
+        if self.deviceSetup:
+            # DensityTreePolicy::constructTree + the cell loop of MediumSystem::setupSelfAfter on the engine's side
+            geom = self.medium.density_geometry()
+            if isinstance(self.grid, PolicyTreeSpatialGrid):
+                _, ncells = engine.build_octree(self.grid.extent, self.grid.tree_policy(self.numDensitySamples), [geom])
+                self.grid.first_child = None  # fetched on demand: fetch_device_setup()
+            else:
+                self.grid.configure(engine)
+                ncells = self.grid.num_cells
+            mark("grid")
+            engine.sample_medium(geom, self.numDensitySamples, ncells)
+        else:
+            self.grid.configure(engine)
+            mark("grid")
+            engine.set_medium(self.density, self.volume)
+        mark("medium")
         mix = self.medium.mix
         engine.set_dustmix(mix.lambda_border, mix.sigma_abs, mix.sigma_sca, mix.asymmpar, mix.mu)
         rf = -1
@@ -883,18 +965,30 @@ class MonteCarloSimulation:
                           "bias_min": self.source_range[0], "bias_max": self.source_range[1]})
             srcs.append(d)
         engine.set_sources(srcs, self.sourceBias)
+        mark("tables")
         instr = []
         for i in self.instruments:
             g = i.wavelengthGrid if (i.wavelengthGrid is not None and not oligo) else self.defaultWavelengthGrid
             instr.append(i.fields([k for k, h in enumerate(self.grids) if h is g][0]))
         engine.set_instruments(instr, self.dustEmissionWLG is not None)
+        mark("instruments")
         if self.dustEmissionWLG is not None:
             mix, eg = self.medium.mix, self.dustEmissionWLG
             lo, hi = eg.wavelength_range()
             engine.set_secondary([k for k, h in enumerate(self.grids) if h is eg][0], self.secondarySpatialBias,
                                  self.dustEmissionWavelengthBias, lo, hi, mix.Tv, mix.planck_abs, mix.rf_sigma_abs,
                                  mix.em_sigma_abs)
+        mark("secondary")
+        # seconds spent per group of engine calls (bench.py reports them under e2e.parts)
+        self.last_configure_parts = {marks[k][0]: marks[k][1] - marks[k - 1][1] for k in range(1, len(marks))}
         return engine
+
+    def fetch_device_setup(self, engine: abi.Engine):
+        """Reads back what configure() built on the engine's side (deviceSetup): node list, densities, volumes."""
+        if isinstance(self.grid, PolicyTreeSpatialGrid):
+            self.grid.adopt(engine.read_octree())
+        self.density, self.volume = engine.read_medium()
+        return self
 
     def run(self, engine: abi.Engine, first=0, count=None, stream_id=0, comm=None):
         """MonteCarloSimulation::runSimulation, MonteCarloSimulation.cpp:58-100: primary emission and, in DustEmission
