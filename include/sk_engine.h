@@ -242,6 +242,12 @@ int sk_engine_set_grid_octree(sk_engine_t* e, const double extent[6], int32_t nu
 int sk_engine_set_grid_voronoi(sk_engine_t* e, const double extent[6], int32_t num_cells, const double* sites,
                                const int64_t* nbr_offset, const int32_t* nbr_index);
 
+/* Optional, after sk_engine_set_grid_voronoi: the enclosing box of every Voronoi cell, boxes[6*m..] = {xmin,ymin,zmin,xmax,
+ * ymax,zmax} of VoronoiMeshSnapshot::Cell (a Box: the bounding box of the cell's vertices, VoronoiMeshSnapshot.cpp:104-135).
+ * Needed only for dust emission from a Voronoi grid: VoronoiMeshSnapshot::generatePosition(m) (.cpp:976-989) draws
+ * Random::position(box) until the point is closest to site m among m's neighbours (isPointClosestTo, .cpp:848-856). */
+int sk_engine_set_voronoi_extents(sk_engine_t* e, int32_t num_cells, const double* boxes);
+
 /* MediumState number densities and volumes for a single medium component
  * (MediumState::numberDensity(m,0), MediumState::volume(m); MediumState.cpp:196-247). */
 int sk_engine_set_medium(sk_engine_t* e, int32_t num_cells, const double* number_density, const double* volume);

@@ -32,6 +32,25 @@ static int fail(int code, const std::string& msg)
             return fail(SK_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));                   \
     } while (0)
 
+// SK_DEBUG_TIMING=1: host wall time of the phases of the set-up calls, to stderr
+#include <chrono>
+namespace
+{
+    struct PhaseTimer {
+        const char* name;
+        std::chrono::steady_clock::time_point t0;
+        bool on;
+        explicit PhaseTimer(const char* n) : name(n), t0(std::chrono::steady_clock::now()), on(getenv("SK_DEBUG_TIMING") != nullptr) {}
+        void lap(const char* what)
+        {
+            if (!on) return;
+            auto t1 = std::chrono::steady_clock::now();
+            fprintf(stderr, "[sk timing] %s: %s %.2f ms\n", name, what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+            t0 = t1;
+        }
+    };
+}
+
 extern "C" const char* sk_last_error(void)
 {
     return g_err.c_str();
@@ -39,6 +58,23 @@ extern "C" const char* sk_last_error(void)
 extern "C" int sk_abi_version(void)
 {
     return SK_ABI_VERSION;
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// device memory: stream-ordered allocations from the device's default pool on the engine's stream.  A plain cudaFree
+// synchronises the whole device and was measured at 0.4 s once the process holds a multi-GB bank; cudaFreeAsync returns
+// the block to the pool (release threshold = never), where the next set_* call or the next engine finds it again.
+// ---------------------------------------------------------------------------------------------------
+static thread_local cudaStream_t g_stream = nullptr;  // stream of the engine the calling thread is working on
+template <class T>
+static cudaError_t dev_malloc(T** p, size_t bytes)
+{
+    return cudaMallocAsync((void**)p, bytes, g_stream);
+}
+static void dev_free(const void* p)
+{
+    if (p) cudaFreeAsync(const_cast<void*>(p), g_stream);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -213,18 +249,28 @@ static int stage_end(sk_engine* e)
     return SK_OK;
 }
 
+static int bind(sk_engine* e)
+{
+    CK(cudaSetDevice(e->cfg.device));
+    g_stream = e->stream;
+    return SK_OK;
+}
 static void free_group(std::vector<void*>& v)
 {
-    for (void* p : v) cudaFree(p);
+    for (void* p : v) dev_free(p);
     v.clear();
 }
 template <class T>
 static int upload(std::vector<void*>& group, const T* host, size_t n, T** out)
 {
     T* d = nullptr;
-    CK(cudaMalloc(&d, std::max<size_t>(n, 1) * sizeof(T)));
+    CK(dev_malloc(&d, std::max<size_t>(n, 1) * sizeof(T)));
     group.push_back(d);
-    if (n) CK(cudaMemcpy(d, host, n * sizeof(T), cudaMemcpyHostToDevice));
+    if (n)
+    {
+        CK(cudaMemcpyAsync(d, host, n * sizeof(T), cudaMemcpyHostToDevice, g_stream));
+        CK(cudaStreamSynchronize(g_stream));  // the caller's array may go away
+    }
     *out = d;
     return SK_OK;
 }
@@ -232,9 +278,9 @@ template <class T>
 static int dalloc_zero(std::vector<void*>& group, size_t n, T** out)
 {
     T* d = nullptr;
-    CK(cudaMalloc(&d, std::max<size_t>(n, 1) * sizeof(T)));
+    CK(dev_malloc(&d, std::max<size_t>(n, 1) * sizeof(T)));
     group.push_back(d);
-    CK(cudaMemset(d, 0, std::max<size_t>(n, 1) * sizeof(T)));
+    CK(cudaMemsetAsync(d, 0, std::max<size_t>(n, 1) * sizeof(T), g_stream));
     *out = d;
     return SK_OK;
 }
@@ -258,12 +304,20 @@ extern "C" int sk_engine_create(const sk_config_t* config, sk_engine_t** out)
     e->M.min_weight_reduction = config->min_weight_reduction;
     e->M.rf_grid = -1;
     CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    g_stream = e->stream;
+    {
+        // keep freed blocks in the pool instead of returning them to the driver at the next synchronisation
+        cudaMemPool_t pool;
+        CK(cudaDeviceGetDefaultMemPool(&pool, config->device));
+        uint64_t threshold = UINT64_MAX;
+        CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+    }
     CK(cudaEventCreate(&e->ev0));
     CK(cudaEventCreate(&e->ev1));
-    CK(cudaMalloc(&e->work_counter, sizeof(unsigned long long)));
-    CK(cudaMalloc(&e->scalar, sizeof(double)));
-    CK(cudaMalloc(&e->M.counters, 16 * sizeof(unsigned long long)));
-    CK(cudaMemset(e->M.counters, 0, 16 * sizeof(unsigned long long)));
+    CK(dev_malloc(&e->work_counter, sizeof(unsigned long long)));
+    CK(dev_malloc(&e->scalar, sizeof(double)));
+    CK(dev_malloc(&e->M.counters, 16 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(e->M.counters, 0, 16 * sizeof(unsigned long long), e->stream));
     *out = e;
     return SK_OK;
 }
@@ -272,6 +326,7 @@ extern "C" void sk_engine_destroy(sk_engine_t* e)
 {
     if (!e) return;
     cudaSetDevice(e->cfg.device);
+    g_stream = e->stream;
     cudaStreamSynchronize(e->stream);
     free_group(e->grid_allocs);
     free_group(e->medium_allocs);
@@ -281,25 +336,27 @@ extern "C" void sk_engine_destroy(sk_engine_t* e)
     free_group(e->instr_allocs);
     free_group(e->rf_allocs);
     free_group(e->sec_allocs);
-    cudaFree(e->work_counter);
-    cudaFree(e->bank.d);
-    cudaFree(e->bank.i);
-    cudaFree(e->bank.list);
-    cudaFree(e->bank.free_list);
-    cudaFree(e->bank.ctl);
+    dev_free(e->work_counter);
+    dev_free(e->bank.d);
+    dev_free(e->bank.i);
+    dev_free(e->bank.list);
+    dev_free(e->bank.free_list);
+    dev_free(e->bank.ctl);
     cudaFreeHost(e->ctl_host);
     if (e->ev_ctl) cudaEventDestroy(e->ev_ctl);
     for (cudaEvent_t ev : e->stage_events) cudaEventDestroy(ev);
-    cudaFree(e->model_dev);
-    cudaFree(e->scratch);
+    dev_free(e->model_dev);
+    dev_free(e->scratch);
     if (e->pinned) cudaFreeHost(e->pinned);
     if (e->pin_ev[0]) cudaEventDestroy(e->pin_ev[0]);
     if (e->pin_ev[1]) cudaEventDestroy(e->pin_ev[1]);
-    cudaFree(e->scalar);
-    cudaFree(e->M.counters);
+    dev_free(e->scalar);
+    dev_free(e->M.counters);
     cudaEventDestroy(e->ev0);
     cudaEventDestroy(e->ev1);
+    cudaStreamSynchronize(e->stream);  // the stream-ordered frees above
     cudaStreamDestroy(e->stream);
+    g_stream = nullptr;
     delete e;
 }
 
@@ -326,7 +383,7 @@ extern "C" int sk_engine_set_grid_cartesian(sk_engine_t* e, int32_t nx, int32_t 
                                             const double* yv, const double* zv)
 {
     if (!e || nx < 1 || ny < 1 || nz < 1 || !xv || !yv || !zv) return fail(SK_ERR_INVALID, "bad cartesian grid");
-    CK(cudaSetDevice(e->cfg.device));
+    if (int rc_bind = bind(e)) return rc_bind;
     free_group(e->grid_allocs);
     e->grid_kind = 1;
     e->M.grid_kind = 1;
@@ -341,6 +398,7 @@ extern "C" int sk_engine_set_grid_cartesian(sk_engine_t* e, int32_t nx, int32_t 
     e->M.ncells = 0;
     e->M.cells = nullptr;
     e->M.vrec = nullptr;
+    e->M.vbox = nullptr;
     return set_tables(e, xv, nx + 1, yv, ny + 1, zv, nz + 1);
 }
 
@@ -368,6 +426,7 @@ static int finish_octree(sk_engine* e, const double extent[6], int nn, int nc, i
                          const int32_t* d_child, const uint32_t* d_nodecoord, const int32_t* d_nodeofcell)
 {
     const int N = 1 << maxlev;
+    PhaseTimer pt("finish_octree");
     std::vector<double> T[3];
     midpoint_tables(extent, N, T);
     e->grid_kind = 2;
@@ -386,15 +445,18 @@ static int finish_octree(sk_engine* e, const double extent[6], int nn, int nc, i
     SkCellRec* d_cells;
     if (int rc = dalloc_zero(e->grid_allocs, 4 * (size_t)nc, &d_coord)) return rc;
     if (int rc = dalloc_zero(e->grid_allocs, (size_t)nc, &d_cells)) return rc;
+    pt.lap("alloc+zero cells");
     sk_build_links_kernel<<<(nc + 127) / 128, 128, 0, e->stream>>>(d_first, d_child, d_nodecoord, d_nodeofcell, nc, N, maxlev,
                                                                   d_cells, d_coord);
     cudaError_t err = cudaGetLastError();
     if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
     if (err != cudaSuccess) return fail(SK_ERR_CUDA, std::string("octree link builder: ") + cudaGetErrorString(err));
+    pt.lap("link kernel + sync");
     e->M.node_child = d_child;
     e->M.cell_coord = d_coord;
     e->M.cells = d_cells;
     e->M.vrec = nullptr;
+    e->M.vbox = nullptr;
     e->first_child_dev = d_first;
     return set_tables(e, T[0].data(), N + 1, T[1].data(), N + 1, T[2].data(), N + 1);
 }
@@ -403,7 +465,9 @@ extern "C" int sk_engine_set_grid_octree(sk_engine_t* e, const double extent[6],
                                          const int32_t* first_child)
 {
     if (!e || !extent || num_nodes < 1 || !first_child) return fail(SK_ERR_INVALID, "bad octree");
-    CK(cudaSetDevice(e->cfg.device));
+    PhaseTimer pt("set_grid_octree");
+    if (int rc_bind = bind(e)) return rc_bind;
+    pt.lap("cudaSetDevice");
     const int nn = num_nodes;
     std::vector<int> lev(nn, -1), parent(nn, -1);
     lev[0] = 0;
@@ -459,16 +523,21 @@ extern "C" int sk_engine_set_grid_octree(sk_engine_t* e, const double extent[6],
         node_coord[4 * (size_t)l + 2] = iz[l];
         node_coord[4 * (size_t)l + 3] = lev[l];
     }
+    pt.lap("host node arrays");
     free_group(e->grid_allocs);
     int32_t *d_child, *d_first, *d_nodeofcell;
     uint32_t* d_nodecoord;
     if (int rc = upload(e->grid_allocs, node_child.data(), (size_t)nn, &d_child)) return rc;
+    pt.lap("first upload");
     if (int rc = upload(e->grid_allocs, first_child, (size_t)nn, &d_first)) return rc;
     std::vector<void*> scratch;
     int rc = upload(scratch, node_coord.data(), node_coord.size(), &d_nodecoord);
     if (!rc) rc = upload(scratch, node_of_cell.data(), (size_t)nc, &d_nodeofcell);
+    pt.lap("other uploads");
     if (!rc) rc = finish_octree(e, extent, nn, nc, maxlev, d_first, d_child, d_nodecoord, d_nodeofcell);
+    pt.lap("finish_octree");
     free_group(scratch);
+    pt.lap("free scratch");
     return rc;
 }
 
@@ -485,7 +554,7 @@ extern "C" int sk_engine_set_grid_voronoi(sk_engine_t* e, const double extent[6]
         for (int64_t i = nbr_offset[m]; i < nbr_offset[m + 1]; ++i)
             if (nbr_index[i] < -6 || nbr_index[i] >= num_cells) return fail(SK_ERR_INVALID, "neighbour index out of range");
     }
-    CK(cudaSetDevice(e->cfg.device));
+    if (int rc_bind = bind(e)) return rc_bind;
     free_group(e->grid_allocs);
     const int nc = num_cells;
     std::vector<double4> rec(nc);
@@ -533,6 +602,7 @@ extern "C" int sk_engine_set_grid_voronoi(sk_engine_t* e, const double extent[6]
     e->M.vnbr_off = d_off;
     e->M.vnbr = d_idx;
     e->M.vblock = d_block;
+    e->M.vbox = nullptr;
     e->M.vnb = nb;
     e->grid_cells = nc;
     e->M.ncells = 0;
@@ -542,13 +612,28 @@ extern "C" int sk_engine_set_grid_voronoi(sk_engine_t* e, const double extent[6]
     return SK_OK;
 }
 
+extern "C" int sk_engine_set_voronoi_extents(sk_engine_t* e, int32_t num_cells, const double* boxes)
+{
+    if (!e || !boxes) return fail(SK_ERR_INVALID, "null argument");
+    if (e->grid_kind != 3) return fail(SK_ERR_STATE, "set the Voronoi grid before its cell extents");
+    if (num_cells != e->grid_cells) return fail(SK_ERR_INVALID, "extents do not match the grid");
+    for (int m = 0; m < num_cells; ++m)
+        for (int a = 0; a < 3; ++a)
+            if (!(boxes[6 * (size_t)m + a] <= boxes[6 * (size_t)m + a + 3])) return fail(SK_ERR_INVALID, "empty cell extent");
+    if (int rc_bind = bind(e)) return rc_bind;
+    double* d;
+    if (int rc = upload(e->grid_allocs, boxes, 6 * (size_t)num_cells, &d)) return rc;
+    e->M.vbox = d;
+    return SK_OK;
+}
+
 extern "C" int sk_engine_set_medium(sk_engine_t* e, int32_t num_cells, const double* number_density,
                                     const double* volume)
 {
     if (!e || !number_density) return fail(SK_ERR_INVALID, "null argument");
     if (!e->grid_kind) return fail(SK_ERR_STATE, "set the grid before the medium");
     if (num_cells != e->grid_cells) return fail(SK_ERR_INVALID, "medium size does not match the grid");
-    CK(cudaSetDevice(e->cfg.device));
+    if (int rc_bind = bind(e)) return rc_bind;
     free_group(e->medium_allocs);
     e->dens_host.assign(number_density, number_density + num_cells);
     if (e->grid_kind == 1)
@@ -621,8 +706,8 @@ namespace
         size_t cap = 0;
         ~TreeArrays()
         {
-            cudaFree(coord);
-            cudaFree(first);
+            dev_free(coord);
+            dev_free(first);
         }
     };
 }
@@ -632,11 +717,11 @@ static int grow_tree(sk_engine* e, TreeArrays& A, size_t need, size_t used)
     size_t cap = std::max<size_t>(need, 2 * A.cap);
     uint4* c = nullptr;
     int32_t* f = nullptr;
-    CK(cudaMalloc(&c, cap * sizeof(uint4)));
-    cudaError_t err = cudaMalloc(&f, cap * sizeof(int32_t));
+    CK(dev_malloc(&c, cap * sizeof(uint4)));
+    cudaError_t err = dev_malloc(&f, cap * sizeof(int32_t));
     if (err != cudaSuccess)
     {
-        cudaFree(c);
+        dev_free(c);
         return fail(SK_ERR_CUDA, std::string("octree node list: ") + cudaGetErrorString(err));
     }
     if (used)
@@ -645,8 +730,8 @@ static int grow_tree(sk_engine* e, TreeArrays& A, size_t need, size_t used)
         cudaMemcpyAsync(f, A.first, used * sizeof(int32_t), cudaMemcpyDeviceToDevice, e->stream);
         cudaStreamSynchronize(e->stream);
     }
-    cudaFree(A.coord);
-    cudaFree(A.first);
+    dev_free(A.coord);
+    dev_free(A.first);
     A.coord = c;
     A.first = f;
     A.cap = cap;
@@ -662,7 +747,7 @@ extern "C" int sk_engine_build_octree(sk_engine_t* e, const double extent[6], co
     if (policy->max_level > SK_MAX_TREE_LEVEL) return fail(SK_ERR_UNSUPPORTED, "octree deeper than 15 levels");
     if (policy->num_samples < 1) return fail(SK_ERR_INVALID, "numDensitySamples must be positive");
     if (!(extent[3] > extent[0] && extent[4] > extent[1] && extent[5] > extent[2])) return fail(SK_ERR_INVALID, "empty extent");
-    CK(cudaSetDevice(e->cfg.device));
+    if (int rc_bind = bind(e)) return rc_bind;
     SkDevGeomSet G;
     memset(&G, 0, sizeof G);
     G.n = num_media;
@@ -772,7 +857,7 @@ extern "C" int sk_engine_read_octree(sk_engine_t* e, int32_t* first_child)
 {
     if (!e || !first_child) return fail(SK_ERR_INVALID, "null argument");
     if (e->grid_kind != 2 || !e->first_child_dev) return fail(SK_ERR_STATE, "the engine holds no octree");
-    CK(cudaSetDevice(e->cfg.device));
+    if (int rc_bind = bind(e)) return rc_bind;
     CK(cudaMemcpyAsync(first_child, e->first_child_dev, (size_t)e->M.nnodes * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     return SK_OK;
@@ -786,7 +871,7 @@ extern "C" int sk_engine_sample_medium(sk_engine_t* e, const sk_density_geometry
         return fail(e->grid_kind ? SK_ERR_UNSUPPORTED : SK_ERR_STATE, "density sampling needs a Cartesian or octree grid");
     SkDevGeom g;
     if (int rc = to_dev_geom(*medium, g)) return rc;
-    CK(cudaSetDevice(e->cfg.device));
+    if (int rc_bind = bind(e)) return rc_bind;
     free_group(e->medium_allocs);
     const int nc = e->grid_cells;
     double *d_vol, *d_dens = nullptr;
@@ -814,7 +899,7 @@ extern "C" int sk_engine_read_medium(sk_engine_t* e, double* number_density, dou
 {
     if (!e) return fail(SK_ERR_INVALID, "null argument");
     if (!e->M.ncells) return fail(SK_ERR_STATE, "the engine holds no medium state");
-    CK(cudaSetDevice(e->cfg.device));
+    if (int rc_bind = bind(e)) return rc_bind;
     const int nc = e->M.ncells;
     if (number_density)
     {
@@ -850,7 +935,7 @@ extern "C" int sk_engine_read_medium(sk_engine_t* e, double* number_density, dou
 extern "C" int sk_engine_set_dustmix(sk_engine_t* e, const sk_dustmix_t* mix)
 {
     if (!e || !mix || mix->num_lambda < 2) return fail(SK_ERR_INVALID, "bad dust mix");
-    CK(cudaSetDevice(e->cfg.device));
+    if (int rc_bind = bind(e)) return rc_bind;
     free_group(e->dust_allocs);
     int n = mix->num_lambda;
     std::vector<double> ext(n);
@@ -877,7 +962,7 @@ extern "C" int sk_engine_set_wavelength_grids(sk_engine_t* e, int32_t n, const s
 {
     if (!e || n < 0 || (n && !grids) || rf_grid >= n) return fail(SK_ERR_INVALID, "bad wavelength grids");
     if (rf_grid >= 0 && e->M.ncells <= 0) return fail(SK_ERR_STATE, "set the medium before a radiation field grid");
-    CK(cudaSetDevice(e->cfg.device));
+    if (int rc_bind = bind(e)) return rc_bind;
     free_group(e->wlg_allocs);
     free_group(e->rf_allocs);
     std::vector<SkDevWlg> dev(n ? n : 1);
@@ -925,7 +1010,7 @@ extern "C" int sk_engine_set_wavelength_grids(sk_engine_t* e, int32_t n, const s
 extern "C" int sk_engine_set_sources(sk_engine_t* e, int32_t n, const sk_source_t* sources, double source_bias)
 {
     if (!e || n < 1 || !sources) return fail(SK_ERR_INVALID, "bad sources");
-    CK(cudaSetDevice(e->cfg.device));
+    if (int rc_bind = bind(e)) return rc_bind;
     free_group(e->src_allocs);
     double L = 0.;
     for (int h = 0; h < n; ++h) L += sources[h].luminosity;
@@ -1009,7 +1094,7 @@ extern "C" int sk_engine_set_instruments(sk_engine_t* e, int32_t n, const sk_ins
 {
     if (!e || n < 0 || (n && !instruments)) return fail(SK_ERR_INVALID, "bad instruments");
     if (n > SK_MAX_INSTR) return fail(SK_ERR_UNSUPPORTED, "more than 8 instruments");
-    CK(cudaSetDevice(e->cfg.device));
+    if (int rc_bind = bind(e)) return rc_bind;
     free_group(e->instr_allocs);
     e->instr.assign(n, HostInstr());
     size_t det = 0, stat = 0;
@@ -1194,13 +1279,14 @@ extern "C" int sk_engine_set_secondary(sk_engine_t* e, const sk_secondary_t* sec
 {
     if (!e || !sec) return fail(SK_ERR_INVALID, "null argument");
     if (e->M.rf_grid < 0) return fail(SK_ERR_STATE, "dust emission needs a radiation field grid");
-    if (e->grid_kind == 3) return fail(SK_ERR_UNSUPPORTED, "dust emission from a Voronoi grid (random positions in a cell)");
+    if (e->grid_kind == 3 && !e->M.vbox)
+        return fail(SK_ERR_STATE, "dust emission from a Voronoi grid needs the cell extents (sk_engine_set_voronoi_extents)");
     if (!e->M.volume) return fail(SK_ERR_STATE, "dust emission needs the cell volumes (sk_engine_set_medium)");
     if (!e->M.nlam) return fail(SK_ERR_STATE, "set the dust mix before the secondary emission tables");
     if (sec->emission_grid < 0 || sec->emission_grid >= e->M.nwlg) return fail(SK_ERR_INVALID, "bad emission grid index");
     if (sec->num_temperatures < 2 || !sec->temperature || !sec->planck_abs || !sec->rf_sigma_abs || !sec->em_sigma_abs)
         return fail(SK_ERR_INVALID, "missing emission calculator tables");
-    CK(cudaSetDevice(e->cfg.device));
+    if (int rc_bind = bind(e)) return rc_bind;
     free_group(e->sec_allocs);
     e->sec = *sec;
     const sk_wavelength_grid_t& g = e->wlg_host[sec->emission_grid];
@@ -1245,7 +1331,7 @@ extern "C" int sk_engine_set_secondary(sk_engine_t* e, const sk_secondary_t* sec
 extern "C" int sk_engine_clear_instruments(sk_engine_t* e)
 {
     if (!e) return fail(SK_ERR_INVALID, "null engine");
-    CK(cudaSetDevice(e->cfg.device));
+    if (int rc_bind = bind(e)) return rc_bind;
     if (e->det_count) CK(cudaMemsetAsync(e->det_block, 0, e->det_count * sizeof(double), e->stream));
     if (e->stat_count) CK(cudaMemsetAsync(e->stat_block, 0, e->stat_count * sizeof(double), e->stream));
     return SK_OK;
@@ -1261,7 +1347,7 @@ extern "C" int sk_engine_cuda_stream(sk_engine_t* e, void** stream)
 extern "C" int sk_engine_clear_rf(sk_engine_t* e, int32_t primary)
 {
     if (!e) return fail(SK_ERR_INVALID, "null engine");
-    CK(cudaSetDevice(e->cfg.device));
+    if (int rc_bind = bind(e)) return rc_bind;
     size_t bytes = (size_t)e->M.ncells * e->M.nrf * sizeof(double);
     if (!bytes) return SK_OK;
     if (primary)
@@ -1281,7 +1367,7 @@ extern "C" int sk_engine_prepare_primary(sk_engine_t* e, uint64_t num_packets)
     if (!e->Ltot)
         return fail(SK_ERR_INVALID, "Cannot launch primary source photon packets when total luminosity is zero");
     if (!num_packets) return fail(SK_ERR_INVALID, "zero packets");
-    CK(cudaSetDevice(e->cfg.device));
+    if (int rc_bind = bind(e)) return rc_bind;
     int Ns = e->M.nsrc;
     std::vector<unsigned long long> Iv(Ns + 1);
     Iv[0] = 0;
@@ -1310,7 +1396,7 @@ extern "C" int sk_engine_prepare_secondary(sk_engine_t* e, uint64_t num_packets,
     if (!e || !luminosity) return fail(SK_ERR_INVALID, "null argument");
     if (!e->has_secondary) return fail(SK_ERR_STATE, "call sk_engine_set_secondary first");
     if (!num_packets) return fail(SK_ERR_INVALID, "zero packets");
-    CK(cudaSetDevice(e->cfg.device));
+    if (int rc_bind = bind(e)) return rc_bind;
     const int M = e->M.ncells;
     const unsigned blocks = (unsigned)((M + 127) / 128);
     if (e->grid_kind == 1)
@@ -1382,20 +1468,20 @@ static int ensure_bank(sk_engine* e, uint64_t count)
     const int ni = SK_BANK_FIELDS_I(e->M.ninstr) + e->num_pix_lists * (SK_PIX_K + 1);
     e->bank.n = (int32_t)cap;
     if ((size_t)e->bank.cap >= cap && e->bank_fields_d == nd && e->bank_fields_i == ni) return SK_OK;
-    cudaFree(e->bank.d);
-    cudaFree(e->bank.i);
-    cudaFree(e->bank.list);
-    cudaFree(e->bank.free_list);
+    dev_free(e->bank.d);
+    dev_free(e->bank.i);
+    dev_free(e->bank.list);
+    dev_free(e->bank.free_list);
     e->bank.d = nullptr;
     e->bank.i = nullptr;
     e->bank.list = nullptr;
     e->bank.free_list = nullptr;
     e->bank.cap = 0;
-    CK(cudaMalloc(&e->bank.d, cap * nd * sizeof(double)));
-    CK(cudaMalloc(&e->bank.i, cap * ni * sizeof(int32_t)));
-    CK(cudaMalloc(&e->bank.list, cap * sizeof(int32_t)));
-    CK(cudaMalloc(&e->bank.free_list, cap * sizeof(int32_t)));
-    if (!e->bank.ctl) CK(cudaMalloc(&e->bank.ctl, SK_CTL_WORDS * sizeof(unsigned int)));
+    CK(dev_malloc(&e->bank.d, cap * nd * sizeof(double)));
+    CK(dev_malloc(&e->bank.i, cap * ni * sizeof(int32_t)));
+    CK(dev_malloc(&e->bank.list, cap * sizeof(int32_t)));
+    CK(dev_malloc(&e->bank.free_list, cap * sizeof(int32_t)));
+    if (!e->bank.ctl) CK(dev_malloc(&e->bank.ctl, SK_CTL_WORDS * sizeof(unsigned int)));
     if (!e->ctl_host) CK(cudaMallocHost(&e->ctl_host, (SK_CTL_WORDS + 2) * sizeof(unsigned int)));
     if (!e->ev_ctl) CK(cudaEventCreateWithFlags(&e->ev_ctl, cudaEventDisableTiming));
     e->bank.cap = (int32_t)cap;
@@ -1561,7 +1647,7 @@ extern "C" int sk_engine_launch_segment(sk_engine_t* e, uint64_t first, uint64_t
     if (store && e->M.rf_grid < 0) return fail(SK_ERR_STATE, "no radiation field grid configured");
     if (store && !e->M.force_scattering)
         return fail(SK_ERR_INVALID, "storing the radiation field requires forced scattering (Configuration.cpp:476-482)");
-    CK(cudaSetDevice(e->cfg.device));
+    if (int rc_bind = bind(e)) return rc_bind;
     if (!e->num_sms)
     {
         cudaDeviceProp prop;
@@ -1607,7 +1693,7 @@ extern "C" int sk_engine_launch_segment(sk_engine_t* e, uint64_t first, uint64_t
         A.stream_id = stream_id;
         A.work_counter = e->work_counter;
         CK(cudaMemsetAsync(e->work_counter, 0, sizeof(unsigned long long), e->stream));
-        if (!e->model_dev) CK(cudaMalloc(&e->model_dev, sizeof(SkDevModel)));
+        if (!e->model_dev) CK(dev_malloc(&e->model_dev, sizeof(SkDevModel)));
         CK(cudaMemcpyAsync(e->model_dev, &e->M, sizeof(SkDevModel), cudaMemcpyHostToDevice, e->stream));
         A.model = e->model_dev;
         int rc = e->grid_kind == 1 ? run_bank<1>(e, A) : e->grid_kind == 2 ? run_bank<2>(e, A) : run_bank<3>(e, A);
@@ -1621,7 +1707,7 @@ extern "C" int sk_engine_launch_segment(sk_engine_t* e, uint64_t first, uint64_t
 extern "C" int sk_engine_synchronize(sk_engine_t* e)
 {
     if (!e) return fail(SK_ERR_INVALID, "null engine");
-    CK(cudaSetDevice(e->cfg.device));
+    if (int rc_bind = bind(e)) return rc_bind;
     CK(cudaStreamSynchronize(e->stream));
     if (e->timing_pending)
     {
@@ -1662,7 +1748,7 @@ extern "C" int sk_engine_last_stage_ms(sk_engine_t* e, float out[SK_STAGE_COUNT]
 extern "C" int sk_engine_communicate_rf(sk_engine_t* e, int32_t primary)
 {
     if (!e) return fail(SK_ERR_INVALID, "null engine");
-    CK(cudaSetDevice(e->cfg.device));
+    if (int rc_bind = bind(e)) return rc_bind;
     if (!primary && e->M.rf2)
     {
         CK(cudaMemcpyAsync(e->M.rf2, e->M.rf2c, (size_t)e->M.ncells * e->M.nrf * sizeof(double),
@@ -1676,13 +1762,13 @@ extern "C" int sk_engine_absorbed_luminosity(sk_engine_t* e, int32_t primary, do
 {
     if (!e || !out) return fail(SK_ERR_INVALID, "null argument");
     if (e->M.rf_grid < 0) return fail(SK_ERR_STATE, "no radiation field");
-    CK(cudaSetDevice(e->cfg.device));
+    if (int rc_bind = bind(e)) return rc_bind;
     // kappa_abs per RF bin: DustMix::sectionAbs(lambda_ell) = _sigmaabsv[indexForLambda(lambda_ell)]
     const std::vector<double>& lam = e->wlg_lambda[e->M.rf_grid];
     std::vector<double> kabs(lam.size());
     for (size_t i = 0; i < lam.size(); ++i) kabs[i] = e->dust_sig_abs[dust_index_for_lambda(e, lam[i])];
     double* dk = nullptr;
-    CK(cudaMalloc(&dk, kabs.size() * sizeof(double)));
+    CK(dev_malloc(&dk, kabs.size() * sizeof(double)));
     CK(cudaMemcpyAsync(dk, kabs.data(), kabs.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemsetAsync(e->scalar, 0, sizeof(double), e->stream));
     sk_absorbed_kernel<<<296, 256, 0, e->stream>>>(primary ? e->M.rf1 : e->M.rf2, e->M.dens, e->M.cells, e->M.vrec, dk,
@@ -1690,7 +1776,7 @@ extern "C" int sk_engine_absorbed_luminosity(sk_engine_t* e, int32_t primary, do
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, e->scalar, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
-    cudaFree(dk);
+    dev_free(dk);
     return SK_OK;
 }
 
@@ -1700,7 +1786,7 @@ extern "C" int sk_engine_read_rf(sk_engine_t* e, int32_t which, double* out)
     if (!e || !out) return fail(SK_ERR_INVALID, "null argument");
     const double* src = which == 0 ? e->M.rf1 : which == 1 ? e->M.rf2 : e->M.rf2c;
     if (!src) return fail(SK_ERR_STATE, "no radiation field");
-    CK(cudaSetDevice(e->cfg.device));
+    if (int rc_bind = bind(e)) return rc_bind;
     return fetch_doubles(e, src, (size_t)e->M.ncells * e->M.nrf, out);
 }
 
@@ -1708,7 +1794,17 @@ extern "C" int sk_engine_read_rf(sk_engine_t* e, int32_t which, double* out)
 static int fetch_doubles(sk_engine* e, const double* dev, size_t n, double* out)
 {
     const size_t bytes = n * sizeof(double);
-    if (bytes < ((size_t)1 << 16))
+    bool direct = bytes < ((size_t)1 << 16);
+    if (!direct)
+    {
+        // a page-locked destination (cudaHostAlloc / cudaHostRegister by the caller) takes the DMA directly
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, out) == cudaSuccess)
+            direct = attr.type == cudaMemoryTypeHost;
+        else
+            cudaGetLastError();
+    }
+    if (direct)
     {
         CK(cudaMemcpyAsync(out, dev, bytes, cudaMemcpyDeviceToHost, e->stream));
         CK(cudaStreamSynchronize(e->stream));
@@ -1746,7 +1842,7 @@ static int read_array(sk_engine* e, int instrument, int component, bool ifu, dou
 {
     if (!e || !out || instrument < 0 || instrument >= (int)e->instr.size() || component < 0 || component >= SK_NUM_COMP)
         return fail(SK_ERR_INVALID, "bad instrument/component");
-    CK(cudaSetDevice(e->cfg.device));
+    if (int rc_bind = bind(e)) return rc_bind;
     const HostInstr& q = e->instr[instrument];
     if (ifu ? !q.include_ifu : !q.include_sed) return fail(SK_ERR_INVALID, "instrument does not record this");
     size_t len = ifu ? q.npix * q.nl : (size_t)q.nl;
@@ -1757,10 +1853,10 @@ static int read_array(sk_engine* e, int instrument, int component, bool ifu, dou
         // the device into scratch, one transfer
         if (e->scratch_len < len)
         {
-            cudaFree(e->scratch);
+            dev_free(e->scratch);
             e->scratch = nullptr;
             e->scratch_len = 0;
-            CK(cudaMalloc(&e->scratch, len * sizeof(double)));
+            CK(dev_malloc(&e->scratch, len * sizeof(double)));
             e->scratch_len = len;
         }
         const bool sec = off[SK_COMP_SECONDARY_DIRECT] >= 0;
@@ -1789,7 +1885,7 @@ extern "C" int sk_engine_read_sed_stats(sk_engine_t* e, int32_t instrument, int3
         return fail(SK_ERR_INVALID, "bad instrument/power");
     const HostInstr& q = e->instr[instrument];
     if (q.wsed_off[k] < 0) return fail(SK_ERR_INVALID, "statistics not recorded");
-    CK(cudaSetDevice(e->cfg.device));
+    if (int rc_bind = bind(e)) return rc_bind;
     CK(cudaMemcpyAsync(out, e->stat_block + q.wsed_off[k], (size_t)q.nl * sizeof(double), cudaMemcpyDeviceToHost,
                        e->stream));
     CK(cudaStreamSynchronize(e->stream));
@@ -1802,14 +1898,14 @@ extern "C" int sk_engine_read_ifu_stats(sk_engine_t* e, int32_t instrument, int3
         return fail(SK_ERR_INVALID, "bad instrument/power");
     const HostInstr& q = e->instr[instrument];
     if (q.wifu_off[k] < 0) return fail(SK_ERR_INVALID, "statistics not recorded");
-    CK(cudaSetDevice(e->cfg.device));
+    if (int rc_bind = bind(e)) return rc_bind;
     return fetch_doubles(e, e->stat_block + q.wifu_off[k], q.npix * (size_t)q.nl, out);
 }
 
 extern "C" int sk_engine_counters(sk_engine_t* e, sk_counters_t* out, int32_t reset)
 {
     if (!e || !out) return fail(SK_ERR_INVALID, "null argument");
-    CK(cudaSetDevice(e->cfg.device));
+    if (int rc_bind = bind(e)) return rc_bind;
     unsigned long long c[16];
     CK(cudaMemcpyAsync(c, e->M.counters, sizeof c, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));

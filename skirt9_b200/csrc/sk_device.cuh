@@ -91,6 +91,7 @@ struct SkDevModel {
     const long long* vnbr_off;
     const int32_t* vnbr;
     const int32_t* vblock;
+    const double* vbox;  // [6*ncells] enclosing boxes of the Voronoi cells (dust emission only), or null
     int32_t vnb;
     const double* volume;        // cell volumes (MediumState::volume)
     // dust

@@ -122,7 +122,8 @@ __global__ void sk_emission_spectrum_kernel(const SkDevModel M)
 
 // SecondarySourceSystem::launch (SecondarySourceSystem.cpp:130-142) + DustSecondarySource::launch
 // (DustSecondarySource.cpp:511-581) without velocities and polarisation; SpatialGrid::randomPositionInCell
-// (TreeSpatialGrid.cpp:125-128, CartesianSpatialGrid.cpp:80-83) = Random::position(box) (Random.cpp:168-176).
+// (TreeSpatialGrid.cpp:125-128, CartesianSpatialGrid.cpp:80-83) = Random::position(box) (Random.cpp:168-176);
+// VoronoiMeshSpatialGrid::randomPositionInCell = VoronoiMeshSnapshot::generatePosition(m) (VoronoiMeshSnapshot.cpp:976-989).
 template <int GRID>
 __device__ __noinline__ void sk_launch_secondary(const SkDevModel* __restrict__ Mg, const SkSmemTables& T, SkRng& g,
                                                  unsigned long long history, SkLaunch& pp)
@@ -175,7 +176,15 @@ __device__ __noinline__ void sk_launch_secondary(const SkDevModel* __restrict__ 
     }
     double b0, b1, b2, b3, b4, b5;
     if (GRID == 3)
-        b0 = b1 = b2 = b3 = b4 = b5 = 0.;  // not reached: dust emission from a Voronoi grid is rejected by set_secondary
+    {
+        const double* b = M.vbox + 6 * (size_t)m;  // VoronoiMeshSnapshot::Cell is a Box: the cell's enclosing box
+        b0 = b[0];
+        b1 = b[1];
+        b2 = b[2];
+        b3 = b[3];
+        b4 = b[4];
+        b5 = b[5];
+    }
     else if (GRID == 1)
     {
         int k = m % M.nz, j = (m / M.nz) % M.ny, i = m / (M.nz * M.ny);
@@ -197,10 +206,53 @@ __device__ __noinline__ void sk_launch_secondary(const SkDevModel* __restrict__ 
         b4 = T.Y[c.y + size];
         b5 = T.Z[c.z + size];
     }
-    const double ux = sk_uniform(g), uy = sk_uniform(g), uz = sk_uniform(g);
-    pp.rx = b0 + ux * (b3 - b0);  // Box::fracPos, SKIRT/utils/Box.hpp:151-154
-    pp.ry = b1 + uy * (b4 - b1);
-    pp.rz = b2 + uz * (b5 - b2);
+    if (GRID == 3)
+    {
+        // VoronoiMeshSnapshot::generatePosition(m), VoronoiMeshSnapshot.cpp:976-989: random points in the enclosing box
+        // until one is closest to site m among the sites of m's neighbours (isPointClosestTo, .cpp:848-856)
+        const double4 sm = sk_ld_rec(&M.vrec[m]);
+        const long long i0 = M.vnbr_off[m], i1 = M.vnbr_off[m + 1];
+        bool found = false;
+        for (int it = 0; it < 10000 && !found; ++it)
+        {
+            const double ux = sk_uniform(g), uy = sk_uniform(g), uz = sk_uniform(g);
+            const double x = b0 + ux * (b3 - b0);
+            const double y = b1 + uy * (b4 - b1);
+            const double z = b2 + uz * (b5 - b2);
+            double dx = x - sm.x, dy = y - sm.y, dz = z - sm.z;
+            const double target = dx * dx + dy * dy + dz * dz;
+            found = true;
+            for (long long i = i0; i < i1; ++i)
+            {
+                const int id = __ldg(&M.vnbr[i]);
+                if (id < 0) continue;
+                const double4 t = sk_ld_rec(&M.vrec[id]);
+                double ex = x - t.x, ey = y - t.y, ez = z - t.z;
+                if (ex * ex + ey * ey + ez * ez < target)
+                {
+                    found = false;
+                    break;
+                }
+            }
+            pp.rx = x;
+            pp.ry = y;
+            pp.rz = z;
+        }
+        if (!found)
+        {
+            // the reference throws a fatal error here; the engine emits from the site, which lies in the cell
+            pp.rx = sm.x;
+            pp.ry = sm.y;
+            pp.rz = sm.z;
+        }
+    }
+    else
+    {
+        const double ux = sk_uniform(g), uy = sk_uniform(g), uz = sk_uniform(g);
+        pp.rx = b0 + ux * (b3 - b0);  // Box::fracPos, SKIRT/utils/Box.hpp:151-154
+        pp.ry = b1 + uy * (b4 - b1);
+        pp.rz = b2 + uz * (b5 - b2);
+    }
     sk_random_direction(g, pp.kx, pp.ky, pp.kz);
     const double L = M.sec_Lpp * 1.;  // _Lv[s]/_Wv[s] = 1 for the single secondary source
     pp.lambda = lambda;
