@@ -91,6 +91,7 @@ typedef struct sko_engine {
     int32_t* vnbr;     /* neighbour cell indices, -1..-6 for the domain walls */
     int vcells, vnb;   /* number of cells; blocks per axis of the start-cell table */
     int32_t* vblock;   /* [vnb^3] a cell whose site lies in (or near) the block: start of the walk to the nearest site */
+    double* vbox;      /* [6*ncells] enclosing boxes of the cells (VoronoiMeshSnapshot::Cell is a Box), or NULL */
     /* medium */
     int ncells;
     double *dens, *vol;
@@ -522,6 +523,8 @@ static void free_grid(sko_engine_t* e)
     free(e->vnbr_off);
     free(e->vnbr);
     free(e->vblock);
+    free(e->vbox);
+    e->vbox = NULL;
     e->vsite = NULL;
     e->vnbr_off = NULL;
     e->vnbr = e->vblock = NULL;
@@ -702,6 +705,20 @@ static int grid_num_cells(const sko_engine_t* e)
     if (e->grid_kind == 1) return e->nx * e->ny * e->nz;
     if (e->grid_kind == 2) return e->nx;
     return 0;
+}
+
+/* The enclosing boxes of the Voronoi cells: VoronoiMeshSnapshot::Cell::init, VoronoiMeshSnapshot.cpp:104-135 */
+int sko_set_voronoi_extents(sko_engine_t* e, int32_t num_cells, const double* boxes)
+{
+    if (!e || !boxes) return fail(SK_ERR_INVALID, "null argument");
+    if (e->grid_kind != 3) return fail(SK_ERR_STATE, "set the Voronoi grid before its cell extents");
+    if (num_cells != e->vcells) return fail(SK_ERR_INVALID, "extents do not match the grid");
+    for (int m = 0; m < num_cells; ++m)
+        for (int a = 0; a < 3; ++a)
+            if (!(boxes[6 * (size_t)m + a] <= boxes[6 * (size_t)m + a + 3])) return fail(SK_ERR_INVALID, "empty cell extent");
+    free(e->vbox);
+    e->vbox = dupd(boxes, 6 * (size_t)num_cells);
+    return SK_OK;
 }
 
 int sko_set_medium(sko_engine_t* e, int32_t num_cells, const double* number_density, const double* volume)
@@ -1126,7 +1143,8 @@ int sko_set_secondary(sko_engine_t* e, const sk_secondary_t* sec)
 {
     if (!e || !sec) return fail(SK_ERR_INVALID, "null argument");
     if (e->rf_grid < 0) return fail(SK_ERR_STATE, "dust emission needs a radiation field grid");
-    if (e->grid_kind == 3) return fail(SK_ERR_UNSUPPORTED, "dust emission from a Voronoi grid (random positions in a cell)");
+    if (e->grid_kind == 3 && !e->vbox)
+        return fail(SK_ERR_STATE, "dust emission from a Voronoi grid needs the cell extents (sko_set_voronoi_extents)");
     if (sec->emission_grid < 0 || sec->emission_grid >= e->nwlg) return fail(SK_ERR_INVALID, "bad emission grid index");
     if (sec->num_temperatures < 2 || !sec->temperature || !sec->planck_abs || !sec->rf_sigma_abs || !sec->em_sigma_abs)
         return fail(SK_ERR_INVALID, "missing emission calculator tables");
@@ -2404,12 +2422,54 @@ static void launch_secondary(sko_engine_t* e, rng_t* g, uint64_t history, packet
             w = sl / ((1 - xi) * sl + xi * b);
         }
     }
-    double box[6];
-    cell_box(e, m, box);
-    double ux = uniform(g), uy = uniform(g), uz = uniform(g);
-    pp->r[0] = box[0] + ux * (box[3] - box[0]); /* Box::fracPos, Box.hpp */
-    pp->r[1] = box[1] + uy * (box[4] - box[1]);
-    pp->r[2] = box[2] + uz * (box[5] - box[2]);
+    if (e->grid_kind == 3)
+    {
+        /* VoronoiMeshSnapshot::generatePosition(m), VoronoiMeshSnapshot.cpp:976-989: random points in the cell's enclosing
+         * box until one is closest to site m among the sites of m's neighbours (isPointClosestTo, .cpp:848-856) */
+        const double* box = e->vbox + 6 * (size_t)m;
+        const double* sm = e->vsite + 3 * (size_t)m;
+        int found = 0;
+        for (int it = 0; it < 10000 && !found; ++it)
+        {
+            double ux = uniform(g), uy = uniform(g), uz = uniform(g);
+            double x = box[0] + ux * (box[3] - box[0]);
+            double y = box[1] + uy * (box[4] - box[1]);
+            double z = box[2] + uz * (box[5] - box[2]);
+            double dx = x - sm[0], dy = y - sm[1], dz = z - sm[2];
+            double target = dx * dx + dy * dy + dz * dz;
+            found = 1;
+            for (int64_t i = e->vnbr_off[m]; i < e->vnbr_off[m + 1]; ++i)
+            {
+                int id = e->vnbr[i];
+                if (id < 0) continue;
+                const double* t = e->vsite + 3 * (size_t)id;
+                double ex = x - t[0], ey = y - t[1], ez = z - t[2];
+                if (ex * ex + ey * ey + ez * ez < target)
+                {
+                    found = 0;
+                    break;
+                }
+            }
+            pp->r[0] = x;
+            pp->r[1] = y;
+            pp->r[2] = z;
+        }
+        if (!found) /* the reference throws a fatal error here; emit from the site */
+        {
+            pp->r[0] = sm[0];
+            pp->r[1] = sm[1];
+            pp->r[2] = sm[2];
+        }
+    }
+    else
+    {
+        double box[6];
+        cell_box(e, m, box);
+        double ux = uniform(g), uy = uniform(g), uz = uniform(g);
+        pp->r[0] = box[0] + ux * (box[3] - box[0]); /* Box::fracPos, Box.hpp */
+        pp->r[1] = box[1] + uy * (box[4] - box[1]);
+        pp->r[2] = box[2] + uz * (box[5] - box[2]);
+    }
     random_direction(g, pp->k);
     double L = e->sec_Lpp * 1.; /* _Lv[s]/_Wv[s] = 1 for the single secondary source */
     pp->lambda = lambda;
@@ -2747,6 +2807,26 @@ int sko_test_voronoi_cell_index(sko_engine_t* e, const double r[3], int brute)
         }
     }
     return best;
+}
+/* the launch position of one history of the prepared secondary segment and the cell it was launched for */
+int sko_test_secondary_launch(sko_engine_t* e, uint64_t history, uint32_t stream_id, double r[3])
+{
+    if (!e || !e->secondary_ready) return -2;
+    rng_t g;
+    rng_init(&g, (uint32_t)e->cfg.seed, stream_id, history);
+    packet_t pp;
+    launch_secondary(e, &g, history, &pp);
+    memcpy(r, pp.r, 3 * sizeof(double));
+    int lo = 0, hi = e->ncells + 1;
+    while (lo < hi)
+    {
+        int mid = (lo + hi) >> 1;
+        if (history < e->sec_Iv[mid])
+            hi = mid;
+        else
+            lo = mid + 1;
+    }
+    return lo - 1;
 }
 void sko_test_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
 {

@@ -203,7 +203,6 @@ std::string GpuLifeCycle::unsupportedReason() const
     auto voronoi = dynamic_cast<VoronoiMeshSpatialGrid*>(grid);
     if (!dynamic_cast<CartesianSpatialGrid*>(grid) && !(tree && dynamic_cast<OctTreeNode*>(tree->_nodev[0])) && !voronoi)
         return "spatial grid " + grid->type();
-    if (voronoi && config->hasSecondaryEmission()) return "dust emission from a Voronoi grid";
     for (auto source : _sim->sourceSystem()->sources())
     {
         auto ns = dynamic_cast<NormalizedSource*>(source);
@@ -275,7 +274,7 @@ void GpuLifeCycle::configure()
         // VoronoiMeshSnapshot::_cells: site positions and neighbour lists as built by the vendored voro++
         auto mesh = v->_mesh;
         size_t n = mesh->_cells.size();
-        vector<double> sites(3 * n);
+        vector<double> sites(3 * n), boxes(6 * n);
         vector<int64_t> offset(n + 1, 0);
         vector<int32_t> index;
         for (size_t m = 0; m != n; ++m)
@@ -284,12 +283,17 @@ void GpuLifeCycle::configure()
             sites[3 * m] = cell->_r.x();
             sites[3 * m + 1] = cell->_r.y();
             sites[3 * m + 2] = cell->_r.z();
+            // the cell's enclosing box (its Box base class, VoronoiMeshSnapshot.cpp:104-135): dust emission positions
+            const Box& cb = *cell;
+            double cbox[6] = {cb.xmin(), cb.ymin(), cb.zmin(), cb.xmax(), cb.ymax(), cb.zmax()};
+            std::copy(cbox, cbox + 6, boxes.begin() + 6 * m);
             index.insert(index.end(), cell->_neighbors.begin(), cell->_neighbors.end());
             offset[m + 1] = static_cast<int64_t>(index.size());
         }
         Box b = mesh->_extent;
         double ext[6] = {b.xmin(), b.ymin(), b.zmin(), b.xmax(), b.ymax(), b.zmax()};
         check(sk_engine_set_grid_voronoi(_e, ext, static_cast<int32_t>(n), sites.data(), offset.data(), index.data()));
+        if (config->hasSecondaryEmission()) check(sk_engine_set_voronoi_extents(_e, static_cast<int32_t>(n), boxes.data()));
     }
     else
     {

@@ -133,7 +133,8 @@ def load_engine_library(path: Optional[str] = None) -> C.CDLL:
 
 
 # names of the C ABI entry points after the prefix; include/sk_engine.h is the authority
-ABI_FUNCTIONS = ["create", "destroy", "set_grid_cartesian", "set_grid_octree", "set_grid_voronoi", "set_medium", "set_dustmix",
+ABI_FUNCTIONS = ["create", "destroy", "set_grid_cartesian", "set_grid_octree", "set_grid_voronoi", "set_voronoi_extents",
+                 "set_medium", "set_dustmix",
                  "set_wavelength_grids", "set_sources", "set_instruments", "set_secondary", "clear_instruments", "clear_rf",
                  "prepare_primary", "prepare_secondary", "run_segment", "communicate_rf", "absorbed_luminosity",
                  "read_rf", "read_sed", "read_ifu", "read_sed_stats", "read_ifu_stats", "counters"]
@@ -229,6 +230,10 @@ class Engine:
         off = np.ascontiguousarray(nbr_offset, dtype=np.int64)
         idx, pi = _i(nbr_index)
         self._call("set_grid_voronoi", self._h, pe, C.c_int32(len(st)), ps, off.ctypes.data_as(C.POINTER(C.c_int64)), pi)
+
+    def set_voronoi_extents(self, boxes):
+        b, pb = _d(np.asarray(boxes, dtype=np.float64).reshape(-1, 6))
+        self._call("set_voronoi_extents", self._h, C.c_int32(len(b)), pb)
 
     def set_medium(self, number_density, volume=None):
         n, pn = _d(number_density)

@@ -1401,8 +1401,10 @@ extern "C" int sk_engine_prepare_secondary(sk_engine_t* e, uint64_t num_packets,
     const unsigned blocks = (unsigned)((M + 127) / 128);
     if (e->grid_kind == 1)
         sk_dust_luminosity_kernel<1><<<blocks, 128, 0, e->stream>>>(e->M);
-    else
+    else if (e->grid_kind == 2)
         sk_dust_luminosity_kernel<2><<<blocks, 128, 0, e->stream>>>(e->M);
+    else
+        sk_dust_luminosity_kernel<3><<<blocks, 128, 0, e->stream>>>(e->M);
     CK(cudaGetLastError());
     std::vector<double>& Lv = e->sec_Lv_host;
     Lv.resize(M);
@@ -1440,8 +1442,10 @@ extern "C" int sk_engine_prepare_secondary(sk_engine_t* e, uint64_t num_packets,
                        e->stream));
     if (e->grid_kind == 1)
         sk_emission_spectrum_kernel<1><<<blocks, 128, 0, e->stream>>>(e->M);
-    else
+    else if (e->grid_kind == 2)
         sk_emission_spectrum_kernel<2><<<blocks, 128, 0, e->stream>>>(e->M);
+    else
+        sk_emission_spectrum_kernel<3><<<blocks, 128, 0, e->stream>>>(e->M);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e->stream));
     e->M.sec_Lpp = L / (double)num_packets;  // SecondarySourceSystem.cpp:119

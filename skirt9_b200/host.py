@@ -624,6 +624,7 @@ class VoronoiMeshSpatialGrid:
         sites = sites[inside]
         self.sites = sites[np.argsort(sites[:, 0], kind="stable")]       # cells in order of increasing x, .cpp:507-508
         self.volumes = None if volumes is None else np.asarray(volumes, dtype=float)
+        self.cell_extents = None   # enclosing boxes of the cells (VoronoiMeshSnapshot::Cell is a Box), [n,6]
         self.nbr_offset = self.nbr_index = None
 
     def setup(self, media, num_density_samples, rng):
@@ -655,8 +656,36 @@ class VoronoiMeshSpatialGrid:
         ext = np.asarray(self.extent)
         return np.full(self.num_cells, np.prod(ext[3:] - ext[:3]) / self.num_cells)  # placeholder: equal shares
 
+    def compute_cell_geometry(self):
+        """Volumes and enclosing boxes of the cells clipped to the domain -- what the reference takes from voro++
+        (VoronoiMeshSnapshot::Cell::init, VoronoiMeshSnapshot.cpp:104-135).  The sites are mirrored in the six domain
+        walls, which makes every cell of the (unbounded) tessellation of all points equal to the bounded cell."""
+        from scipy.spatial import ConvexHull, Voronoi
+        ext = np.asarray(self.extent)
+        lo, hi = ext[:3], ext[3:]
+        pts = [self.sites]
+        for ax in range(3):
+            for wall in (lo[ax], hi[ax]):
+                r = self.sites.copy()
+                r[:, ax] = 2.0 * wall - r[:, ax]
+                pts.append(r)
+        vor = Voronoi(np.concatenate(pts))
+        n = len(self.sites)
+        boxes, vols = np.empty((n, 6)), np.empty(n)
+        for m in range(n):
+            reg = vor.regions[vor.point_region[m]]
+            if -1 in reg or not reg:
+                raise RuntimeError("unbounded Voronoi cell inside the mirrored point set")
+            v = np.clip(vor.vertices[reg], lo, hi)
+            boxes[m, :3], boxes[m, 3:] = v.min(axis=0), v.max(axis=0)
+            vols[m] = ConvexHull(v).volume
+        self.cell_extents, self.volumes = boxes, vols
+        return self
+
     def configure(self, engine):
         engine.set_grid_voronoi(self.extent, self.sites, self.nbr_offset, self.nbr_index)
+        if self.cell_extents is not None:
+            engine.set_voronoi_extents(self.cell_extents)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -887,6 +916,8 @@ class MonteCarloSimulation:
             return self
         self.grid.setup([self.medium], self.numDensitySamples, rng)
         if isinstance(self.grid, VoronoiMeshSpatialGrid):
+            if self.dustEmissionWLG is not None and self.grid.cell_extents is None:
+                self.grid.compute_cell_geometry()  # emission positions need the cells' enclosing boxes, J their volumes
             self.volume = self.grid.cell_volumes()
             n = self.grid.num_cells
             boxes = None

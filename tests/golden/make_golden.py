@@ -160,6 +160,22 @@ def make_cfg4s():
     print("cfg4s:", {k: np.shape(v) for k, v in out.items()}, prim, sec, conv and conv.group(0))
 
 
+def make_cfg7v():
+    with tempfile.TemporaryDirectory() as d:
+        log = run_reference("cfg7v", d)
+        sed = read_columns(os.path.join(d, "cfg7v_sed_sed.dat"))
+        cells = read_columns(os.path.join(d, "cfg7v_cells_cellprops.dat"))
+        T = read_columns(os.path.join(d, "cfg7v_temp_dust_T.dat"))
+        prim = [float(x) for x in re.findall(r"dust-absorbed primary luminosity is ([0-9.eE+-]+) Lsun", log)]
+        sec = [float(x) for x in re.findall(r"dust-absorbed secondary luminosity in iteration \d+ is ([0-9.eE+-]+) Lsun", log)]
+        conv = re.search(r"Convergence reached after (\d+) iterations", log)
+        out = dict(sed=sed, mass_density_msun_pc3=cells[:, 6], cell_center_pc=cells[:, 1:4], cell_volume_pc3=cells[:, 4],
+                   temperature=T[:, 1].astype(np.float32), absorbed_primary_lsun=np.array(prim),
+                   absorbed_secondary_lsun=np.array(sec), converged_after=int(conv.group(1)) if conv else -1, num_packets=2e5)
+    np.savez_compressed(os.path.join(HERE, "cfg7v_ref.npz"), **out)
+    print("cfg7v:", {k: np.shape(v) for k, v in out.items()}, prim, sec, conv and conv.group(0))
+
+
 def sph_particles(n=6000, seed=12345):
     """SURVEY.md 8d cfg5 recipe scaled down: columns x y z h M (pc, pc, pc, pc, Msun)."""
     rng = np.random.default_rng(seed)

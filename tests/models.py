@@ -103,6 +103,24 @@ def small_voronoi(num_packets=20000, seed=11, num_sites=1500, **kw):
     return configs.cfg5(sites, num_packets=num_packets, seed=seed, num_pixels=16, **kw)
 
 
+def small_voronoi_dust_emission(num_packets=20000, seed=17, num_sites=1200, max_secondary_iterations=2):
+    """cfg4's physics (hot point source in an r^-2 dust shell, dust emission with iterations) on a Voronoi grid of random
+    sites concentrated towards the centre: SecondarySourceSystem launching from Voronoi cells
+    (VoronoiMeshSnapshot::generatePosition(m), VoronoiMeshSnapshot.cpp:976-989)."""
+    pc = H.PC
+    rng = np.random.default_rng(5)
+    r = 0.98 * rng.uniform(0.0, 1.0, size=num_sites) ** 1.5
+    mu = rng.uniform(-1.0, 1.0, size=num_sites)
+    phi = rng.uniform(0.0, 2 * np.pi, size=num_sites)
+    st = np.sqrt(1.0 - mu * mu)
+    sites = np.stack([r * st * np.cos(phi), r * st * np.sin(phi), r * mu], axis=1) * pc
+    sim = configs.cfg4(num_packets=num_packets, seed=seed, num_sed_wavelengths=12,
+                       max_secondary_iterations=max_secondary_iterations)
+    sim.grid = H.VoronoiMeshSpatialGrid(-pc, pc, -pc, pc, -pc, pc, sites)
+    sim.numDensitySamples = 1
+    return sim
+
+
 def tabulated_sed_ring_source_high_g(num_packets=20000, seed=13):
     """A ring-shaped source with a tabulated (ListSED) spectrum next to a point source, and a strongly forward-scattering
     dust mix (g = 0.97 > 0.95: the peel-off uses the +-4 degree averaged phase function, DustMix.cpp:395-445)."""

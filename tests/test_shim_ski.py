@@ -183,3 +183,30 @@ def test_cfg6m_ski_many_features_runs_unchanged(tmp_path):
     # the reference's radiation field probe on the engine's tally
     J = read_columns(tmp_path / "cfg6m_rf_J.dat")[:, 1:]
     np.testing.assert_allclose(J.sum(axis=0), g["J_nu"].astype(float).sum(axis=0), rtol=0.01)
+
+
+def test_cfg7v_ski_voronoi_dust_emission_runs_unchanged(tmp_path):
+    """Dust emission with iterations on a Voronoi grid (3000 sites drawn by the reference's set-up): the secondary packets
+    are launched from Voronoi cells by rejection in the cells' enclosing boxes, which the shim reads from the reference's
+    VoronoiMeshSnapshot::Cell objects."""
+    g = np.load(os.path.join(GOLD, "cfg7v_ref.npz"))
+    n = 2e6
+    log = run_ski("cfg7v", tmp_path, n)
+    cells = read_columns(tmp_path / "cfg7v_cells_cellprops.dat")
+    np.testing.assert_array_equal(cells[:, 6], g["mass_density_msun_pc3"])   # same sites, same sampled densities
+    prim = [float(x) for x in re.findall(r"dust-absorbed primary luminosity is ([0-9.eE+-]+) Lsun", log)]
+    sec = [float(x) for x in re.findall(r"dust-absorbed secondary luminosity in iteration \d+ is ([0-9.eE+-]+) Lsun", log)]
+    conv = re.search(r"Convergence reached after (\d+) iterations", log)
+    assert conv and int(conv.group(1)) == int(g["converged_after"])
+    np.testing.assert_allclose(prim, g["absorbed_primary_lsun"], rtol=0.004)
+    np.testing.assert_allclose(sec, g["absorbed_secondary_lsun"], rtol=0.02)
+    sed = read_columns(tmp_path / "cfg7v_sed_sed.dat")
+    ref = g["sed"]
+    peak = ref[:, 1].max()
+    for col in range(1, 8):
+        ok = ref[:, col] > 0.02 * ref[:, col].max()
+        np.testing.assert_allclose(sed[ok, col], ref[ok, col], rtol=0.12, atol=0.003 * peak, err_msg=f"column {col}")
+        assert sed[:, col].sum() == pytest.approx(ref[:, col].sum(), rel=0.02)
+    T = read_columns(tmp_path / "cfg7v_temp_dust_T.dat")[:, 1]
+    ok = g["temperature"] > 0
+    assert np.median(np.abs(T[ok] / g["temperature"][ok] - 1)) < 0.02
