@@ -218,6 +218,11 @@ def native_arm(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
     torch.cuda.set_device(local)
+    # stdout carries the one JSON line only: anything native libraries print (the NCCL version banner under NCCL_DEBUG)
+    # goes to stderr while the bench runs
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     packets_per_gpu = int(args.packets)
@@ -295,11 +300,13 @@ def native_arm(args):
             e2e_parts["configure_" + kk + "_s"] = e2e_parts.get("configure_" + kk + "_s", 0.0) + vv / e2e_steps
         e2.prepare_primary(total)
         e2.run_segment(first, packets_per_gpu, True, True, False, 1000 + k)
+        tseg = time.perf_counter()
         if world > 1:
             with torch.cuda.stream(torch.cuda.ExternalStream(e2.cuda_stream(), device=local)):
                 dist.all_reduce(e2.device_tensor(3))
             e2.synchronize()
         tc = time.perf_counter()
+        e2e_parts["allreduce_s"] = e2e_parts.get("allreduce_s", 0.0) + (tc - tseg) / e2e_steps
         outs = [e2.read_sed(0, c) for c in (0, 1, 2, 3)] + [e2.read_ifu(0, c, out=ifu_host[c]) for c in (0, 1, 2, 3)]
         d2h = sum(o.nbytes for o in outs)
         td = time.perf_counter()
@@ -382,7 +389,8 @@ def native_arm(args):
                     line["ski_e2e"] = run_shim_once(4e8, os.cpu_count() or 1)
                 except Exception as ex:  # the drop-in binary is informational here; the C-ABI e2e above is the contract
                     line["ski_e2e"] = {"error": str(ex)[:200]}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

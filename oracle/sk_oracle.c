@@ -439,7 +439,8 @@ static double planck(double lambda, double T)
     const double h = 6.62606957e-34, c = 2.99792458e8, k = 1.3806488e-23;
     double f1 = h * c / (k * T);
     double f2 = 2.0 * h * c * c;
-    return f2 / pow(lambda, 5) / (exp(f1 / lambda) - 1.0);
+    const double l2 = lambda * lambda; /* lambda^5 by multiplication, as in the CUDA engine (sk_device.cuh sk_planck) */
+    return f2 / (l2 * l2 * lambda) / (exp(f1 / lambda) - 1.0);
 }
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -738,6 +739,13 @@ int sko_set_medium(sko_engine_t* e, int32_t num_cells, const double* number_dens
 /* setup: octree construction by the density policy and medium-state sampling  */
 /* ------------------------------------------------------------------------------------------------ */
 
+/* x^e for the even exponents 2N of SpiralStructureGeometryDecorator::perturbation: x*x is the correctly rounded
+ * pow(x, 2); same rule in the CUDA engine (sk_device.cuh sk_pow_even) */
+static double pow_even(double x, double e)
+{
+    return e == 2.0 ? x * x : pow(x, e);
+}
+
 /* Geometry::density(Position): ShellGeometry.cpp:30-36 (through SpheGeometry), ExpDiskGeometry.cpp:32-42 and
  * RingGeometry.cpp:39-43 (through AxGeometry), SpiralStructureGeometryDecorator.cpp:24-29,71-75 */
 static double geom_density(const sk_density_geometry_t* g, double x, double y, double z)
@@ -769,7 +777,7 @@ static double geom_density(const sk_density_geometry_t* g, double x, double y, d
             double phi = atan2(y, x);
             double m = p[6], tanp = p[7], R0 = p[8], phi0 = p[9], w = p[10], N = p[11], cn = p[12];
             double gamma = log(R / R0) / tanp + phi0 + 0.5 * M_PI / m;
-            double perturbation = (1.0 - w) + w * cn * pow(sin(0.5 * m * (gamma - phi)), 2 * N);
+            double perturbation = (1.0 - w) + w * cn * pow_even(sin(0.5 * m * (gamma - phi)), 2 * N);
             return rho * perturbation;
         }
         case SK_GEOM_RING:
@@ -2260,7 +2268,7 @@ static void generate_position(rng_t* g, const sk_source_t* s, double r[3])
             {
                 phi = 2.0 * M_PI * uniform(g);
                 double gamma = log(R / Rz) / tanp + phiz + 0.5 * M_PI / m;
-                double perturbation = (1.0 - w) + w * cn * pow(sin(0.5 * m * (gamma - phi)), 2 * N);
+                double perturbation = (1.0 - w) + w * cn * pow_even(sin(0.5 * m * (gamma - phi)), 2 * N);
                 t = uniform(g) * c / perturbation;
             } while (t > 1);
             r[0] = R * cos(phi);

@@ -603,11 +603,11 @@ __device__ __noinline__ void sk_generate_position(SkRng& g, const SkDevSource& s
             double m = p[5], tanp = p[6], Rz = p[7], phiz = p[8], w = p[9], N = p[10], cn = p[11];
             double c = 1.0 + (cn - 1.0) * w;
             double phi, t;
+            const double gamma = log(R / Rz) / tanp + phiz + 0.5 * M_PI / m;  // the same value in every trial
             do
             {
                 phi = 2.0 * M_PI * sk_uniform(g);
-                double gamma = log(R / Rz) / tanp + phiz + 0.5 * M_PI / m;
-                double perturbation = (1.0 - w) + w * cn * pow(sin(0.5 * m * (gamma - phi)), 2 * N);
+                double perturbation = (1.0 - w) + w * cn * sk_pow_even(sin(0.5 * m * (gamma - phi)), 2 * N);
                 t = sk_uniform(g) * c / perturbation;
             } while (t > 1);
             x = R * cos(phi);

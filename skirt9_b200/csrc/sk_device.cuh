@@ -293,6 +293,12 @@ __device__ __forceinline__ double sk_interp_loglog(double x, double x1, double x
     }
     return f1 * exp(log(x / x1) / log(x2 / x1) * (log(f2 / f1)));
 }
+// x^e for the small even integer exponents of SpiralStructureGeometryDecorator::perturbation (2N, N = index): x*x is the
+// correctly rounded pow(x, 2); other exponents go through pow()
+__device__ __forceinline__ double sk_pow_even(double x, double e)
+{
+    return e == 2.0 ? x * x : pow(x, e);
+}
 __device__ __forceinline__ double sk_gexp(double p, double x)
 {
     const double q = 1.0 - p;
@@ -380,7 +386,8 @@ __device__ __forceinline__ double sk_planck(double lambda, double T)
     const double h = 6.62606957e-34, c = 2.99792458e8, k = 1.3806488e-23;
     double f1 = h * c / (k * T);
     double f2 = 2.0 * h * c * c;
-    return f2 / pow(lambda, 5) / (exp(f1 / lambda) - 1.0);
+    const double l2 = lambda * lambda;  // lambda^5 by multiplication (the oracle does the same): pow() is the most
+    return f2 / (l2 * l2 * lambda) / (exp(f1 / lambda) - 1.0);  // expensive call of the launch kernel
 }
 // DisjointWavelengthGrid::bin, DisjointWavelengthGrid.cpp:332-341
 __device__ __forceinline__ int sk_wlg_bin(const SkDevWlg& g, double lambda)

@@ -62,7 +62,7 @@ __device__ __forceinline__ double sk_geom_density(const SkDevGeom& g, double x, 
             double phi = atan2(y, x);
             double m = p[6], tanp = p[7], R0 = p[8], phi0 = p[9], w = p[10], N = p[11], cn = p[12];
             double gamma = log(R / R0) / tanp + phi0 + 0.5 * M_PI / m;
-            double perturbation = (1.0 - w) + w * cn * pow(sin(0.5 * m * (gamma - phi)), 2 * N);
+            double perturbation = (1.0 - w) + w * cn * sk_pow_even(sin(0.5 * m * (gamma - phi)), 2 * N);
             return rho * perturbation;
         }
         case SK_GEOM_RING:
