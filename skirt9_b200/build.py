@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libskirt9_b200.so")
 SOURCES = ["engine.cu"]
-HEADERS = ["sk_device.cuh", "sk_blocks.cuh", "sk_wavefront.cuh", "sk_secondary.cuh", os.path.join("..", "..", "include", "sk_engine.h")]
+HEADERS = ["sk_device.cuh", "sk_blocks.cuh", "sk_wavefront.cuh", "sk_secondary.cuh", "sk_setup.cuh", os.path.join("..", "..", "include", "sk_engine.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-shared", "-Xcompiler", "-fPIC"]
 
