@@ -347,7 +347,10 @@ def native_arm(args):
         peak, which = measured_peak()
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("dram_bytes_per_launch")
+            # dram__bytes_read.sum + dram__bytes_write.sum of one captured launch of the dominant kernel (ncu --set full,
+            # profiles/traffic.json), scaled from that launch's algorithmic bytes to this run's average launch
+            cap = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = cap["dram_bytes_per_launch"] * (dom_bytes / max(dom_launches, 1)) / cap["algorithmic_bytes_of_captured_launch"]
         except Exception:
             pass
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -51,13 +51,14 @@ for rep in reps:
         continue
     txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(txt.splitlines()))
-    hdr = rows[0]
+    hdr, units = rows[0], rows[1]
+    scale = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     for r in rows[2:]:
         d = {"report": rep, "kernel": r[hdr.index("Kernel Name")]}
         for k, name in want.items():
             if k in hdr:
                 try:
-                    d[name] = float(r[hdr.index(k)].replace(",", ""))
+                    d[name] = float(r[hdr.index(k)].replace(",", "")) * scale.get(units[hdr.index(k)], 1.0)
                 except ValueError:
                     pass
         stalls = [(h.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""), float(r[i]))
