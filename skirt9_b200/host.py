@@ -443,10 +443,20 @@ class CartesianSpatialGrid:
 
 
 class DensityTreePolicy:
-    """DensityTreePolicy.cpp:116-227 restricted to the dust-mass-fraction criterion."""
+    """DensityTreePolicy.cpp:116-227, dust criteria: mass fraction, optical depth across the node's diagonal at
+    `wavelength`, density dispersion over the samples (a value of 0 disables a criterion, DensityTreePolicy.cpp:64-66)."""
 
-    def __init__(self, minLevel, maxLevel, maxDustFraction):
+    def __init__(self, minLevel, maxLevel, maxDustFraction, maxDustOpticalDepth=0.0, wavelength=0.55e-6,
+                 maxDustDensityDispersion=0.0):
         self.minLevel, self.maxLevel, self.maxDustFraction = minLevel, maxLevel, maxDustFraction
+        self.maxDustOpticalDepth, self.wavelength = maxDustOpticalDepth, wavelength
+        self.maxDustDensityDispersion = maxDustDensityDispersion
+
+    def dust_kappa(self, media):
+        """_dustKappa, DensityTreePolicy.cpp:75-84: sum of the extinction sections over the sum of the masses per entity."""
+        if not self.maxDustOpticalDepth > 0:
+            return 0.0
+        return sum(float(m.mix.section_ext(self.wavelength)) for m in media) / sum(m.mix.mu for m in media)
 
 
 class PolicyTreeSpatialGrid:
@@ -472,17 +482,28 @@ class PolicyTreeSpatialGrid:
             elif level >= pol.maxLevel:
                 divide = np.zeros(n, dtype=bool)
             else:
-                # needsSubdivide: mean of numSamples random density samples times the node volume over the total
-                # dust mass, DensityTreePolicy.cpp:130-154,190-196 (mass density / total mass = geometry density)
-                rho = np.zeros(n)
+                # needsSubdivide, DensityTreePolicy.cpp:130-210: dust mass density at numSamples random positions
+                mass = sum(med.mass for med in media)
+                rho, rhomin, rhomax = np.zeros(n), np.full(n, np.inf), np.zeros(n)
                 for _ in range(num_density_samples):
                     u = rng.random((n, 3))
                     p = cur[:, :3] + u * (cur[:, 3:] - cur[:, :3])
+                    rhoi = np.zeros(n)
                     for med in media:
-                        rho += med.geometry.density(p[:, 0], p[:, 1], p[:, 2]) / len(media)
+                        rhoi += med.mass * med.geometry.density(p[:, 0], p[:, 1], p[:, 2])
+                    rho += rhoi
+                    rhomin, rhomax = np.minimum(rhomin, rhoi), np.maximum(rhomax, rhoi)
                 rho /= num_density_samples
-                vol = np.prod(cur[:, 3:] - cur[:, :3], axis=1)
-                divide = rho * vol > pol.maxDustFraction
+                size = cur[:, 3:] - cur[:, :3]
+                divide = np.zeros(n, dtype=bool)
+                if pol.maxDustFraction > 0:
+                    divide |= rho * np.prod(size, axis=1) / mass > pol.maxDustFraction
+                if pol.maxDustOpticalDepth > 0:
+                    divide |= pol.dust_kappa(media) * rho * np.linalg.norm(size, axis=1) > pol.maxDustOpticalDepth
+                if pol.maxDustDensityDispersion > 0:
+                    with np.errstate(invalid="ignore", divide="ignore"):
+                        q = np.where(rhomax > 0, (rhomax - rhomin) / rhomax, 0.0)
+                    divide |= q > pol.maxDustDensityDispersion
             idx = np.nonzero(divide)[0]
             fc = np.full(n, -1, dtype=np.int64)
             fc[idx] = total + 8 * np.arange(len(idx))
@@ -515,9 +536,10 @@ class PolicyTreeSpatialGrid:
     def configure(self, engine):
         engine.set_grid_octree(self.extent, self.first_child)
 
-    def tree_policy(self, num_density_samples):
+    def tree_policy(self, num_density_samples, media=()):
         pol = self.policy
-        return abi.SkTreePolicy(pol.minLevel, pol.maxLevel, num_density_samples, 0, pol.maxDustFraction, 0.0, 0.0, 0.0)
+        return abi.SkTreePolicy(pol.minLevel, pol.maxLevel, num_density_samples, 0, pol.maxDustFraction,
+                                pol.maxDustOpticalDepth, pol.maxDustDensityDispersion, pol.dust_kappa(media))
 
     def adopt(self, first_child):
         """Takes over a node list built elsewhere (sk_engine_build_octree) and derives the node boxes from it."""
@@ -962,7 +984,8 @@ class MonteCarloSimulation:
             # DensityTreePolicy::constructTree + the cell loop of MediumSystem::setupSelfAfter on the engine's side
             geom = self.medium.density_geometry()
             if isinstance(self.grid, PolicyTreeSpatialGrid):
-                _, ncells = engine.build_octree(self.grid.extent, self.grid.tree_policy(self.numDensitySamples), [geom])
+                _, ncells = engine.build_octree(self.grid.extent,
+                                                self.grid.tree_policy(self.numDensitySamples, [self.medium]), [geom])
                 self.grid.first_child = None  # fetched on demand: fetch_device_setup()
             else:
                 self.grid.configure(engine)

@@ -99,6 +99,41 @@ def test_oracle_tree_statistically_like_host_mirror_and_reference():
     assert m_own == pytest.approx(m_ref, rel=0.02)
 
 
+def shell_with_all_criteria(device_setup):
+    """cfg4's r^-2 shell with the optical-depth and density-dispersion criteria next to the mass fraction
+    (DensityTreePolicy.cpp:199-210)."""
+    sim = configs.cfg4(num_packets=1000, seed=2, max_level=6)
+    pol = sim.grid.policy
+    sim.grid.policy = H.DensityTreePolicy(pol.minLevel, pol.maxLevel, 2e-3, maxDustOpticalDepth=0.2, wavelength=0.55e-6,
+                                          maxDustDensityDispersion=0.9)
+    sim.deviceSetup = device_setup
+    return sim.setup()
+
+
+def test_oracle_tree_with_optical_depth_and_dispersion_criteria():
+    dev = shell_with_all_criteria(True)
+    e = OracleEngine(dev.config_struct())
+    fc, dens, vol = build(e, dev)
+    host = shell_with_all_criteria(False)   # numpy restatement with its own random numbers
+    n_oracle, n_host = int((fc < 0).sum()), host.grid.num_cells
+    assert abs(n_oracle - n_host) < 0.05 * n_host, (n_oracle, n_host)
+    # each criterion matters: dropping it gives a smaller tree
+    for drop in ("maxDustOpticalDepth", "maxDustDensityDispersion"):
+        sim = shell_with_all_criteria(True)
+        setattr(sim.grid.policy, drop, 0.0)
+        e2 = OracleEngine(sim.config_struct())
+        fc2, _, _ = build(e2, sim)
+        assert (fc2 < 0).sum() < 0.985 * n_oracle, drop
+    # the optical-depth criterion holds for the leaves below the maximum level (sampled mean density x diagonal)
+    lev = levels_of(fc)
+    leaf = fc < 0
+    boxes = dev.grid.boxes[leaf]
+    diag = np.linalg.norm(boxes[:, 3:] - boxes[:, :3], axis=1)
+    tau = dev.grid.policy.dust_kappa([dev.medium]) * dens * dev.medium.mix.mu * diag
+    inner = lev[leaf] < dev.grid.policy.maxLevel
+    assert np.quantile(tau[inner], 0.98) < 2.0 * dev.grid.policy.maxDustOpticalDepth
+
+
 def test_oracle_density_sampling_cartesian():
     sim = configs.cfg1(num_packets=1000, seed=0)
     sim.deviceSetup = True
@@ -133,7 +168,7 @@ def test_unsupported_setup_is_refused():
 # ----------------------------------------------------------------------------------------------------------------------
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", ["cfg2s", "cfg2_full", "cfg4_shell"])
+@pytest.mark.parametrize("case", ["cfg2s", "cfg2_full", "cfg4_shell", "all_criteria"])
 def test_device_tree_and_densities_equal_oracle(case):
     def make():
         if case == "cfg2s":
@@ -142,6 +177,8 @@ def test_device_tree_and_densities_equal_oracle(case):
             sim = configs.cfg2(num_packets=1000, seed=0)   # 933 k cells, levels 3-9
             sim.deviceSetup = True
             return sim.setup()
+        if case == "all_criteria":
+            return shell_with_all_criteria(True)
         sim = configs.cfg4(num_packets=1000, seed=2, max_level=6)   # shell geometry (power law), dust emission setup
         sim.deviceSetup = True
         return sim.setup()
