@@ -301,6 +301,8 @@ def native_arm(args):
         e2.prepare_primary(total)
         e2.run_segment(first, packets_per_gpu, True, True, False, 1000 + k)
         tseg = time.perf_counter()
+        e2e_parts["segment_device_s"] = e2e_parts.get("segment_device_s", 0.0) + e2.last_kernel_ms() * 1e-3 / e2e_steps
+        e2e_parts["segment_host_s"] = e2e_parts.get("segment_host_s", 0.0) + (tseg - tb) / e2e_steps
         if world > 1:
             with torch.cuda.stream(torch.cuda.ExternalStream(e2.cuda_stream(), device=local)):
                 dist.all_reduce(e2.device_tensor(3))

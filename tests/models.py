@@ -19,6 +19,14 @@ def small_octree(num_packets=20000, seed=5, **kw):
     return configs.cfg2(num_packets=num_packets, seed=seed, **args)
 
 
+def small_octree_engine_setup(num_packets=20000, seed=5, **kw):
+    """small_octree with the tree and the densities built on the engine's side (sk_engine_build_octree /
+    sk_engine_sample_medium) instead of by the numpy mirror."""
+    sim = small_octree(num_packets=num_packets, seed=seed, **kw)
+    sim.deviceSetup = True
+    return sim
+
+
 def two_sources_three_instruments(num_packets=20000, seed=11, force=True):
     """Point + shell sources, SED (with aperture) + two frames that share one observer, scattering levels,
     statistics, strongly forward-scattering dust (exercises the averaged HG peel-off), ragged 7x5x3 grid."""

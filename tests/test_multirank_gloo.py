@@ -101,3 +101,18 @@ def test_two_ranks_dust_emission_iterations_match_single_rank():
         a, b = got["sed%d" % c], e.read_sed(0, c)
         np.testing.assert_allclose(a, b, rtol=2e-3, atol=1e-6 * b.max())
     np.testing.assert_allclose(got["rf1"], e.read_rf(0), rtol=1e-10, atol=1e-12 * e.read_rf(0).max())
+
+
+def test_two_ranks_build_the_same_grid_without_communication():
+    """Engine-side set-up (octree by the density policy, sampled densities) draws from Philox streams keyed by node and
+    cell index, so every rank builds the identical replica on its own: no broadcast of the grid, unlike the reference,
+    whose ranks share the evaluation and sum the flags (DensityTreePolicy.cpp:283, ProcessManager::sumToAll)."""
+    comps = [abi.SK_COMP_TRANSPARENT, abi.SK_COMP_PRIMARY_DIRECT, abi.SK_COMP_PRIMARY_SCATTERED]
+    got = run_two_ranks("small_octree_engine_setup(num_packets=6000)", comps, 29613)
+    sim = models.small_octree_engine_setup(num_packets=6000).setup()
+    e = sim.configure(OracleEngine(sim.config_struct()))
+    sim.run(e)
+    assert list(got["block"]) == [0, 3000]
+    for c in comps:
+        a, b = got["sed%d" % c], e.read_sed(0, c)
+        np.testing.assert_allclose(a, b, rtol=1e-11, atol=1e-14 * b.max())
