@@ -286,10 +286,15 @@ def native_arm(args):
     nl, npix = sim.defaultWavelengthGrid.num_bins, sim.instruments[0].numPixelsX * sim.instruments[0].numPixelsY
     # (page-locked, as the contract's "pinned host memory"; sk_engine_read_* then skips its own staging buffer)
     ifu_host = [torch.zeros((nl, npix), dtype=torch.float64).pin_memory().numpy() for _ in range(4)]
-    barrier()
-    t0 = time.perf_counter()
     e2e_parts = {"configure_s": 0.0, "run_s": 0.0, "read_s": 0.0, "destroy_s": 0.0}
-    for k in range(e2e_steps):
+    t0 = time.perf_counter()
+    # pass -1 is an untimed warm-up of the whole end-to-end sequence: on first use the device's memory pool grows by a
+    # second packet bank next to the one of the timed steps above
+    for k in range(-1 if e2e_steps else 0, e2e_steps):
+        if k == 0:
+            barrier()
+            t0 = time.perf_counter()
+            e2e_parts = {"configure_s": 0.0, "run_s": 0.0, "read_s": 0.0, "destroy_s": 0.0}
         ta = time.perf_counter()
         e2 = abi.Engine(sim.config_struct(device=local))
         tcreate = time.perf_counter() - ta
@@ -362,7 +367,7 @@ def native_arm(args):
                            "l2": "256 MB buffer written between iterations", "sharding": "contiguous history blocks, "
                            "replicated grid, NCCL all-reduce of the instrument arrays per step" if world > 1 else "single GPU"},
                 "e2e": {"value": total / e2e_s if e2e_steps else None, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                        "includes": "engine create + octree link build + all table uploads + all stage kernels + read-back of 4 SED and 4 IFU arrays into pinned host buffers + engine destroy",
+                        "includes": "engine create + octree link build + all table uploads + all stage kernels + read-back of 4 SED and 4 IFU arrays into pinned host buffers + engine destroy; one untimed pass first",
                         "parts": e2e_parts},
                 "gpu_launches": int(cnt["kernel_launches"]),
                 "kernel": {"name": dom_name, "launches_per_step": dom_launches, "ms_per_step": stages[dom],

@@ -213,7 +213,7 @@ struct sk_engine {
     bool timing_pending = false;
     std::vector<int> instr_same_observer;
     std::vector<std::array<double, 3>> instr_kobs;
-    bool secondary_ready = false, has_secondary = false, l2_policy_set = false;
+    bool secondary_ready = false, has_secondary = false;
     int num_pix_lists = 0;
     void* pinned = nullptr;
     cudaEvent_t pin_ev[2] = {nullptr, nullptr};
@@ -461,84 +461,14 @@ static int finish_octree(sk_engine* e, const double extent[6], int nn, int nc, i
     return set_tables(e, T[0].data(), N + 1, T[1].data(), N + 1, T[2].data(), N + 1);
 }
 
+static int set_grid_octree_device(sk_engine* e, const double extent[6], int nn, const int32_t* first_child);
 extern "C" int sk_engine_set_grid_octree(sk_engine_t* e, const double extent[6], int32_t num_nodes,
                                          const int32_t* first_child)
 {
     if (!e || !extent || num_nodes < 1 || !first_child) return fail(SK_ERR_INVALID, "bad octree");
-    PhaseTimer pt("set_grid_octree");
+    if (num_nodes > SK_LINK_INDEX_MASK) return fail(SK_ERR_UNSUPPORTED, "octree with more than 2^26 nodes");
     if (int rc_bind = bind(e)) return rc_bind;
-    pt.lap("cudaSetDevice");
-    const int nn = num_nodes;
-    std::vector<int> lev(nn, -1), parent(nn, -1);
-    lev[0] = 0;
-    int maxlev = 0;
-    for (int l = 0; l < nn; ++l)
-    {
-        if (lev[l] < 0) return fail(SK_ERR_INVALID, "octree node list is not parent-before-child");
-        int fc = first_child[l];
-        if (fc < 0) continue;
-        if (fc <= l || fc + 8 > nn) return fail(SK_ERR_INVALID, "octree child index out of range");
-        for (int c = 0; c < 8; ++c)
-        {
-            if (lev[fc + c] >= 0) return fail(SK_ERR_INVALID, "octree node has two parents");
-            lev[fc + c] = lev[l] + 1;
-            parent[fc + c] = l;
-        }
-        maxlev = std::max(maxlev, lev[l] + 1);
-    }
-    if (maxlev > SK_MAX_TREE_LEVEL) return fail(SK_ERR_UNSUPPORTED, "octree deeper than 15 levels");
-    if (nn > SK_LINK_INDEX_MASK) return fail(SK_ERR_UNSUPPORTED, "octree with more than 2^26 nodes");
-    const int N = 1 << maxlev;
-    // lattice coordinates
-    std::vector<int> ix(nn, 0), iy(nn, 0), iz(nn, 0);
-    for (int l = 0; l < nn; ++l)
-    {
-        int fc = first_child[l];
-        if (fc < 0) continue;
-        int half = N >> (lev[l] + 1);
-        for (int c = 0; c < 8; ++c)
-        {
-            ix[fc + c] = ix[l] + ((c & 1) ? half : 0);
-            iy[fc + c] = iy[l] + ((c & 2) ? half : 0);
-            iz[fc + c] = iz[l] + ((c & 4) ? half : 0);
-        }
-    }
-    // cells
-    std::vector<int> cell_of_node(nn, -1);
-    std::vector<int> node_of_cell;
-    for (int l = 0; l < nn; ++l)
-        if (first_child[l] < 0)
-        {
-            cell_of_node[l] = (int)node_of_cell.size();
-            node_of_cell.push_back(l);
-        }
-    const int nc = (int)node_of_cell.size();
-    std::vector<int32_t> node_child(nn);
-    for (int l = 0; l < nn; ++l) node_child[l] = first_child[l] >= 0 ? first_child[l] : -(cell_of_node[l] + 1);
-    std::vector<uint32_t> node_coord(4 * (size_t)nn);
-    for (int l = 0; l < nn; ++l)
-    {
-        node_coord[4 * (size_t)l + 0] = ix[l];
-        node_coord[4 * (size_t)l + 1] = iy[l];
-        node_coord[4 * (size_t)l + 2] = iz[l];
-        node_coord[4 * (size_t)l + 3] = lev[l];
-    }
-    pt.lap("host node arrays");
-    free_group(e->grid_allocs);
-    int32_t *d_child, *d_first, *d_nodeofcell;
-    uint32_t* d_nodecoord;
-    if (int rc = upload(e->grid_allocs, node_child.data(), (size_t)nn, &d_child)) return rc;
-    pt.lap("first upload");
-    if (int rc = upload(e->grid_allocs, first_child, (size_t)nn, &d_first)) return rc;
-    std::vector<void*> scratch;
-    int rc = upload(scratch, node_coord.data(), node_coord.size(), &d_nodecoord);
-    if (!rc) rc = upload(scratch, node_of_cell.data(), (size_t)nc, &d_nodeofcell);
-    pt.lap("other uploads");
-    if (!rc) rc = finish_octree(e, extent, nn, nc, maxlev, d_first, d_child, d_nodecoord, d_nodeofcell);
-    pt.lap("finish_octree");
-    free_group(scratch);
-    pt.lap("free scratch");
-    return rc;
+    return set_grid_octree_device(e, extent, num_nodes, first_child);
 }
 
 // VoronoiMeshSnapshot as built by the reference's setup (sites + neighbour lists); the engine adds the start-cell table of
@@ -662,7 +592,6 @@ extern "C" int sk_engine_set_medium(sk_engine_t* e, int32_t num_cells, const dou
         e->M.dens = nullptr;
     }
     e->M.ncells = num_cells;
-    e->l2_policy_set = false;
     e->M.volume = nullptr;
     if (volume)
     {
@@ -736,6 +665,74 @@ static int grow_tree(sk_engine* e, TreeArrays& A, size_t need, size_t used)
     A.first = f;
     A.cap = cap;
     return SK_OK;
+}
+
+// Tail shared by sk_engine_build_octree and sk_engine_set_grid_octree: the node list is on the device (first_child and
+// lattice coordinates at a level `shift` finer than the deepest one reached); numbers the cells (leaves in node order,
+// TreeSpatialGrid.cpp:40-48), takes ownership of copies of the node arrays and builds the neighbour links.
+static int number_cells_and_finish(sk_engine* e, const double extent[6], int nn, int maxlev, int shift, uint4* d_coord,
+                                   const int32_t* d_first_in, std::vector<void*>& scratch, int32_t* d_total, int* num_cells)
+{
+    int32_t *d_leaf, *d_cellrank, *d_sums2, *d_child, *d_first, *d_nodeofcell;
+    if (int rc = dalloc_zero(scratch, (size_t)nn, &d_leaf)) return rc;
+    if (int rc = dalloc_zero(scratch, (size_t)nn, &d_cellrank)) return rc;
+    if (int rc = dalloc_zero(scratch, (size_t)nn / SK_SCAN_BLOCK + 2, &d_sums2)) return rc;
+    sk_tree_leaf_flags_kernel<<<(nn + 255) / 256, 256, 0, e->stream>>>(d_coord, d_first_in, nn, shift, d_leaf);
+    CK(cudaGetLastError());
+    if (int rc = exclusive_scan(e, d_leaf, d_cellrank, nn, d_sums2, d_total)) return rc;
+    int32_t nc = 0;
+    CK(cudaMemcpyAsync(&nc, d_total, sizeof nc, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    free_group(e->grid_allocs);
+    if (int rc = dalloc_zero(e->grid_allocs, (size_t)nn, &d_child)) return rc;
+    if (int rc = dalloc_zero(e->grid_allocs, (size_t)nn, &d_first)) return rc;
+    if (int rc = dalloc_zero(scratch, (size_t)nc, &d_nodeofcell)) return rc;
+    CK(cudaMemcpyAsync(d_first, d_first_in, (size_t)nn * sizeof(int32_t), cudaMemcpyDeviceToDevice, e->stream));
+    sk_tree_number_cells_kernel<<<(nn + 255) / 256, 256, 0, e->stream>>>(d_first_in, d_cellrank, nn, d_child, d_nodeofcell);
+    CK(cudaGetLastError());
+    *num_cells = nc;
+    return finish_octree(e, extent, nn, nc, maxlev, d_first, d_child, reinterpret_cast<const uint32_t*>(d_coord), d_nodeofcell);
+}
+
+// sk_engine_set_grid_octree: only the caller's first_child array crosses the bus; levels, lattice coordinates, the checks of
+// the node list (parent before child, one parent per node, every node reachable, depth) and the cell numbering run on the
+// device, one pass per level
+static int set_grid_octree_device(sk_engine* e, const double extent[6], int nn, const int32_t* first_child)
+{
+    PhaseTimer pt("set_grid_octree");
+    std::vector<void*> scratch;
+    struct Guard {
+        std::vector<void*>& v;
+        ~Guard() { free_group(v); }
+    } guard{scratch};
+    int32_t *d_first, *d_parent, *d_total;
+    int* d_status;
+    uint4* d_coord;
+    if (int rc = upload(scratch, first_child, (size_t)nn, &d_first)) return rc;
+    pt.lap("upload first_child");
+    if (int rc = dalloc_zero(scratch, (size_t)nn, &d_parent)) return rc;
+    if (int rc = dalloc_zero(scratch, (size_t)nn, &d_coord)) return rc;
+    if (int rc = dalloc_zero(scratch, 2, &d_status)) return rc;
+    if (int rc = dalloc_zero(scratch, 1, &d_total)) return rc;
+    const unsigned blocks = (unsigned)((nn + 255) / 256);
+    sk_tree_init_kernel<<<blocks, 256, 0, e->stream>>>(d_coord, d_parent, nn);
+    for (unsigned L = 0; L <= SK_MAX_TREE_LEVEL; ++L)
+        sk_tree_propagate_kernel<<<blocks, 256, 0, e->stream>>>(d_first, nn, L, d_coord, d_parent, d_status);
+    sk_tree_check_kernel<<<blocks, 256, 0, e->stream>>>(d_coord, nn, d_status);
+    CK(cudaGetLastError());
+    int status[2] = {0, 0};
+    CK(cudaMemcpyAsync(status, d_status, sizeof status, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    pt.lap("levels and coordinates");
+    if (status[0] & 1) return fail(SK_ERR_INVALID, "octree child index out of range or not after its parent");
+    if (status[0] & 2) return fail(SK_ERR_INVALID, "octree node has two parents");
+    if (status[0] & 4) return fail(SK_ERR_UNSUPPORTED, "octree deeper than 15 levels");
+    if (status[0] & 8) return fail(SK_ERR_INVALID, "octree node list is not parent-before-child");
+    const int maxlev = status[1];
+    int nc = 0;
+    int rc = number_cells_and_finish(e, extent, nn, maxlev, SK_MAX_TREE_LEVEL - maxlev, d_coord, d_first, scratch, d_total, &nc);
+    pt.lap("cells and links");
+    return rc;
 }
 
 extern "C" int sk_engine_build_octree(sk_engine_t* e, const double extent[6], const sk_tree_policy_t* policy, int32_t num_media,
@@ -828,26 +825,8 @@ extern "C" int sk_engine_build_octree(sk_engine_t* e, const double extent[6], co
         lend = nn_new;
     }
     const int nn = (int)lend;
-    // cells = leaves in node order; lattice coordinates in units of the deepest level reached
-    int32_t *d_leaf, *d_cellrank, *d_sums2, *d_child, *d_first, *d_nodeofcell;
-    if (int rc = dalloc_zero(scratch, (size_t)nn, &d_leaf)) return rc;
-    if (int rc = dalloc_zero(scratch, (size_t)nn, &d_cellrank)) return rc;
-    if (int rc = dalloc_zero(scratch, (size_t)nn / SK_SCAN_BLOCK + 2, &d_sums2)) return rc;
-    sk_tree_leaf_flags_kernel<<<(nn + 255) / 256, 256, 0, e->stream>>>(A.coord, A.first, nn, maxL - maxlev, d_leaf);
-    CK(cudaGetLastError());
-    if (int rc = exclusive_scan(e, d_leaf, d_cellrank, nn, d_sums2, d_total)) return rc;
-    int32_t nc = 0;
-    CK(cudaMemcpyAsync(&nc, d_total, sizeof nc, cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
-    free_group(e->grid_allocs);
-    if (int rc = dalloc_zero(e->grid_allocs, (size_t)nn, &d_child)) return rc;
-    if (int rc = dalloc_zero(e->grid_allocs, (size_t)nn, &d_first)) return rc;
-    if (int rc = dalloc_zero(scratch, (size_t)nc, &d_nodeofcell)) return rc;
-    CK(cudaMemcpyAsync(d_first, A.first, (size_t)nn * sizeof(int32_t), cudaMemcpyDeviceToDevice, e->stream));
-    sk_tree_number_cells_kernel<<<(nn + 255) / 256, 256, 0, e->stream>>>(A.first, d_cellrank, nn, d_child, d_nodeofcell);
-    CK(cudaGetLastError());
-    if (int rc = finish_octree(e, extent, nn, nc, maxlev, d_first, d_child, reinterpret_cast<const uint32_t*>(A.coord), d_nodeofcell))
-        return rc;
+    int nc = 0;
+    if (int rc = number_cells_and_finish(e, extent, nn, maxlev, maxL - maxlev, A.coord, A.first, scratch, d_total, &nc)) return rc;
     if (num_nodes) *num_nodes = (uint64_t)nn;
     if (num_cells) *num_cells = (uint64_t)nc;
     return SK_OK;
@@ -891,7 +870,6 @@ extern "C" int sk_engine_sample_medium(sk_engine_t* e, const sk_density_geometry
     e->M.dens = d_dens;
     e->M.volume = d_vol;
     e->M.ncells = nc;
-    e->l2_policy_set = false;
     return SK_OK;
 }
 
@@ -1652,37 +1630,9 @@ extern "C" int sk_engine_launch_segment(sk_engine_t* e, uint64_t first, uint64_t
     if (store && !e->M.force_scattering)
         return fail(SK_ERR_INVALID, "storing the radiation field requires forced scattering (Configuration.cpp:476-482)");
     if (int rc_bind = bind(e)) return rc_bind;
-    if (!e->num_sms)
-    {
-        cudaDeviceProp prop;
-        CK(cudaGetDeviceProperties(&prop, e->cfg.device));
-        e->num_sms = prop.multiProcessorCount;
-    }
-    if (!e->l2_policy_set)
-    {
-        // keep the cell records (the random-access working set of the crossing loops) resident in L2 while the packet
-        // bank streams through it: persisting access-policy window on the engine's stream
-        const void* base = e->grid_kind == 2 ? (const void*)e->M.cells : e->grid_kind == 3 ? (const void*)e->M.vrec : (const void*)e->M.dens;
-        size_t bytes = e->grid_kind == 1 ? (size_t)e->M.ncells * sizeof(double) : (size_t)e->M.ncells * 32;
-        cudaDeviceProp prop;
-        CK(cudaGetDeviceProperties(&prop, e->cfg.device));
-        size_t window = std::min<size_t>(bytes, (size_t)prop.accessPolicyMaxWindowSize);
-        size_t carve = std::min<size_t>(window, (size_t)prop.persistingL2CacheMaxSize);
-        if (window && carve && !getenv("SK_NO_L2_PERSIST"))
-        {
-            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
-            cudaStreamAttrValue attr;
-            memset(&attr, 0, sizeof attr);
-            attr.accessPolicyWindow.base_ptr = const_cast<void*>(base);
-            attr.accessPolicyWindow.num_bytes = window;
-            attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)window);
-            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-            cudaStreamSetAttribute(e->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
-            cudaGetLastError();  // the policy is an optimisation: failure to set it is not an error
-        }
-        e->l2_policy_set = true;
-    }
+    if (!e->num_sms) CK(cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, e->cfg.device));
+    // (An L2 persisting window over the cell records was measured to make no difference -- the 30 MB of records stay in
+    //  the 126 MB L2 on their own -- and cudaGetDeviceProperties / cudaDeviceSetLimit cost milliseconds per engine.)
     CK(cudaEventRecord(e->ev0, e->stream));
     e->stage_of_pair.clear();
     if (count)

@@ -243,6 +243,56 @@ __global__ void __launch_bounds__(128) sk_tree_subdivide_kernel(int N, uint4* __
                                     c.w + 1u);
 }
 
+// A node list handed in by the caller (sk_engine_set_grid_octree): levels and lattice coordinates of the children of the
+// nodes of level L, one pass per level.  Coordinates are top-aligned on the 2^SK_MAX_TREE_LEVEL lattice (child bit c of a
+// node of level L sits at bit SK_MAX_TREE_LEVEL-1-L) and are shifted down once the depth of the tree is known.
+// flags: bit 0 child index out of range or not after its parent, bit 1 node with two parents, bit 2 deeper than
+// SK_MAX_TREE_LEVEL, bit 3 node not reachable from the root; status[1] = deepest level
+#define SK_TREE_UNKNOWN_LEVEL 0xffffffffu
+__global__ void sk_tree_propagate_kernel(const int32_t* __restrict__ first_child, int nn, unsigned L, uint4* __restrict__ coord,
+                                         int32_t* __restrict__ parent, int* __restrict__ status)
+{
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nn) return;
+    const uint4 c = coord[l];
+    if (c.w != L) return;
+    const int fc = first_child[l];
+    if (fc < 0) return;
+    if (fc <= l || fc + 8 > nn)
+    {
+        atomicOr(&status[0], 1);
+        return;
+    }
+    if (L >= SK_MAX_TREE_LEVEL)
+    {
+        atomicOr(&status[0], 4);
+        return;
+    }
+    const unsigned bit = 1u << (SK_MAX_TREE_LEVEL - 1 - L);
+    for (int ch = 0; ch < 8; ++ch)
+    {
+        if (atomicCAS(&parent[fc + ch], -1, l) != -1)
+        {
+            atomicOr(&status[0], 2);
+            continue;
+        }
+        coord[fc + ch] = make_uint4(c.x | ((ch & 1) ? bit : 0u), c.y | ((ch & 2) ? bit : 0u), c.z | ((ch & 4) ? bit : 0u), L + 1);
+    }
+    atomicMax(&status[1], (int)L + 1);
+}
+__global__ void sk_tree_init_kernel(uint4* __restrict__ coord, int32_t* __restrict__ parent, int nn)
+{
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nn) return;
+    coord[l] = make_uint4(0, 0, 0, l == 0 ? 0u : SK_TREE_UNKNOWN_LEVEL);
+    parent[l] = -1;
+}
+__global__ void sk_tree_check_kernel(const uint4* __restrict__ coord, int nn, int* __restrict__ status)
+{
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l < nn && coord[l].w == SK_TREE_UNKNOWN_LEVEL) atomicOr(&status[0], 8);
+}
+
 // after the last level: rescale the lattice coordinates to the deepest level actually reached, flag the leaves
 __global__ void sk_tree_leaf_flags_kernel(uint4* __restrict__ coord, const int32_t* __restrict__ first_child, int nn, int shift,
                                           int32_t* __restrict__ leaf)

@@ -206,3 +206,14 @@ def test_engine_rejects_unsupported_and_bad_calls(engine_lib):
     with pytest.raises(abi.SkError) as ei:
         abi.Engine(abi.SkConfig(0, 1, 0, 0.5, 1e4, 99, 0), lib=engine_lib)
     assert ei.value.code == abi.SK_ERR_INVALID
+    # malformed octree node lists are caught by the device-side checks of sk_engine_set_grid_octree
+    box = [0, 0, 0, 1, 1, 1]
+    leaves = [-1] * 8
+    for bad in ([5] + leaves,                       # children beyond the end of the list
+                [1] + leaves[:7] + [1] + leaves,    # a node pointing back at an earlier block: two parents / not after
+                [1] + leaves + leaves):             # orphan nodes that no parent points to
+        with pytest.raises(abi.SkError) as ei:
+            e.set_grid_octree(box, bad)
+        assert ei.value.code == abi.SK_ERR_INVALID, bad
+    e.set_grid_octree(box, [1] + leaves[:7] + [9] + leaves)   # a valid two-level tree
+    e.set_medium(np.ones(15))
