@@ -362,17 +362,24 @@ extern "C" void sk_engine_destroy(sk_engine_t* e)
 
 static int set_tables(sk_engine* e, const double* xv, int nx1, const double* yv, int ny1, const double* zv, int nz1)
 {
+    // device copies padded to an even number of entries: the trace kernels stage them with 16-byte-granular bulk copies
     double *dx, *dy, *dz;
-    if (int rc = upload(e->grid_allocs, xv, nx1, &dx)) return rc;
-    if (int rc = upload(e->grid_allocs, yv, ny1, &dy)) return rc;
-    if (int rc = upload(e->grid_allocs, zv, nz1, &dz)) return rc;
+    const double* src[3] = {xv, yv, zv};
+    const int len[3] = {nx1, ny1, nz1};
+    double** dst[3] = {&dx, &dy, &dz};
+    for (int a = 0; a < 3; ++a)
+    {
+        std::vector<double> padded(SK_TABLE_PAD(len[a]), src[a][len[a] - 1]);
+        std::copy(src[a], src[a] + len[a], padded.begin());
+        if (int rc = upload(e->grid_allocs, padded.data(), padded.size(), dst[a])) return rc;
+    }
     e->M.xv = dx;
     e->M.yv = dy;
     e->M.zv = dz;
     e->table_len[0] = nx1;
     e->table_len[1] = ny1;
     e->table_len[2] = nz1;
-    size_t bytes = (size_t)(nx1 + ny1 + nz1) * sizeof(double);
+    size_t bytes = (size_t)(SK_TABLE_PAD(nx1) + SK_TABLE_PAD(ny1) + SK_TABLE_PAD(nz1)) * sizeof(double);
     // keep the tables in shared memory when they leave room for >= 4 CTAs per SM (227 KB per SM)
     e->M.lattice_in_smem = bytes <= 48 * 1024 ? 1 : 0;
     e->smem_bytes = e->M.lattice_in_smem ? bytes : 0;

@@ -39,6 +39,8 @@ struct SkLocalCounters {
     unsigned int packets, fwd_paths, fwd_segs, replay_segs, peel_paths, peel_segs, scatt, rf, det, fallbacks;
 };
 
+// border tables are allocated and staged in multiples of 16 bytes (TMA bulk copies): entries rounded up to even
+#define SK_TABLE_PAD(n) (((n) + 1) & ~1)
 struct SkSmemTables {
     const double *X, *Y, *Z;
 };

@@ -131,6 +131,45 @@ struct SkRunArgs {
 };
 
 // ---------------------------------------------------------------------------------------------------
+// TMA bulk copy global -> shared memory (cp.async.bulk, SASS UBLKCP) completing on an mbarrier: stages the border tables
+// of the trace kernels.  Sizes and both addresses are multiples of 16 bytes.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t sk_shared_addr(const void* p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void sk_mbar_init(unsigned long long* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sk_shared_addr(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void sk_mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sk_shared_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sk_tma_load_bulk(void* dst_shared, const void* src_global, unsigned bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     sk_shared_addr(dst_shared)),
+                 "l"(src_global), "r"(bytes), "r"(sk_shared_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void sk_mbar_wait(unsigned long long* bar, unsigned phase)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "SK_MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra SK_MBAR_DONE;\n"
+        "bra SK_MBAR_WAIT;\n"
+        "SK_MBAR_DONE:\n"
+        "}\n" ::"r"(sk_shared_addr(bar)),
+        "r"(phase)
+        : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Philox4x32-10 counter-based generator (replaces Random.cpp:20-56); identical to oracle/sk_oracle.c
 // ---------------------------------------------------------------------------------------------------
 struct SkRng {

@@ -208,20 +208,28 @@ template <int GRID, int MODE, bool STORE, bool TABLES_IN_SMEM>
 __global__ void __launch_bounds__(SK_TRACE_BLOCK, MODE == 2 ? SK_TRACE_MINBLOCKS_PEEL : SK_TRACE_MINBLOCKS)
     sk_wf_trace(const SkDevModel M, const SkRunArgs A, const SkBank K, const SkRayDir obs)
 {
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem[];
+    __shared__ unsigned long long tma_bar;
     SkSmemTables T;
     if (TABLES_IN_SMEM)
     {
-        // stage the per-axis border tables (Cartesian borders / octree lattice) in shared memory; the instantiation is
+        // stage the per-axis border tables (Cartesian borders / octree lattice) in shared memory with three TMA bulk copies
+        // that complete on one mbarrier (the tables are padded to 16-byte multiples, SK_TABLE_PAD); the instantiation is
         // separate from the global-memory one so that the lookups in the crossing loop compile to LDS
-        const int n0 = M.nx + 1, n1 = M.ny + 1, n2 = M.nz + 1;
-        for (int i = threadIdx.x; i < n0; i += blockDim.x) smem[i] = M.xv[i];
-        for (int i = threadIdx.x; i < n1; i += blockDim.x) smem[n0 + i] = M.yv[i];
-        for (int i = threadIdx.x; i < n2; i += blockDim.x) smem[n0 + n1 + i] = M.zv[i];
+        const int n0 = SK_TABLE_PAD(M.nx + 1), n1 = SK_TABLE_PAD(M.ny + 1), n2 = SK_TABLE_PAD(M.nz + 1);
+        if (threadIdx.x == 0) sk_mbar_init(&tma_bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            sk_mbar_arrive_expect_tx(&tma_bar, (unsigned)((n0 + n1 + n2) * sizeof(double)));
+            sk_tma_load_bulk(smem, M.xv, (unsigned)(n0 * sizeof(double)), &tma_bar);
+            sk_tma_load_bulk(smem + n0, M.yv, (unsigned)(n1 * sizeof(double)), &tma_bar);
+            sk_tma_load_bulk(smem + n0 + n1, M.zv, (unsigned)(n2 * sizeof(double)), &tma_bar);
+        }
+        sk_mbar_wait(&tma_bar, 0);
         T.X = smem;
         T.Y = smem + n0;
         T.Z = smem + n0 + n1;
-        __syncthreads();
     }
     else
     {
