@@ -35,6 +35,9 @@
 #include <valarray>
 #include <vector>
 
+#include <cuda_runtime_api.h>
+#include <nccl.h>
+
 #define private public
 #define protected public
 #include "AllCellsLibrary.hpp"
@@ -164,11 +167,103 @@ namespace
 
 ////////////////////////////////////////////////////////////////////
 
-GpuLifeCycle::GpuLifeCycle(MonteCarloSimulation* sim, int device) : _sim(sim), _device(device) {}
+GpuLifeCycle::GpuLifeCycle(MonteCarloSimulation* sim, const std::vector<int>& devices) : _sim(sim), _devices(devices)
+{
+    if (_devices.empty()) _devices.push_back(0);
+}
 
 GpuLifeCycle::~GpuLifeCycle()
 {
-    if (_e) sk_engine_destroy(_e);
+    for (void* c : _comms) ncclCommDestroy(static_cast<ncclComm_t>(c));
+    for (sk_engine_t* e : _engines) sk_engine_destroy(e);
+}
+
+// every device gets a full replica of the model, like every process of the reference's MPI runs
+void GpuLifeCycle::configure()
+{
+    for (int device : _devices)
+    {
+        _e = nullptr;
+        configureEngine(device);
+        _engines.push_back(_e);
+    }
+    _e = _engines[0];
+    if (_engines.size() > 1) prepareNccl();
+}
+
+void GpuLifeCycle::prepareNccl()
+{
+    std::vector<ncclComm_t> comms(_devices.size());
+    ncclResult_t r = ncclCommInitAll(comms.data(), static_cast<int>(_devices.size()), _devices.data());
+    if (r != ncclSuccess) throw FATALERROR(string("NCCL: ") + ncclGetErrorString(r));
+    for (ncclComm_t c : comms) _comms.push_back(c);
+    _sim->log()->info("GPU life cycle: " + std::to_string(_devices.size()) + " devices, NCCL all-reduce of the tallies");
+}
+
+// one emission segment: contiguous history blocks, one per device, run concurrently
+void GpuLifeCycle::runSegmentOnAll(size_t Npp, int primary, int peel, int store)
+{
+    const size_t n = _engines.size();
+    const uint32_t segment = _segment++;
+    if (n == 1)
+    {
+        check(sk_engine_run_segment(_e, 0, Npp, primary, peel, store, segment));
+        return;
+    }
+    std::vector<int> rc(n, SK_OK);
+    std::vector<string> msg(n);
+    std::vector<std::thread> threads;
+    for (size_t i = 0; i != n; ++i)
+    {
+        const uint64_t first = Npp * i / n, last = Npp * (i + 1) / n;
+        threads.emplace_back([this, i, first, last, primary, peel, store, segment, &rc, &msg]() {
+            rc[i] = sk_engine_run_segment(_engines[i], first, last - first, primary, peel, store, segment);
+            if (rc[i] != SK_OK) msg[i] = sk_last_error();  // the error text is thread-local
+        });
+    }
+    for (auto& t : threads) t.join();
+    for (size_t i = 0; i != n; ++i)
+        if (rc[i] != SK_OK) throw FATALERROR("GPU life-cycle engine (device " + std::to_string(_devices[i]) + "): " + msg[i]);
+}
+
+// in-place sum over the devices of one tally block (sk_engine_device_buffer: 0 rf1, 2 rf2c, 3 detectors, 4 statistics)
+void GpuLifeCycle::allReduce(int which)
+{
+    const size_t n = _engines.size();
+    if (n == 1) return;
+    std::vector<void*> buf(n), stream(n);
+    uint64_t count = 0;
+    for (size_t i = 0; i != n; ++i)
+    {
+        uint64_t c = 0;
+        check(sk_engine_device_buffer(_engines[i], which, &buf[i], &c));
+        check(sk_engine_cuda_stream(_engines[i], &stream[i]));
+        if (i && c != count) throw FATALERROR("GPU life cycle: tally blocks of different size on different devices");
+        count = c;
+        if (!buf[i]) count = 0;
+    }
+    if (!count) return;
+    ncclGroupStart();
+    for (size_t i = 0; i != n; ++i)
+    {
+        ncclResult_t r = ncclAllReduce(buf[i], buf[i], count, ncclDouble, ncclSum, static_cast<ncclComm_t>(_comms[i]),
+                                       static_cast<cudaStream_t>(stream[i]));
+        if (r != ncclSuccess)
+        {
+            ncclGroupEnd();
+            throw FATALERROR(string("NCCL all-reduce: ") + ncclGetErrorString(r));
+        }
+    }
+    ncclResult_t r = ncclGroupEnd();
+    if (r != ncclSuccess) throw FATALERROR(string("NCCL all-reduce: ") + ncclGetErrorString(r));
+    for (size_t i = 0; i != n; ++i) check(sk_engine_synchronize(_engines[i]));
+}
+
+// MediumSystem::communicateRadiationField(primary), MediumSystem.cpp:1304-1313: sum over the devices, then _rf2 = _rf2c
+void GpuLifeCycle::communicateRadiationField(int primary)
+{
+    allReduce(primary ? 0 : 2);
+    for (sk_engine_t* e : _engines) check(sk_engine_communicate_rf(e, primary));
 }
 
 void GpuLifeCycle::check(int rc) const
@@ -248,7 +343,7 @@ std::string GpuLifeCycle::unsupportedReason() const
 
 ////////////////////////////////////////////////////////////////////
 
-void GpuLifeCycle::configure()
+void GpuLifeCycle::configureEngine(int device)
 {
     auto config = _sim->_config;
     auto ms = _sim->mediumSystem();
@@ -261,7 +356,7 @@ void GpuLifeCycle::configure()
     c.min_scatt_events = config->minScattEvents();
     c.path_length_bias = config->pathLengthBias();
     c.min_weight_reduction = config->minWeightReduction();
-    c.device = _device;
+    c.device = device;
     check(sk_engine_create(&c, &_e));
 
     // ---- spatial grid
@@ -497,7 +592,18 @@ void GpuLifeCycle::runSimulation()
             runSecondaryEmission();
         }
     }
-    check(sk_engine_counters(_e, &_counters, 0));
+    memset(&_counters, 0, sizeof _counters);
+    for (sk_engine_t* e : _engines)
+    {
+        sk_counters_t c;
+        check(sk_engine_counters(e, &c, 0));
+        const uint64_t* src = reinterpret_cast<const uint64_t*>(&c);
+        uint64_t* dst = reinterpret_cast<uint64_t*>(&_counters);
+        for (size_t k = 0; k != sizeof(sk_counters_t) / sizeof(uint64_t); ++k) dst[k] += src[k];
+    }
+    // FluxRecorder::calibrateAndWrite -> ProcessManager::sumToRoot, FluxRecorder.cpp:487-493
+    allReduce(3);
+    allReduce(4);
     {
         TimeLogger logger(_sim->log(), "final output");
         returnRadiationField();
@@ -514,7 +620,8 @@ void GpuLifeCycle::runPrimaryEmission()
     auto config = _sim->_config;
     string segment = "primary emission";
     TimeLogger logger(_sim->log(), segment);
-    if (config->hasRadiationField()) check(sk_engine_clear_rf(_e, 1));
+    if (config->hasRadiationField())
+        for (sk_engine_t* e : _engines) check(sk_engine_clear_rf(e, 1));
     size_t Npp = config->numPrimaryPackets();
     if (!Npp)
         _sim->log()->warning("Skipping primary emission because no photon packets were requested");
@@ -523,10 +630,10 @@ void GpuLifeCycle::runPrimaryEmission()
     else
     {
         _sim->log()->info("Launching " + StringUtils::toString(static_cast<double>(Npp)) + " primary emission photon packets on the GPU");
-        check(sk_engine_prepare_primary(_e, Npp));
-        check(sk_engine_run_segment(_e, 0, Npp, 1, 1, config->hasRadiationField(), _segment++));
+        for (sk_engine_t* e : _engines) check(sk_engine_prepare_primary(e, Npp));
+        runSegmentOnAll(Npp, 1, 1, config->hasRadiationField());
     }
-    if (config->hasRadiationField()) check(sk_engine_communicate_rf(_e, 1));
+    if (config->hasRadiationField()) communicateRadiationField(1);
 }
 
 // MonteCarloSimulation::runSecondaryEmission, MonteCarloSimulation.cpp:142-173
@@ -536,24 +643,26 @@ void GpuLifeCycle::runSecondaryEmission()
     string segment = "secondary emission";
     TimeLogger logger(_sim->log(), segment);
     bool storeRF = config->storeEmissionRadiationField();
-    if (storeRF) check(sk_engine_clear_rf(_e, 0));
+    if (storeRF)
+        for (sk_engine_t* e : _engines) check(sk_engine_clear_rf(e, 0));
     size_t Npp = config->numSecondaryPackets();
     double L = 0.;
     if (!Npp)
         _sim->log()->warning("Skipping secondary emission because no photon packets were requested");
     else
     {
-        check(sk_engine_prepare_secondary(_e, Npp, &L));
+        // every device prepares the same secondary sources from its (all-reduced) copy of the radiation field
+        for (sk_engine_t* e : _engines) check(sk_engine_prepare_secondary(e, Npp, &L));
         if (!L)
             _sim->log()->warning("Skipping secondary emission because the total luminosity of secondary sources is zero");
         else
         {
             auto units = _sim->units();
             _sim->log()->info("Dust luminosity: " + StringUtils::toString(units->obolluminosity(L), 'g') + " " + units->ubolluminosity());
-            check(sk_engine_run_segment(_e, 0, Npp, 0, 1, storeRF, _segment++));
+            runSegmentOnAll(Npp, 0, 1, storeRF);
         }
     }
-    if (storeRF) check(sk_engine_communicate_rf(_e, 0));
+    if (storeRF) communicateRadiationField(0);
 }
 
 // MonteCarloSimulation::runSecondaryEmissionIterations (.cpp:335-403) with DustAbsorptionConvergence (.cpp:180-227) and
@@ -577,17 +686,17 @@ void GpuLifeCycle::runSecondaryEmissionIterations()
         {
             string segment = "secondary emission iteration " + std::to_string(iter);
             TimeLogger logger(log, segment);
-            check(sk_engine_clear_rf(_e, 0));
+            for (sk_engine_t* e : _engines) check(sk_engine_clear_rf(e, 0));
             double L = 0.;
-            check(sk_engine_prepare_secondary(_e, Npp, &L));
+            for (sk_engine_t* e : _engines) check(sk_engine_prepare_secondary(e, Npp, &L));
             if (!L)
             {
                 log->warning("Skipping secondary emission iterations because the total luminosity of secondary sources is zero");
                 return;
             }
             log->info("Dust luminosity: " + StringUtils::toString(units->obolluminosity(L), 'g') + " " + units->ubolluminosity());
-            check(sk_engine_run_segment(_e, 0, Npp, 0, 0, 1, _segment++));
-            check(sk_engine_communicate_rf(_e, 0));
+            runSegmentOnAll(Npp, 0, 0, 1);
+            communicateRadiationField(0);
 
             double Labsprim = 0., Labsseco = 0.;
             check(sk_engine_absorbed_luminosity(_e, 1, &Labsprim));

@@ -19,7 +19,11 @@ class MonteCarloSimulation;
 class GpuLifeCycle
 {
 public:
-    GpuLifeCycle(MonteCarloSimulation* sim, int device);
+    // one engine per listed CUDA device; with several devices every emission segment is split into contiguous history
+    // blocks (one per device, run concurrently from one host thread each) and the tallies are all-reduced with NCCL
+    // exactly where the reference calls ProcessManager::sumToAll / sumToRoot (MediumSystem.cpp:1304-1313,
+    // FluxRecorder.cpp:487-493)
+    GpuLifeCycle(MonteCarloSimulation* sim, const std::vector<int>& devices);
     ~GpuLifeCycle();
 
     // returns an empty string when the configured simulation lies on the accelerated path, or the reason why not
@@ -35,6 +39,11 @@ public:
 
 private:
     void check(int rc) const;
+    void configureEngine(int device);
+    void prepareNccl();
+    void runSegmentOnAll(size_t Npp, int primary, int peel, int store);
+    void allReduce(int which);
+    void communicateRadiationField(int primary);
     void runPrimaryEmission();
     void runSecondaryEmission();
     void runSecondaryEmissionIterations();
@@ -42,7 +51,9 @@ private:
     void returnDetectors();
 
     MonteCarloSimulation* _sim;
-    int _device;
+    std::vector<int> _devices;
+    std::vector<sk_engine_t*> _engines;  // one per device; _e is the one being configured, then the first
+    std::vector<void*> _comms;           // ncclComm_t per engine (empty for a single device)
     sk_engine_t* _e{nullptr};
     uint32_t _segment{0};
     sk_counters_t _counters{};

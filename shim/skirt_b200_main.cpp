@@ -2,7 +2,7 @@
 // probes and output writers (linked unmodified from the reference's object files) driven by GpuLifeCycle, which runs
 // every emission segment through libskirt9_b200.so (include/sk_engine.h).
 //
-//   skirt_b200 [-t threads] [-b] [-i indir] [-o outdir] [-g device] [--cpu] file.ski
+//   skirt_b200 [-t threads] [-b] [-i indir] [-o outdir] [-g device[,device...]] [--cpu] file.ski
 //
 // The structure follows SKIRT/main/SkirtMain.cpp:15-31 and SkirtCommandLineHandler::doSimulation
 // (SKIRT/main/SkirtCommandLineHandler.cpp:295-400); `--cpu` runs the reference's own CPU life cycle instead (the same
@@ -68,7 +68,8 @@ int main(int argc, char** argv)
     Console console;
 
     // ---- command line
-    int threads = 0, device = 0;
+    int threads = 0;
+    std::vector<int> devices;
     bool brief = false, cpu = false;
     string inpath, outpath, skipath;
     for (int i = 1; i < argc; ++i)
@@ -83,7 +84,19 @@ int main(int argc, char** argv)
             if (a == "-t")
                 threads = std::stoi(value());
             else if (a == "-g")
-                device = std::stoi(value());
+            {
+                // one CUDA device ordinal or a comma-separated list: the histories of every segment are split over them
+                devices.clear();
+                string list = value();
+                size_t pos = 0;
+                while (pos <= list.size())
+                {
+                    size_t comma = list.find(',', pos);
+                    if (comma == string::npos) comma = list.size();
+                    devices.push_back(std::stoi(list.substr(pos, comma - pos)));
+                    pos = comma + 1;
+                }
+            }
             else if (a == "-i")
                 inpath = value();
             else if (a == "-o")
@@ -105,7 +118,7 @@ int main(int argc, char** argv)
     }
     if (skipath.empty())
     {
-        console.error("usage: skirt_b200 [-t threads] [-b] [-i indir] [-o outdir] [-g device] [--cpu] file.ski");
+        console.error("usage: skirt_b200 [-t threads] [-b] [-i indir] [-o outdir] [-g device[,device...]] [--cpu] file.ski");
         return EXIT_FAILURE;
     }
     if (!StringUtils::endsWith(skipath, ".ski")) skipath += ".ski";
@@ -140,7 +153,7 @@ int main(int argc, char** argv)
             TimeLogger logger(simulation->_log, "simulation " + simulation->_paths->outputPrefix());
             simulation->setupSimulation();
 
-            GpuLifeCycle gpu(simulation, device);
+            GpuLifeCycle gpu(simulation, devices);
             string why = cpu ? string("--cpu was given") : gpu.unsupportedReason();
             if (why.empty())
             {

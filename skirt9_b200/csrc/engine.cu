@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -208,6 +209,8 @@ struct sk_engine {
     double* scalar = nullptr;
     int table_len[3] = {0, 0, 0};
     const int32_t* first_child_dev = nullptr;  // octree: first_child per node (owned by grid_allocs)
+    std::map<const void*, int> occupancy;       // resident blocks per SM of the trace-kernel instantiations ...
+    size_t occupancy_smem = (size_t)-1;         // ... for this dynamic shared-memory size
     size_t smem_bytes = 0;
     float last_ms = 0.f;
     bool timing_pending = false;
@@ -1483,16 +1486,24 @@ template <int GRID, int MODE, bool STORE, bool SMEMT>
 static int launch_trace_impl(sk_engine* e, const SkRunArgs& A, const SkRayDir& dir)
 {
     auto kern = sk_wf_trace<GRID, MODE, STORE, SMEMT>;
-    // occupancy of this instantiation for this engine's shared-memory footprint (cached per footprint)
-    static size_t cached_smem = (size_t)-1;
-    static int per_sm = 0;
+    // occupancy of this instantiation on this engine's device for its shared-memory footprint (cached in the engine:
+    // engines on different devices run from different host threads)
     const size_t smem = e->smem_bytes;
-    if (cached_smem != smem)
+    if (e->occupancy_smem != smem)
+    {
+        e->occupancy.clear();
+        e->occupancy_smem = smem;
+    }
+    int per_sm = 0;
+    auto it = e->occupancy.find((const void*)kern);
+    if (it != e->occupancy.end())
+        per_sm = it->second;
+    else
     {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1)));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SK_TRACE_BLOCK, smem));
         if (per_sm < 1) per_sm = 1;
-        cached_smem = smem;
+        e->occupancy[(const void*)kern] = per_sm;
     }
     // persistent grid: every SM filled to the occupancy this kernel gets, but no more warps than chunks of rays
     unsigned long long chunks = ((unsigned long long)e->bank.n + SK_CHUNK - 1) / SK_CHUNK;

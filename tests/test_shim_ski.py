@@ -21,14 +21,15 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 pytestmark = pytest.mark.gpu
 
 
-def run_ski(name, tmp_path, packets):
+def run_ski(name, tmp_path, packets, devices=None):
     if not os.path.exists(EXE):
         pytest.fail("shim/_build/skirt_b200 has not been built (make -C shim, where /root/reference exists)")
     text = open(os.path.join(GOLD, "ski", name + ".ski")).read()
     text = re.sub(r'numPackets="[^"]*"', 'numPackets="%g"' % packets, text, count=1)
     ski = tmp_path / (name + ".ski")
     ski.write_text(text)
-    subprocess.check_call([EXE, "-t", "1", "-b", "-o", str(tmp_path), str(ski)], stdout=subprocess.DEVNULL)
+    extra = ["-g", devices] if devices else []
+    subprocess.check_call([EXE, "-t", "1", "-b", "-o", str(tmp_path)] + extra + [str(ski)], stdout=subprocess.DEVNULL)
     log = (tmp_path / (name + "_log.txt")).read_text()
     assert "GPU life cycle:" in log, log[-2000:]
     return log
@@ -210,3 +211,48 @@ def test_cfg7v_ski_voronoi_dust_emission_runs_unchanged(tmp_path):
     T = read_columns(tmp_path / "cfg7v_temp_dust_T.dat")[:, 1]
     ok = g["temperature"] > 0
     assert np.median(np.abs(T[ok] / g["temperature"][ok] - 1)) < 0.02
+
+
+def _num_gpus():
+    try:
+        out = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True).stdout
+        return sum(1 for line in out.splitlines() if line.startswith("GPU "))
+    except OSError:
+        return 0
+
+
+@pytest.mark.skipif(_num_gpus() < 2, reason="needs two GPUs (skirt_b200 -g 0,1)")
+def test_two_gpus_from_the_drop_in_binary(tmp_path):
+    """skirt_b200 -g 0,1: one engine per device, contiguous history blocks, NCCL all-reduce of the radiation field after
+    every segment and of the detector arrays before output, from C++ (shim/GpuLifeCycle.cpp)."""
+    # primary emission only: octree, SED against the reference (same checks as the single-GPU test)
+    g = np.load(os.path.join(GOLD, "cfg2s_ref.npz"))
+    hi = np.load(os.path.join(GOLD, "cfg2s_hi_ref.npz"))
+    d1 = tmp_path / "a"
+    d1.mkdir()
+    log = run_ski("cfg2s", d1, 4e6, devices="0,1")
+    assert "2 devices, NCCL all-reduce" in log
+    sed = read_columns(d1 / "cfg2s_i60_sed.dat")
+    stats = read_columns(d1 / "cfg2s_i60_sedstats.dat")
+    m = re.search(r"GPU life cycle: (\d+) packets", log)
+    assert m and 3990000 <= int(m.group(1)) <= 4000000   # every history ran once, on one of the two devices
+    r_own = rel_error(stats[:, 1:].T)
+    for r in (g, hi):
+        tol = 4.0 * np.hypot(rel_error(r["sedstats"][:, 1:].T), r_own)
+        for col in (1, 2, 3, 4):
+            bound = tol * np.maximum(r["sed"][:, col], r["sed"][:, 1])
+            assert np.all(np.abs(sed[:, col] - r["sed"][:, col]) <= bound), col
+    # dust emission with iterations: the radiation field is summed over the devices inside the iteration loop
+    g4 = np.load(os.path.join(GOLD, "cfg4s_ref.npz"))
+    d2 = tmp_path / "b"
+    d2.mkdir()
+    log = run_ski("cfg4s", d2, 2e6, devices="0,1")
+    prim = [float(x) for x in re.findall(r"dust-absorbed primary luminosity is ([0-9.eE+-]+) Lsun", log)]
+    sec = [float(x) for x in re.findall(r"dust-absorbed secondary luminosity in iteration \d+ is ([0-9.eE+-]+) Lsun", log)]
+    conv = re.search(r"Convergence reached after (\d+) iterations", log)
+    assert conv and int(conv.group(1)) == int(g4["converged_after"])
+    np.testing.assert_allclose(prim, g4["absorbed_primary_lsun"], rtol=0.004)
+    np.testing.assert_allclose(sec, g4["absorbed_secondary_lsun"], rtol=0.02)
+    sed4 = read_columns(d2 / "cfg4s_sed_sed.dat")
+    for col in range(1, 8):
+        assert sed4[:, col].sum() == pytest.approx(g4["sed"][:, col].sum(), rel=0.02)
