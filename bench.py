@@ -86,10 +86,25 @@ def run_reference_once(num_packets, threads, workdir):
     subprocess.check_call([REF_EXE, "-t", str(threads), "-b", "-o", out, ski], stdout=subprocess.DEVNULL,
                           stderr=subprocess.DEVNULL)
     log = open(os.path.join(out, "cfg2_log.txt")).read()
-    m = re.search(r"Finished primary emission in ([0-9.]+) s", log)
     LAST_REFERENCE_SETUP.clear()
     LAST_REFERENCE_SETUP.update(reference_setup_times(log, threads))
-    return num_packets / float(m.group(1)), float(m.group(1))
+    secs = emission_seconds(log)
+    return num_packets / secs, secs
+
+
+def log_stamp(log, pattern):
+    """Seconds since midnight of the first log line matching `pattern` (the reference stamps every line to the ms)."""
+    m = re.search(r"\d+/\d+/\d+ (\d+):(\d+):(\d+\.\d+)[ \-!*]+" + pattern, log)
+    return None if m is None else 3600 * int(m.group(1)) + 60 * int(m.group(2)) + float(m.group(3))
+
+
+def emission_seconds(log):
+    """Duration of the primary emission segment of a reference (or skirt_b200) run: the TimeLogger pair 'Starting primary
+    emission...' / 'Finished primary emission in X s' by their millisecond time stamps; X itself has 0.1 s resolution."""
+    t0, t1 = log_stamp(log, "Starting primary emission"), log_stamp(log, "Finished primary emission")
+    if t0 is not None and t1 is not None and (t1 - t0) % 86400 > 0:
+        return (t1 - t0) % 86400
+    return float(re.search(r"Finished primary emission in ([0-9.]+) s", log).group(1))
 
 
 LAST_REFERENCE_SETUP = {}
@@ -99,10 +114,7 @@ def reference_setup_times(log, threads):
     """Grid construction and medium-state sampling times of a reference run, from the millisecond time stamps of its log
     ('Constructing the spatial tree grid...' -> 'Finished construction of the spatial tree grid';
     'Determining medium properties for N cells...' -> 'Done determining medium properties')."""
-    def stamp(pattern):
-        m = re.search(r"\d+/\d+/\d+ (\d+):(\d+):(\d+\.\d+)\s+" + pattern, log)
-        return None if m is None else 3600 * int(m.group(1)) + 60 * int(m.group(2)) + float(m.group(3))
-    t = [stamp(p) for p in ("Constructing the spatial tree grid", "Finished construction of the spatial tree grid",
+    t = [log_stamp(log, p) for p in ("Constructing the spatial tree grid", "Finished construction of the spatial tree grid",
                             r"Determining medium properties for \d+ cells", "Done determining medium properties")]
     if any(v is None for v in t):
         return {}
@@ -123,12 +135,12 @@ def run_shim_once(num_packets, threads):
         subprocess.check_call([SHIM_EXE, "-t", str(threads), "-b", "-o", d, ski], stdout=subprocess.DEVNULL,
                               stderr=subprocess.DEVNULL)
         log = open(os.path.join(d, "cfg2_log.txt")).read()
-    secs = float(re.search(r"Finished primary emission in ([0-9.]+) s", log).group(1))
+    secs = emission_seconds(log)
     cells = re.search(r"Determining medium properties for (\d+) cells", log)
     return {"packets": num_packets, "seconds": secs, "packets_per_s": num_packets / secs,
             "cells": int(cells.group(1)) if cells else None,
             "what": "skirt_b200 -t %d cfg2.ski: reference object model + C++ shim + GPU life cycle, time from the "
-                    "reference's TimeLogger line 'Finished primary emission in %.1f s'" % (threads, secs)}
+                    "time stamps of the reference's TimeLogger lines 'Starting / Finished primary emission' (%.3f s)" % (threads, secs)}
 
 
 def run_port_once(num_packets):
@@ -150,7 +162,7 @@ def cpu_baseline(sample_packets):
             rate, secs = run_reference_once(sample_packets, cores, d)
         return {"value": rate, "unit": UNIT, "cores": cores, "kind": "reference",
                 "sample": f"unmodified SKIRT 9 (oracle/_ref) -t {cores}, same cfg2 ski, {sample_packets:g} packets, "
-                          f"'Finished primary emission in {secs:.1f} s'"}
+                          f"log time stamps 'Starting / Finished primary emission': {secs:.3f} s"}
     rate, secs = run_port_once(min(sample_packets, 2e5))
     return {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
             "sample": f"oracle/sk_oracle.c single thread, {min(sample_packets, 2e5):g} packets in {secs:.1f} s"}
