@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SK_ABI_VERSION 3
+#define SK_ABI_VERSION 4
 
 typedef struct sk_engine sk_engine_t;
 
@@ -137,6 +137,9 @@ typedef struct sk_instrument {
                                        contributions of one history to the same bin combined first
                                        (FluxRecorder.cpp:457-466, 962-1014) */
     int32_t reserved;
+    double redshift;                /* observer-frame redshift z of the instrument's recorder: a packet is binned at
+                                       lambda (1 + z) (FluxRecorder::setObserverFrameRedshift, FluxRecorder.cpp:123-130,
+                                       309-310); 0 for the local universe */
 } sk_instrument_t;
 
 /* Detector array ids: the enum of SKIRT/core/FluxRecorder.cpp:26-56 without the polarisation entries. */
@@ -354,6 +357,11 @@ int sk_engine_counters(sk_engine_t* e, sk_counters_t* out, int32_t reset);
  * shim's own ncclAllReduce) can reduce tallies in place: which = 0 rf1, 1 rf2, 2 rf2c, 3 = all
  * detector arrays of all instruments (one contiguous block), 4 = all statistics arrays. */
 int sk_engine_device_buffer(sk_engine_t* e, int32_t which, void** device_ptr, uint64_t* num_doubles);
+/* Diagnostic for bench.py's second roofline: the measured rate (records/s) at which this device serves chains of
+ * dependent, randomly scattered 32-byte record fetches out of a table of num_records records at full occupancy -- the
+ * memory access pattern of the crossing loop (one cell record per crossing, the next cell index comes out of it)
+ * without its arithmetic.  No counterpart in the reference. */
+int sk_engine_measure_gather_peak(sk_engine_t* e, int32_t num_records, double* records_per_s);
 /* The cudaStream_t all engine work is enqueued on (so that a caller can order its collectives and its CUDA
  * events after the life-cycle kernel without a host synchronisation). */
 int sk_engine_cuda_stream(sk_engine_t* e, void** stream);

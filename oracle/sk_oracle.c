@@ -2017,7 +2017,8 @@ static void detect(sko_engine_t* e, instr_t* q, packet_t* ppp)
     }
     if (!q->include_sed && l < 0) return;
 
-    int ell = wlg_bin(&e->wlg[q->d.wavelength_grid].g, ppp->lambda);
+    /* the packet's redshifted wavelength, FluxRecorder.cpp:309-310 */
+    int ell = wlg_bin(&e->wlg[q->d.wavelength_grid].g, ppp->lambda * (1. + q->d.redshift));
     if (ell < 0) return;
 
     double L = ppp->W / ppp->lambda;

@@ -30,6 +30,8 @@ for path in libs:
         ms.append(e.last_kernel_ms())
     stages = {k: round(v, 1) for k, v in e.last_stage_ms().items()}
     c = e.counters()
+    if os.environ.get("SK_TUNE_GATHER", "1") == "1" and path == libs[0]:
+        print(json.dumps({"gather_peak_records_per_s": e.measure_gather_peak(sim.grid.num_cells), "records": int(sim.grid.num_cells)}), flush=True)
     print(json.dumps({"variant": os.path.basename(path)[4:-3], "packets": packets, "ms": ms,
                       "pkt_per_s": packets / (min(ms[1:]) * 1e-3), "stages_ms": stages, "rounds": c["rounds"] / 3}), flush=True)
     e.close()

@@ -289,7 +289,6 @@ std::string GpuLifeCycle::unsupportedReason() const
     if (config->hasGasEmission()) return "gas emission";
     if (config->hasStochasticDustEmission()) return "stochastic dust emission";
     if (config->includeHeatingByCMB()) return "CMB heating";
-    if (config->redshift() != 0.) return "nonzero redshift";
     if (ProcessManager::isMultiProc()) return "MPI (use one engine per rank through the C ABI instead)";
     auto mix = dynamic_cast<const DustMix*>(ms->media()[0]->mix());
     if (!mix || mix->scatteringMode() != DustMix::ScatteringMode::HenyeyGreenstein) return "a material mix other than a Henyey-Greenstein dust mix";
@@ -329,6 +328,26 @@ std::string GpuLifeCycle::unsupportedReason() const
         if (!dynamic_cast<const DisjointWavelengthGrid*>(ins->_recorder->_lambdagrid)) return "instrument wavelength grid that is not disjoint";
     }
     if (_sim->instrumentSystem()->instruments().size() > 8) return "more than 8 instruments";
+    for (auto ins : _sim->instrumentSystem()->instruments())
+    {
+        if (ins->numScatteringLevels() > 8) return "more than 8 individually recorded scattering levels";
+        auto fi = dynamic_cast<FrameInstrument*>(ins);
+        if (fi && ins->recordStatistics()
+            && static_cast<double>(fi->numPixelsX()) * fi->numPixelsY() * ins->_recorder->_lambdagrid->numBins() > 2147483647.)
+            return "per-pixel statistics on a frame with more than 2^31 pixel bins";
+    }
+    // probes that are called back for every launched packet (LaunchedPacketsProbe, SourceSystem.cpp:101-113,
+    // SecondarySourceSystem.cpp:130-142): the engine launches on the device and never calls them
+    if (!_sim->sourceSystem()->_callbackv.empty()) return "a probe with a launch call-back (e.g. LaunchedPacketsProbe)";
+    if (_sim->_secondarySourceSystem && !_sim->_secondarySourceSystem->_callbackv.empty())
+        return "a probe with a secondary launch call-back (e.g. LaunchedPacketsProbe)";
+    if (tree)
+    {
+        if (tree->_nodev.size() > 0x03FFFFFFu) return "octree with more than 2^26 nodes";
+        int maxlevel = 0;
+        for (auto node : tree->_nodev) maxlevel = std::max(maxlevel, node->level());
+        if (maxlevel > 15) return "octree deeper than 15 levels";
+    }
     if (config->hasSecondaryEmission())
     {
         if (!config->hasDustEmission()) return "secondary emission other than dust";
@@ -553,6 +572,7 @@ void GpuLifeCycle::configureEngine(int device)
         q.record_components = !ins->_recorder->_recordTotalOnly;
         q.num_scattering_levels = ins->numScatteringLevels();
         q.record_statistics = ins->recordStatistics();
+        q.redshift = ins->_recorder->_redshift;  // observer frame: packets are binned at lambda (1 + z), FluxRecorder.cpp:310
     }
     check(sk_engine_set_instruments(_e, static_cast<int32_t>(iv.size()), iv.data(), config->hasSecondaryEmission()));
 

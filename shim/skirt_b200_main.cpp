@@ -5,8 +5,10 @@
 //   skirt_b200 [-t threads] [-b] [-i indir] [-o outdir] [-g device[,device...]] [--cpu] file.ski
 //
 // The structure follows SKIRT/main/SkirtMain.cpp:15-31 and SkirtCommandLineHandler::doSimulation
-// (SKIRT/main/SkirtCommandLineHandler.cpp:295-400); `--cpu` runs the reference's own CPU life cycle instead (the same
-// binary then is the reference), which is also what happens, with a warning, for configurations outside the accelerated path.
+// (SKIRT/main/SkirtCommandLineHandler.cpp:295-400).  There is no CPU fallback: a configuration outside the accelerated
+// path ends with a fatal error that names the reason (the reference's error convention, SkirtCommandLineHandler.cpp:372-400).
+// `--cpu` is an explicit baseline mode: it runs the reference's own CPU life cycle (the same binary then is the reference)
+// and says so in the log ("CPU life cycle (reference)"); it is never chosen on its own.
 #include <algorithm>
 #include <array>
 #include <atomic>
@@ -93,7 +95,11 @@ int main(int argc, char** argv)
                 {
                     size_t comma = list.find(',', pos);
                     if (comma == string::npos) comma = list.size();
-                    devices.push_back(std::stoi(list.substr(pos, comma - pos)));
+                    int device = std::stoi(list.substr(pos, comma - pos));
+                    if (device < 0) throw FATALERROR("Negative CUDA device ordinal in -g " + list);
+                    if (std::find(devices.begin(), devices.end(), device) != devices.end())
+                        throw FATALERROR("CUDA device " + std::to_string(device) + " is listed twice in -g " + list);
+                    devices.push_back(device);
                     pos = comma + 1;
                 }
             }
@@ -153,10 +159,19 @@ int main(int argc, char** argv)
             TimeLogger logger(simulation->_log, "simulation " + simulation->_paths->outputPrefix());
             simulation->setupSimulation();
 
-            GpuLifeCycle gpu(simulation, devices);
-            string why = cpu ? string("--cpu was given") : gpu.unsupportedReason();
-            if (why.empty())
+            if (cpu)
             {
+                // explicit baseline mode, never a fall-back
+                simulation->_log->warning("CPU life cycle (reference): --cpu was given, the GPU engine is not used");
+                simulation->runSimulation();
+            }
+            else
+            {
+                GpuLifeCycle gpu(simulation, devices);
+                string why = gpu.unsupportedReason();
+                if (!why.empty())
+                    throw FATALERROR("This configuration is outside the GPU life cycle (" + why
+                                     + "); skirt_b200 has no CPU fall-back (use the reference, or --cpu for its baseline mode)");
                 {
                     TimeLogger uplog(simulation->_log, "GPU engine configuration");
                     gpu.configure();
@@ -167,13 +182,6 @@ int main(int argc, char** argv)
                                        + std::to_string(c.forward_segments + c.peel_segments) + " path segments, "
                                        + std::to_string(c.scatterings) + " scatterings, " + std::to_string(c.detections)
                                        + " detections, " + std::to_string(c.kernel_launches) + " kernel launches");
-            }
-            else
-            {
-                if (!cpu)
-                    simulation->_log->warning("This configuration is outside the GPU life cycle (" + why
-                                              + "); running the reference CPU path");
-                simulation->runSimulation();
             }
         }
         catch (FatalError& error)

@@ -64,7 +64,7 @@ class SkInstrument(C.Structure):
                 ("num_pixels_x", C.c_int32), ("num_pixels_y", C.c_int32), ("field_of_view_x", C.c_double),
                 ("field_of_view_y", C.c_double), ("center_x", C.c_double), ("center_y", C.c_double),
                 ("record_components", C.c_int32), ("num_scattering_levels", C.c_int32),
-                ("record_statistics", C.c_int32), ("reserved", C.c_int32)]
+                ("record_statistics", C.c_int32), ("reserved", C.c_int32), ("redshift", C.c_double)]
 
 
 class SkSecondary(C.Structure):
@@ -139,7 +139,8 @@ ABI_FUNCTIONS = ["create", "destroy", "set_grid_cartesian", "set_grid_octree", "
                  "prepare_primary", "prepare_secondary", "run_segment", "communicate_rf", "absorbed_luminosity",
                  "read_rf", "read_sed", "read_ifu", "read_sed_stats", "read_ifu_stats", "counters"]
 SETUP_FUNCTIONS = ["build_octree", "read_octree", "sample_medium", "read_medium"]
-ENGINE_ONLY_FUNCTIONS = ["launch_segment", "synchronize", "last_kernel_ms", "last_stage_ms", "device_buffer", "cuda_stream"]
+ENGINE_ONLY_FUNCTIONS = ["launch_segment", "synchronize", "last_kernel_ms", "last_stage_ms", "device_buffer", "cuda_stream",
+                         "measure_gather_peak"]
 
 
 class Engine:
@@ -445,6 +446,12 @@ class Engine:
         c = SkCounters()
         self._call("counters", self._h, C.byref(c), C.c_int32(int(reset)))
         return c.as_dict()
+
+    def measure_gather_peak(self, num_records) -> float:
+        """records/s of dependent scattered 32-byte record fetches on this device (the crossing loop's access pattern)."""
+        out = C.c_double()
+        self._call("measure_gather_peak", self._h, C.c_int32(int(num_records)), C.byref(out))
+        return out.value
 
     def device_buffer(self, which):
         ptr = C.c_void_p()

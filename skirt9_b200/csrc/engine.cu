@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <numeric>
 #include <string>
 #include <vector>
 
@@ -451,6 +452,11 @@ static int finish_octree(sk_engine* e, const double extent[6], int nn, int nc, i
     memcpy(e->M.ext, extent, 6 * sizeof(double));
     double dx = extent[3] - extent[0], dy = extent[4] - extent[1], dz = extent[5] - extent[2];
     e->M.eps = 1e-12 * sqrt(dx * dx + dy * dy + dz * dz);  // TreeSpatialGrid.cpp:28
+    e->M.eps4 = 4. * e->M.eps;
+    e->M.lat_h[0] = dx / N;  // pitch of the finest lattice: the trace kernels walk rays in lattice coordinates
+    e->M.lat_h[1] = dy / N;
+    e->M.lat_h[2] = dz / N;
+    for (int a = 0; a < 3; ++a) e->M.lat_invh[a] = 1. / e->M.lat_h[a];
     uint32_t* d_coord;
     SkCellRec* d_cells;
     if (int rc = dalloc_zero(e->grid_allocs, 4 * (size_t)nc, &d_coord)) return rc;
@@ -1096,6 +1102,7 @@ extern "C" int sk_engine_set_instruments(sk_engine_t* e, int32_t n, const sk_ins
             return fail(SK_ERR_INVALID, "instrument wavelength grid index out of range");
         if (d.num_scattering_levels > SK_MAX_LEVELS) return fail(SK_ERR_UNSUPPORTED, "too many scattering levels");
         if (d.kind < SK_INSTR_SED || d.kind > SK_INSTR_FULL) return fail(SK_ERR_UNSUPPORTED, "unknown instrument kind");
+        if (!(d.redshift > -1.)) return fail(SK_ERR_INVALID, "instrument redshift must exceed -1");
         q.include_sed = d.kind == SK_INSTR_SED || d.kind == SK_INSTR_FULL;
         q.include_ifu = d.kind == SK_INSTR_FRAME || d.kind == SK_INSTR_FULL;
         q.nl = e->wlg_host[d.wavelength_grid].num_bins;
@@ -1205,6 +1212,7 @@ extern "C" int sk_engine_set_instruments(sk_engine_t* e, int32_t n, const sk_ins
             }
         }
         v.radius2 = d.radius * d.radius;
+        v.zp1 = 1. + d.redshift;
         if (q.include_ifu)
         {
             v.xpmin = d.center_x - 0.5 * d.field_of_view_x;
@@ -1483,16 +1491,17 @@ static int ensure_bank(sk_engine* e, uint64_t count)
 }
 
 template <int GRID, int MODE, bool STORE, bool SMEMT>
-static int launch_trace_impl(sk_engine* e, const SkRunArgs& A, const SkRayDir& dir)
+static int launch_trace_impl(sk_engine* e, const SkRunArgs& A, const SkObsDir& dir)
 {
     auto kern = sk_wf_trace<GRID, MODE, STORE, SMEMT>;
     // occupancy of this instantiation on this engine's device for its shared-memory footprint (cached in the engine:
-    // engines on different devices run from different host threads)
-    const size_t smem = e->smem_bytes;
-    if (e->occupancy_smem != smem)
+    // engines on different devices run from different host threads).  The staged tables never exceed 48 KB (set_tables),
+    // the default limit of dynamic shared memory, so no per-device function attribute has to be set.
+    const size_t smem = SMEMT ? e->smem_bytes : 0;
+    if (e->occupancy_smem != e->smem_bytes)
     {
         e->occupancy.clear();
-        e->occupancy_smem = smem;
+        e->occupancy_smem = e->smem_bytes;
     }
     int per_sm = 0;
     auto it = e->occupancy.find((const void*)kern);
@@ -1500,7 +1509,6 @@ static int launch_trace_impl(sk_engine* e, const SkRunArgs& A, const SkRayDir& d
         per_sm = it->second;
     else
     {
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1)));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SK_TRACE_BLOCK, smem));
         if (per_sm < 1) per_sm = 1;
         e->occupancy[(const void*)kern] = per_sm;
@@ -1518,10 +1526,11 @@ static int launch_trace_impl(sk_engine* e, const SkRunArgs& A, const SkRayDir& d
 }
 
 template <int GRID, int MODE, bool STORE>
-static int launch_trace(sk_engine* e, const SkRunArgs& A, const SkRayDir& dir)
+static int launch_trace(sk_engine* e, const SkRunArgs& A, const SkObsDir& dir)
 {
-    return e->M.lattice_in_smem ? launch_trace_impl<GRID, MODE, STORE, true>(e, A, dir)
-                                : launch_trace_impl<GRID, MODE, STORE, false>(e, A, dir);
+    // only the Cartesian grid looks borders up while it walks (TMA-staged tables); the octree walks in lattice coordinates
+    if (GRID == 1 && e->M.lattice_in_smem) return launch_trace_impl<GRID, MODE, STORE, GRID == 1>(e, A, dir);
+    return launch_trace_impl<GRID, MODE, STORE, false>(e, A, dir);
 }
 
 template <int GRID>
@@ -1557,8 +1566,10 @@ static int run_bank(sk_engine* e, const SkRunArgs& A)
         CK(cudaGetLastError());
         return stage_end(e);
     };
-    SkRayDir nodir;
-    nodir.set(0., 0., 1.);
+    SkObsDir nodir;
+    nodir.d.set(0., 0., 1., nullptr);
+    nodir.px = nodir.py = 0.;
+    nodir.pz = 1.;
     CK(cudaMemsetAsync(K.i + (size_t)I_STATE * K.cap, 0, (size_t)K.n * sizeof(int32_t), e->stream));
     for (unsigned long long round = 0;; ++round)
     {
@@ -1592,8 +1603,11 @@ static int run_bank(sk_engine* e, const SkRunArgs& A)
                 CK(cudaGetLastError());
                 if (int rc = stage_end(e)) return rc;
             }
-            SkRayDir obs;
-            obs.set(e->instr_kobs[j0][0], e->instr_kobs[j0][1], e->instr_kobs[j0][2]);
+            SkObsDir obs;
+            obs.px = e->instr_kobs[j0][0];
+            obs.py = e->instr_kobs[j0][1];
+            obs.pz = e->instr_kobs[j0][2];
+            obs.d.set(obs.px, obs.py, obs.pz, GRID == 2 ? M.lat_h : nullptr);
             if (int rc = launch_trace<GRID, 2, false>(e, A, obs)) return rc;
             const int last = gi + 1 == groups.size();
             if (last) CK(cudaMemsetAsync(&K.ctl[SK_CTL_NLIST], 0, sizeof(unsigned int), e->stream));
@@ -1601,15 +1615,19 @@ static int run_bank(sk_engine* e, const SkRunArgs& A)
         }
         if (M.force_scattering)
         {
+            // forward path, interaction optical depth and the walk to the interaction point in one kernel
             if (int rc = A.store ? launch_trace<GRID, 0, true>(e, A, nodir) : launch_trace<GRID, 0, false>(e, A, nodir))
                 return rc;
         }
-        CK(cudaMemsetAsync(&K.ctl[SK_CTL_NLIST], 0, sizeof(unsigned int), e->stream));
-        if (int rc = stage_begin(e, SK_STAGE_SAMPLE)) return rc;
-        sk_wf_sample<<<eblocks, SK_EVENT_BLOCK, 0, e->stream>>>(M, A, K);
-        CK(cudaGetLastError());
-        if (int rc = stage_end(e)) return rc;
-        if (int rc = launch_trace<GRID, 1, false>(e, A, nodir)) return rc;
+        else
+        {
+            CK(cudaMemsetAsync(&K.ctl[SK_CTL_NLIST], 0, sizeof(unsigned int), e->stream));
+            if (int rc = stage_begin(e, SK_STAGE_SAMPLE)) return rc;
+            sk_wf_sample<<<eblocks, SK_EVENT_BLOCK, 0, e->stream>>>(M, A, K);
+            CK(cudaGetLastError());
+            if (int rc = stage_end(e)) return rc;
+            if (int rc = launch_trace<GRID, 1, false>(e, A, nodir)) return rc;
+        }
         // census of this round: stop when the bank is empty and every history has been handed out
         CK(cudaEventSynchronize(e->ev_ctl));
         unsigned long long dispensed;
@@ -1899,6 +1917,78 @@ extern "C" int sk_engine_counters(sk_engine_t* e, sk_counters_t* out, int32_t re
         CK(cudaMemsetAsync(e->M.counters, 0, sizeof c, e->stream));
         e->launches_total = e->rounds_total = 0;
     }
+    return SK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Measured ceiling of the crossing loop's memory access pattern (bench.py's second roofline): every lane follows a
+// chain of dependent 32-byte record fetches (one 256-bit load per step, the next index comes out of the record) through
+// a table of `num_records` records linked in a random cycle -- the cell-record gather of the trace kernels without any
+// of their arithmetic, at full occupancy.  records/s of this kernel bounds the cell crossings/s of ANY walk that needs
+// one dependent record per crossing on this device.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sk_gather_chain_kernel(const SkCellRec* __restrict__ table, int num_records, int steps,
+                                                               unsigned long long* sink)
+{
+    const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
+    int m = (int)(((unsigned long long)tid * 2654435761ull) % (unsigned long long)num_records);
+    double acc = 0.;
+    for (int i = 0; i < steps; ++i)
+    {
+        int4 a, b;
+        sk_ld256(&table[m], a, b);
+        acc += __hiloint2double(a.y, a.x);
+        m = a.z;
+    }
+    if (acc == 12345.678) atomicAdd(sink, (unsigned long long)m);  // keeps the chain alive
+}
+__global__ void sk_gather_init_kernel(SkCellRec* table, int num_records, unsigned long long mult, unsigned long long add)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= num_records) return;
+    SkCellRec r;
+    r.dens = 1.;
+    // an affine map modulo num_records with an odd multiplier coprime to it scatters successive fetches over the table
+    r.link[0] = (int)(((unsigned long long)m * mult + add) % (unsigned long long)num_records);
+    for (int w = 1; w < 6; ++w) r.link[w] = -1;
+    table[m] = r;
+}
+extern "C" int sk_engine_measure_gather_peak(sk_engine_t* e, int32_t num_records, double* records_per_s)
+{
+    if (!e || !records_per_s || num_records < 1024) return fail(SK_ERR_INVALID, "bad argument");
+    if (int rc_bind = bind(e)) return rc_bind;
+    if (!e->num_sms) CK(cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, e->cfg.device));
+    SkCellRec* table = nullptr;
+    unsigned long long* sink = nullptr;
+    CK(dev_malloc(&table, (size_t)num_records * sizeof(SkCellRec)));
+    CK(dev_malloc(&sink, sizeof(unsigned long long)));
+    unsigned long long mult = 2654435761ull;
+    while (std::gcd(mult, (unsigned long long)num_records) != 1) mult += 2;
+    sk_gather_init_kernel<<<(num_records + 255) / 256, 256, 0, e->stream>>>(table, num_records, mult, 40503ull);
+    CK(cudaGetLastError());
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a));
+    CK(cudaEventCreate(&b));
+    const int steps = 512;
+    double best = 0.;
+    // 8 resident blocks of 256 threads per SM = full occupancy; two warm-up launches, best of five
+    const unsigned blocks = (unsigned)e->num_sms * 8u;
+    for (int it = 0; it < 7; ++it)
+    {
+        CK(cudaEventRecord(a, e->stream));
+        sk_gather_chain_kernel<<<blocks, 256, 0, e->stream>>>(table, num_records, steps, sink);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(b, e->stream));
+        CK(cudaEventSynchronize(b));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, a, b));
+        if (it >= 2) best = std::max(best, (double)blocks * 256. * steps / (ms * 1e-3));
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    dev_free(table);
+    dev_free(sink);
+    *records_per_s = best;
     return SK_OK;
 }
 

@@ -8,12 +8,12 @@
 // Per-packet state of the in-flight bank: field-major arrays of `cap` entries (structure of arrays in HBM),
 // the device counterpart of PhotonPacket (SKIRT/utils/PhotonPacket.hpp:337-363).
 enum {
-    D_RX, D_RY, D_RZ, D_KX, D_KY, D_KZ, D_LAMBDA, D_W, D_LTHR, D_SIGEXT, D_TAUPATH, D_TAUINT, D_STOT, D_SINT,
+    D_RX, D_RY, D_RZ, D_KX, D_KY, D_KZ, D_IKX, D_IKY, D_IKZ, D_LAMBDA, D_W, D_LTHR, D_SIGEXT, D_TAUPATH, D_TAUINT, D_SINT,
     D_PEELW, D_PTAU, D_LIMIT, D_HISTW0, SK_ND = D_HISTW0 + SK_MAX_INSTR
 };
 enum {
     I_HLO, I_HHI, I_DRAW, I_NSCATT, I_STATE, I_ILAM, I_M, I_IX, I_IY, I_IZ, I_LEV, I_MINT, I_MIX, I_MIY, I_MIZ,
-    I_MLEV, I_NSEG, I_HELL0, SK_NI = I_HELL0 + SK_MAX_INSTR
+    I_MLEV, I_HELL0, SK_NI = I_HELL0 + SK_MAX_INSTR
 };
 // I_STATE bits
 #define SK_ST_LIVE 1
@@ -128,39 +128,42 @@ __device__ __noinline__ bool sk_move_inside(double& rx, double& ry, double& rz, 
 }
 
 // Octree cell location: TreeNode::leafChild (TreeNode.cpp:65-76) + OctTreeNode::child (OctTreeNode.cpp:37-42) on the
-// integer lattice: a node is (ix,iy,iz,level); its centre (CHILD_0->rmax) is the lattice border at +half size.
-// `fc` is the node id of the first child of the node to descend from.
-__device__ __forceinline__ void sk_tree_descend(const int32_t* __restrict__ node_child, int maxlevel,
-                                                const SkSmemTables& T, int fc, int ix, int iy, int iz, int lev,
-                                                double x, double y, double z, SkCellPos& out)
+// integer lattice: a node is (ix,iy,iz,level) in units of the finest level, so the child that holds the lattice point
+// (fx,fy,fz) is given by one bit of each coordinate per level.  `fc` is the node id of the first child of the node
+// (at level `lev`) to descend from, or -(cell+1) when that node is a leaf already.
+__device__ __forceinline__ void sk_tree_descend(const int32_t* __restrict__ node_child, int maxlevel, int fc, int fx, int fy,
+                                                int fz, int lev, SkCellPos& out)
 {
     while (fc >= 0)
     {
-        int half = 1 << (maxlevel - lev - 1);
-        int l = 0;
-        if (!(x < T.X[ix + half]))
-        {
-            l |= 1;
-            ix += half;
-        }
-        if (!(y < T.Y[iy + half]))
-        {
-            l |= 2;
-            iy += half;
-        }
-        if (!(z < T.Z[iz + half]))
-        {
-            l |= 4;
-            iz += half;
-        }
+        const int b = maxlevel - lev - 1;
+        const int l = ((fx >> b) & 1) | (((fy >> b) & 1) << 1) | (((fz >> b) & 1) << 2);
         lev++;
         fc = __ldg(&node_child[fc + l]);
     }
+    const int mask = ~((1 << (maxlevel - lev)) - 1);
     out.m = -(fc + 1);
-    out.ix = ix;
-    out.iy = iy;
-    out.iz = iz;
+    out.ix = fx & mask;
+    out.iy = fy & mask;
+    out.iz = fz & mask;
     out.lev = lev;
+}
+// Lattice coordinate of a position along one axis of the octree domain, u = (x - min) / pitch, as a multiplication by the
+// reciprocal pitch.  A result within 1e-9 of an integer is that integer: a position that lies exactly on a cell border (a
+// point source at the centre of the grid) then stays exactly on it whatever the rounding of the reciprocal, and so in the
+// cell the reference's comparisons with the recursive midpoints put it in; for any other position the shift (1e-9 of the
+// finest cell) is far below eps.  Every kernel converts with this one function, so they all agree on the cell.
+__device__ __forceinline__ double sk_lat_coord(double x, double xmin, double invh)
+{
+    const double u = (x - xmin) * invh;
+    const double r = rint(u);
+    return fabs(u - r) < 1e-9 ? r : u;
+}
+// the finest lattice cell that holds lattice coordinate u (the domain box is closed: u == N belongs to the last cell)
+__device__ __forceinline__ int sk_lat_index(double u, int N)
+{
+    const int i = __double2int_rd(u);
+    return i < 0 ? 0 : (i >= N ? N - 1 : i);
 }
 
 // one 32-byte Voronoi cell record {site; density} through the read-only path (one 256-bit load, one sector)
@@ -241,50 +244,85 @@ __device__ __noinline__ void sk_locate(const SkDevModel* __restrict__ Mg, const 
         out.m = out.iz + Mg->nz * out.iy + Mg->nz * Mg->ny * out.ix;
     }
     else
-        sk_tree_descend(Mg->node_child, Mg->maxlevel, T, __ldg(&Mg->node_child[0]), 0, 0, 0, 0, x, y, z, out);
-}
-
-// Cold path of the octree step: the full neighbour search of TreeSpatialGrid.cpp:190-207 for the situations the
-// fast path does not decide itself (domain boundary, near-ties between exit walls, grazing directions):
-// the leaf containing the new position (TreeNode::neighbor + root()->leafChild fall-back), the nextafter escape
-// when stuck in the same cell, and termination.
-__device__ __noinline__ void sk_tree_step_rare(const SkDevModel* __restrict__ Mg, const SkSmemTables& T, double& rx,
-                                               double& ry, double& rz, double kx, double ky, double kz, int m_old,
-                                               SkCellPos& q)
-{
-    sk_locate<2>(Mg, T, rx, ry, rz, q);
-    if (q.m == m_old)
     {
-        // PathSegmentGenerator::propagateToNextAfter, PathSegmentGenerator.hpp:148-153
-        rx = nextafter(rx, (kx < 0.) ? -DBL_MAX : DBL_MAX);
-        ry = nextafter(ry, (ky < 0.) ? -DBL_MAX : DBL_MAX);
-        rz = nextafter(rz, (kz < 0.) ? -DBL_MAX : DBL_MAX);
-        sk_locate<2>(Mg, T, rx, ry, rz, q);
-        if (q.m == m_old) q.m = -1;
+        const int N = Mg->nx;
+        const int fx = sk_lat_index(sk_lat_coord(x, Mg->ext[0], Mg->lat_invh[0]), N);
+        const int fy = sk_lat_index(sk_lat_coord(y, Mg->ext[1], Mg->lat_invh[1]), N);
+        const int fz = sk_lat_index(sk_lat_coord(z, Mg->ext[2], Mg->lat_invh[2]), N);
+        sk_tree_descend(Mg->node_child, Mg->maxlevel, __ldg(&Mg->node_child[0]), fx, fy, fz, 0, out);
     }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// One cell crossing.  Returns the segment (m, dens, ds) and moves (r, p) to the next cell; `p.m < 0` afterwards
-// means the path has left the grid.
-//   Cartesian: CartesianSpatialGrid::MySegmentGenerator::next, CartesianSpatialGrid.cpp:95-162
-//   Octree:    TreeSpatialGrid::MySegmentGenerator::next, TreeSpatialGrid.cpp:140-216, with TreeNode::neighbor
-//              (TreeNode.cpp:103-112) served by the per-cell links
-// The ray carries the reciprocals of its direction components (0 where the reference treats the component as
-// zero, fabs(k) <= 1e-15), so the exit distances cost a multiplication instead of a division per axis.
+// Ray direction in traversal coordinates.  The ray carries the reciprocals of its direction components (0 where the
+// reference treats the component as zero, fabs(k) <= 1e-15), so an exit distance costs a multiplication instead of a
+// division per axis, and the sign / zero / grazing tests of the crossing loop as bits of one integer.
+//   Cartesian, Voronoi: k = the unit direction.
+//   Octree: k = direction in lattice units per unit of path length, k_a / pitch_a: the ray is walked in the lattice
+//   coordinates u = (r - min) / pitch, in which the borders of cell (ix, iy, iz, level) are the integers ix and
+//   ix + 2^(maxlevel - level); path lengths (ds, eps) stay physical.
 // ---------------------------------------------------------------------------------------------------
-struct SkRayDir {
+#define SK_DIR_NEG 1u     // bits 0..2: component < 0 (the ray leaves through the lower wall of that axis)
+#define SK_DIR_ZERO 8u    // bits 3..5: fabs(component) <= 1e-15: no exit through the walls of that axis
+#define SK_DIR_GRAZE 64u  // bits 6..8: !(fabs(component) > 1e-3): the eps advance across such a wall may be lost to rounding
+struct SkDir {
     double kx, ky, kz;
     double ikx, iky, ikz;
-    __host__ __device__ __forceinline__ void set(double x, double y, double z)
+    unsigned flags;
+    // (x, y, z) = the unit direction; h = pitch of the finest octree lattice per axis, or null for physical coordinates
+    __host__ __device__ __forceinline__ void set(double x, double y, double z, const double* h)
     {
-        kx = x;
-        ky = y;
-        kz = z;
-        ikx = (fabs(x) > 1e-15) ? 1.0 / x : 0.;
-        iky = (fabs(y) > 1e-15) ? 1.0 / y : 0.;
-        ikz = (fabs(z) > 1e-15) ? 1.0 / z : 0.;
+        unsigned f = 0;
+        if (x < 0.0) f |= SK_DIR_NEG;
+        if (y < 0.0) f |= SK_DIR_NEG << 1;
+        if (z < 0.0) f |= SK_DIR_NEG << 2;
+        if (!(fabs(x) > 1e-15)) f |= SK_DIR_ZERO;
+        if (!(fabs(y) > 1e-15)) f |= SK_DIR_ZERO << 1;
+        if (!(fabs(z) > 1e-15)) f |= SK_DIR_ZERO << 2;
+        if (!(fabs(x) > 1e-3)) f |= SK_DIR_GRAZE;
+        if (!(fabs(y) > 1e-3)) f |= SK_DIR_GRAZE << 1;
+        if (!(fabs(z) > 1e-3)) f |= SK_DIR_GRAZE << 2;
+        flags = f;
+        kx = h ? x / h[0] : x;
+        ky = h ? y / h[1] : y;
+        kz = h ? z / h[2] : z;
+        ikx = (f & SK_DIR_ZERO) ? 0. : (h ? h[0] : 1.0) / x;
+        iky = (f & (SK_DIR_ZERO << 1)) ? 0. : (h ? h[1] : 1.0) / y;
+        ikz = (f & (SK_DIR_ZERO << 2)) ? 0. : (h ? h[2] : 1.0) / z;
     }
+    // the same from the unit direction and the reciprocals an event kernel has stored in the bank (sk_dir_recip):
+    // invh = reciprocal pitch of the octree lattice per axis, or null for physical coordinates
+    __device__ __forceinline__ void load(double x, double y, double z, double ix, double iy, double iz, const double* invh)
+    {
+        unsigned f = 0;
+        if (x < 0.0) f |= SK_DIR_NEG;
+        if (y < 0.0) f |= SK_DIR_NEG << 1;
+        if (z < 0.0) f |= SK_DIR_NEG << 2;
+        if (ix == 0.) f |= SK_DIR_ZERO;
+        if (iy == 0.) f |= SK_DIR_ZERO << 1;
+        if (iz == 0.) f |= SK_DIR_ZERO << 2;
+        if (!(fabs(x) > 1e-3)) f |= SK_DIR_GRAZE;
+        if (!(fabs(y) > 1e-3)) f |= SK_DIR_GRAZE << 1;
+        if (!(fabs(z) > 1e-3)) f |= SK_DIR_GRAZE << 2;
+        flags = f;
+        kx = invh ? x * invh[0] : x;
+        ky = invh ? y * invh[1] : y;
+        kz = invh ? z * invh[2] : z;
+        ikx = ix;
+        iky = iy;
+        ikz = iz;
+    }
+};
+// Reciprocal of a direction component in traversal coordinates (h = lattice pitch of the axis for the octree, 1 otherwise);
+// 0 where the reference treats the component as zero.  Computed once per direction by the event kernel that creates it.
+__device__ __forceinline__ double sk_dir_recip(double k, double h)
+{
+    return (fabs(k) > 1e-15) ? h / k : 0.;
+}
+// the observer's direction of a peel-off trace: traversal form + the unit vector itself (for entering the grid)
+struct SkObsDir {
+    SkDir d;
+    double px, py, pz;
 };
 
 // one 32-byte record with a single 256-bit load through the read-only path (LDG.E.256 on sm_100a): half the L1 tag
@@ -297,24 +335,306 @@ __device__ __forceinline__ void sk_ld256(const void* p, int4& a, int4& b)
     b = make_int4((int)(unsigned)q2, (int)(q2 >> 32), (int)(unsigned)q3, (int)(q3 >> 32));
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Steppers: one lane's walk through the grid, cut in two halves so that a walk can stop INSIDE a cell (the interaction
+// point) without having stepped out of it:
+//     begin(r, cell)   start in `cell` at position r (the caller has located the cell)
+//     exit(...)        the segment through the current cell: its index m, density and length ds; does not move.
+//                      ds < 0 (Voronoi only): the generator ended without a further segment, m() < 0 afterwards
+//     move(...)        step to the next cell; m() < 0 afterwards means the path has left the grid
+//     cell()           the current cell
+//   Cartesian: CartesianSpatialGrid::MySegmentGenerator::next, CartesianSpatialGrid.cpp:95-162
+//   Octree:    TreeSpatialGrid::MySegmentGenerator::next, TreeSpatialGrid.cpp:140-216, with TreeNode::neighbor
+//              (TreeNode.cpp:103-112) served by the per-cell links
+//   Voronoi:   VoronoiMeshSnapshot::MySegmentGenerator::next, VoronoiMeshSnapshot.cpp:1087-1179
+// ---------------------------------------------------------------------------------------------------
 template <int GRID>
-__device__ __forceinline__ void sk_step(const SkDevModel& M, const SkDevModel* __restrict__ Mg, const SkSmemTables& T,
-                                        SkLocalCounters& cnt, double& rx, double& ry, double& rz, const SkRayDir& k,
-                                        SkCellPos& p, int& m_out, double& dens_out, double& ds_out)
-{
-    if (GRID == 3)
+struct SkStepper;
+
+// ---- Cartesian grid
+template <>
+struct SkStepper<1> {
+    double rx, ry, rz;
+    int cm, ix, iy, iz;
+    double ds_;
+    int axis;
+    __device__ __forceinline__ int m() const { return cm; }
+    __device__ __forceinline__ double ds() const { return ds_; }
+    __device__ __forceinline__ SkCellPos cell(const SkDevModel&) const { return SkCellPos{cm, ix, iy, iz, 0}; }
+    __device__ __forceinline__ void begin(const SkDevModel&, double x, double y, double z, const SkCellPos& p)
     {
-        // VoronoiMeshSnapshot::MySegmentGenerator::next, VoronoiMeshSnapshot.cpp:1087-1179: the exit point is the nearest
-        // intersection with the bisecting planes towards the neighbouring sites and with the domain walls
-        int m = p.m;
+        rx = x;
+        ry = y;
+        rz = z;
+        cm = p.m;
+        ix = p.ix;
+        iy = p.iy;
+        iz = p.iz;
+    }
+    __device__ __forceinline__ void exit(const SkDevModel& M, const SkDevModel* __restrict__, const SkSmemTables& T,
+                                         SkLocalCounters&, const SkDir& k, int& m_out, double& dens_out, double& ds_out)
+    {
+        const double dens = __ldg(&M.dens[cm]);
+        const double xE = T.X[ix + ((k.kx < 0.0) ? 0 : 1)];
+        const double yE = T.Y[iy + ((k.ky < 0.0) ? 0 : 1)];
+        const double zE = T.Z[iz + ((k.kz < 0.0) ? 0 : 1)];
+        const double dsx = (k.ikx != 0.) ? (xE - rx) * k.ikx : DBL_MAX;
+        const double dsy = (k.iky != 0.) ? (yE - ry) * k.iky : DBL_MAX;
+        const double dsz = (k.ikz != 0.) ? (zE - rz) * k.ikz : DBL_MAX;
+        if (dsx <= dsy && dsx <= dsz)
+        {
+            axis = 0;
+            ds_ = dsx;
+        }
+        else if (dsy < dsx && dsy <= dsz)
+        {
+            axis = 1;
+            ds_ = dsy;
+        }
+        else
+        {
+            axis = 2;
+            ds_ = dsz;
+        }
+        m_out = cm;
+        dens_out = dens;
+        ds_out = ds_;
+    }
+    __device__ __forceinline__ void move(const SkDevModel& M, const SkDevModel* __restrict__, const SkSmemTables& T,
+                                         SkLocalCounters&, const SkDir& k)
+    {
+        bool outside;
+        if (axis == 0)
+        {
+            rx = T.X[ix + ((k.kx < 0.0) ? 0 : 1)];
+            ry += k.ky * ds_;
+            rz += k.kz * ds_;
+            ix += (k.kx < 0.0) ? -1 : 1;
+            outside = (ix >= M.nx || ix < 0);
+        }
+        else if (axis == 1)
+        {
+            ry = T.Y[iy + ((k.ky < 0.0) ? 0 : 1)];
+            rx += k.kx * ds_;
+            rz += k.kz * ds_;
+            iy += (k.ky < 0.0) ? -1 : 1;
+            outside = (iy >= M.ny || iy < 0);
+        }
+        else
+        {
+            rz = T.Z[iz + ((k.kz < 0.0) ? 0 : 1)];
+            rx += k.kx * ds_;
+            ry += k.ky * ds_;
+            iz += (k.kz < 0.0) ? -1 : 1;
+            outside = (iz >= M.nz || iz < 0);
+        }
+        cm = outside ? -1 : iz + M.nz * iy + M.nz * M.ny * ix;
+    }
+};
+
+// ---- Octree, walked in lattice coordinates.
+// Cold path: the full neighbour search of TreeSpatialGrid.cpp:190-207 for the situations the fast path does not decide
+// itself (near-ties between exit walls, grazing directions, no neighbour across the exit wall although the position is
+// still in the domain): the leaf that contains the new position (TreeNode::neighbor + root()->leafChild fall-back), the
+// nextafter escape when stuck in the same cell, and termination.
+__device__ __noinline__ void sk_tree_step_rare(const SkDevModel* __restrict__ Mg, double& ux, double& uy, double& uz,
+                                               unsigned dirflags, int m_old, SkCellPos& q)
+{
+    const int N = Mg->nx;
+    const double top = (double)N;
+    for (int attempt = 0; attempt < 2; ++attempt)
+    {
+        if (!(ux >= 0. && ux <= top && uy >= 0. && uy <= top && uz >= 0. && uz <= top))
+        {
+            q.m = -1;
+            return;
+        }
+        sk_tree_descend(Mg->node_child, Mg->maxlevel, __ldg(&Mg->node_child[0]), sk_lat_index(ux, N), sk_lat_index(uy, N),
+                        sk_lat_index(uz, N), 0, q);
+        if (q.m != m_old) return;
+        if (attempt == 0)
+        {
+            // PathSegmentGenerator::propagateToNextAfter, PathSegmentGenerator.hpp:148-153
+            ux = nextafter(ux, (dirflags & SK_DIR_NEG) ? -DBL_MAX : DBL_MAX);
+            uy = nextafter(uy, (dirflags & (SK_DIR_NEG << 1)) ? -DBL_MAX : DBL_MAX);
+            uz = nextafter(uz, (dirflags & (SK_DIR_NEG << 2)) ? -DBL_MAX : DBL_MAX);
+        }
+    }
+    q.m = -1;  // still in the same cell: the path ends (TreeSpatialGrid.cpp:205-207)
+}
+
+template <>
+struct SkStepper<2> {
+    double ux, uy, uz;    // position in lattice coordinates
+    int cm, ix, iy, iz;   // current cell: index and the lattice coordinates of its lower corner
+    int sh;               // log2 of its size in lattice units = maxlevel - level
+    double ds_;
+    int link;             // the link across the exit wall
+    int how;              // bits 0..1 exit axis, bit 2: the next cell needs the full search
+    __device__ __forceinline__ int m() const { return cm; }
+    __device__ __forceinline__ double ds() const { return ds_; }
+    __device__ __forceinline__ void begin(const SkDevModel& M, double x, double y, double z, const SkCellPos& p)
+    {
+        ux = sk_lat_coord(x, M.ext[0], M.lat_invh[0]);
+        uy = sk_lat_coord(y, M.ext[1], M.lat_invh[1]);
+        uz = sk_lat_coord(z, M.ext[2], M.lat_invh[2]);
+        cm = p.m;
+        ix = p.ix;
+        iy = p.iy;
+        iz = p.iz;
+        sh = M.maxlevel - p.lev;
+    }
+    __device__ __forceinline__ SkCellPos cell(const SkDevModel& M) const { return SkCellPos{cm, ix, iy, iz, M.maxlevel - sh}; }
+    __device__ __forceinline__ void exit(const SkDevModel& M, const SkDevModel* __restrict__, const SkSmemTables&,
+                                         SkLocalCounters&, const SkDir& k, int& m_out, double& dens_out, double& ds_out)
+    {
+        // one 32-byte sector: density + the six neighbour links of the current cell
+        int4 a, b;
+        sk_ld256(&M.cells[cm], a, b);
+        const unsigned f = k.flags;
+        const int size = 1 << sh;
+        const bool nx = f & SK_DIR_NEG, ny = f & (SK_DIR_NEG << 1), nz = f & (SK_DIR_NEG << 2);
+        // the exit walls are lattice planes: integers, exactly representable
+        const double xnext = (double)(ix + (nx ? 0 : size));
+        const double ynext = (double)(iy + (ny ? 0 : size));
+        const double znext = (double)(iz + (nz ? 0 : size));
+        double dsx = (xnext - ux) * k.ikx;
+        double dsy = (ynext - uy) * k.iky;
+        double dsz = (znext - uz) * k.ikz;
+        if (f & (7u * SK_DIR_ZERO))
+        {
+            // no exit through the walls of an axis the direction has no component along (never for a random direction)
+            if (f & SK_DIR_ZERO) dsx = DBL_MAX;
+            if (f & (SK_DIR_ZERO << 1)) dsy = DBL_MAX;
+            if (f & (SK_DIR_ZERO << 2)) dsz = DBL_MAX;
+        }
+        // exit wall: x if dsx<=dsy && dsx<=dsz, else y if dsy<=dsx && dsy<=dsz, else z (TreeSpatialGrid.cpp:160-178); once x
+        // is ruled out, y wins exactly when dsy<=dsz.  `other` = the nearest of the two walls not taken.
+        const bool cyz = dsy <= dsz;
+        const double mn = cyz ? dsy : dsz, mx = cyz ? dsz : dsy;
+        const bool takex = dsx <= mn;
+        const double ds = takex ? dsx : mn;
+        const double o2 = dsx <= mx ? dsx : mx;
+        const double other = takex ? mn : o2;
+        const int lx = nx ? a.z : a.w, ly = ny ? b.x : b.y, lz = nz ? b.z : b.w;
+        const int lyz = cyz ? ly : lz;
+        link = takex ? lx : lyz;
+        // The link decides the next cell unless the new position may also have crossed a second wall (the exit distances
+        // of two walls differ by less than a few eps) or the direction grazes the exit wall (the eps advance may be lost
+        // to rounding); those cases take the reference's full search.
+        const unsigned gyz = cyz ? (SK_DIR_GRAZE << 1) : (SK_DIR_GRAZE << 2);
+        const unsigned gbit = takex ? SK_DIR_GRAZE : gyz;
+        const bool rare = !(other - ds > M.eps4) || (f & gbit);
+        how = (takex ? 0 : (cyz ? 1 : 2)) | (rare ? 4 : 0);
+        ds_ = ds;
+        m_out = cm;
+        dens_out = __hiloint2double(a.y, a.x);
+        ds_out = ds;
+    }
+    __device__ __forceinline__ void move(const SkDevModel& M, const SkDevModel* __restrict__ Mg, const SkSmemTables&,
+                                         SkLocalCounters& cnt, const SkDir& k)
+    {
+        const double adv = ds_ + M.eps;
+        ux = __fma_rn(k.kx, adv, ux);
+        uy = __fma_rn(k.ky, adv, uy);
+        uz = __fma_rn(k.kz, adv, uz);
+        if (!(how & 4))
+        {
+            // The common way for a path to end: no neighbour across the exit wall, which then is a wall of the domain, and
+            // the position has been advanced eps beyond it (the direction does not graze the wall, the exit is not a
+            // near-tie): TreeNode::neighbor() and root()->leafChild() both come back empty (TreeSpatialGrid.cpp:190-205).
+            if (link < 0)
+            {
+                cm = -1;
+                return;
+            }
+            // step to the lattice point just across the exit wall, then align to the neighbour's level
+            const unsigned f = k.flags;
+            const int size = 1 << sh;
+            const int axis = how & 3;
+            ix += axis == 0 ? ((f & SK_DIR_NEG) ? -1 : size) : 0;
+            iy += axis == 1 ? ((f & (SK_DIR_NEG << 1)) ? -1 : size) : 0;
+            iz += axis == 2 ? ((f & (SK_DIR_NEG << 2)) ? -1 : size) : 0;
+            const int nlev = (link >> SK_LINK_LEVEL_SHIFT) & 15;
+            int nsh = M.maxlevel - nlev;
+            int fc = link & SK_LINK_INDEX_MASK;
+            if (link & SK_LINK_INTERNAL)
+            {
+                // the neighbour is subdivided: descend to the leaf that holds the new position; along the exit axis the
+                // lattice coordinate is the one just across the wall (exact), across it the position decides (it lies
+                // inside the neighbour node: no clamping)
+                const int fx = axis == 0 ? ix : __double2int_rd(ux);
+                const int fy = axis == 1 ? iy : __double2int_rd(uy);
+                const int fz = axis == 2 ? iz : __double2int_rd(uz);
+                do
+                {
+                    nsh--;
+                    const int l = ((fx >> nsh) & 1) | (((fy >> nsh) & 1) << 1) | (((fz >> nsh) & 1) << 2);
+                    fc = __ldg(&M.node_child[fc + l]);
+                } while (fc >= 0);
+                fc = -(fc + 1);
+                ix = fx;
+                iy = fy;
+                iz = fz;
+            }
+            const int mask = -1 << nsh;  // a leaf at the same, a coarser or (after the descent) a finer level
+            cm = fc;
+            ix &= mask;
+            iy &= mask;
+            iz &= mask;
+            sh = nsh;
+            return;
+        }
+        const double top = (double)M.nx;
+        if (link < 0 && !(ux >= 0. && ux <= top && uy >= 0. && uy <= top && uz >= 0. && uz <= top))
+        {
+            cm = -1;
+            return;
+        }
+        // (copies confine the address-taken variables, which live in local memory, to this cold branch)
+        cnt.fallbacks++;
+        double tx = ux, ty = uy, tz = uz;
+        SkCellPos q;
+        sk_tree_step_rare(Mg, tx, ty, tz, k.flags, cm, q);
+        ux = tx;
+        uy = ty;
+        uz = tz;
+        cm = q.m;
+        ix = q.ix;
+        iy = q.iy;
+        iz = q.iz;
+        sh = M.maxlevel - q.lev;
+    }
+};
+
+// ---- Voronoi mesh: the exit point is the nearest intersection with the bisecting planes towards the neighbouring sites
+// and with the domain walls
+template <>
+struct SkStepper<3> {
+    double rx, ry, rz;
+    int cm, mq;
+    double sq;
+    __device__ __forceinline__ int m() const { return cm; }
+    __device__ __forceinline__ double ds() const { return sq; }
+    __device__ __forceinline__ void begin(const SkDevModel&, double x, double y, double z, const SkCellPos& p)
+    {
+        rx = x;
+        ry = y;
+        rz = z;
+        cm = p.m;
+    }
+    __device__ __forceinline__ SkCellPos cell(const SkDevModel&) const { return SkCellPos{cm, 0, 0, 0, 0}; }
+    __device__ __forceinline__ void exit(const SkDevModel& M, const SkDevModel* __restrict__ Mg, const SkSmemTables&,
+                                         SkLocalCounters& cnt, const SkDir& k, int& m_out, double& dens_out, double& ds_out)
+    {
         while (true)
         {
-            const double4 pr = sk_ld_rec(&M.vrec[m]);
-            double sq = DBL_MAX;
+            const double4 pr = sk_ld_rec(&M.vrec[cm]);
+            sq = DBL_MAX;
             const int NO_INDEX = -99;
-            int mq = NO_INDEX;
-            const long long i1 = __ldg(&M.vnbr_off[m + 1]);
-            for (long long i = __ldg(&M.vnbr_off[m]); i < i1; ++i)
+            mq = NO_INDEX;
+            const int i1 = (int)__ldg(&M.vnbr_off[cm + 1]);
+            for (int i = (int)__ldg(&M.vnbr_off[cm]); i < i1; ++i)
             {
                 const int mi = __ldg(&M.vnbr[i]);
                 double si = 0;
@@ -347,161 +667,39 @@ __device__ __forceinline__ void sk_step(const SkDevModel& M, const SkDevModel* _
                     mq = mi;
                 }
             }
-            if (mq == NO_INDEX)
+            if (mq != NO_INDEX)
             {
-                // no exit point (rare): nudge the position, look the cell up again (.cpp:1156-1167)
-                cnt.fallbacks++;
-                rx += k.kx * M.eps;
-                ry += k.ky * M.eps;
-                rz += k.kz * M.eps;
-                m = sk_box_contains(M.ext, rx, ry, rz) ? sk_voronoi_walk(Mg, rx, ry, rz, m) : -1;
-                if (m < 0)
-                {
-                    // outside the domain: the path ends without a further segment
-                    p.m = -1;
-                    m_out = -1;
-                    dens_out = 0.;
-                    ds_out = -1.;
-                    return;
-                }
-                continue;
+                m_out = cm;
+                dens_out = pr.w;
+                ds_out = sq;
+                return;
             }
-            const double adv = sq + M.eps;
-            rx += k.kx * adv;
-            ry += k.ky * adv;
-            rz += k.kz * adv;
-            m_out = m;
-            dens_out = pr.w;
-            ds_out = sq;
-            p.m = mq < 0 ? -1 : mq;
-            return;
+            // no exit point (rare): nudge the position, look the cell up again (.cpp:1156-1167)
+            cnt.fallbacks++;
+            rx += k.kx * M.eps;
+            ry += k.ky * M.eps;
+            rz += k.kz * M.eps;
+            cm = sk_box_contains(M.ext, rx, ry, rz) ? sk_voronoi_walk(Mg, rx, ry, rz, cm) : -1;
+            if (cm < 0)
+            {
+                // outside the domain: the path ends without a further segment
+                m_out = -1;
+                dens_out = 0.;
+                ds_out = -1.;
+                return;
+            }
         }
     }
-    else if (GRID == 1)
+    __device__ __forceinline__ void move(const SkDevModel& M, const SkDevModel* __restrict__, const SkSmemTables&,
+                                         SkLocalCounters&, const SkDir& k)
     {
-        int m = p.m;
-        double dens = __ldg(&M.dens[m]);
-        double xE = T.X[p.ix + ((k.kx < 0.0) ? 0 : 1)];
-        double yE = T.Y[p.iy + ((k.ky < 0.0) ? 0 : 1)];
-        double zE = T.Z[p.iz + ((k.kz < 0.0) ? 0 : 1)];
-        double dsx = (k.ikx != 0.) ? (xE - rx) * k.ikx : DBL_MAX;
-        double dsy = (k.iky != 0.) ? (yE - ry) * k.iky : DBL_MAX;
-        double dsz = (k.ikz != 0.) ? (zE - rz) * k.ikz : DBL_MAX;
-        double ds;
-        bool outside;
-        if (dsx <= dsy && dsx <= dsz)
-        {
-            ds = dsx;
-            rx = xE;
-            ry += k.ky * dsx;
-            rz += k.kz * dsx;
-            p.ix += (k.kx < 0.0) ? -1 : 1;
-            outside = (p.ix >= M.nx || p.ix < 0);
-        }
-        else if (dsy < dsx && dsy <= dsz)
-        {
-            ds = dsy;
-            ry = yE;
-            rx += k.kx * dsy;
-            rz += k.kz * dsy;
-            p.iy += (k.ky < 0.0) ? -1 : 1;
-            outside = (p.iy >= M.ny || p.iy < 0);
-        }
-        else
-        {
-            ds = dsz;
-            rz = zE;
-            rx += k.kx * dsz;
-            ry += k.ky * dsz;
-            p.iz += (k.kz < 0.0) ? -1 : 1;
-            outside = (p.iz >= M.nz || p.iz < 0);
-        }
-        m_out = m;
-        dens_out = dens;
-        ds_out = ds;
-        p.m = outside ? -1 : p.iz + M.nz * p.iy + M.nz * M.ny * p.ix;
-    }
-    else
-    {
-        // one 32-byte sector: density + the six neighbour links of the current cell
-        int4 a, b;
-        sk_ld256(&M.cells[p.m], a, b);
-        const int size = 1 << (M.maxlevel - p.lev);
-        const bool nx = k.kx < 0.0, ny = k.ky < 0.0, nz = k.kz < 0.0;
-        const double xnext = T.X[p.ix + (nx ? 0 : size)];
-        const double ynext = T.Y[p.iy + (ny ? 0 : size)];
-        const double znext = T.Z[p.iz + (nz ? 0 : size)];
-        const double dsx = (k.ikx != 0.) ? (xnext - rx) * k.ikx : DBL_MAX;
-        const double dsy = (k.iky != 0.) ? (ynext - ry) * k.iky : DBL_MAX;
-        const double dsz = (k.ikz != 0.) ? (znext - rz) * k.ikz : DBL_MAX;
-        // exit wall: x if dsx<=dsy && dsx<=dsz, else y if dsy<=dsx && dsy<=dsz, else z (TreeSpatialGrid.cpp:160-178)
-        const bool takex = dsx <= dsy && dsx <= dsz;
-        const bool takey = !takex && dsy <= dsx && dsy <= dsz;
-        const double ds = takex ? dsx : takey ? dsy : dsz;
-        const double other = takex ? fmin(dsy, dsz) : takey ? fmin(dsx, dsz) : fmin(dsx, dsy);
-        const double kexit = takex ? k.kx : takey ? k.ky : k.kz;
-        const int lx = nx ? a.z : a.w, ly = ny ? b.x : b.y, lz = nz ? b.z : b.w;
-        const int link = takex ? lx : takey ? ly : lz;
-        const double adv = ds + M.eps;
+        const double adv = sq + M.eps;
         rx += k.kx * adv;
         ry += k.ky * adv;
         rz += k.kz * adv;
-        m_out = p.m;
-        dens_out = __hiloint2double(a.y, a.x);
-        ds_out = ds;
-        // The link decides the next cell unless the new position may also have crossed a second wall (the exit
-        // distances of two walls differ by less than a few eps), the direction grazes the exit wall (the eps advance may
-        // be lost to rounding), or the path reaches the domain boundary; those cases take the reference's full search.
-        // The common way for a path to end: there is no neighbour across the exit wall and the new position lies outside
-        // the domain, so TreeNode::neighbor() and root()->leafChild() both come back empty (TreeSpatialGrid.cpp:190-205).
-        if (link < 0 && !sk_box_contains(M.ext, rx, ry, rz))
-        {
-            p.m = -1;
-            return;
-        }
-        const bool rare = link < 0 || !(other - ds > 4. * M.eps) || !(fabs(kexit) > 1e-3);
-        if (!rare)
-        {
-            // step to the lattice point just across the exit wall, then align to the neighbour's level
-            int ix = p.ix, iy = p.iy, iz = p.iz;
-            if (takex)
-                ix += nx ? -1 : size;
-            else if (takey)
-                iy += ny ? -1 : size;
-            else
-                iz += nz ? -1 : size;
-            const int nlev = (link >> SK_LINK_LEVEL_SHIFT) & 15;
-            const int mask = ~((1 << (M.maxlevel - nlev)) - 1);
-            ix &= mask;
-            iy &= mask;
-            iz &= mask;
-            const int idx = link & SK_LINK_INDEX_MASK;
-            if (!(link & SK_LINK_INTERNAL))
-            {
-                p.m = idx;  // leaf neighbour at the same or a coarser level
-                p.ix = ix;
-                p.iy = iy;
-                p.iz = iz;
-                p.lev = nlev;
-            }
-            else
-                sk_tree_descend(M.node_child, M.maxlevel, T, idx, ix, iy, iz, nlev, rx, ry, rz, p);
-        }
-        else
-        {
-            // (copies confine the address-taken variables, which live in local memory, to this cold branch)
-            cnt.fallbacks++;
-            double tx = rx, ty = ry, tz = rz;
-            SkCellPos q;
-            sk_tree_step_rare(Mg, T, tx, ty, tz, k.kx, k.ky, k.kz, p.m, q);
-            rx = tx;
-            ry = ty;
-            rz = tz;
-            p = q;
-        }
+        cm = mq < 0 ? -1 : mq;
     }
-}
-
+};
 // ---------------------------------------------------------------------------------------------------
 // Sources: SourceSystem::launch (SourceSystem.cpp:101-113), NormalizedSource::launch (NormalizedSource.cpp:73-110),
 // GeometricSource::launchNormalized (GeometricSource.cpp:66-82), PointSource::launchSpecialty (PointSource.cpp:32-42)
@@ -736,7 +934,7 @@ __device__ __forceinline__ bool sk_detect_geometry(const SkDevModel& M, const Sk
             l = i + q.nx * jj;
     }
     if (!q.include_sed && l < 0) return false;
-    ell = sk_wlg_bin(M.wlg[q.wlg], lambda);
+    ell = sk_wlg_bin(M.wlg[q.wlg], lambda * q.zp1);  // the packet's redshifted wavelength, FluxRecorder.cpp:309-313
     return ell >= 0;
 }
 
@@ -804,12 +1002,18 @@ __device__ __forceinline__ double sk_cell_density(const SkDevModel& M, int m)
 {
     return GRID == 3 ? M.vrec[m].w : GRID == 2 ? M.cells[m].dens : M.dens[m];
 }
-// true when (x,y,z) lies in the half-open box of cell c
+// true when (x,y,z) lies in the half-open box of cell c (octree: in lattice coordinates, like the walk itself)
 template <int GRID>
 __device__ __forceinline__ bool sk_cell_contains(const SkDevModel& M, const SkSmemTables& T, const SkCellPos& c, double x,
                                                  double y, double z)
 {
-    const int size = GRID == 1 ? 1 : 1 << (M.maxlevel - c.lev);
-    return x >= T.X[c.ix] && x < T.X[c.ix + size] && y >= T.Y[c.iy] && y < T.Y[c.iy + size] && z >= T.Z[c.iz]
-           && z < T.Z[c.iz + size];
+    if (GRID == 2)
+    {
+        const int size = 1 << (M.maxlevel - c.lev);
+        const double ux = sk_lat_coord(x, M.ext[0], M.lat_invh[0]), uy = sk_lat_coord(y, M.ext[1], M.lat_invh[1]),
+                     uz = sk_lat_coord(z, M.ext[2], M.lat_invh[2]);
+        return ux >= (double)c.ix && ux < (double)(c.ix + size) && uy >= (double)c.iy && uy < (double)(c.iy + size)
+               && uz >= (double)c.iz && uz < (double)(c.iz + size);
+    }
+    return x >= T.X[c.ix] && x < T.X[c.ix + 1] && y >= T.Y[c.iy] && y < T.Y[c.iy + 1] && z >= T.Z[c.iz] && z < T.Z[c.iz + 1];
 }

@@ -3,8 +3,9 @@
 // Layout in HBM:
 //   * octree: one 32-byte record per CELL {double density; int32 link[6]} -- exactly one 32 B sector per cell
 //     crossing; the cell geometry is NOT stored per cell: a cell is identified by its integer lattice coordinates
-//     (ix,iy,iz at the finest level, carried in registers) and its level, and its bounds come from three per-axis
-//     border tables X/Y/Z[2^maxLevel+1] that are staged in shared memory.  link[w] is the same-level-or-coarser
+//     (ix,iy,iz at the finest level, carried in registers) and its level, and a ray is walked in lattice coordinates
+//     u = (r - min) / pitch, in which the cell borders are those integers (no border look-ups in the crossing loop; the
+//     per-axis border tables X/Y/Z[2^maxLevel+1] remain for the set-up kernels).  link[w] is the same-level-or-coarser
 //     neighbour across wall w: a cell index (+ its level) when that neighbour is a leaf, an internal node id
 //     otherwise (then a short descent through the 4-byte-per-node child table follows), -1 at the domain boundary.
 //   * Cartesian grid: border arrays in shared memory, density[m] 8 B per crossing, neighbours by index arithmetic.
@@ -59,6 +60,7 @@ struct SkDevInstr {
     double kobs[3];
     double costheta, sintheta, cosphi, sinphi, cosomega, sinomega;
     double xpmin, xpsiz, ypmin, ypsiz, radius2;
+    double zp1;         // 1 + observer-frame redshift (FluxRecorder.cpp:310)
     double* sed[SK_NUM_COMP];
     double* ifu[SK_NUM_COMP];
     double* wsed[5];
@@ -79,6 +81,9 @@ struct SkDevModel {
     int32_t lattice_in_smem;
     double ext[6];
     double eps;
+    double eps4;                 // 4 eps: exit distances of two walls closer than this take the full neighbour search
+    double lat_h[3];             // octree: pitch of the finest lattice per axis, (max - min) / 2^maxlevel
+    double lat_invh[3];          // and its reciprocal
     const double *xv, *yv, *zv;  // cartesian borders or octree lattice tables
     const double* dens;          // cartesian: density per cell
     const SkCellRec* cells;      // octree

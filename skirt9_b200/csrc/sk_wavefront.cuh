@@ -195,27 +195,77 @@ __device__ __forceinline__ void sk_finish_history(const SkDevModel& M, const SkB
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Forced scattering: the interaction optical depth, MonteCarloSimulation::simulateForcedPropagation (.cpp:696-722) with
+// Random::exponCutoff (Random.cpp:105-117) and the path-length bias xi.  The reference draws when the forward path is
+// complete; here the work is cut in three so that only a few instructions run in the trace kernel, where the lanes that
+// have just finished a path are a small part of their warp:
+//   sk_predraw_interaction  (launch / detect kernels, full warps) draws the deviates at the place in the history's random
+//                           sequence where the reference draws them -- nothing else draws in between -- and packs them
+//                           into one number: -u when the biased (linear) branch was chosen, +u otherwise
+//   sk_interaction_depth    (trace kernel, at the end of the forward path) turns it into tau_int for the path's tau_path
+//   sk_wf_advance           applies the bias weight p/q to the packet
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double sk_predraw_interaction(SkRng& g, double xi)
+{
+    if (xi == 0.) return sk_uniform(g);
+    const bool biased = sk_uniform(g) < xi;
+    const double u = sk_uniform(g);
+    return biased ? -u : u;
+}
+// Random::exponCutoff's rejection loop (x > xmax can only come from rounding when u is within an ulp of 1): further
+// deviates of the history, drawn here.  Arguments by value so that the kernel's parameter copies never have their address
+// taken.
+__device__ __noinline__ double sk_redraw_interaction(uint32_t seed, uint32_t stream_id, int32_t* bank_i, int cap, int slot,
+                                                     double xmax)
+{
+    SkBank K;
+    K.i = bank_i;
+    K.cap = cap;
+    SkRng g;
+    sk_rng_init(g, seed, stream_id, ((unsigned long long)(uint32_t)K.I(I_HHI, slot) << 32) | (uint32_t)K.I(I_HLO, slot),
+                (uint32_t)K.I(I_DRAW, slot));
+    double x;
+    do
+        x = -log(1.0 - sk_uniform(g) * (1.0 - exp(-xmax)));
+    while (x > xmax);
+    K.I(I_DRAW, slot) = (int)g.draw;
+    return x;
+}
+__device__ __forceinline__ double sk_interaction_depth(double u, double taupath, bool& redraw)
+{
+    redraw = false;
+    if (u < 0.) return -u * taupath;        // uniform * taupath (.cpp:712)
+    if (taupath < 1e-10) return u * taupath;  // Random.cpp:109-110
+    const double x = -log(1.0 - u * (1.0 - exp(-taupath)));
+    redraw = x > taupath;
+    return x;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Trace kernels: walk all rays of the list with dynamic lane refill.
-//   MODE 0  forward path to the boundary: MediumSystem::setExtinctionOpticalDepths (MediumSystem.cpp:849-871); with
-//           STORE fused with MonteCarloSimulation::storeRadiationField (.cpp:638-665)
-//   MODE 1  walk to the interaction point: SpatialGridPath::findInteractionPoint (SpatialGridPath.cpp:164-206), or for
-//           non-forced scattering MediumSystem::setInteractionPointUsingExtinction (MediumSystem.cpp:978-1010)
+//   MODE 0  forced scattering: the forward path to the boundary -- MediumSystem::setExtinctionOpticalDepths
+//           (MediumSystem.cpp:849-871), with STORE fused with MonteCarloSimulation::storeRadiationField (.cpp:638-665) --
+//           then, in the same lane, the interaction optical depth (simulateForcedPropagation, .cpp:696-722) and the walk
+//           to the interaction point, SpatialGridPath::findInteractionPoint (SpatialGridPath.cpp:164-206): paths are
+//           not stored, the second walk repeats the first with identical arithmetic while the cell records are cache-hot
+//   MODE 1  non-forced scattering: walk to the interaction point drawn by sk_wf_sample,
+//           MediumSystem::setInteractionPointUsingExtinction (MediumSystem.cpp:978-1010)
 //   MODE 2  optical depth to the observer: MediumSystem::getExtinctionOpticalDepth (MediumSystem.cpp:1192-1219)
 // Structure: a compact inner loop that only crosses cells, and an outer service block (store the results of finished
 // rays, load new rays) that is entered when at least SK_REFILL_MIN lanes are idle, so that its cost is shared.
 // ---------------------------------------------------------------------------------------------------
 template <int GRID, int MODE, bool STORE, bool TABLES_IN_SMEM>
 __global__ void __launch_bounds__(SK_TRACE_BLOCK, MODE == 2 ? SK_TRACE_MINBLOCKS_PEEL : SK_TRACE_MINBLOCKS)
-    sk_wf_trace(const SkDevModel M, const SkRunArgs A, const SkBank K, const SkRayDir obs)
+    sk_wf_trace(const SkDevModel M, const SkRunArgs A, const SkBank K, const SkObsDir obs)
 {
     extern __shared__ __align__(16) double smem[];
     __shared__ unsigned long long tma_bar;
     SkSmemTables T;
     if (TABLES_IN_SMEM)
     {
-        // stage the per-axis border tables (Cartesian borders / octree lattice) in shared memory with three TMA bulk copies
-        // that complete on one mbarrier (the tables are padded to 16-byte multiples, SK_TABLE_PAD); the instantiation is
-        // separate from the global-memory one so that the lookups in the crossing loop compile to LDS
+        // stage the per-axis border tables of the Cartesian grid in shared memory with three TMA bulk copies that complete
+        // on one mbarrier (the tables are padded to 16-byte multiples, SK_TABLE_PAD); the instantiation is separate from
+        // the global-memory one so that the lookups in the crossing loop compile to LDS
         const int n0 = SK_TABLE_PAD(M.nx + 1), n1 = SK_TABLE_PAD(M.ny + 1), n2 = SK_TABLE_PAD(M.nz + 1);
         if (threadIdx.x == 0) sk_mbar_init(&tma_bar, 1);
         __syncthreads();
@@ -247,51 +297,73 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, MODE == 2 ? SK_TRACE_MINBLOCKS
 
     int chunk_pos = 0, chunk_end = 0;  // the warp's reserved range of the list
     bool exhausted = false;            // the global list has been handed out completely
-    bool active = false, pending = false;
+    // lane state: ACTIVE = walking a ray; PENDING = its ray has ended, results not yet written; REPLAY (MODE 0) = the lane is
+    // on the second walk of its packet, to the interaction point; FOUND = that walk ended at an interaction point
+    enum { ACTIVE = 1, PENDING = 2, REPLAY = 4, FOUND = 8 };
+    unsigned ls = 0;
     int slot = 0;
-    double rx = 0, ry = 0, rz = 0;
-    SkRayDir kray;  // direction of the lane's ray; all peel-off rays (MODE 2) share the observer's direction, which stays in
-    kray.set(0., 0., 1.);  // the kernel's parameter space: no per-lane registers, uniform sign tests
-    const SkRayDir& k = MODE == 2 ? obs : kray;
-    SkCellPos p{-1, 0, 0, 0, 0};
+    SkDir kray;  // direction of the lane's ray; all peel-off rays (MODE 2) share the observer's direction, which stays in
+    kray.set(0., 0., 1., nullptr);  // the kernel's parameter space: no per-lane registers, uniform sign tests
+    const SkDir& k = MODE == 2 ? obs.d : kray;
+    SkStepper<GRID> st;  // while a lane is not ACTIVE its stepper keeps the cell in which the walk ended
+    st.cm = -1;
     double tau = 0, s = 0, limit = 0, section = 0;
     int nseg = 0;
     // MODE 0 + STORE extras
     double lum = 0, lnExtBeg = 0, extBeg = 1;
     int rf_ell = -1;
     double* rf = nullptr;
-    // MODE 1 results
-    SkCellPos hit{-1, 0, 0, 0, 0};
-    double s_int = 0;
-    bool found = false;
+    double s_int = 0;  // result of a walk to the interaction point
 
     while (true)
     {
         // ---------------- service block: results of finished rays out, new rays in
-        if (pending)
+        bool start = false;  // the lane begins a walk in this pass: a new ray, or the second walk of its packet
+        if (ls & PENDING)
         {
-            pending = false;
-            if (MODE == 0)
+            ls &= ~PENDING;
+            if (MODE == 0 && !(ls & REPLAY))
             {
                 K.D(D_TAUPATH, slot) = tau;
-                K.D(D_STOT, slot) = s;
-                K.I(I_NSEG, slot) = nseg;
                 cnt.fwd_paths++;
                 cnt.fwd_segs += nseg;
+                // no extinction along the path: the packet cannot scatter; sk_wf_advance terminates it (.cpp:702-706)
+                if (tau > 0.)
+                {
+                    bool redraw;
+                    limit = sk_interaction_depth(K.D(D_TAUINT, slot), tau, redraw);
+                    if (redraw) limit = sk_redraw_interaction(M.seed, A.stream_id, K.i, K.cap, slot, tau);
+                    K.D(D_TAUINT, slot) = limit;
+                    ls |= REPLAY;
+                    start = true;
+                }
             }
-            else if (MODE == 1)
+            else if (MODE == 0 || MODE == 1)
             {
+                // the interaction cell = the cell in which the walk stopped.  A walk that left the grid is at or beyond the
+                // exit optical depth of its last segment: the interaction point is the end of the path, in the last cell
+                // crossed (SpatialGridPath.cpp:199-205; the stepper holds -2 - m, and sk_wf_advance looks the lattice
+                // position up again: level -1); -1: the path missed the grid.
+                SkCellPos hit = st.cell(M);
+                if (hit.m < -1)
+                {
+                    hit.m = -2 - hit.m;
+                    hit.lev = -1;
+                }
+                // a walk that stopped inside a cell holds the optical depth at the cell's far wall in s_int: linear
+                // interpolation over the segment (SpatialGridPath.cpp:188-194)
+                if (st.m() >= 0) s_int = sk_interp_linlin(limit, tau, s_int, s, s + st.ds());
                 K.D(D_SINT, slot) = s_int;
                 K.I(I_MINT, slot) = hit.m;
                 K.I(I_MIX, slot) = hit.ix;
                 K.I(I_MIY, slot) = hit.iy;
                 K.I(I_MIZ, slot) = hit.iz;
                 K.I(I_MLEV, slot) = hit.lev;
-                if (found) K.I(I_STATE, slot) |= SK_ST_FOUND;
-                if (forced)
+                if (MODE == 0)
                     cnt.replay_segs += nseg;
                 else
                 {
+                    if (ls & FOUND) K.I(I_STATE, slot) |= SK_ST_FOUND;
                     cnt.fwd_paths++;
                     cnt.fwd_segs += nseg;
                 }
@@ -304,7 +376,7 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, MODE == 2 ? SK_TRACE_MINBLOCKS
             }
         }
         {
-            const unsigned idle = __ballot_sync(0xffffffffu, !active);
+            const unsigned idle = __ballot_sync(0xffffffffu, !(ls & ACTIVE) && !start);
             if (chunk_pos >= chunk_end && !exhausted)
             {
                 unsigned b = 0;
@@ -320,46 +392,48 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, MODE == 2 ? SK_TRACE_MINBLOCKS
             }
             const int idx = chunk_pos + __popc(idle & lt_mask);
             const int take = min(__popc(idle), chunk_end - chunk_pos);
-            if (!active && idx < chunk_end)
+            if (!(ls & ACTIVE) && !start && idx < chunk_end)
             {
                 slot = K.list[idx];
-                active = true;
-                rx = K.D(D_RX, slot);
-                ry = K.D(D_RY, slot);
-                rz = K.D(D_RZ, slot);
-                if (MODE != 2) kray.set(K.D(D_KX, slot), K.D(D_KY, slot), K.D(D_KZ, slot));
-                p.m = K.I(I_M, slot);
-                p.ix = K.I(I_IX, slot);
-                p.iy = K.I(I_IY, slot);
-                p.iz = K.I(I_IZ, slot);
-                p.lev = K.I(I_LEV, slot);
+                start = true;
+                ls = 0;
+                if (MODE != 2)
+                    kray.load(K.D(D_KX, slot), K.D(D_KY, slot), K.D(D_KZ, slot), K.D(D_IKX, slot), K.D(D_IKY, slot),
+                              K.D(D_IKZ, slot), GRID == 2 ? M.lat_invh : nullptr);
                 section = K.D(D_SIGEXT, slot);
-                tau = 0.;
-                s = 0.;
-                nseg = 0;
                 if (MODE == 0 && STORE)
                 {
-                    lnExtBeg = 0.;
-                    extBeg = 1.;
                     double lambda = K.D(D_LAMBDA, slot);
                     rf_ell = sk_wlg_bin(M.wlg[M.rf_grid], lambda);  // MonteCarloSimulation.cpp:643
                     rf = A.primary ? M.rf1 : M.rf2c;
                     lum = K.D(D_W, slot) / lambda;
                 }
-                if (MODE == 1)
-                {
-                    limit = K.D(D_TAUINT, slot);
-                    hit = p;
-                    found = false;
-                    s_int = 0.;
-                }
+                if (MODE == 1) limit = K.D(D_TAUINT, slot);
                 if (MODE == 2) limit = K.D(D_LIMIT, slot);
+            }
+            if (start)
+            {
+                double rx = K.D(D_RX, slot), ry = K.D(D_RY, slot), rz = K.D(D_RZ, slot);
+                SkCellPos p{K.I(I_M, slot), K.I(I_IX, slot), K.I(I_IY, slot), K.I(I_IZ, slot), K.I(I_LEV, slot)};
+                ls |= ACTIVE;
+                tau = 0.;
+                s = 0.;
+                nseg = 0;
+                s_int = 0.;
+                if (MODE == 0 && STORE)
+                {
+                    lnExtBeg = 0.;
+                    extBeg = 1.;
+                }
                 if (p.m < 0)
                 {
                     // the path starts outside (or exactly on the border of) the grid: PathSegmentGenerator::moveInside
                     double cumds = 0.;
                     double tx = rx, ty = ry, tz = rz;
-                    if (sk_move_inside(tx, ty, tz, k.kx, k.ky, k.kz, Mg->ext, M.eps, cumds))
+                    const double dkx = MODE == 2 ? obs.px : K.D(D_KX, slot), dky = MODE == 2 ? obs.py : K.D(D_KY, slot),
+                                 dkz = MODE == 2 ? obs.pz : K.D(D_KZ, slot);
+                    p.m = -1;
+                    if (sk_move_inside(tx, ty, tz, dkx, dky, dkz, Mg->ext, M.eps, cumds))
                     {
                         SkCellPos q;
                         sk_locate<GRID>(Mg, T, tx, ty, tz, q);
@@ -377,14 +451,14 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, MODE == 2 ? SK_TRACE_MINBLOCKS
                     if (p.m < 0)
                     {
                         // the path misses the grid: no segments
-                        active = false;
-                        pending = true;
-                        if (MODE == 1) s_int = s;
+                        ls = (ls & ~ACTIVE) | PENDING;
+                        s_int = s;
                     }
                 }
+                st.begin(M, rx, ry, rz, p);
             }
             if (take > 0) chunk_pos += take;
-            if (!__any_sync(0xffffffffu, active || pending))
+            if (!__any_sync(0xffffffffu, (ls & (ACTIVE | PENDING)) != 0))
             {
                 if (exhausted) break;
                 continue;  // the chunk ran out exactly here: reserve the next one
@@ -392,26 +466,31 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, MODE == 2 ? SK_TRACE_MINBLOCKS
         }
         // ---------------- inner loop: cross cells until enough lanes have finished their ray
         const int want_idle = (exhausted && chunk_pos >= chunk_end) ? 32 : (MODE == 1 ? SK_REFILL_MIN_SHORT : SK_REFILL_MIN);
-        int nidle;
         do
         {
-            if (active)
+            if (ls & ACTIVE)
             {
                 int m;
                 double dens, ds;
-                const SkCellPos cur = p;
-                sk_step<GRID>(M, Mg, T, cnt, rx, ry, rz, k, p, m, dens, ds);
+                st.exit(M, Mg, T, cnt, k, m, dens, ds);
                 bool done = false;
                 if (MODE == 0)
                 {
                     if (ds > 0.)  // SpatialGridPath::addSegment, SpatialGridPath.cpp:41-48
                     {
                         nseg++;
-                        s += ds;
-                        tau += section * dens * ds;
-                        if (STORE && rf_ell >= 0)
+                        const double tau1 = __fma_rn(section * dens, ds, tau);
+                        if (ls & REPLAY)
                         {
-                            double lnExtEnd = -tau;
+                            if (limit < tau1)
+                            {
+                                s_int = tau1;  // interaction inside this segment: interpolated by the service block
+                                done = true;
+                            }
+                        }
+                        else if (STORE && rf_ell >= 0)
+                        {
+                            double lnExtEnd = -tau1;
                             double extEnd = exp(lnExtEnd);
                             double extMean = sk_lnmean4(extEnd, extBeg, lnExtEnd, lnExtBeg);
                             double Lds = lum * extMean * ds;
@@ -420,6 +499,11 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, MODE == 2 ? SK_TRACE_MINBLOCKS
                             lnExtBeg = lnExtEnd;
                             extBeg = extEnd;
                         }
+                        if (!done)
+                        {
+                            s += ds;
+                            tau = tau1;
+                        }
                     }
                 }
                 else if (MODE == 1)
@@ -427,43 +511,47 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, MODE == 2 ? SK_TRACE_MINBLOCKS
                     if (forced ? (ds > 0.) : (ds >= 0.))  // ds < 0: the generator ended without a segment (Voronoi)
                     {
                         nseg++;
-                        double tau0 = tau, s0 = s;
-                        s += ds;
-                        tau += section * dens * ds;
-                        hit = cur;
-                        if (limit < tau)
+                        const double tau1 = __fma_rn(section * dens, ds, tau);
+                        if (limit < tau1)
                         {
-                            s_int = sk_interp_linlin(limit, tau0, tau, s0, s);  // interaction inside this segment
-                            found = true;
+                            s_int = tau1;  // interaction inside this segment: interpolated by the service block
+                            ls |= FOUND;
                             done = true;
+                        }
+                        else
+                        {
+                            s += ds;
+                            tau = tau1;
                         }
                     }
                 }
                 else if (ds >= 0.)
                 {
                     nseg++;
-                    tau += section * dens * ds;
+                    tau = __fma_rn(section * dens, ds, tau);
                     if (tau >= limit)
                     {
                         tau = INFINITY;  // MediumSystem.cpp:1215
                         done = true;
                     }
                 }
-                if (!done && p.m < 0)
+                if (!done)
                 {
-                    // the path has left the grid; MODE 1: at or beyond the exit optical depth of the last segment ->
-                    // use the last segment (SpatialGridPath.cpp:199-205); non-forced: no interaction
-                    done = true;
-                    if (MODE == 1) s_int = s;
+                    if (GRID != 3 || st.m() >= 0) st.move(M, Mg, T, cnt, k);
+                    if (st.m() < 0)
+                    {
+                        // the path has left the grid (non-forced: no interaction)
+                        done = true;
+                        if (MODE != 2)
+                        {
+                            s_int = s;
+                            st.cm = -2 - m;  // the last cell crossed
+                        }
+                    }
                 }
-                if (done)
-                {
-                    active = false;
-                    pending = true;
-                }
+                if (done) ls = (ls & ~ACTIVE) | PENDING;
             }
-            nidle = __popc(__ballot_sync(0xffffffffu, !active));
-        } while (nidle < want_idle);
+        } while (__popc(__ballot_sync(0xffffffffu, !(ls & ACTIVE))) < want_idle);
     }
     sk_flush_counters(M, cnt);
 }
@@ -540,6 +628,7 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_advance(const SkDevModel
     const int m = K.I(I_MINT, sl), ilam = K.I(I_ILAM, sl), nscatt = K.I(I_NSCATT, sl);
     const int mix = K.I(I_MIX, sl), miy = K.I(I_MIY, sl), miz = K.I(I_MIZ, sl), mlev = K.I(I_MLEV, sl);
     const double sigext = K.D(D_SIGEXT, sl), W0 = K.D(D_W, sl), taupath = K.D(D_TAUPATH, sl), sint = K.D(D_SINT, sl);
+    const double tauint = K.D(D_TAUINT, sl);
     const double kx = K.D(D_KX, sl), ky = K.D(D_KY, sl), kz = K.D(D_KZ, sl);
     const double rx0 = K.D(D_RX, sl), ry0 = K.D(D_RY, sl), rz0 = K.D(D_RZ, sl);
     const double lambda = K.D(D_LAMBDA, sl), lthr = K.D(D_LTHR, sl);
@@ -551,6 +640,9 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_advance(const SkDevModel
     {
         bool alive = true;
         if (!forced && !(st & SK_ST_FOUND)) alive = false;  // escaped, MonteCarloSimulation.cpp:594
+        // forced scattering without extinction along the path: the packet cannot scatter, terminate it (.cpp:702-706); the
+        // forward trace has found taupath = 0 (no segments, or only empty cells) and drawn no interaction point
+        if (forced && !(taupath > 0.)) alive = false;
         if (alive)
         {
             // MediumSystem::albedoForScattering, MediumSystem.cpp:678-693
@@ -563,7 +655,19 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_advance(const SkDevModel
                 albedo = kext > 0. ? ksca / kext : 0.;
             }
             if (forced)
-                W *= -expm1(-taupath) * albedo;
+            {
+                // the path-length bias weight p/q of the interaction optical depth the trace kernel has used (.cpp:714-718),
+                // then the escape fraction and the albedo (.cpp:729-733)
+                const double em = expm1(-taupath);
+                const double xi = M.path_length_bias;
+                if (xi != 0.)
+                {
+                    const double pw = -exp(-tauint) / em;
+                    const double qw = (1.0 - xi) * pw + xi / taupath;
+                    W *= pw / qw;
+                }
+                W *= -em * albedo;
+            }
             else
                 W *= albedo;
             x = rx0 + sint * kx;  // PhotonPacket::propagate, PhotonPacket.cpp:107-111
@@ -589,7 +693,7 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_advance(const SkDevModel
                 {
                     if (inside) c.m = sk_voronoi_walk(Mg, x, y, z, m);  // a new path looks its cell up (.cpp:1076)
                 }
-                else if (inside && !sk_cell_contains<GRID>(M, T, c, x, y, z))
+                else if (inside && (mlev < 0 || !sk_cell_contains<GRID>(M, T, c, x, y, z)))
                 {
                     SkCellPos c2;
                     sk_locate<GRID>(Mg, T, x, y, z, c2);
@@ -666,6 +770,10 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK, SK_LAUNCH_MINBLOCKS) sk_wf_lau
                 K.D(D_KX, slot) = pp.kx;
                 K.D(D_KY, slot) = pp.ky;
                 K.D(D_KZ, slot) = pp.kz;
+                K.D(D_IKX, slot) = sk_dir_recip(pp.kx, GRID == 2 ? M.lat_h[0] : 1.);
+                K.D(D_IKY, slot) = sk_dir_recip(pp.ky, GRID == 2 ? M.lat_h[1] : 1.);
+                K.D(D_IKZ, slot) = sk_dir_recip(pp.kz, GRID == 2 ? M.lat_h[2] : 1.);
+                if (M.force_scattering) K.D(D_TAUINT, slot) = sk_predraw_interaction(g, M.path_length_bias);
                 K.D(D_LAMBDA, slot) = pp.lambda;
                 K.D(D_W, slot) = pp.W;
                 K.D(D_LTHR, slot) = (pp.W / pp.lambda) / M.min_weight_reduction;  // .cpp:563
@@ -769,6 +877,12 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_detect(const SkDevModel 
                 K.D(D_KX, slot) = kx;
                 K.D(D_KY, slot) = ky;
                 K.D(D_KZ, slot) = kz;
+                const bool lattice = M.grid_kind == 2;  // the octree is walked in lattice coordinates
+                K.D(D_IKX, slot) = sk_dir_recip(kx, lattice ? M.lat_h[0] : 1.);
+                K.D(D_IKY, slot) = sk_dir_recip(ky, lattice ? M.lat_h[1] : 1.);
+                K.D(D_IKZ, slot) = sk_dir_recip(kz, lattice ? M.lat_h[2] : 1.);
+                // the deviates of the interaction that follows this scattering (simulateForcedPropagation is the next to draw)
+                if (M.force_scattering) K.D(D_TAUINT, slot) = sk_predraw_interaction(g, M.path_length_bias);
                 K.I(I_DRAW, slot) = (int)g.draw;
                 K.I(I_NSCATT, slot) += 1;
                 K.I(I_STATE, slot) = st & ~SK_ST_SCATTER;
@@ -794,51 +908,22 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_detect(const SkDevModel 
     }
 }
 
-// sample: the interaction optical depth -- simulateForcedPropagation (.cpp:696-722) or Random::expon for
-// simulateNonForcedPropagation (.cpp:749) -- and the list of rays to walk to the interaction point.
+// sample: the interaction optical depth of non-forced propagation -- Random::expon for simulateNonForcedPropagation
+// (.cpp:749) -- and the list of rays to walk to the interaction point.  (With forced scattering the forward trace kernel
+// draws the interaction optical depth itself, sk_sample_interaction.)
 __global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_sample(const SkDevModel M, const SkRunArgs A, const SkBank K)
 {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = slot < K.n;
-    const bool forced = M.force_scattering != 0;
-    int st = valid ? K.I(I_STATE, slot) : 0;
-    bool live = (st & SK_ST_LIVE) != 0;
+    const int st = valid ? K.I(I_STATE, slot) : 0;
+    const bool live = (st & SK_ST_LIVE) != 0;
     if (live)
     {
         SkRng g;
         sk_rng_load(g, M, A, K, slot);
-        if (forced)
-        {
-            double taupath = K.D(D_TAUPATH, slot);
-            if (!(K.I(I_NSEG, slot) > 0 && taupath > 0.))
-            {
-                // no extinction along the path: the packet cannot scatter, terminate it (.cpp:702-706)
-                sk_finish_history(M, K, slot);
-                live = false;
-            }
-            else
-            {
-                double xi = M.path_length_bias;
-                double tauint;
-                if (xi == 0.)
-                    tauint = sk_expon_cutoff(g, taupath);
-                else
-                {
-                    tauint = sk_uniform(g) < xi ? sk_uniform(g) * taupath : sk_expon_cutoff(g, taupath);
-                    double pw = -exp(-tauint) / expm1(-taupath);
-                    double qw = (1.0 - xi) * pw + xi / taupath;
-                    K.D(D_W, slot) *= pw / qw;
-                }
-                K.D(D_TAUINT, slot) = tauint;
-            }
-        }
-        else
-            K.D(D_TAUINT, slot) = -log(sk_uniform(g));
-        if (live)
-        {
-            K.I(I_DRAW, slot) = (int)g.draw;
-            K.I(I_STATE, slot) = st & ~SK_ST_FOUND;
-        }
+        K.D(D_TAUINT, slot) = -log(sk_uniform(g));
+        K.I(I_DRAW, slot) = (int)g.draw;
+        K.I(I_STATE, slot) = st & ~SK_ST_FOUND;
     }
     sk_block_append(K.list, &K.ctl[SK_CTL_NLIST], live, slot);
 }

@@ -826,6 +826,7 @@ class Instrument:
     numScatteringLevels: int = 0
     recordStatistics: bool = False
     wavelengthGrid: Optional[DisjointWavelengthGrid] = None
+    redshift: float = 0.0  # FluxRecorder::setObserverFrameRedshift (from the simulation's Cosmology)
 
     def fields(self, grid_index):
         return {"kind": self.kind, "wavelength_grid": grid_index, "inclination": self.inclination,
@@ -833,7 +834,8 @@ class Instrument:
                 "num_pixels_x": self.numPixelsX, "num_pixels_y": self.numPixelsY,
                 "field_of_view_x": self.fieldOfViewX, "field_of_view_y": self.fieldOfViewY,
                 "center_x": self.centerX, "center_y": self.centerY, "record_components": self.recordComponents,
-                "num_scattering_levels": self.numScatteringLevels, "record_statistics": self.recordStatistics}
+                "num_scattering_levels": self.numScatteringLevels, "record_statistics": self.recordStatistics,
+                "redshift": self.redshift}
 
 
 def SEDInstrument(**kw):

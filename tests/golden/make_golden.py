@@ -88,6 +88,22 @@ def make_cfg2s():
     print("cfg2s:", {k: np.shape(v) for k, v in out.items()})
 
 
+def make_cfg8z():
+    """cfg2s in the observer frame at redshift 0.5 (instrument distance 0): same tree and densities as cfg2s (same seed,
+    same set-up), the packets binned at lambda (1 + z), the calibration with the luminosity distance."""
+    with tempfile.TemporaryDirectory() as d:
+        run_reference("cfg8z", d, packets=2e6)
+        sed = read_columns(os.path.join(d, "cfg8z_i60_sed.dat"))
+        stats = read_columns(os.path.join(d, "cfg8z_i60_sedstats.dat"))
+        cells = read_columns(os.path.join(d, "cfg8z_cells_cellprops.dat"))
+        base = np.load(os.path.join(HERE, "cfg2s_ref.npz"))["mass_density_msun_pc3"]
+        assert np.array_equal(cells[:, 6], base), "cfg8z must see the tree and the densities of cfg2s"
+        total = read_fits_cube(os.path.join(d, "cfg8z_i60_total.fits"))[0].astype(np.float64)
+        out = dict(sed=sed, sedstats=stats, frame_total_sum=total.sum(axis=0), num_packets=2e6)
+    np.savez_compressed(os.path.join(HERE, "cfg8z_ref.npz"), **out)
+    print("cfg8z:", {k: np.shape(v) for k, v in out.items()})
+
+
 def make_hi(name, packets=2e7):
     """High-statistics companion of a fixture: the same ski with `packets` histories, still with `-t 1` because the
     tree and the cell densities are sampled from the thread's random stream (Random.cpp:31-36) and must stay those of
