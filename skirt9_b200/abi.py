@@ -326,6 +326,7 @@ class Engine:
             q.record_components = int(s.get("record_components", False))
             q.num_scattering_levels = s.get("num_scattering_levels", 0)
             q.record_statistics = int(s.get("record_statistics", False))
+            q.redshift = float(s.get("redshift", 0.0))
             arr[k] = q
             self._instr.append((self._wlg[q.wavelength_grid], q.num_pixels_x * q.num_pixels_y))
         self._call("set_instruments", self._h, C.c_int32(len(instruments)), arr, C.c_int32(int(has_medium_emission)))

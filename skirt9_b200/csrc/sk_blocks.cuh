@@ -268,6 +268,7 @@ __device__ __noinline__ void sk_locate(const SkDevModel* __restrict__ Mg, const 
 struct SkDir {
     double kx, ky, kz;
     double ikx, iky, ikz;
+    double bigx, bigy, bigz;  // observer directions only (set()): DBL_MAX for an axis without exit walls, else 0
     unsigned flags;
     // (x, y, z) = the unit direction; h = pitch of the finest octree lattice per axis, or null for physical coordinates
     __host__ __device__ __forceinline__ void set(double x, double y, double z, const double* h)
@@ -289,6 +290,9 @@ struct SkDir {
         ikx = (f & SK_DIR_ZERO) ? 0. : (h ? h[0] : 1.0) / x;
         iky = (f & (SK_DIR_ZERO << 1)) ? 0. : (h ? h[1] : 1.0) / y;
         ikz = (f & (SK_DIR_ZERO << 2)) ? 0. : (h ? h[2] : 1.0) / z;
+        bigx = (f & SK_DIR_ZERO) ? DBL_MAX : 0.;
+        bigy = (f & (SK_DIR_ZERO << 1)) ? DBL_MAX : 0.;
+        bigz = (f & (SK_DIR_ZERO << 2)) ? DBL_MAX : 0.;
     }
     // the same from the unit direction and the reciprocals an event kernel has stored in the bank (sk_dir_recip):
     // invh = reciprocal pitch of the octree lattice per axis, or null for physical coordinates
@@ -298,9 +302,9 @@ struct SkDir {
         if (x < 0.0) f |= SK_DIR_NEG;
         if (y < 0.0) f |= SK_DIR_NEG << 1;
         if (z < 0.0) f |= SK_DIR_NEG << 2;
-        if (ix == 0.) f |= SK_DIR_ZERO;
-        if (iy == 0.) f |= SK_DIR_ZERO << 1;
-        if (iz == 0.) f |= SK_DIR_ZERO << 2;
+        if (fabs(ix) > 1e290) f |= SK_DIR_ZERO;
+        if (fabs(iy) > 1e290) f |= SK_DIR_ZERO << 1;
+        if (fabs(iz) > 1e290) f |= SK_DIR_ZERO << 2;
         if (!(fabs(x) > 1e-3)) f |= SK_DIR_GRAZE;
         if (!(fabs(y) > 1e-3)) f |= SK_DIR_GRAZE << 1;
         if (!(fabs(z) > 1e-3)) f |= SK_DIR_GRAZE << 2;
@@ -311,13 +315,19 @@ struct SkDir {
         ikx = ix;
         iky = iy;
         ikz = iz;
+        bigx = bigy = bigz = 0.;
     }
 };
-// Reciprocal of a direction component in traversal coordinates (h = lattice pitch of the axis for the octree, 1 otherwise);
-// 0 where the reference treats the component as zero.  Computed once per direction by the event kernel that creates it.
+// Reciprocal of a direction component of a packet's own (random) direction in traversal coordinates (h = lattice pitch of
+// the axis for the octree, 1 otherwise), computed once per direction by the event kernel that creates it.  Where the
+// reference treats the component as zero (fabs(k) <= 1e-15: no exit through the walls of that axis) the reciprocal is
+// +-1e300 with the sign of the component: the exit distance (wall - position) * 1e300 of that axis then loses every
+// comparison, with no test in the crossing loop.  (The observer's direction, where exact zeros are the rule for a face-on
+// instrument, uses exact offsets instead: SkDir::set.)
+#define SK_RECIP_ZERO 1e300
 __device__ __forceinline__ double sk_dir_recip(double k, double h)
 {
-    return (fabs(k) > 1e-15) ? h / k : 0.;
+    return (fabs(k) > 1e-15) ? h / k : (k < 0.0 ? -SK_RECIP_ZERO : SK_RECIP_ZERO);
 }
 // the observer's direction of a peel-off trace: traversal form + the unit vector itself (for entering the grid)
 struct SkObsDir {
@@ -371,6 +381,7 @@ struct SkStepper<1> {
         iy = p.iy;
         iz = p.iz;
     }
+    template <bool OBSERVER>
     __device__ __forceinline__ void exit(const SkDevModel& M, const SkDevModel* __restrict__, const SkSmemTables& T,
                                          SkLocalCounters&, const SkDir& k, int& m_out, double& dens_out, double& ds_out)
     {
@@ -378,9 +389,9 @@ struct SkStepper<1> {
         const double xE = T.X[ix + ((k.kx < 0.0) ? 0 : 1)];
         const double yE = T.Y[iy + ((k.ky < 0.0) ? 0 : 1)];
         const double zE = T.Z[iz + ((k.kz < 0.0) ? 0 : 1)];
-        const double dsx = (k.ikx != 0.) ? (xE - rx) * k.ikx : DBL_MAX;
-        const double dsy = (k.iky != 0.) ? (yE - ry) * k.iky : DBL_MAX;
-        const double dsz = (k.ikz != 0.) ? (zE - rz) * k.ikz : DBL_MAX;
+        const double dsx = (k.flags & SK_DIR_ZERO) ? DBL_MAX : (xE - rx) * k.ikx;
+        const double dsy = (k.flags & (SK_DIR_ZERO << 1)) ? DBL_MAX : (yE - ry) * k.iky;
+        const double dsz = (k.flags & (SK_DIR_ZERO << 2)) ? DBL_MAX : (zE - rz) * k.ikz;
         if (dsx <= dsy && dsx <= dsz)
         {
             axis = 0;
@@ -485,6 +496,7 @@ struct SkStepper<2> {
         sh = M.maxlevel - p.lev;
     }
     __device__ __forceinline__ SkCellPos cell(const SkDevModel& M) const { return SkCellPos{cm, ix, iy, iz, M.maxlevel - sh}; }
+    template <bool OBSERVER>
     __device__ __forceinline__ void exit(const SkDevModel& M, const SkDevModel* __restrict__, const SkSmemTables&,
                                          SkLocalCounters&, const SkDir& k, int& m_out, double& dens_out, double& ds_out)
     {
@@ -498,33 +510,29 @@ struct SkStepper<2> {
         const double xnext = (double)(ix + (nx ? 0 : size));
         const double ynext = (double)(iy + (ny ? 0 : size));
         const double znext = (double)(iz + (nz ? 0 : size));
-        double dsx = (xnext - ux) * k.ikx;
-        double dsy = (ynext - uy) * k.iky;
-        double dsz = (znext - uz) * k.ikz;
-        if (f & (7u * SK_DIR_ZERO))
-        {
-            // no exit through the walls of an axis the direction has no component along (never for a random direction)
-            if (f & SK_DIR_ZERO) dsx = DBL_MAX;
-            if (f & (SK_DIR_ZERO << 1)) dsy = DBL_MAX;
-            if (f & (SK_DIR_ZERO << 2)) dsz = DBL_MAX;
-        }
+        // no exit through the walls of an axis the direction has no component along: the observer's direction adds
+        // DBL_MAX to (wall - position) * 0, a packet's own direction multiplies by +-1e300 (sk_dir_recip)
+        const double dsx = OBSERVER ? __fma_rn(xnext - ux, k.ikx, k.bigx) : (xnext - ux) * k.ikx;
+        const double dsy = OBSERVER ? __fma_rn(ynext - uy, k.iky, k.bigy) : (ynext - uy) * k.iky;
+        const double dsz = OBSERVER ? __fma_rn(znext - uz, k.ikz, k.bigz) : (znext - uz) * k.ikz;
         // exit wall: x if dsx<=dsy && dsx<=dsz, else y if dsy<=dsx && dsy<=dsz, else z (TreeSpatialGrid.cpp:160-178); once x
-        // is ruled out, y wins exactly when dsy<=dsz.  `other` = the nearest of the two walls not taken.
+        // is ruled out, y wins exactly when dsy<=dsz
         const bool cyz = dsy <= dsz;
-        const double mn = cyz ? dsy : dsz, mx = cyz ? dsz : dsy;
+        const double mn = cyz ? dsy : dsz;
         const bool takex = dsx <= mn;
         const double ds = takex ? dsx : mn;
-        const double o2 = dsx <= mx ? dsx : mx;
-        const double other = takex ? mn : o2;
         const int lx = nx ? a.z : a.w, ly = ny ? b.x : b.y, lz = nz ? b.z : b.w;
         const int lyz = cyz ? ly : lz;
         link = takex ? lx : lyz;
-        // The link decides the next cell unless the new position may also have crossed a second wall (the exit distances
-        // of two walls differ by less than a few eps) or the direction grazes the exit wall (the eps advance may be lost
-        // to rounding); those cases take the reference's full search.
+        // The link decides the next cell unless the new position may also have crossed a second wall (the exit distance
+        // of another wall is within a few eps of the nearest) or the direction grazes the exit wall (the eps advance may
+        // be lost to rounding); those cases take the reference's full search.
+        const double near = ds + M.eps4;
+        const bool bx = dsx <= near, by = dsy <= near, bz = dsz <= near;
+        const bool tie = (bx && by) || (bx && bz) || (by && bz);
         const unsigned gyz = cyz ? (SK_DIR_GRAZE << 1) : (SK_DIR_GRAZE << 2);
         const unsigned gbit = takex ? SK_DIR_GRAZE : gyz;
-        const bool rare = !(other - ds > M.eps4) || (f & gbit);
+        const bool rare = tie || (f & gbit);
         how = (takex ? 0 : (cyz ? 1 : 2)) | (rare ? 4 : 0);
         ds_ = ds;
         m_out = cm;
@@ -624,6 +632,7 @@ struct SkStepper<3> {
         cm = p.m;
     }
     __device__ __forceinline__ SkCellPos cell(const SkDevModel&) const { return SkCellPos{cm, 0, 0, 0, 0}; }
+    template <bool OBSERVER>
     __device__ __forceinline__ void exit(const SkDevModel& M, const SkDevModel* __restrict__ Mg, const SkSmemTables&,
                                          SkLocalCounters& cnt, const SkDir& k, int& m_out, double& dens_out, double& ds_out)
     {

@@ -32,16 +32,19 @@
 #define SK_TRACE_BLOCK 128
 #endif
 #ifndef SK_TRACE_MINBLOCKS
-#define SK_TRACE_MINBLOCKS 6
+#define SK_TRACE_MINBLOCKS 8        // the walks wait on L2 latency: resident warps count for more than a few spilled registers
 #endif
 #ifndef SK_TRACE_MINBLOCKS_PEEL
-#define SK_TRACE_MINBLOCKS_PEEL 8   // the peel-off kernel keeps its (shared) direction in parameter space: fewer registers
+#define SK_TRACE_MINBLOCKS_PEEL 10  // the peel-off kernel keeps its (shared) direction in parameter space: fewer registers
 #endif
 #ifndef SK_CHUNK
 #define SK_CHUNK 64
 #endif
 #ifndef SK_REFILL_MIN
 #define SK_REFILL_MIN 6
+#endif
+#ifndef SK_REFILL_MIN_FUSED
+#define SK_REFILL_MIN_FUSED 10  // forward + interaction walk: two path ends per packet, the service block runs twice as often
 #endif
 #ifndef SK_REFILL_MIN_SHORT
 #define SK_REFILL_MIN_SHORT 12  // walks to the interaction point are short (a dozen cells): refill threshold of their own
@@ -465,14 +468,15 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, MODE == 2 ? SK_TRACE_MINBLOCKS
             }
         }
         // ---------------- inner loop: cross cells until enough lanes have finished their ray
-        const int want_idle = (exhausted && chunk_pos >= chunk_end) ? 32 : (MODE == 1 ? SK_REFILL_MIN_SHORT : SK_REFILL_MIN);
+        int want_idle = (exhausted && chunk_pos >= chunk_end) ? 32 : (MODE == 1 ? SK_REFILL_MIN_SHORT : MODE == 0 ? SK_REFILL_MIN_FUSED : SK_REFILL_MIN);
+        asm volatile("" : "+r"(want_idle));  // keeps the threshold in a register instead of re-deriving it every crossing
         do
         {
             if (ls & ACTIVE)
             {
                 int m;
                 double dens, ds;
-                st.exit(M, Mg, T, cnt, k, m, dens, ds);
+                st.template exit<MODE == 2>(M, Mg, T, cnt, k, m, dens, ds);
                 bool done = false;
                 if (MODE == 0)
                 {
@@ -542,14 +546,14 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, MODE == 2 ? SK_TRACE_MINBLOCKS
                     {
                         // the path has left the grid (non-forced: no interaction)
                         done = true;
-                        if (MODE != 2)
+                        if (MODE == 1 || (MODE == 0 && (ls & REPLAY)))
                         {
                             s_int = s;
                             st.cm = -2 - m;  // the last cell crossed
                         }
                     }
                 }
-                if (done) ls = (ls & ~ACTIVE) | PENDING;
+                if (done) ls ^= (ACTIVE | PENDING);  // ACTIVE -> PENDING
             }
         } while (__popc(__ballot_sync(0xffffffffu, !(ls & ACTIVE))) < want_idle);
     }

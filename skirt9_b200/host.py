@@ -826,7 +826,9 @@ class Instrument:
     numScatteringLevels: int = 0
     recordStatistics: bool = False
     wavelengthGrid: Optional[DisjointWavelengthGrid] = None
-    redshift: float = 0.0  # FluxRecorder::setObserverFrameRedshift (from the simulation's Cosmology)
+    redshift: float = 0.0  # FluxRecorder::setObserverFrameRedshift (from the simulation's Cosmology) ...
+    luminosityDistance: float = 0.0  # ... with the distances the Cosmology derives from it (used for calibration only)
+    angularDiameterDistance: float = 0.0
 
     def fields(self, grid_index):
         return {"kind": self.kind, "wavelength_grid": grid_index, "inclination": self.inclination,
@@ -1127,7 +1129,8 @@ class MonteCarloSimulation:
         oligo = self.oligoWavelengths is not None
         g = i.wavelengthGrid if (i.wavelengthGrid is not None and not oligo) else self.defaultWavelengthGrid
         L = engine.read_sed(instrument, component)
-        flam = L / (4 * math.pi * i.distance ** 2) / g.dlambdav
+        d = i.luminosityDistance if i.redshift else i.distance  # FluxRecorder.cpp:503
+        flam = L / (4 * math.pi * d ** 2) / g.dlambdav
         return flam * g.lambdav ** 2 / C_LIGHT * 1e26
 
     def surface_brightness(self, engine, instrument=0, component=abi.SK_COMP_TOTAL):

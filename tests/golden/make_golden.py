@@ -99,7 +99,10 @@ def make_cfg8z():
         base = np.load(os.path.join(HERE, "cfg2s_ref.npz"))["mass_density_msun_pc3"]
         assert np.array_equal(cells[:, 6], base), "cfg8z must see the tree and the densities of cfg2s"
         total = read_fits_cube(os.path.join(d, "cfg8z_i60_total.fits"))[0].astype(np.float64)
-        out = dict(sed=sed, sedstats=stats, frame_total_sum=total.sum(axis=0), num_packets=2e6)
+        head = open(os.path.join(d, "cfg8z_i60_sed.dat")).readline()
+        dl = float(re.search(r"luminosity distance ([0-9.eE+-]+) Mpc", head).group(1))
+        out = dict(sed=sed, sedstats=stats, frame_total_sum=total.sum(axis=0), num_packets=2e6, redshift=0.5,
+                   luminosity_distance_mpc=dl)
     np.savez_compressed(os.path.join(HERE, "cfg8z_ref.npz"), **out)
     print("cfg8z:", {k: np.shape(v) for k, v in out.items()})
 

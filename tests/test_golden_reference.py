@@ -149,6 +149,34 @@ def check_cfg2s(sim, e, g, n, nsigma=4.0):
     assert a.sum() == pytest.approx(c.sum(), rel=0.0012 * scale_hi)
 
 
+def cfg8z_from_reference(num_packets):
+    """cfg2s observed at redshift 0.5 (tests/golden/ski/cfg8z.ski): the reference's tree and densities are those of cfg2s,
+    the instrument's wavelength grid is 0.15-15 micron and every packet is binned at lambda (1 + z)."""
+    sim, _ = cfg2s_from_reference(num_packets)
+    g = load("cfg8z")
+    sim.defaultWavelengthGrid = H.LogWavelengthGrid(0.15e-6, 15e-6, 10)
+    ins = sim.instruments[0]
+    ins.redshift = float(g["redshift"])
+    ins.luminosityDistance = float(g["luminosity_distance_mpc"]) * 1e6 * H.PC
+    ins.distance = 0.0
+    sim.setup()
+    return sim, g
+
+
+def check_cfg8z(sim, e, g, nsigma=4.0):
+    np.testing.assert_allclose(sim.defaultWavelengthGrid.lambdav * 1e6, g["sed"][:, 0], rtol=1e-9)
+    r_own = rel_error(e.read_sed_stats(0))
+    tol = nsigma * np.hypot(rel_error(g["sedstats"][:, 1:].T), r_own)
+    sed = g["sed"]
+    for col, comp in ((1, abi.SK_COMP_TOTAL), (2, abi.SK_COMP_TRANSPARENT), (3, abi.SK_COMP_PRIMARY_DIRECT),
+                      (4, abi.SK_COMP_PRIMARY_SCATTERED)):
+        f = sim.sed_flux_density(e, 0, comp)
+        bound = tol * np.maximum(sed[:, col], sed[:, 1])
+        assert np.all(np.abs(f - sed[:, col]) <= bound), (comp, f / sed[:, col] - 1, tol)
+    # the rest-frame run of the same model has its flux in other bins: the shift is what is being tested
+    assert sim.sed_flux_density(e, 0, abi.SK_COMP_TRANSPARENT)[0] < 1e-3 * sed[:, 2].max()
+
+
 # ---------------------------------------------------------------- CPU: the oracle against the reference
 def test_oracle_matches_reference_cfg1():
     n = 100000
@@ -173,6 +201,23 @@ def test_oracle_matches_reference_cfg2s():
 
 
 # ---------------------------------------------------------------- GPU: the engine against the reference
+def test_oracle_matches_reference_cfg8z_redshift():
+    n = 200000
+    sim, g = cfg8z_from_reference(n)
+    e = sim.configure(OracleEngine(sim.config_struct()))
+    sim.run(e)
+    check_cfg8z(sim, e, g, nsigma=5.0)
+
+
+@pytest.mark.gpu
+def test_engine_matches_reference_cfg8z_redshift(engine_lib):
+    n = 4000000
+    sim, g = cfg8z_from_reference(n)
+    e = sim.configure(abi.Engine(sim.config_struct(device=0), lib=engine_lib))
+    sim.run(e)
+    check_cfg8z(sim, e, g)
+
+
 @pytest.mark.gpu
 def test_engine_matches_reference_cfg1(engine_lib):
     n = 4000000

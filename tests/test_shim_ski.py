@@ -95,6 +95,25 @@ def test_cfg2s_ski_octree_runs_unchanged(tmp_path):
     assert total.astype(float).sum() == pytest.approx(hi["frame_total_sum"].sum(), rel=3e-3)
 
 
+def test_cfg8z_ski_observer_frame_redshift_runs_unchanged(tmp_path):
+    """cfg2s seen from redshift 0.5 (FlatUniverseCosmology, instrument distance 0): the engine bins the packets at
+    lambda (1 + z) (FluxRecorder.cpp:309-310), the reference's writer calibrates with the luminosity distance."""
+    g = np.load(os.path.join(GOLD, "cfg8z_ref.npz"))
+    log = run_ski("cfg8z", tmp_path, 4e6)
+    assert "redshift" not in re.findall(r"outside the GPU life cycle \(([^)]*)\)", log)
+    sed = read_columns(tmp_path / "cfg8z_i60_sed.dat")
+    stats = read_columns(tmp_path / "cfg8z_i60_sedstats.dat")
+    head = open(tmp_path / "cfg8z_i60_sed.dat").readline()
+    assert "redshift 0.5" in head
+    np.testing.assert_allclose(sed[:, 0], g["sed"][:, 0], rtol=1e-9)
+    tol = 4.0 * np.hypot(rel_error(g["sedstats"][:, 1:].T), rel_error(stats[:, 1:].T))
+    for col in (1, 2, 3, 4):
+        bound = tol * np.maximum(g["sed"][:, col], g["sed"][:, 1])
+        assert np.all(np.abs(sed[:, col] - g["sed"][:, col]) <= bound), col
+    total, _ = read_fits_cube(tmp_path / "cfg8z_i60_total.fits")
+    assert total.astype(float).sum() == pytest.approx(g["frame_total_sum"].sum(), rel=4e-3)
+
+
 def test_cfg4s_ski_dust_emission_runs_unchanged(tmp_path):
     g = np.load(os.path.join(GOLD, "cfg4s_ref.npz"))
     n = 2e6
