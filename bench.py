@@ -1,13 +1,15 @@
 #!/usr/bin/env python
-"""bench.py -- photon packets/s of the life-cycle hot path on BASELINE.json configs[1]
-(dusty spiral galaxy, ~9.3e5-cell octree, 50 wavelength bins, 256^2 FullInstrument, 1e8 packets per GPU).
+"""bench.py -- photon packets/s of the life-cycle hot path on the workloads of BASELINE.json `configs`.
 
-  python bench.py --gpus N --steps K --warmup W          # this repo's CUDA engine (one rank per GPU under torchrun)
-  python bench.py --impl reference --steps K --warmup W  # the UNMODIFIED reference (oracle/_ref) on the host cores
+  python bench.py --gpus N --steps K --warmup W                   # this repo's CUDA engine (one rank per GPU under torchrun)
+  python bench.py --impl reference --steps K --warmup W           # the UNMODIFIED reference (oracle/_ref) on the host cores
+  python bench.py --config cfg1|cfg2|cfg4|cfg5 ...                 # another workload (default cfg2 = the headline, configs[1])
 
-A step = one primary-emission segment (MonteCarloSimulation::runPrimaryEmission): all histories of the rank's
-shard through the life-cycle kernel, then (N>1) the reduction of the instrument arrays over NCCL where the reference
-calls ProcessManager::sumToRoot (FluxRecorder.cpp:487-493).  Prints ONE JSON line on rank 0.
+A step = one pass of the hot path over one batch of histories: for cfg1 / cfg2 / cfg5 one primary-emission segment
+(MonteCarloSimulation::runPrimaryEmission), for cfg4 the whole sequence of segments of a dust-emission run (primary
+emission, the secondary-emission iterations, the final secondary emission); all histories of the rank's shard go through
+the stage kernels, then (N>1) the reductions over NCCL where the reference calls ProcessManager::sumToAll / sumToRoot
+(MediumSystem.cpp:1304-1313, FluxRecorder.cpp:487-493).  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -24,10 +26,35 @@ sys.path.insert(0, ROOT)
 
 METRIC = "photon packets/sec"
 UNIT = "packets/s"
-SKI = os.path.join(ROOT, "tests", "golden", "ski", "cfg2.ski")
+SKI_DIR = os.path.join(ROOT, "tests", "golden", "ski")
+SKI = os.path.join(SKI_DIR, "cfg2.ski")
 REF_EXE = os.path.join(ROOT, "oracle", "_ref", "release", "SKIRT", "main", "skirt")
-WORKLOAD = "cfg2: dusty spiral (spiral exp-disk source, ring dust tau_Z=1), OctTree ~9.3e5 cells (levels 3-9), " \
-           "50 log wavelength bins 0.1-10 micron, FullInstrument 256x256 i=60deg, forced scattering, no RF"
+SHIM_EXE = os.path.join(ROOT, "shim", "_build", "skirt_b200")
+PC = 3.0856775814913673e16
+
+WORKLOADS = {
+    "cfg2": {
+        "text": "cfg2: dusty spiral (spiral exp-disk source, ring dust tau_Z=1), OctTree ~9.3e5 cells (levels 3-9), "
+                "50 log wavelength bins 0.1-10 micron, FullInstrument 256x256 i=60deg, forced scattering, no RF",
+        "packets": 1e8, "cpu_packets": 2e6, "ref_packets": 1e6, "parity_packets": 1e8, "ski": "cfg2.ski", "store": False,
+        "grid": 2},
+    "cfg1": {
+        "text": "cfg1: point source in a uniform dust sphere (tau=1), Cartesian 32^3 grid, one wavelength 0.55 micron, "
+                "FullInstrument 64x64 i=60deg, forced scattering, radiation field stored",
+        "packets": 1e7, "cpu_packets": 1e6, "ref_packets": 1e6, "parity_packets": 1e7, "ski": "cfg1.ski", "store": True,
+        "grid": 1},
+    "cfg4": {
+        "text": "cfg4: dust emission with secondary-emission iterations (10000 K point source in an r^-2 dust shell, "
+                "tau_Z=20), OctTree ~1e6 cells (levels 3-8), RF grid 40 bins, emission grid 60 bins, SEDInstrument; a step "
+                "= primary emission + iterations (convergence 1%/3%, at most 5) + final secondary emission",
+        "packets": 1e7, "cpu_packets": 2e5, "ref_packets": 2e5, "parity_packets": 1e7, "ski": "cfg4s.ski", "store": True,
+        "grid": 2},
+    "cfg5": {
+        "text": "cfg5: Voronoi grid on 5e5 SPH-like particle positions (ImportedSites), exp-disk source, one wavelength, "
+                "FullInstrument 256x256, forced scattering, no RF",
+        "packets": 1e8, "cpu_packets": 2e4, "ref_packets": 2e4, "parity_packets": 0, "ski": None, "store": False,
+        "grid": 3},
+}
 
 
 def measured_peak():
@@ -76,26 +103,16 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(sm)}
 
 
-def run_reference_once(num_packets, threads, workdir):
-    """Times the unmodified reference on the same ski: returns packets/s from its own TimeLogger line."""
-    ski = os.path.join(workdir, "cfg2.ski")
-    text = open(SKI).read().replace('numPackets="1e6"', f'numPackets="{num_packets:g}"')
-    open(ski, "w").write(text)
-    out = os.path.join(workdir, "out")
-    os.makedirs(out, exist_ok=True)
-    subprocess.check_call([REF_EXE, "-t", str(threads), "-b", "-o", out, ski], stdout=subprocess.DEVNULL,
-                          stderr=subprocess.DEVNULL)
-    log = open(os.path.join(out, "cfg2_log.txt")).read()
-    LAST_REFERENCE_SETUP.clear()
-    LAST_REFERENCE_SETUP.update(reference_setup_times(log, threads))
-    secs = emission_seconds(log)
-    return num_packets / secs, secs
-
-
-def log_stamp(log, pattern):
-    """Seconds since midnight of the first log line matching `pattern` (the reference stamps every line to the ms)."""
-    m = re.search(r"\d+/\d+/\d+ (\d+):(\d+):(\d+\.\d+)[ \-!*]+" + pattern, log)
-    return None if m is None else 3600 * int(m.group(1)) + 60 * int(m.group(2)) + float(m.group(3))
+# ---------------------------------------------------------------------------------------------------
+# the reference (and the drop-in binary) on a ski file: log parsing
+# ---------------------------------------------------------------------------------------------------
+def log_stamp(log, pattern, last=False):
+    """Seconds since midnight of the first (or last) log line matching `pattern` (the reference stamps every line to the ms)."""
+    ms = list(re.finditer(r"\d+/\d+/\d+ (\d+):(\d+):(\d+\.\d+)[ \-!*]+" + pattern, log))
+    if not ms:
+        return None
+    m = ms[-1] if last else ms[0]
+    return 3600 * int(m.group(1)) + 60 * int(m.group(2)) + float(m.group(3))
 
 
 def emission_seconds(log):
@@ -105,6 +122,32 @@ def emission_seconds(log):
     if t0 is not None and t1 is not None and (t1 - t0) % 86400 > 0:
         return (t1 - t0) % 86400
     return float(re.search(r"Finished primary emission in ([0-9.]+) s", log).group(1))
+
+
+def all_segments_seconds(log):
+    """From the start of the primary emission to the end of the last emission segment of the run (dust-emission runs: the
+    iterations with their per-iteration set-up, and the final secondary emission), and the number of segments."""
+    t0 = log_stamp(log, "Starting primary emission")
+    t1 = log_stamp(log, r"Finished (?:primary|secondary) emission", last=True)
+    nseg = len(re.findall(r"Finished (?:primary|secondary) emission", log))
+    return (t1 - t0) % 86400, nseg
+
+
+def run_phases(log):
+    """Wall time of the phases of a reference / skirt_b200 run from its log stamps: setup, the run, final output, total."""
+    t = {k: log_stamp(log, p, last=l) for k, p, l in (("start", "Starting simulation", False), ("setup", "Finished setup in", False),
+                                                       ("setup_out", "Finished setup output", False),
+                                                       ("run0", "Starting primary emission", False),
+                                                       ("run1", r"Finished (?:primary|secondary) emission", True),
+                                                       ("end", "Finished simulation", True))}
+    out = {}
+    if t["start"] is not None and t["setup"] is not None:
+        out["setup_s"] = (t["setup"] - t["start"]) % 86400
+    if t["run0"] is not None and t["run1"] is not None:
+        out["emission_s"] = (t["run1"] - t["run0"]) % 86400
+    if t["start"] is not None and t["end"] is not None:
+        out["total_s"] = (t["end"] - t["start"]) % 86400
+    return out
 
 
 LAST_REFERENCE_SETUP = {}
@@ -123,62 +166,125 @@ def reference_setup_times(log, threads):
             "medium_properties_s": (t[3] - t[2]) % 86400}
 
 
-SHIM_EXE = os.path.join(ROOT, "shim", "_build", "skirt_b200")
+def ski_text(name, packets, statistics=False):
+    """The workload's ski file with its number of packets (per segment) replaced; cfg4 scales the fixture's octree to the
+    ~1e6 cells of BASELINE.json configs[3]."""
+    w = WORKLOADS[name]
+    text = open(os.path.join(SKI_DIR, w["ski"])).read()
+    text = re.sub(r'numPackets="[^"]*"', 'numPackets="%g"' % packets, text, count=1)
+    if name == "cfg4":
+        text = re.sub(r'maxLevel="\d+"', 'maxLevel="8"', text, count=1)
+        text = re.sub(r'maxDustFraction="[^"]*"', 'maxDustFraction="3.3e-6"', text, count=1)
+    if statistics:
+        text = text.replace('recordStatistics="false"', 'recordStatistics="true"')
+    return text
 
 
-def run_shim_once(num_packets, threads):
-    """The same cfg2 ski through skirt_b200 (the unmodified reference driven by the C++ shim, life cycle on the GPU):
-    packets/s from the reference's own TimeLogger line, exactly as for the CPU reference."""
+def run_ski(exe, name, packets, threads, workdir, statistics=False, extra=()):
+    """Runs `exe` (the reference or skirt_b200) on the workload's ski; returns (log, host wall seconds, output dir, prefix)."""
+    prefix = name
+    ski = os.path.join(workdir, prefix + ".ski")
+    open(ski, "w").write(ski_text(name, packets, statistics))
+    out = os.path.join(workdir, "out")
+    os.makedirs(out, exist_ok=True)
+    t0 = time.perf_counter()
+    subprocess.check_call([exe, "-t", str(threads), "-b", "-o", out, *extra, ski], stdout=subprocess.DEVNULL,
+                          stderr=subprocess.DEVNULL)
+    wall = time.perf_counter() - t0
+    return open(os.path.join(out, prefix + "_log.txt")).read(), wall, out, prefix
+
+
+def run_reference_once(num_packets, threads, workdir, name="cfg2"):
+    """Times the unmodified reference on the workload's ski: returns packets/s from its own TimeLogger lines."""
+    log, wall, _, _ = run_ski(REF_EXE, name, num_packets, threads, workdir)
+    LAST_REFERENCE_SETUP.clear()
+    LAST_REFERENCE_SETUP.update(reference_setup_times(log, threads))
+    LAST_REFERENCE_SETUP.update({"phases": run_phases(log), "wall_s": wall})
+    if name == "cfg4":
+        secs, nseg = all_segments_seconds(log)
+        return nseg * num_packets / secs, secs
+    secs = emission_seconds(log)
+    return num_packets / secs, secs
+
+
+def run_shim_once(num_packets, threads, name="cfg2"):
+    """The same ski through skirt_b200 (the unmodified reference driven by the C++ shim, life cycle on the GPU): packets/s from
+    the reference's own TimeLogger lines, exactly as for the CPU reference, and the wall time of the WHOLE run (set-up by the
+    reference's host code, engine configuration, emission, output files)."""
     with tempfile.TemporaryDirectory() as d:
-        ski = os.path.join(d, "cfg2.ski")
-        open(ski, "w").write(open(SKI).read().replace('numPackets="1e6"', f'numPackets="{num_packets:g}"'))
-        subprocess.check_call([SHIM_EXE, "-t", str(threads), "-b", "-o", d, ski], stdout=subprocess.DEVNULL,
-                              stderr=subprocess.DEVNULL)
-        log = open(os.path.join(d, "cfg2_log.txt")).read()
+        log, wall, _, _ = run_ski(SHIM_EXE, name, num_packets, threads, d)
+    gpu_path = "GPU life cycle:" in log and "CPU life cycle (reference)" not in log
+    if not gpu_path:
+        raise RuntimeError("skirt_b200 did not run the GPU life cycle: " + log[-400:])
     secs = emission_seconds(log)
     cells = re.search(r"Determining medium properties for (\d+) cells", log)
-    return {"packets": num_packets, "seconds": secs, "packets_per_s": num_packets / secs,
+    return {"packets": num_packets, "gpu_path": gpu_path, "seconds": secs, "packets_per_s": num_packets / secs,
+            "total_wall_s": wall, "phases": run_phases(log), "setup": reference_setup_times(log, threads),
             "cells": int(cells.group(1)) if cells else None,
-            "what": "skirt_b200 -t %d cfg2.ski: reference object model + C++ shim + GPU life cycle, time from the "
-                    "time stamps of the reference's TimeLogger lines 'Starting / Finished primary emission' (%.3f s)" % (threads, secs)}
+            "what": "skirt_b200 -t %d %s.ski: reference object model + C++ shim + GPU life cycle; `seconds` from the time "
+                    "stamps of the reference's TimeLogger lines 'Starting / Finished primary emission', `total_wall_s` = "
+                    "the whole process (ski parsing, set-up, engine configuration, emission, FITS/text output)" % (threads, name)}
 
 
-def run_port_once(num_packets):
-    """Fallback when oracle/_ref is absent: times the single-threaded C port of the oracle."""
+def make_sim(name, total_packets, statistics=False):
+    """The workload as host mirror objects (setup() done: grid built, densities sampled)."""
     from skirt9_b200 import configs
+    if name == "cfg2":
+        return configs.cfg2(num_packets=total_packets, record_statistics=statistics).setup()
+    if name == "cfg1":
+        return configs.cfg1(num_packets=total_packets, record_statistics=statistics).setup()
+    if name == "cfg4":
+        return configs.cfg4(num_packets=total_packets, max_level=8, max_dust_fraction=3.3e-6).setup()
+    import numpy as np
+    rng = np.random.default_rng(12345)   # SURVEY.md 8d cfg5 recipe
+    sites = int(os.environ.get("SK_BENCH_SITES", "500000"))
+    R = rng.gamma(2.0, 3000.0, size=2 * sites)
+    R = R[R < 15000.0][:sites]
+    phi = rng.uniform(0, 2 * np.pi, size=len(R))
+    z = np.clip(rng.laplace(0.0, 250.0, size=len(R)), -1900.0, 1900.0)
+    return configs.cfg5(np.stack([R * np.cos(phi), R * np.sin(phi), z], axis=1) * PC, num_packets=total_packets,
+                        num_pixels=256, record_statistics=False).setup()
+
+
+def run_port_once(num_packets, name="cfg2"):
+    """Fallback when oracle/_ref is absent (or the workload has no ski): times the single-threaded C port of the oracle."""
     from tests.oracle_lib import OracleEngine
-    sim = configs.cfg2(num_packets=num_packets).setup()
+    sim = make_sim(name, num_packets)
     e = sim.configure(OracleEngine(sim.config_struct()))
     t = time.time()
     sim.run(e)
     dt = time.time() - t
-    return num_packets / dt, dt
+    return e.counters()["packets"] / dt, dt
 
 
-def cpu_baseline(sample_packets):
+def cpu_baseline(sample_packets, name="cfg2"):
     cores = os.cpu_count() or 1
-    if os.path.exists(REF_EXE):
+    w = WORKLOADS[name]
+    if os.path.exists(REF_EXE) and w["ski"]:
         with tempfile.TemporaryDirectory() as d:
-            rate, secs = run_reference_once(sample_packets, cores, d)
+            rate, secs = run_reference_once(sample_packets, cores, d, name)
         return {"value": rate, "unit": UNIT, "cores": cores, "kind": "reference",
-                "sample": f"unmodified SKIRT 9 (oracle/_ref) -t {cores}, same cfg2 ski, {sample_packets:g} packets, "
-                          f"log time stamps 'Starting / Finished primary emission': {secs:.3f} s"}
-    rate, secs = run_port_once(min(sample_packets, 2e5))
+                "sample": f"unmodified SKIRT 9 (oracle/_ref) -t {cores}, same {name} ski, {sample_packets:g} packets per segment, "
+                          f"log time stamps of the emission segments: {secs:.3f} s"}
+    n = min(sample_packets, 2e5)
+    rate, secs = run_port_once(n, name)
     return {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"oracle/sk_oracle.c single thread, {min(sample_packets, 2e5):g} packets in {secs:.1f} s"}
+            "sample": f"oracle/sk_oracle.c single thread, {n:g} packets in {secs:.1f} s"}
 
 
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    name = args.config
+    w = WORKLOADS[name]
     cores = os.cpu_count() or 1
-    n = args.ref_packets
+    n = args.ref_packets or w["ref_packets"]
     rates = []
+    have_ref = os.path.exists(REF_EXE) and w["ski"] is not None
     with tempfile.TemporaryDirectory() as d:
-        have_ref = os.path.exists(REF_EXE)
         for it in range(args.warmup + args.steps):
-            rate, secs = run_reference_once(n, cores, d) if have_ref else run_port_once(min(n, 2e5))
+            rate, secs = run_reference_once(n, cores, d, name) if have_ref else run_port_once(min(n, 2e5), name)
             if it >= args.warmup:
                 rates.append((rate, secs))
     value = sum(r for r, _ in rates) / len(rates)
@@ -187,11 +293,82 @@ def reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "packets_per_step": n, "timing": "reference TimeLogger 'Finished primary emission'"},
+            "config": {"workload": w["text"], "packets_per_step": n,
+                       "timing": "reference TimeLogger lines of the emission segments (millisecond log stamps)"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores if have_ref else 1, "kind": kind,
-                             "sample": f"{n:g} packets per step, {'skirt -t %d' % cores if have_ref else 'C port, 1 thread'}"},
+                             "sample": f"{n:g} packets per segment per step, {'skirt -t %d' % cores if have_ref else 'C port, 1 thread'}"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+# parity next to the number: the engine's SED against the reference's on the same ski, with both sides' Sum w^k statistics
+# ---------------------------------------------------------------------------------------------------
+def rel_error(stats):
+    """R = sqrt(Sum w^2/(Sum w)^2 - 1/N) per bin (FluxRecorder.hpp:50-63) from rows (N, Sum w, Sum w^2, ...)."""
+    import numpy as np
+    n, w1, w2 = stats[0], stats[1], stats[2]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.sqrt(np.maximum(w2 / (w1 * w1) - 1.0 / np.maximum(n, 1), 0.0))
+
+
+def sed_parity(name, device, ref_packets, gpu_packets):
+    """Runs the unmodified reference (recordStatistics on) and the engine on the workload and compares the calibrated SED
+    columns bin by bin in units of sigma = sqrt(R^2 + R_ref^2) max(F_ref, F_ref_total), R from both sides' Sum w^k
+    (4 sigma per bin).  Sum w^k underestimates the scatter of the composite-biased wavelength sampling (heavy
+    tails), so the same statistic is also evaluated between two reference runs that differ in their seed only: its rms there
+    (1 for a perfect error model) scales the 4 sigma bound."""
+    import numpy as np
+    from skirt9_b200 import abi
+    from tests.skirt_files import read_columns
+    cores = os.cpu_count() or 1
+    instr = "i60"
+    refs = []
+    for seed in (0, 1):
+        with tempfile.TemporaryDirectory() as d:
+            text = ski_text(name, ref_packets, statistics=True).replace('Random seed="0"', 'Random seed="%d"' % seed)
+            ski = os.path.join(d, name + ".ski")
+            open(ski, "w").write(text)
+            subprocess.check_call([REF_EXE, "-t", str(cores), "-b", "-o", d, ski], stdout=subprocess.DEVNULL,
+                                  stderr=subprocess.DEVNULL)
+            refs.append((read_columns(os.path.join(d, f"{name}_{instr}_sed.dat")),
+                         read_columns(os.path.join(d, f"{name}_{instr}_sedstats.dat"))))
+    ref, ref_stats = refs[0]
+    sim = make_sim(name, gpu_packets, statistics=True)
+    e = sim.configure(abi.Engine(sim.config_struct(device=device)))
+    sim.run(e, stream_id=7)
+    own_stats = e.read_sed_stats(0)
+    names = {1: "total", 2: "transparent", 3: "direct", 4: "scattered"}
+    cols = ((1, abi.SK_COMP_TOTAL), (2, abi.SK_COMP_TRANSPARENT), (3, abi.SK_COMP_PRIMARY_DIRECT), (4, abi.SK_COMP_PRIMARY_SCATTERED))
+
+    def zscores(f, stats, col):
+        sigma = np.hypot(rel_error(ref_stats[:, 1:].T), rel_error(stats))
+        scale = np.maximum(ref[:, col], ref[:, 1]) * sigma
+        ok = scale > 0
+        return np.abs(f - ref[:, col])[ok] / scale[ok]
+
+    own, rr = {}, {}
+    for col, comp in cols:
+        own[names[col]] = zscores(sim.sed_flux_density(e, 0, comp), own_stats, col)
+        rr[names[col]] = zscores(refs[1][0][:, col], refs[1][1][:, 1:].T, col)
+    allz, allrr = np.concatenate(list(own.values())), np.concatenate(list(rr.values()))
+    rms_rr = float(np.sqrt((allrr ** 2).mean()))
+    bound = 4.0 * max(1.0, rms_rr)
+    tot_ref, tot_own = ref[:, 1].sum(), sim.sed_flux_density(e, 0, abi.SK_COMP_TOTAL).sum()
+    overflow = e.counters()["pixel_overflows"]
+    e.close()
+    return {"against": f"unmodified reference, same {name} ski with recordStatistics, -t {cores}, {ref_packets:g} packets (its own "
+                       f"set-up from its Mersenne streams); engine {gpu_packets:g} packets on the host mirror's set-up",
+            "quantity": "calibrated SED (Jy): total, transparent, direct, scattered", "bins": int(len(allz)),
+            "criterion": "|F - F_ref| <= 4 max(1, rms_ref_vs_ref) sqrt(R^2 + R_ref^2) max(F_ref, F_ref_total), R from Sum w^k "
+                         "of both sides; rms_ref_vs_ref = rms of the same statistic between two reference runs (seeds 0, 1)",
+            "max_sigma": float(allz.max()), "rms_sigma": float(np.sqrt((allz ** 2).mean())),
+            "bins_over_4_sigma": int((allz > 4).sum()),
+            "max_sigma_per_component": {k: float(v.max()) for k, v in own.items()},
+            "reference_vs_reference": {"max_sigma": float(allrr.max()), "rms_sigma": rms_rr,
+                                       "bins_over_4_sigma": int((allrr > 4).sum())},
+            "bound_sigma": bound, "total_flux_ratio": float(tot_own / tot_ref), "pixel_overflows": int(overflow),
+            "pass": bool(allz.max() <= bound)}
 
 
 def device_setup_times(device):
@@ -222,8 +399,10 @@ def native_arm(args):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from skirt9_b200 import abi, configs, parallel
+    from skirt9_b200 import abi, parallel
 
+    name = args.config
+    w = WORKLOADS[name]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -237,33 +416,72 @@ def native_arm(args):
     os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    packets_per_gpu = int(args.packets)
-    total = packets_per_gpu * world
+    comm = parallel.Comm(dist if world > 1 else None)
+    packets_per_gpu = int(args.packets or w["packets"])
+    total = packets_per_gpu * world     # histories per segment over all ranks (weak scaling)
 
-    sim = configs.cfg2(num_packets=total).setup()
+    t_setup0 = time.perf_counter()
+    sim = make_sim(name, total)
+    host_setup_s = time.perf_counter() - t_setup0
     engine = sim.configure(abi.Engine(sim.config_struct(device=local)))
     stream = torch.cuda.ExternalStream(engine.cuda_stream(), device=local)
     det = engine.device_tensor(3)
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=f"cuda:{local}")  # > 126 MB L2
     first, count = parallel.history_block(total, rank, world)   # contiguous block of this rank
     assert count == packets_per_gpu
+    single_segment = name != "cfg4"
+    # a step may consist of several segments: add up the engine's CUDA-event times of all of them, and the wall time of the
+    # blocking C-ABI calls between them (dust emission: the per-iteration preparation and convergence test)
+    acc = {"kernel_ms": 0.0, "stages": {}, "host_ms": {}}
+    timed_calls = ("run_segment", "prepare_primary", "prepare_secondary", "absorbed_luminosity", "communicate_rf", "clear_rf",
+                   "clear_instruments")
+
+    def wrap(eng):
+        for fn in timed_calls:
+            inner = getattr(eng, fn)
+
+            def call(*a, _inner=inner, _fn=fn, **kw):
+                t0 = time.perf_counter()
+                out = _inner(*a, **kw)
+                acc["host_ms"][_fn] = acc["host_ms"].get(_fn, 0.0) + 1e3 * (time.perf_counter() - t0)
+                if _fn == "run_segment":
+                    acc["kernel_ms"] += eng.last_kernel_ms()
+                    for k, v in eng.last_stage_ms().items():
+                        acc["stages"][k] = acc["stages"].get(k, 0.0) + v
+                return out
+            setattr(eng, fn, call)
+    if not (single_segment and not w["store"]):
+        wrap(engine)
+        if world > 1:
+            ar = comm._all_reduce
+
+            def timed_all_reduce(eng, which, _ar=ar):
+                t0 = time.perf_counter()
+                _ar(eng, which)
+                acc["host_ms"]["all_reduce_%d" % which] = acc["host_ms"].get("all_reduce_%d" % which, 0.0) + 1e3 * (time.perf_counter() - t0)
+            comm._all_reduce = timed_all_reduce
 
     def step(stream_id):
         with torch.cuda.stream(stream):
             flush.zero_()                      # L2 flush between iterations
-            engine.clear_instruments()
-            engine.prepare_primary(total)
-            engine.launch_segment(first, packets_per_gpu, True, True, False, stream_id)
-            if world > 1:
-                dist.all_reduce(det)           # FluxRecorder::calibrateAndWrite -> ProcessManager::sumToRoot
+        engine.clear_instruments()
+        if single_segment and not w["store"]:
+            with torch.cuda.stream(stream):
+                engine.prepare_primary(total)
+                engine.launch_segment(first, packets_per_gpu, True, True, False, stream_id)
+                if world > 1:
+                    dist.all_reduce(det)       # FluxRecorder::calibrateAndWrite -> ProcessManager::sumToRoot
+        else:
+            # the host mirror of MonteCarloSimulation::runSimulation: every segment, with the reference's reductions
+            sim.run(engine, stream_id=stream_id, comm=comm if world > 1 else None)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for w in range(args.warmup):
-        step(w)
+    for k in range(args.warmup):
+        step(k)
         engine.synchronize()
     engine.counters(reset=True)
     barrier()
@@ -273,12 +491,17 @@ def native_arm(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kernel_ms, stage_ms = [], []
     ev0.record(stream)
+    acc["kernel_ms"], acc["stages"], acc["host_ms"] = 0.0, {}, {}
     for k in range(args.steps):
         step(args.warmup + k)
         engine.synchronize()                   # also reads back the engine's own CUDA-event durations
-        kernel_ms.append(engine.last_kernel_ms())
-        stage_ms.append(engine.last_stage_ms())
+        if single_segment and not w["store"]:
+            kernel_ms.append(engine.last_kernel_ms())
+            stage_ms.append(engine.last_stage_ms())
     ev1.record(stream)
+    if not kernel_ms:
+        kernel_ms = [acc["kernel_ms"] / args.steps]
+        stage_ms = [{k: acc["stages"].get(k, 0.0) / args.steps for k in engine.STAGES}]
     barrier()
     ms_total = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if sampler else None
@@ -287,18 +510,35 @@ def native_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     cnt = engine.counters()
+    cvec = torch.tensor([cnt["packets"]], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(cvec)
+    packets_all_ranks = float(cvec[0].item())   # histories launched in the timed steps, all ranks (cfg4: all segments)
 
     # ---- end-to-end through the public API with host buffers: tables H2D, run, tallies D2H, every step
     e2e_steps = 0 if args.no_e2e else max(1, min(args.steps, 2))
-    h2d = (sim.grid.first_child.nbytes + sim.density.nbytes + sim.volume.nbytes
-           + sum(g.borderv.nbytes + g.ellv.nbytes + g.lambdav.nbytes + g.dlambdav.nbytes for g in sim.grids)
-           + 4 * sim.medium.mix.lambda_border.nbytes + sum(3 * s.sed.lambdav.nbytes for s in sim.sources))
+    h2d = sim.density.nbytes + sim.volume.nbytes \
+        + sum(g.borderv.nbytes + g.ellv.nbytes + g.lambdav.nbytes + g.dlambdav.nbytes for g in sim.grids) \
+        + 4 * sim.medium.mix.lambda_border.nbytes + sum(3 * s.sed.lambdav.nbytes for s in sim.sources)
+    if w["grid"] == 2:
+        h2d += sim.grid.first_child.nbytes
+    elif w["grid"] == 1:
+        h2d += sim.grid.xv.nbytes + sim.grid.yv.nbytes + sim.grid.zv.nbytes
+    else:
+        h2d += sim.grid.sites.nbytes + sim.grid.nbr_offset.nbytes + sim.grid.nbr_index.nbytes
     d2h = 0
-    # host buffers of the caller (allocated and touched once, like the reference's own FluxRecorder arrays)
-    nl, npix = sim.defaultWavelengthGrid.num_bins, sim.instruments[0].numPixelsX * sim.instruments[0].numPixelsY
-    # (page-locked, as the contract's "pinned host memory"; sk_engine_read_* then skips its own staging buffer)
-    ifu_host = [torch.zeros((nl, npix), dtype=torch.float64).pin_memory().numpy() for _ in range(4)]
+    comps = [c for c in (0, 1, 2, 3)]
+    ins = sim.instruments[0]
+    has_ifu = ins.kind != abi.SK_INSTR_SED
+    # host buffers of the caller (allocated and touched once, like the reference's own FluxRecorder arrays); page-locked,
+    # as the contract's "pinned host memory": sk_engine_read_* then skips its own staging buffer
+    ifu_host = []
+    if has_ifu:
+        nl = (sim.defaultWavelengthGrid.num_bins if sim.oligoWavelengths is None else len(sim.oligoWavelengths))
+        npix = ins.numPixelsX * ins.numPixelsY
+        ifu_host = [torch.zeros((nl, npix), dtype=torch.float64).pin_memory().numpy() for _ in comps]
     e2e_parts = {"configure_s": 0.0, "run_s": 0.0, "read_s": 0.0, "destroy_s": 0.0}
+    e2e_packets = 0
     t0 = time.perf_counter()
     # pass -1 is an untimed warm-up of the whole end-to-end sequence: on first use the device's memory pool grows by a
     # second packet bank next to the one of the timed steps above
@@ -307,26 +547,27 @@ def native_arm(args):
             barrier()
             t0 = time.perf_counter()
             e2e_parts = {"configure_s": 0.0, "run_s": 0.0, "read_s": 0.0, "destroy_s": 0.0}
+            e2e_packets = 0
         ta = time.perf_counter()
         e2 = abi.Engine(sim.config_struct(device=local))
-        tcreate = time.perf_counter() - ta
         sim.configure(e2)
         tb = time.perf_counter()
-        detail = dict(sim.last_configure_parts, create=tcreate)
-        for kk, vv in detail.items():
-            e2e_parts["configure_" + kk + "_s"] = e2e_parts.get("configure_" + kk + "_s", 0.0) + vv / e2e_steps
-        e2.prepare_primary(total)
-        e2.run_segment(first, packets_per_gpu, True, True, False, 1000 + k)
-        tseg = time.perf_counter()
-        e2e_parts["segment_device_s"] = e2e_parts.get("segment_device_s", 0.0) + e2.last_kernel_ms() * 1e-3 / e2e_steps
-        e2e_parts["segment_host_s"] = e2e_parts.get("segment_host_s", 0.0) + (tseg - tb) / e2e_steps
-        if world > 1:
-            with torch.cuda.stream(torch.cuda.ExternalStream(e2.cuda_stream(), device=local)):
-                dist.all_reduce(e2.device_tensor(3))
-            e2.synchronize()
+        if single_segment and not w["store"]:
+            e2.prepare_primary(total)
+            e2.run_segment(first, packets_per_gpu, True, True, False, 1000 + k)
+            if world > 1:
+                with torch.cuda.stream(torch.cuda.ExternalStream(e2.cuda_stream(), device=local)):
+                    dist.all_reduce(e2.device_tensor(3))
+                e2.synchronize()
+        else:
+            sim.run(e2, stream_id=1000 + k, comm=comm if world > 1 else None)
         tc = time.perf_counter()
-        e2e_parts["allreduce_s"] = e2e_parts.get("allreduce_s", 0.0) + (tc - tseg) / e2e_steps
-        outs = [e2.read_sed(0, c) for c in (0, 1, 2, 3)] + [e2.read_ifu(0, c, out=ifu_host[c]) for c in (0, 1, 2, 3)]
+        e2e_packets += e2.counters()["packets"]
+        outs = [e2.read_sed(0, c) for c in comps]
+        if has_ifu:
+            outs += [e2.read_ifu(0, c, out=ifu_host[c]) for c in comps]
+        if w["store"]:
+            outs.append(e2.read_rf(0))
         d2h = sum(o.nbytes for o in outs)
         td = time.perf_counter()
         e2.close()            # sk_engine_destroy: stream-ordered frees back into the device's memory pool
@@ -337,80 +578,129 @@ def native_arm(args):
         e2e_parts["destroy_s"] += (tf - td) / e2e_steps
     barrier()
     e2e_s = (time.perf_counter() - t0) / max(e2e_steps, 1)
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local}")
+    te = torch.tensor([e2e_s, float(e2e_packets)], dtype=torch.float64, device=f"cuda:{local}")
     if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s = float(te.item())
+        tmax = te.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(te)
+        te[0] = tmax[0]
+    e2e_s, e2e_packets_all = float(te[0].item()), float(te[1].item())
 
     if rank == 0:
         ms_per_step = ms_total / args.steps
-        value = total / (ms_per_step * 1e-3)
+        value = packets_all_ranks / args.steps / (ms_per_step * 1e-3)
         pk = max(cnt["packets"], 1)
         S = (cnt["forward_segments"] + cnt["peel_segments"]) / pk
         S_fwd = cnt["forward_segments"] / pk
         P_peel = cnt["peel_paths"] / pk
-        bytes_per_packet = 60.0 * S + 32.0 * P_peel + 64.0     # SURVEY.md 8d accounting (no RF store in cfg2)
+        # SURVEY.md 8d accounting: per segment 60 B (tree, Cartesian) or 32 B + 28 B per neighbour (Voronoi), + 16 B per RF
+        # deposit, + 32 B per detection, + 64 B per launch
+        if w["grid"] == 3:
+            nbrs = float(sim.grid.nbr_offset[-1]) / sim.grid.num_cells
+            seg_bytes = 32.0 + 28.0 * nbrs
+        else:
+            seg_bytes = 60.0
+        dep = cnt["rf_deposits"] / pk
+        bytes_per_packet = seg_bytes * S + 16.0 * dep + 32.0 * P_peel + 64.0
         kms = sum(kernel_ms) / len(kernel_ms)
         stages = {k: sum(d[k] for d in stage_ms) / len(stage_ms) for k in stage_ms[0]}
-        # the dominant kernel: the trace kernel with the largest share of the step; its algorithmic bytes are 60 B per
-        # segment it crosses (cell bounds 48 B + density 8 B + link 4 B), its time the sum of its launches
-        seg = {"trace_forward": cnt["forward_segments"], "trace_interaction": cnt["replay_segments"],
+        # the dominant kernel: the trace kernel with the largest share of the step.  With forced scattering the forward
+        # kernel also walks to the interaction point (replay segments: the same cell records a second time)
+        seg = {"trace_forward": cnt["forward_segments"] + (cnt["replay_segments"] if stages["trace_interaction"] == 0 else 0),
+               "trace_interaction": cnt["replay_segments"] if stages["trace_interaction"] > 0 else 0,
                "trace_peel": cnt["peel_segments"]}
         dom = max(seg, key=lambda k: stages[k])
-        dom_name = {"trace_forward": "sk_wf_trace<2,0,false>", "trace_interaction": "sk_wf_trace<2,1,false>",
-                    "trace_peel": "sk_wf_trace<2,2,false>"}[dom]
-        dom_bytes = 60.0 * seg[dom] / args.steps
+        g = w["grid"]
+        store_flag = "true" if w["store"] else "false"
+        dom_name = {"trace_forward": f"sk_wf_trace<{g},0,{store_flag}> (forward path + walk to the interaction point)",
+                    "trace_interaction": f"sk_wf_trace<{g},1,false>", "trace_peel": f"sk_wf_trace<{g},2,false>"}[dom]
+        dom_bytes = (seg_bytes * seg[dom] + (16.0 * cnt["rf_deposits"] if dom == "trace_forward" else 0.0)) / args.steps
         dom_launches = cnt["rounds"] / args.steps
         achieved = dom_bytes / (stages[dom] * 1e-3) / 1e9
-        whole_step = bytes_per_packet * packets_per_gpu / (kms * 1e-3) / 1e9
+        whole_step = bytes_per_packet * pk / args.steps / (kms * 1e-3) / 1e9
         peak, which = measured_peak()
         traffic = None
         try:
-            # dram__bytes_read.sum + dram__bytes_write.sum of one captured launch of the dominant kernel (ncu --set full,
-            # profiles/traffic.json), scaled from that launch's algorithmic bytes to this run's average launch
+            # dram__bytes_read.sum + dram__bytes_write.sum of one captured launch of the dominant kernel of THIS build (ncu
+            # --set full, profiles/traffic.json), scaled from that launch's algorithmic bytes to this run's average launch
             cap = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            traffic = cap["dram_bytes_per_launch"] * (dom_bytes / max(dom_launches, 1)) / cap["algorithmic_bytes_of_captured_launch"]
+            if cap.get("workload", "cfg2") == name and cap.get("kernel", dom) == dom:
+                traffic = cap["dram_bytes_per_launch"] * (dom_bytes / max(dom_launches, 1)) / cap["algorithmic_bytes_of_captured_launch"]
         except Exception:
             pass
+        # the second roofline, against the resource that binds: dependent, scattered 32-byte record fetches.  Measured
+        # live on this device with the crossing loop's access pattern and nothing else (sk_engine_measure_gather_peak)
+        binding = None
+        if w["grid"] != 1:
+            try:
+                gp = engine.measure_gather_peak(max(int(sim.grid.num_cells), 1024))
+                per_seg_fetches = 1.0 if w["grid"] == 2 else 1.0 + nbrs
+                ach = seg[dom] * per_seg_fetches / args.steps / (stages[dom] * 1e-3)
+                binding = {"bound": "dependent scattered 32-byte record fetches (L2-resident table, one 256-bit load per "
+                                    "fetch, full occupancy, no arithmetic)", "achieved": ach, "peak": gp,
+                           "unit": "record fetches/s", "frac": ach / gp,
+                           "note": "achieved = cell records the dominant trace kernel fetched / its CUDA-event time; peak = "
+                                   "sk_engine_measure_gather_peak on a table of the grid's size, measured in this run"}
+            except Exception as ex:
+                binding = {"error": str(ex)[:200]}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "packets_per_gpu": packets_per_gpu, "cells": int(sim.grid.num_cells),
+                "config": {"workload": w["text"], "name": name, "packets_per_gpu": packets_per_gpu, "cells": int(sim.grid.num_cells),
                            "l2": "256 MB buffer written between iterations", "sharding": "contiguous history blocks, "
-                           "replicated grid, NCCL all-reduce of the instrument arrays per step" if world > 1 else "single GPU"},
-                "e2e": {"value": total / e2e_s if e2e_steps else None, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                        "includes": "engine create + octree link build + all table uploads + all stage kernels + read-back of 4 SED and 4 IFU arrays into pinned host buffers + engine destroy; one untimed pass first",
-                        "parts": e2e_parts},
+                           "replicated grid, NCCL all-reduce of the instrument arrays per step" + (" and of the radiation "
+                           "field per segment" if w["store"] else "") if world > 1 else "single GPU"},
+                "e2e": {"value": e2e_packets_all / max(e2e_steps, 1) / e2e_s if e2e_steps else None, "unit": UNIT,
+                        "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                        "includes": "engine create + grid / link build + all table uploads + all stage kernels + read-back of the "
+                                    "SED and IFU arrays (and the radiation field when stored) into pinned host buffers + engine "
+                                    "destroy; one untimed pass first", "parts": e2e_parts},
                 "gpu_launches": int(cnt["kernel_launches"]),
                 "kernel": {"name": dom_name, "launches_per_step": dom_launches, "ms_per_step": stages[dom],
                            "ms_per_launch": stages[dom] / max(dom_launches, 1), "share_of_step": stages[dom] / kms,
                            "stage_ms_per_step": stages, "step_ms": kms,
                            "segments_per_packet": S, "forward_segments_per_packet": S_fwd,
                            "replay_segments_per_packet": cnt["replay_segments"] / pk,
+                           "rf_deposits_per_packet": dep,
                            "peel_paths_per_packet": P_peel, "scatterings_per_packet": cnt["scatterings"] / pk,
                            "segments_per_s": (cnt["forward_segments"] + cnt["peel_segments"] + cnt["replay_segments"])
                            / args.steps / (kms * 1e-3), "tree_fallbacks_per_packet": cnt["fallbacks"] / pk,
-                           "rounds_per_step": cnt["rounds"] / args.steps},
+                           "rounds_per_step": cnt["rounds"] / args.steps, "packets_per_step_this_rank": pk / args.steps},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "peak_source": which,
                              "bytes_per_launch": dom_bytes / max(dom_launches, 1),
                              "whole_step_achieved": whole_step, "whole_step_frac": whole_step / peak,
                              "bytes_per_packet": bytes_per_packet,
-                             "note": "achieved = 60 B x segments crossed by the dominant trace kernel / its CUDA-event time; "
-                                     "whole_step = (60 B/segment + 32 B/detection + 64 B/launch) x packets / step time. The "
-                                     "30 MB of cell records are L2-resident, so DRAM traffic is far below the algorithmic "
-                                     "bytes: the kernel is latency / fp64-issue bound, not HBM bound"},
+                             "note": "achieved = algorithmic bytes (SURVEY.md 8d: %g B per segment, +16 B per RF deposit) of the "
+                                     "segments the dominant trace kernel crossed / its CUDA-event time.  The cell records are "
+                                     "L2-resident, so DRAM traffic is far below the algorithmic bytes and this fraction can "
+                                     "exceed what HBM alone could deliver: the kernel is bound by dependent scattered record "
+                                     "fetches, see roofline_binding" % seg_bytes},
+                "roofline_binding": binding,
+                "host_setup_s": host_setup_s,
                 "clocks": clocks}
+        if acc["host_ms"]:
+            line["host_calls_ms_per_step"] = {k: v / args.steps for k, v in sorted(acc["host_ms"].items())}
+        if name == "cfg4":
+            line["iterations"] = len(sim.convergence)
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(args.cpu_packets)
-            line["setup"] = device_setup_times(local)
+            line["cpu_baseline"] = cpu_baseline(args.cpu_packets or w["cpu_packets"], name)
             if LAST_REFERENCE_SETUP:
-                line["setup"]["reference_cpu"] = dict(LAST_REFERENCE_SETUP)
-            if os.path.exists(SHIM_EXE) and not args.no_e2e:
+                line["cpu_baseline"]["whole_run"] = dict(LAST_REFERENCE_SETUP)
+            if name == "cfg2":
+                line["setup"] = device_setup_times(local)
+                if LAST_REFERENCE_SETUP:
+                    line["setup"]["reference_cpu"] = {k: v for k, v in LAST_REFERENCE_SETUP.items() if k not in ("phases", "wall_s")}
+            if os.path.exists(REF_EXE) and w["ski"] and w["parity_packets"] and name in ("cfg1", "cfg2") and not args.no_parity:
                 try:
-                    line["ski_e2e"] = run_shim_once(4e8, os.cpu_count() or 1)
+                    line["parity"] = sed_parity(name, local, args.cpu_packets or w["cpu_packets"], int(w["parity_packets"]))
+                except Exception as ex:
+                    line["parity"] = {"error": str(ex)[:300], "pass": False}
+            if os.path.exists(SHIM_EXE) and w["ski"] and not args.no_e2e and name in ("cfg1", "cfg2"):
+                try:
+                    line["ski_e2e"] = run_shim_once(4e8 if name == "cfg2" else 4e7, os.cpu_count() or 1, name)
                 except Exception as ex:  # the drop-in binary is informational here; the C-ABI e2e above is the contract
-                    line["ski_e2e"] = {"error": str(ex)[:200]}
+                    line["ski_e2e"] = {"error": str(ex)[:300], "gpu_path": False}
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
@@ -423,10 +713,12 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--packets", type=float, default=1e8, help="packets per GPU per step (BASELINE configs[1]: 1e8)")
-    ap.add_argument("--cpu-packets", type=float, default=2e6, help="bounded sample for the cpu_baseline leg")
-    ap.add_argument("--ref-packets", type=float, default=1e6, help="packets per step of --impl reference")
+    ap.add_argument("--config", default="cfg2", choices=sorted(WORKLOADS), help="BASELINE.json workload (default: configs[1])")
+    ap.add_argument("--packets", type=float, default=None, help="packets per GPU per segment (cfg2: 1e8 = BASELINE configs[1])")
+    ap.add_argument("--cpu-packets", type=float, default=None, help="bounded sample for the cpu_baseline leg")
+    ap.add_argument("--ref-packets", type=float, default=None, help="packets per step of --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the SED comparison with the reference")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs only)")
     args = ap.parse_args()
     if args.impl == "reference":

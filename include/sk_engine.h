@@ -213,7 +213,9 @@ typedef struct sk_counters {
     uint64_t fallbacks;      /* tree: top-down relocations after a failed neighbour link */
     uint64_t kernel_launches;/* kernels launched by sk_engine_launch_segment / prepare_secondary (host-side count) */
     uint64_t rounds;         /* rounds of the stage sequence over the bank */
-    uint64_t reserved[4];
+    uint64_t pixel_overflows;/* per-pixel statistics: contributions recorded on their own because the pool of list chunks
+                                ran dry (0 unless SK_PIX_POOL was set too small; then Sum w^k, k >= 2, is biased) */
+    uint64_t reserved[3];
 } sk_counters_t;
 
 /* ---- life cycle of the engine object ---------------------------------------------------------- */

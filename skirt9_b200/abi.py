@@ -100,8 +100,8 @@ class SkTreePolicy(C.Structure):
 class SkCounters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in
                 ("packets", "forward_paths", "forward_segments", "replay_segments", "peel_paths", "peel_segments",
-                 "scatterings", "rf_deposits", "detections", "fallbacks", "kernel_launches", "rounds")] \
-        + [("reserved", C.c_uint64 * 4)]
+                 "scatterings", "rf_deposits", "detections", "fallbacks", "kernel_launches", "rounds", "pixel_overflows")] \
+        + [("reserved", C.c_uint64 * 3)]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_ if n != "reserved"}

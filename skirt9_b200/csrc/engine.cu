@@ -126,6 +126,16 @@ __global__ void sk_build_links_kernel(const int32_t* __restrict__ first_child, c
     }
     cells[m] = r;
 }
+__global__ void sk_pool_reset_kernel(int32_t* __restrict__ pool_free, int* __restrict__ pool_ctl, int nchunks)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < nchunks) pool_free[c] = c;
+    if (c == 0)
+    {
+        pool_ctl[0] = nchunks;
+        pool_ctl[1] = 0;
+    }
+}
 __global__ void sk_set_density_kernel(SkCellRec* __restrict__ cells, const double* __restrict__ dens, int ncells)
 {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
@@ -201,7 +211,9 @@ struct sk_engine {
     double* stat_block = nullptr;
     size_t stat_count = 0;
     unsigned long long* work_counter = nullptr;
-    SkBank bank = {nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0};  // the in-flight packets (sk_wavefront.cuh)
+    SkBank bank = {};  // the in-flight packets (sk_wavefront.cuh)
+    int pool_chunks = 0;                                    // chunks in the pool of per-history pixel lists
+    unsigned long long pixel_overflows = 0;
     int bank_fields_d = 0, bank_fields_i = 0;
     unsigned int* ctl_host = nullptr;                       // pinned copy of the control words + work counter
     cudaEvent_t ev_ctl = nullptr;
@@ -220,6 +232,7 @@ struct sk_engine {
     bool secondary_ready = false, has_secondary = false;
     int num_pix_lists = 0;
     void* pinned = nullptr;
+    size_t pinned_bytes = 0;
     cudaEvent_t pin_ev[2] = {nullptr, nullptr};
     double* scratch = nullptr;
     size_t scratch_len = 0;
@@ -345,6 +358,11 @@ extern "C" void sk_engine_destroy(sk_engine_t* e)
     dev_free(e->bank.i);
     dev_free(e->bank.list);
     dev_free(e->bank.free_list);
+    dev_free(e->bank.pool_lell);
+    dev_free(e->bank.pool_w);
+    dev_free(e->bank.pool_next);
+    dev_free(e->bank.pool_free);
+    dev_free(e->bank.pool_ctl);
     dev_free(e->bank.ctl);
     cudaFreeHost(e->ctl_host);
     if (e->ev_ctl) cudaEventDestroy(e->ev_ctl);
@@ -362,6 +380,37 @@ extern "C" void sk_engine_destroy(sk_engine_t* e)
     cudaStreamDestroy(e->stream);
     g_stream = nullptr;
     delete e;
+}
+
+// A new grid invalidates everything that is sized by its number of cells or points into it: the medium state, the
+// radiation field tables (allocated by sk_engine_set_wavelength_grids) and the secondary-emission tables
+// (sk_engine_set_secondary).  The caller repeats those calls for the new grid; until then the engine reports "not configured"
+// instead of writing beyond buffers that were sized for the old grid.
+static void drop_grid(sk_engine* e)
+{
+    free_group(e->grid_allocs);
+    free_group(e->medium_allocs);
+    free_group(e->rf_allocs);
+    free_group(e->sec_allocs);
+    e->grid_kind = 0;
+    e->grid_cells = 0;
+    e->M.grid_kind = 0;
+    e->M.ncells = 0;
+    e->M.cells = nullptr;
+    e->M.dens = nullptr;
+    e->M.volume = nullptr;
+    e->M.vrec = nullptr;
+    e->M.vbox = nullptr;
+    e->M.node_child = nullptr;
+    e->M.cell_coord = nullptr;
+    e->M.xv = e->M.yv = e->M.zv = nullptr;
+    e->M.rf1 = e->M.rf2 = e->M.rf2c = nullptr;
+    e->M.rf_grid = -1;
+    e->M.nrf = 0;
+    e->has_secondary = false;
+    e->secondary_ready = false;
+    e->first_child_dev = nullptr;
+    e->dens_host.clear();
 }
 
 static int set_tables(sk_engine* e, const double* xv, int nx1, const double* yv, int ny1, const double* zv, int nz1)
@@ -395,7 +444,7 @@ extern "C" int sk_engine_set_grid_cartesian(sk_engine_t* e, int32_t nx, int32_t 
 {
     if (!e || nx < 1 || ny < 1 || nz < 1 || !xv || !yv || !zv) return fail(SK_ERR_INVALID, "bad cartesian grid");
     if (int rc_bind = bind(e)) return rc_bind;
-    free_group(e->grid_allocs);
+    drop_grid(e);
     e->grid_kind = 1;
     e->M.grid_kind = 1;
     e->M.nx = nx;
@@ -440,8 +489,6 @@ static int finish_octree(sk_engine* e, const double extent[6], int nn, int nc, i
     PhaseTimer pt("finish_octree");
     std::vector<double> T[3];
     midpoint_tables(extent, N, T);
-    e->grid_kind = 2;
-    e->M.grid_kind = 2;
     e->M.nx = N;
     e->M.ny = N;
     e->M.nz = N;
@@ -474,7 +521,10 @@ static int finish_octree(sk_engine* e, const double extent[6], int nn, int nc, i
     e->M.vrec = nullptr;
     e->M.vbox = nullptr;
     e->first_child_dev = d_first;
-    return set_tables(e, T[0].data(), N + 1, T[1].data(), N + 1, T[2].data(), N + 1);
+    if (int rc = set_tables(e, T[0].data(), N + 1, T[1].data(), N + 1, T[2].data(), N + 1)) return rc;
+    e->grid_kind = 2;  // only a completely built grid is announced
+    e->M.grid_kind = 2;
+    return SK_OK;
 }
 
 static int set_grid_octree_device(sk_engine* e, const double extent[6], int nn, const int32_t* first_child);
@@ -500,8 +550,9 @@ extern "C" int sk_engine_set_grid_voronoi(sk_engine_t* e, const double extent[6]
         for (int64_t i = nbr_offset[m]; i < nbr_offset[m + 1]; ++i)
             if (nbr_index[i] < -6 || nbr_index[i] >= num_cells) return fail(SK_ERR_INVALID, "neighbour index out of range");
     }
+    if (nbr_offset[num_cells] > 0x7fffffffLL) return fail(SK_ERR_UNSUPPORTED, "Voronoi mesh with more than 2^31 neighbour entries");
     if (int rc_bind = bind(e)) return rc_bind;
-    free_group(e->grid_allocs);
+    drop_grid(e);
     const int nc = num_cells;
     std::vector<double4> rec(nc);
     for (int m = 0; m < nc; ++m) rec[m] = make_double4(sites[3 * (size_t)m], sites[3 * (size_t)m + 1], sites[3 * (size_t)m + 2], 0.);
@@ -699,7 +750,7 @@ static int number_cells_and_finish(sk_engine* e, const double extent[6], int nn,
     int32_t nc = 0;
     CK(cudaMemcpyAsync(&nc, d_total, sizeof nc, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
-    free_group(e->grid_allocs);
+    drop_grid(e);  // from here on a failure leaves the engine without a grid (grid_kind 0), not with dangling tables
     if (int rc = dalloc_zero(e->grid_allocs, (size_t)nn, &d_child)) return rc;
     if (int rc = dalloc_zero(e->grid_allocs, (size_t)nn, &d_first)) return rc;
     if (int rc = dalloc_zero(scratch, (size_t)nc, &d_nodeofcell)) return rc;
@@ -1465,18 +1516,39 @@ static int ensure_bank(sk_engine* e, uint64_t count)
     size_t cap = std::min<uint64_t>(count, bank_capacity_limit());
     cap = std::max<size_t>((cap + 255) / 256 * 256, 256);
     const int nd = SK_BANK_FIELDS_D(e->M.ninstr) + e->num_pix_lists * SK_PIX_K;
-    const int ni = SK_BANK_FIELDS_I(e->M.ninstr) + e->num_pix_lists * (SK_PIX_K + 1);
+    const int ni = SK_BANK_FIELDS_I(e->M.ninstr) + e->num_pix_lists * SK_PIX_INTS;
     e->bank.n = (int32_t)cap;
     if ((size_t)e->bank.cap >= cap && e->bank_fields_d == nd && e->bank_fields_i == ni) return SK_OK;
     dev_free(e->bank.d);
     dev_free(e->bank.i);
     dev_free(e->bank.list);
     dev_free(e->bank.free_list);
+    dev_free(e->bank.pool_lell);
+    dev_free(e->bank.pool_w);
+    dev_free(e->bank.pool_next);
+    dev_free(e->bank.pool_free);
     e->bank.d = nullptr;
     e->bank.i = nullptr;
     e->bank.list = nullptr;
     e->bank.free_list = nullptr;
+    e->bank.pool_lell = e->bank.pool_next = e->bank.pool_free = nullptr;
+    e->bank.pool_w = nullptr;
     e->bank.cap = 0;
+    e->pool_chunks = 0;
+    if (e->num_pix_lists)
+    {
+        // continuation chunks of the per-history pixel lists: one for every fourth slot and list (SK_PIX_POOL overrides;
+        // a history needs one when it reaches more than SK_PIX_K distinct frame pixels)
+        const char* ps = getenv("SK_PIX_POOL");
+        const long long want = ps ? atoll(ps) : 0;
+        const size_t nch = want > 0 ? (size_t)want : std::max<size_t>(1024, cap * e->num_pix_lists / 4);
+        CK(dev_malloc(&e->bank.pool_lell, nch * SK_PIX_C * sizeof(int32_t)));
+        CK(dev_malloc(&e->bank.pool_w, nch * SK_PIX_C * sizeof(double)));
+        CK(dev_malloc(&e->bank.pool_next, nch * sizeof(int32_t)));
+        CK(dev_malloc(&e->bank.pool_free, nch * sizeof(int32_t)));
+        if (!e->bank.pool_ctl) CK(dev_malloc(&e->bank.pool_ctl, 2 * sizeof(int)));
+        e->pool_chunks = (int)nch;
+    }
     CK(dev_malloc(&e->bank.d, cap * nd * sizeof(double)));
     CK(dev_malloc(&e->bank.i, cap * ni * sizeof(int32_t)));
     CK(dev_malloc(&e->bank.list, cap * sizeof(int32_t)));
@@ -1674,6 +1746,13 @@ extern "C" int sk_engine_launch_segment(sk_engine_t* e, uint64_t first, uint64_t
     if (count)
     {
         if (int rc = ensure_bank(e, count)) return rc;
+        if (e->pool_chunks)
+        {
+            // every chunk is free at the start of a segment (all histories of the previous one have ended)
+            sk_pool_reset_kernel<<<(e->pool_chunks + 255) / 256, 256, 0, e->stream>>>(e->bank.pool_free, e->bank.pool_ctl,
+                                                                                    e->pool_chunks);
+            CK(cudaGetLastError());
+        }
         SkRunArgs A;
         A.first = first;
         A.count = count;
@@ -1688,6 +1767,13 @@ extern "C" int sk_engine_launch_segment(sk_engine_t* e, uint64_t first, uint64_t
         A.model = e->model_dev;
         int rc = e->grid_kind == 1 ? run_bank<1>(e, A) : e->grid_kind == 2 ? run_bank<2>(e, A) : run_bank<3>(e, A);
         if (rc) return rc;
+        if (e->pool_chunks)
+        {
+            int ctl[2] = {0, 0};
+            CK(cudaMemcpyAsync(ctl, e->bank.pool_ctl, sizeof ctl, cudaMemcpyDeviceToHost, e->stream));
+            CK(cudaStreamSynchronize(e->stream));
+            e->pixel_overflows += (unsigned long long)ctl[1];
+        }
     }
     CK(cudaEventRecord(e->ev1, e->stream));
     e->timing_pending = true;
@@ -1800,10 +1886,18 @@ static int fetch_doubles(sk_engine* e, const double* dev, size_t n, double* out)
         CK(cudaStreamSynchronize(e->stream));
         return SK_OK;
     }
-    const size_t chunk = (size_t)32 << 20;
-    if (!e->pinned)
+    // staging buffer of two chunks, sized to the transfer (page-locking 64 MB for a small read costs more than the read)
+    const size_t chunk = std::min<size_t>((size_t)32 << 20, (bytes + 4095) / 4096 * 4096);
+    if (e->pinned_bytes < 2 * chunk)
     {
+        if (e->pinned) cudaFreeHost(e->pinned);
+        e->pinned = nullptr;
+        e->pinned_bytes = 0;
         CK(cudaMallocHost(&e->pinned, 2 * chunk));
+        e->pinned_bytes = 2 * chunk;
+    }
+    if (!e->pin_ev[0])
+    {
         CK(cudaEventCreateWithFlags(&e->pin_ev[0], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&e->pin_ev[1], cudaEventDisableTiming));
     }
@@ -1912,10 +2006,12 @@ extern "C" int sk_engine_counters(sk_engine_t* e, sk_counters_t* out, int32_t re
     out->fallbacks = c[9];
     out->kernel_launches = e->launches_total;
     out->rounds = e->rounds_total;
+    out->pixel_overflows = e->pixel_overflows;
     if (reset)
     {
         CK(cudaMemsetAsync(e->M.counters, 0, sizeof c, e->stream));
         e->launches_total = e->rounds_total = 0;
+        e->pixel_overflows = 0;
     }
     return SK_OK;
 }

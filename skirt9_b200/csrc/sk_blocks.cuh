@@ -28,6 +28,14 @@ struct SkBank {
     unsigned int* ctl;  // control words: see SK_CTL_*
     int32_t cap;      // allocated slots = stride of the field-major arrays
     int32_t n;        // slots in use [0, n): the whole bank while histories are handed out, shrinking while it drains
+    // pool of list chunks for histories that reach more than SK_PIX_K distinct frame pixels (per-pixel statistics): chunk c
+    // holds entries pool_lell/pool_w[c*SK_PIX_C ..), pool_next[c] chains to the next older chunk of the same history;
+    // pool_free is a stack of free chunks, pool_ctl = {stack height, contributions recorded early because the pool ran dry}
+    int32_t* pool_lell;
+    double* pool_w;
+    int32_t* pool_next;
+    int32_t* pool_free;
+    int* pool_ctl;
     __device__ __forceinline__ double& D(int f, int s) const { return d[(size_t)f * cap + s]; }
     __device__ __forceinline__ int32_t& I(int f, int s) const { return i[(size_t)f * cap + s]; }
 };

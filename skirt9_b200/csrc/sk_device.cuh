@@ -21,7 +21,10 @@
 #define SK_NUM_COMP (SK_COMP_PRIMARY_SCATTERED_LEVEL + SK_MAX_LEVELS)
 #define SK_MAX_INSTR 8
 #ifndef SK_PIX_K
-#define SK_PIX_K 32  // distinct frame pixels one history can hold before its oldest entry is recorded early
+#define SK_PIX_K 32  // distinct (pixel, bin) entries of a history kept in its bank slot; longer lists continue in chunks of
+#endif
+#ifndef SK_PIX_C
+#define SK_PIX_C 32  // this many entries taken from a pool in device memory (SkBank::pool_*)
 #endif
 #define SK_MAX_TREE_LEVEL 15
 #define SK_LINK_INTERNAL 0x40000000
@@ -122,7 +125,8 @@ struct SkDevModel {
     // instruments
     const SkDevInstr* instr;
     int32_t ninstr;
-    int32_t pix_base_d, pix_base_i;  // first bank field of the per-history pixel lists (SK_PIX_K entries per instrument)
+    int32_t pix_base_d, pix_base_i;  // first bank field of the per-history pixel lists: per instrument SK_PIX_K doubles and
+                                     // SK_PIX_K + 2 ints (pixel-bin indices, number of entries, newest pool chunk or -1)
     // counters
     unsigned long long* counters;
 };

@@ -145,12 +145,16 @@ __device__ __forceinline__ void sk_record_pixel_stats(const SkDevInstr& q, int l
     }
 }
 // A detection's contribution to the history's pixel list (ContributionList::addContribution, FluxRecorder.hpp:331, with the
-// grouping of FluxRecorder.cpp:996-999 done on insertion).  A history that reaches more than SK_PIX_K distinct pixels has
-// its oldest entry recorded early.
+// grouping of FluxRecorder.cpp:996-999 done on insertion): the first SK_PIX_K distinct (pixel, bin) entries live in the
+// history's bank slot, further ones in chunks of SK_PIX_C entries chained from a pool (newest chunk first).  Chunks are only
+// taken here (detect kernel) and only given back by sk_finish_history (advance kernel), never in the same kernel, so one
+// atomic counter is the whole stack discipline.  Should the pool run dry the contribution is recorded on its own
+// (counted in sk_counters_t::pixel_overflows; the pool is sized so that this does not happen).
+#define SK_PIX_INTS (SK_PIX_K + 2)
 __device__ __forceinline__ void sk_add_pixel_contribution(const SkDevModel& M, const SkBank& K, const SkDevInstr& q,
                                                           int slot, int lell, double w)
 {
-    const int fi = M.pix_base_i + q.pix_slot * (SK_PIX_K + 1), fd = M.pix_base_d + q.pix_slot * SK_PIX_K;
+    const int fi = M.pix_base_i + q.pix_slot * SK_PIX_INTS, fd = M.pix_base_d + q.pix_slot * SK_PIX_K;
     const int total = K.I(fi + SK_PIX_K, slot);
     const int n = min(total, SK_PIX_K);
     for (int i = 0; i < n; ++i)
@@ -159,10 +163,41 @@ __device__ __forceinline__ void sk_add_pixel_contribution(const SkDevModel& M, c
             K.D(fd + i, slot) += w;
             return;
         }
-    const int at = total % SK_PIX_K;
-    if (total >= SK_PIX_K) sk_record_pixel_stats(q, K.I(fi + at, slot), K.D(fd + at, slot));
-    K.I(fi + at, slot) = lell;
-    K.D(fd + at, slot) = w;
+    if (total < SK_PIX_K)
+    {
+        K.I(fi + total, slot) = lell;
+        K.D(fd + total, slot) = w;
+        K.I(fi + SK_PIX_K, slot) = total + 1;
+        return;
+    }
+    int head = K.I(fi + SK_PIX_K + 1, slot);
+    const int rem = total - SK_PIX_K;  // entries in the chain; the newest chunk holds ((rem - 1) % C) + 1 of them
+    int cnt = rem ? ((rem - 1) % SK_PIX_C) + 1 : 0;
+    for (int c = head; c >= 0 && rem; c = K.pool_next[c], cnt = SK_PIX_C)
+        for (int j = 0; j < cnt; ++j)
+            if (K.pool_lell[(size_t)c * SK_PIX_C + j] == lell)
+            {
+                K.pool_w[(size_t)c * SK_PIX_C + j] += w;
+                return;
+            }
+    const int at = rem % SK_PIX_C;
+    if (at == 0)
+    {
+        const int top = atomicSub(&K.pool_ctl[0], 1) - 1;
+        if (top < 0)
+        {
+            atomicAdd(&K.pool_ctl[0], 1);
+            atomicAdd(&K.pool_ctl[1], 1);
+            sk_record_pixel_stats(q, lell, w);
+            return;
+        }
+        const int c = K.pool_free[top];
+        K.pool_next[c] = head;
+        head = c;
+        K.I(fi + SK_PIX_K + 1, slot) = c;
+    }
+    K.pool_lell[(size_t)head * SK_PIX_C + at] = lell;
+    K.pool_w[(size_t)head * SK_PIX_C + at] = w;
     K.I(fi + SK_PIX_K, slot) = total + 1;
 }
 
@@ -190,9 +225,23 @@ __device__ __forceinline__ void sk_finish_history(const SkDevModel& M, const SkB
     {
         const SkDevInstr& q = M.instr[j];
         if (q.pix_slot < 0) continue;
-        const int fi = M.pix_base_i + q.pix_slot * (SK_PIX_K + 1), fd = M.pix_base_d + q.pix_slot * SK_PIX_K;
-        const int n = min(K.I(fi + SK_PIX_K, slot), SK_PIX_K);
+        const int fi = M.pix_base_i + q.pix_slot * SK_PIX_INTS, fd = M.pix_base_d + q.pix_slot * SK_PIX_K;
+        const int total = K.I(fi + SK_PIX_K, slot);
+        const int n = min(total, SK_PIX_K);
         for (int i = 0; i < n; ++i) sk_record_pixel_stats(q, K.I(fi + i, slot), K.D(fd + i, slot));
+        const int rem = total - SK_PIX_K;
+        if (rem > 0)
+        {
+            int cnt = ((rem - 1) % SK_PIX_C) + 1;
+            for (int c = K.I(fi + SK_PIX_K + 1, slot); c >= 0; cnt = SK_PIX_C)
+            {
+                for (int i = 0; i < cnt; ++i)
+                    sk_record_pixel_stats(q, K.pool_lell[(size_t)c * SK_PIX_C + i], K.pool_w[(size_t)c * SK_PIX_C + i]);
+                const int next = K.pool_next[c];
+                K.pool_free[atomicAdd(&K.pool_ctl[0], 1)] = c;  // back on the stack of free chunks
+                c = next;
+            }
+        }
     }
     K.I(I_STATE, slot) = 0;
 }
@@ -797,7 +846,11 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK, SK_LAUNCH_MINBLOCKS) sk_wf_lau
                     K.D(D_HISTW0 + j, slot) = 0.;
                     K.I(I_HELL0 + j, slot) = -1;
                     const int ps = M.instr[j].pix_slot;
-                    if (ps >= 0) K.I(M.pix_base_i + ps * (SK_PIX_K + 1) + SK_PIX_K, slot) = 0;
+                    if (ps >= 0)
+                    {
+                        K.I(M.pix_base_i + ps * SK_PIX_INTS + SK_PIX_K, slot) = 0;
+                        K.I(M.pix_base_i + ps * SK_PIX_INTS + SK_PIX_K + 1, slot) = -1;
+                    }
                 }
                 K.I(I_STATE, slot) = SK_ST_LIVE;
                 live = true;

@@ -147,3 +147,21 @@ def tabulated_sed_ring_source_high_g(num_packets=20000, seed=13):
                                   minWavelength=0.15e-6, maxWavelength=8e-6, defaultWavelengthGrid=wlg,
                                   storeRadiationField=True, radiationFieldWLG=H.LogWavelengthGrid(0.15e-6, 8e-6, 5),
                                   numDensitySamples=3, seed=seed)
+
+
+def long_histories_many_pixels(num_packets=1500, seed=21):
+    """Histories that reach hundreds of distinct frame pixels: nearly conservative scattering (albedo 0.995) in an optically
+    thick sphere, no path-length bias, a weight reduction of 1e4 before termination, a 64 x 64 frame with per-pixel statistics.  The per-history
+    pixel list (FluxRecorder's ContributionList, FluxRecorder.cpp:990-1013) then is far longer than the SK_PIX_K entries
+    that fit in a bank slot and continues in chunks from the pool."""
+    pc = H.PC
+    mix = H.MeanListDustMix([0.1e-6, 1e-6], [1000.0, 1000.0], [0.995, 0.995], [0.2, 0.2])
+    medium = H.GeometricMedium(H.ShellGeometry(1e-4 * pc, 1.0 * pc, 0.0), mix, opticalDepth=100.0, wavelength=0.55e-6)
+    grid = H.CartesianSpatialGrid(-pc, pc, -pc, pc, -pc, pc, 12, 12, 12)
+    src = H.PointSource((0.0, 0.0, 0.0), H.BlackBodySED(5000.0), luminosity=1.0 * H.LSUN)
+    instr = H.FullInstrument(instrumentName="i60", distance=1e6 * pc, inclination=60 * DEG, fieldOfViewX=2 * pc,
+                             numPixelsX=64, fieldOfViewY=2 * pc, numPixelsY=64, recordComponents=True, recordStatistics=True)
+    sim = H.MonteCarloSimulation(sources=[src], medium=medium, grid=grid, instruments=[instr], numPackets=num_packets,
+                                 oligoWavelengths=[0.55e-6], storeRadiationField=False, numDensitySamples=4, seed=seed)
+    sim.pathLengthBias = 0.0   # (the bias weights p/q would end the histories after a dozen scatterings)
+    return sim

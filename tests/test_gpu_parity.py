@@ -217,3 +217,25 @@ def test_engine_rejects_unsupported_and_bad_calls(engine_lib):
         assert ei.value.code == abi.SK_ERR_INVALID, bad
     e.set_grid_octree(box, [1] + leaves[:7] + [9] + leaves)   # a valid two-level tree
     e.set_medium(np.ones(15))
+
+
+def test_per_pixel_statistics_of_histories_with_hundreds_of_pixels(engine_lib, monkeypatch):
+    """The per-history pixel list is exact beyond the SK_PIX_K = 32 entries of a bank slot (chunks chained from a pool):
+    Sum w^k per pixel, k = 0..4, equals the oracle's, which keeps a list of any length like the reference's ContributionList."""
+    sim = models.long_histories_many_pixels()
+    gpu, cpu = run_both(sim, engine_lib)
+    c = gpu.counters()
+    assert c["scatterings"] / c["packets"] > 150          # long histories ...
+    st = cpu.read_ifu_stats(0)
+    assert st[0].sum() / c["packets"] > 100                # ... that reach > 100 distinct pixels each, on average
+    assert c["pixel_overflows"] == 0
+    models.compare_engines(sim, gpu, cpu)
+    gpu.close()
+    # a pool that is too small is reported, and leaves the first moments intact (only Sum w^k, k >= 2, sees the split lists)
+    monkeypatch.setenv("SK_PIX_POOL", "8")
+    small = sim.configure(abi.Engine(sim.config_struct(device=0), lib=engine_lib))
+    sim.run(small)
+    assert small.counters()["pixel_overflows"] > 0
+    a, b = small.read_ifu_stats(0), st
+    np.testing.assert_allclose(a[1], b[1], rtol=1e-8, atol=1e-8 * b[1].max())
+    assert a[0].sum() > b[0].sum()
