@@ -357,7 +357,9 @@ int sk_engine_counters(sk_engine_t* e, sk_counters_t* out, int32_t reset);
 
 /* Raw device buffers so that the rank's communicator (NCCL via torch.distributed in bench.py, or the
  * shim's own ncclAllReduce) can reduce tallies in place: which = 0 rf1, 1 rf2, 2 rf2c, 3 = all
- * detector arrays of all instruments (one contiguous block), 4 = all statistics arrays. */
+ * detector arrays of all instruments (one contiguous block), 4 = all statistics arrays.  The radiation field buffers are
+ * wavelength-major on the device, [ell*Ncells + m] (the same on every rank, so element-wise reductions are unaffected);
+ * sk_engine_read_rf hands them out in the reference's [m*Nrf + ell] layout. */
 int sk_engine_device_buffer(sk_engine_t* e, int32_t which, void** device_ptr, uint64_t* num_doubles);
 /* Diagnostic for bench.py's second roofline: the measured rate (records/s) at which this device serves chains of
  * dependent, randomly scattered 32-byte record fetches out of a table of num_records records at full occupancy -- the

@@ -1,13 +1,20 @@
 #!/usr/bin/env python
-"""Kernel-variant tuning on the GPU box: one host setup of cfg2, then every variants/lib_*.so timed on the same input.
-usage: python scripts/tune.py [packets] [names...]"""
+"""Kernel-variant tuning on the GPU box: one host setup of the workload, then every variants/lib_*.so timed on the same input.
+usage: python scripts/tune.py [packets] [--config cfg1|cfg2|cfg4|cfg5] [names...]"""
 import glob, os, sys, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from skirt9_b200 import abi, configs
+from skirt9_b200 import abi
+import bench
 
-packets = int(float(sys.argv[1])) if len(sys.argv) > 1 else 20000000
-names = sys.argv[2:]
+argv = sys.argv[1:]
+config = "cfg2"
+if "--config" in argv:
+    i = argv.index("--config")
+    config = argv[i + 1]
+    del argv[i:i + 2]
+packets = int(float(argv[0])) if argv else 20000000
+names = argv[1:]
 libs = sorted(glob.glob(os.path.join(ROOT, "variants", "lib_*.so")))
 if names:
     libs = [l for l in libs if os.path.basename(l)[4:-3] in names]
@@ -15,23 +22,30 @@ if os.environ.get("SK_TUNE_CHILD") != "1" and len(libs) > 1:
     # one process per variant: the libraries export the same symbols, and in-library calls bind to the first one loaded
     import subprocess
     for path in libs:
-        subprocess.call([sys.executable, __file__, str(packets), os.path.basename(path)[4:-3]],
+        subprocess.call([sys.executable, __file__, str(packets), "--config", config, os.path.basename(path)[4:-3]],
                         env=dict(os.environ, SK_TUNE_CHILD="1"))
     sys.exit(0)
-sim = configs.cfg2(num_packets=packets).setup()
+sim = bench.make_sim(config, packets)
 for path in libs:
     lib = abi.load_engine_library(path)
     e = sim.configure(abi.Engine(sim.config_struct(device=0), lib=lib))
-    e.prepare_primary(packets)
+    acc = {"ms": 0.0, "stages": {}}
+    inner = e.run_segment
+
+    def run_segment(*a, **kw):
+        inner(*a, **kw)
+        acc["ms"] += e.last_kernel_ms()
+        for k, v in e.last_stage_ms().items():
+            acc["stages"][k] = acc["stages"].get(k, 0.0) + v
+    e.run_segment = run_segment
     ms = []
     for k in range(3):
         e.clear_instruments()
-        e.run_segment(0, packets, True, True, False, k)
-        ms.append(e.last_kernel_ms())
-    stages = {k: round(v, 1) for k, v in e.last_stage_ms().items()}
+        acc["ms"], acc["stages"] = 0.0, {}
+        sim.run(e, stream_id=k)
+        ms.append(acc["ms"])
+    stages = {k: round(v, 1) for k, v in acc["stages"].items() if v}
     c = e.counters()
-    if os.environ.get("SK_TUNE_GATHER", "1") == "1" and path == libs[0]:
-        print(json.dumps({"gather_peak_records_per_s": e.measure_gather_peak(sim.grid.num_cells), "records": int(sim.grid.num_cells)}), flush=True)
-    print(json.dumps({"variant": os.path.basename(path)[4:-3], "packets": packets, "ms": ms,
-                      "pkt_per_s": packets / (min(ms[1:]) * 1e-3), "stages_ms": stages, "rounds": c["rounds"] / 3}), flush=True)
+    print(json.dumps({"variant": os.path.basename(path)[4:-3], "config": config, "packets": packets, "ms": ms,
+                      "pkt_per_s": c["packets"] / 3 / (min(ms[1:]) * 1e-3), "stages_ms": stages, "rounds": c["rounds"] / 3}), flush=True)
     e.close()

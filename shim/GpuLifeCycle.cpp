@@ -45,6 +45,7 @@
 #include "CartesianSpatialGrid.hpp"
 #include "Configuration.hpp"
 #include "DefaultWavelengthDistribution.hpp"
+#include "DensityTreePolicy.hpp"
 #include "DisjointWavelengthGrid.hpp"
 #include "DistantInstrument.hpp"
 #include "DustMix.hpp"
@@ -53,6 +54,7 @@
 #include "FluxRecorder.hpp"
 #include "FrameInstrument.hpp"
 #include "FullInstrument.hpp"
+#include "GeometricMedium.hpp"
 #include "GeometricSource.hpp"
 #include "InstrumentSystem.hpp"
 #include "Log.hpp"
@@ -62,6 +64,7 @@
 #include "OctTreeNode.hpp"
 #include "OligoWavelengthDistribution.hpp"
 #include "PointSource.hpp"
+#include "PolicyTreeSpatialGrid.hpp"
 #include "ProbeSystem.hpp"
 #include "ProcessManager.hpp"
 #include "Random.hpp"
@@ -163,6 +166,154 @@ namespace
         }
         return false;
     }
+}
+
+////////////////////////////////////////////////////////////////////
+
+// SURVEY.md 8f row f2 in the drop-in: DensityTreePolicy::constructTree (DensityTreePolicy.cpp:242-309) on the GPU.  The
+// reference calls the policy through the virtual TreePolicy::constructTree, so a subclass that overrides just that function
+// can stand in for the policy object the ski file created; everything else (properties, setupSelfBefore with the media
+// lists, the dust mass and kappa) is the reference's own code, inherited.
+namespace
+{
+    // a medium component as sk_engine_build_octree sees it: geometry kind + the parameters of Geometry::density
+    bool describeMedium(const Medium* medium, sk_density_geometry_t& d, bool setupDone)
+    {
+        memset(&d, 0, sizeof d);
+        auto gm = dynamic_cast<const GeometricMedium*>(medium);
+        if (!gm) return false;
+        const Geometry* geom = gm->geometry();
+        if (setupDone)
+        {
+            d.number = gm->number();
+            d.mass = gm->mass();
+        }
+        if (auto g = dynamic_cast<const ShellGeometry*>(geom))
+        {
+            d.geometry = SK_GEOM_SHELL;
+            double p[] = {g->minRadius(), g->maxRadius(), g->exponent(), g->_A};
+            std::copy(p, p + 4, d.p);
+            return true;
+        }
+        if (auto g = dynamic_cast<const ExpDiskGeometry*>(geom))
+        {
+            d.geometry = SK_GEOM_EXPDISK;
+            double p[] = {g->scaleLength(), g->scaleHeight(), g->minRadius(), g->maxRadius(), g->maxZ(), g->_rho0};
+            std::copy(p, p + 6, d.p);
+            return true;
+        }
+        if (auto g = dynamic_cast<const RingGeometry*>(geom))
+        {
+            d.geometry = SK_GEOM_RING;
+            double p[] = {g->ringRadius(), g->width(), g->height(), g->_A};
+            std::copy(p, p + 4, d.p);
+            return true;
+        }
+        if (auto g = dynamic_cast<const SpiralStructureGeometryDecorator*>(geom))
+        {
+            auto e = dynamic_cast<const ExpDiskGeometry*>(g->geometry());
+            if (!e) return false;
+            d.geometry = SK_GEOM_SPIRAL_EXPDISK;
+            double p[] = {e->scaleLength(), e->scaleHeight(), e->minRadius(), e->maxRadius(), e->maxZ(), e->_rho0,
+                          static_cast<double>(g->numArms()), g->_tanp, g->radiusZeroPoint(), g->phaseZeroPoint(),
+                          g->perturbationWeight(), static_cast<double>(g->index()), g->_cn};
+            std::copy(p, p + 13, d.p);
+            return true;
+        }
+        return false;
+    }
+
+    class GpuDensityTreePolicy : public DensityTreePolicy
+    {
+    public:
+        GpuDensityTreePolicy(const DensityTreePolicy* src, int device) : _device(device)
+        {
+            _minLevel = src->_minLevel;
+            _maxLevel = src->_maxLevel;
+            _maxDustFraction = src->_maxDustFraction;
+            _maxDustOpticalDepth = src->_maxDustOpticalDepth;
+            _wavelength = src->_wavelength;
+            _maxDustDensityDispersion = src->_maxDustDensityDispersion;
+            _maxElectronFraction = src->_maxElectronFraction;
+            _maxGasFraction = src->_maxGasFraction;
+        }
+
+        vector<TreeNode*> constructTree(TreeNode* root) override
+        {
+            auto log = find<Log>();
+            // only dust criteria on geometric media run on the device; anything else is the reference's own loop
+            vector<sk_density_geometry_t> media(_dustMedia.size());
+            bool ok = !_dustMedia.empty() && _electronMedia.empty() && _gasMedia.empty() && _dustMIBv.empty()
+                      && maxLevel() <= 15 && dynamic_cast<OctTreeNode*>(root);
+            for (size_t h = 0; ok && h != media.size(); ++h) ok = describeMedium(_dustMedia[h], media[h], true);
+            if (!ok) return DensityTreePolicy::constructTree(root);
+
+            auto fail = [](int rc) {
+                if (rc != SK_OK) throw FATALERROR(string("GPU tree construction: ") + sk_last_error());
+            };
+            sk_config_t c;
+            memset(&c, 0, sizeof c);
+            c.seed = static_cast<uint32_t>(_random->seed());
+            c.device = _device;
+            sk_engine_t* e = nullptr;
+            fail(sk_engine_create(&c, &e));
+            sk_tree_policy_t p;
+            memset(&p, 0, sizeof p);
+            p.min_level = minLevel();
+            p.max_level = maxLevel();
+            p.num_samples = _numSamples;
+            p.max_dust_fraction = maxDustFraction();
+            p.max_dust_optical_depth = maxDustOpticalDepth();
+            p.max_dust_density_dispersion = maxDustDensityDispersion();
+            p.dust_kappa = _dustKappa;
+            const Box& b = *root;
+            double ext[6] = {b.xmin(), b.ymin(), b.zmin(), b.xmax(), b.ymax(), b.zmax()};
+            uint64_t nn = 0, nc = 0;
+            int rc = sk_engine_build_octree(e, ext, &p, static_cast<int32_t>(media.size()), media.data(), &nn, &nc);
+            vector<int32_t> firstChild(rc == SK_OK ? nn : 0);
+            if (rc == SK_OK) rc = sk_engine_read_octree(e, firstChild.data());
+            sk_engine_destroy(e);
+            fail(rc);
+            log->info("  GPU tree construction: " + std::to_string(nn) + " nodes, " + std::to_string(nc)
+                      + " cells (sk_engine_build_octree)");
+
+            // the reference's node objects in the same breadth-first order (TreeNode::subdivide without the neighbour lists:
+            // nothing on the host walks the tree from cell to cell once the life cycle runs on the device)
+            vector<TreeNode*> nodev{root};
+            nodev.reserve(nn);
+            for (size_t l = 0; l != nn; ++l)
+            {
+                if (firstChild[l] < 0) continue;
+                if (static_cast<size_t>(firstChild[l]) != nodev.size())
+                    throw FATALERROR("GPU tree construction: node list is not breadth-first");
+                TreeNode* node = nodev[l];
+                node->createChildren(static_cast<int>(nodev.size()));
+                nodev.insert(nodev.end(), node->_children.begin(), node->_children.end());
+            }
+            if (nodev.size() != nn) throw FATALERROR("GPU tree construction: node count mismatch");
+            return nodev;
+        }
+
+    private:
+        int _device;
+    };
+}
+
+bool GpuLifeCycle::installDeviceTreeConstruction(MonteCarloSimulation* sim, int device)
+{
+    auto ms = sim->mediumSystem();
+    if (!ms) return false;
+    auto grid = dynamic_cast<PolicyTreeSpatialGrid*>(ms->grid());
+    if (!grid || grid->treeType() != PolicyTreeSpatialGrid::TreeType::OctTree) return false;
+    auto policy = grid->policy();
+    if (!policy || typeid(*policy) != typeid(DensityTreePolicy)) return false;
+    for (auto medium : ms->media())
+    {
+        sk_density_geometry_t d;
+        if (!describeMedium(medium, d, false)) return false;
+    }
+    grid->ii_set_policy(new GpuDensityTreePolicy(static_cast<DensityTreePolicy*>(policy), device));
+    return true;
 }
 
 ////////////////////////////////////////////////////////////////////

@@ -26,6 +26,11 @@ public:
     GpuLifeCycle(MonteCarloSimulation* sim, const std::vector<int>& devices);
     ~GpuLifeCycle();
 
+    // Before setupSimulation(): when the spatial grid is an octree built by a DensityTreePolicy over geometric dust media the
+    // engine knows, replaces the policy object by one whose constructTree() runs sk_engine_build_octree on `device`
+    // (DensityTreePolicy.cpp:242-309).  Returns false (and changes nothing) otherwise.
+    static bool installDeviceTreeConstruction(MonteCarloSimulation* sim, int device);
+
     // returns an empty string when the configured simulation lies on the accelerated path, or the reason why not
     std::string unsupportedReason() const;
 

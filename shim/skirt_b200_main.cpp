@@ -2,7 +2,7 @@
 // probes and output writers (linked unmodified from the reference's object files) driven by GpuLifeCycle, which runs
 // every emission segment through libskirt9_b200.so (include/sk_engine.h).
 //
-//   skirt_b200 [-t threads] [-b] [-i indir] [-o outdir] [-g device[,device...]] [--cpu] file.ski
+//   skirt_b200 [-t threads] [-b] [-i indir] [-o outdir] [-g device[,device...]] [--host-setup] [--cpu] file.ski
 //
 // The structure follows SKIRT/main/SkirtMain.cpp:15-31 and SkirtCommandLineHandler::doSimulation
 // (SKIRT/main/SkirtCommandLineHandler.cpp:295-400).  There is no CPU fallback: a configuration outside the accelerated
@@ -72,7 +72,7 @@ int main(int argc, char** argv)
     // ---- command line
     int threads = 0;
     std::vector<int> devices;
-    bool brief = false, cpu = false;
+    bool brief = false, cpu = false, hostSetup = false;
     string inpath, outpath, skipath;
     for (int i = 1; i < argc; ++i)
     {
@@ -111,6 +111,8 @@ int main(int argc, char** argv)
                 brief = true;
             else if (a == "--cpu")
                 cpu = true;
+            else if (a == "--host-setup")
+                hostSetup = true;
             else if (!a.empty() && a[0] != '-')
                 skipath = a;
             else
@@ -124,7 +126,7 @@ int main(int argc, char** argv)
     }
     if (skipath.empty())
     {
-        console.error("usage: skirt_b200 [-t threads] [-b] [-i indir] [-o outdir] [-g device[,device...]] [--cpu] file.ski");
+        console.error("usage: skirt_b200 [-t threads] [-b] [-i indir] [-o outdir] [-g device[,device...]] [--host-setup] [--cpu] file.ski");
         return EXIT_FAILURE;
     }
     if (!StringUtils::endsWith(skipath, ".ski")) skipath += ".ski";
@@ -157,6 +159,9 @@ int main(int argc, char** argv)
             simulation->_factory->setup();
             simulation->_log->setup();
             TimeLogger logger(simulation->_log, "simulation " + simulation->_paths->outputPrefix());
+            // the octree of a DensityTreePolicy is constructed on the first device (--host-setup keeps the reference's loop)
+            if (!cpu && !hostSetup && GpuLifeCycle::installDeviceTreeConstruction(simulation, devices.empty() ? 0 : devices[0]))
+                simulation->_log->info("The spatial tree will be constructed on the GPU");
             simulation->setupSimulation();
 
             if (cpu)

@@ -48,7 +48,7 @@ def cfg2(num_packets=1e8, max_level=9, max_dust_fraction=3.5e-6, seed=0, num_pix
 
 
 def cfg4(num_packets=2e5, max_level=6, max_dust_fraction=2e-4, seed=0, min_level=3, num_sed_wavelengths=50,
-         max_secondary_iterations=5):
+         max_secondary_iterations=5, record_statistics=False):
     """dust emission with secondary-emission iterations; 1e4 Lsun 10 000 K point source in an r^-2 dust
     shell with tau_Z(0.55 um) = 20, octree, RF grid 40 bins 0.1-1000 um, emission grid 60 bins 1-1000 um,
     SEDInstrument with components.  (BASELINE.json configs[3] scales the tree to ~1e6 cells: max_level=8,
@@ -59,7 +59,8 @@ def cfg4(num_packets=2e5, max_level=6, max_dust_fraction=2e-4, seed=0, min_level
     medium = H.GeometricMedium(H.ShellGeometry(0.01 * pc, 1.0 * pc, 2.0), mix, opticalDepth=20.0, wavelength=0.55e-6)
     grid = H.PolicyTreeSpatialGrid(-pc, pc, -pc, pc, -pc, pc, H.DensityTreePolicy(min_level, max_level, max_dust_fraction))
     src = H.PointSource((0.0, 0.0, 0.0), H.BlackBodySED(10000.0), luminosity=1e4 * H.LSUN)
-    instr = H.SEDInstrument(instrumentName="sed", distance=1e6 * pc, inclination=60 * DEG, recordComponents=True)
+    instr = H.SEDInstrument(instrumentName="sed", distance=1e6 * pc, inclination=60 * DEG, recordComponents=True,
+                            recordStatistics=record_statistics)
     return H.MonteCarloSimulation(sources=[src], medium=medium, grid=grid, instruments=[instr], numPackets=num_packets,
                                   minWavelength=0.1e-6, maxWavelength=20e-6,
                                   defaultWavelengthGrid=H.LogWavelengthGrid(0.1e-6, 1000e-6, num_sed_wavelengths),

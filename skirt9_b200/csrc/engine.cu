@@ -126,6 +126,23 @@ __global__ void sk_build_links_kernel(const int32_t* __restrict__ first_child, c
     }
     cells[m] = r;
 }
+// device layout [ell][m] -> the reference's Table<2> layout [m][ell] (sk_engine_read_rf)
+__global__ void sk_rf_transpose_kernel(const double* __restrict__ in, double* __restrict__ out, int ncells, int nrf)
+{
+    __shared__ double tile[32][33];
+    const int m0 = blockIdx.x * 32, l0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y)
+    {
+        const int ell = l0 + j, m = m0 + threadIdx.x;
+        if (ell < nrf && m < ncells) tile[j][threadIdx.x] = in[(size_t)ell * ncells + m];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y)
+    {
+        const int m = m0 + j, ell = l0 + threadIdx.x;
+        if (ell < nrf && m < ncells) out[(size_t)m * nrf + ell] = tile[threadIdx.x][j];
+    }
+}
 __global__ void sk_pool_reset_kernel(int32_t* __restrict__ pool_free, int* __restrict__ pool_ctl, int nchunks)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -167,7 +184,7 @@ __global__ void sk_absorbed_kernel(const double* __restrict__ rf, const double* 
     {
         double n = dens_or_null ? dens_or_null[m] : cells ? cells[m].dens : vrec[m].w;
         double s = 0.;
-        for (int ell = 0; ell < nrf; ++ell) s += kabs[ell] * n * rf[(size_t)m * nrf + ell];
+        for (int ell = 0; ell < nrf; ++ell) s += kabs[ell] * n * rf[(size_t)ell * ncells + m];  // SK_RF_INDEX
         sum += s;
     }
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
@@ -213,6 +230,7 @@ struct sk_engine {
     unsigned long long* work_counter = nullptr;
     SkBank bank = {};  // the in-flight packets (sk_wavefront.cuh)
     int pool_chunks = 0;                                    // chunks in the pool of per-history pixel lists
+    unsigned int* sort_cursor = nullptr;                    // bin cursors of the wavelength sort of the forward rays
     unsigned long long pixel_overflows = 0;
     int bank_fields_d = 0, bank_fields_i = 0;
     unsigned int* ctl_host = nullptr;                       // pinned copy of the control words + work counter
@@ -363,6 +381,7 @@ extern "C" void sk_engine_destroy(sk_engine_t* e)
     dev_free(e->bank.pool_next);
     dev_free(e->bank.pool_free);
     dev_free(e->bank.pool_ctl);
+    dev_free(e->sort_cursor);
     dev_free(e->bank.ctl);
     cudaFreeHost(e->ctl_host);
     if (e->ev_ctl) cudaEventDestroy(e->ev_ctl);
@@ -1537,11 +1556,11 @@ static int ensure_bank(sk_engine* e, uint64_t count)
     e->pool_chunks = 0;
     if (e->num_pix_lists)
     {
-        // continuation chunks of the per-history pixel lists: one for every fourth slot and list (SK_PIX_POOL overrides;
-        // a history needs one when it reaches more than SK_PIX_K distinct frame pixels)
+        // continuation chunks of the per-history pixel lists: two per slot and list, at least 16384 (388 bytes each;
+        // SK_PIX_POOL overrides).  A history takes one for every SK_PIX_C distinct frame pixels beyond the first SK_PIX_K.
         const char* ps = getenv("SK_PIX_POOL");
         const long long want = ps ? atoll(ps) : 0;
-        const size_t nch = want > 0 ? (size_t)want : std::max<size_t>(1024, cap * e->num_pix_lists / 4);
+        const size_t nch = want > 0 ? (size_t)want : std::max<size_t>(16384, 2 * cap * e->num_pix_lists);
         CK(dev_malloc(&e->bank.pool_lell, nch * SK_PIX_C * sizeof(int32_t)));
         CK(dev_malloc(&e->bank.pool_w, nch * SK_PIX_C * sizeof(double)));
         CK(dev_malloc(&e->bank.pool_next, nch * sizeof(int32_t)));
@@ -1687,8 +1706,27 @@ static int run_bank(sk_engine* e, const SkRunArgs& A)
         }
         if (M.force_scattering)
         {
-            // forward path, interaction optical depth and the walk to the interaction point in one kernel
-            if (int rc = A.store ? launch_trace<GRID, 0, true>(e, A, nodir) : launch_trace<GRID, 0, false>(e, A, nodir))
+            // forward path, interaction optical depth and the walk to the interaction point in one kernel; when the radiation
+            // field is stored the rays are first put in order of their wavelength bin (see SK_RF_INDEX)
+            if (A.store && M.nrf > 1 && M.nrf <= SK_SORT_MAX_BINS)
+            {
+                if (!e->sort_cursor) CK(dev_malloc(&e->sort_cursor, (SK_SORT_MAX_BINS + 1) * sizeof(unsigned int)));
+                CK(cudaMemsetAsync(e->sort_cursor, 0, (M.nrf + 1) * sizeof(unsigned int), e->stream));
+                if (int rc = stage_begin(e, SK_STAGE_PEEL_SETUP)) return rc;
+                const unsigned cblocks = std::min<unsigned>(eblocks, (unsigned)e->num_sms * 8u);
+                sk_wf_bin_count<<<cblocks, SK_EVENT_BLOCK, 0, e->stream>>>(K, M.nrf, e->sort_cursor);
+                sk_wf_bin_scan<<<1, 32, 0, e->stream>>>(e->sort_cursor, M.nrf);
+                const unsigned sblocks = (unsigned)(((size_t)K.n + SK_SORT_TILE - 1) / SK_SORT_TILE);
+                sk_wf_bin_scatter<<<sblocks, SK_EVENT_BLOCK, 0, e->stream>>>(K, M.nrf, e->sort_cursor);
+                CK(cudaGetLastError());
+                e->launches_total += 2;
+                if (int rc = stage_end(e)) return rc;
+                std::swap(e->bank.list, e->bank.free_list);  // the sorted list is the ray list of the trace ...
+                int rc = launch_trace<GRID, 0, true>(e, A, nodir);
+                std::swap(e->bank.list, e->bank.free_list);  // ... and the buffers return to their roles
+                if (rc) return rc;
+            }
+            else if (int rc = A.store ? launch_trace<GRID, 0, true>(e, A, nodir) : launch_trace<GRID, 0, false>(e, A, nodir))
                 return rc;
         }
         else
@@ -1863,7 +1901,20 @@ extern "C" int sk_engine_read_rf(sk_engine_t* e, int32_t which, double* out)
     const double* src = which == 0 ? e->M.rf1 : which == 1 ? e->M.rf2 : e->M.rf2c;
     if (!src) return fail(SK_ERR_STATE, "no radiation field");
     if (int rc_bind = bind(e)) return rc_bind;
-    return fetch_doubles(e, src, (size_t)e->M.ncells * e->M.nrf, out);
+    // the device keeps the tables wavelength-major (SK_RF_INDEX): transpose into scratch, one transfer
+    const size_t len = (size_t)e->M.ncells * e->M.nrf;
+    if (e->scratch_len < len)
+    {
+        dev_free(e->scratch);
+        e->scratch = nullptr;
+        e->scratch_len = 0;
+        CK(dev_malloc(&e->scratch, len * sizeof(double)));
+        e->scratch_len = len;
+    }
+    dim3 grid((unsigned)((e->M.ncells + 31) / 32), (unsigned)((e->M.nrf + 31) / 32));
+    sk_rf_transpose_kernel<<<grid, dim3(32, 8), 0, e->stream>>>(src, e->scratch, e->M.ncells, e->M.nrf);
+    CK(cudaGetLastError());
+    return fetch_doubles(e, e->scratch, len, out);
 }
 
 // device -> caller buffer through a pinned staging buffer (pageable destinations otherwise crawl at page-fault speed)

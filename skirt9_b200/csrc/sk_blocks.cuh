@@ -13,7 +13,7 @@ enum {
 };
 enum {
     I_HLO, I_HHI, I_DRAW, I_NSCATT, I_STATE, I_ILAM, I_M, I_IX, I_IY, I_IZ, I_LEV, I_MINT, I_MIX, I_MIY, I_MIZ,
-    I_MLEV, I_HELL0, SK_NI = I_HELL0 + SK_MAX_INSTR
+    I_MLEV, I_RFELL, I_HELL0, SK_NI = I_HELL0 + SK_MAX_INSTR
 };
 // I_STATE bits
 #define SK_ST_LIVE 1
@@ -956,12 +956,12 @@ __device__ __forceinline__ bool sk_detect_geometry(const SkDevModel& M, const Sk
 }
 
 // Second half of FluxRecorder::detect (FluxRecorder.cpp:320-433): component routing and the tallies.
-// `sed_sm` (optional) is the block's shared-memory copy [SK_NUM_COMP][nl_stride] of this instrument's SED arrays: all
-// packets of a round hit the same few hundred SED bins, so they are combined per block before they reach the L2 atomics.
-__device__ __forceinline__ void sk_record(const SkDevInstr& q, int l, int ell, double L, double Lext, int nscatt,
-                                          bool primary_origin, double* sed_sm, int nl_stride)
+// Component routing by origin and number of scatterings (FluxRecorder.cpp:345-380): the array that takes the extincted
+// luminosity, and -- or -1 -- the transparent array and the array of the individual scattering level.
+__device__ __forceinline__ void sk_route(const SkDevInstr& q, int nscatt, bool primary_origin, int& c_ext, int& c_tr, int& c_lev)
 {
-    int c_ext, c_tr = -1, c_lev = -1;
+    c_tr = -1;
+    c_lev = -1;
     if (q.record_total_only)
         c_ext = SK_COMP_TOTAL;
     else if (primary_origin)
@@ -987,27 +987,66 @@ __device__ __forceinline__ void sk_record(const SkDevInstr& q, int l, int ell, d
         else
             c_ext = SK_COMP_SECONDARY_SCATTERED;
     }
-    if (q.include_sed)
+}
+// The SED arrays.  `sed_sm` (optional) is the block's shared-memory copy [SK_NUM_COMP][nl_stride] of this instrument's SED
+// arrays: all packets of a round hit the same few hundred SED bins, so they are combined per block before they reach the
+// L2 atomics.
+__device__ __forceinline__ void sk_record_sed(const SkDevInstr& q, int ell, double L, double Lext, int nscatt,
+                                              bool primary_origin, double* sed_sm, int nl_stride)
+{
+    int c_ext, c_tr, c_lev;
+    sk_route(q, nscatt, primary_origin, c_ext, c_tr, c_lev);
+    if (sed_sm)
     {
-        if (sed_sm)
+        atomicAdd(&sed_sm[c_ext * nl_stride + ell], Lext);
+        if (c_tr >= 0) atomicAdd(&sed_sm[c_tr * nl_stride + ell], L);
+        if (c_lev >= 0) atomicAdd(&sed_sm[c_lev * nl_stride + ell], Lext);
+    }
+    else
+    {
+        atomicAdd(&q.sed[c_ext][ell], Lext);  // LockFree::add, LockFree.hpp:23-37 -> native fp64 RED
+        if (c_tr >= 0) atomicAdd(&q.sed[c_tr][ell], L);
+        if (c_lev >= 0) atomicAdd(&q.sed[c_lev][ell], Lext);
+    }
+}
+// The frame arrays, index l + ell * Npix (FluxRecorder.cpp:433).  Called by ALL lanes of a warp (`hit` false for lanes
+// without a detection): lanes whose detections land on the same pixel, bin and component set -- the image of a point
+// source, a bright knot -- are summed over the warp with shuffles first, and one lane issues the atomics for them
+// (same-address atomics serialise in the L2).
+__device__ __forceinline__ void sk_record_ifu_warp(const SkDevInstr& q, bool hit, int l, int ell, double L, double Lext,
+                                                   int nscatt, bool primary_origin)
+{
+    const unsigned lane = threadIdx.x & 31;
+    const size_t index = hit ? (size_t)l + (size_t)ell * q.npix : 0;
+    // lanes with the same pixel-bin and the same number of scatterings route to the same arrays
+    const unsigned long long key = hit ? ((index << 8) | (unsigned long long)min(nscatt, 255)) + 1ull : 0ull;
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    const int maxcnt = __reduce_max_sync(0xffffffffu, hit ? __popc(peers) : 0);
+    double sumL = L, sumLext = Lext;
+    if (maxcnt > 1)
+    {
+        sumL = 0.;
+        sumLext = 0.;
+        unsigned rem = hit ? peers : 0u;
+        for (int k = 0; k < maxcnt; ++k)
         {
-            atomicAdd(&sed_sm[c_ext * nl_stride + ell], Lext);
-            if (c_tr >= 0) atomicAdd(&sed_sm[c_tr * nl_stride + ell], L);
-            if (c_lev >= 0) atomicAdd(&sed_sm[c_lev * nl_stride + ell], Lext);
-        }
-        else
-        {
-            atomicAdd(&q.sed[c_ext][ell], Lext);  // LockFree::add, LockFree.hpp:23-37 -> native fp64 RED
-            if (c_tr >= 0) atomicAdd(&q.sed[c_tr][ell], L);
-            if (c_lev >= 0) atomicAdd(&q.sed[c_lev][ell], Lext);
+            const int src = rem ? __ffs(rem) - 1 : (int)lane;
+            const double a = __shfl_sync(0xffffffffu, L, src), b = __shfl_sync(0xffffffffu, Lext, src);
+            if (rem)
+            {
+                sumL += a;
+                sumLext += b;
+            }
+            rem &= rem - 1;
         }
     }
-    if (q.include_ifu && l >= 0)
+    if (hit && lane == (unsigned)(__ffs(peers) - 1))
     {
-        size_t index = (size_t)l + (size_t)ell * q.npix;  // FluxRecorder.cpp:433
-        atomicAdd(&q.ifu[c_ext][index], Lext);
-        if (c_tr >= 0) atomicAdd(&q.ifu[c_tr][index], L);
-        if (c_lev >= 0) atomicAdd(&q.ifu[c_lev][index], Lext);
+        int c_ext, c_tr, c_lev;
+        sk_route(q, nscatt, primary_origin, c_ext, c_tr, c_lev);
+        atomicAdd(&q.ifu[c_ext][index], sumLext);
+        if (c_tr >= 0) atomicAdd(&q.ifu[c_tr][index], sumL);
+        if (c_lev >= 0) atomicAdd(&q.ifu[c_lev][index], sumLext);
     }
 }
 

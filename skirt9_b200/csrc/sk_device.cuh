@@ -108,7 +108,7 @@ struct SkDevModel {
     // wavelength grids
     const SkDevWlg* wlg;
     int32_t nwlg, rf_grid, nrf;
-    double *rf1, *rf2, *rf2c;
+    double *rf1, *rf2, *rf2c;    // radiation field tables, wavelength-major on the device: SK_RF_INDEX
     // sources
     const SkDevSource* src;
     const unsigned long long* Iv;
@@ -130,6 +130,12 @@ struct SkDevModel {
     // counters
     unsigned long long* counters;
 };
+
+// Radiation field tables on the device are wavelength-major, rf[ell * ncells + m] (the reference's Table<2> is [m][ell],
+// MediumSystem.hpp:883-885; sk_engine_read_rf transposes): the forward trace walks its rays in order of their wavelength
+// bin, so that the deposits of the rays in flight go to a few slices of ncells doubles each that stay in the L2 cache,
+// instead of to random 32-byte sectors of a table several times the size of the L2 (a read-modify-write in HBM each).
+#define SK_RF_INDEX(M, m, ell) ((size_t)(ell) * (size_t)(M).ncells + (size_t)(m))
 
 struct SkRunArgs {
     unsigned long long first, count;

@@ -22,8 +22,8 @@ __global__ void sk_dust_luminosity_kernel(const SkDevModel M)
     {
         double opacity = n * M.sec_kabs_rf[ell];
         double rf = 0.;
-        rf += M.rf1[(size_t)m * M.nrf + ell];
-        rf += M.rf2[(size_t)m * M.nrf + ell];
+        rf += M.rf1[SK_RF_INDEX(M, m, ell)];
+        rf += M.rf2[SK_RF_INDEX(M, m, ell)];
         Labs += opacity * rf;
     }
     M.sec_Lv[m] = Labs;
@@ -73,8 +73,8 @@ __global__ void sk_emission_spectrum_kernel(const SkDevModel M)
     for (int ell = 0; ell < nrf; ++ell)
     {
         double rf = 0.;
-        rf += M.rf1[(size_t)m * nrf + ell];
-        rf += M.rf2[(size_t)m * nrf + ell];
+        rf += M.rf1[SK_RF_INDEX(M, m, ell)];
+        rf += M.rf2[SK_RF_INDEX(M, m, ell)];
         double J = rf * factor / rfg.dlambda[ell];
         inputabs += M.sec_rfsig[ell] * (J + 0.) * rfg.dlambda[ell];
     }

@@ -34,6 +34,9 @@
 #ifndef SK_TRACE_MINBLOCKS
 #define SK_TRACE_MINBLOCKS 8        // the walks wait on L2 latency: resident warps count for more than a few spilled registers
 #endif
+#ifndef SK_TRACE_MINBLOCKS_STORE
+#define SK_TRACE_MINBLOCKS_STORE 6  // forward walk with radiation-field deposits: exp + logarithmic mean per segment
+#endif
 #ifndef SK_TRACE_MINBLOCKS_PEEL
 #define SK_TRACE_MINBLOCKS_PEEL 10  // the peel-off kernel keeps its (shared) direction in parameter space: fewer registers
 #endif
@@ -307,7 +310,7 @@ __device__ __forceinline__ double sk_interaction_depth(double u, double taupath,
 // rays, load new rays) that is entered when at least SK_REFILL_MIN lanes are idle, so that its cost is shared.
 // ---------------------------------------------------------------------------------------------------
 template <int GRID, int MODE, bool STORE, bool TABLES_IN_SMEM>
-__global__ void __launch_bounds__(SK_TRACE_BLOCK, MODE == 2 ? SK_TRACE_MINBLOCKS_PEEL : SK_TRACE_MINBLOCKS)
+__global__ void __launch_bounds__(SK_TRACE_BLOCK, MODE == 2 ? SK_TRACE_MINBLOCKS_PEEL : STORE ? SK_TRACE_MINBLOCKS_STORE : SK_TRACE_MINBLOCKS)
     sk_wf_trace(const SkDevModel M, const SkRunArgs A, const SkBank K, const SkObsDir obs)
 {
     extern __shared__ __align__(16) double smem[];
@@ -351,7 +354,7 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, MODE == 2 ? SK_TRACE_MINBLOCKS
     bool exhausted = false;            // the global list has been handed out completely
     // lane state: ACTIVE = walking a ray; PENDING = its ray has ended, results not yet written; REPLAY (MODE 0) = the lane is
     // on the second walk of its packet, to the interaction point; FOUND = that walk ended at an interaction point
-    enum { ACTIVE = 1, PENDING = 2, REPLAY = 4, FOUND = 8 };
+    enum { ACTIVE = 1, PENDING = 2, REPLAY = 4, FOUND = 8, FRONT = 16 };  // FRONT: an empty segment in front of the grid
     unsigned ls = 0;
     int slot = 0;
     SkDir kray;  // direction of the lane's ray; all peel-off rays (MODE 2) share the observer's direction, which stays in
@@ -361,9 +364,9 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, MODE == 2 ? SK_TRACE_MINBLOCKS
     st.cm = -1;
     double tau = 0, s = 0, limit = 0, section = 0;
     int nseg = 0;
-    // MODE 0 + STORE extras
-    double lum = 0, lnExtBeg = 0, extBeg = 1;
-    int rf_ell = -1;
+    // MODE 0 + STORE extras: luminosity of the packet, extinction factor at the start of the current segment, and the
+    // column of the radiation field table for the packet's wavelength bin (null: outside the grid, .cpp:643-644)
+    double lum = 0, extBeg = 1;
     double* rf = nullptr;
     double s_int = 0;  // result of a walk to the interaction point
 
@@ -379,6 +382,7 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, MODE == 2 ? SK_TRACE_MINBLOCKS
                 K.D(D_TAUPATH, slot) = tau;
                 cnt.fwd_paths++;
                 cnt.fwd_segs += nseg;
+                if (STORE && rf) cnt.rf += nseg - ((ls & FRONT) ? 1 : 0);  // one deposit per segment inside the grid
                 // no extinction along the path: the packet cannot scatter; sk_wf_advance terminates it (.cpp:702-706)
                 if (tau > 0.)
                 {
@@ -455,10 +459,9 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, MODE == 2 ? SK_TRACE_MINBLOCKS
                 section = K.D(D_SIGEXT, slot);
                 if (MODE == 0 && STORE)
                 {
-                    double lambda = K.D(D_LAMBDA, slot);
-                    rf_ell = sk_wlg_bin(M.wlg[M.rf_grid], lambda);  // MonteCarloSimulation.cpp:643
-                    rf = A.primary ? M.rf1 : M.rf2c;
-                    lum = K.D(D_W, slot) / lambda;
+                    const int rf_ell = K.I(I_RFELL, slot);
+                    rf = rf_ell >= 0 ? (A.primary ? M.rf1 : M.rf2c) + SK_RF_INDEX(M, 0, rf_ell) : nullptr;
+                    lum = K.D(D_W, slot) / K.D(D_LAMBDA, slot);
                 }
                 if (MODE == 1) limit = K.D(D_TAUINT, slot);
                 if (MODE == 2) limit = K.D(D_LIMIT, slot);
@@ -472,11 +475,7 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, MODE == 2 ? SK_TRACE_MINBLOCKS
                 s = 0.;
                 nseg = 0;
                 s_int = 0.;
-                if (MODE == 0 && STORE)
-                {
-                    lnExtBeg = 0.;
-                    extBeg = 1.;
-                }
+                if (MODE == 0 && STORE) extBeg = 1.;
                 if (p.m < 0)
                 {
                     // the path starts outside (or exactly on the border of) the grid: PathSegmentGenerator::moveInside
@@ -498,6 +497,7 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, MODE == 2 ? SK_TRACE_MINBLOCKS
                             // the empty segment in front of the grid (m = -1)
                             nseg++;
                             s += cumds;
+                            ls |= FRONT;
                         }
                     }
                     if (p.m < 0)
@@ -541,15 +541,37 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, MODE == 2 ? SK_TRACE_MINBLOCKS
                                 done = true;
                             }
                         }
-                        else if (STORE && rf_ell >= 0)
+                        else if (STORE && rf)
                         {
-                            double lnExtEnd = -tau1;
-                            double extEnd = exp(lnExtEnd);
-                            double extMean = sk_lnmean4(extEnd, extBeg, lnExtEnd, lnExtBeg);
-                            double Lds = lum * extMean * ds;
-                            atomicAdd(&rf[(size_t)m * M.nrf + rf_ell], Lds);  // MediumSystem.cpp:1294-1300
-                            cnt.rf++;
-                            lnExtBeg = lnExtEnd;
+                            // the logarithms of the extinction factors at both ends of the segment are -tau and -tau1
+                            const double extEnd = exp(-tau1);
+                            const double extMean = sk_lnmean4(extEnd, extBeg, -tau1, -tau);
+                            const double Lds = lum * extMean * ds;
+#ifdef SK_RF_AGGREGATE
+                            // (experiment, DESIGN.md section 9: lanes of the warp that deposit into the same cell and bin
+                            //  are summed with shuffles and one lane issues the atomic)
+                            {
+                                const unsigned am = __activemask();
+                                const unsigned peers = __match_any_sync(am, (unsigned long long)(rf + m));
+                                const int maxcnt = __reduce_max_sync(am, __popc(peers));
+                                double sum = Lds;
+                                if (maxcnt > 1)
+                                {
+                                    sum = 0.;
+                                    unsigned rem = peers;
+                                    for (int kk = 0; kk < maxcnt; ++kk)
+                                    {
+                                        const int src = rem ? __ffs(rem) - 1 : (int)lane;
+                                        const double t = __shfl_sync(am, Lds, src);
+                                        if (rem) sum += t;
+                                        rem &= rem - 1;
+                                    }
+                                }
+                                if (lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(&rf[m], sum);
+                            }
+#else
+                            atomicAdd(&rf[m], Lds);  // MediumSystem.cpp:1294-1300
+#endif
                             extBeg = extEnd;
                         }
                         if (!done)
@@ -836,6 +858,8 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK, SK_LAUNCH_MINBLOCKS) sk_wf_lau
                 K.I(I_DRAW, slot) = (int)g.draw;
                 K.I(I_NSCATT, slot) = 0;
                 K.I(I_ILAM, slot) = pp.ilam;
+                // the packet's bin of the radiation field grid (MonteCarloSimulation.cpp:643): fixed for its whole life
+                K.I(I_RFELL, slot) = M.rf_grid >= 0 ? sk_wlg_bin(M.wlg[M.rf_grid], pp.lambda) : -1;
                 K.I(I_M, slot) = c.m;
                 K.I(I_IX, slot) = c.ix;
                 K.I(I_IY, slot) = c.iy;
@@ -892,27 +916,42 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_detect(const SkDevModel 
     {
         int st = K.I(I_STATE, slot);
         const bool live = (st & SK_ST_LIVE) != 0;
-        if (live && j1 > j0)
+        if (j1 > j0)
         {
-            double lambda = K.D(D_LAMBDA, slot);
-            double x = K.D(D_RX, slot), y = K.D(D_RY, slot), z = K.D(D_RZ, slot);
-            double L = K.D(D_PEELW, slot) / lambda;
-            int nscatt = (st & SK_ST_SCATTER) ? K.I(I_NSCATT, slot) + 1 : 0;
+            // (every lane of the warp walks the instruments, dead slots with `live` false: the frame tallies are combined
+            //  over the warp, sk_record_ifu_warp)
+            double lambda = 1., x = 0., y = 0., z = 0., L = 0.;
+            int nscatt = 0;
+            if (live)
+            {
+                lambda = K.D(D_LAMBDA, slot);
+                x = K.D(D_RX, slot);
+                y = K.D(D_RY, slot);
+                z = K.D(D_RZ, slot);
+                L = K.D(D_PEELW, slot) / lambda;
+                nscatt = (st & SK_ST_SCATTER) ? K.I(I_NSCATT, slot) + 1 : 0;
+            }
             for (int j = j0; j < j1; ++j)
             {
                 const SkDevInstr& q = M.instr[j];
-                int l, ell;
-                if (!sk_detect_geometry(M, q, x, y, z, lambda, l, ell)) continue;
-                double Lext = L * exp(-K.D(D_PTAU, slot));
-                cnt.det++;
-                sk_record(q, l, ell, L, Lext, nscatt, A.primary != 0, nl_stride ? sed_sm + (j - j0) * per_instr : nullptr,
-                          nl_stride);
-                if (q.record_stats && q.include_sed)
+                int l = -1, ell = -1;
+                const bool hit = live && sk_detect_geometry(M, q, x, y, z, lambda, l, ell);
+                double Lext = 0.;
+                if (hit)
                 {
-                    K.D(D_HISTW0 + j, slot) += Lext;  // FluxRecorder.cpp:457-466
-                    K.I(I_HELL0 + j, slot) = ell;
+                    Lext = L * exp(-K.D(D_PTAU, slot));
+                    cnt.det++;
+                    if (q.include_sed)
+                        sk_record_sed(q, ell, L, Lext, nscatt, A.primary != 0, nl_stride ? sed_sm + (j - j0) * per_instr : nullptr,
+                                      nl_stride);
+                    if (q.record_stats && q.include_sed)
+                    {
+                        K.D(D_HISTW0 + j, slot) += Lext;  // FluxRecorder.cpp:457-466
+                        K.I(I_HELL0 + j, slot) = ell;
+                    }
+                    if (q.pix_slot >= 0 && l >= 0) sk_add_pixel_contribution(M, K, q, slot, l + ell * (int)q.npix, Lext);
                 }
-                if (q.pix_slot >= 0 && l >= 0) sk_add_pixel_contribution(M, K, q, slot, l + ell * (int)q.npix, Lext);
+                if (q.include_ifu) sk_record_ifu_warp(q, hit && l >= 0, l, ell, L, Lext, nscatt, A.primary != 0);
             }
         }
         if (last)
@@ -985,6 +1024,69 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_sample(const SkDevModel 
     sk_block_append(K.list, &K.ctl[SK_CTL_NLIST], live, slot);
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Forward rays in order of their radiation-field wavelength bin (segments that store the radiation field): a counting
+// sort of the ray list by I_RFELL (bin -1 = outside the grid first), list -> free_list (unused at this point of the round).
+// count: histogram of the bins; scan: exclusive prefix sum into the cursors; scatter: every block reserves a range per bin
+// for its tile of the list with one atomic per bin, its threads take ranks inside from shared-memory atomics.
+// ---------------------------------------------------------------------------------------------------
+#define SK_SORT_MAX_BINS 1024
+#define SK_SORT_TILE 2048
+__global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_bin_count(const SkBank K, const int nbins, unsigned int* counts)
+{
+    __shared__ unsigned int h[SK_SORT_MAX_BINS + 1];
+    for (int i = threadIdx.x; i <= nbins; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    const unsigned n = K.ctl[SK_CTL_NLIST];
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        atomicAdd(&h[K.I(I_RFELL, K.list[i]) + 1], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i <= nbins; i += blockDim.x)
+        if (h[i]) atomicAdd(&counts[i], h[i]);
+}
+__global__ void sk_wf_bin_scan(unsigned int* counts, const int nbins)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    unsigned int run = 0;
+    for (int i = 0; i <= nbins; ++i)
+    {
+        const unsigned int c = counts[i];
+        counts[i] = run;  // becomes the cursor of bin i
+        run += c;
+    }
+}
+__global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_bin_scatter(const SkBank K, const int nbins, unsigned int* cursor)
+{
+    __shared__ unsigned int h[SK_SORT_MAX_BINS + 1];
+    __shared__ unsigned int base[SK_SORT_MAX_BINS + 1];
+    const unsigned n = K.ctl[SK_CTL_NLIST];
+    const unsigned t0 = blockIdx.x * SK_SORT_TILE;
+    if (t0 >= n) return;
+    const unsigned t1 = min(t0 + SK_SORT_TILE, n);
+    for (int i = threadIdx.x; i <= nbins; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    int slot[SK_SORT_TILE / SK_EVENT_BLOCK], bin[SK_SORT_TILE / SK_EVENT_BLOCK];
+    unsigned rank[SK_SORT_TILE / SK_EVENT_BLOCK];
+#pragma unroll
+    for (int j = 0; j < SK_SORT_TILE / SK_EVENT_BLOCK; ++j)
+    {
+        const unsigned i = t0 + j * SK_EVENT_BLOCK + threadIdx.x;
+        bin[j] = -1;
+        if (i < t1)
+        {
+            slot[j] = K.list[i];
+            bin[j] = K.I(I_RFELL, slot[j]) + 1;
+            rank[j] = atomicAdd(&h[bin[j]], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i <= nbins; i += blockDim.x) base[i] = h[i] ? atomicAdd(&cursor[i], h[i]) : 0u;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < SK_SORT_TILE / SK_EVENT_BLOCK; ++j)
+        if (bin[j] >= 0) K.free_list[base[bin[j]] + rank[j]] = slot[j];
+}
 
 // ---------------------------------------------------------------------------------------------------
 // Draining: once every history of the segment has been handed out the bank empties geometrically (a packet survives a

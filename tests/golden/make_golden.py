@@ -162,6 +162,7 @@ def make_cfg4s():
     with tempfile.TemporaryDirectory() as d:
         log = run_reference("cfg4s", d)
         sed = read_columns(os.path.join(d, "cfg4s_sed_sed.dat"))
+        stats = read_columns(os.path.join(d, "cfg4s_sed_sedstats.dat"))
         cells = read_columns(os.path.join(d, "cfg4s_cells_cellprops.dat"))
         topo = parse_topology(os.path.join(d, "cfg4s_topo_treetop.dat"))
         rfJ = read_columns(os.path.join(d, "cfg4s_rf_J.dat"))
@@ -171,7 +172,7 @@ def make_cfg4s():
         sec = [float(x) for x in re.findall(r"dust-absorbed secondary luminosity in iteration \d+ is ([0-9.eE+-]+) Lsun", log)]
         dustlum = [float(x) for x in re.findall(r"Dust luminosity: ([0-9.eE+-]+) Lsun", log)]
         conv = re.search(r"Convergence reached after (\d+) iterations", log)
-        out = dict(sed=sed, mass_density_msun_pc3=cells[:, 6], cell_center_pc=cells[:, 1:4], cell_volume_pc3=cells[:, 4],
+        out = dict(sed=sed, sedstats=stats, mass_density_msun_pc3=cells[:, 6], cell_center_pc=cells[:, 1:4], cell_volume_pc3=cells[:, 4],
                    topology=topo, J_nu_shell=shell_average(cells, rfJ[:, 1:]), temperature=T[:, 1].astype(np.float32), absorbed_primary_lsun=np.array(prim),
                    absorbed_secondary_lsun=np.array(sec), dust_luminosity_lsun=np.array(dustlum), converged_after=int(conv.group(1)) if conv else -1,
                    num_packets=2e5)
@@ -179,16 +180,40 @@ def make_cfg4s():
     print("cfg4s:", {k: np.shape(v) for k, v in out.items()}, prim, sec, conv and conv.group(0))
 
 
+def make_cfg4s_hi(packets=2e6):
+    """High-statistics companion of cfg4s: the same ski (same tree and densities: -t 1) with ten times the packets per
+    segment, so that the tests can compare the noisy quantities (SED bins, shell-averaged radiation field, the iteration
+    log) against values whose own Monte-Carlo error is three times smaller."""
+    with tempfile.TemporaryDirectory() as d:
+        log = run_reference("cfg4s", d, packets=packets)
+        cells = read_columns(os.path.join(d, "cfg4s_cells_cellprops.dat"))
+        base = np.load(os.path.join(HERE, "cfg4s_ref.npz"))["mass_density_msun_pc3"]
+        assert np.array_equal(cells[:, 6], base), "the high-statistics run must see the inputs of the base fixture"
+        rfJ = read_columns(os.path.join(d, "cfg4s_rf_J.dat"))
+        prim = [float(x) for x in re.findall(r"dust-absorbed primary luminosity is ([0-9.eE+-]+) Lsun", log)]
+        sec = [float(x) for x in re.findall(r"dust-absorbed secondary luminosity in iteration \d+ is ([0-9.eE+-]+) Lsun", log)]
+        dustlum = [float(x) for x in re.findall(r"Dust luminosity: ([0-9.eE+-]+) Lsun", log)]
+        conv = re.search(r"Convergence reached after (\d+) iterations", log)
+        out = dict(sed=read_columns(os.path.join(d, "cfg4s_sed_sed.dat")),
+                   sedstats=read_columns(os.path.join(d, "cfg4s_sed_sedstats.dat")),
+                   J_nu_shell=shell_average(cells, rfJ[:, 1:]), absorbed_primary_lsun=np.array(prim),
+                   absorbed_secondary_lsun=np.array(sec), dust_luminosity_lsun=np.array(dustlum),
+                   converged_after=int(conv.group(1)) if conv else -1, num_packets=packets)
+    np.savez_compressed(os.path.join(HERE, "cfg4s_hi_ref.npz"), **out)
+    print("cfg4s_hi:", {k: np.shape(v) for k, v in out.items()}, prim, sec, conv and conv.group(0))
+
+
 def make_cfg7v():
     with tempfile.TemporaryDirectory() as d:
         log = run_reference("cfg7v", d)
         sed = read_columns(os.path.join(d, "cfg7v_sed_sed.dat"))
+        stats = read_columns(os.path.join(d, "cfg7v_sed_sedstats.dat"))
         cells = read_columns(os.path.join(d, "cfg7v_cells_cellprops.dat"))
         T = read_columns(os.path.join(d, "cfg7v_temp_dust_T.dat"))
         prim = [float(x) for x in re.findall(r"dust-absorbed primary luminosity is ([0-9.eE+-]+) Lsun", log)]
         sec = [float(x) for x in re.findall(r"dust-absorbed secondary luminosity in iteration \d+ is ([0-9.eE+-]+) Lsun", log)]
         conv = re.search(r"Convergence reached after (\d+) iterations", log)
-        out = dict(sed=sed, mass_density_msun_pc3=cells[:, 6], cell_center_pc=cells[:, 1:4], cell_volume_pc3=cells[:, 4],
+        out = dict(sed=sed, sedstats=stats, mass_density_msun_pc3=cells[:, 6], cell_center_pc=cells[:, 1:4], cell_volume_pc3=cells[:, 4],
                    temperature=T[:, 1].astype(np.float32), absorbed_primary_lsun=np.array(prim),
                    absorbed_secondary_lsun=np.array(sec), converged_after=int(conv.group(1)) if conv else -1, num_packets=2e5)
     np.savez_compressed(os.path.join(HERE, "cfg7v_ref.npz"), **out)

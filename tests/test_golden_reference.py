@@ -236,10 +236,37 @@ def test_engine_matches_reference_cfg2s(engine_lib):
     check_cfg2s(sim, e, g, n)
 
 
+def sed_bins_within_statistics(sim, e, g, nsigma=4.0, nsigma_secondary=5.0):
+    """Every SED column of a dust-emission run against the reference's, bin by bin: |F - F_ref| <= nsigma sqrt(R^2 + R_ref^2)
+    max(F_ref, F_ref_total), R from both sides' Sum w^k statistics (those of the total flux, FluxRecorder.cpp:457-466;
+    SURVEY.md 8d), in the bins whose error estimate is reliable by the reference's own rule (R < 0.1 and VOV < 0.1 on both
+    sides, tests/mcstats.py): in the far-UV bins of this model a handful of heavily weighted packets carry the flux and Sum
+    w^k says nothing about the true scatter (the oracle with other seeds is 14 "sigma" off there).  The columns that
+    contain dust emission get nsigma_secondary: the statistics of the final segment do not know about the noise of the
+    radiation field that set the dust temperatures.  The sums over the reliable bins must agree within the quadrature sum
+    of the bins' errors."""
+    from tests import mcstats
+    sed = g["sed"]
+    own, ref = e.read_sed_stats(0), g["sedstats"][:, 1:].T
+    ok = mcstats.reliable(own) & mcstats.reliable(ref)
+    assert ok.sum() >= 0.8 * len(ok)
+    sigma = np.hypot(mcstats.rel_error(own), mcstats.rel_error(ref))
+    for col, comp in ((2, abi.SK_COMP_TRANSPARENT), (3, abi.SK_COMP_PRIMARY_DIRECT), (4, abi.SK_COMP_PRIMARY_SCATTERED),
+                      (5, abi.SK_COMP_SECONDARY_DIRECT), (6, abi.SK_COMP_SECONDARY_SCATTERED),
+                      (7, abi.SK_COMP_SECONDARY_TRANSPARENT), (1, abi.SK_COMP_TOTAL)):
+        ns = nsigma if col in (2, 3, 4) else nsigma_secondary
+        f = sim.sed_flux_density(e, 0, comp)
+        scale = np.maximum(sed[:, col], sed[:, 1])
+        z = np.abs(f - sed[:, col])[ok] / np.maximum(sigma * scale, 1e-300)[ok]
+        assert np.all(z <= ns), (comp, int(np.argmax(z)), float(z.max()))
+        err_sum = np.sqrt(((sigma * scale)[ok] ** 2).sum())
+        assert abs(f[ok].sum() - sed[ok, col].sum()) <= ns * err_sum, comp
+
+
 # ---------------------------------------------------------------- dust emission with secondary iterations (cfg4s)
 def cfg4s_from_reference(num_packets):
     g = load("cfg4s")
-    sim = configs.cfg4(num_packets=num_packets, seed=0)
+    sim = configs.cfg4(num_packets=num_packets, seed=0, record_statistics=True)
     pc = H.PC
     sim.grid = H.FileTreeSpatialGrid(-pc, pc, -pc, pc, -pc, pc, g["topology"], policyOrder=True)
     sim.density = g["mass_density_msun_pc3"] * RHO / sim.medium.mix.MU
@@ -249,7 +276,7 @@ def cfg4s_from_reference(num_packets):
     return sim, g
 
 
-def check_cfg4s(sim, e, g, n, tol_scale=1.0):
+def check_cfg4s(sim, e, g, n, tol_scale=1.0, nsigma=4.0):
     LSUN = H.LSUN
     conv = sim.convergence
     # the reference's log (MonteCarloSimulation.cpp:193-214): absorbed primary luminosity, then per iteration the
@@ -265,15 +292,8 @@ def check_cfg4s(sim, e, g, n, tol_scale=1.0):
     sed = g["sed"]
     lam = sim.defaultWavelengthGrid.lambdav
     np.testing.assert_allclose(lam * 1e6, sed[:, 0], rtol=1e-9)
-    peak = sed[:, 1].max()
-    for col, comp in ((2, abi.SK_COMP_TRANSPARENT), (3, abi.SK_COMP_PRIMARY_DIRECT), (4, abi.SK_COMP_PRIMARY_SCATTERED),
-                      (5, abi.SK_COMP_SECONDARY_DIRECT), (6, abi.SK_COMP_SECONDARY_SCATTERED),
-                      (7, abi.SK_COMP_SECONDARY_TRANSPARENT), (1, abi.SK_COMP_TOTAL)):
-        f = sim.sed_flux_density(e, 0, comp)
-        ok = sed[:, col] > 0.02 * sed[:, col].max()
-        # 50 bins, 2e5 packets per segment on the reference side: a few per cent of noise per bin
-        np.testing.assert_allclose(f[ok], sed[ok, col], rtol=0.12 * tol_scale, atol=0.003 * peak, err_msg=f"comp {comp}")
-        assert f.sum() == pytest.approx(sed[:, col].sum(), rel=0.02 * tol_scale), comp
+    sed_bins_within_statistics(sim, e, g, nsigma, nsigma + 1.0)
+    sed_bins_within_statistics(sim, e, load("cfg4s_hi"), nsigma, nsigma + 1.0)
     # radiation field rf1+rf2 after the run, volume-weighted in radial shells, per wavelength bin
     J = sim.mean_intensity_nu(e, 0) + sim.mean_intensity_nu(e, 1)
     r = np.linalg.norm(g["cell_center_pc"], axis=1)
@@ -286,10 +306,22 @@ def check_cfg4s(sim, e, g, n, tol_scale=1.0):
     ok = ref > 0.05 * ref.max(axis=0, keepdims=True)
     ok[:3] = False       # the innermost shells hold a handful of cells
     ok[:, 33:] = False   # beyond 150 micron only a few (heavily weighted) packets contribute per shell on either side
-    np.testing.assert_allclose(Jshell[ok], ref[ok], rtol=0.15 * tol_scale)
+    # The reference records no statistics for the radiation field, so its noise is measured from the reference itself:
+    # the fixture run (2e5 packets per segment) against the same ski with ten times the packets (cfg4s_hi) gives the rms
+    # relative noise of a shell value per wavelength bin at 2e5 packets, which scales with 1/sqrt(packets).
+    hi = load("cfg4s_hi")
+    nb, nh = float(g["num_packets"]), float(hi["num_packets"])
+    dev = ((ref - hi["J_nu_shell"]) / hi["J_nu_shell"])[ok]
+    noise_base = math.sqrt(float(np.mean(dev ** 2)) / (1.0 + nb / nh))        # rms over the tested shell values, at nb packets
+    assert 0.01 < noise_base < 0.05
+    for name, target, nt in (("fixture", ref, nb), ("hi", hi["J_nu_shell"], nh)):
+        sigma = noise_base * math.sqrt(nb / n + nb / nt)
+        np.testing.assert_allclose(Jshell[ok], target[ok], rtol=5.0 * sigma, err_msg=name)   # 5 x the rms noise
     tot, tot_ref = (Jshell * den[:, None])[3:].sum(axis=0), (ref * den[:, None])[3:].sum(axis=0)
     strong = tot_ref > 0.01 * tot_ref.max()                           # bins that hold more than 1 % of the peak
     np.testing.assert_allclose(tot[strong], tot_ref[strong], rtol=0.08 * tol_scale)   # per bin, volume-integrated
+    tot_hi = (hi["J_nu_shell"] * den[:, None])[3:].sum(axis=0)
+    np.testing.assert_allclose(tot[strong], tot_hi[strong], rtol=0.04 * tol_scale * max(1.0, math.sqrt(nh / n) / 3))
     assert tot.sum() == pytest.approx(tot_ref.sum(), rel=0.01 * tol_scale)
 
 
@@ -298,7 +330,7 @@ def test_oracle_matches_reference_cfg4s_dust_emission():
     sim, g = cfg4s_from_reference(n)
     e = sim.configure(OracleEngine(sim.config_struct()))
     sim.run(e)
-    check_cfg4s(sim, e, g, n, tol_scale=2.0)
+    check_cfg4s(sim, e, g, n, tol_scale=2.0, nsigma=5.0)
 
 
 @pytest.mark.gpu
