@@ -246,10 +246,13 @@ def make_sim(name, total_packets, statistics=False):
                         num_pixels=256, record_statistics=False).setup()
 
 
-def run_port_once(num_packets, name="cfg2"):
+def run_port_once(num_packets, name="cfg2", sim=None):
     """Fallback when oracle/_ref is absent (or the workload has no ski): times the single-threaded C port of the oracle."""
     from tests.oracle_lib import OracleEngine
-    sim = make_sim(name, num_packets)
+    if sim is None:
+        sim = make_sim(name, num_packets)
+    else:
+        sim.numPackets = num_packets     # the set-up (grid, densities) does not depend on the number of packets
     e = sim.configure(OracleEngine(sim.config_struct()))
     t = time.time()
     sim.run(e)
@@ -257,7 +260,7 @@ def run_port_once(num_packets, name="cfg2"):
     return e.counters()["packets"] / dt, dt
 
 
-def cpu_baseline(sample_packets, name="cfg2"):
+def cpu_baseline(sample_packets, name="cfg2", sim=None):
     cores = os.cpu_count() or 1
     w = WORKLOADS[name]
     if os.path.exists(REF_EXE) and w["ski"]:
@@ -267,7 +270,7 @@ def cpu_baseline(sample_packets, name="cfg2"):
                 "sample": f"unmodified SKIRT 9 (oracle/_ref) -t {cores}, same {name} ski, {sample_packets:g} packets per segment, "
                           f"log time stamps of the emission segments: {secs:.3f} s"}
     n = min(sample_packets, 2e5)
-    rate, secs = run_port_once(n, name)
+    rate, secs = run_port_once(n, name, sim)
     return {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
             "sample": f"oracle/sk_oracle.c single thread, {n:g} packets in {secs:.1f} s"}
 
@@ -684,7 +687,7 @@ def native_arm(args):
         if name == "cfg4":
             line["iterations"] = len(sim.convergence)
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(args.cpu_packets or w["cpu_packets"], name)
+            line["cpu_baseline"] = cpu_baseline(args.cpu_packets or w["cpu_packets"], name, sim)
             if LAST_REFERENCE_SETUP:
                 line["cpu_baseline"]["whole_run"] = dict(LAST_REFERENCE_SETUP)
             if name == "cfg2":

@@ -50,7 +50,9 @@ typedef struct sk_config {
     double path_length_bias;     /* Configuration::pathLengthBias() (PhotonPacketOptions.hpp:83) */
     double min_weight_reduction; /* Configuration::minWeightReduction() (PhotonPacketOptions.hpp:69) */
     int32_t device;              /* CUDA device ordinal this engine instance owns (one engine per GPU) */
-    int32_t reserved;
+    int32_t explicit_absorption; /* Configuration::explicitAbsorption() (PhotonPacketOptions): interaction points are drawn
+                                    in scattering optical depth and the packet is attenuated by exp(-tau_abs) instead of
+                                    being multiplied with the albedo (MonteCarloSimulation.cpp:567-570, 727-731, 757-762) */
 } sk_config_t;
 
 /* ---- Wavelength grids: DisjointWavelengthGrid::bin (DisjointWavelengthGrid.cpp:332-341) -------- */

@@ -69,7 +69,9 @@ typedef struct {
 
 typedef struct {
     int m;
-    double ds, s, tau;
+    double ds, s;
+    double tau;    /* cumulative extinction optical depth, or scattering optical depth with explicit absorption */
+    double tauabs; /* cumulative absorption optical depth with explicit absorption, else zero (SpatialGridPath.hpp:98-99) */
 } seg_t;
 
 typedef struct sko_engine {
@@ -1803,7 +1805,8 @@ static int wlg_bin(const sk_wavelength_grid_t* g, double lambda)
     return g->ell[lo];
 }
 
-/* MediumSystem::setExtinctionOpticalDepths, single constant-section medium branch, MediumSystem.cpp:849-871;
+/* MediumSystem::setExtinctionOpticalDepths, single constant-section medium branch, MediumSystem.cpp:849-871 -- or, with
+ * explicit absorption, MediumSystem::setScatteringAndAbsorptionOpticalDepths (MonteCarloSimulation.cpp:567-570);
  * SpatialGridPath::addSegment, SpatialGridPath.cpp:41-48 */
 static void set_extinction_optical_depths(sko_engine_t* e, const packet_t* pp)
 {
@@ -1826,15 +1829,37 @@ static void set_extinction_optical_depths(sko_engine_t* e, const packet_t* pp)
             sg->ds = g.ds;
             sg->s = s;
             sg->tau = 0.;
+            sg->tauabs = 0.;
         }
     }
-    double tau = 0.;
-    double section = e->sig_ext[pp->ilam];
-    for (int n = 0; n < e->nsegs; ++n)
+    if (e->cfg.explicit_absorption)
     {
-        seg_t* sg = &e->segs[n];
-        if (sg->m >= 0) tau += section * e->dens[sg->m] * sg->ds;
-        sg->tau = tau;
+        /* MediumSystem::setScatteringAndAbsorptionOpticalDepths, single constant-section medium, MediumSystem.cpp:905-934 */
+        double tauSca = 0., tauAbs = 0.;
+        double sectionSca = e->sig_sca[pp->ilam], sectionAbs = e->sig_abs[pp->ilam];
+        for (int n = 0; n < e->nsegs; ++n)
+        {
+            seg_t* sg = &e->segs[n];
+            if (sg->m >= 0)
+            {
+                double ns = e->dens[sg->m] * sg->ds;
+                tauSca += sectionSca * ns;
+                tauAbs += sectionAbs * ns;
+            }
+            sg->tau = tauSca;
+            sg->tauabs = tauAbs;
+        }
+    }
+    else
+    {
+        double tau = 0.;
+        double section = e->sig_ext[pp->ilam];
+        for (int n = 0; n < e->nsegs; ++n)
+        {
+            seg_t* sg = &e->segs[n];
+            if (sg->m >= 0) tau += section * e->dens[sg->m] * sg->ds;
+            sg->tau = tau;
+        }
     }
     e->cnt.forward_paths++;
     e->cnt.forward_segments += e->nsegs;
@@ -1877,7 +1902,7 @@ static void store_radiation_field(sko_engine_t* e, int primary, const packet_t* 
     for (int n = 0; n < e->nsegs; ++n)
     {
         const seg_t* sg = &e->segs[n];
-        double lnExtEnd = -sg->tau;
+        double lnExtEnd = -(sg->tau + sg->tauabs); /* Segment::tauExt(), SpatialGridPath.hpp:108 */
         double extEnd = exp(lnExtEnd);
         if (sg->m >= 0)
         {
@@ -1892,8 +1917,9 @@ static void store_radiation_field(sko_engine_t* e, int primary, const packet_t* 
 }
 
 /* SpatialGridPath::findInteractionPoint, SpatialGridPath.cpp:164-206 (extinction-only members) */
-static void find_interaction_point(const sko_engine_t* e, double tauinteract, int* m_out, double* s_out)
+static void find_interaction_point(const sko_engine_t* e, double tauinteract, int* m_out, double* s_out, double* tauabs_out)
 {
+    *tauabs_out = 0.;
     if (e->nsegs == 0)
     {
         *m_out = -1;
@@ -1914,16 +1940,19 @@ static void find_interaction_point(const sko_engine_t* e, double tauinteract, in
     {
         *m_out = e->segs[0].m;
         *s_out = interp_linlin(tauinteract, 0., e->segs[0].tau, 0., e->segs[0].s);
+        *tauabs_out = interp_linlin(tauinteract, 0., e->segs[0].tau, 0., e->segs[0].tauabs);
     }
     else if (lo < e->nsegs)
     {
         *m_out = e->segs[lo].m;
         *s_out = interp_linlin(tauinteract, e->segs[lo - 1].tau, e->segs[lo].tau, e->segs[lo - 1].s, e->segs[lo].s);
+        *tauabs_out = interp_linlin(tauinteract, e->segs[lo - 1].tau, e->segs[lo].tau, e->segs[lo - 1].tauabs, e->segs[lo].tauabs);
     }
     else
     {
         *m_out = e->segs[lo - 1].m;
         *s_out = e->segs[lo - 1].s;
+        *tauabs_out = e->segs[lo - 1].tauabs;
     }
 }
 
@@ -2517,18 +2546,23 @@ static void simulate_forced_propagation(sko_engine_t* e, rng_t* g, packet_t* pp,
         pp->W *= weight;
     }
     int m;
-    double s;
-    find_interaction_point(e, tau, &m, &s);
-    /* MediumSystem::albedoForScattering, MediumSystem.cpp:678-693 (single dust medium: ksca/kext) */
-    double albedo = 0.;
-    if (m >= 0)
+    double s, tauAbs;
+    find_interaction_point(e, tau, &m, &s, &tauAbs);
+    if (e->cfg.explicit_absorption)
+        pp->W *= -expm1(-taupath) * exp(-tauAbs); /* MonteCarloSimulation.cpp:727-731 */
+    else
     {
-        double n = e->dens[m];
-        double ksca = n * e->sig_sca[pp->ilam];
-        double kext = n * e->sig_ext[pp->ilam];
-        albedo = kext > 0. ? ksca / kext : 0.;
+        /* MediumSystem::albedoForScattering, MediumSystem.cpp:678-693 (single dust medium: ksca/kext) */
+        double albedo = 0.;
+        if (m >= 0)
+        {
+            double n = e->dens[m];
+            double ksca = n * e->sig_sca[pp->ilam];
+            double kext = n * e->sig_ext[pp->ilam];
+            albedo = kext > 0. ? ksca / kext : 0.;
+        }
+        pp->W *= -expm1(-taupath) * albedo;
     }
-    pp->W *= -expm1(-taupath) * albedo;
     /* PhotonPacket::propagate, PhotonPacket.cpp:107-111 */
     pp->r[0] += s * pp->k[0];
     pp->r[1] += s * pp->k[1];
@@ -2544,7 +2578,10 @@ static int simulate_nonforced_propagation(sko_engine_t* e, rng_t* g, packet_t* p
     gen_t gen;
     gen_start(&gen, pp->r, pp->k);
     double tau = 0., s = 0.;
-    double section = e->sig_ext[pp->ilam];
+    /* with explicit absorption the walk is in scattering optical depth, setInteractionPointUsingScatteringAndAbsorption
+       (MediumSystem.cpp:1075-1110), and the weight is the absorption along the way instead of the albedo (.cpp:757-762) */
+    const int explicit_abs = e->cfg.explicit_absorption;
+    double section = explicit_abs ? e->sig_sca[pp->ilam] : e->sig_ext[pp->ilam];
     e->cnt.forward_paths++;
     while (gen_next(e, &gen))
     {
@@ -2561,6 +2598,7 @@ static int simulate_nonforced_propagation(sko_engine_t* e, rng_t* g, packet_t* p
             double ksca = n * e->sig_sca[pp->ilam];
             double kext = n * e->sig_ext[pp->ilam];
             double albedo = kext > 0. ? ksca / kext : 0.;
+            if (explicit_abs) albedo = exp(-(tauinteract * e->sig_abs[pp->ilam] / e->sig_sca[pp->ilam]));
             pp->W *= albedo;
             pp->r[0] += sint * pp->k[0];
             pp->r[1] += sint * pp->k[1];

@@ -434,7 +434,6 @@ std::string GpuLifeCycle::unsupportedReason() const
     if (config->hasPolarization()) return "polarization";
     if (config->hasMovingMedia()) return "moving media";
     if (!config->hasConstantPerceivedWavelength()) return "wavelengths that change during the life cycle";
-    if (config->explicitAbsorption()) return "explicit absorption";
     if (config->hasDynamicState()) return "dynamic medium state";
     if (config->hasPrimaryIterations() || config->hasMergedIterations()) return "primary / merged iterations";
     if (config->hasGasEmission()) return "gas emission";
@@ -526,6 +525,7 @@ void GpuLifeCycle::configureEngine(int device)
     c.min_scatt_events = config->minScattEvents();
     c.path_length_bias = config->pathLengthBias();
     c.min_weight_reduction = config->minWeightReduction();
+    c.explicit_absorption = config->explicitAbsorption();
     c.device = device;
     check(sk_engine_create(&c, &_e));
 

@@ -34,7 +34,7 @@ _ip = C.POINTER(C.c_int32)
 class SkConfig(C.Structure):
     _fields_ = [("seed", C.c_uint32), ("force_scattering", C.c_int32), ("min_scatt_events", C.c_int32),
                 ("path_length_bias", C.c_double), ("min_weight_reduction", C.c_double), ("device", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("explicit_absorption", C.c_int32)]
 
 
 class SkWavelengthGrid(C.Structure):

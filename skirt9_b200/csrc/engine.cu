@@ -335,6 +335,7 @@ extern "C" int sk_engine_create(const sk_config_t* config, sk_engine_t** out)
     e->M.seed = config->seed;
     e->M.force_scattering = config->force_scattering;
     e->M.min_scatt_events = config->min_scatt_events;
+    e->M.explicit_absorption = config->explicit_absorption != 0;
     e->M.path_length_bias = config->path_length_bias;
     e->M.min_weight_reduction = config->min_weight_reduction;
     e->M.rf_grid = -1;

@@ -623,6 +623,9 @@ struct SkStepper<2> {
     }
 };
 
+#ifndef SK_VOR_UNROLL
+#define SK_VOR_UNROLL 2  // neighbour records requested together
+#endif
 // ---- Voronoi mesh: the exit point is the nearest intersection with the bisecting planes towards the neighbouring sites
 // and with the domain walls
 template <>
@@ -640,6 +643,13 @@ struct SkStepper<3> {
         cm = p.m;
     }
     __device__ __forceinline__ SkCellPos cell(const SkDevModel&) const { return SkCellPos{cm, 0, 0, 0, 0}; }
+    // The exit distance towards neighbour i is the quotient s_i = num_i / den_i with den_i = n.k > 0 (bisecting plane,
+    // n = p_i - p_r; VoronoiMeshSnapshot.cpp:1108-1129) or |k_axis| (domain wall, .cpp:1134-1143).  The reference divides
+    // for every neighbour and keeps the smallest positive quotient; here the candidates are compared by cross-multiplication
+    // (s_i < s_q <=> num_i den_q < num_q den_i, all den > 0) and only the winner is divided -- the same operands, so the
+    // same ds; the ~15 divisions per crossing were two thirds of the loop's instructions.  Neighbours are taken four at a
+    // time with all their site records requested before the first is used (a wall index loads record 0, unused), so that
+    // four L2 round trips overlap instead of following each other.
     template <bool OBSERVER>
     __device__ __forceinline__ void exit(const SkDevModel& M, const SkDevModel* __restrict__ Mg, const SkSmemTables&,
                                          SkLocalCounters& cnt, const SkDir& k, int& m_out, double& dens_out, double& ds_out)
@@ -647,45 +657,53 @@ struct SkStepper<3> {
         while (true)
         {
             const double4 pr = sk_ld_rec(&M.vrec[cm]);
-            sq = DBL_MAX;
             const int NO_INDEX = -99;
+            double numq = DBL_MAX, denq = 1.0;
             mq = NO_INDEX;
             const int i1 = (int)__ldg(&M.vnbr_off[cm + 1]);
-            for (int i = (int)__ldg(&M.vnbr_off[cm]); i < i1; ++i)
+            for (int i = (int)__ldg(&M.vnbr_off[cm]); i < i1; i += SK_VOR_UNROLL)
             {
-                const int mi = __ldg(&M.vnbr[i]);
-                double si = 0;
-                if (mi >= 0)
+                int mi[SK_VOR_UNROLL];
+                double4 pj[SK_VOR_UNROLL];
+#pragma unroll
+                for (int u = 0; u < SK_VOR_UNROLL; ++u) mi[u] = __ldg(&M.vnbr[min(i + u, i1 - 1)]);  // (a repeated last entry never wins again)
+#pragma unroll
+                for (int u = 0; u < SK_VOR_UNROLL; ++u) pj[u] = sk_ld_rec(&M.vrec[max(mi[u], 0)]);
+#pragma unroll
+                for (int u = 0; u < SK_VOR_UNROLL; ++u)
                 {
-                    const double4 pi = sk_ld_rec(&M.vrec[mi]);
-                    const double nx = pi.x - pr.x, ny = pi.y - pr.y, nz = pi.z - pr.z;
-                    const double ndotk = nx * k.kx + ny * k.ky + nz * k.kz;
-                    if (ndotk > 0)
+                    double num, den;
+                    if (mi[u] >= 0)
                     {
+                        const double4 pi = pj[u];
+                        const double nx = pi.x - pr.x, ny = pi.y - pr.y, nz = pi.z - pr.z;
+                        den = nx * k.kx + ny * k.ky + nz * k.kz;
                         const double px = 0.5 * (pi.x + pr.x), py = 0.5 * (pi.y + pr.y), pz = 0.5 * (pi.z + pr.z);
-                        si = (nx * (px - rx) + ny * (py - ry) + nz * (pz - rz)) / ndotk;
+                        num = nx * (px - rx) + ny * (py - ry) + nz * (pz - rz);
                     }
-                }
-                else
-                {
-                    switch (mi)
+                    else
                     {
-                        case -1: si = (M.ext[0] - rx) / k.kx; break;
-                        case -2: si = (M.ext[3] - rx) / k.kx; break;
-                        case -3: si = (M.ext[1] - ry) / k.ky; break;
-                        case -4: si = (M.ext[4] - ry) / k.ky; break;
-                        case -5: si = (M.ext[2] - rz) / k.kz; break;
-                        default: si = (M.ext[5] - rz) / k.kz; break;
+                        const int axis = (-mi[u] - 1) >> 1;
+                        const double wall = M.ext[axis + (((-mi[u] - 1) & 1) ? 3 : 0)];
+                        num = wall - (axis == 0 ? rx : axis == 1 ? ry : rz);
+                        den = axis == 0 ? k.kx : axis == 1 ? k.ky : k.kz;
+                        if (den < 0.)
+                        {
+                            num = -num;
+                            den = -den;
+                        }
                     }
-                }
-                if (si > 0 && si < sq)
-                {
-                    sq = si;
-                    mq = mi;
+                    if (den > 0. && num > 0. && num * denq < numq * den)
+                    {
+                        numq = num;
+                        denq = den;
+                        mq = mi[u];
+                    }
                 }
             }
             if (mq != NO_INDEX)
             {
+                sq = numq / denq;
                 m_out = cm;
                 dens_out = pr.w;
                 ds_out = sq;

@@ -76,6 +76,7 @@ struct SkDevModel {
     // configuration
     uint32_t seed;
     int32_t force_scattering, min_scatt_events;
+    int32_t explicit_absorption;  // interaction points in scattering optical depth, weight exp(-tau_abs) (.cpp:567-570,727-731)
     double path_length_bias, min_weight_reduction;
     // grid
     int32_t grid_kind;  // 1 cartesian, 2 octree, 3 voronoi

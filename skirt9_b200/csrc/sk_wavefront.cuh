@@ -37,6 +37,9 @@
 #ifndef SK_TRACE_MINBLOCKS_STORE
 #define SK_TRACE_MINBLOCKS_STORE 6  // forward walk with radiation-field deposits: exp + logarithmic mean per segment
 #endif
+#ifndef SK_TRACE_MINBLOCKS_VORONOI
+#define SK_TRACE_MINBLOCKS_VORONOI 8  // (measured: 8 blocks with two neighbour records in flight beat 5 blocks with four)
+#endif
 #ifndef SK_TRACE_MINBLOCKS_PEEL
 #define SK_TRACE_MINBLOCKS_PEEL 10  // the peel-off kernel keeps its (shared) direction in parameter space: fewer registers
 #endif
@@ -310,7 +313,10 @@ __device__ __forceinline__ double sk_interaction_depth(double u, double taupath,
 // rays, load new rays) that is entered when at least SK_REFILL_MIN lanes are idle, so that its cost is shared.
 // ---------------------------------------------------------------------------------------------------
 template <int GRID, int MODE, bool STORE, bool TABLES_IN_SMEM>
-__global__ void __launch_bounds__(SK_TRACE_BLOCK, MODE == 2 ? SK_TRACE_MINBLOCKS_PEEL : STORE ? SK_TRACE_MINBLOCKS_STORE : SK_TRACE_MINBLOCKS)
+__global__ void __launch_bounds__(SK_TRACE_BLOCK, GRID == 3   ? SK_TRACE_MINBLOCKS_VORONOI
+                                                  : MODE == 2 ? SK_TRACE_MINBLOCKS_PEEL
+                                                  : STORE     ? SK_TRACE_MINBLOCKS_STORE
+                                                              : SK_TRACE_MINBLOCKS)
     sk_wf_trace(const SkDevModel M, const SkRunArgs A, const SkBank K, const SkObsDir obs)
 {
     extern __shared__ __align__(16) double smem[];
@@ -354,7 +360,9 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, MODE == 2 ? SK_TRACE_MINBLOCKS
     bool exhausted = false;            // the global list has been handed out completely
     // lane state: ACTIVE = walking a ray; PENDING = its ray has ended, results not yet written; REPLAY (MODE 0) = the lane is
     // on the second walk of its packet, to the interaction point; FOUND = that walk ended at an interaction point
-    enum { ACTIVE = 1, PENDING = 2, REPLAY = 4, FOUND = 8, FRONT = 16 };  // FRONT: an empty segment in front of the grid
+    // FRONT: an empty segment in front of the grid; NOSCAT: explicit absorption in a medium that does not scatter at this
+    // wavelength (the walk then accumulates the extinction for the radiation field and reports a zero path optical depth)
+    enum { ACTIVE = 1, PENDING = 2, REPLAY = 4, FOUND = 8, FRONT = 16, NOSCAT = 32 };
     unsigned ls = 0;
     int slot = 0;
     SkDir kray;  // direction of the lane's ray; all peel-off rays (MODE 2) share the observer's direction, which stays in
@@ -366,7 +374,7 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, MODE == 2 ? SK_TRACE_MINBLOCKS
     int nseg = 0;
     // MODE 0 + STORE extras: luminosity of the packet, extinction factor at the start of the current segment, and the
     // column of the radiation field table for the packet's wavelength bin (null: outside the grid, .cpp:643-644)
-    double lum = 0, extBeg = 1;
+    double lum = 0, extBeg = 1, extfac = 1;  // extfac: extinction over interaction optical depth (1 unless explicit absorption)
     double* rf = nullptr;
     double s_int = 0;  // result of a walk to the interaction point
 
@@ -379,6 +387,7 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, MODE == 2 ? SK_TRACE_MINBLOCKS
             ls &= ~PENDING;
             if (MODE == 0 && !(ls & REPLAY))
             {
+                if (ls & NOSCAT) tau = 0.;
                 K.D(D_TAUPATH, slot) = tau;
                 cnt.fwd_paths++;
                 cnt.fwd_segs += nseg;
@@ -457,6 +466,22 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, MODE == 2 ? SK_TRACE_MINBLOCKS
                     kray.load(K.D(D_KX, slot), K.D(D_KY, slot), K.D(D_KZ, slot), K.D(D_IKX, slot), K.D(D_IKY, slot),
                               K.D(D_IKZ, slot), GRID == 2 ? M.lat_invh : nullptr);
                 section = K.D(D_SIGEXT, slot);
+                if (MODE != 2 && M.explicit_absorption)
+                {
+                    // the walk to the interaction point is in scattering optical depth (MediumSystem.cpp:905-934, 1075-1110);
+                    // the extinction that attenuates the radiation field deposits is a fixed multiple of it
+                    const double sca = M.sig_sca[K.I(I_ILAM, slot)];
+                    if (sca > 0.)
+                    {
+                        if (STORE) extfac = section / sca;
+                        section = sca;
+                    }
+                    else
+                    {
+                        if (STORE) extfac = 1.;
+                        ls |= NOSCAT;
+                    }
+                }
                 if (MODE == 0 && STORE)
                 {
                     const int rf_ell = K.I(I_RFELL, slot);
@@ -544,8 +569,9 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, MODE == 2 ? SK_TRACE_MINBLOCKS
                         else if (STORE && rf)
                         {
                             // the logarithms of the extinction factors at both ends of the segment are -tau and -tau1
-                            const double extEnd = exp(-tau1);
-                            const double extMean = sk_lnmean4(extEnd, extBeg, -tau1, -tau);
+                            const double lnBeg = -(tau * extfac), lnEnd = -(tau1 * extfac);
+                            const double extEnd = exp(lnEnd);
+                            const double extMean = sk_lnmean4(extEnd, extBeg, lnEnd, lnBeg);
                             const double Lds = lum * extMean * ds;
 #ifdef SK_RF_AGGREGATE
                             // (experiment, DESIGN.md section 9: lanes of the warp that deposit into the same cell and bin
@@ -586,7 +612,7 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, MODE == 2 ? SK_TRACE_MINBLOCKS
                     if (forced ? (ds > 0.) : (ds >= 0.))  // ds < 0: the generator ended without a segment (Voronoi)
                     {
                         nseg++;
-                        const double tau1 = __fma_rn(section * dens, ds, tau);
+                        const double tau1 = (ls & NOSCAT) ? 0. : __fma_rn(section * dens, ds, tau);
                         if (limit < tau1)
                         {
                             s_int = tau1;  // interaction inside this segment: interpolated by the service block
@@ -741,10 +767,12 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_advance(const SkDevModel
                     const double qw = (1.0 - xi) * pw + xi / taupath;
                     W *= pw / qw;
                 }
-                W *= -em * albedo;
+                // explicit absorption: the absorption optical depth up to the interaction point, a fixed multiple of the
+                // scattering optical depth for one medium with constant sections (SpatialGridPath.cpp:185-195)
+                W *= -em * (M.explicit_absorption ? exp(-(tauint * M.sig_abs[ilam] / M.sig_sca[ilam])) : albedo);
             }
             else
-                W *= albedo;
+                W *= M.explicit_absorption ? exp(-(tauint * M.sig_abs[ilam] / M.sig_sca[ilam])) : albedo;  // .cpp:757-773
             x = rx0 + sint * kx;  // PhotonPacket::propagate, PhotonPacket.cpp:107-111
             y = ry0 + sint * ky;
             z = rz0 + sint * kz;

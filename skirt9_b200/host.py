@@ -872,6 +872,7 @@ class MonteCarloSimulation:
     radiationFieldWLG: Optional[DisjointWavelengthGrid] = None
     storeRadiationField: bool = False
     forceScattering: bool = True
+    explicitAbsorption: bool = False   # PhotonPacketOptions::explicitAbsorption
     minWeightReduction: float = 1e4
     minScattEvents: int = 0
     pathLengthBias: float = 0.5
@@ -975,7 +976,8 @@ class MonteCarloSimulation:
     def config_struct(self, device=0):
         xi = self.pathLengthBias if self.forceScattering else 0.0  # Configuration.cpp:497-504
         force = self.forceScattering or self.storeRadiationField   # Configuration.cpp:476-482
-        return abi.SkConfig(self.seed, int(force), self.minScattEvents, xi, self.minWeightReduction, device, 0)
+        return abi.SkConfig(self.seed, int(force), self.minScattEvents, xi, self.minWeightReduction, device,
+                            int(self.explicitAbsorption))
 
     def configure(self, engine: abi.Engine):
         """Hands every table to the engine (the extractor step of INTEGRATION.md)."""

@@ -88,6 +88,22 @@ def make_cfg2s():
     print("cfg2s:", {k: np.shape(v) for k, v in out.items()})
 
 
+def make_cfg9e():
+    """cfg1 with explicit absorption: same grid and densities (same seed, same set-up), 1e6 packets."""
+    with tempfile.TemporaryDirectory() as d:
+        run_reference("cfg9e", d)
+        sed = read_columns(os.path.join(d, "cfg9e_i60_sed.dat"))
+        stats = read_columns(os.path.join(d, "cfg9e_i60_sedstats.dat"))
+        cells = read_columns(os.path.join(d, "cfg9e_cells_cellprops.dat"))
+        base = np.load(os.path.join(HERE, "cfg1_ref.npz"))["mass_density_msun_pc3"]
+        assert np.array_equal(cells[:, 6], base), "cfg9e must see the densities of cfg1"
+        rfJ = read_columns(os.path.join(d, "cfg9e_rf_J.dat"))
+        out = dict(sed=sed, sedstats=stats, J_nu=rfJ[:, 1:], num_packets=1e6)
+        out.update(frames(d, "cfg9e_i60", ["total", "primaryscattered"]))
+    np.savez_compressed(os.path.join(HERE, "cfg9e_ref.npz"), **out)
+    print("cfg9e:", {k: np.shape(v) for k, v in out.items()}, sed)
+
+
 def make_cfg8z():
     """cfg2s in the observer frame at redshift 0.5 (instrument distance 0): same tree and densities as cfg2s (same seed,
     same set-up), the packets binned at lambda (1 + z), the calibration with the luminosity distance."""
@@ -218,6 +234,24 @@ def make_cfg7v():
                    absorbed_secondary_lsun=np.array(sec), converged_after=int(conv.group(1)) if conv else -1, num_packets=2e5)
     np.savez_compressed(os.path.join(HERE, "cfg7v_ref.npz"), **out)
     print("cfg7v:", {k: np.shape(v) for k, v in out.items()}, prim, sec, conv and conv.group(0))
+
+
+def make_cfg7v_hi(packets=2e6):
+    """High-statistics companion of cfg7v (same sites and densities: -t 1, same seed): ten times the packets per segment."""
+    with tempfile.TemporaryDirectory() as d:
+        log = run_reference("cfg7v", d, packets=packets)
+        cells = read_columns(os.path.join(d, "cfg7v_cells_cellprops.dat"))
+        base = np.load(os.path.join(HERE, "cfg7v_ref.npz"))["mass_density_msun_pc3"]
+        assert np.array_equal(cells[:, 6], base), "the high-statistics run must see the inputs of the base fixture"
+        prim = [float(x) for x in re.findall(r"dust-absorbed primary luminosity is ([0-9.eE+-]+) Lsun", log)]
+        sec = [float(x) for x in re.findall(r"dust-absorbed secondary luminosity in iteration \d+ is ([0-9.eE+-]+) Lsun", log)]
+        conv = re.search(r"Convergence reached after (\d+) iterations", log)
+        out = dict(sed=read_columns(os.path.join(d, "cfg7v_sed_sed.dat")),
+                   sedstats=read_columns(os.path.join(d, "cfg7v_sed_sedstats.dat")), absorbed_primary_lsun=np.array(prim),
+                   absorbed_secondary_lsun=np.array(sec), converged_after=int(conv.group(1)) if conv else -1,
+                   num_packets=packets)
+    np.savez_compressed(os.path.join(HERE, "cfg7v_hi_ref.npz"), **out)
+    print("cfg7v_hi:", {k: np.shape(v) for k, v in out.items()}, prim, sec, conv and conv.group(0))
 
 
 def sph_particles(n=6000, seed=12345):

@@ -201,6 +201,49 @@ def test_oracle_matches_reference_cfg2s():
 
 
 # ---------------------------------------------------------------- GPU: the engine against the reference
+def cfg9e_from_reference(num_packets):
+    """cfg1 with explicit absorption (tests/golden/ski/cfg9e.ski): same grid and densities as cfg1."""
+    sim, _ = cfg1_from_reference(num_packets)
+    sim.explicitAbsorption = True
+    return sim, load("cfg9e")
+
+
+def check_cfg9e(sim, e, g, n, nsigma=4.0):
+    """Explicit absorption changes the estimator, not the physics: transparent and direct flux are the noise-free values of
+    cfg1, the scattered flux and the radiation field agree with the reference's explicit-absorption run within the noise."""
+    sed = g["sed"][0]
+    tr = sim.sed_flux_density(e, 0, abi.SK_COMP_TRANSPARENT)[0]
+    di = sim.sed_flux_density(e, 0, abi.SK_COMP_PRIMARY_DIRECT)[0]
+    sc = sim.sed_flux_density(e, 0, abi.SK_COMP_PRIMARY_SCATTERED)[0]
+    assert tr == pytest.approx(sed[2], rel=1e-8)
+    assert di == pytest.approx(sed[3], rel=1e-7)
+    tol = nsigma * math.hypot(rel_error(g["sedstats"][0, 1:]), rel_error(e.read_sed_stats(0)[:, 0]))
+    assert abs(sc - sed[4]) <= tol * sed[1], (sc, sed[4], tol)
+    J = sim.mean_intensity_nu(e, 0)[:, 0]
+    scale = max(1.0, math.sqrt(g["num_packets"] / n))
+    assert J.sum() == pytest.approx(g["J_nu"][:, 0].sum(), rel=0.004 * scale)
+    # ... and it IS another estimator: with the same random numbers the packets carry other weights than in cfg1
+    c = e.counters()
+    assert c["scatterings"] / c["packets"] != pytest.approx(5.16, abs=0.05)
+
+
+def test_oracle_matches_reference_cfg9e_explicit_absorption():
+    n = 100000
+    sim, g = cfg9e_from_reference(n)
+    e = sim.configure(OracleEngine(sim.config_struct()))
+    sim.run(e)
+    check_cfg9e(sim, e, g, n)
+
+
+@pytest.mark.gpu
+def test_engine_matches_reference_cfg9e_explicit_absorption(engine_lib):
+    n = 4000000
+    sim, g = cfg9e_from_reference(n)
+    e = sim.configure(abi.Engine(sim.config_struct(device=0), lib=engine_lib))
+    sim.run(e)
+    check_cfg9e(sim, e, g, n)
+
+
 def test_oracle_matches_reference_cfg8z_redshift():
     n = 200000
     sim, g = cfg8z_from_reference(n)

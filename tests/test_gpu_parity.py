@@ -239,3 +239,19 @@ def test_per_pixel_statistics_of_histories_with_hundreds_of_pixels(engine_lib, m
     a, b = small.read_ifu_stats(0), st
     np.testing.assert_allclose(a[1], b[1], rtol=1e-8, atol=1e-8 * b[1].max())
     assert a[0].sum() > b[0].sum()
+
+
+@pytest.mark.parametrize("force", [True, False])
+def test_explicit_absorption(engine_lib, force):
+    """PhotonPacketOptions explicitAbsorption: interaction points in scattering optical depth, weight exp(-tau_abs)
+    (MonteCarloSimulation.cpp:567-570, 727-731, 757-762), with forced (radiation field stored) and non-forced scattering,
+    on an octree and on the ragged Cartesian grid with two sources and three instruments."""
+    sim = models.two_sources_three_instruments(num_packets=20000, force=force)
+    sim.explicitAbsorption = True
+    gpu, cpu = run_both(sim, engine_lib)
+    models.compare_engines(sim, gpu, cpu)
+    sim = models.small_octree(num_packets=20000, record_statistics=True)
+    sim.explicitAbsorption = True
+    sim.forceScattering = force
+    gpu, cpu = run_both(sim, engine_lib)
+    models.compare_engines(sim, gpu, cpu)

@@ -43,12 +43,14 @@ def rel_error(stats_row):
         return np.sqrt(np.maximum(w2 / (w1 * w1) - 1.0 / np.maximum(n, 1), 0.0))
 
 
-def sed_columns_within_statistics(sed, stats, ref, ref_stats, cols, nsigma=4.0, nsigma_secondary=5.0):
+def sed_columns_within_statistics(sed, stats, ref, ref_stats, cols, nsigma=4.0, nsigma_secondary=5.0, secondary_per_bin=True):
     """|F - F_ref| <= nsigma sqrt(R^2 + R_ref^2) max(F_ref, F_ref_total) for the bins of the given columns whose error
     estimate is reliable on both sides by the reference's own rule (R < 0.1, VOV < 0.1; tests/mcstats.py), R from both
     sides' Sum w^k statistics; the columns with dust emission (5-7 and the total) get nsigma_secondary,
     because the statistics of the last segment do not contain the noise of the radiation field behind the dust
-    temperatures.  The sums over those bins agree within the quadrature sum of the bins' errors."""
+    temperatures -- against a fixture with few packets (2e5 per segment) that noise dominates, and those columns are then
+    compared through their sums only (secondary_per_bin=False).  The sums over the bins agree within the quadrature sum of
+    the bins' errors."""
     from tests import mcstats
     own, rst = stats[:, 1:].T, ref_stats[:, 1:].T
     ok = mcstats.reliable(own) & mcstats.reliable(rst)
@@ -58,7 +60,8 @@ def sed_columns_within_statistics(sed, stats, ref, ref_stats, cols, nsigma=4.0, 
         ns = nsigma if col in (2, 3, 4) else nsigma_secondary
         scale = np.maximum(ref[:, col], ref[:, 1]) * sigma
         z = np.abs(sed[:, col] - ref[:, col])[ok] / np.maximum(scale, 1e-300)[ok]
-        assert np.all(z <= ns), (col, int(np.argmax(z)), float(z.max()))
+        if col in (2, 3, 4) or secondary_per_bin:
+            assert np.all(z <= ns), (col, int(np.argmax(z)), float(z.max()))
         assert abs(sed[ok, col].sum() - ref[ok, col].sum()) <= ns * np.sqrt((scale[ok] ** 2).sum()), col
 
 
@@ -140,6 +143,23 @@ def test_cfg2s_ski_with_the_octree_constructed_on_the_gpu(tmp_path):
         assert np.all(np.abs(sed[:, col] - hi["sed"][:, col]) <= bound), col
 
 
+def test_cfg9e_ski_explicit_absorption_runs_unchanged(tmp_path):
+    """cfg1 with explicitAbsorption="true" (MonteCarloSimulation.cpp:567-570, 727-731) against the reference's run of it."""
+    g = np.load(os.path.join(GOLD, "cfg9e_ref.npz"))
+    n = 4e6
+    run_ski("cfg9e", tmp_path, n)
+    sed = read_columns(tmp_path / "cfg9e_i60_sed.dat")[0]
+    stats = read_columns(tmp_path / "cfg9e_i60_sedstats.dat")[0]
+    ref = g["sed"][0]
+    assert sed[2] == pytest.approx(ref[2], rel=1e-8)     # transparent flux: noise free
+    assert sed[3] == pytest.approx(ref[3], rel=1e-8)     # direct flux: same densities, same optical depth
+    tol = 4.0 * math.hypot(rel_error(g["sedstats"][0, 1:]), rel_error(stats[1:]))
+    assert abs(sed[1] - ref[1]) <= tol * ref[1]
+    assert abs(sed[4] - ref[4]) <= tol * ref[1]
+    J = read_columns(tmp_path / "cfg9e_rf_J.dat")[:, 1]
+    assert J.sum() == pytest.approx(g["J_nu"][:, 0].sum(), rel=0.004)
+
+
 def test_cfg8z_ski_observer_frame_redshift_runs_unchanged(tmp_path):
     """cfg2s seen from redshift 0.5 (FlatUniverseCosmology, instrument distance 0): the engine bins the packets at
     lambda (1 + z) (FluxRecorder.cpp:309-310), the reference's writer calibrates with the luminosity distance."""
@@ -171,7 +191,9 @@ def test_cfg4s_ski_dust_emission_runs_unchanged(tmp_path):
     np.testing.assert_allclose(sec, g["absorbed_secondary_lsun"], rtol=0.02)
     sed = read_columns(tmp_path / "cfg4s_sed_sed.dat")
     stats = read_columns(tmp_path / "cfg4s_sed_sedstats.dat")
-    sed_columns_within_statistics(sed, stats, g["sed"], g["sedstats"], range(1, 8))
+    hi = np.load(os.path.join(GOLD, "cfg4s_hi_ref.npz"))   # the same ski with 2e6 packets per segment
+    sed_columns_within_statistics(sed, stats, g["sed"], g["sedstats"], range(1, 8), secondary_per_bin=False)
+    sed_columns_within_statistics(sed, stats, hi["sed"], hi["sedstats"], range(1, 8))
     # the reference's TemperatureProbe evaluated on the radiation field the engine handed back
     T = read_columns(tmp_path / "cfg4s_temp_dust_T.dat")[:, 1]
     ok = g["temperature"] > 0
@@ -263,7 +285,9 @@ def test_cfg7v_ski_voronoi_dust_emission_runs_unchanged(tmp_path):
     np.testing.assert_allclose(sec, g["absorbed_secondary_lsun"], rtol=0.02)
     sed = read_columns(tmp_path / "cfg7v_sed_sed.dat")
     stats = read_columns(tmp_path / "cfg7v_sed_sedstats.dat")
-    sed_columns_within_statistics(sed, stats, g["sed"], g["sedstats"], range(1, 8))
+    hi = np.load(os.path.join(GOLD, "cfg7v_hi_ref.npz"))   # the same ski with 2e6 packets per segment
+    sed_columns_within_statistics(sed, stats, g["sed"], g["sedstats"], range(1, 8), secondary_per_bin=False)
+    sed_columns_within_statistics(sed, stats, hi["sed"], hi["sedstats"], range(1, 8))
     T = read_columns(tmp_path / "cfg7v_temp_dust_T.dat")[:, 1]
     ok = g["temperature"] > 0
     assert np.median(np.abs(T[ok] / g["temperature"][ok] - 1)) < 0.02
