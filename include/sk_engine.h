@@ -324,7 +324,11 @@ int sk_engine_prepare_secondary(sk_engine_t* e, uint64_t num_packets, double* lu
  * includes InstrumentSystem::flush() (FluxRecorder.cpp:472-480). */
 int sk_engine_run_segment(sk_engine_t* e, uint64_t first, uint64_t count, int32_t primary, int32_t peel,
                           int32_t store, uint32_t stream_id);
-/* Same, but only enqueues the work on the engine's stream; pair with sk_engine_synchronize(). */
+/* The same without the final stream synchronisation and without reading the per-stage timings back: the host drives the
+ * rounds of the stage sequence (it looks at the census of the bank one round behind the device, so the device never waits
+ * for it) and returns when the last round has been ENQUEUED and the census says the bank is empty; work that the caller
+ * enqueues on sk_engine_cuda_stream() afterwards -- an NCCL all-reduce of the tallies -- is ordered behind the segment
+ * without a host synchronisation.  Pair with sk_engine_synchronize(). */
 int sk_engine_launch_segment(sk_engine_t* e, uint64_t first, uint64_t count, int32_t primary, int32_t peel,
                              int32_t store, uint32_t stream_id);
 int sk_engine_synchronize(sk_engine_t* e);

@@ -542,6 +542,27 @@ void GpuLifeCycle::configureEngine(int device)
         vector<double> sites(3 * n), boxes(6 * n);
         vector<int64_t> offset(n + 1, 0);
         vector<int32_t> index;
+        // The shim reads the cells through its own declaration of the reference's private Cell class (top of this file).
+        // Check that view against what the reference's PUBLIC accessors say about the same cells -- site position,
+        // enclosing box, volume -- and the neighbour lists for plausibility (at least 4 faces, indices that exist): a
+        // layout that has drifted apart ends the run here instead of feeding garbage to the engine.
+        for (size_t m = 0; m < n; m += std::max<size_t>(1, n / 64))
+        {
+            const VoronoiMeshSnapshot::Cell* cell = mesh->_cells[m];
+            const Position site = mesh->position(static_cast<int>(m));
+            const Box box = mesh->extent(static_cast<int>(m));
+            const Box& cb = *cell;
+            bool same = cell->_r.x() == site.x() && cell->_r.y() == site.y() && cell->_r.z() == site.z()
+                        && cell->_volume == mesh->volume(static_cast<int>(m)) && cb.xmin() == box.xmin()
+                        && cb.ymin() == box.ymin() && cb.zmin() == box.zmin() && cb.xmax() == box.xmax()
+                        && cb.ymax() == box.ymax() && cb.zmax() == box.zmax() && cell->_neighbors.size() >= 4
+                        && cell->_neighbors.size() < 1000;
+            for (size_t i = 0; same && i != cell->_neighbors.size(); ++i)
+                same = cell->_neighbors[i] >= -6 && cell->_neighbors[i] < static_cast<int>(n);
+            if (!same)
+                throw FATALERROR("GPU life-cycle shim: the layout of VoronoiMeshSnapshot::Cell differs from the shim's "
+                                 "declaration (cell " + std::to_string(m) + ")");
+        }
         for (size_t m = 0; m != n; ++m)
         {
             const VoronoiMeshSnapshot::Cell* cell = mesh->_cells[m];

@@ -255,3 +255,22 @@ def test_explicit_absorption(engine_lib, force):
     sim.forceScattering = force
     gpu, cpu = run_both(sim, engine_lib)
     models.compare_engines(sim, gpu, cpu)
+
+
+def test_engine_limits_are_reported_as_unsupported(engine_lib):
+    """More than 8 instruments or more than 8 individually recorded scattering levels are refused with SK_ERR_UNSUPPORTED
+    (the shim lists the same limits in GpuLifeCycle::unsupportedReason), never silently truncated."""
+    import copy
+    sim = models.small_cartesian(num_packets=100)
+    sim.setup()
+    many = copy.copy(sim)
+    many.instruments = [copy.copy(sim.instruments[0]) for _ in range(9)]
+    with pytest.raises(abi.SkError) as err:
+        many.configure(abi.Engine(many.config_struct(device=0), lib=engine_lib))
+    assert err.value.code == abi.SK_ERR_UNSUPPORTED and "8 instruments" in str(err.value)
+    deep = copy.copy(sim)
+    deep.instruments = [copy.copy(sim.instruments[0])]
+    deep.instruments[0].numScatteringLevels = 9
+    with pytest.raises(abi.SkError) as err:
+        deep.configure(abi.Engine(deep.config_struct(device=0), lib=engine_lib))
+    assert err.value.code == abi.SK_ERR_UNSUPPORTED and "scattering levels" in str(err.value)
