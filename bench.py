@@ -430,8 +430,9 @@ def native_arm(args):
     stream = torch.cuda.ExternalStream(engine.cuda_stream(), device=local)
     det = engine.device_tensor(3)
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=f"cuda:{local}")  # > 126 MB L2
-    first, count = parallel.history_block(total, rank, world)   # contiguous block of this rank
-    assert count == packets_per_gpu
+    # every rank is given the whole segment and runs its interleaved share of it (blocks of 16384 histories)
+    first, seg_count = 0, total
+    engine.set_history_interleave(parallel.INTERLEAVE_BLOCK, world, rank)
     single_segment = name != "cfg4"
     # a step may consist of several segments: add up the engine's CUDA-event times of all of them, and the wall time of the
     # blocking C-ABI calls between them (dust emission: the per-iteration preparation and convergence test)
@@ -471,7 +472,7 @@ def native_arm(args):
         if single_segment and not w["store"]:
             with torch.cuda.stream(stream):
                 engine.prepare_primary(total)
-                engine.launch_segment(first, packets_per_gpu, True, True, False, stream_id)
+                engine.launch_segment(first, seg_count, True, True, False, stream_id)
                 if world > 1:
                     dist.all_reduce(det)       # FluxRecorder::calibrateAndWrite -> ProcessManager::sumToRoot
         else:
@@ -554,10 +555,11 @@ def native_arm(args):
         ta = time.perf_counter()
         e2 = abi.Engine(sim.config_struct(device=local))
         sim.configure(e2)
+        e2.set_history_interleave(parallel.INTERLEAVE_BLOCK, world, rank)
         tb = time.perf_counter()
         if single_segment and not w["store"]:
             e2.prepare_primary(total)
-            e2.run_segment(first, packets_per_gpu, True, True, False, 1000 + k)
+            e2.run_segment(first, seg_count, True, True, False, 1000 + k)
             if world > 1:
                 with torch.cuda.stream(torch.cuda.ExternalStream(e2.cuda_stream(), device=local)):
                     dist.all_reduce(e2.device_tensor(3))
@@ -650,7 +652,7 @@ def native_arm(args):
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": w["text"], "name": name, "packets_per_gpu": packets_per_gpu, "cells": int(sim.grid.num_cells),
-                           "l2": "256 MB buffer written between iterations", "sharding": "contiguous history blocks, "
+                           "l2": "256 MB buffer written between iterations", "sharding": "interleaved blocks of 16384 histories, "
                            "replicated grid, NCCL all-reduce of the instrument arrays per step" + (" and of the radiation "
                            "field per segment" if w["store"] else "") if world > 1 else "single GPU"},
                 "e2e": {"value": e2e_packets_all / max(e2e_steps, 1) / e2e_s if e2e_steps else None, "unit": UNIT,

@@ -317,6 +317,17 @@ int sk_engine_prepare_primary(sk_engine_t* e, uint64_t num_packets);
  * MonteCarloSimulation.cpp:156-159). */
 int sk_engine_prepare_secondary(sk_engine_t* e, uint64_t num_packets, double* luminosity);
 
+/* Sharding of a segment over several engines (GPUs, ranks) without a chunk server (the reference hands out chunks of
+ * history indices dynamically, MultiHybridParallel.cpp:26-144, ChunkMaker.cpp:14-50): after this call the engine runs,
+ * of the range [first, first+count) given to sk_engine_run_segment, only the histories i with
+ * ((i - first) / block) % num_parts == part, i.e. every num_parts-th block of `block` consecutive histories (block a
+ * power of two).  All engines of a run are then given the SAME range.  Interleaved blocks balance the load where
+ * contiguous shares do not: the histories of a secondary emission segment are ordered by cell
+ * (DustSecondarySource.cpp:133-145), and a contiguous share is a region of the model with its own path lengths.  The
+ * random streams are keyed by history index, so the tallies do not depend on the sharding.  num_parts = 1 (the default)
+ * runs the whole range. */
+int sk_engine_set_history_interleave(sk_engine_t* e, uint64_t block, uint32_t num_parts, uint32_t part);
+
 /* THE hot path: performLifeCycle(firstIndex, numIndices, primary, peel, store)
  * (MonteCarloSimulation.cpp:538-613) for histories [first, first+count) of the segment prepared by
  * sk_engine_prepare_*; stream_id distinguishes the random streams of successive segments (Philox key

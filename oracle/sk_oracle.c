@@ -76,6 +76,8 @@ typedef struct {
 
 typedef struct sko_engine {
     sk_config_t cfg;
+    uint64_t il_block; /* interleaved sharding (sk_engine_set_history_interleave): block length, parts, this part */
+    uint32_t il_parts, il_part;
     /* grid */
     int grid_kind; /* 1 cartesian, 2 octree, 3 voronoi */
     int nx, ny, nz;
@@ -2685,7 +2687,23 @@ int sko_run_segment(sko_engine_t* e, uint64_t first, uint64_t count, int32_t pri
     if (store && e->rf_grid < 0) return fail(SK_ERR_STATE, "no radiation field grid configured");
     if (store && !e->cfg.force_scattering)
         return fail(SK_ERR_INVALID, "storing the radiation field requires forced scattering (Configuration.cpp:476-482)");
-    for (uint64_t i = first; i != first + count; ++i) life_cycle(e, i, primary, peel, store, stream_id);
+    for (uint64_t i = 0; i != count; ++i)
+    {
+        /* sk_engine_set_history_interleave: every num_parts-th block of `block` histories */
+        if (e->il_parts > 1 && (i / e->il_block) % e->il_parts != e->il_part) continue;
+        life_cycle(e, first + i, primary, peel, store, stream_id);
+    }
+    return SK_OK;
+}
+
+int sko_set_history_interleave(sko_engine_t* e, uint64_t block, uint32_t num_parts, uint32_t part)
+{
+    if (!e) return fail(SK_ERR_INVALID, "null engine");
+    if (num_parts < 1 || part >= num_parts) return fail(SK_ERR_INVALID, "part must be below num_parts");
+    if (num_parts > 1 && (block == 0 || (block & (block - 1)))) return fail(SK_ERR_INVALID, "block must be a power of two");
+    e->il_block = block;
+    e->il_parts = num_parts;
+    e->il_part = part;
     return SK_OK;
 }
 

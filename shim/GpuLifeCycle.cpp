@@ -339,7 +339,13 @@ void GpuLifeCycle::configure()
         _engines.push_back(_e);
     }
     _e = _engines[0];
-    if (_engines.size() > 1) prepareNccl();
+    if (_engines.size() > 1)
+    {
+        for (size_t i = 0; i != _engines.size(); ++i)
+            check(sk_engine_set_history_interleave(_engines[i], 16384, static_cast<uint32_t>(_engines.size()),
+                                                   static_cast<uint32_t>(i)));
+        prepareNccl();
+    }
 }
 
 void GpuLifeCycle::prepareNccl()
@@ -366,9 +372,10 @@ void GpuLifeCycle::runSegmentOnAll(size_t Npp, int primary, int peel, int store)
     std::vector<std::thread> threads;
     for (size_t i = 0; i != n; ++i)
     {
-        const uint64_t first = Npp * i / n, last = Npp * (i + 1) / n;
-        threads.emplace_back([this, i, first, last, primary, peel, store, segment, &rc, &msg]() {
-            rc[i] = sk_engine_run_segment(_engines[i], first, last - first, primary, peel, store, segment);
+        // every engine is given the whole segment and runs its interleaved share of it (set in configure():
+        // sk_engine_set_history_interleave), which keeps the devices balanced also where the histories are ordered by cell
+        threads.emplace_back([this, i, Npp, primary, peel, store, segment, &rc, &msg]() {
+            rc[i] = sk_engine_run_segment(_engines[i], 0, Npp, primary, peel, store, segment);
             if (rc[i] != SK_OK) msg[i] = sk_last_error();  // the error text is thread-local
         });
     }

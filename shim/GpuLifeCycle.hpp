@@ -19,8 +19,8 @@ class MonteCarloSimulation;
 class GpuLifeCycle
 {
 public:
-    // one engine per listed CUDA device; with several devices every emission segment is split into contiguous history
-    // blocks (one per device, run concurrently from one host thread each) and the tallies are all-reduced with NCCL
+    // one engine per listed CUDA device; with several devices every emission segment is split into interleaved blocks of
+    // 16384 histories (device i runs every n-th block; one host thread per device) and the tallies are all-reduced with NCCL
     // exactly where the reference calls ProcessManager::sumToAll / sumToRoot (MediumSystem.cpp:1304-1313,
     // FluxRecorder.cpp:487-493)
     GpuLifeCycle(MonteCarloSimulation* sim, const std::vector<int>& devices);

@@ -136,7 +136,8 @@ def load_engine_library(path: Optional[str] = None) -> C.CDLL:
 ABI_FUNCTIONS = ["create", "destroy", "set_grid_cartesian", "set_grid_octree", "set_grid_voronoi", "set_voronoi_extents",
                  "set_medium", "set_dustmix",
                  "set_wavelength_grids", "set_sources", "set_instruments", "set_secondary", "clear_instruments", "clear_rf",
-                 "prepare_primary", "prepare_secondary", "run_segment", "communicate_rf", "absorbed_luminosity",
+                 "prepare_primary", "prepare_secondary", "set_history_interleave", "run_segment", "communicate_rf",
+                 "absorbed_luminosity",
                  "read_rf", "read_sed", "read_ifu", "read_sed_stats", "read_ifu_stats", "counters"]
 SETUP_FUNCTIONS = ["build_octree", "read_octree", "sample_medium", "read_medium"]
 ENGINE_ONLY_FUNCTIONS = ["launch_segment", "synchronize", "last_kernel_ms", "last_stage_ms", "device_buffer", "cuda_stream",
@@ -372,6 +373,10 @@ class Engine:
         lum = C.c_double()
         self._call("prepare_secondary", self._h, C.c_uint64(int(num_packets)), C.byref(lum))
         return lum.value
+
+    def set_history_interleave(self, block, num_parts, part):
+        """This engine runs every num_parts-th block of `block` histories of the ranges given to run_segment."""
+        self._call("set_history_interleave", self._h, C.c_uint64(int(block)), C.c_uint32(int(num_parts)), C.c_uint32(int(part)))
 
     def run_segment(self, first, count, primary=True, peel=True, store=False, stream_id=0):
         self._call("run_segment", self._h, C.c_uint64(int(first)), C.c_uint64(int(count)), C.c_int32(int(primary)),

@@ -13,6 +13,9 @@
 #include <string>
 #include <vector>
 
+#ifdef SK_SORT_RAYS
+#include <cub/device/device_radix_sort.cuh>  // (experiment only: rays in order of their start cell)
+#endif
 #include "sk_secondary.cuh"
 #include "sk_setup.cuh"
 #include "sk_wavefront.cuh"
@@ -230,6 +233,8 @@ struct sk_engine {
     unsigned long long* work_counter = nullptr;
     SkBank bank = {};  // the in-flight packets (sk_wavefront.cuh)
     int pool_chunks = 0;                                    // chunks in the pool of per-history pixel lists
+    unsigned long long il_block = 0;                       // interleaved sharding (sk_engine_set_history_interleave)
+    unsigned il_parts = 1, il_part = 0;
     unsigned int* sort_cursor = nullptr;                    // bin cursors of the wavelength sort of the forward rays
     unsigned long long pixel_overflows = 0;
     int bank_fields_d = 0, bank_fields_i = 0;
@@ -1617,9 +1622,42 @@ static int launch_trace_impl(sk_engine* e, const SkRunArgs& A, const SkObsDir& d
     return stage_end(e);
 }
 
+#ifdef SK_SORT_RAYS
+__global__ void sk_ray_keys_kernel(const SkBank K, unsigned int* keys)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < K.ctl[SK_CTL_NLIST]) keys[i] = (unsigned)(K.I(I_M, K.list[i]) + 1);
+    else if (i < (unsigned)K.n) keys[i] = 0xffffffffu;
+}
+static int sort_rays_by_cell(sk_engine* e)
+{
+    static unsigned int *keys = nullptr, *keys2 = nullptr;
+    static void* tmp = nullptr;
+    static size_t tmp_bytes = 0, cap = 0;
+    const size_t n = (size_t)e->bank.n;
+    if (cap < n)
+    {
+        CK(cudaMalloc(&keys, e->bank.cap * sizeof(unsigned)));
+        CK(cudaMalloc(&keys2, e->bank.cap * sizeof(unsigned)));
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, e->bank.list, e->bank.free_list, (int)e->bank.cap, 0, 21);
+        CK(cudaMalloc(&tmp, tmp_bytes));
+        cap = e->bank.cap;
+    }
+    sk_ray_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->bank, keys);
+    // entries beyond the list length carry the largest key: they stay behind the rays
+    cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, e->bank.list, e->bank.free_list, (int)n, 0, 32, e->stream);
+    CK(cudaMemcpyAsync(e->bank.list, e->bank.free_list, n * sizeof(int32_t), cudaMemcpyDeviceToDevice, e->stream));
+    return SK_OK;
+}
+#endif
+
 template <int GRID, int MODE, bool STORE>
 static int launch_trace(sk_engine* e, const SkRunArgs& A, const SkObsDir& dir)
 {
+#ifdef SK_SORT_RAYS
+    if (GRID == 2 && (MODE == 2 || SK_SORT_RAYS > 1) && !STORE)
+        if (int rc = sort_rays_by_cell(e)) return rc;
+#endif
     // only the Cartesian grid looks borders up while it walks (TMA-staged tables); the octree walks in lattice coordinates
     if (GRID == 1 && e->M.lattice_in_smem) return launch_trace_impl<GRID, MODE, STORE, GRID == 1>(e, A, dir);
     return launch_trace_impl<GRID, MODE, STORE, false>(e, A, dir);
@@ -1765,6 +1803,17 @@ static int run_bank(sk_engine* e, const SkRunArgs& A)
     return SK_OK;
 }
 
+extern "C" int sk_engine_set_history_interleave(sk_engine_t* e, uint64_t block, uint32_t num_parts, uint32_t part)
+{
+    if (!e) return fail(SK_ERR_INVALID, "null engine");
+    if (num_parts < 1 || part >= num_parts) return fail(SK_ERR_INVALID, "part must be below num_parts");
+    if (num_parts > 1 && (block == 0 || (block & (block - 1)))) return fail(SK_ERR_INVALID, "block must be a power of two");
+    e->il_block = block;
+    e->il_parts = num_parts;
+    e->il_part = part;
+    return SK_OK;
+}
+
 extern "C" int sk_engine_launch_segment(sk_engine_t* e, uint64_t first, uint64_t count, int32_t primary,
                                         int32_t peel, int32_t store, uint32_t stream_id)
 {
@@ -1782,9 +1831,16 @@ extern "C" int sk_engine_launch_segment(sk_engine_t* e, uint64_t first, uint64_t
     //  the 126 MB L2 on their own -- and cudaGetDeviceProperties / cudaDeviceSetLimit cost milliseconds per engine.)
     CK(cudaEventRecord(e->ev0, e->stream));
     e->stage_of_pair.clear();
-    if (count)
+    // this engine's share of [first, first+count): everything, or every il_parts-th block of il_block histories
+    unsigned long long share = count;
+    if (count && e->il_parts > 1)
     {
-        if (int rc = ensure_bank(e, count)) return rc;
+        const unsigned long long B = e->il_block, cycle = B * e->il_parts, rem = count % cycle, lo = (unsigned long long)e->il_part * B;
+        share = count / cycle * B + (rem > lo ? std::min<unsigned long long>(rem - lo, B) : 0ull);
+    }
+    if (share)
+    {
+        if (int rc = ensure_bank(e, share)) return rc;
         if (e->pool_chunks)
         {
             // every chunk is free at the start of a segment (all histories of the previous one have ended)
@@ -1794,7 +1850,16 @@ extern "C" int sk_engine_launch_segment(sk_engine_t* e, uint64_t first, uint64_t
         }
         SkRunArgs A;
         A.first = first;
-        A.count = count;
+        A.count = share;
+        A.il_shift = -1;
+        A.il_stride = A.il_offset = 0;
+        if (e->il_parts > 1)
+        {
+            A.il_shift = 0;
+            while ((1ull << A.il_shift) < e->il_block) A.il_shift++;
+            A.il_stride = e->il_block * e->il_parts;
+            A.il_offset = (unsigned long long)e->il_part * e->il_block;
+        }
         A.primary = primary;
         A.peel = peel && !e->instr.empty();
         A.store = store;

@@ -139,12 +139,21 @@ struct SkDevModel {
 #define SK_RF_INDEX(M, m, ell) ((size_t)(ell) * (size_t)(M).ncells + (size_t)(m))
 
 struct SkRunArgs {
-    unsigned long long first, count;
+    unsigned long long first, count;   // histories of this engine: count indices h, mapped to first + sk_history_of(h)
+    unsigned long long il_stride, il_offset;  // interleaved sharding: h -> (h >> il_shift) * il_stride + il_offset + (h & mask)
+    int32_t il_shift;                  // log2 of the block length, or -1 for a contiguous range
     int32_t primary, peel, store;
     uint32_t stream_id;
     unsigned long long* work_counter;  // dynamic history dispenser
     const SkDevModel* model;           // copy of the model in global memory for the cold, non-inlined paths
 };
+
+// the history index (relative to A.first) of the h-th history this engine runs (sk_engine_set_history_interleave)
+__device__ __forceinline__ unsigned long long sk_history_of(const SkRunArgs& A, unsigned long long h)
+{
+    if (A.il_shift < 0) return h;
+    return (h >> A.il_shift) * A.il_stride + A.il_offset + (h & ((1ull << A.il_shift) - 1ull));
+}
 
 // ---------------------------------------------------------------------------------------------------
 // TMA bulk copy global -> shared memory (cp.async.bulk, SASS UBLKCP) completing on an mbarrier: stages the border tables

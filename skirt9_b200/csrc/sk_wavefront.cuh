@@ -853,7 +853,7 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK, SK_LAUNCH_MINBLOCKS) sk_wf_lau
         const unsigned long long h = sk_block_reserve(A.work_counter, want);
         if (want && h < A.count)
         {
-            const unsigned long long history = A.first + h;
+            const unsigned long long history = A.first + sk_history_of(A, h);
             SkRng g;
             sk_rng_init(g, M.seed, A.stream_id, history, 0);
             SkLaunch pp;

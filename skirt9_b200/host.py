@@ -1070,7 +1070,7 @@ class MonteCarloSimulation:
             engine.clear_rf(True)
         engine.prepare_primary(n)
         if comm is not None:
-            first, count = comm.block(n)
+            first, count = comm.block(engine, n)
         engine.run_segment(first, n if count is None else count, primary=True, peel=True, store=store,
                            stream_id=stream_id)
         if store:
@@ -1086,7 +1086,7 @@ class MonteCarloSimulation:
         n = int(self.numPackets * self.secondaryPacketsMultiplier)
         self.dust_luminosity = engine.prepare_secondary(n)
         if self.dust_luminosity > 0:
-            first, count = comm.block(n) if comm is not None else (0, n)
+            first, count = comm.block(engine, n) if comm is not None else (0, n)
             engine.run_segment(first, count, primary=False, peel=True, store=store, stream_id=stream_id)
         if store:
             if comm is not None:
@@ -1106,7 +1106,7 @@ class MonteCarloSimulation:
             lum = engine.prepare_secondary(n)
             if not lum > 0:
                 return
-            first, count = comm.block(n) if comm is not None else (0, n)
+            first, count = comm.block(engine, n) if comm is not None else (0, n)
             engine.run_segment(first, count, primary=False, peel=False, store=True, stream_id=stream_id + it)
             if comm is not None:
                 comm.allreduce_rf(engine, False)

@@ -274,3 +274,27 @@ def test_engine_limits_are_reported_as_unsupported(engine_lib):
     with pytest.raises(abi.SkError) as err:
         deep.configure(abi.Engine(deep.config_struct(device=0), lib=engine_lib))
     assert err.value.code == abi.SK_ERR_UNSUPPORTED and "scattering levels" in str(err.value)
+
+
+def test_interleaved_shares_add_up_to_the_single_run(engine_lib):
+    """sk_engine_set_history_interleave: three engines that each run every third block of 256 histories of the same
+    segment -- the sharding of the multi-GPU drivers -- together give the tallies of one engine running all of it."""
+    sim = models.small_octree(num_packets=10000, record_statistics=True)
+    sim.setup()
+    one = sim.configure(abi.Engine(sim.config_struct(device=0), lib=engine_lib))
+    sim.run(one)
+    parts = []
+    for part in range(3):
+        e = sim.configure(abi.Engine(sim.config_struct(device=0), lib=engine_lib))
+        e.set_history_interleave(256, 3, part)
+        sim.run(e)
+        parts.append(e)
+    assert sum(e.counters()["packets"] for e in parts) == one.counters()["packets"] == 10000
+    assert [e.counters()["packets"] for e in parts] == [3344, 3328, 3328]
+    for comp in (abi.SK_COMP_TRANSPARENT, abi.SK_COMP_PRIMARY_DIRECT, abi.SK_COMP_PRIMARY_SCATTERED):
+        np.testing.assert_allclose(sum(e.read_sed(0, comp) for e in parts), one.read_sed(0, comp), rtol=1e-10)
+        a, b = sum(e.read_ifu(0, comp) for e in parts), one.read_ifu(0, comp)
+        np.testing.assert_allclose(a, b, rtol=1e-10, atol=1e-12 * b.max())
+    np.testing.assert_allclose(sum(e.read_sed_stats(0) for e in parts), one.read_sed_stats(0), rtol=1e-9)
+    with pytest.raises(abi.SkError):
+        parts[0].set_history_interleave(100, 3, 0)     # not a power of two

@@ -1,6 +1,6 @@
 """The N>1 path on CPU: two processes over gloo run the sharded simulation driver (skirt9_b200.parallel.Comm) with the
-oracle engine and must reproduce the single-rank tallies.  This covers the host logic of the multi-GPU path -- history
-blocks, the all-reduce of the radiation field inside the secondary-emission iteration loop, the final all-reduce of
+oracle engine and must reproduce the single-rank tallies.  This covers the host logic of the multi-GPU path -- interleaved
+history blocks, the all-reduce of the radiation field inside the secondary-emission iteration loop, the final all-reduce of
 the detector arrays -- without a GPU; the same code drives the CUDA engine over NCCL in bench.py."""
 import os
 import subprocess
@@ -26,10 +26,10 @@ from tests import models
 from tests.oracle_lib import OracleEngine
 
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
-comm = parallel.Comm(dist)
+comm = parallel.Comm(dist, block=256)   # small blocks: the test models have a few thousand histories
 sim = models.{model}.setup()
 e = sim.configure(OracleEngine(sim.config_struct()))
-first, count = comm.block(int(sim.numPackets))
+first, count = comm.block(e, int(sim.numPackets))
 sim.run(e, comm=comm)
 # the oracle keeps one allocation per detector array: reduce what was read back (the CUDA engine reduces its contiguous block)
 import torch
@@ -43,7 +43,7 @@ if sim.storeRadiationField:
 if sim.dustEmissionWLG is not None:
     out["rf2"] = e.read_rf(1)
     out["conv"] = np.array([[c["dust_luminosity"], c["absorbed_primary"], c["absorbed_secondary"]] for c in sim.convergence])
-out["block"] = np.array([first, count])
+out["block"] = np.array([first, count, e.counters()["packets"]])
 if comm.rank == 0:
     np.savez({out!r}, **out)
 dist.barrier()
@@ -62,6 +62,19 @@ def run_two_ranks(model, comps, port):
         return dict(np.load(out))
 
 
+def test_interleaved_shares_tile_the_range():
+    for n in (1, 7, 1000, 16384 * 3 + 5, 10**9 + 7):
+        for world in (1, 2, 3, 8):
+            for block in (256, 16384):
+                shares = [parallel.interleaved_count(n, r, world, block) for r in range(world)]
+                assert sum(shares) == n
+                assert max(shares) - min(shares) <= block
+                # the same by enumeration
+                if n <= 100000:
+                    idx = np.arange(n)
+                    assert shares == [int(((idx // block) % world == r).sum()) for r in range(world)]
+
+
 def test_history_blocks_tile_the_range():
     for n in (1, 7, 1000, 10**9 + 7):
         for world in (1, 2, 3, 8):
@@ -78,7 +91,9 @@ def test_two_ranks_primary_emission_matches_single_rank():
     sim = models.small_cartesian(num_packets=6001).setup()
     e = sim.configure(OracleEngine(sim.config_struct()))
     sim.run(e)
-    assert list(got["block"]) == [0, 3000]
+    # every rank is handed the whole segment and runs its interleaved share: rank 0 the blocks 0, 2, 4, ...
+    assert list(got["block"][:2]) == [0, 6001]
+    assert got["block"][2] <= parallel.interleaved_count(6001, 0, 2, 256) < 6001
     for c in comps:
         np.testing.assert_allclose(got["sed%d" % c], e.read_sed(0, c), rtol=1e-11)
     ref = e.read_rf(0)
@@ -112,7 +127,7 @@ def test_two_ranks_build_the_same_grid_without_communication():
     sim = models.small_octree_engine_setup(num_packets=6000).setup()
     e = sim.configure(OracleEngine(sim.config_struct()))
     sim.run(e)
-    assert list(got["block"]) == [0, 3000]
+    assert list(got["block"][:2]) == [0, 6000]
     for c in comps:
         a, b = got["sed%d" % c], e.read_sed(0, c)
         np.testing.assert_allclose(a, b, rtol=1e-11, atol=1e-14 * b.max())
