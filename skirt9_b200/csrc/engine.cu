@@ -13,9 +13,6 @@
 #include <string>
 #include <vector>
 
-#ifdef SK_SORT_RAYS
-#include <cub/device/device_radix_sort.cuh>  // (experiment only: rays in order of their start cell)
-#endif
 #include "sk_secondary.cuh"
 #include "sk_setup.cuh"
 #include "sk_wavefront.cuh"
@@ -1622,42 +1619,9 @@ static int launch_trace_impl(sk_engine* e, const SkRunArgs& A, const SkObsDir& d
     return stage_end(e);
 }
 
-#ifdef SK_SORT_RAYS
-__global__ void sk_ray_keys_kernel(const SkBank K, unsigned int* keys)
-{
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < K.ctl[SK_CTL_NLIST]) keys[i] = (unsigned)(K.I(I_M, K.list[i]) + 1);
-    else if (i < (unsigned)K.n) keys[i] = 0xffffffffu;
-}
-static int sort_rays_by_cell(sk_engine* e)
-{
-    static unsigned int *keys = nullptr, *keys2 = nullptr;
-    static void* tmp = nullptr;
-    static size_t tmp_bytes = 0, cap = 0;
-    const size_t n = (size_t)e->bank.n;
-    if (cap < n)
-    {
-        CK(cudaMalloc(&keys, e->bank.cap * sizeof(unsigned)));
-        CK(cudaMalloc(&keys2, e->bank.cap * sizeof(unsigned)));
-        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, e->bank.list, e->bank.free_list, (int)e->bank.cap, 0, 21);
-        CK(cudaMalloc(&tmp, tmp_bytes));
-        cap = e->bank.cap;
-    }
-    sk_ray_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->bank, keys);
-    // entries beyond the list length carry the largest key: they stay behind the rays
-    cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, e->bank.list, e->bank.free_list, (int)n, 0, 32, e->stream);
-    CK(cudaMemcpyAsync(e->bank.list, e->bank.free_list, n * sizeof(int32_t), cudaMemcpyDeviceToDevice, e->stream));
-    return SK_OK;
-}
-#endif
-
 template <int GRID, int MODE, bool STORE>
 static int launch_trace(sk_engine* e, const SkRunArgs& A, const SkObsDir& dir)
 {
-#ifdef SK_SORT_RAYS
-    if (GRID == 2 && (MODE == 2 || SK_SORT_RAYS > 1) && !STORE)
-        if (int rc = sort_rays_by_cell(e)) return rc;
-#endif
     // only the Cartesian grid looks borders up while it walks (TMA-staged tables); the octree walks in lattice coordinates
     if (GRID == 1 && e->M.lattice_in_smem) return launch_trace_impl<GRID, MODE, STORE, GRID == 1>(e, A, dir);
     return launch_trace_impl<GRID, MODE, STORE, false>(e, A, dir);
