@@ -28,6 +28,7 @@
 #include <string>
 #include <thread>
 #include <tuple>
+#include <chrono>
 #include <typeinfo>
 #include <unordered_map>
 #include <unordered_set>
@@ -125,6 +126,14 @@ namespace
     }
 
     const double* ptr(const Array& a) { return &a[0]; }
+
+    bool sameValues(const Array& a, const Array& b)
+    {
+        if (a.size() != b.size()) return false;
+        for (size_t i = 0; i != a.size(); ++i)
+            if (a[i] != b[i]) return false;
+        return true;
+    }
 
     // the geometries that have a device-side sampler (include/sk_engine.h sk_geometry_kind)
     bool fillGeometry(const Geometry* geom, sk_source_t& s)
@@ -251,12 +260,18 @@ namespace
             auto fail = [](int rc) {
                 if (rc != SK_OK) throw FATALERROR(string("GPU tree construction: ") + sk_last_error());
             };
+            auto now = []() { return std::chrono::steady_clock::now(); };
+            auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+                return StringUtils::toString(std::chrono::duration<double, std::milli>(b - a).count(), 'f', 1);
+            };
+            auto t0 = now();
             sk_config_t c;
             memset(&c, 0, sizeof c);
             c.seed = static_cast<uint32_t>(_random->seed());
             c.device = _device;
             sk_engine_t* e = nullptr;
-            fail(sk_engine_create(&c, &e));
+            fail(sk_engine_create(&c, &e));  // the first CUDA call of the process: creates the device context
+            auto t1 = now();
             sk_tree_policy_t p;
             memset(&p, 0, sizeof p);
             p.min_level = minLevel();
@@ -274,8 +289,7 @@ namespace
             if (rc == SK_OK) rc = sk_engine_read_octree(e, firstChild.data());
             sk_engine_destroy(e);
             fail(rc);
-            log->info("  GPU tree construction: " + std::to_string(nn) + " nodes, " + std::to_string(nc)
-                      + " cells (sk_engine_build_octree)");
+            auto t2 = now();
 
             // the reference's node objects in the same breadth-first order (TreeNode::subdivide without the neighbour lists:
             // nothing on the host walks the tree from cell to cell once the life cycle runs on the device)
@@ -291,6 +305,9 @@ namespace
                 nodev.insert(nodev.end(), node->_children.begin(), node->_children.end());
             }
             if (nodev.size() != nn) throw FATALERROR("GPU tree construction: node count mismatch");
+            log->info("  GPU tree construction: " + std::to_string(nn) + " nodes, " + std::to_string(nc) + " cells (CUDA context "
+                      + ms(t0, t1) + " ms, sk_engine_build_octree + read-back " + ms(t1, t2) + " ms, TreeNode objects "
+                      + ms(t2, now()) + " ms)");
             return nodev;
         }
 
@@ -437,7 +454,7 @@ std::string GpuLifeCycle::unsupportedReason() const
     auto config = _sim->_config;
     auto ms = _sim->mediumSystem();
     if (!config->hasMedium() || !ms) return "no medium";
-    if (ms->numMedia() != 1 || !config->hasSingleConstantSectionMedium()) return "more than one medium or variable cross sections";
+    if (!config->hasSingleConstantSectionMedium() && !config->hasMultipleConstantSectionMedia()) return "variable cross sections";
     if (config->hasPolarization()) return "polarization";
     if (config->hasMovingMedia()) return "moving media";
     if (!config->hasConstantPerceivedWavelength()) return "wavelengths that change during the life cycle";
@@ -449,6 +466,16 @@ std::string GpuLifeCycle::unsupportedReason() const
     if (ProcessManager::isMultiProc()) return "MPI (use one engine per rank through the C ABI instead)";
     auto mix = dynamic_cast<const DustMix*>(ms->media()[0]->mix());
     if (!mix || mix->scatteringMode() != DustMix::ScatteringMode::HenyeyGreenstein) return "a material mix other than a Henyey-Greenstein dust mix";
+    // several media (MediumSystem.cpp:874-885, 697-767): the cell record holds ONE density, so they must share one material
+    // mix; opacity, albedo, phase function and emissivity are then those of a single medium with the summed density
+    for (int h = 1; h < ms->numMedia(); ++h)
+    {
+        auto other = dynamic_cast<const DustMix*>(ms->media()[h]->mix());
+        if (!other || other->type() != mix->type() || other->scatteringMode() != mix->scatteringMode() || other->mass() != mix->mass()
+            || !sameValues(other->_lambdav, mix->_lambdav) || !sameValues(other->_sigmaabsv, mix->_sigmaabsv)
+            || !sameValues(other->_sigmascav, mix->_sigmascav) || !sameValues(other->_asymmparv, mix->_asymmparv))
+            return "more than one medium with different material mixes";
+    }
     auto grid = ms->grid();
     auto tree = dynamic_cast<TreeSpatialGrid*>(grid);
     auto voronoi = dynamic_cast<VoronoiMeshSpatialGrid*>(grid);
@@ -606,9 +633,11 @@ void GpuLifeCycle::configureEngine(int device)
     // ---- medium state (MediumState.cpp:196-247)
     int M = ms->numCells();
     vector<double> nv(M), Vv(M);
+    const int numMedia = ms->numMedia();  // all with the same material mix (unsupportedReason): the densities add up
     for (int m = 0; m != M; ++m)
     {
         nv[m] = ms->numberDensity(m, 0);
+        for (int h = 1; h < numMedia; ++h) nv[m] += ms->numberDensity(m, h);
         Vv[m] = ms->volume(m);
     }
     check(sk_engine_set_medium(_e, M, nv.data(), Vv.data()));

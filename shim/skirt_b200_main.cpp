@@ -44,6 +44,8 @@
 #undef private
 #undef protected
 
+#include <cuda_runtime_api.h>
+
 #include "BuildInfo.hpp"
 #include "Console.hpp"
 #include "FatalError.hpp"
@@ -130,6 +132,19 @@ int main(int argc, char** argv)
         return EXIT_FAILURE;
     }
     if (!StringUtils::endsWith(skipath, ".ski")) skipath += ".ski";
+
+    // The CUDA context of the first device takes a few hundred milliseconds to create: start that now, on a thread of its
+    // own, so that it overlaps with reading the ski file and building the simulation hierarchy instead of delaying the first
+    // engine call (the octree construction during set-up).
+    std::thread warmup;
+    if (!cpu)
+        warmup = std::thread([device = devices.empty() ? 0 : devices[0]]() {
+            if (cudaSetDevice(device) == cudaSuccess) cudaFree(nullptr);
+        });
+    struct Joiner {
+        std::thread& t;
+        ~Joiner() { if (t.joinable()) t.join(); }
+    } joiner{warmup};
 
     string producer = "SKIRT " + version + " + B200 life-cycle engine (ABI " + std::to_string(sk_abi_version()) + ")";
     console.info("Welcome to " + producer);

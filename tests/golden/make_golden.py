@@ -123,6 +123,22 @@ def make_cfg8z():
     print("cfg8z:", {k: np.shape(v) for k, v in out.items()})
 
 
+def make_cfg10d():
+    """cfg2s with two dust media sharing one mix (ring + exponential disk): the reference's several-media code path; the fixture
+    holds the tree and the TOTAL dust density the reference sampled.  2e6 packets."""
+    with tempfile.TemporaryDirectory() as d:
+        run_reference("cfg10d", d, packets=2e6)
+        sed = read_columns(os.path.join(d, "cfg10d_i60_sed.dat"))
+        stats = read_columns(os.path.join(d, "cfg10d_i60_sedstats.dat"))
+        cells = read_columns(os.path.join(d, "cfg10d_cells_cellprops.dat"))
+        topo = parse_topology(os.path.join(d, "cfg10d_topo_treetop.dat"))
+        total = read_fits_cube(os.path.join(d, "cfg10d_i60_total.fits"))[0].astype(np.float64)
+        out = dict(sed=sed, sedstats=stats, mass_density_msun_pc3=cells[:, 6], cell_center_pc=cells[:, 1:4],
+                   cell_volume_pc3=cells[:, 4], topology=topo, num_packets=2e6, frame_total_sum=total.sum(axis=0))
+    np.savez_compressed(os.path.join(HERE, "cfg10d_ref.npz"), **out)
+    print("cfg10d:", {k: np.shape(v) for k, v in out.items()})
+
+
 def make_hi(name, packets=2e7):
     """High-statistics companion of a fixture: the same ski with `packets` histories, still with `-t 1` because the
     tree and the cell densities are sampled from the thread's random stream (Random.cpp:31-36) and must stay those of

@@ -40,8 +40,8 @@ def cfg1_from_reference(num_packets):
     return sim, g
 
 
-def cfg2s_from_reference(num_packets):
-    g = load("cfg2s")
+def cfg2s_from_reference(num_packets, fixture="cfg2s"):
+    g = load(fixture)
     sim = configs.cfg2(num_packets=num_packets, seed=0, max_level=6, max_dust_fraction=1e-4, num_pixels=64,
                        num_wavelengths=10, record_statistics=True)
     pc = H.PC
@@ -163,6 +163,34 @@ def cfg8z_from_reference(num_packets):
     return sim, g
 
 
+def cfg10d_from_reference(num_packets):
+    """cfg2s with two dust media that share one material mix (tests/golden/ski/cfg10d.ski: ring + exponential disk).  The
+    reference runs its several-media code (MediumSystem.cpp:874-885, peel-off :697-767); the engine is given the tree and the
+    TOTAL density the reference sampled -- with one shared mix that is the same transfer problem."""
+    return cfg2s_from_reference(num_packets, "cfg10d")
+
+
+def check_cfg10d(sim, e, g, n, nsigma=4.0):
+    np.testing.assert_allclose(sim.defaultWavelengthGrid.lambdav * 1e6, g["sed"][:, 0], rtol=1e-9)
+    r_own = rel_error(e.read_sed_stats(0))
+    tol = nsigma * np.hypot(rel_error(g["sedstats"][:, 1:].T), r_own)
+    sed = g["sed"]
+    for col, comp in ((1, abi.SK_COMP_TOTAL), (2, abi.SK_COMP_TRANSPARENT), (3, abi.SK_COMP_PRIMARY_DIRECT),
+                      (4, abi.SK_COMP_PRIMARY_SCATTERED)):
+        f = sim.sed_flux_density(e, 0, comp)
+        bound = tol * np.maximum(sed[:, col], sed[:, 1])
+        assert np.all(np.abs(f - sed[:, col]) <= bound), (comp, f / sed[:, col] - 1, tol)
+    di, tr = sim.sed_flux_density(e, 0, abi.SK_COMP_PRIMARY_DIRECT), sim.sed_flux_density(e, 0, abi.SK_COMP_TRANSPARENT)
+    assert np.all(np.abs(di / tr - sed[:, 3] / sed[:, 2]) <= tol * sed[:, 3] / sed[:, 2])
+    a = sim.surface_brightness(e, 0, abi.SK_COMP_TOTAL).sum(axis=0)
+    blk = lambda x: x.reshape(8, 8, 8, 8).sum(axis=(1, 3))
+    a, c = blk(a), blk(g["frame_total_sum"])
+    ok = c > 0.05 * c.max()
+    scale = max(1.0, math.sqrt(g["num_packets"] / n))
+    np.testing.assert_allclose(a[ok], c[ok], rtol=0.06 * scale)
+    assert a.sum() == pytest.approx(c.sum(), rel=0.004 * scale)
+
+
 def check_cfg8z(sim, e, g, nsigma=4.0):
     np.testing.assert_allclose(sim.defaultWavelengthGrid.lambdav * 1e6, g["sed"][:, 0], rtol=1e-9)
     r_own = rel_error(e.read_sed_stats(0))
@@ -250,6 +278,23 @@ def test_oracle_matches_reference_cfg8z_redshift():
     e = sim.configure(OracleEngine(sim.config_struct()))
     sim.run(e)
     check_cfg8z(sim, e, g, nsigma=5.0)
+
+
+def test_oracle_matches_reference_cfg10d_two_media_one_mix():
+    n = 300000
+    sim, g = cfg10d_from_reference(n)
+    e = sim.configure(OracleEngine(sim.config_struct()))
+    sim.run(e)
+    check_cfg10d(sim, e, g, n, nsigma=5.0)
+
+
+@pytest.mark.gpu
+def test_engine_matches_reference_cfg10d_two_media_one_mix(engine_lib):
+    n = 4000000
+    sim, g = cfg10d_from_reference(n)
+    e = sim.configure(abi.Engine(sim.config_struct(device=0), lib=engine_lib))
+    sim.run(e)
+    check_cfg10d(sim, e, g, n)
 
 
 @pytest.mark.gpu

@@ -27,14 +27,15 @@ def small(name, packets="2e4"):
     return re.sub(r'numPackets="[^"]*"', f'numPackets="{packets}"', open(os.path.join(SKI, name + ".ski")).read(), count=1)
 
 
-def two_media(text):
-    """Duplicates the GeometricMedium element: two dust components (MediumSystem.cpp:874-885 is not on the accelerated path)."""
+def two_mixes(text):
+    """Duplicates the GeometricMedium element and changes the copy's albedo: two dust components with DIFFERENT material mixes
+    (MediumSystem.cpp:874-885; several media that share one mix are on the accelerated path, tests/golden/ski/cfg10d.ski)."""
     a, b = text.index("<GeometricMedium"), text.index("</GeometricMedium>") + len("</GeometricMedium>")
-    return text[:b] + text[a:b] + text[b:]
+    return text[:b] + text[a:b].replace('albedos="0.6, 0.6"', 'albedos="0.4, 0.4"') + text[b:]
 
 
 @pytest.mark.parametrize("edit, reason", [
-    (two_media, "more than one medium"),
+    (two_mixes, "more than one medium with different material mixes"),
     (lambda s: s.replace('<RadiationFieldProbe', '<LaunchedPacketsProbe probeName="lpp"/><RadiationFieldProbe', 1),
      "launch call-back"),
     (lambda s: s.replace('recordPolarization="false"', 'recordPolarization="true"'), "polarization"),

@@ -179,6 +179,34 @@ def test_cfg8z_ski_observer_frame_redshift_runs_unchanged(tmp_path):
     assert total.astype(float).sum() == pytest.approx(g["frame_total_sum"].sum(), rel=4e-3)
 
 
+def test_cfg10d_ski_two_media_sharing_one_mix_runs_unchanged(tmp_path):
+    """Two dust media with the same material mix (ring + exponential disk): the reference's several-media configuration
+    (MediumSystem.cpp:874-885); the shim hands the engine the summed density.  Once with the reference's own set-up (same tree
+    and densities as the fixture), once with the tree built on the device from BOTH geometries."""
+    g = np.load(os.path.join(GOLD, "cfg10d_ref.npz"))
+    for host_setup in (True, False):
+        d = tmp_path / ("host" if host_setup else "device")
+        d.mkdir()
+        log = run_ski("cfg10d", d, 4e6, host_setup=host_setup)
+        assert "GPU life cycle:" in log and "outside the GPU life cycle" not in log
+        cells = read_columns(d / "cfg10d_cells_cellprops.dat")
+        if host_setup:
+            np.testing.assert_array_equal(cells[:, 6], g["mass_density_msun_pc3"])   # both media, summed by the probe
+        else:
+            assert "GPU tree construction" in log
+            assert len(cells) == pytest.approx(len(g["mass_density_msun_pc3"]), rel=0.03)
+            mass = lambda c, rho: float((c * rho).sum())
+            assert mass(cells[:, 4], cells[:, 6]) == pytest.approx(mass(g["cell_volume_pc3"], g["mass_density_msun_pc3"]), rel=0.01)
+        sed = read_columns(d / "cfg10d_i60_sed.dat")
+        stats = read_columns(d / "cfg10d_i60_sedstats.dat")
+        tol = 4.0 * np.hypot(rel_error(g["sedstats"][:, 1:].T), rel_error(stats[:, 1:].T)) + (0.0 if host_setup else 0.01)
+        for col in (1, 2, 3, 4):
+            bound = tol * np.maximum(g["sed"][:, col], g["sed"][:, 1])
+            assert np.all(np.abs(sed[:, col] - g["sed"][:, col]) <= bound), (host_setup, col)
+        total, _ = read_fits_cube(d / "cfg10d_i60_total.fits")
+        assert total.astype(float).sum() == pytest.approx(g["frame_total_sum"].sum(), rel=4e-3 if host_setup else 1.2e-2)
+
+
 def test_cfg4s_ski_dust_emission_runs_unchanged(tmp_path):
     g = np.load(os.path.join(GOLD, "cfg4s_ref.npz"))
     n = 2e6
