@@ -213,6 +213,8 @@ def run_shim_once(num_packets, threads, name="cfg2"):
     reference's host code, engine configuration, emission, output files)."""
     with tempfile.TemporaryDirectory() as d:
         log, wall, _, _ = run_ski(SHIM_EXE, name, num_packets, threads, d)
+    if os.environ.get("SK_KEEP_LOG"):  # diagnostic: keep the drop-in's log next to the bench line
+        open(os.environ["SK_KEEP_LOG"], "w").write(log)
     gpu_path = "GPU life cycle:" in log and "CPU life cycle (reference)" not in log
     if not gpu_path:
         raise RuntimeError("skirt_b200 did not run the GPU life cycle: " + log[-400:])
