@@ -30,7 +30,8 @@
 extern "C" {
 #endif
 
-#define SK_ABI_VERSION 4
+#define SK_ABI_VERSION 5
+#define SK_MAX_MEDIA 4 /* medium components with their own material mix (sk_engine_set_media) */
 
 typedef struct sk_engine sk_engine_t;
 
@@ -283,6 +284,20 @@ int sk_engine_read_medium(sk_engine_t* e, double* number_density, double* volume
 
 int sk_engine_set_dustmix(sk_engine_t* e, const sk_dustmix_t* mix);
 
+/* Several medium components, each with its own material mix (Configuration::hasMultipleConstantSectionMedia; f4 of SURVEY.md
+ * section 8): the medium state MediumState::numberDensity(m,h) for h = 0..num_media-1, number_density[h*num_cells + m], and
+ * the mix of every component.  All dust mixes of one simulation share the wavelength grid of their property tables
+ * (DustMix.cpp:52-98 derives it from the configuration alone), so lambda_border must be the same in all of them.  What changes
+ * on the path: optical depths sum sigma_h n_h over the components (MediumSystem.cpp:874-885, 1222-1240, 1012-1040), the
+ * albedo is sum k_sca / sum k_ext in the interaction cell (:678-693), a scattering peel-off is the sum of the components'
+ * phase functions weighted with their scattering opacities (:697-767), the scattering component is drawn from those weights
+ * with one extra deviate (:796-823), and the absorbed luminosity and the dust emission spectrum sum over the components, each
+ * with the equilibrium temperature of its own mix (:1317-1356, 1452-1476).  sk_engine_set_medium / sk_engine_set_dustmix are
+ * the num_media = 1 forms.  Up to SK_MAX_MEDIA components; explicit absorption is limited to one component. */
+int sk_engine_set_media(sk_engine_t* e, int32_t num_cells, int32_t num_media, const double* number_density,
+                        const double* volume);
+int sk_engine_set_dustmixes(sk_engine_t* e, int32_t num_media, const sk_dustmix_t* mixes);
+
 /* All wavelength grids used by instruments, the radiation field and dust emission, addressed by index.
  * rf_grid = index of Configuration::radiationFieldWLG() or -1 when no radiation field is stored. */
 int sk_engine_set_wavelength_grids(sk_engine_t* e, int32_t n, const sk_wavelength_grid_t* grids, int32_t rf_grid);
@@ -296,6 +311,9 @@ int sk_engine_set_sources(sk_engine_t* e, int32_t n, const sk_source_t* sources,
 int sk_engine_set_instruments(sk_engine_t* e, int32_t n, const sk_instrument_t* instruments, int32_t has_medium_emission);
 
 int sk_engine_set_secondary(sk_engine_t* e, const sk_secondary_t* sec);
+/* The same for several dust components: sec[h] holds the calculator tables of component h's mix (planck_abs, rf_sigma_abs,
+ * em_sigma_abs); the grid, the temperature grid and the bias settings must agree in all entries. */
+int sk_engine_set_secondary_media(sk_engine_t* e, int32_t num_media, const sk_secondary_t* sec);
 
 /* Zeroes all detector and statistics arrays (what FluxRecorder::finalizeConfiguration leaves behind,
  * FluxRecorder.cpp:185-300) so that one engine can run several simulations back to back. */

@@ -96,11 +96,11 @@ typedef struct sko_engine {
     int vcells, vnb;   /* number of cells; blocks per axis of the start-cell table */
     int32_t* vblock;   /* [vnb^3] a cell whose site lies in (or near) the block: start of the walk to the nearest site */
     double* vbox;      /* [6*ncells] enclosing boxes of the cells (VoronoiMeshSnapshot::Cell is a Box), or NULL */
-    /* medium */
-    int ncells;
+    /* medium: nmed components (Configuration::hasMultipleConstantSectionMedia when > 1); dens[h*ncells + m] */
+    int ncells, nmed;
     double *dens, *vol;
-    /* dust */
-    int nlam;
+    /* dust: one table set per component, [h*nlam + i]; the wavelength grid lam_border is common (DustMix.cpp:52-98) */
+    int nlam, nmix;
     double *lam_border, *sig_abs, *sig_sca, *sig_ext, *gpar;
     double mu;
     /* wavelength grids */
@@ -125,7 +125,9 @@ typedef struct sko_engine {
     /* secondary (dust) emission */
     int has_secondary;
     sk_secondary_t sec;
-    double *sec_T, *sec_planckabs, *sec_rfsig, *sec_emsig; /* EquilibriumDustEmissionCalculator tables */
+    int sec_nmed;
+    double *sec_T, *sec_planckabs, *sec_rfsig, *sec_emsig; /* EquilibriumDustEmissionCalculator tables, one set per dust
+                                                              component: [h*nT + i], [h*nrf + ell], [h*sec_nem + i] */
     int sec_nem;             /* N_em + 2 points of DisjointWavelengthGrid::extlambdav() */
     double* sec_lambda;      /* [sec_nem] */
     double *sec_pv, *sec_Pv; /* [ncells][sec_nem] normalised emission spectrum and cdf of every cell */
@@ -726,17 +728,23 @@ int sko_set_voronoi_extents(sko_engine_t* e, int32_t num_cells, const double* bo
     return SK_OK;
 }
 
-int sko_set_medium(sko_engine_t* e, int32_t num_cells, const double* number_density, const double* volume)
+int sko_set_media(sko_engine_t* e, int32_t num_cells, int32_t num_media, const double* number_density, const double* volume)
 {
     if (!e || !number_density) return fail(SK_ERR_INVALID, "null argument");
+    if (num_media < 1 || num_media > SK_MAX_MEDIA) return fail(SK_ERR_UNSUPPORTED, "number of medium components");
     if (!e->grid_kind) return fail(SK_ERR_STATE, "set the grid before the medium");
     if (num_cells != grid_num_cells(e)) return fail(SK_ERR_INVALID, "medium size does not match the grid");
     free(e->dens);
     free(e->vol);
     e->ncells = num_cells;
-    e->dens = dupd(number_density, num_cells);
+    e->nmed = num_media;
+    e->dens = dupd(number_density, (size_t)num_media * num_cells);
     e->vol = volume ? dupd(volume, num_cells) : NULL;
     return SK_OK;
+}
+int sko_set_medium(sko_engine_t* e, int32_t num_cells, const double* number_density, const double* volume)
+{
+    return sko_set_media(e, num_cells, 1, number_density, volume);
 }
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -910,6 +918,7 @@ int sko_sample_medium(sko_engine_t* e, const sk_density_geometry_t* medium, int3
     e->dens = (double*)malloc((size_t)nc * sizeof(double));
     e->vol = (double*)malloc((size_t)nc * sizeof(double));
     e->ncells = nc;
+    e->nmed = 1;
     for (int m = 0; m < nc; ++m)
     {
         double b[6];
@@ -963,24 +972,39 @@ int sko_read_medium(sko_engine_t* e, double* number_density, double* volume)
     return SK_OK;
 }
 
-int sko_set_dustmix(sko_engine_t* e, const sk_dustmix_t* mix)
+int sko_set_dustmixes(sko_engine_t* e, int32_t num_media, const sk_dustmix_t* mixes)
 {
-    if (!e || !mix || mix->num_lambda < 2) return fail(SK_ERR_INVALID, "bad dust mix");
-    int n = mix->num_lambda;
+    if (!e || !mixes || num_media < 1 || mixes[0].num_lambda < 2) return fail(SK_ERR_INVALID, "bad dust mix");
+    if (num_media > SK_MAX_MEDIA) return fail(SK_ERR_UNSUPPORTED, "number of medium components");
+    int n = mixes[0].num_lambda;
+    for (int h = 1; h < num_media; ++h)
+        if (mixes[h].num_lambda != n || memcmp(mixes[h].lambda_border, mixes[0].lambda_border, n * sizeof(double)))
+            return fail(SK_ERR_INVALID, "the dust mixes of one simulation share one wavelength grid (DustMix.cpp:52-98)");
     free(e->lam_border);
     free(e->sig_abs);
     free(e->sig_sca);
     free(e->sig_ext);
     free(e->gpar);
     e->nlam = n;
-    e->lam_border = dupd(mix->lambda_border, n);
-    e->sig_abs = dupd(mix->sigma_abs, n);
-    e->sig_sca = dupd(mix->sigma_sca, n);
-    e->gpar = dupd(mix->asymmpar, n);
-    e->sig_ext = (double*)malloc(n * sizeof(double));
-    for (int i = 0; i < n; ++i) e->sig_ext[i] = e->sig_abs[i] + e->sig_sca[i]; /* DustMix.cpp:160-163 */
-    e->mu = mix->mu;
+    e->nmix = num_media;
+    e->lam_border = dupd(mixes[0].lambda_border, n);
+    e->sig_abs = (double*)malloc((size_t)num_media * n * sizeof(double));
+    e->sig_sca = (double*)malloc((size_t)num_media * n * sizeof(double));
+    e->gpar = (double*)malloc((size_t)num_media * n * sizeof(double));
+    e->sig_ext = (double*)malloc((size_t)num_media * n * sizeof(double));
+    for (int h = 0; h < num_media; ++h)
+    {
+        memcpy(e->sig_abs + (size_t)h * n, mixes[h].sigma_abs, n * sizeof(double));
+        memcpy(e->sig_sca + (size_t)h * n, mixes[h].sigma_sca, n * sizeof(double));
+        memcpy(e->gpar + (size_t)h * n, mixes[h].asymmpar, n * sizeof(double));
+    }
+    for (int i = 0; i < num_media * n; ++i) e->sig_ext[i] = e->sig_abs[i] + e->sig_sca[i]; /* DustMix.cpp:160-163 */
+    e->mu = mixes[0].mu;
     return SK_OK;
+}
+int sko_set_dustmix(sko_engine_t* e, const sk_dustmix_t* mix)
+{
+    return sko_set_dustmixes(e, 1, mix);
 }
 
 static void alloc_rf(sko_engine_t* e)
@@ -1151,24 +1175,39 @@ static void free_secondary(sko_engine_t* e)
     e->has_secondary = e->secondary_ready = 0;
 }
 
-int sko_set_secondary(sko_engine_t* e, const sk_secondary_t* sec)
+int sko_set_secondary_media(sko_engine_t* e, int32_t num_media, const sk_secondary_t* sec)
 {
-    if (!e || !sec) return fail(SK_ERR_INVALID, "null argument");
+    if (!e || !sec || num_media < 1) return fail(SK_ERR_INVALID, "null argument");
+    if (num_media > SK_MAX_MEDIA) return fail(SK_ERR_UNSUPPORTED, "number of medium components");
     if (e->rf_grid < 0) return fail(SK_ERR_STATE, "dust emission needs a radiation field grid");
     if (e->grid_kind == 3 && !e->vbox)
         return fail(SK_ERR_STATE, "dust emission from a Voronoi grid needs the cell extents (sko_set_voronoi_extents)");
     if (sec->emission_grid < 0 || sec->emission_grid >= e->nwlg) return fail(SK_ERR_INVALID, "bad emission grid index");
-    if (sec->num_temperatures < 2 || !sec->temperature || !sec->planck_abs || !sec->rf_sigma_abs || !sec->em_sigma_abs)
-        return fail(SK_ERR_INVALID, "missing emission calculator tables");
+    for (int h = 0; h < num_media; ++h)
+    {
+        if (sec[h].num_temperatures < 2 || !sec[h].temperature || !sec[h].planck_abs || !sec[h].rf_sigma_abs || !sec[h].em_sigma_abs)
+            return fail(SK_ERR_INVALID, "missing emission calculator tables");
+        if (sec[h].emission_grid != sec->emission_grid || sec[h].num_temperatures != sec->num_temperatures
+            || memcmp(sec[h].temperature, sec->temperature, sec->num_temperatures * sizeof(double)))
+            return fail(SK_ERR_INVALID, "the emission calculators of the dust components must share their grids");
+    }
     free_secondary(e);
     e->sec = *sec;
+    e->sec_nmed = num_media;
     const sk_wavelength_grid_t* g = &e->wlg[sec->emission_grid].g;
     int n = g->num_bins;
+    const int nT = sec->num_temperatures;
     e->sec_nem = n + 2;
-    e->sec_T = dupd(sec->temperature, sec->num_temperatures);
-    e->sec_planckabs = dupd(sec->planck_abs, sec->num_temperatures);
-    e->sec_rfsig = dupd(sec->rf_sigma_abs, e->nrf);
-    e->sec_emsig = dupd(sec->em_sigma_abs, n + 2);
+    e->sec_T = dupd(sec->temperature, nT);
+    e->sec_planckabs = (double*)malloc((size_t)num_media * nT * sizeof(double));
+    e->sec_rfsig = (double*)malloc((size_t)num_media * e->nrf * sizeof(double));
+    e->sec_emsig = (double*)malloc((size_t)num_media * (n + 2) * sizeof(double));
+    for (int h = 0; h < num_media; ++h)
+    {
+        memcpy(e->sec_planckabs + (size_t)h * nT, sec[h].planck_abs, nT * sizeof(double));
+        memcpy(e->sec_rfsig + (size_t)h * e->nrf, sec[h].rf_sigma_abs, e->nrf * sizeof(double));
+        memcpy(e->sec_emsig + (size_t)h * (n + 2), sec[h].em_sigma_abs, (n + 2) * sizeof(double));
+    }
     /* DisjointWavelengthGrid::extlambdav, DisjointWavelengthGrid.cpp:346-356 */
     e->sec_lambda = (double*)malloc((n + 2) * sizeof(double));
     e->sec_lambda[0] = g->borders[0];
@@ -1176,6 +1215,10 @@ int sko_set_secondary(sko_engine_t* e, const sk_secondary_t* sec)
     e->sec_lambda[n + 1] = g->borders[g->num_borders - 1];
     e->has_secondary = 1;
     return SK_OK;
+}
+int sko_set_secondary(sko_engine_t* e, const sk_secondary_t* sec)
+{
+    return sko_set_secondary_media(e, 1, sec);
 }
 
 int sko_clear_instruments(sko_engine_t* e)
@@ -1269,7 +1312,10 @@ int sko_prepare_secondary(sko_engine_t* e, uint64_t num_packets, double* luminos
         double Labs = 0.;
         for (int ell = 0; ell < nrf; ++ell)
         {
-            double opacity = e->dens[m] * e->sig_abs[index_for_lambda(e, rfg->lambda[ell])];
+            /* MediumSystem::opacityAbs(lambda, m, Dust): sum over the dust components, MediumSystem.cpp:619-630 */
+            double opacity = 0.;
+            for (int h = 0; h < e->nmed; ++h)
+                opacity += e->dens[(size_t)h * M + m] * e->sig_abs[(size_t)h * e->nlam + index_for_lambda(e, rfg->lambda[ell])];
             double rf = 0.;
             rf += e->rf1[(size_t)m * nrf + ell];
             rf += e->rf2[(size_t)m * nrf + ell];
@@ -1315,31 +1361,41 @@ int sko_prepare_secondary(sko_engine_t* e, uint64_t num_packets, double* luminos
             memset(Pv, 0, nem * sizeof(double));
             continue;
         }
-        /* meanIntensity + equilibriumTemperature */
+        /* MediumSystem::dustEmissionSpectrum (MediumSystem.cpp:1466-1476): the sum over the dust components of
+           DustMix::emissionSpectrum = number density times the emissivity of the component's own mix at its own equilibrium
+           temperature in the cell's radiation field (meanIntensity + equilibriumTemperature) */
         double factor = 1. / (4. * M_PI * e->vol[m]);
-        double inputabs = 0.;
-        for (int ell = 0; ell < nrf; ++ell)
+        for (int i = 0; i < nem; ++i) pv[i] = 0.;
+        for (int h = 0; h < e->nmed; ++h)
         {
-            double rf = 0.;
-            rf += e->rf1[(size_t)m * nrf + ell];
-            rf += e->rf2[(size_t)m * nrf + ell];
-            double J = rf * factor / rfg->dlambda[ell];
-            inputabs += e->sec_rfsig[ell] * (J + 0.) * rfg->dlambda[ell];
+            const double* rfsig = e->sec_rfsig + (size_t)h * nrf;
+            const double* planckabs = e->sec_planckabs + (size_t)h * nT;
+            const double* emsig = e->sec_emsig + (size_t)h * nem;
+            double inputabs = 0.;
+            for (int ell = 0; ell < nrf; ++ell)
+            {
+                double rf = 0.;
+                rf += e->rf1[(size_t)m * nrf + ell];
+                rf += e->rf2[(size_t)m * nrf + ell];
+                double J = rf * factor / rfg->dlambda[ell];
+                inputabs += rfsig[ell] * (J + 0.) * rfg->dlambda[ell];
+            }
+            double T = 0.;
+            if (inputabs > 0.)
+            {
+                /* NR::clampedValue<interpolateLinLin>(inputabs, _planckabsvv, _Tv), NR.hpp:391-399 with NR::locate */
+                int i = inputabs == planckabs[nT - 1] ? nT - 2 : locate_basic(planckabs, inputabs, nT);
+                if (i < 0)
+                    T = e->sec_T[0];
+                else if (i >= nT - 1)
+                    T = e->sec_T[nT - 1];
+                else
+                    T = interp_linlin(inputabs, planckabs[i], planckabs[i + 1], e->sec_T[i], e->sec_T[i + 1]);
+            }
+            /* emissivity times number density on the extended emission grid */
+            const double n = e->dens[(size_t)h * M + m];
+            for (int i = 0; i < nem; ++i) pv[i] += n * (emsig[i] * planck(e->sec_lambda[i], T));
         }
-        double T = 0.;
-        if (inputabs > 0.)
-        {
-            /* NR::clampedValue<interpolateLinLin>(inputabs, _planckabsvv, _Tv), NR.hpp:391-399 with NR::locate */
-            int i = inputabs == e->sec_planckabs[nT - 1] ? nT - 2 : locate_basic(e->sec_planckabs, inputabs, nT);
-            if (i < 0)
-                T = e->sec_T[0];
-            else if (i >= nT - 1)
-                T = e->sec_T[nT - 1];
-            else
-                T = interp_linlin(inputabs, e->sec_planckabs[i], e->sec_planckabs[i + 1], e->sec_T[i], e->sec_T[i + 1]);
-        }
-        /* emissivity times number density on the extended emission grid */
-        for (int i = 0; i < nem; ++i) pv[i] = e->dens[m] * (e->sec_emsig[i] * planck(e->sec_lambda[i], T));
         /* NR::cdf<interpolateLogLog>(xv,pv,Pv, extlambdav, ev, range of the grid): the range is [ext[0], ext[n+1]], so
            the axis is the extended grid itself and the two outer values are the log-log interpolants evaluated at the
            end points of the first and last interval */
@@ -1783,7 +1839,17 @@ typedef struct {
     int has_tau;
     double tau_obs;
     int ilam; /* DustMix::indexForLambda(lambda), constant during the life cycle (no kinematics) */
+    int m_int; /* PhotonPacket::interactionCellIndex(): the cell of the last interaction point (SpatialGridPath.hpp:150) */
 } packet_t;
+
+/* the opacity sum over the medium components in cell m with the sections sig[h*nlam + ilam]: MediumSystem::opacitySca/Ext
+ * for spatially constant sections (MediumSystem.cpp:632-662), n_h * sigma_h each (MaterialMix::opacity*) */
+static double opacity_sum(const sko_engine_t* e, const double* sig, int ilam, int m)
+{
+    double result = 0.;
+    for (int h = 0; h < e->nmed; ++h) result += e->dens[(size_t)h * e->ncells + m] * sig[(size_t)h * e->nlam + ilam];
+    return result;
+}
 
 /* DustMix::indexForLambda, DustMix.cpp:276-279 */
 static int index_for_lambda(const sko_engine_t* e, double lambda)
@@ -1837,29 +1903,32 @@ static void set_extinction_optical_depths(sko_engine_t* e, const packet_t* pp)
     if (e->cfg.explicit_absorption)
     {
         /* MediumSystem::setScatteringAndAbsorptionOpticalDepths, single constant-section medium, MediumSystem.cpp:905-934 */
+        /* (several components: MediumSystem.cpp:937-955) */
         double tauSca = 0., tauAbs = 0.;
-        double sectionSca = e->sig_sca[pp->ilam], sectionAbs = e->sig_abs[pp->ilam];
         for (int n = 0; n < e->nsegs; ++n)
         {
             seg_t* sg = &e->segs[n];
             if (sg->m >= 0)
-            {
-                double ns = e->dens[sg->m] * sg->ds;
-                tauSca += sectionSca * ns;
-                tauAbs += sectionAbs * ns;
-            }
+                for (int h = 0; h < e->nmed; ++h)
+                {
+                    double ns = e->dens[(size_t)h * e->ncells + sg->m] * sg->ds;
+                    tauSca += e->sig_sca[(size_t)h * e->nlam + pp->ilam] * ns;
+                    tauAbs += e->sig_abs[(size_t)h * e->nlam + pp->ilam] * ns;
+                }
             sg->tau = tauSca;
             sg->tauabs = tauAbs;
         }
     }
     else
     {
+        /* single medium, MediumSystem.cpp:863-871; several media with constant sections, MediumSystem.cpp:874-885 */
         double tau = 0.;
-        double section = e->sig_ext[pp->ilam];
         for (int n = 0; n < e->nsegs; ++n)
         {
             seg_t* sg = &e->segs[n];
-            if (sg->m >= 0) tau += section * e->dens[sg->m] * sg->ds;
+            if (sg->m >= 0)
+                for (int h = 0; h < e->nmed; ++h)
+                    tau += e->sig_ext[(size_t)h * e->nlam + pp->ilam] * e->dens[(size_t)h * e->ncells + sg->m] * sg->ds;
             sg->tau = tau;
         }
     }
@@ -1876,14 +1945,15 @@ static double get_extinction_optical_depth(sko_engine_t* e, const packet_t* ppp)
     gen_t g;
     gen_start(&g, ppp->r, ppp->k);
     double tau = 0.;
-    double section = e->sig_ext[ppp->ilam];
     e->cnt.peel_paths++;
     while (gen_next(e, &g))
     {
         e->cnt.peel_segments++;
         if (g.m >= 0)
         {
-            tau += section * e->dens[g.m] * g.ds;
+            /* (several media: MediumSystem.cpp:1222-1240) */
+            for (int h = 0; h < e->nmed; ++h)
+                tau += e->sig_ext[(size_t)h * e->nlam + ppp->ilam] * e->dens[(size_t)h * e->ncells + g.m] * g.ds;
             if (tau >= taumax) return INFINITY;
         }
     }
@@ -2167,10 +2237,29 @@ static void peel_off_scattering(sko_engine_t* e, const packet_t* pp)
         if (!q->same_as_preceding)
         {
             double costheta = pp->k[0] * q->kobs[0] + pp->k[1] * q->kobs[1] + pp->k[2] * q->kobs[2];
-            double g = e->gpar[pp->ilam];
-            double value = fabs(g) > glarge ? mean_hg(g, costheta) : value_hg(g, costheta);
+            /* MediumSystem::weightsForScattering (MediumSystem.cpp:697-730): 1 for a single medium, else the scattering
+               opacities of the components in the interaction cell, normalised; none scatters: no peel-off at all
+               (MonteCarloSimulation.cpp:790-792) */
+            double wv[SK_MAX_MEDIA] = {1., 0., 0., 0.};
+            if (e->nmed > 1)
+            {
+                double sum = 0.;
+                for (int h = 0; h < e->nmed; ++h)
+                {
+                    wv[h] = e->dens[(size_t)h * e->ncells + pp->m_int] * e->sig_sca[(size_t)h * e->nlam + pp->ilam];
+                    sum += wv[h];
+                }
+                if (!(sum > 0.)) return;
+                for (int h = 0; h < e->nmed; ++h) wv[h] /= sum;
+            }
             double I = 0.;
-            I += value * 1.; /* single medium: weight wv[0] = 1, MediumSystem.cpp:703-708 */
+            for (int h = 0; h < e->nmed; ++h)
+                if (wv[h] > 0.)
+                {
+                    double g = e->gpar[(size_t)h * e->nlam + pp->ilam];
+                    double value = fabs(g) > glarge ? mean_hg(g, costheta) : value_hg(g, costheta);
+                    I += value * wv[h]; /* MediumSystem.cpp:745-754 */
+                }
             ppp = *pp;
             ppp.W = pp->W * I;
             ppp.nscatt = pp->nscatt + 1;
@@ -2558,13 +2647,13 @@ static void simulate_forced_propagation(sko_engine_t* e, rng_t* g, packet_t* pp,
         double albedo = 0.;
         if (m >= 0)
         {
-            double n = e->dens[m];
-            double ksca = n * e->sig_sca[pp->ilam];
-            double kext = n * e->sig_ext[pp->ilam];
+            double ksca = opacity_sum(e, e->sig_sca, pp->ilam, m);
+            double kext = opacity_sum(e, e->sig_ext, pp->ilam, m);
             albedo = kext > 0. ? ksca / kext : 0.;
         }
         pp->W *= -expm1(-taupath) * albedo;
     }
+    pp->m_int = m;
     /* PhotonPacket::propagate, PhotonPacket.cpp:107-111 */
     pp->r[0] += s * pp->k[0];
     pp->r[1] += s * pp->k[1];
@@ -2583,7 +2672,7 @@ static int simulate_nonforced_propagation(sko_engine_t* e, rng_t* g, packet_t* p
     /* with explicit absorption the walk is in scattering optical depth, setInteractionPointUsingScatteringAndAbsorption
        (MediumSystem.cpp:1075-1110), and the weight is the absorption along the way instead of the albedo (.cpp:757-762) */
     const int explicit_abs = e->cfg.explicit_absorption;
-    double section = explicit_abs ? e->sig_sca[pp->ilam] : e->sig_ext[pp->ilam];
+    const double* section = explicit_abs ? e->sig_sca : e->sig_ext; /* (several media: MediumSystem.cpp:1012-1040) */
     e->cnt.forward_paths++;
     while (gen_next(e, &gen))
     {
@@ -2591,15 +2680,17 @@ static int simulate_nonforced_propagation(sko_engine_t* e, rng_t* g, packet_t* p
         double tau0 = tau, s0 = s;
         double ds = gen.ds;
         int m = gen.m;
-        if (m >= 0) tau += section * e->dens[m] * gen.ds;
+        if (m >= 0)
+            for (int h = 0; h < e->nmed; ++h)
+                tau += section[(size_t)h * e->nlam + pp->ilam] * e->dens[(size_t)h * e->ncells + m] * gen.ds;
         s += ds;
         if (tauinteract < tau)
         {
             double sint = interp_linlin(tauinteract, tau0, tau, s0, s);
-            double n = e->dens[m];
-            double ksca = n * e->sig_sca[pp->ilam];
-            double kext = n * e->sig_ext[pp->ilam];
+            double ksca = opacity_sum(e, e->sig_sca, pp->ilam, m);
+            double kext = opacity_sum(e, e->sig_ext, pp->ilam, m);
             double albedo = kext > 0. ? ksca / kext : 0.;
+            pp->m_int = m;
             if (explicit_abs) albedo = exp(-(tauinteract * e->sig_abs[pp->ilam] / e->sig_sca[pp->ilam]));
             pp->W *= albedo;
             pp->r[0] += sint * pp->k[0];
@@ -2615,7 +2706,19 @@ static int simulate_nonforced_propagation(sko_engine_t* e, rng_t* g, packet_t* p
  * (DustMix.cpp:496-511), PhotonPacket::scatter (PhotonPacket.cpp:115-122) */
 static void simulate_scattering(sko_engine_t* e, rng_t* g, packet_t* pp)
 {
-    double gp = e->gpar[pp->ilam];
+    /* select a medium component within the cell: NR::cdf over the scattering opacities (NR.hpp:446-463: cumulative sums
+       divided by the total, first element zero) and NR::locateClip of one uniform deviate, MediumSystem.cpp:805-818 */
+    int hsel = 0;
+    if (e->nmed > 1)
+    {
+        double Xv[SK_MAX_MEDIA + 1];
+        Xv[0] = 0.;
+        for (int h = 0; h < e->nmed; ++h)
+            Xv[h + 1] = Xv[h] + e->dens[(size_t)h * e->ncells + pp->m_int] * e->sig_sca[(size_t)h * e->nlam + pp->ilam];
+        for (int h = 0; h <= e->nmed; ++h) Xv[h] /= Xv[e->nmed];
+        hsel = locate_clip(Xv, e->nmed + 1, uniform(g));
+    }
+    double gp = e->gpar[(size_t)hsel * e->nlam + pp->ilam];
     double knew[3];
     if (fabs(gp) < 1e-6)
         random_direction(g, knew);
@@ -2684,6 +2787,10 @@ int sko_run_segment(sko_engine_t* e, uint64_t first, uint64_t count, int32_t pri
     if (primary && !e->nsrc) return fail(SK_ERR_STATE, "engine is not fully configured");
     if (primary && !e->npackets) return fail(SK_ERR_STATE, "call prepare_primary first");
     if (!primary && !e->secondary_ready) return fail(SK_ERR_STATE, "call prepare_secondary first");
+    if (e->nmed != e->nmix) return fail(SK_ERR_STATE, "the number of dust mixes does not match the number of medium components");
+    if (e->nmed > 1 && e->cfg.explicit_absorption)
+        return fail(SK_ERR_UNSUPPORTED, "explicit absorption with several medium components");
+    if (!primary && e->sec_nmed != e->nmed) return fail(SK_ERR_STATE, "emission tables do not match the medium components");
     if (store && e->rf_grid < 0) return fail(SK_ERR_STATE, "no radiation field grid configured");
     if (store && !e->cfg.force_scattering)
         return fail(SK_ERR_INVALID, "storing the radiation field requires forced scattering (Configuration.cpp:476-482)");
@@ -2729,7 +2836,9 @@ int sko_absorbed_luminosity(sko_engine_t* e, int32_t primary, double* out)
         for (int ell = 0; ell < e->nrf; ++ell)
         {
             int il = index_for_lambda(e, g->lambda[ell]);
-            sum += e->sig_abs[il] * e->dens[m] * rf[(size_t)m * e->nrf + ell];
+            double opacity = 0.; /* MediumSystem::opacityAbs over the dust components */
+            for (int h = 0; h < e->nmed; ++h) opacity += e->sig_abs[(size_t)h * e->nlam + il] * e->dens[(size_t)h * e->ncells + m];
+            sum += opacity * rf[(size_t)m * e->nrf + ell];
         }
         Labs += sum;
     }

@@ -254,6 +254,26 @@ class Engine:
         mix = SkDustMix(len(lb), 0, p0, p1, p2, p3, mu)
         self._call("set_dustmix", self._h, C.byref(mix))
 
+    def set_media(self, number_density, volume=None):
+        """Several medium components: number_density[h][m] (sk_engine_set_media)."""
+        n, pn = _d(np.asarray(number_density, dtype=np.float64).reshape(len(number_density), -1))
+        if volume is not None:
+            v, pv = _d(volume)
+        else:
+            pv = None
+        self._call("set_media", self._h, C.c_int32(n.shape[1]), C.c_int32(n.shape[0]), pn, pv)
+        self.num_cells = n.shape[1]
+
+    def set_dustmixes(self, mixes: Sequence[tuple]):
+        """mixes: (lambda_border, sigma_abs, sigma_sca, asymmpar, mu) per medium component (sk_engine_set_dustmixes)."""
+        arr = (SkDustMix * len(mixes))()
+        keep = []
+        for h, (lambda_border, sigma_abs, sigma_sca, asymmpar, mu) in enumerate(mixes):
+            k = [_d(lambda_border), _d(sigma_abs), _d(sigma_sca), _d(asymmpar)]
+            keep.append(k)
+            arr[h] = SkDustMix(len(k[0][0]), 0, k[0][1], k[1][1], k[2][1], k[3][1], mu)
+        self._call("set_dustmixes", self._h, C.c_int32(len(mixes)), arr)
+
     def set_wavelength_grids(self, grids: Sequence[dict], rf_grid: int = -1):
         """grids: dicts with keys borders, ell, lambda, dlambda (see host.DisjointWavelengthGrid.table())."""
         arr = (SkWavelengthGrid * max(1, len(grids)))()
@@ -338,6 +358,17 @@ class Engine:
         sec = SkSecondary(emission_grid, len(keep[0][0]), spatial_bias, wavelength_bias, bias_min, bias_max,
                           keep[0][1], keep[1][1], keep[2][1], keep[3][1])
         self._call("set_secondary", self._h, C.byref(sec))
+
+    def set_secondary_media(self, emission_grid, spatial_bias, wavelength_bias, bias_min, bias_max, tables: Sequence[tuple]):
+        """tables: (temperature, planck_abs, rf_sigma_abs, em_sigma_abs) per dust component (sk_engine_set_secondary_media)."""
+        arr = (SkSecondary * len(tables))()
+        keep = []
+        for h, t in enumerate(tables):
+            k = [_d(x) for x in t]
+            keep.append(k)
+            arr[h] = SkSecondary(emission_grid, len(k[0][0]), spatial_bias, wavelength_bias, bias_min, bias_max,
+                                 k[0][1], k[1][1], k[2][1], k[3][1])
+        self._call("set_secondary_media", self._h, C.c_int32(len(tables)), arr)
 
     # -- running --------------------------------------------------------------------------------
     def clear_instruments(self):

@@ -896,6 +896,13 @@ class MonteCarloSimulation:
     # (sk_engine_build_octree / sk_engine_sample_medium) instead of with the numpy code of setup()
     deviceSetup: bool = False
     density: Optional[np.ndarray] = field(default=None, repr=False)
+    # further medium components, each with its own material mix (Configuration::hasMultipleConstantSectionMedia); `density`
+    # is then [component][cell]
+    extraMedia: List[GeometricMedium] = field(default_factory=list)
+
+    @property
+    def media(self):
+        return [self.medium] + list(self.extraMedia)
 
     def setup(self):
         """Simulation::setup(): digests the hierarchy into the flat tables the engine needs."""
@@ -916,7 +923,7 @@ class MonteCarloSimulation:
                 self.grids.append(g)
         # Configuration::simulationWavelengthRange / simulationWavelengths, Configuration.cpp:566-662
         lo, hi = self.source_range
-        extra = [self.medium.norm_wavelength]
+        extra = [md.norm_wavelength for md in self.media]
         for g in self.grids:
             a, b = g.wavelength_range()
             lo, hi = min(lo, a), max(hi, b)
@@ -924,12 +931,15 @@ class MonteCarloSimulation:
         if self.storeRadiationField and not oligo:
             lo, hi = min(lo, 0.09e-6), max(hi, 2000e-6)
         lo, hi = lo / 1.01, hi * 1.01
-        self.medium.mix.setup((lo, hi), extra)
+        for md in self.media:
+            md.mix.setup((lo, hi), extra)
         if self.dustEmissionWLG is not None:
             if not self.storeRadiationField or self.radiationFieldWLG is None:
                 raise ValueError("DustEmission mode needs a stored radiation field")
-            self.medium.mix.precalculate(self.radiationFieldWLG, self.dustEmissionWLG)
-        self.medium.setup()
+            for md in self.media:
+                md.mix.precalculate(self.radiationFieldWLG, self.dustEmissionWLG)
+        for md in self.media:
+            md.setup()
         for s in self.sources:
             s.sed.setup(self.source_range)
         # grid and medium state (MediumSystem.cpp:286-399)
@@ -937,11 +947,13 @@ class MonteCarloSimulation:
             if not isinstance(self.grid, (CartesianSpatialGrid, PolicyTreeSpatialGrid)) \
                     or isinstance(self.grid, FileTreeSpatialGrid):
                 raise ValueError("deviceSetup needs a Cartesian or policy octree grid")
+            if self.extraMedia:
+                raise ValueError("deviceSetup samples a single medium component")
             if isinstance(self.grid, CartesianSpatialGrid):
                 self.grid.setup([self.medium], self.numDensitySamples, rng)
             self.density = self.volume = None  # both come from the engine in configure()
             return self
-        self.grid.setup([self.medium], self.numDensitySamples, rng)
+        self.grid.setup(self.media, self.numDensitySamples, rng)
         if isinstance(self.grid, VoronoiMeshSpatialGrid):
             if self.dustEmissionWLG is not None and self.grid.cell_extents is None:
                 self.grid.compute_cell_geometry()  # emission positions need the cells' enclosing boxes, J their volumes
@@ -951,26 +963,31 @@ class MonteCarloSimulation:
             if self.density is None:
                 # MediumSystem.cpp:286-399 with numDensitySamples = 1: the density at the cell's site
                 st = self.grid.sites
-                self.density = self.medium.number_density(st[:, 0], st[:, 1], st[:, 2])
+                self.density = np.stack([md.number_density(st[:, 0], st[:, 1], st[:, 2]) for md in self.media])
+                if not self.extraMedia:
+                    self.density = self.density[0]
         else:
             boxes = self.grid.cell_boxes()
             self.volume = np.prod(boxes[:, 3:] - boxes[:, :3], axis=1)
             n = len(boxes)
-        dens = np.zeros(n)
+        nmed = len(self.media)
+        dens = np.zeros((nmed, n))
         if self.density is not None:
-            # medium state imported from a SpatialCellPropertiesProbe file of a reference run (tests/golden)
-            if len(self.density) != n:
+            # medium state imported from a SpatialCellPropertiesProbe / DensityProbe file of a reference run (tests/golden)
+            dens = np.asarray(self.density, dtype=float).reshape(nmed, -1)
+            if dens.shape[1] != n:
                 raise ValueError("imported density does not match the grid")
-            dens = np.asarray(self.density, dtype=float)
         elif self.numDensitySamples == 1:
             c = 0.5 * (boxes[:, :3] + boxes[:, 3:])
-            dens = self.medium.number_density(c[:, 0], c[:, 1], c[:, 2])
+            for h, md in enumerate(self.media):
+                dens[h] = md.number_density(c[:, 0], c[:, 1], c[:, 2])
         else:
             for _ in range(self.numDensitySamples):
                 p = boxes[:, :3] + rng.random((n, 3)) * (boxes[:, 3:] - boxes[:, :3])
-                dens += self.medium.number_density(p[:, 0], p[:, 1], p[:, 2])
+                for h, md in enumerate(self.media):
+                    dens[h] += md.number_density(p[:, 0], p[:, 1], p[:, 2])
             dens /= self.numDensitySamples
-        self.density = dens
+        self.density = dens if self.extraMedia else dens[0]
         return self
 
     def config_struct(self, device=0):
@@ -1001,10 +1018,17 @@ class MonteCarloSimulation:
         else:
             self.grid.configure(engine)
             mark("grid")
-            engine.set_medium(self.density, self.volume)
+            if self.extraMedia:
+                engine.set_media(self.density, self.volume)
+            else:
+                engine.set_medium(self.density, self.volume)
         mark("medium")
         mix = self.medium.mix
-        engine.set_dustmix(mix.lambda_border, mix.sigma_abs, mix.sigma_sca, mix.asymmpar, mix.mu)
+        if self.extraMedia:
+            engine.set_dustmixes([(md.mix.lambda_border, md.mix.sigma_abs, md.mix.sigma_sca, md.mix.asymmpar, md.mix.mu)
+                                  for md in self.media])
+        else:
+            engine.set_dustmix(mix.lambda_border, mix.sigma_abs, mix.sigma_sca, mix.asymmpar, mix.mu)
         rf = -1
         if self.storeRadiationField:
             rf = [k for k, g in enumerate(self.grids) if g is self.radiationFieldWLG][0]
@@ -1035,9 +1059,15 @@ class MonteCarloSimulation:
         if self.dustEmissionWLG is not None:
             mix, eg = self.medium.mix, self.dustEmissionWLG
             lo, hi = eg.wavelength_range()
-            engine.set_secondary([k for k, h in enumerate(self.grids) if h is eg][0], self.secondarySpatialBias,
-                                 self.dustEmissionWavelengthBias, lo, hi, mix.Tv, mix.planck_abs, mix.rf_sigma_abs,
-                                 mix.em_sigma_abs)
+            if self.extraMedia:
+                engine.set_secondary_media([k for k, h in enumerate(self.grids) if h is eg][0], self.secondarySpatialBias,
+                                           self.dustEmissionWavelengthBias, lo, hi,
+                                           [(md.mix.Tv, md.mix.planck_abs, md.mix.rf_sigma_abs, md.mix.em_sigma_abs)
+                                            for md in self.media])
+            else:
+                engine.set_secondary([k for k, h in enumerate(self.grids) if h is eg][0], self.secondarySpatialBias,
+                                     self.dustEmissionWavelengthBias, lo, hi, mix.Tv, mix.planck_abs, mix.rf_sigma_abs,
+                                     mix.em_sigma_abs)
         mark("secondary")
         # seconds spent per group of engine calls (bench.py reports them under e2e.parts)
         self.last_configure_parts = {marks[k][0]: marks[k][1] - marks[k - 1][1] for k in range(1, len(marks))}

@@ -139,6 +139,55 @@ def make_cfg10d():
     print("cfg10d:", {k: np.shape(v) for k, v in out.items()})
 
 
+def make_cfg11m():
+    """Two dust media with DIFFERENT material mixes on the cfg2s octree (extinction only): the fixture holds the tree and the
+    mass density of EACH component (DensityProbe, aggregation Component) as the reference sampled them.  2e6 packets."""
+    with tempfile.TemporaryDirectory() as d:
+        run_reference("cfg11m", d, packets=2e6)
+        cells = read_columns(os.path.join(d, "cfg11m_cells_cellprops.dat"))
+        rho = np.stack([read_columns(os.path.join(d, "cfg11m_dns_%d_rho.dat" % h))[:, 1] for h in range(2)])
+        total = read_fits_cube(os.path.join(d, "cfg11m_i60_total.fits"))[0].astype(np.float64)
+        out = dict(sed=read_columns(os.path.join(d, "cfg11m_i60_sed.dat")),
+                   sedstats=read_columns(os.path.join(d, "cfg11m_i60_sedstats.dat")), component_mass_density_msun_pc3=rho,
+                   cell_center_pc=cells[:, 1:4], cell_volume_pc3=cells[:, 4],
+                   topology=parse_topology(os.path.join(d, "cfg11m_topo_treetop.dat")), num_packets=2e6,
+                   frame_total_sum=total.sum(axis=0))
+    np.savez_compressed(os.path.join(HERE, "cfg11m_ref.npz"), **out)
+    print("cfg11m:", {k: np.shape(v) for k, v in out.items()})
+
+
+def make_cfg12me(packets=None, tag="cfg12me_ref"):
+    """Dust emission with iterations from two dust media with different mixes (cfg4s with a second, uniform shell)."""
+    with tempfile.TemporaryDirectory() as d:
+        log = run_reference("cfg12me", d, packets=packets)
+        cells = read_columns(os.path.join(d, "cfg12me_cells_cellprops.dat"))
+        rho = np.stack([read_columns(os.path.join(d, "cfg12me_dns_%d_rho.dat" % h))[:, 1] for h in range(2)])
+        rfJ = read_columns(os.path.join(d, "cfg12me_rf_J.dat"))
+        prim = [float(x) for x in re.findall(r"dust-absorbed primary luminosity is ([0-9.eE+-]+) Lsun", log)]
+        sec = [float(x) for x in re.findall(r"dust-absorbed secondary luminosity in iteration \d+ is ([0-9.eE+-]+) Lsun", log)]
+        dustlum = [float(x) for x in re.findall(r"Dust luminosity: ([0-9.eE+-]+) Lsun", log)]
+        conv = re.search(r"Convergence reached after (\d+) iterations", log)
+        out = dict(sed=read_columns(os.path.join(d, "cfg12me_sed_sed.dat")),
+                   sedstats=read_columns(os.path.join(d, "cfg12me_sed_sedstats.dat")),
+                   J_nu_shell=shell_average(cells, rfJ[:, 1:]), absorbed_primary_lsun=np.array(prim),
+                   absorbed_secondary_lsun=np.array(sec), dust_luminosity_lsun=np.array(dustlum),
+                   converged_after=int(conv.group(1)) if conv else -1, num_packets=packets or 2e5)
+        if packets is None:
+            T = read_columns(os.path.join(d, "cfg12me_temp_dust_T.dat"))
+            out.update(component_mass_density_msun_pc3=rho, cell_center_pc=cells[:, 1:4], cell_volume_pc3=cells[:, 4],
+                       topology=parse_topology(os.path.join(d, "cfg12me_topo_treetop.dat")),
+                       temperature=T[:, 1].astype(np.float32))
+        else:
+            base = np.load(os.path.join(HERE, "cfg12me_ref.npz"))["component_mass_density_msun_pc3"]
+            assert np.array_equal(rho, base), "the high-statistics run must see the inputs of the base fixture"
+    np.savez_compressed(os.path.join(HERE, tag + ".npz"), **out)
+    print(tag + ":", {k: np.shape(v) for k, v in out.items()}, prim, sec, conv and conv.group(0))
+
+
+def make_cfg12me_hi():
+    make_cfg12me(packets=2e6, tag="cfg12me_hi_ref")
+
+
 def make_hi(name, packets=2e7):
     """High-statistics companion of a fixture: the same ski with `packets` histories, still with `-t 1` because the
     tree and the cell densities are sampled from the thread's random stream (Random.cpp:31-36) and must stay those of

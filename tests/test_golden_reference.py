@@ -297,6 +297,51 @@ def test_engine_matches_reference_cfg10d_two_media_one_mix(engine_lib):
     check_cfg10d(sim, e, g, n)
 
 
+def cfg11m_from_reference(num_packets):
+    """cfg2s with two dust media with DIFFERENT material mixes (tests/golden/ski/cfg11m.ski): the tree and the density of
+    each component as the reference sampled them (DensityProbe per component)."""
+    g = load("cfg11m")
+    sim = configs.cfg2(num_packets=num_packets, seed=0, max_level=6, max_dust_fraction=1e-4, num_pixels=64,
+                       num_wavelengths=10, record_statistics=True)
+    pc = H.PC
+    sim.medium.tau = 0.7
+    mix2 = H.MeanListDustMix([0.1e-6, 0.55e-6, 10e-6], [1500.0, 1200.0, 400.0], [0.8, 0.7, 0.5], [0.3, 0.2, 0.0])
+    sim.extraMedia = [H.GeometricMedium(H.ExpDiskGeometry(5000 * pc, 250 * pc, 0.0, 20000 * pc, 2000 * pc), mix2,
+                                        opticalDepth=0.5, wavelength=0.55e-6)]
+    sim.grid = H.FileTreeSpatialGrid(-20000 * pc, 20000 * pc, -20000 * pc, 20000 * pc, -2000 * pc, 2000 * pc,
+                                     g["topology"], policyOrder=True)
+    sim.density = g["component_mass_density_msun_pc3"] * RHO / sim.medium.mix.MU
+    sim.setup()
+    boxes = sim.grid.cell_boxes()
+    np.testing.assert_allclose(0.5 * (boxes[:, :3] + boxes[:, 3:]) / pc, g["cell_center_pc"], rtol=1e-8, atol=1e-6)
+    assert sim.density.shape == (2, len(boxes))
+    return sim, g
+
+
+def test_oracle_matches_reference_cfg11m_two_media_two_mixes():
+    n = 300000
+    sim, g = cfg11m_from_reference(n)
+    e = sim.configure(OracleEngine(sim.config_struct()))
+    sim.run(e)
+    check_cfg10d(sim, e, g, n, nsigma=5.0)
+    # the test must be able to fail: the same model with the second component given the first one's mix is far off
+    sim2, _ = cfg11m_from_reference(n)
+    sim2.extraMedia[0].mix = sim2.medium.mix
+    e2 = sim2.configure(OracleEngine(sim2.config_struct()))
+    sim2.run(e2)
+    with pytest.raises(AssertionError):
+        check_cfg10d(sim2, e2, g, n, nsigma=5.0)
+
+
+@pytest.mark.gpu
+def test_engine_matches_reference_cfg11m_two_media_two_mixes(engine_lib):
+    n = 4000000
+    sim, g = cfg11m_from_reference(n)
+    e = sim.configure(abi.Engine(sim.config_struct(device=0), lib=engine_lib))
+    sim.run(e)
+    check_cfg10d(sim, e, g, n)
+
+
 @pytest.mark.gpu
 def test_engine_matches_reference_cfg8z_redshift(engine_lib):
     n = 4000000
@@ -364,7 +409,7 @@ def cfg4s_from_reference(num_packets):
     return sim, g
 
 
-def check_cfg4s(sim, e, g, n, tol_scale=1.0, nsigma=4.0):
+def check_cfg4s(sim, e, g, n, tol_scale=1.0, nsigma=4.0, hi_name="cfg4s_hi"):
     LSUN = H.LSUN
     conv = sim.convergence
     # the reference's log (MonteCarloSimulation.cpp:193-214): absorbed primary luminosity, then per iteration the
@@ -381,7 +426,7 @@ def check_cfg4s(sim, e, g, n, tol_scale=1.0, nsigma=4.0):
     lam = sim.defaultWavelengthGrid.lambdav
     np.testing.assert_allclose(lam * 1e6, sed[:, 0], rtol=1e-9)
     sed_bins_within_statistics(sim, e, g, nsigma, nsigma + 1.0)
-    sed_bins_within_statistics(sim, e, load("cfg4s_hi"), nsigma, nsigma + 1.0)
+    sed_bins_within_statistics(sim, e, load(hi_name), nsigma, nsigma + 1.0)
     # radiation field rf1+rf2 after the run, volume-weighted in radial shells, per wavelength bin
     J = sim.mean_intensity_nu(e, 0) + sim.mean_intensity_nu(e, 1)
     r = np.linalg.norm(g["cell_center_pc"], axis=1)
@@ -397,7 +442,7 @@ def check_cfg4s(sim, e, g, n, tol_scale=1.0, nsigma=4.0):
     # The reference records no statistics for the radiation field, so its noise is measured from the reference itself:
     # the fixture run (2e5 packets per segment) against the same ski with ten times the packets (cfg4s_hi) gives the rms
     # relative noise of a shell value per wavelength bin at 2e5 packets, which scales with 1/sqrt(packets).
-    hi = load("cfg4s_hi")
+    hi = load(hi_name)
     nb, nh = float(g["num_packets"]), float(hi["num_packets"])
     dev = ((ref - hi["J_nu_shell"]) / hi["J_nu_shell"])[ok]
     noise_base = math.sqrt(float(np.mean(dev ** 2)) / (1.0 + nb / nh))        # rms over the tested shell values, at nb packets
@@ -411,6 +456,41 @@ def check_cfg4s(sim, e, g, n, tol_scale=1.0, nsigma=4.0):
     tot_hi = (hi["J_nu_shell"] * den[:, None])[3:].sum(axis=0)
     np.testing.assert_allclose(tot[strong], tot_hi[strong], rtol=0.04 * tol_scale * max(1.0, math.sqrt(nh / n) / 3))
     assert tot.sum() == pytest.approx(tot_ref.sum(), rel=0.01 * tol_scale)
+
+
+def cfg12me_from_reference(num_packets):
+    """cfg4s with a second dust component of another mix (tests/golden/ski/cfg12me.ski): dust emission summed over the
+    components, each at the equilibrium temperature of its own mix (MediumSystem.cpp:1452-1476)."""
+    g = load("cfg12me")
+    sim = configs.cfg4(num_packets=num_packets, seed=0, record_statistics=True)
+    pc = H.PC
+    sim.medium.tau = 12.0
+    mix2 = H.MeanListDustMix([0.05e-6, 0.55e-6, 10e-6, 100e-6, 2000e-6], [2500.0, 1500.0, 300.0, 30.0, 0.1],
+                             [0.7, 0.75, 0.4, 0.05, 0.001], [0.3, 0.2, 0.0, 0.0, 0.0])
+    sim.extraMedia = [H.GeometricMedium(H.ShellGeometry(0.2 * pc, 0.9 * pc, 0.0), mix2, opticalDepth=6.0, wavelength=0.55e-6)]
+    sim.grid = H.FileTreeSpatialGrid(-pc, pc, -pc, pc, -pc, pc, g["topology"], policyOrder=True)
+    sim.density = g["component_mass_density_msun_pc3"] * RHO / sim.medium.mix.MU
+    sim.setup()
+    boxes = sim.grid.cell_boxes()
+    np.testing.assert_allclose(0.5 * (boxes[:, :3] + boxes[:, 3:]) / pc, g["cell_center_pc"], rtol=1e-8, atol=1e-9)
+    return sim, g
+
+
+def test_oracle_matches_reference_cfg12me_dust_emission_two_mixes():
+    n = 50000
+    sim, g = cfg12me_from_reference(n)
+    e = sim.configure(OracleEngine(sim.config_struct()))
+    sim.run(e)
+    check_cfg4s(sim, e, g, n, tol_scale=2.0, nsigma=5.0, hi_name="cfg12me_hi")
+
+
+@pytest.mark.gpu
+def test_engine_matches_reference_cfg12me_dust_emission_two_mixes(engine_lib):
+    n = 2000000
+    sim, g = cfg12me_from_reference(n)
+    e = sim.configure(abi.Engine(sim.config_struct(device=0), lib=engine_lib))
+    sim.run(e)
+    check_cfg4s(sim, e, g, n, hi_name="cfg12me_hi")
 
 
 def test_oracle_matches_reference_cfg4s_dust_emission():
