@@ -234,7 +234,16 @@ def make_sim(name, total_packets, statistics=False):
     """The workload as host mirror objects (setup() done: grid built, densities sampled)."""
     from skirt9_b200 import configs
     if name == "cfg2":
-        return configs.cfg2(num_packets=total_packets, record_statistics=statistics).setup()
+        sim = configs.cfg2(num_packets=total_packets, record_statistics=statistics)
+        if os.environ.get("SK_BENCH_SECOND_MIX"):
+            # diagnostic (not a BASELINE workload): cfg2 with a second dust component of another material mix, the cost of the
+            # several-component trace kernels next to the single-medium ones
+            from skirt9_b200 import host as H
+            mix2 = H.MeanListDustMix([0.1e-6, 0.55e-6, 10e-6], [1500.0, 1200.0, 400.0], [0.8, 0.7, 0.5], [0.3, 0.2, 0.0])
+            sim.medium.tau = 0.6
+            sim.extraMedia = [H.GeometricMedium(H.ExpDiskGeometry(5000 * PC, 250 * PC, 0.0, 20000 * PC, 2000 * PC), mix2,
+                                                opticalDepth=0.4, wavelength=0.55e-6)]
+        return sim.setup()
     if name == "cfg1":
         return configs.cfg1(num_packets=total_packets, record_statistics=statistics).setup()
     if name == "cfg4":

@@ -449,6 +449,23 @@ void GpuLifeCycle::check(int rc) const
 
 ////////////////////////////////////////////////////////////////////
 
+// true when every medium component has the tables of the first one's dust mix
+bool GpuLifeCycle::mediaShareOneMix() const
+{
+    auto ms = _sim->mediumSystem();
+    auto mix = dynamic_cast<const DustMix*>(ms->media()[0]->mix());
+    for (int h = 1; h < ms->numMedia(); ++h)
+    {
+        auto other = dynamic_cast<const DustMix*>(ms->media()[h]->mix());
+        if (!mix || !other || other->type() != mix->type() || other->scatteringMode() != mix->scatteringMode()
+            || other->mass() != mix->mass() || !sameValues(other->_lambdav, mix->_lambdav)
+            || !sameValues(other->_sigmaabsv, mix->_sigmaabsv) || !sameValues(other->_sigmascav, mix->_sigmascav)
+            || !sameValues(other->_asymmparv, mix->_asymmparv))
+            return false;
+    }
+    return true;
+}
+
 std::string GpuLifeCycle::unsupportedReason() const
 {
     auto config = _sim->_config;
@@ -466,15 +483,20 @@ std::string GpuLifeCycle::unsupportedReason() const
     if (ProcessManager::isMultiProc()) return "MPI (use one engine per rank through the C ABI instead)";
     auto mix = dynamic_cast<const DustMix*>(ms->media()[0]->mix());
     if (!mix || mix->scatteringMode() != DustMix::ScatteringMode::HenyeyGreenstein) return "a material mix other than a Henyey-Greenstein dust mix";
-    // several media (MediumSystem.cpp:874-885, 697-767): the cell record holds ONE density, so they must share one material
-    // mix; opacity, albedo, phase function and emissivity are then those of a single medium with the summed density
+    // several media (MediumSystem.cpp:874-885, 697-767): components that share one material mix are a single medium with the
+    // summed density (opacity, albedo, phase function and emissivity are the same); components with different mixes run on the
+    // engine's several-component path (sk_engine_set_media), up to SK_MAX_MEDIA of them and without explicit absorption
     for (int h = 1; h < ms->numMedia(); ++h)
     {
         auto other = dynamic_cast<const DustMix*>(ms->media()[h]->mix());
-        if (!other || other->type() != mix->type() || other->scatteringMode() != mix->scatteringMode() || other->mass() != mix->mass()
-            || !sameValues(other->_lambdav, mix->_lambdav) || !sameValues(other->_sigmaabsv, mix->_sigmaabsv)
-            || !sameValues(other->_sigmascav, mix->_sigmascav) || !sameValues(other->_asymmparv, mix->_asymmparv))
-            return "more than one medium with different material mixes";
+        if (!other || other->scatteringMode() != DustMix::ScatteringMode::HenyeyGreenstein)
+            return "a material mix other than a Henyey-Greenstein dust mix";
+        if (!sameValues(other->_lambdav, mix->_lambdav)) return "dust mixes with different property wavelength grids";
+    }
+    if (!mediaShareOneMix())
+    {
+        if (ms->numMedia() > SK_MAX_MEDIA) return "more than " + std::to_string(SK_MAX_MEDIA) + " media with different material mixes";
+        if (config->explicitAbsorption()) return "explicit absorption with several different material mixes";
     }
     auto grid = ms->grid();
     auto tree = dynamic_cast<TreeSpatialGrid*>(grid);
@@ -632,27 +654,39 @@ void GpuLifeCycle::configureEngine(int device)
 
     // ---- medium state (MediumState.cpp:196-247)
     int M = ms->numCells();
-    vector<double> nv(M), Vv(M);
-    const int numMedia = ms->numMedia();  // all with the same material mix (unsupportedReason): the densities add up
+    const int numMedia = ms->numMedia();
+    // components with the same material mix: the densities add up to one medium; different mixes: one engine component each
+    const int numComponents = mediaShareOneMix() ? 1 : numMedia;
+    vector<double> nv(static_cast<size_t>(numComponents) * M), Vv(M);
     for (int m = 0; m != M; ++m)
     {
-        nv[m] = ms->numberDensity(m, 0);
-        for (int h = 1; h < numMedia; ++h) nv[m] += ms->numberDensity(m, h);
+        if (numComponents == 1)
+        {
+            nv[m] = ms->numberDensity(m, 0);
+            for (int h = 1; h < numMedia; ++h) nv[m] += ms->numberDensity(m, h);
+        }
+        else
+            for (int h = 0; h < numMedia; ++h) nv[static_cast<size_t>(h) * M + m] = ms->numberDensity(m, h);
         Vv[m] = ms->volume(m);
     }
-    check(sk_engine_set_medium(_e, M, nv.data(), Vv.data()));
+    check(sk_engine_set_media(_e, M, numComponents, nv.data(), Vv.data()));
 
-    // ---- dust mix tables (DustMix.cpp:47-246)
+    // ---- dust mix tables (DustMix.cpp:47-246), one set per engine component
     auto mix = dynamic_cast<const DustMix*>(ms->media()[0]->mix());
-    sk_dustmix_t d;
-    memset(&d, 0, sizeof d);
-    d.num_lambda = static_cast<int32_t>(mix->_lambdav.size());
-    d.lambda_border = ptr(mix->_lambdav);
-    d.sigma_abs = ptr(mix->_sigmaabsv);
-    d.sigma_sca = ptr(mix->_sigmascav);
-    d.asymmpar = ptr(mix->_asymmparv);
-    d.mu = mix->mass();
-    check(sk_engine_set_dustmix(_e, &d));
+    vector<sk_dustmix_t> dv(numComponents);
+    for (int h = 0; h < numComponents; ++h)
+    {
+        auto mh = dynamic_cast<const DustMix*>(ms->media()[h]->mix());
+        sk_dustmix_t& d = dv[h];
+        memset(&d, 0, sizeof d);
+        d.num_lambda = static_cast<int32_t>(mh->_lambdav.size());
+        d.lambda_border = ptr(mh->_lambdav);
+        d.sigma_abs = ptr(mh->_sigmaabsv);
+        d.sigma_sca = ptr(mh->_sigmascav);
+        d.asymmpar = ptr(mh->_asymmparv);
+        d.mu = mh->mass();
+    }
+    check(sk_engine_set_dustmixes(_e, numComponents, dv.data()));
 
     // ---- wavelength grids: every distinct grid used by the instruments, the radiation field and dust emission
     vector<DisjointWavelengthGrid*> grids;
@@ -787,21 +821,25 @@ void GpuLifeCycle::configureEngine(int device)
     // ---- dust emission (EquilibriumDustEmissionCalculator.cpp:18-93)
     if (config->hasSecondaryEmission())
     {
-        auto& calc = mix->_calc;
-        sk_secondary_t sec;
-        memset(&sec, 0, sizeof sec);
-        sec.emission_grid = emGrid;
-        sec.num_temperatures = static_cast<int32_t>(calc._Tv.size());
-        sec.spatial_bias = config->secondarySpatialBias();
-        sec.wavelength_bias = config->dustEmissionWavelengthBias();
+        vector<sk_secondary_t> secv(numComponents);
         Range r = config->dustEmissionWLG()->wavelengthRange();
-        sec.bias_min = r.min();
-        sec.bias_max = r.max();
-        sec.temperature = ptr(calc._Tv);
-        sec.planck_abs = ptr(calc._planckabsvv[0]);
-        sec.rf_sigma_abs = ptr(calc._rfsigmaabsvv[0]);
-        sec.em_sigma_abs = ptr(calc._emsigmaabsvv[0]);
-        check(sk_engine_set_secondary(_e, &sec));
+        for (int h = 0; h < numComponents; ++h)
+        {
+            auto& calc = dynamic_cast<const DustMix*>(ms->media()[h]->mix())->_calc;
+            sk_secondary_t& sec = secv[h];
+            memset(&sec, 0, sizeof sec);
+            sec.emission_grid = emGrid;
+            sec.num_temperatures = static_cast<int32_t>(calc._Tv.size());
+            sec.spatial_bias = config->secondarySpatialBias();
+            sec.wavelength_bias = config->dustEmissionWavelengthBias();
+            sec.bias_min = r.min();
+            sec.bias_max = r.max();
+            sec.temperature = ptr(calc._Tv);
+            sec.planck_abs = ptr(calc._planckabsvv[0]);
+            sec.rf_sigma_abs = ptr(calc._rfsigmaabsvv[0]);
+            sec.em_sigma_abs = ptr(calc._emsigmaabsvv[0]);
+        }
+        check(sk_engine_set_secondary_media(_e, numComponents, secv.data()));
     }
 }
 

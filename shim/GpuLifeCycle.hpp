@@ -33,6 +33,7 @@ public:
 
     // returns an empty string when the configured simulation lies on the accelerated path, or the reason why not
     std::string unsupportedReason() const;
+    bool mediaShareOneMix() const;  // all medium components have the tables of one dust mix (they then run as one medium)
 
     // hands all tables to the engine (the extractor of INTEGRATION.md section 1); call after setupSimulation()
     void configure();

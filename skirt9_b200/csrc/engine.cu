@@ -177,6 +177,7 @@ __global__ void sk_sum_kernel(double* __restrict__ out, const double* __restrict
 // MediumSystem::totalDustAbsorbedLuminosity, MediumSystem.cpp:1317-1356 (single dust medium, constant sections)
 __global__ void sk_absorbed_kernel(const double* __restrict__ rf, const double* __restrict__ dens_or_null,
                                    const SkCellRec* __restrict__ cells, const double4* __restrict__ vrec,
+                                   const double* __restrict__ densx, int nmed,
                                    const double* __restrict__ kabs, int ncells, int nrf, double* out)
 {
     double sum = 0.;
@@ -184,7 +185,13 @@ __global__ void sk_absorbed_kernel(const double* __restrict__ rf, const double* 
     {
         double n = dens_or_null ? dens_or_null[m] : cells ? cells[m].dens : vrec[m].w;
         double s = 0.;
-        for (int ell = 0; ell < nrf; ++ell) s += kabs[ell] * n * rf[(size_t)ell * ncells + m];  // SK_RF_INDEX
+        for (int ell = 0; ell < nrf; ++ell)
+        {
+            // MediumSystem::opacityAbs over the dust components; kabs[h*nrf + ell]
+            double opacity = kabs[ell] * n;
+            for (int h = 1; h < nmed; ++h) opacity += kabs[h * nrf + ell] * densx[(size_t)(h - 1) * ncells + m];
+            s += opacity * rf[(size_t)ell * ncells + m];  // SK_RF_INDEX
+        }
         sum += s;
     }
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
@@ -250,6 +257,8 @@ struct sk_engine {
     std::vector<int> instr_same_observer;
     std::vector<std::array<double, 3>> instr_kobs;
     bool secondary_ready = false, has_secondary = false;
+    int num_mixes = 0;      // dust mixes given by sk_engine_set_dustmixes; must equal M.nmed when a segment runs
+    int sec_num_media = 0;  // dust components the secondary-emission tables were given for
     int num_pix_lists = 0;
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
@@ -341,6 +350,7 @@ extern "C" int sk_engine_create(const sk_config_t* config, sk_engine_t** out)
     e->M.path_length_bias = config->path_length_bias;
     e->M.min_weight_reduction = config->min_weight_reduction;
     e->M.rf_grid = -1;
+    e->M.nmed = 1;
     CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     g_stream = e->stream;
     {
@@ -420,6 +430,8 @@ static void drop_grid(sk_engine* e)
     e->M.ncells = 0;
     e->M.cells = nullptr;
     e->M.dens = nullptr;
+    e->M.densx = nullptr;
+    e->M.nmed = 1;
     e->M.volume = nullptr;
     e->M.vrec = nullptr;
     e->M.vbox = nullptr;
@@ -428,6 +440,7 @@ static void drop_grid(sk_engine* e)
     e->M.xv = e->M.yv = e->M.zv = nullptr;
     e->M.rf1 = e->M.rf2 = e->M.rf2c = nullptr;
     e->M.rf_grid = -1;
+    e->M.nmed = 1;
     e->M.nrf = 0;
     e->has_secondary = false;
     e->secondary_ready = false;
@@ -649,11 +662,28 @@ extern "C" int sk_engine_set_voronoi_extents(sk_engine_t* e, int32_t num_cells, 
 extern "C" int sk_engine_set_medium(sk_engine_t* e, int32_t num_cells, const double* number_density,
                                     const double* volume)
 {
+    return sk_engine_set_media(e, num_cells, 1, number_density, volume);
+}
+
+extern "C" int sk_engine_set_media(sk_engine_t* e, int32_t num_cells, int32_t num_media, const double* number_density,
+                                   const double* volume)
+{
     if (!e || !number_density) return fail(SK_ERR_INVALID, "null argument");
+    if (num_media < 1 || num_media > SK_MAX_MEDIA)
+        return fail(SK_ERR_UNSUPPORTED, "between 1 and " + std::to_string(SK_MAX_MEDIA) + " medium components are supported");
     if (!e->grid_kind) return fail(SK_ERR_STATE, "set the grid before the medium");
     if (num_cells != e->grid_cells) return fail(SK_ERR_INVALID, "medium size does not match the grid");
     if (int rc_bind = bind(e)) return rc_bind;
     free_group(e->medium_allocs);
+    e->M.densx = nullptr;
+    e->M.nmed = num_media;
+    if (num_media > 1)
+    {
+        // the components beyond the first: densx[(h-1)*ncells + m]
+        double* dx;
+        if (int rc = upload(e->medium_allocs, number_density + num_cells, (size_t)(num_media - 1) * num_cells, &dx)) return rc;
+        e->M.densx = dx;
+    }
     e->dens_host.assign(number_density, number_density + num_cells);
     if (e->grid_kind == 1)
     {
@@ -957,6 +987,8 @@ extern "C" int sk_engine_sample_medium(sk_engine_t* e, const sk_density_geometry
     CK(cudaStreamSynchronize(e->stream));
     e->dens_host.clear();
     e->M.dens = d_dens;
+    e->M.densx = nullptr;
+    e->M.nmed = 1;
     e->M.volume = d_vol;
     e->M.ncells = nc;
     return SK_OK;
@@ -1001,26 +1033,50 @@ extern "C" int sk_engine_read_medium(sk_engine_t* e, double* number_density, dou
 
 extern "C" int sk_engine_set_dustmix(sk_engine_t* e, const sk_dustmix_t* mix)
 {
-    if (!e || !mix || mix->num_lambda < 2) return fail(SK_ERR_INVALID, "bad dust mix");
+    return sk_engine_set_dustmixes(e, 1, mix);
+}
+
+extern "C" int sk_engine_set_dustmixes(sk_engine_t* e, int32_t num_media, const sk_dustmix_t* mixes)
+{
+    if (!e || !mixes || num_media < 1 || mixes[0].num_lambda < 2) return fail(SK_ERR_INVALID, "bad dust mix");
+    if (num_media > SK_MAX_MEDIA)
+        return fail(SK_ERR_UNSUPPORTED, "between 1 and " + std::to_string(SK_MAX_MEDIA) + " medium components are supported");
+    const int n = mixes[0].num_lambda;
+    for (int h = 0; h < num_media; ++h)
+    {
+        if (!mixes[h].lambda_border || !mixes[h].sigma_abs || !mixes[h].sigma_sca || !mixes[h].asymmpar)
+            return fail(SK_ERR_INVALID, "bad dust mix");
+        if (mixes[h].num_lambda != n || memcmp(mixes[h].lambda_border, mixes[0].lambda_border, (size_t)n * sizeof(double)))
+            return fail(SK_ERR_INVALID, "the dust mixes of one simulation share one wavelength grid (DustMix.cpp:52-98)");
+    }
     if (int rc_bind = bind(e)) return rc_bind;
     free_group(e->dust_allocs);
-    int n = mix->num_lambda;
-    std::vector<double> ext(n);
-    for (int i = 0; i < n; ++i) ext[i] = mix->sigma_abs[i] + mix->sigma_sca[i];  // DustMix.cpp:160-163
+    // one table set per component, [h*n + i]
+    std::vector<double> abs((size_t)num_media * n), sca((size_t)num_media * n), ext((size_t)num_media * n), gp((size_t)num_media * n);
+    for (int h = 0; h < num_media; ++h)
+        for (int i = 0; i < n; ++i)
+        {
+            const size_t k = (size_t)h * n + i;
+            abs[k] = mixes[h].sigma_abs[i];
+            sca[k] = mixes[h].sigma_sca[i];
+            ext[k] = mixes[h].sigma_abs[i] + mixes[h].sigma_sca[i];  // DustMix.cpp:160-163
+            gp[k] = mixes[h].asymmpar[i];
+        }
     double *a, *b, *c, *d, *g;
-    if (int rc = upload(e->dust_allocs, mix->lambda_border, (size_t)n, &a)) return rc;
-    if (int rc = upload(e->dust_allocs, mix->sigma_abs, (size_t)n, &b)) return rc;
-    if (int rc = upload(e->dust_allocs, mix->sigma_sca, (size_t)n, &c)) return rc;
-    if (int rc = upload(e->dust_allocs, ext.data(), (size_t)n, &d)) return rc;
-    if (int rc = upload(e->dust_allocs, mix->asymmpar, (size_t)n, &g)) return rc;
+    if (int rc = upload(e->dust_allocs, mixes[0].lambda_border, (size_t)n, &a)) return rc;
+    if (int rc = upload(e->dust_allocs, abs.data(), abs.size(), &b)) return rc;
+    if (int rc = upload(e->dust_allocs, sca.data(), sca.size(), &c)) return rc;
+    if (int rc = upload(e->dust_allocs, ext.data(), ext.size(), &d)) return rc;
+    if (int rc = upload(e->dust_allocs, gp.data(), gp.size(), &g)) return rc;
     e->M.nlam = n;
     e->M.lam_border = a;
     e->M.sig_abs = b;
     e->M.sig_sca = c;
     e->M.sig_ext = d;
     e->M.gpar = g;
-    e->dust_lam_border.assign(mix->lambda_border, mix->lambda_border + n);
-    e->dust_sig_abs.assign(mix->sigma_abs, mix->sigma_abs + n);
+    e->num_mixes = num_media;
+    e->dust_lam_border.assign(mixes[0].lambda_border, mixes[0].lambda_border + n);
+    e->dust_sig_abs = abs;
     return SK_OK;
 }
 
@@ -1346,15 +1402,27 @@ static int dust_index_for_lambda(const sk_engine* e, double lambda)
 
 extern "C" int sk_engine_set_secondary(sk_engine_t* e, const sk_secondary_t* sec)
 {
-    if (!e || !sec) return fail(SK_ERR_INVALID, "null argument");
+    return sk_engine_set_secondary_media(e, 1, sec);
+}
+
+extern "C" int sk_engine_set_secondary_media(sk_engine_t* e, int32_t num_media, const sk_secondary_t* sec)
+{
+    if (!e || !sec || num_media < 1) return fail(SK_ERR_INVALID, "null argument");
+    if (num_media != e->num_mixes) return fail(SK_ERR_INVALID, "one set of emission tables per dust mix is needed");
     if (e->M.rf_grid < 0) return fail(SK_ERR_STATE, "dust emission needs a radiation field grid");
     if (e->grid_kind == 3 && !e->M.vbox)
         return fail(SK_ERR_STATE, "dust emission from a Voronoi grid needs the cell extents (sk_engine_set_voronoi_extents)");
     if (!e->M.volume) return fail(SK_ERR_STATE, "dust emission needs the cell volumes (sk_engine_set_medium)");
     if (!e->M.nlam) return fail(SK_ERR_STATE, "set the dust mix before the secondary emission tables");
     if (sec->emission_grid < 0 || sec->emission_grid >= e->M.nwlg) return fail(SK_ERR_INVALID, "bad emission grid index");
-    if (sec->num_temperatures < 2 || !sec->temperature || !sec->planck_abs || !sec->rf_sigma_abs || !sec->em_sigma_abs)
-        return fail(SK_ERR_INVALID, "missing emission calculator tables");
+    for (int h = 0; h < num_media; ++h)
+    {
+        if (sec[h].num_temperatures < 2 || !sec[h].temperature || !sec[h].planck_abs || !sec[h].rf_sigma_abs || !sec[h].em_sigma_abs)
+            return fail(SK_ERR_INVALID, "missing emission calculator tables");
+        if (sec[h].emission_grid != sec->emission_grid || sec[h].num_temperatures != sec->num_temperatures
+            || memcmp(sec[h].temperature, sec->temperature, (size_t)sec->num_temperatures * sizeof(double)))
+            return fail(SK_ERR_INVALID, "the emission calculators of the dust components must share their grids");
+    }
     if (int rc_bind = bind(e)) return rc_bind;
     free_group(e->sec_allocs);
     e->sec = *sec;
@@ -1366,16 +1434,25 @@ extern "C" int sk_engine_set_secondary(sk_engine_t* e, const sk_secondary_t* sec
     ext[0] = e->wlg_border_lo[sec->emission_grid];
     for (int ell = 0; ell < n; ++ell) ext[ell + 1] = glam[ell];
     ext[nem - 1] = e->wlg_border_hi[sec->emission_grid];
-    std::vector<double> kabs(nrf);
+    const int nT = sec->num_temperatures, nlam = e->M.nlam;
+    std::vector<double> kabs((size_t)num_media * nrf), emsig((size_t)num_media * nem), rfsig((size_t)num_media * nrf),
+        planckabs((size_t)num_media * nT);
     const std::vector<double>& rflam = e->wlg_lambda[e->M.rf_grid];
-    for (int ell = 0; ell < nrf; ++ell) kabs[ell] = e->dust_sig_abs[dust_index_for_lambda(e, rflam[ell])];
+    for (int h = 0; h < num_media; ++h)
+    {
+        for (int ell = 0; ell < nrf; ++ell)
+            kabs[(size_t)h * nrf + ell] = e->dust_sig_abs[(size_t)h * nlam + dust_index_for_lambda(e, rflam[ell])];
+        std::copy(sec[h].em_sigma_abs, sec[h].em_sigma_abs + nem, emsig.begin() + (size_t)h * nem);
+        std::copy(sec[h].rf_sigma_abs, sec[h].rf_sigma_abs + nrf, rfsig.begin() + (size_t)h * nrf);
+        std::copy(sec[h].planck_abs, sec[h].planck_abs + nT, planckabs.begin() + (size_t)h * nT);
+    }
     double *a, *b, *c, *d, *f, *k;
     if (int rc = upload(e->sec_allocs, ext.data(), (size_t)nem, &a)) return rc;
-    if (int rc = upload(e->sec_allocs, sec->em_sigma_abs, (size_t)nem, &b)) return rc;
-    if (int rc = upload(e->sec_allocs, sec->rf_sigma_abs, (size_t)nrf, &c)) return rc;
-    if (int rc = upload(e->sec_allocs, sec->temperature, (size_t)sec->num_temperatures, &d)) return rc;
-    if (int rc = upload(e->sec_allocs, sec->planck_abs, (size_t)sec->num_temperatures, &f)) return rc;
-    if (int rc = upload(e->sec_allocs, kabs.data(), (size_t)nrf, &k)) return rc;
+    if (int rc = upload(e->sec_allocs, emsig.data(), emsig.size(), &b)) return rc;
+    if (int rc = upload(e->sec_allocs, rfsig.data(), rfsig.size(), &c)) return rc;
+    if (int rc = upload(e->sec_allocs, sec->temperature, (size_t)nT, &d)) return rc;
+    if (int rc = upload(e->sec_allocs, planckabs.data(), planckabs.size(), &f)) return rc;
+    if (int rc = upload(e->sec_allocs, kabs.data(), kabs.size(), &k)) return rc;
     e->M.sec_nem = nem;
     e->M.sec_nT = sec->num_temperatures;
     e->M.sec_lambda = a;
@@ -1393,6 +1470,7 @@ extern "C" int sk_engine_set_secondary(sk_engine_t* e, const sk_secondary_t* sec
     e->M.sec_bias_min = sec->bias_min;
     e->M.sec_bias_max = sec->bias_max;
     e->has_secondary = true;
+    e->sec_num_media = num_media;
     e->secondary_ready = false;
     return SK_OK;
 }
@@ -1584,10 +1662,10 @@ static int ensure_bank(sk_engine* e, uint64_t count)
     return SK_OK;
 }
 
-template <int GRID, int MODE, bool STORE, bool SMEMT>
+template <int GRID, int MODE, bool STORE, bool SMEMT, bool MULTI>
 static int launch_trace_impl(sk_engine* e, const SkRunArgs& A, const SkObsDir& dir)
 {
-    auto kern = sk_wf_trace<GRID, MODE, STORE, SMEMT>;
+    auto kern = sk_wf_trace<GRID, MODE, STORE, SMEMT, MULTI>;
     // occupancy of this instantiation on this engine's device for its shared-memory footprint (cached in the engine:
     // engines on different devices run from different host threads).  The staged tables never exceed 48 KB (set_tables),
     // the default limit of dynamic shared memory, so no per-device function attribute has to be set.
@@ -1623,8 +1701,14 @@ template <int GRID, int MODE, bool STORE>
 static int launch_trace(sk_engine* e, const SkRunArgs& A, const SkObsDir& dir)
 {
     // only the Cartesian grid looks borders up while it walks (TMA-staged tables); the octree walks in lattice coordinates
-    if (GRID == 1 && e->M.lattice_in_smem) return launch_trace_impl<GRID, MODE, STORE, GRID == 1>(e, A, dir);
-    return launch_trace_impl<GRID, MODE, STORE, false>(e, A, dir);
+    // several medium components with their own mixes: the instantiation that sums the opacities
+    if (e->M.nmed > 1)
+    {
+        if (GRID == 1 && e->M.lattice_in_smem) return launch_trace_impl<GRID, MODE, STORE, GRID == 1, true>(e, A, dir);
+        return launch_trace_impl<GRID, MODE, STORE, false, true>(e, A, dir);
+    }
+    if (GRID == 1 && e->M.lattice_in_smem) return launch_trace_impl<GRID, MODE, STORE, GRID == 1, false>(e, A, dir);
+    return launch_trace_impl<GRID, MODE, STORE, false, false>(e, A, dir);
 }
 
 template <int GRID>
@@ -1693,7 +1777,7 @@ static int run_bank(sk_engine* e, const SkRunArgs& A)
             {
                 CK(cudaMemsetAsync(&K.ctl[SK_CTL_NLIST], 0, sizeof(unsigned int), e->stream));
                 if (int rc = stage_begin(e, SK_STAGE_PEEL_SETUP)) return rc;
-                sk_wf_peel_setup<<<eblocks, SK_EVENT_BLOCK, 0, e->stream>>>(M, K, j0, j1);
+                sk_wf_peel_setup<<<eblocks, SK_EVENT_BLOCK, 0, e->stream>>>(M, A.model, K, j0, j1);
                 CK(cudaGetLastError());
                 if (int rc = stage_end(e)) return rc;
             }
@@ -1786,6 +1870,10 @@ extern "C" int sk_engine_launch_segment(sk_engine_t* e, uint64_t first, uint64_t
     if (primary && !e->M.nsrc) return fail(SK_ERR_STATE, "engine is not fully configured");
     if (primary && !e->npackets) return fail(SK_ERR_STATE, "call sk_engine_prepare_primary first");
     if (!primary && !e->secondary_ready) return fail(SK_ERR_STATE, "call sk_engine_prepare_secondary first");
+    if (e->num_mixes != e->M.nmed) return fail(SK_ERR_STATE, "the number of dust mixes does not match the number of medium components");
+    if (e->M.nmed > 1 && e->M.explicit_absorption)
+        return fail(SK_ERR_UNSUPPORTED, "explicit absorption with several medium components");
+    if (!primary && e->sec_num_media != e->M.nmed) return fail(SK_ERR_STATE, "emission tables do not match the medium components");
     if (store && e->M.rf_grid < 0) return fail(SK_ERR_STATE, "no radiation field grid configured");
     if (store && !e->M.force_scattering)
         return fail(SK_ERR_INVALID, "storing the radiation field requires forced scattering (Configuration.cpp:476-482)");
@@ -1909,14 +1997,17 @@ extern "C" int sk_engine_absorbed_luminosity(sk_engine_t* e, int32_t primary, do
     if (int rc_bind = bind(e)) return rc_bind;
     // kappa_abs per RF bin: DustMix::sectionAbs(lambda_ell) = _sigmaabsv[indexForLambda(lambda_ell)]
     const std::vector<double>& lam = e->wlg_lambda[e->M.rf_grid];
-    std::vector<double> kabs(lam.size());
-    for (size_t i = 0; i < lam.size(); ++i) kabs[i] = e->dust_sig_abs[dust_index_for_lambda(e, lam[i])];
+    if (e->num_mixes != e->M.nmed) return fail(SK_ERR_STATE, "the number of dust mixes does not match the number of medium components");
+    std::vector<double> kabs(lam.size() * (size_t)e->M.nmed);
+    for (int h = 0; h < e->M.nmed; ++h)
+        for (size_t i = 0; i < lam.size(); ++i)
+            kabs[(size_t)h * lam.size() + i] = e->dust_sig_abs[(size_t)h * e->M.nlam + dust_index_for_lambda(e, lam[i])];
     double* dk = nullptr;
     CK(dev_malloc(&dk, kabs.size() * sizeof(double)));
     CK(cudaMemcpyAsync(dk, kabs.data(), kabs.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemsetAsync(e->scalar, 0, sizeof(double), e->stream));
-    sk_absorbed_kernel<<<296, 256, 0, e->stream>>>(primary ? e->M.rf1 : e->M.rf2, e->M.dens, e->M.cells, e->M.vrec, dk,
-                                                   e->M.ncells, e->M.nrf, e->scalar);
+    sk_absorbed_kernel<<<296, 256, 0, e->stream>>>(primary ? e->M.rf1 : e->M.rf2, e->M.dens, e->M.cells, e->M.vrec, e->M.densx,
+                                                   e->M.nmed, dk, e->M.ncells, e->M.nrf, e->scalar);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, e->scalar, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));

@@ -1076,6 +1076,26 @@ __device__ __forceinline__ double sk_cell_density(const SkDevModel& M, int m)
 {
     return GRID == 3 ? M.vrec[m].w : GRID == 2 ? M.cells[m].dens : M.dens[m];
 }
+// number density of medium component h in cell m (MediumState::numberDensity(m,h))
+template <int GRID>
+__device__ __forceinline__ double sk_component_density(const SkDevModel& M, int m, int h)
+{
+    return h == 0 ? sk_cell_density<GRID>(M, m) : M.densx[(size_t)(h - 1) * (size_t)M.ncells + (size_t)m];
+}
+// the same without the grid as a template parameter (kernels that serve every grid kind)
+__device__ __forceinline__ double sk_component_density_any(const SkDevModel& M, int m, int h)
+{
+    if (h > 0) return M.densx[(size_t)(h - 1) * (size_t)M.ncells + (size_t)m];
+    return M.grid_kind == 3 ? M.vrec[m].w : M.grid_kind == 2 ? M.cells[m].dens : M.dens[m];
+}
+// MediumSystem::opacitySca / opacityExt in cell m for sections that are constant in space (MediumSystem.cpp:632-662): the
+// sum over the components of n_h sigma_h, sigma from the table sig[h*nlam + ilam]
+__device__ __forceinline__ double sk_opacity_sum(const SkDevModel& M, const double* __restrict__ sig, int ilam, int m)
+{
+    double result = 0.;
+    for (int h = 0; h < M.nmed; ++h) result += sk_component_density_any(M, m, h) * sig[h * M.nlam + ilam];
+    return result;
+}
 // true when (x,y,z) lies in the half-open box of cell c (octree: in lattice coordinates, like the walk itself)
 template <int GRID>
 __device__ __forceinline__ bool sk_cell_contains(const SkDevModel& M, const SkSmemTables& T, const SkCellPos& c, double x,

@@ -103,7 +103,11 @@ struct SkDevModel {
     const double* vbox;  // [6*ncells] enclosing boxes of the Voronoi cells (dust emission only), or null
     int32_t vnb;
     const double* volume;        // cell volumes (MediumState::volume)
-    // dust
+    // several medium components with their own material mixes (sk_engine_set_media): the density of component 0 lives where
+    // the single medium's does (cell record / dens[]), the others in densx[(h-1)*ncells + m]
+    int32_t nmed;
+    const double* densx;
+    // dust: one table set per component, [h*nlam + i]; lam_border is common to all mixes (DustMix.cpp:52-98)
     int32_t nlam;
     const double *lam_border, *sig_abs, *sig_sca, *sig_ext, *gpar;
     // wavelength grids
@@ -117,8 +121,8 @@ struct SkDevModel {
     double Lpp;
     // secondary (dust) emission, sk_secondary.cuh
     int32_t sec_nem, sec_nT;         // points of the extended emission grid; size of the temperature grid
-    const double *sec_lambda, *sec_emsig, *sec_rfsig, *sec_T, *sec_planckabs;
-    const double* sec_kabs_rf;       // sigma_abs at the characteristic wavelengths of the radiation field grid
+    const double *sec_lambda, *sec_emsig, *sec_rfsig, *sec_T, *sec_planckabs;  // per component: [h*sec_nem+i], [h*nrf+ell], -, [h*sec_nT+i]
+    const double* sec_kabs_rf;       // sigma_abs at the characteristic wavelengths of the radiation field grid, [h*nrf + ell]
     double *sec_pv, *sec_Pv;         // [ncells][sec_nem] normalised emission spectrum and its cdf
     double *sec_Lv, *sec_ws;         // [ncells] absorbed luminosity; launch weight _Lv[m]/_Wv[m]
     unsigned long long* sec_Iv;      // [ncells+1] history index -> cell map

@@ -16,11 +16,14 @@ __global__ void sk_dust_luminosity_kernel(const SkDevModel M)
 {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= M.ncells) return;
-    const double n = sk_cell_density<GRID>(M, m);
+    double nh[SK_MAX_MEDIA];
+    for (int h = 0; h < M.nmed; ++h) nh[h] = sk_component_density<GRID>(M, m, h);
     double Labs = 0.;
     for (int ell = 0; ell < M.nrf; ++ell)
     {
-        double opacity = n * M.sec_kabs_rf[ell];
+        // MediumSystem::opacityAbs(lambda, m, Dust): the sum over the dust components (MediumSystem.cpp:619-630)
+        double opacity = nh[0] * M.sec_kabs_rf[ell];
+        for (int h = 1; h < M.nmed; ++h) opacity += nh[h] * M.sec_kabs_rf[h * M.nrf + ell];
         double rf = 0.;
         rf += M.rf1[SK_RF_INDEX(M, m, ell)];
         rf += M.rf2[SK_RF_INDEX(M, m, ell)];
@@ -69,29 +72,40 @@ __global__ void sk_emission_spectrum_kernel(const SkDevModel M)
     }
     const SkDevWlg& rfg = M.wlg[M.rf_grid];
     const double factor = 1. / (4. * M_PI * M.volume[m]);
-    double inputabs = 0.;
-    for (int ell = 0; ell < nrf; ++ell)
-    {
-        double rf = 0.;
-        rf += M.rf1[SK_RF_INDEX(M, m, ell)];
-        rf += M.rf2[SK_RF_INDEX(M, m, ell)];
-        double J = rf * factor / rfg.dlambda[ell];
-        inputabs += M.sec_rfsig[ell] * (J + 0.) * rfg.dlambda[ell];
-    }
-    double T = 0.;
-    if (inputabs > 0.)
-    {
-        int i = inputabs == M.sec_planckabs[nT - 1] ? nT - 2 : sk_locate_basic(M.sec_planckabs, inputabs, nT);
-        if (i < 0)
-            T = M.sec_T[0];
-        else if (i >= nT - 1)
-            T = M.sec_T[nT - 1];
-        else
-            T = sk_interp_linlin(inputabs, M.sec_planckabs[i], M.sec_planckabs[i + 1], M.sec_T[i], M.sec_T[i + 1]);
-    }
-    const double n = sk_cell_density<GRID>(M, m);
     const double* x = M.sec_lambda;
-    for (int i = 0; i < nem; ++i) pv[i] = n * (M.sec_emsig[i] * sk_planck(x[i], T));
+    // MediumSystem::dustEmissionSpectrum (MediumSystem.cpp:1466-1476): the sum over the dust components of the number
+    // density times the emissivity of the component's mix at its own equilibrium temperature
+    for (int h = 0; h < M.nmed; ++h)
+    {
+        const double* __restrict__ rfsig = M.sec_rfsig + h * nrf;
+        const double* __restrict__ planckabs = M.sec_planckabs + h * nT;
+        const double* __restrict__ emsig = M.sec_emsig + h * nem;
+        double inputabs = 0.;
+        for (int ell = 0; ell < nrf; ++ell)
+        {
+            double rf = 0.;
+            rf += M.rf1[SK_RF_INDEX(M, m, ell)];
+            rf += M.rf2[SK_RF_INDEX(M, m, ell)];
+            double J = rf * factor / rfg.dlambda[ell];
+            inputabs += rfsig[ell] * (J + 0.) * rfg.dlambda[ell];
+        }
+        double T = 0.;
+        if (inputabs > 0.)
+        {
+            int i = inputabs == planckabs[nT - 1] ? nT - 2 : sk_locate_basic(planckabs, inputabs, nT);
+            if (i < 0)
+                T = M.sec_T[0];
+            else if (i >= nT - 1)
+                T = M.sec_T[nT - 1];
+            else
+                T = sk_interp_linlin(inputabs, planckabs[i], planckabs[i + 1], M.sec_T[i], M.sec_T[i + 1]);
+        }
+        const double n = sk_component_density<GRID>(M, m, h);
+        if (h == 0)
+            for (int i = 0; i < nem; ++i) pv[i] = n * (emsig[i] * sk_planck(x[i], T));
+        else
+            for (int i = 0; i < nem; ++i) pv[i] += n * (emsig[i] * sk_planck(x[i], T));
+    }
     {
         double first = sk_interp_loglog(x[0], x[0], x[1], pv[0], pv[1]);
         double last = sk_interp_loglog(x[nem - 1], x[nem - 2], x[nem - 1], pv[nem - 2], pv[nem - 1]);

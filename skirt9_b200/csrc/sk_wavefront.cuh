@@ -312,7 +312,11 @@ __device__ __forceinline__ double sk_interaction_depth(double u, double taupath,
 // Structure: a compact inner loop that only crosses cells, and an outer service block (store the results of finished
 // rays, load new rays) that is entered when at least SK_REFILL_MIN lanes are idle, so that its cost is shared.
 // ---------------------------------------------------------------------------------------------------
-template <int GRID, int MODE, bool STORE, bool TABLES_IN_SMEM>
+// MULTI: several medium components with their own mixes (MediumSystem.cpp:874-885, 1012-1040, 1222-1240): the opacity of a
+// cell is the sum of sigma_h n_h; the sections of the components beyond the first live in lane registers and their
+// densities are fetched from densx once the cell is known.  A separate instantiation, so that the single-medium kernels
+// keep their registers and instruction count.
+template <int GRID, int MODE, bool STORE, bool TABLES_IN_SMEM, bool MULTI>
 __global__ void __launch_bounds__(SK_TRACE_BLOCK, GRID == 3   ? SK_TRACE_MINBLOCKS_VORONOI
                                                   : MODE == 2 ? SK_TRACE_MINBLOCKS_PEEL
                                                   : STORE     ? SK_TRACE_MINBLOCKS_STORE
@@ -371,6 +375,7 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, GRID == 3   ? SK_TRACE_MINBLOC
     SkStepper<GRID> st;  // while a lane is not ACTIVE its stepper keeps the cell in which the walk ended
     st.cm = -1;
     double tau = 0, s = 0, limit = 0, section = 0;
+    double secx[MULTI ? SK_MAX_MEDIA - 1 : 1] = {0.};  // MULTI: extinction sections of the components 1..
     int nseg = 0;
     // MODE 0 + STORE extras: luminosity of the packet, extinction factor at the start of the current segment, and the
     // column of the radiation field table for the packet's wavelength bin (null: outside the grid, .cpp:643-644)
@@ -466,6 +471,12 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, GRID == 3   ? SK_TRACE_MINBLOC
                     kray.load(K.D(D_KX, slot), K.D(D_KY, slot), K.D(D_KZ, slot), K.D(D_IKX, slot), K.D(D_IKY, slot),
                               K.D(D_IKZ, slot), GRID == 2 ? M.lat_invh : nullptr);
                 section = K.D(D_SIGEXT, slot);
+                if (MULTI)
+                {
+                    const int il = K.I(I_ILAM, slot);
+#pragma unroll
+                    for (int h = 1; h < SK_MAX_MEDIA; ++h) secx[h - 1] = h < M.nmed ? M.sig_ext[h * M.nlam + il] : 0.;
+                }
                 if (MODE != 2 && M.explicit_absorption)
                 {
                     // the walk to the interaction point is in scattering optical depth (MediumSystem.cpp:905-934, 1075-1110);
@@ -552,12 +563,19 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, GRID == 3   ? SK_TRACE_MINBLOC
                 double dens, ds;
                 st.template exit<MODE == 2>(M, Mg, T, cnt, k, m, dens, ds);
                 bool done = false;
+                double kappa = section * dens;  // opacity of the cell at the ray's wavelength
+                if (MULTI && m >= 0)
+                {
+#pragma unroll
+                    for (int h = 1; h < SK_MAX_MEDIA; ++h)
+                        if (h < M.nmed) kappa = __fma_rn(secx[h - 1], __ldg(&M.densx[(size_t)(h - 1) * (size_t)M.ncells + (size_t)m]), kappa);
+                }
                 if (MODE == 0)
                 {
                     if (ds > 0.)  // SpatialGridPath::addSegment, SpatialGridPath.cpp:41-48
                     {
                         nseg++;
-                        const double tau1 = __fma_rn(section * dens, ds, tau);
+                        const double tau1 = __fma_rn(kappa, ds, tau);
                         if (ls & REPLAY)
                         {
                             if (limit < tau1)
@@ -612,7 +630,7 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, GRID == 3   ? SK_TRACE_MINBLOC
                     if (forced ? (ds > 0.) : (ds >= 0.))  // ds < 0: the generator ended without a segment (Voronoi)
                     {
                         nseg++;
-                        const double tau1 = (ls & NOSCAT) ? 0. : __fma_rn(section * dens, ds, tau);
+                        const double tau1 = (ls & NOSCAT) ? 0. : __fma_rn(kappa, ds, tau);
                         if (limit < tau1)
                         {
                             s_int = tau1;  // interaction inside this segment: interpolated by the service block
@@ -629,7 +647,7 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, GRID == 3   ? SK_TRACE_MINBLOC
                 else if (ds >= 0.)
                 {
                     nseg++;
-                    tau = __fma_rn(section * dens, ds, tau);
+                    tau = __fma_rn(kappa, ds, tau);
                     if (tau >= limit)
                     {
                         tau = INFINITY;  // MediumSystem.cpp:1215
@@ -665,9 +683,56 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, GRID == 3   ? SK_TRACE_MINBLOC
 // consolidated branch), DustMix::peeloffScattering HG branch (DustMix.cpp:430-445), MediumSystem::peelOffScattering
 // (MediumSystem.cpp:734-767) with the single-medium weight 1, PhotonPacket::launchScatteringPeelOff / launchEmissionPeelOff
 // (PhotonPacket.cpp:66-103).  Returns true when the slot joins the peel-off ray list.
-__device__ __forceinline__ bool sk_peel_setup_values(const SkDevModel& M, const SkBank& K, int slot, bool scattering,
+// Several medium components (cold paths, kept out of line so that the single-medium kernels keep their registers):
+// MediumSystem::weightsForScattering (MediumSystem.cpp:697-730) -- the scattering opacities of the components in the
+// interaction cell, normalised -- and the weighted sum of the components' phase functions towards the observer
+// (MediumSystem::peelOffScattering, MediumSystem.cpp:745-754; DustMix::peeloffScattering HG branch, DustMix.cpp:430-445)
+__device__ __noinline__ double sk_peel_intensity_media(const SkDevModel* __restrict__ Mg, int mint, int ilam, double costheta)
+{
+    const SkDevModel& M = *Mg;
+    double wv[SK_MAX_MEDIA], sum = 0.;
+    for (int h = 0; h < M.nmed; ++h)
+    {
+        wv[h] = mint >= 0 ? sk_component_density_any(M, mint, h) * M.sig_sca[h * M.nlam + ilam] : 0.;
+        sum += wv[h];
+    }
+    double I = 0.;
+    for (int h = 0; h < M.nmed; ++h)
+    {
+        const double w = sum > 0. ? wv[h] / sum : 0.;
+        if (w > 0.)
+        {
+            double gp = M.gpar[h * M.nlam + ilam];
+            double value = fabs(gp) > 0.95 ? sk_mean_hg(gp, costheta) : sk_value_hg(gp, costheta);
+            I += value * w;
+        }
+    }
+    return I;
+}
+// MediumSystem::albedoForScattering (MediumSystem.cpp:678-693): sum k_sca / sum k_ext over the components
+__device__ __noinline__ double sk_albedo_media(const SkDevModel* __restrict__ Mg, int m, int ilam)
+{
+    const SkDevModel& M = *Mg;
+    const double ksca = sk_opacity_sum(M, M.sig_sca, ilam, m), kext = sk_opacity_sum(M, M.sig_ext, ilam, m);
+    return kext > 0. ? ksca / kext : 0.;
+}
+// MediumSystem::simulateScattering (MediumSystem.cpp:805-818): the scattering component, from NR::cdf over the scattering
+// opacities in the interaction cell and NR::locateClip of the deviate u
+__device__ __noinline__ int sk_scattering_component(const SkDevModel* __restrict__ Mg, int mint, int ilam, double u)
+{
+    const SkDevModel& M = *Mg;
+    double Xv[SK_MAX_MEDIA + 1];
+    Xv[0] = 0.;
+    for (int h = 0; h < M.nmed; ++h) Xv[h + 1] = Xv[h] + sk_component_density_any(M, mint, h) * M.sig_sca[h * M.nlam + ilam];
+    const double norm = Xv[M.nmed];
+    int hsel = 0;
+    for (int h = 1; h < M.nmed; ++h)
+        if (u >= Xv[h] / norm) hsel = h;
+    return hsel;
+}
+__device__ __forceinline__ bool sk_peel_setup_values(const SkDevModel& M, const SkDevModel* __restrict__ Mg, const SkBank& K, int slot, bool scattering,
                                                      int j0, int j1, double W, double lambda, double x, double y, double z,
-                                                     double kx, double ky, double kz, int ilam)
+                                                     double kx, double ky, double kz, int ilam, int mint)
 {
     const SkDevInstr& q0 = M.instr[j0];
     const double ox = q0.kobs[0], oy = q0.kobs[1], oz = q0.kobs[2];
@@ -675,10 +740,15 @@ __device__ __forceinline__ bool sk_peel_setup_values(const SkDevModel& M, const 
     if (scattering)
     {
         double costheta = kx * ox + ky * oy + kz * oz;
-        double gp = M.gpar[ilam];
-        double value = fabs(gp) > 0.95 ? sk_mean_hg(gp, costheta) : sk_value_hg(gp, costheta);
         double I = 0.;
-        I += value * 1.;
+        if (M.nmed == 1)
+        {
+            double gp = M.gpar[ilam];
+            double value = fabs(gp) > 0.95 ? sk_mean_hg(gp, costheta) : sk_value_hg(gp, costheta);
+            I += value * 1.;
+        }
+        else
+            I = sk_peel_intensity_media(Mg, mint, ilam, costheta);
         peelW = W * I;
     }
     else
@@ -703,17 +773,21 @@ __device__ __forceinline__ bool sk_peel_setup_values(const SkDevModel& M, const 
     }
     return need;
 }
-__device__ __forceinline__ bool sk_peel_setup(const SkDevModel& M, const SkBank& K, int slot, int st, int j0, int j1)
+__device__ __forceinline__ bool sk_peel_setup(const SkDevModel& M, const SkDevModel* __restrict__ Mg, const SkBank& K, int slot, int st,
+                                              int j0, int j1)
 {
-    return sk_peel_setup_values(M, K, slot, (st & SK_ST_SCATTER) != 0, j0, j1, K.D(D_W, slot), K.D(D_LAMBDA, slot),
+    return sk_peel_setup_values(M, Mg, K, slot, (st & SK_ST_SCATTER) != 0, j0, j1, K.D(D_W, slot), K.D(D_LAMBDA, slot),
                                 K.D(D_RX, slot), K.D(D_RY, slot), K.D(D_RZ, slot), K.D(D_KX, slot), K.D(D_KY, slot),
-                                K.D(D_KZ, slot), K.I(I_ILAM, slot));
+                                K.D(D_KZ, slot), K.I(I_ILAM, slot), (st & SK_ST_SCATTER) ? K.I(I_MINT, slot) : -1);
 }
 
 // advance: the interaction that ends the previous round and, for the surviving packets, the peel-off set-up towards
 // the first observer group; free slots are collected for the launch kernel.
+#ifndef SK_ADVANCE_MINBLOCKS
+#define SK_ADVANCE_MINBLOCKS 1
+#endif
 template <int GRID>
-__global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_advance(const SkDevModel M, const SkRunArgs A, const SkBank K,
+__global__ void __launch_bounds__(SK_EVENT_BLOCK, SK_ADVANCE_MINBLOCKS) sk_wf_advance(const SkDevModel M, const SkRunArgs A, const SkBank K,
                                                                  const int j0, const int j1)
 {
     const SkSmemTables T{M.xv, M.yv, M.zv};
@@ -754,6 +828,7 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_advance(const SkDevModel
                 double ksca = dn * M.sig_sca[ilam];
                 double kext = dn * sigext;
                 albedo = kext > 0. ? ksca / kext : 0.;
+                if (M.nmed > 1) albedo = sk_albedo_media(Mg, m, ilam);
             }
             if (forced)
             {
@@ -826,7 +901,7 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_advance(const SkDevModel
     sk_block_append(K.free_list, &K.ctl[SK_CTL_NFREE], valid && !live, slot, &K.ctl[SK_CTL_NLIVE], live);
     if (A.peel && j1 > j0)
     {
-        bool need = survivor && sk_peel_setup_values(M, K, slot, true, j0, j1, W, lambda, x, y, z, kx, ky, kz, ilam);
+        bool need = survivor && sk_peel_setup_values(M, Mg, K, slot, true, j0, j1, W, lambda, x, y, z, kx, ky, kz, ilam, m);
         sk_block_append(K.list, &K.ctl[SK_CTL_NLIST], need, slot);
     }
 }
@@ -910,19 +985,19 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK, SK_LAUNCH_MINBLOCKS) sk_wf_lau
         }
     }
     {
-        const bool need = A.peel && j1 > j0 && live && sk_peel_setup(M, K, slot, SK_ST_LIVE, j0, j1);
+        const bool need = A.peel && j1 > j0 && live && sk_peel_setup(M, Mg, K, slot, SK_ST_LIVE, j0, j1);
         // (the launched packets are counted -- sk_counters_t::packets -- in the same pass)
         sk_block_append(K.list, &K.ctl[SK_CTL_NLIST], need, slot, &K.ctl[SK_CTL_NLIVE], live, &M.counters[0]);
     }
 }
 
 // peel-off set-up towards a further observer group
-__global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_peel_setup(const SkDevModel M, const SkBank K, const int j0,
-                                                                    const int j1)
+__global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_peel_setup(const SkDevModel M, const SkDevModel* __restrict__ Mg, const SkBank K,
+                                                                    const int j0, const int j1)
 {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     const int st = slot < K.n ? K.I(I_STATE, slot) : 0;
-    bool need = (st & SK_ST_LIVE) && sk_peel_setup(M, K, slot, st, j0, j1);
+    bool need = (st & SK_ST_LIVE) && sk_peel_setup(M, Mg, K, slot, st, j0, j1);
     sk_block_append(K.list, &K.ctl[SK_CTL_NLIST], need, slot);
 }
 
@@ -988,7 +1063,9 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_detect(const SkDevModel 
             {
                 SkRng g;
                 sk_rng_load(g, M, A, K, slot);
-                double gp = M.gpar[K.I(I_ILAM, slot)];
+                int hsel = 0;
+                if (M.nmed > 1) hsel = sk_scattering_component(A.model, K.I(I_MINT, slot), K.I(I_ILAM, slot), sk_uniform(g));
+                double gp = M.gpar[hsel * M.nlam + K.I(I_ILAM, slot)];
                 double kx = K.D(D_KX, slot), ky = K.D(D_KY, slot), kz = K.D(D_KZ, slot);
                 if (fabs(gp) < 1e-6)
                     sk_random_direction(g, kx, ky, kz);

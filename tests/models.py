@@ -165,3 +165,22 @@ def long_histories_many_pixels(num_packets=1500, seed=21):
                                  oligoWavelengths=[0.55e-6], storeRadiationField=False, numDensitySamples=4, seed=seed)
     sim.pathLengthBias = 0.0   # (the bias weights p/q would end the histories after a dozen scatterings)
     return sim
+
+
+def with_second_component(sim, kind="disk"):
+    """Adds a second dust component with its own, greyer and more isotropically scattering mix to a model (the
+    several-media paths of MediumSystem.cpp:678-823, 874-885, 1012-1040, 1222-1240, 1452-1476)."""
+    pc = H.PC
+    lam = sim.medium.mix.inlam
+    n = len(lam)
+    kappa = np.linspace(1800.0, 300.0, n)
+    albedo = np.linspace(0.85, 0.35, n)
+    g = np.linspace(0.35, 0.0, n)
+    mix2 = H.MeanListDustMix(lam, kappa, albedo, g)
+    scale = abs(sim.grid.extent[3]) if hasattr(sim.grid, "extent") else pc
+    if kind == "disk":
+        geom = H.ExpDiskGeometry(0.25 * scale, 0.05 * scale, 0.0, scale, 0.1 * scale)
+    else:
+        geom = H.ShellGeometry(0.2 * scale, 0.9 * scale, 0.0)
+    sim.extraMedia = [H.GeometricMedium(geom, mix2, opticalDepth=0.5 * sim.medium.tau, wavelength=sim.medium.norm_wavelength)]
+    return sim

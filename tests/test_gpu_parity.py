@@ -298,3 +298,78 @@ def test_interleaved_shares_add_up_to_the_single_run(engine_lib):
     np.testing.assert_allclose(sum(e.read_sed_stats(0) for e in parts), one.read_sed_stats(0), rtol=1e-9)
     with pytest.raises(abi.SkError):
         parts[0].set_history_interleave(100, 3, 0)     # not a power of two
+
+
+# ---------------------------------------------------------------- several medium components with their own mixes
+def test_two_components_cartesian_forced_with_radiation_field(engine_lib):
+    sim = models.with_second_component(models.two_sources_three_instruments(num_packets=20000, force=True), "shell")
+    gpu, cpu = run_both(sim, engine_lib)
+    models.compare_engines(sim, gpu, cpu)
+    assert gpu.counters()["scatterings"] > 20000
+    # the second component matters: the same model without it gives other tallies
+    ref = models.two_sources_three_instruments(num_packets=20000, force=True)
+    one, _ = run_both(ref, engine_lib)
+    assert not np.allclose(one.read_sed(0, abi.SK_COMP_PRIMARY_SCATTERED), gpu.read_sed(0, abi.SK_COMP_PRIMARY_SCATTERED), rtol=1e-3)
+
+
+def test_two_components_cartesian_nonforced(engine_lib):
+    sim = models.with_second_component(models.two_sources_three_instruments(num_packets=20000, force=False), "shell")
+    gpu, cpu = run_both(sim, engine_lib)
+    models.compare_engines(sim, gpu, cpu)
+
+
+def test_two_components_octree(engine_lib):
+    sim = models.with_second_component(models.small_octree(num_packets=30000, record_statistics=True), "disk")
+    gpu, cpu = run_both(sim, engine_lib)
+    models.compare_engines(sim, gpu, cpu)
+    assert sim.density.shape[0] == 2 and (sim.density[1] > 0).any()
+
+
+def test_three_components_voronoi(engine_lib):
+    from skirt9_b200 import host as H
+    sim = models.with_second_component(models.small_voronoi(num_packets=20000), "disk")
+    third = H.MeanListDustMix([0.1e-6, 1e-6], [500.0, 700.0], [0.2, 0.9], [0.0, 0.8])
+    sim.extraMedia.append(H.GeometricMedium(H.ExpDiskGeometry(5000 * H.PC, 400 * H.PC, 0.0, 15000 * H.PC, 1900 * H.PC), third,
+                                            opticalDepth=0.3, wavelength=0.55e-6))
+    gpu, cpu = run_both(sim, engine_lib)
+    models.compare_engines(sim, gpu, cpu)
+
+
+def test_two_components_dust_emission_iterations(engine_lib):
+    import copy
+    sim = models.with_second_component(models.small_dust_emission(num_packets=20000), "shell").setup()
+    simc = copy.copy(sim)
+    gpu = sim.configure(abi.Engine(sim.config_struct(device=0), lib=engine_lib))
+    cpu = simc.configure(OracleEngine(simc.config_struct()))
+    sim.run(gpu)
+    simc.run(cpu)
+    assert len(sim.convergence) == len(simc.convergence) >= 1
+    for a, b in zip(sim.convergence, simc.convergence):
+        for key in ("dust_luminosity", "absorbed_primary", "absorbed_secondary"):
+            assert a[key] == pytest.approx(b[key], rel=1e-9), key
+    models.compare_engines(sim, gpu, cpu, rtol=1e-8)
+    assert gpu.read_sed(0, abi.SK_COMP_SECONDARY_DIRECT).sum() > 0
+
+
+def test_component_limits_are_reported(engine_lib):
+    """More than SK_MAX_MEDIA components, mixes on different wavelength grids, a mix count that does not match the medium
+    state, explicit absorption with several components: reported, never run."""
+    sim = models.with_second_component(models.small_cartesian(num_packets=1000), "shell").setup()
+    e = abi.Engine(sim.config_struct(device=0), lib=engine_lib)
+    sim.grid.configure(e)
+    with pytest.raises(abi.SkError):
+        e.set_media(np.zeros((5, sim.grid.num_cells)), sim.volume)
+    mixes = [(md.mix.lambda_border, md.mix.sigma_abs, md.mix.sigma_sca, md.mix.asymmpar, md.mix.mu) for md in sim.media]
+    shifted = (mixes[1][0] * 1.01,) + mixes[1][1:]
+    with pytest.raises(abi.SkError):
+        e.set_dustmixes([mixes[0], shifted])
+    e2 = sim.configure(abi.Engine(sim.config_struct(device=0), lib=engine_lib))
+    e2.set_dustmix(*mixes[0])          # one mix for two components
+    e2.prepare_primary(1000)
+    with pytest.raises(abi.SkError):
+        e2.run_segment(0, 1000, True, True, False, 0)
+    sim.explicitAbsorption = True
+    e3 = sim.configure(abi.Engine(sim.config_struct(device=0), lib=engine_lib))
+    e3.prepare_primary(1000)
+    with pytest.raises(abi.SkError):
+        e3.run_segment(0, 1000, True, True, False, 0)

@@ -29,13 +29,16 @@ def small(name, packets="2e4"):
 
 def two_mixes(text):
     """Duplicates the GeometricMedium element and changes the copy's albedo: two dust components with DIFFERENT material mixes
-    (MediumSystem.cpp:874-885; several media that share one mix are on the accelerated path, tests/golden/ski/cfg10d.ski)."""
+    (MediumSystem.cpp:874-885) -- on the accelerated path (tests/golden/ski/cfg11m.ski) unless combined with explicit
+    absorption (MediumSystem.cpp:937-955), which the engine runs for one component only."""
     a, b = text.index("<GeometricMedium"), text.index("</GeometricMedium>") + len("</GeometricMedium>")
-    return text[:b] + text[a:b].replace('albedos="0.6, 0.6"', 'albedos="0.4, 0.4"') + text[b:]
+    text = text[:b] + text[a:b].replace('albedos="0.6, 0.6"', 'albedos="0.4, 0.4"') + text[b:]
+    assert 'explicitAbsorption="false"' in text
+    return text.replace('explicitAbsorption="false"', 'explicitAbsorption="true"')
 
 
 @pytest.mark.parametrize("edit, reason", [
-    (two_mixes, "more than one medium with different material mixes"),
+    (two_mixes, "explicit absorption with several different material mixes"),
     (lambda s: s.replace('<RadiationFieldProbe', '<LaunchedPacketsProbe probeName="lpp"/><RadiationFieldProbe', 1),
      "launch call-back"),
     (lambda s: s.replace('recordPolarization="false"', 'recordPolarization="true"'), "polarization"),

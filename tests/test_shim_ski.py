@@ -207,6 +207,41 @@ def test_cfg10d_ski_two_media_sharing_one_mix_runs_unchanged(tmp_path):
         assert total.astype(float).sum() == pytest.approx(g["frame_total_sum"].sum(), rel=4e-3 if host_setup else 1.2e-2)
 
 
+def test_cfg11m_ski_two_media_with_different_mixes_runs_unchanged(tmp_path):
+    """Two dust media with DIFFERENT material mixes: the shim hands the engine one component per medium
+    (sk_engine_set_media / sk_engine_set_dustmixes) and the several-media life cycle runs on the device."""
+    g = np.load(os.path.join(GOLD, "cfg11m_ref.npz"))
+    log = run_ski("cfg11m", tmp_path, 4e6)
+    assert "GPU life cycle:" in log and "outside the GPU life cycle" not in log
+    for h in range(2):   # same inputs as the fixture: the reference's own set-up, -t 1, seed 0
+        rho = read_columns(tmp_path / ("cfg11m_dns_%d_rho.dat" % h))[:, 1]
+        np.testing.assert_array_equal(rho, g["component_mass_density_msun_pc3"][h])
+    sed = read_columns(tmp_path / "cfg11m_i60_sed.dat")
+    stats = read_columns(tmp_path / "cfg11m_i60_sedstats.dat")
+    tol = 4.0 * np.hypot(rel_error(g["sedstats"][:, 1:].T), rel_error(stats[:, 1:].T))
+    for col in (1, 2, 3, 4):
+        bound = tol * np.maximum(g["sed"][:, col], g["sed"][:, 1])
+        assert np.all(np.abs(sed[:, col] - g["sed"][:, col]) <= bound), col
+    total, _ = read_fits_cube(tmp_path / "cfg11m_i60_total.fits")
+    assert total.astype(float).sum() == pytest.approx(g["frame_total_sum"].sum(), rel=4e-3)
+
+
+def test_cfg12me_ski_dust_emission_from_two_mixes_runs_unchanged(tmp_path):
+    g = np.load(os.path.join(GOLD, "cfg12me_ref.npz"))
+    log = run_ski("cfg12me", tmp_path, 2e6)
+    prim = [float(x) for x in re.findall(r"dust-absorbed primary luminosity is ([0-9.eE+-]+) Lsun", log)]
+    sec = [float(x) for x in re.findall(r"dust-absorbed secondary luminosity in iteration \d+ is ([0-9.eE+-]+) Lsun", log)]
+    conv = re.search(r"Convergence reached after (\d+) iterations", log)
+    assert conv and int(conv.group(1)) == int(g["converged_after"])
+    np.testing.assert_allclose(prim, g["absorbed_primary_lsun"], rtol=0.004)
+    np.testing.assert_allclose(sec, g["absorbed_secondary_lsun"], rtol=0.02)
+    sed = read_columns(tmp_path / "cfg12me_sed_sed.dat")
+    stats = read_columns(tmp_path / "cfg12me_sed_sedstats.dat")
+    hi = np.load(os.path.join(GOLD, "cfg12me_hi_ref.npz"))
+    sed_columns_within_statistics(sed, stats, g["sed"], g["sedstats"], range(1, 8), secondary_per_bin=False)
+    sed_columns_within_statistics(sed, stats, hi["sed"], hi["sedstats"], range(1, 8))
+
+
 def test_cfg4s_ski_dust_emission_runs_unchanged(tmp_path):
     g = np.load(os.path.join(GOLD, "cfg4s_ref.npz"))
     n = 2e6
