@@ -1754,7 +1754,10 @@ static int run_bank(sk_engine* e, const SkRunArgs& A)
         CK(cudaMemsetAsync(K.ctl, 0, SK_CTL_WORDS * sizeof(unsigned int), e->stream));
         const int g0a = groups.empty() ? 0 : groups[0].first, g0b = groups.empty() ? 0 : groups[0].second;
         if (int rc = stage_begin(e, SK_STAGE_ADVANCE)) return rc;
-        sk_wf_advance<GRID><<<eblocks, SK_EVENT_BLOCK, 0, e->stream>>>(M, A, K, g0a, g0b);
+        if (M.nmed > 1)
+            sk_wf_advance<GRID, true><<<eblocks, SK_EVENT_BLOCK, 0, e->stream>>>(M, A, K, g0a, g0b);
+        else
+            sk_wf_advance<GRID, false><<<eblocks, SK_EVENT_BLOCK, 0, e->stream>>>(M, A, K, g0a, g0b);
         CK(cudaGetLastError());
         if (int rc = stage_end(e)) return rc;
         if (int rc = stage_begin(e, SK_STAGE_LAUNCH)) return rc;

@@ -43,6 +43,9 @@
 #ifndef SK_TRACE_MINBLOCKS_PEEL
 #define SK_TRACE_MINBLOCKS_PEEL 10  // the peel-off kernel keeps its (shared) direction in parameter space: fewer registers
 #endif
+#ifndef SK_TRACE_MINBLOCKS_MULTI_LESS
+#define SK_TRACE_MINBLOCKS_MULTI_LESS 1  // several components: one resident block fewer pays for the extra lane state (measured)
+#endif
 #ifndef SK_CHUNK
 #define SK_CHUNK 64
 #endif
@@ -317,10 +320,11 @@ __device__ __forceinline__ double sk_interaction_depth(double u, double taupath,
 // densities are fetched from densx once the cell is known.  A separate instantiation, so that the single-medium kernels
 // keep their registers and instruction count.
 template <int GRID, int MODE, bool STORE, bool TABLES_IN_SMEM, bool MULTI>
-__global__ void __launch_bounds__(SK_TRACE_BLOCK, GRID == 3   ? SK_TRACE_MINBLOCKS_VORONOI
-                                                  : MODE == 2 ? SK_TRACE_MINBLOCKS_PEEL
-                                                  : STORE     ? SK_TRACE_MINBLOCKS_STORE
-                                                              : SK_TRACE_MINBLOCKS)
+__global__ void __launch_bounds__(SK_TRACE_BLOCK, (GRID == 3   ? SK_TRACE_MINBLOCKS_VORONOI
+                                                   : MODE == 2 ? SK_TRACE_MINBLOCKS_PEEL
+                                                   : STORE     ? SK_TRACE_MINBLOCKS_STORE
+                                                               : SK_TRACE_MINBLOCKS)
+                                                      - (MULTI ? SK_TRACE_MINBLOCKS_MULTI_LESS : 0))
     sk_wf_trace(const SkDevModel M, const SkRunArgs A, const SkBank K, const SkObsDir obs)
 {
     extern __shared__ __align__(16) double smem[];
@@ -375,7 +379,17 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, GRID == 3   ? SK_TRACE_MINBLOC
     SkStepper<GRID> st;  // while a lane is not ACTIVE its stepper keeps the cell in which the walk ended
     st.cm = -1;
     double tau = 0, s = 0, limit = 0, section = 0;
-    double secx[MULTI ? SK_MAX_MEDIA - 1 : 1] = {0.};  // MULTI: extinction sections of the components 1..
+    // MULTI: the second component's extinction section and its density in cell mpre live in lane registers; the density is
+    // requested as soon as the walk knows its next cell, so that it travels together with the cell record.  Further
+    // components (rare) are read from the tables at each crossing.
+    double sec1 = 0., dn1 = 0.;
+    int mpre = -1, ilam_ray = 0;
+#define SK_FETCH_DENSX()                                                                          \
+    if (MULTI)                                                                                    \
+    {                                                                                             \
+        mpre = st.m();                                                                            \
+        if (mpre >= 0) dn1 = __ldg(&M.densx[(size_t)mpre]);                                       \
+    }
     int nseg = 0;
     // MODE 0 + STORE extras: luminosity of the packet, extinction factor at the start of the current segment, and the
     // column of the radiation field table for the packet's wavelength bin (null: outside the grid, .cpp:643-644)
@@ -473,9 +487,8 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, GRID == 3   ? SK_TRACE_MINBLOC
                 section = K.D(D_SIGEXT, slot);
                 if (MULTI)
                 {
-                    const int il = K.I(I_ILAM, slot);
-#pragma unroll
-                    for (int h = 1; h < SK_MAX_MEDIA; ++h) secx[h - 1] = h < M.nmed ? M.sig_ext[h * M.nlam + il] : 0.;
+                    ilam_ray = K.I(I_ILAM, slot);
+                    sec1 = M.sig_ext[M.nlam + ilam_ray];
                 }
                 if (MODE != 2 && M.explicit_absorption)
                 {
@@ -544,6 +557,7 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, GRID == 3   ? SK_TRACE_MINBLOC
                     }
                 }
                 st.begin(M, rx, ry, rz, p);
+                SK_FETCH_DENSX();
             }
             if (take > 0) chunk_pos += take;
             if (!__any_sync(0xffffffffu, (ls & (ACTIVE | PENDING)) != 0))
@@ -566,9 +580,11 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, GRID == 3   ? SK_TRACE_MINBLOC
                 double kappa = section * dens;  // opacity of the cell at the ray's wavelength
                 if (MULTI && m >= 0)
                 {
-#pragma unroll
-                    for (int h = 1; h < SK_MAX_MEDIA; ++h)
-                        if (h < M.nmed) kappa = __fma_rn(secx[h - 1], __ldg(&M.densx[(size_t)(h - 1) * (size_t)M.ncells + (size_t)m]), kappa);
+                    if (m != mpre) SK_FETCH_DENSX();  // (the Voronoi walk may re-locate its cell inside exit())
+                    kappa = __fma_rn(sec1, dn1, kappa);
+                    for (int h = 2; h < M.nmed; ++h)
+                        kappa = __fma_rn(__ldg(&M.sig_ext[h * M.nlam + ilam_ray]),
+                                         __ldg(&M.densx[(size_t)(h - 1) * (size_t)M.ncells + (size_t)m]), kappa);
                 }
                 if (MODE == 0)
                 {
@@ -657,6 +673,7 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, GRID == 3   ? SK_TRACE_MINBLOC
                 if (!done)
                 {
                     if (GRID != 3 || st.m() >= 0) st.move(M, Mg, T, cnt, k);
+                    SK_FETCH_DENSX();
                     if (st.m() < 0)
                     {
                         // the path has left the grid (non-forced: no interaction)
@@ -673,6 +690,7 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, GRID == 3   ? SK_TRACE_MINBLOC
         } while (__popc(__ballot_sync(0xffffffffu, !(ls & ACTIVE))) < want_idle);
     }
     sk_flush_counters(M, cnt);
+#undef SK_FETCH_DENSX
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -730,6 +748,7 @@ __device__ __noinline__ int sk_scattering_component(const SkDevModel* __restrict
         if (u >= Xv[h] / norm) hsel = h;
     return hsel;
 }
+template <bool MULTI>
 __device__ __forceinline__ bool sk_peel_setup_values(const SkDevModel& M, const SkDevModel* __restrict__ Mg, const SkBank& K, int slot, bool scattering,
                                                      int j0, int j1, double W, double lambda, double x, double y, double z,
                                                      double kx, double ky, double kz, int ilam, int mint)
@@ -741,7 +760,7 @@ __device__ __forceinline__ bool sk_peel_setup_values(const SkDevModel& M, const 
     {
         double costheta = kx * ox + ky * oy + kz * oz;
         double I = 0.;
-        if (M.nmed == 1)
+        if (!MULTI)
         {
             double gp = M.gpar[ilam];
             double value = fabs(gp) > 0.95 ? sk_mean_hg(gp, costheta) : sk_value_hg(gp, costheta);
@@ -776,18 +795,24 @@ __device__ __forceinline__ bool sk_peel_setup_values(const SkDevModel& M, const 
 __device__ __forceinline__ bool sk_peel_setup(const SkDevModel& M, const SkDevModel* __restrict__ Mg, const SkBank& K, int slot, int st,
                                               int j0, int j1)
 {
-    return sk_peel_setup_values(M, Mg, K, slot, (st & SK_ST_SCATTER) != 0, j0, j1, K.D(D_W, slot), K.D(D_LAMBDA, slot),
+    if (M.nmed > 1)
+        return sk_peel_setup_values<true>(M, Mg, K, slot, (st & SK_ST_SCATTER) != 0, j0, j1, K.D(D_W, slot), K.D(D_LAMBDA, slot),
+                                          K.D(D_RX, slot), K.D(D_RY, slot), K.D(D_RZ, slot), K.D(D_KX, slot), K.D(D_KY, slot),
+                                          K.D(D_KZ, slot), K.I(I_ILAM, slot), (st & SK_ST_SCATTER) ? K.I(I_MINT, slot) : -1);
+    return sk_peel_setup_values<false>(M, Mg, K, slot, (st & SK_ST_SCATTER) != 0, j0, j1, K.D(D_W, slot), K.D(D_LAMBDA, slot),
                                 K.D(D_RX, slot), K.D(D_RY, slot), K.D(D_RZ, slot), K.D(D_KX, slot), K.D(D_KY, slot),
                                 K.D(D_KZ, slot), K.I(I_ILAM, slot), (st & SK_ST_SCATTER) ? K.I(I_MINT, slot) : -1);
 }
 
 // advance: the interaction that ends the previous round and, for the surviving packets, the peel-off set-up towards
 // the first observer group; free slots are collected for the launch kernel.
-#ifndef SK_ADVANCE_MINBLOCKS
-#define SK_ADVANCE_MINBLOCKS 1
+#ifdef SK_ADVANCE_MINBLOCKS  // (tuning variants; by default the compiler's own choice for 256-thread blocks)
+#define SK_ADVANCE_BOUNDS __launch_bounds__(SK_EVENT_BLOCK, SK_ADVANCE_MINBLOCKS)
+#else
+#define SK_ADVANCE_BOUNDS __launch_bounds__(SK_EVENT_BLOCK)
 #endif
-template <int GRID>
-__global__ void __launch_bounds__(SK_EVENT_BLOCK, SK_ADVANCE_MINBLOCKS) sk_wf_advance(const SkDevModel M, const SkRunArgs A, const SkBank K,
+template <int GRID, bool MULTI>
+__global__ void SK_ADVANCE_BOUNDS sk_wf_advance(const SkDevModel M, const SkRunArgs A, const SkBank K,
                                                                  const int j0, const int j1)
 {
     const SkSmemTables T{M.xv, M.yv, M.zv};
@@ -828,7 +853,7 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK, SK_ADVANCE_MINBLOCKS) sk_wf_ad
                 double ksca = dn * M.sig_sca[ilam];
                 double kext = dn * sigext;
                 albedo = kext > 0. ? ksca / kext : 0.;
-                if (M.nmed > 1) albedo = sk_albedo_media(Mg, m, ilam);
+                if (MULTI) albedo = sk_albedo_media(Mg, m, ilam);
             }
             if (forced)
             {
@@ -901,7 +926,7 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK, SK_ADVANCE_MINBLOCKS) sk_wf_ad
     sk_block_append(K.free_list, &K.ctl[SK_CTL_NFREE], valid && !live, slot, &K.ctl[SK_CTL_NLIVE], live);
     if (A.peel && j1 > j0)
     {
-        bool need = survivor && sk_peel_setup_values(M, Mg, K, slot, true, j0, j1, W, lambda, x, y, z, kx, ky, kz, ilam, m);
+        bool need = survivor && sk_peel_setup_values<MULTI>(M, Mg, K, slot, true, j0, j1, W, lambda, x, y, z, kx, ky, kz, ilam, m);
         sk_block_append(K.list, &K.ctl[SK_CTL_NLIST], need, slot);
     }
 }

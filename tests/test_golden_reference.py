@@ -369,15 +369,35 @@ def test_engine_matches_reference_cfg2s(engine_lib):
     check_cfg2s(sim, e, g, n)
 
 
-def sed_bins_within_statistics(sim, e, g, nsigma=4.0, nsigma_secondary=5.0):
+def reference_scatter(g, hi):
+    """How far two runs of the UNMODIFIED REFERENCE on the same inputs (the base fixture and its high-statistics companion) lie
+    apart in a dust-emission column, in units of the Sum w^k error estimate: the rms over the reliable bins of
+    |F - F_hi| / (sqrt(R^2 + R_hi^2) max(F_hi, F_hi,total)), per SED column.  Above 1 where the noise of the radiation field
+    behind the dust temperatures, which the statistics of the last segment know nothing about, matters (it scales with
+    1/sqrt(packets) like R itself, so the ratio holds for any number of packets)."""
+    from tests import mcstats
+    a, b = g["sedstats"][:, 1:].T, hi["sedstats"][:, 1:].T
+    ok = mcstats.reliable(a) & mcstats.reliable(b)
+    sigma = np.hypot(mcstats.rel_error(a), mcstats.rel_error(b))
+    out = {}
+    for col in (5, 6, 7, 1):
+        scale = np.maximum(hi["sed"][:, col], hi["sed"][:, 1])
+        z = (np.abs(g["sed"][:, col] - hi["sed"][:, col]) / np.maximum(sigma * scale, 1e-300))[ok & (hi["sed"][:, col] > 0)]
+        out[col] = max(1.0, float(np.sqrt(np.mean(z ** 2)))) if len(z) else 1.0
+    return out
+
+
+def sed_bins_within_statistics(sim, e, g, nsigma=4.0, nsigma_secondary=5.0, secondary_per_bin=True, scatter=None):
     """Every SED column of a dust-emission run against the reference's, bin by bin: |F - F_ref| <= nsigma sqrt(R^2 + R_ref^2)
     max(F_ref, F_ref_total), R from both sides' Sum w^k statistics (those of the total flux, FluxRecorder.cpp:457-466;
     SURVEY.md 8d), in the bins whose error estimate is reliable by the reference's own rule (R < 0.1 and VOV < 0.1 on both
     sides, tests/mcstats.py): in the far-UV bins of this model a handful of heavily weighted packets carry the flux and Sum
     w^k says nothing about the true scatter (the oracle with other seeds is 14 "sigma" off there).  The columns that
     contain dust emission get nsigma_secondary: the statistics of the final segment do not know about the noise of the
-    radiation field that set the dust temperatures.  The sums over the reliable bins must agree within the quadrature sum
-    of the bins' errors."""
+    radiation field that set the dust temperatures, and against a fixture whose own radiation field is noisy (the base
+    fixtures: 2e5 packets per segment) they are compared through their sums only (secondary_per_bin=False; the drop-in's
+    tests do the same, tests/test_shim_ski.py) -- per bin they are held to the high-statistics fixtures.  The sums over the
+    reliable bins must agree within the quadrature sum of the bins' errors."""
     from tests import mcstats
     sed = g["sed"]
     own, ref = e.read_sed_stats(0), g["sedstats"][:, 1:].T
@@ -387,11 +407,13 @@ def sed_bins_within_statistics(sim, e, g, nsigma=4.0, nsigma_secondary=5.0):
     for col, comp in ((2, abi.SK_COMP_TRANSPARENT), (3, abi.SK_COMP_PRIMARY_DIRECT), (4, abi.SK_COMP_PRIMARY_SCATTERED),
                       (5, abi.SK_COMP_SECONDARY_DIRECT), (6, abi.SK_COMP_SECONDARY_SCATTERED),
                       (7, abi.SK_COMP_SECONDARY_TRANSPARENT), (1, abi.SK_COMP_TOTAL)):
-        ns = nsigma if col in (2, 3, 4) else nsigma_secondary
+        # (dust-emission columns: times the reference's own run-to-run scatter in units of that estimate, reference_scatter)
+        ns = nsigma if col in (2, 3, 4) else nsigma_secondary * (scatter[col] if scatter else 1.0)
         f = sim.sed_flux_density(e, 0, comp)
         scale = np.maximum(sed[:, col], sed[:, 1])
         z = np.abs(f - sed[:, col])[ok] / np.maximum(sigma * scale, 1e-300)[ok]
-        assert np.all(z <= ns), (comp, int(np.argmax(z)), float(z.max()))
+        if secondary_per_bin or col in (2, 3, 4):
+            assert np.all(z <= ns), (comp, int(np.argmax(z)), float(z.max()))
         err_sum = np.sqrt(((sigma * scale)[ok] ** 2).sum())
         assert abs(f[ok].sum() - sed[ok, col].sum()) <= ns * err_sum, comp
 
@@ -425,8 +447,9 @@ def check_cfg4s(sim, e, g, n, tol_scale=1.0, nsigma=4.0, hi_name="cfg4s_hi"):
     sed = g["sed"]
     lam = sim.defaultWavelengthGrid.lambdav
     np.testing.assert_allclose(lam * 1e6, sed[:, 0], rtol=1e-9)
-    sed_bins_within_statistics(sim, e, g, nsigma, nsigma + 1.0)
-    sed_bins_within_statistics(sim, e, load(hi_name), nsigma, nsigma + 1.0)
+    scatter = reference_scatter(g, load(hi_name))
+    sed_bins_within_statistics(sim, e, g, nsigma, nsigma + 1.0, secondary_per_bin=False, scatter=scatter)
+    sed_bins_within_statistics(sim, e, load(hi_name), nsigma, nsigma + 1.0, scatter=scatter)
     # radiation field rf1+rf2 after the run, volume-weighted in radial shells, per wavelength bin
     J = sim.mean_intensity_nu(e, 0) + sim.mean_intensity_nu(e, 1)
     r = np.linalg.norm(g["cell_center_pc"], axis=1)
