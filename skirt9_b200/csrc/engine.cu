@@ -434,6 +434,7 @@ static void drop_grid(sk_engine* e)
     e->M.nmed = 1;
     e->M.volume = nullptr;
     e->M.vrec = nullptr;
+    e->M.vnrec = nullptr;
     e->M.vbox = nullptr;
     e->M.node_child = nullptr;
     e->M.cell_coord = nullptr;
@@ -493,6 +494,7 @@ extern "C" int sk_engine_set_grid_cartesian(sk_engine_t* e, int32_t nx, int32_t 
     e->M.ncells = 0;
     e->M.cells = nullptr;
     e->M.vrec = nullptr;
+    e->M.vnrec = nullptr;
     e->M.vbox = nullptr;
     return set_tables(e, xv, nx + 1, yv, ny + 1, zv, nz + 1);
 }
@@ -554,6 +556,7 @@ static int finish_octree(sk_engine* e, const double extent[6], int nn, int nc, i
     e->M.cell_coord = d_coord;
     e->M.cells = d_cells;
     e->M.vrec = nullptr;
+    e->M.vnrec = nullptr;
     e->M.vbox = nullptr;
     e->first_child_dev = d_first;
     if (int rc = set_tables(e, T[0].data(), N + 1, T[1].data(), N + 1, T[2].data(), N + 1)) return rc;
@@ -614,6 +617,18 @@ extern "C" int sk_engine_set_grid_voronoi(sk_engine_t* e, const double extent[6]
             last = block[b];
     }
     std::vector<long long> off(nbr_offset, nbr_offset + nc + 1);
+    // the neighbour records of the crossing loop: the neighbour's site next to its index, contiguous per cell
+    std::vector<double4> nrec((size_t)nbr_offset[nc]);
+    for (size_t i = 0; i < nrec.size(); ++i)
+    {
+        const int32_t mi = nbr_index[i];
+        const long long bits = (long long)mi;
+        double w;
+        memcpy(&w, &bits, sizeof w);
+        nrec[i] = mi >= 0 ? make_double4(rec[mi].x, rec[mi].y, rec[mi].z, w) : make_double4(0., 0., 0., w);
+    }
+    double4* d_nrec;
+    if (int rc = upload(e->grid_allocs, nrec.data(), nrec.size(), &d_nrec)) return rc;
     double4* d_rec;
     long long* d_off;
     int32_t *d_idx, *d_block;
@@ -633,6 +648,7 @@ extern "C" int sk_engine_set_grid_voronoi(sk_engine_t* e, const double extent[6]
     e->M.vrec = d_rec;
     e->M.vnbr_off = d_off;
     e->M.vnbr = d_idx;
+    e->M.vnrec = d_nrec;
     e->M.vblock = d_block;
     e->M.vbox = nullptr;
     e->M.vnb = nb;

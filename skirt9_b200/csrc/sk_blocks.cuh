@@ -666,9 +666,9 @@ struct SkStepper<3> {
                 int mi[SK_VOR_UNROLL];
                 double4 pj[SK_VOR_UNROLL];
 #pragma unroll
-                for (int u = 0; u < SK_VOR_UNROLL; ++u) mi[u] = __ldg(&M.vnbr[min(i + u, i1 - 1)]);  // (a repeated last entry never wins again)
+                for (int u = 0; u < SK_VOR_UNROLL; ++u) pj[u] = sk_ld_rec(&M.vnrec[min(i + u, i1 - 1)]);  // (a repeated last entry never wins again)
 #pragma unroll
-                for (int u = 0; u < SK_VOR_UNROLL; ++u) pj[u] = sk_ld_rec(&M.vrec[max(mi[u], 0)]);
+                for (int u = 0; u < SK_VOR_UNROLL; ++u) mi[u] = (int)__double_as_longlong(pj[u].w);
 #pragma unroll
                 for (int u = 0; u < SK_VOR_UNROLL; ++u)
                 {

@@ -99,6 +99,9 @@ struct SkDevModel {
     const double4* vrec;
     const long long* vnbr_off;
     const int32_t* vnbr;
+    const double4* vnrec;  // per neighbour entry (same order as vnbr): {site x,y,z of the neighbour; its index in the low 32 bits
+                           // of w}, so that a crossing reads its ~15 candidates as one contiguous run of 32-byte records
+                           // instead of an index list plus as many scattered site records
     const int32_t* vblock;
     const double* vbox;  // [6*ncells] enclosing boxes of the Voronoi cells (dust emission only), or null
     int32_t vnb;

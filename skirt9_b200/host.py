@@ -654,14 +654,37 @@ class VoronoiMeshSpatialGrid:
         n = len(self.sites)
         tri = Delaunay(self.sites)
         indptr, indices = tri.vertex_neighbor_vertices
-        counts = np.diff(indptr) + 6
+        # The domain walls a cell lists (VoronoiMeshSnapshot.cpp:1134-1143: voro++ reports the walls that bound the cell): the
+        # vertices of a bounded Voronoi cell are the circumcentres of the Delaunay tetrahedra around its site, so the cell
+        # reaches beyond a wall exactly when one of them does; the unbounded cells of the hull sites list all six.
+        S = tri.simplices
+        A = self.sites[S[:, 0]]
+        B, C, D = self.sites[S[:, 1]] - A, self.sites[S[:, 2]] - A, self.sites[S[:, 3]] - A
+        mat = np.stack([B, C, D], axis=1)
+        rhs = 0.5 * np.stack([(B * B).sum(1), (C * C).sum(1), (D * D).sum(1)], axis=1)
+        good = np.abs(np.linalg.det(mat)) > 1e-12 * np.prod(np.linalg.norm(mat, axis=2), axis=1)
+        cc = np.full_like(A, np.nan)
+        cc[good] = np.linalg.solve(mat[good], rhs[good][..., None])[..., 0] + A[good]
+        lo, hi = np.full((n, 3), np.inf), np.full((n, 3), -np.inf)
+        sliver = np.zeros(n, dtype=bool)     # a flat tetrahedron has its circumcentre (nearly) at infinity: all walls
+        for j in range(4):
+            np.minimum.at(lo, S[good, j], cc[good])
+            np.maximum.at(hi, S[good, j], cc[good])
+            sliver[S[~good, j]] = True
+        every = sliver
+        every[np.unique(tri.convex_hull)] = True
+        ext = np.asarray(self.extent)
+        touch = np.concatenate([(lo < ext[:3]) | every[:, None], (hi > ext[3:]) | every[:, None]], axis=1)  # xmin ymin zmin xmax ymax zmax
+        touch = touch[:, [0, 3, 1, 4, 2, 5]]                                                              # walls -1 .. -6
+        counts = np.diff(indptr) + touch.sum(axis=1)
         self.nbr_offset = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
         idx = np.empty(self.nbr_offset[-1], dtype=np.int32)
         walls = np.array([-1, -2, -3, -4, -5, -6], dtype=np.int32)
         for m in range(n):
             a, b = self.nbr_offset[m], self.nbr_offset[m + 1]
-            idx[a:b - 6] = indices[indptr[m]:indptr[m + 1]]
-            idx[b - 6:b] = walls
+            k = indptr[m + 1] - indptr[m]
+            idx[a:a + k] = indices[indptr[m]:indptr[m + 1]]
+            idx[a + k:b] = walls[touch[m]]
         self.nbr_index = idx
 
     @property
