@@ -624,7 +624,8 @@ struct SkStepper<2> {
 };
 
 #ifndef SK_VOR_UNROLL
-#define SK_VOR_UNROLL 2  // neighbour records requested together
+#define SK_VOR_UNROLL 3  // neighbour records requested together (measured on 2e5 cells, 1e7 packets: 1: 407 ms, 2: 324 ms, 3: 313 ms,
+                         // 4: 366 ms per segment; the index-list layout of round 1 with 2: 352 ms)
 #endif
 // ---- Voronoi mesh: the exit point is the nearest intersection with the bisecting planes towards the neighbouring sites
 // and with the domain walls
@@ -647,9 +648,13 @@ struct SkStepper<3> {
     // n = p_i - p_r; VoronoiMeshSnapshot.cpp:1108-1129) or |k_axis| (domain wall, .cpp:1134-1143).  The reference divides
     // for every neighbour and keeps the smallest positive quotient; here the candidates are compared by cross-multiplication
     // (s_i < s_q <=> num_i den_q < num_q den_i, all den > 0) and only the winner is divided -- the same operands, so the
-    // same ds; the ~15 divisions per crossing were two thirds of the loop's instructions.  Neighbours are taken four at a
-    // time with all their site records requested before the first is used (a wall index loads record 0, unused), so that
-    // four L2 round trips overlap instead of following each other.
+    // same ds; the ~15 divisions per crossing were two thirds of the loop's instructions.  The candidates of a cell are one
+    // contiguous run of 32-byte records {site of the neighbour; its index} (M.vnrec) instead of an index list plus as many
+    // scattered site records, and SK_VOR_UNROLL of them are requested before the first is used, so that their L2 round
+    // trips overlap: the loop is bound by the chain of dependent loads per crossing (offsets -> records -> next cell), not by
+    // its arithmetic.  (Rejected, measured: plane records {n; |n|^2/2} relative to the cell's site -- 12 instead of 27 fp64
+    // instructions per neighbour, rounding-level differences only, parity tests green -- were SLOWER, 394 vs 313 ms, because
+    // the winner's index then is one more dependent load per crossing.)
     template <bool OBSERVER>
     __device__ __forceinline__ void exit(const SkDevModel& M, const SkDevModel* __restrict__ Mg, const SkSmemTables&,
                                          SkLocalCounters& cnt, const SkDir& k, int& m_out, double& dens_out, double& ds_out)
