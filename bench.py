@@ -337,8 +337,9 @@ def sed_parity(name, device, ref_packets, gpu_packets):
     import numpy as np
     from skirt9_b200 import abi
     from tests.skirt_files import read_columns
+    from tests import mcstats
     cores = os.cpu_count() or 1
-    instr = "i60"
+    instr = "sed" if name == "cfg4" else "i60"
     refs = []
     for seed in (0, 1):
         with tempfile.TemporaryDirectory() as d:
@@ -354,13 +355,20 @@ def sed_parity(name, device, ref_packets, gpu_packets):
     e = sim.configure(abi.Engine(sim.config_struct(device=device)))
     sim.run(e, stream_id=7)
     own_stats = e.read_sed_stats(0)
-    names = {1: "total", 2: "transparent", 3: "direct", 4: "scattered"}
+    names = {1: "total", 2: "transparent", 3: "direct", 4: "scattered", 5: "secondary direct", 6: "secondary scattered",
+             7: "secondary transparent"}
     cols = ((1, abi.SK_COMP_TOTAL), (2, abi.SK_COMP_TRANSPARENT), (3, abi.SK_COMP_PRIMARY_DIRECT), (4, abi.SK_COMP_PRIMARY_SCATTERED))
+    if sim.dustEmissionWLG is not None:
+        cols += ((5, abi.SK_COMP_SECONDARY_DIRECT), (6, abi.SK_COMP_SECONDARY_SCATTERED), (7, abi.SK_COMP_SECONDARY_TRANSPARENT))
 
     def zscores(f, stats, col):
+        # (dust emission: only the bins whose error estimate is reliable by the reference's own rule, R < 0.1 and VOV < 0.1 on both
+        #  sides -- in the far-UV bins of that workload a handful of heavily weighted packets carry the flux)
         sigma = np.hypot(rel_error(ref_stats[:, 1:].T), rel_error(stats))
         scale = np.maximum(ref[:, col], ref[:, 1]) * sigma
         ok = scale > 0
+        if sim.dustEmissionWLG is not None:
+            ok &= mcstats.reliable(ref_stats[:, 1:].T) & mcstats.reliable(stats)
         return np.abs(f - ref[:, col])[ok] / scale[ok]
 
     own, rr = {}, {}
@@ -375,7 +383,7 @@ def sed_parity(name, device, ref_packets, gpu_packets):
     e.close()
     return {"against": f"unmodified reference, same {name} ski with recordStatistics, -t {cores}, {ref_packets:g} packets (its own "
                        f"set-up from its Mersenne streams); engine {gpu_packets:g} packets on the host mirror's set-up",
-            "quantity": "calibrated SED (Jy): total, transparent, direct, scattered", "bins": int(len(allz)),
+            "quantity": "calibrated SED (Jy): " + ", ".join(names[c] for c, _ in cols), "bins": int(len(allz)),
             "criterion": "|F - F_ref| <= 4 max(1, rms_ref_vs_ref) sqrt(R^2 + R_ref^2) max(F_ref, F_ref_total), R from Sum w^k "
                          "of both sides; rms_ref_vs_ref = rms of the same statistic between two reference runs (seeds 0, 1)",
             "max_sigma": float(allz.max()), "rms_sigma": float(np.sqrt((allz ** 2).mean())),
@@ -709,9 +717,11 @@ def native_arm(args):
                 line["setup"] = device_setup_times(local)
                 if LAST_REFERENCE_SETUP:
                     line["setup"]["reference_cpu"] = {k: v for k, v in LAST_REFERENCE_SETUP.items() if k not in ("phases", "wall_s")}
-            if os.path.exists(REF_EXE) and w["ski"] and w["parity_packets"] and name in ("cfg1", "cfg2") and not args.no_parity:
+            if os.path.exists(REF_EXE) and w["ski"] and w["parity_packets"] and name in ("cfg1", "cfg2", "cfg4") and not args.no_parity:
                 try:
-                    line["parity"] = sed_parity(name, local, args.cpu_packets or w["cpu_packets"], int(w["parity_packets"]))
+                    # (cfg4: five times the packets of the timing sample, the dust-emission columns need the statistics)
+                    line["parity"] = sed_parity(name, local, (args.cpu_packets or w["cpu_packets"]) * (5 if name == "cfg4" else 1),
+                                                int(w["parity_packets"]))
                 except Exception as ex:
                     line["parity"] = {"error": str(ex)[:300], "pass": False}
             if os.path.exists(SHIM_EXE) and w["ski"] and not args.no_e2e and name in ("cfg1", "cfg2"):
