@@ -96,6 +96,7 @@ typedef struct sko_engine {
     int vcells, vnb;   /* number of cells; blocks per axis of the start-cell table */
     int32_t* vblock;   /* [vnb^3] a cell whose site lies in (or near) the block: start of the walk to the nearest site */
     double* vbox;      /* [6*ncells] enclosing boxes of the cells (VoronoiMeshSnapshot::Cell is a Box), or NULL */
+    double* vvol;      /* [ncells] cell volumes when the tessellation was built here (sko_build_voronoi), or NULL */
     /* medium: nmed components (Configuration::hasMultipleConstantSectionMedia when > 1); dens[h*ncells + m] */
     int ncells, nmed;
     double *dens, *vol;
@@ -531,7 +532,9 @@ static void free_grid(sko_engine_t* e)
     free(e->vnbr);
     free(e->vblock);
     free(e->vbox);
+    free(e->vvol);
     e->vbox = NULL;
+    e->vvol = NULL;
     e->vsite = NULL;
     e->vnbr_off = NULL;
     e->vnbr = e->vblock = NULL;
@@ -725,6 +728,380 @@ int sko_set_voronoi_extents(sko_engine_t* e, int32_t num_cells, const double* bo
             if (!(boxes[6 * (size_t)m + a] <= boxes[6 * (size_t)m + a + 3])) return fail(SK_ERR_INVALID, "empty cell extent");
     free(e->vbox);
     e->vbox = dupd(boxes, 6 * (size_t)num_cells);
+    return SK_OK;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* Voronoi tessellation: VoronoiMeshSnapshot::buildMesh (VoronoiMeshSnapshot.cpp:491-730), which the  */
+/* reference delegates to the vendored voro++ (SKIRT/voro: container::compute_cell for every site, then                    */
+/* voronoicell_neighbor::neighbors / volume / vertices).  voro++'s published algorithm (Rycroft 2009) starts from the       */
+/* domain box around the site and cuts it with the bisecting planes towards the other sites in order of increasing        */
+/* distance, visiting the blocks of a uniform search grid outwards, until no unvisited site can cut the cell any more     */
+/* (every unvisited site is farther than twice the cell's largest vertex distance).  Restated here with the cell held as  */
+/* a list of vertices, each the intersection of three planes (the cell is simple for sites in general position), in       */
+/* coordinates relative to the site.  Output per cell: the neighbours whose plane carries a face (in order of cutting),    */
+/* then the domain walls that do (-1..-6 = xmin,xmax,ymin,ymax,zmin,zmax), the volume and the enclosing box.               */
+/* ------------------------------------------------------------------------------------------------ */
+#define VC_MAXP 96  /* planes kept per cell (6 walls + the bisectors that have cut it so far) */
+#define VC_MAXT 192 /* vertices */
+typedef struct {
+    int np, nt;
+    double pn[VC_MAXP][3], pd[VC_MAXP]; /* plane j: pn.x <= pd, x relative to the site */
+    int pid[VC_MAXP];                   /* neighbour index, or -1..-6 */
+    unsigned char ta[VC_MAXT], tb[VC_MAXT], tc[VC_MAXT];
+    double vx[VC_MAXT], vy[VC_MAXT], vz[VC_MAXT];
+    double rmax2; /* largest squared vertex distance */
+} vcell_t;
+
+/* the point where three planes meet (Cramer's rule); returns 0 when they do not meet in a point */
+static int vc_vertex(const vcell_t* c, int a, int b, int d, double* x, double* y, double* z)
+{
+    const double* A = c->pn[a];
+    const double* B = c->pn[b];
+    const double* C = c->pn[d];
+    const double bcx = B[1] * C[2] - B[2] * C[1], bcy = B[2] * C[0] - B[0] * C[2], bcz = B[0] * C[1] - B[1] * C[0];
+    const double det = A[0] * bcx + A[1] * bcy + A[2] * bcz;
+    if (det == 0.) return 0;
+    const double cax = C[1] * A[2] - C[2] * A[1], cay = C[2] * A[0] - C[0] * A[2], caz = C[0] * A[1] - C[1] * A[0];
+    const double abx = A[1] * B[2] - A[2] * B[1], aby = A[2] * B[0] - A[0] * B[2], abz = A[0] * B[1] - A[1] * B[0];
+    const double da = c->pd[a], db = c->pd[b], dd = c->pd[d];
+    *x = (da * bcx + db * cax + dd * abx) / det;
+    *y = (da * bcy + db * cay + dd * aby) / det;
+    *z = (da * bcz + db * caz + dd * abz) / det;
+    return 1;
+}
+static void vc_rmax(vcell_t* c)
+{
+    double r = 0.;
+    for (int t = 0; t < c->nt; ++t)
+    {
+        double q = c->vx[t] * c->vx[t] + c->vy[t] * c->vy[t] + c->vz[t] * c->vz[t];
+        if (q > r) r = q;
+    }
+    c->rmax2 = r;
+}
+static void vc_init(vcell_t* c, const double extent[6], const double p[3])
+{
+    c->np = 6;
+    c->nt = 0;
+    for (int w = 0; w < 6; ++w)
+    {
+        const int axis = w >> 1, upper = w & 1;
+        c->pn[w][0] = c->pn[w][1] = c->pn[w][2] = 0.;
+        c->pn[w][axis] = upper ? 1. : -1.;
+        c->pd[w] = upper ? extent[axis + 3] - p[axis] : -(extent[axis] - p[axis]);
+        c->pid[w] = -(w + 1);
+    }
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j)
+            for (int k = 0; k < 2; ++k)
+            {
+                const int t = c->nt++;
+                c->ta[t] = (unsigned char)i;
+                c->tb[t] = (unsigned char)(2 + j);
+                c->tc[t] = (unsigned char)(4 + k);
+                vc_vertex(c, i, 2 + j, 4 + k, &c->vx[t], &c->vy[t], &c->vz[t]);
+            }
+    vc_rmax(c);
+}
+/* cuts the cell with the plane n.x <= d of neighbour `id`; returns 0 on success, a negative code when the cell is not simple
+ * or outgrows the buffers */
+static int vc_clip(vcell_t* c, double nx, double ny, double nz, double d, int id)
+{
+    unsigned char out[VC_MAXT];
+    int nout = 0;
+    for (int t = 0; t < c->nt; ++t)
+    {
+        out[t] = (nx * c->vx[t] + ny * c->vy[t] + nz * c->vz[t] - d) > 0.;
+        nout += out[t];
+    }
+    if (!nout) return 0;             /* the plane does not reach the cell */
+    if (nout == c->nt) return -1;    /* cannot happen for a bisector: the site itself is inside */
+    if (c->np >= VC_MAXP)
+    {
+        /* drop the planes that no longer carry a vertex (cut away again by nearer neighbours) and renumber */
+        unsigned char map[VC_MAXP], keep[VC_MAXP];
+        for (int j = 0; j < c->np; ++j) keep[j] = j < 6;
+        for (int t = 0; t < c->nt; ++t) keep[c->ta[t]] = keep[c->tb[t]] = keep[c->tc[t]] = 1;
+        int np = 0;
+        for (int j = 0; j < c->np; ++j)
+        {
+            map[j] = (unsigned char)np;
+            if (!keep[j]) continue;
+            c->pn[np][0] = c->pn[j][0];
+            c->pn[np][1] = c->pn[j][1];
+            c->pn[np][2] = c->pn[j][2];
+            c->pd[np] = c->pd[j];
+            c->pid[np] = c->pid[j];
+            np++;
+        }
+        c->np = np;
+        for (int t = 0; t < c->nt; ++t)
+        {
+            c->ta[t] = map[c->ta[t]];
+            c->tb[t] = map[c->tb[t]];
+            c->tc[t] = map[c->tc[t]];
+        }
+        if (c->np >= VC_MAXP) return -2;
+    }
+    const int P = c->np++;
+    c->pn[P][0] = nx;
+    c->pn[P][1] = ny;
+    c->pn[P][2] = nz;
+    c->pd[P] = d;
+    c->pid[P] = id;
+    /* the edges (pairs of planes) of the removed vertices that lead to a kept vertex: those that occur once among them */
+    unsigned char ea[3 * VC_MAXT], eb[3 * VC_MAXT], eo[3 * VC_MAXT];
+    int ne = 0;
+    for (int t = 0; t < c->nt; ++t)
+    {
+        if (!out[t]) continue;
+        const unsigned char pa[3] = {c->ta[t], c->ta[t], c->tb[t]}, pb[3] = {c->tb[t], c->tc[t], c->tc[t]};
+        for (int k = 0; k < 3; ++k)
+        {
+            int found = -1;
+            for (int q = 0; q < ne; ++q)
+                if (ea[q] == pa[k] && eb[q] == pb[k]) found = q;
+            if (found >= 0)
+                eo[found]++;
+            else
+            {
+                ea[ne] = pa[k];
+                eb[ne] = pb[k];
+                eo[ne] = 1;
+                ne++;
+            }
+        }
+    }
+    /* compact the kept vertices, then one new vertex per boundary edge */
+    int nt = 0;
+    for (int t = 0; t < c->nt; ++t)
+        if (!out[t])
+        {
+            c->ta[nt] = c->ta[t];
+            c->tb[nt] = c->tb[t];
+            c->tc[nt] = c->tc[t];
+            c->vx[nt] = c->vx[t];
+            c->vy[nt] = c->vy[t];
+            c->vz[nt] = c->vz[t];
+            nt++;
+        }
+    for (int q = 0; q < ne; ++q)
+    {
+        if (eo[q] > 2) return -3; /* more than three planes through a vertex: not a simple cell */
+        if (eo[q] != 1) continue;
+        if (nt >= VC_MAXT) return -2;
+        c->ta[nt] = ea[q];
+        c->tb[nt] = eb[q];
+        c->tc[nt] = (unsigned char)P;
+        if (!vc_vertex(c, ea[q], eb[q], P, &c->vx[nt], &c->vy[nt], &c->vz[nt])) return -3;
+        nt++;
+    }
+    c->nt = nt;
+    vc_rmax(c);
+    return 0;
+}
+/* volume and enclosing box (relative to the site) from the faces: the vertices of a face are ordered by walking from one to
+ * the next across the plane they share besides the face's own; the volume is the sum of the pyramids site-face */
+static int vc_measure(const vcell_t* c, double* volume, double box[6], unsigned char used[VC_MAXP])
+{
+    for (int j = 0; j < c->np; ++j) used[j] = 0;
+    box[0] = box[1] = box[2] = DBL_MAX;
+    box[3] = box[4] = box[5] = -DBL_MAX;
+    for (int t = 0; t < c->nt; ++t)
+    {
+        used[c->ta[t]] = used[c->tb[t]] = used[c->tc[t]] = 1;
+        if (c->vx[t] < box[0]) box[0] = c->vx[t];
+        if (c->vy[t] < box[1]) box[1] = c->vy[t];
+        if (c->vz[t] < box[2]) box[2] = c->vz[t];
+        if (c->vx[t] > box[3]) box[3] = c->vx[t];
+        if (c->vy[t] > box[4]) box[4] = c->vy[t];
+        if (c->vz[t] > box[5]) box[5] = c->vz[t];
+    }
+    double V = 0.;
+    for (int f = 0; f < c->np; ++f)
+    {
+        if (!used[f]) continue;
+        int t0 = -1;
+        for (int t = 0; t < c->nt && t0 < 0; ++t)
+            if (c->ta[t] == f || c->tb[t] == f || c->tc[t] == f) t0 = t;
+        /* the two other planes of the first vertex; leave through the second */
+        int o1 = c->ta[t0] == f ? c->tb[t0] : c->ta[t0];
+        int via = c->tc[t0] == f ? c->tb[t0] : c->tc[t0];
+        if (via == o1) via = c->tc[t0];
+        int cur = t0, steps = 0;
+        double sum = 0.;
+        double px = 0., py = 0., pz = 0.; /* previous vertex of the fan */
+        while (1)
+        {
+            int next = -1;
+            for (int t = 0; t < c->nt; ++t)
+            {
+                if (t == cur) continue;
+                const int a = c->ta[t], b = c->tb[t], d = c->tc[t];
+                if ((a == f || b == f || d == f) && (a == via || b == via || d == via)) next = t;
+            }
+            if (next < 0 || ++steps > c->nt) return -3;
+            const int a = c->ta[next], b = c->tb[next], d = c->tc[next];
+            const int other = (a != f && a != via) ? a : (b != f && b != via) ? b : d;
+            if (next == t0) break;
+            if (steps >= 2)
+            {
+                /* triangle (t0, previous, next) of the fan: 6 x signed volume of the pyramid with the site */
+                const double ax = c->vx[t0], ay = c->vy[t0], az = c->vz[t0];
+                const double bx = c->vx[next], by = c->vy[next], bz = c->vz[next];
+                sum += ax * (py * bz - pz * by) + ay * (pz * bx - px * bz) + az * (px * by - py * bx);
+            }
+            px = c->vx[next];
+            py = c->vy[next];
+            pz = c->vz[next];
+            via = other;
+            cur = next;
+        }
+        V += fabs(sum);
+    }
+    *volume = V / 6.;
+    return 0;
+}
+
+int sko_build_voronoi(sko_engine_t* e, const double extent[6], int32_t num_sites, const double* sites, uint64_t* num_entries)
+{
+    if (!e || !extent || num_sites < 1 || !sites) return fail(SK_ERR_INVALID, "bad voronoi sites");
+    const int n = num_sites;
+    for (int m = 0; m < n; ++m)
+        for (int a = 0; a < 3; ++a)
+            if (!(sites[3 * (size_t)m + a] > extent[a] && sites[3 * (size_t)m + a] < extent[a + 3]))
+                return fail(SK_ERR_INVALID, "site outside the domain");
+    /* search grid: cubic blocks holding two sites on average; sites of a block in ascending index */
+    const double wx = extent[3] - extent[0], wy = extent[4] - extent[1], wz = extent[5] - extent[2];
+    const double w = cbrt(2. * wx * wy * wz / n);
+    int gx = (int)ceil(wx / w), gy = (int)ceil(wy / w), gz = (int)ceil(wz / w);
+    gx = gx < 1 ? 1 : gx;
+    gy = gy < 1 ? 1 : gy;
+    gz = gz < 1 ? 1 : gz;
+    const size_t ng = (size_t)gx * gy * gz;
+    int32_t* start = (int32_t*)calloc(ng + 1, sizeof(int32_t));
+    int32_t* blk = (int32_t*)malloc((size_t)n * sizeof(int32_t));
+    int32_t* order = (int32_t*)malloc((size_t)n * sizeof(int32_t));
+    for (int m = 0; m < n; ++m)
+    {
+        int i = (int)((sites[3 * (size_t)m] - extent[0]) / w), j = (int)((sites[3 * (size_t)m + 1] - extent[1]) / w),
+            k = (int)((sites[3 * (size_t)m + 2] - extent[2]) / w);
+        i = i >= gx ? gx - 1 : i;
+        j = j >= gy ? gy - 1 : j;
+        k = k >= gz ? gz - 1 : k;
+        blk[m] = (int32_t)(((size_t)i * gy + j) * gz + k);
+        start[blk[m] + 1]++;
+    }
+    for (size_t b = 0; b < ng; ++b) start[b + 1] += start[b];
+    {
+        int32_t* fill = (int32_t*)malloc(ng * sizeof(int32_t));
+        memcpy(fill, start, ng * sizeof(int32_t));
+        for (int m = 0; m < n; ++m) order[fill[blk[m]]++] = m;
+        free(fill);
+    }
+    int64_t* off = (int64_t*)malloc(((size_t)n + 1) * sizeof(int64_t));
+    int32_t* idx = (int32_t*)malloc((size_t)n * VC_MAXP * sizeof(int32_t));
+    double* vol = (double*)malloc((size_t)n * sizeof(double));
+    double* box = (double*)malloc(6 * (size_t)n * sizeof(double));
+    int rc = 0;
+    off[0] = 0;
+    vcell_t c;
+    for (int m = 0; m < n && !rc; ++m)
+    {
+        const double* p = sites + 3 * (size_t)m;
+        vc_init(&c, extent, p);
+        const int bi = blk[m] / (gy * gz), bj = (blk[m] / gz) % gy, bk = blk[m] % gz;
+        const int smax = (gx > gy ? (gx > gz ? gx : gz) : (gy > gz ? gy : gz));
+        for (int s = 0; s <= smax && !rc; ++s)
+        {
+            /* every site in a block at Chebyshev distance s or more is at least (s-1) w away */
+            if (s >= 2 && (double)(s - 1) * w * (double)(s - 1) * w >= 4. * c.rmax2) break;
+            for (int i = bi - s; i <= bi + s && !rc; ++i)
+            {
+                if (i < 0 || i >= gx) continue;
+                for (int j = bj - s; j <= bj + s && !rc; ++j)
+                {
+                    if (j < 0 || j >= gy) continue;
+                    const int shell = (i == bi - s || i == bi + s || j == bj - s || j == bj + s);
+                    for (int k = bk - s; k <= bk + s && !rc; k += (shell || s == 0) ? 1 : 2 * s)
+                    {
+                        if (k < 0 || k >= gz) continue;
+                        const size_t b = ((size_t)i * gy + j) * gz + k;
+                        for (int32_t q = start[b]; q < start[b + 1] && !rc; ++q)
+                        {
+                            const int mi = order[q];
+                            if (mi == m) continue;
+                            const double nx = sites[3 * (size_t)mi] - p[0], ny = sites[3 * (size_t)mi + 1] - p[1],
+                                         nz = sites[3 * (size_t)mi + 2] - p[2];
+                            const double n2 = nx * nx + ny * ny + nz * nz;
+                            if (n2 >= 4. * c.rmax2) continue; /* its bisector lies beyond the farthest vertex */
+                            if (n2 == 0.) rc = -4;
+                            else rc = vc_clip(&c, nx, ny, nz, 0.5 * n2, mi);
+                        }
+                    }
+                }
+            }
+        }
+        if (rc) break;
+        unsigned char used[VC_MAXP];
+        double b6[6];
+        rc = vc_measure(&c, &vol[m], b6, used);
+        if (rc) break;
+        int64_t o = off[m];
+        for (int j = 6; j < c.np; ++j)
+            if (used[j]) idx[o++] = c.pid[j];
+        for (int j = 0; j < 6; ++j)
+            if (used[j]) idx[o++] = c.pid[j];
+        off[m + 1] = o;
+        for (int a = 0; a < 3; ++a)
+        {
+            box[6 * (size_t)m + a] = p[a] + b6[a];
+            box[6 * (size_t)m + a + 3] = p[a] + b6[a + 3];
+        }
+    }
+    free(start);
+    free(blk);
+    free(order);
+    int out = SK_OK;
+    if (rc)
+        out = fail(SK_ERR_UNSUPPORTED, rc == -2   ? "Voronoi cell with more faces than the builder holds"
+                                       : rc == -4 ? "coinciding Voronoi sites"
+                                                  : "Voronoi sites in degenerate position (a cell that is not simple)");
+    else
+    {
+        out = sko_set_grid_voronoi(e, extent, n, sites, off, idx);
+        if (!out) out = sko_set_voronoi_extents(e, n, box);
+        if (!out)
+        {
+            free(e->vvol);
+            e->vvol = vol;
+            vol = NULL;
+            if (num_entries) *num_entries = (uint64_t)off[n];
+        }
+    }
+    free(off);
+    free(idx);
+    free(vol);
+    free(box);
+    return out;
+}
+/* the tessellation the engine holds: neighbour lists, cell volumes and enclosing boxes (any pointer may be NULL) */
+int sko_read_voronoi(sko_engine_t* e, int64_t* nbr_offset, int32_t* nbr_index, double* volume, double* boxes)
+{
+    if (!e || e->grid_kind != 3) return fail(SK_ERR_STATE, "the engine holds no Voronoi grid");
+    if (nbr_offset) memcpy(nbr_offset, e->vnbr_off, ((size_t)e->vcells + 1) * sizeof(int64_t));
+    if (nbr_index) memcpy(nbr_index, e->vnbr, (size_t)e->vnbr_off[e->vcells] * sizeof(int32_t));
+    if (volume)
+    {
+        if (!e->vvol) return fail(SK_ERR_STATE, "the grid was not built by build_voronoi: no volumes");
+        memcpy(volume, e->vvol, (size_t)e->vcells * sizeof(double));
+    }
+    if (boxes)
+    {
+        if (!e->vbox) return fail(SK_ERR_STATE, "no cell extents");
+        memcpy(boxes, e->vbox, 6 * (size_t)e->vcells * sizeof(double));
+    }
     return SK_OK;
 }
 

@@ -233,6 +233,27 @@ class Engine:
         idx, pi = _i(nbr_index)
         self._call("set_grid_voronoi", self._h, pe, C.c_int32(len(st)), ps, off.ctypes.data_as(C.POINTER(C.c_int64)), pi)
 
+    def build_voronoi(self, extent, sites):
+        """VoronoiMeshSnapshot::buildMesh on the engine's side (sk_engine_build_voronoi): returns the number of neighbour entries."""
+        ext, pe = _d(extent)
+        st, ps = _d(np.asarray(sites, dtype=np.float64).reshape(-1, 3))
+        n = C.c_uint64()
+        self._call("build_voronoi", self._h, pe, C.c_int32(len(st)), ps, C.byref(n))
+        self.num_cells = len(st)
+        self._voronoi_entries = int(n.value)
+        return int(n.value)
+
+    def read_voronoi(self):
+        """(nbr_offset, nbr_index, volumes, boxes) of the tessellation built by build_voronoi."""
+        n = self.num_cells
+        off = np.empty(n + 1, dtype=np.int64)
+        idx = np.empty(self._voronoi_entries, dtype=np.int32)
+        vol = np.empty(n)
+        box = np.empty((n, 6))
+        self._call("read_voronoi", self._h, off.ctypes.data_as(C.POINTER(C.c_int64)), idx.ctypes.data_as(C.POINTER(C.c_int32)),
+                   vol.ctypes.data_as(_dp), box.ctypes.data_as(_dp))
+        return off, idx, vol, box
+
     def set_voronoi_extents(self, boxes):
         b, pb = _d(np.asarray(boxes, dtype=np.float64).reshape(-1, 6))
         self._call("set_voronoi_extents", self._h, C.c_int32(len(b)), pb)
