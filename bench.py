@@ -255,8 +255,11 @@ def make_sim(name, total_packets, statistics=False):
     R = R[R < 15000.0][:sites]
     phi = rng.uniform(0, 2 * np.pi, size=len(R))
     z = np.clip(rng.laplace(0.0, 250.0, size=len(R)), -1900.0, 1900.0)
-    return configs.cfg5(np.stack([R * np.cos(phi), R * np.sin(phi), z], axis=1) * PC, num_packets=total_packets,
-                        num_pixels=256, record_statistics=False).setup()
+    sim = configs.cfg5(np.stack([R * np.cos(phi), R * np.sin(phi), z], axis=1) * PC, num_packets=total_packets,
+                       num_pixels=256, record_statistics=False)
+    # the tessellation (VoronoiMeshSnapshot::buildMesh) is built by the engine when it is configured: sk_engine_build_voronoi
+    sim.deviceSetup = os.environ.get("SK_BENCH_HOST_TESSELLATION") is None
+    return sim.setup()
 
 
 def run_port_once(num_packets, name="cfg2", sim=None):

@@ -250,6 +250,23 @@ int sk_engine_set_grid_octree(sk_engine_t* e, const double extent[6], int32_t nu
 int sk_engine_set_grid_voronoi(sk_engine_t* e, const double extent[6], int32_t num_cells, const double* sites,
                                const int64_t* nbr_offset, const int32_t* nbr_index);
 
+/* VoronoiMeshSnapshot::buildMesh (VoronoiMeshSnapshot.cpp:491-730) on the device: the tessellation of the domain box by the
+ * given sites -- what the reference obtains from the vendored voro++ (container::compute_cell per site; neighbors, volume,
+ * vertices of every cell).  sites[3*m..] as in sk_engine_set_grid_voronoi, all strictly inside the domain and in the order the
+ * cells are to be numbered (the reference sorts them by x and drops sites outside the domain or closer than 1e-12 of its
+ * diagonal to another, VoronoiMeshSnapshot.cpp:500-540; the caller does that).  One thread builds one cell: the box around the
+ * site is cut with the bisecting planes towards the other sites, visiting the blocks of a uniform search grid outwards, until
+ * every unvisited site is farther away than twice the cell's largest vertex distance.  Leaves the engine in the state
+ * sk_engine_set_grid_voronoi + sk_engine_set_voronoi_extents would, and keeps the cell volumes (MediumState::volume).  Sites in
+ * degenerate position (more than three planes through a vertex, as in a regular lattice) are reported as SK_ERR_UNSUPPORTED --
+ * the caller then falls back to its own tessellation.  *num_entries = total length of the neighbour lists. */
+int sk_engine_build_voronoi(sk_engine_t* e, const double extent[6], int32_t num_sites, const double* sites,
+                            uint64_t* num_entries);
+/* The tessellation the engine holds after sk_engine_build_voronoi (any pointer may be NULL): nbr_offset[num_cells+1],
+ * nbr_index[num_entries] (per cell the neighbours that share a face with it, then the domain walls -1..-6 that bound it),
+ * volume[num_cells], boxes[6*num_cells]. */
+int sk_engine_read_voronoi(sk_engine_t* e, int64_t* nbr_offset, int32_t* nbr_index, double* volume, double* boxes);
+
 /* Optional, after sk_engine_set_grid_voronoi: the enclosing box of every Voronoi cell, boxes[6*m..] = {xmin,ymin,zmin,xmax,
  * ymax,zmax} of VoronoiMeshSnapshot::Cell (a Box: the bounding box of the cell's vertices, VoronoiMeshSnapshot.cpp:104-135).
  * Needed only for dust emission from a Voronoi grid: VoronoiMeshSnapshot::generatePosition(m) (.cpp:976-989) draws

@@ -257,6 +257,10 @@ struct sk_engine {
     std::vector<int> instr_same_observer;
     std::vector<std::array<double, 3>> instr_kobs;
     bool secondary_ready = false, has_secondary = false;
+    // the tessellation built by sk_engine_build_voronoi, kept for sk_engine_read_voronoi
+    std::vector<int64_t> voronoi_off;
+    std::vector<int32_t> voronoi_idx;
+    std::vector<double> voronoi_volume, voronoi_box;
     int num_mixes = 0;      // dust mixes given by sk_engine_set_dustmixes; must equal M.nmed when a segment runs
     int sec_num_media = 0;  // dust components the secondary-emission tables were given for
     int num_pix_lists = 0;
@@ -447,6 +451,10 @@ static void drop_grid(sk_engine* e)
     e->secondary_ready = false;
     e->first_child_dev = nullptr;
     e->dens_host.clear();
+    e->voronoi_off.clear();
+    e->voronoi_idx.clear();
+    e->voronoi_volume.clear();
+    e->voronoi_box.clear();
 }
 
 static int set_tables(sk_engine* e, const double* xv, int nx1, const double* yv, int ny1, const double* zv, int nz1)
@@ -672,6 +680,127 @@ extern "C" int sk_engine_set_voronoi_extents(sk_engine_t* e, int32_t num_cells, 
     double* d;
     if (int rc = upload(e->grid_allocs, boxes, 6 * (size_t)num_cells, &d)) return rc;
     e->M.vbox = d;
+    return SK_OK;
+}
+
+static int exclusive_scan(sk_engine* e, const int32_t* in, int32_t* out, int n, int32_t* sums, int32_t* total);
+// VoronoiMeshSnapshot::buildMesh on the device (sk_setup.cuh): search grid on the host (a counting sort of the sites into cubic
+// blocks of two sites on average, as oracle/sk_oracle.c sko_build_voronoi), one thread per cell, the neighbour slots packed
+// into lists on the device; the lists then take the same route as a tessellation handed in by the caller.
+extern "C" int sk_engine_build_voronoi(sk_engine_t* e, const double extent[6], int32_t num_sites, const double* sites,
+                                       uint64_t* num_entries)
+{
+    if (!e || !extent || num_sites < 1 || !sites) return fail(SK_ERR_INVALID, "bad voronoi sites");
+    const int n = num_sites;
+    for (int m = 0; m < n; ++m)
+        for (int a = 0; a < 3; ++a)
+            if (!(sites[3 * (size_t)m + a] > extent[a] && sites[3 * (size_t)m + a] < extent[a + 3]))
+                return fail(SK_ERR_INVALID, "site outside the domain");
+    if (int rc_bind = bind(e)) return rc_bind;
+    PhaseTimer pt("build_voronoi");
+    const double wx = extent[3] - extent[0], wy = extent[4] - extent[1], wz = extent[5] - extent[2];
+    const double w = cbrt(2. * wx * wy * wz / n);
+    int gx = std::max(1, (int)ceil(wx / w)), gy = std::max(1, (int)ceil(wy / w)), gz = std::max(1, (int)ceil(wz / w));
+    const size_t ng = (size_t)gx * gy * gz;
+    std::vector<int32_t> start(ng + 1, 0), blk(n), order(n);
+    for (int m = 0; m < n; ++m)
+    {
+        int i = (int)((sites[3 * (size_t)m] - extent[0]) / w), j = (int)((sites[3 * (size_t)m + 1] - extent[1]) / w),
+            k = (int)((sites[3 * (size_t)m + 2] - extent[2]) / w);
+        i = i >= gx ? gx - 1 : i;
+        j = j >= gy ? gy - 1 : j;
+        k = k >= gz ? gz - 1 : k;
+        blk[m] = (int32_t)(((size_t)i * gy + j) * gz + k);
+        start[blk[m] + 1]++;
+    }
+    for (size_t b = 0; b < ng; ++b) start[b + 1] += start[b];
+    {
+        std::vector<int32_t> fill(start.begin(), start.end() - 1);
+        for (int m = 0; m < n; ++m) order[fill[blk[m]]++] = m;
+    }
+    pt.lap("search grid (host)");
+    std::vector<void*> scratch;
+    struct Guard {
+        std::vector<void*>& v;
+        ~Guard() { free_group(v); }
+    } guard{scratch};
+    SkVoronoiBuild B;
+    memcpy(B.ext, extent, sizeof B.ext);
+    B.w = w;
+    B.gx = gx;
+    B.gy = gy;
+    B.gz = gz;
+    B.n = n;
+    double *d_sites, *d_vol, *d_box;
+    int32_t *d_start, *d_order, *d_blk, *d_nbr, *d_count, *d_off, *d_sums, *d_total, *d_idx;
+    int* d_err;
+    if (int rc = upload(scratch, sites, 3 * (size_t)n, &d_sites)) return rc;
+    if (int rc = upload(scratch, start.data(), start.size(), &d_start)) return rc;
+    if (int rc = upload(scratch, order.data(), order.size(), &d_order)) return rc;
+    if (int rc = upload(scratch, blk.data(), blk.size(), &d_blk)) return rc;
+    if (int rc = dalloc_zero(scratch, (size_t)n * SK_VC_MAXNB, &d_nbr)) return rc;
+    if (int rc = dalloc_zero(scratch, (size_t)n, &d_count)) return rc;
+    if (int rc = dalloc_zero(scratch, (size_t)n, &d_off)) return rc;
+    if (int rc = dalloc_zero(scratch, (size_t)(n + SK_SCAN_BLOCK - 1) / SK_SCAN_BLOCK + 1, &d_sums)) return rc;
+    if (int rc = dalloc_zero(scratch, (size_t)1, &d_total)) return rc;
+    if (int rc = dalloc_zero(scratch, (size_t)n, &d_vol)) return rc;
+    if (int rc = dalloc_zero(scratch, 6 * (size_t)n, &d_box)) return rc;
+    if (int rc = dalloc_zero(scratch, (size_t)1, &d_err)) return rc;
+    B.sites = d_sites;
+    B.start = d_start;
+    B.order = d_order;
+    B.blk = d_blk;
+    B.nbr = d_nbr;
+    B.count = d_count;
+    B.volume = d_vol;
+    B.box = d_box;
+    B.error = d_err;
+    sk_voronoi_build_kernel<<<(n + 63) / 64, 64, 0, e->stream>>>(B);
+    CK(cudaGetLastError());
+    if (int rc = exclusive_scan(e, d_count, d_off, n, d_sums, d_total)) return rc;
+    int32_t total = 0;
+    int err = 0;
+    CK(cudaMemcpyAsync(&total, d_total, sizeof total, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(&err, d_err, sizeof err, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    pt.lap("cells (device)");
+    if (err)
+        return fail(SK_ERR_UNSUPPORTED, err == -2   ? "Voronoi cell with more faces than the builder holds"
+                                        : err == -4 ? "coinciding Voronoi sites"
+                                        : err == -5 ? "Voronoi cell with more than 64 faces"
+                                                    : "Voronoi sites in degenerate position (a cell that is not simple)");
+    if (int rc = dalloc_zero(scratch, (size_t)std::max(total, 1), &d_idx)) return rc;
+    sk_voronoi_compact_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(d_nbr, d_count, d_off, n, d_idx);
+    CK(cudaGetLastError());
+    std::vector<int32_t> off32(n), idx((size_t)total);
+    std::vector<double> vol(n), box(6 * (size_t)n);
+    CK(cudaMemcpyAsync(off32.data(), d_off, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(idx.data(), d_idx, (size_t)total * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(vol.data(), d_vol, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(box.data(), d_box, 6 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    std::vector<int64_t> off((size_t)n + 1);
+    for (int m = 0; m < n; ++m) off[m] = off32[m];
+    off[n] = total;
+    pt.lap("lists to the host");
+    if (int rc = sk_engine_set_grid_voronoi(e, extent, n, sites, off.data(), idx.data())) return rc;
+    if (int rc = sk_engine_set_voronoi_extents(e, n, box.data())) return rc;
+    e->voronoi_off = std::move(off);
+    e->voronoi_idx = std::move(idx);
+    e->voronoi_volume = std::move(vol);
+    e->voronoi_box = std::move(box);
+    if (num_entries) *num_entries = (uint64_t)total;
+    return SK_OK;
+}
+
+extern "C" int sk_engine_read_voronoi(sk_engine_t* e, int64_t* nbr_offset, int32_t* nbr_index, double* volume, double* boxes)
+{
+    if (!e) return fail(SK_ERR_INVALID, "null engine");
+    if (e->grid_kind != 3 || e->voronoi_off.empty()) return fail(SK_ERR_STATE, "the engine holds no tessellation built by sk_engine_build_voronoi");
+    if (nbr_offset) memcpy(nbr_offset, e->voronoi_off.data(), e->voronoi_off.size() * sizeof(int64_t));
+    if (nbr_index) memcpy(nbr_index, e->voronoi_idx.data(), e->voronoi_idx.size() * sizeof(int32_t));
+    if (volume) memcpy(volume, e->voronoi_volume.data(), e->voronoi_volume.size() * sizeof(double));
+    if (boxes) memcpy(boxes, e->voronoi_box.data(), e->voronoi_box.size() * sizeof(double));
     return SK_OK;
 }
 

@@ -391,3 +391,324 @@ __global__ void sk_gather_density_kernel(const SkCellRec* __restrict__ cells, co
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m < ncells) out[m] = cells ? cells[m].dens : vrec[m].w;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Voronoi tessellation on the device: VoronoiMeshSnapshot::buildMesh (VoronoiMeshSnapshot.cpp:491-730),
+// which the reference delegates to the vendored voro++ (container::compute_cell per site, then neighbors / volume / vertices).
+// One thread builds one cell the way voro++ does: the domain box around the site is cut with the bisecting planes towards
+// the other sites, visiting the blocks of a uniform search grid outwards, until every unvisited site is farther than twice
+// the cell's largest vertex distance.  The cell is a list of vertices, each the meeting point of three planes (simple cells:
+// sites in general position), in coordinates relative to the site; per-thread state lives in local memory (a cell has a few
+// dozen planes and vertices).  Same operations in the same order as oracle/sk_oracle.c (vc_*), so lists, volumes and boxes
+// are bit-identical.  Output per cell: the neighbours whose plane carries a face, in the order they cut the cell, then the
+// walls -1..-6 that do; volume; enclosing box.
+// ---------------------------------------------------------------------------------------------------
+#define SK_VC_MAXP 96   // planes kept per cell: 6 walls + the bisectors that have cut it so far (unused ones are dropped when full)
+#define SK_VC_MAXT 192  // vertices
+#define SK_VC_MAXNB 64  // faces of a finished cell (slots of the temporary neighbour table)
+struct SkVCell {
+    int np, nt;
+    double pn[SK_VC_MAXP][3], pd[SK_VC_MAXP];
+    int pid[SK_VC_MAXP];
+    unsigned char ta[SK_VC_MAXT], tb[SK_VC_MAXT], tc[SK_VC_MAXT];
+    double vx[SK_VC_MAXT], vy[SK_VC_MAXT], vz[SK_VC_MAXT];
+    double rmax2;
+};
+struct SkVoronoiBuild {
+    double ext[6];
+    double w;            // width of the cubic search blocks
+    int gx, gy, gz, n;
+    const double* sites; // [3n]
+    const int32_t* start; // [blocks+1] first entry of each block in `order`
+    const int32_t* order; // site indices block by block, ascending inside a block
+    const int32_t* blk;   // block of every site
+    int32_t* nbr;         // [n * SK_VC_MAXNB]
+    int32_t* count;       // [n]
+    double* volume;       // [n]
+    double* box;          // [6n]
+    int* error;           // first failure: -2 buffers, -3 degenerate sites, -4 coinciding sites, -5 too many faces
+};
+
+__device__ __forceinline__ bool sk_vc_vertex(const SkVCell& c, int a, int b, int d, double& x, double& y, double& z)
+{
+    const double* A = c.pn[a];
+    const double* B = c.pn[b];
+    const double* C = c.pn[d];
+    const double bcx = B[1] * C[2] - B[2] * C[1], bcy = B[2] * C[0] - B[0] * C[2], bcz = B[0] * C[1] - B[1] * C[0];
+    const double det = A[0] * bcx + A[1] * bcy + A[2] * bcz;
+    if (det == 0.) return false;
+    const double cax = C[1] * A[2] - C[2] * A[1], cay = C[2] * A[0] - C[0] * A[2], caz = C[0] * A[1] - C[1] * A[0];
+    const double abx = A[1] * B[2] - A[2] * B[1], aby = A[2] * B[0] - A[0] * B[2], abz = A[0] * B[1] - A[1] * B[0];
+    const double da = c.pd[a], db = c.pd[b], dd = c.pd[d];
+    x = (da * bcx + db * cax + dd * abx) / det;
+    y = (da * bcy + db * cay + dd * aby) / det;
+    z = (da * bcz + db * caz + dd * abz) / det;
+    return true;
+}
+__device__ __forceinline__ void sk_vc_rmax(SkVCell& c)
+{
+    double r = 0.;
+    for (int t = 0; t < c.nt; ++t)
+    {
+        const double q = c.vx[t] * c.vx[t] + c.vy[t] * c.vy[t] + c.vz[t] * c.vz[t];
+        if (q > r) r = q;
+    }
+    c.rmax2 = r;
+}
+__device__ __noinline__ int sk_vc_clip(SkVCell& c, double nx, double ny, double nz, double d, int id)
+{
+    unsigned char out[SK_VC_MAXT];
+    int nout = 0;
+    for (int t = 0; t < c.nt; ++t)
+    {
+        out[t] = (nx * c.vx[t] + ny * c.vy[t] + nz * c.vz[t] - d) > 0.;
+        nout += out[t];
+    }
+    if (!nout) return 0;
+    if (nout == c.nt) return -1;
+    if (c.np >= SK_VC_MAXP)
+    {
+        unsigned char map[SK_VC_MAXP], keep[SK_VC_MAXP];
+        for (int j = 0; j < c.np; ++j) keep[j] = j < 6;
+        for (int t = 0; t < c.nt; ++t) keep[c.ta[t]] = keep[c.tb[t]] = keep[c.tc[t]] = 1;
+        int np = 0;
+        for (int j = 0; j < c.np; ++j)
+        {
+            map[j] = (unsigned char)np;
+            if (!keep[j]) continue;
+            c.pn[np][0] = c.pn[j][0];
+            c.pn[np][1] = c.pn[j][1];
+            c.pn[np][2] = c.pn[j][2];
+            c.pd[np] = c.pd[j];
+            c.pid[np] = c.pid[j];
+            np++;
+        }
+        c.np = np;
+        for (int t = 0; t < c.nt; ++t)
+        {
+            c.ta[t] = map[c.ta[t]];
+            c.tb[t] = map[c.tb[t]];
+            c.tc[t] = map[c.tc[t]];
+        }
+        if (c.np >= SK_VC_MAXP) return -2;
+    }
+    const int P = c.np++;
+    c.pn[P][0] = nx;
+    c.pn[P][1] = ny;
+    c.pn[P][2] = nz;
+    c.pd[P] = d;
+    c.pid[P] = id;
+    // the edges (pairs of planes) of the removed vertices that lead to a kept vertex: those that occur once among them
+    unsigned char ea[3 * SK_VC_MAXT], eb[3 * SK_VC_MAXT], eo[3 * SK_VC_MAXT];
+    int ne = 0;
+    for (int t = 0; t < c.nt; ++t)
+    {
+        if (!out[t]) continue;
+        const unsigned char pa[3] = {c.ta[t], c.ta[t], c.tb[t]}, pb[3] = {c.tb[t], c.tc[t], c.tc[t]};
+        for (int k = 0; k < 3; ++k)
+        {
+            int found = -1;
+            for (int q = 0; q < ne; ++q)
+                if (ea[q] == pa[k] && eb[q] == pb[k]) found = q;
+            if (found >= 0)
+                eo[found]++;
+            else
+            {
+                ea[ne] = pa[k];
+                eb[ne] = pb[k];
+                eo[ne] = 1;
+                ne++;
+            }
+        }
+    }
+    int nt = 0;
+    for (int t = 0; t < c.nt; ++t)
+        if (!out[t])
+        {
+            c.ta[nt] = c.ta[t];
+            c.tb[nt] = c.tb[t];
+            c.tc[nt] = c.tc[t];
+            c.vx[nt] = c.vx[t];
+            c.vy[nt] = c.vy[t];
+            c.vz[nt] = c.vz[t];
+            nt++;
+        }
+    for (int q = 0; q < ne; ++q)
+    {
+        if (eo[q] > 2) return -3;
+        if (eo[q] != 1) continue;
+        if (nt >= SK_VC_MAXT) return -2;
+        c.ta[nt] = ea[q];
+        c.tb[nt] = eb[q];
+        c.tc[nt] = (unsigned char)P;
+        if (!sk_vc_vertex(c, ea[q], eb[q], P, c.vx[nt], c.vy[nt], c.vz[nt])) return -3;
+        nt++;
+    }
+    c.nt = nt;
+    sk_vc_rmax(c);
+    return 0;
+}
+__device__ __noinline__ int sk_vc_measure(const SkVCell& c, double& volume, double box[6], unsigned char* used)
+{
+    for (int j = 0; j < c.np; ++j) used[j] = 0;
+    box[0] = box[1] = box[2] = DBL_MAX;
+    box[3] = box[4] = box[5] = -DBL_MAX;
+    for (int t = 0; t < c.nt; ++t)
+    {
+        used[c.ta[t]] = used[c.tb[t]] = used[c.tc[t]] = 1;
+        if (c.vx[t] < box[0]) box[0] = c.vx[t];
+        if (c.vy[t] < box[1]) box[1] = c.vy[t];
+        if (c.vz[t] < box[2]) box[2] = c.vz[t];
+        if (c.vx[t] > box[3]) box[3] = c.vx[t];
+        if (c.vy[t] > box[4]) box[4] = c.vy[t];
+        if (c.vz[t] > box[5]) box[5] = c.vz[t];
+    }
+    double V = 0.;
+    for (int f = 0; f < c.np; ++f)
+    {
+        if (!used[f]) continue;
+        int t0 = -1;
+        for (int t = 0; t < c.nt && t0 < 0; ++t)
+            if (c.ta[t] == f || c.tb[t] == f || c.tc[t] == f) t0 = t;
+        int o1 = c.ta[t0] == f ? c.tb[t0] : c.ta[t0];
+        int via = c.tc[t0] == f ? c.tb[t0] : c.tc[t0];
+        if (via == o1) via = c.tc[t0];
+        int cur = t0, steps = 0;
+        double sum = 0.;
+        double px = 0., py = 0., pz = 0.;
+        while (true)
+        {
+            int next = -1;
+            for (int t = 0; t < c.nt; ++t)
+            {
+                if (t == cur) continue;
+                const int a = c.ta[t], b = c.tb[t], d = c.tc[t];
+                if ((a == f || b == f || d == f) && (a == via || b == via || d == via)) next = t;
+            }
+            if (next < 0 || ++steps > c.nt) return -3;
+            const int a = c.ta[next], b = c.tb[next], d = c.tc[next];
+            const int other = (a != f && a != via) ? a : (b != f && b != via) ? b : d;
+            if (next == t0) break;
+            if (steps >= 2)
+            {
+                const double ax = c.vx[t0], ay = c.vy[t0], az = c.vz[t0];
+                const double bx = c.vx[next], by = c.vy[next], bz = c.vz[next];
+                sum += ax * (py * bz - pz * by) + ay * (pz * bx - px * bz) + az * (px * by - py * bx);
+            }
+            px = c.vx[next];
+            py = c.vy[next];
+            pz = c.vz[next];
+            via = other;
+            cur = next;
+        }
+        V += fabs(sum);
+    }
+    volume = V / 6.;
+    return 0;
+}
+
+__global__ void __launch_bounds__(64) sk_voronoi_build_kernel(const SkVoronoiBuild B)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= B.n) return;
+    SkVCell c;
+    const double p[3] = {B.sites[3 * (size_t)m], B.sites[3 * (size_t)m + 1], B.sites[3 * (size_t)m + 2]};
+    c.np = 6;
+    c.nt = 0;
+    for (int w = 0; w < 6; ++w)
+    {
+        const int axis = w >> 1, upper = w & 1;
+        c.pn[w][0] = c.pn[w][1] = c.pn[w][2] = 0.;
+        c.pn[w][axis] = upper ? 1. : -1.;
+        c.pd[w] = upper ? B.ext[axis + 3] - p[axis] : -(B.ext[axis] - p[axis]);
+        c.pid[w] = -(w + 1);
+    }
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j)
+            for (int k = 0; k < 2; ++k)
+            {
+                const int t = c.nt++;
+                c.ta[t] = (unsigned char)i;
+                c.tb[t] = (unsigned char)(2 + j);
+                c.tc[t] = (unsigned char)(4 + k);
+                sk_vc_vertex(c, i, 2 + j, 4 + k, c.vx[t], c.vy[t], c.vz[t]);
+            }
+    sk_vc_rmax(c);
+    const int gx = B.gx, gy = B.gy, gz = B.gz;
+    const int b0 = B.blk[m];
+    const int bi = b0 / (gy * gz), bj = (b0 / gz) % gy, bk = b0 % gz;
+    const int smax = gx > gy ? (gx > gz ? gx : gz) : (gy > gz ? gy : gz);
+    int rc = 0;
+    for (int s = 0; s <= smax && !rc; ++s)
+    {
+        // every site in a block at Chebyshev distance s or more is at least (s-1) w away
+        if (s >= 2 && (double)(s - 1) * B.w * (double)(s - 1) * B.w >= 4. * c.rmax2) break;
+        for (int i = bi - s; i <= bi + s && !rc; ++i)
+        {
+            if (i < 0 || i >= gx) continue;
+            for (int j = bj - s; j <= bj + s && !rc; ++j)
+            {
+                if (j < 0 || j >= gy) continue;
+                const bool shell = (i == bi - s || i == bi + s || j == bj - s || j == bj + s);
+                for (int k = bk - s; k <= bk + s && !rc; k += (shell || s == 0) ? 1 : 2 * s)
+                {
+                    if (k < 0 || k >= gz) continue;
+                    const size_t b = ((size_t)i * gy + j) * gz + k;
+                    const int q1 = B.start[b + 1];
+                    for (int q = B.start[b]; q < q1 && !rc; ++q)
+                    {
+                        const int mi = B.order[q];
+                        if (mi == m) continue;
+                        const double nx = B.sites[3 * (size_t)mi] - p[0], ny = B.sites[3 * (size_t)mi + 1] - p[1],
+                                     nz = B.sites[3 * (size_t)mi + 2] - p[2];
+                        const double n2 = nx * nx + ny * ny + nz * nz;
+                        if (n2 >= 4. * c.rmax2) continue;  // its bisector lies beyond the farthest vertex
+                        rc = n2 == 0. ? -4 : sk_vc_clip(c, nx, ny, nz, 0.5 * n2, mi);
+                    }
+                }
+            }
+        }
+    }
+    unsigned char used[SK_VC_MAXP];
+    double b6[6], vol = 0.;
+    if (!rc) rc = sk_vc_measure(c, vol, b6, used);
+    int cnt = 0;
+    if (!rc)
+    {
+        int32_t* out = B.nbr + (size_t)m * SK_VC_MAXNB;
+        for (int j = 6; j < c.np && !rc; ++j)
+            if (used[j])
+            {
+                if (cnt >= SK_VC_MAXNB) rc = -5;
+                else out[cnt++] = c.pid[j];
+            }
+        for (int j = 0; j < 6 && !rc; ++j)
+            if (used[j])
+            {
+                if (cnt >= SK_VC_MAXNB) rc = -5;
+                else out[cnt++] = c.pid[j];
+            }
+    }
+    if (rc)
+    {
+        atomicCAS(B.error, 0, rc);
+        B.count[m] = 0;
+        return;
+    }
+    B.count[m] = cnt;
+    B.volume[m] = vol;
+    for (int a = 0; a < 3; ++a)
+    {
+        B.box[6 * (size_t)m + a] = p[a] + b6[a];
+        B.box[6 * (size_t)m + a + 3] = p[a] + b6[a + 3];
+    }
+}
+// packs the per-cell neighbour slots into the lists the grid takes (offsets from an exclusive scan of the counts)
+__global__ void sk_voronoi_compact_kernel(const int32_t* __restrict__ nbr, const int32_t* __restrict__ count,
+                                          const int32_t* __restrict__ offset, int n, int32_t* __restrict__ out)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n) return;
+    const int c = count[m], o = offset[m];
+    for (int i = 0; i < c; ++i) out[o + i] = nbr[(size_t)m * SK_VC_MAXNB + i];
+}

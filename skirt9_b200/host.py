@@ -728,6 +728,11 @@ class VoronoiMeshSpatialGrid:
         return self
 
     def configure(self, engine):
+        if self.nbr_offset is None:
+            # no tessellation yet (MonteCarloSimulation.deviceSetup): VoronoiMeshSnapshot::buildMesh on the engine's side
+            engine.build_voronoi(self.extent, self.sites)
+            self.nbr_offset, self.nbr_index, self.volumes, self.cell_extents = engine.read_voronoi()
+            return
         engine.set_grid_voronoi(self.extent, self.sites, self.nbr_offset, self.nbr_index)
         if self.cell_extents is not None:
             engine.set_voronoi_extents(self.cell_extents)
@@ -966,10 +971,20 @@ class MonteCarloSimulation:
         for s in self.sources:
             s.sed.setup(self.source_range)
         # grid and medium state (MediumSystem.cpp:286-399)
+        if self.deviceSetup and isinstance(self.grid, VoronoiMeshSpatialGrid):
+            # the tessellation (neighbour lists, volumes, enclosing boxes) is built by the engine in configure()
+            # (sk_engine_build_voronoi); the medium state is the density at the sites (numDensitySamples = 1)
+            if self.density is None:
+                st = self.grid.sites
+                self.density = np.stack([md.number_density(st[:, 0], st[:, 1], st[:, 2]) for md in self.media])
+                if not self.extraMedia:
+                    self.density = self.density[0]
+            self.volume = None
+            return self
         if self.deviceSetup:
             if not isinstance(self.grid, (CartesianSpatialGrid, PolicyTreeSpatialGrid)) \
                     or isinstance(self.grid, FileTreeSpatialGrid):
-                raise ValueError("deviceSetup needs a Cartesian or policy octree grid")
+                raise ValueError("deviceSetup needs a Cartesian, policy octree or Voronoi grid")
             if self.extraMedia:
                 raise ValueError("deviceSetup samples a single medium component")
             if isinstance(self.grid, CartesianSpatialGrid):
@@ -1026,7 +1041,15 @@ class MonteCarloSimulation:
 
         def mark(name):
             marks.append((name, time.perf_counter()))
-        if self.deviceSetup:
+        if self.deviceSetup and isinstance(self.grid, VoronoiMeshSpatialGrid):
+            self.grid.configure(engine)          # builds the tessellation on the device
+            self.volume = self.grid.volumes
+            mark("grid")
+            if self.extraMedia:
+                engine.set_media(self.density, self.volume)
+            else:
+                engine.set_medium(self.density, self.volume)
+        elif self.deviceSetup:
             # DensityTreePolicy::constructTree + the cell loop of MediumSystem::setupSelfAfter on the engine's side
             geom = self.medium.density_geometry()
             if isinstance(self.grid, PolicyTreeSpatialGrid):

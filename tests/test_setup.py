@@ -234,3 +234,121 @@ def test_simulation_set_up_on_the_device_matches_reference_fluxes():
         r_own = np.sqrt(np.maximum(st[2] / (st[1] * st[1]) - 1.0 / np.maximum(st[0], 1), 0.0))
     assert np.all(np.abs(tr - sed[:, 2]) <= (4 * r_own + 1e-6) * sed[:, 2])
     assert np.all(np.abs(tot - sed[:, 1]) <= (4 * r_own + 0.01) * sed[:, 1]), (tot / sed[:, 1])
+
+
+# ---------------------------------------------------------------- Voronoi tessellation (VoronoiMeshSnapshot::buildMesh, voro++)
+def disk_sites(n, seed=99):
+    rng = np.random.default_rng(seed)
+    R = np.minimum(rng.gamma(2.0, 3000.0, size=n), 15000.0)
+    phi = rng.uniform(0, 2 * np.pi, size=n)
+    z = np.clip(rng.laplace(0.0, 300.0, size=n), -1900.0, 1900.0)
+    s = np.stack([R * np.cos(phi), R * np.sin(phi), z], axis=1) * PC
+    return s[np.argsort(s[:, 0], kind="stable")]
+
+
+VOR_EXTENT = (-16000 * PC, -16000 * PC, -2000 * PC, 16000 * PC, 16000 * PC, 2000 * PC)
+
+
+def test_oracle_voronoi_tessellation_is_a_partition_with_symmetric_faces():
+    """The cells fill the domain box exactly, every face is shared by the two cells it separates, and volumes, enclosing
+    boxes and neighbours agree with an independent construction (scipy's Qhull on the sites mirrored in the six walls)."""
+    sites = disk_sites(2500)
+    e = OracleEngine(configs.cfg1(num_packets=10).config_struct())
+    entries = e.build_voronoi(VOR_EXTENT, sites)
+    off, idx, vol, box = e.read_voronoi()
+    n = len(sites)
+    assert off[0] == 0 and off[-1] == entries == len(idx) and np.all(np.diff(off) >= 4)
+    ext = np.asarray(VOR_EXTENT)
+    assert vol.sum() == pytest.approx(np.prod(ext[3:] - ext[:3]), rel=1e-13)
+    sets = [set(idx[off[m]:off[m + 1]].tolist()) for m in range(n)]
+    assert all(m in sets[j] for m in range(n) for j in sets[m] if j >= 0)
+    assert all(len(sets[m]) == off[m + 1] - off[m] for m in range(n))        # no neighbour listed twice
+    grid = H.VoronoiMeshSpatialGrid(*(VOR_EXTENT[i] for i in (0, 3, 1, 4, 2, 5)), sites)
+    grid.setup([], 1, None)
+    grid.compute_cell_geometry()
+    np.testing.assert_allclose(vol, grid.volumes, rtol=1e-11)
+    np.testing.assert_allclose(box, grid.cell_extents, rtol=0, atol=1e-12 * (ext[3] - ext[0]))
+    # every face neighbour is a Delaunay neighbour; Delaunay neighbours without a face have it outside the domain box
+    for m in range(n):
+        delaunay = set(x for x in grid.nbr_index[grid.nbr_offset[m]:grid.nbr_offset[m + 1]].tolist() if x >= 0)
+        assert set(x for x in sets[m] if x >= 0) <= delaunay
+    # the walls a cell lists are those its enclosing box touches
+    for w in range(6):
+        axis, upper = w >> 1, w & 1
+        touches = box[:, axis + 3] >= ext[axis + 3] * (1 - 1e-14) if upper else box[:, axis] <= ext[axis] * (1 - 1e-14)
+        listed = np.array([-(w + 1) in sets[m] for m in range(n)])
+        assert np.array_equal(touches, listed), w
+
+
+def test_oracle_voronoi_volumes_equal_the_reference():
+    """All cell volumes of the cfg5s fixture -- written by the unmodified reference, whose tessellation is voro++'s -- to the
+    10 digits of its text output.  The reference read the sites with the 9 digits of the particle file."""
+    g = np.load(os.path.join(GOLD, "cfg5s_ref.npz"))
+    pos = np.array([[float("%.8e" % v) for v in row[:3]] for row in g["particles"]]) * PC
+    pos = pos[np.argsort(pos[:, 0], kind="stable")]          # cells in order of increasing x, VoronoiMeshSnapshot.cpp:507-508
+    e = OracleEngine(configs.cfg1(num_packets=10).config_struct())
+    e.build_voronoi(VOR_EXTENT, pos)
+    vol = e.read_voronoi()[2]
+    np.testing.assert_allclose(vol, g["cell_volume_pc3"] * PC ** 3, rtol=1e-9)
+
+
+def test_voronoi_builder_refuses_what_it_cannot_do():
+    e = OracleEngine(configs.cfg1(num_packets=10).config_struct())
+    x = (np.arange(4) + 0.5) / 4 * 2 - 1
+    lattice = np.stack(np.meshgrid(x, x, x, indexing="ij"), axis=-1).reshape(-1, 3) * PC      # four planes through every vertex
+    with pytest.raises(abi.SkError):
+        e.build_voronoi((-PC, -PC, -PC, PC, PC, PC), lattice)
+    with pytest.raises(abi.SkError):
+        e.build_voronoi((-PC, -PC, -PC, PC, PC, PC), np.array([[0.1, 0.2, 0.3], [0.1, 0.2, 0.3]]) * PC)   # coinciding sites
+    with pytest.raises(abi.SkError):
+        e.build_voronoi((-PC, -PC, -PC, PC, PC, PC), np.array([[0.1, 0.2, 1.5]]) * PC)                      # outside the domain
+
+
+def test_life_cycle_on_the_built_tessellation_equals_the_delaunay_lists():
+    """The face neighbours are all a walk needs: the same run on the built lists and on the (larger) Delaunay neighbour lists."""
+    from tests import models
+    runs = []
+    for device_setup in (True, False):
+        sim = models.small_voronoi(num_packets=4000)
+        sim.deviceSetup = device_setup
+        sim.setup()
+        e = sim.configure(OracleEngine(sim.config_struct()))
+        sim.run(e)
+        runs.append((sim, e))
+    assert runs[0][0].grid.nbr_offset[-1] < runs[1][0].grid.nbr_offset[-1]
+    models.compare_engines(runs[0][0], runs[0][1], runs[1][1])
+
+
+@pytest.mark.gpu
+def test_device_voronoi_tessellation_equals_oracle():
+    """sk_voronoi_build_kernel against the oracle: the same lists in the same order, volumes and boxes bit for bit."""
+    for n in (300, 20000):
+        sites = disk_sites(n, seed=n)
+        cfg = configs.cfg1(num_packets=10).config_struct(device=0)
+        gpu, cpu = abi.Engine(cfg), OracleEngine(cfg)
+        assert gpu.build_voronoi(VOR_EXTENT, sites) == cpu.build_voronoi(VOR_EXTENT, sites)
+        a, b = gpu.read_voronoi(), cpu.read_voronoi()
+        np.testing.assert_array_equal(a[0], b[0])
+        np.testing.assert_array_equal(a[1], b[1])
+        np.testing.assert_array_equal(a[2], b[2])
+        np.testing.assert_array_equal(a[3], b[3])
+    x = (np.arange(4) + 0.5) / 4 * 2 - 1
+    lattice = np.stack(np.meshgrid(x, x, x, indexing="ij"), axis=-1).reshape(-1, 3) * PC
+    with pytest.raises(abi.SkError):
+        abi.Engine(cfg).build_voronoi((-PC, -PC, -PC, PC, PC, PC), lattice)
+
+
+@pytest.mark.gpu
+def test_voronoi_simulation_set_up_on_the_device_equals_oracle():
+    from tests import models
+    sim = models.small_voronoi_dust_emission(num_packets=6000)
+    sim.deviceSetup = True
+    sim.setup()
+    gpu = sim.configure(abi.Engine(sim.config_struct(device=0)))
+    import copy
+    simc = copy.copy(sim)
+    cpu = simc.configure(OracleEngine(simc.config_struct()))
+    sim.run(gpu)
+    simc.run(cpu)
+    models.compare_engines(sim, gpu, cpu, rtol=1e-8)
+    assert sim.sed_flux_density(gpu, 0, abi.SK_COMP_SECONDARY_DIRECT).sum() > 0
