@@ -685,7 +685,7 @@ extern "C" int sk_engine_set_voronoi_extents(sk_engine_t* e, int32_t num_cells, 
 
 static int exclusive_scan(sk_engine* e, const int32_t* in, int32_t* out, int n, int32_t* sums, int32_t* total);
 // VoronoiMeshSnapshot::buildMesh on the device (sk_setup.cuh): search grid on the host (a counting sort of the sites into cubic
-// blocks of two sites on average, as oracle/sk_oracle.c sko_build_voronoi), one thread per cell, the neighbour slots packed
+// blocks of two sites on average), one thread per cell, the neighbour slots packed
 // into lists on the device; the lists then take the same route as a tessellation handed in by the caller.
 extern "C" int sk_engine_build_voronoi(sk_engine_t* e, const double extent[6], int32_t num_sites, const double* sites,
                                        uint64_t* num_entries)
