@@ -296,6 +296,17 @@ int sk_engine_read_octree(sk_engine_t* e, int32_t* first_child);
  * (TreeSpatialGrid::randomPositionInCell, TreeSpatialGrid.cpp:125-128).  Generator key = (seed, 0x43454c4c "CELL"),
  * counter = (cell index, draw).  Replaces sk_engine_set_medium. */
 int sk_engine_sample_medium(sk_engine_t* e, const sk_density_geometry_t* medium, int32_t num_samples);
+/* The same cell loop for a ParticleMedium: the smoothed-particle density of ParticleSnapshot::density(Position)
+ * (ParticleSnapshot.cpp:248-258) -- sum over the particles, in ascending index, of W(|r - c_m| / h_m) M_m / h_m^3 with the
+ * CubicSplineSmoothingKernel (CubicSplineSmoothingKernel.cpp:39-47) -- times density_scale (ImportedMedium::numberDensity,
+ * ImportedMedium.cpp:198-203: 1/mu for a snapshot that holds masses, times the mass fraction), averaged over num_samples random
+ * positions in the cell: Random::position(box) for Cartesian and octree cells, VoronoiMeshSnapshot::generatePosition(m)
+ * (VoronoiMeshSnapshot.cpp:976-989) for Voronoi cells, which needs the cells' extents; num_samples = 1 takes the centre of the
+ * box (not available for Voronoi cells, whose central position is the centroid).  particles[5*m..] = x y z h M.  Volumes: box
+ * volumes, or the volumes of a tessellation built by sk_engine_build_voronoi.  Same generator key and counter as
+ * sk_engine_sample_medium. */
+int sk_engine_sample_medium_particles(sk_engine_t* e, int32_t num_particles, const double* particles, double density_scale,
+                                      int32_t num_samples);
 /* MediumState::numberDensity(m,0) and MediumState::volume(m) as the engine holds them (either array may be NULL). */
 int sk_engine_read_medium(sk_engine_t* e, double* number_density, double* volume);
 

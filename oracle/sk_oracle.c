@@ -1337,6 +1337,143 @@ int sko_sample_medium(sko_engine_t* e, const sk_density_geometry_t* medium, int3
     return SK_OK;
 }
 
+/* ParticleMedium: the smoothed-particle density of ParticleSnapshot::density(Position) (ParticleSnapshot.cpp:248-258) with the
+ * CubicSplineSmoothingKernel (CubicSplineSmoothingKernel.cpp:39-47), sampled per cell like any medium by the cell loop of
+ * MediumSystem::setupSelfAfter (MediumSystem.cpp:286-330, PropertySampler :46-106).  The reference sums over the particles
+ * of the search block that holds the position (BoxSearch::entitiesFor, BoxSearch.cpp:201-207: ascending particle index);
+ * particles that do not reach the position contribute an exact zero, so the sum over ALL particles in ascending index is
+ * the same number -- which is what this restatement does.  particles[5*m..] = x y z h M. */
+static double sph_kernel_density(double u)
+{
+    if (u < 0.0 || u >= 1.0)
+        return 0.0;
+    else if (u < 0.5)
+        return 8.0 / M_PI * (1.0 - 6.0 * u * u * (1.0 - u));
+    else
+        return 8.0 / M_PI * 2.0 * (1.0 - u) * (1.0 - u) * (1.0 - u);
+}
+static double sph_density(const double* particles, int np, double x, double y, double z)
+{
+    double sum = 0.;
+    for (int m = 0; m < np; ++m)
+    {
+        const double* q = particles + 5 * (size_t)m;
+        const double dx = x - q[0], dy = y - q[1], dz = z - q[2];
+        const double h = q[3];
+        const double r2 = dx * dx + dy * dy + dz * dz;
+        if (r2 >= h * h) continue; /* u >= 1: an exact zero */
+        const double u = sqrt(r2) / h;
+        sum += sph_kernel_density(u) * (q[4] / (h * h * h)); /* Particle::density(), ParticleSnapshot.cpp:45 */
+    }
+    return sum > 0. ? sum : 0.;
+}
+int sko_sample_medium_particles(sko_engine_t* e, int32_t num_particles, const double* particles, double density_scale,
+                                int32_t num_samples)
+{
+    if (!e || !particles || num_particles < 1 || num_samples < 1) return fail(SK_ERR_INVALID, "bad particle medium");
+    if (!e->grid_kind) return fail(SK_ERR_STATE, "set the grid before the medium");
+    if (e->grid_kind == 3 && !e->vbox) return fail(SK_ERR_STATE, "sampling in Voronoi cells needs their extents");
+    if (e->grid_kind == 3 && num_samples == 1)
+        return fail(SK_ERR_UNSUPPORTED, "the density at the centroid of a Voronoi cell (numDensitySamples = 1)");
+    for (int m = 0; m < num_particles; ++m)
+        if (!(particles[5 * (size_t)m + 3] > 0.)) return fail(SK_ERR_INVALID, "smoothing length must be positive");
+    const int nc = grid_num_cells(e);
+    double* dens = (double*)malloc((size_t)nc * sizeof(double));
+    double* vol = NULL;
+    if (e->grid_kind != 3)
+        vol = (double*)malloc((size_t)nc * sizeof(double));
+    else if (e->vvol)
+        vol = dupd(e->vvol, nc);
+    for (int m = 0; m < nc; ++m)
+    {
+        double b[6];
+        if (e->grid_kind == 1)
+        {
+            int k = m % e->nz, j = (m / e->nz) % e->ny, i = m / (e->nz * e->ny);
+            b[0] = e->xv[i];
+            b[3] = e->xv[i + 1];
+            b[1] = e->yv[j];
+            b[4] = e->yv[j + 1];
+            b[2] = e->zv[k];
+            b[5] = e->zv[k + 1];
+        }
+        else if (e->grid_kind == 2)
+            memcpy(b, e->node_box + 6 * (size_t)e->node_of_cell[m], sizeof b);
+        else
+            memcpy(b, e->vbox + 6 * (size_t)m, sizeof b);
+        double n;
+        if (num_samples == 1)
+            n = sph_density(particles, num_particles, 0.5 * (b[0] + b[3]), 0.5 * (b[1] + b[4]), 0.5 * (b[2] + b[5])) * density_scale;
+        else
+        {
+            rng_t g;
+            rng_init(&g, (uint32_t)e->cfg.seed, 0x43454c4cu, (uint64_t)m);
+            double sum = 0.;
+            for (int i = 0; i != num_samples; ++i)
+            {
+                double x, y, z;
+                if (e->grid_kind == 3)
+                {
+                    /* VoronoiMeshSnapshot::generatePosition(m), VoronoiMeshSnapshot.cpp:976-989 */
+                    const double* sm = e->vsite + 3 * (size_t)m;
+                    int found = 0;
+                    x = sm[0];
+                    y = sm[1];
+                    z = sm[2];
+                    for (int it = 0; it < 10000 && !found; ++it)
+                    {
+                        double ux = uniform(&g), uy = uniform(&g), uz = uniform(&g);
+                        double px = b[0] + ux * (b[3] - b[0]);
+                        double py = b[1] + uy * (b[4] - b[1]);
+                        double pz = b[2] + uz * (b[5] - b[2]);
+                        double dx = px - sm[0], dy = py - sm[1], dz = pz - sm[2];
+                        double target = dx * dx + dy * dy + dz * dz;
+                        found = 1;
+                        for (int64_t q = e->vnbr_off[m]; q < e->vnbr_off[m + 1]; ++q)
+                        {
+                            int id = e->vnbr[q];
+                            if (id < 0) continue;
+                            const double* t = e->vsite + 3 * (size_t)id;
+                            double ex = px - t[0], ey = py - t[1], ez = pz - t[2];
+                            if (ex * ex + ey * ey + ez * ez < target)
+                            {
+                                found = 0;
+                                break;
+                            }
+                        }
+                        if (found)
+                        {
+                            x = px;
+                            y = py;
+                            z = pz;
+                        }
+                    }
+                }
+                else
+                {
+                    double ux = uniform(&g);
+                    double uy = uniform(&g);
+                    double uz = uniform(&g);
+                    x = b[0] + ux * (b[3] - b[0]);
+                    y = b[1] + uy * (b[4] - b[1]);
+                    z = b[2] + uz * (b[5] - b[2]);
+                }
+                sum += sph_density(particles, num_particles, x, y, z) * density_scale;
+            }
+            n = sum / num_samples;
+        }
+        dens[m] = n;
+        if (e->grid_kind != 3) vol[m] = (b[3] - b[0]) * (b[4] - b[1]) * (b[5] - b[2]);
+    }
+    free(e->dens);
+    free(e->vol);
+    e->dens = dens;
+    e->vol = vol;
+    e->ncells = nc;
+    e->nmed = 1;
+    return SK_OK;
+}
+
 int sko_read_medium(sko_engine_t* e, double* number_density, double* volume)
 {
     if (!e || !e->ncells) return fail(SK_ERR_STATE, "the engine holds no medium state");

@@ -220,6 +220,12 @@ class Engine:
         self._call("sample_medium", self._h, C.byref(medium), C.c_int32(num_samples))
         self.num_cells = num_cells
 
+    def sample_medium_particles(self, particles, density_scale: float, num_samples: int, num_cells: int):
+        """ParticleMedium sampled on the engine's side: particles[n][5] = x y z h M (sk_engine_sample_medium_particles)."""
+        p, pp = _d(np.asarray(particles, dtype=np.float64).reshape(-1, 5))
+        self._call("sample_medium_particles", self._h, C.c_int32(len(p)), pp, C.c_double(density_scale), C.c_int32(num_samples))
+        self.num_cells = num_cells
+
     def read_medium(self):
         dens = np.empty(self.num_cells)
         vol = np.empty(self.num_cells)

@@ -1139,6 +1139,139 @@ extern "C" int sk_engine_sample_medium(sk_engine_t* e, const sk_density_geometry
     return SK_OK;
 }
 
+// ParticleMedium sampled on the device (sk_setup.cuh): the search blocks and their particle lists are built on the host
+extern "C" int sk_engine_sample_medium_particles(sk_engine_t* e, int32_t num_particles, const double* particles,
+                                                 double density_scale, int32_t num_samples)
+{
+    if (!e || !particles || num_particles < 1 || num_samples < 1) return fail(SK_ERR_INVALID, "bad particle medium");
+    if (!e->grid_kind) return fail(SK_ERR_STATE, "set the grid before the medium");
+    if (e->grid_kind == 3 && !e->M.vbox) return fail(SK_ERR_STATE, "sampling in Voronoi cells needs their extents");
+    if (e->grid_kind == 3 && num_samples == 1)
+        return fail(SK_ERR_UNSUPPORTED, "the density at the centroid of a Voronoi cell (numDensitySamples = 1)");
+    const int np = num_particles;
+    double hsum = 0.;
+    for (int m = 0; m < np; ++m)
+    {
+        if (!(particles[5 * (size_t)m + 3] > 0.)) return fail(SK_ERR_INVALID, "smoothing length must be positive");
+        hsum += particles[5 * (size_t)m + 3];
+    }
+    if (int rc_bind = bind(e)) return rc_bind;
+    // search blocks: cubic, about 32768 of them but not much smaller than a typical particle
+    const double* ext = e->M.ext;
+    const double wx = ext[3] - ext[0], wy = ext[4] - ext[1], wz = ext[5] - ext[2];
+    const double bw = std::max(cbrt(wx * wy * wz / 32768.), 0.75 * hsum / np);
+    SkSphSearch S;
+    memcpy(S.ext, ext, sizeof S.ext);
+    S.nbx = std::max(1, std::min(256, (int)ceil(wx / bw)));
+    S.nby = std::max(1, std::min(256, (int)ceil(wy / bw)));
+    S.nbz = std::max(1, std::min(256, (int)ceil(wz / bw)));
+    S.inv[0] = S.nbx / wx;
+    S.inv[1] = S.nby / wy;
+    S.inv[2] = S.nbz / wz;
+    S.np = np;
+    const size_t nblocks = (size_t)S.nbx * S.nby * S.nbz;
+    auto range = [&](double lo, double hi, int axis, int nb, int& a, int& b) {
+        a = (int)floor((lo - ext[axis]) * S.inv[axis]);
+        b = (int)floor((hi - ext[axis]) * S.inv[axis]);
+        a = std::max(a - 1, 0);          // one block of margin: the device rounds the block of a position on its own
+        b = std::min(b + 1, nb - 1);
+    };
+    std::vector<int32_t> start(nblocks + 1, 0);
+    for (int pass = 0; pass < 2; ++pass)
+    {
+        std::vector<int32_t> fill;
+        std::vector<int32_t> list;
+        if (pass == 1)
+        {
+            for (size_t b = 0; b < nblocks; ++b) start[b + 1] += start[b];
+            if ((uint64_t)start[nblocks] > 0x7fffffffu) return fail(SK_ERR_UNSUPPORTED, "particle search lists beyond 2^31 entries");
+            fill.assign(start.begin(), start.end() - 1);
+            list.resize((size_t)start[nblocks]);
+        }
+        for (int m = 0; m < np; ++m)
+        {
+            const double* q = particles + 5 * (size_t)m;
+            int i0, i1, j0, j1, k0, k1;
+            range(q[0] - q[3], q[0] + q[3], 0, S.nbx, i0, i1);
+            range(q[1] - q[3], q[1] + q[3], 1, S.nby, j0, j1);
+            range(q[2] - q[3], q[2] + q[3], 2, S.nbz, k0, k1);
+            for (int i = i0; i <= i1; ++i)
+                for (int j = j0; j <= j1; ++j)
+                    for (int k = k0; k <= k1; ++k)
+                    {
+                        const size_t b = ((size_t)i * S.nby + j) * S.nbz + k;
+                        if (pass == 0)
+                            start[b + 1]++;
+                        else
+                            list[fill[b]++] = m;   // particles in ascending index within every block
+                    }
+        }
+        if (pass == 1)
+        {
+            std::vector<void*> scratch;
+            struct Guard {
+                std::vector<void*>& v;
+                ~Guard() { free_group(v); }
+            } guard{scratch};
+            int32_t *d_start, *d_list;
+            double *d_part, *d_dens;
+            if (int rc = upload(scratch, start.data(), start.size(), &d_start)) return rc;
+            if (int rc = upload(scratch, list.data(), std::max<size_t>(list.size(), 1), &d_list)) return rc;
+            if (int rc = upload(scratch, particles, 5 * (size_t)np, &d_part)) return rc;
+            S.start = d_start;
+            S.list = d_list;
+            S.part = d_part;
+            const int nc = e->grid_cells;
+            // the medium state: densities through a scratch array into the cell records; volumes of the boxes, or of the
+            // tessellation this engine built
+            free_group(e->medium_allocs);
+            e->M.densx = nullptr;
+            e->M.nmed = 1;
+            e->M.dens = nullptr;
+            e->M.volume = nullptr;
+            double* d_vol = nullptr;
+            if (e->grid_kind != 3)
+            {
+                if (int rc = dalloc_zero(e->medium_allocs, (size_t)nc, &d_vol)) return rc;
+            }
+            else if (!e->voronoi_volume.empty())
+            {
+                if (int rc = upload(e->medium_allocs, e->voronoi_volume.data(), (size_t)nc, &d_vol)) return rc;
+            }
+            if (e->grid_kind == 1)
+            {
+                if (int rc = dalloc_zero(e->medium_allocs, (size_t)nc, &d_dens)) return rc;
+                sk_sample_particles_kernel<1><<<(nc + 127) / 128, 128, 0, e->stream>>>(e->M, S, density_scale, num_samples, (uint32_t)e->cfg.seed,
+                                                                                      nc, nullptr, nullptr, d_dens, d_vol);
+                e->M.dens = d_dens;
+            }
+            else
+            {
+                if (int rc = dalloc_zero(scratch, (size_t)nc, &d_dens)) return rc;
+                if (e->grid_kind == 2)
+                {
+                    sk_sample_particles_kernel<2><<<(nc + 127) / 128, 128, 0, e->stream>>>(e->M, S, density_scale, num_samples,
+                                                                                          (uint32_t)e->cfg.seed, nc, nullptr, nullptr, d_dens, d_vol);
+                    sk_set_density_kernel<<<(nc + 255) / 256, 256, 0, e->stream>>>(const_cast<SkCellRec*>(e->M.cells), d_dens, nc);
+                }
+                else
+                {
+                    sk_sample_particles_kernel<3><<<(nc + 127) / 128, 128, 0, e->stream>>>(e->M, S, density_scale, num_samples,
+                                                                                          (uint32_t)e->cfg.seed, nc, nullptr,
+                                                                                          const_cast<double4*>(e->M.vrec), d_dens, d_vol);
+                    sk_set_density_voronoi_kernel<<<(nc + 255) / 256, 256, 0, e->stream>>>(const_cast<double4*>(e->M.vrec), d_dens, nc);
+                }
+            }
+            CK(cudaGetLastError());
+            CK(cudaStreamSynchronize(e->stream));
+            e->dens_host.clear();
+            e->M.volume = d_vol;
+            e->M.ncells = nc;
+        }
+    }
+    return SK_OK;
+}
+
 extern "C" int sk_engine_read_medium(sk_engine_t* e, double* number_density, double* volume)
 {
     if (!e) return fail(SK_ERR_INVALID, "null argument");

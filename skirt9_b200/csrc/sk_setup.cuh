@@ -712,3 +712,161 @@ __global__ void sk_voronoi_compact_kernel(const int32_t* __restrict__ nbr, const
     const int c = count[m], o = offset[m];
     for (int i = 0; i < c; ++i) out[o + i] = nbr[(size_t)m * SK_VC_MAXNB + i];
 }
+
+// ---------------------------------------------------------------------------------------------------
+// ParticleMedium: the smoothed-particle density of ParticleSnapshot::density(Position) (ParticleSnapshot.cpp:248-258) with the
+// CubicSplineSmoothingKernel (CubicSplineSmoothingKernel.cpp:39-47), sampled per cell by the cell loop of
+// MediumSystem::setupSelfAfter (MediumSystem.cpp:286-330, PropertySampler :46-106).  Like the reference's BoxSearch
+// (BoxSearch.cpp:201-207) the sum runs over the particles listed for the search block that holds the position, in ascending
+// particle index; particles that do not reach the position contribute an exact zero, so the value is that of the sum over all
+// particles in ascending index.  One thread per cell, its samples in sequence.
+// ---------------------------------------------------------------------------------------------------
+struct SkSphSearch {
+    double ext[6];
+    double inv[3];         // blocks per unit length
+    int nbx, nby, nbz, np;
+    const int32_t* start;  // [blocks+1]
+    const int32_t* list;   // particle indices per block, ascending
+    const double* part;    // [5 np] x y z h M
+};
+__device__ __forceinline__ double sk_sph_kernel_density(double u)
+{
+    if (u < 0.0 || u >= 1.0)
+        return 0.0;
+    else if (u < 0.5)
+        return 8.0 / M_PI * (1.0 - 6.0 * u * u * (1.0 - u));
+    else
+        return 8.0 / M_PI * 2.0 * (1.0 - u) * (1.0 - u) * (1.0 - u);
+}
+__device__ __forceinline__ double sk_sph_density(const SkSphSearch& S, double x, double y, double z)
+{
+    int i = (int)((x - S.ext[0]) * S.inv[0]), j = (int)((y - S.ext[1]) * S.inv[1]), k = (int)((z - S.ext[2]) * S.inv[2]);
+    i = i < 0 ? 0 : i >= S.nbx ? S.nbx - 1 : i;
+    j = j < 0 ? 0 : j >= S.nby ? S.nby - 1 : j;
+    k = k < 0 ? 0 : k >= S.nbz ? S.nbz - 1 : k;
+    const size_t b = ((size_t)i * S.nby + j) * S.nbz + k;
+    const int q1 = S.start[b + 1];
+    double sum = 0.;
+    for (int q = S.start[b]; q < q1; ++q)
+    {
+        const double* p = S.part + 5 * (size_t)__ldg(&S.list[q]);
+        const double dx = x - __ldg(p), dy = y - __ldg(p + 1), dz = z - __ldg(p + 2);
+        const double h = __ldg(p + 3);
+        const double r2 = dx * dx + dy * dy + dz * dz;
+        if (r2 >= h * h) continue;
+        const double u = sqrt(r2) / h;
+        sum += sk_sph_kernel_density(u) * (__ldg(p + 4) / (h * h * h));  // Particle::density(), ParticleSnapshot.cpp:45
+    }
+    return sum > 0. ? sum : 0.;
+}
+template <int GRID>
+__global__ void __launch_bounds__(128) sk_sample_particles_kernel(SkDevModel M, SkSphSearch S, double scale, int num_samples, uint32_t seed,
+                                                                  int ncells, SkCellRec* __restrict__ cells, double4* __restrict__ vrec,
+                                                                  double* __restrict__ dens, double* __restrict__ volume)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= ncells) return;
+    double b0, b1, b2, b3, b4, b5;
+    if (GRID == 3)
+    {
+        const double* bx = M.vbox + 6 * (size_t)m;
+        b0 = bx[0];
+        b1 = bx[1];
+        b2 = bx[2];
+        b3 = bx[3];
+        b4 = bx[4];
+        b5 = bx[5];
+    }
+    else
+    {
+        int ix, iy, iz, size;
+        if (GRID == 1)
+        {
+            iz = m % M.nz;
+            iy = (m / M.nz) % M.ny;
+            ix = m / (M.nz * M.ny);
+            size = 1;
+        }
+        else
+        {
+            const uint4 c = reinterpret_cast<const uint4*>(M.cell_coord)[m];
+            ix = (int)c.x;
+            iy = (int)c.y;
+            iz = (int)c.z;
+            size = 1 << (M.maxlevel - (int)c.w);
+        }
+        b0 = M.xv[ix];
+        b3 = M.xv[ix + size];
+        b1 = M.yv[iy];
+        b4 = M.yv[iy + size];
+        b2 = M.zv[iz];
+        b5 = M.zv[iz + size];
+    }
+    double n;
+    if (num_samples == 1)
+        n = sk_sph_density(S, 0.5 * (b0 + b3), 0.5 * (b1 + b4), 0.5 * (b2 + b5)) * scale;
+    else
+    {
+        SkRng r;
+        sk_rng_init(r, seed, SK_STREAM_CELL, (unsigned long long)m, 0);
+        double sum = 0.;
+        for (int i = 0; i != num_samples; ++i)
+        {
+            double x, y, z;
+            if (GRID == 3)
+            {
+                // VoronoiMeshSnapshot::generatePosition(m), VoronoiMeshSnapshot.cpp:976-989
+                const double4 sm = vrec[m];
+                const long long i0 = M.vnbr_off[m], i1 = M.vnbr_off[m + 1];
+                bool found = false;
+                x = sm.x;
+                y = sm.y;
+                z = sm.z;
+                for (int it = 0; it < 10000 && !found; ++it)
+                {
+                    const double ux = sk_uniform(r), uy = sk_uniform(r), uz = sk_uniform(r);
+                    const double px = b0 + ux * (b3 - b0);
+                    const double py = b1 + uy * (b4 - b1);
+                    const double pz = b2 + uz * (b5 - b2);
+                    const double dx = px - sm.x, dy = py - sm.y, dz = pz - sm.z;
+                    const double target = dx * dx + dy * dy + dz * dz;
+                    found = true;
+                    for (long long q = i0; q < i1; ++q)
+                    {
+                        const int id = __ldg(&M.vnbr[q]);
+                        if (id < 0) continue;
+                        const double4 t = vrec[id];
+                        const double ex = px - t.x, ey = py - t.y, ez = pz - t.z;
+                        if (ex * ex + ey * ey + ez * ez < target)
+                        {
+                            found = false;
+                            break;
+                        }
+                    }
+                    if (found)
+                    {
+                        x = px;
+                        y = py;
+                        z = pz;
+                    }
+                }
+            }
+            else
+            {
+                const double ux = sk_uniform(r);
+                const double uy = sk_uniform(r);
+                const double uz = sk_uniform(r);
+                x = b0 + ux * (b3 - b0);
+                y = b1 + uy * (b4 - b1);
+                z = b2 + uz * (b5 - b2);
+            }
+            sum += sk_sph_density(S, x, y, z) * scale;
+        }
+        n = sum / num_samples;
+    }
+    if (GRID == 1)
+        dens[m] = n;
+    else
+        dens[m] = n;  // written into the cell records by the caller's kernel (octree: SkCellRec::dens, Voronoi: vrec.w)
+    if (GRID != 3) volume[m] = (b3 - b0) * (b4 - b1) * (b5 - b2);
+}

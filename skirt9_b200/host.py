@@ -412,6 +412,29 @@ class GeometricMedium:
         return abi.SkDensityGeometry.make(kind, params, self.number, self.mass)
 
 
+class ParticleMedium:
+    """ParticleMedium (ImportedMedium.cpp:198-203) on a ParticleSnapshot with the CubicSplineSmoothingKernel: particles[n][5] =
+    x y z h M (m, m, m, m, kg).  The mirror does not evaluate the smoothed density itself: the cell densities are imported
+    (MonteCarloSimulation.density, e.g. from a reference run) or sampled by the engine (deviceSetup:
+    sk_engine_sample_medium_particles)."""
+
+    def __init__(self, particles, materialMix, massFraction=1.0):
+        self.particles = np.ascontiguousarray(particles, dtype=float).reshape(-1, 5)
+        self.mix, self.massFraction = materialMix, massFraction
+        self.norm_wavelength = None
+
+    def setup(self):
+        self.mass = float(self.particles[:, 4].sum()) * self.massFraction
+        self.number = self.mass / self.mix.mu
+
+    @property
+    def density_scale(self):
+        return self.massFraction / self.mix.mu
+
+    def number_density(self, x, y, z):
+        raise NotImplementedError("the smoothed-particle density is sampled on the engine's side (deviceSetup)")
+
+
 # ---------------------------------------------------------------------------------------------------
 # spatial grids
 # ---------------------------------------------------------------------------------------------------
@@ -951,7 +974,7 @@ class MonteCarloSimulation:
                 self.grids.append(g)
         # Configuration::simulationWavelengthRange / simulationWavelengths, Configuration.cpp:566-662
         lo, hi = self.source_range
-        extra = [md.norm_wavelength for md in self.media]
+        extra = [md.norm_wavelength for md in self.media if md.norm_wavelength is not None]
         for g in self.grids:
             a, b = g.wavelength_range()
             lo, hi = min(lo, a), max(hi, b)
@@ -974,7 +997,7 @@ class MonteCarloSimulation:
         if self.deviceSetup and isinstance(self.grid, VoronoiMeshSpatialGrid):
             # the tessellation (neighbour lists, volumes, enclosing boxes) is built by the engine in configure()
             # (sk_engine_build_voronoi); the medium state is the density at the sites (numDensitySamples = 1)
-            if self.density is None:
+            if self.density is None and not isinstance(self.medium, ParticleMedium):
                 st = self.grid.sites
                 self.density = np.stack([md.number_density(st[:, 0], st[:, 1], st[:, 2]) for md in self.media])
                 if not self.extraMedia:
@@ -1045,22 +1068,32 @@ class MonteCarloSimulation:
             self.grid.configure(engine)          # builds the tessellation on the device
             self.volume = self.grid.volumes
             mark("grid")
-            if self.extraMedia:
+            if isinstance(self.medium, ParticleMedium) and self.density is None:
+                # the cell loop of MediumSystem::setupSelfAfter for a ParticleMedium, on the engine's side
+                engine.sample_medium_particles(self.medium.particles, self.medium.density_scale, self.numDensitySamples,
+                                               self.grid.num_cells)
+            elif self.extraMedia:
                 engine.set_media(self.density, self.volume)
             else:
                 engine.set_medium(self.density, self.volume)
         elif self.deviceSetup:
             # DensityTreePolicy::constructTree + the cell loop of MediumSystem::setupSelfAfter on the engine's side
-            geom = self.medium.density_geometry()
-            if isinstance(self.grid, PolicyTreeSpatialGrid):
-                _, ncells = engine.build_octree(self.grid.extent,
-                                                self.grid.tree_policy(self.numDensitySamples, [self.medium]), [geom])
-                self.grid.first_child = None  # fetched on demand: fetch_device_setup()
+            if isinstance(self.medium, ParticleMedium):
+                self.grid.configure(engine)      # (the tree policy needs a geometric medium: Cartesian grid, or a tree given)
+                mark("grid")
+                engine.sample_medium_particles(self.medium.particles, self.medium.density_scale, self.numDensitySamples,
+                                               self.grid.num_cells)
             else:
-                self.grid.configure(engine)
-                ncells = self.grid.num_cells
-            mark("grid")
-            engine.sample_medium(geom, self.numDensitySamples, ncells)
+                geom = self.medium.density_geometry()
+                if isinstance(self.grid, PolicyTreeSpatialGrid):
+                    _, ncells = engine.build_octree(self.grid.extent,
+                                                    self.grid.tree_policy(self.numDensitySamples, [self.medium]), [geom])
+                    self.grid.first_child = None  # fetched on demand: fetch_device_setup()
+                else:
+                    self.grid.configure(engine)
+                    ncells = self.grid.num_cells
+                mark("grid")
+                engine.sample_medium(geom, self.numDensitySamples, ncells)
         else:
             self.grid.configure(engine)
             mark("grid")

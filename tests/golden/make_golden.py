@@ -352,6 +352,18 @@ def make_cfg5s():
     print("cfg5s:", {k: np.shape(v) for k, v in out.items()})
 
 
+def make_cfg13p():
+    """ParticleMedium sampled at the centres of Cartesian cells (numDensitySamples = 1): the reference's smoothed-particle density,
+    deterministic."""
+    p = sph_particles()
+    with tempfile.TemporaryDirectory() as d:
+        run_reference("cfg13p", d, {"sph.txt": sph_text(p)})
+        cells = read_columns(os.path.join(d, "cfg13p_cells_cellprops.dat"))
+        out = dict(particles=p, mass_density_msun_pc3=cells[:, 6], cell_center_pc=cells[:, 1:4], cell_volume_pc3=cells[:, 4])
+    np.savez_compressed(os.path.join(HERE, "cfg13p_ref.npz"), **out)
+    print("cfg13p:", {k: np.shape(v) for k, v in out.items()})
+
+
 if __name__ == "__main__":
     if not os.path.exists(SKIRT):
         raise SystemExit("oracle/_ref is not built: run `make -C oracle -f ref.mk -j8` where /root/reference exists")

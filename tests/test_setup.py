@@ -352,3 +352,104 @@ def test_voronoi_simulation_set_up_on_the_device_equals_oracle():
     simc.run(cpu)
     models.compare_engines(sim, gpu, cpu, rtol=1e-8)
     assert sim.sed_flux_density(gpu, 0, abi.SK_COMP_SECONDARY_DIRECT).sum() > 0
+
+
+# ---------------------------------------------------------------- ParticleMedium: smoothed-particle density per cell
+MSUN = H.MSUN
+
+
+def sph_fixture(name):
+    """The particle table of a fixture as the reference read it (9 digits in the text file), in SI units."""
+    g = np.load(os.path.join(GOLD, name + "_ref.npz"))
+    part = np.array([[float("%.8e" % v) for v in row] for row in g["particles"]])
+    part[:, :4] *= PC
+    part[:, 4] *= MSUN
+    return g, part
+
+
+def cartesian_24_20_10(engine):
+    engine.set_grid_cartesian(np.linspace(-16000 * PC, 16000 * PC, 25), np.linspace(-16000 * PC, 16000 * PC, 21),
+                              np.linspace(-2000 * PC, 2000 * PC, 11))
+    return 24 * 20 * 10
+
+
+def test_oracle_particle_density_equals_the_reference():
+    """tests/golden/ski/cfg13p.ski: ParticleMedium on a Cartesian grid with numDensitySamples = 1 -- the reference's
+    ParticleSnapshot::density at every cell centre, deterministic; to the 10 digits of its text output, and the same set of
+    empty cells."""
+    g, part = sph_fixture("cfg13p")
+    e = OracleEngine(configs.cfg1(num_packets=10).config_struct())
+    nc = cartesian_24_20_10(e)
+    e.sample_medium_particles(part, 1.0, 1, nc)
+    dens, vol = e.read_medium()
+    ref = g["mass_density_msun_pc3"] * MSUN / PC ** 3
+    assert np.array_equal(dens > 0, ref > 0) and (ref > 0).sum() > 1500
+    np.testing.assert_allclose(dens[ref > 0], ref[ref > 0], rtol=1e-9)
+    np.testing.assert_allclose(vol, g["cell_volume_pc3"] * PC ** 3, rtol=1e-9)
+
+
+def test_oracle_particle_density_in_voronoi_cells_like_the_reference():
+    """cfg5s: ten random positions per Voronoi cell.  The reference draws them from its Mersenne twister, so the agreement is
+    statistical: total mass, and the cell values around the reference's within the scatter of ten samples."""
+    g, part = sph_fixture("cfg5s")
+    sites = part[:, :3][np.argsort(part[:, 0], kind="stable")]
+    e = OracleEngine(configs.cfg1(num_packets=10).config_struct())
+    e.build_voronoi(VOR_EXTENT, sites)
+    e.sample_medium_particles(part, 1.0, 10, len(sites))
+    dens, vol = e.read_medium()
+    ref = g["mass_density_msun_pc3"] * MSUN / PC ** 3
+    refvol = g["cell_volume_pc3"] * PC ** 3
+    np.testing.assert_allclose(vol, refvol, rtol=1e-9)
+    assert (dens * vol).sum() == pytest.approx((ref * refvol).sum(), rel=0.02)
+    ok = (ref > 0) & (dens > 0)
+    assert ok.mean() > 0.99
+    assert np.median(dens[ok] / ref[ok]) == pytest.approx(1.0, abs=0.02)
+    assert np.corrcoef(np.log(dens[ok]), np.log(ref[ok]))[0, 1] > 0.85
+    with pytest.raises(abi.SkError):
+        e.sample_medium_particles(part, 1.0, 1, len(sites))      # the centroid of a Voronoi cell is not available
+
+
+@pytest.mark.gpu
+def test_device_particle_density_equals_oracle():
+    """sk_sample_particles_kernel against the oracle on a Cartesian grid (cell centres and random positions), an octree and a
+    Voronoi grid built on the device: the same positions, the same particles in the same order."""
+    g, part = sph_fixture("cfg13p")
+    cfg = configs.cfg1(num_packets=10, seed=4).config_struct(device=0)
+    for kind in ("cartesian1", "cartesian7", "octree", "voronoi"):
+        gpu, cpu = abi.Engine(cfg), OracleEngine(cfg)
+        if kind.startswith("cartesian"):
+            nc = [cartesian_24_20_10(x) for x in (gpu, cpu)][0]
+            ns = int(kind[-1])
+        elif kind == "octree":
+            sim = cfg2s(False, num_packets=10)
+            for x in (gpu, cpu):
+                sim.grid.configure(x)
+            nc, ns = sim.grid.num_cells, 3
+        else:
+            sites = part[:, :3][np.argsort(part[:, 0], kind="stable")][::3]
+            for x in (gpu, cpu):
+                x.build_voronoi(VOR_EXTENT, sites)
+            nc, ns = len(sites), 4
+        for x in (gpu, cpu):
+            x.sample_medium_particles(part, 2.5, ns, nc)
+        (da, va), (db, vb) = gpu.read_medium(), cpu.read_medium()
+        assert (db > 0).sum() > 0.3 * nc, kind
+        np.testing.assert_allclose(da, db, rtol=1e-13, atol=0, err_msg=kind)
+        np.testing.assert_array_equal(va, vb, err_msg=kind)
+
+
+@pytest.mark.gpu
+def test_particle_medium_on_a_device_built_voronoi_grid_runs_like_the_reference():
+    """cfg5s end to end with nothing but the particle table: sites sorted and tessellated, densities sampled and the life cycle run
+    on the device; fluxes against the reference's (its set-up differs in the random positions only)."""
+    from tests.test_golden_reference import check_cfg5s
+    g, part = sph_fixture("cfg5s")
+    n = 2000000
+    sim = configs.cfg5(part[:, :3], num_packets=n, seed=0)
+    sim.medium = H.ParticleMedium(part, sim.medium.mix)
+    sim.numDensitySamples = 10
+    sim.deviceSetup = True
+    sim.setup()
+    e = sim.configure(abi.Engine(sim.config_struct(device=0)))
+    sim.run(e)
+    check_cfg5s(sim, e, g, n)
