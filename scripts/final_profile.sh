@@ -18,6 +18,9 @@ if [[ $PARTS == *bench* ]]; then
   done
   timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_ref_cfg2.json 2> gpurun_out/${TAG}_ref_cfg2.err
   cut -c1-200 gpurun_out/${TAG}_ref_cfg2.json
+  # diagnostic, not a BASELINE workload: cfg2 with a second dust component of another material mix (several-component kernels)
+  SK_BENCH_SECOND_MIX=1 timeout 600 python bench.py --no-cpu-baseline --no-parity > gpurun_out/${TAG}_bench_cfg2_second_mix.json 2> gpurun_out/${TAG}_bench_cfg2_second_mix.err
+  cut -c1-200 gpurun_out/${TAG}_bench_cfg2_second_mix.json
 fi
 if [[ $PARTS == *ncu* ]]; then
   B="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e"
@@ -30,7 +33,7 @@ if [[ $PARTS == *ncu* ]]; then
   ls -la gpurun_out | grep ${TAG} | grep ncu-rep
 fi
 if [[ $PARTS == *san* ]]; then
-  timeout 900 compute-sanitizer --tool memcheck --error-exitcode 1 python -m pytest tests/test_gpu_parity.py -q -x -k "cartesian_cfg1 or octree_cfg2_small or explicit or interleaved or dust_emission or voronoi" > gpurun_out/${TAG}_memcheck.log 2>&1
+  timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 1 python -m pytest tests/test_gpu_parity.py tests/test_setup.py -q -x -k "cartesian_cfg1 or octree_cfg2_small or explicit or interleaved or dust_emission or voronoi or two_components or three_components or particle_density" > gpurun_out/${TAG}_memcheck.log 2>&1
   echo "memcheck rc=$?" >> gpurun_out/${TAG}_memcheck.log
   tail -5 gpurun_out/${TAG}_memcheck.log
 fi
