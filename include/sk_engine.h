@@ -321,7 +321,9 @@ int sk_engine_set_dustmix(sk_engine_t* e, const sk_dustmix_t* mix);
  * phase functions weighted with their scattering opacities (:697-767), the scattering component is drawn from those weights
  * with one extra deviate (:796-823), and the absorbed luminosity and the dust emission spectrum sum over the components, each
  * with the equilibrium temperature of its own mix (:1317-1356, 1452-1476).  sk_engine_set_medium / sk_engine_set_dustmix are
- * the num_media = 1 forms.  Up to SK_MAX_MEDIA components; explicit absorption is limited to one component. */
+ * the num_media = 1 forms.  Up to SK_MAX_MEDIA components.  With explicit absorption the walks are in scattering optical depth and
+ * the absorption optical depth is accumulated next to it and interpolated at the interaction point (MediumSystem.cpp:937-955,
+ * 1112-1150). */
 int sk_engine_set_media(sk_engine_t* e, int32_t num_cells, int32_t num_media, const double* number_density,
                         const double* volume);
 int sk_engine_set_dustmixes(sk_engine_t* e, int32_t num_media, const sk_dustmix_t* mixes);

@@ -3182,19 +3182,28 @@ static int simulate_nonforced_propagation(sko_engine_t* e, rng_t* g, packet_t* p
     double tauinteract = -log(uniform(g)); /* Random::expon, Random.cpp:98-101 */
     gen_t gen;
     gen_start(&gen, pp->r, pp->k);
-    double tau = 0., s = 0.;
+    double tau = 0., s = 0., tauabs = 0.;
     /* with explicit absorption the walk is in scattering optical depth, setInteractionPointUsingScatteringAndAbsorption
-       (MediumSystem.cpp:1075-1110), and the weight is the absorption along the way instead of the albedo (.cpp:757-762) */
+       (MediumSystem.cpp:1075-1110; several media :1112-1150: the absorption optical depth is accumulated next to it and
+       interpolated at the interaction point), and the weight is the absorption along the way instead of the albedo
+       (MonteCarloSimulation.cpp:757-762) */
     const int explicit_abs = e->cfg.explicit_absorption;
     const double* section = explicit_abs ? e->sig_sca : e->sig_ext; /* (several media: MediumSystem.cpp:1012-1040) */
     e->cnt.forward_paths++;
     while (gen_next(e, &gen))
     {
         e->cnt.forward_segments++;
-        double tau0 = tau, s0 = s;
+        double tau0 = tau, s0 = s, tauabs0 = tauabs;
         double ds = gen.ds;
         int m = gen.m;
-        if (m >= 0)
+        if (m >= 0 && explicit_abs && e->nmed > 1)
+            for (int h = 0; h < e->nmed; ++h)
+            {
+                double ns = e->dens[(size_t)h * e->ncells + m] * ds;
+                tau += e->sig_sca[(size_t)h * e->nlam + pp->ilam] * ns;
+                tauabs += e->sig_abs[(size_t)h * e->nlam + pp->ilam] * ns;
+            }
+        else if (m >= 0)
             for (int h = 0; h < e->nmed; ++h)
                 tau += section[(size_t)h * e->nlam + pp->ilam] * e->dens[(size_t)h * e->ncells + m] * gen.ds;
         s += ds;
@@ -3205,7 +3214,9 @@ static int simulate_nonforced_propagation(sko_engine_t* e, rng_t* g, packet_t* p
             double kext = opacity_sum(e, e->sig_ext, pp->ilam, m);
             double albedo = kext > 0. ? ksca / kext : 0.;
             pp->m_int = m;
-            if (explicit_abs) albedo = exp(-(tauinteract * e->sig_abs[pp->ilam] / e->sig_sca[pp->ilam]));
+            if (explicit_abs)
+                albedo = e->nmed > 1 ? exp(-interp_linlin(tauinteract, tau0, tau, tauabs0, tauabs))
+                                     : exp(-(tauinteract * e->sig_abs[pp->ilam] / e->sig_sca[pp->ilam]));
             pp->W *= albedo;
             pp->r[0] += sint * pp->k[0];
             pp->r[1] += sint * pp->k[1];
@@ -3302,8 +3313,6 @@ int sko_run_segment(sko_engine_t* e, uint64_t first, uint64_t count, int32_t pri
     if (primary && !e->npackets) return fail(SK_ERR_STATE, "call prepare_primary first");
     if (!primary && !e->secondary_ready) return fail(SK_ERR_STATE, "call prepare_secondary first");
     if (e->nmed != e->nmix) return fail(SK_ERR_STATE, "the number of dust mixes does not match the number of medium components");
-    if (e->nmed > 1 && e->cfg.explicit_absorption)
-        return fail(SK_ERR_UNSUPPORTED, "explicit absorption with several medium components");
     if (!primary && e->sec_nmed != e->nmed) return fail(SK_ERR_STATE, "emission tables do not match the medium components");
     if (store && e->rf_grid < 0) return fail(SK_ERR_STATE, "no radiation field grid configured");
     if (store && !e->cfg.force_scattering)

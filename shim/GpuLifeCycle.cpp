@@ -485,7 +485,7 @@ std::string GpuLifeCycle::unsupportedReason() const
     if (!mix || mix->scatteringMode() != DustMix::ScatteringMode::HenyeyGreenstein) return "a material mix other than a Henyey-Greenstein dust mix";
     // several media (MediumSystem.cpp:874-885, 697-767): components that share one material mix are a single medium with the
     // summed density (opacity, albedo, phase function and emissivity are the same); components with different mixes run on the
-    // engine's several-component path (sk_engine_set_media), up to SK_MAX_MEDIA of them and without explicit absorption
+    // engine's several-component path (sk_engine_set_media), up to SK_MAX_MEDIA of them
     for (int h = 1; h < ms->numMedia(); ++h)
     {
         auto other = dynamic_cast<const DustMix*>(ms->media()[h]->mix());
@@ -496,7 +496,6 @@ std::string GpuLifeCycle::unsupportedReason() const
     if (!mediaShareOneMix())
     {
         if (ms->numMedia() > SK_MAX_MEDIA) return "more than " + std::to_string(SK_MAX_MEDIA) + " media with different material mixes";
-        if (config->explicitAbsorption()) return "explicit absorption with several different material mixes";
     }
     auto grid = ms->grid();
     auto tree = dynamic_cast<TreeSpatialGrid*>(grid);

@@ -2152,8 +2152,6 @@ extern "C" int sk_engine_launch_segment(sk_engine_t* e, uint64_t first, uint64_t
     if (primary && !e->npackets) return fail(SK_ERR_STATE, "call sk_engine_prepare_primary first");
     if (!primary && !e->secondary_ready) return fail(SK_ERR_STATE, "call sk_engine_prepare_secondary first");
     if (e->num_mixes != e->M.nmed) return fail(SK_ERR_STATE, "the number of dust mixes does not match the number of medium components");
-    if (e->M.nmed > 1 && e->M.explicit_absorption)
-        return fail(SK_ERR_UNSUPPORTED, "explicit absorption with several medium components");
     if (!primary && e->sec_num_media != e->M.nmed) return fail(SK_ERR_STATE, "emission tables do not match the medium components");
     if (store && e->M.rf_grid < 0) return fail(SK_ERR_STATE, "no radiation field grid configured");
     if (store && !e->M.force_scattering)

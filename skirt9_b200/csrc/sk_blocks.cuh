@@ -15,6 +15,9 @@ enum {
     I_HLO, I_HHI, I_DRAW, I_NSCATT, I_STATE, I_ILAM, I_M, I_IX, I_IY, I_IZ, I_LEV, I_MINT, I_MIX, I_MIY, I_MIZ,
     I_MLEV, I_RFELL, I_HELL0, SK_NI = I_HELL0 + SK_MAX_INSTR
 };
+// the absorption optical depth at the interaction point (explicit absorption with several medium components) travels from the
+// forward trace to the advance kernel of the next round in the field of the peel-off limit, which is idle in between
+#define D_TAUABS D_LIMIT
 // I_STATE bits
 #define SK_ST_LIVE 1
 #define SK_ST_SCATTER 2    // a scattering event is pending (peel-off of kind "scattering", then new direction)

@@ -384,6 +384,10 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, (GRID == 3   ? SK_TRACE_MINBLO
     // components (rare) are read from the tables at each crossing.
     double sec1 = 0., dn1 = 0.;
     int mpre = -1, ilam_ray = 0;
+    // MULTI with explicit absorption (MediumSystem.cpp:937-955, 1112-1150): the walk is in scattering optical depth and the
+    // absorption optical depth is accumulated next to it -- the ratio of the two varies from cell to cell
+    const bool multi_explicit = MULTI && MODE != 2 && M.explicit_absorption;
+    double seca0 = 0., seca1 = 0., taua = 0., taua_end = 0.;
 #define SK_FETCH_DENSX()                                                                          \
     if (MULTI)                                                                                    \
     {                                                                                             \
@@ -436,6 +440,8 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, (GRID == 3   ? SK_TRACE_MINBLO
                 }
                 // a walk that stopped inside a cell holds the optical depth at the cell's far wall in s_int: linear
                 // interpolation over the segment (SpatialGridPath.cpp:188-194)
+                if (multi_explicit)  // SpatialGridPath.cpp:185-195 / MediumSystem.cpp:1143-1147: interpolated like the distance
+                    K.D(D_TAUABS, slot) = st.m() >= 0 ? sk_interp_linlin(limit, tau, s_int, taua, taua_end) : taua;
                 if (st.m() >= 0) s_int = sk_interp_linlin(limit, tau, s_int, s, s + st.ds());
                 K.D(D_SINT, slot) = s_int;
                 K.I(I_MINT, slot) = hit.m;
@@ -489,8 +495,15 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, (GRID == 3   ? SK_TRACE_MINBLO
                 {
                     ilam_ray = K.I(I_ILAM, slot);
                     sec1 = M.sig_ext[M.nlam + ilam_ray];
+                    if (multi_explicit)
+                    {
+                        section = M.sig_sca[ilam_ray];
+                        sec1 = M.sig_sca[M.nlam + ilam_ray];
+                        seca0 = M.sig_abs[ilam_ray];
+                        seca1 = M.sig_abs[M.nlam + ilam_ray];
+                    }
                 }
-                if (MODE != 2 && M.explicit_absorption)
+                if (!MULTI && MODE != 2 && M.explicit_absorption)
                 {
                     // the walk to the interaction point is in scattering optical depth (MediumSystem.cpp:905-934, 1075-1110);
                     // the extinction that attenuates the radiation field deposits is a fixed multiple of it
@@ -524,6 +537,7 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, (GRID == 3   ? SK_TRACE_MINBLO
                 s = 0.;
                 nseg = 0;
                 s_int = 0.;
+                if (MULTI) taua = 0.;
                 if (MODE == 0 && STORE) extBeg = 1.;
                 if (p.m < 0)
                 {
@@ -582,9 +596,18 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, (GRID == 3   ? SK_TRACE_MINBLO
                 {
                     if (m != mpre) SK_FETCH_DENSX();  // (the Voronoi walk may re-locate its cell inside exit())
                     kappa = __fma_rn(sec1, dn1, kappa);
+                    const double* __restrict__ sigx = multi_explicit ? M.sig_sca : M.sig_ext;
                     for (int h = 2; h < M.nmed; ++h)
-                        kappa = __fma_rn(__ldg(&M.sig_ext[h * M.nlam + ilam_ray]),
+                        kappa = __fma_rn(__ldg(&sigx[h * M.nlam + ilam_ray]),
                                          __ldg(&M.densx[(size_t)(h - 1) * (size_t)M.ncells + (size_t)m]), kappa);
+                    if (multi_explicit)
+                    {
+                        double kappa_abs = __fma_rn(seca1, dn1, seca0 * dens);
+                        for (int h = 2; h < M.nmed; ++h)
+                            kappa_abs = __fma_rn(__ldg(&M.sig_abs[h * M.nlam + ilam_ray]),
+                                                 __ldg(&M.densx[(size_t)(h - 1) * (size_t)M.ncells + (size_t)m]), kappa_abs);
+                        taua_end = __fma_rn(kappa_abs, ds > 0. ? ds : 0., taua);  // absorption optical depth at the far wall
+                    }
                 }
                 if (MODE == 0)
                 {
@@ -603,7 +626,8 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, (GRID == 3   ? SK_TRACE_MINBLO
                         else if (STORE && rf)
                         {
                             // the logarithms of the extinction factors at both ends of the segment are -tau and -tau1
-                            const double lnBeg = -(tau * extfac), lnEnd = -(tau1 * extfac);
+                            const double lnBeg = multi_explicit ? -(tau + taua) : -(tau * extfac),
+                                         lnEnd = multi_explicit ? -(tau1 + taua_end) : -(tau1 * extfac);
                             const double extEnd = exp(lnEnd);
                             const double extMean = sk_lnmean4(extEnd, extBeg, lnEnd, lnBeg);
                             const double Lds = lum * extMean * ds;
@@ -638,6 +662,7 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, (GRID == 3   ? SK_TRACE_MINBLO
                         {
                             s += ds;
                             tau = tau1;
+                            if (MULTI) taua = taua_end;
                         }
                     }
                 }
@@ -657,6 +682,7 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, (GRID == 3   ? SK_TRACE_MINBLO
                         {
                             s += ds;
                             tau = tau1;
+                            if (MULTI) taua = taua_end;
                         }
                     }
                 }
@@ -869,8 +895,13 @@ __global__ void SK_ADVANCE_BOUNDS sk_wf_advance(const SkDevModel M, const SkRunA
                 }
                 // explicit absorption: the absorption optical depth up to the interaction point, a fixed multiple of the
                 // scattering optical depth for one medium with constant sections (SpatialGridPath.cpp:185-195)
-                W *= -em * (M.explicit_absorption ? exp(-(tauint * M.sig_abs[ilam] / M.sig_sca[ilam])) : albedo);
+                if (MULTI)  // (several components: the absorption optical depth accumulated by the walk)
+                    W *= -em * (M.explicit_absorption ? exp(-K.D(D_TAUABS, sl)) : albedo);
+                else
+                    W *= -em * (M.explicit_absorption ? exp(-(tauint * M.sig_abs[ilam] / M.sig_sca[ilam])) : albedo);
             }
+            else if (MULTI)
+                W *= M.explicit_absorption ? exp(-K.D(D_TAUABS, sl)) : albedo;
             else
                 W *= M.explicit_absorption ? exp(-(tauint * M.sig_abs[ilam] / M.sig_sca[ilam])) : albedo;  // .cpp:757-773
             x = rx0 + sint * kx;  // PhotonPacket::propagate, PhotonPacket.cpp:107-111

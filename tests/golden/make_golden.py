@@ -156,6 +156,22 @@ def make_cfg11m():
     print("cfg11m:", {k: np.shape(v) for k, v in out.items()})
 
 
+def make_cfg14em():
+    """cfg11m with explicit absorption: two dust media with different mixes, interaction points in scattering optical depth, the
+    absorption optical depth interpolated along the path (MediumSystem.cpp:937-955).  Same tree and densities as cfg11m."""
+    with tempfile.TemporaryDirectory() as d:
+        run_reference("cfg14em", d, packets=2e6)
+        rho = np.stack([read_columns(os.path.join(d, "cfg14em_dns_%d_rho.dat" % h))[:, 1] for h in range(2)])
+        base = np.load(os.path.join(HERE, "cfg11m_ref.npz"))["component_mass_density_msun_pc3"]
+        assert np.array_equal(rho, base), "cfg14em must see the inputs of cfg11m"
+        total = read_fits_cube(os.path.join(d, "cfg14em_i60_total.fits"))[0].astype(np.float64)
+        out = dict(sed=read_columns(os.path.join(d, "cfg14em_i60_sed.dat")),
+                   sedstats=read_columns(os.path.join(d, "cfg14em_i60_sedstats.dat")), num_packets=2e6,
+                   frame_total_sum=total.sum(axis=0))
+    np.savez_compressed(os.path.join(HERE, "cfg14em_ref.npz"), **out)
+    print("cfg14em:", {k: np.shape(v) for k, v in out.items()})
+
+
 def make_cfg12me(packets=None, tag="cfg12me_ref"):
     """Dust emission with iterations from two dust media with different mixes (cfg4s with a second, uniform shell)."""
     with tempfile.TemporaryDirectory() as d:

@@ -353,7 +353,7 @@ def test_two_components_dust_emission_iterations(engine_lib):
 
 def test_component_limits_are_reported(engine_lib):
     """More than SK_MAX_MEDIA components, mixes on different wavelength grids, a mix count that does not match the medium
-    state, explicit absorption with several components: reported, never run."""
+    state: reported, never run."""
     sim = models.with_second_component(models.small_cartesian(num_packets=1000), "shell").setup()
     e = abi.Engine(sim.config_struct(device=0), lib=engine_lib)
     sim.grid.configure(e)
@@ -368,8 +368,30 @@ def test_component_limits_are_reported(engine_lib):
     e2.prepare_primary(1000)
     with pytest.raises(abi.SkError):
         e2.run_segment(0, 1000, True, True, False, 0)
+
+
+@pytest.mark.parametrize("force", [True, False])
+def test_two_components_with_explicit_absorption(engine_lib, force):
+    """Explicit absorption with several mixes (MediumSystem.cpp:937-955, 1112-1150): the walks are in scattering optical depth,
+    the absorption optical depth -- whose ratio to it now varies from cell to cell -- is accumulated next to it and interpolated
+    at the interaction point; the radiation field sees the sum of the two."""
+    sim = models.with_second_component(models.two_sources_three_instruments(num_packets=20000, force=force), "shell")
     sim.explicitAbsorption = True
-    e3 = sim.configure(abi.Engine(sim.config_struct(device=0), lib=engine_lib))
-    e3.prepare_primary(1000)
-    with pytest.raises(abi.SkError):
-        e3.run_segment(0, 1000, True, True, False, 0)
+    gpu, cpu = run_both(sim, engine_lib)
+    models.compare_engines(sim, gpu, cpu)
+    assert gpu.counters()["scatterings"] > 10000
+    # against the same model with the albedo weighting: other weights, so other tallies
+    ref = models.with_second_component(models.two_sources_three_instruments(num_packets=20000, force=force), "shell")
+    one, _ = run_both(ref, engine_lib)
+    assert not np.allclose(one.read_sed(0, abi.SK_COMP_PRIMARY_SCATTERED), gpu.read_sed(0, abi.SK_COMP_PRIMARY_SCATTERED), rtol=1e-3)
+
+
+def test_three_components_octree_with_explicit_absorption(engine_lib):
+    from skirt9_b200 import host as H
+    sim = models.with_second_component(models.small_octree(num_packets=20000, record_statistics=True), "disk")
+    third = H.MeanListDustMix([0.1e-6, 0.55e-6, 10e-6], [800.0, 900.0, 100.0], [0.0, 0.9, 0.5], [0.0, 0.7, 0.2])   # no scattering in the UV
+    sim.extraMedia.append(H.GeometricMedium(H.ExpDiskGeometry(6000 * H.PC, 500 * H.PC, 0.0, 20000 * H.PC, 2000 * H.PC), third,
+                                            opticalDepth=0.3, wavelength=0.55e-6))
+    sim.explicitAbsorption = True
+    gpu, cpu = run_both(sim, engine_lib)
+    models.compare_engines(sim, gpu, cpu)

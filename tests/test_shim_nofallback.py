@@ -27,18 +27,17 @@ def small(name, packets="2e4"):
     return re.sub(r'numPackets="[^"]*"', f'numPackets="{packets}"', open(os.path.join(SKI, name + ".ski")).read(), count=1)
 
 
-def two_mixes(text):
-    """Duplicates the GeometricMedium element and changes the copy's albedo: two dust components with DIFFERENT material mixes
-    (MediumSystem.cpp:874-885) -- on the accelerated path (tests/golden/ski/cfg11m.ski) unless combined with explicit
-    absorption (MediumSystem.cpp:937-955), which the engine runs for one component only."""
+def five_mixes(text):
+    """Four copies of the GeometricMedium element with other albedos: five dust components with DIFFERENT material mixes
+    (MediumSystem.cpp:874-885) -- up to SK_MAX_MEDIA = 4 run on the accelerated path (tests/golden/ski/cfg11m.ski)."""
     a, b = text.index("<GeometricMedium"), text.index("</GeometricMedium>") + len("</GeometricMedium>")
-    text = text[:b] + text[a:b].replace('albedos="0.6, 0.6"', 'albedos="0.4, 0.4"') + text[b:]
-    assert 'explicitAbsorption="false"' in text
-    return text.replace('explicitAbsorption="false"', 'explicitAbsorption="true"')
+    copies = "".join(text[a:b].replace('albedos="0.6, 0.6"', 'albedos="0.%d, 0.%d"' % (k, k)) for k in (2, 3, 4, 5))
+    assert 'albedos="0.6, 0.6"' in text
+    return text[:b] + copies + text[b:]
 
 
 @pytest.mark.parametrize("edit, reason", [
-    (two_mixes, "explicit absorption with several different material mixes"),
+    (five_mixes, "more than 4 media with different material mixes"),
     (lambda s: s.replace('<RadiationFieldProbe', '<LaunchedPacketsProbe probeName="lpp"/><RadiationFieldProbe', 1),
      "launch call-back"),
     (lambda s: s.replace('recordPolarization="false"', 'recordPolarization="true"'), "polarization"),

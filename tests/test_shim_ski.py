@@ -226,6 +226,20 @@ def test_cfg11m_ski_two_media_with_different_mixes_runs_unchanged(tmp_path):
     assert total.astype(float).sum() == pytest.approx(g["frame_total_sum"].sum(), rel=4e-3)
 
 
+def test_cfg14em_ski_two_mixes_with_explicit_absorption_runs_unchanged(tmp_path):
+    g = np.load(os.path.join(GOLD, "cfg14em_ref.npz"))
+    log = run_ski("cfg14em", tmp_path, 4e6)
+    assert "GPU life cycle:" in log and "outside the GPU life cycle" not in log
+    sed = read_columns(tmp_path / "cfg14em_i60_sed.dat")
+    stats = read_columns(tmp_path / "cfg14em_i60_sedstats.dat")
+    tol = 4.0 * np.hypot(rel_error(g["sedstats"][:, 1:].T), rel_error(stats[:, 1:].T))
+    for col in (1, 2, 3, 4):
+        bound = tol * np.maximum(g["sed"][:, col], g["sed"][:, 1])
+        assert np.all(np.abs(sed[:, col] - g["sed"][:, col]) <= bound), col
+    total, _ = read_fits_cube(tmp_path / "cfg14em_i60_total.fits")
+    assert total.astype(float).sum() == pytest.approx(g["frame_total_sum"].sum(), rel=4e-3)
+
+
 def test_cfg12me_ski_dust_emission_from_two_mixes_runs_unchanged(tmp_path):
     g = np.load(os.path.join(GOLD, "cfg12me_ref.npz"))
     log = run_ski("cfg12me", tmp_path, 2e6)
