@@ -31,6 +31,15 @@ if [[ $PARTS == *ncu* ]]; then
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:sk_wf_trace -s 4 -c 2 -o gpurun_out/${TAG}_cfg1 -f $B --config cfg1 --packets 1e7 > gpurun_out/${TAG}_cfg1_bench.log 2>&1
   SK_BENCH_SITES=200000 timeout 900 ncu --set full --clock-control none --import-source on -k regex:sk_wf_trace -s 4 -c 2 -o gpurun_out/${TAG}_cfg5 -f $B --config cfg5 --packets 4e6 > gpurun_out/${TAG}_cfg5_bench.log 2>&1
   ls -la gpurun_out | grep ${TAG} | grep ncu-rep
+  # gpurun brings back at most 64 MiB: the raw metric pages of every capture as CSV (what scripts/make_profile_summaries.py reads),
+  # and only the report of the dominant trace kernels itself (source page, scripts/make_traffic.py)
+  for r in prof events cfg4 cfg1 cfg5; do
+    if [ -f gpurun_out/${TAG}_$r.ncu-rep ]; then
+      ncu -i gpurun_out/${TAG}_$r.ncu-rep --page raw --csv > gpurun_out/${TAG}_${r}_raw.csv 2>/dev/null
+      [ $r != prof ] && rm -f gpurun_out/${TAG}_$r.ncu-rep
+    fi
+  done
+  du -sh gpurun_out
 fi
 if [[ $PARTS == *san* ]]; then
   timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 1 python -m pytest tests/test_gpu_parity.py tests/test_setup.py -q -x -k "cartesian_cfg1 or octree_cfg2_small or explicit or interleaved or dust_emission or voronoi or two_components or three_components or particle_density" > gpurun_out/${TAG}_memcheck.log 2>&1

@@ -47,9 +47,13 @@ out = []
 reps = sys.argv[2:] or [tag + "_prof", tag + "_events", tag + "_launch"]
 for rep in reps:
     path = os.path.join(G, rep + ".ncu-rep")
-    if not os.path.exists(path):
+    raw = os.path.join(G, rep + "_raw.csv")   # the raw page exported on the GPU box (scripts/final_profile.sh)
+    if os.path.exists(raw):
+        txt = open(raw).read()
+    elif os.path.exists(path):
+        txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    else:
         continue
-    txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(txt.splitlines()))
     hdr, units = rows[0], rows[1]
     scale = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
