@@ -247,7 +247,7 @@ def make_sim(name, total_packets, statistics=False):
     if name == "cfg1":
         return configs.cfg1(num_packets=total_packets, record_statistics=statistics).setup()
     if name == "cfg4":
-        return configs.cfg4(num_packets=total_packets, max_level=8, max_dust_fraction=3.3e-6).setup()
+        return configs.cfg4(num_packets=total_packets, max_level=8, max_dust_fraction=3.3e-6, record_statistics=statistics).setup()
     import numpy as np
     rng = np.random.default_rng(12345)   # SURVEY.md 8d cfg5 recipe
     sites = int(os.environ.get("SK_BENCH_SITES", "500000"))

@@ -597,12 +597,14 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, (GRID == 3   ? SK_TRACE_MINBLO
                     if (m != mpre) SK_FETCH_DENSX();  // (the Voronoi walk may re-locate its cell inside exit())
                     kappa = __fma_rn(sec1, dn1, kappa);
                     const double* __restrict__ sigx = multi_explicit ? M.sig_sca : M.sig_ext;
-                    for (int h = 2; h < M.nmed; ++h)
+#pragma unroll 1
+                    for (int h = 2; h < M.nmed; ++h)  // (third and fourth component: rare, kept out of the unrolled code)
                         kappa = __fma_rn(__ldg(&sigx[h * M.nlam + ilam_ray]),
                                          __ldg(&M.densx[(size_t)(h - 1) * (size_t)M.ncells + (size_t)m]), kappa);
                     if (multi_explicit)
                     {
                         double kappa_abs = __fma_rn(seca1, dn1, seca0 * dens);
+#pragma unroll 1
                         for (int h = 2; h < M.nmed; ++h)
                             kappa_abs = __fma_rn(__ldg(&M.sig_abs[h * M.nlam + ilam_ray]),
                                                  __ldg(&M.densx[(size_t)(h - 1) * (size_t)M.ncells + (size_t)m]), kappa_abs);
