@@ -381,6 +381,14 @@ def sed_parity(name, device, ref_packets, gpu_packets):
     allz, allrr = np.concatenate(list(own.values())), np.concatenate(list(rr.values()))
     rms_rr = float(np.sqrt((allrr ** 2).mean()))
     bound = 4.0 * max(1.0, rms_rr)
+    # per column: in a dust-emission run the columns differ by orders of magnitude in how well Sum w^k describes their scatter
+    # (the secondary transparent flux has nearly equal weights, so a tiny R, but carries the noise of the radiation field behind
+    # the dust temperatures in full), so each column is held to the reference's own run-to-run scatter IN THAT COLUMN
+    rms_rr_col = {k: (float(np.sqrt((v ** 2).mean())) if len(v) else 0.0) for k, v in rr.items()}
+    bound_col = {k: 4.0 * max(1.0, v) for k, v in rms_rr_col.items()}
+    passed = bool(allz.max() <= bound)
+    if sim.dustEmissionWLG is not None:
+        passed = all((len(v) == 0 or float(v.max()) <= bound_col[k]) for k, v in own.items())
     tot_ref, tot_own = ref[:, 1].sum(), sim.sed_flux_density(e, 0, abi.SK_COMP_TOTAL).sum()
     overflow = e.counters()["pixel_overflows"]
     e.close()
@@ -394,8 +402,10 @@ def sed_parity(name, device, ref_packets, gpu_packets):
             "max_sigma_per_component": {k: float(v.max()) for k, v in own.items()},
             "reference_vs_reference": {"max_sigma": float(allrr.max()), "rms_sigma": rms_rr,
                                        "bins_over_4_sigma": int((allrr > 4).sum())},
-            "bound_sigma": bound, "total_flux_ratio": float(tot_own / tot_ref), "pixel_overflows": int(overflow),
-            "pass": bool(allz.max() <= bound)}
+            "bound_sigma": bound, "rms_sigma_per_component": {k: (float(np.sqrt((v ** 2).mean())) if len(v) else 0.0) for k, v in own.items()},
+            "reference_vs_reference_rms_per_component": rms_rr_col, "bound_sigma_per_component": bound_col,
+            "pass_rule": "per component (dust emission)" if sim.dustEmissionWLG is not None else "all bins against bound_sigma",
+            "total_flux_ratio": float(tot_own / tot_ref), "pixel_overflows": int(overflow), "pass": passed}
 
 
 def device_setup_times(device):
