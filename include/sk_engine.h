@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SK_ABI_VERSION 5
+#define SK_ABI_VERSION 6
 #define SK_MAX_MEDIA 4 /* medium components with their own material mix (sk_engine_set_media) */
 
 typedef struct sk_engine sk_engine_t;
@@ -122,7 +122,16 @@ typedef struct sk_source {
     int32_t reserved;
     const double* oligo_lambda;  /* [oligo_n] */
     double oligo_probability;    /* OligoWavelengthDistribution::_probability */
+    int32_t velocity_kind;       /* sk_velocity_kind: the bulk velocity of the source, Source::hasVelocity() -- the packet is
+                                    launched at lambda (1 - k.v/c) (PhotonPacket::launch, PhotonPacket.cpp:33) */
+    int32_t reserved2;
+    double velocity[3];          /* SK_VEL_CONSTANT: the vector (m/s); SK_VEL_RADIAL / SK_VEL_CYLINDRICAL: {magnitude,
+                                    unityRadius, exponent} of GeometricSource::velocityMagnitude() times the field */
 } sk_source_t;
+/* The velocity of a source at the launch position: PointSource velocityX/Y/Z (SpecialtySource.cpp) or
+ * GeometricSource::velocityMagnitude() * velocityDistribution()->vector(r) (GeometricSource.cpp:66-82) for the vector fields
+ * UnidirectionalVectorField (as a constant vector), RadialVectorField.cpp:19-37 and CylindricalVectorField.cpp:19-38. */
+enum sk_velocity_kind { SK_VEL_NONE = 0, SK_VEL_CONSTANT = 1, SK_VEL_RADIAL = 2, SK_VEL_CYLINDRICAL = 3 };
 
 /* ---- Instruments: DistantInstrument / SEDInstrument / FrameInstrument / FullInstrument --------- */
 enum sk_instrument_kind { SK_INSTR_SED = 1, SK_INSTR_FRAME = 2, SK_INSTR_FULL = 3 };
@@ -311,6 +320,19 @@ int sk_engine_sample_medium_particles(sk_engine_t* e, int32_t num_particles, con
 int sk_engine_read_medium(sk_engine_t* e, double* number_density, double* volume);
 
 int sk_engine_set_dustmix(sk_engine_t* e, const sk_dustmix_t* mix);
+
+/* Kinematics (f4 of SURVEY.md section 8): MediumState::bulkVelocity(m) (MediumSystem.cpp:330-365), velocity[3*m + c] in m/s,
+ * after the medium state; NULL (or num_cells = 0) returns to media at rest.  With moving media -- Configuration::
+ * hasMovingMedia(), and here also with moving sources alone -- the wavelength a cell perceives differs from cell to cell,
+ * lambda / (1 - k.v_m/c) (PhotonPacket::perceivedWavelength, PhotonPacket.cpp:133-151), and every use of a cross section
+ * follows it: the optical depths of the forward and peel-off paths look the sections up per segment (the "spatially variable
+ * cross sections" branches, MediumSystem.cpp:888-900, 958-972, 1242-1258), the radiation field is binned at the perceived
+ * wavelength with the perceived luminosity (MonteCarloSimulation.cpp:667-691), albedo, peel-off weights and the scattering
+ * component use the wavelength perceived in the interaction cell (MediumSystem.cpp:667-693), a scattered or peeled-off packet
+ * leaves at lambda_perceived (1 - k_new.v_m/c) (PhotonPacket::scatter / launchScatteringPeelOff, PhotonPacket.cpp:89-122), and
+ * a packet emitted by a dust cell carries the cell's bulk velocity (DustSecondarySource.cpp:562-580).  The caller passes the
+ * path length bias the configuration ends up with (0 with moving media and forced scattering, Configuration.cpp:492-498). */
+int sk_engine_set_velocities(sk_engine_t* e, int32_t num_cells, const double* velocity);
 
 /* Several medium components, each with its own material mix (Configuration::hasMultipleConstantSectionMedia; f4 of SURVEY.md
  * section 8): the medium state MediumState::numberDensity(m,h) for h = 0..num_media-1, number_density[h*num_cells + m], and

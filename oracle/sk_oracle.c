@@ -100,6 +100,9 @@ typedef struct sko_engine {
     /* medium: nmed components (Configuration::hasMultipleConstantSectionMedia when > 1); dens[h*ncells + m] */
     int ncells, nmed;
     double *dens, *vol;
+    /* kinematics: MediumState::bulkVelocity(m), [3*m + c], or NULL for media at rest; kin = moving media or moving sources */
+    double* vel;
+    int kin;
     /* dust: one table set per component, [h*nlam + i]; the wavelength grid lam_border is common (DustMix.cpp:52-98) */
     int nlam, nmix;
     double *lam_border, *sig_abs, *sig_sca, *sig_ext, *gpar;
@@ -143,6 +146,7 @@ typedef struct sko_engine {
 } sko_engine_t;
 
 static char g_err[512] = "";
+static void update_kin(sko_engine_t* e);
 static int fail(int code, const char* msg)
 {
     snprintf(g_err, sizeof g_err, "%s", msg);
@@ -554,6 +558,7 @@ void sko_destroy(sko_engine_t* e)
     free_grid(e);
     free(e->dens);
     free(e->vol);
+    free(e->vel);
     free(e->lam_border);
     free(e->sig_abs);
     free(e->sig_sca);
@@ -1113,6 +1118,9 @@ int sko_set_media(sko_engine_t* e, int32_t num_cells, int32_t num_media, const d
     if (num_cells != grid_num_cells(e)) return fail(SK_ERR_INVALID, "medium size does not match the grid");
     free(e->dens);
     free(e->vol);
+    free(e->vel); /* a new medium state is at rest until sko_set_velocities says otherwise */
+    e->vel = NULL;
+    update_kin(e);
     e->ncells = num_cells;
     e->nmed = num_media;
     e->dens = dupd(number_density, (size_t)num_media * num_cells);
@@ -1292,6 +1300,9 @@ int sko_sample_medium(sko_engine_t* e, const sk_density_geometry_t* medium, int3
     int nc = grid_num_cells(e);
     free(e->dens);
     free(e->vol);
+    free(e->vel);
+    e->vel = NULL;
+    update_kin(e);
     e->dens = (double*)malloc((size_t)nc * sizeof(double));
     e->vol = (double*)malloc((size_t)nc * sizeof(double));
     e->ncells = nc;
@@ -1467,6 +1478,9 @@ int sko_sample_medium_particles(sko_engine_t* e, int32_t num_particles, const do
     }
     free(e->dens);
     free(e->vol);
+    free(e->vel);
+    e->vel = NULL;
+    update_kin(e);
     e->dens = dens;
     e->vol = vol;
     e->ncells = nc;
@@ -1483,6 +1497,28 @@ int sko_read_medium(sko_engine_t* e, double* number_density, double* volume)
         if (!e->vol) return fail(SK_ERR_STATE, "the engine holds no cell volumes");
         memcpy(volume, e->vol, (size_t)e->ncells * sizeof(double));
     }
+    return SK_OK;
+}
+
+static void update_kin(sko_engine_t* e)
+{
+    e->kin = e->vel != NULL;
+    for (int h = 0; h < e->nsrc; ++h)
+        if (e->src[h].s.velocity_kind != SK_VEL_NONE) e->kin = 1;
+}
+
+/* MediumState::bulkVelocity(m) for every cell (sk_engine_set_velocities) */
+int sko_set_velocities(sko_engine_t* e, int32_t num_cells, const double* velocity)
+{
+    if (!e) return fail(SK_ERR_INVALID, "null engine");
+    free(e->vel);
+    e->vel = NULL;
+    if (velocity && num_cells > 0)
+    {
+        if (!e->dens || num_cells != e->ncells) return fail(SK_ERR_INVALID, "velocities do not match the medium state");
+        e->vel = dupd(velocity, 3 * (size_t)num_cells);
+    }
+    update_kin(e);
     return SK_OK;
 }
 
@@ -1584,6 +1620,7 @@ int sko_set_sources(sko_engine_t* e, int32_t n, const sk_source_t* sources, doub
     double L = 0.;
     for (int h = 0; h < n; ++h) L += sources[h].luminosity;
     e->Ltot = L;
+    update_kin(e);
     if (!L) return SK_OK;
     double wLsum = 0., wsum = 0.;
     for (int h = 0; h < n; ++h)
@@ -2352,9 +2389,27 @@ typedef struct {
     uint64_t history;
     int has_tau;
     double tau_obs;
-    int ilam; /* DustMix::indexForLambda(lambda), constant during the life cycle (no kinematics) */
+    int ilam; /* DustMix::indexForLambda(lambda); without kinematics constant during the life cycle */
     int m_int; /* PhotonPacket::interactionCellIndex(): the cell of the last interaction point (SpatialGridPath.hpp:150) */
+    /* kinematics: the rest-frame emission wavelength and the velocity of the emitter (PhotonPacket::_lambda0, _bvi) */
+    double lambda0, vsrc[3];
+    int has_vsrc;
 } packet_t;
+
+/* ---- kinematics: PhotonPacket::shiftedEmissionWavelength / shiftedReceptionWavelength / perceivedWavelength,
+ * PhotonPacket.cpp:133-151 (no Hubble flow) */
+#define SK_C_LIGHT 299792458. /* Constants::c() */
+static double shifted_emission_wavelength(double lambda, const double k[3], const double v[3])
+{
+    return lambda * (1 - (k[0] * v[0] + k[1] * v[1] + k[2] * v[2]) / SK_C_LIGHT);
+}
+/* the wavelength cell m perceives for a packet of wavelength lambda travelling along k */
+static double perceived_wavelength(const sko_engine_t* e, double lambda, const double k[3], int m)
+{
+    if (!e->vel || m < 0) return lambda;
+    const double* v = e->vel + 3 * (size_t)m;
+    return lambda / (1 - (k[0] * v[0] + k[1] * v[1] + k[2] * v[2]) / SK_C_LIGHT);
+}
 
 /* the opacity sum over the medium components in cell m with the sections sig[h*nlam + ilam]: MediumSystem::opacitySca/Ext
  * for spatially constant sections (MediumSystem.cpp:632-662), n_h * sigma_h each (MaterialMix::opacity*) */
@@ -2369,6 +2424,14 @@ static double opacity_sum(const sko_engine_t* e, const double* sig, int ilam, in
 static int index_for_lambda(const sko_engine_t* e, double lambda)
 {
     return locate_clip(e->lam_border, e->nlam, lambda);
+}
+
+/* the index of the dust property tables for the packet in cell m: fixed for the packet without kinematics, else looked up
+ * at the wavelength the cell perceives (the "spatially variable cross sections" branches of MediumSystem.cpp) */
+static int ilam_in_cell(const sko_engine_t* e, const packet_t* pp, int m)
+{
+    if (!e->kin) return pp->ilam;
+    return index_for_lambda(e, perceived_wavelength(e, pp->lambda, pp->k, m));
 }
 
 /* DisjointWavelengthGrid::bin, DisjointWavelengthGrid.cpp:332-341 */
@@ -2423,12 +2486,15 @@ static void set_extinction_optical_depths(sko_engine_t* e, const packet_t* pp)
         {
             seg_t* sg = &e->segs[n];
             if (sg->m >= 0)
+            {
+                const int il = ilam_in_cell(e, pp, sg->m); /* (kinematics: MediumSystem.cpp:958-972) */
                 for (int h = 0; h < e->nmed; ++h)
                 {
                     double ns = e->dens[(size_t)h * e->ncells + sg->m] * sg->ds;
-                    tauSca += e->sig_sca[(size_t)h * e->nlam + pp->ilam] * ns;
-                    tauAbs += e->sig_abs[(size_t)h * e->nlam + pp->ilam] * ns;
+                    tauSca += e->sig_sca[(size_t)h * e->nlam + il] * ns;
+                    tauAbs += e->sig_abs[(size_t)h * e->nlam + il] * ns;
                 }
+            }
             sg->tau = tauSca;
             sg->tauabs = tauAbs;
         }
@@ -2441,8 +2507,11 @@ static void set_extinction_optical_depths(sko_engine_t* e, const packet_t* pp)
         {
             seg_t* sg = &e->segs[n];
             if (sg->m >= 0)
+            {
+                const int il = ilam_in_cell(e, pp, sg->m); /* (kinematics: MediumSystem.cpp:888-900) */
                 for (int h = 0; h < e->nmed; ++h)
-                    tau += e->sig_ext[(size_t)h * e->nlam + pp->ilam] * e->dens[(size_t)h * e->ncells + sg->m] * sg->ds;
+                    tau += e->sig_ext[(size_t)h * e->nlam + il] * e->dens[(size_t)h * e->ncells + sg->m] * sg->ds;
+            }
             sg->tau = tau;
         }
     }
@@ -2465,9 +2534,10 @@ static double get_extinction_optical_depth(sko_engine_t* e, const packet_t* ppp)
         e->cnt.peel_segments++;
         if (g.m >= 0)
         {
-            /* (several media: MediumSystem.cpp:1222-1240) */
+            /* (several media: MediumSystem.cpp:1222-1240; kinematics: MediumSystem.cpp:1242-1258) */
+            const int il = ilam_in_cell(e, ppp, g.m);
             for (int h = 0; h < e->nmed; ++h)
-                tau += e->sig_ext[(size_t)h * e->nlam + ppp->ilam] * e->dens[(size_t)h * e->ncells + g.m] * g.ds;
+                tau += e->sig_ext[(size_t)h * e->nlam + il] * e->dens[(size_t)h * e->ncells + g.m] * g.ds;
             if (tau >= taumax) return INFINITY;
         }
     }
@@ -2479,6 +2549,34 @@ static double get_extinction_optical_depth(sko_engine_t* e, const packet_t* ppp)
 static void store_radiation_field(sko_engine_t* e, int primary, const packet_t* pp)
 {
     if (e->rf_grid < 0) return;
+    if (e->kin)
+    {
+        /* the branch for perceived wavelengths that vary along the path, MonteCarloSimulation.cpp:667-691 */
+        double lnExtBeg = 0.;
+        double extBeg = 1.;
+        double* rf = primary ? e->rf1 : e->rf2c;
+        for (int n = 0; n < e->nsegs; ++n)
+        {
+            const seg_t* sg = &e->segs[n];
+            double lnExtEnd = -(sg->tau + sg->tauabs);
+            double extEnd = exp(lnExtEnd);
+            if (sg->m >= 0)
+            {
+                double lambda = perceived_wavelength(e, pp->lambda, pp->k, sg->m);
+                int ell = wlg_bin(&e->wlg[e->rf_grid].g, lambda);
+                if (ell >= 0)
+                {
+                    double extMean = lnmean4(extEnd, extBeg, lnExtEnd, lnExtBeg);
+                    double Lds = (pp->W / lambda) * extMean * sg->ds; /* PhotonPacket::perceivedLuminosity */
+                    rf[(size_t)sg->m * e->nrf + ell] += Lds;
+                    e->cnt.rf_deposits++;
+                }
+            }
+            lnExtBeg = lnExtEnd;
+            extBeg = extEnd;
+        }
+        return;
+    }
     int ell = wlg_bin(&e->wlg[e->rf_grid].g, pp->lambda);
     if (ell < 0) return;
     double luminosity = pp->W / pp->lambda;
@@ -2732,6 +2830,11 @@ static void peel_off_emission(sko_engine_t* e, const packet_t* pp)
             ppp.nscatt = 0;
             memcpy(ppp.k, q->kobs, sizeof ppp.k);
             ppp.has_tau = 0;
+            if (pp->has_vsrc) /* PhotonPacket.cpp:77 */
+            {
+                ppp.lambda = shifted_emission_wavelength(pp->lambda0, q->kobs, pp->vsrc);
+                ppp.ilam = index_for_lambda(e, ppp.lambda);
+            }
         }
         detect(e, q, &ppp);
     }
@@ -2754,13 +2857,17 @@ static void peel_off_scattering(sko_engine_t* e, const packet_t* pp)
             /* MediumSystem::weightsForScattering (MediumSystem.cpp:697-730): 1 for a single medium, else the scattering
                opacities of the components in the interaction cell, normalised; none scatters: no peel-off at all
                (MonteCarloSimulation.cpp:790-792) */
+            /* the wavelength the interaction cell perceives, MediumSystem::perceivedWavelengthForScattering
+               (MediumSystem.cpp:667-674) */
+            const double lamp = perceived_wavelength(e, pp->lambda, pp->k, pp->m_int);
+            const int ilp = e->kin ? index_for_lambda(e, lamp) : pp->ilam;
             double wv[SK_MAX_MEDIA] = {1., 0., 0., 0.};
             if (e->nmed > 1)
             {
                 double sum = 0.;
                 for (int h = 0; h < e->nmed; ++h)
                 {
-                    wv[h] = e->dens[(size_t)h * e->ncells + pp->m_int] * e->sig_sca[(size_t)h * e->nlam + pp->ilam];
+                    wv[h] = e->dens[(size_t)h * e->ncells + pp->m_int] * e->sig_sca[(size_t)h * e->nlam + ilp];
                     sum += wv[h];
                 }
                 if (!(sum > 0.)) return;
@@ -2770,11 +2877,23 @@ static void peel_off_scattering(sko_engine_t* e, const packet_t* pp)
             for (int h = 0; h < e->nmed; ++h)
                 if (wv[h] > 0.)
                 {
-                    double g = e->gpar[(size_t)h * e->nlam + pp->ilam];
+                    double g = e->gpar[(size_t)h * e->nlam + ilp];
                     double value = fabs(g) > glarge ? mean_hg(g, costheta) : value_hg(g, costheta);
                     I += value * wv[h]; /* MediumSystem.cpp:745-754 */
                 }
             ppp = *pp;
+            if (e->kin)
+            {
+                /* PhotonPacket::launchScatteringPeelOff (PhotonPacket.cpp:89-103): the perceived wavelength, shifted by the
+                   bulk velocity of the cell for the direction towards the observer */
+                ppp.lambda = lamp;
+                if (e->vel && pp->m_int >= 0)
+                {
+                    const double* v = e->vel + 3 * (size_t)pp->m_int;
+                    if (v[0] != 0. || v[1] != 0. || v[2] != 0.) ppp.lambda = shifted_emission_wavelength(lamp, q->kobs, v);
+                }
+                ppp.ilam = index_for_lambda(e, ppp.lambda);
+            }
             ppp.W = pp->W * I;
             ppp.nscatt = pp->nscatt + 1;
             memcpy(ppp.k, q->kobs, sizeof ppp.k);
@@ -2915,6 +3034,47 @@ static void generate_position(rng_t* g, const sk_source_t* s, double r[3])
     }
 }
 
+/* the bulk velocity of a source at the launch position: PointSource velocityX/Y/Z, or GeometricSource::velocityMagnitude()
+ * times the vector field (GeometricSource.cpp:73-79; RadialVectorField.cpp:19-37, CylindricalVectorField.cpp:19-38) */
+static void source_velocity(const sk_source_t* s, const double r[3], double v[3])
+{
+    v[0] = v[1] = v[2] = 0.;
+    if (s->velocity_kind == SK_VEL_CONSTANT)
+    {
+        v[0] = s->velocity[0];
+        v[1] = s->velocity[1];
+        v[2] = s->velocity[2];
+    }
+    else if (s->velocity_kind == SK_VEL_RADIAL || s->velocity_kind == SK_VEL_CYLINDRICAL)
+    {
+        const double mag = s->velocity[0], unity = s->velocity[1], expon = s->velocity[2];
+        double u[3];
+        if (s->velocity_kind == SK_VEL_RADIAL)
+        {
+            u[0] = r[0];
+            u[1] = r[1];
+            u[2] = r[2];
+        }
+        else
+        {
+            u[0] = -r[1];
+            u[1] = r[0];
+            u[2] = 0.;
+        }
+        double rr = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+        if (rr == 0.) return;
+        u[0] /= rr;
+        u[1] /= rr;
+        u[2] /= rr;
+        double f = 1.;
+        if (unity > 0.)
+            if ((expon > 0. && rr < unity) || (expon < 0. && rr > unity)) f = pow(rr / unity, expon);
+        v[0] = mag * (f * u[0]);
+        v[1] = mag * (f * u[1]);
+        v[2] = mag * (f * u[2]);
+    }
+}
+
 /* SourceSystem::launch (SourceSystem.cpp:101-113), NormalizedSource::launch (NormalizedSource.cpp:73-110),
  * GeometricSource::launchNormalized (GeometricSource.cpp:66-82), PointSource::launchSpecialty (PointSource.cpp:32-42),
  * PhotonPacket::launch (PhotonPacket.cpp:18-40) */
@@ -2993,7 +3153,17 @@ static void launch_primary(sko_engine_t* e, rng_t* g, uint64_t history, packet_t
     pp->primary_origin = 1;
     pp->history = history;
     pp->has_tau = 0;
-    pp->ilam = index_for_lambda(e, lambda);
+    pp->lambda0 = lambda;
+    pp->has_vsrc = 0;
+    if (s->velocity_kind != SK_VEL_NONE)
+    {
+        /* PhotonPacket::launch with a velocity interface (PhotonPacket.cpp:33): the wavelength is Doppler-shifted for the
+           launch direction, the weight keeps the rest-frame wavelength */
+        source_velocity(s, pp->r, pp->vsrc);
+        pp->has_vsrc = 1;
+        pp->lambda = shifted_emission_wavelength(lambda, pp->k, pp->vsrc);
+    }
+    pp->ilam = index_for_lambda(e, pp->lambda);
 }
 
 /* SecondarySourceSystem::launch (SecondarySourceSystem.cpp:130-142) + DustSecondarySource::launch
@@ -3121,7 +3291,20 @@ static void launch_secondary(sko_engine_t* e, rng_t* g, uint64_t history, packet
     pp->primary_origin = 0;
     pp->history = history;
     pp->has_tau = 0;
-    pp->ilam = index_for_lambda(e, lambda);
+    pp->lambda0 = lambda;
+    pp->has_vsrc = 0;
+    if (e->vel)
+    {
+        /* the bulk velocity of the emitting cell, if it is nonzero (DustSecondarySource.cpp:271, 562-563) */
+        const double* v = e->vel + 3 * (size_t)m;
+        if (v[0] != 0. || v[1] != 0. || v[2] != 0.)
+        {
+            memcpy(pp->vsrc, v, sizeof pp->vsrc);
+            pp->has_vsrc = 1;
+            pp->lambda = shifted_emission_wavelength(lambda, pp->k, pp->vsrc);
+        }
+    }
+    pp->ilam = index_for_lambda(e, pp->lambda);
 }
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -3161,8 +3344,9 @@ static void simulate_forced_propagation(sko_engine_t* e, rng_t* g, packet_t* pp,
         double albedo = 0.;
         if (m >= 0)
         {
-            double ksca = opacity_sum(e, e->sig_sca, pp->ilam, m);
-            double kext = opacity_sum(e, e->sig_ext, pp->ilam, m);
+            const int il = ilam_in_cell(e, pp, m); /* perceivedWavelengthForScattering */
+            double ksca = opacity_sum(e, e->sig_sca, il, m);
+            double kext = opacity_sum(e, e->sig_ext, il, m);
             albedo = kext > 0. ? ksca / kext : 0.;
         }
         pp->W *= -expm1(-taupath) * albedo;
@@ -3196,26 +3380,27 @@ static int simulate_nonforced_propagation(sko_engine_t* e, rng_t* g, packet_t* p
         double tau0 = tau, s0 = s, tauabs0 = tauabs;
         double ds = gen.ds;
         int m = gen.m;
-        if (m >= 0 && explicit_abs && e->nmed > 1)
+        const int il = m >= 0 ? ilam_in_cell(e, pp, m) : pp->ilam; /* (kinematics: MediumSystem.cpp:1042-1070, 1152-1188) */
+        if (m >= 0 && explicit_abs && (e->nmed > 1 || e->kin))
             for (int h = 0; h < e->nmed; ++h)
             {
                 double ns = e->dens[(size_t)h * e->ncells + m] * ds;
-                tau += e->sig_sca[(size_t)h * e->nlam + pp->ilam] * ns;
-                tauabs += e->sig_abs[(size_t)h * e->nlam + pp->ilam] * ns;
+                tau += e->sig_sca[(size_t)h * e->nlam + il] * ns;
+                tauabs += e->sig_abs[(size_t)h * e->nlam + il] * ns;
             }
         else if (m >= 0)
             for (int h = 0; h < e->nmed; ++h)
-                tau += section[(size_t)h * e->nlam + pp->ilam] * e->dens[(size_t)h * e->ncells + m] * gen.ds;
+                tau += section[(size_t)h * e->nlam + il] * e->dens[(size_t)h * e->ncells + m] * gen.ds;
         s += ds;
         if (tauinteract < tau)
         {
             double sint = interp_linlin(tauinteract, tau0, tau, s0, s);
-            double ksca = opacity_sum(e, e->sig_sca, pp->ilam, m);
-            double kext = opacity_sum(e, e->sig_ext, pp->ilam, m);
+            double ksca = opacity_sum(e, e->sig_sca, il, m);
+            double kext = opacity_sum(e, e->sig_ext, il, m);
             double albedo = kext > 0. ? ksca / kext : 0.;
             pp->m_int = m;
             if (explicit_abs)
-                albedo = e->nmed > 1 ? exp(-interp_linlin(tauinteract, tau0, tau, tauabs0, tauabs))
+                albedo = (e->nmed > 1 || e->kin) ? exp(-interp_linlin(tauinteract, tau0, tau, tauabs0, tauabs))
                                      : exp(-(tauinteract * e->sig_abs[pp->ilam] / e->sig_sca[pp->ilam]));
             pp->W *= albedo;
             pp->r[0] += sint * pp->k[0];
@@ -3234,16 +3419,18 @@ static void simulate_scattering(sko_engine_t* e, rng_t* g, packet_t* pp)
     /* select a medium component within the cell: NR::cdf over the scattering opacities (NR.hpp:446-463: cumulative sums
        divided by the total, first element zero) and NR::locateClip of one uniform deviate, MediumSystem.cpp:805-818 */
     int hsel = 0;
+    const double lamp = perceived_wavelength(e, pp->lambda, pp->k, pp->m_int); /* MediumSystem.cpp:802 */
+    const int ilp = e->kin ? index_for_lambda(e, lamp) : pp->ilam;
     if (e->nmed > 1)
     {
         double Xv[SK_MAX_MEDIA + 1];
         Xv[0] = 0.;
         for (int h = 0; h < e->nmed; ++h)
-            Xv[h + 1] = Xv[h] + e->dens[(size_t)h * e->ncells + pp->m_int] * e->sig_sca[(size_t)h * e->nlam + pp->ilam];
+            Xv[h + 1] = Xv[h] + e->dens[(size_t)h * e->ncells + pp->m_int] * e->sig_sca[(size_t)h * e->nlam + ilp];
         for (int h = 0; h <= e->nmed; ++h) Xv[h] /= Xv[e->nmed];
         hsel = locate_clip(Xv, e->nmed + 1, uniform(g));
     }
-    double gp = e->gpar[(size_t)hsel * e->nlam + pp->ilam];
+    double gp = e->gpar[(size_t)hsel * e->nlam + ilp];
     double knew[3];
     if (fabs(gp) < 1e-6)
         random_direction(g, knew);
@@ -3255,6 +3442,18 @@ static void simulate_scattering(sko_engine_t* e, rng_t* g, packet_t* pp)
     }
     pp->nscatt++;
     memcpy(pp->k, knew, sizeof knew);
+    if (e->kin)
+    {
+        /* PhotonPacket::scatter(bfk, bfv, lambda), PhotonPacket.cpp:115-122: the packet leaves at the perceived wavelength,
+           shifted by the bulk velocity of the cell for its new direction */
+        pp->lambda = lamp;
+        if (e->vel && pp->m_int >= 0)
+        {
+            const double* v = e->vel + 3 * (size_t)pp->m_int;
+            if (v[0] != 0. || v[1] != 0. || v[2] != 0.) pp->lambda = shifted_emission_wavelength(lamp, knew, v);
+        }
+        pp->ilam = index_for_lambda(e, pp->lambda);
+    }
     e->cnt.scatterings++;
 }
 

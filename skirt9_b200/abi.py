@@ -22,6 +22,7 @@ SK_SRC_POINT, SK_SRC_GEOMETRIC = 1, 2
 SK_GEOM_NONE, SK_GEOM_SHELL, SK_GEOM_EXPDISK, SK_GEOM_RING, SK_GEOM_SPIRAL_EXPDISK = range(5)
 SK_SED_TABULATED, SK_SED_BLACKBODY = 1, 2
 SK_BIAS_NONE, SK_BIAS_LOGUNIFORM, SK_BIAS_OLIGO = 0, 1, 2
+SK_VEL_NONE, SK_VEL_CONSTANT, SK_VEL_RADIAL, SK_VEL_CYLINDRICAL = 0, 1, 2, 3
 SK_INSTR_SED, SK_INSTR_FRAME, SK_INSTR_FULL = 1, 2, 3
 (SK_COMP_TOTAL, SK_COMP_TRANSPARENT, SK_COMP_PRIMARY_DIRECT, SK_COMP_PRIMARY_SCATTERED, SK_COMP_SECONDARY_DIRECT,
  SK_COMP_SECONDARY_SCATTERED, SK_COMP_SECONDARY_TRANSPARENT, SK_COMP_PRIMARY_SCATTERED_LEVEL) = range(8)
@@ -55,7 +56,8 @@ class SkSource(C.Structure):
                 ("bias_kind", C.c_int32), ("sed_lambda", _dp), ("sed_p", _dp), ("sed_P", _dp),
                 ("sed_temperature", C.c_double), ("sed_norm", C.c_double), ("wavelength_bias", C.c_double),
                 ("bias_min", C.c_double), ("bias_max", C.c_double), ("oligo_n", C.c_int32), ("reserved", C.c_int32),
-                ("oligo_lambda", _dp), ("oligo_probability", C.c_double)]
+                ("oligo_lambda", _dp), ("oligo_probability", C.c_double), ("velocity_kind", C.c_int32),
+                ("reserved2", C.c_int32), ("velocity", C.c_double * 3)]
 
 
 class SkInstrument(C.Structure):
@@ -273,6 +275,14 @@ class Engine:
         self._call("set_medium", self._h, C.c_int32(len(n)), pn, pv)
         self.num_cells = len(n)
 
+    def set_velocities(self, velocity):
+        """MediumState::bulkVelocity(m) per cell, [num_cells][3] in m/s; None returns to media at rest."""
+        if velocity is None:
+            self._call("set_velocities", self._h, C.c_int32(0), None)
+            return
+        v, pv = _d(np.ascontiguousarray(velocity, dtype=float).reshape(-1))
+        self._call("set_velocities", self._h, C.c_int32(len(v) // 3), pv)
+
     def set_dustmix(self, lambda_border, sigma_abs, sigma_sca, asymmpar, mu):
         lb, p0 = _d(lambda_border)
         sa, p1 = _d(sigma_abs)
@@ -350,6 +360,8 @@ class Engine:
                 keep.append(a)
                 q.oligo_n, q.oligo_lambda = len(a), pa
                 q.oligo_probability = s["oligo_probability"]
+            q.velocity_kind = s.get("velocity_kind", SK_VEL_NONE)
+            q.velocity = (C.c_double * 3)(*s.get("velocity", (0., 0., 0.)))
             arr[k] = q
         self._call("set_sources", self._h, C.c_int32(len(sources)), arr, C.c_double(source_bias))
 

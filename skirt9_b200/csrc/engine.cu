@@ -218,6 +218,8 @@ struct sk_engine {
     SkDevModel M;
     // owned device allocations by group
     std::vector<void*> grid_allocs, medium_allocs, dust_allocs, wlg_allocs, src_allocs, instr_allocs, rf_allocs, sec_allocs;
+    std::vector<void*> vel_allocs;  // kinematics: the per-cell bulk velocities (given, or zeros when only sources move)
+    bool vel_given = false, src_moving = false;
     // host mirrors
     int grid_kind = 0;
     int grid_cells = 0;
@@ -310,6 +312,15 @@ static void free_group(std::vector<void*>& v)
     for (void* p : v) dev_free(p);
     v.clear();
 }
+// kinematics are on when the media or any source move; a new medium state is at rest until the caller says otherwise
+static void drop_velocities(sk_engine* e)
+{
+    free_group(e->vel_allocs);
+    e->M.vel = nullptr;
+    e->vel_given = false;
+    e->M.kin = e->src_moving ? 1 : 0;
+}
+
 template <class T>
 static int upload(std::vector<void*>& group, const T* host, size_t n, T** out)
 {
@@ -382,6 +393,7 @@ extern "C" void sk_engine_destroy(sk_engine_t* e)
     cudaStreamSynchronize(e->stream);
     free_group(e->grid_allocs);
     free_group(e->medium_allocs);
+    free_group(e->vel_allocs);
     free_group(e->dust_allocs);
     free_group(e->wlg_allocs);
     free_group(e->src_allocs);
@@ -428,6 +440,7 @@ static void drop_grid(sk_engine* e)
     free_group(e->medium_allocs);
     free_group(e->rf_allocs);
     free_group(e->sec_allocs);
+    drop_velocities(e);
     e->grid_kind = 0;
     e->grid_cells = 0;
     e->M.grid_kind = 0;
@@ -804,6 +817,23 @@ extern "C" int sk_engine_read_voronoi(sk_engine_t* e, int64_t* nbr_offset, int32
     return SK_OK;
 }
 
+// MediumState::bulkVelocity(m) (MediumSystem.cpp:330-365) for the walks with kinematics (sk_wavefront.cuh)
+extern "C" int sk_engine_set_velocities(sk_engine_t* e, int32_t num_cells, const double* velocity)
+{
+    if (!e) return fail(SK_ERR_INVALID, "null engine");
+    if (int rc_bind = bind(e)) return rc_bind;
+    drop_velocities(e);
+    if (!velocity || num_cells <= 0) return SK_OK;
+    if (!e->grid_kind || !e->M.ncells) return fail(SK_ERR_STATE, "set the medium state before the velocities");
+    if (num_cells != e->M.ncells) return fail(SK_ERR_INVALID, "velocities do not match the medium state");
+    double* v;
+    if (int rc = upload(e->vel_allocs, velocity, 3 * (size_t)num_cells, &v)) return rc;
+    e->M.vel = v;
+    e->vel_given = true;
+    e->M.kin = 1;
+    return SK_OK;
+}
+
 extern "C" int sk_engine_set_medium(sk_engine_t* e, int32_t num_cells, const double* number_density,
                                     const double* volume)
 {
@@ -820,6 +850,7 @@ extern "C" int sk_engine_set_media(sk_engine_t* e, int32_t num_cells, int32_t nu
     if (num_cells != e->grid_cells) return fail(SK_ERR_INVALID, "medium size does not match the grid");
     if (int rc_bind = bind(e)) return rc_bind;
     free_group(e->medium_allocs);
+    drop_velocities(e);
     e->M.densx = nullptr;
     e->M.nmed = num_media;
     if (num_media > 1)
@@ -1131,6 +1162,7 @@ extern "C" int sk_engine_sample_medium(sk_engine_t* e, const sk_density_geometry
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e->stream));
     e->dens_host.clear();
+    drop_velocities(e);
     e->M.dens = d_dens;
     e->M.densx = nullptr;
     e->M.nmed = 1;
@@ -1225,6 +1257,7 @@ extern "C" int sk_engine_sample_medium_particles(sk_engine_t* e, int32_t num_par
             // the medium state: densities through a scratch array into the cell records; volumes of the boxes, or of the
             // tessellation this engine built
             free_group(e->medium_allocs);
+            drop_velocities(e);
             e->M.densx = nullptr;
             e->M.nmed = 1;
             e->M.dens = nullptr;
@@ -1432,6 +1465,7 @@ extern "C" int sk_engine_set_sources(sk_engine_t* e, int32_t n, const sk_source_
                        + source_bias * sources[h].source_weight / wsum;
     }
     std::vector<SkDevSource> dev(n);
+    bool moving = false;
     for (int h = 0; h < n; ++h)
     {
         const sk_source_t& s = sources[h];
@@ -1476,7 +1510,13 @@ extern "C" int sk_engine_set_sources(sk_engine_t* e, int32_t n, const sk_source_
         d.bias_max = s.bias_max;
         d.oligo_probability = s.oligo_probability;
         d.Lw = L ? e->Lv[h] / e->Wv[h] : 0.;
+        if (s.velocity_kind < SK_VEL_NONE || s.velocity_kind > SK_VEL_CYLINDRICAL) return fail(SK_ERR_UNSUPPORTED, "unknown source velocity kind");
+        d.velocity_kind = s.velocity_kind;
+        memcpy(d.velocity, s.velocity, sizeof d.velocity);
+        if (s.velocity_kind != SK_VEL_NONE) moving = true;
     }
+    e->src_moving = moving;
+    e->M.kin = (e->vel_given || moving) ? 1 : 0;
     SkDevSource* ds;
     if (int rc = upload(e->src_allocs, dev.data(), dev.size(), &ds)) return rc;
     unsigned long long* iv;
@@ -1893,8 +1933,15 @@ static int ensure_bank(sk_engine* e, uint64_t count)
 {
     size_t cap = std::min<uint64_t>(count, bank_capacity_limit());
     cap = std::max<size_t>((cap + 255) / 256 * 256, 256);
-    const int nd = SK_BANK_FIELDS_D(e->M.ninstr) + e->num_pix_lists * SK_PIX_K;
-    const int ni = SK_BANK_FIELDS_I(e->M.ninstr) + e->num_pix_lists * SK_PIX_INTS;
+    int nd = SK_BANK_FIELDS_D(e->M.ninstr) + e->num_pix_lists * SK_PIX_K;
+    int ni = SK_BANK_FIELDS_I(e->M.ninstr) + e->num_pix_lists * SK_PIX_INTS;
+    e->M.kin_base_d = nd;  // the extra per-packet fields of a run with kinematics follow the pixel lists
+    e->M.kin_base_i = ni;
+    if (e->M.kin)
+    {
+        nd += SK_KD_COUNT;
+        ni += SK_KI_COUNT;
+    }
     e->bank.n = (int32_t)cap;
     if ((size_t)e->bank.cap >= cap && e->bank_fields_d == nd && e->bank_fields_i == ni) return SK_OK;
     dev_free(e->bank.d);
@@ -1980,7 +2027,7 @@ static int launch_trace(sk_engine* e, const SkRunArgs& A, const SkObsDir& dir)
 {
     // only the Cartesian grid looks borders up while it walks (TMA-staged tables); the octree walks in lattice coordinates
     // several medium components with their own mixes: the instantiation that sums the opacities
-    if (e->M.nmed > 1)
+    if (e->M.nmed > 1 || e->M.kin)
     {
         if (GRID == 1 && e->M.lattice_in_smem) return launch_trace_impl<GRID, MODE, STORE, GRID == 1, true>(e, A, dir);
         return launch_trace_impl<GRID, MODE, STORE, false, true>(e, A, dir);
@@ -2018,7 +2065,10 @@ static int run_bank(sk_engine* e, const SkRunArgs& A)
             smem = 0;
         }
         if (int rc = stage_begin(e, SK_STAGE_DETECT)) return rc;
-        sk_wf_detect<<<dblocks, SK_EVENT_BLOCK, smem, e->stream>>>(M, A, K, j0, j1, last, nl);
+        if (M.kin)
+            sk_wf_detect<true><<<dblocks, SK_EVENT_BLOCK, smem, e->stream>>>(M, A, K, j0, j1, last, nl);
+        else
+            sk_wf_detect<false><<<dblocks, SK_EVENT_BLOCK, smem, e->stream>>>(M, A, K, j0, j1, last, nl);
         CK(cudaGetLastError());
         return stage_end(e);
     };
@@ -2032,7 +2082,7 @@ static int run_bank(sk_engine* e, const SkRunArgs& A)
         CK(cudaMemsetAsync(K.ctl, 0, SK_CTL_WORDS * sizeof(unsigned int), e->stream));
         const int g0a = groups.empty() ? 0 : groups[0].first, g0b = groups.empty() ? 0 : groups[0].second;
         if (int rc = stage_begin(e, SK_STAGE_ADVANCE)) return rc;
-        if (M.nmed > 1)
+        if (M.nmed > 1 || M.kin)
             sk_wf_advance<GRID, true><<<eblocks, SK_EVENT_BLOCK, 0, e->stream>>>(M, A, K, g0a, g0b);
         else
             sk_wf_advance<GRID, false><<<eblocks, SK_EVENT_BLOCK, 0, e->stream>>>(M, A, K, g0a, g0b);
@@ -2168,6 +2218,13 @@ extern "C" int sk_engine_launch_segment(sk_engine_t* e, uint64_t first, uint64_t
     {
         const unsigned long long B = e->il_block, cycle = B * e->il_parts, rem = count % cycle, lo = (unsigned long long)e->il_part * B;
         share = count / cycle * B + (rem > lo ? std::min<unsigned long long>(rem - lo, B) : 0ull);
+    }
+    if (e->M.kin && !e->M.vel)
+    {
+        // only the sources move: the walks with kinematics read a velocity per cell all the same
+        double* v;
+        if (int rc = dalloc_zero(e->vel_allocs, 3 * (size_t)e->M.ncells, &v)) return rc;
+        e->M.vel = v;
     }
     if (share)
     {

@@ -18,6 +18,11 @@ enum {
 // the absorption optical depth at the interaction point (explicit absorption with several medium components) travels from the
 // forward trace to the advance kernel of the next round in the field of the peel-off limit, which is idle in between
 #define D_TAUABS D_LIMIT
+// extra fields of a bank with kinematics (SkDevModel::kin), relative to kin_base_d / kin_base_i: the wavelength of the current
+// peel-off packet, the wavelength the interaction cell perceives and its index in the dust tables, the rest wavelength at
+// emission and the velocity of the emitter (PhotonPacket::_lambda0, _bvi: needed for the emission peel-offs)
+enum { SK_KD_PLAMBDA, SK_KD_LAMP, SK_KD_LAMBDA0, SK_KD_VSX, SK_KD_VSY, SK_KD_VSZ, SK_KD_COUNT };
+enum { SK_KI_ILAMP, SK_KI_COUNT };
 // I_STATE bits
 #define SK_ST_LIVE 1
 #define SK_ST_SCATTER 2    // a scattering event is pending (peel-off of kind "scattering", then new direction)
@@ -865,7 +870,50 @@ __device__ __noinline__ void sk_generate_position(SkRng& g, const SkDevSource& s
 struct SkLaunch {
     double lambda, W, rx, ry, rz, kx, ky, kz;
     int ilam;
+    double vx, vy, vz;  // velocity of the emitter (kinematics): the source at the launch position, or the emitting dust cell
 };
+
+// the bulk velocity of a source at the launch position: PointSource velocityX/Y/Z, or GeometricSource::velocityMagnitude()
+// times the vector field (GeometricSource.cpp:73-79; RadialVectorField.cpp:19-37, CylindricalVectorField.cpp:19-38)
+__device__ __forceinline__ void sk_source_velocity(const SkDevSource& s, double x, double y, double z, double& vx, double& vy,
+                                                   double& vz)
+{
+    vx = vy = vz = 0.;
+    if (s.velocity_kind == SK_VEL_CONSTANT)
+    {
+        vx = s.velocity[0];
+        vy = s.velocity[1];
+        vz = s.velocity[2];
+    }
+    else if (s.velocity_kind == SK_VEL_RADIAL || s.velocity_kind == SK_VEL_CYLINDRICAL)
+    {
+        const double mag = s.velocity[0], unity = s.velocity[1], expon = s.velocity[2];
+        double ux, uy, uz;
+        if (s.velocity_kind == SK_VEL_RADIAL)
+        {
+            ux = x;
+            uy = y;
+            uz = z;
+        }
+        else
+        {
+            ux = -y;
+            uy = x;
+            uz = 0.;
+        }
+        const double rr = sqrt(ux * ux + uy * uy + uz * uz);
+        if (rr == 0.) return;
+        ux /= rr;
+        uy /= rr;
+        uz /= rr;
+        double f = 1.;
+        if (unity > 0.)
+            if ((expon > 0. && rr < unity) || (expon < 0. && rr > unity)) f = pow(rr / unity, expon);
+        vx = mag * (f * ux);
+        vy = mag * (f * uy);
+        vz = mag * (f * uz);
+    }
+}
 
 __device__ __noinline__ void sk_launch_primary(const SkDevModel* __restrict__ Mg, SkRng& g, unsigned long long history,
                                                SkLaunch& pp)
@@ -936,6 +984,7 @@ __device__ __noinline__ void sk_launch_primary(const SkDevModel* __restrict__ Mg
     pp.lambda = lambda;
     pp.W = Lw * lambda;  // PhotonPacket::launch, PhotonPacket.cpp:18-40
     pp.ilam = sk_locate_clip(M.lam_border, M.nlam, lambda);
+    sk_source_velocity(s, pp.rx, pp.ry, pp.rz, pp.vx, pp.vy, pp.vz);
 }
 
 // DustSecondarySource::launch (DustSecondarySource.cpp:511-581): implemented in sk_secondary.cuh

@@ -54,6 +54,8 @@ struct SkDevSource {
     const double* oligo_lambda;
     double sed_temperature, sed_norm, wavelength_bias, bias_min, bias_max, oligo_probability;
     double Lw;  // _Lv[h]/_Wv[h]  (SourceSystem.cpp:105)
+    int32_t velocity_kind, pad3;  // sk_velocity_kind and its parameters (sk_source_t::velocity)
+    double velocity[3];
 };
 
 struct SkDevInstr {
@@ -137,6 +139,11 @@ struct SkDevModel {
                                      // SK_PIX_K + 2 ints (pixel-bin indices, number of entries, newest pool chunk or -1)
     // counters
     unsigned long long* counters;
+    // kinematics (sk_engine_set_velocities; also set when only sources move): vel[3*m + c] = MediumState::bulkVelocity(m),
+    // all zero for media at rest.  The walks then run in the several-component instantiation with per-cell section look-ups,
+    // and the bank holds the extra per-packet fields SK_KD_* / SK_KI_* from kin_base_d / kin_base_i on.
+    int32_t kin, kin_base_d, kin_base_i, kin_pad;
+    const double* vel;
 };
 
 // Radiation field tables on the device are wavelength-major, rf[ell * ncells + m] (the reference's Table<2> is [m][ell],
@@ -460,7 +467,41 @@ __device__ __forceinline__ double sk_planck(double lambda, double T)
     const double l2 = lambda * lambda;  // lambda^5 by multiplication (the oracle does the same): pow() is the most
     return f2 / (l2 * l2 * lambda) / (exp(f1 / lambda) - 1.0);  // expensive call of the launch kernel
 }
+// the same with a guess: i is returned when it is the answer (two comparisons), else the search runs.  The walks with
+// kinematics look the dust tables up in every cell, and the perceived wavelength moves by parts in a thousand from cell to cell.
+__device__ __forceinline__ int sk_locate_clip_hint(const double* __restrict__ xv, int n, double x, int i)
+{
+    if ((i == 0 || xv[i] <= x) && (i == n - 2 || x < xv[i + 1])) return i;
+    return sk_locate_clip(xv, n, x);
+}
+// Doppler shifts, PhotonPacket.cpp:133-151 (no Hubble flow): the wavelength a packet of rest wavelength lambda leaves with in
+// direction k from an emitter moving with v, and the wavelength a receiver moving with v perceives
+#define SK_C_LIGHT 299792458.  // Constants::c()
+__device__ __forceinline__ double sk_shifted_emission(double lambda, double kx, double ky, double kz, double vx, double vy,
+                                                      double vz)
+{
+    return lambda * (1 - (kx * vx + ky * vy + kz * vz) / SK_C_LIGHT);
+}
+__device__ __forceinline__ double sk_perceived(double lambda, double kx, double ky, double kz, double vx, double vy, double vz)
+{
+    return lambda / (1 - (kx * vx + ky * vy + kz * vz) / SK_C_LIGHT);
+}
 // DisjointWavelengthGrid::bin, DisjointWavelengthGrid.cpp:332-341
+// (the border index std::upper_bound returns, with a guess: see sk_locate_clip_hint)
+__device__ __forceinline__ int sk_wlg_upper_hint(const SkDevWlg& g, double lambda, int lo0)
+{
+    if ((lo0 == 0 || g.borders[lo0 - 1] <= lambda) && (lo0 == g.num_borders || lambda < g.borders[lo0])) return lo0;
+    int lo = 0, hi = g.num_borders;
+    while (lo < hi)
+    {
+        int mid = (lo + hi) >> 1;
+        if (lambda < g.borders[mid])
+            hi = mid;
+        else
+            lo = mid + 1;
+    }
+    return lo;
+}
 __device__ __forceinline__ int sk_wlg_bin(const SkDevWlg& g, double lambda)
 {
     int lo = 0, hi = g.num_borders;

@@ -272,4 +272,8 @@ __device__ __noinline__ void sk_launch_secondary(const SkDevModel* __restrict__ 
     pp.lambda = lambda;
     pp.W = (L * ws * w) * lambda;
     pp.ilam = sk_locate_clip(M.lam_border, M.nlam, lambda);
+    // the bulk velocity of the emitting cell (DustSecondarySource.cpp:271, 562-580)
+    pp.vx = M.vel ? M.vel[3 * (size_t)m] : 0.;
+    pp.vy = M.vel ? M.vel[3 * (size_t)m + 1] : 0.;
+    pp.vz = M.vel ? M.vel[3 * (size_t)m + 2] : 0.;
 }

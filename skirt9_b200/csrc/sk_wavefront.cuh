@@ -388,11 +388,29 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, (GRID == 3   ? SK_TRACE_MINBLO
     // absorption optical depth is accumulated next to it -- the ratio of the two varies from cell to cell
     const bool multi_explicit = MULTI && MODE != 2 && M.explicit_absorption;
     double seca0 = 0., seca1 = 0., taua = 0., taua_end = 0.;
+    // MULTI with kinematics (sk_engine_set_velocities): the cell perceives lam_ray / (1 - k.v_m/c) and the sections are those
+    // of that wavelength (MediumSystem.cpp:888-900, 958-972, 1242-1258); ilam_ray follows it from cell to cell, and the sections
+    // in the lane registers are reloaded when it changes.  pk = the ray's direction in physical coordinates.
+    const bool kin = MULTI && M.kin;
+    const bool more_media = MULTI && M.nmed > 1;
+    double lam_ray = 0., lamp = 0., pkx = 0., pky = 0., pkz = 0.;
+    int rf_lo = 0;
 #define SK_FETCH_DENSX()                                                                          \
-    if (MULTI)                                                                                    \
+    if (more_media)                                                                               \
     {                                                                                             \
         mpre = st.m();                                                                            \
         if (mpre >= 0) dn1 = __ldg(&M.densx[(size_t)mpre]);                                       \
+    }
+#define SK_LOAD_SECTIONS()                                                                        \
+    {                                                                                             \
+        const double* __restrict__ sg_ = multi_explicit ? M.sig_sca : M.sig_ext;                 \
+        section = sg_[ilam_ray];                                                                  \
+        sec1 = more_media ? sg_[M.nlam + ilam_ray] : 0.;                                          \
+        if (multi_explicit)                                                                       \
+        {                                                                                         \
+            seca0 = M.sig_abs[ilam_ray];                                                          \
+            seca1 = more_media ? M.sig_abs[M.nlam + ilam_ray] : 0.;                               \
+        }                                                                                         \
     }
     int nseg = 0;
     // MODE 0 + STORE extras: luminosity of the packet, extinction factor at the start of the current segment, and the
@@ -414,7 +432,7 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, (GRID == 3   ? SK_TRACE_MINBLO
                 K.D(D_TAUPATH, slot) = tau;
                 cnt.fwd_paths++;
                 cnt.fwd_segs += nseg;
-                if (STORE && rf) cnt.rf += nseg - ((ls & FRONT) ? 1 : 0);  // one deposit per segment inside the grid
+                if (STORE && rf && !kin) cnt.rf += nseg - ((ls & FRONT) ? 1 : 0);  // one deposit per segment inside the grid
                 // no extinction along the path: the packet cannot scatter; sk_wf_advance terminates it (.cpp:702-706)
                 if (tau > 0.)
                 {
@@ -494,14 +512,16 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, (GRID == 3   ? SK_TRACE_MINBLO
                 if (MULTI)
                 {
                     ilam_ray = K.I(I_ILAM, slot);
-                    sec1 = M.sig_ext[M.nlam + ilam_ray];
-                    if (multi_explicit)
+                    if (kin)
                     {
-                        section = M.sig_sca[ilam_ray];
-                        sec1 = M.sig_sca[M.nlam + ilam_ray];
-                        seca0 = M.sig_abs[ilam_ray];
-                        seca1 = M.sig_abs[M.nlam + ilam_ray];
+                        // a peel-off ray travels at the wavelength of the peel-off packet (sk_peel_setup_values)
+                        lam_ray = MODE == 2 ? K.D(M.kin_base_d + SK_KD_PLAMBDA, slot) : K.D(D_LAMBDA, slot);
+                        if (MODE == 2) ilam_ray = sk_locate_clip_hint(M.lam_border, M.nlam, lam_ray, ilam_ray);
+                        pkx = MODE == 2 ? obs.px : K.D(D_KX, slot);
+                        pky = MODE == 2 ? obs.py : K.D(D_KY, slot);
+                        pkz = MODE == 2 ? obs.pz : K.D(D_KZ, slot);
                     }
+                    SK_LOAD_SECTIONS();
                 }
                 if (!MULTI && MODE != 2 && M.explicit_absorption)
                 {
@@ -524,6 +544,13 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, (GRID == 3   ? SK_TRACE_MINBLO
                     const int rf_ell = K.I(I_RFELL, slot);
                     rf = rf_ell >= 0 ? (A.primary ? M.rf1 : M.rf2c) + SK_RF_INDEX(M, 0, rf_ell) : nullptr;
                     lum = K.D(D_W, slot) / K.D(D_LAMBDA, slot);
+                    if (kin)
+                    {
+                        // the bin follows the perceived wavelength from cell to cell (MonteCarloSimulation.cpp:667-691):
+                        // rf = the whole table, lum = the weight W (the perceived luminosity is W / lambda_perceived)
+                        rf = A.primary ? M.rf1 : M.rf2c;
+                        lum = K.D(D_W, slot);
+                    }
                 }
                 if (MODE == 1) limit = K.D(D_TAUINT, slot);
                 if (MODE == 2) limit = K.D(D_LIMIT, slot);
@@ -594,7 +621,19 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, (GRID == 3   ? SK_TRACE_MINBLO
                 double kappa = section * dens;  // opacity of the cell at the ray's wavelength
                 if (MULTI && m >= 0)
                 {
-                    if (m != mpre) SK_FETCH_DENSX();  // (the Voronoi walk may re-locate its cell inside exit())
+                    if (kin)
+                    {
+                        const double* __restrict__ vm = M.vel + 3 * (size_t)m;
+                        lamp = sk_perceived(lam_ray, pkx, pky, pkz, __ldg(vm), __ldg(vm + 1), __ldg(vm + 2));
+                        const int il = sk_locate_clip_hint(M.lam_border, M.nlam, lamp, ilam_ray);
+                        if (il != ilam_ray)
+                        {
+                            ilam_ray = il;
+                            SK_LOAD_SECTIONS();
+                        }
+                        kappa = section * dens;
+                    }
+                    if (more_media && m != mpre) SK_FETCH_DENSX();  // (the Voronoi walk may re-locate its cell inside exit())
                     kappa = __fma_rn(sec1, dn1, kappa);
                     const double* __restrict__ sigx = multi_explicit ? M.sig_sca : M.sig_ext;
 #pragma unroll 1
@@ -633,6 +672,21 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, (GRID == 3   ? SK_TRACE_MINBLO
                             const double extEnd = exp(lnEnd);
                             const double extMean = sk_lnmean4(extEnd, extBeg, lnEnd, lnBeg);
                             const double Lds = lum * extMean * ds;
+                            if (kin)
+                            {
+                                if (m >= 0)
+                                {
+                                    const SkDevWlg& wg = M.wlg[M.rf_grid];
+                                    rf_lo = sk_wlg_upper_hint(wg, lamp, rf_lo);
+                                    const int ell = wg.ell[rf_lo];
+                                    if (ell >= 0)
+                                    {
+                                        atomicAdd(&rf[SK_RF_INDEX(M, m, ell)], (lum / lamp) * extMean * ds);
+                                        cnt.rf++;
+                                    }
+                                }
+                            }
+                            else
 #ifdef SK_RF_AGGREGATE
                             // (experiment, DESIGN.md section 9: lanes of the warp that deposit into the same cell and bin
                             //  are summed with shuffles and one lane issues the atomic)
@@ -718,6 +772,7 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, (GRID == 3   ? SK_TRACE_MINBLO
         } while (__popc(__ballot_sync(0xffffffffu, !(ls & ACTIVE))) < want_idle);
     }
     sk_flush_counters(M, cnt);
+#undef SK_LOAD_SECTIONS
 #undef SK_FETCH_DENSX
 }
 
@@ -784,6 +839,23 @@ __device__ __forceinline__ bool sk_peel_setup_values(const SkDevModel& M, const 
     const SkDevInstr& q0 = M.instr[j0];
     const double ox = q0.kobs[0], oy = q0.kobs[1], oz = q0.kobs[2];
     double peelW;
+    if (MULTI && M.kin)
+    {
+        // kinematics: `lambda` is the wavelength the interaction cell perceives (scattering) and the peel-off packet leaves
+        // Doppler-shifted for the direction towards the observer by the bulk velocity of the cell
+        // (PhotonPacket::launchScatteringPeelOff, PhotonPacket.cpp:89-103), or by the velocity of the emitter from the rest
+        // wavelength at emission (launchEmissionPeelOff, PhotonPacket.cpp:66-85)
+        const int kb = M.kin_base_d;
+        if (scattering)
+        {
+            const double* __restrict__ vm = M.vel + 3 * (size_t)(mint >= 0 ? mint : 0);
+            lambda = sk_shifted_emission(lambda, ox, oy, oz, mint >= 0 ? vm[0] : 0., mint >= 0 ? vm[1] : 0., mint >= 0 ? vm[2] : 0.);
+        }
+        else
+            lambda = sk_shifted_emission(K.D(kb + SK_KD_LAMBDA0, slot), ox, oy, oz, K.D(kb + SK_KD_VSX, slot),
+                                         K.D(kb + SK_KD_VSY, slot), K.D(kb + SK_KD_VSZ, slot));
+        K.D(kb + SK_KD_PLAMBDA, slot) = lambda;
+    }
     if (scattering)
     {
         double costheta = kx * ox + ky * oy + kz * oz;
@@ -823,7 +895,11 @@ __device__ __forceinline__ bool sk_peel_setup_values(const SkDevModel& M, const 
 __device__ __forceinline__ bool sk_peel_setup(const SkDevModel& M, const SkDevModel* __restrict__ Mg, const SkBank& K, int slot, int st,
                                               int j0, int j1)
 {
-    if (M.nmed > 1)
+    if (M.kin && (st & SK_ST_SCATTER))  // the wavelength the interaction cell perceives and its index (sk_wf_advance)
+        return sk_peel_setup_values<true>(M, Mg, K, slot, true, j0, j1, K.D(D_W, slot), K.D(M.kin_base_d + SK_KD_LAMP, slot),
+                                          K.D(D_RX, slot), K.D(D_RY, slot), K.D(D_RZ, slot), K.D(D_KX, slot), K.D(D_KY, slot),
+                                          K.D(D_KZ, slot), K.I(M.kin_base_i + SK_KI_ILAMP, slot), K.I(I_MINT, slot));
+    if (M.nmed > 1 || M.kin)
         return sk_peel_setup_values<true>(M, Mg, K, slot, (st & SK_ST_SCATTER) != 0, j0, j1, K.D(D_W, slot), K.D(D_LAMBDA, slot),
                                           K.D(D_RX, slot), K.D(D_RY, slot), K.D(D_RZ, slot), K.D(D_KX, slot), K.D(D_KY, slot),
                                           K.D(D_KZ, slot), K.I(I_ILAM, slot), (st & SK_ST_SCATTER) ? K.I(I_MINT, slot) : -1);
@@ -834,11 +910,13 @@ __device__ __forceinline__ bool sk_peel_setup(const SkDevModel& M, const SkDevMo
 
 // advance: the interaction that ends the previous round and, for the surviving packets, the peel-off set-up towards
 // the first observer group; free slots are collected for the launch kernel.
-#ifdef SK_ADVANCE_MINBLOCKS  // (tuning variants; by default the compiler's own choice for 256-thread blocks)
-#define SK_ADVANCE_BOUNDS __launch_bounds__(SK_EVENT_BLOCK, SK_ADVANCE_MINBLOCKS)
-#else
-#define SK_ADVANCE_BOUNDS __launch_bounds__(SK_EVENT_BLOCK)
+// (five resident blocks of 256 threads = 48 registers for the single-medium instantiation: what the compiler chose on its own
+//  for the kernels profiled in DESIGN.md section 9, and measured level with the alternatives there; pinned so that unrelated
+//  changes of the model structure do not flip the choice)
+#ifndef SK_ADVANCE_MINBLOCKS
+#define SK_ADVANCE_MINBLOCKS (MULTI ? 4 : 5)
 #endif
+#define SK_ADVANCE_BOUNDS __launch_bounds__(SK_EVENT_BLOCK, SK_ADVANCE_MINBLOCKS)
 template <int GRID, bool MULTI>
 __global__ void SK_ADVANCE_BOUNDS sk_wf_advance(const SkDevModel M, const SkRunArgs A, const SkBank K,
                                                                  const int j0, const int j1)
@@ -862,6 +940,8 @@ __global__ void SK_ADVANCE_BOUNDS sk_wf_advance(const SkDevModel M, const SkRunA
     const double lambda = K.D(D_LAMBDA, sl), lthr = K.D(D_LTHR, sl);
     bool survivor = false;
     double W = W0, x = rx0, y = ry0, z = rz0;
+    double lamp = lambda;  // kinematics: wavelength perceived by the interaction cell, and its index in the dust tables
+    int ilamp = ilam;
 
     // ---- the interaction: albedo weight, move, termination test (.cpp:724-741, 576-580)
     if (st & SK_ST_LIVE)
@@ -875,13 +955,21 @@ __global__ void SK_ADVANCE_BOUNDS sk_wf_advance(const SkDevModel M, const SkRunA
         {
             // MediumSystem::albedoForScattering, MediumSystem.cpp:678-693
             double albedo = 0.;
+            if (MULTI && M.kin)
+            {
+                // the wavelength the interaction cell perceives (MediumSystem::perceivedWavelengthForScattering,
+                // MediumSystem.cpp:667-674): albedo, peel-off weights and the scattering itself use it
+                const double* __restrict__ vm = M.vel + 3 * (size_t)(m >= 0 ? m : 0);
+                lamp = m >= 0 ? sk_perceived(lambda, kx, ky, kz, vm[0], vm[1], vm[2]) : lambda;
+                ilamp = sk_locate_clip_hint(M.lam_border, M.nlam, lamp, ilam);
+            }
             if (m >= 0)
             {
                 double dn = sk_cell_density<GRID>(M, m);
                 double ksca = dn * M.sig_sca[ilam];
                 double kext = dn * sigext;
                 albedo = kext > 0. ? ksca / kext : 0.;
-                if (MULTI) albedo = sk_albedo_media(Mg, m, ilam);
+                if (MULTI) albedo = sk_albedo_media(Mg, m, ilamp);
             }
             if (forced)
             {
@@ -944,6 +1032,11 @@ __global__ void SK_ADVANCE_BOUNDS sk_wf_advance(const SkDevModel M, const SkRunA
                 st = SK_ST_LIVE | SK_ST_SCATTER;
                 K.I(I_STATE, slot) = st;
                 survivor = true;
+                if (MULTI && M.kin)
+                {
+                    K.D(M.kin_base_d + SK_KD_LAMP, slot) = lamp;
+                    K.I(M.kin_base_i + SK_KI_ILAMP, slot) = ilamp;
+                }
             }
         }
         if (!alive)
@@ -959,7 +1052,7 @@ __global__ void SK_ADVANCE_BOUNDS sk_wf_advance(const SkDevModel M, const SkRunA
     sk_block_append(K.free_list, &K.ctl[SK_CTL_NFREE], valid && !live, slot, &K.ctl[SK_CTL_NLIVE], live);
     if (A.peel && j1 > j0)
     {
-        bool need = survivor && sk_peel_setup_values<MULTI>(M, Mg, K, slot, true, j0, j1, W, lambda, x, y, z, kx, ky, kz, ilam, m);
+        bool need = survivor && sk_peel_setup_values<MULTI>(M, Mg, K, slot, true, j0, j1, W, lamp, x, y, z, kx, ky, kz, ilamp, m);
         sk_block_append(K.list, &K.ctl[SK_CTL_NLIST], need, slot);
     }
 }
@@ -994,6 +1087,14 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK, SK_LAUNCH_MINBLOCKS) sk_wf_lau
                 sk_launch_primary(Mg, g, history, pp);
             else
                 sk_launch_secondary<GRID>(Mg, T, g, history, pp);
+            const double lambda0 = pp.lambda;
+            if (M.kin)
+            {
+                // PhotonPacket::launch with a velocity interface (PhotonPacket.cpp:33): the wavelength is Doppler-shifted for
+                // the launch direction, the weight keeps the rest wavelength
+                pp.lambda = sk_shifted_emission(lambda0, pp.kx, pp.ky, pp.kz, pp.vx, pp.vy, pp.vz);
+                pp.ilam = sk_locate_clip_hint(M.lam_border, M.nlam, pp.lambda, pp.ilam);
+            }
             if (pp.W / pp.lambda > 0)  // MonteCarloSimulation.cpp:553
             {
                 SkCellPos c;
@@ -1037,6 +1138,14 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK, SK_LAUNCH_MINBLOCKS) sk_wf_lau
                         K.I(M.pix_base_i + ps * SK_PIX_INTS + SK_PIX_K + 1, slot) = -1;
                     }
                 }
+                if (M.kin)
+                {
+                    const int kb = M.kin_base_d;
+                    K.D(kb + SK_KD_LAMBDA0, slot) = lambda0;
+                    K.D(kb + SK_KD_VSX, slot) = pp.vx;
+                    K.D(kb + SK_KD_VSY, slot) = pp.vy;
+                    K.D(kb + SK_KD_VSZ, slot) = pp.vz;
+                }
                 K.I(I_STATE, slot) = SK_ST_LIVE;
                 live = true;
             }
@@ -1063,6 +1172,8 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_peel_setup(const SkDevMo
 // pending scattering events -- MediumSystem::simulateScattering (MediumSystem.cpp:796-823) + DustMix::performScattering
 // HG branch (DustMix.cpp:496-511) -- and the list of forward rays.  Persistent grid-stride kernel: each block keeps the
 // SED arrays of the group in shared memory (nl_stride > 0) and adds them to the global arrays once at its end.
+// (KIN: the instantiation for runs with kinematics, so that the other keeps its registers)
+template <bool KIN>
 __global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_detect(const SkDevModel M, const SkRunArgs A, const SkBank K,
                                                                 const int j0, const int j1, const int last,
                                                                 const int nl_stride)
@@ -1085,7 +1196,7 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_detect(const SkDevModel 
             int nscatt = 0;
             if (live)
             {
-                lambda = K.D(D_LAMBDA, slot);
+                lambda = KIN ? K.D(M.kin_base_d + SK_KD_PLAMBDA, slot) : K.D(D_LAMBDA, slot);  // of the peel-off packet
                 x = K.D(D_RX, slot);
                 y = K.D(D_RY, slot);
                 z = K.D(D_RZ, slot);
@@ -1122,8 +1233,10 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_detect(const SkDevModel 
                 SkRng g;
                 sk_rng_load(g, M, A, K, slot);
                 int hsel = 0;
-                if (M.nmed > 1) hsel = sk_scattering_component(A.model, K.I(I_MINT, slot), K.I(I_ILAM, slot), sk_uniform(g));
-                double gp = M.gpar[hsel * M.nlam + K.I(I_ILAM, slot)];
+                // (kinematics: the index of the wavelength the interaction cell perceives, MediumSystem.cpp:802)
+                const int ilam_s = KIN ? K.I(M.kin_base_i + SK_KI_ILAMP, slot) : K.I(I_ILAM, slot);
+                if (M.nmed > 1) hsel = sk_scattering_component(A.model, K.I(I_MINT, slot), ilam_s, sk_uniform(g));
+                double gp = M.gpar[hsel * M.nlam + ilam_s];
                 double kx = K.D(D_KX, slot), ky = K.D(D_KY, slot), kz = K.D(D_KZ, slot);
                 if (fabs(gp) < 1e-6)
                     sk_random_direction(g, kx, ky, kz);
@@ -1140,6 +1253,20 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_detect(const SkDevModel 
                 K.D(D_IKX, slot) = sk_dir_recip(kx, lattice ? M.lat_h[0] : 1.);
                 K.D(D_IKY, slot) = sk_dir_recip(ky, lattice ? M.lat_h[1] : 1.);
                 K.D(D_IKZ, slot) = sk_dir_recip(kz, lattice ? M.lat_h[2] : 1.);
+                if (KIN)
+                {
+                    // PhotonPacket::scatter(bfk, bfv, lambda), PhotonPacket.cpp:115-122: the packet leaves at the perceived
+                    // wavelength, shifted by the bulk velocity of the cell for its new direction
+                    const int mint = K.I(I_MINT, slot);
+                    const double* __restrict__ vm = M.vel + 3 * (size_t)(mint >= 0 ? mint : 0);
+                    const double lnew = sk_shifted_emission(K.D(M.kin_base_d + SK_KD_LAMP, slot), kx, ky, kz, mint >= 0 ? vm[0] : 0.,
+                                                            mint >= 0 ? vm[1] : 0., mint >= 0 ? vm[2] : 0.);
+                    const int inew = sk_locate_clip_hint(M.lam_border, M.nlam, lnew, ilam_s);
+                    K.D(D_LAMBDA, slot) = lnew;
+                    K.I(I_ILAM, slot) = inew;
+                    K.D(D_SIGEXT, slot) = M.sig_ext[inew];
+                    if (M.rf_grid >= 0) K.I(I_RFELL, slot) = sk_wlg_bin(M.wlg[M.rf_grid], lnew);
+                }
                 // the deviates of the interaction that follows this scattering (simulateForcedPropagation is the next to draw)
                 if (M.force_scattering) K.D(D_TAUINT, slot) = sk_predraw_interaction(g, M.path_length_bias);
                 K.I(I_DRAW, slot) = (int)g.draw;

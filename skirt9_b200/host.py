@@ -390,13 +390,80 @@ class MeanListDustMix:
         return self.sigma_abs[i] + self.sigma_sca[i]
 
 
-class GeometricMedium:
-    """GeometricMedium.cpp:14-20 with OpticalDepthMaterialNormalization (axis Z), .cpp:12-31."""
+class _PowerLawVectorField:
+    """Common part of RadialVectorField / CylindricalVectorField: a unit vector times (r/unityRadius)^exponent inside
+    (exponent > 0) or outside (exponent < 0) the unity radius, 1 elsewhere; null on the axis / at the origin."""
+    kind = abi.SK_VEL_NONE
 
-    def __init__(self, geometry, materialMix, opticalDepth, wavelength):
+    def __init__(self, unityRadius=0.0, exponent=0.0):
+        self.unityRadius, self.exponent = unityRadius, exponent
+
+    def _unit(self, r):
+        raise NotImplementedError
+
+    def vector(self, r):
+        r = np.atleast_2d(np.asarray(r, dtype=float))
+        u = self._unit(r)
+        rr = np.sqrt((u * u).sum(axis=1))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            u = np.where(rr[:, None] > 0, u / rr[:, None], 0.0)
+            f = np.ones_like(rr)
+            if self.unityRadius > 0:
+                sel = (rr < self.unityRadius) if self.exponent > 0 else (rr > self.unityRadius) if self.exponent < 0 \
+                    else np.zeros_like(rr, dtype=bool)
+                f = np.where(sel & (rr > 0), (rr / self.unityRadius) ** self.exponent, 1.0)
+        return f[:, None] * u
+
+    def source_fields(self, magnitude):
+        return {"velocity_kind": self.kind, "velocity": (magnitude, self.unityRadius, self.exponent)}
+
+
+class RadialVectorField(_PowerLawVectorField):
+    """RadialVectorField.cpp:19-37."""
+    kind = abi.SK_VEL_RADIAL
+
+    def _unit(self, r):
+        return r.copy()
+
+
+class CylindricalVectorField(_PowerLawVectorField):
+    """CylindricalVectorField.cpp:19-38: rotation about the z axis."""
+    kind = abi.SK_VEL_CYLINDRICAL
+
+    def _unit(self, r):
+        return np.stack([-r[:, 1], r[:, 0], np.zeros(len(r))], axis=1)
+
+
+class UnidirectionalVectorField:
+    """UnidirectionalVectorField: the same unit vector everywhere."""
+
+    def __init__(self, x=0.0, y=0.0, z=1.0):
+        n = math.sqrt(x * x + y * y + z * z)
+        self.u = (x / n, y / n, z / n)
+
+    def vector(self, r):
+        r = np.atleast_2d(np.asarray(r, dtype=float))
+        return np.tile(np.array(self.u), (len(r), 1))
+
+    def source_fields(self, magnitude):
+        return {"velocity_kind": abi.SK_VEL_CONSTANT, "velocity": tuple(magnitude * c for c in self.u)}
+
+
+class GeometricMedium:
+    """GeometricMedium.cpp:14-20 with OpticalDepthMaterialNormalization (axis Z), .cpp:12-31; optionally with a bulk velocity
+    velocityMagnitude * velocityDistribution(r) (GeometricMedium.cpp:51-68)."""
+
+    def __init__(self, geometry, materialMix, opticalDepth, wavelength, velocityMagnitude=0.0, velocityDistribution=None):
         self.geometry, self.mix = geometry, materialMix
         self.tau, self.norm_wavelength = opticalDepth, wavelength
         self.number = None
+        self.velocityMagnitude, self.velocityDistribution = velocityMagnitude, velocityDistribution
+
+    def has_velocity(self):
+        return self.velocityDistribution is not None and self.velocityMagnitude != 0
+
+    def bulk_velocity(self, r):
+        return self.velocityMagnitude * self.velocityDistribution.vector(r)
 
     def setup(self):
         section = float(self.mix.section_ext(self.norm_wavelength))
@@ -835,9 +902,16 @@ class PointSource:
     luminosity: float  # IntegratedLuminosityNormalization over the source range (W)
     sourceWeight: float = 1.0
     wavelengthBias: float = 0.5
+    velocity: Optional[Sequence[float]] = None  # SpecialtySource velocityX/Y/Z (m/s)
+
+    def has_velocity(self):
+        return self.velocity is not None and any(self.velocity)
 
     def fields(self):
-        return {"kind": abi.SK_SRC_POINT, "position": tuple(self.position)}
+        d = {"kind": abi.SK_SRC_POINT, "position": tuple(self.position)}
+        if self.has_velocity():
+            d.update({"velocity_kind": abi.SK_VEL_CONSTANT, "velocity": tuple(self.velocity)})
+        return d
 
 
 @dataclass
@@ -847,10 +921,17 @@ class GeometricSource:
     luminosity: float
     sourceWeight: float = 1.0
     wavelengthBias: float = 0.5
+    velocityMagnitude: float = 0.0  # GeometricSource::velocityMagnitude / velocityDistribution
+    velocityDistribution: object = None
+
+    def has_velocity(self):
+        return self.velocityDistribution is not None and self.velocityMagnitude != 0
 
     def fields(self):
         d = {"kind": abi.SK_SRC_GEOMETRIC}
         d.update(self.geometry.source_fields())
+        if self.has_velocity():
+            d.update(self.velocityDistribution.source_fields(self.velocityMagnitude))
         return d
 
 
@@ -979,6 +1060,17 @@ class MonteCarloSimulation:
             a, b = g.wavelength_range()
             lo, hi = min(lo, a), max(hi, b)
             extra += list(g.lambdav)
+        # kinematics (Configuration.cpp:81, 320, 573): a wide margin for Doppler shifts
+        self.hasMovingMedia = any(getattr(md, "has_velocity", lambda: False)() for md in self.media)
+        self.hasMovingSources = any(s.has_velocity() for s in self.sources)
+        if (self.hasMovingMedia or self.hasMovingSources) and oligo:
+            raise ValueError("velocities are refused in oligochromatic simulations (GeometricMedium.cpp:55-60)")
+        if self.hasMovingSources or self.hasMovingMedia:
+            lo0, hi0 = self.source_range
+            if self.dustEmissionWLG is not None:
+                a, b = self.dustEmissionWLG.wavelength_range()
+                lo0, hi0 = min(lo0, a), max(hi0, b)
+            lo, hi = min(lo, lo0 / (1.0 + 1.0 / 3.0)), max(hi, hi0 * (1.0 + 1.0 / 3.0))
         if self.storeRadiationField and not oligo:
             lo, hi = min(lo, 0.09e-6), max(hi, 2000e-6)
         lo, hi = lo / 1.01, hi * 1.01
@@ -1049,10 +1141,26 @@ class MonteCarloSimulation:
                     dens[h] += md.number_density(p[:, 0], p[:, 1], p[:, 2])
             dens /= self.numDensitySamples
         self.density = dens if self.extraMedia else dens[0]
+        self.velocity = None
+        if self.hasMovingMedia:
+            # MediumSystem.cpp:330-365 with numPropertySamples = 1 and AggregatePolicy::Average: the number-density weighted
+            # mean of the components' bulk velocities at the central position of the cell; zero where there is no material
+            if boxes is None:
+                raise ValueError("moving media need a Cartesian or tree grid here (central positions of Voronoi cells are centroids)")
+            c = 0.5 * (boxes[:, :3] + boxes[:, 3:])
+            ntot = dens.sum(axis=0)
+            v = np.zeros((n, 3))
+            for h, md in enumerate(self.media):
+                if md.has_velocity():
+                    v += dens[h][:, None] * md.bulk_velocity(c)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                self.velocity = np.where(ntot[:, None] > 0, v / ntot[:, None], 0.0)
         return self
 
     def config_struct(self, device=0):
         xi = self.pathLengthBias if self.forceScattering else 0.0  # Configuration.cpp:497-504
+        if getattr(self, "hasMovingMedia", False):
+            xi = 0.0  # "Disabling path length stretching to allow Doppler shifts to be properly sampled", Configuration.cpp:492-498
         force = self.forceScattering or self.storeRadiationField   # Configuration.cpp:476-482
         return abi.SkConfig(self.seed, int(force), self.minScattEvents, xi, self.minWeightReduction, device,
                             int(self.explicitAbsorption))
@@ -1101,6 +1209,8 @@ class MonteCarloSimulation:
                 engine.set_media(self.density, self.volume)
             else:
                 engine.set_medium(self.density, self.volume)
+        if getattr(self, "velocity", None) is not None:
+            engine.set_velocities(self.velocity)
         mark("medium")
         mix = self.medium.mix
         if self.extraMedia:

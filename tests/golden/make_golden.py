@@ -380,6 +380,27 @@ def make_cfg13p():
     print("cfg13p:", {k: np.shape(v) for k, v in out.items()})
 
 
+def make_cfg15k():
+    """Kinematics: a moving point source with a narrow emission feature in an expanding dust shell, dust emission without
+    iterations (tests/golden/ski/cfg15k.ski).  Three SED instruments (two opposite lines of sight along the source's velocity
+    with a fine wavelength grid around the feature, one on the default grid), the radiation field on a grid that is fine around
+    the feature (volume-weighted in 16 radial shells), the dust luminosity from the log."""
+    with tempfile.TemporaryDirectory() as d:
+        log = run_reference("cfg15k", d)
+        cells = read_columns(os.path.join(d, "cfg15k_cells_cellprops.dat"))
+        rfJ = read_columns(os.path.join(d, "cfg15k_rf_J.dat"))
+        out = dict(mass_density_msun_pc3=cells[:, 6], cell_center_pc=cells[:, 1:4], cell_volume_pc3=cells[:, 4],
+                   J_nu_shell=shell_average(cells, rfJ[:, 1:], nshell=16),
+                   rf_wavelengths_micron=read_columns(os.path.join(d, "cfg15k_rf_wavelengths.dat"))[:, 0],
+                   dust_luminosity_lsun=float(re.search(r"Dust luminosity: ([0-9.eE+-]+) Lsun", log).group(1)),
+                   num_packets=1e6)
+        for name in ("fwd", "bwd", "sed"):
+            out["sed_" + name] = read_columns(os.path.join(d, "cfg15k_%s_sed.dat" % name))
+            out["sedstats_" + name] = read_columns(os.path.join(d, "cfg15k_%s_sedstats.dat" % name))
+    np.savez_compressed(os.path.join(HERE, "cfg15k_ref.npz"), **out)
+    print("cfg15k:", {k: np.shape(v) for k, v in out.items()}, out["dust_luminosity_lsun"])
+
+
 if __name__ == "__main__":
     if not os.path.exists(SKIRT):
         raise SystemExit("oracle/_ref is not built: run `make -C oracle -f ref.mk -j8` where /root/reference exists")

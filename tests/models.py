@@ -184,3 +184,24 @@ def with_second_component(sim, kind="disk"):
         geom = H.ShellGeometry(0.2 * scale, 0.9 * scale, 0.0)
     sim.extraMedia = [H.GeometricMedium(geom, mix2, opticalDepth=0.5 * sim.medium.tau, wavelength=sim.medium.norm_wavelength)]
     return sim
+
+
+def with_kinematics(sim, source=True, media=True, speed=6e6):
+    """Gives a panchromatic model moving sources and / or moving media (PhotonPacket.cpp:133-151; Configuration::
+    hasMovingSources / hasMovingMedia): the first medium component expands radially, a second one rotates about the z axis;
+    a point source moves along a fixed direction, a geometric source expands.  `speed` of 6e6 m/s = 0.02 c shifts a wavelength
+    over two dozen points of the dust property tables (1000 per dex)."""
+    pc = H.PC
+    scale = abs(sim.grid.extent[3]) if hasattr(sim.grid, "extent") else pc
+    if media:
+        for h, md in enumerate(sim.media):
+            md.velocityMagnitude = speed * (1.0 if h == 0 else -0.7)
+            md.velocityDistribution = H.RadialVectorField(scale, 1.0) if h == 0 else H.CylindricalVectorField(0.3 * scale, -0.5)
+    if source:
+        for s in sim.sources:
+            if isinstance(s, H.PointSource):
+                s.velocity = (0.8 * speed, -0.5 * speed, 0.3 * speed)
+            else:
+                s.velocityMagnitude = 0.6 * speed
+                s.velocityDistribution = H.RadialVectorField(0.5 * scale, 0.5)
+    return sim

@@ -26,7 +26,7 @@ def test_engine_library_exports_every_declared_symbol():
     for n in declared_symbols():
         assert hasattr(lib, n), n
     lib.sk_abi_version.restype = ctypes.c_int
-    assert lib.sk_abi_version() == 5
+    assert lib.sk_abi_version() == 6
 
 
 def test_struct_sizes_match_the_c_header():

@@ -636,3 +636,102 @@ def test_engine_matches_reference_cfg5s_voronoi(engine_lib):
     e = sim.configure(abi.Engine(sim.config_struct(device=0), lib=engine_lib))
     sim.run(e)
     check_cfg5s(sim, e, g, n)
+
+
+# ---------------------------------------------------------------- kinematics: moving source, expanding dust shell (cfg15k)
+def cfg15k_from_reference(num_packets):
+    """tests/golden/ski/cfg15k.ski through the host mirror: a point source moving at 6000 km/s along +x with a narrow
+    emission feature, a dust shell expanding at 9000 km/s x r/pc, dust emission without iterations."""
+    import re
+    g = load("cfg15k")
+    pc = H.PC
+    ski = open(os.path.join(GOLD, "ski", "cfg15k.ski")).read()
+    rfw = [float(x) * 1e-6 for x in re.findall(r"([0-9.]+) micron", re.search(r'<ListWavelengthGrid wavelengths="([^"]*)"', ski).group(1))]
+    mix = H.MeanListDustMix([0.05e-6, 0.55e-6, 10e-6, 100e-6, 2000e-6], [5000.0, 1000.0, 100.0, 5.0, 0.01],
+                            [0.4, 0.6, 0.2, 0.01, 0.0001], [0.6, 0.5, 0.05, 0.0, 0.0])
+    medium = H.GeometricMedium(H.ShellGeometry(0.05 * pc, 1.0 * pc, 1.0), mix, opticalDepth=3.0, wavelength=0.55e-6,
+                               velocityMagnitude=9e6, velocityDistribution=H.RadialVectorField(1.0 * pc, 1.0))
+    grid = H.CartesianSpatialGrid(-pc, pc, -pc, pc, -pc, pc, 16, 16, 16)
+    sed = H.ListSED([0.2e-6, 0.499e-6, 0.5e-6, 0.51e-6, 0.511e-6, 2e-6], [0.02, 0.02, 1.0, 1.0, 0.02, 0.02])
+    src = H.PointSource((0.0, 0.0, 0.0), sed, luminosity=1e4 * H.LSUN, velocity=(6e6, 0.0, 0.0))
+    fine = H.LogWavelengthGrid(0.46e-6, 0.56e-6, 40)
+    kw = dict(distance=1e6 * pc, recordComponents=True, recordStatistics=True)
+    instr = [H.SEDInstrument(instrumentName="fwd", inclination=90 * DEG, azimuth=0.0, wavelengthGrid=fine, **kw),
+             H.SEDInstrument(instrumentName="bwd", inclination=90 * DEG, azimuth=180 * DEG, wavelengthGrid=fine, **kw),
+             H.SEDInstrument(instrumentName="sed", inclination=60 * DEG, azimuth=30 * DEG, **kw)]
+    sim = H.MonteCarloSimulation(sources=[src], medium=medium, grid=grid, instruments=instr, numPackets=num_packets,
+                                 minWavelength=0.2e-6, maxWavelength=2e-6,
+                                 defaultWavelengthGrid=H.LogWavelengthGrid(0.1e-6, 1000e-6, 40), storeRadiationField=True,
+                                 radiationFieldWLG=H.ListWavelengthGrid(rfw), dustEmissionWLG=H.LogWavelengthGrid(1e-6, 1000e-6, 40),
+                                 iterateSecondaryEmission=False, numDensitySamples=20, seed=0)
+    sim.density = g["mass_density_msun_pc3"] * RHO / mix.MU
+    sim.setup()
+    np.testing.assert_allclose(sim.radiationFieldWLG.lambdav * 1e6, g["rf_wavelengths_micron"], rtol=1e-6)
+    assert sim.config_struct().path_length_bias == 0.0   # Configuration.cpp:492-498
+    return sim, g
+
+
+DEG = math.pi / 180.0
+
+
+def check_cfg15k(sim, e, g, n, nsigma=4.0, min_reliable=0.7):
+    from tests import mcstats
+    LSUN = H.LSUN
+    assert sim.dust_luminosity / LSUN == pytest.approx(float(g["dust_luminosity_lsun"]), rel=0.01)
+    worst = 0.0
+    for j, name in enumerate(("fwd", "bwd", "sed")):
+        sed, ref = g["sed_" + name], g["sedstats_" + name][:, 1:].T
+        own = e.read_sed_stats(j)
+        # (N of FluxRecorder.hpp:50-63: the packets launched in the two peel-off segments, primary and secondary emission)
+        n_own, n_ref = 2.0 * n, 2.0 * float(g["num_packets"])
+        ok = mcstats.reliable(own, launched=n_own) & mcstats.reliable(ref, launched=n_ref)
+        assert ok.sum() >= min_reliable * len(ok), (name, int(ok.sum()))
+        sigma = np.hypot(mcstats.rel_error(own, n_own), mcstats.rel_error(ref, n_ref))
+        for col, comp in ((1, abi.SK_COMP_TOTAL), (2, abi.SK_COMP_TRANSPARENT), (3, abi.SK_COMP_PRIMARY_DIRECT),
+                          (4, abi.SK_COMP_PRIMARY_SCATTERED), (5, abi.SK_COMP_SECONDARY_DIRECT),
+                          (6, abi.SK_COMP_SECONDARY_SCATTERED), (7, abi.SK_COMP_SECONDARY_TRANSPARENT)):
+            f = sim.sed_flux_density(e, j, comp)
+            scale = np.maximum(sed[:, col], sed[:, 1])
+            z = (np.abs(f - sed[:, col]) / np.maximum(sigma * scale, 1e-300))[ok]
+            # (dust emission columns: the statistics do not know the noise of the radiation field behind the temperatures)
+            ns = nsigma if col <= 4 else nsigma + 2.0
+            assert np.all(z <= ns), (name, comp, int(np.argmax(z)), float(z.max()))
+            worst = max(worst, float(z.max()))
+    # the Doppler shifts themselves: the direct light of the feature (0.5-0.51 micron at rest) arrives blue-shifted by 2 % on
+    # the line of sight the source approaches and red-shifted on the opposite one
+    lam = sim.instruments[0].wavelengthGrid.lambdav
+    for j, factor in ((0, 1.0 - 6e6 / H.C_LIGHT), (1, 1.0 + 6e6 / H.C_LIGHT)):
+        d = e.read_sed(j, abi.SK_COMP_TRANSPARENT)
+        d = np.where(d > 0.5 * d.max(), d, 0.0)   # (the bins of the feature, without the continuum under it)
+        centre = float((d * lam).sum() / d.sum())
+        assert centre == pytest.approx(0.505e-6 * factor, rel=3e-3), (j, centre)
+    # radiation field per shell and bin of the grid that resolves the feature, against the reference's own run
+    J = sim.mean_intensity_nu(e, 0)
+    r = np.linalg.norm(g["cell_center_pc"], axis=1)
+    V = g["cell_volume_pc3"]
+    k = np.minimum((r / (1.0 / 16)).astype(int), 15)
+    num = np.stack([np.bincount(k, weights=V * J[:, ell], minlength=16) for ell in range(J.shape[1])], axis=1)
+    Jshell = num / np.bincount(k, weights=V, minlength=16)[:, None]
+    ref = g["J_nu_shell"]
+    ok = ref > 0.02 * ref.max()
+    ok[:2] = False
+    tol = 0.05 * math.hypot(1.0, math.sqrt(float(g["num_packets"]) / n))
+    np.testing.assert_allclose(Jshell[ok], ref[ok], rtol=tol)
+    return worst
+
+
+def test_oracle_matches_reference_cfg15k_kinematics():
+    n = 100000
+    sim, g = cfg15k_from_reference(n)
+    e = sim.configure(OracleEngine(sim.config_struct()))
+    sim.run(e)
+    check_cfg15k(sim, e, g, n, nsigma=5.0, min_reliable=0.25)
+
+
+@pytest.mark.gpu
+def test_engine_matches_reference_cfg15k_kinematics(engine_lib):
+    n = 2000000
+    sim, g = cfg15k_from_reference(n)
+    e = sim.configure(abi.Engine(sim.config_struct(device=0), lib=engine_lib))
+    sim.run(e)
+    check_cfg15k(sim, e, g, n)

@@ -3,6 +3,7 @@ import numpy as np
 import pytest
 
 from skirt9_b200 import abi
+from skirt9_b200 import host as H
 from tests import models
 from tests.oracle_lib import OracleEngine
 
@@ -395,3 +396,95 @@ def test_three_components_octree_with_explicit_absorption(engine_lib):
     sim.explicitAbsorption = True
     gpu, cpu = run_both(sim, engine_lib)
     models.compare_engines(sim, gpu, cpu)
+
+
+# ---------------------------------------------------------------- kinematics (sk_engine_set_velocities, moving sources)
+@pytest.mark.parametrize("force", [True, False])
+def test_kinematics_cartesian_two_sources(engine_lib, force):
+    """Moving point and shell sources in an expanding medium on the ragged Cartesian grid: per-cell perceived wavelengths for
+    the optical depths and (forced) the radiation field, Doppler shifts at launch, scattering and peel-off."""
+    sim = models.with_kinematics(models.two_sources_three_instruments(num_packets=20000, force=force))
+    if force:
+        sim.radiationFieldWLG = H.LogWavelengthGrid(0.15e-6, 8e-6, 120)   # bins of 3 %: the shifts cross them
+    gpu, cpu = run_both(sim, engine_lib)
+    models.compare_engines(sim, gpu, cpu)
+    assert gpu.counters()["scatterings"] > 0
+
+
+def test_kinematics_velocity_table_at_rest_equals_the_static_engine(engine_lib):
+    """A velocity table of zeros sends the run through the kernels with per-cell look-ups; the tallies must be those of the
+    single-medium kernels."""
+    sim = models.small_octree(num_packets=20000, record_statistics=True)
+    sim.setup()
+    a = sim.configure(abi.Engine(sim.config_struct(device=0), lib=engine_lib))
+    b = sim.configure(abi.Engine(sim.config_struct(device=0), lib=engine_lib))
+    b.set_velocities(np.zeros((sim.grid.num_cells, 3)))
+    sim.run(a)
+    sim.run(b)
+    models.compare_engines(sim, a, b, rtol=1e-11)
+
+
+def test_kinematics_octree_moving_source_only(engine_lib):
+    """Only the source moves (Configuration::hasMovingSources): the engine makes up the table of velocities at rest."""
+    sim = models.with_kinematics(models.small_octree(num_packets=20000, record_statistics=True), media=False)
+    gpu, cpu = run_both(sim, engine_lib)
+    models.compare_engines(sim, gpu, cpu)
+
+
+def test_kinematics_octree_ring_source_with_radiation_field(engine_lib):
+    sim = models.with_kinematics(models.tabulated_sed_ring_source_high_g(num_packets=20000))
+    sim.radiationFieldWLG = H.LogWavelengthGrid(0.15e-6, 8e-6, 80)
+    gpu, cpu = run_both(sim, engine_lib)
+    models.compare_engines(sim, gpu, cpu)
+
+
+def test_kinematics_dust_emission_iterations(engine_lib):
+    """Dust cells emit with their bulk velocity (DustSecondarySource.cpp:562-580); the radiation field of the secondary
+    segments is binned at the perceived wavelengths too."""
+    sim = models.with_kinematics(models.small_dust_emission(num_packets=20000))
+    gpu, cpu = run_both(sim, engine_lib)
+    models.compare_engines(sim, gpu, cpu)
+    assert len(sim.convergence) >= 1
+
+
+@pytest.mark.parametrize("force", [True, False])
+def test_kinematics_two_components_with_explicit_absorption(engine_lib, force):
+    sim = models.with_second_component(models.two_sources_three_instruments(num_packets=15000, force=force), kind="shell")
+    sim = models.with_kinematics(sim)
+    sim.explicitAbsorption = True
+    gpu, cpu = run_both(sim, engine_lib)
+    models.compare_engines(sim, gpu, cpu)
+
+
+def test_kinematics_single_component_with_explicit_absorption(engine_lib):
+    sim = models.with_kinematics(models.small_octree(num_packets=15000))
+    sim.explicitAbsorption = True
+    gpu, cpu = run_both(sim, engine_lib)
+    models.compare_engines(sim, gpu, cpu)
+
+
+def test_kinematics_voronoi(engine_lib):
+    """Velocities per Voronoi cell handed over directly (the host mirror computes them for box-shaped cells only)."""
+    sim = models.small_voronoi(num_packets=15000)
+    sim.setup()
+    rng = np.random.default_rng(4)
+    sim.velocity = rng.normal(0.0, 3e6, size=(sim.grid.num_cells, 3))
+    gpu = sim.configure(abi.Engine(sim.config_struct(device=0), lib=engine_lib))
+    cpu = sim.configure(OracleEngine(sim.config_struct()))
+    sim.run(gpu)
+    sim.run(cpu)
+    models.compare_engines(sim, gpu, cpu)
+
+
+def test_velocities_are_dropped_with_the_medium_state(engine_lib):
+    sim = models.small_cartesian(num_packets=2000)
+    sim.setup()
+    e = sim.configure(abi.Engine(sim.config_struct(device=0), lib=engine_lib))
+    with pytest.raises(abi.SkError):
+        e.set_velocities(np.zeros((sim.grid.num_cells + 1, 3)))
+    e.set_velocities(np.zeros((sim.grid.num_cells, 3)))
+    e.set_medium(sim.density, sim.volume)      # a new medium state is at rest
+    ref = sim.configure(abi.Engine(sim.config_struct(device=0), lib=engine_lib))
+    sim.run(e)
+    sim.run(ref)
+    models.compare_engines(sim, e, ref, rtol=1e-12)

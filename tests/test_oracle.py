@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 
 from skirt9_b200 import abi
+from skirt9_b200 import host as H
 from tests import models
 from tests.oracle_lib import OracleEngine, oracle_library
 
@@ -210,3 +211,62 @@ def test_voronoi_secondary_launch_positions_lie_in_their_cell():
     b = sim.grid.cell_extents[m_big]
     spread = (sel.max(axis=0) - sel.min(axis=0)) / (b[3:] - b[:3])
     assert np.all(spread > 0.5)   # the samples span the cell's box, not a corner of it
+
+
+# ---------------------------------------------------------------- kinematics (PhotonPacket.cpp:133-151)
+def _run_oracle(sim):
+    sim.setup()
+    e = sim.configure(OracleEngine(sim.config_struct()))
+    sim.run(e)
+    return e
+
+
+def test_kinematics_with_everything_at_rest_changes_nothing():
+    """A velocity table of zeros switches the per-cell look-ups on (the branches for spatially variable cross sections,
+    MediumSystem.cpp:888-900) without changing a single number: perceived wavelength = wavelength."""
+    a = _run_oracle(models.two_sources_three_instruments(num_packets=3000))
+    sim = models.two_sources_three_instruments(num_packets=3000)
+    sim.setup()
+    b = sim.configure(OracleEngine(sim.config_struct()))
+    b.set_velocities(np.zeros((sim.grid.num_cells, 3)))
+    sim.run(b)
+    models.compare_engines(sim, a, b, rtol=1e-13)
+
+
+def test_moving_source_shifts_the_observed_wavelengths():
+    """A point source receding from one observer and approaching the opposite one, no medium to speak of: the transparent
+    SEDs are the rest-frame SED shifted by -+ v/c; the luminosity W / lambda follows the shift."""
+    pc = H.PC
+    beta = 0.05
+    mix = H.MeanListDustMix([0.1e-6, 10e-6], [1000.0, 1000.0], [0.5, 0.5], [0.0, 0.0])
+    medium = H.GeometricMedium(H.ShellGeometry(0.1 * pc, 1.0 * pc, 0.0), mix, opticalDepth=1e-6, wavelength=0.55e-6)
+    grid = H.CartesianSpatialGrid(-pc, pc, -pc, pc, -pc, pc, 3, 3, 3)
+    sed = H.ListSED([0.3e-6, 0.499e-6, 0.5e-6, 0.52e-6, 0.521e-6, 0.9e-6], [1e-6, 1e-6, 1.0, 1.0, 1e-6, 1e-6])
+    src = H.PointSource((0.0, 0.0, 0.0), sed, luminosity=H.LSUN, velocity=(beta * H.C_LIGHT, 0.0, 0.0), wavelengthBias=0.0)
+    wlg = H.LogWavelengthGrid(0.4e-6, 0.65e-6, 200)
+    kw = dict(distance=1e6 * pc, inclination=math.pi / 2, recordComponents=True)
+    instr = [H.SEDInstrument(instrumentName="a", azimuth=0.0, **kw), H.SEDInstrument(instrumentName="b", azimuth=math.pi, **kw)]
+    sim = H.MonteCarloSimulation(sources=[src], medium=medium, grid=grid, instruments=instr, numPackets=20000,
+                                 minWavelength=0.3e-6, maxWavelength=0.9e-6, defaultWavelengthGrid=wlg, numDensitySamples=1, seed=2)
+    e = _run_oracle(sim)
+    for j, factor in ((0, 1.0 - beta), (1, 1.0 + beta)):
+        f = e.read_sed(j, abi.SK_COMP_TRANSPARENT)
+        centre = float((f * wlg.lambdav).sum() / f.sum())
+        assert centre == pytest.approx(0.51e-6 * factor, rel=2e-3)
+        # L = W / lambda with W = L0 lambda0: the detected luminosity is L0 / (1 -+ beta)
+        assert f.sum() == pytest.approx(H.LSUN / factor, rel=1e-2)
+
+
+@pytest.mark.parametrize("force", [True, False])
+def test_kinematics_conserve_the_bookkeeping(force):
+    """Moving sources and media on the two-source model: every launched packet is followed to its end, the counters obey the
+    identities of the life cycle, and the result differs from the model at rest (the look-ups really follow the shifts)."""
+    rest = _run_oracle(models.two_sources_three_instruments(num_packets=3000, force=force))
+    sim = models.with_kinematics(models.two_sources_three_instruments(num_packets=3000, force=force))
+    e = _run_oracle(sim)
+    c = e.counters()
+    assert c["packets"] == 3000
+    assert 0 < c["peel_paths"] <= 2 * (c["packets"] + c["scatterings"])   # two observer groups, apertures and frames cut
+    assert c["scatterings"] > 0 and c["detections"] > 0
+    assert abs(e.read_sed(0, abi.SK_COMP_TOTAL).sum() / rest.read_sed(0, abi.SK_COMP_TOTAL).sum() - 1.0) > 1e-6
+    assert sim.config_struct().path_length_bias == 0.0
