@@ -45,6 +45,7 @@
 #include "BlackBodySED.hpp"
 #include "CartesianSpatialGrid.hpp"
 #include "Configuration.hpp"
+#include "CylindricalVectorField.hpp"
 #include "DefaultWavelengthDistribution.hpp"
 #include "DensityTreePolicy.hpp"
 #include "DisjointWavelengthGrid.hpp"
@@ -68,6 +69,7 @@
 #include "PolicyTreeSpatialGrid.hpp"
 #include "ProbeSystem.hpp"
 #include "ProcessManager.hpp"
+#include "RadialVectorField.hpp"
 #include "Random.hpp"
 #include "RingGeometry.hpp"
 #include "SEDInstrument.hpp"
@@ -79,6 +81,7 @@
 #include "TabulatedSED.hpp"
 #include "TimeLogger.hpp"
 #include "TreeSpatialGrid.hpp"
+#include "UnidirectionalVectorField.hpp"
 #include "Units.hpp"
 #include "VoronoiMeshSnapshot.hpp"
 #include "VoronoiMeshSpatialGrid.hpp"
@@ -466,15 +469,57 @@ bool GpuLifeCycle::mediaShareOneMix() const
     return true;
 }
 
+namespace
+{
+    // GeometricSource::velocityMagnitude() * velocityDistribution()->vector(r) (GeometricSource.cpp:73-79) for the vector
+    // fields the engine evaluates at the launch position
+    bool fillVelocity(const GeometricSource* gs, sk_source_t& s)
+    {
+        auto field = gs->velocityDistribution();
+        if (auto u = dynamic_cast<const UnidirectionalVectorField*>(field))
+        {
+            Vec d = u->vector(Position());
+            s.velocity_kind = SK_VEL_CONSTANT;
+            s.velocity[0] = gs->velocityMagnitude() * d.x();
+            s.velocity[1] = gs->velocityMagnitude() * d.y();
+            s.velocity[2] = gs->velocityMagnitude() * d.z();
+            return true;
+        }
+        // (exact types only: a subclass may evaluate another field)
+        if (field->type() == "RadialVectorField")
+        {
+            auto r = dynamic_cast<const RadialVectorField*>(field);
+            s.velocity_kind = SK_VEL_RADIAL;
+            s.velocity[0] = gs->velocityMagnitude();
+            s.velocity[1] = r->unityRadius();
+            s.velocity[2] = r->exponent();
+            return true;
+        }
+        if (field->type() == "CylindricalVectorField")
+        {
+            auto c = dynamic_cast<const CylindricalVectorField*>(field);
+            s.velocity_kind = SK_VEL_CYLINDRICAL;
+            s.velocity[0] = gs->velocityMagnitude();
+            s.velocity[1] = c->unityRadius();
+            s.velocity[2] = c->exponent();
+            return true;
+        }
+        return false;
+    }
+}
+
 std::string GpuLifeCycle::unsupportedReason() const
 {
     auto config = _sim->_config;
     auto ms = _sim->mediumSystem();
     if (!config->hasMedium() || !ms) return "no medium";
-    if (!config->hasSingleConstantSectionMedium() && !config->hasMultipleConstantSectionMedia()) return "variable cross sections";
+    // moving media (and moving sources) run on the engine's path with per-cell perceived wavelengths (sk_engine_set_velocities);
+    // the other reasons for spatially variable cross sections do not
+    if (config->hasVariableMedia()) return "spatially variable material mixes";
+    if (config->hubbleExpansionRate()) return "Hubble flow";
+    if (!config->hasMovingMedia() && !config->hasSingleConstantSectionMedium() && !config->hasMultipleConstantSectionMedia())
+        return "variable cross sections";
     if (config->hasPolarization()) return "polarization";
-    if (config->hasMovingMedia()) return "moving media";
-    if (!config->hasConstantPerceivedWavelength()) return "wavelengths that change during the life cycle";
     if (config->hasDynamicState()) return "dynamic medium state";
     if (config->hasPrimaryIterations() || config->hasMergedIterations()) return "primary / merged iterations";
     if (config->hasGasEmission()) return "gas emission";
@@ -512,14 +557,13 @@ std::string GpuLifeCycle::unsupportedReason() const
         if (auto ps = dynamic_cast<PointSource*>(source))
         {
             if (ps->angularDistribution() || ps->polarizationProfile()) return "anisotropic or polarized point source";
-            if (ps->velocityX() || ps->velocityY() || ps->velocityZ()) return "moving source";
         }
         else if (auto gs = dynamic_cast<GeometricSource*>(source))
         {
             sk_source_t probe;
             memset(&probe, 0, sizeof probe);
             if (!fillGeometry(gs->geometry(), probe)) return "source geometry " + gs->geometry()->type();
-            if (gs->velocityMagnitude()) return "moving source";
+            if (gs->hasVelocity() && !fillVelocity(gs, probe)) return "source velocity field " + gs->velocityDistribution()->type();
         }
         else
             return "source " + source->type();
@@ -669,6 +713,20 @@ void GpuLifeCycle::configureEngine(int device)
         Vv[m] = ms->volume(m);
     }
     check(sk_engine_set_media(_e, M, numComponents, nv.data(), Vv.data()));
+    if (config->hasMovingMedia())
+    {
+        // MediumState::bulkVelocity(m): the aggregate over the components the reference's set-up has stored per cell
+        // (MediumSystem.cpp:330-365)
+        vector<double> vv(3 * static_cast<size_t>(M));
+        for (int m = 0; m != M; ++m)
+        {
+            Vec v = ms->bulkVelocity(m);
+            vv[3 * static_cast<size_t>(m)] = v.x();
+            vv[3 * static_cast<size_t>(m) + 1] = v.y();
+            vv[3 * static_cast<size_t>(m) + 2] = v.z();
+        }
+        check(sk_engine_set_velocities(_e, M, vv.data()));
+    }
 
     // ---- dust mix tables (DustMix.cpp:47-246), one set per engine component
     auto mix = dynamic_cast<const DustMix*>(ms->media()[0]->mix());
@@ -737,11 +795,20 @@ void GpuLifeCycle::configureEngine(int device)
             s.position[0] = ps->positionX();
             s.position[1] = ps->positionY();
             s.position[2] = ps->positionZ();
+            if (ps->hasVelocity())  // SpecialtySource: velocityX/Y/Z
+            {
+                s.velocity_kind = SK_VEL_CONSTANT;
+                s.velocity[0] = ps->velocityX();
+                s.velocity[1] = ps->velocityY();
+                s.velocity[2] = ps->velocityZ();
+            }
         }
         else
         {
             s.kind = SK_SRC_GEOMETRIC;
-            fillGeometry(dynamic_cast<GeometricSource*>(ns)->geometry(), s);
+            auto gs = dynamic_cast<GeometricSource*>(ns);
+            fillGeometry(gs->geometry(), s);
+            if (gs->hasVelocity()) fillVelocity(gs, s);
         }
         if (auto bb = dynamic_cast<BlackBodySED*>(ns->sed()))
         {
