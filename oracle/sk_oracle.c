@@ -58,9 +58,11 @@ typedef struct {
     double* wsed[5];
     double* wifu[5];
     /* per-history statistics accumulator (FluxRecorder::ContributionList, FluxRecorder.hpp:327-339) */
-    int hist_active;
-    int hist_ell;
-    double hist_w;
+    /* SED: one entry per wavelength bin the history has reached (with kinematics its peel-off packets differ in wavelength),
+       FluxRecorder.cpp:962-986 */
+    int hist_nsed, hist_capsed;
+    int* hist_sed_ell;
+    double* hist_sed_w;
     /* the history's contributions per frame pixel: index l + ell*Npix and summed weight, in order of first detection */
     int hist_npix, hist_cappix;
     size_t* hist_lell;
@@ -483,6 +485,8 @@ static void free_instruments(sko_engine_t* e)
         for (int k = 0; k < 5; ++k) free(e->instr[i].wifu[k]);
         free(e->instr[i].hist_lell);
         free(e->instr[i].hist_wpix);
+        free(e->instr[i].hist_sed_ell);
+        free(e->instr[i].hist_sed_w);
     }
     free(e->instr);
     e->instr = NULL;
@@ -2673,17 +2677,16 @@ static double mean_hg(double g, double costheta)
 /* FluxRecorder::recordContributions for the SED arrays, FluxRecorder.cpp:962-986 */
 static void flush_history_stats(instr_t* q)
 {
-    if (q->hist_active && q->wsed[0])
+    for (int i = 0; i < q->hist_nsed && q->wsed[0]; ++i)
     {
         double wn = 1.;
         for (int k = 0; k <= 4; ++k)
         {
-            q->wsed[k][q->hist_ell] += wn;
-            wn *= q->hist_w;
+            q->wsed[k][q->hist_sed_ell[i]] += wn;
+            wn *= q->hist_sed_w[i];
         }
     }
-    q->hist_active = 0;
-    q->hist_w = 0.;
+    q->hist_nsed = 0;
     /* FluxRecorder::recordContributions for the frame, FluxRecorder.cpp:990-1013 (the list already holds one entry per
        pixel and wavelength bin, which is what sorting and grouping the raw contributions produces) */
     for (int i = 0; i < q->hist_npix; ++i)
@@ -2790,9 +2793,21 @@ static void detect(sko_engine_t* e, instr_t* q, packet_t* ppp)
     }
     if (q->d.record_statistics && q->include_sed)
     {
-        q->hist_active = 1;
-        q->hist_ell = ell;
-        q->hist_w += Lext;
+        int i = 0;
+        while (i < q->hist_nsed && q->hist_sed_ell[i] != ell) i++;
+        if (i == q->hist_nsed)
+        {
+            if (q->hist_nsed == q->hist_capsed)
+            {
+                q->hist_capsed = q->hist_capsed ? 2 * q->hist_capsed : 16;
+                q->hist_sed_ell = (int*)realloc(q->hist_sed_ell, q->hist_capsed * sizeof(int));
+                q->hist_sed_w = (double*)realloc(q->hist_sed_w, q->hist_capsed * sizeof(double));
+            }
+            q->hist_sed_ell[i] = ell;
+            q->hist_sed_w[i] = 0.;
+            q->hist_nsed++;
+        }
+        q->hist_sed_w[i] += Lext;
     }
     if (q->d.record_statistics && q->include_ifu && l >= 0)
     {

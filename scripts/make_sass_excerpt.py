@@ -13,12 +13,12 @@ import sys
 
 LIB = "skirt9_b200/csrc/libskirt9_b200.so"
 KERNELS = [
-    ("_Z11sk_wf_traceILi2ELi2ELb0ELb0ELb0EE", "sk_wf_trace<2,2,0,0,0>: octree, peel-off paths (observer direction shared by the launch)"),
-    ("_Z11sk_wf_traceILi2ELi0ELb0ELb0ELb0EE", "sk_wf_trace<2,0,0,0,0>: octree, fused forward path + walk to the interaction point"),
-    ("_Z11sk_wf_traceILi2ELi0ELb1ELb0ELb0EE", "sk_wf_trace<2,0,1,0,0>: octree, fused, radiation field stored (cfg4)"),
-    ("_Z11sk_wf_traceILi1ELi0ELb1ELb1ELb0EE", "sk_wf_trace<1,0,1,1,0>: Cartesian, fused, radiation field stored, mesh tables in shared memory (cfg1)"),
-    ("_Z11sk_wf_traceILi3ELi0ELb0ELb0ELb0EE", "sk_wf_trace<3,0,0,0,0>: Voronoi, fused (cfg5)"),
-    ("_Z11sk_wf_traceILi2ELi0ELb0ELb0ELb1EE", "sk_wf_trace<2,0,0,0,1>: octree, fused, several medium components (MULTI)"),
+    ("_Z11sk_wf_traceILi2ELi2ELb0ELb0ELb0ELb0EE", "sk_wf_trace<2,2,0,0,0>: octree, peel-off paths (observer direction shared by the launch)"),
+    ("_Z11sk_wf_traceILi2ELi0ELb0ELb0ELb0ELb0EE", "sk_wf_trace<2,0,0,0,0>: octree, fused forward path + walk to the interaction point"),
+    ("_Z11sk_wf_traceILi2ELi0ELb1ELb0ELb0ELb0EE", "sk_wf_trace<2,0,1,0,0>: octree, fused, radiation field stored (cfg4)"),
+    ("_Z11sk_wf_traceILi1ELi0ELb1ELb1ELb0ELb0EE", "sk_wf_trace<1,0,1,1,0>: Cartesian, fused, radiation field stored, mesh tables in shared memory (cfg1)"),
+    ("_Z11sk_wf_traceILi3ELi0ELb0ELb0ELb0ELb0EE", "sk_wf_trace<3,0,0,0,0>: Voronoi, fused (cfg5)"),
+    ("_Z11sk_wf_traceILi2ELi0ELb0ELb0ELb1ELb0EE", "sk_wf_trace<2,0,0,0,1>: octree, fused, several medium components (MULTI)"),
 ]
 INS = re.compile(r"^\s*/\*([0-9a-f]{4,5})\*/\s+(.*?);")
 

@@ -209,6 +209,7 @@ struct HostInstr {
     long long sed_off[SK_NUM_COMP], ifu_off[SK_NUM_COMP];  // offsets (doubles) into the detector block, -1 = absent
     long long wsed_off[5], wifu_off[5];
     int pix_slot = -1;
+    int sed_slot = -1;  // relative to the pixel lists: the list of SED bins a run with kinematics keeps per history
 };
 
 struct sk_engine {
@@ -266,6 +267,7 @@ struct sk_engine {
     int num_mixes = 0;      // dust mixes given by sk_engine_set_dustmixes; must equal M.nmed when a segment runs
     int sec_num_media = 0;  // dust components the secondary-emission tables were given for
     int num_pix_lists = 0;
+    int num_sed_lists = 0;  // SED instruments with statistics: one more list each in runs with kinematics
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
     cudaEvent_t pin_ev[2] = {nullptr, nullptr};
@@ -1539,7 +1541,7 @@ extern "C" int sk_engine_set_instruments(sk_engine_t* e, int32_t n, const sk_ins
     free_group(e->instr_allocs);
     e->instr.assign(n, HostInstr());
     size_t det = 0, stat = 0;
-    int num_pix_lists = 0;
+    int num_pix_lists = 0, num_sed_lists = 0;
     for (int i = 0; i < n; ++i)
     {
         HostInstr& q = e->instr[i];
@@ -1581,6 +1583,7 @@ extern "C" int sk_engine_set_instruments(sk_engine_t* e, int32_t n, const sk_ins
                 det += lenifu;
             }
         }
+        q.sed_slot = (d.record_statistics && lensed) ? num_sed_lists++ : -1;
         q.pix_slot = -1;
         if (d.record_statistics && lenifu)
         {
@@ -1682,6 +1685,7 @@ extern "C" int sk_engine_set_instruments(sk_engine_t* e, int32_t n, const sk_ins
         for (int k = 0; k < 5; ++k) v.wsed[k] = q.wsed_off[k] >= 0 ? e->stat_block + q.wsed_off[k] : nullptr;
         for (int k = 0; k < 5; ++k) v.wifu[k] = q.wifu_off[k] >= 0 ? e->stat_block + q.wifu_off[k] : nullptr;
         v.pix_slot = q.pix_slot;
+        v.sed_slot = q.sed_slot >= 0 ? num_pix_lists + q.sed_slot : -1;  // (the lists of SED bins follow the pixel lists)
     }
     e->instr_same_observer.assign(n, 0);
     e->instr_kobs.assign(n, std::array<double, 3>{0., 0., 1.});
@@ -1695,6 +1699,7 @@ extern "C" int sk_engine_set_instruments(sk_engine_t* e, int32_t n, const sk_ins
     e->M.instr = di;
     e->M.ninstr = n;
     e->num_pix_lists = num_pix_lists;
+    e->num_sed_lists = num_sed_lists;
     e->M.pix_base_d = SK_BANK_FIELDS_D(n);
     e->M.pix_base_i = SK_BANK_FIELDS_I(n);
     return SK_OK;
@@ -1933,8 +1938,9 @@ static int ensure_bank(sk_engine* e, uint64_t count)
 {
     size_t cap = std::min<uint64_t>(count, bank_capacity_limit());
     cap = std::max<size_t>((cap + 255) / 256 * 256, 256);
-    int nd = SK_BANK_FIELDS_D(e->M.ninstr) + e->num_pix_lists * SK_PIX_K;
-    int ni = SK_BANK_FIELDS_I(e->M.ninstr) + e->num_pix_lists * SK_PIX_INTS;
+    const int nlists = e->num_pix_lists + (e->M.kin ? e->num_sed_lists : 0);
+    int nd = SK_BANK_FIELDS_D(e->M.ninstr) + nlists * SK_PIX_K;
+    int ni = SK_BANK_FIELDS_I(e->M.ninstr) + nlists * SK_PIX_INTS;
     e->M.kin_base_d = nd;  // the extra per-packet fields of a run with kinematics follow the pixel lists
     e->M.kin_base_i = ni;
     if (e->M.kin)
@@ -1960,13 +1966,13 @@ static int ensure_bank(sk_engine* e, uint64_t count)
     e->bank.pool_w = nullptr;
     e->bank.cap = 0;
     e->pool_chunks = 0;
-    if (e->num_pix_lists)
+    if (nlists)
     {
         // continuation chunks of the per-history pixel lists: two per slot and list, at least 16384 (388 bytes each;
         // SK_PIX_POOL overrides).  A history takes one for every SK_PIX_C distinct frame pixels beyond the first SK_PIX_K.
         const char* ps = getenv("SK_PIX_POOL");
         const long long want = ps ? atoll(ps) : 0;
-        const size_t nch = want > 0 ? (size_t)want : std::max<size_t>(16384, 2 * cap * e->num_pix_lists);
+        const size_t nch = want > 0 ? (size_t)want : std::max<size_t>(16384, 2 * cap * nlists);
         CK(dev_malloc(&e->bank.pool_lell, nch * SK_PIX_C * sizeof(int32_t)));
         CK(dev_malloc(&e->bank.pool_w, nch * SK_PIX_C * sizeof(double)));
         CK(dev_malloc(&e->bank.pool_next, nch * sizeof(int32_t)));
@@ -1987,10 +1993,10 @@ static int ensure_bank(sk_engine* e, uint64_t count)
     return SK_OK;
 }
 
-template <int GRID, int MODE, bool STORE, bool SMEMT, bool MULTI>
+template <int GRID, int MODE, bool STORE, bool SMEMT, bool MULTI, bool KIN = false>
 static int launch_trace_impl(sk_engine* e, const SkRunArgs& A, const SkObsDir& dir)
 {
-    auto kern = sk_wf_trace<GRID, MODE, STORE, SMEMT, MULTI>;
+    auto kern = sk_wf_trace<GRID, MODE, STORE, SMEMT, MULTI, KIN>;
     // occupancy of this instantiation on this engine's device for its shared-memory footprint (cached in the engine:
     // engines on different devices run from different host threads).  The staged tables never exceed 48 KB (set_tables),
     // the default limit of dynamic shared memory, so no per-device function attribute has to be set.
@@ -2027,7 +2033,13 @@ static int launch_trace(sk_engine* e, const SkRunArgs& A, const SkObsDir& dir)
 {
     // only the Cartesian grid looks borders up while it walks (TMA-staged tables); the octree walks in lattice coordinates
     // several medium components with their own mixes: the instantiation that sums the opacities
-    if (e->M.nmed > 1 || e->M.kin)
+    // kinematics: the instantiation that looks the sections up in every cell at the wavelength the cell perceives
+    if (e->M.kin)
+    {
+        if (GRID == 1 && e->M.lattice_in_smem) return launch_trace_impl<GRID, MODE, STORE, GRID == 1, true, true>(e, A, dir);
+        return launch_trace_impl<GRID, MODE, STORE, false, true, true>(e, A, dir);
+    }
+    if (e->M.nmed > 1)
     {
         if (GRID == 1 && e->M.lattice_in_smem) return launch_trace_impl<GRID, MODE, STORE, GRID == 1, true>(e, A, dir);
         return launch_trace_impl<GRID, MODE, STORE, false, true>(e, A, dir);

@@ -71,7 +71,8 @@ struct SkDevInstr {
     double* wsed[5];
     double* wifu[5];    // per-pixel statistics (FluxRecorder::_wifu) or null
     int32_t pix_slot;   // index of this instrument's per-history pixel list in the bank, or -1
-    int32_t pad2;
+    int32_t sed_slot;   // index of its per-history list of SED bins, used in runs with kinematics (the peel-off packets of one
+                        // history then differ in wavelength, FluxRecorder.cpp:962-986), or -1
 };
 
 struct SkDevModel {

@@ -144,12 +144,13 @@ __device__ __forceinline__ void sk_rng_load(SkRng& g, const SkDevModel& M, const
                 (uint32_t)K.I(I_DRAW, slot));
 }
 
-__device__ __forceinline__ void sk_record_pixel_stats(const SkDevInstr& q, int lell, double w)
+// (to_sed: the entry is a wavelength bin of the SED statistics instead of a pixel and bin of the frame statistics)
+__device__ __forceinline__ void sk_record_pixel_stats(const SkDevInstr& q, int lell, double w, bool to_sed = false)
 {
     double wn = 1.;
     for (int kk = 0; kk <= 4; ++kk)
     {
-        atomicAdd(&q.wifu[kk][lell], wn);
+        atomicAdd(to_sed ? &q.wsed[kk][lell] : &q.wifu[kk][lell], wn);
         wn *= w;
     }
 }
@@ -160,10 +161,13 @@ __device__ __forceinline__ void sk_record_pixel_stats(const SkDevInstr& q, int l
 // atomic counter is the whole stack discipline.  Should the pool run dry the contribution is recorded on its own
 // (counted in sk_counters_t::pixel_overflows; the pool is sized so that this does not happen).
 #define SK_PIX_INTS (SK_PIX_K + 2)
+// With kinematics the same lists, keyed by wavelength bin, hold the history's contributions to the SED statistics (to_sed,
+// list q.sed_slot): its peel-off packets then differ in wavelength (FluxRecorder.cpp:962-986).
 __device__ __forceinline__ void sk_add_pixel_contribution(const SkDevModel& M, const SkBank& K, const SkDevInstr& q,
-                                                          int slot, int lell, double w)
+                                                          int slot, int lell, double w, bool to_sed = false)
 {
-    const int fi = M.pix_base_i + q.pix_slot * SK_PIX_INTS, fd = M.pix_base_d + q.pix_slot * SK_PIX_K;
+    const int ls = to_sed ? q.sed_slot : q.pix_slot;
+    const int fi = M.pix_base_i + ls * SK_PIX_INTS, fd = M.pix_base_d + ls * SK_PIX_K;
     const int total = K.I(fi + SK_PIX_K, slot);
     const int n = min(total, SK_PIX_K);
     for (int i = 0; i < n; ++i)
@@ -197,7 +201,7 @@ __device__ __forceinline__ void sk_add_pixel_contribution(const SkDevModel& M, c
         {
             atomicAdd(&K.pool_ctl[0], 1);
             atomicAdd(&K.pool_ctl[1], 1);
-            sk_record_pixel_stats(q, lell, w);
+            sk_record_pixel_stats(q, lell, w, to_sed);
             return;
         }
         const int c = K.pool_free[top];
@@ -211,12 +215,13 @@ __device__ __forceinline__ void sk_add_pixel_contribution(const SkDevModel& M, c
 }
 
 // Ends a history: FluxRecorder::recordContributions for the SED arrays (FluxRecorder.cpp:962-986); frees the slot.
-__device__ __forceinline__ void sk_finish_history(const SkDevModel& M, const SkBank& K, int slot)
+__device__ __forceinline__ void sk_finish_history(const SkDevModel& M, const SkBank& K, int slot, bool kin = false)
 {
     for (int j = 0; j < M.ninstr; ++j)
     {
         const SkDevInstr& q = M.instr[j];
         if (!q.record_stats) continue;
+        if (kin && q.sed_slot >= 0) continue;  // (its SED bins are in a list, below)
         int ell = K.I(I_HELL0 + j, slot);
         if (ell >= 0)
         {
@@ -230,14 +235,16 @@ __device__ __forceinline__ void sk_finish_history(const SkDevModel& M, const SkB
         }
     }
     // the same per frame pixel (FluxRecorder.cpp:990-1013): the history's list holds one entry per pixel and bin
-    for (int j = 0; j < M.ninstr; ++j)
+    for (int jj = 0; jj < (kin ? 2 : 1) * M.ninstr; ++jj)
     {
-        const SkDevInstr& q = M.instr[j];
-        if (q.pix_slot < 0) continue;
-        const int fi = M.pix_base_i + q.pix_slot * SK_PIX_INTS, fd = M.pix_base_d + q.pix_slot * SK_PIX_K;
+        const bool to_sed = jj >= M.ninstr;  // second pass (kinematics): the lists of SED bins
+        const SkDevInstr& q = M.instr[to_sed ? jj - M.ninstr : jj];
+        const int ls = to_sed ? q.sed_slot : q.pix_slot;
+        if (ls < 0) continue;
+        const int fi = M.pix_base_i + ls * SK_PIX_INTS, fd = M.pix_base_d + ls * SK_PIX_K;
         const int total = K.I(fi + SK_PIX_K, slot);
         const int n = min(total, SK_PIX_K);
-        for (int i = 0; i < n; ++i) sk_record_pixel_stats(q, K.I(fi + i, slot), K.D(fd + i, slot));
+        for (int i = 0; i < n; ++i) sk_record_pixel_stats(q, K.I(fi + i, slot), K.D(fd + i, slot), to_sed);
         const int rem = total - SK_PIX_K;
         if (rem > 0)
         {
@@ -245,7 +252,7 @@ __device__ __forceinline__ void sk_finish_history(const SkDevModel& M, const SkB
             for (int c = K.I(fi + SK_PIX_K + 1, slot); c >= 0; cnt = SK_PIX_C)
             {
                 for (int i = 0; i < cnt; ++i)
-                    sk_record_pixel_stats(q, K.pool_lell[(size_t)c * SK_PIX_C + i], K.pool_w[(size_t)c * SK_PIX_C + i]);
+                    sk_record_pixel_stats(q, K.pool_lell[(size_t)c * SK_PIX_C + i], K.pool_w[(size_t)c * SK_PIX_C + i], to_sed);
                 const int next = K.pool_next[c];
                 K.pool_free[atomicAdd(&K.pool_ctl[0], 1)] = c;  // back on the stack of free chunks
                 c = next;
@@ -319,7 +326,8 @@ __device__ __forceinline__ double sk_interaction_depth(double u, double taupath,
 // cell is the sum of sigma_h n_h; the sections of the components beyond the first live in lane registers and their
 // densities are fetched from densx once the cell is known.  A separate instantiation, so that the single-medium kernels
 // keep their registers and instruction count.
-template <int GRID, int MODE, bool STORE, bool TABLES_IN_SMEM, bool MULTI>
+// KIN (with MULTI): kinematics, the per-cell look-ups at the perceived wavelength; its own instantiation for the same reason.
+template <int GRID, int MODE, bool STORE, bool TABLES_IN_SMEM, bool MULTI, bool KIN>
 __global__ void __launch_bounds__(SK_TRACE_BLOCK, (GRID == 3   ? SK_TRACE_MINBLOCKS_VORONOI
                                                    : MODE == 2 ? SK_TRACE_MINBLOCKS_PEEL
                                                    : STORE     ? SK_TRACE_MINBLOCKS_STORE
@@ -391,7 +399,7 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, (GRID == 3   ? SK_TRACE_MINBLO
     // MULTI with kinematics (sk_engine_set_velocities): the cell perceives lam_ray / (1 - k.v_m/c) and the sections are those
     // of that wavelength (MediumSystem.cpp:888-900, 958-972, 1242-1258); ilam_ray follows it from cell to cell, and the sections
     // in the lane registers are reloaded when it changes.  pk = the ray's direction in physical coordinates.
-    const bool kin = MULTI && M.kin;
+    constexpr bool kin = MULTI && KIN;
     const bool more_media = MULTI && M.nmed > 1;
     double lam_ray = 0., lamp = 0., pkx = 0., pky = 0., pkz = 0.;
     int rf_lo = 0;
@@ -1041,7 +1049,7 @@ __global__ void SK_ADVANCE_BOUNDS sk_wf_advance(const SkDevModel M, const SkRunA
         }
         if (!alive)
         {
-            sk_finish_history(M, K, slot);
+            sk_finish_history(M, K, slot, MULTI && M.kin);
             st = 0;
         }
     }
@@ -1137,6 +1145,12 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK, SK_LAUNCH_MINBLOCKS) sk_wf_lau
                         K.I(M.pix_base_i + ps * SK_PIX_INTS + SK_PIX_K, slot) = 0;
                         K.I(M.pix_base_i + ps * SK_PIX_INTS + SK_PIX_K + 1, slot) = -1;
                     }
+                    const int ss = M.kin ? M.instr[j].sed_slot : -1;
+                    if (ss >= 0)
+                    {
+                        K.I(M.pix_base_i + ss * SK_PIX_INTS + SK_PIX_K, slot) = 0;
+                        K.I(M.pix_base_i + ss * SK_PIX_INTS + SK_PIX_K + 1, slot) = -1;
+                    }
                 }
                 if (M.kin)
                 {
@@ -1216,7 +1230,9 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_detect(const SkDevModel 
                     if (q.include_sed)
                         sk_record_sed(q, ell, L, Lext, nscatt, A.primary != 0, nl_stride ? sed_sm + (j - j0) * per_instr : nullptr,
                                       nl_stride);
-                    if (q.record_stats && q.include_sed)
+                    if (KIN && q.sed_slot >= 0)
+                        sk_add_pixel_contribution(M, K, q, slot, ell, Lext, true);
+                    else if (q.record_stats && q.include_sed)
                     {
                         K.D(D_HISTW0 + j, slot) += Lext;  // FluxRecorder.cpp:457-466
                         K.I(I_HELL0 + j, slot) = ell;
