@@ -243,6 +243,15 @@ def make_sim(name, total_packets, statistics=False):
             sim.medium.tau = 0.6
             sim.extraMedia = [H.GeometricMedium(H.ExpDiskGeometry(5000 * PC, 250 * PC, 0.0, 20000 * PC, 2000 * PC), mix2,
                                                 opticalDepth=0.4, wavelength=0.55e-6)]
+        if os.environ.get("SK_BENCH_KINEMATICS"):
+            # diagnostic (not a BASELINE workload): cfg2 with a rotating dust ring (220 km/s, flat rotation curve) and a source
+            # that rotates with it -- the cost of the trace kernels that look the sections up per cell at the perceived wavelength
+            from skirt9_b200 import host as H
+            sim.medium.velocityMagnitude = 220e3
+            sim.medium.velocityDistribution = H.CylindricalVectorField()
+            for s in sim.sources:
+                s.velocityMagnitude = 220e3
+                s.velocityDistribution = H.CylindricalVectorField()
         return sim.setup()
     if name == "cfg1":
         return configs.cfg1(num_packets=total_packets, record_statistics=statistics).setup()
