@@ -51,6 +51,8 @@
 #include "DisjointWavelengthGrid.hpp"
 #include "DistantInstrument.hpp"
 #include "DustMix.hpp"
+#include "DynamicStateOptions.hpp"
+#include "DynamicStateRecipe.hpp"
 #include "ExpDiskGeometry.hpp"
 #include "FatalError.hpp"
 #include "FluxRecorder.hpp"
@@ -520,8 +522,12 @@ std::string GpuLifeCycle::unsupportedReason() const
     if (!config->hasMovingMedia() && !config->hasSingleConstantSectionMedium() && !config->hasMultipleConstantSectionMedia())
         return "variable cross sections";
     if (config->hasPolarization()) return "polarization";
-    if (config->hasDynamicState()) return "dynamic medium state";
-    if (config->hasPrimaryIterations() || config->hasMergedIterations()) return "primary / merged iterations";
+    // dynamic medium state: the recipes run on the host between the segments (the reference's own code on the radiation field the
+    // engine hands back) and the new densities go to the engine; media that keep a dynamic state of their own (gas) do not
+    if (config->hasPrimaryDynamicStateMedia() || config->hasSecondaryDynamicStateMedia()) return "media with a dynamic state of their own";
+    if (config->hasDynamicStateRecipes())
+        for (auto recipe : ms->dynamicStateOptions()->recipes())
+            if (recipe->type() != "ClearDensityRecipe") return "dynamic state recipe " + recipe->type();
     if (config->hasGasEmission()) return "gas emission";
     if (config->hasStochasticDustEmission()) return "stochastic dust emission";
     if (config->includeHeatingByCMB()) return "CMB heating";
@@ -611,6 +617,47 @@ std::string GpuLifeCycle::unsupportedReason() const
 
 ////////////////////////////////////////////////////////////////////
 
+// The medium state the engine walks through: number densities per component and cell volumes (MediumState.cpp:196-247) and,
+// with moving media, the bulk velocities.  Called when the engine is configured and again after every update of a dynamic
+// medium state (MediumSystem::updateDynamicStateRecipes, MediumSystem.cpp:1498-1558), which changes densities on the host.
+void GpuLifeCycle::uploadMediumState(sk_engine_t* engine)
+{
+    auto config = _sim->_config;
+    auto ms = _sim->mediumSystem();
+    sk_engine_t* _e = engine;
+    int M = ms->numCells();
+    const int numMedia = ms->numMedia();
+    // components with the same material mix: the densities add up to one medium; different mixes: one engine component each
+    const int numComponents = mediaShareOneMix() ? 1 : numMedia;
+    vector<double> nv(static_cast<size_t>(numComponents) * M), Vv(M);
+    for (int m = 0; m != M; ++m)
+    {
+        if (numComponents == 1)
+        {
+            nv[m] = ms->numberDensity(m, 0);
+            for (int h = 1; h < numMedia; ++h) nv[m] += ms->numberDensity(m, h);
+        }
+        else
+            for (int h = 0; h < numMedia; ++h) nv[static_cast<size_t>(h) * M + m] = ms->numberDensity(m, h);
+        Vv[m] = ms->volume(m);
+    }
+    check(sk_engine_set_media(_e, M, numComponents, nv.data(), Vv.data()));
+    if (config->hasMovingMedia())
+    {
+        // MediumState::bulkVelocity(m): the aggregate over the components the reference's set-up has stored per cell
+        // (MediumSystem.cpp:330-365)
+        vector<double> vv(3 * static_cast<size_t>(M));
+        for (int m = 0; m != M; ++m)
+        {
+            Vec v = ms->bulkVelocity(m);
+            vv[3 * static_cast<size_t>(m)] = v.x();
+            vv[3 * static_cast<size_t>(m) + 1] = v.y();
+            vv[3 * static_cast<size_t>(m) + 2] = v.z();
+        }
+        check(sk_engine_set_velocities(_e, M, vv.data()));
+    }
+}
+
 void GpuLifeCycle::configureEngine(int device)
 {
     auto config = _sim->_config;
@@ -695,38 +742,10 @@ void GpuLifeCycle::configureEngine(int device)
         check(sk_engine_set_grid_octree(_e, ext, static_cast<int32_t>(n), firstChild.data()));
     }
 
-    // ---- medium state (MediumState.cpp:196-247)
-    int M = ms->numCells();
+    // ---- medium state (MediumState.cpp:196-247) and, with moving media, the bulk velocities
+    uploadMediumState(_e);
     const int numMedia = ms->numMedia();
-    // components with the same material mix: the densities add up to one medium; different mixes: one engine component each
     const int numComponents = mediaShareOneMix() ? 1 : numMedia;
-    vector<double> nv(static_cast<size_t>(numComponents) * M), Vv(M);
-    for (int m = 0; m != M; ++m)
-    {
-        if (numComponents == 1)
-        {
-            nv[m] = ms->numberDensity(m, 0);
-            for (int h = 1; h < numMedia; ++h) nv[m] += ms->numberDensity(m, h);
-        }
-        else
-            for (int h = 0; h < numMedia; ++h) nv[static_cast<size_t>(h) * M + m] = ms->numberDensity(m, h);
-        Vv[m] = ms->volume(m);
-    }
-    check(sk_engine_set_media(_e, M, numComponents, nv.data(), Vv.data()));
-    if (config->hasMovingMedia())
-    {
-        // MediumState::bulkVelocity(m): the aggregate over the components the reference's set-up has stored per cell
-        // (MediumSystem.cpp:330-365)
-        vector<double> vv(3 * static_cast<size_t>(M));
-        for (int m = 0; m != M; ++m)
-        {
-            Vec v = ms->bulkVelocity(m);
-            vv[3 * static_cast<size_t>(m)] = v.x();
-            vv[3 * static_cast<size_t>(m) + 1] = v.y();
-            vv[3 * static_cast<size_t>(m) + 2] = v.z();
-        }
-        check(sk_engine_set_velocities(_e, M, vv.data()));
-    }
 
     // ---- dust mix tables (DustMix.cpp:47-246), one set per engine component
     auto mix = dynamic_cast<const DustMix*>(ms->media()[0]->mix());
@@ -917,11 +936,24 @@ void GpuLifeCycle::runSimulation()
     auto config = _sim->_config;
     {
         TimeLogger logger(_sim->log(), "the run");
-        runPrimaryEmission();
-        if (config->hasSecondaryEmission())
+        // MonteCarloSimulation::runSimulation, MonteCarloSimulation.cpp:58-86
+        bool hasPrimaryLuminosity = _sim->sourceSystem()->luminosity() > 0.;
+        if (config->hasMergedIterations() && hasPrimaryLuminosity)
         {
-            if (config->hasSecondaryIterations()) runSecondaryEmissionIterations();
+            if (config->hasPrimaryIterations()) runPrimaryEmissionIterations();
+            runMergedEmissionIterations();
+            runPrimaryEmission();
             runSecondaryEmission();
+        }
+        else
+        {
+            if (config->hasPrimaryIterations() && hasPrimaryLuminosity) runPrimaryEmissionIterations();
+            runPrimaryEmission();
+            if (config->hasSecondaryEmission())
+            {
+                if (config->hasSecondaryIterations()) runSecondaryEmissionIterations();
+                runSecondaryEmission();
+            }
         }
     }
     memset(&_counters, 0, sizeof _counters);
@@ -997,8 +1029,158 @@ void GpuLifeCycle::runSecondaryEmission()
     if (storeRF) communicateRadiationField(0);
 }
 
-// MonteCarloSimulation::runSecondaryEmissionIterations (.cpp:335-403) with DustAbsorptionConvergence (.cpp:180-227) and
-// logLoopConvergence (.cpp:233-261); the log lines are the reference's
+// DustAbsorptionConvergence::logConvergenceInfo (MonteCarloSimulation.cpp:180-227): the absorbed luminosities from the
+// engine's radiation field tables; the log lines are the reference's
+bool GpuLifeCycle::logDustConvergence(int iter, double& prevLabsseco)
+{
+    auto config = _sim->_config;
+    auto log = _sim->log();
+    auto units = _sim->units();
+    double fractionOfPrimary = config->maxFractionOfPrimary();
+    double fractionOfPrevious = config->maxFractionOfPrevious();
+    double Labsprim = 0., Labsseco = 0.;
+    check(sk_engine_absorbed_luminosity(_e, 1, &Labsprim));
+    check(sk_engine_absorbed_luminosity(_e, 0, &Labsseco));
+    log->info("The total dust-absorbed primary luminosity is " + StringUtils::toString(units->obolluminosity(Labsprim), 'g')
+              + " " + units->ubolluminosity());
+    log->info("The total dust-absorbed secondary luminosity in iteration " + std::to_string(iter) + " is "
+              + StringUtils::toString(units->obolluminosity(Labsseco), 'g') + " " + units->ubolluminosity());
+    if (Labsprim > 0. && Labsseco > 0.)
+    {
+        if (iter == 1)
+            log->info("--> absorbed secondary luminosity is " + StringUtils::toString(Labsseco / Labsprim * 100., 'f', 2)
+                      + "% of absorbed primary luminosity (convergence criterion is "
+                      + StringUtils::toString(fractionOfPrimary * 100., 'f', 2) + "%)");
+        else
+            log->info("--> absorbed secondary luminosity changed by "
+                      + StringUtils::toString(std::abs((Labsseco - prevLabsseco) / Labsseco) * 100., 'f', 2)
+                      + "% compared to previous iteration (convergence criterion is "
+                      + StringUtils::toString(fractionOfPrevious * 100., 'f', 2) + "%)");
+    }
+    bool converged = Labsprim <= 0. || Labsseco <= 0. || Labsseco / Labsprim < fractionOfPrimary
+                     || std::abs((Labsseco - prevLabsseco) / Labsseco) < fractionOfPrevious;
+    prevLabsseco = Labsseco;
+    return converged;
+}
+
+// logLoopConvergence (MonteCarloSimulation.cpp:233-261): true when the loop ends
+bool GpuLifeCycle::logLoopConvergence(bool converged, int iter, int minIters, int maxIters)
+{
+    auto log = _sim->log();
+    if (converged && iter < minIters)
+    {
+        log->info("Convergence reached but continuing until " + std::to_string(minIters) + " iterations have been performed");
+        return false;
+    }
+    if (converged)
+    {
+        log->info("Convergence reached after " + std::to_string(iter) + " iterations");
+        return true;
+    }
+    if (iter < maxIters)
+    {
+        log->info("Convergence not yet reached after " + std::to_string(iter) + " iterations");
+        return false;
+    }
+    log->error("Convergence not yet reached after " + std::to_string(iter) + " iterations");
+    return true;
+}
+
+// MediumSystem::updatePrimaryDynamicMediumState (MediumSystem.cpp:1626-1632) between two segments: the reference's recipes
+// read the mean intensity from the reference's tables, so the engine's radiation field goes back to the host first; the
+// densities they change go to every engine afterwards
+bool GpuLifeCycle::updateDynamicMediumState()
+{
+    returnRadiationField();
+    bool converged = _sim->mediumSystem()->updatePrimaryDynamicMediumState();
+    for (sk_engine_t* e : _engines) uploadMediumState(e);
+    return converged;
+}
+
+// MonteCarloSimulation::runPrimaryEmissionIterations, MonteCarloSimulation.cpp:266-330
+void GpuLifeCycle::runPrimaryEmissionIterations()
+{
+    auto config = _sim->_config;
+    auto log = _sim->log();
+    double minNpp = std::max(1., config->numPrimaryIterationPackets() * config->primaryIterationInitialPacketsFraction());
+    double maxNpp = std::max(1., static_cast<double>(config->numPrimaryIterationPackets()));
+    double ramp = config->primaryIterationPacketsRamp();
+    int minIters = config->minPrimaryIterations();
+    int maxIters = config->maxPrimaryIterations();
+    size_t prevNpp = 0;
+    int iter = 0;
+    while (true)
+    {
+        ++iter;
+        size_t Npp = std::min(maxNpp, minNpp * std::pow(ramp, iter - 1));
+        if (Npp != prevNpp)
+        {
+            for (sk_engine_t* e : _engines) check(sk_engine_prepare_primary(e, Npp));
+            prevNpp = Npp;
+        }
+        bool converged = true;
+        {
+            string segment = "primary emission iteration " + std::to_string(iter);
+            TimeLogger logger(log, segment);
+            _sim->mediumSystem()->beginDynamicMediumStateIteration();
+            for (sk_engine_t* e : _engines) check(sk_engine_clear_rf(e, 1));
+            log->info("Launching " + StringUtils::toString(static_cast<double>(Npp)) + " primary emission photon packets on the GPU");
+            runSegmentOnAll(Npp, 1, 0, 1);
+            communicateRadiationField(1);
+            converged = updateDynamicMediumState();
+        }
+        _sim->probeSystem()->probePrimary(iter);
+        if (logLoopConvergence(converged, iter, minIters, maxIters)) break;
+    }
+}
+
+// MonteCarloSimulation::runMergedEmissionIterations, MonteCarloSimulation.cpp:407-496
+void GpuLifeCycle::runMergedEmissionIterations()
+{
+    auto config = _sim->_config;
+    auto log = _sim->log();
+    auto units = _sim->units();
+    size_t Npp1 = config->numPrimaryIterationPackets();
+    size_t Npp2 = config->numSecondaryIterationPackets();
+    int minIters = config->minSecondaryIterations();
+    int maxIters = config->maxSecondaryIterations();
+    for (sk_engine_t* e : _engines) check(sk_engine_prepare_primary(e, Npp1));
+    double prevLabsseco = 0.;
+    int iter = 0;
+    while (true)
+    {
+        ++iter;
+        bool converged = true;
+        {
+            string segment = "merged primary and secondary emission iteration " + std::to_string(iter);
+            TimeLogger logger(log, segment);
+            _sim->mediumSystem()->beginDynamicMediumStateIteration();
+            for (sk_engine_t* e : _engines) check(sk_engine_clear_rf(e, 1));
+            runSegmentOnAll(Npp1, 1, 0, 1);
+            communicateRadiationField(1);
+            // (updateSecondaryDynamicMediumState, MediumSystem.cpp:1636-1641: only media with a dynamic state of their own,
+            //  which unsupportedReason() excludes)
+            for (sk_engine_t* e : _engines) check(sk_engine_clear_rf(e, 0));
+            double L = 0.;
+            for (sk_engine_t* e : _engines) check(sk_engine_prepare_secondary(e, Npp2, &L));
+            if (!L)
+            {
+                log->warning("Skipping merged emission iterations because the total luminosity of secondary sources is zero");
+                return;
+            }
+            log->info("Dust luminosity: " + StringUtils::toString(units->obolluminosity(L), 'g') + " " + units->ubolluminosity());
+            runSegmentOnAll(Npp2, 0, 0, 1);
+            communicateRadiationField(0);
+            // (in the reference's order: the absorbed luminosities are evaluated with the updated densities)
+            converged &= updateDynamicMediumState();
+            converged &= logDustConvergence(iter, prevLabsseco);
+        }
+        _sim->probeSystem()->probeSecondary(iter);
+        if (logLoopConvergence(converged, iter, minIters, maxIters)) break;
+    }
+}
+
+// MonteCarloSimulation::runSecondaryEmissionIterations (.cpp:335-403)
 void GpuLifeCycle::runSecondaryEmissionIterations()
 {
     auto config = _sim->_config;
@@ -1007,8 +1189,6 @@ void GpuLifeCycle::runSecondaryEmissionIterations()
     size_t Npp = config->numSecondaryIterationPackets();
     int minIters = config->minSecondaryIterations();
     int maxIters = config->maxSecondaryIterations();
-    double fractionOfPrimary = config->maxFractionOfPrimary();
-    double fractionOfPrevious = config->maxFractionOfPrevious();
     double prevLabsseco = 0.;
     int iter = 0;
     while (true)
@@ -1029,51 +1209,12 @@ void GpuLifeCycle::runSecondaryEmissionIterations()
             log->info("Dust luminosity: " + StringUtils::toString(units->obolluminosity(L), 'g') + " " + units->ubolluminosity());
             runSegmentOnAll(Npp, 0, 0, 1);
             communicateRadiationField(0);
-
-            double Labsprim = 0., Labsseco = 0.;
-            check(sk_engine_absorbed_luminosity(_e, 1, &Labsprim));
-            check(sk_engine_absorbed_luminosity(_e, 0, &Labsseco));
-            log->info("The total dust-absorbed primary luminosity is " + StringUtils::toString(units->obolluminosity(Labsprim), 'g')
-                      + " " + units->ubolluminosity());
-            log->info("The total dust-absorbed secondary luminosity in iteration " + std::to_string(iter) + " is "
-                      + StringUtils::toString(units->obolluminosity(Labsseco), 'g') + " " + units->ubolluminosity());
-            if (Labsprim > 0. && Labsseco > 0.)
-            {
-                if (iter == 1)
-                    log->info("--> absorbed secondary luminosity is " + StringUtils::toString(Labsseco / Labsprim * 100., 'f', 2)
-                              + "% of absorbed primary luminosity (convergence criterion is "
-                              + StringUtils::toString(fractionOfPrimary * 100., 'f', 2) + "%)");
-                else
-                    log->info("--> absorbed secondary luminosity changed by "
-                              + StringUtils::toString(std::abs((Labsseco - prevLabsseco) / Labsseco) * 100., 'f', 2)
-                              + "% compared to previous iteration (convergence criterion is "
-                              + StringUtils::toString(fractionOfPrevious * 100., 'f', 2) + "%)");
-            }
-            converged = Labsprim <= 0. || Labsseco <= 0. || Labsseco / Labsprim < fractionOfPrimary
-                        || std::abs((Labsseco - prevLabsseco) / Labsseco) < fractionOfPrevious;
-            prevLabsseco = Labsseco;
+            converged = logDustConvergence(iter, prevLabsseco);
         }
         // probes that fire after every iteration read the radiation field from the reference's tables
         returnRadiationField();
         _sim->probeSystem()->probeSecondary(iter);
-
-        if (converged && iter < minIters)
-        {
-            log->info("Convergence reached but continuing until " + std::to_string(minIters) + " iterations have been performed");
-            continue;
-        }
-        if (converged)
-        {
-            log->info("Convergence reached after " + std::to_string(iter) + " iterations");
-            break;
-        }
-        if (iter < maxIters)
-        {
-            log->info("Convergence not yet reached after " + std::to_string(iter) + " iterations");
-            continue;
-        }
-        log->error("Convergence not yet reached after " + std::to_string(iter) + " iterations");
-        break;
+        if (logLoopConvergence(converged, iter, minIters, maxIters)) break;
     }
 }
 

@@ -53,6 +53,12 @@ private:
     void runPrimaryEmission();
     void runSecondaryEmission();
     void runSecondaryEmissionIterations();
+    void runPrimaryEmissionIterations();
+    void runMergedEmissionIterations();
+    bool logDustConvergence(int iter, double& prevLabsseco);
+    bool logLoopConvergence(bool converged, int iter, int minIters, int maxIters);
+    bool updateDynamicMediumState();
+    void uploadMediumState(sk_engine_t* engine);
     void returnRadiationField();
     void returnDetectors();
 

@@ -1023,6 +1023,16 @@ class MonteCarloSimulation:
     storeEmissionRadiationField: bool = False
     secondaryPacketsMultiplier: float = 1.0
     secondaryIterationPacketsMultiplier: float = 1.0
+    # dynamic medium state (DynamicStateOptions with a ClearDensityRecipe; IterationOptions): the recipe runs on the host between
+    # the segments, on the radiation field the engine hands back, and the new densities go to the engine
+    clearDensityThreshold: Optional[float] = None   # ClearDensityRecipe::fieldStrengthThreshold; given => the recipe is present
+    iteratePrimaryEmission: bool = False            # MonteCarloSimulation::iteratePrimaryEmission
+    includePrimaryEmission: bool = False            # IterationOptions::includePrimaryEmission (merged iterations)
+    minPrimaryIterations: int = 1
+    maxPrimaryIterations: int = 10
+    primaryIterationPacketsMultiplier: float = 1.0
+    primaryIterationInitialPacketsFraction: float = 1.0
+    primaryIterationPacketsRamp: float = 1.0
     setup_seed: int = 12345  # host-side sampling of densities / tree policy (numpy RNG)
     # build the octree and sample the medium state on the engine's side
     # (sk_engine_build_octree / sk_engine_sample_medium) instead of with the numpy code of setup()
@@ -1273,9 +1283,16 @@ class MonteCarloSimulation:
         """MonteCarloSimulation::runSimulation, MonteCarloSimulation.cpp:58-100: primary emission and, in DustEmission
         mode, the secondary emission iterations and the final secondary emission.  `comm` (skirt9_b200.parallel.Comm)
         shards the histories of every segment over the ranks and performs the reference's reductions."""
+        dynamic = self.clearDensityThreshold is not None                      # Configuration.cpp:139-226
+        primary_iterations = self.iteratePrimaryEmission and dynamic
+        merged = (self.dustEmissionWLG is not None and self.iterateSecondaryEmission and self.includePrimaryEmission and dynamic)
+        if primary_iterations:
+            self.run_primary_emission_iterations(engine, stream_id + 3000, comm)
+        if merged:
+            self.run_merged_emission_iterations(engine, stream_id + 4000, comm)
         self.run_primary_emission(engine, first, count, stream_id, comm)
         if self.dustEmissionWLG is not None:
-            if self.iterateSecondaryEmission:
+            if self.iterateSecondaryEmission and not merged:
                 self.run_secondary_emission_iterations(engine, stream_id + 1000, comm)
             self.run_secondary_emission(engine, stream_id + 2000, comm)
         if comm is not None:
@@ -1296,6 +1313,99 @@ class MonteCarloSimulation:
             if comm is not None:
                 comm.allreduce_rf(engine, True)
             engine.communicate_rf(True)
+
+    # -- dynamic medium state ------------------------------------------------------------------------
+    def update_dynamic_state(self, engine):
+        """MediumSystem::updateDynamicStateRecipes (MediumSystem.cpp:1498-1558) with a ClearDensityRecipe
+        (ClearDensityRecipe.cpp:17-35): a cell whose radiation field strength U = Sum_l J_l dlambda_l / 1.7623e-6 W/m2/sr exceeds
+        the threshold loses its material.  Returns (cells updated, converged); the new densities go to the engine."""
+        rf = engine.read_rf(0)
+        if self.dustEmissionWLG is not None:
+            rf = rf + engine.read_rf(1)                      # MediumSystem::radiationField, MediumSystem.cpp:1360-1366
+        U = rf.sum(axis=1) / (4 * math.pi * self.volume) / 1.7623e-06
+        dens = np.asarray(self.density, dtype=float)
+        total = dens if dens.ndim == 1 else dens.sum(axis=0)
+        hit = (U > self.clearDensityThreshold)
+        updated = int(np.count_nonzero(hit & (total > 0))) if dens.ndim == 1 else int(np.count_nonzero(hit[None, :] & (dens > 0)))
+        cells = int(np.count_nonzero(hit & (total > 0)))
+        if dens.ndim == 1:
+            dens = np.where(hit, 0.0, dens)
+        else:
+            dens = np.where(hit[None, :], 0.0, dens)
+        self.density = dens
+        if self.extraMedia:
+            engine.set_media(self.density, self.volume)
+        else:
+            engine.set_medium(self.density, self.volume)
+        if getattr(self, "velocity", None) is not None:
+            engine.set_velocities(self.velocity)
+        return cells, updated == 0                            # DynamicStateRecipe::endUpdate with maxNotConvergedCells = 0
+
+    @staticmethod
+    def _loop_ends(converged, it, min_iters, max_iters):
+        """logLoopConvergence, MonteCarloSimulation.cpp:233-261."""
+        return (converged and it >= min_iters) or (not converged and it >= max_iters)
+
+    def run_primary_emission_iterations(self, engine, stream_id=3000, comm=None):
+        """MonteCarloSimulation::runPrimaryEmissionIterations, MonteCarloSimulation.cpp:266-330."""
+        n_it = self.numPackets * self.primaryIterationPacketsMultiplier
+        min_n = max(1.0, n_it * self.primaryIterationInitialPacketsFraction)
+        max_n = max(1.0, n_it)
+        self.primary_iterations = []
+        it, prev = 0, 0
+        while True:
+            it += 1
+            n = int(min(max_n, min_n * self.primaryIterationPacketsRamp ** (it - 1)))
+            if n != prev:
+                engine.prepare_primary(n)
+                prev = n
+            engine.clear_rf(True)
+            first, count = comm.block(engine, n) if comm is not None else (0, n)
+            engine.run_segment(first, count, primary=True, peel=False, store=True, stream_id=stream_id + it)
+            if comm is not None:
+                comm.allreduce_rf(engine, True)
+            engine.communicate_rf(True)
+            updated, converged = self.update_dynamic_state(engine)
+            self.primary_iterations.append({"iteration": it, "packets": n, "updated_cells": updated, "converged": converged})
+            if self._loop_ends(converged, it, self.minPrimaryIterations, self.maxPrimaryIterations):
+                break
+
+    def run_merged_emission_iterations(self, engine, stream_id=4000, comm=None):
+        """MonteCarloSimulation::runMergedEmissionIterations, MonteCarloSimulation.cpp:407-496."""
+        n1 = int(self.numPackets * self.primaryIterationPacketsMultiplier)
+        n2 = int(self.numPackets * self.secondaryIterationPacketsMultiplier)
+        engine.prepare_primary(n1)
+        self.convergence = []
+        prev, it = 0.0, 0
+        while True:
+            it += 1
+            engine.clear_rf(True)
+            first, count = comm.block(engine, n1) if comm is not None else (0, n1)
+            engine.run_segment(first, count, primary=True, peel=False, store=True, stream_id=stream_id + 2 * it)
+            if comm is not None:
+                comm.allreduce_rf(engine, True)
+            engine.communicate_rf(True)
+            engine.clear_rf(False)
+            lum = engine.prepare_secondary(n2)
+            if not lum > 0:
+                return
+            first, count = comm.block(engine, n2) if comm is not None else (0, n2)
+            engine.run_segment(first, count, primary=False, peel=False, store=True, stream_id=stream_id + 2 * it + 1)
+            if comm is not None:
+                comm.allreduce_rf(engine, False)
+            engine.communicate_rf(False)
+            updated, converged = self.update_dynamic_state(engine)
+            # (the reference evaluates the absorbed luminosities after the update, with the new densities)
+            Lprim, Lseco = engine.absorbed_luminosity(True), engine.absorbed_luminosity(False)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                dust = (Lprim <= 0 or Lseco <= 0 or Lseco / Lprim < self.maxFractionOfPrimary
+                        or abs((Lseco - prev) / Lseco) < self.maxFractionOfPrevious)
+            prev = Lseco
+            converged = bool(converged and dust)
+            self.convergence.append({"iteration": it, "dust_luminosity": lum, "absorbed_primary": Lprim,
+                                     "absorbed_secondary": Lseco, "updated_cells": updated, "converged": converged})
+            if self._loop_ends(converged, it, self.minSecondaryIterations, self.maxSecondaryIterations):
+                break
 
     def run_secondary_emission(self, engine, stream_id=2000, comm=None):
         """MonteCarloSimulation::runSecondaryEmission, MonteCarloSimulation.cpp:142-173."""

@@ -401,6 +401,34 @@ def make_cfg15k():
     print("cfg15k:", {k: np.shape(v) for k, v in out.items()}, out["dust_luminosity_lsun"])
 
 
+def make_cfg16d():
+    """Dynamic medium state: a ClearDensityRecipe carves a cavity around the source in primary emission iterations, merged primary
+    and secondary iterations follow, then the regular segments (tests/golden/ski/cfg16d.ski).  The fixture holds the initial
+    densities (a run of the same ski without the recipe's effect: threshold 1e30), the final ones, the per-iteration log values
+    and the SED."""
+    with tempfile.TemporaryDirectory() as d:
+        text = open(os.path.join(HERE, "ski", "cfg16d.ski")).read()
+        open(os.path.join(d, "cfg16d0.ski"), "w").write(
+            text.replace('fieldStrengthThreshold="300"', 'fieldStrengthThreshold="1e30"').replace('numPackets="4e5"', 'numPackets="100"'))
+        subprocess.check_call([SKIRT, "-t", "1", "-b", "-o", d, os.path.join(d, "cfg16d0.ski")], stdout=subprocess.DEVNULL)
+        initial = read_columns(os.path.join(d, "cfg16d0_cells_cellprops.dat"))
+        log = run_reference("cfg16d", d)
+        cells = read_columns(os.path.join(d, "cfg16d_cells_cellprops.dat"))
+        assert np.array_equal(initial[:, 1:5], cells[:, 1:5])
+        out = dict(initial_mass_density_msun_pc3=initial[:, 6], final_mass_density_msun_pc3=cells[:, 6],
+                   cell_center_pc=cells[:, 1:4], cell_volume_pc3=cells[:, 4],
+                   updated_cells=np.array([int(x) for x in re.findall(r"Updated cells: (\d+) out of", log)]),
+                   dust_luminosity_lsun=np.array([float(x) for x in re.findall(r"Dust luminosity: ([0-9.eE+-]+) Lsun", log)]),
+                   absorbed_primary_lsun=np.array([float(x) for x in re.findall(r"dust-absorbed primary luminosity is ([0-9.eE+-]+) Lsun", log)]),
+                   absorbed_secondary_lsun=np.array([float(x) for x in re.findall(r"dust-absorbed secondary luminosity in iteration \d+ is ([0-9.eE+-]+) Lsun", log)]),
+                   primary_iterations=len(re.findall(r"Finished primary emission iteration", log)),
+                   merged_iterations=len(re.findall(r"Finished merged primary and secondary emission iteration", log)),
+                   sed=read_columns(os.path.join(d, "cfg16d_sed_sed.dat")),
+                   sedstats=read_columns(os.path.join(d, "cfg16d_sed_sedstats.dat")), num_packets=4e5)
+    np.savez_compressed(os.path.join(HERE, "cfg16d_ref.npz"), **out)
+    print("cfg16d:", {k: (np.shape(v) if np.ndim(v) > 1 else v) for k, v in out.items() if "density" not in k and "cell" not in k and "sed" not in k})
+
+
 if __name__ == "__main__":
     if not os.path.exists(SKIRT):
         raise SystemExit("oracle/_ref is not built: run `make -C oracle -f ref.mk -j8` where /root/reference exists")

@@ -735,3 +735,74 @@ def test_engine_matches_reference_cfg15k_kinematics(engine_lib):
     e = sim.configure(abi.Engine(sim.config_struct(device=0), lib=engine_lib))
     sim.run(e)
     check_cfg15k(sim, e, g, n)
+
+
+# ---------------------------------------------------------------- dynamic medium state: primary and merged iterations (cfg16d)
+def cfg16d_from_reference(num_packets):
+    """tests/golden/ski/cfg16d.ski through the host mirror: a ClearDensityRecipe (threshold U = 300) in primary emission
+    iterations (0.5 x packets, ramp 1.5 from half of that) and merged primary + secondary iterations, then the regular segments."""
+    g = load("cfg16d")
+    pc = H.PC
+    mix = H.MeanListDustMix([0.05e-6, 0.55e-6, 10e-6, 100e-6, 2000e-6], [5000.0, 1000.0, 100.0, 5.0, 0.01],
+                            [0.4, 0.6, 0.2, 0.01, 0.0001], [0.6, 0.5, 0.05, 0.0, 0.0])
+    medium = H.GeometricMedium(H.ShellGeometry(0.02 * pc, 1.0 * pc, 1.0), mix, opticalDepth=6.0, wavelength=0.55e-6)
+    grid = H.CartesianSpatialGrid(-pc, pc, -pc, pc, -pc, pc, 21, 21, 21)
+    src = H.PointSource((0.0, 0.0, 0.0), H.BlackBodySED(10000.0), luminosity=1e4 * H.LSUN)
+    instr = H.SEDInstrument(instrumentName="sed", distance=1e6 * pc, inclination=60 * DEG, recordComponents=True, recordStatistics=True)
+    sim = H.MonteCarloSimulation(sources=[src], medium=medium, grid=grid, instruments=[instr], numPackets=num_packets,
+                                 minWavelength=0.1e-6, maxWavelength=20e-6,
+                                 defaultWavelengthGrid=H.LogWavelengthGrid(0.1e-6, 1000e-6, 40), storeRadiationField=True,
+                                 radiationFieldWLG=H.LogWavelengthGrid(0.1e-6, 1000e-6, 40),
+                                 dustEmissionWLG=H.LogWavelengthGrid(1e-6, 1000e-6, 40), iterateSecondaryEmission=True,
+                                 minSecondaryIterations=1, maxSecondaryIterations=6, secondaryIterationPacketsMultiplier=0.5,
+                                 clearDensityThreshold=300.0, iteratePrimaryEmission=True, includePrimaryEmission=True,
+                                 minPrimaryIterations=1, maxPrimaryIterations=8, primaryIterationPacketsMultiplier=0.5,
+                                 primaryIterationInitialPacketsFraction=0.5, primaryIterationPacketsRamp=1.5,
+                                 numDensitySamples=20, seed=0)
+    sim.density = g["initial_mass_density_msun_pc3"] * RHO / mix.MU
+    sim.setup()
+    return sim, g
+
+
+def check_cfg16d(sim, e, g, n, tol_scale=1.0):
+    LSUN = H.LSUN
+    # the cavity: the reference clears 81 of the 5564 filled cells in three primary and two merged iterations; which cells near the
+    # threshold go is a matter of the noise in their radiation field, so the counts agree statistically
+    ref_cleared = (g["final_mass_density_msun_pc3"] == 0) & (g["initial_mass_density_msun_pc3"] > 0)
+    own_cleared = (np.asarray(sim.density) == 0) & (g["initial_mass_density_msun_pc3"] > 0)
+    assert int(ref_cleared.sum()) == int(g["updated_cells"].sum()) == 81
+    assert abs(int(own_cleared.sum()) - 81) <= 12 * tol_scale
+    # the cleared cells are the ones nearest to the source, on both sides
+    r = np.linalg.norm(g["cell_center_pc"], axis=1)
+    assert r[own_cleared].max() < 1.25 * r[ref_cleared].max()
+    assert np.count_nonzero(own_cleared & ref_cleared) >= 0.8 * min(own_cleared.sum(), ref_cleared.sum())
+    assert 2 <= len(sim.primary_iterations) <= 5 and sim.primary_iterations[-1]["converged"]
+    assert sim.primary_iterations[0]["packets"] == int(0.25 * n) and sim.primary_iterations[1]["packets"] == int(0.375 * n)
+    assert 1 <= len(sim.convergence) <= 4
+    # luminosities of the last merged iteration and of the final secondary emission (converged state)
+    assert sim.convergence[-1]["absorbed_primary"] / LSUN == pytest.approx(g["absorbed_primary_lsun"][-1], rel=0.03 * tol_scale)
+    assert sim.convergence[-1]["absorbed_secondary"] / LSUN == pytest.approx(g["absorbed_secondary_lsun"][-1], rel=0.08 * tol_scale)
+    assert sim.dust_luminosity / LSUN == pytest.approx(g["dust_luminosity_lsun"][-1], rel=0.03 * tol_scale)
+    # SED: the sums per column (the bins individually depend on the exact shape of the cavity)
+    sed = g["sed"]
+    for col, comp in ((1, abi.SK_COMP_TOTAL), (2, abi.SK_COMP_TRANSPARENT), (3, abi.SK_COMP_PRIMARY_DIRECT),
+                      (4, abi.SK_COMP_PRIMARY_SCATTERED), (5, abi.SK_COMP_SECONDARY_DIRECT)):
+        f = sim.sed_flux_density(e, 0, comp)
+        assert f.sum() == pytest.approx(sed[:, col].sum(), rel=(0.01 if col == 2 else 0.05) * tol_scale), comp
+
+
+def test_oracle_matches_reference_cfg16d_dynamic_state_iterations():
+    n = 100000
+    sim, g = cfg16d_from_reference(n)
+    e = sim.configure(OracleEngine(sim.config_struct()))
+    sim.run(e)
+    check_cfg16d(sim, e, g, n, tol_scale=2.0)
+
+
+@pytest.mark.gpu
+def test_engine_matches_reference_cfg16d_dynamic_state_iterations(engine_lib):
+    n = 400000
+    sim, g = cfg16d_from_reference(n)
+    e = sim.configure(abi.Engine(sim.config_struct(device=0), lib=engine_lib))
+    sim.run(e)
+    check_cfg16d(sim, e, g, n)

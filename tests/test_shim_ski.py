@@ -308,6 +308,36 @@ def test_cfg15k_ski_kinematics_runs_unchanged(tmp_path):
         assert float((f * sed[:, 0]).sum() / f.sum()) == pytest.approx(0.505 * factor, rel=3e-3)
 
 
+def test_cfg16d_ski_dynamic_state_iterations_run_unchanged(tmp_path):
+    """Primary emission iterations and merged iterations with a ClearDensityRecipe (the call sites MonteCarloSimulation.cpp:314,
+    451, 474): the segments run on the engine, the reference's own recipe code updates the medium state on the host from the
+    radiation field handed back, and the new densities go to the engine.  Same packets as the fixture run: the sequence of
+    cleared cells is the reference's up to the noise of the cells at the threshold."""
+    g = np.load(os.path.join(GOLD, "cfg16d_ref.npz"))
+    log = run_ski("cfg16d", tmp_path, 4e5)
+    updated = [int(x) for x in re.findall(r"Updated cells: (\d+) out of", log)]
+    nprim = len(re.findall(r"Finished primary emission iteration", log))
+    nmerged = len(re.findall(r"Finished merged primary and secondary emission iteration", log))
+    assert 2 <= nprim <= 5 and 1 <= nmerged <= 4
+    assert len(updated) == nprim + nmerged and updated[0] > 0
+    assert abs(sum(updated) - int(g["updated_cells"].sum())) <= 12
+    lum = [float(x) for x in re.findall(r"Dust luminosity: ([0-9.eE+-]+) Lsun", log)]
+    prim = [float(x) for x in re.findall(r"dust-absorbed primary luminosity is ([0-9.eE+-]+) Lsun", log)]
+    sec = [float(x) for x in re.findall(r"dust-absorbed secondary luminosity in iteration \d+ is ([0-9.eE+-]+) Lsun", log)]
+    assert lum[-1] == pytest.approx(g["dust_luminosity_lsun"][-1], rel=0.03)
+    assert prim[-1] == pytest.approx(g["absorbed_primary_lsun"][-1], rel=0.03)
+    assert sec[-1] == pytest.approx(g["absorbed_secondary_lsun"][-1], rel=0.08)
+    # the medium state the reference's probe writes after the run: the cavity
+    cells = read_columns(tmp_path / "cfg16d_cells_cellprops.dat")
+    own = (cells[:, 6] == 0) & (g["initial_mass_density_msun_pc3"] > 0)
+    ref = (g["final_mass_density_msun_pc3"] == 0) & (g["initial_mass_density_msun_pc3"] > 0)
+    assert own.sum() == sum(updated)
+    assert np.count_nonzero(own & ref) >= 0.8 * min(own.sum(), ref.sum())
+    sed = read_columns(tmp_path / "cfg16d_sed_sed.dat")
+    for col in (1, 2, 3, 4, 5):
+        assert sed[:, col].sum() == pytest.approx(g["sed"][:, col].sum(), rel=0.01 if col == 2 else 0.05), col
+
+
 def test_cfg5s_ski_voronoi_particles_runs_unchanged(tmp_path):
     """ParticleMedium import + VoronoiMeshSpatialGrid (voro++ tessellation, SPH kernel density sampling) all done by the
     reference's own setup code; only the life cycle runs on the GPU."""
