@@ -828,8 +828,10 @@ extern "C" int sk_engine_set_velocities(sk_engine_t* e, int32_t num_cells, const
     if (!velocity || num_cells <= 0) return SK_OK;
     if (!e->grid_kind || !e->M.ncells) return fail(SK_ERR_STATE, "set the medium state before the velocities");
     if (num_cells != e->M.ncells) return fail(SK_ERR_INVALID, "velocities do not match the medium state");
-    double* v;
-    if (int rc = upload(e->vel_allocs, velocity, 3 * (size_t)num_cells, &v)) return rc;
+    std::vector<double4> v4((size_t)num_cells);
+    for (int m = 0; m < num_cells; ++m) v4[m] = make_double4(velocity[3 * (size_t)m], velocity[3 * (size_t)m + 1], velocity[3 * (size_t)m + 2], 0.);
+    double4* v;
+    if (int rc = upload(e->vel_allocs, v4.data(), (size_t)num_cells, &v)) return rc;
     e->M.vel = v;
     e->vel_given = true;
     e->M.kin = 1;
@@ -2234,8 +2236,8 @@ extern "C" int sk_engine_launch_segment(sk_engine_t* e, uint64_t first, uint64_t
     if (e->M.kin && !e->M.vel)
     {
         // only the sources move: the walks with kinematics read a velocity per cell all the same
-        double* v;
-        if (int rc = dalloc_zero(e->vel_allocs, 3 * (size_t)e->M.ncells, &v)) return rc;
+        double4* v;
+        if (int rc = dalloc_zero(e->vel_allocs, (size_t)e->M.ncells, &v)) return rc;
         e->M.vel = v;
     }
     if (share)

@@ -140,11 +140,11 @@ struct SkDevModel {
                                      // SK_PIX_K + 2 ints (pixel-bin indices, number of entries, newest pool chunk or -1)
     // counters
     unsigned long long* counters;
-    // kinematics (sk_engine_set_velocities; also set when only sources move): vel[3*m + c] = MediumState::bulkVelocity(m),
+    // kinematics (sk_engine_set_velocities; also set when only sources move): vel[m] = MediumState::bulkVelocity(m),
     // all zero for media at rest.  The walks then run in the several-component instantiation with per-cell section look-ups,
     // and the bank holds the extra per-packet fields SK_KD_* / SK_KI_* from kin_base_d / kin_base_i on.
     int32_t kin, kin_base_d, kin_base_i, kin_pad;
-    const double* vel;
+    const double4* vel;  // {vx, vy, vz, 0} per cell: one 32-byte request per crossing, like the cell record
 };
 
 // Radiation field tables on the device are wavelength-major, rf[ell * ncells + m] (the reference's Table<2> is [m][ell],
@@ -470,9 +470,20 @@ __device__ __forceinline__ double sk_planck(double lambda, double T)
 }
 // the same with a guess: i is returned when it is the answer (two comparisons), else the search runs.  The walks with
 // kinematics look the dust tables up in every cell, and the perceived wavelength moves by parts in a thousand from cell to cell.
+// (a few steps up or down the table first: the answer is the index i with (i == 0 or xv[i] <= x) and (i == n-2 or x < xv[i+1]),
+//  however it is found)
 __device__ __forceinline__ int sk_locate_clip_hint(const double* __restrict__ xv, int n, double x, int i)
 {
-    if ((i == 0 || xv[i] <= x) && (i == n - 2 || x < xv[i + 1])) return i;
+#pragma unroll 1
+    for (int step = 0; step < 6; ++step)
+    {
+        if (i > 0 && x < xv[i])
+            --i;
+        else if (i < n - 2 && !(x < xv[i + 1]))
+            ++i;
+        else
+            return i;
+    }
     return sk_locate_clip(xv, n, x);
 }
 // Doppler shifts, PhotonPacket.cpp:133-151 (no Hubble flow): the wavelength a packet of rest wavelength lambda leaves with in
@@ -491,7 +502,17 @@ __device__ __forceinline__ double sk_perceived(double lambda, double kx, double 
 // (the border index std::upper_bound returns, with a guess: see sk_locate_clip_hint)
 __device__ __forceinline__ int sk_wlg_upper_hint(const SkDevWlg& g, double lambda, int lo0)
 {
-    if ((lo0 == 0 || g.borders[lo0 - 1] <= lambda) && (lo0 == g.num_borders || lambda < g.borders[lo0])) return lo0;
+    // (the answer is the index lo with (lo == 0 or borders[lo-1] <= lambda) and (lo == num_borders or lambda < borders[lo]))
+#pragma unroll 1
+    for (int step = 0; step < 3; ++step)
+    {
+        if (lo0 > 0 && lambda < g.borders[lo0 - 1])
+            --lo0;
+        else if (lo0 < g.num_borders && !(lambda < g.borders[lo0]))
+            ++lo0;
+        else
+            return lo0;
+    }
     int lo = 0, hi = g.num_borders;
     while (lo < hi)
     {

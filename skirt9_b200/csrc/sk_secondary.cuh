@@ -273,7 +273,7 @@ __device__ __noinline__ void sk_launch_secondary(const SkDevModel* __restrict__ 
     pp.W = (L * ws * w) * lambda;
     pp.ilam = sk_locate_clip(M.lam_border, M.nlam, lambda);
     // the bulk velocity of the emitting cell (DustSecondarySource.cpp:271, 562-580)
-    pp.vx = M.vel ? M.vel[3 * (size_t)m] : 0.;
-    pp.vy = M.vel ? M.vel[3 * (size_t)m + 1] : 0.;
-    pp.vz = M.vel ? M.vel[3 * (size_t)m + 2] : 0.;
+    pp.vx = M.vel ? M.vel[m].x : 0.;
+    pp.vy = M.vel ? M.vel[m].y : 0.;
+    pp.vz = M.vel ? M.vel[m].z : 0.;
 }

@@ -46,6 +46,9 @@
 #ifndef SK_TRACE_MINBLOCKS_MULTI_LESS
 #define SK_TRACE_MINBLOCKS_MULTI_LESS 1  // several components: one resident block fewer pays for the extra lane state (measured)
 #endif
+#ifndef SK_TRACE_MINBLOCKS_KIN_LESS
+#define SK_TRACE_MINBLOCKS_KIN_LESS 1  // kinematics: perceived wavelength, table index and k.v of the next cell in lane registers (measured: 1 beats 2 and 3)
+#endif
 #ifndef SK_CHUNK
 #define SK_CHUNK 64
 #endif
@@ -332,7 +335,7 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, (GRID == 3   ? SK_TRACE_MINBLO
                                                    : MODE == 2 ? SK_TRACE_MINBLOCKS_PEEL
                                                    : STORE     ? SK_TRACE_MINBLOCKS_STORE
                                                                : SK_TRACE_MINBLOCKS)
-                                                      - (MULTI ? SK_TRACE_MINBLOCKS_MULTI_LESS : 0))
+                                                      - (KIN ? SK_TRACE_MINBLOCKS_KIN_LESS : MULTI ? SK_TRACE_MINBLOCKS_MULTI_LESS : 0))
     sk_wf_trace(const SkDevModel M, const SkRunArgs A, const SkBank K, const SkObsDir obs)
 {
     extern __shared__ __align__(16) double smem[];
@@ -402,12 +405,18 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, (GRID == 3   ? SK_TRACE_MINBLO
     constexpr bool kin = MULTI && KIN;
     const bool more_media = MULTI && M.nmed > 1;
     double lam_ray = 0., lamp = 0., pkx = 0., pky = 0., pkz = 0.;
+    double kv = 0.;  // k . v of cell mpre, requested like the second component's density as soon as the next cell is known
     int rf_lo = 0;
 #define SK_FETCH_DENSX()                                                                          \
-    if (more_media)                                                                               \
+    if (more_media || kin)                                                                        \
     {                                                                                             \
         mpre = st.m();                                                                            \
-        if (mpre >= 0) dn1 = __ldg(&M.densx[(size_t)mpre]);                                       \
+        if (more_media && mpre >= 0) dn1 = __ldg(&M.densx[(size_t)mpre]);                         \
+        if (kin && mpre >= 0)                                                                     \
+        {                                                                                         \
+            const double4 v_ = sk_ld_rec(&M.vel[mpre]);                                           \
+            kv = pkx * v_.x + pky * v_.y + pkz * v_.z;                                            \
+        }                                                                                         \
     }
 #define SK_LOAD_SECTIONS()                                                                        \
     {                                                                                             \
@@ -631,8 +640,8 @@ __global__ void __launch_bounds__(SK_TRACE_BLOCK, (GRID == 3   ? SK_TRACE_MINBLO
                 {
                     if (kin)
                     {
-                        const double* __restrict__ vm = M.vel + 3 * (size_t)m;
-                        lamp = sk_perceived(lam_ray, pkx, pky, pkz, __ldg(vm), __ldg(vm + 1), __ldg(vm + 2));
+                        if (m != mpre) SK_FETCH_DENSX();  // (the Voronoi walk may re-locate its cell inside exit())
+                        lamp = lam_ray / (1 - kv / SK_C_LIGHT);  // sk_perceived
                         const int il = sk_locate_clip_hint(M.lam_border, M.nlam, lamp, ilam_ray);
                         if (il != ilam_ray)
                         {
@@ -856,8 +865,8 @@ __device__ __forceinline__ bool sk_peel_setup_values(const SkDevModel& M, const 
         const int kb = M.kin_base_d;
         if (scattering)
         {
-            const double* __restrict__ vm = M.vel + 3 * (size_t)(mint >= 0 ? mint : 0);
-            lambda = sk_shifted_emission(lambda, ox, oy, oz, mint >= 0 ? vm[0] : 0., mint >= 0 ? vm[1] : 0., mint >= 0 ? vm[2] : 0.);
+            const double4 vm = M.vel[mint >= 0 ? mint : 0];
+            lambda = sk_shifted_emission(lambda, ox, oy, oz, mint >= 0 ? vm.x : 0., mint >= 0 ? vm.y : 0., mint >= 0 ? vm.z : 0.);
         }
         else
             lambda = sk_shifted_emission(K.D(kb + SK_KD_LAMBDA0, slot), ox, oy, oz, K.D(kb + SK_KD_VSX, slot),
@@ -967,8 +976,8 @@ __global__ void SK_ADVANCE_BOUNDS sk_wf_advance(const SkDevModel M, const SkRunA
             {
                 // the wavelength the interaction cell perceives (MediumSystem::perceivedWavelengthForScattering,
                 // MediumSystem.cpp:667-674): albedo, peel-off weights and the scattering itself use it
-                const double* __restrict__ vm = M.vel + 3 * (size_t)(m >= 0 ? m : 0);
-                lamp = m >= 0 ? sk_perceived(lambda, kx, ky, kz, vm[0], vm[1], vm[2]) : lambda;
+                const double4 vm = M.vel[m >= 0 ? m : 0];
+                lamp = m >= 0 ? sk_perceived(lambda, kx, ky, kz, vm.x, vm.y, vm.z) : lambda;
                 ilamp = sk_locate_clip_hint(M.lam_border, M.nlam, lamp, ilam);
             }
             if (m >= 0)
@@ -1274,9 +1283,9 @@ __global__ void __launch_bounds__(SK_EVENT_BLOCK) sk_wf_detect(const SkDevModel 
                     // PhotonPacket::scatter(bfk, bfv, lambda), PhotonPacket.cpp:115-122: the packet leaves at the perceived
                     // wavelength, shifted by the bulk velocity of the cell for its new direction
                     const int mint = K.I(I_MINT, slot);
-                    const double* __restrict__ vm = M.vel + 3 * (size_t)(mint >= 0 ? mint : 0);
-                    const double lnew = sk_shifted_emission(K.D(M.kin_base_d + SK_KD_LAMP, slot), kx, ky, kz, mint >= 0 ? vm[0] : 0.,
-                                                            mint >= 0 ? vm[1] : 0., mint >= 0 ? vm[2] : 0.);
+                    const double4 vm = M.vel[mint >= 0 ? mint : 0];
+                    const double lnew = sk_shifted_emission(K.D(M.kin_base_d + SK_KD_LAMP, slot), kx, ky, kz, mint >= 0 ? vm.x : 0.,
+                                                            mint >= 0 ? vm.y : 0., mint >= 0 ? vm.z : 0.);
                     const int inew = sk_locate_clip_hint(M.lam_border, M.nlam, lnew, ilam_s);
                     K.D(D_LAMBDA, slot) = lnew;
                     K.I(I_ILAM, slot) = inew;
