@@ -21,6 +21,9 @@ if [[ $PARTS == *bench* ]]; then
   # diagnostic, not a BASELINE workload: cfg2 with a second dust component of another material mix (several-component kernels)
   SK_BENCH_SECOND_MIX=1 timeout 600 python bench.py --no-cpu-baseline --no-parity > gpurun_out/${TAG}_bench_cfg2_second_mix.json 2> gpurun_out/${TAG}_bench_cfg2_second_mix.err
   cut -c1-200 gpurun_out/${TAG}_bench_cfg2_second_mix.json
+  # diagnostic: cfg2 with a rotating ring and source (kinematics kernels; path-length stretching is off then, as in the reference)
+  SK_BENCH_KINEMATICS=1 timeout 600 python bench.py --no-cpu-baseline --no-parity --packets 3e7 > gpurun_out/${TAG}_bench_cfg2_kinematics.json 2> gpurun_out/${TAG}_bench_cfg2_kinematics.err
+  cut -c1-200 gpurun_out/${TAG}_bench_cfg2_kinematics.json
 fi
 if [[ $PARTS == *ncu* ]]; then
   B="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e"
@@ -42,7 +45,7 @@ if [[ $PARTS == *ncu* ]]; then
   du -sh gpurun_out
 fi
 if [[ $PARTS == *san* ]]; then
-  timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 1 python -m pytest tests/test_gpu_parity.py tests/test_setup.py -q -x -k "cartesian_cfg1 or octree_cfg2_small or explicit or interleaved or dust_emission or voronoi or two_components or three_components or particle_density" > gpurun_out/${TAG}_memcheck.log 2>&1
+  timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 1 python -m pytest tests/test_gpu_parity.py tests/test_setup.py -q -x -k "cartesian_cfg1 or octree_cfg2_small or explicit or interleaved or dust_emission or voronoi or two_components or three_components or particle_density or kinematics" > gpurun_out/${TAG}_memcheck.log 2>&1
   echo "memcheck rc=$?" >> gpurun_out/${TAG}_memcheck.log
   tail -5 gpurun_out/${TAG}_memcheck.log
 fi
