@@ -205,3 +205,25 @@ def with_kinematics(sim, source=True, media=True, speed=6e6):
                 s.velocityMagnitude = 0.6 * speed
                 s.velocityDistribution = H.RadialVectorField(0.5 * scale, 0.5)
     return sim
+
+
+def small_dynamic_state(num_packets=20000, seed=9):
+    """cfg16d in small: a ClearDensityRecipe carves a cavity around a point source in primary emission iterations (packet
+    ramp), merged primary + secondary iterations follow, then the regular segments (MonteCarloSimulation.cpp:266-330, 407-496)."""
+    pc = H.PC
+    mix = H.MeanListDustMix([0.05e-6, 0.55e-6, 10e-6, 100e-6, 2000e-6], [5000.0, 1000.0, 100.0, 5.0, 0.01],
+                            [0.4, 0.6, 0.2, 0.01, 0.0001], [0.6, 0.5, 0.05, 0.0, 0.0])
+    medium = H.GeometricMedium(H.ShellGeometry(0.02 * pc, 1.0 * pc, 1.0), mix, opticalDepth=6.0, wavelength=0.55e-6)
+    grid = H.CartesianSpatialGrid(-pc, pc, -pc, pc, -pc, pc, 11, 11, 11)
+    src = H.PointSource((0.0, 0.0, 0.0), H.BlackBodySED(10000.0), luminosity=1e4 * H.LSUN)
+    instr = H.SEDInstrument(instrumentName="sed", distance=1e6 * pc, inclination=60 * DEG, recordComponents=True, recordStatistics=True)
+    return H.MonteCarloSimulation(sources=[src], medium=medium, grid=grid, instruments=[instr], numPackets=num_packets,
+                                  minWavelength=0.1e-6, maxWavelength=20e-6,
+                                  defaultWavelengthGrid=H.LogWavelengthGrid(0.1e-6, 1000e-6, 20), storeRadiationField=True,
+                                  radiationFieldWLG=H.LogWavelengthGrid(0.1e-6, 1000e-6, 20),
+                                  dustEmissionWLG=H.LogWavelengthGrid(1e-6, 1000e-6, 20), iterateSecondaryEmission=True,
+                                  minSecondaryIterations=1, maxSecondaryIterations=4, secondaryIterationPacketsMultiplier=0.5,
+                                  clearDensityThreshold=100.0, iteratePrimaryEmission=True, includePrimaryEmission=True,
+                                  minPrimaryIterations=1, maxPrimaryIterations=6, primaryIterationPacketsMultiplier=0.5,
+                                  primaryIterationInitialPacketsFraction=0.5, primaryIterationPacketsRamp=1.5,
+                                  numDensitySamples=4, seed=seed)

@@ -488,3 +488,20 @@ def test_velocities_are_dropped_with_the_medium_state(engine_lib):
     sim.run(e)
     sim.run(ref)
     models.compare_engines(sim, e, ref, rtol=1e-12)
+
+
+def test_dynamic_state_iterations_match_oracle(engine_lib):
+    """Primary and merged iterations with a ClearDensityRecipe through the host mirror: the engine is handed new densities between
+    segments (sk_engine_set_medium on a configured engine keeps links, tables, radiation field and detector arrays)."""
+    sim = models.small_dynamic_state(num_packets=20000)
+    sim.setup()
+    initial = np.array(sim.density, copy=True)
+    gpu = sim.configure(abi.Engine(sim.config_struct(device=0), lib=engine_lib))
+    sim.run(gpu)
+    cleared_gpu, its_gpu = np.array(sim.density == 0), [it["updated_cells"] for it in sim.primary_iterations]
+    sim.density = initial.copy()     # (the recipe has changed the model's densities: the oracle starts from the same state)
+    cpu = sim.configure(OracleEngine(sim.config_struct()))
+    sim.run(cpu)
+    assert its_gpu == [it["updated_cells"] for it in sim.primary_iterations] and sum(its_gpu) > 0
+    assert np.array_equal(cleared_gpu, sim.density == 0)
+    models.compare_engines(sim, gpu, cpu, rtol=1e-8)

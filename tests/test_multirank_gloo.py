@@ -131,3 +131,32 @@ def test_two_ranks_build_the_same_grid_without_communication():
     for c in comps:
         a, b = got["sed%d" % c], e.read_sed(0, c)
         np.testing.assert_allclose(a, b, rtol=1e-11, atol=1e-14 * b.max())
+
+
+def test_two_ranks_dynamic_state_iterations_match_single_rank():
+    """Primary and merged iterations over a dynamic medium state: the radiation field is all-reduced before the recipe looks at
+    it, so both ranks clear the same cells and hand the same densities to their engines."""
+    comps = [abi.SK_COMP_PRIMARY_DIRECT, abi.SK_COMP_PRIMARY_SCATTERED, abi.SK_COMP_SECONDARY_DIRECT]
+    got = run_two_ranks("small_dynamic_state(num_packets=8000)", comps, 29614)
+    sim = models.small_dynamic_state(num_packets=8000).setup()
+    e = sim.configure(OracleEngine(sim.config_struct()))
+    sim.run(e)
+    assert sum(it["updated_cells"] for it in sim.primary_iterations) > 0
+    conv = np.array([[c["dust_luminosity"], c["absorbed_primary"], c["absorbed_secondary"]] for c in sim.convergence])
+    assert got["conv"].shape == conv.shape
+    np.testing.assert_allclose(got["conv"], conv, rtol=2e-4)
+    for c in comps:
+        a, b = got["sed%d" % c], e.read_sed(0, c)
+        np.testing.assert_allclose(a, b, rtol=2e-3, atol=1e-6 * b.max())
+
+
+def test_two_ranks_kinematics_match_single_rank():
+    comps = [abi.SK_COMP_TRANSPARENT, abi.SK_COMP_PRIMARY_DIRECT, abi.SK_COMP_PRIMARY_SCATTERED]
+    got = run_two_ranks("with_kinematics(models.two_sources_three_instruments(num_packets=6000))", comps, 29615)
+    sim = models.with_kinematics(models.two_sources_three_instruments(num_packets=6000)).setup()
+    e = sim.configure(OracleEngine(sim.config_struct()))
+    sim.run(e)
+    for c in comps:
+        np.testing.assert_allclose(got["sed%d" % c], e.read_sed(0, c), rtol=1e-11)
+    ref = e.read_rf(0)
+    np.testing.assert_allclose(got["rf1"], ref, rtol=1e-10, atol=1e-12 * ref.max())
