@@ -1928,19 +1928,21 @@ extern "C" int sk_engine_prepare_secondary(sk_engine_t* e, uint64_t num_packets,
 // ---------------------------------------------------------------------------------------------------
 // the segment driver: performLifeCycle(firstIndex, numIndices, primary, peel, store) over the bank
 // ---------------------------------------------------------------------------------------------------
-static size_t bank_capacity_limit()
+static size_t bank_capacity_limit(int nlists)
 {
-    // in-flight packets per GPU; ~230 B of state each.  SK_BANK overrides (tests use small banks to exercise refill).
+    // in-flight packets per GPU; ~230 B of state each, 3.9 GB at 2^24 (measured on cfg2, 1e8 packets: 2^22 462 ms, 2^23 442 ms,
+    // 2^24 432 ms, 2^25 435 ms per step: fewer rounds, a shorter drain).  Per-history pixel / bin lists add 392 B per slot and
+    // list plus their pool of chunks: those runs keep 2^23.  SK_BANK overrides (tests use small banks to exercise refill).
     const char* s = getenv("SK_BANK");
     long long v = s ? atoll(s) : 0;
-    return v > 0 ? (size_t)v : (size_t)1 << 23;
+    return v > 0 ? (size_t)v : (size_t)1 << (nlists > 0 ? 23 : 24);
 }
 
 static int ensure_bank(sk_engine* e, uint64_t count)
 {
-    size_t cap = std::min<uint64_t>(count, bank_capacity_limit());
-    cap = std::max<size_t>((cap + 255) / 256 * 256, 256);
     const int nlists = e->num_pix_lists + (e->M.kin ? e->num_sed_lists : 0);
+    size_t cap = std::min<uint64_t>(count, bank_capacity_limit(nlists));
+    cap = std::max<size_t>((cap + 255) / 256 * 256, 256);
     int nd = SK_BANK_FIELDS_D(e->M.ninstr) + nlists * SK_PIX_K;
     int ni = SK_BANK_FIELDS_I(e->M.ninstr) + nlists * SK_PIX_INTS;
     e->M.kin_base_d = nd;  // the extra per-packet fields of a run with kinematics follow the pixel lists
