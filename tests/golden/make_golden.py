@@ -429,6 +429,37 @@ def make_cfg16d():
     print("cfg16d:", {k: (np.shape(v) if np.ndim(v) > 1 else v) for k, v in out.items() if "density" not in k and "cell" not in k and "sed" not in k})
 
 
+def make_cfg1_formats():
+    """The text headers and FITS cards of the files the reference writes for cfg1 (formats only: 1e4 packets), for the test of
+    skirt9_b200/output.py."""
+    import json
+    with tempfile.TemporaryDirectory() as d:
+        run_reference("cfg1", d, packets=1e4)
+        def comments(name, limit=None):
+            lines = [ln.rstrip("\n") for ln in open(os.path.join(d, name)) if ln.startswith("#")]
+            return lines[:limit] if limit else lines
+        def cards(name):
+            raw = open(os.path.join(d, name), "rb").read()
+            out, blocks, pos = [], 0, 0
+            while blocks < 2:       # primary header and the header of the table extension
+                c = raw[pos:pos + 80].decode("ascii")
+                pos += 80
+                if c.startswith("END"):
+                    blocks += 1
+                    out.append("END")
+                    pos = (pos + 2879) // 2880 * 2880
+                    if blocks == 1:
+                        pos += (64 * 64 * 4 + 2879) // 2880 * 2880
+                elif not c.startswith("DATE"):
+                    out.append(c.rstrip())
+            return out, raw[pos:pos + 16].decode("ascii")
+        c, row = cards("cfg1_i60_total.fits")
+        out = dict(sed=comments("cfg1_i60_sed.dat"), sedstats=comments("cfg1_i60_sedstats.dat"), rf=comments("cfg1_rf_J.dat"),
+                   fits_cards=c, fits_table_row=row, files=sorted(f for f in os.listdir(d) if f.startswith("cfg1_i60_") and "stats" not in f))
+    json.dump(out, open(os.path.join(HERE, "cfg1_formats.json"), "w"), indent=1)
+    print("cfg1_formats:", {k: len(v) for k, v in out.items()})
+
+
 if __name__ == "__main__":
     if not os.path.exists(SKIRT):
         raise SystemExit("oracle/_ref is not built: run `make -C oracle -f ref.mk -j8` where /root/reference exists")
