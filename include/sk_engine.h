@@ -346,6 +346,10 @@ int sk_engine_set_velocities(sk_engine_t* e, int32_t num_cells, const double* ve
  * the num_media = 1 forms.  Up to SK_MAX_MEDIA components.  With explicit absorption the walks are in scattering optical depth and
  * the absorption optical depth is accumulated next to it and interpolated at the interaction point (MediumSystem.cpp:937-955,
  * 1112-1150). */
+/* May be called again on a configured engine with the same grid -- a dynamic medium state whose recipes have changed densities
+ * between two segments (MediumSystem::updateDynamicStateRecipes, MediumSystem.cpp:1498-1558; the primary / merged iteration
+ * loops of MonteCarloSimulation.cpp:266-330, 407-496): grid links, dust tables, radiation field and detector arrays stay; the
+ * new medium state is at rest until sk_engine_set_velocities is called again. */
 int sk_engine_set_media(sk_engine_t* e, int32_t num_cells, int32_t num_media, const double* number_density,
                         const double* volume);
 int sk_engine_set_dustmixes(sk_engine_t* e, int32_t num_media, const sk_dustmix_t* mixes);
