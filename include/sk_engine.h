@@ -181,6 +181,9 @@ typedef struct sk_secondary {
     const double* rf_sigma_abs;  /* [N_rf]   _rfsigmaabsvv[0]: sigma_abs resampled on the radiation field grid (.cpp:59) */
     const double* em_sigma_abs;  /* [N_em+2] _emsigmaabsvv[0]: sigma_abs on DisjointWavelengthGrid::extlambdav() of the
                                     emission grid (.cpp:62-65, DisjointWavelengthGrid.cpp:346-356) */
+    const double* rf_cmb;        /* [N_rf] _Bcmbv: the CMB source term B_lambda(T_cmb (1 + z)) at the wavelengths of the radiation
+                                    field grid, added to the mean intensity in the energy balance when DustEmissionOptions::
+                                    includeHeatingByCMB (.cpp:37-44, 120-131); NULL = none */
 } sk_secondary_t;
 
 /* ---- Setup on the device: octree construction and medium-state sampling ----

@@ -132,6 +132,7 @@ typedef struct sko_engine {
     int has_secondary;
     sk_secondary_t sec;
     int sec_nmed;
+    double* sec_cmb; /* [nrf] the CMB source term of the energy balance (zeros without CMB heating) */
     double *sec_T, *sec_planckabs, *sec_rfsig, *sec_emsig; /* EquilibriumDustEmissionCalculator tables, one set per dust
                                                               component: [h*nT + i], [h*nrf + ell], [h*sec_nem + i] */
     int sec_nem;             /* N_em + 2 points of DisjointWavelengthGrid::extlambdav() */
@@ -1717,6 +1718,8 @@ static void free_secondary(sko_engine_t* e)
     free(e->sec_T);
     free(e->sec_planckabs);
     free(e->sec_rfsig);
+    free(e->sec_cmb);
+    e->sec_cmb = NULL;
     free(e->sec_emsig);
     free(e->sec_lambda);
     free(e->sec_pv);
@@ -1756,6 +1759,8 @@ int sko_set_secondary_media(sko_engine_t* e, int32_t num_media, const sk_seconda
     e->sec_T = dupd(sec->temperature, nT);
     e->sec_planckabs = (double*)malloc((size_t)num_media * nT * sizeof(double));
     e->sec_rfsig = (double*)malloc((size_t)num_media * e->nrf * sizeof(double));
+    e->sec_cmb = (double*)calloc(e->nrf ? e->nrf : 1, sizeof(double));
+    if (sec->rf_cmb) memcpy(e->sec_cmb, sec->rf_cmb, e->nrf * sizeof(double));
     e->sec_emsig = (double*)malloc((size_t)num_media * (n + 2) * sizeof(double));
     for (int h = 0; h < num_media; ++h)
     {
@@ -1933,7 +1938,7 @@ int sko_prepare_secondary(sko_engine_t* e, uint64_t num_packets, double* luminos
                 rf += e->rf1[(size_t)m * nrf + ell];
                 rf += e->rf2[(size_t)m * nrf + ell];
                 double J = rf * factor / rfg->dlambda[ell];
-                inputabs += rfsig[ell] * (J + 0.) * rfg->dlambda[ell];
+                inputabs += rfsig[ell] * (J + e->sec_cmb[ell]) * rfg->dlambda[ell]; /* (Jv + _Bcmbv), .cpp:123 */
             }
             double T = 0.;
             if (inputabs > 0.)

@@ -530,7 +530,6 @@ std::string GpuLifeCycle::unsupportedReason() const
             if (recipe->type() != "ClearDensityRecipe") return "dynamic state recipe " + recipe->type();
     if (config->hasGasEmission()) return "gas emission";
     if (config->hasStochasticDustEmission()) return "stochastic dust emission";
-    if (config->includeHeatingByCMB()) return "CMB heating";
     if (ProcessManager::isMultiProc()) return "MPI (use one engine per rank through the C ABI instead)";
     auto mix = dynamic_cast<const DustMix*>(ms->media()[0]->mix());
     if (!mix || mix->scatteringMode() != DustMix::ScatteringMode::HenyeyGreenstein) return "a material mix other than a Henyey-Greenstein dust mix";
@@ -923,6 +922,8 @@ void GpuLifeCycle::configureEngine(int device)
             sec.planck_abs = ptr(calc._planckabsvv[0]);
             sec.rf_sigma_abs = ptr(calc._rfsigmaabsvv[0]);
             sec.em_sigma_abs = ptr(calc._emsigmaabsvv[0]);
+            // the CMB source term of the energy balance (all zero unless DustEmissionOptions::includeHeatingByCMB)
+            sec.rf_cmb = calc._Bcmbv.size() ? ptr(calc._Bcmbv) : nullptr;
         }
         check(sk_engine_set_secondary_media(_e, numComponents, secv.data()));
     }

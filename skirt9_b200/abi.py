@@ -72,7 +72,7 @@ class SkInstrument(C.Structure):
 class SkSecondary(C.Structure):
     _fields_ = [("emission_grid", C.c_int32), ("num_temperatures", C.c_int32), ("spatial_bias", C.c_double),
                 ("wavelength_bias", C.c_double), ("bias_min", C.c_double), ("bias_max", C.c_double),
-                ("temperature", _dp), ("planck_abs", _dp), ("rf_sigma_abs", _dp), ("em_sigma_abs", _dp)]
+                ("temperature", _dp), ("planck_abs", _dp), ("rf_sigma_abs", _dp), ("em_sigma_abs", _dp), ("rf_cmb", _dp)]
 
 
 SK_DENSITY_MAX_PARAMS = 16
@@ -392,21 +392,24 @@ class Engine:
         self._call("set_instruments", self._h, C.c_int32(len(instruments)), arr, C.c_int32(int(has_medium_emission)))
 
     def set_secondary(self, emission_grid, spatial_bias, wavelength_bias, bias_min, bias_max, temperature, planck_abs,
-                      rf_sigma_abs, em_sigma_abs):
+                      rf_sigma_abs, em_sigma_abs, rf_cmb=None):
         keep = [_d(temperature), _d(planck_abs), _d(rf_sigma_abs), _d(em_sigma_abs)]
+        cmb = _d(rf_cmb) if rf_cmb is not None else (None, None)
         sec = SkSecondary(emission_grid, len(keep[0][0]), spatial_bias, wavelength_bias, bias_min, bias_max,
-                          keep[0][1], keep[1][1], keep[2][1], keep[3][1])
+                          keep[0][1], keep[1][1], keep[2][1], keep[3][1], cmb[1])
         self._call("set_secondary", self._h, C.byref(sec))
 
-    def set_secondary_media(self, emission_grid, spatial_bias, wavelength_bias, bias_min, bias_max, tables: Sequence[tuple]):
+    def set_secondary_media(self, emission_grid, spatial_bias, wavelength_bias, bias_min, bias_max, tables: Sequence[tuple],
+                            rf_cmb=None):
         """tables: (temperature, planck_abs, rf_sigma_abs, em_sigma_abs) per dust component (sk_engine_set_secondary_media)."""
         arr = (SkSecondary * len(tables))()
         keep = []
+        cmb = _d(rf_cmb) if rf_cmb is not None else (None, None)
         for h, t in enumerate(tables):
             k = [_d(x) for x in t]
             keep.append(k)
             arr[h] = SkSecondary(emission_grid, len(k[0][0]), spatial_bias, wavelength_bias, bias_min, bias_max,
-                                 k[0][1], k[1][1], k[2][1], k[3][1])
+                                 k[0][1], k[1][1], k[2][1], k[3][1], cmb[1])
         self._call("set_secondary_media", self._h, C.c_int32(len(tables)), arr)
 
     # -- running --------------------------------------------------------------------------------

@@ -1771,7 +1771,11 @@ extern "C" int sk_engine_set_secondary_media(sk_engine_t* e, int32_t num_media, 
         std::copy(sec[h].rf_sigma_abs, sec[h].rf_sigma_abs + nrf, rfsig.begin() + (size_t)h * nrf);
         std::copy(sec[h].planck_abs, sec[h].planck_abs + nT, planckabs.begin() + (size_t)h * nT);
     }
-    double *a, *b, *c, *d, *f, *k;
+    double *a, *b, *c, *d, *f, *k, *cmb;
+    std::vector<double> cmbv((size_t)std::max(nrf, 1), 0.);
+    if (sec->rf_cmb) std::copy(sec->rf_cmb, sec->rf_cmb + nrf, cmbv.begin());
+    if (int rc = upload(e->sec_allocs, cmbv.data(), cmbv.size(), &cmb)) return rc;
+    e->M.sec_cmb = cmb;
     if (int rc = upload(e->sec_allocs, ext.data(), (size_t)nem, &a)) return rc;
     if (int rc = upload(e->sec_allocs, emsig.data(), emsig.size(), &b)) return rc;
     if (int rc = upload(e->sec_allocs, rfsig.data(), rfsig.size(), &c)) return rc;

@@ -128,6 +128,7 @@ struct SkDevModel {
     // secondary (dust) emission, sk_secondary.cuh
     int32_t sec_nem, sec_nT;         // points of the extended emission grid; size of the temperature grid
     const double *sec_lambda, *sec_emsig, *sec_rfsig, *sec_T, *sec_planckabs;  // per component: [h*sec_nem+i], [h*nrf+ell], -, [h*sec_nT+i]
+    const double* sec_cmb;           // [nrf] CMB source term of the energy balance (zeros without CMB heating)
     const double* sec_kabs_rf;       // sigma_abs at the characteristic wavelengths of the radiation field grid, [h*nrf + ell]
     double *sec_pv, *sec_Pv;         // [ncells][sec_nem] normalised emission spectrum and its cdf
     double *sec_Lv, *sec_ws;         // [ncells] absorbed luminosity; launch weight _Lv[m]/_Wv[m]

@@ -87,7 +87,7 @@ __global__ void sk_emission_spectrum_kernel(const SkDevModel M)
             rf += M.rf1[SK_RF_INDEX(M, m, ell)];
             rf += M.rf2[SK_RF_INDEX(M, m, ell)];
             double J = rf * factor / rfg.dlambda[ell];
-            inputabs += rfsig[ell] * (J + 0.) * rfg.dlambda[ell];
+            inputabs += rfsig[ell] * (J + M.sec_cmb[ell]) * rfg.dlambda[ell];  // (Jv + _Bcmbv), .cpp:123
         }
         double T = 0.;
         if (inputabs > 0.)

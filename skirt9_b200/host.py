@@ -75,7 +75,8 @@ def planck(lam, T):
     """PlanckFunction::value, SKIRT/utils/PlanckFunction.cpp:24-27."""
     f1 = H_PLANCK * C_LIGHT / (K_BOLTZ * T)
     f2 = 2.0 * H_PLANCK * C_LIGHT * C_LIGHT
-    return f2 / np.power(lam, 5) / np.expm1(f1 / lam)
+    with np.errstate(over="ignore"):   # (far on the Wien side expm1 overflows to inf and the value is 0, as in the reference)
+        return f2 / np.power(lam, 5) / np.expm1(f1 / lam)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -1025,6 +1026,8 @@ class MonteCarloSimulation:
     secondaryIterationPacketsMultiplier: float = 1.0
     # dynamic medium state (DynamicStateOptions with a ClearDensityRecipe; IterationOptions): the recipe runs on the host between
     # the segments, on the radiation field the engine hands back, and the new densities go to the engine
+    includeHeatingByCMB: bool = False  # DustEmissionOptions::includeHeatingByCMB, with the redshift of the simulation's Cosmology
+    cosmologyRedshift: float = 0.0
     clearDensityThreshold: Optional[float] = None   # ClearDensityRecipe::fieldStrengthThreshold; given => the recipe is present
     iteratePrimaryEmission: bool = False            # MonteCarloSimulation::iteratePrimaryEmission
     includePrimaryEmission: bool = False            # IterationOptions::includePrimaryEmission (merged iterations)
@@ -1258,15 +1261,17 @@ class MonteCarloSimulation:
         if self.dustEmissionWLG is not None:
             mix, eg = self.medium.mix, self.dustEmissionWLG
             lo, hi = eg.wavelength_range()
+            # the CMB source term of the energy balance, EquilibriumDustEmissionCalculator.cpp:37-44 (Constants::Tcmb = 2.725 K)
+            cmb = planck(self.radiationFieldWLG.lambdav, 2.725 * (1.0 + self.cosmologyRedshift)) if self.includeHeatingByCMB else None
             if self.extraMedia:
                 engine.set_secondary_media([k for k, h in enumerate(self.grids) if h is eg][0], self.secondarySpatialBias,
                                            self.dustEmissionWavelengthBias, lo, hi,
                                            [(md.mix.Tv, md.mix.planck_abs, md.mix.rf_sigma_abs, md.mix.em_sigma_abs)
-                                            for md in self.media])
+                                            for md in self.media], rf_cmb=cmb)
             else:
                 engine.set_secondary([k for k, h in enumerate(self.grids) if h is eg][0], self.secondarySpatialBias,
                                      self.dustEmissionWavelengthBias, lo, hi, mix.Tv, mix.planck_abs, mix.rf_sigma_abs,
-                                     mix.em_sigma_abs)
+                                     mix.em_sigma_abs, rf_cmb=cmb)
         mark("secondary")
         # seconds spent per group of engine calls (bench.py reports them under e2e.parts)
         self.last_configure_parts = {marks[k][0]: marks[k][1] - marks[k - 1][1] for k in range(1, len(marks))}

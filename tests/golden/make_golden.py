@@ -429,6 +429,24 @@ def make_cfg16d():
     print("cfg16d:", {k: (np.shape(v) if np.ndim(v) > 1 else v) for k, v in out.items() if "density" not in k and "cell" not in k and "sed" not in k})
 
 
+def make_cfg17c():
+    """Dust heated by the CMB at redshift 6 (tests/golden/ski/cfg17c.ski): SED of the observer-frame instrument, the dust
+    temperatures of the TemperatureProbe, the dust luminosity; the sampled densities as input."""
+    with tempfile.TemporaryDirectory() as d:
+        log = run_reference("cfg17c", d)
+        cells = read_columns(os.path.join(d, "cfg17c_cells_cellprops.dat"))
+        head = open(os.path.join(d, "cfg17c_sed_sed.dat")).readline()
+        out = dict(mass_density_msun_pc3=cells[:, 6], cell_center_pc=cells[:, 1:4], cell_volume_pc3=cells[:, 4],
+                   sed=read_columns(os.path.join(d, "cfg17c_sed_sed.dat")),
+                   sedstats=read_columns(os.path.join(d, "cfg17c_sed_sedstats.dat")),
+                   temperature=read_columns(os.path.join(d, "cfg17c_temp_dust_T.dat"))[:, 1].astype(np.float32),
+                   dust_luminosity_lsun=float(re.search(r"Dust luminosity: ([0-9.eE+-]+) Lsun", log).group(1)),
+                   redshift=6.0, luminosity_distance_mpc=float(re.search(r"luminosity distance ([0-9.eE+-]+) Mpc", head).group(1)),
+                   num_packets=4e5)
+    np.savez_compressed(os.path.join(HERE, "cfg17c_ref.npz"), **out)
+    print("cfg17c:", {k: np.shape(v) for k, v in out.items()}, out["dust_luminosity_lsun"], out["luminosity_distance_mpc"])
+
+
 def make_cfg1_formats():
     """The text headers and FITS cards of the files the reference writes for cfg1 (formats only: 1e4 packets), for the test of
     skirt9_b200/output.py."""

@@ -806,3 +806,74 @@ def test_engine_matches_reference_cfg16d_dynamic_state_iterations(engine_lib):
     e = sim.configure(abi.Engine(sim.config_struct(device=0), lib=engine_lib))
     sim.run(e)
     check_cfg16d(sim, e, g, n)
+
+
+# ---------------------------------------------------------------- dust heated by the CMB at redshift 6 (cfg17c)
+def cfg17c_from_reference(num_packets, cmb=True):
+    """tests/golden/ski/cfg17c.ski through the host mirror: a 3 Lsun point source in a dust shell at z = 6; the CMB (19 K) enters
+    the energy balance of the dust (EquilibriumDustEmissionCalculator.cpp:37-44, 120-131)."""
+    g = load("cfg17c")
+    pc = H.PC
+    mix = H.MeanListDustMix([0.05e-6, 0.55e-6, 10e-6, 100e-6, 2000e-6], [5000.0, 1000.0, 100.0, 5.0, 0.01],
+                            [0.4, 0.6, 0.2, 0.01, 0.0001], [0.6, 0.5, 0.05, 0.0, 0.0])
+    medium = H.GeometricMedium(H.ShellGeometry(0.05 * pc, 1.0 * pc, 1.0), mix, opticalDepth=3.0, wavelength=0.55e-6)
+    grid = H.CartesianSpatialGrid(-pc, pc, -pc, pc, -pc, pc, 16, 16, 16)
+    src = H.PointSource((0.0, 0.0, 0.0), H.BlackBodySED(6000.0), luminosity=3.0 * H.LSUN)
+    instr = H.SEDInstrument(instrumentName="sed", distance=0.0, inclination=60 * DEG, azimuth=30 * DEG, recordComponents=True,
+                            recordStatistics=True, redshift=6.0, luminosityDistance=float(g["luminosity_distance_mpc"]) * 1e6 * pc)
+    sim = H.MonteCarloSimulation(sources=[src], medium=medium, grid=grid, instruments=[instr], numPackets=num_packets,
+                                 minWavelength=0.2e-6, maxWavelength=2e-6,
+                                 defaultWavelengthGrid=H.LogWavelengthGrid(0.5e-6, 20000e-6, 40), storeRadiationField=True,
+                                 radiationFieldWLG=H.LogWavelengthGrid(0.1e-6, 3000e-6, 50),
+                                 dustEmissionWLG=H.LogWavelengthGrid(1e-6, 3000e-6, 50), iterateSecondaryEmission=False,
+                                 includeHeatingByCMB=cmb, cosmologyRedshift=6.0, numDensitySamples=20, seed=0)
+    sim.density = g["mass_density_msun_pc3"] * RHO / mix.MU
+    sim.setup()
+    return sim, g
+
+
+def check_cfg17c(sim, e, g, n, nsigma=4.0):
+    from tests import mcstats
+    assert sim.dust_luminosity / H.LSUN == pytest.approx(float(g["dust_luminosity_lsun"]), rel=0.01)
+    sed, ref, own = g["sed"], g["sedstats"][:, 1:].T, e.read_sed_stats(0)
+    n_own, n_ref = 2.0 * n, 2.0 * float(g["num_packets"])
+    ok = mcstats.reliable(own, launched=n_own) & mcstats.reliable(ref, launched=n_ref)
+    assert ok.sum() >= 15
+    sigma = np.hypot(mcstats.rel_error(own, n_own), mcstats.rel_error(ref, n_ref))
+    for col, comp in ((1, abi.SK_COMP_TOTAL), (2, abi.SK_COMP_TRANSPARENT), (3, abi.SK_COMP_PRIMARY_DIRECT),
+                      (4, abi.SK_COMP_PRIMARY_SCATTERED), (5, abi.SK_COMP_SECONDARY_DIRECT),
+                      (6, abi.SK_COMP_SECONDARY_SCATTERED), (7, abi.SK_COMP_SECONDARY_TRANSPARENT)):
+        f = sim.sed_flux_density(e, 0, comp)
+        scale = np.maximum(sed[:, col], sed[:, 1])
+        z = (np.abs(f - sed[:, col]) / np.maximum(sigma * scale, 1e-300))[ok]
+        assert np.all(z <= (nsigma if col <= 4 else nsigma + 2.0)), (comp, int(np.argmax(z)), float(z.max()))
+    # where the dust emission peaks in the observer frame: set by the dust temperature, hence by the CMB term
+    lam = sim.defaultWavelengthGrid.lambdav
+    peak = lambda f: float(np.exp((np.log(lam) * f).sum() / f.sum()))
+    own_peak, ref_peak = peak(sim.sed_flux_density(e, 0, abi.SK_COMP_SECONDARY_DIRECT)), peak(sed[:, 5])
+    assert own_peak == pytest.approx(ref_peak, rel=0.02)
+    return own_peak
+
+
+def test_oracle_matches_reference_cfg17c_cmb_heating():
+    n = 100000
+    sim, g = cfg17c_from_reference(n)
+    e = sim.configure(OracleEngine(sim.config_struct()))
+    sim.run(e)
+    with_cmb = check_cfg17c(sim, e, g, n, nsigma=5.0)
+    # the same model without the CMB term is colder: its emission peaks at clearly longer wavelengths
+    sim0, _ = cfg17c_from_reference(n, cmb=False)
+    e0 = sim0.configure(OracleEngine(sim0.config_struct()))
+    sim0.run(e0)
+    lam = sim0.defaultWavelengthGrid.lambdav
+    f0 = sim0.sed_flux_density(e0, 0, abi.SK_COMP_SECONDARY_DIRECT)
+    assert float(np.exp((np.log(lam) * f0).sum() / f0.sum())) > 1.5 * with_cmb
+
+
+@pytest.mark.gpu
+def test_engine_matches_reference_cfg17c_cmb_heating(engine_lib):
+    n = 1000000
+    sim, g = cfg17c_from_reference(n)
+    e = sim.configure(abi.Engine(sim.config_struct(device=0), lib=engine_lib))
+    sim.run(e)
+    check_cfg17c(sim, e, g, n)

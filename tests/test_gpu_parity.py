@@ -505,3 +505,12 @@ def test_dynamic_state_iterations_match_oracle(engine_lib):
     assert its_gpu == [it["updated_cells"] for it in sim.primary_iterations] and sum(its_gpu) > 0
     assert np.array_equal(cleared_gpu, sim.density == 0)
     models.compare_engines(sim, gpu, cpu, rtol=1e-8)
+
+
+def test_dust_emission_with_cmb_heating(engine_lib):
+    """DustEmissionOptions::includeHeatingByCMB at redshift 6: the CMB source term in the energy balance of every cell."""
+    sim = models.small_dust_emission(num_packets=20000)
+    sim.sources[0].luminosity = 3.0 * H.LSUN      # faint source: the 19 K background sets most dust temperatures
+    sim.includeHeatingByCMB, sim.cosmologyRedshift = True, 6.0
+    gpu, cpu = run_both(sim, engine_lib)
+    models.compare_engines(sim, gpu, cpu)

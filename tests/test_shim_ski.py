@@ -338,6 +338,30 @@ def test_cfg16d_ski_dynamic_state_iterations_run_unchanged(tmp_path):
         assert sed[:, col].sum() == pytest.approx(g["sed"][:, col].sum(), rel=0.01 if col == 2 else 0.05), col
 
 
+def test_cfg17c_ski_cmb_heating_runs_unchanged(tmp_path):
+    """Dust heated by the CMB at redshift 6, observer-frame instrument: the shim hands the calculator's CMB source term to the
+    engine (sk_secondary_t::rf_cmb); the reference's TemperatureProbe then shows the 19 K floor."""
+    from tests import mcstats
+    g = np.load(os.path.join(GOLD, "cfg17c_ref.npz"))
+    n = 1e6
+    log = run_ski("cfg17c", tmp_path, n)
+    lum = float(re.search(r"Dust luminosity: ([0-9.eE+-]+) Lsun", log).group(1))
+    assert lum == pytest.approx(float(g["dust_luminosity_lsun"]), rel=0.01)
+    sed = read_columns(tmp_path / "cfg17c_sed_sed.dat")
+    own = read_columns(tmp_path / "cfg17c_sed_sedstats.dat")[:, 1:].T
+    ref = g["sedstats"][:, 1:].T
+    ok = mcstats.reliable(own, launched=2 * n) & mcstats.reliable(ref, launched=2 * float(g["num_packets"]))
+    sigma = np.hypot(mcstats.rel_error(own, 2 * n), mcstats.rel_error(ref, 2 * float(g["num_packets"])))
+    for col in range(1, 8):
+        scale = np.maximum(g["sed"][:, col], g["sed"][:, 1])
+        z = (np.abs(sed[:, col] - g["sed"][:, col]) / np.maximum(sigma * scale, 1e-300))[ok]
+        assert np.all(z <= (4.5 if col <= 4 else 6.5)), (col, int(np.argmax(z)), float(z.max()))
+    T = read_columns(tmp_path / "cfg17c_temp_dust_T.dat")[:, 1]
+    filled = g["temperature"] > 0
+    assert np.array_equal(T > 0, filled)
+    assert T[filled].min() > 19.0 and np.median(np.abs(T[filled] / g["temperature"][filled] - 1)) < 0.01
+
+
 def test_cfg5s_ski_voronoi_particles_runs_unchanged(tmp_path):
     """ParticleMedium import + VoronoiMeshSpatialGrid (voro++ tessellation, SPH kernel density sampling) all done by the
     reference's own setup code; only the life cycle runs on the GPU."""
