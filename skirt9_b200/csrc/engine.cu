@@ -274,7 +274,10 @@ struct sk_engine {
     double* scratch = nullptr;
     size_t scratch_len = 0;
     sk_secondary_t sec;
-    std::vector<double> sec_Lv_host;
+    // page-locked staging of the per-cell arrays of sk_engine_prepare_secondary (luminosities down, launch weights and packet
+    // map up: 32 bytes per cell and call), allocated once per cell count
+    double* sec_pin = nullptr;
+    size_t sec_pin_cells = 0;
     unsigned long long rounds_total = 0, launches_total = 0;
     // per-stage timing of the last segment: event pairs around every launch
     std::vector<cudaEvent_t> stage_events;  // pool, grown on demand
@@ -420,6 +423,7 @@ extern "C" void sk_engine_destroy(sk_engine_t* e)
     dev_free(e->model_dev);
     dev_free(e->scratch);
     if (e->pinned) cudaFreeHost(e->pinned);
+    if (e->sec_pin) cudaFreeHost(e->sec_pin);
     if (e->pin_ev[0]) cudaEventDestroy(e->pin_ev[0]);
     if (e->pin_ev[1]) cudaEventDestroy(e->pin_ev[1]);
     dev_free(e->scalar);
@@ -1882,21 +1886,31 @@ extern "C" int sk_engine_prepare_secondary(sk_engine_t* e, uint64_t num_packets,
     else
         sk_dust_luminosity_kernel<3><<<blocks, 128, 0, e->stream>>>(e->M);
     CK(cudaGetLastError());
-    std::vector<double>& Lv = e->sec_Lv_host;
-    Lv.resize(M);
-    CK(cudaMemcpyAsync(Lv.data(), e->M.sec_Lv, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    if (e->sec_pin_cells != (size_t)M)
+    {
+        if (e->sec_pin) cudaFreeHost(e->sec_pin);
+        e->sec_pin = nullptr;
+        e->sec_pin_cells = 0;
+        CK(cudaMallocHost(&e->sec_pin, (3 * (size_t)M + 2) * sizeof(double)));
+        e->sec_pin_cells = (size_t)M;
+    }
+    double* Lv = e->sec_pin;                                                         // [M]
+    double* ws = e->sec_pin + (size_t)M;                                              // [M]
+    unsigned long long* Iv = reinterpret_cast<unsigned long long*>(e->sec_pin + 2 * (size_t)M);  // [M + 1]
+    CK(cudaMemcpyAsync(Lv, e->M.sec_Lv, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     double L = 0.;
     for (int m = 0; m < M; ++m) L += Lv[m];
     *luminosity = L;
     e->secondary_ready = false;
     if (!L) return SK_OK;
-    for (int m = 0; m < M; ++m) Lv[m] /= L;
     double wsum = 0.;
-    for (int m = 0; m < M; ++m) wsum += Lv[m] > 0 ? 1. : 0.;
+    for (int m = 0; m < M; ++m)
+    {
+        Lv[m] /= L;
+        wsum += Lv[m] > 0 ? 1. : 0.;
+    }
     const double xi = e->sec.spatial_bias;
-    std::vector<double> ws(M);
-    std::vector<unsigned long long> Iv((size_t)M + 1);
     Iv[0] = 0;
     double W = 0.;
     for (int m = 0; m < M; ++m)
@@ -1912,10 +1926,9 @@ extern "C" int sk_engine_prepare_secondary(sk_engine_t* e, uint64_t num_packets,
         }
     }
     Iv[M] = num_packets;
-    CK(cudaMemcpyAsync(e->M.sec_Lv, Lv.data(), (size_t)M * sizeof(double), cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemcpyAsync(e->M.sec_ws, ws.data(), (size_t)M * sizeof(double), cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemcpyAsync(e->M.sec_Iv, Iv.data(), ((size_t)M + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice,
-                       e->stream));
+    CK(cudaMemcpyAsync(e->M.sec_Lv, Lv, (size_t)M * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->M.sec_ws, ws, (size_t)M * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->M.sec_Iv, Iv, ((size_t)M + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, e->stream));
     if (e->grid_kind == 1)
         sk_emission_spectrum_kernel<1><<<blocks, 128, 0, e->stream>>>(e->M);
     else if (e->grid_kind == 2)
