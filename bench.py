@@ -627,6 +627,7 @@ def native_arm(args):
         nl = (sim.defaultWavelengthGrid.num_bins if sim.oligoWavelengths is None else len(sim.oligoWavelengths))
         npix = ins.numPixelsX * ins.numPixelsY
         ifu_host = [torch.zeros((nl, npix), dtype=torch.float64).pin_memory().numpy() for _ in comps]
+    rf_host = None
     e2e_parts = {"configure_s": 0.0, "run_s": 0.0, "read_s": 0.0, "destroy_s": 0.0}
     e2e_packets = 0
     t0 = time.perf_counter()
@@ -658,7 +659,9 @@ def native_arm(args):
         if has_ifu:
             outs += [e2.read_ifu(0, c, out=ifu_host[c]) for c in comps]
         if w["store"]:
-            outs.append(e2.read_rf(0))
+            if rf_host is None:   # (allocated in the untimed pass: the caller's table, like MediumSystem::_rf1)
+                rf_host = torch.zeros((e2.num_cells, e2.num_rf), dtype=torch.float64).pin_memory().numpy()
+            outs.append(e2.read_rf(0, out=rf_host))
         d2h = sum(o.nbytes for o in outs)
         td = time.perf_counter()
         e2.close()            # sk_engine_destroy: stream-ordered frees back into the device's memory pool

@@ -483,8 +483,12 @@ class Engine:
         return out.value
 
     # -- outputs --------------------------------------------------------------------------------
-    def read_rf(self, which=0):
-        out = np.empty((self.num_cells, self.num_rf), dtype=np.float64)
+    def read_rf(self, which=0, out=None):
+        """[cell][bin] radiation field table; `out` may be a caller-owned C-contiguous float64 array of that shape (page-locked:
+        the engine then copies straight into it)."""
+        if out is None:
+            out = np.empty((self.num_cells, self.num_rf), dtype=np.float64)
+        assert out.shape == (self.num_cells, self.num_rf) and out.dtype == np.float64 and out.flags["C_CONTIGUOUS"]
         self._call("read_rf", self._h, C.c_int32(which), out.ctypes.data_as(_dp))
         return out
 
