@@ -67,3 +67,37 @@ def test_cfg1_files_have_the_reference_formats(tmp_path):
         cube, c = read_fits_cube("%s_i60_%s.fits" % (prefix, name))
         assert cube.shape == (1, 64, 64) and c["BUNIT"] == "MJy/sr"
         np.testing.assert_allclose(cube, sim.surface_brightness(e, 0, comp).astype(np.float32), rtol=1e-6)
+
+
+def test_multi_wavelength_cube_and_its_table_extension(tmp_path):
+    """A FullInstrument with several wavelength bins, scattering levels and a FrameInstrument without components: one cube per
+    component, the wavelengths in the ASCII table extension, the SED columns of the scattering levels."""
+    from tests import models
+    sim = models.two_sources_three_instruments(num_packets=4000)
+    sim.setup()
+    e = sim.configure(OracleEngine(sim.config_struct()))
+    sim.run(e)
+    prefix = str(tmp_path / "m")
+    paths = [os.path.basename(p) for p in output.write_all(sim, e, prefix)]
+    assert "m_sed_sed.dat" in paths and "m_sed_sedstats.dat" in paths and "m_f1_total.fits" in paths
+    assert "m_f1_transparent.fits" not in paths            # (f1 does not record components)
+    assert "m_f2_primaryscattered.fits" in paths and "m_rf_J.dat" in paths
+    # the aperture SED instrument records two scattering levels: the wavelength, the 7 flux columns, then the two levels
+    head = comments(prefix + "_sed_sed.dat")
+    assert head[0] == "# SED at inclination 30 deg, azimuth 40 deg, distance 1 Mpc"
+    assert head[-2:] == ["# column 9: 1-times scattered primary flux; F_nu (Jy)", "# column 10: 2-times scattered primary flux; F_nu (Jy)"]
+    sed = read_columns(prefix + "_sed_sed.dat")
+    g = sim.defaultWavelengthGrid
+    assert sed.shape == (g.num_bins, 10)
+    np.testing.assert_allclose(sed[:, 0], g.lambdav * 1e6, rtol=1e-9)
+    np.testing.assert_allclose(sed[:, 8], sim.sed_flux_density(e, 0, abi.SK_COMP_PRIMARY_SCATTERED_LEVEL), rtol=1e-9)
+    cube, cards = read_fits_cube(prefix + "_f2_total.fits")
+    assert cube.shape == (g.num_bins, 4, 4) and int(cards["NAXIS3"]) == g.num_bins
+    np.testing.assert_allclose(cube, sim.surface_brightness(e, 2, abi.SK_COMP_TOTAL).astype(np.float32), rtol=1e-6)
+    assert float(cards["CROTA1"]) == 100.0 and float(cards["CROTA3"]) == 15.0
+    # the table extension: one row of 16 characters per wavelength, after the padded cube
+    raw = open(prefix + "_f2_total.fits", "rb").read()
+    pos = 2880 + (g.num_bins * 16 * 4 + 2879) // 2880 * 2880 + 2880
+    rows = [float(raw[pos + 16 * k:pos + 16 * (k + 1)]) for k in range(g.num_bins)]
+    np.testing.assert_allclose(rows, g.lambdav * 1e6, rtol=1e-9)
+    assert len(raw) % 2880 == 0
