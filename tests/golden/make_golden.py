@@ -401,6 +401,26 @@ def make_cfg15k():
     print("cfg15k:", {k: np.shape(v) for k, v in out.items()}, out["dust_luminosity_lsun"])
 
 
+def make_cfg18ke():
+    """cfg15k with a second, rotating dust component of another mix and explicit absorption (tests/golden/ski/cfg18ke.ski); the
+    mass density of each component from the reference's DensityProbe.  4e5 packets (a history is ten scatterings long)."""
+    with tempfile.TemporaryDirectory() as d:
+        log = run_reference("cfg18ke", d, packets=4e5)
+        cells = read_columns(os.path.join(d, "cfg18ke_cells_cellprops.dat"))
+        rho = np.stack([read_columns(os.path.join(d, "cfg18ke_dns_%d_rho.dat" % h))[:, 1] for h in range(2)])
+        rfJ = read_columns(os.path.join(d, "cfg18ke_rf_J.dat"))
+        out = dict(component_mass_density_msun_pc3=rho, cell_center_pc=cells[:, 1:4], cell_volume_pc3=cells[:, 4],
+                   J_nu_shell=shell_average(cells, rfJ[:, 1:], nshell=16),
+                   rf_wavelengths_micron=read_columns(os.path.join(d, "cfg18ke_rf_wavelengths.dat"))[:, 0],
+                   dust_luminosity_lsun=float(re.search(r"Dust luminosity: ([0-9.eE+-]+) Lsun", log).group(1)),
+                   num_packets=4e5)
+        for name in ("fwd", "bwd", "sed"):
+            out["sed_" + name] = read_columns(os.path.join(d, "cfg18ke_%s_sed.dat" % name))
+            out["sedstats_" + name] = read_columns(os.path.join(d, "cfg18ke_%s_sedstats.dat" % name))
+    np.savez_compressed(os.path.join(HERE, "cfg18ke_ref.npz"), **out)
+    print("cfg18ke:", {k: np.shape(v) for k, v in out.items()}, out["dust_luminosity_lsun"])
+
+
 def make_cfg16d():
     """Dynamic medium state: a ClearDensityRecipe carves a cavity around the source in primary emission iterations, merged primary
     and secondary iterations follow, then the regular segments (tests/golden/ski/cfg16d.ski).  The fixture holds the initial

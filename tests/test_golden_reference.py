@@ -674,6 +674,23 @@ def cfg15k_from_reference(num_packets):
 DEG = math.pi / 180.0
 
 
+def cfg18ke_from_reference(num_packets):
+    """tests/golden/ski/cfg18ke.ski: cfg15k with explicit absorption and a second, rotating dust component of another mix; the
+    bulk velocity of a cell is the density-weighted mean of the two components' velocities (MediumSystem.cpp:330-345)."""
+    sim, _ = cfg15k_from_reference(num_packets)
+    g = load("cfg18ke")
+    pc = H.PC
+    mix2 = H.MeanListDustMix([0.05e-6, 0.55e-6, 10e-6, 100e-6, 2000e-6], [2500.0, 1500.0, 300.0, 30.0, 0.1],
+                             [0.7, 0.75, 0.4, 0.05, 0.001], [0.3, 0.2, 0.0, 0.0, 0.0])
+    sim.extraMedia = [H.GeometricMedium(H.ShellGeometry(0.2 * pc, 0.9 * pc, 0.0), mix2, opticalDepth=1.5, wavelength=0.55e-6,
+                                        velocityMagnitude=-5e6, velocityDistribution=H.CylindricalVectorField(0.5 * pc, -0.5))]
+    sim.explicitAbsorption = True
+    sim.density = g["component_mass_density_msun_pc3"] * RHO / sim.medium.mix.MU
+    sim.setup()
+    assert sim.density.shape == (2, 4096) and sim.velocity.shape == (4096, 3)
+    return sim, g
+
+
 def check_cfg15k(sim, e, g, n, nsigma=4.0, min_reliable=0.7):
     from tests import mcstats
     LSUN = H.LSUN
@@ -789,6 +806,23 @@ def check_cfg16d(sim, e, g, n, tol_scale=1.0):
                       (4, abi.SK_COMP_PRIMARY_SCATTERED), (5, abi.SK_COMP_SECONDARY_DIRECT)):
         f = sim.sed_flux_density(e, 0, comp)
         assert f.sum() == pytest.approx(sed[:, col].sum(), rel=(0.01 if col == 2 else 0.05) * tol_scale), comp
+
+
+def test_oracle_matches_reference_cfg18ke_kinematics_two_mixes_explicit_absorption():
+    n = 60000
+    sim, g = cfg18ke_from_reference(n)
+    e = sim.configure(OracleEngine(sim.config_struct()))
+    sim.run(e)
+    check_cfg15k(sim, e, g, n, nsigma=5.0, min_reliable=0.2)
+
+
+@pytest.mark.gpu
+def test_engine_matches_reference_cfg18ke_kinematics_two_mixes_explicit_absorption(engine_lib):
+    n = 1000000
+    sim, g = cfg18ke_from_reference(n)
+    e = sim.configure(abi.Engine(sim.config_struct(device=0), lib=engine_lib))
+    sim.run(e)
+    check_cfg15k(sim, e, g, n, nsigma=4.5)
 
 
 def test_oracle_matches_reference_cfg16d_dynamic_state_iterations():
