@@ -278,21 +278,22 @@ def test_cfg4s_ski_dust_emission_runs_unchanged(tmp_path):
     assert np.array_equal(T > 0, g["temperature"] > 0) or np.mean((T > 0) != ok) < 0.01
 
 
-def test_cfg15k_ski_kinematics_runs_unchanged(tmp_path):
+@pytest.mark.parametrize("name, n", [("cfg15k", 2e6), ("cfg18ke", 1e6)])
+def test_cfg15k_ski_kinematics_runs_unchanged(tmp_path, name, n):
     """Moving source, expanding dust shell, dust emission: the ski of the cfg15k fixture through the drop-in.  The reference's
     set-up samples densities and bulk velocities; the shim hands MediumState::bulkVelocity(m) and the source's velocity to the
-    engine.  The two fine-grid SED instruments on opposite lines of sight resolve the Doppler shifts."""
+    engine.  The two fine-grid SED instruments on opposite lines of sight resolve the Doppler shifts.  cfg18ke: the same with a
+    second, rotating component of another mix and explicit absorption."""
     from tests import mcstats
-    g = np.load(os.path.join(GOLD, "cfg15k_ref.npz"))
-    n = 2e6
-    log = run_ski("cfg15k", tmp_path, n)
+    g = np.load(os.path.join(GOLD, name + "_ref.npz"))
+    log = run_ski(name, tmp_path, n)
     assert "Including support for kinematics" in log
     lum = float(re.search(r"Dust luminosity: ([0-9.eE+-]+) Lsun", log).group(1))
     assert lum == pytest.approx(float(g["dust_luminosity_lsun"]), rel=0.005)
-    for name in ("fwd", "bwd", "sed"):
-        sed = read_columns(tmp_path / ("cfg15k_%s_sed.dat" % name))
-        own = read_columns(tmp_path / ("cfg15k_%s_sedstats.dat" % name))[:, 1:].T
-        ref_sed, ref = g["sed_" + name], g["sedstats_" + name][:, 1:].T
+    for ins in ("fwd", "bwd", "sed"):
+        sed = read_columns(tmp_path / ("%s_%s_sed.dat" % (name, ins)))
+        own = read_columns(tmp_path / ("%s_%s_sedstats.dat" % (name, ins)))[:, 1:].T
+        ref_sed, ref = g["sed_" + ins], g["sedstats_" + ins][:, 1:].T
         # (N of FluxRecorder.hpp:50-63: the packets launched in the two peel-off segments)
         ok = mcstats.reliable(own, launched=2 * n) & mcstats.reliable(ref, launched=2 * float(g["num_packets"]))
         assert ok.sum() >= 0.7 * len(ok)
@@ -300,10 +301,10 @@ def test_cfg15k_ski_kinematics_runs_unchanged(tmp_path):
         for col in range(1, 8):
             scale = np.maximum(ref_sed[:, col], ref_sed[:, 1])
             z = (np.abs(sed[:, col] - ref_sed[:, col]) / np.maximum(sigma * scale, 1e-300))[ok]
-            assert np.all(z <= (4.5 if col <= 4 else 6.5)), (name, col, int(np.argmax(z)), float(z.max()))
+            assert np.all(z <= (4.5 if col <= 4 else 6.5)), (ins, col, int(np.argmax(z)), float(z.max()))
     # the shifted feature: 0.5-0.51 micron at rest, the source moves at 0.02 c along the line of sight of "fwd"
-    for name, factor in (("fwd", 1 - 0.02001), ("bwd", 1 + 0.02001)):
-        sed = read_columns(tmp_path / ("cfg15k_%s_sed.dat" % name))
+    for ins, factor in (("fwd", 1 - 0.02001), ("bwd", 1 + 0.02001)):
+        sed = read_columns(tmp_path / ("%s_%s_sed.dat" % (name, ins)))
         f = np.where(sed[:, 2] > 0.5 * sed[:, 2].max(), sed[:, 2] / sed[:, 0] ** 2, 0.0)   # F_nu -> F_lambda
         assert float((f * sed[:, 0]).sum() / f.sum()) == pytest.approx(0.505 * factor, rel=3e-3)
 
