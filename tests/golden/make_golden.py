@@ -421,6 +421,23 @@ def make_cfg18ke():
     print("cfg18ke:", {k: np.shape(v) for k, v in out.items()}, out["dust_luminosity_lsun"])
 
 
+def make_cfg18ke_velocity():
+    """The per-cell bulk velocities the reference's set-up stores for cfg18ke (VelocityProbe, per-cell form): two moving components,
+    aggregated by number density (MediumSystem.cpp:330-345).  Pins the host mirror's vector fields and aggregation."""
+    with tempfile.TemporaryDirectory() as d:
+        text = open(os.path.join(HERE, "ski", "cfg18ke.ski")).read()
+        text = text.replace('<SpatialCellPropertiesProbe probeName="cells" wavelength="0.55 micron"/>',
+                            '<SpatialCellPropertiesProbe probeName="cells" wavelength="0.55 micron"/>'
+                            '<VelocityProbe probeName="vel"><form type="Form"><PerCellForm/></form></VelocityProbe>')
+        text = re.sub(r'numPackets="[^"]*"', 'numPackets="100"', text, count=1)
+        ski = os.path.join(d, "v.ski")
+        open(ski, "w").write(text)
+        subprocess.check_call([SKIRT, "-t", "1", "-b", "-o", d, ski], stdout=subprocess.DEVNULL)
+        v = read_columns(os.path.join(d, "v_vel_v.dat"))[:, 1:]
+    np.savez_compressed(os.path.join(HERE, "cfg18ke_velocity_ref.npz"), velocity_km_s=v)
+    print("cfg18ke_velocity:", v.shape, np.abs(v).max())
+
+
 def make_cfg16d():
     """Dynamic medium state: a ClearDensityRecipe carves a cavity around the source in primary emission iterations, merged primary
     and secondary iterations follow, then the regular segments (tests/golden/ski/cfg16d.ski).  The fixture holds the initial

@@ -911,3 +911,13 @@ def test_engine_matches_reference_cfg17c_cmb_heating(engine_lib):
     e = sim.configure(abi.Engine(sim.config_struct(device=0), lib=engine_lib))
     sim.run(e)
     check_cfg17c(sim, e, g, n)
+
+
+def test_host_mirror_bulk_velocities_match_reference_cfg18ke():
+    """MediumState::bulkVelocity per cell as the reference's VelocityProbe writes it for cfg18ke (radial and cylindrical vector
+    fields with power-law magnitudes, two components aggregated by number density) against the host mirror's table, which is
+    what the oracle and the engine are handed."""
+    sim, _ = cfg18ke_from_reference(1000)
+    v = load("cfg18ke_velocity")["velocity_km_s"] * 1e3
+    assert np.abs(v).max() > 5e6
+    np.testing.assert_allclose(sim.velocity, v, rtol=1e-8, atol=1e-8 * np.abs(v).max())
