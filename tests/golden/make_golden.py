@@ -438,6 +438,24 @@ def make_cfg18ke_velocity():
     print("cfg18ke_velocity:", v.shape, np.abs(v).max())
 
 
+def make_cfg19ks():
+    """A rotating ring source (GeometricSource with a CylindricalVectorField velocity) in dust at rest: tests/golden/ski/cfg19ks.ski."""
+    with tempfile.TemporaryDirectory() as d:
+        log = run_reference("cfg19ks", d)
+        cells = read_columns(os.path.join(d, "cfg19ks_cells_cellprops.dat"))
+        rfJ = read_columns(os.path.join(d, "cfg19ks_rf_J.dat"))
+        out = dict(mass_density_msun_pc3=cells[:, 6], cell_center_pc=cells[:, 1:4], cell_volume_pc3=cells[:, 4],
+                   J_nu_shell=shell_average(cells, rfJ[:, 1:], nshell=16),
+                   rf_wavelengths_micron=read_columns(os.path.join(d, "cfg19ks_rf_wavelengths.dat"))[:, 0],
+                   dust_luminosity_lsun=float(re.search(r"Dust luminosity: ([0-9.eE+-]+) Lsun", log).group(1)),
+                   num_packets=1e6)
+        for name in ("fwd", "bwd", "sed"):
+            out["sed_" + name] = read_columns(os.path.join(d, "cfg19ks_%s_sed.dat" % name))
+            out["sedstats_" + name] = read_columns(os.path.join(d, "cfg19ks_%s_sedstats.dat" % name))
+    np.savez_compressed(os.path.join(HERE, "cfg19ks_ref.npz"), **out)
+    print("cfg19ks:", {k: np.shape(v) for k, v in out.items()}, out["dust_luminosity_lsun"])
+
+
 def make_cfg16d():
     """Dynamic medium state: a ClearDensityRecipe carves a cavity around the source in primary emission iterations, merged primary
     and secondary iterations follow, then the regular segments (tests/golden/ski/cfg16d.ski).  The fixture holds the initial

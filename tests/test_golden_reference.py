@@ -691,7 +691,23 @@ def cfg18ke_from_reference(num_packets):
     return sim, g
 
 
-def check_cfg15k(sim, e, g, n, nsigma=4.0, min_reliable=0.7):
+def cfg19ks_from_reference(num_packets):
+    """tests/golden/ski/cfg19ks.ski: cfg15k's emission feature from a ring source that rotates at 6000 km/s (a GeometricSource with
+    a CylindricalVectorField velocity), the dust at rest -- Configuration::hasMovingSources only, so path-length stretching stays."""
+    sim, _ = cfg15k_from_reference(num_packets)
+    g = load("cfg19ks")
+    pc = H.PC
+    old = sim.sources[0]
+    sim.sources = [H.GeometricSource(H.RingGeometry(0.5 * pc, 0.05 * pc, 0.02 * pc), old.sed, luminosity=old.luminosity,
+                                     velocityMagnitude=6e6, velocityDistribution=H.CylindricalVectorField())]
+    sim.medium.velocityMagnitude, sim.medium.velocityDistribution = 0.0, None
+    sim.density = g["mass_density_msun_pc3"] * RHO / sim.medium.mix.MU
+    sim.setup()
+    assert sim.velocity is None and sim.hasMovingSources and sim.config_struct().path_length_bias == 0.5
+    return sim, g
+
+
+def check_cfg15k(sim, e, g, n, nsigma=4.0, min_reliable=0.7, shifts=(-6e6 / H.C_LIGHT, 6e6 / H.C_LIGHT), rf_rms=False):
     from tests import mcstats
     LSUN = H.LSUN
     assert sim.dust_luminosity / LSUN == pytest.approx(float(g["dust_luminosity_lsun"]), rel=0.01)
@@ -717,7 +733,7 @@ def check_cfg15k(sim, e, g, n, nsigma=4.0, min_reliable=0.7):
     # the Doppler shifts themselves: the direct light of the feature (0.5-0.51 micron at rest) arrives blue-shifted by 2 % on
     # the line of sight the source approaches and red-shifted on the opposite one
     lam = sim.instruments[0].wavelengthGrid.lambdav
-    for j, factor in ((0, 1.0 - 6e6 / H.C_LIGHT), (1, 1.0 + 6e6 / H.C_LIGHT)):
+    for j, factor in ((0, 1.0 + shifts[0]), (1, 1.0 + shifts[1])):
         d = e.read_sed(j, abi.SK_COMP_TRANSPARENT)
         d = np.where(d > 0.5 * d.max(), d, 0.0)   # (the bins of the feature, without the continuum under it)
         centre = float((d * lam).sum() / d.sum())
@@ -732,8 +748,15 @@ def check_cfg15k(sim, e, g, n, nsigma=4.0, min_reliable=0.7):
     ref = g["J_nu_shell"]
     ok = ref > 0.02 * ref.max()
     ok[:2] = False
-    tol = 0.05 * math.hypot(1.0, math.sqrt(float(g["num_packets"]) / n))
-    np.testing.assert_allclose(Jshell[ok], ref[ok], rtol=tol)
+    scale = math.hypot(1.0, math.sqrt(float(g["num_packets"]) / n))
+    if rf_rms:
+        # (a ring source: the shells around its radius hold a few strongly lit cells and the values per shell and fine bin are
+        #  noisy on both sides -- 3 % rms in the reference's 1e6-packet run, measured against the oracle at 1e5 and 1e6 packets,
+        #  falling with 1/sqrt(packets) and unbiased; held to that as a whole)
+        rel = Jshell[ok] / ref[ok] - 1.0
+        assert math.sqrt(float(np.mean(rel ** 2))) <= 0.07 * scale and abs(float(rel.mean())) <= 0.01 * scale
+    else:
+        np.testing.assert_allclose(Jshell[ok], ref[ok], rtol=0.05 * scale)
     return worst
 
 
@@ -823,6 +846,28 @@ def test_engine_matches_reference_cfg18ke_kinematics_two_mixes_explicit_absorpti
     e = sim.configure(abi.Engine(sim.config_struct(device=0), lib=engine_lib))
     sim.run(e)
     check_cfg15k(sim, e, g, n, nsigma=4.5)
+
+
+def test_oracle_matches_reference_cfg19ks_rotating_ring_source():
+    n = 100000
+    sim, g = cfg19ks_from_reference(n)
+    e = sim.configure(OracleEngine(sim.config_struct()))
+    sim.run(e)
+    check_cfg15k(sim, e, g, n, nsigma=5.0, min_reliable=0.25, shifts=(0.0, 0.0), rf_rms=True)
+    # the rotation profile: the feature is spread over +- 2 % with horns at the ends, not a 2 % wide line
+    lam = sim.instruments[0].wavelengthGrid.lambdav
+    d = e.read_sed(0, abi.SK_COMP_TRANSPARENT)
+    strong = lam[d > 0.5 * d.max()]
+    assert strong.min() < 0.497e-6 and strong.max() > 0.514e-6
+
+
+@pytest.mark.gpu
+def test_engine_matches_reference_cfg19ks_rotating_ring_source(engine_lib):
+    n = 2000000
+    sim, g = cfg19ks_from_reference(n)
+    e = sim.configure(abi.Engine(sim.config_struct(device=0), lib=engine_lib))
+    sim.run(e)
+    check_cfg15k(sim, e, g, n, nsigma=4.5, shifts=(0.0, 0.0), rf_rms=True)
 
 
 def test_oracle_matches_reference_cfg16d_dynamic_state_iterations():
