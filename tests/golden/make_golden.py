@@ -456,6 +456,22 @@ def make_cfg19ks():
     print("cfg19ks:", {k: np.shape(v) for k, v in out.items()}, out["dust_luminosity_lsun"])
 
 
+def make_cfg20kn():
+    """cfg2s with a rotating disk (source and dust ring at 9000 km/s), a narrow emission feature and NON-forced scattering: same
+    seed and set-up as cfg2s, hence its tree and densities.  2e5 packets (the reference spends 1e-3 s per history on this path)."""
+    with tempfile.TemporaryDirectory() as d:
+        run_reference("cfg20kn", d, packets=2e5)
+        cells = read_columns(os.path.join(d, "cfg20kn_cells_cellprops.dat"))
+        base = np.load(os.path.join(HERE, "cfg2s_ref.npz"))["mass_density_msun_pc3"]
+        assert np.array_equal(cells[:, 6], base), "cfg20kn must see the tree and the densities of cfg2s"
+        out = dict(num_packets=2e5)
+        for name in ("edge", "i60"):
+            out["sed_" + name] = read_columns(os.path.join(d, "cfg20kn_%s_sed.dat" % name))
+            out["sedstats_" + name] = read_columns(os.path.join(d, "cfg20kn_%s_sedstats.dat" % name))
+    np.savez_compressed(os.path.join(HERE, "cfg20kn_ref.npz"), **out)
+    print("cfg20kn:", {k: np.shape(v) for k, v in out.items()})
+
+
 def make_cfg16d():
     """Dynamic medium state: a ClearDensityRecipe carves a cavity around the source in primary emission iterations, merged primary
     and secondary iterations follow, then the regular segments (tests/golden/ski/cfg16d.ski).  The fixture holds the initial

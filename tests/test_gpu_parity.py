@@ -514,3 +514,13 @@ def test_dust_emission_with_cmb_heating(engine_lib):
     sim.includeHeatingByCMB, sim.cosmologyRedshift = True, 6.0
     gpu, cpu = run_both(sim, engine_lib)
     models.compare_engines(sim, gpu, cpu)
+
+
+def test_kinematics_octree_nonforced(engine_lib):
+    """Moving source and medium on the octree without forced scattering: the walk to the interaction point with per-cell
+    look-ups (MediumSystem.cpp:1042-1070)."""
+    sim = models.with_kinematics(models.small_octree(num_packets=30000, record_statistics=True))
+    sim.forceScattering = False
+    gpu, cpu = run_both(sim, engine_lib)
+    models.compare_engines(sim, gpu, cpu)
+    assert gpu.counters()["scatterings"] > 0

@@ -311,6 +311,27 @@ def test_cfg15k_ski_kinematics_runs_unchanged(tmp_path, name, n):
         assert float((f * sed[:, 0]).sum() / f.sum()) == pytest.approx(0.505 * factor, rel=3e-3)
 
 
+def test_cfg20kn_ski_kinematics_octree_nonforced_runs_unchanged(tmp_path):
+    """A rotating disk (source velocity field, moving dust ring) on the octree without forced scattering: the ski of the cfg20kn
+    fixture through the drop-in, with the reference's own (CPU, -t 1) tree so that grid and densities are the fixture's."""
+    from tests import mcstats
+    g = np.load(os.path.join(GOLD, "cfg20kn_ref.npz"))
+    n = 4e6
+    log = run_ski("cfg20kn", tmp_path, n)
+    assert "Including support for kinematics" in log and "no forced scattering" in log
+    for ins in ("edge", "i60"):
+        sed = read_columns(tmp_path / ("cfg20kn_%s_sed.dat" % ins))
+        own = read_columns(tmp_path / ("cfg20kn_%s_sedstats.dat" % ins))[:, 1:].T
+        ref_sed, ref = g["sed_" + ins], g["sedstats_" + ins][:, 1:].T
+        ok = mcstats.reliable(own, launched=n) & mcstats.reliable(ref, launched=float(g["num_packets"]))
+        assert ok.sum() >= 4
+        sigma = np.hypot(mcstats.rel_error(own, n), mcstats.rel_error(ref, float(g["num_packets"])))
+        for col in range(1, 5):
+            scale = np.maximum(ref_sed[:, col], ref_sed[:, 1])
+            z = (np.abs(sed[:, col] - ref_sed[:, col]) / np.maximum(sigma * scale, 1e-300))[ok]
+            assert np.all(z <= 4.5), (ins, col, int(np.argmax(z)), float(z.max()))
+
+
 def test_cfg16d_ski_dynamic_state_iterations_run_unchanged(tmp_path):
     """Primary emission iterations and merged iterations with a ClearDensityRecipe (the call sites MonteCarloSimulation.cpp:314,
     451, 474): the segments run on the engine, the reference's own recipe code updates the medium state on the host from the
