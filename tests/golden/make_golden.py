@@ -392,6 +392,8 @@ def make_cfg15k():
         out = dict(mass_density_msun_pc3=cells[:, 6], cell_center_pc=cells[:, 1:4], cell_volume_pc3=cells[:, 4],
                    J_nu_shell=shell_average(cells, rfJ[:, 1:], nshell=16),
                    rf_wavelengths_micron=read_columns(os.path.join(d, "cfg15k_rf_wavelengths.dat"))[:, 0],
+                   # characteristic wavelength, effective width, left and right border of every bin of the ListWavelengthGrid
+                   rf_grid_micron=read_columns(os.path.join(d, "cfg15k_rf_wavelengths.dat")),
                    dust_luminosity_lsun=float(re.search(r"Dust luminosity: ([0-9.eE+-]+) Lsun", log).group(1)),
                    num_packets=1e6)
         for name in ("fwd", "bwd", "sed"):

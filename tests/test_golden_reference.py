@@ -1027,3 +1027,16 @@ def test_engine_matches_reference_cfg20kn_kinematics_octree_nonforced(engine_lib
     e = sim.configure(abi.Engine(sim.config_struct(device=0), lib=engine_lib))
     sim.run(e)
     check_cfg20kn(sim, e, g, n, nsigma=4.5)
+
+
+def test_host_mirror_list_wavelength_grid_matches_reference_cfg15k():
+    """The bins of the ListWavelengthGrid of cfg15k (36 fine + 19 coarse characteristic wavelengths, logarithmic borders) as the
+    reference's RadiationFieldProbe lists them (characteristic wavelength, effective width, left and right border) against the
+    host mirror's grid, whose borders the oracle and the engine bin the radiation field with."""
+    sim, g = cfg15k_from_reference(1000)
+    ref = g["rf_grid_micron"] * 1e-6
+    grid = sim.radiationFieldWLG
+    np.testing.assert_allclose(grid.lambdav, ref[:, 0], rtol=1e-9)
+    np.testing.assert_allclose(grid.dlambdav, ref[:, 1], rtol=1e-8)
+    np.testing.assert_allclose(grid.borderv[:-1], ref[:, 2], rtol=1e-9)
+    np.testing.assert_allclose(grid.borderv[1:], ref[:, 3], rtol=1e-9)
