@@ -474,6 +474,26 @@ def make_cfg20kn():
     print("cfg20kn:", {k: np.shape(v) for k, v in out.items()})
 
 
+def make_cfg15k_opticalprops():
+    """Cross sections and asymmetry parameter of cfg15k's MeanListDustMix at 400 wavelengths as the reference's
+    OpticalMaterialPropertiesProbe writes them (the probe's wavelengths join the grid of the dust property tables, so the values
+    are the mix's own interpolation at exactly those wavelengths).  Pins the host mirror's MeanListDustMix."""
+    with tempfile.TemporaryDirectory() as d:
+        text = open(os.path.join(HERE, "ski", "cfg15k.ski")).read()
+        text = text.replace('<SpatialCellPropertiesProbe probeName="cells" wavelength="0.55 micron"/>',
+                            '<SpatialCellPropertiesProbe probeName="cells" wavelength="0.55 micron"/>'
+                            '<OpticalMaterialPropertiesProbe probeName="opt"><wavelengthGrid type="WavelengthGrid">'
+                            '<LogWavelengthGrid minWavelength="0.16 micron" maxWavelength="900 micron" numWavelengths="400"/>'
+                            '</wavelengthGrid></OpticalMaterialPropertiesProbe>')
+        text = re.sub(r'numPackets="[^"]*"', 'numPackets="100"', text, count=1)
+        ski = os.path.join(d, "o.ski")
+        open(ski, "w").write(text)
+        subprocess.check_call([SKIRT, "-t", "1", "-b", "-o", d, ski], stdout=subprocess.DEVNULL)
+        t = read_columns(os.path.join(d, "o_opt_opticalprops_0.dat"))
+    np.savez_compressed(os.path.join(HERE, "cfg15k_opticalprops_ref.npz"), table=t)
+    print("cfg15k_opticalprops:", t.shape)
+
+
 def make_cfg16d():
     """Dynamic medium state: a ClearDensityRecipe carves a cavity around the source in primary emission iterations, merged primary
     and secondary iterations follow, then the regular segments (tests/golden/ski/cfg16d.ski).  The fixture holds the initial

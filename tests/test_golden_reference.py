@@ -1040,3 +1040,21 @@ def test_host_mirror_list_wavelength_grid_matches_reference_cfg15k():
     np.testing.assert_allclose(grid.dlambdav, ref[:, 1], rtol=1e-8)
     np.testing.assert_allclose(grid.borderv[:-1], ref[:, 2], rtol=1e-9)
     np.testing.assert_allclose(grid.borderv[1:], ref[:, 3], rtol=1e-9)
+
+
+def test_host_mirror_dust_mix_matches_reference_optical_properties():
+    """MeanListDustMix through the host mirror against the reference's OpticalMaterialPropertiesProbe for cfg15k's mix: extinction,
+    absorption and scattering cross sections per hydrogen atom and the asymmetry parameter at 400 wavelengths from 0.16 to 900
+    micron (log-log interpolation of the five tabulated points, clamped outside; the dust mass per hydrogen atom)."""
+    t = load("cfg15k_opticalprops")["table"]
+    lam = t[:, 0] * 1e-6
+    mix = H.MeanListDustMix([0.05e-6, 0.55e-6, 10e-6, 100e-6, 2000e-6], [5000.0, 1000.0, 100.0, 5.0, 0.01],
+                            [0.4, 0.6, 0.2, 0.01, 0.0001], [0.6, 0.5, 0.05, 0.0, 0.0])
+    mix.setup((0.1e-6, 2000e-6), list(lam))     # (the probe's wavelengths join the property grid, as in the reference's run)
+    i = np.array([mix.index_for_lambda(x) for x in lam])
+    np.testing.assert_allclose(mix.lambdav[i], lam, rtol=1e-14)
+    np.testing.assert_allclose((mix.sigma_abs + mix.sigma_sca)[i], t[:, 1], rtol=1e-8)
+    np.testing.assert_allclose(mix.sigma_abs[i], t[:, 2], rtol=1e-8)
+    np.testing.assert_allclose(mix.sigma_sca[i], t[:, 3], rtol=1e-8)
+    np.testing.assert_allclose(mix.sigma_abs[i] / mix.mu, t[:, 5], rtol=1e-8)
+    np.testing.assert_allclose(mix.asymmpar[i], t[:, 8], rtol=0, atol=1e-9)
