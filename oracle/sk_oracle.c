@@ -7,7 +7,7 @@
  *
  * Parity pinning: the reference has no golden vectors or tests for this path.  The
  * oracle is pinned instead against outputs of the unmodified reference compiled here into
- * oracle/_ref (see oracle/Makefile, tests/golden/make_golden.py, tests/test_oracle_vs_reference.py):
+ * oracle/_ref (see oracle/ref.mk, tests/golden/make_golden.py, tests/test_golden_reference.py):
  * agreement is statistical (the reference draws from per-thread MT19937-64, this file and the CUDA
  * engine draw from Philox4x32-10 keyed by history index), within the Monte-Carlo error the reference
  * itself reports through recordStatistics.  Against the CUDA engine the agreement is deterministic
